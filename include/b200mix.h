@@ -1,0 +1,189 @@
+/* b200mix.h — C ABI of the Blackwell (sm_100a) mixer backend for OpenAL Soft.
+ *
+ * This is the drop-in boundary: one level above the reference's per-kernel
+ * function pointers, it replaces the body of DeviceBase::renderSamples(unsigned)
+ * between "parameters updated" and "RealOut ready" —
+ *   the voice loop      alc/alu.cpp:2201-2206  (Voice::mix, core/voice.cpp:988-1233)
+ *   the slot loop       alc/alu.cpp:2252-2256  (EffectState::process)
+ *   the post-process    alc/alu.cpp:2439-2443  (DeviceBase::Process, alc/alu.cpp:284-312)
+ * The host keeps ProcessParamUpdates (alc/alu.cpp:2153), clocks, events and
+ * Write<T>.  Everything here is plain C: pointers and sizes, no C++/torch types.
+ * All float data is IEEE fp32.  All functions return B200MIX_OK (0) or a
+ * negative error; b200mix_last_error() gives the text.  A failing render is
+ * what the host turns into DeviceBase::handleDisconnect (alc/alu.cpp:2521).
+ *
+ * Threading follows the reference: create/destroy/buffer_* from API threads
+ * (serialised by the host's BufferLock), everything else from the single mixer
+ * thread of the device.  No entry point is re-entrant per device.
+ */
+#ifndef B200MIX_H
+#define B200MIX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200MIX_API __declspec(dllexport)
+#else
+#define B200MIX_API __attribute__((visibility("default")))
+#endif
+
+/* ---- constants mirrored from the reference ------------------------------ */
+#define B200MIX_LINE_SIZE        1024u /* BufferLineSize          core/bufferline.h:11 */
+#define B200MIX_HRIR_LENGTH       128u /* HrirLength              core/mixer/hrtfdefs.h:19 */
+#define B200MIX_HRTF_HISTORY       64u /* HrtfHistoryLength       core/mixer/hrtfdefs.h:15 */
+#define B200MIX_MAX_SENDS           6u /* MaxSendCount            core/voice.h:31 */
+#define B200MIX_MAX_DRY_CHANNELS   32u /* MaxOutputChannels       core/devformat.h:81 */
+#define B200MIX_MAX_WET_CHANNELS   25u /* MaxAmbiChannels         core/ambidefs.h:19 */
+#define B200MIX_RESAMPLER_PADDING  48u /* MaxResamplerPadding     core/resampler_limits.h:8 */
+#define B200MIX_NO_SLOT   0xffffffffu
+
+enum { B200MIX_OK = 0, B200MIX_ERR_INVALID = -1, B200MIX_ERR_CUDA = -2,
+       B200MIX_ERR_NOMEM = -3, B200MIX_ERR_UNSUPPORTED = -4 };
+
+/* enum class Resampler, core/mixer/defs.h:31-44 (same order and values). */
+enum b200mix_resampler {
+    B200MIX_RESAMPLER_POINT = 0, B200MIX_RESAMPLER_LINEAR, B200MIX_RESAMPLER_SPLINE,
+    B200MIX_RESAMPLER_GAUSSIAN, B200MIX_RESAMPLER_FAST_BSINC12, B200MIX_RESAMPLER_BSINC12,
+    B200MIX_RESAMPLER_FAST_BSINC24, B200MIX_RESAMPLER_BSINC24, B200MIX_RESAMPLER_FAST_BSINC48,
+    B200MIX_RESAMPLER_BSINC48
+};
+
+/* enum FmtType, core/storage_formats.h (PCM subset; IMA4/MSADPCM are §8f-next). */
+enum b200mix_sample_type {
+    B200MIX_FMT_U8 = 0, B200MIX_FMT_I16, B200MIX_FMT_I32, B200MIX_FMT_F32, B200MIX_FMT_F64,
+    B200MIX_FMT_MULAW, B200MIX_FMT_ALAW
+};
+
+/* PostProcess variant of DeviceBase (core/device.h:200-222). */
+enum b200mix_post_process {
+    B200MIX_POST_NONE = 0,   /* RealOut aliases Dry (e.g. ALC_BFORMAT3D_SOFT output) */
+    B200MIX_POST_AMBIDEC,    /* BFormatDec::process        core/bformatdec.cpp:60-97 */
+    B200MIX_POST_HRTF,       /* MixDirectHrtf              core/mixer/hrtfbase.h:91-133 */
+    B200MIX_POST_UHJ         /* UhjEncoderIIR::encode      core/uhjfilter.cpp:231-283 */
+};
+
+typedef struct b200mix_device b200mix_device;
+
+/* What aluInitRenderer / UpdateDeviceParams decided (alc/panning.cpp:1220-1438). */
+typedef struct b200mix_device_desc {
+    uint32_t struct_size;     /* sizeof(b200mix_device_desc) */
+    int32_t  cuda_device;     /* ordinal; -1 = current */
+    uint32_t sample_rate;     /* DeviceBase::mSampleRate */
+    uint32_t dry_channels;    /* Dry.Buffer.size()  (C_d) */
+    uint32_t real_channels;   /* RealOut.Buffer.size() */
+    uint32_t wet_channels;    /* per-slot Wet.Buffer.size() (C_w); 0 = no sends */
+    uint32_t num_sends;       /* DeviceBase::NumAuxSends */
+    uint32_t ir_size;         /* DeviceBase::mIrSize (0 when no HRTF) */
+    uint32_t post_process;    /* enum b200mix_post_process */
+    uint32_t real_left;       /* RealOut.ChannelIndex[FrontLeft]  (HRTF/UHJ output) */
+    uint32_t real_right;      /* RealOut.ChannelIndex[FrontRight] */
+    uint32_t max_voices;      /* capacity of the voice array */
+    uint32_t max_buffers;     /* capacity of the buffer table */
+    uint32_t max_slots;       /* capacity of the aux-slot table */
+} b200mix_device_desc;
+
+B200MIX_API int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out);
+B200MIX_API void b200mix_destroy(b200mix_device *dev);
+/* Text of the last error on this device (or the last create failure if dev==NULL). */
+B200MIX_API const char *b200mix_last_error(const b200mix_device *dev);
+/* Library/ABI version: (major<<16)|minor. */
+B200MIX_API uint32_t b200mix_version(void);
+
+/* ---- post-process constant data ----------------------------------------- */
+/* DirectHrtfState (core/hrtf.h:84-110): per dry channel the pre-summed
+ * virtual-speaker HRIR, the HF scale and the band-splitter coefficient.
+ * ir_size is DirectHrtfState::mIrSize (may exceed the per-voice ir_size, <=128);
+ * coeffs is [channels][ir_size][2]. */
+B200MIX_API int b200mix_set_hrtf_decoder(b200mix_device *dev, uint32_t channels,
+    uint32_t ir_size, const float *coeffs, const float *hf_scale, const float *splitter_coeff);
+/* BFormatDec (core/bformatdec.h): gains_hf/gains_lf are [in_channels][real_channels];
+ * gains_lf==NULL selects the single-band decoder; xover_coeff is the splitter's mCoeff. */
+B200MIX_API int b200mix_set_ambi_decoder(b200mix_device *dev, uint32_t in_channels,
+    const float *gains_hf, const float *gains_lf, float xover_coeff);
+
+/* ---- buffers: BufferStorage (core/buffer_storage.h:52-75) ---------------- */
+/* Uploads an immutable copy (AL semantics: a buffer cannot change while attached). */
+B200MIX_API int b200mix_buffer_data(b200mix_device *dev, uint32_t buffer, uint32_t sample_type,
+    uint32_t channels, uint32_t frames, const void *data, size_t bytes);
+B200MIX_API int b200mix_buffer_free(b200mix_device *dev, uint32_t buffer);
+
+/* ---- voices: the post-ALU snapshot of Voice (core/voice.h:157-272) ------- */
+enum {
+    B200MIX_VF_PLAYING   = 1u<<0, /* Voice::Playing */
+    B200MIX_VF_STOPPING  = 1u<<1, /* Voice::Stopping: fade to silence this update, then stop */
+    B200MIX_VF_STATIC    = 1u<<2, /* VoiceFlag::IsStatic */
+    B200MIX_VF_LOOPING   = 1u<<3, /* mLoopBuffer != nullptr */
+    B200MIX_VF_HRTF      = 1u<<4, /* VoiceFlag::HasHrtf: direct path is the per-voice HRIR */
+    B200MIX_VF_RESET     = 1u<<5, /* fresh voice (Voice::prepare): zero histories, take position,
+                                     clear IsFading */
+    B200MIX_VF_FADING    = 1u<<6, /* with RESET: start with IsFading set (al/source.cpp:775,2714) */
+    B200MIX_VF_STOPPED   = 1u<<7  /* Voice::Stopped: remove from the active set */
+};
+
+typedef struct b200mix_voice_params {
+    uint32_t voice;           /* index in the device voice array, < max_voices */
+    uint32_t flags;           /* B200MIX_VF_* */
+    uint32_t buffer;          /* buffer id of mCurrentBuffer (static sources) */
+    uint32_t resampler;       /* enum b200mix_resampler (VoiceProps::mResampler) */
+    int32_t  position;        /* mPosition      (RESET only) */
+    uint32_t position_frac;   /* mPositionFrac  (RESET only) */
+    uint32_t loop_start;      /* VoiceBufferItem::mLoopStart */
+    uint32_t loop_end;        /* VoiceBufferItem::mLoopEnd */
+    uint32_t step;            /* mStep, 16.16 fixed point */
+    uint32_t hrtf_delay[2];   /* Hrtf.Target.Delay */
+    float    hrtf_gain;       /* Hrtf.Target.Gain */
+    uint32_t send_slot[B200MIX_MAX_SENDS]; /* aux slot id per send or B200MIX_NO_SLOT */
+} b200mix_voice_params;
+
+/* Applies n parameter snapshots.  Side arrays are indexed like params[]:
+ *   hrtf_coeffs [n][ir_size][2]              Hrtf.Target.Coeffs (HRTF voices; may be NULL)
+ *   dry_gains   [n][dry_channels]            mDryParams.Gains.Target (non-HRTF; may be NULL)
+ *   send_gains  [n][num_sends][wet_channels] mWetParams[s].Gains.Target (may be NULL)
+ * A NULL side array leaves the corresponding targets unchanged. */
+B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
+    const b200mix_voice_params *params, const float *hrtf_coeffs, const float *dry_gains,
+    const float *send_gains);
+
+typedef struct b200mix_voice_result {
+    int32_t  position;        /* new mPosition */
+    uint32_t position_frac;   /* new mPositionFrac */
+    uint32_t flags;           /* B200MIX_VF_PLAYING / _STOPPING / _STOPPED after this update */
+    uint32_t buffers_done;    /* for AsyncBufferCompleteEvent (queues; 0 for static) */
+} b200mix_voice_result;
+
+/* ---- the hot path -------------------------------------------------------- */
+/* One mix update of `frames` (1..1024) sample frames:
+ * zero MixBuffer, mix every active voice, run the aux slots, post-process.
+ * real_out[c] (c < real_channels) are HOST pointers to >= frames floats each
+ * (the planar RealOut the host's Write<T> then converts/interleaves).
+ * results (nullable) receives max_voices entries. */
+B200MIX_API int b200mix_render(b200mix_device *dev, uint32_t frames, float *const *real_out,
+    b200mix_voice_result *results);
+
+/* Same update with the output left in device memory (for callers that keep
+ * going on the GPU, and for device-timed benchmarking): *real_out_dev is a
+ * device pointer to [real_channels][1024] floats valid until the next call. */
+B200MIX_API int b200mix_render_device(b200mix_device *dev, uint32_t frames,
+    const float **real_out_dev);
+
+/* ---- introspection (tests, profiling) ------------------------------------ */
+/* Copies the Dry mix of the last update: [dry_channels][1024]. */
+B200MIX_API int b200mix_get_dry(b200mix_device *dev, float *dry);
+/* Copies resampler tables as the device holds them (bit-compared with the
+ * reference's in tests): which = enum b200mix_resampler; returns float count. */
+B200MIX_API int64_t b200mix_get_resampler_table(b200mix_device *dev, uint32_t which,
+    float *out, size_t max_floats);
+/* Number of CUDA kernels this device has launched so far. */
+B200MIX_API uint64_t b200mix_launch_count(const b200mix_device *dev);
+/* CUDA stream the device launches on (a cudaStream_t), for event timing. */
+B200MIX_API void *b200mix_stream(b200mix_device *dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MIX_H */

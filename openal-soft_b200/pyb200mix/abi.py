@@ -1,0 +1,43 @@
+"""ctypes mirror of include/b200mix.h (structs + constants) shared by the tests,
+the reference harness wrapper and bench.py.  Pure declarations, no compute."""
+import ctypes as C
+
+LINE = 1024
+HRIR_LENGTH = 128
+HRTF_HISTORY = 64
+MAX_SENDS = 6
+MAX_DRY = 32
+MAX_WET = 25
+PADDING = 48
+NO_SLOT = 0xFFFFFFFF
+
+(RS_POINT, RS_LINEAR, RS_SPLINE, RS_GAUSSIAN, RS_FAST_BSINC12, RS_BSINC12, RS_FAST_BSINC24,
+ RS_BSINC24, RS_FAST_BSINC48, RS_BSINC48) = range(10)
+FMT_U8, FMT_I16, FMT_I32, FMT_F32, FMT_F64, FMT_MULAW, FMT_ALAW = range(7)
+POST_NONE, POST_AMBIDEC, POST_HRTF, POST_UHJ = range(4)
+VF_PLAYING, VF_STOPPING, VF_STATIC, VF_LOOPING, VF_HRTF, VF_RESET, VF_FADING, VF_STOPPED = (
+    1 << i for i in range(8))
+
+
+class DeviceDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("cuda_device", C.c_int32),
+                ("sample_rate", C.c_uint32), ("dry_channels", C.c_uint32),
+                ("real_channels", C.c_uint32), ("wet_channels", C.c_uint32),
+                ("num_sends", C.c_uint32), ("ir_size", C.c_uint32),
+                ("post_process", C.c_uint32), ("real_left", C.c_uint32),
+                ("real_right", C.c_uint32), ("max_voices", C.c_uint32),
+                ("max_buffers", C.c_uint32), ("max_slots", C.c_uint32)]
+
+
+class VoiceParams(C.Structure):
+    _fields_ = [("voice", C.c_uint32), ("flags", C.c_uint32), ("buffer", C.c_uint32),
+                ("resampler", C.c_uint32), ("position", C.c_int32),
+                ("position_frac", C.c_uint32), ("loop_start", C.c_uint32),
+                ("loop_end", C.c_uint32), ("step", C.c_uint32),
+                ("hrtf_delay", C.c_uint32 * 2), ("hrtf_gain", C.c_float),
+                ("send_slot", C.c_uint32 * MAX_SENDS)]
+
+
+class VoiceResult(C.Structure):
+    _fields_ = [("position", C.c_int32), ("position_frac", C.c_uint32),
+                ("flags", C.c_uint32), ("buffers_done", C.c_uint32)]

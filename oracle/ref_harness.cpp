@@ -1,0 +1,403 @@
+/* ref_harness.cpp — TEST INFRASTRUCTURE ONLY (never linked or loaded by the product).
+ *
+ * A thin window into the UNMODIFIED reference (oracle/_ref/libopenal_ref.so,
+ * built from /root/reference by oracle/refbuild/Makefile).  Compiled against
+ * the reference's private headers where they lie; no reference source is copied.
+ *
+ * It does two jobs:
+ *  1. "reference-side binding": converts the reference's live post-ALU objects
+ *     (DeviceBase, Voice, BufferStorage) into the b200mix C-ABI structs of
+ *     include/b200mix.h — exactly what a maintainer's seam in
+ *     DeviceBase::renderSamples (alc/alu.cpp:2412) would do, see INTEGRATION.md.
+ *  2. kernel-level taps: calls Resample_*_C/SSE, and dumps the static-init
+ *     coefficient tables, so the oracle restatement (oracle/almix_oracle.c) and
+ *     the CUDA tables can be pinned bit-for-bit.
+ */
+#include "config.h"
+
+/* The only private members we need are plain floats/arrays; open them up for
+ * reading instead of patching the reference. */
+#include <algorithm>
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <span>
+#include <variant>
+#include <vector>
+
+/* pre-include their dependencies so only the two class bodies see the macros */
+#include "opthelpers.h"
+#include "core/ambidefs.h"
+#include "core/bufferline.h"
+#include "core/devformat.h"
+#define class struct
+#define private public
+#include "core/filters/splitter.h"
+#include "core/bformatdec.h"
+#undef private
+#undef class
+
+#include "AL/al.h"
+#include "AL/alc.h"
+#include "alc/context.hpp"
+#include "alc/device.h"
+#include "alc/alu.h"
+#include "core/bsinc_tables.h"
+#include "core/context.h"
+#include "core/cubic_tables.h"
+#include "core/device.h"
+#include "core/effectslot.h"
+#include "core/fpu_ctrl.h"
+#include "core/hrtf.h"
+#include "core/mixer/defs.h"
+#include "core/mixer/hrtfdefs.h"
+#include "core/voice.h"
+
+#include "../include/b200mix.h"
+
+namespace {
+auto dev_of(ALCdevice *d) -> al::Device* { return static_cast<al::Device*>(d); }
+auto ctx_of(ALCcontext *c) -> al::Context* { return static_cast<al::Context*>(c); }
+} // namespace
+
+extern "C" {
+
+/* Extra per-voice mixer state the ABI does not carry (it is device-resident in
+ * the product); used by tests to compare state evolution, and to seed it. */
+struct refh_voice_state {
+    int32_t  play_state;      /* Voice::State */
+    uint32_t is_fading;
+    int32_t  position;
+    uint32_t position_frac;
+    uint32_t buffer_frames;   /* VoiceBufferItem::mSampleLen */
+    uint32_t buffer_type;     /* b200mix_sample_type or 0xffffffff */
+    uint32_t buffer_channels; /* mFrameStep */
+    uint32_t bsinc_m, bsinc_l;
+    float    bsinc_sf;
+    const void *buffer_data;  /* host pointer into the reference's BufferStorage */
+    float    prev_samples[B200MIX_RESAMPLER_PADDING];
+    float    hrtf_history[B200MIX_HRTF_HISTORY];
+    float    old_coeffs[B200MIX_HRIR_LENGTH][2];
+    uint32_t old_delay[2];
+    float    old_gain;
+    float    cur_dry_gains[B200MIX_MAX_DRY_CHANNELS];
+    float    cur_send_gains[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
+};
+
+int refh_device_desc(ALCdevice *adev, b200mix_device_desc *out)
+{
+    auto *dev = dev_of(adev);
+    std::memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(*out);
+    out->cuda_device = -1;
+    out->sample_rate = dev->mSampleRate;
+    out->dry_channels = static_cast<uint32_t>(dev->Dry.Buffer.size());
+    out->real_channels = static_cast<uint32_t>(dev->RealOut.Buffer.size());
+    out->num_sends = dev->NumAuxSends;
+    out->ir_size = dev->mIrSize;
+    out->wet_channels = 0; /* filled by refh_wet_channels once a slot exists */
+    if(std::holds_alternative<AmbiDecPostProcess>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_AMBIDEC;
+    else if(std::holds_alternative<HrtfPostProcess>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_HRTF;
+    else if(std::holds_alternative<UhjPostProcess>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_UHJ;
+    else if(std::holds_alternative<std::monostate>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_NONE;
+    else
+        return -1;
+    out->real_left = dev->RealOut.ChannelIndex[FrontLeft].c_val;
+    out->real_right = dev->RealOut.ChannelIndex[FrontRight].c_val;
+    /* RealOut aliases Dry when no decode is needed. */
+    if(out->post_process == B200MIX_POST_NONE
+        && dev->RealOut.Buffer.data() != dev->Dry.Buffer.data())
+        return -2;
+    return 0;
+}
+
+/* Returns the channel count; *ir_size receives DirectHrtfState::mIrSize (which can
+ * exceed the device's per-voice mIrSize); arrays sized [channels][*ir_size][2],
+ * [channels], [channels].  Call with NULL arrays first to learn the sizes. */
+int refh_hrtf_decoder(ALCdevice *adev, uint32_t *ir_size, float *coeffs, float *hf_scale,
+    float *splitter_coeff)
+{
+    auto *dev = dev_of(adev);
+    auto *proc = std::get_if<HrtfPostProcess>(&dev->mPostProcess);
+    if(!proc) return -1;
+    auto &st = *proc->mHrtfState;
+    const auto ir = st.mIrSize;
+    *ir_size = ir;
+    auto c = 0u;
+    for(auto &chan : st.mChannels)
+    {
+        if(coeffs)
+            for(auto j = 0u;j < ir;++j)
+            {
+                coeffs[(c*ir + j)*2 + 0] = chan.mCoeffs[j][0];
+                coeffs[(c*ir + j)*2 + 1] = chan.mCoeffs[j][1];
+            }
+        if(hf_scale) hf_scale[c] = chan.mHfScale;
+        if(splitter_coeff) splitter_coeff[c] = chan.mSplitter.mCoeff;
+        ++c;
+    }
+    return static_cast<int>(c);
+}
+
+/* Returns in_channels; gains are [in][real_channels]. *dual = 1 if dual-band. */
+int refh_ambi_decoder(ALCdevice *adev, float *gains_hf, float *gains_lf, float *xover_coeff,
+    int *dual)
+{
+    auto *dev = dev_of(adev);
+    auto *proc = std::get_if<AmbiDecPostProcess>(&dev->mPostProcess);
+    if(!proc) return -1;
+    auto &dec = *proc->mAmbiDecoder;
+    const auto outs = dev->RealOut.Buffer.size();
+    if(auto *sb = std::get_if<BFormatDec::SBandDecoderVector>(&dec.mChannelDec))
+    {
+        *dual = 0;
+        for(auto i = 0_uz;i < sb->size();++i)
+            for(auto o = 0_uz;o < outs;++o)
+                gains_hf[i*outs + o] = (*sb)[i].mGains[o];
+        return static_cast<int>(sb->size());
+    }
+    auto &db = std::get<BFormatDec::DBandDecoderVector>(dec.mChannelDec);
+    *dual = 1;
+    for(auto i = 0_uz;i < db.size();++i)
+        for(auto o = 0_uz;o < outs;++o)
+        {
+            gains_hf[i*outs + o] = db[i].mGains[BFormatDec::sHFBand][o];
+            gains_lf[i*outs + o] = db[i].mGains[BFormatDec::sLFBand][o];
+        }
+    *xover_coeff = db.empty() ? 0.0f : db[0].mXOver.mCoeff;
+    return static_cast<int>(db.size());
+}
+
+int refh_voice_count(ALCcontext *actx)
+{ return static_cast<int>(ctx_of(actx)->getVoicesSpan().size()); }
+
+/* Snapshot of every voice slot [0, count): ABI params + side arrays + state.
+ * Any output pointer may be NULL.  dry_gains is [n][dry_channels], hrtf_coeffs
+ * [n][ir_size][2], send_gains [n][num_sends][wet_channels]. */
+int refh_snapshot_voices(ALCcontext *actx, b200mix_voice_params *params, float *hrtf_coeffs,
+    float *dry_gains, float *send_gains, uint32_t wet_channels, refh_voice_state *state)
+{
+    auto *ctx = ctx_of(actx);
+    auto *dev = static_cast<DeviceBase*>(ctx->mDevice);
+    const auto voices = ctx->getVoicesSpan();
+    const auto ir = dev->mIrSize;
+    const auto cd = dev->Dry.Buffer.size();
+    const auto ns = dev->NumAuxSends;
+    auto slots = std::span<EffectSlotBase*>{};
+    if(auto *arr = ctx->mActiveAuxSlots.load(std::memory_order_acquire))
+    {
+        auto all = std::span{*arr};
+        slots = all.first(all.size()>>1);
+    }
+
+    auto n = 0u;
+    for(auto *voice : voices)
+    {
+        auto &ch = voice->mChans[0];
+        const auto pstate = voice->mPlayState.load();
+        auto *item = voice->mCurrentBuffer.load();
+        auto *loop = voice->mLoopBuffer.load();
+        if(params)
+        {
+            auto &p = params[n];
+            std::memset(&p, 0, sizeof(p));
+            p.voice = n;
+            if(pstate == Voice::Playing) p.flags |= B200MIX_VF_PLAYING;
+            else if(pstate == Voice::Stopping) p.flags |= B200MIX_VF_STOPPING;
+            else p.flags |= B200MIX_VF_STOPPED;
+            if(voice->mFlags.test(VoiceFlag::IsStatic)) p.flags |= B200MIX_VF_STATIC;
+            if(loop) p.flags |= B200MIX_VF_LOOPING;
+            if(voice->mFlags.test(VoiceFlag::HasHrtf)) p.flags |= B200MIX_VF_HRTF;
+            p.buffer = 0;
+            p.resampler = static_cast<uint32_t>(voice->mProps.mResampler);
+            p.position = voice->mPosition.load();
+            p.position_frac = voice->mPositionFrac.load();
+            p.loop_start = item ? item->mLoopStart : 0u;
+            p.loop_end = item ? item->mLoopEnd : 0u;
+            p.step = voice->mStep;
+            p.hrtf_delay[0] = ch.mDryParams.Hrtf.Target.Delay[0];
+            p.hrtf_delay[1] = ch.mDryParams.Hrtf.Target.Delay[1];
+            p.hrtf_gain = ch.mDryParams.Hrtf.Target.Gain;
+            for(auto s = 0u;s < B200MIX_MAX_SENDS;++s)
+            {
+                p.send_slot[s] = B200MIX_NO_SLOT;
+                if(s >= ns || voice->mSend[s].Buffer.empty()) continue;
+                for(auto k = 0_uz;k < slots.size();++k)
+                    if(slots[k]->Wet.Buffer.data() == voice->mSend[s].Buffer.data())
+                        p.send_slot[s] = static_cast<uint32_t>(k);
+            }
+        }
+        if(hrtf_coeffs)
+            for(auto j = 0u;j < ir;++j)
+            {
+                hrtf_coeffs[(n*ir + j)*2 + 0] = ch.mDryParams.Hrtf.Target.Coeffs[j][0];
+                hrtf_coeffs[(n*ir + j)*2 + 1] = ch.mDryParams.Hrtf.Target.Coeffs[j][1];
+            }
+        if(dry_gains)
+            for(auto c = 0_uz;c < cd;++c)
+                dry_gains[n*cd + c] = ch.mDryParams.Gains.Target[c];
+        if(send_gains)
+            for(auto s = 0u;s < ns;++s)
+                for(auto c = 0u;c < wet_channels;++c)
+                    send_gains[(n*ns + s)*wet_channels + c] = ch.mWetParams[s].Gains.Target[c];
+        if(state)
+        {
+            auto &st = state[n];
+            std::memset(&st, 0, sizeof(st));
+            st.play_state = static_cast<int32_t>(pstate);
+            st.is_fading = voice->mFlags.test(VoiceFlag::IsFading);
+            st.position = voice->mPosition.load();
+            st.position_frac = voice->mPositionFrac.load();
+            st.buffer_type = 0xffffffffu;
+            if(item)
+            {
+                st.buffer_frames = item->mSampleLen;
+                st.buffer_channels = voice->mFrameStep;
+                std::visit([&st]<typename T>(std::span<T> const &spl)
+                {
+                    st.buffer_data = spl.data();
+                    if constexpr(std::is_same_v<T,u8>) st.buffer_type = B200MIX_FMT_U8;
+                    else if constexpr(std::is_same_v<T,i16>) st.buffer_type = B200MIX_FMT_I16;
+                    else if constexpr(std::is_same_v<T,i32>) st.buffer_type = B200MIX_FMT_I32;
+                    else if constexpr(std::is_same_v<T,f32>) st.buffer_type = B200MIX_FMT_F32;
+                    else if constexpr(std::is_same_v<T,f64>) st.buffer_type = B200MIX_FMT_F64;
+                    else if constexpr(std::is_same_v<T,MulawSample>) st.buffer_type = B200MIX_FMT_MULAW;
+                    else if constexpr(std::is_same_v<T,AlawSample>) st.buffer_type = B200MIX_FMT_ALAW;
+                }, item->mSamples);
+            }
+            if(auto *bs = std::get_if<BsincState>(&voice->mResampleState))
+            {
+                st.bsinc_m = bs->m.c_val;
+                st.bsinc_l = bs->l.c_val;
+                st.bsinc_sf = bs->sf;
+            }
+            std::copy_n(voice->mPrevSamples[0].begin(), B200MIX_RESAMPLER_PADDING, st.prev_samples);
+            std::copy_n(ch.mDryParams.Hrtf.History.begin(), B200MIX_HRTF_HISTORY, st.hrtf_history);
+            for(auto j = 0u;j < B200MIX_HRIR_LENGTH;++j)
+            {
+                st.old_coeffs[j][0] = ch.mDryParams.Hrtf.Old.Coeffs[j][0];
+                st.old_coeffs[j][1] = ch.mDryParams.Hrtf.Old.Coeffs[j][1];
+            }
+            st.old_delay[0] = ch.mDryParams.Hrtf.Old.Delay[0];
+            st.old_delay[1] = ch.mDryParams.Hrtf.Old.Delay[1];
+            st.old_gain = ch.mDryParams.Hrtf.Old.Gain;
+            std::copy_n(ch.mDryParams.Gains.Current.begin(), B200MIX_MAX_DRY_CHANNELS,
+                st.cur_dry_gains);
+            for(auto s = 0u;s < B200MIX_MAX_SENDS;++s)
+                std::copy_n(ch.mWetParams[s].Gains.Current.begin(), B200MIX_MAX_WET_CHANNELS,
+                    st.cur_send_gains[s]);
+        }
+        ++n;
+    }
+    return static_cast<int>(n);
+}
+
+/* HrtfAccumData as [1024+128][2]. */
+void refh_get_hrtf_accum(ALCdevice *adev, float *out)
+{
+    auto *dev = dev_of(adev);
+    for(auto i = 0_uz;i < dev->HrtfAccumData.size();++i)
+    {
+        out[i*2 + 0] = dev->HrtfAccumData[i][0];
+        out[i*2 + 1] = dev->HrtfAccumData[i][1];
+    }
+}
+
+/* Dry mix of the last update, [dry_channels][1024]. */
+void refh_get_dry(ALCdevice *adev, float *out)
+{
+    auto *dev = dev_of(adev);
+    for(auto c = 0_uz;c < dev->Dry.Buffer.size();++c)
+        std::copy_n(dev->Dry.Buffer[c].begin(), BufferLineSize, out + c*BufferLineSize);
+}
+
+/* ---- kernel-level taps --------------------------------------------------- */
+
+/* Runs the reference resampler exactly as Voice::mix would call it:
+ * src is mResampleData (position 0 at index MaxResamplerEdge=24).
+ * simd=0 forces the *_C kernels, simd=1 uses PrepareResampler's CPU selection. */
+int refh_resample(uint32_t resampler, int simd, uint32_t increment, uint32_t frac,
+    const float *src, uint32_t src_len, float *dst, uint32_t dst_len)
+{
+    auto mixer_mode = FPUCtl{};
+    auto state = InterpState{};
+    auto func = PrepareResampler(static_cast<Resampler>(resampler), increment, &state);
+    if(!simd)
+    {
+        switch(static_cast<Resampler>(resampler))
+        {
+        case Resampler::Point: func = Resample_Point_C; break;
+        case Resampler::Linear: func = Resample_Linear_C; break;
+        case Resampler::Spline: case Resampler::Gaussian: func = Resample_Cubic_C; break;
+        case Resampler::BSinc12: case Resampler::BSinc24: case Resampler::BSinc48:
+            func = (increment > MixerFracOne) ? Resample_BSinc_C : Resample_FastBSinc_C; break;
+        default: func = Resample_FastBSinc_C; break;
+        }
+    }
+    func(&state, std::span{src, src_len}, frac, increment, std::span{dst, dst_len});
+    return 0;
+}
+
+/* BsincPrepare's result for one increment (alc/alu.cpp:140-165): sf, m, l and the
+ * offset of the scale's sub-table.  The tables themselves are hidden symbols
+ * (DECL_HIDDEN), so they are reached through PrepareResampler's state. */
+namespace {
+auto bsinc_state(uint32_t resampler, uint32_t increment) -> BsincState
+{
+    auto state = InterpState{};
+    std::ignore = PrepareResampler(static_cast<Resampler>(resampler), increment, &state);
+    return std::get<BsincState>(state);
+}
+auto bsinc_base(uint32_t resampler) -> const float*
+{
+    /* scale index 0 (offset 0) is selected by the largest down-sampling ratio */
+    return bsinc_state(resampler, MaxPitch<<MixerFracBits).filter.data();
+}
+} // namespace
+
+int refh_bsinc_state(uint32_t resampler, uint32_t increment, float *sf, uint32_t *m, uint32_t *l,
+    uint32_t *offset)
+{
+    const auto st = bsinc_state(resampler, increment);
+    *sf = st.sf; *m = st.m.c_val; *l = st.l.c_val;
+    *offset = static_cast<uint32_t>(st.filter.data() - bsinc_base(resampler));
+    return 0;
+}
+
+/* resampler = BSinc12/24/48 enum value.  Returns the float count of the table
+ * (offset of the last scale + its size). */
+int64_t refh_bsinc_table(uint32_t resampler, float *out, size_t max_floats)
+{
+    const auto *base = bsinc_base(resampler);
+    const auto last = bsinc_state(resampler, MixerFracOne); /* si = 15 */
+    const auto total = static_cast<size_t>(last.filter.data() - base)
+        + size_t{last.m.c_val}*4u*BSincPhaseCount;
+    if(out) std::copy_n(base, std::min(max_floats, total), out);
+    return static_cast<int64_t>(total);
+}
+
+/* which: 0 = spline, 1 = gaussian.  out is [32][8] (coeffs[4], deltas[4]). */
+void refh_cubic_table(int which, float *out)
+{
+    auto state = InterpState{};
+    std::ignore = PrepareResampler(which ? Resampler::Gaussian : Resampler::Spline, MixerFracOne,
+        &state);
+    const auto t = std::get<CubicState>(state).filter;
+    for(auto pi = 0u;pi < CubicPhaseCount;++pi)
+        for(auto k = 0u;k < 4;++k)
+        {
+            out[pi*8 + k] = t[pi].mCoeffs[k];
+            out[pi*8 + 4 + k] = t[pi].mDeltas[k];
+        }
+}
+
+/* gCubicTable (used by the reverb's modulated taps): 513 floats. */
+void refh_cubic_filter(float *out)
+{ std::copy(gCubicTable.mFilter.begin(), gCubicTable.mFilter.end(), out); }
+
+} // extern "C"

@@ -1,0 +1,253 @@
+"""ctypes driver for the UNMODIFIED reference (oracle/_ref/libopenal_ref.so) through
+its public loopback API (include/AL/alext.h:318-345), plus the state/kernel taps
+of oracle/ref_harness.cpp.  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "openal-soft_b200"))
+from pyb200mix import abi  # noqa: E402
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+# AL / ALC enums (include/AL/al.h, alc.h, alext.h, efx.h)
+AL_NONE = 0
+AL_SOURCE_RELATIVE = 0x202
+AL_PITCH = 0x1003
+AL_POSITION = 0x1004
+AL_LOOPING = 0x1007
+AL_BUFFER = 0x1009
+AL_GAIN = 0x100A
+AL_SOURCE_STATE = 0x1010
+AL_PLAYING = 0x1012
+AL_ROLLOFF_FACTOR = 0x1021
+AL_FORMAT_MONO8 = 0x1100
+AL_FORMAT_MONO16 = 0x1101
+AL_FORMAT_MONO_FLOAT32 = 0x10010
+AL_DISTANCE_MODEL = 0xD000
+AL_SOURCE_RESAMPLER_SOFT = 0x1212
+AL_SOURCE_SPATIALIZE_SOFT = 0x1214
+AL_SAMPLE_OFFSET = 0x1025
+AL_AUXILIARY_SEND_FILTER = 0x20006
+AL_EFFECT_TYPE = 0x8001
+AL_EFFECT_EAXREVERB = 0x8000
+AL_EFFECTSLOT_EFFECT = 0x0001
+AL_FILTER_NULL = 0
+ALC_FREQUENCY = 0x1007
+ALC_MONO_SOURCES = 0x1010
+ALC_STEREO_SOURCES = 0x1011
+ALC_FORMAT_CHANNELS_SOFT = 0x1990
+ALC_FORMAT_TYPE_SOFT = 0x1991
+ALC_FLOAT_SOFT = 0x1406
+ALC_STEREO_SOFT = 0x1501
+ALC_BFORMAT3D_SOFT = 0x1507
+ALC_HRTF_SOFT = 0x1992
+ALC_HRTF_STATUS_SOFT = 0x1993
+ALC_AMBISONIC_LAYOUT_SOFT = 0x1997
+ALC_AMBISONIC_SCALING_SOFT = 0x1998
+ALC_AMBISONIC_ORDER_SOFT = 0x1999
+ALC_ACN_SOFT = 1
+ALC_N3D_SOFT = 2
+ALC_OUTPUT_MODE_SOFT = 0x19AC
+ALC_STEREO_BASIC_SOFT = 0x19AE
+ALC_STEREO_UHJ_SOFT = 0x19AF
+ALC_STEREO_HRTF_SOFT = 0x19B2
+ALC_MAX_AUXILIARY_SENDS = 0x20003
+ALC_OUTPUT_LIMITER_SOFT = 0x199A
+
+
+class VoiceState(C.Structure):
+    _fields_ = [("play_state", C.c_int32), ("is_fading", C.c_uint32), ("position", C.c_int32),
+                ("position_frac", C.c_uint32), ("buffer_frames", C.c_uint32),
+                ("buffer_type", C.c_uint32), ("buffer_channels", C.c_uint32),
+                ("bsinc_m", C.c_uint32), ("bsinc_l", C.c_uint32), ("bsinc_sf", C.c_float),
+                ("buffer_data", C.c_void_p),
+                ("prev_samples", C.c_float * abi.PADDING),
+                ("hrtf_history", C.c_float * abi.HRTF_HISTORY),
+                ("old_coeffs", (C.c_float * 2) * abi.HRIR_LENGTH),
+                ("old_delay", C.c_uint32 * 2), ("old_gain", C.c_float),
+                ("cur_dry_gains", C.c_float * abi.MAX_DRY),
+                ("cur_send_gains", (C.c_float * abi.MAX_WET) * abi.MAX_SENDS)]
+
+
+def available() -> bool:
+    return (os.path.exists(os.path.join(REF_DIR, "libopenal_ref.so"))
+            and os.path.exists(os.path.join(REF_DIR, "libref_harness.so")))
+
+
+_libs = None
+
+
+def libs(conf_text: str | None = None):
+    """Loads the reference once per process.  conf_text (alsoft.conf syntax) must be
+    given on the FIRST call: the reference reads ALSOFT_CONF at its first use."""
+    global _libs
+    if _libs is not None:
+        return _libs
+    conf_path = os.path.join(REF_DIR, f"alsoft_{os.getpid()}.conf")
+    with open(conf_path, "w") as f:
+        f.write(conf_text or "[general]\n")
+    os.environ["ALSOFT_CONF"] = conf_path
+    os.environ.setdefault("ALSOFT_LOGLEVEL", "1")
+    al = C.CDLL(os.path.join(REF_DIR, "libopenal_ref.so"), mode=C.RTLD_GLOBAL)
+    hz = C.CDLL(os.path.join(REF_DIR, "libref_harness.so"))
+    al.alcLoopbackOpenDeviceSOFT.restype = C.c_void_p
+    al.alcLoopbackOpenDeviceSOFT.argtypes = [C.c_char_p]
+    al.alcCreateContext.restype = C.c_void_p
+    al.alcCreateContext.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    al.alcMakeContextCurrent.argtypes = [C.c_void_p]
+    al.alcDestroyContext.argtypes = [C.c_void_p]
+    al.alcCloseDevice.argtypes = [C.c_void_p]
+    al.alcGetIntegerv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    al.alcRenderSamplesSOFT.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    al.alcGetError.argtypes = [C.c_void_p]
+    al.alGenBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alGenSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alBufferData.argtypes = [C.c_uint, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    al.alSourcei.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alSourcef.argtypes = [C.c_uint, C.c_int, C.c_float]
+    al.alSource3f.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_float, C.c_float]
+    al.alSource3i.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+    al.alSourcePlayv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alSourceStopv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alDistanceModel.argtypes = [C.c_int]
+    al.alGetSourcei.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_int)]
+    al.alcDevicePauseSOFT.argtypes = [C.c_void_p]
+    hz.refh_device_desc.argtypes = [C.c_void_p, C.POINTER(abi.DeviceDesc)]
+    hz.refh_hrtf_decoder.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+    hz.refh_ambi_decoder.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+    hz.refh_voice_count.argtypes = [C.c_void_p]
+    hz.refh_snapshot_voices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_uint32, C.c_void_p]
+    hz.refh_get_hrtf_accum.argtypes = [C.c_void_p, C.c_void_p]
+    hz.refh_get_dry.argtypes = [C.c_void_p, C.c_void_p]
+    hz.refh_resample.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
+                                 C.c_uint32, C.c_void_p, C.c_uint32]
+    hz.refh_bsinc_state.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32)]
+    hz.refh_bsinc_table.restype = C.c_int64
+    hz.refh_bsinc_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+    hz.refh_cubic_table.argtypes = [C.c_int, C.c_void_p]
+    hz.refh_cubic_filter.argtypes = [C.c_void_p]
+    _libs = (al, hz)
+    return _libs
+
+
+class RefDevice:
+    """A loopback device + context on the reference.  Stereo float32 by default."""
+
+    def __init__(self, attrs: dict, conf_text: str | None = None):
+        self.al, self.hz = libs(conf_text)
+        self.dev = self.al.alcLoopbackOpenDeviceSOFT(None)
+        assert self.dev, "alcLoopbackOpenDeviceSOFT failed"
+        a = {ALC_FORMAT_CHANNELS_SOFT: ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT: ALC_FLOAT_SOFT,
+             ALC_FREQUENCY: 48000}
+        a.update(attrs)
+        flat = []
+        for k, v in a.items():
+            flat += [k, v]
+        flat.append(0)
+        arr = (C.c_int * len(flat))(*flat)
+        self.ctx = self.al.alcCreateContext(self.dev, arr)
+        assert self.ctx, f"alcCreateContext failed: {self.al.alcGetError(self.dev):#x}"
+        self.al.alcMakeContextCurrent(self.ctx)
+        self.buffers = []
+        self.sources = []
+        self._keep = []
+        self.desc = abi.DeviceDesc()
+        rc = self.hz.refh_device_desc(self.dev, C.byref(self.desc))
+        assert rc == 0, f"refh_device_desc {rc}"
+        self.out_channels = 2
+
+    def close(self):
+        self.al.alcMakeContextCurrent(None)
+        self.al.alcDestroyContext(self.ctx)
+        self.al.alcCloseDevice(self.dev)
+
+    def hrtf_enabled(self) -> bool:
+        v = C.c_int(0)
+        self.al.alcGetIntegerv(self.dev, ALC_HRTF_STATUS_SOFT, 1, C.byref(v))
+        return v.value == 1
+
+    def add_voice(self, pcm: np.ndarray, rate: int, pitch: float, pos, gain: float,
+                  resampler: int | None, looping: bool = True, fmt=AL_FORMAT_MONO16):
+        b = C.c_uint(0)
+        s = C.c_uint(0)
+        self.al.alGenBuffers(1, C.byref(b))
+        pcm = np.ascontiguousarray(pcm)
+        self.al.alBufferData(b, fmt, pcm.ctypes.data, pcm.nbytes, rate)
+        self.al.alGenSources(1, C.byref(s))
+        self.al.alSourcei(s, AL_BUFFER, b.value)
+        self.al.alSourcei(s, AL_LOOPING, 1 if looping else 0)
+        self.al.alSourcef(s, AL_PITCH, pitch)
+        self.al.alSourcef(s, AL_GAIN, gain)
+        self.al.alSource3f(s, AL_POSITION, *[float(x) for x in pos])
+        if resampler is not None:
+            self.al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x}"
+        self.buffers.append(b.value)
+        self.sources.append(s.value)
+        self._keep.append(pcm)
+        return s.value
+
+    def play_all(self):
+        arr = (C.c_uint * len(self.sources))(*self.sources)
+        self.al.alSourcePlayv(len(self.sources), arr)
+
+    def render(self, frames: int = 1024, channels: int | None = None) -> np.ndarray:
+        """Returns planar [channels][frames] float32 (de-interleaved)."""
+        ch = channels or self.out_channels
+        buf = np.zeros((frames, ch), dtype=np.float32)
+        self.al.alcRenderSamplesSOFT(self.dev, buf.ctypes.data, frames)
+        return np.ascontiguousarray(buf.T)
+
+    # ---- taps ----
+    def snapshot(self, wet_channels: int = 0):
+        n = self.hz.refh_voice_count(self.ctx)
+        d = self.desc
+        params = (abi.VoiceParams * max(n, 1))()
+        state = (VoiceState * max(n, 1))()
+        coeffs = np.zeros((max(n, 1), max(d.ir_size, 1), 2), dtype=np.float32)
+        dry = np.zeros((max(n, 1), d.dry_channels), dtype=np.float32)
+        send = np.zeros((max(n, 1), max(d.num_sends, 1), max(wet_channels, 1)), dtype=np.float32)
+        got = self.hz.refh_snapshot_voices(self.ctx, params, coeffs.ctypes.data, dry.ctypes.data,
+                                           send.ctypes.data if wet_channels else None,
+                                           wet_channels, state)
+        assert got == n
+        return n, params, coeffs[:n], dry[:n], send[:n], state
+
+    def hrtf_accum(self) -> np.ndarray:
+        out = np.zeros((abi.LINE + abi.HRIR_LENGTH, 2), dtype=np.float32)
+        self.hz.refh_get_hrtf_accum(self.dev, out.ctypes.data)
+        return out
+
+    def dry(self) -> np.ndarray:
+        out = np.zeros((self.desc.dry_channels, abi.LINE), dtype=np.float32)
+        self.hz.refh_get_dry(self.dev, out.ctypes.data)
+        return out
+
+    def hrtf_decoder(self):
+        ir = C.c_uint32(0)
+        n = self.hz.refh_hrtf_decoder(self.dev, C.byref(ir), None, None, None)
+        assert n == self.desc.dry_channels, (n, self.desc.dry_channels)
+        coeffs = np.zeros((n, ir.value, 2), dtype=np.float32)
+        hf = np.zeros(n, dtype=np.float32)
+        sc = np.zeros(n, dtype=np.float32)
+        self.hz.refh_hrtf_decoder(self.dev, C.byref(ir), coeffs.ctypes.data, hf.ctypes.data,
+                                  sc.ctypes.data)
+        return coeffs, hf, sc
+
+    def ambi_decoder(self):
+        d = self.desc
+        hfm = np.zeros((d.dry_channels, d.real_channels), dtype=np.float32)
+        lfm = np.zeros((d.dry_channels, d.real_channels), dtype=np.float32)
+        xo = C.c_float(0)
+        dual = C.c_int(0)
+        got = self.hz.refh_ambi_decoder(self.dev, hfm.ctypes.data, lfm.ctypes.data,
+                                        C.byref(xo), C.byref(dual))
+        assert got == d.dry_channels, (got, d.dry_channels)
+        return hfm, (lfm if dual.value else None), xo.value
