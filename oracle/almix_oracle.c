@@ -1,0 +1,896 @@
+/* oracle/almix_oracle.c — TEST INFRASTRUCTURE ONLY (see almix_oracle.h).
+ *
+ * Scalar C restatement of one OpenAL Soft mix update.  Each function cites the
+ * reference code it follows (paths relative to the reference root).  The order
+ * of floating-point operations follows the reference's C kernels
+ * (core/mixer/mixer_c.cpp) so that results are bit-identical to the reference
+ * built with disable-cpu-exts=all, and within fp32 rounding of its SSE kernels.
+ * Build with -ffp-contract=off (no FMA contraction; the reference's x86-64
+ * build has none either).
+ */
+#include "almix_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define LINE   B200MIX_LINE_SIZE
+#define HRIR   B200MIX_HRIR_LENGTH
+#define HIST   B200MIX_HRTF_HISTORY
+#define EDGE   24u                      /* MaxResamplerEdge     core/resampler_limits.h:10 */
+#define PAD    B200MIX_RESAMPLER_PADDING/* MaxResamplerPadding  core/resampler_limits.h:8 */
+#define FRAC_BITS 16
+#define FRAC_ONE  (1u<<FRAC_BITS)
+#define FRAC_MASK (FRAC_ONE-1u)
+#define DECODER_MAX_PADDING 256u        /* DecoderBase::sMaxPadding core/decoderbase.hpp */
+#define RESBUF (LINE + DECODER_MAX_PADDING + PAD) /* DeviceBase::mResampleData core/device.h:282 */
+#define SILENCE_THRESHOLD 0.00001f      /* GainSilenceThreshold core/mixer/defs.h:28 */
+
+/* ---- tables (static-init in the reference) ------------------------------- */
+static oracle_bsinc_table g_bsinc12, g_bsinc24, g_bsinc48;
+static float g_spline[ORACLE_CUBIC_PHASES][8], g_gaussian[ORACLE_CUBIC_PHASES][8];
+static int g_tables_ready;
+
+static int ensure_tables(void)
+{
+    if(g_tables_ready) return 0;
+    /* core/bsinc_tables.cpp:150-155 */
+    if(oracle_build_bsinc(&g_bsinc12, 60, 11, 2)) return -1;
+    if(oracle_build_bsinc(&g_bsinc24, 60, 23, 2)) return -1;
+    if(oracle_build_bsinc(&g_bsinc48, 80, 47, 1)) return -1;
+    oracle_build_spline(g_spline);
+    oracle_build_gaussian(g_gaussian);
+    g_tables_ready = 1;
+    return 0;
+}
+
+static const oracle_bsinc_table *bsinc_for(uint32_t which)
+{
+    switch(which)
+    {
+    case B200MIX_RESAMPLER_FAST_BSINC12: case B200MIX_RESAMPLER_BSINC12: return &g_bsinc12;
+    case B200MIX_RESAMPLER_FAST_BSINC24: case B200MIX_RESAMPLER_BSINC24: return &g_bsinc24;
+    case B200MIX_RESAMPLER_FAST_BSINC48: case B200MIX_RESAMPLER_BSINC48: return &g_bsinc48;
+    }
+    return NULL;
+}
+
+int64_t oracle_get_resampler_table(uint32_t which, float *out, size_t max_floats)
+{
+    if(ensure_tables()) return -1;
+    const float *src; size_t n;
+    if(which == B200MIX_RESAMPLER_SPLINE) { src = &g_spline[0][0]; n = ORACLE_CUBIC_PHASES*8; }
+    else if(which == B200MIX_RESAMPLER_GAUSSIAN) { src = &g_gaussian[0][0]; n = ORACLE_CUBIC_PHASES*8; }
+    else
+    {
+        const oracle_bsinc_table *t = bsinc_for(which);
+        if(!t) return -1;
+        src = t->tab; n = t->total;
+    }
+    if(out) memcpy(out, src, sizeof(float)*(n < max_floats ? n : max_floats));
+    return (int64_t)n;
+}
+
+int oracle_get_bsinc_state(uint32_t which, uint32_t increment, float *sf, uint32_t *m, uint32_t *l,
+    uint32_t *offset)
+{
+    if(ensure_tables()) return -1;
+    const oracle_bsinc_table *t = bsinc_for(which);
+    if(!t) return -1;
+    oracle_bsinc_state st;
+    oracle_bsinc_prepare(t, increment, &st);
+    *sf = st.sf; *m = st.m; *l = st.l; *offset = (uint32_t)(st.filter - t->tab);
+    return 0;
+}
+
+/* ---- resamplers: core/mixer/mixer_c.cpp:39-137,190-221 ------------------- */
+static float lerpf(float a, float b, float mu) { return a + (b-a)*mu; } /* alnumeric.h:115 */
+
+int oracle_resample(uint32_t resampler, uint32_t increment, uint32_t frac, const float *src,
+    float *dst, uint32_t dst_len)
+{
+    if(ensure_tables()) return -1;
+    size_t pos = 0;
+    switch(resampler)
+    {
+    case B200MIX_RESAMPLER_POINT: {
+        const float *vals = src + EDGE;
+        for(uint32_t i = 0;i < dst_len;++i)
+        {
+            dst[i] = vals[pos];
+            frac += increment; pos += frac>>FRAC_BITS; frac &= FRAC_MASK;
+        }
+        return 0; }
+    case B200MIX_RESAMPLER_LINEAR: {
+        const float *vals = src + EDGE;
+        for(uint32_t i = 0;i < dst_len;++i)
+        {
+            dst[i] = lerpf(vals[pos+0], vals[pos+1], (float)frac*(1.0f/FRAC_ONE));
+            frac += increment; pos += frac>>FRAC_BITS; frac &= FRAC_MASK;
+        }
+        return 0; }
+    case B200MIX_RESAMPLER_SPLINE:
+    case B200MIX_RESAMPLER_GAUSSIAN: {
+        /* do_cubic, mixer_c.cpp:48-61; CubicPhaseDiffBits = 16-5 = 11 */
+        const float (*tab)[8] = (resampler == B200MIX_RESAMPLER_SPLINE) ? g_spline : g_gaussian;
+        const float *vals = src + EDGE-1;
+        for(uint32_t i = 0;i < dst_len;++i)
+        {
+            const unsigned pi = frac>>11;
+            const float pf = (float)(frac&2047u)*(1.0f/2048.0f);
+            const float *fil = tab[pi], *phd = tab[pi]+4;
+            dst[i] = (fil[0] + pf*phd[0])*vals[pos+0] + (fil[1] + pf*phd[1])*vals[pos+1]
+                + (fil[2] + pf*phd[2])*vals[pos+2] + (fil[3] + pf*phd[3])*vals[pos+3];
+            frac += increment; pos += frac>>FRAC_BITS; frac &= FRAC_MASK;
+        }
+        return 0; }
+    default: break;
+    }
+    const oracle_bsinc_table *t = bsinc_for(resampler);
+    if(!t) return -1;
+    oracle_bsinc_state st;
+    oracle_bsinc_prepare(t, increment, &st);
+    const size_t m = st.m;
+    const float *vals = src + EDGE - st.l;
+    /* SelectResampler, alc/alu.cpp:203-235: full BSinc only when down-sampling with
+     * a non-"fast" kind; otherwise FastBSinc (phase interpolation only). */
+    const int full = (increment > FRAC_ONE) && (resampler == B200MIX_RESAMPLER_BSINC12
+        || resampler == B200MIX_RESAMPLER_BSINC24 || resampler == B200MIX_RESAMPLER_BSINC48);
+    for(uint32_t i = 0;i < dst_len;++i)
+    {
+        const unsigned pi = frac>>11;
+        const float pf = (float)(frac&2047u)*(1.0f/2048.0f);
+        const float *fil = st.filter + 2*pi*m;
+        const float *phd = fil + m;
+        float r = 0.0f;
+        if(full)
+        {
+            /* do_bsinc, mixer_c.cpp:84-105 */
+            const float *scd = fil + ORACLE_BSINC_PHASES*2*m;
+            const float *spd = scd + m;
+            for(size_t j = 0;j < m;++j)
+                r += (fil[j] + st.sf*scd[j] + pf*(phd[j] + st.sf*spd[j])) * vals[pos+j];
+        }
+        else
+        {
+            /* do_fastbsinc, mixer_c.cpp:63-82 */
+            for(size_t j = 0;j < m;++j)
+                r += (fil[j] + pf*phd[j]) * vals[pos+j];
+        }
+        dst[i] = r;
+        frac += increment; pos += frac>>FRAC_BITS; frac &= FRAC_MASK;
+    }
+    return 0;
+}
+
+/* ---- device state --------------------------------------------------------- */
+typedef struct { uint32_t type, channels, frames; void *data; } obuffer;
+
+typedef struct {
+    int state;                 /* 0 stopped, 1 playing, 2 stopping (Voice::State) */
+    uint32_t flags;            /* STATIC / LOOPING / HRTF */
+    int fading;                /* VoiceFlag::IsFading */
+    int have_buffer;           /* mCurrentBuffer != nullptr */
+    uint32_t buffer, resampler;
+    int32_t pos; uint32_t frac;
+    uint32_t loop_start, loop_end, step;
+    float prev[PAD];                          /* mPrevSamples[0] */
+    float hist[HIST];                         /* Hrtf.History */
+    float tgt_coef[HRIR][2], old_coef[HRIR][2];
+    uint32_t tgt_delay[2], old_delay[2];
+    float tgt_gain, old_gain;
+    float dry_cur[B200MIX_MAX_DRY_CHANNELS], dry_tgt[B200MIX_MAX_DRY_CHANNELS];
+    uint32_t send_slot[B200MIX_MAX_SENDS];
+    float send_cur[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
+    float send_tgt[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
+} ovoice;
+
+typedef struct { float coeff, lp_z1, lp_z2, ap_z1; } osplitter; /* core/filters/splitter.h */
+
+struct oracle_device {
+    b200mix_device_desc desc;
+    obuffer *buffers;
+    ovoice *voices;
+    float (*dry)[LINE];        /* Dry.Buffer */
+    float (*real)[LINE];       /* RealOut.Buffer (== dry when POST_NONE) */
+    float (*wet)[LINE];        /* [slot*wet_channels + c] */
+    float accum[LINE+HRIR][2]; /* HrtfAccumData core/device.h:288 */
+    /* HRTF decoder (DirectHrtfState) */
+    uint32_t dec_channels, dec_ir;
+    float (*dec_coef)[HRIR][2];
+    float *dec_hfscale;
+    osplitter *dec_split;
+    /* ambi decoder (BFormatDec) */
+    uint32_t amb_in; int amb_dual;
+    float *amb_hf, *amb_lf;    /* [in][real] */
+    osplitter *amb_split;
+    /* scratch */
+    float resample_data[RESBUF];
+    float samples[LINE];
+    float hrtf_samples[LINE+HIST];
+    float temp[LINE], temp2[LINE];
+};
+
+int oracle_create(const b200mix_device_desc *desc, oracle_device **out)
+{
+    if(!desc || !out || desc->dry_channels > B200MIX_MAX_DRY_CHANNELS
+        || desc->wet_channels > B200MIX_MAX_WET_CHANNELS || desc->num_sends > B200MIX_MAX_SENDS)
+        return B200MIX_ERR_INVALID;
+    if(ensure_tables()) return B200MIX_ERR_NOMEM;
+    oracle_device *d = calloc(1, sizeof(*d));
+    if(!d) return B200MIX_ERR_NOMEM;
+    d->desc = *desc;
+    d->buffers = calloc(desc->max_buffers ? desc->max_buffers : 1, sizeof(obuffer));
+    d->voices = calloc(desc->max_voices ? desc->max_voices : 1, sizeof(ovoice));
+    d->dry = calloc(desc->dry_channels ? desc->dry_channels : 1, sizeof(float[LINE]));
+    if(desc->post_process == B200MIX_POST_NONE) d->real = d->dry;
+    else d->real = calloc(desc->real_channels ? desc->real_channels : 1, sizeof(float[LINE]));
+    size_t nwet = (size_t)desc->max_slots*desc->wet_channels;
+    d->wet = calloc(nwet ? nwet : 1, sizeof(float[LINE]));
+    *out = d;
+    return B200MIX_OK;
+}
+
+void oracle_destroy(oracle_device *d)
+{
+    if(!d) return;
+    for(uint32_t i = 0;i < d->desc.max_buffers;++i) free(d->buffers[i].data);
+    free(d->buffers); free(d->voices);
+    if(d->real != d->dry) free(d->real);
+    free(d->dry); free(d->wet);
+    free(d->dec_coef); free(d->dec_hfscale); free(d->dec_split);
+    free(d->amb_hf); free(d->amb_lf); free(d->amb_split);
+    free(d);
+}
+
+int oracle_set_hrtf_decoder(oracle_device *d, uint32_t channels, uint32_t ir_size,
+    const float *coeffs, const float *hf_scale, const float *splitter_coeff)
+{
+    if(channels != d->desc.dry_channels || ir_size > HRIR) return B200MIX_ERR_INVALID;
+    d->dec_channels = channels; d->dec_ir = ir_size;
+    d->dec_coef = calloc(channels, sizeof(float[HRIR][2]));
+    d->dec_hfscale = calloc(channels, sizeof(float));
+    d->dec_split = calloc(channels, sizeof(osplitter));
+    for(uint32_t c = 0;c < channels;++c)
+    {
+        for(uint32_t j = 0;j < ir_size;++j)
+        {
+            d->dec_coef[c][j][0] = coeffs[(c*ir_size + j)*2 + 0];
+            d->dec_coef[c][j][1] = coeffs[(c*ir_size + j)*2 + 1];
+        }
+        d->dec_hfscale[c] = hf_scale[c];
+        d->dec_split[c].coeff = splitter_coeff[c];
+    }
+    return B200MIX_OK;
+}
+
+int oracle_set_ambi_decoder(oracle_device *d, uint32_t in_channels, const float *gains_hf,
+    const float *gains_lf, float xover_coeff)
+{
+    if(in_channels != d->desc.dry_channels) return B200MIX_ERR_INVALID;
+    const size_t n = (size_t)in_channels*d->desc.real_channels;
+    d->amb_in = in_channels; d->amb_dual = gains_lf != NULL;
+    d->amb_hf = malloc(n*sizeof(float)); memcpy(d->amb_hf, gains_hf, n*sizeof(float));
+    if(gains_lf) { d->amb_lf = malloc(n*sizeof(float)); memcpy(d->amb_lf, gains_lf, n*sizeof(float)); }
+    d->amb_split = calloc(in_channels, sizeof(osplitter));
+    for(uint32_t c = 0;c < in_channels;++c) d->amb_split[c].coeff = xover_coeff;
+    return B200MIX_OK;
+}
+
+static size_t sample_bytes(uint32_t type)
+{
+    switch(type)
+    {
+    case B200MIX_FMT_U8: case B200MIX_FMT_MULAW: case B200MIX_FMT_ALAW: return 1;
+    case B200MIX_FMT_I16: return 2;
+    case B200MIX_FMT_I32: case B200MIX_FMT_F32: return 4;
+    case B200MIX_FMT_F64: return 8;
+    }
+    return 0;
+}
+
+int oracle_buffer_data(oracle_device *d, uint32_t buffer, uint32_t type, uint32_t channels,
+    uint32_t frames, const void *data, size_t bytes)
+{
+    if(buffer >= d->desc.max_buffers || !sample_bytes(type) || channels < 1) return B200MIX_ERR_INVALID;
+    if(type == B200MIX_FMT_MULAW || type == B200MIX_FMT_ALAW) return B200MIX_ERR_UNSUPPORTED;
+    if(bytes < (size_t)frames*channels*sample_bytes(type)) return B200MIX_ERR_INVALID;
+    obuffer *b = &d->buffers[buffer];
+    free(b->data);
+    b->data = malloc(bytes ? bytes : 1);
+    memcpy(b->data, data, bytes);
+    b->type = type; b->channels = channels; b->frames = frames;
+    return B200MIX_OK;
+}
+
+int oracle_buffer_free(oracle_device *d, uint32_t buffer)
+{
+    if(buffer >= d->desc.max_buffers) return B200MIX_ERR_INVALID;
+    free(d->buffers[buffer].data);
+    memset(&d->buffers[buffer], 0, sizeof(obuffer));
+    return B200MIX_OK;
+}
+
+int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_params *params,
+    const float *hrtf_coeffs, const float *dry_gains, const float *send_gains)
+{
+    const uint32_t ir = d->desc.ir_size, cd = d->desc.dry_channels;
+    const uint32_t ns = d->desc.num_sends, cw = d->desc.wet_channels;
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const b200mix_voice_params *p = &params[i];
+        if(p->voice >= d->desc.max_voices) return B200MIX_ERR_INVALID;
+        ovoice *v = &d->voices[p->voice];
+        if(p->flags & B200MIX_VF_RESET)
+        {
+            /* Voice::prepare + InitVoice: core/voice.cpp:1235-1400, al/source.cpp:639-669 */
+            memset(v, 0, sizeof(*v));
+            v->pos = p->position; v->frac = p->position_frac;
+            v->fading = (p->flags & B200MIX_VF_FADING) != 0;
+            v->have_buffer = 1;
+        }
+        if(p->flags & B200MIX_VF_STOPPED) v->state = 0;
+        else if(p->flags & B200MIX_VF_STOPPING) v->state = 2;
+        else if(p->flags & B200MIX_VF_PLAYING) v->state = 1;
+        v->flags = p->flags & (B200MIX_VF_STATIC|B200MIX_VF_LOOPING|B200MIX_VF_HRTF);
+        v->buffer = p->buffer; v->resampler = p->resampler;
+        v->loop_start = p->loop_start; v->loop_end = p->loop_end; v->step = p->step;
+        v->tgt_delay[0] = p->hrtf_delay[0]; v->tgt_delay[1] = p->hrtf_delay[1];
+        v->tgt_gain = p->hrtf_gain;
+        memcpy(v->send_slot, p->send_slot, sizeof(v->send_slot));
+        if(hrtf_coeffs)
+            for(uint32_t j = 0;j < ir;++j)
+            {
+                v->tgt_coef[j][0] = hrtf_coeffs[((size_t)i*ir + j)*2 + 0];
+                v->tgt_coef[j][1] = hrtf_coeffs[((size_t)i*ir + j)*2 + 1];
+            }
+        if(dry_gains)
+            for(uint32_t c = 0;c < cd;++c) v->dry_tgt[c] = dry_gains[(size_t)i*cd + c];
+        if(send_gains)
+            for(uint32_t s = 0;s < ns;++s)
+                for(uint32_t c = 0;c < cw;++c)
+                    v->send_tgt[s][c] = send_gains[((size_t)i*ns + s)*cw + c];
+    }
+    return B200MIX_OK;
+}
+
+/* ---- sample loading: core/voice.cpp:271-288 (LoadSamples), fmt_traits.h:88-131 */
+static float to_float(const obuffer *b, size_t idx)
+{
+    switch(b->type)
+    {
+    case B200MIX_FMT_U8: return ((float)((const uint8_t*)b->data)[idx]-128.0f) * (1.0f/128.0f);
+    case B200MIX_FMT_I16: return (float)((const int16_t*)b->data)[idx] * (1.0f/32768.0f);
+    case B200MIX_FMT_I32: return (float)((const int32_t*)b->data)[idx] * (1.0f/2147483648.0f);
+    case B200MIX_FMT_F32: return ((const float*)b->data)[idx];
+    case B200MIX_FMT_F64: return (float)((const double*)b->data)[idx];
+    }
+    return 0.0f;
+}
+static void load_samples(float *dst, size_t count, const obuffer *b, size_t offset)
+{
+    for(size_t i = 0;i < count;++i)
+        dst[i] = to_float(b, (offset+i)*b->channels);
+}
+
+/* LoadBufferStatic, core/voice.cpp:500-544 */
+static void load_buffer_static(const obuffer *b, int looping, uint32_t loop_start,
+    uint32_t loop_end, size_t dataPosInt, float *dst, size_t count)
+{
+    if(!looping)
+    {
+        float lastSample = 0.0f;
+        if(b->frames > dataPosInt)
+        {
+            size_t remaining = b->frames - dataPosInt;
+            if(remaining > count) remaining = count;
+            load_samples(dst, remaining, b, dataPosInt);
+            lastSample = dst[remaining-1];
+            dst += remaining; count -= remaining;
+        }
+        for(size_t i = 0;i < count;++i) dst[i] = lastSample;
+    }
+    else
+    {
+        const size_t loopStart = loop_start, loopEnd = loop_end;
+        const size_t intPos = (dataPosInt < loopEnd) ? dataPosInt
+            : (((dataPosInt-loopStart)%(loopEnd-loopStart)) + loopStart);
+        size_t remaining = loopEnd-intPos;
+        if(remaining > count) remaining = count;
+        load_samples(dst, remaining, b, intPos);
+        dst += remaining; count -= remaining;
+        const size_t loopSize = loopEnd - loopStart;
+        while(count > 0)
+        {
+            const size_t toFill = (count < loopSize) ? count : loopSize;
+            load_samples(dst, toFill, b, loopStart);
+            dst += toFill; count -= toFill;
+        }
+    }
+}
+
+/* CalculateBufferSize, core/voice.cpp:601-640 */
+static void calc_buffer_size(uint32_t fracPos, uint32_t increment, uint32_t dstRemaining,
+    uint32_t *dst, uint32_t *src)
+{
+    const uint32_t SrcSizeMax = RESBUF - EDGE;
+    const uint32_t ext = increment <= FRAC_ONE;
+    const uint64_t srcSize64 = (((uint64_t)(dstRemaining - ext)*increment + fracPos) >> FRAC_BITS)
+        + ext + EDGE;
+    if(srcSize64 <= SrcSizeMax) { *dst = dstRemaining; *src = (uint32_t)srcSize64; return; }
+    const uint64_t dstSize64 = (((uint64_t)(SrcSizeMax - EDGE)<<FRAC_BITS) - fracPos) / increment;
+    if(dstSize64 < dstRemaining) { *dst = (uint32_t)dstSize64 & ~3u; *src = SrcSizeMax; return; }
+    *dst = dstRemaining; *src = SrcSizeMax;
+}
+
+static int32_t add_sat_i32(int32_t a, int32_t b)
+{
+    int64_t r = (int64_t)a + b;
+    if(r > INT32_MAX) r = INT32_MAX;
+    if(r < INT32_MIN) r = INT32_MIN;
+    return (int32_t)r;
+}
+
+/* LoadResampledSamples for one mono static voice, core/voice.cpp:642-822 */
+static void load_resampled(oracle_device *d, ovoice *v, int vstate, int looping,
+    uint32_t samplesToMix)
+{
+    float *rd = d->resample_data;
+    float *srcBuffer = rd + EDGE;
+    memcpy(rd, v->prev, sizeof(v->prev));
+    int32_t intPos = v->pos;
+    uint32_t fracPos = v->frac;
+    const uint32_t increment = v->step;
+    const obuffer *buf = v->have_buffer ? &d->buffers[v->buffer] : NULL;
+
+    for(uint32_t loaded = 0;loaded < samplesToMix;)
+    {
+        uint32_t dstn, srcn;
+        calc_buffer_size(fracPos, increment, samplesToMix-loaded, &dstn, &srcn);
+
+        uint32_t srcSampleDelay = 0;
+        int silent = 0;
+        if(intPos < 0)
+        {
+            srcSampleDelay = (uint32_t)(-intPos);
+            if(srcSampleDelay >= srcn)
+            {
+                memset(d->samples+loaded, 0, sizeof(float)*dstn);
+                memset(srcBuffer, 0, sizeof(float)*srcn);
+                loaded += dstn;
+                if(loaded < samplesToMix)
+                {
+                    fracPos += dstn*increment;
+                    const uint32_t srcOffset = fracPos >> FRAC_BITS;
+                    fracPos &= FRAC_MASK;
+                    intPos = add_sat_i32(intPos, (int32_t)srcOffset);
+                }
+                silent = 1;
+            }
+            else
+                memset(srcBuffer, 0, sizeof(float)*srcSampleDelay);
+        }
+        if(silent) continue;
+
+        if(!buf)
+        {
+            /* voice ended prematurely: hold the sample closest to 0, voice.cpp:704-719 */
+            const uint32_t avail = (srcn < EDGE) ? srcn : EDGE;
+            const uint32_t tofill = (srcn > EDGE) ? srcn : EDGE;
+            uint32_t best = 0;
+            for(uint32_t i = 1;i < avail;++i)
+                if(fabsf(srcBuffer[i]) < fabsf(srcBuffer[best])) best = i;
+            for(uint32_t i = best+1;i < tofill;++i) srcBuffer[i] = srcBuffer[best];
+        }
+        else
+        {
+            const uint32_t uintPos = (intPos < 0) ? 0u : (uint32_t)intPos;
+            load_buffer_static(buf, looping, v->loop_start, v->loop_end, uintPos,
+                srcBuffer+srcSampleDelay, srcn-srcSampleDelay);
+        }
+
+        if(increment == FRAC_ONE && fracPos == 0)
+            memcpy(d->samples+loaded, srcBuffer, sizeof(float)*dstn); /* bypass, :764-766 */
+        else
+            oracle_resample(v->resampler, increment, fracPos, rd, d->samples+loaded, dstn);
+
+        if(vstate == 1)
+        {
+            const uint32_t loadEnd = loaded + dstn;
+            if(samplesToMix > loaded && samplesToMix <= loadEnd)
+            {
+                const size_t dstOffset = samplesToMix - loaded;
+                const size_t srcOffset = (dstOffset*increment + fracPos) >> FRAC_BITS;
+                memmove(v->prev, rd+srcOffset, sizeof(v->prev));
+            }
+        }
+
+        loaded += dstn;
+        if(loaded < samplesToMix)
+        {
+            fracPos += dstn*increment;
+            const uint32_t srcOffset = fracPos >> FRAC_BITS;
+            fracPos &= FRAC_MASK;
+            if(intPos < 0) intPos += (int32_t)srcOffset;
+            else intPos = add_sat_i32(intPos, (int32_t)srcOffset);
+            memmove(rd, rd+srcOffset, sizeof(float)*PAD);
+        }
+    }
+}
+
+/* MixLine + Mix_C, core/mixer/mixer_c.cpp:150-186,247-258 */
+static void mix_line(const float *in, size_t n, float *dst, float *cur, float target, float delta,
+    size_t fade_len, size_t counter)
+{
+    const float step = (target - *cur) * delta;
+    size_t pos = 0;
+    if(fabsf(step) > 1.1920929e-07f)
+    {
+        const float gain = *cur;
+        float step_count = 0.0f;
+        for(;pos < fade_len;++pos)
+        {
+            dst[pos] += in[pos] * (gain + step*step_count);
+            step_count += 1.0f;
+        }
+        if(fade_len < counter)
+        {
+            *cur = gain + step*step_count;
+            return;
+        }
+    }
+    *cur = target;
+    if(!(fabsf(target) > SILENCE_THRESHOLD))
+        return;
+    for(;pos < n;++pos)
+        dst[pos] += in[pos]*target;
+}
+
+static void mix_samples(const float *in, size_t n, float (*out)[LINE], size_t nchan, float *cur,
+    const float *tgt, size_t counter)
+{
+    const float delta = (counter > 0) ? 1.0f/(float)counter : 0.0f;
+    const size_t fade_len = (counter < n) ? counter : n;
+    for(size_t c = 0;c < nchan;++c)
+        mix_line(in, n, out[c], &cur[c], tgt[c], delta, fade_len, counter);
+}
+
+/* ApplyCoeffs, mixer_c.cpp:139-148 */
+static void apply_coeffs(float (*values)[2], size_t ir, const float (*coeffs)[2], float left,
+    float right)
+{
+    for(size_t c = 0;c < ir;++c)
+    {
+        values[c][0] = values[c][0] + coeffs[c][0]*left;
+        values[c][1] = values[c][1] + coeffs[c][1]*right;
+    }
+}
+
+/* MixHrtfBase, core/mixer/hrtfbase.h:17-42 */
+static void mix_hrtf(const float *in, float (*accum)[2], size_t ir, const float (*coeffs)[2],
+    const uint32_t delay[2], float gain, float gainstep, size_t todo)
+{
+    size_t ldelay = HIST - delay[0], rdelay = HIST - delay[1];
+    float stepcount = 0.0f;
+    for(size_t i = 0;i < todo;++i)
+    {
+        const float g = gain + gainstep*stepcount;
+        const float left = in[ldelay++] * g;
+        const float right = in[rdelay++] * g;
+        apply_coeffs(accum+i, ir, coeffs, left, right);
+        stepcount += 1.0f;
+    }
+}
+
+/* MixHrtfBlendBase, core/mixer/hrtfbase.h:44-89 */
+static void mix_hrtf_blend(const float *in, float (*accum)[2], size_t ir,
+    const float (*oldc)[2], const uint32_t olddelay[2], float oldgain,
+    const float (*newc)[2], const uint32_t newdelay[2], float newGainStep, size_t todo)
+{
+    const float oldGainStep = oldgain / (float)todo;
+    if(oldgain > SILENCE_THRESHOLD)
+    {
+        size_t ldelay = HIST - olddelay[0], rdelay = HIST - olddelay[1];
+        float stepcount = (float)todo;
+        for(size_t i = 0;i < todo;++i)
+        {
+            const float g = oldGainStep*stepcount;
+            const float left = in[ldelay++] * g;
+            const float right = in[rdelay++] * g;
+            apply_coeffs(accum+i, ir, oldc, left, right);
+            stepcount -= 1.0f;
+        }
+    }
+    if(newGainStep*(float)todo > SILENCE_THRESHOLD)
+    {
+        size_t ldelay = HIST+1 - newdelay[0], rdelay = HIST+1 - newdelay[1];
+        float stepcount = 1.0f;
+        for(size_t i = 1;i < todo;++i)
+        {
+            const float g = newGainStep*stepcount;
+            const float left = in[ldelay++] * g;
+            const float right = in[rdelay++] * g;
+            apply_coeffs(accum+i, ir, newc, left, right);
+            stepcount += 1.0f;
+        }
+    }
+}
+
+/* DoHrtfMix, core/voice.cpp:827-902 (outPos == 0) */
+static void do_hrtf_mix(oracle_device *d, ovoice *v, const float *samples, size_t n,
+    float targetGain, size_t counter, int isPlaying)
+{
+    const size_t ir = d->desc.ir_size;
+    float *hs = d->hrtf_samples;
+    memcpy(hs, v->hist, sizeof(v->hist));
+    memcpy(hs+HIST, samples, sizeof(float)*n);
+    if(isPlaying)
+        memcpy(v->hist, hs+n, sizeof(v->hist));
+
+    size_t fademix = 0, outPos = 0;
+    if(counter)
+    {
+        fademix = (n < counter) ? n : counter;
+        float gain = targetGain;
+        if(counter > fademix)
+        {
+            const float a = (float)fademix / (float)counter;
+            gain = lerpf(v->old_gain, targetGain, a);
+        }
+        mix_hrtf_blend(hs, d->accum+outPos, ir, (const float(*)[2])v->old_coef, v->old_delay,
+            v->old_gain, (const float(*)[2])v->tgt_coef, v->tgt_delay, gain/(float)fademix,
+            fademix);
+        memcpy(v->old_coef, v->tgt_coef, sizeof(v->old_coef));
+        v->old_delay[0] = v->tgt_delay[0]; v->old_delay[1] = v->tgt_delay[1];
+        v->old_gain = gain;
+        outPos += fademix;
+    }
+    if(fademix < n)
+    {
+        const size_t todo = n - fademix;
+        float gain = targetGain;
+        if(counter > n)
+        {
+            const float a = (float)todo / (float)(counter-fademix);
+            gain = lerpf(v->old_gain, targetGain, a);
+        }
+        mix_hrtf(hs+fademix, d->accum+outPos, ir, (const float(*)[2])v->tgt_coef, v->tgt_delay,
+            v->old_gain, (gain - v->old_gain) / (float)todo, todo);
+        v->old_gain = gain;
+    }
+}
+
+/* Voice::mix for a mono static voice, core/voice.cpp:988-1233 */
+static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_result *res)
+{
+    static const float silent[B200MIX_MAX_DRY_CHANNELS];
+    const int vstate = v->state;
+    const uint32_t increment = v->step;
+    if(increment < 1)
+    {
+        if(vstate == 2) v->state = 0;
+        return;
+    }
+    const obuffer *buf = v->have_buffer ? &d->buffers[v->buffer] : NULL;
+    int looping = (v->flags & B200MIX_VF_LOOPING) != 0;
+    if((v->flags & B200MIX_VF_STATIC) && looping && buf)
+    {
+        if(v->pos >= 0 && (uint32_t)v->pos >= v->loop_end) looping = 0; /* :1015-1019 */
+    }
+
+    load_resampled(d, v, vstate, looping, n);
+
+    const size_t counter = v->fading ? (n < 64u ? n : 64u) : 0u;
+    const uint32_t cd = d->desc.dry_channels, ns = d->desc.num_sends, cw = d->desc.wet_channels;
+    if(!counter)
+    {
+        /* :1094-1112 */
+        if(!(v->flags & B200MIX_VF_HRTF))
+            memcpy(v->dry_cur, v->dry_tgt, sizeof(v->dry_cur));
+        else
+        {
+            memcpy(v->old_coef, v->tgt_coef, sizeof(v->old_coef));
+            v->old_delay[0] = v->tgt_delay[0]; v->old_delay[1] = v->tgt_delay[1];
+            v->old_gain = v->tgt_gain;
+        }
+        for(uint32_t s = 0;s < ns;++s)
+            if(v->send_slot[s] != B200MIX_NO_SLOT)
+                memcpy(v->send_cur[s], v->send_tgt[s], sizeof(v->send_cur[s]));
+    }
+
+    /* DoMix, :934-984 (filters inactive) */
+    if(v->flags & B200MIX_VF_HRTF)
+    {
+        const float targetGain = v->tgt_gain * (float)(vstate == 1);
+        do_hrtf_mix(d, v, d->samples, n, targetGain, counter, vstate == 1);
+    }
+    else
+    {
+        const float *tg = (vstate == 1) ? v->dry_tgt : silent;
+        mix_samples(d->samples, n, d->dry, cd, v->dry_cur, tg, counter);
+    }
+    for(uint32_t s = 0;s < ns;++s)
+    {
+        if(v->send_slot[s] == B200MIX_NO_SLOT) continue;
+        const float *tg = (vstate == 1) ? v->send_tgt[s] : silent;
+        mix_samples(d->samples, n, d->wet + (size_t)v->send_slot[s]*cw, cw, v->send_cur[s], tg,
+            counter);
+    }
+
+    v->fading = 1;
+    if(vstate == 2)
+    {
+        v->state = 0;
+        return;
+    }
+
+    /* position update, :1126-1153 */
+    uint32_t frac = v->frac + increment*n;
+    const uint32_t samplesDone = frac >> FRAC_BITS;
+    int32_t pos = add_sat_i32(v->pos, (int32_t)samplesDone);
+    frac &= FRAC_MASK;
+    if(buf && pos > 0)
+    {
+        if(looping)
+        {
+            uint32_t up = (uint32_t)pos;
+            if(up >= v->loop_end)
+            {
+                up = ((up-v->loop_start)%(v->loop_end-v->loop_start)) + v->loop_start;
+                pos = (int32_t)up;
+            }
+        }
+        else if((uint32_t)pos >= buf->frames)
+            v->have_buffer = 0;
+    }
+    v->pos = pos; v->frac = frac;
+    if(!v->have_buffer)
+        v->state = 2; /* Stopping: fade out on the next update, :1224-1232 */
+    (void)res;
+}
+
+/* BandSplitter::processHfScale(input, output, hfscale), core/filters/splitter.cpp:64-95.
+ * NOTE the reference's quirk at :79: lp_z1 = lp_y0 + d0*lp_coeff in this overload. */
+static void splitter_hfscale(osplitter *s, const float *in, float *out, size_t n, float hfscale)
+{
+    const float ap_coeff = s->coeff;
+    const float lp_coeff = s->coeff*0.5f + 0.5f;
+    float lp_z1 = s->lp_z1, lp_z2 = s->lp_z2, ap_z1 = s->ap_z1;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x = in[i];
+        const float d0 = (x - lp_z1) * lp_coeff;
+        const float lp_y0 = lp_z1 + d0;
+        lp_z1 = lp_y0 + d0*lp_coeff;
+        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+        const float lp_y1 = lp_z2 + d1;
+        lp_z2 = lp_y1 + d1;
+        const float ap_y = x*ap_coeff + ap_z1;
+        ap_z1 = x - ap_y*ap_coeff;
+        out[i] = (ap_y-lp_y1)*hfscale + lp_y1;
+    }
+    s->lp_z1 = lp_z1; s->lp_z2 = lp_z2; s->ap_z1 = ap_z1;
+}
+
+/* BandSplitter::process, core/filters/splitter.cpp:28-62 */
+static void splitter_process(osplitter *s, const float *in, float *hp, float *lp, size_t n)
+{
+    const float ap_coeff = s->coeff;
+    const float lp_coeff = s->coeff*0.5f + 0.5f;
+    float lp_z1 = s->lp_z1, lp_z2 = s->lp_z2, ap_z1 = s->ap_z1;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x = in[i];
+        const float d0 = (x - lp_z1) * lp_coeff;
+        const float lp_y0 = lp_z1 + d0;
+        lp_z1 = lp_y0 + d0;
+        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+        const float lp_y1 = lp_z2 + d1;
+        lp_z2 = lp_y1 + d1;
+        lp[i] = lp_y1;
+        const float ap_y = x*ap_coeff + ap_z1;
+        ap_z1 = x - ap_y*ap_coeff;
+        hp[i] = ap_y - lp_y1;
+    }
+    s->lp_z1 = lp_z1; s->lp_z2 = lp_z2; s->ap_z1 = ap_z1;
+}
+
+/* MixDirectHrtfBase, core/mixer/hrtfbase.h:91-133 */
+static void post_hrtf(oracle_device *d, size_t n)
+{
+    for(uint32_t c = 0;c < d->dec_channels;++c)
+    {
+        splitter_hfscale(&d->dec_split[c], d->dry[c], d->temp, n, d->dec_hfscale[c]);
+        for(size_t i = 0;i < n;++i)
+            apply_coeffs(d->accum+i, d->dec_ir, (const float(*)[2])d->dec_coef[c], d->temp[i],
+                d->temp[i]);
+    }
+    float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
+    for(size_t i = 0;i < n;++i)
+    {
+        left[i] += d->accum[i][0];
+        right[i] += d->accum[i][1];
+    }
+    memmove(d->accum, d->accum+n, sizeof(float[2])*HRIR);
+    memset(d->accum+HRIR, 0, sizeof(float[2])*n);
+}
+
+/* BFormatDec::process, core/bformatdec.cpp:60-97 */
+static void post_ambidec(oracle_device *d, size_t n)
+{
+    const uint32_t outs = d->desc.real_channels;
+    for(uint32_t c = 0;c < d->amb_in;++c)
+    {
+        if(d->amb_dual)
+        {
+            splitter_process(&d->amb_split[c], d->dry[c], d->temp, d->temp2, n);
+            float *g = d->amb_hf + (size_t)c*outs;
+            float tmp[B200MIX_MAX_DRY_CHANNELS];
+            memcpy(tmp, g, sizeof(float)*outs);
+            mix_samples(d->temp, n, d->real, outs, tmp, g, 0);
+            g = d->amb_lf + (size_t)c*outs;
+            memcpy(tmp, g, sizeof(float)*outs);
+            mix_samples(d->temp2, n, d->real, outs, tmp, g, 0);
+        }
+        else
+        {
+            float *g = d->amb_hf + (size_t)c*outs;
+            float tmp[B200MIX_MAX_DRY_CHANNELS];
+            memcpy(tmp, g, sizeof(float)*outs);
+            mix_samples(d->dry[c], n, d->real, outs, tmp, g, 0);
+        }
+    }
+}
+
+/* DeviceBase::renderSamples(unsigned) + ProcessContexts, alc/alu.cpp:2412-2459,2177-2273 */
+int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
+    b200mix_voice_result *results)
+{
+    if(frames < 1 || frames > LINE) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc *dd = &d->desc;
+    memset(d->dry, 0, sizeof(float[LINE])*dd->dry_channels);
+    if(d->real != d->dry) memset(d->real, 0, sizeof(float[LINE])*dd->real_channels);
+    memset(d->wet, 0, sizeof(float[LINE])*(size_t)dd->max_slots*dd->wet_channels);
+
+    for(uint32_t i = 0;i < dd->max_voices;++i)
+    {
+        ovoice *v = &d->voices[i];
+        if(v->state == 1 || v->state == 2)
+            voice_mix(d, v, frames, NULL);
+    }
+    /* effect slots: none configured in the oracle yet */
+
+    switch(dd->post_process)
+    {
+    case B200MIX_POST_HRTF: if(d->dec_channels) post_hrtf(d, frames); break;
+    case B200MIX_POST_AMBIDEC: if(d->amb_in) post_ambidec(d, frames); break;
+    case B200MIX_POST_NONE: break;
+    default: return B200MIX_ERR_UNSUPPORTED;
+    }
+
+    if(real_out)
+        for(uint32_t c = 0;c < dd->real_channels;++c)
+            if(real_out[c]) memcpy(real_out[c], d->real[c], sizeof(float)*frames);
+    if(results)
+        for(uint32_t i = 0;i < dd->max_voices;++i)
+        {
+            const ovoice *v = &d->voices[i];
+            results[i].position = v->pos; results[i].position_frac = v->frac;
+            results[i].flags = (v->state == 1) ? B200MIX_VF_PLAYING
+                : (v->state == 2) ? B200MIX_VF_STOPPING : B200MIX_VF_STOPPED;
+            results[i].buffers_done = 0;
+        }
+    return B200MIX_OK;
+}
+
+int oracle_get_dry(oracle_device *d, float *dry)
+{
+    memcpy(dry, d->dry, sizeof(float[LINE])*d->desc.dry_channels);
+    return B200MIX_OK;
+}
+
+int oracle_get_hrtf_accum(oracle_device *d, float *accum)
+{
+    memcpy(accum, d->accum, sizeof(d->accum));
+    return B200MIX_OK;
+}

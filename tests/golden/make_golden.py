@@ -1,0 +1,105 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the UNMODIFIED reference compiled under
+oracle/_ref (see oracle/refbuild/Makefile).  Run from the repo root:
+    python tests/golden/make_golden.py
+Each fixture holds, for one seeded synthetic scene (openal-soft_b200/pyb200mix/scene.py):
+the device description and decoder constants the reference chose, the post-ALU
+voice parameters it computed (b200mix_voice_params + side arrays), and its
+rendered output for U consecutive 1024-frame updates from BOTH kernel sets:
+  out_sse : default CPU extensions (SSE..SSE4.1)
+  out_c   : disable-cpu-exts=all (the plain C kernels)
+The PCM inputs are regenerated from the seeds at test time.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "openal-soft_b200"))
+
+SCENES = {
+    # name: (voices, hrtf, resampler, updates, looping, buffer_frames)
+    "hrtf_bsinc24_v8": (8, 1, 7, 6, True, 48000),
+    "hrtf_fastbsinc12_v6": (6, 1, 4, 3, True, 48000),
+    "hrtf_bsinc48_v4": (4, 1, 9, 3, True, 48000),
+    "stereo_spline_v64": (64, 0, 2, 4, True, 48000),
+    "stereo_linear_v5": (5, 0, 1, 2, True, 48000),
+    "stereo_point_v5": (5, 0, 0, 2, True, 48000),
+    "stereo_gaussian_v5": (5, 0, 3, 2, True, 48000),
+    "stereo_bsinc12_v5": (5, 0, 5, 2, True, 48000),
+    # short non-looping buffers: voices end, go Stopping, fade out
+    "hrtf_bsinc24_oneshot_v6": (6, 1, 7, 5, False, 2500),
+    "stereo_spline_oneshot_v6": (6, 0, 2, 5, False, 2500),
+}
+
+
+def run_scene(name):
+    from helpers import refal, scenes
+    from pyb200mix import abi
+    V, hrtf, rs, U, looping, frames = SCENES[name]
+    ref, pcms = scenes.make_ref_scene(V, hrtf, rs, looping=looping, frames=frames)
+    ref.play_all()
+    outs = []
+    snap = None
+    for u in range(U):
+        outs.append(ref.render())
+        if u == 0:
+            snap = ref.snapshot()
+    n, params, coeffs, dry, send, state = snap
+    d = ref.desc
+    res = dict(out=np.stack(outs),
+               desc=np.frombuffer(bytes(d), dtype=np.uint8).copy(),
+               params=np.frombuffer(bytes(params), dtype=np.uint8)[:V * C.sizeof(abi.VoiceParams)].copy(),
+               coeffs=coeffs[:V].copy(), dry=dry[:V].copy())
+    if d.post_process == abi.POST_HRTF:
+        c, hf, sc = ref.hrtf_decoder()
+        res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)
+    elif d.post_process == abi.POST_AMBIDEC:
+        hfm, lfm, xo = ref.ambi_decoder()
+        res.update(amb_hf=hfm, amb_xover=np.float32(xo))
+        if lfm is not None:
+            res.update(amb_lf=lfm)
+    ref.close()
+    return res
+
+
+def child(name, mode, path):
+    from helpers import refal
+    conf = "[general]\n" + ("disable-cpu-exts = all\n" if mode == "c" else "")
+    refal.libs(conf)
+    res = run_scene(name)
+    np.savez(path, **res)
+
+
+def main():
+    if len(sys.argv) == 4:
+        child(sys.argv[1], sys.argv[2], sys.argv[3])
+        return
+    for name in SCENES:
+        parts = {}
+        for mode in ("sse", "c"):
+            tmp = os.path.join(HERE, f"_tmp_{name}_{mode}.npz")
+            subprocess.check_call([sys.executable, __file__, name, mode, tmp])
+            parts[mode] = dict(np.load(tmp))
+            os.remove(tmp)
+        a, b = parts["sse"], parts["c"]
+        for k in a:
+            if k != "out":
+                assert np.array_equal(a[k], b[k]), (name, k)
+        out = {k: v for k, v in a.items() if k != "out"}
+        out["out_sse"] = a["out"]
+        out["out_c"] = b["out"]
+        V, hrtf, rs, U, looping, frames = SCENES[name]
+        out["meta"] = np.array([V, hrtf, rs, U, int(looping), frames], dtype=np.int64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        d = np.abs(a["out"].astype(np.float64) - b["out"]).max()
+        print(f"{name}: wrote, |sse-c|max = {d:.3e}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Replays a committed golden fixture (tests/golden/*.npz, produced from the compiled
+reference by tests/golden/make_golden.py) on a b200mix-surface implementation."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from pyb200mix import abi, scene
+from .mixlib import MixDevice
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden")
+
+
+def names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def replay(mixlib, fx, updates=None, frames=abi.LINE):
+    """Returns (out [U][ch][frames], final voice results)."""
+    V, hrtf, rs, U, looping, buf_frames = [int(x) for x in fx["meta"]]
+    desc = abi.DeviceDesc.from_buffer_copy(fx["desc"].tobytes())
+    desc.max_voices = V
+    desc.max_buffers = V
+    desc.max_slots = 0
+    dev = MixDevice(mixlib, desc)
+    try:
+        if desc.post_process == abi.POST_HRTF:
+            dev.set_hrtf_decoder(fx["dec_coeffs"], fx["dec_hf"], fx["dec_sc"])
+        elif desc.post_process == abi.POST_AMBIDEC:
+            dev.set_ambi_decoder(fx["amb_hf"], fx.get("amb_lf"), float(fx["amb_xover"]))
+        for i in range(V):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_i16(i, buf_frames))
+        params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
+        plist = []
+        for k in range(V):
+            q = abi.VoiceParams()
+            C.memmove(C.byref(q), C.byref(params[k]), C.sizeof(q))
+            q.buffer = k
+            # the snapshot was taken after the reference's first update: restart the voice
+            q.flags = (q.flags & ~(abi.VF_STOPPING | abi.VF_STOPPED)) | abi.VF_PLAYING | abi.VF_RESET
+            q.position = 0
+            q.position_frac = 0
+            plist.append(q)
+        dev.voices_update(plist, fx["coeffs"], fx["dry"], None)
+        outs = []
+        res = None
+        for _ in range(updates or U):
+            o, res = dev.render(frames, want_results=True)
+            outs.append(o)
+        return np.stack(outs), res
+    finally:
+        dev.close()

@@ -1,0 +1,133 @@
+"""Uniform ctypes front-end over the two implementations of the include/b200mix.h
+surface: the CUDA product (libb200mix.so, prefix b200mix_) and the CPU oracle
+(oracle/liboracle.so, prefix oracle_).  Tests drive both with the same calls."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "openal-soft_b200"))
+from pyb200mix import abi  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+PRODUCT_SO = os.path.join(ROOT, "openal-soft_b200", "libb200mix.so")
+
+
+class MixLib:
+    def __init__(self, path: str, prefix: str):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        L = self.lib
+        f = lambda name: getattr(L, prefix + name)  # noqa: E731
+        self.create = f("create")
+        self.create.argtypes = [C.POINTER(abi.DeviceDesc), C.POINTER(C.c_void_p)]
+        self.destroy = f("destroy")
+        self.destroy.argtypes = [C.c_void_p]
+        self.destroy.restype = None
+        self.set_hrtf_decoder = f("set_hrtf_decoder")
+        self.set_hrtf_decoder.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 3
+        self.set_ambi_decoder = f("set_ambi_decoder")
+        self.set_ambi_decoder.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float]
+        self.buffer_data = f("buffer_data")
+        self.buffer_data.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_void_p, C.c_size_t]
+        self.voices_update = f("voices_update")
+        self.voices_update.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        self.render = f("render")
+        self.render.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]
+        self.get_dry = f("get_dry")
+        self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
+
+
+class MixDevice:
+    """One device on either implementation."""
+
+    def __init__(self, mixlib: MixLib, desc: abi.DeviceDesc):
+        self.m = mixlib
+        self.desc = abi.DeviceDesc()
+        C.memmove(C.byref(self.desc), C.byref(desc), C.sizeof(desc))
+        self.desc.struct_size = C.sizeof(abi.DeviceDesc)
+        h = C.c_void_p()
+        rc = self.m.create(C.byref(self.desc), C.byref(h))
+        assert rc == 0, f"{mixlib.prefix}create -> {rc}"
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.m.destroy(self.h)
+            self.h = None
+
+    def set_hrtf_decoder(self, coeffs, hf, sc):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float32)
+        hf = np.ascontiguousarray(hf, dtype=np.float32)
+        sc = np.ascontiguousarray(sc, dtype=np.float32)
+        rc = self.m.set_hrtf_decoder(self.h, coeffs.shape[0], coeffs.shape[1], coeffs.ctypes.data,
+                                     hf.ctypes.data, sc.ctypes.data)
+        assert rc == 0, rc
+
+    def set_ambi_decoder(self, hfm, lfm, xover):
+        hfm = np.ascontiguousarray(hfm, dtype=np.float32)
+        lfp = None
+        if lfm is not None:
+            lfm = np.ascontiguousarray(lfm, dtype=np.float32)
+            lfp = lfm.ctypes.data
+        rc = self.m.set_ambi_decoder(self.h, hfm.shape[0], hfm.ctypes.data, lfp, xover)
+        assert rc == 0, rc
+
+    def buffer_data(self, buf_id, sample_type, pcm):
+        pcm = np.ascontiguousarray(pcm)
+        rc = self.m.buffer_data(self.h, buf_id, sample_type, 1, pcm.shape[0], pcm.ctypes.data,
+                                pcm.nbytes)
+        assert rc == 0, rc
+
+    def voices_update(self, params, coeffs=None, dry=None, send=None):
+        n = len(params)
+        arr = params if not isinstance(params, list) else (abi.VoiceParams * n)(*params)
+        cp = dp = sp = None
+        if coeffs is not None:
+            coeffs = np.ascontiguousarray(coeffs, dtype=np.float32)
+            cp = coeffs.ctypes.data
+        if dry is not None:
+            dry = np.ascontiguousarray(dry, dtype=np.float32)
+            dp = dry.ctypes.data
+        if send is not None:
+            send = np.ascontiguousarray(send, dtype=np.float32)
+            sp = send.ctypes.data
+        rc = self.m.voices_update(self.h, n, arr, cp, dp, sp)
+        assert rc == 0, rc
+
+    def render(self, frames=1024, want_results=False):
+        ch = self.desc.real_channels
+        out = np.zeros((ch, frames), dtype=np.float32)
+        ptrs = (C.c_void_p * ch)(*[out[c].ctypes.data for c in range(ch)])
+        res = (abi.VoiceResult * max(self.desc.max_voices, 1))() if want_results else None
+        rc = self.m.render(self.h, frames, ptrs, res)
+        assert rc == 0, f"render -> {rc}"
+        return (out, res) if want_results else out
+
+    def dry(self):
+        out = np.zeros((self.desc.dry_channels, abi.LINE), dtype=np.float32)
+        self.m.get_dry(self.h, out.ctypes.data)
+        return out
+
+
+_oracle = None
+
+
+def oracle() -> MixLib:
+    global _oracle
+    if _oracle is None:
+        _oracle = MixLib(ORACLE_SO, "oracle_")
+    return _oracle
+
+
+_product = None
+
+
+def product() -> MixLib:
+    global _product
+    if _product is None:
+        _product = MixLib(PRODUCT_SO, "b200mix_")
+    return _product

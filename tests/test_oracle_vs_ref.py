@@ -1,0 +1,85 @@
+"""Pins the oracle restatement against the compiled reference (oracle/_ref) live:
+coefficient tables and BsincPrepare bit-for-bit, resampler kernels bit-for-bit vs
+the reference's C kernels and within rounding of its SSE kernels.
+Skipped when oracle/_ref is absent (it is built by __graft_entry__.build() when
+/root/reference exists, and travels to the GPU box)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import mixlib, refal
+from pyb200mix import abi
+
+pytestmark = pytest.mark.ref
+
+
+def _oracle_lib():
+    lib = mixlib.oracle().lib
+    lib.oracle_get_resampler_table.restype = C.c_int64
+    lib.oracle_get_resampler_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+    lib.oracle_get_bsinc_state.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_uint32)]
+    lib.oracle_resample.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.c_uint32]
+    return lib
+
+
+@pytest.mark.parametrize("which", [abi.RS_BSINC12, abi.RS_BSINC24, abi.RS_BSINC48])
+def test_bsinc_tables_bit_exact(which):
+    _, hz = refal.libs()
+    lib = _oracle_lib()
+    n_ref = hz.refh_bsinc_table(which, None, 0)
+    n = lib.oracle_get_resampler_table(which, None, 0)
+    assert n == n_ref and n > 0
+    a = np.zeros(n, dtype=np.float32)
+    b = np.zeros(n, dtype=np.float32)
+    hz.refh_bsinc_table(which, a.ctypes.data, n)
+    lib.oracle_get_resampler_table(which, b.ctypes.data, n)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("which,idx", [(abi.RS_SPLINE, 0), (abi.RS_GAUSSIAN, 1)])
+def test_cubic_tables_bit_exact(which, idx):
+    _, hz = refal.libs()
+    lib = _oracle_lib()
+    a = np.zeros(256, dtype=np.float32)
+    b = np.zeros(256, dtype=np.float32)
+    hz.refh_cubic_table(idx, a.ctypes.data)
+    assert lib.oracle_get_resampler_table(which, b.ctypes.data, 256) == 256
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("which", [abi.RS_BSINC12, abi.RS_BSINC24, abi.RS_BSINC48])
+def test_bsinc_prepare_bit_exact(which):
+    _, hz = refal.libs()
+    lib = _oracle_lib()
+    rng = np.random.default_rng(1)
+    incs = list(rng.integers(1, 10 << 16, size=400)) + [65535, 65536, 65537, 131072, 655360]
+    for inc in incs:
+        r = [C.c_float(), C.c_uint32(), C.c_uint32(), C.c_uint32()]
+        o = [C.c_float(), C.c_uint32(), C.c_uint32(), C.c_uint32()]
+        hz.refh_bsinc_state(which, int(inc), *[C.byref(x) for x in r])
+        lib.oracle_get_bsinc_state(which, int(inc), *[C.byref(x) for x in o])
+        assert [x.value for x in r] == [x.value for x in o], inc
+
+
+@pytest.mark.parametrize("resampler", range(10))
+def test_resamplers_vs_reference_kernels(resampler):
+    _, hz = refal.libs()
+    lib = _oracle_lib()
+    rng = np.random.default_rng(resampler)
+    for inc in [1, 7000, 32768, 65535, 65536, 65537, 70000, 98304, 131072, 200000, 655360]:
+        for frac in [0, 1, 2047, 2048, 40000, 65535]:
+            n_out = 257
+            need = ((n_out * inc + frac) >> 16) + 100
+            src = rng.uniform(-1, 1, size=need).astype(np.float32)
+            a = np.zeros(n_out, dtype=np.float32)
+            b = np.zeros(n_out, dtype=np.float32)
+            s = np.zeros(n_out, dtype=np.float32)
+            hz.refh_resample(resampler, 0, inc, frac, src.ctypes.data, need, a.ctypes.data, n_out)
+            hz.refh_resample(resampler, 1, inc, frac, src.ctypes.data, need, s.ctypes.data, n_out)
+            lib.oracle_resample(resampler, inc, frac, src.ctypes.data, b.ctypes.data, n_out)
+            assert np.array_equal(a, b), (resampler, inc, frac)
+            assert np.abs(s.astype(np.float64) - b).max() <= 2e-6, (resampler, inc, frac)
