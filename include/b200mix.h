@@ -178,6 +178,11 @@ B200MIX_API int b200mix_get_dry(b200mix_device *dev, float *dry);
  * reference's in tests): which = enum b200mix_resampler; returns float count. */
 B200MIX_API int64_t b200mix_get_resampler_table(b200mix_device *dev, uint32_t which,
     float *out, size_t max_floats);
+/* Kernel timing for roofline reports: when enabled, the voice kernel of every update is
+ * bracketed by CUDA events on the device's stream; b200mix_last_mix_kernel_ms returns the
+ * duration of the most recent one (synchronises the stream), <0 if unavailable. */
+B200MIX_API int b200mix_profile(b200mix_device *dev, int enable);
+B200MIX_API float b200mix_last_mix_kernel_ms(b200mix_device *dev);
 /* Number of CUDA kernels this device has launched so far. */
 B200MIX_API uint64_t b200mix_launch_count(const b200mix_device *dev);
 /* CUDA stream the device launches on (a cudaStream_t), for event timing. */

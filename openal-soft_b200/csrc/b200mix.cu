@@ -1,0 +1,699 @@
+// b200mix.cu — host side of the C ABI in include/b200mix.h.
+//
+// Owns the device-resident mirrors of the reference's mixer state (voices, buffers,
+// mix buffers, HRTF accumulator carry) and issues the per-update launch sequence:
+//   [k_apply_updates]  k_mix_voices  k_reduce_rows  post-process  (D2H)
+// on one CUDA stream.  No CPU mixing path exists: every entry point fails with
+// B200MIX_ERR_CUDA when the CUDA runtime/device is unusable.
+#include "../../include/b200mix.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "mixer_kernels.cuh"
+#include "resampler_tables.hpp"
+
+using namespace b200mix;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {           // cudaMalloc'ed array with size bookkeeping
+    void *ptr{nullptr}; size_t bytes{0};
+};
+
+} // namespace
+
+struct b200mix_device {
+    b200mix_device_desc desc{};
+    int cuda_dev{0};
+    int num_sms{0};
+    cudaStream_t stream{nullptr};
+    std::string error;
+    uint64_t launches{0};
+
+    // tables
+    BsincTable bsinc[3];
+    float *d_bsinc[3]{};
+    float *d_cubic[2]{};
+
+    // state
+    VoiceRec *d_voices{nullptr};
+    BufferRec *d_buffers{nullptr};
+    std::vector<BufferRec> h_buffers;
+    float2 *d_hrtf_tgt{nullptr}, *d_hrtf_old{nullptr};
+    float *d_dry_cur{nullptr}, *d_dry_tgt{nullptr}, *d_send_cur{nullptr}, *d_send_tgt{nullptr};
+    VoiceResult *d_results{nullptr};
+    b200mix_voice_result *h_results{nullptr};     // pinned
+
+    // mix buffers
+    uint32_t dry_alloc_ch{0};
+    float *d_dry{nullptr}, *d_real{nullptr}, *d_wet{nullptr};
+    float *d_partial{nullptr}; size_t partial_floats{0};
+    float *d_accum_sum{nullptr};                  // [2][kAccumLen]
+    float *d_carry[2]{};                          // [2][kHrirLen] ping-pong
+    int carry_idx{0};
+    float *h_real{nullptr};                       // pinned [real][1024]
+
+    // decoders
+    uint32_t dec_channels{0}, dec_ir{0};
+    float2 *d_dec_coef{nullptr}; float *d_dec_hfscale{nullptr}, *d_dec_state{nullptr};
+    float *d_temp{nullptr}, *d_temp2{nullptr};
+    uint32_t amb_in{0}; bool amb_dual{false};
+    float *d_amb_hf{nullptr}, *d_amb_lf{nullptr}, *d_amb_state{nullptr};
+    bool dry_active{false};
+
+    // update staging (pinned host + device)
+    VoiceUpdate *h_upd{nullptr}, *d_upd{nullptr};
+    float *h_coef{nullptr}, *d_coef{nullptr};
+    float *h_dryg{nullptr}, *d_dryg{nullptr};
+    float *h_sendg{nullptr}, *d_sendg{nullptr};
+    uint32_t stage_cap{0};
+    cudaEvent_t stage_done{nullptr};
+    bool stage_busy{false};
+
+    bool profile{false};
+    cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
+    bool ev_valid{false};
+
+    uint32_t ir_pad{0};
+    uint32_t voice_hi{0};          // 1 + highest voice index ever configured
+    // launch geometry (resolved at create)
+    int mix_variant{0}; int mix_groups{2}; int mix_gs{64}; int mix_cdr{0};
+    size_t mix_smem{0}; int mix_blocks_per_sm{1};
+};
+
+namespace {
+
+#define CUDA_TRY(dev, expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) {            \
+    (dev)->error = std::string(#expr) + ": " + cudaGetErrorString(e_); return B200MIX_ERR_CUDA; } } while(0)
+
+template<typename T>
+int dev_alloc(b200mix_device *d, T *&p, size_t count, bool zero = true)
+{
+    p = nullptr;
+    if(count == 0) return B200MIX_OK;
+    CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&p), count*sizeof(T)));
+    if(zero) CUDA_TRY(d, cudaMemsetAsync(p, 0, count*sizeof(T), d->stream));
+    return B200MIX_OK;
+}
+
+using MixKernel = void(*)(const MixParams);
+
+struct Variant { MixKernel fn; int gs, groups, cdr; size_t smem; bool hrtf; };
+
+template<int GS, int GROUPS, bool HRTF, int CDR, int OPT, int FP>
+Variant make_variant()
+{
+    return Variant{k_mix_voices<GS, GROUPS, HRTF, CDR, OPT, FP>, GS, GROUPS, CDR,
+        sizeof(GroupSmem<GS, OPT, FP>)*GROUPS, HRTF};
+}
+
+// 0: HRTF ir<=64, 1: HRTF ir<=128, 2: dry <=4 channels in registers, 3: dry <=16 channels
+Variant get_variant(int idx)
+{
+    switch(idx)
+    {
+    case 0: return make_variant<64, 2, true, 0, 17, 64>();
+    case 1: return make_variant<64, 2, true, 0, 19, 128>();
+    case 2: return make_variant<64, 2, false, 4, 1, 8>();
+    default: return make_variant<256, 1, false, 16, 1, 8>();
+    }
+}
+
+int ensure_stage(b200mix_device *d, uint32_t n)
+{
+    if(n <= d->stage_cap) return B200MIX_OK;
+    const b200mix_device_desc &dd = d->desc;
+    if(d->stage_cap)
+    {
+        cudaStreamSynchronize(d->stream);
+        cudaFreeHost(d->h_upd); cudaFree(d->d_upd);
+        cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
+        cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg);
+        cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
+        d->h_upd = nullptr; d->h_coef = d->h_dryg = d->h_sendg = nullptr;
+        d->d_upd = nullptr; d->d_coef = d->d_dryg = d->d_sendg = nullptr;
+    }
+    const uint32_t cap = std::max<uint32_t>(n, 256u);
+    CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_upd), cap*sizeof(VoiceUpdate)));
+    CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_upd), cap*sizeof(VoiceUpdate)));
+    if(dd.ir_size)
+    {
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_coef), size_t(cap)*dd.ir_size*2*sizeof(float)));
+        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_coef), size_t(cap)*dd.ir_size*2*sizeof(float)));
+    }
+    if(dd.dry_channels)
+    {
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_dryg), size_t(cap)*dd.dry_channels*sizeof(float)));
+        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_dryg), size_t(cap)*dd.dry_channels*sizeof(float)));
+    }
+    if(dd.num_sends && dd.wet_channels)
+    {
+        const size_t per = size_t(dd.num_sends)*dd.wet_channels;
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_sendg), cap*per*sizeof(float)));
+        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_sendg), cap*per*sizeof(float)));
+    }
+    d->stage_cap = cap;
+    return B200MIX_OK;
+}
+
+const BsincTable *bsinc_for(const b200mix_device *d, uint32_t resampler)
+{
+    if(resampler < B200MIX_RESAMPLER_FAST_BSINC12 || resampler > B200MIX_RESAMPLER_BSINC48)
+        return nullptr;
+    return &d->bsinc[(resampler - B200MIX_RESAMPLER_FAST_BSINC12) >> 1];
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t b200mix_version(void) { return (1u<<16) | 0u; }
+
+const char *b200mix_last_error(const b200mix_device *dev)
+{ return dev ? dev->error.c_str() : g_create_error.c_str(); }
+
+int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
+{
+    if(!desc || !out || desc->struct_size != sizeof(b200mix_device_desc))
+    { g_create_error = "bad descriptor"; return B200MIX_ERR_INVALID; }
+    if(desc->dry_channels > B200MIX_MAX_DRY_CHANNELS || desc->wet_channels > B200MIX_MAX_WET_CHANNELS
+        || desc->num_sends > B200MIX_MAX_SENDS || desc->ir_size > B200MIX_HRIR_LENGTH
+        || desc->real_channels > B200MIX_MAX_DRY_CHANNELS || desc->max_voices == 0)
+    { g_create_error = "descriptor out of range"; return B200MIX_ERR_INVALID; }
+    if(desc->post_process == B200MIX_POST_UHJ)
+    { g_create_error = "UHJ post-process not implemented yet"; return B200MIX_ERR_UNSUPPORTED; }
+
+    auto *d = new(std::nothrow) b200mix_device{};
+    if(!d) { g_create_error = "out of host memory"; return B200MIX_ERR_NOMEM; }
+    d->desc = *desc;
+    auto fail = [&](int code) { g_create_error = d->error; b200mix_destroy(d); return code; };
+
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
+    { d->error = "no CUDA device: the b200mix mixer has no CPU path"; return fail(B200MIX_ERR_CUDA); }
+    if(desc->cuda_device >= 0) d->cuda_dev = desc->cuda_device;
+    else if(cudaGetDevice(&d->cuda_dev) != cudaSuccess) d->cuda_dev = 0;
+    if(cudaSetDevice(d->cuda_dev) != cudaSuccess)
+    { d->error = "cudaSetDevice failed"; return fail(B200MIX_ERR_CUDA); }
+    cudaDeviceProp prop{};
+    if(cudaGetDeviceProperties(&prop, d->cuda_dev) != cudaSuccess)
+    { d->error = "cudaGetDeviceProperties failed"; return fail(B200MIX_ERR_CUDA); }
+    d->num_sms = prop.multiProcessorCount;
+    if(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess)
+    { d->error = "cudaStreamCreate failed"; return fail(B200MIX_ERR_CUDA); }
+    if(cudaEventCreateWithFlags(&d->stage_done, cudaEventDisableTiming) != cudaSuccess)
+    { d->error = "cudaEventCreate failed"; return fail(B200MIX_ERR_CUDA); }
+
+    auto run = [&]() -> int {
+        // resampler tables (core/bsinc_tables.cpp:150-155)
+        d->bsinc[0] = BuildBsincTable(60, 11, 2);
+        d->bsinc[1] = BuildBsincTable(60, 23, 2);
+        d->bsinc[2] = BuildBsincTable(80, 47, 1);
+        for(int i = 0;i < 3;++i)
+        {
+            if(int rc = dev_alloc(d, d->d_bsinc[i], d->bsinc[i].tab.size(), false)) return rc;
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_bsinc[i], d->bsinc[i].tab.data(),
+                d->bsinc[i].tab.size()*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        }
+        const std::vector<float> cubic[2] = {BuildSplineTable(), BuildGaussianTable()};
+        for(int i = 0;i < 2;++i)
+        {
+            if(int rc = dev_alloc(d, d->d_cubic[i], cubic[i].size(), false)) return rc;
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_cubic[i], cubic[i].data(), cubic[i].size()*sizeof(float),
+                cudaMemcpyHostToDevice, d->stream));
+        }
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));   // cubic[] goes out of scope
+
+        const b200mix_device_desc &dd = d->desc;
+        d->ir_pad = (dd.ir_size + 7u) & ~7u;
+        if(int rc = dev_alloc(d, d->d_voices, dd.max_voices)) return rc;
+        if(int rc = dev_alloc(d, d->d_buffers, std::max(dd.max_buffers, 1u))) return rc;
+        d->h_buffers.assign(std::max(dd.max_buffers, 1u), BufferRec{});
+        if(dd.ir_size)
+        {
+            if(int rc = dev_alloc(d, d->d_hrtf_tgt, size_t(dd.max_voices)*d->ir_pad)) return rc;
+            if(int rc = dev_alloc(d, d->d_hrtf_old, size_t(dd.max_voices)*d->ir_pad)) return rc;
+        }
+        if(int rc = dev_alloc(d, d->d_dry_cur, size_t(dd.max_voices)*std::max(dd.dry_channels, 1u))) return rc;
+        if(int rc = dev_alloc(d, d->d_dry_tgt, size_t(dd.max_voices)*std::max(dd.dry_channels, 1u))) return rc;
+        if(dd.num_sends && dd.wet_channels)
+        {
+            const size_t per = size_t(dd.num_sends)*dd.wet_channels;
+            if(int rc = dev_alloc(d, d->d_send_cur, dd.max_voices*per)) return rc;
+            if(int rc = dev_alloc(d, d->d_send_tgt, dd.max_voices*per)) return rc;
+        }
+        if(int rc = dev_alloc(d, d->d_results, dd.max_voices)) return rc;
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_results),
+            size_t(dd.max_voices)*sizeof(b200mix_voice_result)));
+
+        // launch variant
+        const bool hrtfDev = dd.ir_size > 0;
+        d->mix_variant = hrtfDev ? (dd.ir_size <= 64 ? 0 : 1) : (dd.dry_channels <= 4 ? 2 : 3);
+        const Variant var = get_variant(d->mix_variant);
+        d->mix_gs = var.gs; d->mix_groups = var.groups; d->mix_cdr = var.cdr; d->mix_smem = var.smem;
+        CUDA_TRY(d, cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(var.smem)));
+        int perSm = 0;
+        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, var.fn, var.gs*var.groups, var.smem));
+        d->mix_blocks_per_sm = std::max(perSm, 1);
+
+        d->dry_alloc_ch = std::max<uint32_t>(std::max(dd.dry_channels, 1u), uint32_t(var.cdr));
+        if(int rc = dev_alloc(d, d->d_dry, size_t(d->dry_alloc_ch)*kLine)) return rc;
+        if(dd.post_process == B200MIX_POST_NONE) d->d_real = d->d_dry;
+        else if(int rc = dev_alloc(d, d->d_real, size_t(std::max(dd.real_channels, 1u))*kLine)) return rc;
+        if(dd.max_slots && dd.wet_channels)
+            if(int rc = dev_alloc(d, d->d_wet, size_t(dd.max_slots)*dd.wet_channels*kLine)) return rc;
+        const size_t maxRows = size_t(d->num_sms)*d->mix_blocks_per_sm*var.groups;
+        d->partial_floats = maxRows*(hrtfDev ? 2*kAccumLen : 0) + maxRows*size_t(var.cdr)*kLine;
+        if(int rc = dev_alloc(d, d->d_partial, std::max<size_t>(d->partial_floats, 4))) return rc;
+        if(int rc = dev_alloc(d, d->d_accum_sum, 2*kAccumLen)) return rc;
+        if(int rc = dev_alloc(d, d->d_carry[0], 2*kHrirLen)) return rc;
+        if(int rc = dev_alloc(d, d->d_carry[1], 2*kHrirLen)) return rc;
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_real),
+            size_t(std::max(dd.real_channels, 1u))*kLine*sizeof(float)));
+        if(int rc = dev_alloc(d, d->d_temp, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
+        if(int rc = dev_alloc(d, d->d_temp2, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
+        if(int rc = ensure_stage(d, std::min(dd.max_voices, 4096u))) return rc;
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        return B200MIX_OK;
+    };
+    int rc;
+    try { rc = run(); }
+    catch(const std::exception &e) { d->error = e.what(); rc = B200MIX_ERR_NOMEM; }
+    if(rc != B200MIX_OK) return fail(rc);
+    *out = d;
+    return B200MIX_OK;
+}
+
+void b200mix_destroy(b200mix_device *d)
+{
+    if(!d) return;
+    if(d->stream) cudaStreamSynchronize(d->stream);
+    for(auto &b : d->h_buffers) if(b.data) cudaFree(const_cast<void*>(b.data));
+    for(int i = 0;i < 3;++i) cudaFree(d->d_bsinc[i]);
+    for(int i = 0;i < 2;++i) cudaFree(d->d_cubic[i]);
+    cudaFree(d->d_voices); cudaFree(d->d_buffers); cudaFree(d->d_hrtf_tgt); cudaFree(d->d_hrtf_old);
+    cudaFree(d->d_dry_cur); cudaFree(d->d_dry_tgt); cudaFree(d->d_send_cur); cudaFree(d->d_send_tgt);
+    cudaFree(d->d_results); cudaFreeHost(d->h_results);
+    if(d->d_real != d->d_dry) cudaFree(d->d_real);
+    cudaFree(d->d_dry); cudaFree(d->d_wet); cudaFree(d->d_partial); cudaFree(d->d_accum_sum);
+    cudaFree(d->d_carry[0]); cudaFree(d->d_carry[1]); cudaFreeHost(d->h_real);
+    cudaFree(d->d_dec_coef); cudaFree(d->d_dec_hfscale); cudaFree(d->d_dec_state);
+    cudaFree(d->d_temp); cudaFree(d->d_temp2);
+    cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
+    cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
+    cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
+    if(d->stage_done) cudaEventDestroy(d->stage_done);
+    if(d->ev_mix0) cudaEventDestroy(d->ev_mix0);
+    if(d->ev_mix1) cudaEventDestroy(d->ev_mix1);
+    if(d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int b200mix_set_hrtf_decoder(b200mix_device *d, uint32_t channels, uint32_t ir_size,
+    const float *coeffs, const float *hf_scale, const float *splitter_coeff)
+{
+    if(!d || channels != d->desc.dry_channels || ir_size > B200MIX_HRIR_LENGTH || !coeffs
+        || !hf_scale || !splitter_coeff || d->desc.post_process != B200MIX_POST_HRTF)
+    { if(d) d->error = "set_hrtf_decoder: bad arguments"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    cudaFree(d->d_dec_coef); cudaFree(d->d_dec_hfscale); cudaFree(d->d_dec_state);
+    d->dec_channels = channels; d->dec_ir = ir_size;
+    if(int rc = dev_alloc(d, d->d_dec_coef, size_t(channels)*ir_size, false)) return rc;
+    if(int rc = dev_alloc(d, d->d_dec_hfscale, channels, false)) return rc;
+    if(int rc = dev_alloc(d, d->d_dec_state, size_t(channels)*4)) return rc;
+    std::vector<float> st(size_t(channels)*4, 0.0f);
+    for(uint32_t c = 0;c < channels;++c) st[c*4] = splitter_coeff[c];
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_dec_coef, coeffs, size_t(channels)*ir_size*2*sizeof(float),
+        cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_dec_hfscale, hf_scale, channels*sizeof(float),
+        cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_dec_state, st.data(), st.size()*sizeof(float),
+        cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return B200MIX_OK;
+}
+
+int b200mix_set_ambi_decoder(b200mix_device *d, uint32_t in_channels, const float *gains_hf,
+    const float *gains_lf, float xover_coeff)
+{
+    if(!d || in_channels != d->desc.dry_channels || !gains_hf
+        || d->desc.post_process != B200MIX_POST_AMBIDEC)
+    { if(d) d->error = "set_ambi_decoder: bad arguments"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
+    d->d_amb_lf = nullptr;
+    const size_t n = size_t(in_channels)*d->desc.real_channels;
+    d->amb_in = in_channels; d->amb_dual = gains_lf != nullptr;
+    if(int rc = dev_alloc(d, d->d_amb_hf, n, false)) return rc;
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_amb_hf, gains_hf, n*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    if(gains_lf)
+    {
+        if(int rc = dev_alloc(d, d->d_amb_lf, n, false)) return rc;
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_amb_lf, gains_lf, n*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    }
+    std::vector<float> st(size_t(in_channels)*4, 0.0f);
+    for(uint32_t c = 0;c < in_channels;++c) st[c*4] = xover_coeff;
+    if(int rc = dev_alloc(d, d->d_amb_state, st.size(), false)) return rc;
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_amb_state, st.data(), st.size()*sizeof(float),
+        cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return B200MIX_OK;
+}
+
+int b200mix_buffer_data(b200mix_device *d, uint32_t buffer, uint32_t sample_type, uint32_t channels,
+    uint32_t frames, const void *data, size_t bytes)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
+    if(buffer >= d->desc.max_buffers || sample_type > B200MIX_FMT_ALAW || channels < 1 || !data)
+    { d->error = "buffer_data: bad arguments"; return B200MIX_ERR_INVALID; }
+    if(sample_type == B200MIX_FMT_MULAW || sample_type == B200MIX_FMT_ALAW)
+    { d->error = "buffer_data: mu-law/A-law not implemented yet"; return B200MIX_ERR_UNSUPPORTED; }
+    const size_t need = size_t(frames)*channels*sz[sample_type];
+    if(bytes < need) { d->error = "buffer_data: short data"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    BufferRec &h = d->h_buffers[buffer];
+    if(h.data)
+    {
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        cudaFree(const_cast<void*>(h.data));
+        h = BufferRec{};
+    }
+    void *p = nullptr;
+    // +16 bytes so vector/tail reads past the last frame stay inside the allocation
+    CUDA_TRY(d, cudaMalloc(&p, need + 16));
+    CUDA_TRY(d, cudaMemcpyAsync(p, data, need, cudaMemcpyHostToDevice, d->stream));
+    h.data = p; h.frames = frames; h.type = sample_type; h.channels = channels;
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_buffers + buffer, &h, sizeof(BufferRec), cudaMemcpyHostToDevice,
+        d->stream));
+    return B200MIX_OK;
+}
+
+int b200mix_buffer_free(b200mix_device *d, uint32_t buffer)
+{
+    if(!d || buffer >= d->desc.max_buffers) return B200MIX_ERR_INVALID;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    BufferRec &h = d->h_buffers[buffer];
+    if(h.data)
+    {
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        cudaFree(const_cast<void*>(h.data));
+        h = BufferRec{};
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_buffers + buffer, &h, sizeof(BufferRec),
+            cudaMemcpyHostToDevice, d->stream));
+    }
+    return B200MIX_OK;
+}
+
+int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
+    const float *hrtf_coeffs, const float *dry_gains, const float *send_gains)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(n == 0) return B200MIX_OK;
+    if(!params) { d->error = "voices_update: null params"; return B200MIX_ERR_INVALID; }
+    const b200mix_device_desc &dd = d->desc;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    if(d->stage_busy)
+    {
+        CUDA_TRY(d, cudaEventSynchronize(d->stage_done));
+        d->stage_busy = false;
+    }
+    if(int rc = ensure_stage(d, n)) return rc;
+
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const b200mix_voice_params &p = params[i];
+        if(p.voice >= dd.max_voices || p.resampler > B200MIX_RESAMPLER_BSINC48
+            || (!(p.flags & B200MIX_VF_STOPPED) && p.buffer >= dd.max_buffers))
+        { d->error = "voices_update: voice/buffer/resampler out of range"; return B200MIX_ERR_INVALID; }
+        if((p.flags & B200MIX_VF_LOOPING) && p.loop_end <= p.loop_start)
+        { d->error = "voices_update: empty loop"; return B200MIX_ERR_INVALID; }
+        VoiceUpdate &u = d->h_upd[i];
+        u.voice = p.voice; u.flags = p.flags; u.buffer = p.buffer; u.resampler = p.resampler;
+        u.position = p.position; u.position_frac = p.position_frac;
+        u.loop_start = p.loop_start; u.loop_end = p.loop_end; u.step = p.step;
+        u.bsinc_sf = 0.0f; u.bsinc_m = 0; u.bsinc_l = 0; u.bsinc_off = 0;
+        if(const BsincTable *t = bsinc_for(d, p.resampler))
+        {
+            const BsincState st = PrepareBsinc(*t, p.step);
+            u.bsinc_sf = st.sf; u.bsinc_m = st.m; u.bsinc_l = st.l; u.bsinc_off = st.offset;
+        }
+        u.delay0 = p.hrtf_delay[0]; u.delay1 = p.hrtf_delay[1]; u.gain = p.hrtf_gain;
+        if(u.delay0 >= B200MIX_HRTF_HISTORY || u.delay1 >= B200MIX_HRTF_HISTORY)
+        { d->error = "voices_update: HRTF delay out of range"; return B200MIX_ERR_INVALID; }
+        for(uint32_t s = 0;s < B200MIX_MAX_SENDS;++s)
+        {
+            u.send_slot[s] = (s < dd.num_sends) ? p.send_slot[s] : B200MIX_NO_SLOT;
+            if(u.send_slot[s] != B200MIX_NO_SLOT && u.send_slot[s] >= dd.max_slots)
+            { d->error = "voices_update: send slot out of range"; return B200MIX_ERR_INVALID; }
+        }
+        u.has_coeffs = hrtf_coeffs != nullptr && dd.ir_size > 0;
+        u.has_dry = dry_gains != nullptr;
+        if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED)) d->dry_active = true;
+        d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
+    }
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_upd, d->h_upd, n*sizeof(VoiceUpdate), cudaMemcpyHostToDevice, d->stream));
+    ApplyParams A{};
+    A.voices = d->d_voices; A.updates = d->d_upd;
+    if(hrtf_coeffs && dd.ir_size)
+    {
+        const size_t cnt = size_t(n)*dd.ir_size*2;
+        std::memcpy(d->h_coef, hrtf_coeffs, cnt*sizeof(float));
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_coef, d->h_coef, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        A.coeffs = d->d_coef;
+    }
+    if(dry_gains && dd.dry_channels)
+    {
+        const size_t cnt = size_t(n)*dd.dry_channels;
+        std::memcpy(d->h_dryg, dry_gains, cnt*sizeof(float));
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_dryg, d->h_dryg, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        A.dry = d->d_dryg;
+    }
+    if(send_gains && dd.num_sends && dd.wet_channels)
+    {
+        const size_t cnt = size_t(n)*dd.num_sends*dd.wet_channels;
+        std::memcpy(d->h_sendg, send_gains, cnt*sizeof(float));
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_sendg, d->h_sendg, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        A.send = d->d_sendg;
+    }
+    A.hrtf_tgt = d->d_hrtf_tgt; A.hrtf_old = d->d_hrtf_old;
+    A.dry_cur = d->d_dry_cur; A.dry_tgt = d->d_dry_tgt;
+    A.send_cur = d->d_send_cur; A.send_tgt = d->d_send_tgt;
+    A.ir = dd.ir_size; A.ir_pad = d->ir_pad; A.cd = dd.dry_channels; A.cw = dd.wet_channels;
+    A.num_sends = dd.num_sends;
+    k_apply_updates<<<n, 64, 0, d->stream>>>(A);
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
+    CUDA_TRY(d, cudaEventRecord(d->stage_done, d->stream));
+    d->stage_busy = true;
+    return B200MIX_OK;
+}
+
+static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
+{
+    const b200mix_device_desc &dd = d->desc;
+    if(frames < 1 || frames > B200MIX_LINE_SIZE)
+    { d->error = "render: frames out of range"; return B200MIX_ERR_INVALID; }
+    if(dd.post_process == B200MIX_POST_HRTF && !d->dec_channels)
+    { d->error = "render: HRTF decoder not set"; return B200MIX_ERR_INVALID; }
+    if(dd.post_process == B200MIX_POST_AMBIDEC && !d->amb_in)
+    { d->error = "render: ambisonic decoder not set"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+
+    // clear MixBuffer (alc/alu.cpp:2417) and the wet buffers (alc/alu.cpp:2196-2198)
+    CUDA_TRY(d, cudaMemsetAsync(d->d_dry, 0, size_t(d->dry_alloc_ch)*kLine*sizeof(float), d->stream));
+    if(d->d_real != d->d_dry)
+        CUDA_TRY(d, cudaMemsetAsync(d->d_real, 0, size_t(dd.real_channels)*kLine*sizeof(float), d->stream));
+    if(d->d_wet)
+        CUDA_TRY(d, cudaMemsetAsync(d->d_wet, 0, size_t(dd.max_slots)*dd.wet_channels*kLine*sizeof(float), d->stream));
+
+    const Variant var = get_variant(d->mix_variant);
+    const uint32_t nv = std::max(d->voice_hi, 1u);
+    const uint32_t maxBlocks = uint32_t(d->num_sms*d->mix_blocks_per_sm);
+    const uint32_t blocks = std::max(1u, std::min(maxBlocks, (nv + var.groups - 1)/var.groups));
+    const size_t rows = size_t(blocks)*var.groups;
+
+    MixParams P{};
+    P.voices = d->d_voices; P.buffers = d->d_buffers;
+    P.hrtf_tgt = d->d_hrtf_tgt; P.hrtf_old = d->d_hrtf_old;
+    P.dry_cur = d->d_dry_cur; P.dry_tgt = d->d_dry_tgt;
+    P.send_cur = d->d_send_cur; P.send_tgt = d->d_send_tgt;
+    P.dry = d->d_dry; P.wet = d->d_wet; P.partial = d->d_partial;
+    P.results = want_results ? d->d_results : nullptr;
+    for(int i = 0;i < 3;++i) P.bsinc_tab[i] = d->d_bsinc[i];
+    for(int i = 0;i < 2;++i) P.cubic_tab[i] = d->d_cubic[i];
+    P.max_voices = nv; P.frames = frames; P.ir = dd.ir_size; P.ir_pad = d->ir_pad;
+    P.cd = dd.dry_channels; P.cw = dd.wet_channels; P.num_sends = dd.num_sends;
+    P.max_buffers = dd.max_buffers;
+    if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
+    var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
+    if(d->profile) { cudaEventRecord(d->ev_mix1, d->stream); d->ev_valid = true; }
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
+
+    if(var.hrtf)
+    {
+        const uint32_t len = 2*kAccumLen;
+        k_reduce_rows<4><<<(len/4 + 63)/64, 256, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
+            d->d_accum_sum, 0);
+        ++d->launches;
+    }
+    if(var.cdr > 0)
+    {
+        const uint32_t len = uint32_t(var.cdr)*kLine;
+        const float *pd = d->d_partial + (var.hrtf ? rows*(2*kAccumLen) : 0);
+        k_reduce_rows<4><<<(len/4 + 63)/64, 256, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
+        ++d->launches;
+    }
+    CUDA_TRY(d, cudaGetLastError());
+
+    // effect slots: not implemented in this round (no slot can be configured)
+
+    switch(dd.post_process)
+    {
+    case B200MIX_POST_HRTF:
+    {
+        PostHrtfParams Q{};
+        Q.accum_sum = d->d_accum_sum; Q.carry_in = d->d_carry[d->carry_idx];
+        Q.carry_out = d->d_carry[d->carry_idx^1];
+        Q.dry = d->d_dry; Q.real = d->d_real; Q.dec_coef = d->d_dec_coef;
+        Q.dec_hfscale = d->d_dec_hfscale; Q.dec_state = d->d_dec_state; Q.temp = d->d_temp;
+        Q.frames = frames; Q.cd = dd.dry_channels; Q.dec_ir = d->dec_ir;
+        Q.real_left = dd.real_left; Q.real_right = dd.real_right; Q.dry_active = d->dry_active;
+        if(d->dry_active)
+        {
+            k_post_hrtf_split<<<1, 32, 0, d->stream>>>(Q);
+            ++d->launches;
+        }
+        const uint32_t total = 2u*(frames + kHrirLen);
+        k_post_hrtf_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
+        ++d->launches;
+        d->carry_idx ^= 1;
+        break;
+    }
+    case B200MIX_POST_AMBIDEC:
+    {
+        PostAmbiParams Q{};
+        Q.dry = d->d_dry; Q.real = d->d_real; Q.gains_hf = d->d_amb_hf; Q.gains_lf = d->d_amb_lf;
+        Q.split_state = d->d_amb_state; Q.temp_hf = d->d_temp; Q.temp_lf = d->d_temp2;
+        Q.frames = frames; Q.cd = dd.dry_channels; Q.real_channels = dd.real_channels;
+        Q.dual = d->amb_dual;
+        if(d->amb_dual)
+        {
+            k_post_ambi_split<<<1, 32, 0, d->stream>>>(Q);
+            ++d->launches;
+        }
+        const uint32_t total = dd.real_channels*frames;
+        k_post_ambi_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
+        ++d->launches;
+        break;
+    }
+    default: break;
+    }
+    CUDA_TRY(d, cudaGetLastError());
+    return B200MIX_OK;
+}
+
+int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
+    b200mix_voice_result *results)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(int rc = render_launch(d, frames, results != nullptr)) return rc;
+    const b200mix_device_desc &dd = d->desc;
+    if(real_out)
+        CUDA_TRY(d, cudaMemcpyAsync(d->h_real, d->d_real, size_t(dd.real_channels)*kLine*sizeof(float),
+            cudaMemcpyDeviceToHost, d->stream));
+    const uint32_t nv = std::max(d->voice_hi, 1u);
+    if(results)
+        CUDA_TRY(d, cudaMemcpyAsync(d->h_results, d->d_results, size_t(nv)*sizeof(VoiceResult),
+            cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    d->stage_busy = false;
+    if(real_out)
+        for(uint32_t c = 0;c < dd.real_channels;++c)
+            if(real_out[c]) std::memcpy(real_out[c], d->h_real + size_t(c)*kLine, frames*sizeof(float));
+    if(results)
+    {
+        std::memcpy(results, d->h_results, size_t(nv)*sizeof(b200mix_voice_result));
+        for(uint32_t v = nv;v < dd.max_voices;++v)
+            results[v] = b200mix_voice_result{0, 0u, B200MIX_VF_STOPPED, 0u};
+    }
+    return B200MIX_OK;
+}
+
+int b200mix_render_device(b200mix_device *d, uint32_t frames, const float **real_out_dev)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(int rc = render_launch(d, frames, false)) return rc;
+    if(real_out_dev) *real_out_dev = d->d_real;
+    return B200MIX_OK;
+}
+
+int b200mix_get_dry(b200mix_device *d, float *dry)
+{
+    if(!d || !dry) return B200MIX_ERR_INVALID;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    CUDA_TRY(d, cudaMemcpy(dry, d->d_dry, size_t(d->desc.dry_channels)*kLine*sizeof(float),
+        cudaMemcpyDeviceToHost));
+    return B200MIX_OK;
+}
+
+int64_t b200mix_get_resampler_table(b200mix_device *d, uint32_t which, float *out, size_t max_floats)
+{
+    if(!d) return -1;
+    if(cudaSetDevice(d->cuda_dev) != cudaSuccess) return -1;
+    const float *src = nullptr; size_t n = 0;
+    if(which == B200MIX_RESAMPLER_SPLINE) { src = d->d_cubic[0]; n = 256; }
+    else if(which == B200MIX_RESAMPLER_GAUSSIAN) { src = d->d_cubic[1]; n = 256; }
+    else if(bsinc_for(d, which))
+    {
+        const int i = int(which - B200MIX_RESAMPLER_FAST_BSINC12) >> 1;
+        src = d->d_bsinc[i]; n = d->bsinc[i].tab.size();
+    }
+    else return -1;
+    if(out)
+    {
+        cudaStreamSynchronize(d->stream);
+        if(cudaMemcpy(out, src, std::min(n, max_floats)*sizeof(float), cudaMemcpyDeviceToHost)
+            != cudaSuccess) return -1;
+    }
+    return int64_t(n);
+}
+
+int b200mix_profile(b200mix_device *d, int enable)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    if(enable && !d->ev_mix0)
+    {
+        CUDA_TRY(d, cudaEventCreate(&d->ev_mix0));
+        CUDA_TRY(d, cudaEventCreate(&d->ev_mix1));
+    }
+    d->profile = enable != 0;
+    d->ev_valid = false;
+    return B200MIX_OK;
+}
+
+float b200mix_last_mix_kernel_ms(b200mix_device *d)
+{
+    if(!d || !d->ev_valid) return -1.0f;
+    if(cudaEventSynchronize(d->ev_mix1) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if(cudaEventElapsedTime(&ms, d->ev_mix0, d->ev_mix1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+uint64_t b200mix_launch_count(const b200mix_device *d) { return d ? d->launches : 0; }
+void *b200mix_stream(b200mix_device *d) { return d ? static_cast<void*>(d->stream) : nullptr; }
+
+} // extern "C"

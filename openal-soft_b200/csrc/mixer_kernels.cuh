@@ -1,0 +1,936 @@
+// mixer_kernels.cuh — sm_100a kernels of the b200mix hot path (device code only).
+//
+// Work decomposition: the voice loop of ProcessContexts
+// (alc/alu.cpp:2201-2206) becomes ONE persistent launch.  A CTA holds GROUPS voice
+// groups of GS threads; a group walks its share of the voice array and, per voice,
+//   1. rebuilds the reference's resample window chunk by chunk in shared memory
+//      (LoadResampledSamples, core/voice.cpp:642-822), decoding the source straight
+//      from HBM, and resamples it with a per-voice pre-combined phase table,
+//   2. turns the resampled line into the per-ear, gain-ramped FIR inputs
+//      (DoHrtfMix, core/voice.cpp:827-902; MixHrtfBlend/MixHrtf, hrtfbase.h:17-89),
+//   3. runs the HRIR FIR in gather form with OPT contiguous outputs per thread held
+//      in registers ACROSS all voices of the group (the cross-voice reduction of
+//      `Accum[i+j] += ...` happens in registers, not memory),
+// and finally stores one partial accumulator row per group; k_reduce_* sums the
+// rows in a fixed order (deterministic output).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200mix {
+
+constexpr int kLine = 1024;          // BufferLineSize
+constexpr int kHrirLen = 128;        // HrirLength
+constexpr int kHist = 64;            // HrtfHistoryLength
+constexpr int kEdge = 24;            // MaxResamplerEdge
+constexpr int kPad = 48;             // MaxResamplerPadding
+constexpr int kResBuf = kLine + 256 + kPad;   // DeviceBase::mResampleData (core/device.h:282)
+constexpr int kSrcSizeMax = kResBuf - kEdge;
+constexpr int kMaxSends = 6;
+constexpr int kAccumLen = kLine + kHrirLen;   // HrtfAccumData (core/device.h:288)
+constexpr float kSilence = 0.00001f;          // GainSilenceThreshold
+constexpr float kEps = 1.1920929e-07f;
+
+// internal voice flag bits (low 8 bits are the ABI's B200MIX_VF_*)
+constexpr uint32_t kVfStatic = 1u<<2, kVfLooping = 1u<<3, kVfHrtf = 1u<<4;
+constexpr uint32_t kVfFading = 1u<<8, kVfHaveBuffer = 1u<<9, kVfCoefDirty = 1u<<10;
+
+struct alignas(16) BufferRec {
+    const void *data;
+    uint32_t frames, type, channels, pad;
+};
+
+// Device-resident mirror of the mixing state of one Voice (core/voice.h:157-272).
+struct alignas(16) VoiceRec {
+    uint32_t state;            // 0 stopped, 1 playing, 2 stopping
+    uint32_t flags;
+    uint32_t buffer, resampler;
+    int32_t  pos; uint32_t frac, step, loop_start;
+    uint32_t loop_end; float bsinc_sf; uint32_t bsinc_m, bsinc_l;
+    uint32_t bsinc_off, tgt_delay0, tgt_delay1; float tgt_gain;
+    uint32_t old_delay0, old_delay1; float old_gain; uint32_t send_mask;
+    uint32_t send_slot[kMaxSends]; uint32_t pad2[2];
+    float prev[kPad];          // mPrevSamples[0]
+    float hist[kHist];         // Hrtf.History
+};
+
+struct alignas(16) VoiceUpdate {   // staged by b200mix_voices_update
+    uint32_t voice, flags, buffer, resampler;
+    int32_t  position; uint32_t position_frac, loop_start, loop_end;
+    uint32_t step; float bsinc_sf; uint32_t bsinc_m, bsinc_l;
+    uint32_t bsinc_off, delay0, delay1; float gain;
+    uint32_t send_slot[kMaxSends]; uint32_t has_coeffs, has_dry;
+};
+
+struct VoiceResult { int32_t position; uint32_t position_frac, flags, buffers_done; };
+
+struct MixParams {
+    VoiceRec *voices; const BufferRec *buffers;
+    float2 *hrtf_tgt; float2 *hrtf_old;       // [max_voices][ir_pad]
+    float *dry_cur; float *dry_tgt;           // [max_voices][cd]
+    float *send_cur; float *send_tgt;         // [max_voices][num_sends][cw]
+    float *dry;                               // [cd][1024]   (atomics path)
+    float *wet;                               // [slots][cw][1024]
+    float *partial;                           // see k_reduce_*
+    VoiceResult *results;
+    const float *bsinc_tab[3];                // bsinc12, 24, 48
+    const float *cubic_tab[2];                // spline, gaussian [32][8]
+    uint32_t max_voices, frames, ir, ir_pad, cd, cw, num_sends, max_buffers;
+};
+
+__device__ __forceinline__ void group_sync(int id, int count)
+{ asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+__device__ __forceinline__ float load_sample(const BufferRec &b, size_t idx)
+{
+    // SampleInfo<T>::to_float, core/fmt_traits.h:88-131
+    switch(b.type)
+    {
+    case 0: return (float(static_cast<const uint8_t*>(b.data)[idx]) - 128.0f) * (1.0f/128.0f);
+    case 1: return float(static_cast<const int16_t*>(b.data)[idx]) * (1.0f/32768.0f);
+    case 2: return float(static_cast<const int32_t*>(b.data)[idx]) * (1.0f/2147483648.0f);
+    case 3: return static_cast<const float*>(b.data)[idx];
+    case 4: return float(static_cast<const double*>(b.data)[idx]);
+    }
+    return 0.0f;
+}
+
+// CalculateBufferSize, core/voice.cpp:601-640
+__device__ __forceinline__ void calc_buffer_size(uint32_t fracPos, uint32_t increment,
+    uint32_t dstRemaining, uint32_t &dst, uint32_t &src)
+{
+    const uint32_t ext = increment <= 65536u;
+    const uint64_t srcSize64 = ((uint64_t(dstRemaining - ext)*increment + fracPos) >> 16)
+        + ext + kEdge;
+    if(srcSize64 <= uint64_t(kSrcSizeMax)) { dst = dstRemaining; src = uint32_t(srcSize64); return; }
+    const uint64_t dstSize64 = ((uint64_t(kSrcSizeMax - kEdge)<<16) - fracPos) / increment;
+    if(dstSize64 < dstRemaining) { dst = uint32_t(dstSize64) & ~3u; src = kSrcSizeMax; return; }
+    dst = dstRemaining; src = kSrcSizeMax;
+}
+
+__device__ __forceinline__ int32_t add_sat(int32_t a, int32_t b)
+{
+    long long r = (long long)a + b;
+    r = r > 2147483647ll ? 2147483647ll : (r < -2147483648ll ? -2147483648ll : r);
+    return int32_t(r);
+}
+
+// Shared-memory carve-up of one voice group.
+template<int GS, int OPT, int FP>
+struct GroupSmem {
+    static constexpr int kTabStride = kPad + 1;         // odd: conflict-free phase rows
+    static constexpr int kLLen = FP + OPT*GS;           // FIR input incl. front zero pad
+    static constexpr int kOLen = FP + kHist + FP + 32;  // old-coefficient pass input
+    float win[kResBuf + 8];
+    float x[kHist + kLine];
+    float tabF[32*kTabStride];
+    float tabD[32*kTabStride];
+    float lL[kLLen], lR[kLLen];
+    float oL[kOLen], oR[kOLen];
+    float2 coefT[kHrirLen], coefO[kHrirLen];
+    float newGain[32 + kMaxSends*25];   // Current gains written back after the voice
+};
+
+// One FIR pass: acc[r] += sum_j c[j] * in[FP + t0 + r - j]   (gather form of
+// MixHrtfBase's scatter, hrtfbase.h:28-40), taps in blocks of 8 with a register
+// window so each input value is loaded once per block.
+template<int OPT, int FP, bool LEFT>
+__device__ __forceinline__ void fir_pass(float (&acc)[OPT], const float *__restrict__ in,
+    const float2 *__restrict__ coef, int irpad, int t0)
+{
+    for(int jb = 0;jb < irpad;jb += 8)
+    {
+        float w[OPT+7];
+        const float *p = in + FP + t0 - jb - 7;
+        #pragma unroll
+        for(int k = 0;k < OPT+7;++k) w[k] = p[k];
+        #pragma unroll
+        for(int jj = 0;jj < 8;++jj)
+        {
+            const float2 c2 = coef[jb+jj];
+            const float c = LEFT ? c2.x : c2.y;
+            #pragma unroll
+            for(int r = 0;r < OPT;++r)
+                acc[r] = fmaf(c, w[r - jj + 7], acc[r]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The voice kernel.  GS threads per voice group, GROUPS groups per CTA.
+//   HRTF   : device has per-voice HRIR mixing (HrtfAccumData partial rows)
+//   CDR    : dry channels accumulated in registers (non-HRTF voices), 0 = use atomics
+//   OPT/FP : FIR outputs per thread / front pad (17/64 for ir<=64, 19/128 for ir<=128)
+// ---------------------------------------------------------------------------
+template<int GS, int GROUPS, bool HRTF, int CDR, int OPT, int FP>
+__global__ void __launch_bounds__(GS*GROUPS)
+k_mix_voices(const MixParams P)
+{
+    using Smem = GroupSmem<GS, OPT, FP>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / GS;
+    const int t = threadIdx.x % GS;
+    Smem &S = reinterpret_cast<Smem*>(smem_raw)[g];
+    const int bar = 1 + g;
+    constexpr int SPT = kLine / GS;               // resampled samples per thread
+
+    float accL[OPT], accR[OPT];
+    #pragma unroll
+    for(int r = 0;r < OPT;++r) { accL[r] = 0.0f; accR[r] = 0.0f; }
+    float accD[CDR > 0 ? CDR : 1][SPT];
+    #pragma unroll
+    for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
+        #pragma unroll
+        for(int r = 0;r < SPT;++r) accD[c][r] = 0.0f;
+
+    const uint32_t n = P.frames;
+    const int t0 = OPT*t;
+
+    for(uint32_t v = blockIdx.x*GROUPS + g;v < P.max_voices;v += gridDim.x*GROUPS)
+    {
+        VoiceRec &rec = P.voices[v];
+        const uint32_t vstate = rec.state;
+        if(vstate != 1u && vstate != 2u)
+        {
+            if(t == 0 && P.results)
+                P.results[v] = VoiceResult{rec.pos, rec.frac, 1u<<7, 0u};
+            continue;
+        }
+        const uint32_t increment = rec.step;
+        uint32_t flags = rec.flags;
+        if(increment < 1u)
+        {
+            if(t == 0)
+            {
+                if(vstate == 2u) rec.state = 0u;
+                if(P.results)
+                    P.results[v] = VoiceResult{rec.pos, rec.frac, (vstate == 2u) ? (1u<<7) : 1u, 0u};
+            }
+            continue;
+        }
+        const bool haveBuffer = (flags & kVfHaveBuffer) != 0;
+        const BufferRec buf = P.buffers[haveBuffer ? rec.buffer : 0u];
+        const uint32_t loopStart = rec.loop_start, loopEnd = rec.loop_end;
+        int32_t intPos = rec.pos;
+        uint32_t fracPos = rec.frac;
+        bool looping = (flags & kVfLooping) != 0;
+        if((flags & kVfStatic) && looping && haveBuffer && intPos >= 0
+            && uint32_t(intPos) >= loopEnd)
+            looping = false;                                     // core/voice.cpp:1015-1019
+        const uint32_t resampler = rec.resampler;
+        const bool isHrtf = HRTF && (flags & kVfHrtf);
+        const bool dirty = (flags & kVfCoefDirty) != 0;
+
+        // ---- stage per-voice constants into shared memory ----
+        for(int k = t;k < kPad;k += GS) S.win[k] = rec.prev[k];
+        if(isHrtf)
+        {
+            for(int k = t;k < kHist;k += GS) S.x[k] = rec.hist[k];
+            const float2 *ct = P.hrtf_tgt + size_t(v)*P.ir_pad;
+            const float2 *co = P.hrtf_old + size_t(v)*P.ir_pad;
+            for(int k = t;k < int(P.ir_pad);k += GS)
+            {
+                const float2 c = ct[k];
+                S.coefT[k] = c;
+                S.coefO[k] = dirty ? co[k] : c;
+            }
+        }
+        // pre-combined phase table: coef(phase,pf)[j] = F[phase][j] + pf*D[phase][j]
+        //   BSinc      F = fil + sf*scd, D = phd + sf*spd   (mixer_c.cpp:84-105)
+        //   FastBSinc  F = fil,          D = phd            (mixer_c.cpp:63-82)
+        //   cubic      F = mCoeffs,      D = mDeltas        (mixer_c.cpp:48-61)
+        uint32_t m = 0, tapOff = 0;                  // taps and left offset into the window
+        const bool bypass = false;
+        (void)bypass;
+        if(resampler >= 4u)
+        {
+            m = rec.bsinc_m;
+            tapOff = kEdge - rec.bsinc_l;
+            const float *tab = P.bsinc_tab[(resampler-4u)>>1] + rec.bsinc_off;
+            const bool full = (increment > 65536u) && (resampler & 1u);
+            const float sf = rec.bsinc_sf;
+            const uint32_t cnt = 32u*m;
+            for(uint32_t e = t;e < cnt;e += GS)
+            {
+                const uint32_t pi = e / m, j = e - pi*m;
+                const float *fil = tab + 2u*pi*m;
+                float f = fil[j], d = fil[m + j];
+                if(full)
+                {
+                    const float *scd = fil + 32u*2u*m;
+                    f = f + sf*scd[j];
+                    d = d + sf*scd[m + j];
+                }
+                S.tabF[pi*Smem::kTabStride + j] = f;
+                S.tabD[pi*Smem::kTabStride + j] = d;
+            }
+        }
+        else if(resampler >= 2u)
+        {
+            m = 4; tapOff = kEdge - 1;
+            const float *tab = P.cubic_tab[resampler-2u];
+            for(uint32_t e = t;e < 128u;e += GS)
+            {
+                const uint32_t pi = e>>2, j = e&3u;
+                S.tabF[pi*Smem::kTabStride + j] = tab[pi*8u + j];
+                S.tabD[pi*Smem::kTabStride + j] = tab[pi*8u + 4u + j];
+            }
+        }
+
+        // ---- LoadResampledSamples, chunk by chunk (core/voice.cpp:668-811) ----
+        float *xs = S.x + kHist;
+        for(uint32_t loaded = 0;loaded < n;)
+        {
+            uint32_t dstn, srcn;
+            calc_buffer_size(fracPos, increment, n-loaded, dstn, srcn);
+            uint32_t srcDelay = 0;
+            bool silent = false;
+            if(intPos < 0)
+            {
+                srcDelay = uint32_t(-intPos);
+                if(srcDelay >= srcn) silent = true;
+            }
+            group_sync(bar, GS);           // window history in place / previous chunk consumed
+            if(silent)
+            {
+                for(uint32_t k = t;k < dstn;k += GS) xs[loaded+k] = 0.0f;
+                for(uint32_t k = t;k < srcn;k += GS) S.win[kEdge+k] = 0.0f;
+            }
+            else
+            {
+                float *srcBuffer = S.win + kEdge;
+                if(!haveBuffer)
+                {
+                    // voice ended: hold the sample closest to 0 (core/voice.cpp:704-719)
+                    const uint32_t avail = srcn < uint32_t(kEdge) ? srcn : uint32_t(kEdge);
+                    const uint32_t tofill = srcn > uint32_t(kEdge) ? srcn : uint32_t(kEdge);
+                    uint32_t best = 0;
+                    for(uint32_t i = 1;i < avail;++i)
+                        if(fabsf(srcBuffer[i]) < fabsf(srcBuffer[best])) best = i;
+                    const float held = srcBuffer[best];
+                    group_sync(bar, GS);
+                    for(uint32_t k = best+1+t;k < tofill;k += GS) srcBuffer[k] = held;
+                }
+                else
+                {
+                    const uint32_t uintPos = intPos < 0 ? 0u : uint32_t(intPos);
+                    const uint32_t count = srcn - srcDelay;
+                    float *dst = srcBuffer + srcDelay;
+                    for(uint32_t k = t;k < srcDelay;k += GS) srcBuffer[k] = 0.0f;
+                    if(!looping)
+                    {
+                        // LoadBufferStatic, non-looping (core/voice.cpp:504-519)
+                        const float last = (buf.frames > uintPos)
+                            ? load_sample(buf, size_t(buf.frames-1u)*buf.channels) : 0.0f;
+                        for(uint32_t k = t;k < count;k += GS)
+                        {
+                            const uint64_t q = uint64_t(uintPos) + k;
+                            dst[k] = (q < buf.frames) ? load_sample(buf, size_t(q)*buf.channels) : last;
+                        }
+                    }
+                    else
+                    {
+                        // LoadBufferStatic, looping (core/voice.cpp:520-543)
+                        const uint32_t loopSize = loopEnd - loopStart;
+                        const uint32_t q0 = (uintPos < loopEnd) ? uintPos
+                            : ((uintPos-loopStart)%loopSize + loopStart);
+                        const uint32_t firstRun = loopEnd - q0;
+                        for(uint32_t k = t;k < count;k += GS)
+                        {
+                            const uint32_t q = (k < firstRun) ? q0 + k
+                                : loopStart + (k - firstRun)%loopSize;
+                            dst[k] = load_sample(buf, size_t(q)*buf.channels);
+                        }
+                    }
+                }
+                group_sync(bar, GS);       // window complete
+
+                // ---- resample dstn outputs (core/voice.cpp:764-769) ----
+                if(increment == 65536u && fracPos == 0u)
+                {
+                    for(uint32_t k = t;k < dstn;k += GS) xs[loaded+k] = srcBuffer[k];
+                }
+                else if(resampler >= 2u)
+                {
+                    const float *vals = S.win + tapOff;
+                    for(uint32_t k = t;k < dstn;k += GS)
+                    {
+                        const uint64_t fp = uint64_t(k)*increment + fracPos;
+                        const uint32_t pos = uint32_t(fp>>16), frac = uint32_t(fp) & 0xffffu;
+                        const uint32_t pi = frac>>11;
+                        const float pf = float(frac & 2047u) * (1.0f/2048.0f);
+                        const float *F = S.tabF + pi*Smem::kTabStride;
+                        const float *D = S.tabD + pi*Smem::kTabStride;
+                        const float *sv = vals + pos;
+                        float r = 0.0f;
+                        for(uint32_t j = 0;j < m;j += 4)
+                        {
+                            r = fmaf(fmaf(pf, D[j+0], F[j+0]), sv[j+0], r);
+                            r = fmaf(fmaf(pf, D[j+1], F[j+1]), sv[j+1], r);
+                            r = fmaf(fmaf(pf, D[j+2], F[j+2]), sv[j+2], r);
+                            r = fmaf(fmaf(pf, D[j+3], F[j+3]), sv[j+3], r);
+                        }
+                        xs[loaded+k] = r;
+                    }
+                }
+                else
+                {
+                    const float *vals = srcBuffer;
+                    for(uint32_t k = t;k < dstn;k += GS)
+                    {
+                        const uint64_t fp = uint64_t(k)*increment + fracPos;
+                        const uint32_t pos = uint32_t(fp>>16), frac = uint32_t(fp) & 0xffffu;
+                        if(resampler == 0u) xs[loaded+k] = vals[pos];
+                        else
+                        {
+                            const float a = vals[pos], b = vals[pos+1];
+                            xs[loaded+k] = a + (b-a)*(float(frac)*(1.0f/65536.0f));
+                        }
+                    }
+                }
+            }
+
+            // ---- history for the next update (core/voice.cpp:772-785) ----
+            const uint32_t loadEnd = loaded + dstn;
+            if(!silent && vstate == 1u && n > loaded && n <= loadEnd)
+            {
+                const uint32_t dstOffset = n - loaded;
+                const uint32_t srcOffset = uint32_t((uint64_t(dstOffset)*increment + fracPos) >> 16);
+                for(int k = t;k < kPad;k += GS) rec.prev[k] = S.win[srcOffset + k];
+            }
+            loaded = loadEnd;
+            if(loaded < n)
+            {
+                fracPos += dstn*increment;
+                const uint32_t srcOffset = fracPos >> 16;
+                fracPos &= 0xffffu;
+                if(silent) intPos = add_sat(intPos, int32_t(srcOffset));
+                else
+                {
+                    if(intPos < 0) intPos += int32_t(srcOffset);
+                    else intPos = add_sat(intPos, int32_t(srcOffset));
+                    // slide the window tail to the front (core/voice.cpp:808-809)
+                    float carry = 0.0f;
+                    if(t < kPad) carry = S.win[srcOffset + t];
+                    float carry2 = 0.0f;
+                    if(GS < kPad && t + GS < kPad) carry2 = S.win[srcOffset + t + GS];
+                    group_sync(bar, GS);
+                    if(t < kPad) S.win[t] = carry;
+                    if(GS < kPad && t + GS < kPad) S.win[t + GS] = carry2;
+                }
+            }
+        }
+        group_sync(bar, GS);               // xs complete
+
+        // ---- fade bookkeeping (core/voice.cpp:1093-1112) ----
+        const bool fading = (flags & kVfFading) != 0;
+        const uint32_t counter = fading ? (n < 64u ? n : 64u) : 0u;
+        const bool playing = vstate == 1u;
+
+        if(isHrtf)
+        {
+            // DoHrtfMix (core/voice.cpp:827-902), outPos == 0
+            if(playing)
+                for(int k = t;k < kHist;k += GS) rec.hist[k] = S.x[n + k];
+            uint32_t oD0 = rec.old_delay0, oD1 = rec.old_delay1;
+            float oGain = rec.old_gain;
+            const uint32_t tD0 = rec.tgt_delay0, tD1 = rec.tgt_delay1;
+            if(!counter) { oD0 = tD0; oD1 = tD1; oGain = rec.tgt_gain; }
+            const bool sameFilter = !counter || (!dirty && oD0 == tD0 && oD1 == tD1);
+            const float targetGain = rec.tgt_gain * (playing ? 1.0f : 0.0f);
+            const uint32_t fademix = counter;                     // counter <= n always
+            float blendNewStep = 0.0f, oldStep = 0.0f;
+            bool oldOn = false, newOn = false;
+            float gainA = oGain;                                  // Old.Gain entering part 2
+            if(fademix)
+            {
+                const float gain = targetGain;                    // counter == fademix
+                blendNewStep = gain / float(fademix);
+                oldStep = oGain / float(fademix);
+                oldOn = oGain > kSilence;
+                newOn = blendNewStep*float(fademix) > kSilence;
+                gainA = gain;
+            }
+            const uint32_t todo = n - fademix;
+            const float step2 = todo ? (targetGain - gainA) / float(todo) : 0.0f;
+
+            const float *hs = S.x;                                // [History | samples]
+            for(int i = t;i < Smem::kLLen;i += GS)
+            {
+                const int s = i - FP;                             // input sample index
+                float l = 0.0f, r = 0.0f;
+                if(s >= 0 && s < int(n))
+                {
+                    float gnew;
+                    if(uint32_t(s) < fademix)
+                        gnew = (newOn && s >= 1) ? blendNewStep*float(s) : 0.0f;
+                    else
+                        gnew = gainA + step2*float(uint32_t(s) - fademix);
+                    l = hs[kHist - tD0 + s] * gnew;
+                    r = hs[kHist - tD1 + s] * gnew;
+                    if(sameFilter && oldOn && uint32_t(s) < fademix)
+                    {
+                        const float gold = oldStep*float(fademix - uint32_t(s));
+                        l += hs[kHist - oD0 + s] * gold;
+                        r += hs[kHist - oD1 + s] * gold;
+                    }
+                }
+                S.lL[i] = l; S.lR[i] = r;
+            }
+            const bool oldPass = !sameFilter && oldOn;
+            if(oldPass)
+                for(int i = t;i < Smem::kOLen;i += GS)
+                {
+                    const int s = i - FP;
+                    float l = 0.0f, r = 0.0f;
+                    if(s >= 0 && uint32_t(s) < fademix)
+                    {
+                        const float gold = oldStep*float(fademix - uint32_t(s));
+                        l = hs[kHist - oD0 + s] * gold;
+                        r = hs[kHist - oD1 + s] * gold;
+                    }
+                    S.oL[i] = l; S.oR[i] = r;
+                }
+            group_sync(bar, GS);
+
+            const int irpad = int(P.ir_pad);
+            fir_pass<OPT, FP, true >(accL, S.lL, S.coefT, irpad, t0);
+            fir_pass<OPT, FP, false>(accR, S.lR, S.coefT, irpad, t0);
+            if(oldPass && t0 < int(kHist) + irpad)
+            {
+                fir_pass<OPT, FP, true >(accL, S.oL, S.coefO, irpad, t0);
+                fir_pass<OPT, FP, false>(accR, S.oR, S.coefO, irpad, t0);
+            }
+            if(t == 0)
+            {
+                rec.old_delay0 = tD0; rec.old_delay1 = tD1;
+                rec.old_gain = targetGain;
+            }
+        }
+        else
+        {
+            // MixSamples -> Mix_ (core/mixer.h:27-41, mixer_c.cpp:150-186,247-258)
+            const uint32_t cd = P.cd;
+            const float delta = counter ? 1.0f/float(counter) : 0.0f;
+            const uint32_t fadeLen = counter < n ? counter : n;
+            float *cur = P.dry_cur + size_t(v)*cd;
+            const float *tgt = P.dry_tgt + size_t(v)*cd;
+            for(uint32_t c = 0;c < cd;++c)
+            {
+                const float cg = counter ? cur[c] : tgt[c];
+                const float tg = playing ? tgt[c] : 0.0f;
+                const float step = (tg - cg)*delta;
+                const bool fade = fabsf(step) > kEps;
+                const bool early = fade && fadeLen < counter;
+                const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
+                const uint32_t start = fade ? fadeLen : 0u;
+                #pragma unroll
+                for(int r = 0;r < SPT;++r)
+                {
+                    const uint32_t i = t + r*GS;
+                    float gsel = 0.0f;
+                    if(i < n)
+                        gsel = (fade && i < fadeLen) ? (cg + step*float(i)) : (i >= start ? flat : 0.0f);
+                    const float val = xs[i < n ? i : 0]*gsel;
+                    if(CDR > 0 && c < uint32_t(CDR))
+                    {
+                        #pragma unroll
+                        for(int cc = 0;cc < (CDR > 0 ? CDR : 1);++cc)
+                            if(cc == int(c)) accD[cc][r] += val;
+                    }
+                    else if(gsel != 0.0f)
+                        atomicAdd(P.dry + size_t(c)*kLine + i, val);
+                }
+                if(t == 0)
+                    S.newGain[c] = early ? (cg + step*float(fadeLen)) : tg;
+            }
+        }
+
+        // ---- auxiliary sends (core/voice.cpp:967-980) ----
+        if(P.num_sends && rec.send_mask)
+        {
+            const uint32_t cw = P.cw;
+            const float delta = counter ? 1.0f/float(counter) : 0.0f;
+            const uint32_t fadeLen = counter < n ? counter : n;
+            for(uint32_t s = 0;s < P.num_sends;++s)
+            {
+                const uint32_t slot = rec.send_slot[s];
+                if(slot == 0xffffffffu) continue;
+                float *cur = P.send_cur + (size_t(v)*P.num_sends + s)*cw;
+                const float *tgt = P.send_tgt + (size_t(v)*P.num_sends + s)*cw;
+                float *wet = P.wet + size_t(slot)*cw*kLine;
+                for(uint32_t c = 0;c < cw;++c)
+                {
+                    const float cg = counter ? cur[c] : tgt[c];
+                    const float tg = playing ? tgt[c] : 0.0f;
+                    const float step = (tg - cg)*delta;
+                    const bool fade = fabsf(step) > kEps;
+                    const bool early = fade && fadeLen < counter;
+                    const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
+                    const uint32_t start = fade ? fadeLen : 0u;
+                    for(uint32_t i = t;i < n;i += GS)
+                    {
+                        const float gsel = (fade && i < fadeLen) ? (cg + step*float(i))
+                            : (i >= start ? flat : 0.0f);
+                        if(gsel != 0.0f)
+                            atomicAdd(wet + size_t(c)*kLine + i, xs[i]*gsel);
+                    }
+                    if(t == 0)
+                        S.newGain[32 + s*25 + c] = early ? (cg + step*float(fadeLen)) : tg;
+                }
+            }
+        }
+
+        // ---- position / state update (core/voice.cpp:1116-1232) ----
+        if(t == 0)
+        {
+            uint32_t newFlags = (flags | kVfFading) & ~kVfCoefDirty;
+            uint32_t newState = vstate;
+            int32_t pos = rec.pos; uint32_t frac = rec.frac;
+            if(vstate == 2u) newState = 0u;
+            else
+            {
+                frac += increment*n;
+                const uint32_t done = frac >> 16;
+                pos = add_sat(pos, int32_t(done));
+                frac &= 0xffffu;
+                if(haveBuffer && pos > 0)
+                {
+                    if(looping)
+                    {
+                        uint32_t up = uint32_t(pos);
+                        if(up >= loopEnd)
+                            pos = int32_t((up-loopStart)%(loopEnd-loopStart) + loopStart);
+                    }
+                    else if(uint32_t(pos) >= buf.frames)
+                    {
+                        newFlags &= ~kVfHaveBuffer;
+                        newState = 2u;
+                    }
+                }
+                rec.pos = pos; rec.frac = frac;
+            }
+            rec.flags = newFlags;
+            rec.state = newState;
+            if(P.results)
+                P.results[v] = VoiceResult{pos, frac,
+                    newState == 1u ? 1u : (newState == 2u ? 2u : (1u<<7)), 0u};
+        }
+        group_sync(bar, GS);               // smem free for the next voice
+        if(t == 0)
+        {
+            // Gains.Current write-back, after every thread has read the old values
+            if(!isHrtf)
+                for(uint32_t c = 0;c < P.cd;++c)
+                    P.dry_cur[size_t(v)*P.cd + c] = S.newGain[c];
+            if(P.num_sends && rec.send_mask)
+                for(uint32_t s = 0;s < P.num_sends;++s)
+                    if(rec.send_slot[s] != 0xffffffffu)
+                        for(uint32_t c = 0;c < P.cw;++c)
+                            P.send_cur[(size_t(v)*P.num_sends + s)*P.cw + c] = S.newGain[32 + s*25 + c];
+        }
+        group_sync(bar, GS);
+    }
+
+    // ---- one partial row per group ----
+    const size_t row = size_t(blockIdx.x)*GROUPS + g;
+    if(HRTF)
+    {
+        float *pl = P.partial + row*(2*kAccumLen);
+        float *pr = pl + kAccumLen;
+        #pragma unroll
+        for(int r = 0;r < OPT;++r)
+        {
+            const int o = t0 + r;
+            if(o < kAccumLen) { pl[o] = accL[r]; pr[o] = accR[r]; }
+        }
+        if(GS*OPT < kAccumLen)
+            for(int o = GS*OPT + t;o < kAccumLen;o += GS) { pl[o] = 0.0f; pr[o] = 0.0f; }
+    }
+    if(CDR > 0)
+    {
+        const size_t rows = size_t(gridDim.x)*GROUPS;
+        float *pd = P.partial + (HRTF ? rows*(2*kAccumLen) : 0) + row*(size_t(CDR)*kLine);
+        #pragma unroll
+        for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
+            #pragma unroll
+            for(int r = 0;r < SPT;++r)
+                pd[c*kLine + t + r*GS] = accD[c][r];
+    }
+}
+
+// Sums `rows` partial rows of `len` floats in a fixed order into out (+= if accumulate).
+// One thread per 4 elements x SEG row segments; deterministic.
+template<int SEG>
+__global__ void __launch_bounds__(64*SEG)
+k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
+    float *__restrict__ out, int accumulate)
+{
+    __shared__ float4 sm[SEG][64];
+    const uint32_t e4 = blockIdx.x*64 + (threadIdx.x & 63);
+    const uint32_t seg = threadIdx.x >> 6;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(e4*4 < len)
+    {
+        const uint32_t per = (rows + SEG - 1)/SEG;
+        const uint32_t r0 = seg*per, r1 = (r0 + per < rows) ? r0 + per : rows;
+        const float4 *p = reinterpret_cast<const float4*>(partial) + e4;
+        const size_t stride4 = len/4;
+        uint32_t r = r0;
+        for(;r + 4 <= r1;r += 4)
+        {
+            const float4 a = p[size_t(r)*stride4], b = p[size_t(r+1)*stride4];
+            const float4 c = p[size_t(r+2)*stride4], d = p[size_t(r+3)*stride4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+            s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        }
+        for(;r < r1;++r)
+        {
+            const float4 a = p[size_t(r)*stride4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    sm[seg][threadIdx.x & 63] = s;
+    __syncthreads();
+    if(seg == 0 && e4*4 < len)
+    {
+        float4 tot = sm[0][threadIdx.x];
+        #pragma unroll
+        for(int k = 1;k < SEG;++k)
+        {
+            const float4 a = sm[k][threadIdx.x];
+            tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
+        }
+        float4 *o = reinterpret_cast<float4*>(out) + e4;
+        if(accumulate)
+        {
+            const float4 a = *o;
+            tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
+        }
+        *o = tot;
+    }
+}
+
+// Applies staged parameter snapshots to the voice records (the device half of
+// b200mix_voices_update).  One CTA of 64 threads per update.
+struct ApplyParams {
+    VoiceRec *voices; const VoiceUpdate *updates;
+    const float *coeffs; const float *dry; const float *send;   // staged side arrays (or null)
+    float2 *hrtf_tgt; float2 *hrtf_old; float *dry_cur, *dry_tgt, *send_cur, *send_tgt;
+    uint32_t ir, ir_pad, cd, cw, num_sends;
+};
+
+__global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
+{
+    const uint32_t u = blockIdx.x;
+    const VoiceUpdate up = A.updates[u];
+    VoiceRec &rec = A.voices[up.voice];
+    const int t = threadIdx.x;
+    const bool reset = (up.flags & (1u<<5)) != 0;
+    const uint32_t oldFlags = reset ? 0u : rec.flags;
+    const bool wasDirty = (oldFlags & kVfCoefDirty) != 0;
+    __syncthreads();
+    if(reset)
+    {
+        for(int k = t;k < kPad;k += 64) rec.prev[k] = 0.0f;
+        for(int k = t;k < kHist;k += 64) rec.hist[k] = 0.0f;
+        if(A.dry_cur) for(uint32_t c = t;c < A.cd;c += 64) A.dry_cur[size_t(up.voice)*A.cd + c] = 0.0f;
+        if(A.send_cur)
+            for(uint32_t c = t;c < A.num_sends*A.cw;c += 64)
+                A.send_cur[size_t(up.voice)*A.num_sends*A.cw + c] = 0.0f;
+    }
+    if(up.has_coeffs && A.hrtf_tgt)
+    {
+        float2 *tg = A.hrtf_tgt + size_t(up.voice)*A.ir_pad;
+        float2 *ol = A.hrtf_old + size_t(up.voice)*A.ir_pad;
+        const float *src = A.coeffs + size_t(u)*A.ir*2;
+        for(uint32_t k = t;k < A.ir_pad;k += 64)
+        {
+            // keep "old" = the filter used by the last mix unless a newer target is
+            // already pending
+            if(!wasDirty && !reset) ol[k] = tg[k];
+            tg[k] = (k < A.ir) ? make_float2(src[k*2], src[k*2+1]) : make_float2(0.f, 0.f);
+        }
+    }
+    if(up.has_dry && A.dry_tgt)
+        for(uint32_t c = t;c < A.cd;c += 64)
+            A.dry_tgt[size_t(up.voice)*A.cd + c] = A.dry[size_t(u)*A.cd + c];
+    if(A.send && A.send_tgt)
+        for(uint32_t c = t;c < A.num_sends*A.cw;c += 64)
+            A.send_tgt[size_t(up.voice)*A.num_sends*A.cw + c] = A.send[size_t(u)*A.num_sends*A.cw + c];
+    if(t == 0)
+    {
+        uint32_t fl = up.flags & (kVfStatic|kVfLooping|kVfHrtf);
+        if(reset)
+        {
+            rec.pos = up.position; rec.frac = up.position_frac;
+            fl |= kVfHaveBuffer;
+            if(up.flags & (1u<<6)) fl |= kVfFading;
+            rec.old_delay0 = 0; rec.old_delay1 = 0; rec.old_gain = 0.0f;
+        }
+        else
+        {
+            fl |= oldFlags & (kVfFading|kVfHaveBuffer|kVfCoefDirty);
+        }
+        if(up.has_coeffs && !reset) fl |= kVfCoefDirty;
+        rec.flags = fl;
+        if(up.flags & (1u<<7)) rec.state = 0u;
+        else if(up.flags & (1u<<1)) rec.state = 2u;
+        else if(up.flags & (1u<<0)) rec.state = 1u;
+        rec.buffer = up.buffer; rec.resampler = up.resampler;
+        rec.loop_start = up.loop_start; rec.loop_end = up.loop_end; rec.step = up.step;
+        rec.bsinc_sf = up.bsinc_sf; rec.bsinc_m = up.bsinc_m; rec.bsinc_l = up.bsinc_l;
+        rec.bsinc_off = up.bsinc_off;
+        rec.tgt_delay0 = up.delay0; rec.tgt_delay1 = up.delay1; rec.tgt_gain = up.gain;
+        uint32_t mask = 0;
+        for(int s = 0;s < kMaxSends;++s)
+        {
+            rec.send_slot[s] = up.send_slot[s];
+            if(up.send_slot[s] != 0xffffffffu) mask |= 1u<<s;
+        }
+        rec.send_mask = mask;
+    }
+}
+
+// Post-process for HRTF output (DeviceBase::Process(HrtfPostProcess), alc/alu.cpp:289-298
+// -> MixDirectHrtfBase, hrtfbase.h:91-133).
+struct PostHrtfParams {
+    const float *accum_sum;      // [2][kAccumLen] this update's voice contributions
+    const float *carry_in;       // [2][kHrirLen]  accumulator tail from the last update
+    float *carry_out;            // [2][kHrirLen]
+    const float *dry;            // [cd][1024]
+    float *real;                 // [real][1024]
+    const float2 *dec_coef;      // [cd][dec_ir]
+    const float *dec_hfscale; float *dec_state;   // state: [cd][4] = coeff, lp_z1, lp_z2, ap_z1
+    float *temp;                 // [cd][1024] band-split dry
+    uint32_t frames, cd, dec_ir, real_left, real_right, dry_active;
+};
+
+// Stage 1 (only when the dry mix is non-silent): BandSplitter::processHfScale per dry
+// channel (core/filters/splitter.cpp:64-95) — a serial recurrence, one thread each.
+__global__ void k_post_hrtf_split(const PostHrtfParams Q)
+{
+    const uint32_t c = blockIdx.x*blockDim.x + threadIdx.x;
+    if(c >= Q.cd) return;
+    float *st = Q.dec_state + c*4;
+    const float ap_coeff = st[0];
+    const float lp_coeff = st[0]*0.5f + 0.5f;
+    float lp_z1 = st[1], lp_z2 = st[2], ap_z1 = st[3];
+    const float hfscale = Q.dec_hfscale[c];
+    const float *in = Q.dry + size_t(c)*kLine;
+    float *out = Q.temp + size_t(c)*kLine;
+    for(uint32_t i = 0;i < Q.frames;++i)
+    {
+        const float x = in[i];
+        const float d0 = (x - lp_z1) * lp_coeff;
+        const float lp_y0 = lp_z1 + d0;
+        lp_z1 = lp_y0 + d0*lp_coeff;
+        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+        const float lp_y1 = lp_z2 + d1;
+        lp_z2 = lp_y1 + d1;
+        const float ap_y = x*ap_coeff + ap_z1;
+        ap_z1 = x - ap_y*ap_coeff;
+        out[i] = (ap_y-lp_y1)*hfscale + lp_y1;
+    }
+    st[1] = lp_z1; st[2] = lp_z2; st[3] = ap_z1;
+}
+
+// Stage 2: total[t] = carry[t] + voices[t] + decoder FIR of the dry channels;
+// RealOut L/R += total[0..n); carry_out = total[n..n+128).
+__global__ void __launch_bounds__(128) k_post_hrtf_mix(const PostHrtfParams Q)
+{
+    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;   // [ear][t]
+    const uint32_t span = Q.frames + kHrirLen;
+    if(idx >= 2u*span) return;
+    const uint32_t ear = idx / span, tt = idx - ear*span;
+    float tot = Q.accum_sum[ear*kAccumLen + tt];
+    if(tt < uint32_t(kHrirLen)) tot += Q.carry_in[ear*kHrirLen + tt];
+    if(Q.dry_active)
+    {
+        for(uint32_t c = 0;c < Q.cd;++c)
+        {
+            const float *x = Q.temp + size_t(c)*kLine;
+            const float2 *cf = Q.dec_coef + size_t(c)*Q.dec_ir;
+            float s = 0.0f;
+            const uint32_t jmax = Q.dec_ir;
+            for(uint32_t j = 0;j < jmax;++j)
+            {
+                const int src = int(tt) - int(j);
+                if(src >= 0 && src < int(Q.frames))
+                    s = fmaf(ear ? cf[j].y : cf[j].x, x[src], s);
+            }
+            tot += s;
+        }
+    }
+    if(tt < Q.frames)
+    {
+        float *o = Q.real + size_t(ear ? Q.real_right : Q.real_left)*kLine + tt;
+        *o += tot;
+    }
+    else
+        Q.carry_out[ear*kHrirLen + (tt - Q.frames)] = tot;
+}
+
+// BFormatDec::process, single band (core/bformatdec.cpp:85-95): real[o] += G[c][o]*dry[c],
+// summed in channel order like the reference's MixSamples loop.
+struct PostAmbiParams {
+    const float *dry; float *real; const float *gains_hf; const float *gains_lf;
+    float *split_state; float *temp_hf; float *temp_lf;
+    uint32_t frames, cd, real_channels, dual;
+};
+
+__global__ void k_post_ambi_split(const PostAmbiParams Q)
+{
+    // BandSplitter::process, core/filters/splitter.cpp:28-62 (dual-band decoders)
+    const uint32_t c = blockIdx.x*blockDim.x + threadIdx.x;
+    if(c >= Q.cd) return;
+    float *st = Q.split_state + c*4;
+    const float ap_coeff = st[0];
+    const float lp_coeff = st[0]*0.5f + 0.5f;
+    float lp_z1 = st[1], lp_z2 = st[2], ap_z1 = st[3];
+    const float *in = Q.dry + size_t(c)*kLine;
+    float *hp = Q.temp_hf + size_t(c)*kLine, *lp = Q.temp_lf + size_t(c)*kLine;
+    for(uint32_t i = 0;i < Q.frames;++i)
+    {
+        const float x = in[i];
+        const float d0 = (x - lp_z1) * lp_coeff;
+        const float lp_y0 = lp_z1 + d0;
+        lp_z1 = lp_y0 + d0;
+        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+        const float lp_y1 = lp_z2 + d1;
+        lp_z2 = lp_y1 + d1;
+        lp[i] = lp_y1;
+        const float ap_y = x*ap_coeff + ap_z1;
+        ap_z1 = x - ap_y*ap_coeff;
+        hp[i] = ap_y - lp_y1;
+    }
+    st[1] = lp_z1; st[2] = lp_z2; st[3] = ap_z1;
+}
+
+__global__ void __launch_bounds__(128) k_post_ambi_mix(const PostAmbiParams Q)
+{
+    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;   // [out][i]
+    if(idx >= Q.real_channels*Q.frames) return;
+    const uint32_t o = idx / Q.frames, i = idx - o*Q.frames;
+    float acc = Q.real[size_t(o)*kLine + i];
+    for(uint32_t c = 0;c < Q.cd;++c)
+    {
+        if(Q.dual)
+        {
+            const float gh = Q.gains_hf[c*Q.real_channels + o];
+            const float gl = Q.gains_lf[c*Q.real_channels + o];
+            if(fabsf(gh) > kSilence) acc += Q.temp_hf[size_t(c)*kLine + i]*gh;
+            if(fabsf(gl) > kSilence) acc += Q.temp_lf[size_t(c)*kLine + i]*gl;
+        }
+        else
+        {
+            const float gh = Q.gains_hf[c*Q.real_channels + o];
+            if(fabsf(gh) > kSilence) acc += Q.dry[size_t(c)*kLine + i]*gh;
+        }
+    }
+    Q.real[size_t(o)*kLine + i] = acc;
+}
+
+} // namespace b200mix
