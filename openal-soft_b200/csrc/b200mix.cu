@@ -69,6 +69,7 @@ struct b200mix_device {
     uint32_t amb_in{0}; bool amb_dual{false};
     float *d_amb_hf{nullptr}, *d_amb_lf{nullptr}, *d_amb_state{nullptr};
     bool dry_active{false};
+    float *d_uhj_state{nullptr}, *d_uhj_scratch{nullptr};
 
     // update staging (pinned host + device)
     VoiceUpdate *h_upd{nullptr}, *d_upd{nullptr};
@@ -189,8 +190,8 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         || desc->num_sends > B200MIX_MAX_SENDS || desc->ir_size > B200MIX_HRIR_LENGTH
         || desc->real_channels > B200MIX_MAX_DRY_CHANNELS || desc->max_voices == 0)
     { g_create_error = "descriptor out of range"; return B200MIX_ERR_INVALID; }
-    if(desc->post_process == B200MIX_POST_UHJ)
-    { g_create_error = "UHJ post-process not implemented yet"; return B200MIX_ERR_UNSUPPORTED; }
+    if(desc->post_process == B200MIX_POST_UHJ && desc->dry_channels < 3)
+    { g_create_error = "UHJ post-process needs W,X,Y dry channels"; return B200MIX_ERR_INVALID; }
 
     auto *d = new(std::nothrow) b200mix_device{};
     if(!d) { g_create_error = "out of host memory"; return B200MIX_ERR_NOMEM; }
@@ -281,6 +282,11 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             size_t(std::max(dd.real_channels, 1u))*kLine*sizeof(float)));
         if(int rc = dev_alloc(d, d->d_temp, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
         if(int rc = dev_alloc(d, d->d_temp2, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
+        if(dd.post_process == B200MIX_POST_UHJ)
+        {
+            if(int rc = dev_alloc(d, d->d_uhj_state, 64)) return rc;
+            if(int rc = dev_alloc(d, d->d_uhj_scratch, 5*1025)) return rc;
+        }
         if(int rc = ensure_stage(d, std::min(dd.max_voices, 4096u))) return rc;
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
         return B200MIX_OK;
@@ -309,6 +315,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_dec_coef); cudaFree(d->d_dec_hfscale); cudaFree(d->d_dec_state);
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
+    cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
     cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
     cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
     if(d->stage_done) cudaEventDestroy(d->stage_done);
@@ -376,8 +383,6 @@ int b200mix_buffer_data(b200mix_device *d, uint32_t buffer, uint32_t sample_type
     static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
     if(buffer >= d->desc.max_buffers || sample_type > B200MIX_FMT_ALAW || channels < 1 || !data)
     { d->error = "buffer_data: bad arguments"; return B200MIX_ERR_INVALID; }
-    if(sample_type == B200MIX_FMT_MULAW || sample_type == B200MIX_FMT_ALAW)
-    { d->error = "buffer_data: mu-law/A-law not implemented yet"; return B200MIX_ERR_UNSUPPORTED; }
     const size_t need = size_t(frames)*channels*sz[sample_type];
     if(bytes < need) { d->error = "buffer_data: short data"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
@@ -543,7 +548,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     if(var.hrtf)
     {
         const uint32_t len = 2*kAccumLen;
-        k_reduce_rows<4><<<(len/4 + 63)/64, 256, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
+        k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
             d->d_accum_sum, 0);
         ++d->launches;
     }
@@ -551,7 +556,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     {
         const uint32_t len = uint32_t(var.cdr)*kLine;
         const float *pd = d->d_partial + (var.hrtf ? rows*(2*kAccumLen) : 0);
-        k_reduce_rows<4><<<(len/4 + 63)/64, 256, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
+        k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
         ++d->launches;
     }
     CUDA_TRY(d, cudaGetLastError());
@@ -594,6 +599,15 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         }
         const uint32_t total = dd.real_channels*frames;
         k_post_ambi_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
+        ++d->launches;
+        break;
+    }
+    case B200MIX_POST_UHJ:
+    {
+        PostUhjParams Q{};
+        Q.dry = d->d_dry; Q.real = d->d_real; Q.state = d->d_uhj_state; Q.scratch = d->d_uhj_scratch;
+        Q.frames = frames; Q.real_left = dd.real_left; Q.real_right = dd.real_right;
+        k_post_uhj<<<1, 1024, 0, d->stream>>>(Q);
         ++d->launches;
         break;
     }

@@ -81,6 +81,25 @@ struct MixParams {
 __device__ __forceinline__ void group_sync(int id, int count)
 { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{ asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+__device__ __forceinline__ uint32_t sample_bytes(uint32_t type)
+{ return type == 1u ? 2u : ((type == 0u || type >= 5u) ? 1u : (type == 4u ? 8u : 4u)); }
+
+// Pulls the lines a voice will read next update into L2: its record + HRIR two voices
+// ahead (plain address arithmetic), and one voice ahead the source span its resampler
+// will consume (needs that voice's header, already prefetched the round before).
+__device__ __forceinline__ void prefetch_span(const char *base, size_t bytes, size_t off,
+    size_t len, int t, int gs)
+{
+    if(off >= bytes) return;
+    if(off + len > bytes) len = bytes - off;
+    const size_t first = off & ~size_t(127);
+    for(size_t a = first + size_t(t)*128u;a < off + len;a += size_t(gs)*128u)
+        prefetch_l2(base + a);
+}
+
 __device__ __forceinline__ float load_sample(const BufferRec &b, size_t idx)
 {
     // SampleInfo<T>::to_float, core/fmt_traits.h:88-131
@@ -115,43 +134,108 @@ __device__ __forceinline__ int32_t add_sat(int32_t a, int32_t b)
     return int32_t(r);
 }
 
+// SampleInfo<T>::to_float, core/fmt_traits.h:88-131
+__device__ __forceinline__ float to_float(uint8_t v) { return (float(v) - 128.0f) * (1.0f/128.0f); }
+__device__ __forceinline__ float to_float(int16_t v) { return float(v) * (1.0f/32768.0f); }
+__device__ __forceinline__ float to_float(int32_t v) { return float(v) * (1.0f/2147483648.0f); }
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(double v) { return float(v); }
+// ITU-T G.711 expansion == muLaw/aLawDecompressionTable (core/fmt_traits.h:12-81)
+struct MulawByte { uint8_t v; };
+struct AlawByte { uint8_t v; };
+__device__ __forceinline__ float to_float(MulawByte b)
+{
+    const uint32_t u = (~uint32_t(b.v)) & 0xffu;
+    const int s = int((((u & 0x0fu)<<3) + 0x84u) << ((u>>4)&7u)) - 0x84;
+    return float((u & 0x80u) ? -s : s) * (1.0f/32768.0f);
+}
+__device__ __forceinline__ float to_float(AlawByte b)
+{
+    const uint32_t a = uint32_t(b.v) ^ 0x55u;
+    const uint32_t e = (a>>4)&7u, m = a & 0x0fu;
+    const int s = (e == 0u) ? int((m<<4) + 8u) : int(((m<<4) + 0x108u) << (e-1u));
+    return float((a & 0x80u) ? s : -s) * (1.0f/32768.0f);
+}
+
+template<typename T> __device__ __forceinline__ T ld_raw(const T *p) { return __ldg(p); }
+template<> __device__ __forceinline__ MulawByte ld_raw(const MulawByte *p)
+{ return MulawByte{__ldg(reinterpret_cast<const uint8_t*>(p))}; }
+template<> __device__ __forceinline__ AlawByte ld_raw(const AlawByte *p)
+{ return AlawByte{__ldg(reinterpret_cast<const uint8_t*>(p))}; }
+
+struct FillArgs {
+    float *dst; uint32_t count, uintPos, q0, firstRun, loopStart, loopSize, lastFrame, channels;
+    bool looping, pastEnd, simpleWrap;
+};
+
+// LoadBufferStatic (core/voice.cpp:500-544) for one window run: element k maps to buffer
+// frame q(k) (loop wrap / end hold); 8 independent loads are issued before any use.
+template<typename T, int GS>
+__device__ __forceinline__ void fill_window(const FillArgs &A, const T *__restrict__ src, int t)
+{
+    for(uint32_t k0 = t;k0 < A.count;k0 += 8u*GS)
+    {
+        T raw[8];
+        #pragma unroll
+        for(int u = 0;u < 8;++u)
+        {
+            uint32_t k = k0 + uint32_t(u)*GS;
+            k = k < A.count ? k : A.count-1u;
+            uint32_t q;
+            if(!A.looping) q = min(A.uintPos + k, A.lastFrame);
+            else if(k < A.firstRun) q = A.q0 + k;
+            else if(A.simpleWrap) q = A.loopStart + (k - A.firstRun);
+            else q = A.loopStart + (k - A.firstRun)%A.loopSize;
+            raw[u] = ld_raw(src + size_t(q)*A.channels);
+        }
+        #pragma unroll
+        for(int u = 0;u < 8;++u)
+        {
+            const uint32_t k = k0 + uint32_t(u)*GS;
+            if(k < A.count) A.dst[k] = A.pastEnd ? 0.0f : to_float(raw[u]);
+        }
+    }
+}
+
 // Shared-memory carve-up of one voice group.
 template<int GS, int OPT, int FP>
 struct GroupSmem {
-    static constexpr int kTabStride = kPad + 1;         // odd: conflict-free phase rows
+    static constexpr int kTabStride = kPad + 2;         // max row stride; rows use m+2 (even, half odd:
+                                                        // 8-byte aligned AND conflict-free for LDS.64)
     static constexpr int kLLen = FP + OPT*GS;           // FIR input incl. front zero pad
     static constexpr int kOLen = FP + kHist + FP + 32;  // old-coefficient pass input
-    float win[kResBuf + 8];
+    // The resample stage (window + phase tables) and the FIR stage (per-ear inputs) never
+    // live at the same time: they share storage.
+    struct ResampleStage { float win[kResBuf + 8]; alignas(8) float tabF[32*kTabStride]; alignas(8) float tabD[32*kTabStride]; };
+    struct FirStage { float2 lLR[kLLen]; float2 oLR[kOLen]; };   // {left, right} per input sample
+    union { ResampleStage rs; FirStage fs; } u;
     float x[kHist + kLine];
-    float tabF[32*kTabStride];
-    float tabD[32*kTabStride];
-    float lL[kLLen], lR[kLLen];
-    float oL[kOLen], oR[kOLen];
     float2 coefT[kHrirLen], coefO[kHrirLen];
     float newGain[32 + kMaxSends*25];   // Current gains written back after the voice
 };
 
-// One FIR pass: acc[r] += sum_j c[j] * in[FP + t0 + r - j]   (gather form of
-// MixHrtfBase's scatter, hrtfbase.h:28-40), taps in blocks of 8 with a register
-// window so each input value is loaded once per block.
-template<int OPT, int FP, bool LEFT>
-__device__ __forceinline__ void fir_pass(float (&acc)[OPT], const float *__restrict__ in,
+// One FIR pass for BOTH ears: acc[r].{x,y} += sum_j c[j].{x,y} * in[FP + t0 + r - j].{x,y}
+// (gather form of MixHrtfBase's scatter, hrtfbase.h:28-40).  Left/right travel as the two
+// halves of Blackwell's packed FFMA2 (fma.rn.f32x2): one instruction issues both ears'
+// MACs.  Taps go in blocks of JB with a register window so each input is loaded once per block.
+template<int OPT, int FP>
+__device__ __forceinline__ void fir_pass(float2 (&acc)[OPT], const float2 *__restrict__ in,
     const float2 *__restrict__ coef, int irpad, int t0)
 {
-    for(int jb = 0;jb < irpad;jb += 8)
+    constexpr int JB = 8;                       // taps per register-window block
+    for(int jb = 0;jb < irpad;jb += JB)
     {
-        float w[OPT+7];
-        const float *p = in + FP + t0 - jb - 7;
+        float2 w[OPT+JB-1];
+        const float2 *p = in + FP + t0 - jb - (JB-1);
         #pragma unroll
-        for(int k = 0;k < OPT+7;++k) w[k] = p[k];
+        for(int k = 0;k < OPT+JB-1;++k) w[k] = p[k];
         #pragma unroll
-        for(int jj = 0;jj < 8;++jj)
+        for(int jj = 0;jj < JB;++jj)
         {
-            const float2 c2 = coef[jb+jj];
-            const float c = LEFT ? c2.x : c2.y;
+            const float2 c = coef[jb+jj];
             #pragma unroll
             for(int r = 0;r < OPT;++r)
-                acc[r] = fmaf(c, w[r - jj + 7], acc[r]);
+                acc[r] = __ffma2_rn(c, w[r - jj + (JB-1)], acc[r]);
         }
     }
 }
@@ -163,7 +247,7 @@ __device__ __forceinline__ void fir_pass(float (&acc)[OPT], const float *__restr
 //   OPT/FP : FIR outputs per thread / front pad (17/64 for ir<=64, 19/128 for ir<=128)
 // ---------------------------------------------------------------------------
 template<int GS, int GROUPS, bool HRTF, int CDR, int OPT, int FP>
-__global__ void __launch_bounds__(GS*GROUPS)
+__global__ void __launch_bounds__(GS*GROUPS, (HRTF && GS*GROUPS == 128) ? 4 : 1)
 k_mix_voices(const MixParams P)
 {
     using Smem = GroupSmem<GS, OPT, FP>;
@@ -174,9 +258,9 @@ k_mix_voices(const MixParams P)
     const int bar = 1 + g;
     constexpr int SPT = kLine / GS;               // resampled samples per thread
 
-    float accL[OPT], accR[OPT];
+    float2 acc[OPT];
     #pragma unroll
-    for(int r = 0;r < OPT;++r) { accL[r] = 0.0f; accR[r] = 0.0f; }
+    for(int r = 0;r < OPT;++r) acc[r] = make_float2(0.0f, 0.0f);
     float accD[CDR > 0 ? CDR : 1][SPT];
     #pragma unroll
     for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
@@ -189,40 +273,43 @@ k_mix_voices(const MixParams P)
     for(uint32_t v = blockIdx.x*GROUPS + g;v < P.max_voices;v += gridDim.x*GROUPS)
     {
         VoiceRec &rec = P.voices[v];
-        const uint32_t vstate = rec.state;
+        // one batch of vector loads for the scalar part of the record
+        const uint4 *hp = reinterpret_cast<const uint4*>(&rec);
+        const uint4 h0 = hp[0], h1 = hp[1], h2 = hp[2], h3 = hp[3], h4 = hp[4];
+        const uint32_t vstate = h0.x;
         if(vstate != 1u && vstate != 2u)
         {
             if(t == 0 && P.results)
-                P.results[v] = VoiceResult{rec.pos, rec.frac, 1u<<7, 0u};
+                P.results[v] = VoiceResult{int32_t(h1.x), h1.y, 1u<<7, 0u};
             continue;
         }
-        const uint32_t increment = rec.step;
-        uint32_t flags = rec.flags;
+        const uint32_t increment = h1.z;
+        uint32_t flags = h0.y;
         if(increment < 1u)
         {
             if(t == 0)
             {
                 if(vstate == 2u) rec.state = 0u;
                 if(P.results)
-                    P.results[v] = VoiceResult{rec.pos, rec.frac, (vstate == 2u) ? (1u<<7) : 1u, 0u};
+                    P.results[v] = VoiceResult{int32_t(h1.x), h1.y, (vstate == 2u) ? (1u<<7) : 1u, 0u};
             }
             continue;
         }
         const bool haveBuffer = (flags & kVfHaveBuffer) != 0;
-        const BufferRec buf = P.buffers[haveBuffer ? rec.buffer : 0u];
-        const uint32_t loopStart = rec.loop_start, loopEnd = rec.loop_end;
-        int32_t intPos = rec.pos;
-        uint32_t fracPos = rec.frac;
+        const BufferRec buf = P.buffers[haveBuffer ? h0.z : 0u];
+        const uint32_t loopStart = h1.w, loopEnd = h2.x;
+        int32_t intPos = int32_t(h1.x);
+        uint32_t fracPos = h1.y;
         bool looping = (flags & kVfLooping) != 0;
         if((flags & kVfStatic) && looping && haveBuffer && intPos >= 0
             && uint32_t(intPos) >= loopEnd)
             looping = false;                                     // core/voice.cpp:1015-1019
-        const uint32_t resampler = rec.resampler;
+        const uint32_t resampler = h0.w;
         const bool isHrtf = HRTF && (flags & kVfHrtf);
         const bool dirty = (flags & kVfCoefDirty) != 0;
 
         // ---- stage per-voice constants into shared memory ----
-        for(int k = t;k < kPad;k += GS) S.win[k] = rec.prev[k];
+        for(int k = t;k < kPad;k += GS) S.u.rs.win[k] = rec.prev[k];
         if(isHrtf)
         {
             for(int k = t;k < kHist;k += GS) S.x[k] = rec.hist[k];
@@ -239,41 +326,50 @@ k_mix_voices(const MixParams P)
         //   BSinc      F = fil + sf*scd, D = phd + sf*spd   (mixer_c.cpp:84-105)
         //   FastBSinc  F = fil,          D = phd            (mixer_c.cpp:63-82)
         //   cubic      F = mCoeffs,      D = mDeltas        (mixer_c.cpp:48-61)
-        uint32_t m = 0, tapOff = 0;                  // taps and left offset into the window
+        uint32_t m = 0, tapOff = 0, ms = 6;          // taps, left offset into the window, row stride
         const bool bypass = false;
         (void)bypass;
         if(resampler >= 4u)
         {
-            m = rec.bsinc_m;
-            tapOff = kEdge - rec.bsinc_l;
-            const float *tab = P.bsinc_tab[(resampler-4u)>>1] + rec.bsinc_off;
+            m = h2.z;
+            tapOff = kEdge - h2.w;
+            const float *tab = P.bsinc_tab[(resampler-4u)>>1] + h3.x;
             const bool full = (increment > 65536u) && (resampler & 1u);
-            const float sf = rec.bsinc_sf;
-            const uint32_t cnt = 32u*m;
-            for(uint32_t e = t;e < cnt;e += GS)
+            const float sf = __uint_as_float(h2.y);
+            // The sub-table of one scale is [32 phases][fil m | phd m] followed by
+            // [32 phases][scd m | spd m].  A thread owns one column of the 2m-wide rows and
+            // walks the 32 phases (coalesced across threads, 8 loads in flight).
+            const uint32_t rowLen = 2u*m;
+            const float *tab2 = tab + 64u*m;
+            ms = m + 2u;
+            for(uint32_t c = t;c < rowLen;c += GS)
             {
-                const uint32_t pi = e / m, j = e - pi*m;
-                const float *fil = tab + 2u*pi*m;
-                float f = fil[j], d = fil[m + j];
-                if(full)
+                float *dstc = (c < m) ? (S.u.rs.tabF + c) : (S.u.rs.tabD + (c - m));
+                #pragma unroll 1
+                for(uint32_t p0 = 0;p0 < 32u;p0 += 8u)
                 {
-                    const float *scd = fil + 32u*2u*m;
-                    f = f + sf*scd[j];
-                    d = d + sf*scd[m + j];
+                    float a[8], b[8];
+                    #pragma unroll
+                    for(int u = 0;u < 8;++u)
+                    {
+                        a[u] = __ldg(tab + (p0+u)*rowLen + c);
+                        b[u] = full ? __ldg(tab2 + (p0+u)*rowLen + c) : 0.0f;
+                    }
+                    #pragma unroll
+                    for(int u = 0;u < 8;++u)
+                        dstc[(p0+u)*ms] = full ? fmaf(sf, b[u], a[u]) : a[u];
                 }
-                S.tabF[pi*Smem::kTabStride + j] = f;
-                S.tabD[pi*Smem::kTabStride + j] = d;
             }
         }
         else if(resampler >= 2u)
         {
-            m = 4; tapOff = kEdge - 1;
+            m = 4; tapOff = kEdge - 1; ms = 6;
             const float *tab = P.cubic_tab[resampler-2u];
             for(uint32_t e = t;e < 128u;e += GS)
             {
                 const uint32_t pi = e>>2, j = e&3u;
-                S.tabF[pi*Smem::kTabStride + j] = tab[pi*8u + j];
-                S.tabD[pi*Smem::kTabStride + j] = tab[pi*8u + 4u + j];
+                S.u.rs.tabF[pi*ms + j] = tab[pi*8u + j];
+                S.u.rs.tabD[pi*ms + j] = tab[pi*8u + 4u + j];
             }
         }
 
@@ -294,11 +390,11 @@ k_mix_voices(const MixParams P)
             if(silent)
             {
                 for(uint32_t k = t;k < dstn;k += GS) xs[loaded+k] = 0.0f;
-                for(uint32_t k = t;k < srcn;k += GS) S.win[kEdge+k] = 0.0f;
+                for(uint32_t k = t;k < srcn;k += GS) S.u.rs.win[kEdge+k] = 0.0f;
             }
             else
             {
-                float *srcBuffer = S.win + kEdge;
+                float *srcBuffer = S.u.rs.win + kEdge;
                 if(!haveBuffer)
                 {
                     // voice ended: hold the sample closest to 0 (core/voice.cpp:704-719)
@@ -317,30 +413,26 @@ k_mix_voices(const MixParams P)
                     const uint32_t count = srcn - srcDelay;
                     float *dst = srcBuffer + srcDelay;
                     for(uint32_t k = t;k < srcDelay;k += GS) srcBuffer[k] = 0.0f;
-                    if(!looping)
+                    // LoadBufferStatic (core/voice.cpp:500-544).  Element k of the run maps to
+                    // buffer frame q(k); loads are issued 8 at a time before any conversion.
+                    const uint32_t loopSize = looping ? (loopEnd - loopStart) : 1u;
+                    const uint32_t q0 = !looping ? uintPos : ((uintPos < loopEnd) ? uintPos
+                        : ((uintPos-loopStart)%loopSize + loopStart));
+                    const uint32_t firstRun = looping ? (loopEnd - q0) : 0u;
+                    const uint32_t lastFrame = buf.frames ? buf.frames-1u : 0u;
+                    const bool pastEnd = !looping && !(buf.frames > uintPos);
+                    const bool simpleWrap = looping && count <= firstRun + loopSize;
+                    const FillArgs fa{dst, count, uintPos, q0, firstRun, loopStart, loopSize,
+                        lastFrame, buf.channels, looping, pastEnd, simpleWrap};
+                    switch(buf.type)
                     {
-                        // LoadBufferStatic, non-looping (core/voice.cpp:504-519)
-                        const float last = (buf.frames > uintPos)
-                            ? load_sample(buf, size_t(buf.frames-1u)*buf.channels) : 0.0f;
-                        for(uint32_t k = t;k < count;k += GS)
-                        {
-                            const uint64_t q = uint64_t(uintPos) + k;
-                            dst[k] = (q < buf.frames) ? load_sample(buf, size_t(q)*buf.channels) : last;
-                        }
-                    }
-                    else
-                    {
-                        // LoadBufferStatic, looping (core/voice.cpp:520-543)
-                        const uint32_t loopSize = loopEnd - loopStart;
-                        const uint32_t q0 = (uintPos < loopEnd) ? uintPos
-                            : ((uintPos-loopStart)%loopSize + loopStart);
-                        const uint32_t firstRun = loopEnd - q0;
-                        for(uint32_t k = t;k < count;k += GS)
-                        {
-                            const uint32_t q = (k < firstRun) ? q0 + k
-                                : loopStart + (k - firstRun)%loopSize;
-                            dst[k] = load_sample(buf, size_t(q)*buf.channels);
-                        }
+                    case 0: fill_window<uint8_t, GS>(fa, static_cast<const uint8_t*>(buf.data), t); break;
+                    case 1: fill_window<int16_t, GS>(fa, static_cast<const int16_t*>(buf.data), t); break;
+                    case 2: fill_window<int32_t, GS>(fa, static_cast<const int32_t*>(buf.data), t); break;
+                    case 3: fill_window<float, GS>(fa, static_cast<const float*>(buf.data), t); break;
+                    case 4: fill_window<double, GS>(fa, static_cast<const double*>(buf.data), t); break;
+                    case 5: fill_window<MulawByte, GS>(fa, static_cast<const MulawByte*>(buf.data), t); break;
+                    default: fill_window<AlawByte, GS>(fa, static_cast<const AlawByte*>(buf.data), t); break;
                     }
                 }
                 group_sync(bar, GS);       // window complete
@@ -352,24 +444,27 @@ k_mix_voices(const MixParams P)
                 }
                 else if(resampler >= 2u)
                 {
-                    const float *vals = S.win + tapOff;
+                    const float *vals = S.u.rs.win + tapOff;
                     for(uint32_t k = t;k < dstn;k += GS)
                     {
                         const uint64_t fp = uint64_t(k)*increment + fracPos;
                         const uint32_t pos = uint32_t(fp>>16), frac = uint32_t(fp) & 0xffffu;
                         const uint32_t pi = frac>>11;
                         const float pf = float(frac & 2047u) * (1.0f/2048.0f);
-                        const float *F = S.tabF + pi*Smem::kTabStride;
-                        const float *D = S.tabD + pi*Smem::kTabStride;
+                        const float2 *F = reinterpret_cast<const float2*>(S.u.rs.tabF + pi*ms);
+                        const float2 *D = reinterpret_cast<const float2*>(S.u.rs.tabD + pi*ms);
                         const float *sv = vals + pos;
-                        float r = 0.0f;
+                        const float2 pf2 = make_float2(pf, pf);
+                        float2 r0 = make_float2(0.0f, 0.0f), r1 = r0;
                         for(uint32_t j = 0;j < m;j += 4)
                         {
-                            r = fmaf(fmaf(pf, D[j+0], F[j+0]), sv[j+0], r);
-                            r = fmaf(fmaf(pf, D[j+1], F[j+1]), sv[j+1], r);
-                            r = fmaf(fmaf(pf, D[j+2], F[j+2]), sv[j+2], r);
-                            r = fmaf(fmaf(pf, D[j+3], F[j+3]), sv[j+3], r);
+                            // two taps per packed FFMA2: c = F + pf*D ; r += c*s
+                            const float2 c0 = __ffma2_rn(pf2, D[j>>1], F[j>>1]);
+                            const float2 c1 = __ffma2_rn(pf2, D[(j>>1)+1], F[(j>>1)+1]);
+                            r0 = __ffma2_rn(c0, make_float2(sv[j+0], sv[j+1]), r0);
+                            r1 = __ffma2_rn(c1, make_float2(sv[j+2], sv[j+3]), r1);
                         }
+                        const float r = (r0.x + r1.x) + (r0.y + r1.y);
                         xs[loaded+k] = r;
                     }
                 }
@@ -396,7 +491,7 @@ k_mix_voices(const MixParams P)
             {
                 const uint32_t dstOffset = n - loaded;
                 const uint32_t srcOffset = uint32_t((uint64_t(dstOffset)*increment + fracPos) >> 16);
-                for(int k = t;k < kPad;k += GS) rec.prev[k] = S.win[srcOffset + k];
+                for(int k = t;k < kPad;k += GS) rec.prev[k] = S.u.rs.win[srcOffset + k];
             }
             loaded = loadEnd;
             if(loaded < n)
@@ -411,12 +506,12 @@ k_mix_voices(const MixParams P)
                     else intPos = add_sat(intPos, int32_t(srcOffset));
                     // slide the window tail to the front (core/voice.cpp:808-809)
                     float carry = 0.0f;
-                    if(t < kPad) carry = S.win[srcOffset + t];
+                    if(t < kPad) carry = S.u.rs.win[srcOffset + t];
                     float carry2 = 0.0f;
-                    if(GS < kPad && t + GS < kPad) carry2 = S.win[srcOffset + t + GS];
+                    if(GS < kPad && t + GS < kPad) carry2 = S.u.rs.win[srcOffset + t + GS];
                     group_sync(bar, GS);
-                    if(t < kPad) S.win[t] = carry;
-                    if(GS < kPad && t + GS < kPad) S.win[t + GS] = carry2;
+                    if(t < kPad) S.u.rs.win[t] = carry;
+                    if(GS < kPad && t + GS < kPad) S.u.rs.win[t + GS] = carry2;
                 }
             }
         }
@@ -432,12 +527,13 @@ k_mix_voices(const MixParams P)
             // DoHrtfMix (core/voice.cpp:827-902), outPos == 0
             if(playing)
                 for(int k = t;k < kHist;k += GS) rec.hist[k] = S.x[n + k];
-            uint32_t oD0 = rec.old_delay0, oD1 = rec.old_delay1;
-            float oGain = rec.old_gain;
-            const uint32_t tD0 = rec.tgt_delay0, tD1 = rec.tgt_delay1;
-            if(!counter) { oD0 = tD0; oD1 = tD1; oGain = rec.tgt_gain; }
+            uint32_t oD0 = h4.x, oD1 = h4.y;
+            float oGain = __uint_as_float(h4.z);
+            const uint32_t tD0 = h3.y, tD1 = h3.z;
+            const float tgtGain = __uint_as_float(h3.w);
+            if(!counter) { oD0 = tD0; oD1 = tD1; oGain = tgtGain; }
             const bool sameFilter = !counter || (!dirty && oD0 == tD0 && oD1 == tD1);
-            const float targetGain = rec.tgt_gain * (playing ? 1.0f : 0.0f);
+            const float targetGain = tgtGain * (playing ? 1.0f : 0.0f);
             const uint32_t fademix = counter;                     // counter <= n always
             float blendNewStep = 0.0f, oldStep = 0.0f;
             bool oldOn = false, newOn = false;
@@ -475,7 +571,7 @@ k_mix_voices(const MixParams P)
                         r += hs[kHist - oD1 + s] * gold;
                     }
                 }
-                S.lL[i] = l; S.lR[i] = r;
+                S.u.fs.lLR[i] = make_float2(l, r);
             }
             const bool oldPass = !sameFilter && oldOn;
             if(oldPass)
@@ -489,18 +585,42 @@ k_mix_voices(const MixParams P)
                         l = hs[kHist - oD0 + s] * gold;
                         r = hs[kHist - oD1 + s] * gold;
                     }
-                    S.oL[i] = l; S.oR[i] = r;
+                    S.u.fs.oLR[i] = make_float2(l, r);
                 }
             group_sync(bar, GS);
 
-            const int irpad = int(P.ir_pad);
-            fir_pass<OPT, FP, true >(accL, S.lL, S.coefT, irpad, t0);
-            fir_pass<OPT, FP, false>(accR, S.lR, S.coefT, irpad, t0);
-            if(oldPass && t0 < int(kHist) + irpad)
-            {
-                fir_pass<OPT, FP, true >(accL, S.oL, S.coefO, irpad, t0);
-                fir_pass<OPT, FP, false>(accR, S.oR, S.coefO, irpad, t0);
+            // software prefetch for the voices this group mixes next (overlaps the FIR)
+    {
+                const uint32_t stride = gridDim.x*GROUPS;
+                const uint32_t v2 = v + 2u*stride, v1 = v + stride;
+                if(v2 < P.max_voices)
+                {
+                    if(t < 5) prefetch_l2(reinterpret_cast<const char*>(&P.voices[v2]) + t*128);
+                    else if(HRTF && t < 5 + int((P.ir_pad*8u + 127u)/128u))
+                        prefetch_l2(reinterpret_cast<const char*>(P.hrtf_tgt + size_t(v2)*P.ir_pad) + (t-5)*128);
+                }
+                if(v1 < P.max_voices)
+                {
+                    const VoiceRec &nx = P.voices[v1];
+                    if((nx.state == 1u || nx.state == 2u) && (nx.flags & kVfHaveBuffer) && nx.step >= 1u)
+                    {
+                        const BufferRec nb = P.buffers[nx.buffer];
+                        const size_t fb = size_t(sample_bytes(nb.type))*nb.channels;
+                        const size_t bytes = size_t(nb.frames)*fb;
+                        const uint32_t p0 = nx.pos < 0 ? 0u : uint32_t(nx.pos);
+                        const size_t need = size_t((uint64_t(P.frames)*nx.step + nx.frac) >> 16) + kPad;
+                        const char *base = static_cast<const char*>(nb.data);
+                        prefetch_span(base, bytes, size_t(p0)*fb, need*fb, t, GS);
+                        if((nx.flags & kVfLooping) && p0 + need > nx.loop_end && nx.loop_end > p0)
+                            prefetch_span(base, bytes, size_t(nx.loop_start)*fb,
+                                (p0 + need - nx.loop_end)*fb, t, GS);
+                    }
+                }
             }
+            const int irpad = int(P.ir_pad);
+            fir_pass<OPT, FP>(acc, S.u.fs.lLR, S.coefT, irpad, t0);
+            if(oldPass && t0 < int(kHist) + irpad)
+                fir_pass<OPT, FP>(acc, S.u.fs.oLR, S.coefO, irpad, t0);
             if(t == 0)
             {
                 rec.old_delay0 = tD0; rec.old_delay1 = tD1;
@@ -547,7 +667,7 @@ k_mix_voices(const MixParams P)
         }
 
         // ---- auxiliary sends (core/voice.cpp:967-980) ----
-        if(P.num_sends && rec.send_mask)
+        if(P.num_sends && h4.w)
         {
             const uint32_t cw = P.cw;
             const float delta = counter ? 1.0f/float(counter) : 0.0f;
@@ -586,7 +706,7 @@ k_mix_voices(const MixParams P)
         {
             uint32_t newFlags = (flags | kVfFading) & ~kVfCoefDirty;
             uint32_t newState = vstate;
-            int32_t pos = rec.pos; uint32_t frac = rec.frac;
+            int32_t pos = int32_t(h1.x); uint32_t frac = h1.y;
             if(vstate == 2u) newState = 0u;
             else
             {
@@ -642,7 +762,7 @@ k_mix_voices(const MixParams P)
         for(int r = 0;r < OPT;++r)
         {
             const int o = t0 + r;
-            if(o < kAccumLen) { pl[o] = accL[r]; pr[o] = accR[r]; }
+            if(o < kAccumLen) { pl[o] = acc[r].x; pr[o] = acc[r].y; }
         }
         if(GS*OPT < kAccumLen)
             for(int o = GS*OPT + t;o < kAccumLen;o += GS) { pl[o] = 0.0f; pr[o] = 0.0f; }
@@ -660,27 +780,28 @@ k_mix_voices(const MixParams P)
 }
 
 // Sums `rows` partial rows of `len` floats in a fixed order into out (+= if accumulate).
-// One thread per 4 elements x SEG row segments; deterministic.
-template<int SEG>
-__global__ void __launch_bounds__(64*SEG)
+// A CTA owns 32 float4 columns; its 32 warps each sum a contiguous segment of rows
+// (4 independent loads in flight), then warp 0 adds the 32 segment sums in order.
+// Deterministic: the summation tree depends only on (rows, len).
+__global__ void __launch_bounds__(1024)
 k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
     float *__restrict__ out, int accumulate)
 {
-    __shared__ float4 sm[SEG][64];
-    const uint32_t e4 = blockIdx.x*64 + (threadIdx.x & 63);
-    const uint32_t seg = threadIdx.x >> 6;
+    __shared__ float4 sm[32][33];
+    const uint32_t lane = threadIdx.x & 31u, seg = threadIdx.x >> 5;
+    const uint32_t e4 = blockIdx.x*32u + lane;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if(e4*4 < len)
+    if(e4*4u < len)
     {
-        const uint32_t per = (rows + SEG - 1)/SEG;
+        const uint32_t per = (rows + 31u)/32u;
         const uint32_t r0 = seg*per, r1 = (r0 + per < rows) ? r0 + per : rows;
         const float4 *p = reinterpret_cast<const float4*>(partial) + e4;
-        const size_t stride4 = len/4;
+        const size_t stride4 = len/4u;
         uint32_t r = r0;
-        for(;r + 4 <= r1;r += 4)
+        for(;r + 4u <= r1;r += 4u)
         {
-            const float4 a = p[size_t(r)*stride4], b = p[size_t(r+1)*stride4];
-            const float4 c = p[size_t(r+2)*stride4], d = p[size_t(r+3)*stride4];
+            const float4 a = __ldg(p + size_t(r)*stride4), b = __ldg(p + size_t(r+1)*stride4);
+            const float4 c = __ldg(p + size_t(r+2)*stride4), d = __ldg(p + size_t(r+3)*stride4);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
             s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
             s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
@@ -688,19 +809,19 @@ k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
         }
         for(;r < r1;++r)
         {
-            const float4 a = p[size_t(r)*stride4];
+            const float4 a = __ldg(p + size_t(r)*stride4);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
     }
-    sm[seg][threadIdx.x & 63] = s;
+    sm[seg][lane] = s;
     __syncthreads();
-    if(seg == 0 && e4*4 < len)
+    if(seg == 0 && e4*4u < len)
     {
-        float4 tot = sm[0][threadIdx.x];
+        float4 tot = sm[0][lane];
         #pragma unroll
-        for(int k = 1;k < SEG;++k)
+        for(int k = 1;k < 32;++k)
         {
-            const float4 a = sm[k][threadIdx.x];
+            const float4 a = sm[k][lane];
             tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
         }
         float4 *o = reinterpret_cast<float4*>(out) + e4;
@@ -931,6 +1052,70 @@ __global__ void __launch_bounds__(128) k_post_ambi_mix(const PostAmbiParams Q)
         }
     }
     Q.real[size_t(o)*kLine + i] = acc;
+}
+
+// UhjEncoderIIR::encode (core/uhjfilter.cpp:231-283): five 4-stage all-pass chains
+// (core/allpass_iir.hpp:53-70), each a serial recurrence -> one thread per chain, then
+// the whole block combines.  state: [5 chains][4 stages][2] + 4 delay samples.
+struct PostUhjParams {
+    const float *dry; float *real; float *state; float *scratch;   // scratch [5][1025]
+    uint32_t frames, real_left, real_right;
+};
+
+__global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
+{
+    constexpr float F1[4] = {0.479400865589f, 0.876218493539f, 0.976597589508f, 0.997499255936f};
+    constexpr float F2[4] = {0.161758498368f, 0.733028932341f, 0.945349700329f, 0.990599156684f};
+    const uint32_t n = Q.frames;
+    const float *w = Q.dry, *x = Q.dry + kLine, *y = Q.dry + 2*kLine;
+    float *left = Q.real + size_t(Q.real_left)*kLine, *right = Q.real + size_t(Q.real_right)*kLine;
+    float *outS = Q.scratch, *outWX = Q.scratch + 1025, *outD = Q.scratch + 2*1025;
+    float *outL = Q.scratch + 3*1025, *outR = Q.scratch + 4*1025;
+    const int chain = threadIdx.x;
+    if(chain < 5)
+    {
+        float *st = Q.state + chain*8;
+        float z0[4], z1[4];
+        #pragma unroll
+        for(int i = 0;i < 4;++i) { z0[i] = st[i*2]; z1[i] = st[i*2+1]; }
+        const bool second = chain == 1;
+        float *dst = chain == 0 ? outS+1 : chain == 1 ? outWX : chain == 2 ? outD+1
+            : chain == 3 ? outL+1 : outR+1;
+        for(uint32_t k = 0;k < n;++k)
+        {
+            float v;
+            if(chain == 0) v = 0.4698463f*w[k] + 0.0757602682546f*x[k];
+            else if(chain == 1) v = -0.17101005f*w[k] + 0.208149636675f*x[k];
+            else if(chain == 2) v = y[k];
+            else if(chain == 3) v = left[k];
+            else v = right[k];
+            #pragma unroll
+            for(int i = 0;i < 4;++i)
+            {
+                const float c = second ? F2[i] : F1[i];
+                const float yy = v*c + z0[i];
+                z0[i] = z1[i];
+                z1[i] = yy*c - v;
+                v = yy;
+            }
+            dst[k] = v;
+        }
+        #pragma unroll
+        for(int i = 0;i < 4;++i) { st[i*2] = z0[i]; st[i*2+1] = z1[i]; }
+        // the one-sample output delay of the Filter1 chains
+        float *delay = Q.state + 40;
+        if(chain == 0) { outS[0] = delay[0]; delay[0] = outS[n]; }
+        else if(chain == 2) { outD[0] = delay[1]; delay[1] = outD[n]; }
+        else if(chain == 3) { outL[0] = delay[2]; delay[2] = outL[n]; }
+        else if(chain == 4) { outR[0] = delay[3]; delay[3] = outR[n]; }
+    }
+    __syncthreads();
+    for(uint32_t i = threadIdx.x;i < n;i += blockDim.x)
+    {
+        const float dd = outWX[i] + 0.267586995182f*outD[i];
+        left[i] = outS[i] + dd + outL[i];
+        right[i] = outS[i] - dd + outR[i];
+    }
 }
 
 } // namespace b200mix

@@ -69,3 +69,23 @@ def voice_buffer_fast(i: int, frames: int = BUFFER_FRAMES) -> np.ndarray:
 
 def voice_gain(num_voices: int) -> float:
     return 1.0 / math.sqrt(num_voices)
+
+
+# sample formats for the format-coverage scenes: (abi FMT_*, AL format enum)
+FORMATS = {"i16": (1, 0x1101), "u8": (0, 0x1100), "f32": (3, 0x10010), "mulaw": (5, 0x10014),
+           "alaw": (6, 0x10016)}
+
+
+def voice_buffer_fmt(i: int, frames: int, fmt: str) -> np.ndarray:
+    """The voice's synthetic signal in another storage format (core/fmt_traits.h)."""
+    pcm = voice_buffer_i16(i, frames)
+    if fmt == "i16":
+        return pcm
+    if fmt == "u8":
+        return ((pcm.astype(np.int32) >> 8) + 128).astype(np.uint8)
+    if fmt == "f32":
+        return (pcm.astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+    if fmt in ("mulaw", "alaw"):
+        # any byte is a valid G.711 code: use a deterministic byte pattern of the signal
+        return ((pcm.astype(np.int32) >> 7) & 0xFF).astype(np.uint8)
+    raise ValueError(fmt)

@@ -204,6 +204,10 @@ struct oracle_device {
     uint32_t amb_in; int amb_dual;
     float *amb_hf, *amb_lf;    /* [in][real] */
     osplitter *amb_split;
+    /* UHJ IIR encoder state (UhjEncoderIIR, core/uhjfilter.h) */
+    float uhj_f1wx[4][2], uhj_f2wx[4][2], uhj_f1y[4][2], uhj_f1d[2][4][2];
+    float uhj_delay_wx, uhj_delay_y, uhj_delay_d[2];
+    float uhj_s[LINE+1], uhj_d[LINE+1], uhj_wx[LINE], uhj_t[LINE+1];
     /* scratch */
     float resample_data[RESBUF];
     float samples[LINE];
@@ -293,7 +297,6 @@ int oracle_buffer_data(oracle_device *d, uint32_t buffer, uint32_t type, uint32_
     uint32_t frames, const void *data, size_t bytes)
 {
     if(buffer >= d->desc.max_buffers || !sample_bytes(type) || channels < 1) return B200MIX_ERR_INVALID;
-    if(type == B200MIX_FMT_MULAW || type == B200MIX_FMT_ALAW) return B200MIX_ERR_UNSUPPORTED;
     if(bytes < (size_t)frames*channels*sample_bytes(type)) return B200MIX_ERR_INVALID;
     obuffer *b = &d->buffers[buffer];
     free(b->data);
@@ -354,7 +357,23 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
     return B200MIX_OK;
 }
 
-/* ---- sample loading: core/voice.cpp:271-288 (LoadSamples), fmt_traits.h:88-131 */
+/* ITU-T G.711 expansion; equals muLawDecompressionTable / aLawDecompressionTable
+ * (core/fmt_traits.h:12-81), computed instead of tabulated. */
+static int mulaw_decode(uint8_t b)
+{
+    const unsigned u = (~b) & 0xffu;
+    const int s = (int)((((u & 0x0fu)<<3) + 0x84u) << ((u>>4)&7u)) - 0x84;
+    return (u & 0x80u) ? -s : s;
+}
+static int alaw_decode(uint8_t b)
+{
+    const unsigned a = b ^ 0x55u;
+    const unsigned e = (a>>4)&7u, m = a & 0x0fu;
+    const int s = (e == 0) ? (int)((m<<4) + 8u) : (int)(((m<<4) + 0x108u) << (e-1u));
+    return (a & 0x80u) ? s : -s;
+}
+
+/* ---- sample loading: core/voice.cpp:271-288 (LoadSamples), fmt_traits.h:88-161 */
 static float to_float(const obuffer *b, size_t idx)
 {
     switch(b->type)
@@ -364,6 +383,8 @@ static float to_float(const obuffer *b, size_t idx)
     case B200MIX_FMT_I32: return (float)((const int32_t*)b->data)[idx] * (1.0f/2147483648.0f);
     case B200MIX_FMT_F32: return ((const float*)b->data)[idx];
     case B200MIX_FMT_F64: return (float)((const double*)b->data)[idx];
+    case B200MIX_FMT_MULAW: return (float)mulaw_decode(((const uint8_t*)b->data)[idx]) * (1.0f/32768.0f);
+    case B200MIX_FMT_ALAW: return (float)alaw_decode(((const uint8_t*)b->data)[idx]) * (1.0f/32768.0f);
     }
     return 0.0f;
 }
@@ -842,6 +863,53 @@ static void post_ambidec(oracle_device *d, size_t n)
     }
 }
 
+/* process(AllPassFilter&...), core/allpass_iir.hpp:53-70 */
+static void allpass_process(float st[4][2], const float coeffs[4], const float *src, float *dst,
+    size_t n)
+{
+    for(size_t k = 0;k < n;++k)
+    {
+        float x = src[k];
+        for(int i = 0;i < 4;++i)
+        {
+            const float y = x*coeffs[i] + st[i][0];
+            st[i][0] = st[i][1];
+            st[i][1] = y*coeffs[i] - x;
+            x = y;
+        }
+        dst[k] = x;
+    }
+}
+
+/* UhjEncoderIIR::encode, core/uhjfilter.cpp:231-283 (DeviceBase::Process(UhjPostProcess),
+ * alc/alu.cpp:300-312) */
+static void post_uhj(oracle_device *d, size_t n)
+{
+    static const float F1[4] = {0.479400865589f, 0.876218493539f, 0.976597589508f, 0.997499255936f};
+    static const float F2[4] = {0.161758498368f, 0.733028932341f, 0.945349700329f, 0.990599156684f};
+    const float *w = d->dry[0], *x = d->dry[1], *y = d->dry[2];
+    float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
+
+    for(size_t i = 0;i < n;++i) d->temp[i] = 0.4698463f*w[i] + 0.0757602682546f*x[i];
+    allpass_process(d->uhj_f1wx, F1, d->temp, d->uhj_s+1, n);
+    d->uhj_s[0] = d->uhj_delay_wx; d->uhj_delay_wx = d->uhj_s[n];
+
+    for(size_t i = 0;i < n;++i) d->temp[i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    allpass_process(d->uhj_f2wx, F2, d->temp, d->uhj_wx, n);
+
+    allpass_process(d->uhj_f1y, F1, y, d->uhj_d+1, n);
+    d->uhj_d[0] = d->uhj_delay_y; d->uhj_delay_y = d->uhj_d[n];
+    for(size_t i = 0;i < n;++i) d->uhj_d[i] = d->uhj_wx[i] + 0.267586995182f*d->uhj_d[i];
+
+    allpass_process(d->uhj_f1d[0], F1, left, d->uhj_t+1, n);
+    d->uhj_t[0] = d->uhj_delay_d[0]; d->uhj_delay_d[0] = d->uhj_t[n];
+    for(size_t i = 0;i < n;++i) left[i] = d->uhj_s[i] + d->uhj_d[i] + d->uhj_t[i];
+
+    allpass_process(d->uhj_f1d[1], F1, right, d->uhj_t+1, n);
+    d->uhj_t[0] = d->uhj_delay_d[1]; d->uhj_delay_d[1] = d->uhj_t[n];
+    for(size_t i = 0;i < n;++i) right[i] = d->uhj_s[i] - d->uhj_d[i] + d->uhj_t[i];
+}
+
 /* DeviceBase::renderSamples(unsigned) + ProcessContexts, alc/alu.cpp:2412-2459,2177-2273 */
 int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     b200mix_voice_result *results)
@@ -864,6 +932,7 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     {
     case B200MIX_POST_HRTF: if(d->dec_channels) post_hrtf(d, frames); break;
     case B200MIX_POST_AMBIDEC: if(d->amb_in) post_ambidec(d, frames); break;
+    case B200MIX_POST_UHJ: if(dd->dry_channels >= 3) post_uhj(d, frames); break;
     case B200MIX_POST_NONE: break;
     default: return B200MIX_ERR_UNSUPPORTED;
     }

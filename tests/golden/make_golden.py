@@ -35,14 +35,33 @@ SCENES = {
     # short non-looping buffers: voices end, go Stopping, fade out
     "hrtf_bsinc24_oneshot_v6": (6, 1, 7, 5, False, 2500),
     "stereo_spline_oneshot_v6": (6, 0, 2, 5, False, 2500),
+    # config 4b: stereo UHJ output (2-D first order dry mix + UhjEncoderIIR)
+    "uhj_spline_v8": (8, 0, 2, 4, True, 48000, "uhj"),
+    # config 4a: third-order ambisonic output (16 dry channels, RealOut aliases Dry)
+    "ambi3_bsinc24_v12": (12, 0, 7, 3, True, 48000, "ambi3"),
+    # storage formats (core/fmt_traits.h)
+    "hrtf_spline_mulaw_v4": (4, 1, 2, 2, True, 48000, None, "mulaw"),
+    "hrtf_spline_alaw_v4": (4, 1, 2, 2, True, 48000, None, "alaw"),
+    "stereo_spline_u8_v4": (4, 0, 2, 2, True, 48000, None, "u8"),
+    "stereo_spline_f32_v4": (4, 0, 2, 2, True, 48000, None, "f32"),
+}
+
+ATTRS = {
+    "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
+    "ambi3": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 3,
+                        r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
+                        r.ALC_AMBISONIC_SCALING_SOFT: r.ALC_N3D_SOFT},
 }
 
 
 def run_scene(name):
     from helpers import refal, scenes
     from pyb200mix import abi
-    V, hrtf, rs, U, looping, frames = SCENES[name]
-    ref, pcms = scenes.make_ref_scene(V, hrtf, rs, looping=looping, frames=frames)
+    V, hrtf, rs, U, looping, frames = SCENES[name][:6]
+    spec = SCENES[name]
+    attrs = ATTRS[spec[6]](refal) if len(spec) > 6 and spec[6] else None
+    fmt = spec[7] if len(spec) > 7 else "i16"
+    ref, pcms = scenes.make_ref_scene(V, hrtf, rs, attrs=attrs, looping=looping, frames=frames, fmt=fmt)
     ref.play_all()
     outs = []
     snap = None
@@ -94,8 +113,9 @@ def main():
         out = {k: v for k, v in a.items() if k != "out"}
         out["out_sse"] = a["out"]
         out["out_c"] = b["out"]
-        V, hrtf, rs, U, looping, frames = SCENES[name]
+        V, hrtf, rs, U, looping, frames = SCENES[name][:6]
         out["meta"] = np.array([V, hrtf, rs, U, int(looping), frames], dtype=np.int64)
+        out["fmt"] = np.array(SCENES[name][7] if len(SCENES[name]) > 7 else "i16")
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         d = np.abs(a["out"].astype(np.float64) - b["out"]).max()
         print(f"{name}: wrote, |sse-c|max = {d:.3e}")

@@ -33,8 +33,9 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             dev.set_hrtf_decoder(fx["dec_coeffs"], fx["dec_hf"], fx["dec_sc"])
         elif desc.post_process == abi.POST_AMBIDEC:
             dev.set_ambi_decoder(fx["amb_hf"], fx.get("amb_lf"), float(fx["amb_xover"]))
+        fmt = str(fx["fmt"]) if "fmt" in fx else "i16"
         for i in range(V):
-            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_i16(i, buf_frames))
+            dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, buf_frames, fmt))
         params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
         plist = []
         for k in range(V):

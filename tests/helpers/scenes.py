@@ -9,18 +9,20 @@ from pyb200mix import abi, scene
 
 
 def make_ref_scene(num_voices, hrtf, resampler, attrs=None, pitch_fn=scene.voice_pitch,
-                   looping=True, frames=scene.BUFFER_FRAMES, max_sources=None):
+                   looping=True, frames=scene.BUFFER_FRAMES, max_sources=None, fmt="i16"):
     a = {refal.ALC_HRTF_SOFT: 1 if hrtf else 0,
          refal.ALC_MONO_SOURCES: max_sources or max(num_voices, 1)}
     if attrs:
         a.update(attrs)
     ref = refal.RefDevice(a)
+    ref.out_channels = ref.desc.real_channels
     pcms = []
     for i in range(num_voices):
-        pcm = scene.voice_buffer_i16(i, frames)
+        pcm = scene.voice_buffer_fmt(i, frames, fmt)
         pcms.append(pcm)
         ref.add_voice(pcm, scene.BUFFER_RATE, pitch_fn(i), scene.voice_position(i),
-                      scene.voice_gain(num_voices), resampler, looping=looping)
+                      scene.voice_gain(num_voices), resampler, looping=looping,
+                      fmt=scene.FORMATS[fmt][1])
     return ref, pcms
 
 

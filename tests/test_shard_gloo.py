@@ -1,0 +1,86 @@
+"""The N>1 path on CPU: world_size-2 gloo.  Each rank mixes its shard of the voices
+(with the CPU oracle standing in for the device mixer — the host-side sharding and the
+collective are what is under test) and the reduced RealOut must equal the single-process
+mix of all voices."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pyb200mix import shard
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_shard_ranges_partition_the_voices():
+    for total, world in [(4096, 8), (10, 4), (3, 8), (65536, 8), (1, 1)]:
+        seen = []
+        for r in range(world):
+            first, count = shard.shard_range(total, world, r)
+            seen += list(range(first, first + count))
+            for v in range(first, first + count):
+                assert shard.owner_of(v, total, world) == r
+        assert seen == list(range(total))
+
+
+def _mix(voices, total, updates):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "openal-soft_b200"))
+    from helpers import mixlib, synth
+    from helpers.mixlib import MixDevice
+    from pyb200mix import abi, scene
+    rng = np.random.default_rng(11)
+    desc = synth.hrtf_desc(total, 64)
+    params, coeffs, dry = synth.voice_set(rng, total, 64)
+    dev = MixDevice(mixlib.oracle(), desc)
+    dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+    for i in voices:
+        dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i, 6000))
+    for p in params:
+        p.loop_end = 6000
+        p.position %= 3000
+    dev.voices_update([params[i] for i in voices], coeffs[voices], dry[voices], None)
+    out = np.stack([dev.render() for _ in range(updates)])
+    dev.close()
+    return out
+
+
+def _worker(rank, world, port, total, updates, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard.shard_range(total, world, rank)
+    out = _mix(list(range(first, first + count)), total, updates)
+    block = torch.from_numpy(out.copy())
+    shard.reduce_real_out(block, dst=0)
+    if rank == 0:
+        ret.put(block.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_reduce_equals_single_process_mix():
+    total, updates, world = 24, 3, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, updates, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    reduced = ret.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    full = _mix(list(range(total)), total, updates)
+    err = np.abs(reduced.astype(np.float64) - full)
+    assert np.abs(full).max() > 1e-3
+    scale = max(1.0, float(np.abs(full).max()))   # fp32 re-association of the two partial sums
+    assert err.max() <= 5e-6 * scale and np.sqrt((err ** 2).mean()) <= 5e-7 * scale
