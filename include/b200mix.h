@@ -112,6 +112,25 @@ B200MIX_API int b200mix_buffer_data(b200mix_device *dev, uint32_t buffer, uint32
     uint32_t channels, uint32_t frames, const void *data, size_t bytes);
 B200MIX_API int b200mix_buffer_free(b200mix_device *dev, uint32_t buffer);
 
+/* ---- auxiliary effect slots: EffectSlotBase + EffectState (core/effectslot.h:50-82,
+ *      core/effects/base.h:197-222) ------------------------------------------------ */
+enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1 };
+
+/* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
+ * device-rate impulse response (planar [ir_channels][ir_frames] floats; the host applies
+ * the reference's polyphase resampling first when the IR buffer's rate differs) on aux
+ * slot `slot` and resets its history.  The slot reads wet channel 0 of its input
+ * (alc/effects/convolution.cpp:636) and mixes ir_channels output lines into the Dry mix. */
+B200MIX_API int b200mix_slot_convolution(b200mix_device *dev, uint32_t slot, uint32_t ir_channels,
+    uint32_t ir_frames, const float *ir);
+/* Result of EffectState::update for the slot's output mix: Target gains
+ * [lines][dry_channels] (ConvolutionState::ChannelData::Target); Current is kept on the
+ * device and fades to Target over the whole update like MixSamples(..., Counter=samplesToDo). */
+B200MIX_API int b200mix_slot_output_gains(b200mix_device *dev, uint32_t slot, uint32_t lines,
+    const float *gains);
+/* Detaches the effect (EffectSlotType::None): the slot's wet input is ignored. */
+B200MIX_API int b200mix_slot_disable(b200mix_device *dev, uint32_t slot);
+
 /* ---- voices: the post-ALU snapshot of Voice (core/voice.h:157-272) ------- */
 enum {
     B200MIX_VF_PLAYING   = 1u<<0, /* Voice::Playing */

@@ -84,6 +84,14 @@ struct b200mix_device {
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
     bool ev_valid{false};
 
+    // mixing order (host mirror of which voices are configured active, and their cost)
+    std::vector<uint8_t> h_active;
+    std::vector<uint32_t> h_cost;
+    std::vector<uint32_t> h_order;
+    uint32_t *d_order{nullptr};
+    uint32_t num_order{0};
+    bool order_dirty{true};
+
     uint32_t ir_pad{0};
     uint32_t voice_hi{0};          // 1 + highest voice index ever configured
     // launch geometry (resolved at create)
@@ -253,6 +261,9 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             if(int rc = dev_alloc(d, d->d_send_tgt, dd.max_voices*per)) return rc;
         }
         if(int rc = dev_alloc(d, d->d_results, dd.max_voices)) return rc;
+        if(int rc = dev_alloc(d, d->d_order, dd.max_voices)) return rc;
+        d->h_active.assign(dd.max_voices, 0);
+        d->h_cost.assign(dd.max_voices, 0);
         CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_results),
             size_t(dd.max_voices)*sizeof(b200mix_voice_result)));
 
@@ -308,7 +319,7 @@ void b200mix_destroy(b200mix_device *d)
     for(int i = 0;i < 2;++i) cudaFree(d->d_cubic[i]);
     cudaFree(d->d_voices); cudaFree(d->d_buffers); cudaFree(d->d_hrtf_tgt); cudaFree(d->d_hrtf_old);
     cudaFree(d->d_dry_cur); cudaFree(d->d_dry_tgt); cudaFree(d->d_send_cur); cudaFree(d->d_send_tgt);
-    cudaFree(d->d_results); cudaFreeHost(d->h_results);
+    cudaFree(d->d_results); cudaFreeHost(d->h_results); cudaFree(d->d_order);
     if(d->d_real != d->d_dry) cudaFree(d->d_real);
     cudaFree(d->d_dry); cudaFree(d->d_wet); cudaFree(d->d_partial); cudaFree(d->d_accum_sum);
     cudaFree(d->d_carry[0]); cudaFree(d->d_carry[1]); cudaFreeHost(d->h_real);
@@ -464,6 +475,13 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
         u.has_coeffs = hrtf_coeffs != nullptr && dd.ir_size > 0;
         u.has_dry = dry_gains != nullptr;
         if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED)) d->dry_active = true;
+        {
+            // mixing-order bookkeeping: membership and a cost key (resampler taps per output)
+            const uint8_t act = (p.flags & B200MIX_VF_STOPPED) ? 0 : 1;
+            uint32_t cost = (p.step == 65536u) ? 1u : (u.bsinc_m ? u.bsinc_m : (p.resampler >= 2u ? 4u : 2u));
+            if(d->h_active[p.voice] != act || d->h_cost[p.voice] != cost) d->order_dirty = true;
+            d->h_active[p.voice] = act; d->h_cost[p.voice] = cost;
+        }
         d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
     }
     CUDA_TRY(d, cudaMemcpyAsync(d->d_upd, d->h_upd, n*sizeof(VoiceUpdate), cudaMemcpyHostToDevice, d->stream));
@@ -521,10 +539,26 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     if(d->d_wet)
         CUDA_TRY(d, cudaMemsetAsync(d->d_wet, 0, size_t(dd.max_slots)*dd.wet_channels*kLine*sizeof(float), d->stream));
 
+    if(d->order_dirty)
+    {
+        d->h_order.clear();
+        for(uint32_t v = 0;v < d->voice_hi;++v) if(d->h_active[v]) d->h_order.push_back(v);
+        std::stable_sort(d->h_order.begin(), d->h_order.end(),
+            [d](uint32_t a, uint32_t b) { return d->h_cost[a] > d->h_cost[b]; });
+        d->num_order = uint32_t(d->h_order.size());
+        if(d->num_order)
+        {
+            // the vector may be reused before the copy completes: synchronise (rare path)
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_order, d->h_order.data(), d->num_order*sizeof(uint32_t),
+                cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        }
+        d->order_dirty = false;
+    }
     const Variant var = get_variant(d->mix_variant);
     const uint32_t nv = std::max(d->voice_hi, 1u);
     const uint32_t maxBlocks = uint32_t(d->num_sms*d->mix_blocks_per_sm);
-    const uint32_t blocks = std::max(1u, std::min(maxBlocks, (nv + var.groups - 1)/var.groups));
+    const uint32_t blocks = std::max(1u, std::min(maxBlocks, (d->num_order + var.groups - 1)/var.groups));
     const size_t rows = size_t(blocks)*var.groups;
 
     MixParams P{};
@@ -539,6 +573,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     P.max_voices = nv; P.frames = frames; P.ir = dd.ir_size; P.ir_pad = d->ir_pad;
     P.cd = dd.dry_channels; P.cw = dd.wet_channels; P.num_sends = dd.num_sends;
     P.max_buffers = dd.max_buffers;
+    P.order = d->d_order; P.num_order = d->num_order;
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
     if(d->profile) { cudaEventRecord(d->ev_mix1, d->stream); d->ev_valid = true; }

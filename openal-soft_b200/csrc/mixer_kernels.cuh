@@ -76,6 +76,8 @@ struct MixParams {
     const float *bsinc_tab[3];                // bsinc12, 24, 48
     const float *cubic_tab[2];                // spline, gaussian [32][8]
     uint32_t max_voices, frames, ir, ir_pad, cd, cw, num_sends, max_buffers;
+    const uint32_t *order;                    // mixing order: voice indices, cost-sorted
+    uint32_t num_order;
 };
 
 __device__ __forceinline__ void group_sync(int id, int count)
@@ -270,8 +272,12 @@ k_mix_voices(const MixParams P)
     const uint32_t n = P.frames;
     const int t0 = OPT*t;
 
-    for(uint32_t v = blockIdx.x*GROUPS + g;v < P.max_voices;v += gridDim.x*GROUPS)
+    // Voices are visited in the host's mixing order (active voices only, sorted by
+    // resampler cost) with a grid-strided assignment: every round of the persistent loop
+    // hands all groups voices of similar cost, which balances the rounds.
+    for(uint32_t oi = blockIdx.x*GROUPS + g;oi < P.num_order;oi += gridDim.x*GROUPS)
     {
+        const uint32_t v = P.order[oi];
         VoiceRec &rec = P.voices[v];
         // one batch of vector loads for the scalar part of the record
         const uint4 *hp = reinterpret_cast<const uint4*>(&rec);
@@ -592,7 +598,9 @@ k_mix_voices(const MixParams P)
             // software prefetch for the voices this group mixes next (overlaps the FIR)
     {
                 const uint32_t stride = gridDim.x*GROUPS;
-                const uint32_t v2 = v + 2u*stride, v1 = v + stride;
+                const uint32_t o2 = oi + 2u*stride, o1 = oi + stride;
+                const uint32_t v2 = o2 < P.num_order ? P.order[o2] : 0xffffffffu;
+                const uint32_t v1 = o1 < P.num_order ? P.order[o1] : 0xffffffffu;
                 if(v2 < P.max_voices)
                 {
                     if(t < 5) prefetch_l2(reinterpret_cast<const char*>(&P.voices[v2]) + t*128);

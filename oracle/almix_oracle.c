@@ -187,6 +187,21 @@ typedef struct {
 
 typedef struct { float coeff, lp_z1, lp_z2, ap_z1; } osplitter; /* core/filters/splitter.h */
 
+/* One aux slot with a ConvolutionState (alc/effects/convolution.cpp:254-300).
+ * RESTATEMENT NOTE: the reference evaluates the convolution as a 128-tap time-domain head
+ * plus 256-point FFT partitions (pffft).  Both compute the linear convolution
+ * y[n] = sum_k h[k] x[n-k]; this oracle evaluates that definition directly with a double
+ * accumulator (no FFT), so it is not bit-exact with pffft's float butterflies — it is
+ * pinned against the compiled reference to <= 1e-6 (tests/test_oracle_vs_ref.py,
+ * tests/golden conv scene). */
+typedef struct {
+    uint32_t type, channels, frames;
+    float *ir;                 /* [channels][frames] */
+    float *hist;               /* input history ring, frames+1024 long (newest at hist_pos-1) */
+    uint32_t hist_pos;
+    float *cur, *tgt;          /* output mix gains [channels][MAX_DRY] */
+} oslot;
+
 struct oracle_device {
     b200mix_device_desc desc;
     obuffer *buffers;
@@ -194,6 +209,7 @@ struct oracle_device {
     float (*dry)[LINE];        /* Dry.Buffer */
     float (*real)[LINE];       /* RealOut.Buffer (== dry when POST_NONE) */
     float (*wet)[LINE];        /* [slot*wet_channels + c] */
+    oslot *slots;
     float accum[LINE+HRIR][2]; /* HrtfAccumData core/device.h:288 */
     /* HRTF decoder (DirectHrtfState) */
     uint32_t dec_channels, dec_ir;
@@ -231,6 +247,7 @@ int oracle_create(const b200mix_device_desc *desc, oracle_device **out)
     else d->real = calloc(desc->real_channels ? desc->real_channels : 1, sizeof(float[LINE]));
     size_t nwet = (size_t)desc->max_slots*desc->wet_channels;
     d->wet = calloc(nwet ? nwet : 1, sizeof(float[LINE]));
+    d->slots = calloc(desc->max_slots ? desc->max_slots : 1, sizeof(oslot));
     *out = d;
     return B200MIX_OK;
 }
@@ -241,6 +258,9 @@ void oracle_destroy(oracle_device *d)
     for(uint32_t i = 0;i < d->desc.max_buffers;++i) free(d->buffers[i].data);
     free(d->buffers); free(d->voices);
     if(d->real != d->dry) free(d->real);
+    for(uint32_t i = 0;i < d->desc.max_slots;++i)
+    { free(d->slots[i].ir); free(d->slots[i].hist); free(d->slots[i].cur); free(d->slots[i].tgt); }
+    free(d->slots);
     free(d->dry); free(d->wet);
     free(d->dec_coef); free(d->dec_hfscale); free(d->dec_split);
     free(d->amb_hf); free(d->amb_lf); free(d->amb_split);
@@ -278,6 +298,41 @@ int oracle_set_ambi_decoder(oracle_device *d, uint32_t in_channels, const float 
     if(gains_lf) { d->amb_lf = malloc(n*sizeof(float)); memcpy(d->amb_lf, gains_lf, n*sizeof(float)); }
     d->amb_split = calloc(in_channels, sizeof(osplitter));
     for(uint32_t c = 0;c < in_channels;++c) d->amb_split[c].coeff = xover_coeff;
+    return B200MIX_OK;
+}
+
+int oracle_slot_disable(oracle_device *d, uint32_t slot)
+{
+    if(slot >= d->desc.max_slots) return B200MIX_ERR_INVALID;
+    oslot *s = &d->slots[slot];
+    free(s->ir); free(s->hist); free(s->cur); free(s->tgt);
+    memset(s, 0, sizeof(*s));
+    return B200MIX_OK;
+}
+
+int oracle_slot_convolution(oracle_device *d, uint32_t slot, uint32_t ir_channels,
+    uint32_t ir_frames, const float *ir)
+{
+    if(slot >= d->desc.max_slots || !ir_channels || !ir_frames || !ir) return B200MIX_ERR_INVALID;
+    oracle_slot_disable(d, slot);
+    oslot *s = &d->slots[slot];
+    s->type = B200MIX_EFFECT_CONVOLUTION; s->channels = ir_channels; s->frames = ir_frames;
+    s->ir = malloc(sizeof(float)*(size_t)ir_channels*ir_frames);
+    memcpy(s->ir, ir, sizeof(float)*(size_t)ir_channels*ir_frames);
+    s->hist = calloc((size_t)ir_frames + LINE, sizeof(float));
+    s->cur = calloc((size_t)ir_channels*B200MIX_MAX_DRY_CHANNELS, sizeof(float));
+    s->tgt = calloc((size_t)ir_channels*B200MIX_MAX_DRY_CHANNELS, sizeof(float));
+    return B200MIX_OK;
+}
+
+int oracle_slot_output_gains(oracle_device *d, uint32_t slot, uint32_t lines, const float *gains)
+{
+    if(slot >= d->desc.max_slots || !d->slots[slot].type || lines != d->slots[slot].channels)
+        return B200MIX_ERR_INVALID;
+    oslot *s = &d->slots[slot];
+    for(uint32_t c = 0;c < lines;++c)
+        for(uint32_t o = 0;o < d->desc.dry_channels;++o)
+            s->tgt[c*B200MIX_MAX_DRY_CHANNELS + o] = gains[c*d->desc.dry_channels + o];
     return B200MIX_OK;
 }
 
@@ -910,6 +965,39 @@ static void post_uhj(oracle_device *d, size_t n)
     for(size_t i = 0;i < n;++i) right[i] = d->uhj_s[i] - d->uhj_d[i] + d->uhj_t[i];
 }
 
+/* ConvolutionState::process + NormalMix (alc/effects/convolution.cpp:623-714,298-304):
+ * out_c[i] = sum_k ir_c[k] * x[i-k] over the slot's whole input history, then
+ * MixSamples(out_c, Dry, Current, Target, Counter = samplesToDo). */
+static void slot_convolution_process(oracle_device *d, oslot *s, const float *in, size_t n)
+{
+    const uint32_t L = s->frames;
+    const uint32_t R = L + LINE;        /* ring: every output of this update still sees L taps */
+    /* append the new input to the history ring */
+    for(size_t i = 0;i < n;++i)
+    {
+        s->hist[s->hist_pos] = in[i];
+        s->hist_pos = (s->hist_pos+1u) % R;
+    }
+    for(uint32_t c = 0;c < s->channels;++c)
+    {
+        const float *h = s->ir + (size_t)c*L;
+        for(size_t i = 0;i < n;++i)
+        {
+            /* newest sample of output i sits (n-1-i) behind the ring head */
+            uint32_t p = (s->hist_pos + R - 1u - (uint32_t)(n-1-i)) % R;
+            double acc = 0.0;
+            for(uint32_t k = 0;k < L;++k)
+            {
+                acc += (double)h[k] * (double)s->hist[p];
+                p = p ? p-1u : R-1u;
+            }
+            d->temp[i] = (float)acc;
+        }
+        mix_samples(d->temp, n, d->dry, d->desc.dry_channels, s->cur + c*B200MIX_MAX_DRY_CHANNELS,
+            s->tgt + c*B200MIX_MAX_DRY_CHANNELS, n);
+    }
+}
+
 /* DeviceBase::renderSamples(unsigned) + ProcessContexts, alc/alu.cpp:2412-2459,2177-2273 */
 int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     b200mix_voice_result *results)
@@ -926,7 +1014,11 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
         if(v->state == 1 || v->state == 2)
             voice_mix(d, v, frames, NULL);
     }
-    /* effect slots: none configured in the oracle yet */
+    /* EffectState::process for every slot (alc/alu.cpp:2252-2256); slots here have no
+     * slot targets, so each mixes straight into Dry (mOutTarget, alc/alu.cpp:626-633). */
+    for(uint32_t si = 0;si < dd->max_slots;++si)
+        if(d->slots[si].type == B200MIX_EFFECT_CONVOLUTION)
+            slot_convolution_process(d, &d->slots[si], d->wet[(size_t)si*dd->wet_channels], frames);
 
     switch(dd->post_process)
     {
@@ -955,6 +1047,13 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
 int oracle_get_dry(oracle_device *d, float *dry)
 {
     memcpy(dry, d->dry, sizeof(float[LINE])*d->desc.dry_channels);
+    return B200MIX_OK;
+}
+
+int oracle_get_wet(oracle_device *d, uint32_t slot, float *wet)
+{
+    if(slot >= d->desc.max_slots) return B200MIX_ERR_INVALID;
+    memcpy(wet, d->wet[(size_t)slot*d->desc.wet_channels], sizeof(float[LINE])*d->desc.wet_channels);
     return B200MIX_OK;
 }
 

@@ -72,7 +72,13 @@ int  oracle_voices_update(oracle_device *dev, uint32_t n, const b200mix_voice_pa
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains);
 int  oracle_render(oracle_device *dev, uint32_t frames, float *const *real_out,
     b200mix_voice_result *results);
+int  oracle_slot_convolution(oracle_device *dev, uint32_t slot, uint32_t ir_channels,
+    uint32_t ir_frames, const float *ir);
+int  oracle_slot_output_gains(oracle_device *dev, uint32_t slot, uint32_t lines, const float *gains);
+int  oracle_slot_disable(oracle_device *dev, uint32_t slot);
 int  oracle_get_dry(oracle_device *dev, float *dry);
+/* test-only: wet mix of one slot [wet_channels][1024] */
+int  oracle_get_wet(oracle_device *dev, uint32_t slot, float *wet);
 /* test-only: device-wide HRTF accumulator [1024+128][2] */
 int  oracle_get_hrtf_accum(oracle_device *dev, float *accum);
 

@@ -51,6 +51,7 @@
 #include "core/fpu_ctrl.h"
 #include "core/hrtf.h"
 #include "core/mixer/defs.h"
+#include "core/mixer.h"
 #include "core/mixer/hrtfdefs.h"
 #include "core/voice.h"
 
@@ -295,6 +296,56 @@ int refh_snapshot_voices(ALCcontext *actx, b200mix_voice_params *params, float *
         ++n;
     }
     return static_cast<int>(n);
+}
+
+/* Active aux slots of the context (ContextBase::mActiveAuxSlots, core/context.h:142). */
+int refh_slot_count(ALCcontext *actx)
+{
+    auto *arr = ctx_of(actx)->mActiveAuxSlots.load(std::memory_order_acquire);
+    return arr ? static_cast<int>(arr->size()>>1) : 0;
+}
+
+/* Wet.Buffer.size() of active slot `idx` (aluInitEffectPanning, alc/panning.cpp:1441). */
+int refh_slot_wet_channels(ALCcontext *actx, int idx)
+{
+    auto *arr = ctx_of(actx)->mActiveAuxSlots.load(std::memory_order_acquire);
+    if(!arr || idx < 0 || size_t(idx) >= (arr->size()>>1)) return -1;
+    return static_cast<int>((*arr)[size_t(idx)]->Wet.Buffer.size());
+}
+
+/* Wet mix of active slot idx after the last update: [wet_channels][1024]. */
+int refh_get_wet(ALCcontext *actx, int idx, float *out)
+{
+    auto *arr = ctx_of(actx)->mActiveAuxSlots.load(std::memory_order_acquire);
+    if(!arr || idx < 0 || size_t(idx) >= (arr->size()>>1)) return -1;
+    auto &wet = (*arr)[size_t(idx)]->Wet.Buffer;
+    for(auto c = 0_uz;c < wet.size();++c)
+        std::copy_n(wet[c].begin(), BufferLineSize, out + c*BufferLineSize);
+    return static_cast<int>(wet.size());
+}
+
+/* Per-voice send filter activity (Voice::mSend[s].FilterActive) and direct filter. */
+int refh_voice_filters_active(ALCcontext *actx, int voice, int *direct, int *sends)
+{
+    auto voices = ctx_of(actx)->getVoicesSpan();
+    if(voice < 0 || size_t(voice) >= voices.size()) return -1;
+    *direct = voices[size_t(voice)]->mDirect.FilterActive;
+    for(auto s = 0u;s < MaxSendCount;++s) sends[s] = voices[size_t(voice)]->mSend[s].FilterActive;
+    return 0;
+}
+
+/* What ConvolutionState::update computes for a MONO impulse response
+ * (alc/effects/convolution.cpp:541-600, MonoMap -> front centre): the pan gains of one
+ * output line into the Dry mix, scaled by the slot gain.  out has dry_channels entries. */
+void refh_mono_line_gains(ALCdevice *adev, float slot_gain, float *out)
+{
+    auto *dev = dev_of(adev);
+    const auto pos = std::array{0.0f, 0.0f, -1.0f};
+    const auto coeffs = CalcDirectionCoeffs(pos, 0.0f);
+    auto gains = std::array<float, MaxAmbiChannels>{};
+    ComputePanGains(&dev->Dry, coeffs, slot_gain, gains);
+    for(auto c = 0_uz;c < dev->Dry.Buffer.size() && c < MaxAmbiChannels;++c)
+        out[c] = gains[c];
 }
 
 /* HrtfAccumData as [1024+128][2]. */

@@ -37,6 +37,12 @@ class MixLib:
                                        C.c_void_p]
         self.render = f("render")
         self.render.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]
+        self.slot_convolution = f("slot_convolution")
+        self.slot_convolution.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        self.slot_output_gains = f("slot_output_gains")
+        self.slot_output_gains.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        self.slot_disable = f("slot_disable")
+        self.slot_disable.argtypes = [C.c_void_p, C.c_uint32]
         self.get_dry = f("get_dry")
         self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
 
@@ -74,6 +80,15 @@ class MixDevice:
             lfm = np.ascontiguousarray(lfm, dtype=np.float32)
             lfp = lfm.ctypes.data
         rc = self.m.set_ambi_decoder(self.h, hfm.shape[0], hfm.ctypes.data, lfp, xover)
+        assert rc == 0, rc
+
+    def slot_convolution(self, slot, ir, gains):
+        """ir: [channels][frames] float32; gains: [channels][dry_channels]."""
+        ir = np.ascontiguousarray(np.atleast_2d(ir), dtype=np.float32)
+        gains = np.ascontiguousarray(np.atleast_2d(gains), dtype=np.float32)
+        rc = self.m.slot_convolution(self.h, slot, ir.shape[0], ir.shape[1], ir.ctypes.data)
+        assert rc == 0, rc
+        rc = self.m.slot_output_gains(self.h, slot, gains.shape[0], gains.ctypes.data)
         assert rc == 0, rc
 
     def buffer_data(self, buf_id, sample_type, pcm):

@@ -33,6 +33,8 @@ AL_SAMPLE_OFFSET = 0x1025
 AL_AUXILIARY_SEND_FILTER = 0x20006
 AL_EFFECT_TYPE = 0x8001
 AL_EFFECT_EAXREVERB = 0x8000
+AL_EFFECT_CONVOLUTION_SOFT = 0xA000
+AL_EFFECTSLOT_GAIN = 0x0002
 AL_EFFECTSLOT_EFFECT = 0x0001
 AL_FILTER_NULL = 0
 ALC_FREQUENCY = 0x1007
@@ -121,6 +123,14 @@ def libs(conf_text: str | None = None):
     hz.refh_voice_count.argtypes = [C.c_void_p]
     hz.refh_snapshot_voices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_uint32, C.c_void_p]
+    hz.refh_slot_count.argtypes = [C.c_void_p]
+    hz.refh_slot_wet_channels.argtypes = [C.c_void_p, C.c_int]
+    hz.refh_mono_line_gains.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    for fn in ("alGenEffects", "alGenAuxiliaryEffectSlots"):
+        getattr(al, fn).argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alEffecti.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alAuxiliaryEffectSloti.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alAuxiliaryEffectSlotf.argtypes = [C.c_uint, C.c_int, C.c_float]
     hz.refh_get_hrtf_accum.argtypes = [C.c_void_p, C.c_void_p]
     hz.refh_get_dry.argtypes = [C.c_void_p, C.c_void_p]
     hz.refh_resample.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -193,6 +203,40 @@ class RefDevice:
         self.sources.append(s.value)
         self._keep.append(pcm)
         return s.value
+
+    def add_convolution_slot(self, ir_pcm: np.ndarray, rate: int, slot_gain: float = 1.0,
+                             fmt=AL_FORMAT_MONO_FLOAT32):
+        """examples/alconvolve.c:448-450: IR buffer on an aux slot + the convolution effect."""
+        b = C.c_uint(0)
+        e = C.c_uint(0)
+        s = C.c_uint(0)
+        ir_pcm = np.ascontiguousarray(ir_pcm)
+        self.al.alGenBuffers(1, C.byref(b))
+        self.al.alBufferData(b, fmt, ir_pcm.ctypes.data, ir_pcm.nbytes, rate)
+        self.al.alGenEffects(1, C.byref(e))
+        self.al.alEffecti(e, AL_EFFECT_TYPE, AL_EFFECT_CONVOLUTION_SOFT)
+        self.al.alGenAuxiliaryEffectSlots(1, C.byref(s))
+        self.al.alAuxiliaryEffectSloti(s, AL_BUFFER, b.value)
+        self.al.alAuxiliaryEffectSlotf(s, AL_EFFECTSLOT_GAIN, slot_gain)
+        self.al.alAuxiliaryEffectSloti(s, AL_EFFECTSLOT_EFFECT, e.value)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} creating convolution slot"
+        self._keep.append(ir_pcm)
+        return s.value
+
+    def connect_send(self, source: int, slot: int, send: int = 0):
+        self.al.alSource3i(source, AL_AUXILIARY_SEND_FILTER, slot, send, AL_FILTER_NULL)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} connecting send"
+
+    def slot_info(self):
+        n = self.hz.refh_slot_count(self.ctx)
+        return n, [self.hz.refh_slot_wet_channels(self.ctx, i) for i in range(n)]
+
+    def mono_line_gains(self, slot_gain: float) -> np.ndarray:
+        out = np.zeros(self.desc.dry_channels, dtype=np.float32)
+        self.hz.refh_mono_line_gains(self.dev, slot_gain, out.ctypes.data)
+        return out
 
     def play_all(self):
         arr = (C.c_uint * len(self.sources))(*self.sources)

@@ -26,27 +26,30 @@ def make_ref_scene(num_voices, hrtf, resampler, attrs=None, pitch_fn=scene.voice
     return ref, pcms
 
 
-def mirror_device(mixlib, ref, max_voices, pcms):
+def mirror_device(mixlib, ref, max_voices, pcms, fmt=abi.FMT_I16):
     """Creates the b200mix-surface device that mirrors a reference device."""
     desc = abi.DeviceDesc()
     C.memmove(C.byref(desc), C.byref(ref.desc), C.sizeof(desc))
     desc.max_voices = max_voices
     desc.max_buffers = max(len(pcms), 1)
-    desc.max_slots = 0
+    nslots, wet = ref.slot_info()
+    desc.max_slots = nslots
+    desc.wet_channels = wet[0] if nslots else 0
     dev = MixDevice(mixlib, desc)
     if desc.post_process == abi.POST_HRTF:
         dev.set_hrtf_decoder(*ref.hrtf_decoder())
     elif desc.post_process == abi.POST_AMBIDEC:
         dev.set_ambi_decoder(*ref.ambi_decoder())
     for i, pcm in enumerate(pcms):
-        dev.buffer_data(i, abi.FMT_I16, pcm)
+        dev.buffer_data(i, fmt, pcm)
     return dev
 
 
 def feed_params(dev, ref, first, nv):
     """Copies the reference's current post-ALU voice targets into dev.
     Voice slot k of the reference plays source k (sources are started in order)."""
-    n, params, coeffs, dry, send, state = ref.snapshot()
+    wet = dev.desc.wet_channels
+    n, params, coeffs, dry, send, state = ref.snapshot(wet_channels=wet)
     plist = []
     for k in range(nv):
         p = params[k]
@@ -58,7 +61,7 @@ def feed_params(dev, ref, first, nv):
             q.position = 0
             q.position_frac = 0
         plist.append(q)
-    dev.voices_update(plist, coeffs[:nv], dry[:nv], None)
+    dev.voices_update(plist, coeffs[:nv], dry[:nv], send[:nv] if wet else None)
     return state
 
 
