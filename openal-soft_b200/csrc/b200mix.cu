@@ -8,6 +8,7 @@
 #include "../../include/b200mix.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -17,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "mixer_kernels.cuh"
+#include "effect_kernels.cuh"
 #include "resampler_tables.hpp"
 
 using namespace b200mix;
@@ -79,6 +81,22 @@ struct b200mix_device {
     uint32_t stage_cap{0};
     cudaEvent_t stage_done{nullptr};
     bool stage_busy{false};
+
+    // aux sends and effect slots
+    std::vector<SlotRec> h_slots;            // host mirror (device pointers inside)
+    SlotRec *d_slots{nullptr};
+    std::vector<std::vector<void*>> slot_allocs;
+    uint32_t active_slots{0};
+    float *d_xscratch{nullptr};
+    uint32_t *d_sendinfo{nullptr};
+    std::vector<uint32_t> h_send_slot;       // [max_voices][MAX_SENDS] host mirror
+    std::vector<uint32_t> h_slot_start;
+    std::vector<SendEntry> h_entries;
+    uint32_t *d_slot_start{nullptr};
+    SendEntry *d_entries{nullptr};
+    uint32_t num_entries{0};
+    bool sends_dirty{true};
+    float2 *d_twiddle{nullptr};
 
     bool profile{false};
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
@@ -293,6 +311,27 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             size_t(std::max(dd.real_channels, 1u))*kLine*sizeof(float)));
         if(int rc = dev_alloc(d, d->d_temp, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
         if(int rc = dev_alloc(d, d->d_temp2, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
+        if(dd.max_slots && dd.wet_channels && dd.num_sends)
+        {
+            d->h_slots.assign(dd.max_slots, SlotRec{});
+            d->slot_allocs.assign(dd.max_slots, {});
+            if(int rc = dev_alloc(d, d->d_slots, dd.max_slots)) return rc;
+            if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine, false)) return rc;
+            if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
+            d->h_send_slot.assign(size_t(dd.max_voices)*B200MIX_MAX_SENDS, B200MIX_NO_SLOT);
+            if(int rc = dev_alloc(d, d->d_slot_start, dd.max_slots + 1)) return rc;
+            if(int rc = dev_alloc(d, d->d_entries, size_t(dd.max_voices)*dd.num_sends)) return rc;
+            std::vector<float2> tw(128);
+            for(int k = 0;k < 128;++k)
+            {
+                const double a = -2.0*3.14159265358979323846*double(k)/256.0;
+                tw[k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+            if(int rc = dev_alloc(d, d->d_twiddle, 128, false)) return rc;
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_twiddle, tw.data(), 128*sizeof(float2),
+                cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        }
         if(dd.post_process == B200MIX_POST_UHJ)
         {
             if(int rc = dev_alloc(d, d->d_uhj_state, 64)) return rc;
@@ -327,6 +366,9 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
+    for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
+    cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
+    cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle);
     cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
     cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
     if(d->stage_done) cudaEventDestroy(d->stage_done);
@@ -430,6 +472,110 @@ int b200mix_buffer_free(b200mix_device *d, uint32_t buffer)
     return B200MIX_OK;
 }
 
+static void free_slot(b200mix_device *d, uint32_t slot)
+{
+    cudaStreamSynchronize(d->stream);
+    for(void *p : d->slot_allocs[slot]) cudaFree(p);
+    d->slot_allocs[slot].clear();
+    if(d->h_slots[slot].type) --d->active_slots;
+    d->h_slots[slot] = SlotRec{};
+}
+
+int b200mix_slot_disable(b200mix_device *d, uint32_t slot)
+{
+    if(!d || slot >= d->h_slots.size()) { if(d) d->error = "slot_disable: bad slot"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    free_slot(d, slot);
+    CUDA_TRY(d, cudaMemcpy(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice));
+    return B200MIX_OK;
+}
+
+int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_channels,
+    uint32_t ir_frames, const float *ir)
+{
+    if(!d || slot >= d->h_slots.size() || !ir_channels || ir_channels > 16 || !ir_frames || !ir)
+    { if(d) d->error = "slot_convolution: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    free_slot(d, slot);
+    SlotRec r{};
+    r.type = B200MIX_EFFECT_CONVOLUTION; r.channels = ir_channels; r.frames = ir_frames;
+    // mNumConvolveSegs (alc/effects/convolution.cpp:375-376)
+    const uint32_t nseg = std::max<uint32_t>((ir_frames + kConvBlock - 1)/kConvBlock, 2u) - 1u;
+    r.segs = nseg;
+    auto alloc = [&](auto *&p, size_t count) -> int {
+        if(int rc = dev_alloc(d, p, count)) return rc;
+        d->slot_allocs[slot].push_back(p);
+        return B200MIX_OK;
+    };
+    if(int rc = alloc(r.H, size_t(ir_channels)*nseg*kConvFft)) return rc;
+    if(int rc = alloc(r.X, size_t(nseg + kConvMaxBlocks)*kConvFft)) return rc;
+    if(int rc = alloc(r.head, size_t(ir_channels)*kConvBlock)) return rc;
+    if(int rc = alloc(r.inbuf, kConvFft)) return rc;
+    if(int rc = alloc(r.ov, size_t(ir_channels)*kConvFft)) return rc;
+    if(int rc = alloc(r.yspec, size_t(ir_channels)*kConvMaxBlocks*kConvFft)) return rc;
+    if(int rc = alloc(r.lines, size_t(ir_channels)*kLine)) return rc;
+    if(int rc = alloc(r.gains, size_t(2)*ir_channels*32)) return rc;
+    if(int rc = alloc(r.gtgt, size_t(ir_channels)*32)) return rc;
+
+    // Filter spectra: segment s holds taps [128(s+1), 128(s+2)), zero padded to 256,
+    // transformed in f64 and scaled by 1/256 (convolution.cpp:425-468); layout is ours.
+    std::vector<float> H(size_t(ir_channels)*nseg*kConvFft, 0.0f), head(size_t(ir_channels)*kConvBlock, 0.0f);
+    std::vector<double> cs(kConvFft), sn(kConvFft);
+    for(int k = 0;k < kConvFft;++k)
+    {
+        cs[k] = std::cos(2.0*3.14159265358979323846*k/kConvFft);
+        sn[k] = std::sin(2.0*3.14159265358979323846*k/kConvFft);
+    }
+    for(uint32_t c = 0;c < ir_channels;++c)
+    {
+        const float *h = ir + size_t(c)*ir_frames;
+        for(uint32_t k = 0;k < uint32_t(kConvBlock) && k < ir_frames;++k) head[c*kConvBlock + k] = h[k];
+        for(uint32_t sg = 0;sg < nseg;++sg)
+        {
+            const size_t base = size_t(kConvBlock)*(sg + 1);
+            float *dst = H.data() + (size_t(c)*nseg + sg)*kConvFft;
+            const uint32_t cnt = base < ir_frames ? std::min<uint32_t>(kConvBlock, uint32_t(ir_frames - base)) : 0u;
+            for(int bin = 0;bin <= kConvBlock;++bin)
+            {
+                double re = 0.0, im = 0.0;
+                for(uint32_t j = 0;j < cnt;++j)
+                {
+                    const int ph = int((uint64_t(bin)*j) % kConvFft);
+                    re += double(h[base + j])*cs[ph];
+                    im -= double(h[base + j])*sn[ph];
+                }
+                const double sc = 1.0/double(kConvFft);
+                if(bin == 0) dst[0] = float(re*sc);
+                else if(bin == kConvBlock) dst[1] = float(re*sc);
+                else { dst[bin*2] = float(re*sc); dst[bin*2+1] = float(im*sc); }
+            }
+        }
+    }
+    CUDA_TRY(d, cudaMemcpyAsync(r.H, H.data(), H.size()*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaMemcpyAsync(r.head, head.data(), head.size()*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    d->h_slots[slot] = r;
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    ++d->active_slots;
+    d->dry_active = true;
+    return B200MIX_OK;
+}
+
+int b200mix_slot_output_gains(b200mix_device *d, uint32_t slot, uint32_t lines, const float *gains)
+{
+    if(!d || slot >= d->h_slots.size() || !d->h_slots[slot].type || lines != d->h_slots[slot].channels || !gains)
+    { if(d) d->error = "slot_output_gains: bad arguments"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    std::vector<float> g(size_t(lines)*32, 0.0f);
+    for(uint32_t c = 0;c < lines;++c)
+        for(uint32_t o = 0;o < d->desc.dry_channels;++o)
+            g[c*32 + o] = gains[c*d->desc.dry_channels + o];
+    CUDA_TRY(d, cudaMemcpyAsync(d->h_slots[slot].gtgt, g.data(), g.size()*sizeof(float),
+        cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return B200MIX_OK;
+}
+
 int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains)
 {
@@ -472,6 +618,13 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
             if(u.send_slot[s] != B200MIX_NO_SLOT && u.send_slot[s] >= dd.max_slots)
             { d->error = "voices_update: send slot out of range"; return B200MIX_ERR_INVALID; }
         }
+        if(!d->h_send_slot.empty())
+            for(uint32_t s2 = 0;s2 < B200MIX_MAX_SENDS;++s2)
+            {
+                uint32_t &m = d->h_send_slot[size_t(p.voice)*B200MIX_MAX_SENDS + s2];
+                const uint32_t nv2 = (p.flags & B200MIX_VF_STOPPED) ? B200MIX_NO_SLOT : u.send_slot[s2];
+                if(m != nv2) { m = nv2; d->sends_dirty = true; }
+            }
         u.has_coeffs = hrtf_coeffs != nullptr && dd.ir_size > 0;
         u.has_dry = dry_gains != nullptr;
         if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED)) d->dry_active = true;
@@ -574,6 +727,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     P.cd = dd.dry_channels; P.cw = dd.wet_channels; P.num_sends = dd.num_sends;
     P.max_buffers = dd.max_buffers;
     P.order = d->d_order; P.num_order = d->num_order;
+    P.xscratch = d->d_xscratch; P.sendinfo = d->d_sendinfo;
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
     if(d->profile) { cudaEventRecord(d->ev_mix1, d->stream); d->ev_valid = true; }
@@ -596,7 +750,60 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     }
     CUDA_TRY(d, cudaGetLastError());
 
-    // effect slots: not implemented in this round (no slot can be configured)
+    // ---- aux sends + effect slots (alc/alu.cpp:2196-2198, 2252-2256) ----
+    if(d->active_slots)
+    {
+        if(d->sends_dirty)
+        {
+            // CSR of (voice, send) pairs per slot, voices in index order (deterministic sums)
+            d->h_slot_start.assign(dd.max_slots + 1, 0);
+            d->h_entries.clear();
+            for(uint32_t sl = 0;sl < dd.max_slots;++sl)
+            {
+                d->h_slot_start[sl] = uint32_t(d->h_entries.size());
+                for(uint32_t v = 0;v < d->voice_hi;++v)
+                    for(uint32_t s2 = 0;s2 < dd.num_sends;++s2)
+                        if(d->h_send_slot[size_t(v)*B200MIX_MAX_SENDS + s2] == sl)
+                            d->h_entries.push_back(SendEntry{v, s2});
+            }
+            d->h_slot_start[dd.max_slots] = uint32_t(d->h_entries.size());
+            d->num_entries = uint32_t(d->h_entries.size());
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_slot_start, d->h_slot_start.data(),
+                (dd.max_slots + 1)*sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+            if(d->num_entries)
+                CUDA_TRY(d, cudaMemcpyAsync(d->d_entries, d->h_entries.data(),
+                    d->num_entries*sizeof(SendEntry), cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+            d->sends_dirty = false;
+        }
+        SendMixParams SM{};
+        SM.slot_start = d->d_slot_start; SM.entries = d->d_entries; SM.sendinfo = d->d_sendinfo;
+        SM.xscratch = d->d_xscratch; SM.send_cur = d->d_send_cur; SM.send_tgt = d->d_send_tgt;
+        SM.wet = d->d_wet; SM.frames = frames; SM.cw = dd.wet_channels; SM.num_sends = dd.num_sends;
+        k_send_mix<<<dim3(dd.max_slots, (frames + 255)/256), 256, 0, d->stream>>>(SM);
+        ++d->launches;
+        if(d->num_entries)
+        {
+            const uint32_t tot = d->num_entries*dd.wet_channels;
+            k_send_gains_update<<<(tot + 127)/128, 128, 0, d->stream>>>(SM, d->num_entries);
+            ++d->launches;
+        }
+        ConvParams CP{};
+        CP.slots = d->d_slots; CP.wet = d->d_wet; CP.twiddle = d->d_twiddle;
+        CP.frames = frames; CP.cw = dd.wet_channels; CP.num_slots = dd.max_slots;
+        uint32_t maxch = 1;
+        for(const SlotRec &sr : d->h_slots) if(sr.type) maxch = std::max(maxch, sr.channels);
+        k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
+        k_conv_mac<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
+        k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
+        SlotMixParams SP{};
+        SP.slots = d->d_slots; SP.dry = d->d_dry; SP.frames = frames; SP.cd = dd.dry_channels;
+        SP.num_slots = dd.max_slots;
+        k_slot_output_mix<<<dim3((frames + 255)/256, dd.dry_channels), 256, 0, d->stream>>>(SP);
+        k_slot_gains_commit<<<dd.max_slots, 64, 0, d->stream>>>(SP);
+        d->launches += 5;
+        CUDA_TRY(d, cudaGetLastError());
+    }
 
     switch(dd.post_process)
     {

@@ -1,0 +1,360 @@
+// effect_kernels.cuh — aux-send wet mix and the convolution effect slot on sm_100a.
+//
+//  k_send_mix        MixSamples of every (voice, send) into the slot wet buffers
+//                    (core/voice.cpp:967-980), slot-major and in a fixed order (no atomics)
+//  k_conv_input      ConvolutionState::process, input side (alc/effects/convolution.cpp:
+//                    636-667): FIFO bookkeeping, 256-point FFTs of the completed 128-sample
+//                    blocks into the spectrum ring, and the 128-tap time-domain head (apply_fir)
+//  k_conv_mac        sum_s X[(cur+s) mod S] * H[s] for ALL blocks completed in this update in
+//                    ONE pass over the filter spectra (the reference re-reads them per block)
+//  k_conv_output     inverse FFTs + overlap-add (convolution.cpp:699-706)
+//  k_slot_output_mix the slots' output lines -> Dry with MixSamples(Counter = samplesToDo)
+//
+// The FFT is an in-shared-memory radix-2 complex FFT of 256 points (cuFFT-free); only the
+// RESULT has to match the reference's pffft path, the spectrum layout is our own:
+// packed [re0, nyquist, re1, im1, ... re127, im127].
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "mixer_kernels.cuh"
+
+namespace b200mix {
+
+constexpr int kConvBlock = 128;     // ConvolveUpdateSamples
+constexpr int kConvFft = 256;       // ConvolveUpdateSize
+constexpr int kConvMaxBlocks = 9;   // blocks that can complete in one 1024-frame update
+
+struct SlotRec {
+    uint32_t type, channels, frames, segs;     // segs = mNumConvolveSegs
+    uint32_t cur, fifo, nb_last, f_last;       // ring position, FIFO fill; last update's record
+    uint32_t cur_last, pad0, pad1, pad2;
+    float *H;         // [channels][segs][256]  filter spectra (pre-scaled by 1/256)
+    float *X;         // [segs+kConvMaxBlocks][256] input spectra ring (our own ring: long enough that
+                      //                        a whole update's blocks never overwrite live history)
+    float *head;      // [channels][128]        first 128 IR taps
+    float *inbuf;     // [256]                  mInput
+    float *ov;        // [channels][256]        mOutput
+    float *yspec;     // [channels][kConvMaxBlocks][256]
+    float *lines;     // [channels][1024]       this update's output lines
+    float *gains;     // [2][channels][32]      ping-pong Current gains
+    float *gtgt;      // [channels][32]         Target gains
+    uint32_t gsel, pad3;
+};
+
+// ---- send mix --------------------------------------------------------------------------
+struct SendEntry { uint32_t voice, send; };
+
+struct SendMixParams {
+    const uint32_t *slot_start;     // [slots+1] CSR over entries
+    const SendEntry *entries;
+    const uint32_t *sendinfo;       // per voice: bit0 valid, bit1 playing, bits 8.. counter
+    const float *xscratch;          // [max_voices][1024] resampled lines of voices with sends
+    float *send_cur; const float *send_tgt;   // [max_voices][num_sends][cw]
+    float *wet;                     // [slots][cw][1024]
+    uint32_t frames, cw, num_sends;
+};
+
+// grid (slot, tile of 256 samples), 256 threads; up to 4 wet channels per pass in registers.
+__global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
+{
+    const uint32_t slot = blockIdx.x;
+    const uint32_t i = blockIdx.y*256u + threadIdx.x;
+    const uint32_t n = Q.frames;
+    const uint32_t e0 = Q.slot_start[slot], e1 = Q.slot_start[slot+1];
+    for(uint32_t c0 = 0;c0 < Q.cw;c0 += 4u)
+    {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for(uint32_t e = e0;e < e1;++e)
+        {
+            const SendEntry en = Q.entries[e];
+            const uint32_t info = Q.sendinfo[en.voice];
+            if(!(info & 1u)) continue;
+            const bool playing = (info & 2u) != 0;
+            const uint32_t counter = info >> 8;
+            const float x = (i < n) ? Q.xscratch[size_t(en.voice)*kLine + i] : 0.0f;
+            const float delta = counter ? 1.0f/float(counter) : 0.0f;
+            const uint32_t fadeLen = counter < n ? counter : n;
+            const size_t gbase = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw;
+            #pragma unroll
+            for(uint32_t cc = 0;cc < 4u;++cc)
+            {
+                const uint32_t c = c0 + cc;
+                if(c >= Q.cw) break;
+                // Mix_ semantics (core/mixer/mixer_c.cpp:150-186)
+                const float tg0 = Q.send_tgt[gbase + c];
+                const float cg = counter ? Q.send_cur[gbase + c] : tg0;
+                const float tg = playing ? tg0 : 0.0f;
+                const float step = (tg - cg)*delta;
+                const bool fade = fabsf(step) > kEps;
+                const bool early = fade && fadeLen < counter;
+                const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
+                const uint32_t start = fade ? fadeLen : 0u;
+                const float g = (fade && i < fadeLen) ? (cg + step*float(i)) : (i >= start ? flat : 0.0f);
+                acc[cc] += x*g;
+            }
+        }
+        #pragma unroll
+        for(uint32_t cc = 0;cc < 4u;++cc)
+            if(c0 + cc < Q.cw && i < n)
+                Q.wet[(size_t(slot)*Q.cw + c0 + cc)*kLine + i] = acc[cc];
+    }
+}
+
+// New Current gains of the sends (runs after k_send_mix; one thread per entry-channel).
+__global__ void k_send_gains_update(const SendMixParams Q, uint32_t num_entries)
+{
+    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;
+    const uint32_t e = idx / Q.cw, c = idx - e*Q.cw;
+    if(e >= num_entries) return;
+    const SendEntry en = Q.entries[e];
+    const uint32_t info = Q.sendinfo[en.voice];
+    if(!(info & 1u)) return;
+    const bool playing = (info & 2u) != 0;
+    const uint32_t counter = info >> 8, n = Q.frames;
+    const float delta = counter ? 1.0f/float(counter) : 0.0f;
+    const uint32_t fadeLen = counter < n ? counter : n;
+    const size_t g = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw + c;
+    const float tg0 = Q.send_tgt[g];
+    const float cg = counter ? Q.send_cur[g] : tg0;
+    const float tg = playing ? tg0 : 0.0f;
+    const float step = (tg - cg)*delta;
+    const bool early = (fabsf(step) > kEps) && fadeLen < counter;
+    Q.send_cur[g] = early ? (cg + step*float(fadeLen)) : tg;
+}
+
+// ---- 256-point complex FFT in shared memory (128 threads, radix-2 DIT) -------------------
+// tw[k] = exp(-2 pi i k/256), k < 128.  data must hold the input in bit-reversed order.
+__device__ __forceinline__ uint32_t bitrev8(uint32_t v) { return __brev(v) >> 24; }
+
+__device__ __forceinline__ void fft256_inplace(float2 *data, const float2 *__restrict__ tw, int t)
+{
+    #pragma unroll
+    for(int stage = 0;stage < 8;++stage)
+    {
+        const int half = 1 << stage;
+        const int grp = t >> stage, pos = t & (half-1);
+        const int i0 = (grp << (stage+1)) + pos, i1 = i0 + half;
+        const float2 w = tw[pos << (7-stage)];
+        const float2 a = data[i0], b = data[i1];
+        const float2 bw = make_float2(b.x*w.x - b.y*w.y, b.x*w.y + b.y*w.x);
+        __syncthreads();
+        data[i0] = make_float2(a.x + bw.x, a.y + bw.y);
+        data[i1] = make_float2(a.x - bw.x, a.y - bw.y);
+        __syncthreads();
+    }
+}
+
+struct ConvParams {
+    SlotRec *slots; const float *wet; const float2 *twiddle;
+    uint32_t frames, cw, num_slots;
+};
+
+// grid = slots, 128 threads
+__global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
+{
+    __shared__ float stream[kConvFft + kLine + 8];
+    __shared__ float2 fbuf[kConvFft];
+    __shared__ float hsm[kConvBlock];
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 1u) return;
+    const int t = threadIdx.x;
+    const uint32_t n = Q.frames, f = S.fifo, cur = S.cur, ring = S.segs + kConvMaxBlocks;
+    const uint32_t nb = (f + n) / kConvBlock;
+    const float *in = Q.wet + size_t(blockIdx.x)*Q.cw*kLine;          // wet channel 0
+    // stream = [previous block | partial block (f) | new samples (n)]
+    for(uint32_t k = t;k < kConvBlock + f;k += 128) stream[k] = S.inbuf[k];
+    for(uint32_t k = t;k < n;k += 128) stream[kConvBlock + f + k] = in[k];
+    __syncthreads();
+
+    // spectra of the blocks completed by this update -> ring slots cur, cur-1, ...
+    for(uint32_t b = 0;b < nb;++b)
+    {
+        const float *blk = stream + kConvBlock + b*kConvBlock;
+        // [128 samples | 128 zeros], loaded in bit-reversed order
+        for(int k = t;k < kConvFft;k += 128)
+        {
+            const uint32_t r = bitrev8(uint32_t(k));
+            fbuf[k] = make_float2(r < uint32_t(kConvBlock) ? blk[r] : 0.0f, 0.0f);
+        }
+        __syncthreads();
+        fft256_inplace(fbuf, Q.twiddle, t);
+        const uint32_t slotIdx = (cur + ring - b) % ring;
+        float2 *dst = reinterpret_cast<float2*>(S.X + size_t(slotIdx)*kConvFft);
+        dst[t] = (t == 0) ? make_float2(fbuf[0].x, fbuf[128].x) : fbuf[t];
+        __syncthreads();
+    }
+
+    // 128-tap time-domain head (apply_fir, convolution.cpp:205-251)
+    for(uint32_t c = 0;c < S.channels;++c)
+    {
+        hsm[t] = S.head[c*kConvBlock + t];
+        __syncthreads();
+        for(uint32_t i = t;i < n;i += 128)
+        {
+            const float *p = stream + kConvBlock + f + i;      // newest sample of output i
+            float a0 = 0.0f, a1 = 0.0f;
+            #pragma unroll 8
+            for(int k = 0;k < kConvBlock;k += 2)
+            {
+                a0 = fmaf(hsm[k], p[-k], a0);
+                a1 = fmaf(hsm[k+1], p[-k-1], a1);
+            }
+            S.lines[size_t(c)*kLine + i] = a0 + a1;
+        }
+        __syncthreads();
+    }
+
+    // new mInput: [last complete block | partial block]
+    const uint32_t fNew = (f + n) - nb*kConvBlock;
+    float keep0 = stream[nb*kConvBlock + t];
+    float keep1 = (uint32_t(t) < fNew) ? stream[(nb+1)*kConvBlock + t] : 0.0f;
+    S.inbuf[t] = keep0;
+    S.inbuf[kConvBlock + t] = keep1;
+    if(t == 0)
+    {
+        S.nb_last = nb; S.f_last = f; S.cur_last = cur;
+        S.fifo = fNew;
+        S.cur = (cur + ring - nb) % ring;
+    }
+}
+
+// grid (slots, channels), 128 threads (one packed bin each)
+__global__ void __launch_bounds__(128) k_conv_mac(const ConvParams Q)
+{
+    const SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 1u || blockIdx.y >= S.channels) return;
+    const uint32_t nb = S.nb_last;
+    if(nb == 0) return;
+    const int t = threadIdx.x;
+    const uint32_t segs = S.segs, cur0 = S.cur_last, ring = segs + kConvMaxBlocks;
+    const float2 *X = reinterpret_cast<const float2*>(S.X) + t;
+    const float2 *H = reinterpret_cast<const float2*>(S.H + size_t(blockIdx.y)*segs*kConvFft) + t;
+    float2 acc[kConvMaxBlocks];
+    float2 xw[kConvMaxBlocks];          // xw[b] = X[(cur0 - b + s) mod segs]
+    #pragma unroll
+    for(int b = 0;b < kConvMaxBlocks;++b)
+    {
+        acc[b] = make_float2(0.f, 0.f);
+        const uint32_t q = (cur0 + 2u*ring - uint32_t(b) - 1u) % ring;   // value for s = -1
+        xw[b] = (uint32_t(b) < nb) ? X[size_t(q)*128] : make_float2(0.f, 0.f);
+    }
+    for(uint32_t s = 0;s < segs;++s)
+    {
+        // slide: block b at segment s uses what block b-1 used at s-1
+        #pragma unroll
+        for(int b = kConvMaxBlocks-1;b > 0;--b) xw[b] = xw[b-1];
+        xw[0] = X[size_t((cur0 + s) % ring)*128];
+        const float2 h = H[size_t(s)*128];
+        #pragma unroll
+        for(int b = 0;b < kConvMaxBlocks;++b)
+        {
+            if(t == 0)
+            {   // packed DC / Nyquist: two independent real products
+                acc[b].x = fmaf(xw[b].x, h.x, acc[b].x);
+                acc[b].y = fmaf(xw[b].y, h.y, acc[b].y);
+            }
+            else
+            {
+                acc[b].x = fmaf(xw[b].x, h.x, fmaf(-xw[b].y, h.y, acc[b].x));
+                acc[b].y = fmaf(xw[b].x, h.y, fmaf(xw[b].y, h.x, acc[b].y));
+            }
+        }
+    }
+    float2 *Y = reinterpret_cast<float2*>(S.yspec + size_t(blockIdx.y)*kConvMaxBlocks*kConvFft) + t;
+    #pragma unroll
+    for(int b = 0;b < kConvMaxBlocks;++b)
+        if(uint32_t(b) < nb) Y[size_t(b)*128] = acc[b];
+}
+
+// grid (slots, channels), 128 threads
+__global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
+{
+    __shared__ float2 fbuf[kConvFft];
+    __shared__ float first[kConvBlock], tail[kConvBlock];
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 1u || blockIdx.y >= S.channels) return;
+    const int t = threadIdx.x;
+    const uint32_t c = blockIdx.y, n = Q.frames, nb = S.nb_last, f = S.f_last;
+    float *ov = S.ov + size_t(c)*kConvFft;
+    float *line = S.lines + size_t(c)*kLine;
+    first[t] = ov[t]; tail[t] = ov[kConvBlock + t];
+    __syncthreads();
+    // samples of the block that was in progress when the update started
+    {
+        const uint32_t cnt = (kConvBlock - f < n) ? kConvBlock - f : n;
+        if(uint32_t(t) < cnt) line[t] += first[f + t];
+    }
+    for(uint32_t b = 0;b < nb;++b)
+    {
+        // inverse FFT of the accumulated spectrum: ifft(x) = conj(fft(conj(x)))
+        const float2 *Y = reinterpret_cast<const float2*>(S.yspec + (size_t(c)*kConvMaxBlocks + b)*kConvFft);
+        const float2 y0 = Y[0];
+        __syncthreads();
+        for(int k = t;k < kConvFft;k += 128)
+        {
+            float2 v;
+            if(k == 0) v = make_float2(y0.x, 0.0f);
+            else if(k == 128) v = make_float2(y0.y, 0.0f);
+            else if(k < 128) { const float2 a = Y[k]; v = make_float2(a.x, -a.y); }       // conj(x_k)
+            else { const float2 a = Y[256-k]; v = make_float2(a.x, a.y); }                // conj(conj(x_{N-k}))
+            fbuf[bitrev8(uint32_t(k))] = v;
+        }
+        __syncthreads();
+        fft256_inplace(fbuf, Q.twiddle, t);
+        // O_b = y[0..128) + previous tail ; new tail = y[128..256)   (convolution.cpp:702-706)
+        const float o = fbuf[t].x + tail[t];
+        const float tl = fbuf[kConvBlock + t].x;
+        __syncthreads();
+        first[t] = o; tail[t] = tl;
+        __syncthreads();
+        // the samples following this block boundary
+        const uint32_t base = (b+1u)*kConvBlock - f;       // output index of the block start
+        if(base < n)
+        {
+            const uint32_t cnt = (n - base < uint32_t(kConvBlock)) ? n - base : uint32_t(kConvBlock);
+            if(uint32_t(t) < cnt) line[base + t] += first[t];
+        }
+    }
+    ov[t] = first[t]; ov[kConvBlock + t] = tail[t];
+}
+
+// Dry[o][i] += sum over slots/lines of line[i]*gain(i): MixSamples(Counter = samplesToDo)
+// (ConvolutionState::NormalMix, convolution.cpp:298-304), slots and lines in index order.
+struct SlotMixParams { SlotRec *slots; float *dry; uint32_t frames, cd, num_slots; };
+
+__global__ void __launch_bounds__(256) k_slot_output_mix(const SlotMixParams Q)
+{
+    const uint32_t o = blockIdx.y;
+    const uint32_t i = blockIdx.x*256u + threadIdx.x;
+    const uint32_t n = Q.frames;
+    float acc = (i < n) ? Q.dry[size_t(o)*kLine + i] : 0.0f;
+    const float delta = 1.0f/float(n);
+    for(uint32_t s = 0;s < Q.num_slots;++s)
+    {
+        const SlotRec &S = Q.slots[s];
+        if(S.type != 1u) continue;
+        const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
+        for(uint32_t c = 0;c < S.channels;++c)
+        {
+            const float cg = gcur[c*32u + o], tg = S.gtgt[c*32u + o];
+            const float step = (tg - cg)*delta;
+            const float x = (i < n) ? S.lines[size_t(c)*kLine + i] : 0.0f;
+            if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
+            else if(fabsf(tg) > kSilence) acc += x*tg;
+        }
+    }
+    if(i < n) Q.dry[size_t(o)*kLine + i] = acc;
+}
+
+// Current <- Target for every slot line (the fade always completes: Counter == frames).
+__global__ void k_slot_gains_commit(const SlotMixParams Q)
+{
+    const uint32_t s = blockIdx.x;
+    SlotRec &S = Q.slots[s];
+    if(S.type != 1u) return;
+    float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
+    for(uint32_t k = threadIdx.x;k < S.channels*32u;k += blockDim.x) gcur[k] = S.gtgt[k];
+}
+
+} // namespace b200mix

@@ -76,6 +76,8 @@ struct MixParams {
     const float *bsinc_tab[3];                // bsinc12, 24, 48
     const float *cubic_tab[2];                // spline, gaussian [32][8]
     uint32_t max_voices, frames, ir, ir_pad, cd, cw, num_sends, max_buffers;
+    float *xscratch;                          // [max_voices][1024] lines of voices with sends
+    uint32_t *sendinfo;                       // per voice: bit0 mixed, bit1 playing, bits8.. counter
     const uint32_t *order;                    // mixing order: voice indices, cost-sorted
     uint32_t num_order;
 };
@@ -285,8 +287,11 @@ k_mix_voices(const MixParams P)
         const uint32_t vstate = h0.x;
         if(vstate != 1u && vstate != 2u)
         {
-            if(t == 0 && P.results)
-                P.results[v] = VoiceResult{int32_t(h1.x), h1.y, 1u<<7, 0u};
+            if(t == 0)
+            {
+                if(P.results) P.results[v] = VoiceResult{int32_t(h1.x), h1.y, 1u<<7, 0u};
+                if(P.sendinfo) P.sendinfo[v] = 0u;
+            }
             continue;
         }
         const uint32_t increment = h1.z;
@@ -296,6 +301,7 @@ k_mix_voices(const MixParams P)
             if(t == 0)
             {
                 if(vstate == 2u) rec.state = 0u;
+                if(P.sendinfo) P.sendinfo[v] = 0u;
                 if(P.results)
                     P.results[v] = VoiceResult{int32_t(h1.x), h1.y, (vstate == 2u) ? (1u<<7) : 1u, 0u};
             }
@@ -674,39 +680,15 @@ k_mix_voices(const MixParams P)
             }
         }
 
-        // ---- auxiliary sends (core/voice.cpp:967-980) ----
-        if(P.num_sends && h4.w)
+        // ---- auxiliary sends (core/voice.cpp:967-980): the resampled line is parked in
+        // HBM; k_send_mix sums all (voice, send) pairs slot by slot in a fixed order ----
+        if(P.sendinfo)
         {
-            const uint32_t cw = P.cw;
-            const float delta = counter ? 1.0f/float(counter) : 0.0f;
-            const uint32_t fadeLen = counter < n ? counter : n;
-            for(uint32_t s = 0;s < P.num_sends;++s)
-            {
-                const uint32_t slot = rec.send_slot[s];
-                if(slot == 0xffffffffu) continue;
-                float *cur = P.send_cur + (size_t(v)*P.num_sends + s)*cw;
-                const float *tgt = P.send_tgt + (size_t(v)*P.num_sends + s)*cw;
-                float *wet = P.wet + size_t(slot)*cw*kLine;
-                for(uint32_t c = 0;c < cw;++c)
-                {
-                    const float cg = counter ? cur[c] : tgt[c];
-                    const float tg = playing ? tgt[c] : 0.0f;
-                    const float step = (tg - cg)*delta;
-                    const bool fade = fabsf(step) > kEps;
-                    const bool early = fade && fadeLen < counter;
-                    const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
-                    const uint32_t start = fade ? fadeLen : 0u;
-                    for(uint32_t i = t;i < n;i += GS)
-                    {
-                        const float gsel = (fade && i < fadeLen) ? (cg + step*float(i))
-                            : (i >= start ? flat : 0.0f);
-                        if(gsel != 0.0f)
-                            atomicAdd(wet + size_t(c)*kLine + i, xs[i]*gsel);
-                    }
-                    if(t == 0)
-                        S.newGain[32 + s*25 + c] = early ? (cg + step*float(fadeLen)) : tg;
-                }
-            }
+            const bool sends = P.num_sends && h4.w;
+            if(sends)
+                for(uint32_t k = t;k < n;k += GS) P.xscratch[size_t(v)*kLine + k] = xs[k];
+            if(t == 0)
+                P.sendinfo[v] = sends ? (1u | (playing ? 2u : 0u) | (counter << 8)) : 0u;
         }
 
         // ---- position / state update (core/voice.cpp:1116-1232) ----
@@ -751,11 +733,6 @@ k_mix_voices(const MixParams P)
             if(!isHrtf)
                 for(uint32_t c = 0;c < P.cd;++c)
                     P.dry_cur[size_t(v)*P.cd + c] = S.newGain[c];
-            if(P.num_sends && rec.send_mask)
-                for(uint32_t s = 0;s < P.num_sends;++s)
-                    if(rec.send_slot[s] != 0xffffffffu)
-                        for(uint32_t c = 0;c < P.cw;++c)
-                            P.send_cur[(size_t(v)*P.num_sends + s)*P.cw + c] = S.newGain[32 + s*25 + c];
         }
         group_sync(bar, GS);
     }

@@ -44,7 +44,16 @@ SCENES = {
     "hrtf_spline_alaw_v4": (4, 1, 2, 2, True, 48000, None, "alaw"),
     "stereo_spline_u8_v4": (4, 0, 2, 2, True, 48000, None, "u8"),
     "stereo_spline_f32_v4": (4, 0, 2, 2, True, 48000, None, "f32"),
+    # aux send -> convolution slot (alc/effects/convolution.cpp), mono IR of N taps, slot gain 0.5
+    "hrtf_bsinc24_conv3000_v6": (6, 1, 7, 5, True, 48000, None, "i16", 3000),
+    "hrtf_spline_conv100_v4": (4, 1, 2, 3, True, 48000, None, "i16", 100),
+    "stereo_spline_conv1500_v4": (4, 0, 2, 4, True, 48000, None, "i16", 1500),
 }
+
+
+def conv_ir(taps):
+    rng = np.random.default_rng(taps)
+    return (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
 
 ATTRS = {
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
@@ -62,19 +71,28 @@ def run_scene(name):
     attrs = ATTRS[spec[6]](refal) if len(spec) > 6 and spec[6] else None
     fmt = spec[7] if len(spec) > 7 else "i16"
     ref, pcms = scenes.make_ref_scene(V, hrtf, rs, attrs=attrs, looping=looping, frames=frames, fmt=fmt)
+    taps = spec[8] if len(spec) > 8 else 0
+    if taps:
+        slot = ref.add_convolution_slot(conv_ir(taps), 48000, 0.5)
+        for src in ref.sources:
+            ref.connect_send(src, slot)
     ref.play_all()
     outs = []
     snap = None
+    nslots, wet = ref.slot_info() if taps else (0, [])
     for u in range(U):
         outs.append(ref.render())
         if u == 0:
-            snap = ref.snapshot()
+            snap = ref.snapshot(wet_channels=wet[0] if nslots else 0)
     n, params, coeffs, dry, send, state = snap
     d = ref.desc
     res = dict(out=np.stack(outs),
                desc=np.frombuffer(bytes(d), dtype=np.uint8).copy(),
                params=np.frombuffer(bytes(params), dtype=np.uint8)[:V * C.sizeof(abi.VoiceParams)].copy(),
                coeffs=coeffs[:V].copy(), dry=dry[:V].copy())
+    if taps:
+        res.update(conv_taps=np.int64(taps), conv_gains=ref.mono_line_gains(0.5), send=send[:V].copy(),
+                   wet_channels=np.int64(wet[0]))
     if d.post_process == abi.POST_HRTF:
         c, hf, sc = ref.hrtf_decoder()
         res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)

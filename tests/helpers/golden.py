@@ -27,6 +27,10 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
     desc.max_voices = V
     desc.max_buffers = V
     desc.max_slots = 0
+    taps = int(fx["conv_taps"]) if "conv_taps" in fx else 0
+    if taps:
+        desc.max_slots = 1
+        desc.wet_channels = int(fx["wet_channels"])
     dev = MixDevice(mixlib, desc)
     try:
         if desc.post_process == abi.POST_HRTF:
@@ -36,6 +40,10 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
         fmt = str(fx["fmt"]) if "fmt" in fx else "i16"
         for i in range(V):
             dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, buf_frames, fmt))
+        if taps:
+            rng = np.random.default_rng(taps)      # same IR as tests/golden/make_golden.py:conv_ir
+            ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
+            dev.slot_convolution(0, ir[None, :], fx["conv_gains"][None, :])
         params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
         plist = []
         for k in range(V):
@@ -47,7 +55,7 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             q.position = 0
             q.position_frac = 0
             plist.append(q)
-        dev.voices_update(plist, fx["coeffs"], fx["dry"], None)
+        dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if taps else None)
         outs = []
         res = None
         for _ in range(updates or U):

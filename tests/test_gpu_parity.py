@@ -146,3 +146,36 @@ def test_config2_size_linearity_and_subsample():
     sub = list(range(0, nv, k))
     _check(parts[0], run(mixlib.oracle(), sub), "1/16 subsample vs oracle")
     assert np.sqrt((full ** 2).mean()) > 1e-3
+
+
+def test_convolution_slot_vs_oracle_long_ir_and_ragged_updates():
+    """Aux sends -> convolution slot (2 IR channels, 20000 taps = 156 FFT segments), ragged
+    update sizes so FFT blocks complete mid-update; HRTF voices + a non-silent Dry mix."""
+    rng = np.random.default_rng(77)
+    nv, ir = 40, 64
+    desc = synth.hrtf_desc(nv, ir)
+    desc.num_sends = 2
+    desc.wet_channels = 4
+    desc.max_slots = 3
+    params, coeffs, dry = synth.voice_set(rng, nv, ir)
+    send = (rng.standard_normal((nv, 2, 4)) * 0.3).astype(np.float32)
+    for k, p in enumerate(params):
+        p.send_slot[0] = k % 3 if k % 5 else abi.NO_SLOT
+        p.send_slot[1] = (k + 1) % 3 if k % 2 else abi.NO_SLOT
+    taps = [20000, 300, 1153]
+    irs = [(rng.standard_normal((2 if s == 0 else 1, t)) * np.exp(-np.arange(t) / (t / 4.0)) * 0.03
+            ).astype(np.float32) for s, t in enumerate(taps)]
+    gains = [(rng.standard_normal((x.shape[0], desc.dry_channels)) * 0.5).astype(np.float32) for x in irs]
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        for s in range(3):
+            dev.slot_convolution(s, irs[s], gains[s])
+        dev.voices_update(params, coeffs, dry, send)
+        o = [dev.render(f) for f in (1024, 100, 1024, 28, 640, 1024, 1, 255, 1024)]
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], "convolution slots")
