@@ -114,7 +114,7 @@ B200MIX_API int b200mix_buffer_free(b200mix_device *dev, uint32_t buffer);
 
 /* ---- auxiliary effect slots: EffectSlotBase + EffectState (core/effectslot.h:50-82,
  *      core/effects/base.h:197-222) ------------------------------------------------ */
-enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1 };
+enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B200MIX_EFFECT_REVERB = 2 };
 
 /* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
  * device-rate impulse response (planar [ir_channels][ir_frames] floats; the host applies
@@ -128,6 +128,41 @@ B200MIX_API int b200mix_slot_convolution(b200mix_device *dev, uint32_t slot, uin
  * device and fades to Target over the whole update like MixSamples(..., Counter=samplesToDo). */
 B200MIX_API int b200mix_slot_output_gains(b200mix_device *dev, uint32_t slot, uint32_t lines,
     const float *gains);
+/* EAX / standard reverb (alc/effects/reverb.cpp).  The host's ReverbState::update
+ * (reverb.cpp:1222-1351, with updateDelayLine/updateLines/updateModulator/CalcMatrixCoeffs)
+ * stays the parameter stage; this struct is its RESULT for the current pipeline, i.e. the
+ * state ReverbState::process consumes.  Biquads are {b0, b1, b2, a1, a2} (a0 pre-applied).
+ * Tap/offset values are in samples.  Line lengths come from ReverbState::allocLines. */
+typedef struct b200mix_reverb_params {
+    uint32_t struct_size;
+    uint32_t main_len, late_in_len, early_ap_len, early_len, late_ap_len, late_len; /* per line, pow2 */
+    uint32_t early_tap[4];        /* mEarlyDelayTap[j][1] */
+    float    early_tap_coeff;     /* mEarlyDelayCoeff[1] */
+    uint32_t late_tap[4];         /* mLateDelayTap[j][1] */
+    float    mix_x, mix_y;        /* mMixX, mMixY */
+    float    filter_lp[5], filter_hp[5];   /* mFilter[*].Lp / .Hp */
+    float    early_ap_coeff;      /* mEarly.Allpass.Coeff */
+    uint32_t early_ap_offset[4];  /* mEarly.Allpass.Offset */
+    uint32_t early_offset[4];     /* mEarly.Offset */
+    float    early_coeff;         /* mEarly.Coeff */
+    uint32_t late_offset[4];      /* mLate.Offset */
+    float    density_gain;        /* mLate.DensityGain */
+    float    t60_mid_gain[4];     /* mLate.T60[j].mMidGain */
+    float    t60_hf[4][5], t60_lf[4][5];   /* mLate.T60[j].mHFFilter / mLFFilter */
+    uint32_t mod_step;            /* mLate.Mod.Step */
+    float    mod_depth;           /* mLate.Mod.Depth */
+    float    late_ap_coeff;       /* mLate.VecAp.Coeff */
+    uint32_t late_ap_offset[4];   /* mLate.VecAp.Offset */
+} b200mix_reverb_params;
+
+/* ReverbState::deviceUpdate + the first (full) update: allocates and clears the delay
+ * lines and installs the parameters.  Output mix gains (8 lines: 4 early then 4 late,
+ * EarlyReflections::Gains / LateReverb::Gains) go through b200mix_slot_output_gains.
+ * Only the plain output path (MixOutPlain, device ambisonic order 1) is implemented;
+ * a later full parameter change (pipeline cross-fade) must re-install the slot. */
+B200MIX_API int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot,
+    const b200mix_reverb_params *params);
+
 /* Detaches the effect (EffectSlotType::None): the slot's wet input is ignored. */
 B200MIX_API int b200mix_slot_disable(b200mix_device *dev, uint32_t slot);
 

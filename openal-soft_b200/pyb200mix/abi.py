@@ -41,3 +41,19 @@ class VoiceParams(C.Structure):
 class VoiceResult(C.Structure):
     _fields_ = [("position", C.c_int32), ("position_frac", C.c_uint32),
                 ("flags", C.c_uint32), ("buffers_done", C.c_uint32)]
+
+
+class ReverbParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32),
+                ("main_len", C.c_uint32), ("late_in_len", C.c_uint32), ("early_ap_len", C.c_uint32),
+                ("early_len", C.c_uint32), ("late_ap_len", C.c_uint32), ("late_len", C.c_uint32),
+                ("early_tap", C.c_uint32 * 4), ("early_tap_coeff", C.c_float),
+                ("late_tap", C.c_uint32 * 4), ("mix_x", C.c_float), ("mix_y", C.c_float),
+                ("filter_lp", C.c_float * 5), ("filter_hp", C.c_float * 5),
+                ("early_ap_coeff", C.c_float), ("early_ap_offset", C.c_uint32 * 4),
+                ("early_offset", C.c_uint32 * 4), ("early_coeff", C.c_float),
+                ("late_offset", C.c_uint32 * 4), ("density_gain", C.c_float),
+                ("t60_mid_gain", C.c_float * 4),
+                ("t60_hf", (C.c_float * 5) * 4), ("t60_lf", (C.c_float * 5) * 4),
+                ("mod_step", C.c_uint32), ("mod_depth", C.c_float),
+                ("late_ap_coeff", C.c_float), ("late_ap_offset", C.c_uint32 * 4)]

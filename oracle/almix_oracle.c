@@ -9,6 +9,7 @@
  * build has none either).
  */
 #include "almix_oracle.h"
+#include "reverb_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -200,6 +201,7 @@ typedef struct {
     float *hist;               /* input history ring, frames+1024 long (newest at hist_pos-1) */
     uint32_t hist_pos;
     float *cur, *tgt;          /* output mix gains [channels][MAX_DRY] */
+    oreverb *reverb;           /* type == B200MIX_EFFECT_REVERB */
 } oslot;
 
 struct oracle_device {
@@ -259,7 +261,10 @@ void oracle_destroy(oracle_device *d)
     free(d->buffers); free(d->voices);
     if(d->real != d->dry) free(d->real);
     for(uint32_t i = 0;i < d->desc.max_slots;++i)
-    { free(d->slots[i].ir); free(d->slots[i].hist); free(d->slots[i].cur); free(d->slots[i].tgt); }
+    {
+        free(d->slots[i].ir); free(d->slots[i].hist); free(d->slots[i].cur); free(d->slots[i].tgt);
+        oreverb_destroy(d->slots[i].reverb);
+    }
     free(d->slots);
     free(d->dry); free(d->wet);
     free(d->dec_coef); free(d->dec_hfscale); free(d->dec_split);
@@ -306,7 +311,20 @@ int oracle_slot_disable(oracle_device *d, uint32_t slot)
     if(slot >= d->desc.max_slots) return B200MIX_ERR_INVALID;
     oslot *s = &d->slots[slot];
     free(s->ir); free(s->hist); free(s->cur); free(s->tgt);
+    oreverb_destroy(s->reverb);
     memset(s, 0, sizeof(*s));
+    return B200MIX_OK;
+}
+
+int oracle_slot_reverb(oracle_device *d, uint32_t slot, const b200mix_reverb_params *params)
+{
+    if(slot >= d->desc.max_slots || !params || params->struct_size != sizeof(*params))
+        return B200MIX_ERR_INVALID;
+    oracle_slot_disable(d, slot);
+    oslot *s = &d->slots[slot];
+    s->reverb = oreverb_create(params);
+    if(!s->reverb) return B200MIX_ERR_NOMEM;
+    s->type = B200MIX_EFFECT_REVERB; s->channels = 8;
     return B200MIX_OK;
 }
 
@@ -330,6 +348,11 @@ int oracle_slot_output_gains(oracle_device *d, uint32_t slot, uint32_t lines, co
     if(slot >= d->desc.max_slots || !d->slots[slot].type || lines != d->slots[slot].channels)
         return B200MIX_ERR_INVALID;
     oslot *s = &d->slots[slot];
+    if(s->type == B200MIX_EFFECT_REVERB)
+    {
+        oreverb_set_gains(s->reverb, gains, d->desc.dry_channels);
+        return B200MIX_OK;
+    }
     for(uint32_t c = 0;c < lines;++c)
         for(uint32_t o = 0;o < d->desc.dry_channels;++o)
             s->tgt[c*B200MIX_MAX_DRY_CHANNELS + o] = gains[c*d->desc.dry_channels + o];
@@ -965,6 +988,13 @@ static void post_uhj(oracle_device *d, size_t n)
     for(size_t i = 0;i < n;++i) right[i] = d->uhj_s[i] - d->uhj_d[i] + d->uhj_t[i];
 }
 
+/* MixSamples(line, Dry, Current, Target, Counter = n): ReverbState::MixOutPlain */
+static void reverb_mix_cb(void *ctx, const float *in, size_t n, float *cur, const float *tgt)
+{
+    oracle_device *d = ctx;
+    mix_samples(in, n, d->dry, d->desc.dry_channels, cur, tgt, n);
+}
+
 /* ConvolutionState::process + NormalMix (alc/effects/convolution.cpp:623-714,298-304):
  * out_c[i] = sum_k ir_c[k] * x[i-k] over the slot's whole input history, then
  * MixSamples(out_c, Dry, Current, Target, Counter = samplesToDo). */
@@ -1017,8 +1047,14 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     /* EffectState::process for every slot (alc/alu.cpp:2252-2256); slots here have no
      * slot targets, so each mixes straight into Dry (mOutTarget, alc/alu.cpp:626-633). */
     for(uint32_t si = 0;si < dd->max_slots;++si)
+    {
         if(d->slots[si].type == B200MIX_EFFECT_CONVOLUTION)
             slot_convolution_process(d, &d->slots[si], d->wet[(size_t)si*dd->wet_channels], frames);
+        else if(d->slots[si].type == B200MIX_EFFECT_REVERB)
+            oreverb_process(d->slots[si].reverb, frames,
+                (const float(*)[LINE])d->wet[(size_t)si*dd->wet_channels], dd->wet_channels,
+                reverb_mix_cb, d);
+    }
 
     switch(dd->post_process)
     {

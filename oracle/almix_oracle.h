@@ -75,6 +75,7 @@ int  oracle_render(oracle_device *dev, uint32_t frames, float *const *real_out,
 int  oracle_slot_convolution(oracle_device *dev, uint32_t slot, uint32_t ir_channels,
     uint32_t ir_frames, const float *ir);
 int  oracle_slot_output_gains(oracle_device *dev, uint32_t slot, uint32_t lines, const float *gains);
+int  oracle_slot_reverb(oracle_device *dev, uint32_t slot, const b200mix_reverb_params *params);
 int  oracle_slot_disable(oracle_device *dev, uint32_t slot);
 int  oracle_get_dry(oracle_device *dev, float *dry);
 /* test-only: wet mix of one slot [wet_channels][1024] */

@@ -41,6 +41,8 @@ class MixLib:
         self.slot_convolution.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         self.slot_output_gains = f("slot_output_gains")
         self.slot_output_gains.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        self.slot_reverb = f("slot_reverb")
+        self.slot_reverb.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams)]
         self.slot_disable = f("slot_disable")
         self.slot_disable.argtypes = [C.c_void_p, C.c_uint32]
         self.get_dry = f("get_dry")
@@ -89,6 +91,15 @@ class MixDevice:
         rc = self.m.slot_convolution(self.h, slot, ir.shape[0], ir.shape[1], ir.ctypes.data)
         assert rc == 0, rc
         rc = self.m.slot_output_gains(self.h, slot, gains.shape[0], gains.ctypes.data)
+        assert rc == 0, rc
+
+    def slot_reverb(self, slot, params, gains):
+        """params: abi.ReverbParams; gains: [8][dry_channels] (early 0-3, late 0-3)."""
+        params.struct_size = C.sizeof(abi.ReverbParams)
+        rc = self.m.slot_reverb(self.h, slot, C.byref(params))
+        assert rc == 0, rc
+        gains = np.ascontiguousarray(gains, dtype=np.float32)
+        rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)
         assert rc == 0, rc
 
     def buffer_data(self, buf_id, sample_type, pcm):

@@ -129,6 +129,7 @@ def libs(conf_text: str | None = None):
     for fn in ("alGenEffects", "alGenAuxiliaryEffectSlots"):
         getattr(al, fn).argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alEffecti.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alEffectf.argtypes = [C.c_uint, C.c_int, C.c_float]
     al.alAuxiliaryEffectSloti.argtypes = [C.c_uint, C.c_int, C.c_int]
     al.alAuxiliaryEffectSlotf.argtypes = [C.c_uint, C.c_int, C.c_float]
     hz.refh_get_hrtf_accum.argtypes = [C.c_void_p, C.c_void_p]
@@ -223,6 +224,33 @@ class RefDevice:
         assert err == 0, f"AL error {err:#x} creating convolution slot"
         self._keep.append(ir_pcm)
         return s.value
+
+    def add_reverb_slot(self, eax: bool = True, props: dict | None = None, slot_gain: float = 1.0):
+        """examples/alreverb.c: an (EAX) reverb effect on an aux slot; props = {AL_param: float}."""
+        e = C.c_uint(0)
+        s = C.c_uint(0)
+        self.al.alGenEffects(1, C.byref(e))
+        self.al.alEffecti(e, AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB if eax else 0x0001)
+        for k, v in (props or {}).items():
+            self.al.alEffectf(e, k, float(v))
+        self.al.alGenAuxiliaryEffectSlots(1, C.byref(s))
+        self.al.alAuxiliaryEffectSlotf(s, AL_EFFECTSLOT_GAIN, slot_gain)
+        self.al.alAuxiliaryEffectSloti(s, AL_EFFECTSLOT_EFFECT, e.value)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} creating reverb slot"
+        return s.value
+
+    def reverb_params(self, idx: int):
+        if not hasattr(self, "_rv"):
+            self._rv = C.CDLL(os.path.join(REF_DIR, "libref_reverb_tap.so"))
+            self._rv.refh_reverb_params.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.ReverbParams),
+                                                    C.c_void_p, C.POINTER(C.c_int)]
+        p = abi.ReverbParams()
+        gains = np.zeros((8, self.desc.dry_channels), dtype=np.float32)
+        st = C.c_int(0)
+        rc = self._rv.refh_reverb_params(self.ctx, idx, C.byref(p), gains.ctypes.data, C.byref(st))
+        assert rc == 0, f"refh_reverb_params -> {rc}"
+        return p, gains, st.value
 
     def connect_send(self, source: int, slot: int, send: int = 0):
         self.al.alSource3i(source, AL_AUXILIARY_SEND_FILTER, slot, send, AL_FILTER_NULL)
