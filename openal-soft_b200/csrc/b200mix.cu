@@ -97,6 +97,8 @@ struct b200mix_device {
     uint32_t num_entries{0};
     bool sends_dirty{true};
     float2 *d_twiddle{nullptr};
+    float *d_cubic_filter{nullptr};          // gCubicTable (reverb modulation taps)
+    uint32_t reverb_slots{0};
 
     bool profile{false};
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
@@ -327,6 +329,11 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
                 const double a = -2.0*3.14159265358979323846*double(k)/256.0;
                 tw[k] = make_float2(float(std::cos(a)), float(std::sin(a)));
             }
+            const std::vector<float> cf = BuildCubicFilter();
+            if(int rc = dev_alloc(d, d->d_cubic_filter, cf.size(), false)) return rc;
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_cubic_filter, cf.data(), cf.size()*sizeof(float),
+                cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
             if(int rc = dev_alloc(d, d->d_twiddle, 128, false)) return rc;
             CUDA_TRY(d, cudaMemcpyAsync(d->d_twiddle, tw.data(), 128*sizeof(float2),
                 cudaMemcpyHostToDevice, d->stream));
@@ -368,7 +375,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
-    cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle);
+    cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
     cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
     cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
     if(d->stage_done) cudaEventDestroy(d->stage_done);
@@ -478,6 +485,7 @@ static void free_slot(b200mix_device *d, uint32_t slot)
     for(void *p : d->slot_allocs[slot]) cudaFree(p);
     d->slot_allocs[slot].clear();
     if(d->h_slots[slot].type) --d->active_slots;
+    if(d->h_slots[slot].type == B200MIX_EFFECT_REVERB) --d->reverb_slots;
     d->h_slots[slot] = SlotRec{};
 }
 
@@ -557,6 +565,65 @@ int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_chann
     CUDA_TRY(d, cudaMemcpyAsync(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     ++d->active_slots;
+    d->dry_active = true;
+    return B200MIX_OK;
+}
+
+int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_params *p)
+{
+    if(!d || slot >= d->h_slots.size() || !p || p->struct_size != sizeof(*p))
+    { if(d) d->error = "slot_reverb: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
+    auto pow2 = [](uint32_t v) { return v >= 4u && !(v & (v-1u)); };
+    if(!pow2(p->main_len) || !pow2(p->late_in_len) || !pow2(p->early_ap_len) || !pow2(p->early_len)
+        || !pow2(p->late_ap_len) || !pow2(p->late_len) || !p->late_offset[0] || !p->late_ap_offset[0])
+    { d->error = "slot_reverb: line lengths must be powers of two, feedback delays non-zero"; return B200MIX_ERR_INVALID; }
+    for(int j = 0;j < 4;++j)
+        if(!p->early_ap_offset[j] || p->late_ap_offset[j] < p->late_ap_offset[0])
+        { d->error = "slot_reverb: all-pass delays must be non-zero, late all-pass sorted"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    free_slot(d, slot);
+    SlotRec r{};
+    r.type = B200MIX_EFFECT_REVERB; r.channels = 8;
+    auto alloc = [&](auto *&ptr, size_t count) -> int {
+        if(int rc = dev_alloc(d, ptr, count)) return rc;
+        d->slot_allocs[slot].push_back(ptr);
+        return B200MIX_OK;
+    };
+    ReverbDev h{};
+    h.main_len = p->main_len; h.late_in_len = p->late_in_len; h.early_ap_len = p->early_ap_len;
+    h.early_len = p->early_len; h.late_ap_len = p->late_ap_len; h.late_len = p->late_len;
+    std::memcpy(h.early_tap, p->early_tap, sizeof(h.early_tap)); h.early_tap_coeff = p->early_tap_coeff;
+    std::memcpy(h.late_tap, p->late_tap, sizeof(h.late_tap));
+    h.mix_x = p->mix_x; h.mix_y = p->mix_y;
+    std::memcpy(h.filter_lp, p->filter_lp, sizeof(h.filter_lp));
+    std::memcpy(h.filter_hp, p->filter_hp, sizeof(h.filter_hp));
+    h.early_ap_coeff = p->early_ap_coeff;
+    std::memcpy(h.early_ap_offset, p->early_ap_offset, sizeof(h.early_ap_offset));
+    std::memcpy(h.early_offset, p->early_offset, sizeof(h.early_offset));
+    h.early_coeff = p->early_coeff;
+    std::memcpy(h.late_offset, p->late_offset, sizeof(h.late_offset));
+    h.density_gain = p->density_gain;
+    std::memcpy(h.t60_mid_gain, p->t60_mid_gain, sizeof(h.t60_mid_gain));
+    std::memcpy(h.t60_hf, p->t60_hf, sizeof(h.t60_hf)); std::memcpy(h.t60_lf, p->t60_lf, sizeof(h.t60_lf));
+    h.mod_step = p->mod_step; h.mod_depth = p->mod_depth; h.late_ap_coeff = p->late_ap_coeff;
+    std::memcpy(h.late_ap_offset, p->late_ap_offset, sizeof(h.late_ap_offset));
+    if(int rc = alloc(h.main_d, size_t(4)*p->main_len)) return rc;
+    if(int rc = alloc(h.late_in, size_t(4)*p->late_in_len)) return rc;
+    if(int rc = alloc(h.early_ap, size_t(4)*p->early_ap_len)) return rc;
+    if(int rc = alloc(h.early_d, size_t(4)*p->early_len)) return rc;
+    if(int rc = alloc(h.late_ap, size_t(4)*p->late_ap_len)) return rc;
+    if(int rc = alloc(h.late_d, size_t(4)*p->late_len)) return rc;
+    ReverbDev *dh = nullptr;
+    if(int rc = alloc(dh, 1)) return rc;
+    r.H = reinterpret_cast<float*>(dh);            // SlotRec::H carries the ReverbDev block
+    if(int rc = alloc(r.lines, size_t(8)*kLine)) return rc;
+    if(int rc = alloc(r.gains, size_t(2)*8*32)) return rc;
+    if(int rc = alloc(r.gtgt, size_t(8)*32)) return rc;
+    CUDA_TRY(d, cudaMemcpyAsync(dh, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
+    d->h_slots[slot] = r;
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    ++d->active_slots; ++d->reverb_slots;
     d->dry_active = true;
     return B200MIX_OK;
 }
@@ -793,6 +860,14 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         CP.frames = frames; CP.cw = dd.wet_channels; CP.num_slots = dd.max_slots;
         uint32_t maxch = 1;
         for(const SlotRec &sr : d->h_slots) if(sr.type) maxch = std::max(maxch, sr.channels);
+        if(d->reverb_slots)
+        {
+            ReverbParamsK RP{};
+            RP.slots = d->d_slots; RP.wet = d->d_wet; RP.cubic = d->d_cubic_filter;
+            RP.frames = frames; RP.cw = dd.wet_channels;
+            k_reverb_process<<<dd.max_slots, 128, 0, d->stream>>>(RP);
+            ++d->launches;
+        }
         k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
         k_conv_mac<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
         k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) k_slot_output_mix(const SlotMixParams Q)
     for(uint32_t s = 0;s < Q.num_slots;++s)
     {
         const SlotRec &S = Q.slots[s];
-        if(S.type != 1u) continue;
+        if(S.type == 0u) continue;
         const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
         for(uint32_t c = 0;c < S.channels;++c)
         {
@@ -352,9 +352,287 @@ __global__ void k_slot_gains_commit(const SlotMixParams Q)
 {
     const uint32_t s = blockIdx.x;
     SlotRec &S = Q.slots[s];
-    if(S.type != 1u) return;
+    if(S.type == 0u) return;
     float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
     for(uint32_t k = threadIdx.x;k < S.channels*32u;k += blockDim.x) gcur[k] = S.gtgt[k];
+}
+
+} // namespace b200mix
+
+// =====================================================================================
+// EAX / standard reverb: ReverbState::process for one pipeline in the Normal state
+// (alc/effects/reverb.cpp:1813-1845).  One CTA per slot, 4 warps = the 4 A-format lines.
+// Sample-parallel wherever the reference's data flow allows it (delay taps, all-pass
+// sub-chunks bounded by the feedback delay, scatter matrices, modulated cubic taps);
+// the biquad recurrences (master shelves, T60) run serially on lane 0 of each line warp.
+// =====================================================================================
+namespace b200mix {
+
+struct ReverbDev {
+    // parameters (b200mix_reverb_params)
+    uint32_t main_len, late_in_len, early_ap_len, early_len, late_ap_len, late_len;
+    uint32_t early_tap[4]; float early_tap_coeff; uint32_t late_tap[4];
+    float mix_x, mix_y;
+    float filter_lp[5], filter_hp[5];
+    float early_ap_coeff; uint32_t early_ap_offset[4]; uint32_t early_offset[4]; float early_coeff;
+    uint32_t late_offset[4]; float density_gain; float t60_mid_gain[4];
+    float t60_hf[4][5], t60_lf[4][5];
+    uint32_t mod_step; float mod_depth; float late_ap_coeff; uint32_t late_ap_offset[4];
+    // state
+    float z_lp[4][2], z_hp[4][2], z_t60hf[4][2], z_t60lf[4][2];
+    uint32_t early_tap_cur[4], late_tap_cur[4]; float early_coeff_cur;
+    uint32_t mod_index; uint32_t offset;
+    // delay lines
+    float *main_d, *late_in, *early_ap, *early_d, *late_ap, *late_d;
+};
+
+struct ReverbParamsK { SlotRec *slots; const float *wet; const float *cubic; uint32_t frames, cw; };
+
+__device__ __forceinline__ void scatter4(const float in[4], float x, float y, float out[4])
+{
+    // VectorPartialScatter, reverb.cpp:1396-1405
+    out[0] = x*in[0] + y*(          in[1] + -in[2] + in[3]);
+    out[1] = x*in[1] + y*(-in[0]          +  in[2] + in[3]);
+    out[2] = x*in[2] + y*( in[0] + -in[1]          + in[3]);
+    out[3] = x*in[3] + y*(-in[0] + -in[1] + -in[2]        );
+}
+
+// BiquadFilter::dualProcess (core/filters/biquad.cpp:254-283), in place, one thread.
+__device__ __forceinline__ void dual_biquad_serial(const float *c0, const float *c1, float *z0,
+    float *z1, float *buf, uint32_t n)
+{
+    const float b00 = c0[0], b01 = c0[1], b02 = c0[2], a01 = c0[3], a02 = c0[4];
+    const float b10 = c1[0], b11 = c1[1], b12 = c1[2], a11 = c1[3], a12 = c1[4];
+    float z01 = z0[0], z02 = z0[1], z11 = z1[0], z12 = z1[1];
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const float x0 = buf[i];
+        const float y0 = x0*b00 + z01;
+        z01 = x0*b01 - y0*a01 + z02;
+        z02 = x0*b02 - y0*a02;
+        const float y1 = y0*b10 + z11;
+        z11 = y0*b11 - y1*a11 + z12;
+        z12 = y0*b12 - y1*a12;
+        buf[i] = y1;
+    }
+    z0[0] = z01; z0[1] = z02; z1[0] = z11; z1[1] = z12;
+}
+
+__global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
+{
+    constexpr int NL = 4;
+    constexpr uint32_t MAXUPD = 256;
+    __shared__ float temp[NL][MAXUPD];
+    __shared__ uint32_t moddel[MAXUPD];
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 2u) return;
+    ReverbDev &R = *reinterpret_cast<ReverbDev*>(S.H);
+    const int tid = threadIdx.x, line = tid >> 5, lane = tid & 31;
+    const uint32_t n = Q.frames;
+    const uint32_t offset0 = R.offset;
+    const float *wet = Q.wet + size_t(blockIdx.x)*Q.cw*kLine;
+    const uint32_t numInput = Q.cw < 4u ? Q.cw : 4u;
+    float *earlyOut = S.lines, *lateOut = S.lines + 4*kLine;
+
+    // B-Format -> A-Format into the main delay (reverb.cpp:1824-1838, B2A :91-97)
+    {
+        const float B2A[4][4] = {{0.5f, 0.5f, 0.5f, 0.5f}, {0.5f, -0.5f, -0.5f, 0.5f},
+            {0.5f, 0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, 0.5f, -0.5f}};
+        float *dl = R.main_d + size_t(line)*R.main_len;
+        for(uint32_t i = lane;i < n;i += 32)
+        {
+            float a = 0.0f;
+            for(uint32_t k = 0;k < numInput;++k) a = a + wet[size_t(k)*kLine + i]*B2A[line][k];
+            dl[(offset0 + i) & (R.main_len-1)] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---- processEarly, reverb.cpp:1558-1660 ----
+    uint32_t offset = offset0;
+    float coeffCur = R.early_coeff_cur;
+    uint32_t tapCur = R.early_tap_cur[line];
+    for(uint32_t base = 0;base < n;)
+    {
+        const uint32_t todo = (n-base < MAXUPD) ? n-base : MAXUPD;
+        const float fadeStep = 1.0f/float(todo);
+        const float c0 = coeffCur, c1 = R.early_tap_coeff;
+        coeffCur = c1;
+        {
+            const float *input = R.main_d + size_t(line)*R.main_len;
+            const uint32_t t0 = offset - tapCur, t1 = offset - R.early_tap[line];
+            tapCur = R.early_tap[line];
+            for(uint32_t i = lane;i < todo;i += 32)
+            {
+                const float in0 = input[(t0+i) & (R.main_len-1)], in1 = input[(t1+i) & (R.main_len-1)];
+                const float a = in0*c0, b = in1*c1;
+                temp[line][i] = a + (b-a)*(fadeStep*float(i));
+            }
+        }
+        __syncwarp();
+        if(lane == 0)
+            dual_biquad_serial(R.filter_lp, R.filter_hp, R.z_lp[line], R.z_hp[line], temp[line], todo);
+        __syncwarp();
+        // Allpass4::process (reverb.cpp:1508-1538): sub-chunks no longer than the feedback delay
+        {
+            float *buf = R.early_ap + size_t(line)*R.early_ap_len;
+            const uint32_t m = R.early_ap_len-1, off = R.early_ap_offset[line];
+            const float fc = R.early_ap_coeff;
+            for(uint32_t sb = 0;sb < todo;sb += off)
+            {
+                const uint32_t td = (todo - sb < off) ? todo - sb : off;
+                for(uint32_t i = lane;i < td;i += 32)
+                {
+                    const float x = temp[line][sb+i];
+                    const float y = buf[(offset + sb + i - off) & m] - fc*x;
+                    buf[(offset + sb + i) & m] = x + fc*y;
+                    temp[line][sb+i] = y;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // writeReflected (reverb.cpp:340-365)
+        for(uint32_t i = tid;i < todo;i += 128)
+        {
+            const float s0 = temp[0][i], s1 = temp[1][i], s2 = temp[2][i], s3 = temp[3][i];
+            const uint32_t o = (offset+i) & (R.early_len-1);
+            R.early_d[0*size_t(R.early_len) + o] = (s0      - s1 - s2 - s3) * 0.5f;
+            R.early_d[1*size_t(R.early_len) + o] = (s1 - s0      - s2 - s3) * 0.5f;
+            R.early_d[2*size_t(R.early_len) + o] = (s2 - s0 - s1      - s3) * 0.5f;
+            R.early_d[3*size_t(R.early_len) + o] = (s3 - s0 - s1 - s2     ) * 0.5f;
+        }
+        __syncthreads();
+        {
+            const float *dl = R.early_d + size_t(line)*R.early_len;
+            const uint32_t tap = offset - R.early_offset[line];
+            for(uint32_t i = lane;i < todo;i += 32)
+                earlyOut[size_t(line)*kLine + base + i] = dl[(tap+i) & (R.early_len-1)]*R.early_coeff + temp[line][i];
+        }
+        __syncthreads();
+        // VectorScatter + late-input write (reverb.cpp:1649-1655)
+        for(uint32_t i = tid;i < todo;i += 128)
+        {
+            const float in[4] = {temp[0][i], temp[1][i], temp[2][i], temp[3][i]};
+            float f[4];
+            scatter4(in, R.mix_x, R.mix_y, f);
+            const uint32_t o = (offset+i) & (R.late_in_len-1);
+            #pragma unroll
+            for(int j = 0;j < NL;++j) R.late_in[size_t(j)*R.late_in_len + o] = f[j];
+        }
+        __syncthreads();
+        base += todo; offset += todo;
+    }
+
+    // ---- processLate, reverb.cpp:1696-1811 ----
+    offset = offset0;
+    uint32_t modIdx = R.mod_index;
+    uint32_t ltapCur = R.late_tap_cur[line];
+    for(uint32_t base = 0;base < n;)
+    {
+        uint32_t todo = R.late_offset[0] < MAXUPD ? R.late_offset[0] : MAXUPD;
+        if(n-base < todo) todo = n-base;
+        // Modulation::calcDelays (reverb.cpp:1662-1681)
+        {
+            const float depth = R.mod_depth*256.0f;
+            for(uint32_t i = tid;i < todo;i += 128)
+            {
+                const uint32_t idx = modIdx + i*R.mod_step;
+                const float x = float(idx & 0xffffffu) * (1.0f/16777216.0f);
+                const float lfo = !(idx & 0x800000u) ? ((-16.0f*x*x) + (8.0f*x))
+                    : ((16.0f*x*x) + (-8.0f*x) + (-16.0f*x) + 8.0f);
+                const float v = (lfo+1.0f)*depth;
+                moddel[i] = v > 0.0f ? uint32_t(v) : 0u;
+            }
+            modIdx += todo*R.mod_step;
+        }
+        __syncthreads();
+        {
+            const float *input = R.late_d + size_t(line)*R.late_len;
+            const uint32_t m = R.late_len-1;
+            const float midGain = R.t60_mid_gain[line];
+            const uint32_t tap = offset - R.late_offset[line];
+            for(uint32_t i = lane;i < todo;i += 32)
+            {
+                const uint32_t idelay = moddel[i];
+                const uint32_t delay = tap + i - (idelay>>8), doff = idelay & 255u;
+                const float o0 = input[delay & m], o1 = input[(delay-1u) & m];
+                const float o2 = input[(delay-2u) & m], o3 = input[(delay-3u) & m];
+                const float out = o0*Q.cubic[256u+doff] + o1*Q.cubic[doff] + o2*Q.cubic[256u-doff]
+                    + o3*Q.cubic[512u-doff];
+                temp[line][i] = out*midGain;
+            }
+        }
+        __syncwarp();
+        if(lane == 0)
+            dual_biquad_serial(R.t60_hf[line], R.t60_lf[line], R.z_t60hf[line], R.z_t60lf[line],
+                temp[line], todo);
+        __syncwarp();
+        {
+            const float *input = R.late_in + size_t(line)*R.late_in_len;
+            const uint32_t m = R.late_in_len-1;
+            const uint32_t t0 = offset - ltapCur, t1 = offset - R.late_tap[line];
+            ltapCur = R.late_tap[line];
+            const float fadeStep = 1.0f/float(todo);
+            const float dg = R.density_gain;
+            const float ds = (t0 != t1) ? dg*fadeStep : 0.0f;
+            for(uint32_t i = lane;i < todo;i += 32)
+            {
+                const float fc = float(i);
+                const float fade0 = dg - ds*fc, fade1 = ds*fc;
+                temp[line][i] = input[(t0+i) & m]*fade0 + input[(t1+i) & m]*fade1 + temp[line][i];
+            }
+        }
+        __syncthreads();
+        // VecAllpass::process (reverb.cpp:1452-1503), interleaved delay: frame*4 + line
+        {
+            float *buf = R.late_ap;
+            const uint32_t m = R.late_ap_len-1, minOff = R.late_ap_offset[0];
+            const uint32_t myOff = R.late_ap_offset[line];
+            const float fc = R.late_ap_coeff;
+            for(uint32_t sb = 0;sb < todo;sb += minOff)
+            {
+                const uint32_t td = (todo - sb < minOff) ? todo - sb : minOff;
+                for(uint32_t i = lane;i < td;i += 32)
+                {
+                    const float input = temp[line][sb+i];
+                    const float out = buf[size_t((offset + sb + i - myOff) & m)*NL + line] - fc*input;
+                    buf[size_t((offset + sb + i) & m)*NL + line] = input + fc*out;
+                    temp[line][sb+i] = out;
+                }
+                __syncthreads();
+                for(uint32_t i = tid;i < td;i += 128)
+                {
+                    float *d = buf + size_t((offset + sb + i) & m)*NL;
+                    const float in[4] = {d[0], d[1], d[2], d[3]};
+                    float f[4];
+                    scatter4(in, R.mix_x, R.mix_y, f);
+                    d[0] = f[0]; d[1] = f[1]; d[2] = f[2]; d[3] = f[3];
+                }
+                __syncthreads();
+            }
+        }
+        for(uint32_t i = lane;i < todo;i += 32) lateOut[size_t(line)*kLine + base + i] = temp[line][i];
+        __syncthreads();
+        // VectorScatterRev + feedback write (reverb.cpp:1800-1806)
+        for(uint32_t i = tid;i < todo;i += 128)
+        {
+            const float in[4] = {temp[3][i], temp[2][i], temp[1][i], temp[0][i]};
+            float f[4];
+            scatter4(in, R.mix_x, R.mix_y, f);
+            const uint32_t o = (offset+i) & (R.late_len-1);
+            #pragma unroll
+            for(int j = 0;j < NL;++j) R.late_d[size_t(j)*R.late_len + o] = f[j];
+        }
+        __syncthreads();
+        base += todo; offset += todo;
+    }
+
+    if(lane == 0)
+    {
+        R.early_tap_cur[line] = tapCur; R.late_tap_cur[line] = ltapCur;
+        if(line == 0) { R.early_coeff_cur = coeffCur; R.mod_index = modIdx; R.offset = offset0 + n; }
+    }
 }
 
 } // namespace b200mix

@@ -48,6 +48,12 @@ SCENES = {
     "hrtf_bsinc24_conv3000_v6": (6, 1, 7, 5, True, 48000, None, "i16", 3000),
     "hrtf_spline_conv100_v4": (4, 1, 2, 3, True, 48000, None, "i16", 100),
     "stereo_spline_conv1500_v4": (4, 0, 2, 4, True, 48000, None, "i16", 1500),
+    # aux send -> EAX reverb slot (alc/effects/reverb.cpp): default preset; min density + modulation
+    "hrtf_bsinc24_reverb_v6": (6, 1, 7, 8, True, 48000, None, "i16", 0, {}),
+    "hrtf_spline_reverb_dens0_mod_v4": (4, 1, 2, 6, True, 48000, None, "i16", 0,
+                                        {0x0001: 0.0, 0x0002: 0.7, 0x0012: 1.0, 0x0011: 0.8, 0x0006: 2.5,
+                                         0x0004: 0.5}),
+    "stereo_spline_reverb_v4": (4, 0, 2, 5, True, 48000, None, "i16", 0, {0x0006: 0.8}),
 }
 
 
@@ -76,14 +82,22 @@ def run_scene(name):
         slot = ref.add_convolution_slot(conv_ir(taps), 48000, 0.5)
         for src in ref.sources:
             ref.connect_send(src, slot)
+    rvprops = spec[9] if len(spec) > 9 else None
+    if rvprops is not None:
+        slot = ref.add_reverb_slot(props=rvprops)
+        for src in ref.sources:
+            ref.connect_send(src, slot)
     ref.play_all()
     outs = []
     snap = None
-    nslots, wet = ref.slot_info() if taps else (0, [])
+    nslots, wet = ref.slot_info() if (taps or rvprops is not None) else (0, [])
     for u in range(U):
         outs.append(ref.render())
         if u == 0:
             snap = ref.snapshot(wet_channels=wet[0] if nslots else 0)
+            if rvprops is not None:
+                rvp, rvg, rvstate = ref.reverb_params(0)
+                assert rvstate == 4, rvstate     # ReverbState::Normal
     n, params, coeffs, dry, send, state = snap
     d = ref.desc
     res = dict(out=np.stack(outs),
@@ -93,6 +107,9 @@ def run_scene(name):
     if taps:
         res.update(conv_taps=np.int64(taps), conv_gains=ref.mono_line_gains(0.5), send=send[:V].copy(),
                    wet_channels=np.int64(wet[0]))
+    if rvprops is not None:
+        res.update(reverb_params=np.frombuffer(bytes(rvp), dtype=np.uint8).copy(), reverb_gains=rvg,
+                   send=send[:V].copy(), wet_channels=np.int64(wet[0]))
     if d.post_process == abi.POST_HRTF:
         c, hf, sc = ref.hrtf_decoder()
         res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)

@@ -28,7 +28,8 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
     desc.max_buffers = V
     desc.max_slots = 0
     taps = int(fx["conv_taps"]) if "conv_taps" in fx else 0
-    if taps:
+    reverb = "reverb_params" in fx
+    if taps or reverb:
         desc.max_slots = 1
         desc.wet_channels = int(fx["wet_channels"])
     dev = MixDevice(mixlib, desc)
@@ -44,6 +45,9 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             rng = np.random.default_rng(taps)      # same IR as tests/golden/make_golden.py:conv_ir
             ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
             dev.slot_convolution(0, ir[None, :], fx["conv_gains"][None, :])
+        if reverb:
+            dev.slot_reverb(0, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                            fx["reverb_gains"])
         params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
         plist = []
         for k in range(V):
@@ -55,7 +59,7 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             q.position = 0
             q.position_frac = 0
             plist.append(q)
-        dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if taps else None)
+        dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if (taps or reverb) else None)
         outs = []
         res = None
         for _ in range(updates or U):

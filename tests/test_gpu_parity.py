@@ -179,3 +179,33 @@ def test_convolution_slot_vs_oracle_long_ir_and_ragged_updates():
         dev.close()
         outs.append(np.concatenate(o, axis=1))
     _check(outs[1], outs[0], "convolution slots")
+
+
+def test_reverb_slots_vs_oracle_ragged_updates():
+    """EAX reverb slots driven by the reference's own parameter blocks (taken from two golden
+    fixtures: default preset and min-density + modulation), ragged update sizes."""
+    rng = np.random.default_rng(5150)
+    nv, ir = 24, 64
+    desc = synth.hrtf_desc(nv, ir)
+    desc.num_sends = 1
+    desc.wet_channels = 4
+    desc.max_slots = 2
+    params, coeffs, dry = synth.voice_set(rng, nv, ir)
+    send = (rng.standard_normal((nv, 1, 4)) * 0.3).astype(np.float32)
+    for k, p in enumerate(params):
+        p.send_slot[0] = k % 2
+    fxs = [golden.load("hrtf_bsinc24_reverb_v6"), golden.load("hrtf_spline_reverb_dens0_mod_v4")]
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        for s, fx in enumerate(fxs):
+            dev.slot_reverb(s, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                            fx["reverb_gains"])
+        dev.voices_update(params, coeffs, dry, send)
+        o = [dev.render(f) for f in (1024, 300, 1024, 17, 1024, 1024, 700, 1024)]
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], "reverb slots")
