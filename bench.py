@@ -62,16 +62,43 @@ def load_product():
     lib.b200mix_launch_count.argtypes = [C.c_void_p]
     lib.b200mix_stream.restype = C.c_void_p
     lib.b200mix_stream.argtypes = [C.c_void_p]
+    lib.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_void_p, C.POINTER(C.c_uint32)]
     return lib
 
 
-def synth_voices(first, count, total):
+MHR_PATH = os.path.join(ROOT, "openal-soft_b200", "data", "Default HRTF.mhr")
+
+
+def load_hrtf(lib):
+    """The reference's default data set through the product's own MHR loader, or None."""
+    if not os.path.exists(MHR_PATH):
+        return None
+    data = open(MHR_PATH, "rb").read()
+    h = C.c_void_p()
+    return h if lib.b200mix_hrtf_load(data, len(data), C.byref(h)) == 0 else None
+
+
+def hrir_for(lib, hrtf, pos, out, delays):
+    """CalcHrtfPanning's lookup (alc/alu.cpp:1210-1216) for a source at `pos`."""
+    x, y, z = pos
+    d = math.sqrt(x * x + y * y + z * z)
+    ev = math.asin(max(-1.0, min(1.0, y / d)))
+    az = math.atan2(x / d, -z / d)
+    lib.b200mix_hrtf_get_coeffs(hrtf, ev, az, d, 0.0, out.ctypes.data, delays)
+
+
+def synth_voices(first, count, total, lib=None, hrtf=None, shift=0.0):
     """Post-ALU parameter snapshots for voices [first, first+count) of a `total`-voice
-    scene: decaying 64-tap HRIR pairs, ITD-like delays, gain 1/sqrt(total)."""
+    scene (SURVEY §8d positions): HRIR pair + delays from Default HRTF.mhr via the product's
+    HrtfStore::getCoeffs restatement (synthetic decaying filters only if the data set is
+    not staged), gain 1/sqrt(total).  `shift` rotates the azimuths (moving sources)."""
     rng = np.random.default_rng(0xB200 + first)
     coeffs = (rng.standard_normal((count, IR, 2)) * np.exp(-np.arange(IR) / 10.0)[None, :, None]
               ).astype(np.float32)
     params = (abi.VoiceParams * count)()
+    dl = (C.c_uint32 * 2)()
     pitches = []
     for k in range(count):
         i = first + k
@@ -89,6 +116,13 @@ def synth_voices(first, count, total):
         p.step = max(1, min(int(pitch * 65536.0), 10 << 16))
         p.hrtf_delay[0] = int(rng.integers(0, 40))
         p.hrtf_delay[1] = int(rng.integers(0, 40))
+        if hrtf is not None:
+            x, y, z = scene.voice_position(i)
+            if shift:
+                cs, sn = math.cos(shift), math.sin(shift)
+                x, z = x * cs - z * sn, x * sn + z * cs
+            hrir_for(lib, hrtf, (x, y, z), coeffs[k], dl)
+            p.hrtf_delay[0], p.hrtf_delay[1] = dl[0], dl[1]
         p.hrtf_gain = scene.voice_gain(total)
         for s in range(abi.MAX_SENDS):
             p.send_slot[s] = abi.NO_SLOT
@@ -270,7 +304,8 @@ def main_cuda(args):
     for k in range(nv):
         pcm = scene.voice_buffer_fast(first + k)
         ck(lib.b200mix_buffer_data(h, k, abi.FMT_I16, 1, pcm.shape[0], pcm.ctypes.data, pcm.nbytes), "buffer_data")
-    params, coeffs, pitches = synth_voices(first, nv, total)
+    hrtf = load_hrtf(lib)
+    params, coeffs, pitches = synth_voices(first, nv, total, lib, hrtf)
     ck(lib.b200mix_voices_update(h, nv, params, coeffs.ctypes.data, None, None), "voices_update")
 
     stream = torch.cuda.ExternalStream(lib.b200mix_stream(h))
@@ -338,13 +373,16 @@ def main_cuda(args):
     # front: 8 rotating sets, each moving a different eighth of the voices
     move_sets = []
     for base in range(8):
+        # the moved eighth gets the HRIRs of a rotated position (new coefficients AND delays)
+        p2, c2, _ = synth_voices(first, nv, total, lib, hrtf, shift=0.05 * (base + 1))
         mp = (abi.VoiceParams * nmove)()
         for j in range(nmove):
             k = base + 8 * j
-            C.memmove(C.byref(mp[j]), C.byref(params[k]), C.sizeof(abi.VoiceParams))
+            C.memmove(C.byref(mp[j]), C.byref(p2[k]), C.sizeof(abi.VoiceParams))
             mp[j].flags &= ~abi.VF_RESET
-            mp[j].hrtf_delay[0] = (params[k].hrtf_delay[0] + 3 * base + 1) % 40
-        mc = np.ascontiguousarray(coeffs[base::8][:nmove] * np.float32(1.0 - 0.02 * base))
+            if hrtf is None:
+                mp[j].hrtf_delay[0] = (params[k].hrtf_delay[0] + 3 * base + 1) % 40
+        mc = np.ascontiguousarray(c2[base::8][:nmove] * np.float32(1.0 if hrtf is not None else 1.0 - 0.02 * base))
         move_sets.append((mp, mc))
 
     def step_e2e(it):
@@ -387,7 +425,8 @@ def main_cuda(args):
             "config": {"workload": "config2: 4096 mono 48k voices per GPU, 64-tap HRIR pair per voice, "
                                    "bsinc24, pitch U[0.5,2) (1/16 at 1.0)",
                        "voices": total, "voices_per_gpu": nv, "update_frames": FRAMES,
-                       "hrir": "synthetic decaying 64-tap pairs (parameter stage not on this path)",
+                       "hrir": ("Default HRTF.mhr (MinPHR03, 48 kHz, Ir=64) via b200mix_hrtf_get_coeffs"
+                                if hrtf is not None else "synthetic decaying 64-tap pairs (data set not staged)"),
                        "l2": "flushed between timed updates (256 MiB memset)",
                        "parallelism": f"voices sharded over {world} GPU(s); one NCCL reduce of RealOut per update"},
             "rt_voices": total * UPDATE_MS / ms_per_step,

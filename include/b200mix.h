@@ -225,6 +225,18 @@ B200MIX_API int b200mix_render(b200mix_device *dev, uint32_t frames, float *cons
 B200MIX_API int b200mix_render_device(b200mix_device *dev, uint32_t frames,
     const float **real_out_dev);
 
+/* ---- host-side parameter helpers (no GPU involved) -------------------------- */
+/* The HRTF data set and the per-voice HRIR lookup of the parameter stage:
+ * LoadHrtf03 (core/hrtf_loader.cpp:583-721, "MinPHR03" files such as hrtf/Default HRTF.mhr)
+ * and HrtfStore::getCoeffs (core/hrtf.cpp:192-260).  coeffs is [ir_size][2]. */
+typedef struct b200mix_hrtf b200mix_hrtf;
+B200MIX_API int b200mix_hrtf_load(const void *mhr_data, size_t bytes, b200mix_hrtf **out);
+B200MIX_API void b200mix_hrtf_free(b200mix_hrtf *hrtf);
+B200MIX_API int b200mix_hrtf_info(const b200mix_hrtf *hrtf, uint32_t *sample_rate, uint32_t *ir_size,
+    uint32_t *ir_count);
+B200MIX_API int b200mix_hrtf_get_coeffs(const b200mix_hrtf *hrtf, float elevation, float azimuth,
+    float distance, float spread, float *coeffs, uint32_t delays[2]);
+
 /* ---- introspection (tests, profiling) ------------------------------------ */
 /* Copies the Dry mix of the last update: [dry_channels][1024]. */
 B200MIX_API int b200mix_get_dry(b200mix_device *dev, float *dry);
