@@ -234,7 +234,7 @@ def main_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
         return
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
+    procs = max(1, cores)
     # bounded sample of the same workload: `sample_voices` of the 4096*N voices, so that
     # the whole run ends within minutes (~30 us per voice-update per core)
     total = VOICES_PER_GPU * args.gpus

@@ -303,7 +303,7 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         else if(int rc = dev_alloc(d, d->d_real, size_t(std::max(dd.real_channels, 1u))*kLine)) return rc;
         if(dd.max_slots && dd.wet_channels)
             if(int rc = dev_alloc(d, d->d_wet, size_t(dd.max_slots)*dd.wet_channels*kLine)) return rc;
-        const size_t maxRows = size_t(d->num_sms)*d->mix_blocks_per_sm*var.groups;
+        const size_t maxRows = size_t(d->num_sms)*d->mix_blocks_per_sm;
         d->partial_floats = maxRows*(hrtfDev ? 2*kAccumLen : 0) + maxRows*size_t(var.cdr)*kLine;
         if(int rc = dev_alloc(d, d->d_partial, std::max<size_t>(d->partial_floats, 4))) return rc;
         if(int rc = dev_alloc(d, d->d_accum_sum, 2*kAccumLen)) return rc;
@@ -779,7 +779,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     const uint32_t nv = std::max(d->voice_hi, 1u);
     const uint32_t maxBlocks = uint32_t(d->num_sms*d->mix_blocks_per_sm);
     const uint32_t blocks = std::max(1u, std::min(maxBlocks, (d->num_order + var.groups - 1)/var.groups));
-    const size_t rows = size_t(blocks)*var.groups;
+    const size_t rows = size_t(blocks);        // one partial row per CTA
 
     MixParams P{};
     P.voices = d->d_voices; P.buffers = d->d_buffers;

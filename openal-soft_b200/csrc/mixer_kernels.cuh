@@ -338,7 +338,7 @@ k_mix_voices(const MixParams P)
         //   BSinc      F = fil + sf*scd, D = phd + sf*spd   (mixer_c.cpp:84-105)
         //   FastBSinc  F = fil,          D = phd            (mixer_c.cpp:63-82)
         //   cubic      F = mCoeffs,      D = mDeltas        (mixer_c.cpp:48-61)
-        uint32_t m = 0, tapOff = 0, ms = 6;          // taps, left offset into the window, row stride
+        uint32_t m = 0, tapOff = 0, ms = 5;          // taps, left offset into the window, row stride
         const bool bypass = false;
         (void)bypass;
         if(resampler >= 4u)
@@ -353,7 +353,7 @@ k_mix_voices(const MixParams P)
             // walks the 32 phases (coalesced across threads, 8 loads in flight).
             const uint32_t rowLen = 2u*m;
             const float *tab2 = tab + 64u*m;
-            ms = m + 2u;
+            ms = m + 1u;
             for(uint32_t c = t;c < rowLen;c += GS)
             {
                 float *dstc = (c < m) ? (S.u.rs.tabF + c) : (S.u.rs.tabD + (c - m));
@@ -375,7 +375,7 @@ k_mix_voices(const MixParams P)
         }
         else if(resampler >= 2u)
         {
-            m = 4; tapOff = kEdge - 1; ms = 6;
+            m = 4; tapOff = kEdge - 1; ms = 5;
             const float *tab = P.cubic_tab[resampler-2u];
             for(uint32_t e = t;e < 128u;e += GS)
             {
@@ -463,16 +463,18 @@ k_mix_voices(const MixParams P)
                         const uint32_t pos = uint32_t(fp>>16), frac = uint32_t(fp) & 0xffffu;
                         const uint32_t pi = frac>>11;
                         const float pf = float(frac & 2047u) * (1.0f/2048.0f);
-                        const float2 *F = reinterpret_cast<const float2*>(S.u.rs.tabF + pi*ms);
-                        const float2 *D = reinterpret_cast<const float2*>(S.u.rs.tabD + pi*ms);
+                        // scalar coefficient loads from rows with an ODD stride: every lane reads
+                        // its own phase row without bank conflicts; pairs are packed for FFMA2
+                        const float *F = S.u.rs.tabF + pi*ms;
+                        const float *D = S.u.rs.tabD + pi*ms;
                         const float *sv = vals + pos;
                         const float2 pf2 = make_float2(pf, pf);
                         float2 r0 = make_float2(0.0f, 0.0f), r1 = r0;
                         for(uint32_t j = 0;j < m;j += 4)
                         {
                             // two taps per packed FFMA2: c = F + pf*D ; r += c*s
-                            const float2 c0 = __ffma2_rn(pf2, D[j>>1], F[j>>1]);
-                            const float2 c1 = __ffma2_rn(pf2, D[(j>>1)+1], F[(j>>1)+1]);
+                            const float2 c0 = __ffma2_rn(pf2, make_float2(D[j+0], D[j+1]), make_float2(F[j+0], F[j+1]));
+                            const float2 c1 = __ffma2_rn(pf2, make_float2(D[j+2], D[j+3]), make_float2(F[j+2], F[j+3]));
                             r0 = __ffma2_rn(c0, make_float2(sv[j+0], sv[j+1]), r0);
                             r1 = __ffma2_rn(c1, make_float2(sv[j+2], sv[j+3]), r1);
                         }
@@ -737,30 +739,67 @@ k_mix_voices(const MixParams P)
         group_sync(bar, GS);
     }
 
-    // ---- one partial row per group ----
-    const size_t row = size_t(blockIdx.x)*GROUPS + g;
+    // ---- one partial row per CTA: the groups' register accumulators are summed through
+    //      shared memory in group order (deterministic), halving the rows k_reduce_rows reads
+    const size_t row = blockIdx.x;
+    __syncthreads();                         // every group is done with its voice storage
+    float *stage = reinterpret_cast<float*>(smem_raw);     // >= 2*kAccumLen floats (group 0's area)
     if(HRTF)
     {
-        float *pl = P.partial + row*(2*kAccumLen);
-        float *pr = pl + kAccumLen;
-        #pragma unroll
-        for(int r = 0;r < OPT;++r)
+        for(int gg = 0;gg < GROUPS;++gg)
         {
-            const int o = t0 + r;
-            if(o < kAccumLen) { pl[o] = acc[r].x; pr[o] = acc[r].y; }
+            if(g == gg)
+            {
+                #pragma unroll
+                for(int r = 0;r < OPT;++r)
+                {
+                    const int o = t0 + r;
+                    if(o < kAccumLen)
+                    {
+                        if(gg == 0) { stage[o] = acc[r].x; stage[kAccumLen + o] = acc[r].y; }
+                        else { stage[o] += acc[r].x; stage[kAccumLen + o] += acc[r].y; }
+                    }
+                }
+                if(gg == 0 && GS*OPT < kAccumLen)
+                    for(int o = GS*OPT + t;o < kAccumLen;o += GS) { stage[o] = 0.0f; stage[kAccumLen + o] = 0.0f; }
+            }
+            __syncthreads();
         }
-        if(GS*OPT < kAccumLen)
-            for(int o = GS*OPT + t;o < kAccumLen;o += GS) { pl[o] = 0.0f; pr[o] = 0.0f; }
+        float *pl = P.partial + row*(2*kAccumLen);
+        for(int o = threadIdx.x;o < 2*kAccumLen;o += GS*GROUPS) pl[o] = stage[o];
+        __syncthreads();
     }
     if(CDR > 0)
     {
-        const size_t rows = size_t(gridDim.x)*GROUPS;
+        const size_t rows = gridDim.x;
         float *pd = P.partial + (HRTF ? rows*(2*kAccumLen) : 0) + row*(size_t(CDR)*kLine);
-        #pragma unroll
-        for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
+        if(GROUPS == 1)
+        {
             #pragma unroll
-            for(int r = 0;r < SPT;++r)
-                pd[c*kLine + t + r*GS] = accD[c][r];
+            for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
+                #pragma unroll
+                for(int r = 0;r < SPT;++r)
+                    pd[c*kLine + t + r*GS] = accD[c][r];
+        }
+        else
+        {
+            for(int gg = 0;gg < GROUPS;++gg)
+            {
+                if(g == gg)
+                {
+                    #pragma unroll
+                    for(int c = 0;c < (CDR > 0 ? CDR : 1);++c)
+                        #pragma unroll
+                        for(int r = 0;r < SPT;++r)
+                        {
+                            float *dst = stage + c*kLine + t + r*GS;
+                            if(gg == 0) *dst = accD[c][r]; else *dst += accD[c][r];
+                        }
+                }
+                __syncthreads();
+            }
+            for(int o = threadIdx.x;o < CDR*kLine;o += GS*GROUPS) pd[o] = stage[o];
+        }
     }
 }
 
