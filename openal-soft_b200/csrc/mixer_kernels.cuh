@@ -215,7 +215,7 @@ struct GroupSmem {
     union { ResampleStage rs; FirStage fs; } u;
     float x[kHist + kLine];
     float2 coefT[kHrirLen], coefO[kHrirLen];
-    float newGain[32 + kMaxSends*25];   // Current gains written back after the voice
+    float newGain[32];                  // dry Current gains written back after the voice
 };
 
 // One FIR pass for BOTH ears: acc[r].{x,y} += sum_j c[j].{x,y} * in[FP + t0 + r - j].{x,y}
