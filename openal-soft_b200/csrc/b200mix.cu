@@ -318,7 +318,7 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             d->h_slots.assign(dd.max_slots, SlotRec{});
             d->slot_allocs.assign(dd.max_slots, {});
             if(int rc = dev_alloc(d, d->d_slots, dd.max_slots)) return rc;
-            if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine, false)) return rc;
+            if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
             if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
             d->h_send_slot.assign(size_t(dd.max_voices)*B200MIX_MAX_SENDS, B200MIX_NO_SLOT);
             if(int rc = dev_alloc(d, d->d_slot_start, dd.max_slots + 1)) return rc;
@@ -847,7 +847,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         SM.slot_start = d->d_slot_start; SM.entries = d->d_entries; SM.sendinfo = d->d_sendinfo;
         SM.xscratch = d->d_xscratch; SM.send_cur = d->d_send_cur; SM.send_tgt = d->d_send_tgt;
         SM.wet = d->d_wet; SM.frames = frames; SM.cw = dd.wet_channels; SM.num_sends = dd.num_sends;
-        k_send_mix<<<dim3(dd.max_slots, (frames + 255)/256), 256, 0, d->stream>>>(SM);
+        k_send_mix<<<dim3(dd.max_slots, (frames + 127)/128), 256, 0, d->stream>>>(SM);
         ++d->launches;
         if(d->num_entries)
         {
@@ -869,12 +869,12 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
             ++d->launches;
         }
         k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
-        k_conv_mac<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
+        k_conv_mac<<<dim3(dd.max_slots, maxch), 512, 0, d->stream>>>(CP);
         k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
         SlotMixParams SP{};
         SP.slots = d->d_slots; SP.dry = d->d_dry; SP.frames = frames; SP.cd = dd.dry_channels;
         SP.num_slots = dd.max_slots;
-        k_slot_output_mix<<<dim3((frames + 255)/256, dd.dry_channels), 256, 0, d->stream>>>(SP);
+        k_slot_output_mix<<<dim3((frames + 127)/128, dd.dry_channels), 128, 0, d->stream>>>(SP);
         k_slot_gains_commit<<<dd.max_slots, 64, 0, d->stream>>>(SP);
         d->launches += 5;
         CUDA_TRY(d, cudaGetLastError());
@@ -893,7 +893,7 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         Q.real_left = dd.real_left; Q.real_right = dd.real_right; Q.dry_active = d->dry_active;
         if(d->dry_active)
         {
-            k_post_hrtf_split<<<1, 32, 0, d->stream>>>(Q);
+            k_post_hrtf_split<<<dd.dry_channels, 32, 0, d->stream>>>(Q);
             ++d->launches;
         }
         const uint32_t total = 2u*(frames + kHrirLen);

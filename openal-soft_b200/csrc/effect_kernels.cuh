@@ -55,24 +55,33 @@ struct SendMixParams {
     uint32_t frames, cw, num_sends;
 };
 
-// grid (slot, tile of 256 samples), 256 threads; up to 4 wet channels per pass in registers.
+// grid (slot, tile of 128 samples), 256 threads = 8 warps.  Each warp takes every 8th
+// (voice, send) entry of the slot; a lane owns 4 consecutive samples (one float4 load of the
+// parked line) and up to 4 wet channels.  The 8 warps' partial sums are combined through
+// shared memory in warp order, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
 {
+    __shared__ float part[8][4][128];
     const uint32_t slot = blockIdx.x;
-    const uint32_t i = blockIdx.y*256u + threadIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t i0 = blockIdx.y*128u + lane*4u;
     const uint32_t n = Q.frames;
     const uint32_t e0 = Q.slot_start[slot], e1 = Q.slot_start[slot+1];
     for(uint32_t c0 = 0;c0 < Q.cw;c0 += 4u)
     {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for(uint32_t e = e0;e < e1;++e)
+        float acc[4][4];
+        #pragma unroll
+        for(int c = 0;c < 4;++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f; }
+        for(uint32_t e = e0 + warp;e < e1;e += 8u)
         {
             const SendEntry en = Q.entries[e];
             const uint32_t info = Q.sendinfo[en.voice];
             if(!(info & 1u)) continue;
             const bool playing = (info & 2u) != 0;
             const uint32_t counter = info >> 8;
-            const float x = (i < n) ? Q.xscratch[size_t(en.voice)*kLine + i] : 0.0f;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if(i0 < n) x = *reinterpret_cast<const float4*>(Q.xscratch + size_t(en.voice)*kLine + i0);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
             const float delta = counter ? 1.0f/float(counter) : 0.0f;
             const uint32_t fadeLen = counter < n ? counter : n;
             const size_t gbase = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw;
@@ -80,24 +89,50 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
             for(uint32_t cc = 0;cc < 4u;++cc)
             {
                 const uint32_t c = c0 + cc;
-                if(c >= Q.cw) break;
-                // Mix_ semantics (core/mixer/mixer_c.cpp:150-186)
-                const float tg0 = Q.send_tgt[gbase + c];
-                const float cg = counter ? Q.send_cur[gbase + c] : tg0;
-                const float tg = playing ? tg0 : 0.0f;
-                const float step = (tg - cg)*delta;
-                const bool fade = fabsf(step) > kEps;
-                const bool early = fade && fadeLen < counter;
-                const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
-                const uint32_t start = fade ? fadeLen : 0u;
-                const float g = (fade && i < fadeLen) ? (cg + step*float(i)) : (i >= start ? flat : 0.0f);
-                acc[cc] += x*g;
+                if(c < Q.cw)
+                {
+                    // Mix_ semantics (core/mixer/mixer_c.cpp:150-186)
+                    const float tg0 = Q.send_tgt[gbase + c];
+                    const float cg = counter ? Q.send_cur[gbase + c] : tg0;
+                    const float tg = playing ? tg0 : 0.0f;
+                    const float step = (tg - cg)*delta;
+                    const bool fade = fabsf(step) > kEps;
+                    const bool early = fade && fadeLen < counter;
+                    const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
+                    const uint32_t start = fade ? fadeLen : 0u;
+                    #pragma unroll
+                    for(uint32_t k = 0;k < 4u;++k)
+                    {
+                        const uint32_t i = i0 + k;
+                        const float g = (i >= n) ? 0.0f : ((fade && i < fadeLen) ? (cg + step*float(i))
+                            : (i >= start ? flat : 0.0f));
+                        acc[cc][k] += xs[k]*g;
+                    }
+                }
             }
         }
         #pragma unroll
-        for(uint32_t cc = 0;cc < 4u;++cc)
-            if(c0 + cc < Q.cw && i < n)
-                Q.wet[(size_t(slot)*Q.cw + c0 + cc)*kLine + i] = acc[cc];
+        for(int cc = 0;cc < 4;++cc)
+            #pragma unroll
+            for(int k = 0;k < 4;++k) part[warp][cc][lane*4 + k] = acc[cc][k];
+        __syncthreads();
+        // threads 0..127 own one sample each; sum the 8 warp partials in order
+        if(threadIdx.x < 128u)
+        {
+            const uint32_t i = blockIdx.y*128u + threadIdx.x;
+            #pragma unroll
+            for(uint32_t cc = 0;cc < 4u;++cc)
+            {
+                if(c0 + cc < Q.cw && i < n)
+                {
+                    float sum = part[0][cc][threadIdx.x];
+                    #pragma unroll
+                    for(int wv = 1;wv < 8;++wv) sum += part[wv][cc][threadIdx.x];
+                    Q.wet[(size_t(slot)*Q.cw + c0 + cc)*kLine + i] = sum;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -219,52 +254,100 @@ __global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
     }
 }
 
-// grid (slots, channels), 128 threads (one packed bin each)
-__global__ void __launch_bounds__(128) k_conv_mac(const ConvParams Q)
+// grid (slots, channels), 512 threads = 4 segment ranges x 128 packed bins.  A thread keeps the
+// accumulators of ALL blocks completed this update (<= 9) and walks its range of filter
+// segments once: X[(cur0 - b + s)] is a sliding window over the spectrum ring, so each
+// iteration loads ONE new input spectrum bin and ONE filter bin for up to 9 complex MACs.
+// The loop is unrolled by 9 so the window rotation is a compile-time renaming and the 18
+// loads of a round are issued before their use.  Range partials are combined in order.
+__global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
 {
+    constexpr int NB = kConvMaxBlocks;
+    __shared__ float2 part[3][NB][128];
     const SlotRec &S = Q.slots[blockIdx.x];
     if(S.type != 1u || blockIdx.y >= S.channels) return;
     const uint32_t nb = S.nb_last;
     if(nb == 0) return;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x & 127, grp = threadIdx.x >> 7;
     const uint32_t segs = S.segs, cur0 = S.cur_last, ring = segs + kConvMaxBlocks;
-    const float2 *X = reinterpret_cast<const float2*>(S.X) + t;
-    const float2 *H = reinterpret_cast<const float2*>(S.H + size_t(blockIdx.y)*segs*kConvFft) + t;
-    float2 acc[kConvMaxBlocks];
-    float2 xw[kConvMaxBlocks];          // xw[b] = X[(cur0 - b + s) mod segs]
+    const uint32_t per = (segs + 3u)/4u;
+    const uint32_t s0 = uint32_t(grp)*per, s1 = (s0 + per < segs) ? s0 + per : segs;
+    const float2 *__restrict__ X = reinterpret_cast<const float2*>(S.X) + t;
+    const float2 *__restrict__ H = reinterpret_cast<const float2*>(S.H + size_t(blockIdx.y)*segs*kConvFft) + t;
+    float2 acc[NB], xw[NB];          // xw[s mod NB] holds X[(cur0 + s) mod ring]
     #pragma unroll
-    for(int b = 0;b < kConvMaxBlocks;++b)
+    for(int b = 0;b < NB;++b) acc[b] = make_float2(0.f, 0.f);
+    #pragma unroll
+    for(int u = 0;u < NB;++u) xw[u] = make_float2(0.f, 0.f);
+    if(s0 < s1)
     {
-        acc[b] = make_float2(0.f, 0.f);
-        const uint32_t q = (cur0 + 2u*ring - uint32_t(b) - 1u) % ring;   // value for s = -1
-        xw[b] = (uint32_t(b) < nb) ? X[size_t(q)*128] : make_float2(0.f, 0.f);
-    }
-    for(uint32_t s = 0;s < segs;++s)
-    {
-        // slide: block b at segment s uses what block b-1 used at s-1
-        #pragma unroll
-        for(int b = kConvMaxBlocks-1;b > 0;--b) xw[b] = xw[b-1];
-        xw[0] = X[size_t((cur0 + s) % ring)*128];
-        const float2 h = H[size_t(s)*128];
-        #pragma unroll
-        for(int b = 0;b < kConvMaxBlocks;++b)
+        // history the first segments of the range look back at: X[cur0 + s0 - d], d = 1..NB-1
+        for(int d = 1;d < NB;++d)
         {
-            if(t == 0)
-            {   // packed DC / Nyquist: two independent real products
-                acc[b].x = fmaf(xw[b].x, h.x, acc[b].x);
-                acc[b].y = fmaf(xw[b].y, h.y, acc[b].y);
-            }
-            else
+            const uint32_t q = (cur0 + 2u*ring + s0 - uint32_t(d)) % ring;
+            const int slotIdx = int((s0 + uint32_t(NB)*8u - uint32_t(d)) % uint32_t(NB));
+            const float2 v = X[size_t(q)*128];
+            #pragma unroll
+            for(int u = 0;u < NB;++u) if(u == slotIdx) xw[u] = v;
+        }
+    }
+    // rounds of NB segments aligned to multiples of NB: the window slot (s mod NB) is static
+    const uint32_t r0 = s0 - (s0 % uint32_t(NB));
+    for(uint32_t sb = r0;sb < s1;sb += uint32_t(NB))
+    {
+        float2 xn[NB], hn[NB];
+        #pragma unroll
+        for(int u = 0;u < NB;++u)
+        {
+            const uint32_t s = sb + uint32_t(u);
+            const bool ok = s >= s0 && s < s1;
+            xn[u] = ok ? X[size_t((cur0 + s) % ring)*128] : make_float2(0.f, 0.f);
+            hn[u] = ok ? H[size_t(s)*128] : make_float2(0.f, 0.f);
+        }
+        #pragma unroll
+        for(int u = 0;u < NB;++u)
+        {
+            const uint32_t s = sb + uint32_t(u);
+            if(s >= s0 && s < s1)
             {
-                acc[b].x = fmaf(xw[b].x, h.x, fmaf(-xw[b].y, h.y, acc[b].x));
-                acc[b].y = fmaf(xw[b].x, h.y, fmaf(xw[b].y, h.x, acc[b].y));
+                xw[u] = xn[u];
+                const float2 h = hn[u];
+                #pragma unroll
+                for(int b = 0;b < NB;++b)
+                {
+                    const float2 xv = xw[(u - b + NB) % NB];   // X[cur0 + s - b]
+                    if(t == 0)
+                    {   // packed DC / Nyquist: two independent real products
+                        acc[b].x = fmaf(xv.x, h.x, acc[b].x);
+                        acc[b].y = fmaf(xv.y, h.y, acc[b].y);
+                    }
+                    else
+                    {
+                        acc[b].x = fmaf(xv.x, h.x, fmaf(-xv.y, h.y, acc[b].x));
+                        acc[b].y = fmaf(xv.x, h.y, fmaf(xv.y, h.x, acc[b].y));
+                    }
+                }
             }
         }
     }
-    float2 *Y = reinterpret_cast<float2*>(S.yspec + size_t(blockIdx.y)*kConvMaxBlocks*kConvFft) + t;
-    #pragma unroll
-    for(int b = 0;b < kConvMaxBlocks;++b)
-        if(uint32_t(b) < nb) Y[size_t(b)*128] = acc[b];
+    if(grp > 0)
+    {
+        #pragma unroll
+        for(int b = 0;b < NB;++b) part[grp-1][b][t] = acc[b];
+    }
+    __syncthreads();
+    if(grp == 0)
+    {
+        float2 *Y = reinterpret_cast<float2*>(S.yspec + size_t(blockIdx.y)*kConvMaxBlocks*kConvFft) + t;
+        #pragma unroll
+        for(int b = 0;b < NB;++b)
+        {
+            float2 v = acc[b];
+            #pragma unroll
+            for(int gq = 0;gq < 3;++gq) { v.x += part[gq][b][t].x; v.y += part[gq][b][t].y; }
+            if(uint32_t(b) < nb) Y[size_t(b)*128] = v;
+        }
+    }
 }
 
 // grid (slots, channels), 128 threads
@@ -323,25 +406,50 @@ __global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
 // (ConvolutionState::NormalMix, convolution.cpp:298-304), slots and lines in index order.
 struct SlotMixParams { SlotRec *slots; float *dry; uint32_t frames, cd, num_slots; };
 
-__global__ void __launch_bounds__(256) k_slot_output_mix(const SlotMixParams Q)
+__global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
 {
+    // per-(slot,line) constants are staged once per CTA; the sample loop then only streams
+    // the output lines (coalesced, independent loads)
+    constexpr int kMaxLines = 8;
+    __shared__ float s_cg[64][kMaxLines], s_tg[64][kMaxLines];
+    __shared__ const float *s_line[64];
+    __shared__ uint32_t s_ch[64];
     const uint32_t o = blockIdx.y;
-    const uint32_t i = blockIdx.x*256u + threadIdx.x;
+    const uint32_t i = blockIdx.x*128u + threadIdx.x;
     const uint32_t n = Q.frames;
     float acc = (i < n) ? Q.dry[size_t(o)*kLine + i] : 0.0f;
     const float delta = 1.0f/float(n);
-    for(uint32_t s = 0;s < Q.num_slots;++s)
+    for(uint32_t sb = 0;sb < Q.num_slots;sb += 64u)
     {
-        const SlotRec &S = Q.slots[s];
-        if(S.type == 0u) continue;
-        const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
-        for(uint32_t c = 0;c < S.channels;++c)
+        const uint32_t cnt = (Q.num_slots - sb < 64u) ? Q.num_slots - sb : 64u;
+        __syncthreads();
+        if(threadIdx.x < cnt)
         {
-            const float cg = gcur[c*32u + o], tg = S.gtgt[c*32u + o];
-            const float step = (tg - cg)*delta;
-            const float x = (i < n) ? S.lines[size_t(c)*kLine + i] : 0.0f;
-            if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
-            else if(fabsf(tg) > kSilence) acc += x*tg;
+            const SlotRec &S = Q.slots[sb + threadIdx.x];
+            const uint32_t ch = (S.type == 0u) ? 0u : (S.channels < uint32_t(kMaxLines) ? S.channels : uint32_t(kMaxLines));
+            s_ch[threadIdx.x] = ch;
+            s_line[threadIdx.x] = S.lines;
+            const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
+            for(uint32_t c = 0;c < ch;++c)
+            {
+                s_cg[threadIdx.x][c] = gcur[c*32u + o];
+                s_tg[threadIdx.x][c] = S.gtgt[c*32u + o];
+            }
+        }
+        __syncthreads();
+        for(uint32_t s = 0;s < cnt;++s)
+        {
+            const uint32_t ch = s_ch[s];
+            const float *lines = s_line[s];
+            #pragma unroll 4
+            for(uint32_t c = 0;c < ch;++c)
+            {
+                const float cg = s_cg[s][c], tg = s_tg[s][c];
+                const float step = (tg - cg)*delta;
+                const float x = (i < n) ? lines[size_t(c)*kLine + i] : 0.0f;
+                if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
+                else if(fabsf(tg) > kSilence) acc += x*tg;
+            }
         }
     }
     if(i < n) Q.dry[size_t(o)*kLine + i] = acc;
@@ -397,23 +505,34 @@ __device__ __forceinline__ void scatter4(const float in[4], float x, float y, fl
     out[3] = x*in[3] + y*(-in[0] + -in[1] + -in[2]        );
 }
 
-// BiquadFilter::dualProcess (core/filters/biquad.cpp:254-283), in place, one thread.
+// BiquadFilter::dualProcess (core/filters/biquad.cpp:254-283), in place, one thread; inputs and
+// outputs move in 8-sample register batches so only the z-state is on the dependency chain.
 __device__ __forceinline__ void dual_biquad_serial(const float *c0, const float *c1, float *z0,
     float *z1, float *buf, uint32_t n)
 {
     const float b00 = c0[0], b01 = c0[1], b02 = c0[2], a01 = c0[3], a02 = c0[4];
     const float b10 = c1[0], b11 = c1[1], b12 = c1[2], a11 = c1[3], a12 = c1[4];
     float z01 = z0[0], z02 = z0[1], z11 = z1[0], z12 = z1[1];
-    for(uint32_t i = 0;i < n;++i)
+    for(uint32_t i0 = 0;i0 < n;i0 += 8)
     {
-        const float x0 = buf[i];
-        const float y0 = x0*b00 + z01;
-        z01 = x0*b01 - y0*a01 + z02;
-        z02 = x0*b02 - y0*a02;
-        const float y1 = y0*b10 + z11;
-        z11 = y0*b11 - y1*a11 + z12;
-        z12 = y0*b12 - y1*a12;
-        buf[i] = y1;
+        float x[8], y[8];
+        #pragma unroll
+        for(int k = 0;k < 8;++k) x[k] = (i0 + k < n) ? buf[i0+k] : 0.0f;
+        #pragma unroll
+        for(int k = 0;k < 8;++k)
+        {
+            const float x0 = x[k];
+            const float y0 = x0*b00 + z01;
+            const float n01 = x0*b01 - y0*a01 + z02;
+            const float n02 = x0*b02 - y0*a02;
+            const float y1 = y0*b10 + z11;
+            const float n11 = y0*b11 - y1*a11 + z12;
+            const float n12 = y0*b12 - y1*a12;
+            y[k] = y1;
+            if(i0 + k < n) { z01 = n01; z02 = n02; z11 = n11; z12 = n12; }
+        }
+        #pragma unroll
+        for(int k = 0;k < 8;++k) if(i0 + k < n) buf[i0+k] = y[k];
     }
     z0[0] = z01; z0[1] = z02; z1[0] = z11; z1[1] = z12;
 }

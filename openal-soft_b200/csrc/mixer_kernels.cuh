@@ -457,29 +457,38 @@ k_mix_voices(const MixParams P)
                 else if(resampler >= 2u)
                 {
                     const float *vals = S.u.rs.win + tapOff;
-                    for(uint32_t k = t;k < dstn;k += GS)
+                    // two outputs per thread per pass (k and k+GS): twice the independent
+                    // FFMA2 chains and loads in flight per warp
+                    for(uint32_t k = t;k < dstn;k += 2u*GS)
                     {
-                        const uint64_t fp = uint64_t(k)*increment + fracPos;
-                        const uint32_t pos = uint32_t(fp>>16), frac = uint32_t(fp) & 0xffffu;
-                        const uint32_t pi = frac>>11;
-                        const float pf = float(frac & 2047u) * (1.0f/2048.0f);
+                        const uint32_t kB = k + GS;
+                        const bool hasB = kB < dstn;
+                        const uint64_t fpA = uint64_t(k)*increment + fracPos;
+                        const uint64_t fpB = uint64_t(hasB ? kB : k)*increment + fracPos;
+                        const uint32_t fracA = uint32_t(fpA) & 0xffffu, fracB = uint32_t(fpB) & 0xffffu;
+                        const float pfA = float(fracA & 2047u) * (1.0f/2048.0f);
+                        const float pfB = float(fracB & 2047u) * (1.0f/2048.0f);
                         // scalar coefficient loads from rows with an ODD stride: every lane reads
                         // its own phase row without bank conflicts; pairs are packed for FFMA2
-                        const float *F = S.u.rs.tabF + pi*ms;
-                        const float *D = S.u.rs.tabD + pi*ms;
-                        const float *sv = vals + pos;
-                        const float2 pf2 = make_float2(pf, pf);
-                        float2 r0 = make_float2(0.0f, 0.0f), r1 = r0;
+                        const float *FA = S.u.rs.tabF + (fracA>>11)*ms, *DA = S.u.rs.tabD + (fracA>>11)*ms;
+                        const float *FB = S.u.rs.tabF + (fracB>>11)*ms, *DB = S.u.rs.tabD + (fracB>>11)*ms;
+                        const float *svA = vals + uint32_t(fpA>>16), *svB = vals + uint32_t(fpB>>16);
+                        const float2 pA = make_float2(pfA, pfA), pB = make_float2(pfB, pfB);
+                        float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, b0 = a0, b1 = a0;
                         for(uint32_t j = 0;j < m;j += 4)
                         {
                             // two taps per packed FFMA2: c = F + pf*D ; r += c*s
-                            const float2 c0 = __ffma2_rn(pf2, make_float2(D[j+0], D[j+1]), make_float2(F[j+0], F[j+1]));
-                            const float2 c1 = __ffma2_rn(pf2, make_float2(D[j+2], D[j+3]), make_float2(F[j+2], F[j+3]));
-                            r0 = __ffma2_rn(c0, make_float2(sv[j+0], sv[j+1]), r0);
-                            r1 = __ffma2_rn(c1, make_float2(sv[j+2], sv[j+3]), r1);
+                            const float2 cA0 = __ffma2_rn(pA, make_float2(DA[j+0], DA[j+1]), make_float2(FA[j+0], FA[j+1]));
+                            const float2 cB0 = __ffma2_rn(pB, make_float2(DB[j+0], DB[j+1]), make_float2(FB[j+0], FB[j+1]));
+                            const float2 cA1 = __ffma2_rn(pA, make_float2(DA[j+2], DA[j+3]), make_float2(FA[j+2], FA[j+3]));
+                            const float2 cB1 = __ffma2_rn(pB, make_float2(DB[j+2], DB[j+3]), make_float2(FB[j+2], FB[j+3]));
+                            a0 = __ffma2_rn(cA0, make_float2(svA[j+0], svA[j+1]), a0);
+                            b0 = __ffma2_rn(cB0, make_float2(svB[j+0], svB[j+1]), b0);
+                            a1 = __ffma2_rn(cA1, make_float2(svA[j+2], svA[j+3]), a1);
+                            b1 = __ffma2_rn(cB1, make_float2(svB[j+2], svB[j+3]), b1);
                         }
-                        const float r = (r0.x + r1.x) + (r0.y + r1.y);
-                        xs[loaded+k] = r;
+                        xs[loaded+k] = (a0.x + a1.x) + (a0.y + a1.y);
+                        if(hasB) xs[loaded+kB] = (b0.x + b1.x) + (b0.y + b1.y);
                     }
                 }
                 else
@@ -954,32 +963,52 @@ struct PostHrtfParams {
 };
 
 // Stage 1 (only when the dry mix is non-silent): BandSplitter::processHfScale per dry
-// channel (core/filters/splitter.cpp:64-95) — a serial recurrence, one thread each.
-__global__ void k_post_hrtf_split(const PostHrtfParams Q)
+// channel (core/filters/splitter.cpp:64-95) — a serial recurrence.  One warp per channel:
+// the lanes stage the line through shared memory (coalesced), lane 0 runs the recurrence
+// with 8-sample register batches so the loads/stores stay off the dependency chain.
+__global__ void __launch_bounds__(32) k_post_hrtf_split(const PostHrtfParams Q)
 {
-    const uint32_t c = blockIdx.x*blockDim.x + threadIdx.x;
+    __shared__ float line[kLine];
+    const uint32_t c = blockIdx.x;
     if(c >= Q.cd) return;
-    float *st = Q.dec_state + c*4;
-    const float ap_coeff = st[0];
-    const float lp_coeff = st[0]*0.5f + 0.5f;
-    float lp_z1 = st[1], lp_z2 = st[2], ap_z1 = st[3];
-    const float hfscale = Q.dec_hfscale[c];
+    const uint32_t lane = threadIdx.x, n = Q.frames;
     const float *in = Q.dry + size_t(c)*kLine;
     float *out = Q.temp + size_t(c)*kLine;
-    for(uint32_t i = 0;i < Q.frames;++i)
+    for(uint32_t i = lane;i < kLine;i += 32) line[i] = (i < n) ? in[i] : 0.0f;
+    __syncwarp();
+    if(lane == 0)
     {
-        const float x = in[i];
-        const float d0 = (x - lp_z1) * lp_coeff;
-        const float lp_y0 = lp_z1 + d0;
-        lp_z1 = lp_y0 + d0*lp_coeff;
-        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
-        const float lp_y1 = lp_z2 + d1;
-        lp_z2 = lp_y1 + d1;
-        const float ap_y = x*ap_coeff + ap_z1;
-        ap_z1 = x - ap_y*ap_coeff;
-        out[i] = (ap_y-lp_y1)*hfscale + lp_y1;
+        float *st = Q.dec_state + c*4;
+        const float ap_coeff = st[0];
+        const float lp_coeff = st[0]*0.5f + 0.5f;
+        float lp_z1 = st[1], lp_z2 = st[2], ap_z1 = st[3];
+        const float hfscale = Q.dec_hfscale[c];
+        for(uint32_t i0 = 0;i0 < n;i0 += 8)
+        {
+            float x[8], y[8];
+            #pragma unroll
+            for(int k = 0;k < 8;++k) x[k] = line[i0+k];
+            #pragma unroll
+            for(int k = 0;k < 8;++k)
+            {
+                const float d0 = (x[k] - lp_z1) * lp_coeff;
+                const float lp_y0 = lp_z1 + d0;
+                const float nz1 = lp_y0 + d0*lp_coeff;
+                const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+                const float lp_y1 = lp_z2 + d1;
+                const float nz2 = lp_y1 + d1;
+                const float ap_y = x[k]*ap_coeff + ap_z1;
+                const float naz = x[k] - ap_y*ap_coeff;
+                y[k] = (ap_y-lp_y1)*hfscale + lp_y1;
+                if(i0 + k < n) { lp_z1 = nz1; lp_z2 = nz2; ap_z1 = naz; }
+            }
+            #pragma unroll
+            for(int k = 0;k < 8;++k) line[i0+k] = y[k];
+        }
+        st[1] = lp_z1; st[2] = lp_z2; st[3] = ap_z1;
     }
-    st[1] = lp_z1; st[2] = lp_z2; st[3] = ap_z1;
+    __syncwarp();
+    for(uint32_t i = lane;i < n;i += 32) out[i] = line[i];
 }
 
 // Stage 2: total[t] = carry[t] + voices[t] + decoder FIR of the dry channels;
