@@ -203,6 +203,36 @@ B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
     const b200mix_voice_params *params, const float *hrtf_coeffs, const float *dry_gains,
     const float *send_gains);
 
+/* Direct and send filters: DoFilters -> BiquadInterpFilter::dualProcess
+ * (core/voice.cpp:255-268, core/filters/biquad.cpp:254-343).  One entry is the RESULT of
+ * the parameter stage's filter block for one path of one voice (alc/alu.cpp:1619-1656):
+ * FilterActive plus the two mTargetCoeffs {b0,b1,b2,a1,a2} that
+ * lowpass.setParamsFromSlope(HighShelf, hfNorm, gainHF, 1) and
+ * highpass.setParamsFromSlope(LowShelf, lfNorm, gainLF, 1) produced.  The library keeps
+ * the filter state (z1/z2, current coefficients, mCounter) on the device and applies
+ * BiquadInterpFilter::setParams' rule itself: a target that moved by more than 1/64 in
+ * any coefficient starts the 8x32-sample interpolation, otherwise Current snaps to Target
+ * once the counter has run out.  Forward every setParams call of the reference (once per
+ * CalcVoiceParams of that voice); a voice that never had a filter set costs nothing.
+ * B200MIX_VF_RESET returns every path of the voice to BiquadInterpFilter's initial state. */
+typedef struct b200mix_voice_filter {
+    uint32_t voice;
+    uint32_t path;            /* 0 = direct (mDryParams), 1+s = send s (mWetParams[s]) */
+    uint32_t active;          /* mDirect.FilterActive / mSend[s].FilterActive */
+    float    lowpass[5];      /* LowPass.mTargetCoeffs  (high-shelf) */
+    float    highpass[5];     /* HighPass.mTargetCoeffs (low-shelf) */
+} b200mix_voice_filter;
+
+B200MIX_API int b200mix_voices_filters(b200mix_device *dev, uint32_t n,
+    const b200mix_voice_filter *filters);
+
+/* Host helper, no GPU: BiquadFilter::SetParams via setParamsFromSlope
+ * (core/filters/biquad.h:92-97, biquad.cpp:48-129).  type follows enum BiquadType:
+ * 0 HighShelf, 1 LowShelf, 2 Peaking, 3 LowPass, 4 HighPass, 5 BandPass.
+ * coeffs receives {b0,b1,b2,a1,a2} with a0 pre-applied. */
+B200MIX_API int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope,
+    float coeffs[5]);
+
 typedef struct b200mix_voice_result {
     int32_t  position;        /* new mPosition */
     uint32_t position_frac;   /* new mPositionFrac */

@@ -89,6 +89,20 @@ struct b200mix_device {
     uint32_t active_slots{0};
     float *d_xscratch{nullptr};
     uint32_t *d_sendinfo{nullptr};
+    // direct/send filters (allocated by the first b200mix_voices_filters)
+    FilterRec *d_filt{nullptr};
+    FilterUpdate *h_fupd{nullptr}, *d_fupd{nullptr};
+    uint32_t fupd_cap{0};
+    cudaEvent_t fstage_done{nullptr};
+    bool fstage_busy{false};
+    float *d_fscratch{nullptr};
+    uint32_t fscratch_rows{0};
+    float *d_dline{nullptr};                 // [max_voices][1024] filtered direct-path lines
+    std::vector<uint8_t> h_dfilt;            // host mirror: direct filter active per voice
+    std::vector<uint32_t> h_order2;          // active voices with an active direct filter
+    uint32_t *d_order2{nullptr};
+    uint32_t num_order2{0};
+    bool order2_dirty{false};
     std::vector<uint32_t> h_send_slot;       // [max_voices][MAX_SENDS] host mirror
     std::vector<uint32_t> h_slot_start;
     std::vector<SendEntry> h_entries;
@@ -305,7 +319,8 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             if(int rc = dev_alloc(d, d->d_wet, size_t(dd.max_slots)*dd.wet_channels*kLine)) return rc;
         const size_t maxRows = size_t(d->num_sms)*d->mix_blocks_per_sm;
         d->partial_floats = maxRows*(hrtfDev ? 2*kAccumLen : 0) + maxRows*size_t(var.cdr)*kLine;
-        if(int rc = dev_alloc(d, d->d_partial, std::max<size_t>(d->partial_floats, 4))) return rc;
+        // two regions: the main pass and the deferred pass of voices with direct filters
+        if(int rc = dev_alloc(d, d->d_partial, std::max<size_t>(2*d->partial_floats, 4))) return rc;
         if(int rc = dev_alloc(d, d->d_accum_sum, 2*kAccumLen)) return rc;
         if(int rc = dev_alloc(d, d->d_carry[0], 2*kHrirLen)) return rc;
         if(int rc = dev_alloc(d, d->d_carry[1], 2*kHrirLen)) return rc;
@@ -375,6 +390,10 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
+    cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
+    cudaFree(d->d_dline); cudaFree(d->d_order2);
+    if(d->h_fupd) cudaFreeHost(d->h_fupd);
+    if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
     cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
     cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
@@ -703,6 +722,8 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
             d->h_active[p.voice] = act; d->h_cost[p.voice] = cost;
         }
         d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
+        if((p.flags & B200MIX_VF_RESET) && !d->h_dfilt.empty() && d->h_dfilt[p.voice])
+        { d->h_dfilt[p.voice] = 0; d->order2_dirty = true; }
     }
     CUDA_TRY(d, cudaMemcpyAsync(d->d_upd, d->h_upd, n*sizeof(VoiceUpdate), cudaMemcpyHostToDevice, d->stream));
     ApplyParams A{};
@@ -733,11 +754,116 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
     A.send_cur = d->d_send_cur; A.send_tgt = d->d_send_tgt;
     A.ir = dd.ir_size; A.ir_pad = d->ir_pad; A.cd = dd.dry_channels; A.cw = dd.wet_channels;
     A.num_sends = dd.num_sends;
+    A.filt = d->d_filt; A.filt_paths = 1u + dd.num_sends;
     k_apply_updates<<<n, 64, 0, d->stream>>>(A);
     ++d->launches;
     CUDA_TRY(d, cudaGetLastError());
     CUDA_TRY(d, cudaEventRecord(d->stage_done, d->stream));
     d->stage_busy = true;
+    return B200MIX_OK;
+}
+
+int b200mix_voices_filters(b200mix_device *d, uint32_t n, const b200mix_voice_filter *filters)
+{
+    static_assert(sizeof(FilterUpdate) == sizeof(b200mix_voice_filter), "FilterUpdate mirrors the ABI struct");
+    if(!d) return B200MIX_ERR_INVALID;
+    if(n == 0) return B200MIX_OK;
+    if(!filters) { d->error = "voices_filters: null filters"; return B200MIX_ERR_INVALID; }
+    const b200mix_device_desc &dd = d->desc;
+    const uint32_t paths = 1u + dd.num_sends;
+    for(uint32_t i = 0;i < n;++i)
+        if(filters[i].voice >= dd.max_voices || filters[i].path >= paths)
+        { d->error = "voices_filters: voice/path out of range"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    if(!d->d_filt)
+    {
+        const size_t count = size_t(dd.max_voices)*paths;
+        if(int rc = dev_alloc(d, d->d_filt, count, false)) return rc;
+        k_filter_init<<<unsigned((count*32u + 255u)/256u), 256, 0, d->stream>>>(d->d_filt, count);
+        ++d->launches;
+        CUDA_TRY(d, cudaGetLastError());
+        CUDA_TRY(d, cudaEventCreateWithFlags(&d->fstage_done, cudaEventDisableTiming));
+        if(!d->d_xscratch)
+            if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
+        if(!d->d_sendinfo)
+            if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
+        if(int rc = dev_alloc(d, d->d_dline, size_t(dd.max_voices)*kLine)) return rc;
+        if(int rc = dev_alloc(d, d->d_order2, dd.max_voices)) return rc;
+        d->h_dfilt.assign(dd.max_voices, 0);
+    }
+    for(uint32_t i = 0;i < n;++i)
+        if(filters[i].path == 0)
+        {
+            const uint8_t act = filters[i].active ? 1 : 0;
+            if(d->h_dfilt[filters[i].voice] != act) { d->h_dfilt[filters[i].voice] = act; d->order2_dirty = true; }
+        }
+    if(d->fstage_busy)
+    {
+        CUDA_TRY(d, cudaEventSynchronize(d->fstage_done));
+        d->fstage_busy = false;
+    }
+    if(n > d->fupd_cap)
+    {
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        if(d->h_fupd) cudaFreeHost(d->h_fupd);
+        cudaFree(d->d_fupd);
+        d->h_fupd = nullptr; d->d_fupd = nullptr;
+        const uint32_t cap = std::max(n, 2u*d->fupd_cap);
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_fupd), size_t(cap)*sizeof(FilterUpdate)));
+        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_fupd), size_t(cap)*sizeof(FilterUpdate)));
+        d->fupd_cap = cap;
+    }
+    std::memcpy(d->h_fupd, filters, size_t(n)*sizeof(FilterUpdate));
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_fupd, d->h_fupd, size_t(n)*sizeof(FilterUpdate),
+        cudaMemcpyHostToDevice, d->stream));
+    k_apply_filter_updates<<<(2u*n + 127u)/128u, 128, 0, d->stream>>>(d->d_filt, paths, d->d_fupd, n);
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
+    CUDA_TRY(d, cudaEventRecord(d->fstage_done, d->stream));
+    d->fstage_busy = true;
+    return B200MIX_OK;
+}
+
+// BiquadFilter::SetParams behind setParamsFromSlope (core/filters/biquad.h:61-62,92-97;
+// biquad.cpp:48-129).  Host arithmetic only.
+int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5])
+{
+    if(type > 5u || !coeffs || !(slope > 0.0f)) return B200MIX_ERR_INVALID;
+    gain = std::max(gain, 0.001f);
+    const float rcpQ = std::sqrt((gain + 1.0f/gain)*(1.0f/slope - 1.0f) + 2.0f);
+    gain = std::max(gain, 0.00001f);
+    const float w0 = 3.14159265358979323846f*2.0f * std::min(f0norm, 0.49f);
+    const float sin_w0 = std::sin(w0), cos_w0 = std::cos(w0);
+    const float alpha = sin_w0/2.0f * rcpQ;
+    float a[3] = {1.0f, 0.0f, 0.0f}, b[3] = {1.0f, 0.0f, 0.0f};
+    const float gp = gain + 1.0f, gm = gain - 1.0f;
+    if(type <= 1u)
+    {
+        // shelves: the low shelf is the high shelf with cos(w0) negated
+        const float sg = 2.0f * std::sqrt(gain) * alpha;
+        const float sgn = type == 0u ? 1.0f : -1.0f;
+        const float cw = sgn*cos_w0;
+        b[0] =            gain*(gp + gm*cw + sg);
+        b[1] = sgn*-2.0f*gain*(gm + gp*cw);
+        b[2] =            gain*(gp + gm*cw - sg);
+        a[0] =                  gp - gm*cw + sg;
+        a[1] = sgn*2.0f*       (gm - gp*cw);
+        a[2] =                  gp - gm*cw - sg;
+    }
+    else if(type == 2u)
+    {
+        b[0] = 1.0f + alpha*gain; b[1] = -2.0f*cos_w0; b[2] = 1.0f - alpha*gain;
+        a[0] = 1.0f + alpha/gain; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha/gain;
+    }
+    else
+    {
+        a[0] = 1.0f + alpha; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha;
+        if(type == 3u) { b[0] = (1.0f - cos_w0)/2.0f; b[1] = 1.0f - cos_w0; b[2] = b[0]; }
+        else if(type == 4u) { b[0] = (1.0f + cos_w0)/2.0f; b[1] = -(1.0f + cos_w0); b[2] = b[0]; }
+        else { b[0] = alpha; b[1] = 0.0f; b[2] = -alpha; }
+    }
+    coeffs[0] = b[0]/a[0]; coeffs[1] = b[1]/a[0]; coeffs[2] = b[2]/a[0];
+    coeffs[3] = a[1]/a[0]; coeffs[4] = a[2]/a[0];
     return B200MIX_OK;
 }
 
@@ -774,6 +900,20 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
             CUDA_TRY(d, cudaStreamSynchronize(d->stream));
         }
         d->order_dirty = false;
+        d->order2_dirty = true;
+    }
+    if(d->d_filt && d->order2_dirty)
+    {
+        d->h_order2.clear();
+        for(uint32_t v : d->h_order) if(d->h_dfilt[v]) d->h_order2.push_back(v);
+        d->num_order2 = uint32_t(d->h_order2.size());
+        if(d->num_order2)
+        {
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_order2, d->h_order2.data(), d->num_order2*sizeof(uint32_t),
+                cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        }
+        d->order2_dirty = false;
     }
     const Variant var = get_variant(d->mix_variant);
     const uint32_t nv = std::max(d->voice_hi, 1u);
@@ -795,11 +935,34 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     P.max_buffers = dd.max_buffers;
     P.order = d->d_order; P.num_order = d->num_order;
     P.xscratch = d->d_xscratch; P.sendinfo = d->d_sendinfo;
+    P.filt = d->d_filt; P.filt_paths = 1u + dd.num_sends;
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
     if(d->profile) { cudaEventRecord(d->ev_mix1, d->stream); d->ev_valid = true; }
     ++d->launches;
     CUDA_TRY(d, cudaGetLastError());
+
+    // ---- voices with an active direct filter: filter the parked lines, then mix them ----
+    size_t rows2 = 0;
+    if(d->d_filt && d->num_order2)
+    {
+        FilterRunParams FP{};
+        FP.filt = d->d_filt; FP.filt_paths = 1u + dd.num_sends; FP.sendinfo = d->d_sendinfo;
+        FP.direct_order = d->d_order2; FP.num_direct = d->num_order2;
+        FP.xscratch = d->d_xscratch; FP.dline = d->d_dline; FP.frames = frames;
+        k_filters<<<(d->num_order2 + 31u)/32u, 32, 0, d->stream>>>(FP);
+        ++d->launches;
+        const uint32_t blocks2 = std::max(1u, std::min(maxBlocks, (d->num_order2 + var.groups - 1)/var.groups));
+        rows2 = blocks2;
+        MixParams P2 = P;
+        P2.pass = 1u; P2.dline = d->d_dline;
+        P2.order = d->d_order2; P2.num_order = d->num_order2;
+        P2.partial = d->d_partial + d->partial_floats;
+        P2.results = nullptr;
+        var.fn<<<blocks2, var.gs*var.groups, var.smem, d->stream>>>(P2);
+        ++d->launches;
+        CUDA_TRY(d, cudaGetLastError());
+    }
 
     if(var.hrtf)
     {
@@ -807,6 +970,12 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
             d->d_accum_sum, 0);
         ++d->launches;
+        if(rows2)
+        {
+            k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(d->d_partial + d->partial_floats,
+                uint32_t(rows2), len, d->d_accum_sum, 1);
+            ++d->launches;
+        }
     }
     if(var.cdr > 0)
     {
@@ -814,6 +983,12 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         const float *pd = d->d_partial + (var.hrtf ? rows*(2*kAccumLen) : 0);
         k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
         ++d->launches;
+        if(rows2)
+        {
+            const float *pd2 = d->d_partial + d->partial_floats + (var.hrtf ? rows2*(2*kAccumLen) : 0);
+            k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(pd2, uint32_t(rows2), len, d->d_dry, 1);
+            ++d->launches;
+        }
     }
     CUDA_TRY(d, cudaGetLastError());
 
@@ -847,6 +1022,25 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
         SM.slot_start = d->d_slot_start; SM.entries = d->d_entries; SM.sendinfo = d->d_sendinfo;
         SM.xscratch = d->d_xscratch; SM.send_cur = d->d_send_cur; SM.send_tgt = d->d_send_tgt;
         SM.wet = d->d_wet; SM.frames = frames; SM.cw = dd.wet_channels; SM.num_sends = dd.num_sends;
+        if(d->d_filt && d->num_entries)
+        {
+            if(d->fscratch_rows < d->num_entries)
+            {
+                CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+                cudaFree(d->d_fscratch); d->d_fscratch = nullptr; d->fscratch_rows = 0;
+                const uint32_t rows = std::max(d->num_entries, 64u);
+                CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_fscratch), size_t(rows)*kLine*sizeof(float)));
+                CUDA_TRY(d, cudaMemsetAsync(d->d_fscratch, 0, size_t(rows)*kLine*sizeof(float), d->stream));
+                d->fscratch_rows = rows;
+            }
+            SM.filt = d->d_filt; SM.filt_paths = 1u + dd.num_sends; SM.fscratch = d->d_fscratch;
+            FilterRunParams FP{};
+            FP.filt = d->d_filt; FP.filt_paths = 1u + dd.num_sends; FP.sendinfo = d->d_sendinfo;
+            FP.entries = d->d_entries; FP.num_entries = d->num_entries;
+            FP.xscratch = d->d_xscratch; FP.fscratch = d->d_fscratch; FP.frames = frames;
+            k_filters<<<(d->num_entries + 31u)/32u, 32, 0, d->stream>>>(FP);
+            ++d->launches;
+        }
         k_send_mix<<<dim3(dd.max_slots, (frames + 127)/128), 256, 0, d->stream>>>(SM);
         ++d->launches;
         if(d->num_entries)

@@ -53,7 +53,181 @@ struct SendMixParams {
     float *send_cur; const float *send_tgt;   // [max_voices][num_sends][cw]
     float *wet;                     // [slots][cw][1024]
     uint32_t frames, cw, num_sends;
+    FilterRec *filt; uint32_t filt_paths;   // send filters (null: none ever set)
+    const float *fscratch;          // [entries][1024] filtered lines of entries with an active filter
 };
+
+// ---- direct and send filters ------------------------------------------------------------
+// DoFilters -> BiquadInterpFilter::dualProcess (core/voice.cpp:255-268,
+// core/filters/biquad.cpp:254-343).  The two cascaded transposed-direct-form-II biquads are a
+// serial recurrence per line, and with the EFX shelves (poles close to z = 1) its fp32
+// rounding noise is amplified ~1000x: any re-association (scan, FMA contraction) moves the
+// result by 1e-5 relative.  So the recurrence is evaluated exactly as the reference does —
+// one thread per line, same operation order, explicit round-to-nearest mul/add/sub so the
+// compiler cannot contract to FMA — and the parallelism comes from the lines: a warp takes
+// 32 (voice, path) items, stages 32x32-sample tiles through shared memory (coalesced
+// loads/stores, conflict-free column walks) and prefetches the next tile into registers.
+// Items: [0, num_direct) = voices of `direct_order` (parked line xscratch[v] -> dline[v]),
+//        [num_direct, num_direct + num_entries) = send entries (xscratch[v] -> fscratch[e]).
+struct FilterRunParams {
+    FilterRec *filt; uint32_t filt_paths;
+    const uint32_t *sendinfo;
+    const uint32_t *direct_order; uint32_t num_direct;
+    const SendEntry *entries; uint32_t num_entries;
+    const float *xscratch; float *dline; float *fscratch;
+    uint32_t frames;
+};
+
+struct BiquadCoefs { float b0, b1, b2, a1, a2; };
+
+__device__ __forceinline__ float lerp_rn(float a, float b, float mu)     // lerpf, alnumeric.h:115
+{ return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), mu)); }
+
+__global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
+{
+    __shared__ float tile[32][33];
+    __shared__ const float *inp[32];
+    __shared__ float *outp[32];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t item = blockIdx.x*32u + lane;
+    const uint32_t n = Q.frames;
+
+    FilterRec *fr = nullptr;
+    const float *in = nullptr; float *out = nullptr;
+    if(item < Q.num_direct)
+    {
+        const uint32_t v = Q.direct_order[item];
+        if(Q.sendinfo[v] & kSiDeferred)
+        { fr = Q.filt + size_t(v)*Q.filt_paths; in = Q.xscratch + size_t(v)*kLine; out = Q.dline + size_t(v)*kLine; }
+    }
+    else if(item - Q.num_direct < Q.num_entries)
+    {
+        const uint32_t e = item - Q.num_direct;
+        const SendEntry en = Q.entries[e];
+        if(Q.sendinfo[en.voice] & kSiSend)
+        {
+            fr = Q.filt + size_t(en.voice)*Q.filt_paths + 1u + en.send;
+            in = Q.xscratch + size_t(en.voice)*kLine; out = Q.fscratch + size_t(e)*kLine;
+        }
+    }
+    bool run = false;
+    if(fr)
+    {
+        run = fr->active != 0u;
+        if(!run)
+        {
+            // lpfilter.clear(); hpfilter.clear() (core/voice.cpp:265-266)
+            #pragma unroll
+            for(int f = 0;f < 2;++f)
+            {
+                #pragma unroll
+                for(int k = 0;k < 5;++k) fr->cur[f][k] = fr->tgt[f][k];
+                fr->z[f][0] = 0.0f; fr->z[f][1] = 0.0f; fr->counter[f] = 0;
+            }
+        }
+    }
+    inp[lane] = run ? in : nullptr;
+    outp[lane] = run ? out : nullptr;
+    if(!__any_sync(0xffffffffu, run)) return;
+
+    BiquadCoefs c0{1.f,0.f,0.f,0.f,0.f}, c1 = c0, t0 = c0, t1 = c0;
+    float z01 = 0.f, z02 = 0.f, z11 = 0.f, z12 = 0.f;
+    int counter = 0;              // remaining interpolation steps
+    uint32_t steprem = 0xffffffffu;   // samples until the next coefficient step
+    int maxc = 0;
+    if(run)
+    {
+        c0 = BiquadCoefs{fr->cur[0][0], fr->cur[0][1], fr->cur[0][2], fr->cur[0][3], fr->cur[0][4]};
+        c1 = BiquadCoefs{fr->cur[1][0], fr->cur[1][1], fr->cur[1][2], fr->cur[1][3], fr->cur[1][4]};
+        t0 = BiquadCoefs{fr->tgt[0][0], fr->tgt[0][1], fr->tgt[0][2], fr->tgt[0][3], fr->tgt[0][4]};
+        t1 = BiquadCoefs{fr->tgt[1][0], fr->tgt[1][1], fr->tgt[1][2], fr->tgt[1][3], fr->tgt[1][4]};
+        z01 = fr->z[0][0]; z02 = fr->z[0][1]; z11 = fr->z[1][0]; z12 = fr->z[1][1];
+        maxc = max(fr->counter[0], fr->counter[1]);
+        if(maxc > 0) { counter = maxc >> 5; steprem = 32u - uint32_t(maxc & 31); }
+    }
+    __syncwarp();
+
+    const uint32_t tiles = (n + 31u) >> 5;
+    float nx[32];
+    // prefetch tile 0: row r = item r's 32 consecutive samples, one coalesced load per row
+    #pragma unroll
+    for(int r = 0;r < 32;++r)
+    {
+        const float *p = inp[r];
+        nx[r] = (p && lane < n) ? __ldg(p + lane) : 0.0f;
+    }
+    for(uint32_t tb = 0;tb < tiles;++tb)
+    {
+        #pragma unroll
+        for(int r = 0;r < 32;++r) tile[r][lane] = nx[r];
+        __syncwarp();
+        if(tb + 1u < tiles)
+        {
+            const uint32_t s = (tb + 1u)*32u + lane;
+            #pragma unroll
+            for(int r = 0;r < 32;++r)
+            {
+                const float *p = inp[r];
+                nx[r] = (p && s < n) ? __ldg(p + s) : 0.0f;
+            }
+        }
+        if(run)
+        {
+            const uint32_t cnt = min(32u, n - tb*32u);
+            for(uint32_t i = 0;i < cnt;++i)
+            {
+                // BiquadFilter::dualProcess body (biquad.cpp:264-275)
+                const float x0 = tile[lane][i];
+                const float y0 = __fadd_rn(__fmul_rn(x0, c0.b0), z01);
+                z01 = __fadd_rn(__fsub_rn(__fmul_rn(x0, c0.b1), __fmul_rn(y0, c0.a1)), z02);
+                z02 = __fsub_rn(__fmul_rn(x0, c0.b2), __fmul_rn(y0, c0.a2));
+                const float y1 = __fadd_rn(__fmul_rn(y0, c1.b0), z11);
+                z11 = __fadd_rn(__fsub_rn(__fmul_rn(y0, c1.b1), __fmul_rn(y1, c1.a1)), z12);
+                z12 = __fsub_rn(__fmul_rn(y0, c1.b2), __fmul_rn(y1, c1.a2));
+                tile[lane][i] = y1;
+                // BiquadInterpFilter::dualProcess stepping (biquad.cpp:293-338)
+                if(counter > 0 && --steprem == 0u)
+                {
+                    steprem = 32u;
+                    if(--counter == 0) { c0 = t0; c1 = t1; }
+                    else
+                    {
+                        const float a = __fdiv_rn(1.0f, float(counter + 1));
+                        c0.b0 = lerp_rn(c0.b0, t0.b0, a); c0.b1 = lerp_rn(c0.b1, t0.b1, a);
+                        c0.b2 = lerp_rn(c0.b2, t0.b2, a); c0.a1 = lerp_rn(c0.a1, t0.a1, a);
+                        c0.a2 = lerp_rn(c0.a2, t0.a2, a);
+                        c1.b0 = lerp_rn(c1.b0, t1.b0, a); c1.b1 = lerp_rn(c1.b1, t1.b1, a);
+                        c1.b2 = lerp_rn(c1.b2, t1.b2, a); c1.a1 = lerp_rn(c1.a1, t1.a1, a);
+                        c1.a2 = lerp_rn(c1.a2, t1.a2, a);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        {
+            const uint32_t s = tb*32u + lane;
+            #pragma unroll
+            for(int r = 0;r < 32;++r)
+            {
+                float *p = outp[r];
+                if(p && s < n) p[s] = tile[r][lane];
+            }
+        }
+        __syncwarp();
+    }
+    if(run)
+    {
+        fr->z[0][0] = z01; fr->z[0][1] = z02; fr->z[1][0] = z11; fr->z[1][1] = z12;
+        if(maxc > 0)
+        {
+            fr->cur[0][0] = c0.b0; fr->cur[0][1] = c0.b1; fr->cur[0][2] = c0.b2; fr->cur[0][3] = c0.a1; fr->cur[0][4] = c0.a2;
+            fr->cur[1][0] = c1.b0; fr->cur[1][1] = c1.b1; fr->cur[1][2] = c1.b2; fr->cur[1][3] = c1.a1; fr->cur[1][4] = c1.a2;
+            // mCounter = (counter*SamplesPerStep) | samples already done in the current step
+            const int nc = counter > 0 ? ((counter << 5) | int(32u - steprem)) : 0;
+            fr->counter[0] = nc; fr->counter[1] = nc;
+        }
+    }
+}
 
 // grid (slot, tile of 128 samples), 256 threads = 8 warps.  Each warp takes every 8th
 // (voice, send) entry of the slot; a lane owns 4 consecutive samples (one float4 load of the
@@ -76,11 +250,14 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
         {
             const SendEntry en = Q.entries[e];
             const uint32_t info = Q.sendinfo[en.voice];
-            if(!(info & 1u)) continue;
+            if(!(info & kSiSend)) continue;
             const bool playing = (info & 2u) != 0;
             const uint32_t counter = info >> 8;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if(i0 < n) x = *reinterpret_cast<const float4*>(Q.xscratch + size_t(en.voice)*kLine + i0);
+            const float *line = Q.xscratch + size_t(en.voice)*kLine;
+            if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active)
+                line = Q.fscratch + size_t(e)*kLine;
+            if(i0 < n) x = *reinterpret_cast<const float4*>(line + i0);
             const float xs[4] = {x.x, x.y, x.z, x.w};
             const float delta = counter ? 1.0f/float(counter) : 0.0f;
             const uint32_t fadeLen = counter < n ? counter : n;
@@ -144,7 +321,7 @@ __global__ void k_send_gains_update(const SendMixParams Q, uint32_t num_entries)
     if(e >= num_entries) return;
     const SendEntry en = Q.entries[e];
     const uint32_t info = Q.sendinfo[en.voice];
-    if(!(info & 1u)) return;
+    if(!(info & kSiSend)) return;
     const bool playing = (info & 2u) != 0;
     const uint32_t counter = info >> 8, n = Q.frames;
     const float delta = counter ? 1.0f/float(counter) : 0.0f;

@@ -64,6 +64,22 @@ struct alignas(16) VoiceUpdate {   // staged by b200mix_voices_update
 
 struct VoiceResult { int32_t position; uint32_t position_frac, flags, buffers_done; };
 
+// Device-resident BiquadInterpFilter pair of one voice path (core/voice.h:50-53,70-73;
+// core/filters/biquad.h:137-198): [0] = LowPass (high-shelf), [1] = HighPass (low-shelf).
+// Coefficient sets are {b0,b1,b2,a1,a2}.
+struct alignas(16) FilterRec {
+    float cur[2][5]; float tgt[2][5];
+    float z[2][2];
+    int32_t counter[2];
+    uint32_t active;
+    uint32_t pad[5];
+};
+static_assert(sizeof(FilterRec) == 128, "FilterRec layout");
+
+struct FilterUpdate {      // == b200mix_voice_filter
+    uint32_t voice, path, active; float lp[5], hp[5];
+};
+
 struct MixParams {
     VoiceRec *voices; const BufferRec *buffers;
     float2 *hrtf_tgt; float2 *hrtf_old;       // [max_voices][ir_pad]
@@ -80,7 +96,16 @@ struct MixParams {
     uint32_t *sendinfo;                       // per voice: bit0 mixed, bit1 playing, bits8.. counter
     const uint32_t *order;                    // mixing order: voice indices, cost-sorted
     uint32_t num_order;
+    FilterRec *filt;                          // [max_voices][filt_paths] or null (no filter ever set)
+    uint32_t filt_paths;                      // 1 + num_sends
+    // Voices whose direct-path filter is active are mixed in two passes around k_filters:
+    // pass 0 resamples and parks the line (xscratch), pass 1 mixes the filtered line (dline).
+    uint32_t pass;
+    const float *dline;                       // [max_voices][1024] filtered direct-path lines
 };
+
+// sendinfo bits
+constexpr uint32_t kSiSend = 1u, kSiPlaying = 2u, kSiDeferred = 4u, kSiDirty = 8u;
 
 __device__ __forceinline__ void group_sync(int id, int count)
 { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
@@ -171,6 +196,14 @@ struct FillArgs {
     float *dst; uint32_t count, uintPos, q0, firstRun, loopStart, loopSize, lastFrame, channels;
     bool looping, pastEnd, simpleWrap;
 };
+
+// DoFilters with an inactive pair: lpfilter.clear(); hpfilter.clear() (biquad.h:152-157).
+__device__ __forceinline__ void filter_clear(FilterRec &fr, int t)
+{
+    if(t < 10) fr.cur[t/5][t%5] = fr.tgt[t/5][t%5];
+    else if(t < 14) fr.z[(t-10)>>1][(t-10)&1] = 0.0f;
+    else if(t < 16) fr.counter[t-14] = 0;
+}
 
 // LoadBufferStatic (core/voice.cpp:500-544) for one window run: element k maps to buffer
 // frame q(k) (loop wrap / end hold); 8 independent loads are issued before any use.
@@ -284,7 +317,14 @@ k_mix_voices(const MixParams P)
         // one batch of vector loads for the scalar part of the record
         const uint4 *hp = reinterpret_cast<const uint4*>(&rec);
         const uint4 h0 = hp[0], h1 = hp[1], h2 = hp[2], h3 = hp[3], h4 = hp[4];
-        const uint32_t vstate = h0.x;
+        const bool second = P.pass != 0u;
+        uint32_t info = 0u;
+        if(second)
+        {
+            info = P.sendinfo[v];
+            if(!(info & kSiDeferred)) continue;
+        }
+        const uint32_t vstate = second ? ((info & kSiPlaying) ? 1u : 2u) : h0.x;
         if(vstate != 1u && vstate != 2u)
         {
             if(t == 0)
@@ -296,7 +336,7 @@ k_mix_voices(const MixParams P)
         }
         const uint32_t increment = h1.z;
         uint32_t flags = h0.y;
-        if(increment < 1u)
+        if(!second && increment < 1u)
         {
             if(t == 0)
             {
@@ -318,11 +358,15 @@ k_mix_voices(const MixParams P)
             looping = false;                                     // core/voice.cpp:1015-1019
         const uint32_t resampler = h0.w;
         const bool isHrtf = HRTF && (flags & kVfHrtf);
-        const bool dirty = (flags & kVfCoefDirty) != 0;
+        const bool dirty = second ? ((info & kSiDirty) != 0) : ((flags & kVfCoefDirty) != 0);
+        FilterRec *dfilt = P.filt ? P.filt + size_t(v)*P.filt_paths : nullptr;
+        // pass 0 only resamples a voice with an active direct filter; its mix is deferred
+        const bool defer = !second && dfilt && dfilt->active;
 
         // ---- stage per-voice constants into shared memory ----
-        for(int k = t;k < kPad;k += GS) S.u.rs.win[k] = rec.prev[k];
-        if(isHrtf)
+        if(!second)
+            for(int k = t;k < kPad;k += GS) S.u.rs.win[k] = rec.prev[k];
+        if(isHrtf && !defer)
         {
             for(int k = t;k < kHist;k += GS) S.x[k] = rec.hist[k];
             const float2 *ct = P.hrtf_tgt + size_t(v)*P.ir_pad;
@@ -339,8 +383,15 @@ k_mix_voices(const MixParams P)
         //   FastBSinc  F = fil,          D = phd            (mixer_c.cpp:63-82)
         //   cubic      F = mCoeffs,      D = mDeltas        (mixer_c.cpp:48-61)
         uint32_t m = 0, tapOff = 0, ms = 5;          // taps, left offset into the window, row stride
-        const bool bypass = false;
-        (void)bypass;
+        float *xs = S.x + kHist;
+        if(second)
+        {
+            // the filtered line k_filters left for this voice
+            const float *fl = P.dline + size_t(v)*kLine;
+            for(uint32_t k = t;k < n;k += GS) xs[k] = fl[k];
+        }
+        else
+        {
         if(resampler >= 4u)
         {
             m = h2.z;
@@ -386,7 +437,6 @@ k_mix_voices(const MixParams P)
         }
 
         // ---- LoadResampledSamples, chunk by chunk (core/voice.cpp:668-811) ----
-        float *xs = S.x + kHist;
         for(uint32_t loaded = 0;loaded < n;)
         {
             uint32_t dstn, srcn;
@@ -538,13 +588,30 @@ k_mix_voices(const MixParams P)
                 }
             }
         }
+        }   // !second
         group_sync(bar, GS);               // xs complete
 
         // ---- fade bookkeeping (core/voice.cpp:1093-1112) ----
         const bool fading = (flags & kVfFading) != 0;
-        const uint32_t counter = fading ? (n < 64u ? n : 64u) : 0u;
+        const uint32_t counter = second ? ((info >> 8) & 0xffu) : (fading ? (n < 64u ? n : 64u) : 0u);
         const bool playing = vstate == 1u;
 
+        // ---- auxiliary sends (core/voice.cpp:967-980): the UNFILTERED resampled line is
+        // parked in HBM; k_send_filters / k_send_mix take it from there slot by slot ----
+        if(P.sendinfo && !second)
+        {
+            const bool sends = P.num_sends && h4.w;
+            if(sends || defer)
+                for(uint32_t k = t;k < n;k += GS) P.xscratch[size_t(v)*kLine + k] = xs[k];
+            if(t == 0)
+                P.sendinfo[v] = (sends || defer) ? ((sends ? kSiSend : 0u) | (playing ? kSiPlaying : 0u)
+                    | (defer ? kSiDeferred : 0u) | (dirty ? kSiDirty : 0u) | (counter << 8)) : 0u;
+        }
+        // direct-path DoFilters (core/voice.cpp:943-946) with an inactive pair: clear()
+        if(dfilt && !second && !defer) filter_clear(*dfilt, t);
+
+        if(!defer)
+        {
         if(isHrtf)
         {
             // DoHrtfMix (core/voice.cpp:827-902), outPos == 0
@@ -691,19 +758,10 @@ k_mix_voices(const MixParams P)
             }
         }
 
-        // ---- auxiliary sends (core/voice.cpp:967-980): the resampled line is parked in
-        // HBM; k_send_mix sums all (voice, send) pairs slot by slot in a fixed order ----
-        if(P.sendinfo)
-        {
-            const bool sends = P.num_sends && h4.w;
-            if(sends)
-                for(uint32_t k = t;k < n;k += GS) P.xscratch[size_t(v)*kLine + k] = xs[k];
-            if(t == 0)
-                P.sendinfo[v] = sends ? (1u | (playing ? 2u : 0u) | (counter << 8)) : 0u;
-        }
+        }   // !defer
 
         // ---- position / state update (core/voice.cpp:1116-1232) ----
-        if(t == 0)
+        if(t == 0 && !second)
         {
             uint32_t newFlags = (flags | kVfFading) & ~kVfCoefDirty;
             uint32_t newState = vstate;
@@ -741,7 +799,7 @@ k_mix_voices(const MixParams P)
         if(t == 0)
         {
             // Gains.Current write-back, after every thread has read the old values
-            if(!isHrtf)
+            if(!isHrtf && !defer)
                 for(uint32_t c = 0;c < P.cd;++c)
                     P.dry_cur[size_t(v)*P.cd + c] = S.newGain[c];
         }
@@ -874,7 +932,62 @@ struct ApplyParams {
     const float *coeffs; const float *dry; const float *send;   // staged side arrays (or null)
     float2 *hrtf_tgt; float2 *hrtf_old; float *dry_cur, *dry_tgt, *send_cur, *send_tgt;
     uint32_t ir, ir_pad, cd, cw, num_sends;
+    FilterRec *filt; uint32_t filt_paths;
 };
+
+// BiquadInterpFilter::reset (biquad.h:144-150) for one record; lane k < 32 writes word k.
+__device__ __forceinline__ void filter_reset_word(FilterRec *fr, int k)
+{
+    uint32_t *w = reinterpret_cast<uint32_t*>(fr);
+    uint32_t val = 0u;
+    if(k == 0 || k == 5 || k == 10 || k == 15) val = __float_as_uint(1.0f);   // b0 of cur/tgt
+    else if(k == 24 || k == 25) val = 0xffffffffu;                             // mCounter = -1
+    w[k] = val;
+}
+
+__global__ void k_filter_init(FilterRec *filt, size_t count)
+{
+    const size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+    if(i < count*32u) filter_reset_word(filt + (i >> 5), int(i & 31u));
+}
+
+// The device half of b200mix_voices_filters: BiquadInterpFilter::setParams once
+// SetParams has produced the new targets (biquad.cpp:36-43,123-147).
+__global__ void k_apply_filter_updates(FilterRec *filt, uint32_t paths, const FilterUpdate *upd,
+    uint32_t n)
+{
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if(i >= n*2u) return;
+    const FilterUpdate &u = upd[i >> 1];
+    const int f = int(i & 1u);
+    FilterRec &fr = filt[size_t(u.voice)*paths + u.path];
+    const float *nt = f ? u.hp : u.lp;
+    bool diff = false;
+    #pragma unroll
+    for(int k = 0;k < 5;++k)
+    {
+        diff |= !(fabsf(nt[k] - fr.tgt[f][k]) <= 0.015625f);          // check_set
+        fr.tgt[f][k] = nt[k];
+    }
+    const int c = fr.counter[f];
+    if(!diff)
+    {
+        if(c <= 0)
+        {
+            fr.counter[f] = 0;
+            #pragma unroll
+            for(int k = 0;k < 5;++k) fr.cur[f][k] = nt[k];
+        }
+    }
+    else if(c >= 0) fr.counter[f] = 8*32;                            // InterpSteps*SamplesPerStep
+    else
+    {
+        fr.counter[f] = 0;
+        #pragma unroll
+        for(int k = 0;k < 5;++k) fr.cur[f][k] = nt[k];
+    }
+    if(f == 0) fr.active = u.active ? 1u : 0u;
+}
 
 __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
 {
@@ -894,6 +1007,9 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
         if(A.send_cur)
             for(uint32_t c = t;c < A.num_sends*A.cw;c += 64)
                 A.send_cur[size_t(up.voice)*A.num_sends*A.cw + c] = 0.0f;
+        if(A.filt)          // chandata.mDryParams = DirectParams{}; mWetParams = SendParams{} (voice.cpp:1387-1394)
+            for(uint32_t k = t;k < A.filt_paths*32u;k += 64)
+                filter_reset_word(A.filt + size_t(up.voice)*A.filt_paths + (k >> 5), int(k & 31u));
     }
     if(up.has_coeffs && A.hrtf_tgt)
     {

@@ -38,6 +38,11 @@ class VoiceParams(C.Structure):
                 ("send_slot", C.c_uint32 * MAX_SENDS)]
 
 
+class VoiceFilter(C.Structure):
+    _fields_ = [("voice", C.c_uint32), ("path", C.c_uint32), ("active", C.c_uint32),
+                ("lowpass", C.c_float * 5), ("highpass", C.c_float * 5)]
+
+
 class VoiceResult(C.Structure):
     _fields_ = [("position", C.c_int32), ("position_frac", C.c_uint32),
                 ("flags", C.c_uint32), ("buffers_done", C.c_uint32)]

@@ -167,6 +167,24 @@ int oracle_resample(uint32_t resampler, uint32_t increment, uint32_t frac, const
 /* ---- device state --------------------------------------------------------- */
 typedef struct { uint32_t type, channels, frames; void *data; } obuffer;
 
+/* BiquadInterpFilter (core/filters/biquad.h:137-198): coefficient sets are
+ * {b0,b1,b2,a1,a2}; z = {mZ1,mZ2}; counter = mCounter. */
+typedef struct { float cur[5], tgt[5], z[2]; int counter; } obiquad;
+
+static void obiquad_reset(obiquad *f)      /* BiquadInterpFilter::reset, biquad.h:144-150 */
+{
+    static const float ident[5] = {1.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    memcpy(f->cur, ident, sizeof(ident)); memcpy(f->tgt, ident, sizeof(ident));
+    f->z[0] = f->z[1] = 0.0f;
+    f->counter = -1;
+}
+static void obiquad_clear(obiquad *f)      /* BiquadInterpFilter::clear, biquad.h:152-157 */
+{
+    f->z[0] = f->z[1] = 0.0f;
+    memcpy(f->cur, f->tgt, sizeof(f->cur));
+    f->counter = 0;
+}
+
 typedef struct {
     int state;                 /* 0 stopped, 1 playing, 2 stopping (Voice::State) */
     uint32_t flags;            /* STATIC / LOOPING / HRTF */
@@ -184,6 +202,8 @@ typedef struct {
     uint32_t send_slot[B200MIX_MAX_SENDS];
     float send_cur[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
     float send_tgt[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
+    /* DirectParams/SendParams LowPass+HighPass, path 0 = direct, 1+s = send s */
+    struct { obiquad lp, hp; int active; } filt[1 + B200MIX_MAX_SENDS];
 } ovoice;
 
 typedef struct { float coeff, lp_z1, lp_z2, ap_z1; } osplitter; /* core/filters/splitter.h */
@@ -229,6 +249,7 @@ struct oracle_device {
     /* scratch */
     float resample_data[RESBUF];
     float samples[LINE];
+    float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
     float hrtf_samples[LINE+HIST];
     float temp[LINE], temp2[LINE];
 };
@@ -406,6 +427,8 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
         {
             /* Voice::prepare + InitVoice: core/voice.cpp:1235-1400, al/source.cpp:639-669 */
             memset(v, 0, sizeof(*v));
+            for(uint32_t f = 0;f < 1 + B200MIX_MAX_SENDS;++f)
+            { obiquad_reset(&v->filt[f].lp); obiquad_reset(&v->filt[f].hp); }
             v->pos = p->position; v->frac = p->position_frac;
             v->fading = (p->flags & B200MIX_VF_FADING) != 0;
             v->have_buffer = 1;
@@ -433,6 +456,175 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
                     v->send_tgt[s][c] = send_gains[((size_t)i*ns + s)*cw + c];
     }
     return B200MIX_OK;
+}
+
+/* BiquadInterpFilter::setParams after SetParams filled mTargetCoeffs
+ * (core/filters/biquad.cpp:36-43,123-147): check_set's 1/64 hysteresis decides whether
+ * the 8-step interpolation starts. */
+static void obiquad_set_target(obiquad *f, const float tgt[5])
+{
+    int is_diff = 0;
+    for(int k = 0;k < 5;++k)
+    {
+        is_diff |= !(fabsf(tgt[k] - f->tgt[k]) <= 0.015625f);
+        f->tgt[k] = tgt[k];
+    }
+    if(!is_diff)
+    {
+        if(f->counter <= 0) { f->counter = 0; memcpy(f->cur, f->tgt, sizeof(f->cur)); }
+    }
+    else if(f->counter >= 0)
+        f->counter = 8*32;                         /* InterpSteps*SamplesPerStep */
+    else
+    { f->counter = 0; memcpy(f->cur, f->tgt, sizeof(f->cur)); }
+}
+
+int oracle_voices_filters(oracle_device *d, uint32_t n, const b200mix_voice_filter *filters)
+{
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const b200mix_voice_filter *q = &filters[i];
+        if(q->voice >= d->desc.max_voices || q->path > d->desc.num_sends) return B200MIX_ERR_INVALID;
+        ovoice *v = &d->voices[q->voice];
+        v->filt[q->path].active = q->active != 0;
+        obiquad_set_target(&v->filt[q->path].lp, q->lowpass);
+        obiquad_set_target(&v->filt[q->path].hp, q->highpass);
+    }
+    return B200MIX_OK;
+}
+
+/* BiquadFilter::SetParams behind setParamsFromSlope (core/filters/biquad.h:92-97 with
+ * rcpQFromSlope :61-62; biquad.cpp:48-129). */
+int oracle_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5])
+{
+    if(type > 5u) return B200MIX_ERR_INVALID;
+    gain = fmaxf(gain, 0.001f);
+    const float rcpQ = sqrtf((gain + 1.0f/gain)*(1.0f/slope - 1.0f) + 2.0f);
+    gain = fmaxf(gain, 0.00001f);
+    const float w0 = 3.14159265358979323846f*2.0f * fminf(f0norm, 0.49f);
+    const float sin_w0 = sinf(w0), cos_w0 = cosf(w0);
+    const float alpha = sin_w0/2.0f * rcpQ;
+    float a[3] = {1.0f, 0.0f, 0.0f}, b[3] = {1.0f, 0.0f, 0.0f}, sg;
+    switch(type)
+    {
+    case 0: /* HighShelf */
+        sg = 2.0f * sqrtf(gain) * alpha;
+        b[0] =       gain*((gain+1.0f) + (gain-1.0f)*cos_w0 + sg);
+        b[1] = -2.0f*gain*((gain-1.0f) + (gain+1.0f)*cos_w0     );
+        b[2] =       gain*((gain+1.0f) + (gain-1.0f)*cos_w0 - sg);
+        a[0] =             (gain+1.0f) - (gain-1.0f)*cos_w0 + sg;
+        a[1] =  2.0f*     ((gain-1.0f) - (gain+1.0f)*cos_w0     );
+        a[2] =             (gain+1.0f) - (gain-1.0f)*cos_w0 - sg;
+        break;
+    case 1: /* LowShelf */
+        sg = 2.0f * sqrtf(gain) * alpha;
+        b[0] =       gain*((gain+1.0f) - (gain-1.0f)*cos_w0 + sg);
+        b[1] =  2.0f*gain*((gain-1.0f) - (gain+1.0f)*cos_w0     );
+        b[2] =       gain*((gain+1.0f) - (gain-1.0f)*cos_w0 - sg);
+        a[0] =             (gain+1.0f) + (gain-1.0f)*cos_w0 + sg;
+        a[1] = -2.0f*     ((gain-1.0f) + (gain+1.0f)*cos_w0     );
+        a[2] =             (gain+1.0f) + (gain-1.0f)*cos_w0 - sg;
+        break;
+    case 2: /* Peaking */
+        b[0] = 1.0f + alpha*gain; b[1] = -2.0f*cos_w0; b[2] = 1.0f - alpha*gain;
+        a[0] = 1.0f + alpha/gain; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha/gain;
+        break;
+    case 3: /* LowPass */
+        b[0] = (1.0f - cos_w0)/2.0f; b[1] = 1.0f - cos_w0; b[2] = (1.0f - cos_w0)/2.0f;
+        a[0] = 1.0f + alpha; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha;
+        break;
+    case 4: /* HighPass */
+        b[0] = (1.0f + cos_w0)/2.0f; b[1] = -(1.0f + cos_w0); b[2] = (1.0f + cos_w0)/2.0f;
+        a[0] = 1.0f + alpha; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha;
+        break;
+    default: /* BandPass */
+        b[0] = alpha; b[1] = 0.0f; b[2] = -alpha;
+        a[0] = 1.0f + alpha; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha;
+        break;
+    }
+    coeffs[0] = b[0]/a[0]; coeffs[1] = b[1]/a[0]; coeffs[2] = b[2]/a[0];
+    coeffs[3] = a[1]/a[0]; coeffs[4] = a[2]/a[0];
+    return B200MIX_OK;
+}
+
+/* BiquadFilter::dualProcess, core/filters/biquad.cpp:254-281 (transposed direct form II,
+ * f0 then f1 per sample). */
+static void obiquad_dual_run(obiquad *f0, obiquad *f1, const float *src, float *dst, size_t n)
+{
+    float z01 = f0->z[0], z02 = f0->z[1], z11 = f1->z[0], z12 = f1->z[1];
+    const float *c0 = f0->cur, *c1 = f1->cur;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x0 = src[i];
+        const float y0 = x0*c0[0] + z01;
+        z01 = x0*c0[1] - y0*c0[3] + z02;
+        z02 = x0*c0[2] - y0*c0[4];
+        const float x1 = y0;
+        const float y1 = x1*c1[0] + z11;
+        z11 = x1*c1[1] - y1*c1[3] + z12;
+        z12 = x1*c1[2] - y1*c1[4];
+        dst[i] = y1;
+    }
+    f0->z[0] = z01; f0->z[1] = z02; f1->z[0] = z11; f1->z[1] = z12;
+}
+
+/* BiquadInterpFilter::dualProcess, core/filters/biquad.cpp:283-343. */
+static void obiquad_dual_interp(obiquad *f0, obiquad *f1, const float *src, float *dst, size_t n)
+{
+    const int maxcounter = f0->counter > f1->counter ? f0->counter : f1->counter;
+    if(maxcounter > 0)
+    {
+        int counter = maxcounter / 32;
+        size_t steprem = (size_t)(32 - (maxcounter & 31));
+        while(counter > 0)
+        {
+            const size_t td = steprem < n ? steprem : n;
+            obiquad_dual_run(f0, f1, src, dst, td);
+            steprem -= td;
+            if(steprem)
+            {
+                steprem = 32 - steprem;
+                f0->counter = (counter*32) | (int)steprem;
+                f1->counter = f0->counter;
+                return;
+            }
+            src += td; dst += td; n -= td;
+            steprem = 32;
+            --counter;
+            if(!counter)
+            {
+                f0->counter = 0; memcpy(f0->cur, f0->tgt, sizeof(f0->cur));
+                f1->counter = 0; memcpy(f1->cur, f1->tgt, sizeof(f1->cur));
+                break;
+            }
+            const float a = 1.0f / (float)(counter+1);
+            for(int k = 0;k < 5;++k)
+            {
+                f0->cur[k] = lerpf(f0->cur[k], f0->tgt[k], a);
+                f1->cur[k] = lerpf(f1->cur[k], f1->tgt[k], a);
+            }
+            if(!n)
+            {
+                f0->counter = counter*32;
+                f1->counter = f0->counter;
+                return;
+            }
+        }
+    }
+    obiquad_dual_run(f0, f1, src, dst, n);
+}
+
+/* DoFilters, core/voice.cpp:255-268 */
+static const float *do_filters(ovoice *v, uint32_t path, float *dst, const float *src, size_t n)
+{
+    if(v->filt[path].active)
+    {
+        obiquad_dual_interp(&v->filt[path].lp, &v->filt[path].hp, src, dst, n);
+        return dst;
+    }
+    obiquad_clear(&v->filt[path].lp);
+    obiquad_clear(&v->filt[path].hp);
+    return src;
 }
 
 /* ITU-T G.711 expansion; equals muLawDecompressionTable / aLawDecompressionTable
@@ -797,22 +989,24 @@ static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_res
                 memcpy(v->send_cur[s], v->send_tgt[s], sizeof(v->send_cur[s]));
     }
 
-    /* DoMix, :934-984 (filters inactive) */
+    /* DoMix, :934-984 */
+    const float *samples = do_filters(v, 0, d->filtered, d->samples, n);
     if(v->flags & B200MIX_VF_HRTF)
     {
         const float targetGain = v->tgt_gain * (float)(vstate == 1);
-        do_hrtf_mix(d, v, d->samples, n, targetGain, counter, vstate == 1);
+        do_hrtf_mix(d, v, samples, n, targetGain, counter, vstate == 1);
     }
     else
     {
         const float *tg = (vstate == 1) ? v->dry_tgt : silent;
-        mix_samples(d->samples, n, d->dry, cd, v->dry_cur, tg, counter);
+        mix_samples(samples, n, d->dry, cd, v->dry_cur, tg, counter);
     }
     for(uint32_t s = 0;s < ns;++s)
     {
         if(v->send_slot[s] == B200MIX_NO_SLOT) continue;
+        samples = do_filters(v, 1 + s, d->filtered, d->samples, n);
         const float *tg = (vstate == 1) ? v->send_tgt[s] : silent;
-        mix_samples(d->samples, n, d->wet + (size_t)v->send_slot[s]*cw, cw, v->send_cur[s], tg,
+        mix_samples(samples, n, d->wet + (size_t)v->send_slot[s]*cw, cw, v->send_cur[s], tg,
             counter);
     }
 

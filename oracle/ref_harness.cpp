@@ -31,10 +31,16 @@
 #include "core/ambidefs.h"
 #include "core/bufferline.h"
 #include "core/devformat.h"
+#include <cmath>
+#include <numbers>
+#include "alnumeric.h"
 #define class struct
 #define private public
+#define protected public
 #include "core/filters/splitter.h"
 #include "core/bformatdec.h"
+#include "core/filters/biquad.h"
+#undef protected
 #undef private
 #undef class
 
@@ -332,6 +338,45 @@ int refh_voice_filters_active(ALCcontext *actx, int voice, int *direct, int *sen
     *direct = voices[size_t(voice)]->mDirect.FilterActive;
     for(auto s = 0u;s < MaxSendCount;++s) sends[s] = voices[size_t(voice)]->mSend[s].FilterActive;
     return 0;
+}
+
+/* Direct/send filter targets of one voice as CalcVoiceParams left them
+ * (alc/alu.cpp:1619-1656): per path p (0 = direct, 1+s = send s) the FilterActive flag,
+ * LowPass/HighPass mTargetCoeffs {b0,b1,b2,a1,a2} and mCounter.
+ * coeffs is [7][2][5], active [7], counters [7][2]. */
+int refh_voice_filters(ALCcontext *actx, int voice, float *coeffs, int *active, int *counters)
+{
+    auto voices = ctx_of(actx)->getVoicesSpan();
+    if(voice < 0 || size_t(voice) >= voices.size()) return -1;
+    auto *v = voices[size_t(voice)];
+    auto &ch = v->mChans[0];
+    const auto put = [&](size_t p, BiquadInterpFilter &lp, BiquadInterpFilter &hp, bool act)
+    {
+        const auto one = [](float *o, const BiquadInterpFilter &f)
+        {
+            o[0] = f.mTargetCoeffs.mB0; o[1] = f.mTargetCoeffs.mB1; o[2] = f.mTargetCoeffs.mB2;
+            o[3] = f.mTargetCoeffs.mA1; o[4] = f.mTargetCoeffs.mA2;
+        };
+        one(coeffs + (p*2 + 0)*5, lp);
+        one(coeffs + (p*2 + 1)*5, hp);
+        active[p] = act;
+        counters[p*2 + 0] = lp.mCounter;
+        counters[p*2 + 1] = hp.mCounter;
+    };
+    put(0, ch.mDryParams.LowPass, ch.mDryParams.HighPass, v->mDirect.FilterActive);
+    for(auto s = 0_uz;s < MaxSendCount;++s)
+        put(1 + s, ch.mWetParams[s].LowPass, ch.mWetParams[s].HighPass, v->mSend[s].FilterActive);
+    return 0;
+}
+
+/* BiquadFilter::SetParams through setParamsFromSlope (core/filters/biquad.h:92-97,
+ * biquad.cpp:48-129): type 0 = HighShelf, 1 = LowShelf, ... as enum BiquadType. */
+void refh_biquad_coeffs(int type, float f0norm, float gain, float slope, float *out)
+{
+    auto f = BiquadFilter{};
+    f.setParamsFromSlope(static_cast<BiquadType>(type), f0norm, gain, slope);
+    out[0] = f.mCoeffs.mB0; out[1] = f.mCoeffs.mB1; out[2] = f.mCoeffs.mB2;
+    out[3] = f.mCoeffs.mA1; out[4] = f.mCoeffs.mA2;
 }
 
 /* What ConvolutionState::update computes for a MONO impulse response

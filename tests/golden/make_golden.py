@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generates tests/golden/*.npz from the UNMODIFIED reference compiled under
 oracle/_ref (see oracle/refbuild/Makefile).  Run from the repo root:
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [scene names...]      (default: all scenes)
 Each fixture holds, for one seeded synthetic scene (openal-soft_b200/pyb200mix/scene.py):
 the device description and decoder constants the reference chose, the post-ALU
 voice parameters it computed (b200mix_voice_params + side arrays), and its
@@ -54,7 +54,37 @@ SCENES = {
                                         {0x0001: 0.0, 0x0002: 0.7, 0x0012: 1.0, 0x0011: 0.8, 0x0006: 2.5,
                                          0x0004: 0.5}),
     "stereo_spline_reverb_v4": (4, 0, 2, 5, True, 48000, None, "i16", 0, {0x0006: 0.8}),
+    # direct / send filters (DoFilters -> BiquadInterpFilter, core/filters/biquad.cpp): FILTER_SCRIPTS
+    # below changes filters between updates so the 8x32-sample coefficient interpolation runs
+    "hrtf_bsinc24_dfilter_v6": (6, 1, 7, 6, True, 48000, None, "i16", 0, None, "direct"),
+    "stereo_spline_dfilter_v5": (5, 0, 2, 5, True, 48000, None, "i16", 0, None, "direct"),
+    "hrtf_spline_reverb_sfilter_v4": (4, 1, 2, 6, True, 48000, None, "i16", 0, {}, "send"),
 }
+
+# Filter scripts: {update index (applied BEFORE that render; 0 = before play):
+#                  [(voice, path, gainHF, gainLF or None)]}; path 0 = direct, 1 = send 0.
+# gainHF == 1 and no gainLF detaches the filter.  The filter objects' GAIN stays 1 so the
+# voices' dry/send gain targets (snapshotted once) do not change.
+FILTER_SCRIPTS = {
+    "direct": {0: [(0, 0, 0.25, None), (1, 0, 0.5, 0.3), (2, 0, 0.25, None), (4, 0, 0.05, None)],
+               2: [(0, 0, 0.9, None), (3, 0, 0.1, None)],
+               3: [(1, 0, 0.5, 0.9)],
+               4: [(2, 0, 1.0, None)]},
+    "send": {0: [(0, 1, 0.2, None), (1, 1, 0.6, 0.4), (2, 0, 0.3, None)],
+             2: [(0, 1, 0.8, None), (3, 1, 0.15, None)],
+             4: [(1, 1, 1.0, None), (2, 0, 0.7, 0.5)]},
+}
+
+
+def apply_filter_script(ref, script, u, slot):
+    from helpers import refal
+    for voice, path, ghf, glf in script.get(u, []):
+        src = ref.sources[voice]
+        filt = refal.AL_FILTER_NULL if (ghf == 1.0 and glf is None) else ref.make_filter(1.0, ghf, glf)
+        if path == 0:
+            ref.set_direct_filter(src, filt)
+        else:
+            ref.connect_send(src, slot, path - 1, filt)
 
 
 def conv_ir(taps):
@@ -83,16 +113,27 @@ def run_scene(name):
         for src in ref.sources:
             ref.connect_send(src, slot)
     rvprops = spec[9] if len(spec) > 9 else None
+    slot = 0
     if rvprops is not None:
         slot = ref.add_reverb_slot(props=rvprops)
         for src in ref.sources:
             ref.connect_send(src, slot)
+    script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 else None
+    if script:
+        apply_filter_script(ref, script, 0, slot)
     ref.play_all()
     outs = []
     snap = None
+    filt_meta, filt_coef = [], []
     nslots, wet = ref.slot_info() if (taps or rvprops is not None) else (0, [])
     for u in range(U):
+        if script and u:
+            apply_filter_script(ref, script, u, slot)
         outs.append(ref.render())
+        if script:
+            ents, _ = ref.voice_filters(V)
+            filt_meta.append(np.array([[v, p, a] for v, p, a, _, _ in ents], dtype=np.int32))
+            filt_coef.append(np.array([[lp, hp] for _, _, _, lp, hp in ents], dtype=np.float32))
         if u == 0:
             snap = ref.snapshot(wet_channels=wet[0] if nslots else 0)
             if rvprops is not None:
@@ -110,6 +151,8 @@ def run_scene(name):
     if rvprops is not None:
         res.update(reverb_params=np.frombuffer(bytes(rvp), dtype=np.uint8).copy(), reverb_gains=rvg,
                    send=send[:V].copy(), wet_channels=np.int64(wet[0]))
+    if script:
+        res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if d.post_process == abi.POST_HRTF:
         c, hf, sc = ref.hrtf_decoder()
         res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)
@@ -131,14 +174,17 @@ def child(name, mode, path):
 
 
 def main():
-    if len(sys.argv) == 4:
-        child(sys.argv[1], sys.argv[2], sys.argv[3])
+    if len(sys.argv) == 5 and sys.argv[1] == "--child":
+        child(sys.argv[2], sys.argv[3], sys.argv[4])
         return
+    only = [a for a in sys.argv[1:]]
     for name in SCENES:
+        if only and name not in only:
+            continue
         parts = {}
         for mode in ("sse", "c"):
             tmp = os.path.join(HERE, f"_tmp_{name}_{mode}.npz")
-            subprocess.check_call([sys.executable, __file__, name, mode, tmp])
+            subprocess.check_call([sys.executable, __file__, "--child", name, mode, tmp])
             parts[mode] = dict(np.load(tmp))
             os.remove(tmp)
         a, b = parts["sse"], parts["c"]

@@ -62,7 +62,11 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
         dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if (taps or reverb) else None)
         outs = []
         res = None
-        for _ in range(updates or U):
+        for u in range(updates or U):
+            if "filt_meta" in fx:
+                # the reference's filter targets during update u, every path of every voice
+                dev.voices_filters((int(m[0]), int(m[1]), int(m[2]), c[0], c[1])
+                                   for m, c in zip(fx["filt_meta"][u], fx["filt_coef"][u]))
             o, res = dev.render(frames, want_results=True)
             outs.append(o)
         return np.stack(outs), res

@@ -45,6 +45,10 @@ class MixLib:
         self.slot_reverb.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams)]
         self.slot_disable = f("slot_disable")
         self.slot_disable.argtypes = [C.c_void_p, C.c_uint32]
+        self.voices_filters = f("voices_filters")
+        self.voices_filters.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        self.biquad_coeffs = f("biquad_coeffs")
+        self.biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
         self.get_dry = f("get_dry")
         self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
 
@@ -122,6 +126,17 @@ class MixDevice:
             send = np.ascontiguousarray(send, dtype=np.float32)
             sp = send.ctypes.data
         rc = self.m.voices_update(self.h, n, arr, cp, dp, sp)
+        assert rc == 0, rc
+
+    def voices_filters(self, entries):
+        """entries: iterable of (voice, path, active, lowpass[5], highpass[5])."""
+        entries = list(entries)
+        arr = (abi.VoiceFilter * max(len(entries), 1))()
+        for i, (v, path, act, lp, hp) in enumerate(entries):
+            arr[i].voice, arr[i].path, arr[i].active = int(v), int(path), int(act)
+            arr[i].lowpass[:] = [float(x) for x in lp]
+            arr[i].highpass[:] = [float(x) for x in hp]
+        rc = self.m.voices_filters(self.h, len(entries), arr)
         assert rc == 0, rc
 
     def render(self, frames=1024, want_results=False):

@@ -37,6 +37,16 @@ AL_EFFECT_CONVOLUTION_SOFT = 0xA000
 AL_EFFECTSLOT_GAIN = 0x0002
 AL_EFFECTSLOT_EFFECT = 0x0001
 AL_FILTER_NULL = 0
+AL_DIRECT_FILTER = 0x20005
+AL_FILTER_TYPE = 0x8001
+AL_FILTER_LOWPASS = 0x0001
+AL_FILTER_HIGHPASS = 0x0002
+AL_FILTER_BANDPASS = 0x0003
+AL_LOWPASS_GAIN = 0x0001
+AL_LOWPASS_GAINHF = 0x0002
+AL_BANDPASS_GAIN = 0x0001
+AL_BANDPASS_GAINLF = 0x0002
+AL_BANDPASS_GAINHF = 0x0003
 ALC_FREQUENCY = 0x1007
 ALC_MONO_SOURCES = 0x1010
 ALC_STEREO_SOURCES = 0x1011
@@ -126,7 +136,12 @@ def libs(conf_text: str | None = None):
     hz.refh_slot_count.argtypes = [C.c_void_p]
     hz.refh_slot_wet_channels.argtypes = [C.c_void_p, C.c_int]
     hz.refh_mono_line_gains.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
-    for fn in ("alGenEffects", "alGenAuxiliaryEffectSlots"):
+    hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_biquad_coeffs.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    hz.refh_biquad_coeffs.restype = None
+    al.alFilteri.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alFilterf.argtypes = [C.c_uint, C.c_int, C.c_float]
+    for fn in ("alGenEffects", "alGenAuxiliaryEffectSlots", "alGenFilters"):
         getattr(al, fn).argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alEffecti.argtypes = [C.c_uint, C.c_int, C.c_int]
     al.alEffectf.argtypes = [C.c_uint, C.c_int, C.c_float]
@@ -252,8 +267,46 @@ class RefDevice:
         assert rc == 0, f"refh_reverb_params -> {rc}"
         return p, gains, st.value
 
-    def connect_send(self, source: int, slot: int, send: int = 0):
-        self.al.alSource3i(source, AL_AUXILIARY_SEND_FILTER, slot, send, AL_FILTER_NULL)
+    def make_filter(self, gain: float, gain_hf: float, gain_lf: float | None = None) -> int:
+        """A low-pass (gain, gainHF) or, with gain_lf, band-pass EFX filter object."""
+        f = C.c_uint(0)
+        self.al.alGenFilters(1, C.byref(f))
+        if gain_lf is None:
+            self.al.alFilteri(f, AL_FILTER_TYPE, AL_FILTER_LOWPASS)
+            self.al.alFilterf(f, AL_LOWPASS_GAIN, gain)
+            self.al.alFilterf(f, AL_LOWPASS_GAINHF, gain_hf)
+        else:
+            self.al.alFilteri(f, AL_FILTER_TYPE, AL_FILTER_BANDPASS)
+            self.al.alFilterf(f, AL_BANDPASS_GAIN, gain)
+            self.al.alFilterf(f, AL_BANDPASS_GAINHF, gain_hf)
+            self.al.alFilterf(f, AL_BANDPASS_GAINLF, gain_lf)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} creating filter"
+        return f.value
+
+    def set_direct_filter(self, source: int, filt: int):
+        self.al.alSourcei(source, AL_DIRECT_FILTER, filt)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} setting direct filter"
+
+    def voice_filters(self, nv: int):
+        """[(voice, path, active, lowpass[5], highpass[5])] for voices < nv and every path
+        (0 = direct, 1+s = send s < num_sends), plus the mCounter pairs."""
+        out, counters = [], []
+        ns = self.desc.num_sends
+        for v in range(nv):
+            co = np.zeros((7, 2, 5), dtype=np.float32)
+            act = (C.c_int * 7)()
+            cnt = (C.c_int * 14)()
+            rc = self.hz.refh_voice_filters(self.ctx, v, co.ctypes.data, act, cnt)
+            assert rc == 0
+            for p in range(1 + ns):
+                out.append((v, p, act[p], co[p, 0].copy(), co[p, 1].copy()))
+                counters.append((cnt[2 * p], cnt[2 * p + 1]))
+        return out, counters
+
+    def connect_send(self, source: int, slot: int, send: int = 0, filt: int = AL_FILTER_NULL):
+        self.al.alSource3i(source, AL_AUXILIARY_SEND_FILTER, slot, send, filt)
         err = self.al.alGetError()
         assert err == 0, f"AL error {err:#x} connecting send"
 

@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 RMS_TOL, MAX_TOL = 1e-6, 1e-5
 
 
-def _check(out, ref, what=""):
+def _check(out, ref, what="", rms_tol=RMS_TOL, max_tol=MAX_TOL):
     err = out.astype(np.float64) - ref.astype(np.float64)
     rms = float(np.sqrt((err ** 2).mean()))
     mx = float(np.abs(err).max())
-    assert rms <= RMS_TOL and mx <= MAX_TOL, f"{what}: rms {rms:.3e} max {mx:.3e}"
+    assert rms <= rms_tol and mx <= max_tol, f"{what}: rms {rms:.3e} max {mx:.3e}"
     assert np.abs(ref).max() > 1e-4, "reference output is silent"
 
 
@@ -209,3 +209,73 @@ def test_reverb_slots_vs_oracle_ragged_updates():
         dev.close()
         outs.append(np.concatenate(o, axis=1))
     _check(outs[1], outs[0], "reverb slots")
+
+
+def _shelf_pair(lib, gain_hf, gain_lf):
+    """What alc/alu.cpp:1630-1631 hands the filters: high-shelf at 5 kHz, low-shelf at 250 Hz."""
+    lp = np.zeros(5, dtype=np.float32)
+    hp = np.zeros(5, dtype=np.float32)
+    assert lib.biquad_coeffs(0, 5000.0 / 48000.0, gain_hf, 1.0, lp.ctypes.data) == 0
+    assert lib.biquad_coeffs(1, 250.0 / 48000.0, gain_lf, 1.0, hp.ctypes.data) == 0
+    return lp, hp
+
+
+@pytest.mark.parametrize("hrtf", [True, False])
+def test_direct_and_send_filters_vs_oracle_ragged_updates(hrtf):
+    """DoFilters on the direct path and on a send, with targets changing between ragged
+    updates so coefficient interpolation starts, straddles update boundaries mid-step,
+    restarts while running, and filters get detached (clear) and re-attached."""
+    rng = np.random.default_rng(2024)
+    nv, ir = 40, 64
+    desc = synth.hrtf_desc(nv, ir) if hrtf else synth.stereo_desc(nv)
+    desc.num_sends = 1
+    desc.wet_channels = 4
+    desc.max_slots = 1
+    params, coeffs, dry = synth.voice_set(rng, nv, ir if hrtf else 0, hrtf=hrtf,
+                                          dry_channels=desc.dry_channels)
+    send = (rng.standard_normal((nv, 1, 4)) * 0.3).astype(np.float32)
+    for k, p in enumerate(params):
+        p.send_slot[0] = 0 if k % 3 else abi.NO_SLOT
+    fx = golden.load("hrtf_bsinc24_reverb_v6")
+    sizes = (1024, 37, 512, 1, 1000, 64, 1024, 333, 1024)
+    # (update index, voice stride/offset, path, gainHF, gainLF)
+    script = {0: [(2, 0, 0, 0.2, 1.0), (3, 1, 1, 0.1, 0.5), (5, 2, 0, 0.7, 0.3)],
+              1: [(2, 0, 0, 0.9, 1.0), (4, 1, 0, 0.05, 1.0)],
+              2: [(2, 0, 0, 0.3, 0.6), (3, 1, 1, 1.0, 1.0)],
+              4: [(5, 2, 0, 1.0, 1.0), (3, 1, 1, 0.4, 1.0)],
+              6: [(4, 1, 0, 0.6, 0.9), (5, 2, 0, 0.25, 1.0)]}
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        if hrtf:
+            dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        else:
+            dev.set_ambi_decoder((np.random.default_rng(3).standard_normal((desc.dry_channels, 2)) * 0.5
+                                  ).astype(np.float32), None, 0.0)
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.slot_reverb(0, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                        np.ascontiguousarray(fx["reverb_gains"][:, :desc.dry_channels]))
+        dev.voices_update(params, coeffs if hrtf else None, dry, send)
+        o = []
+        for u, f in enumerate(sizes):
+            ents = []
+            for stride, off, path, ghf, glf in script.get(u, []):
+                lp, hp = _shelf_pair(mixlib.product(), ghf, glf)
+                for v in range(off, nv, stride):
+                    if path == 1 and params[v].send_slot[0] == abi.NO_SLOT:
+                        continue
+                    ents.append((v, path, int(ghf != 1.0 or glf != 1.0), lp, hp))
+            # one entry per (voice, path) per call: later script lines win
+            uniq = {(e[0], e[1]): e for e in ents}
+            if uniq:
+                dev.voices_filters(uniq.values())
+            o.append(dev.render(f))
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    # The EFX low-shelf at 250 Hz has poles at |z| ~ 0.98: the fp32 recurrence amplifies its own
+    # rounding noise ~1000x (a 0.25-amplitude line is only good to ~4e-6 in the reference itself),
+    # and that noise decorrelates as soon as the input differs in the last bit (the CUDA resampler
+    # uses FMA).  The CUDA filter runs the reference's exact operation order; what is left is this
+    # noise floor, so the bound here is 3x the usual one — still 3x inside north_star's tolerance.
+    _check(outs[1], outs[0], "direct + send filters", rms_tol=3e-6, max_tol=3e-5)

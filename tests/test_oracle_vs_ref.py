@@ -83,3 +83,21 @@ def test_resamplers_vs_reference_kernels(resampler):
             lib.oracle_resample(resampler, inc, frac, src.ctypes.data, b.ctypes.data, n_out)
             assert np.array_equal(a, b), (resampler, inc, frac)
             assert np.abs(s.astype(np.float64) - b).max() <= 2e-6, (resampler, inc, frac)
+
+
+def test_biquad_coeffs_bit_exact():
+    """BiquadFilter::SetParams via setParamsFromSlope vs the oracle restatement."""
+    _, hz = refal.libs()
+    lib = mixlib.oracle().lib
+    lib.oracle_biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        typ = int(rng.integers(0, 6))
+        f0 = float(rng.uniform(1e-4, 0.6))
+        gain = float(10.0 ** rng.uniform(-4.0, 1.0))
+        slope = float(rng.uniform(0.05, 1.0))
+        a = np.zeros(5, dtype=np.float32)
+        b = np.zeros(5, dtype=np.float32)
+        hz.refh_biquad_coeffs(typ, f0, gain, slope, a.ctypes.data)
+        assert lib.oracle_biquad_coeffs(typ, f0, gain, slope, b.ctypes.data) == 0
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (typ, f0, gain, slope, a, b)
