@@ -967,12 +967,12 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     if(var.hrtf)
     {
         const uint32_t len = 2*kAccumLen;
-        k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
+        k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(d->d_partial, uint32_t(rows), len,
             d->d_accum_sum, 0);
         ++d->launches;
         if(rows2)
         {
-            k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(d->d_partial + d->partial_floats,
+            k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(d->d_partial + d->partial_floats,
                 uint32_t(rows2), len, d->d_accum_sum, 1);
             ++d->launches;
         }
@@ -981,12 +981,12 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     {
         const uint32_t len = uint32_t(var.cdr)*kLine;
         const float *pd = d->d_partial + (var.hrtf ? rows*(2*kAccumLen) : 0);
-        k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
+        k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(pd, uint32_t(rows), len, d->d_dry, 1);
         ++d->launches;
         if(rows2)
         {
             const float *pd2 = d->d_partial + d->partial_floats + (var.hrtf ? rows2*(2*kAccumLen) : 0);
-            k_reduce_rows<<<(len/4 + 31)/32, 1024, 0, d->stream>>>(pd2, uint32_t(rows2), len, d->d_dry, 1);
+            k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(pd2, uint32_t(rows2), len, d->d_dry, 1);
             ++d->launches;
         }
     }

@@ -871,20 +871,22 @@ k_mix_voices(const MixParams P)
 }
 
 // Sums `rows` partial rows of `len` floats in a fixed order into out (+= if accumulate).
-// A CTA owns 32 float4 columns; its 32 warps each sum a contiguous segment of rows
-// (4 independent loads in flight), then warp 0 adds the 32 segment sums in order.
-// Deterministic: the summation tree depends only on (rows, len).
+// A CTA owns 8 float4 columns (one 128-byte line of every row); its 1024 threads are 128
+// row segments x 8 lanes, so every thread has only rows/128 loads to chain and 72+ SMs pull
+// from L2 at once; the 128 segment sums are then combined in shared memory, 4 at a time in
+// fixed order.  Deterministic: the summation tree depends only on (rows, len).
+constexpr int kReduceCols = 8, kReduceSegs = 128;
 __global__ void __launch_bounds__(1024)
 k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
     float *__restrict__ out, int accumulate)
 {
-    __shared__ float4 sm[32][33];
-    const uint32_t lane = threadIdx.x & 31u, seg = threadIdx.x >> 5;
-    const uint32_t e4 = blockIdx.x*32u + lane;
+    __shared__ float4 sm[kReduceSegs][kReduceCols];
+    const uint32_t col = threadIdx.x & (kReduceCols-1), seg = threadIdx.x / kReduceCols;
+    const uint32_t e4 = blockIdx.x*kReduceCols + col;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if(e4*4u < len)
     {
-        const uint32_t per = (rows + 31u)/32u;
+        const uint32_t per = (rows + kReduceSegs - 1u)/kReduceSegs;
         const uint32_t r0 = seg*per, r1 = (r0 + per < rows) ? r0 + per : rows;
         const float4 *p = reinterpret_cast<const float4*>(partial) + e4;
         const size_t stride4 = len/4u;
@@ -904,17 +906,34 @@ k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
     }
-    sm[seg][lane] = s;
+    sm[seg][col] = s;
     __syncthreads();
+    // 128 -> 32 -> 8 -> 2 -> 1 partial sums per column, each level adding 4 neighbours in order
+    #pragma unroll
+    for(uint32_t width = kReduceSegs/4u;width >= 1u;width /= 4u)
+    {
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool on = seg < width;
+        if(on)
+        {
+            tot = sm[seg*4u][col];
+            #pragma unroll
+            for(uint32_t k = 1;k < 4u;++k)
+            {
+                const float4 a = sm[seg*4u + k][col];
+                tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
+            }
+        }
+        __syncthreads();
+        if(on) sm[seg][col] = tot;
+        __syncthreads();
+        if(width == 2u) break;
+    }
     if(seg == 0 && e4*4u < len)
     {
-        float4 tot = sm[0][lane];
-        #pragma unroll
-        for(int k = 1;k < 32;++k)
-        {
-            const float4 a = sm[k][lane];
-            tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
-        }
+        float4 tot = sm[0][col];
+        const float4 b = sm[1][col];
+        tot.x += b.x; tot.y += b.y; tot.z += b.z; tot.w += b.w;
         float4 *o = reinterpret_cast<float4*>(out) + e4;
         if(accumulate)
         {
