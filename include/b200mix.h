@@ -255,6 +255,21 @@ B200MIX_API int b200mix_render(b200mix_device *dev, uint32_t frames, float *cons
 B200MIX_API int b200mix_render_device(b200mix_device *dev, uint32_t frames,
     const float **real_out_dev);
 
+/* The same update in two halves, for voice-sharded multi-GPU mixing: effects
+ * consume the SUMMED wet input of all ranks, so the host reduces the wet buffers between
+ * the halves.  b200mix_render_begin clears the mix buffers, mixes this device's voices and
+ * finishes its aux sends; *wet_dev is then a DEVICE pointer to the slots' Wet buffers
+ * [max_slots][wet_channels][1024] (wet_floats floats) — sum it across ranks in place, on
+ * the stream b200mix_stream() returns (e.g. ncclAllReduce).  b200mix_render_end runs the
+ * effect slots installed on THIS device (a rank installs only the slots it owns), mixes
+ * their output into Dry and post-processes; real_out/results as for b200mix_render (both
+ * may be NULL), *real_out_dev (nullable) gets the device pointer like b200mix_render_device.
+ * The post-process is linear, so the ranks' RealOut blocks sum to the single-device result. */
+B200MIX_API int b200mix_render_begin(b200mix_device *dev, uint32_t frames, float **wet_dev,
+    size_t *wet_floats);
+B200MIX_API int b200mix_render_end(b200mix_device *dev, float *const *real_out,
+    b200mix_voice_result *results, const float **real_out_dev);
+
 /* ---- host-side parameter helpers (no GPU involved) -------------------------- */
 /* The HRTF data set and the per-voice HRIR lookup of the parameter stage:
  * LoadHrtf03 (core/hrtf_loader.cpp:583-721, "MinPHR03" files such as hrtf/Default HRTF.mhr)

@@ -114,6 +114,7 @@ struct b200mix_device {
     float *d_cubic_filter{nullptr};          // gCubicTable (reverb modulation taps)
     uint32_t reverb_slots{0};
 
+    bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool profile{false};
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
     bool ev_valid{false};
@@ -867,7 +868,9 @@ int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, 
     return B200MIX_OK;
 }
 
-static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
+// Phase A of an update: clear the mix buffers, mix every voice, reduce the partial rows and
+// finish the aux sends -> the slots' Wet buffers are complete (alc/alu.cpp:2196-2206).
+static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results, bool force_sends)
 {
     const b200mix_device_desc &dd = d->desc;
     if(frames < 1 || frames > B200MIX_LINE_SIZE)
@@ -992,8 +995,8 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     }
     CUDA_TRY(d, cudaGetLastError());
 
-    // ---- aux sends + effect slots (alc/alu.cpp:2196-2198, 2252-2256) ----
-    if(d->active_slots)
+    // ---- aux sends (core/voice.cpp:967-980) ----
+    if((d->active_slots || force_sends) && d->d_wet && d->d_slot_start)
     {
         if(d->sends_dirty)
         {
@@ -1049,6 +1052,18 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
             k_send_gains_update<<<(tot + 127)/128, 128, 0, d->stream>>>(SM, d->num_entries);
             ++d->launches;
         }
+        CUDA_TRY(d, cudaGetLastError());
+    }
+    return B200MIX_OK;
+}
+
+// Phase B: run the effect slots on their Wet input, mix their output into Dry, post-process
+// (alc/alu.cpp:2252-2256, 2439-2443).
+static int render_phase_b(b200mix_device *d, uint32_t frames)
+{
+    const b200mix_device_desc &dd = d->desc;
+    if(d->active_slots)
+    {
         ConvParams CP{};
         CP.slots = d->d_slots; CP.wet = d->d_wet; CP.twiddle = d->d_twiddle;
         CP.frames = frames; CP.cw = dd.wet_channels; CP.num_slots = dd.max_slots;
@@ -1128,11 +1143,16 @@ static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
     return B200MIX_OK;
 }
 
-int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
+static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
+{
+    if(d->mid_render) { d->error = "render: a render_begin is pending"; return B200MIX_ERR_INVALID; }
+    if(int rc = render_phase_a(d, frames, want_results, false)) return rc;
+    return render_phase_b(d, frames);
+}
+
+static int render_collect(b200mix_device *d, uint32_t frames, float *const *real_out,
     b200mix_voice_result *results)
 {
-    if(!d) return B200MIX_ERR_INVALID;
-    if(int rc = render_launch(d, frames, results != nullptr)) return rc;
     const b200mix_device_desc &dd = d->desc;
     if(real_out)
         CUDA_TRY(d, cudaMemcpyAsync(d->h_real, d->d_real, size_t(dd.real_channels)*kLine*sizeof(float),
@@ -1153,6 +1173,37 @@ int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
             results[v] = b200mix_voice_result{0, 0u, B200MIX_VF_STOPPED, 0u};
     }
     return B200MIX_OK;
+}
+
+int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
+    b200mix_voice_result *results)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(int rc = render_launch(d, frames, results != nullptr)) return rc;
+    return render_collect(d, frames, real_out, results);
+}
+
+int b200mix_render_begin(b200mix_device *d, uint32_t frames, float **wet_dev, size_t *wet_floats)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(d->mid_render) { d->error = "render_begin: already begun"; return B200MIX_ERR_INVALID; }
+    if(int rc = render_phase_a(d, frames, true, true)) return rc;
+    d->mid_render = true; d->mid_frames = frames;
+    if(wet_dev) *wet_dev = d->d_wet;
+    if(wet_floats) *wet_floats = d->d_wet ? size_t(d->desc.max_slots)*d->desc.wet_channels*kLine : 0;
+    return B200MIX_OK;
+}
+
+int b200mix_render_end(b200mix_device *d, float *const *real_out, b200mix_voice_result *results,
+    const float **real_out_dev)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(!d->mid_render) { d->error = "render_end: no render_begin pending"; return B200MIX_ERR_INVALID; }
+    d->mid_render = false;
+    if(int rc = render_phase_b(d, d->mid_frames)) return rc;
+    if(real_out_dev) *real_out_dev = d->d_real;
+    if(!real_out && !results) return B200MIX_OK;
+    return render_collect(d, d->mid_frames, real_out, results);
 }
 
 int b200mix_render_device(b200mix_device *d, uint32_t frames, const float **real_out_dev)

@@ -30,3 +30,18 @@ def reduce_real_out(block, dst: int = 0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(block, dst=dst, op=dist.ReduceOp.SUM)
     return block
+
+
+def slot_owner(slot: int, world: int) -> int:
+    """Effect slots are independent of each other: slot s runs on rank s mod G."""
+    return slot % world
+
+
+def allreduce_wet(wet):
+    """Sums the slots' Wet buffers of all ranks in place (torch tensor viewing the device's
+    wet storage between b200mix_render_begin and b200mix_render_end): effects consume the
+    summed send input.  Under NCCL call it with the mixer's stream current."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(wet, op=dist.ReduceOp.SUM)
+    return wet

@@ -250,6 +250,7 @@ struct oracle_device {
     float resample_data[RESBUF];
     float samples[LINE];
     float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
+    uint32_t mid_frames;       /* between oracle_render_begin and oracle_render_end */
     float hrtf_samples[LINE+HIST];
     float temp[LINE], temp2[LINE];
 };
@@ -1223,8 +1224,9 @@ static void slot_convolution_process(oracle_device *d, oslot *s, const float *in
 }
 
 /* DeviceBase::renderSamples(unsigned) + ProcessContexts, alc/alu.cpp:2412-2459,2177-2273 */
-int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
-    b200mix_voice_result *results)
+/* First half of an update: clear, voice loop (alc/alu.cpp:2196-2206).  *wet_host is the
+ * oracle's own wet storage [max_slots][wet_channels][1024] (a HOST pointer here). */
+int oracle_render_begin(oracle_device *d, uint32_t frames, float **wet_host, size_t *wet_floats)
 {
     if(frames < 1 || frames > LINE) return B200MIX_ERR_INVALID;
     const b200mix_device_desc *dd = &d->desc;
@@ -1238,6 +1240,20 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
         if(v->state == 1 || v->state == 2)
             voice_mix(d, v, frames, NULL);
     }
+    d->mid_frames = frames;
+    if(wet_host) *wet_host = &d->wet[0][0];
+    if(wet_floats) *wet_floats = (size_t)dd->max_slots*dd->wet_channels*LINE;
+    return B200MIX_OK;
+}
+
+/* Second half: slot loop and post-process (alc/alu.cpp:2252-2256, 2439-2443). */
+int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_result *results,
+    const float **real_out_host)
+{
+    const b200mix_device_desc *dd = &d->desc;
+    const uint32_t frames = d->mid_frames;
+    if(frames < 1) return B200MIX_ERR_INVALID;
+    d->mid_frames = 0;
     /* EffectState::process for every slot (alc/alu.cpp:2252-2256); slots here have no
      * slot targets, so each mixes straight into Dry (mOutTarget, alc/alu.cpp:626-633). */
     for(uint32_t si = 0;si < dd->max_slots;++si)
@@ -1259,6 +1275,7 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     default: return B200MIX_ERR_UNSUPPORTED;
     }
 
+    if(real_out_host) *real_out_host = &d->real[0][0];
     if(real_out)
         for(uint32_t c = 0;c < dd->real_channels;++c)
             if(real_out[c]) memcpy(real_out[c], d->real[c], sizeof(float)*frames);
@@ -1272,6 +1289,14 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
             results[i].buffers_done = 0;
         }
     return B200MIX_OK;
+}
+
+int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
+    b200mix_voice_result *results)
+{
+    const int rc = oracle_render_begin(d, frames, NULL, NULL);
+    if(rc) return rc;
+    return oracle_render_end(d, real_out, results, NULL);
 }
 
 int oracle_get_dry(oracle_device *d, float *dry)

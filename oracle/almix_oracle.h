@@ -74,6 +74,9 @@ int  oracle_voices_filters(oracle_device *dev, uint32_t n, const b200mix_voice_f
 int  oracle_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5]);
 int  oracle_render(oracle_device *dev, uint32_t frames, float *const *real_out,
     b200mix_voice_result *results);
+int  oracle_render_begin(oracle_device *dev, uint32_t frames, float **wet_host, size_t *wet_floats);
+int  oracle_render_end(oracle_device *dev, float *const *real_out, b200mix_voice_result *results,
+    const float **real_out_host);
 int  oracle_slot_convolution(oracle_device *dev, uint32_t slot, uint32_t ir_channels,
     uint32_t ir_frames, const float *ir);
 int  oracle_slot_output_gains(oracle_device *dev, uint32_t slot, uint32_t lines, const float *gains);

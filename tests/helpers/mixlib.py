@@ -49,6 +49,10 @@ class MixLib:
         self.voices_filters.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         self.biquad_coeffs = f("biquad_coeffs")
         self.biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        self.render_begin = f("render_begin")
+        self.render_begin.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        self.render_end = f("render_end")
+        self.render_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
         self.get_dry = f("get_dry")
         self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
 
@@ -147,6 +151,24 @@ class MixDevice:
         rc = self.m.render(self.h, frames, ptrs, res)
         assert rc == 0, f"render -> {rc}"
         return (out, res) if want_results else out
+
+    def render_begin(self, frames=1024):
+        """Returns (wet pointer, float count): a host pointer on the oracle, a device pointer
+        on the product."""
+        self._frames = frames
+        ptr = C.c_void_p()
+        cnt = C.c_size_t()
+        rc = self.m.render_begin(self.h, frames, C.byref(ptr), C.byref(cnt))
+        assert rc == 0, f"render_begin -> {rc}"
+        return ptr.value, cnt.value
+
+    def render_end(self):
+        ch = self.desc.real_channels
+        out = np.zeros((ch, self._frames), dtype=np.float32)
+        ptrs = (C.c_void_p * ch)(*[out[c].ctypes.data for c in range(ch)])
+        rc = self.m.render_end(self.h, ptrs, None, None)
+        assert rc == 0, f"render_end -> {rc}"
+        return out
 
     def dry(self):
         out = np.zeros((self.desc.dry_channels, abi.LINE), dtype=np.float32)

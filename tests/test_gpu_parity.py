@@ -279,3 +279,78 @@ def test_direct_and_send_filters_vs_oracle_ragged_updates(hrtf):
     # uses FMA).  The CUDA filter runs the reference's exact operation order; what is left is this
     # noise floor, so the bound here is 3x the usual one — still 3x inside north_star's tolerance.
     _check(outs[1], outs[0], "direct + send filters", rms_tol=3e-6, max_tol=3e-5)
+
+
+def _cuda_view(ptr, count):
+    import torch
+
+    class _W:
+        pass
+    w = _W()
+    w.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(w, device=torch.device("cuda", 0))
+
+
+def test_two_device_slot_ownership_equals_single_device():
+    """SURVEY §8e on one GPU: two b200mix devices stand for two ranks — voices split in
+    halves, each reverb slot installed only on its owner, the Wet buffers summed between
+    render_begin and render_end (what ncclAllReduce does across GPUs), RealOut blocks added.
+    The result must equal one device mixing everything."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(77)
+    nv, ir = 32, 64
+    desc = synth.hrtf_desc(nv, ir)
+    desc.num_sends = 1
+    desc.wet_channels = 4
+    desc.max_slots = 2
+    params, coeffs, dry = synth.voice_set(rng, nv, ir)
+    send = (rng.standard_normal((nv, 1, 4)) * 0.3).astype(np.float32)
+    for k, p in enumerate(params):
+        p.send_slot[0] = k % 2
+    fxs = [golden.load("hrtf_bsinc24_reverb_v6"), golden.load("hrtf_spline_reverb_dens0_mod_v4")]
+    sizes = (1024, 300, 1024, 1024, 17, 1024)
+    lib = mixlib.product()
+    lib.lib.b200mix_stream.restype = C.c_void_p
+    lib.lib.b200mix_stream.argtypes = [C.c_void_p]
+
+    def make(voices, owned):
+        dev = MixDevice(lib, desc)
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in voices:
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        for s, fx in enumerate(fxs):
+            if s in owned:
+                dev.slot_reverb(s, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                                fx["reverb_gains"])
+        dev.voices_update([params[i] for i in voices], coeffs[voices], dry[voices], send[voices])
+        return dev
+
+    single = make(list(range(nv)), {0, 1})
+    ref = np.concatenate([single.render(f) for f in sizes], axis=1)
+    # begin/end on one device is the same update as render
+    single2 = make(list(range(nv)), {0, 1})
+    o = []
+    for f in sizes:
+        single2.render_begin(f)
+        o.append(single2.render_end())
+    assert np.array_equal(np.concatenate(o, axis=1), ref)
+    single.close()
+    single2.close()
+
+    ranks = [make(list(range(0, nv // 2)), {0}), make(list(range(nv // 2, nv)), {1})]
+    outs = []
+    for f in sizes:
+        wets = []
+        for dev in ranks:
+            ptr, cnt = dev.render_begin(f)
+            wets.append(_cuda_view(ptr, cnt))
+        torch.cuda.synchronize()
+        total = wets[0] + wets[1]
+        for w in wets:
+            w.copy_(total)
+        torch.cuda.synchronize()
+        outs.append(sum(dev.render_end() for dev in ranks))
+    for dev in ranks:
+        dev.close()
+    _check(np.concatenate(outs, axis=1), ref, "two-device slot ownership")

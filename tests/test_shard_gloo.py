@@ -84,3 +84,79 @@ def test_two_rank_reduce_equals_single_process_mix():
     assert np.abs(full).max() > 1e-3
     scale = max(1.0, float(np.abs(full).max()))   # fp32 re-association of the two partial sums
     assert err.max() <= 5e-6 * scale and np.sqrt((err ** 2).mean()) <= 5e-7 * scale
+
+
+# ---- effect slots: wet all-reduce between the two halves of the update --------------------
+def _mix_slots(voices, total, updates, rank, world):
+    """Voices `voices` on this rank; 2 reverb slots, each installed only on its owner rank;
+    the wet buffers are summed across ranks between render_begin and render_end."""
+    import ctypes as C
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "openal-soft_b200"))
+    from helpers import golden, mixlib, synth
+    from helpers.mixlib import MixDevice
+    from pyb200mix import abi, scene
+    rng = np.random.default_rng(21)
+    desc = synth.hrtf_desc(total, 64)
+    desc.num_sends = 1
+    desc.wet_channels = 4
+    desc.max_slots = 2
+    params, coeffs, dry = synth.voice_set(rng, total, 64)
+    send = (rng.standard_normal((total, 1, 4)) * 0.3).astype(np.float32)
+    for k, p in enumerate(params):
+        p.send_slot[0] = k % 2
+        p.loop_end = 6000
+        p.position %= 3000
+    fxs = [golden.load("hrtf_bsinc24_reverb_v6"), golden.load("hrtf_spline_reverb_dens0_mod_v4")]
+    dev = MixDevice(mixlib.oracle(), desc)
+    dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+    for i in voices:
+        dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i, 6000))
+    for s_, fx in enumerate(fxs):
+        if shard.slot_owner(s_, world) == rank:
+            dev.slot_reverb(s_, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                            fx["reverb_gains"])
+    dev.voices_update([params[i] for i in voices], coeffs[voices], dry[voices], send[voices])
+    outs = []
+    for _ in range(updates):
+        ptr, cnt = dev.render_begin()
+        wet = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(cnt,))
+        shard.allreduce_wet(torch.from_numpy(wet))        # in place on the oracle's storage
+        outs.append(dev.render_end())
+    dev.close()
+    return np.stack(outs)
+
+
+def _slot_worker(rank, world, port, total, updates, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard.shard_range(total, world, rank)
+    out = _mix_slots(list(range(first, first + count)), total, updates, rank, world)
+    block = torch.from_numpy(out.copy())
+    shard.reduce_real_out(block, dst=0)
+    if rank == 0:
+        ret.put(block.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_slot_ownership_equals_single_process_mix():
+    total, updates, world = 16, 4, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_slot_worker, args=(r, world, port, total, updates, ret))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    reduced = ret.get(timeout=150)
+    for p in procs:
+        p.join(timeout=30)
+    single = _mix_slots(list(range(total)), total, updates, 0, 1)
+    scale = float(np.abs(single).max())
+    assert scale > 1e-3
+    assert np.abs(reduced - single).max() <= 5e-6 * max(scale, 1.0)
