@@ -115,6 +115,14 @@ struct b200mix_device {
     uint32_t reverb_slots{0};
 
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
+    // parked dry bus (kernel variants without register dry accumulators)
+    std::vector<uint8_t> h_hrtf;             // host mirror: voice mixes through its own HRIR
+    std::vector<SendEntry> h_dry_entries;
+    SendEntry *d_dry_entries{nullptr};
+    uint32_t *d_dry_slot_start{nullptr};
+    uint32_t num_dry_entries{0};
+    bool dry_entries_dirty{true};
+    float *d_dry_partial{nullptr};           // [kDryChunksMax][cd][1024]
     bool profile{false};
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
     bool ev_valid{false};
@@ -160,7 +168,8 @@ Variant make_variant()
         sizeof(GroupSmem<GS, OPT, FP>)*GROUPS, HRTF};
 }
 
-// 0: HRTF ir<=64, 1: HRTF ir<=128, 2: dry <=4 channels in registers, 3: dry <=16 channels
+// 0: HRTF ir<=64, 1: HRTF ir<=128, 2: dry <=4 channels in registers,
+// 3: wider dry mixes: resample + park, the dry bus is summed by k_send_mix
 Variant get_variant(int idx)
 {
     switch(idx)
@@ -168,8 +177,25 @@ Variant get_variant(int idx)
     case 0: return make_variant<64, 2, true, 0, 17, 64>();
     case 1: return make_variant<64, 2, true, 0, 19, 128>();
     case 2: return make_variant<64, 2, false, 4, 1, 8>();
-    default: return make_variant<256, 1, false, 16, 1, 8>();
+    default: return make_variant<64, 2, false, 0, 1, 8>();
     }
+}
+
+constexpr uint32_t kDryChunksMax = 32;
+
+// Storage of the parked dry bus (variants with CDR == 0 that meet a non-HRTF voice).
+int ensure_dry_park(b200mix_device *d)
+{
+    const b200mix_device_desc &dd = d->desc;
+    if(d->d_dry_entries) return B200MIX_OK;
+    if(!d->d_xscratch)
+        if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
+    if(!d->d_sendinfo)
+        if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
+    if(int rc = dev_alloc(d, d->d_dry_entries, dd.max_voices)) return rc;
+    if(int rc = dev_alloc(d, d->d_dry_slot_start, 2)) return rc;
+    if(int rc = dev_alloc(d, d->d_dry_partial, size_t(kDryChunksMax)*dd.dry_channels*kLine)) return rc;
+    return B200MIX_OK;
 }
 
 int ensure_stage(b200mix_device *d, uint32_t n)
@@ -299,6 +325,7 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         if(int rc = dev_alloc(d, d->d_order, dd.max_voices)) return rc;
         d->h_active.assign(dd.max_voices, 0);
         d->h_cost.assign(dd.max_voices, 0);
+        d->h_hrtf.assign(dd.max_voices, 0);
         CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_results),
             size_t(dd.max_voices)*sizeof(b200mix_voice_result)));
 
@@ -393,6 +420,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
     cudaFree(d->d_dline); cudaFree(d->d_order2);
+    cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     if(d->h_fupd) cudaFreeHost(d->h_fupd);
     if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
@@ -714,7 +742,16 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
             }
         u.has_coeffs = hrtf_coeffs != nullptr && dd.ir_size > 0;
         u.has_dry = dry_gains != nullptr;
-        if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED)) d->dry_active = true;
+        if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED))
+        {
+            d->dry_active = true;
+            if(d->mix_cdr == 0)
+                if(int rc = ensure_dry_park(d)) return rc;
+        }
+        {
+            const uint8_t hv = (p.flags & B200MIX_VF_HRTF) ? 1 : 0;
+            if(d->h_hrtf[p.voice] != hv) { d->h_hrtf[p.voice] = hv; d->dry_entries_dirty = true; }
+        }
         {
             // mixing-order bookkeeping: membership and a cost key (resampler taps per output)
             const uint8_t act = (p.flags & B200MIX_VF_STOPPED) ? 0 : 1;
@@ -904,6 +941,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
         }
         d->order_dirty = false;
         d->order2_dirty = true;
+        d->dry_entries_dirty = true;
     }
     if(d->d_filt && d->order2_dirty)
     {
@@ -995,6 +1033,50 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     }
     CUDA_TRY(d, cudaGetLastError());
 
+    // ---- parked dry bus: non-HRTF voices of a variant without register accumulators ----
+    if(var.cdr == 0 && d->d_dry_entries)
+    {
+        if(d->dry_entries_dirty)
+        {
+            d->h_dry_entries.clear();
+            for(uint32_t v = 0;v < d->voice_hi;++v)
+                if(d->h_active[v] && !d->h_hrtf[v]) d->h_dry_entries.push_back(SendEntry{v, 0u});
+            d->num_dry_entries = uint32_t(d->h_dry_entries.size());
+            const uint32_t ss[2] = {0u, d->num_dry_entries};
+            CUDA_TRY(d, cudaMemcpyAsync(d->d_dry_slot_start, ss, sizeof(ss), cudaMemcpyHostToDevice, d->stream));
+            if(d->num_dry_entries)
+                CUDA_TRY(d, cudaMemcpyAsync(d->d_dry_entries, d->h_dry_entries.data(),
+                    d->num_dry_entries*sizeof(SendEntry), cudaMemcpyHostToDevice, d->stream));
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+            d->dry_entries_dirty = false;
+        }
+        if(d->num_dry_entries)
+        {
+            SendMixParams DM{};
+            DM.slot_start = d->d_dry_slot_start; DM.entries = d->d_dry_entries; DM.sendinfo = d->d_sendinfo;
+            DM.xscratch = d->d_xscratch; DM.send_cur = d->d_dry_cur; DM.send_tgt = d->d_dry_tgt;
+            DM.wet = d->d_dry; DM.frames = frames; DM.cw = dd.dry_channels; DM.num_sends = 1;
+            DM.valid_bit = kSiDry; DM.dline = d->d_dline ? d->d_dline : d->d_xscratch;
+            // enough CTAs to fill the GPU: 8 sample tiles x chunks of >= 64 entries
+            const uint32_t chunks = std::max(1u, std::min(kDryChunksMax, (d->num_dry_entries + 63u)/64u));
+            DM.chunks = chunks; DM.partial = d->d_dry_partial;
+            const uint32_t tiles = chunks > 1u ? uint32_t(kLine/128) : (frames + 127u)/128u;
+            k_send_mix<<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
+            ++d->launches;
+            if(chunks > 1u)
+            {
+                const uint32_t len = dd.dry_channels*kLine;
+                k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(
+                    d->d_dry_partial, chunks, len, d->d_dry, 1);
+                ++d->launches;
+            }
+            const uint32_t tot = d->num_dry_entries*dd.dry_channels;
+            k_send_gains_update<<<(tot + 127)/128, 128, 0, d->stream>>>(DM, d->num_dry_entries);
+            ++d->launches;
+            CUDA_TRY(d, cudaGetLastError());
+        }
+    }
+
     // ---- aux sends (core/voice.cpp:967-980) ----
     if((d->active_slots || force_sends) && d->d_wet && d->d_slot_start)
     {
@@ -1025,6 +1107,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
         SM.slot_start = d->d_slot_start; SM.entries = d->d_entries; SM.sendinfo = d->d_sendinfo;
         SM.xscratch = d->d_xscratch; SM.send_cur = d->d_send_cur; SM.send_tgt = d->d_send_tgt;
         SM.wet = d->d_wet; SM.frames = frames; SM.cw = dd.wet_channels; SM.num_sends = dd.num_sends;
+        SM.valid_bit = kSiSend; SM.chunks = 1;
         if(d->d_filt && d->num_entries)
         {
             if(d->fscratch_rows < d->num_entries)
@@ -1044,7 +1127,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             k_filters<<<(d->num_entries + 31u)/32u, 32, 0, d->stream>>>(FP);
             ++d->launches;
         }
-        k_send_mix<<<dim3(dd.max_slots, (frames + 127)/128), 256, 0, d->stream>>>(SM);
+        k_send_mix<<<dim3(dd.max_slots, (frames + 127)/128, 1), 256, 0, d->stream>>>(SM);
         ++d->launches;
         if(d->num_entries)
         {

@@ -48,13 +48,19 @@ struct SendEntry { uint32_t voice, send; };
 struct SendMixParams {
     const uint32_t *slot_start;     // [slots+1] CSR over entries
     const SendEntry *entries;
-    const uint32_t *sendinfo;       // per voice: bit0 valid, bit1 playing, bits 8.. counter
+    const uint32_t *sendinfo;       // per voice: kSi* bits, bits 8.. fade counter
     const float *xscratch;          // [max_voices][1024] resampled lines of voices with sends
     float *send_cur; const float *send_tgt;   // [max_voices][num_sends][cw]
     float *wet;                     // [slots][cw][1024]
     uint32_t frames, cw, num_sends;
     FilterRec *filt; uint32_t filt_paths;   // send filters (null: none ever set)
     const float *fscratch;          // [entries][1024] filtered lines of entries with an active filter
+    // The same kernel sums the DRY bus of parked non-HRTF voices: one pseudo slot whose
+    // entries are (voice, 0), gains dry_cur/dry_tgt, valid bit kSiDry, filtered line dline[v].
+    uint32_t valid_bit;             // kSiSend or kSiDry
+    const float *dline;             // dry bus only: [max_voices][1024] (deferred voices), else null
+    uint32_t chunks;                // gridDim.z: entry ranges summed by separate CTAs
+    float *partial;                 // [chunks][slots][cw][1024] when chunks > 1 (then k_reduce_rows)
 };
 
 // ---- direct and send filters ------------------------------------------------------------
@@ -174,8 +180,34 @@ __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
         if(run)
         {
             const uint32_t cnt = min(32u, n - tb*32u);
-            for(uint32_t i = 0;i < cnt;++i)
+            uint32_t i = 0;
+            while(i < cnt)
             {
+                if(cnt - i >= 8u && (counter <= 0 || steprem > 8u))
+                {
+                    // 8 samples with constant coefficients: straight-line code, so the input
+                    // products are off the recurrence's critical path
+                    float xin[8], yout[8];
+                    #pragma unroll
+                    for(int u = 0;u < 8;++u) xin[u] = tile[lane][i + u];
+                    #pragma unroll
+                    for(int u = 0;u < 8;++u)
+                    {
+                        const float x0 = xin[u];
+                        const float y0 = __fadd_rn(__fmul_rn(x0, c0.b0), z01);
+                        z01 = __fadd_rn(__fsub_rn(__fmul_rn(x0, c0.b1), __fmul_rn(y0, c0.a1)), z02);
+                        z02 = __fsub_rn(__fmul_rn(x0, c0.b2), __fmul_rn(y0, c0.a2));
+                        const float y1 = __fadd_rn(__fmul_rn(y0, c1.b0), z11);
+                        z11 = __fadd_rn(__fsub_rn(__fmul_rn(y0, c1.b1), __fmul_rn(y1, c1.a1)), z12);
+                        z12 = __fsub_rn(__fmul_rn(y0, c1.b2), __fmul_rn(y1, c1.a2));
+                        yout[u] = y1;
+                    }
+                    #pragma unroll
+                    for(int u = 0;u < 8;++u) tile[lane][i + u] = yout[u];
+                    if(counter > 0) steprem -= 8u;
+                    i += 8u;
+                    continue;
+                }
                 // BiquadFilter::dualProcess body (biquad.cpp:264-275)
                 const float x0 = tile[lane][i];
                 const float y0 = __fadd_rn(__fmul_rn(x0, c0.b0), z01);
@@ -185,6 +217,7 @@ __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
                 z11 = __fadd_rn(__fsub_rn(__fmul_rn(y0, c1.b1), __fmul_rn(y1, c1.a1)), z12);
                 z12 = __fsub_rn(__fmul_rn(y0, c1.b2), __fmul_rn(y1, c1.a2));
                 tile[lane][i] = y1;
+                ++i;
                 // BiquadInterpFilter::dualProcess stepping (biquad.cpp:293-338)
                 if(counter > 0 && --steprem == 0u)
                 {
@@ -229,10 +262,11 @@ __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
     }
 }
 
-// grid (slot, tile of 128 samples), 256 threads = 8 warps.  Each warp takes every 8th
-// (voice, send) entry of the slot; a lane owns 4 consecutive samples (one float4 load of the
-// parked line) and up to 4 wet channels.  The 8 warps' partial sums are combined through
-// shared memory in warp order, so the result does not depend on scheduling.
+// grid (slot, tile of 128 samples, entry chunk), 256 threads = 8 warps.  Each warp takes
+// every 8th (voice, send) entry of the chunk; a lane owns 4 consecutive samples (one float4
+// load of the parked line) and up to 4 wet channels.  The 8 warps' partial sums are combined
+// through shared memory in warp order, chunks through k_reduce_rows, so the result does not
+// depend on scheduling.
 __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
 {
     __shared__ float part[8][4][128];
@@ -240,7 +274,16 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t i0 = blockIdx.y*128u + lane*4u;
     const uint32_t n = Q.frames;
-    const uint32_t e0 = Q.slot_start[slot], e1 = Q.slot_start[slot+1];
+    uint32_t e0 = Q.slot_start[slot], e1 = Q.slot_start[slot+1];
+    if(Q.chunks > 1u)
+    {
+        const uint32_t per = (e1 - e0 + Q.chunks - 1u)/Q.chunks;
+        e0 = min(e0 + blockIdx.z*per, e1);
+        e1 = min(e0 + per, e1);
+    }
+    float *outBase = Q.chunks > 1u
+        ? Q.partial + (size_t(blockIdx.z)*gridDim.x + slot)*Q.cw*kLine
+        : Q.wet + size_t(slot)*Q.cw*kLine;
     for(uint32_t c0 = 0;c0 < Q.cw;c0 += 4u)
     {
         float acc[4][4];
@@ -250,12 +293,16 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
         {
             const SendEntry en = Q.entries[e];
             const uint32_t info = Q.sendinfo[en.voice];
-            if(!(info & kSiSend)) continue;
-            const bool playing = (info & 2u) != 0;
-            const uint32_t counter = info >> 8;
+            if(!(info & Q.valid_bit)) continue;
+            const bool playing = (info & kSiPlaying) != 0;
+            const uint32_t counter = (info >> 8) & 0xffu;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             const float *line = Q.xscratch + size_t(en.voice)*kLine;
-            if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active)
+            if(Q.dline)
+            {
+                if(info & kSiDeferred) line = Q.dline + size_t(en.voice)*kLine;
+            }
+            else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active)
                 line = Q.fscratch + size_t(e)*kLine;
             if(i0 < n) x = *reinterpret_cast<const float4*>(line + i0);
             const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -300,12 +347,12 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
             #pragma unroll
             for(uint32_t cc = 0;cc < 4u;++cc)
             {
-                if(c0 + cc < Q.cw && i < n)
+                if(c0 + cc < Q.cw && (i < n || Q.chunks > 1u))
                 {
                     float sum = part[0][cc][threadIdx.x];
                     #pragma unroll
                     for(int wv = 1;wv < 8;++wv) sum += part[wv][cc][threadIdx.x];
-                    Q.wet[(size_t(slot)*Q.cw + c0 + cc)*kLine + i] = sum;
+                    outBase[size_t(c0 + cc)*kLine + i] = sum;
                 }
             }
         }
@@ -321,9 +368,9 @@ __global__ void k_send_gains_update(const SendMixParams Q, uint32_t num_entries)
     if(e >= num_entries) return;
     const SendEntry en = Q.entries[e];
     const uint32_t info = Q.sendinfo[en.voice];
-    if(!(info & kSiSend)) return;
-    const bool playing = (info & 2u) != 0;
-    const uint32_t counter = info >> 8, n = Q.frames;
+    if(!(info & Q.valid_bit)) return;
+    const bool playing = (info & kSiPlaying) != 0;
+    const uint32_t counter = (info >> 8) & 0xffu, n = Q.frames;
     const float delta = counter ? 1.0f/float(counter) : 0.0f;
     const uint32_t fadeLen = counter < n ? counter : n;
     const size_t g = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw + c;

@@ -105,7 +105,7 @@ struct MixParams {
 };
 
 // sendinfo bits
-constexpr uint32_t kSiSend = 1u, kSiPlaying = 2u, kSiDeferred = 4u, kSiDirty = 8u;
+constexpr uint32_t kSiSend = 1u, kSiPlaying = 2u, kSiDeferred = 4u, kSiDirty = 8u, kSiDry = 16u;
 
 __device__ __forceinline__ void group_sync(int id, int count)
 { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
@@ -598,19 +598,24 @@ k_mix_voices(const MixParams P)
 
         // ---- auxiliary sends (core/voice.cpp:967-980): the UNFILTERED resampled line is
         // parked in HBM; k_send_filters / k_send_mix take it from there slot by slot ----
+        // Non-HRTF voices of a kernel variant without register dry accumulators (CDR == 0:
+        // HRTF devices, or more than 4 dry channels) do not mix here at all: the line is
+        // parked and k_send_mix sums the dry bus like one more slot (deterministic, no atomics).
+        const bool parkDry = CDR == 0 && !isHrtf;
         if(P.sendinfo && !second)
         {
             const bool sends = P.num_sends && h4.w;
-            if(sends || defer)
+            if(sends || defer || parkDry)
                 for(uint32_t k = t;k < n;k += GS) P.xscratch[size_t(v)*kLine + k] = xs[k];
             if(t == 0)
-                P.sendinfo[v] = (sends || defer) ? ((sends ? kSiSend : 0u) | (playing ? kSiPlaying : 0u)
-                    | (defer ? kSiDeferred : 0u) | (dirty ? kSiDirty : 0u) | (counter << 8)) : 0u;
+                P.sendinfo[v] = (sends || defer || parkDry) ? ((sends ? kSiSend : 0u)
+                    | (playing ? kSiPlaying : 0u) | (defer ? kSiDeferred : 0u) | (dirty ? kSiDirty : 0u)
+                    | (parkDry ? kSiDry : 0u) | (counter << 8)) : 0u;
         }
         // direct-path DoFilters (core/voice.cpp:943-946) with an inactive pair: clear()
         if(dfilt && !second && !defer) filter_clear(*dfilt, t);
 
-        if(!defer)
+        if(!defer && !parkDry)
         {
         if(isHrtf)
         {
@@ -750,8 +755,7 @@ k_mix_voices(const MixParams P)
                         for(int cc = 0;cc < (CDR > 0 ? CDR : 1);++cc)
                             if(cc == int(c)) accD[cc][r] += val;
                     }
-                    else if(gsel != 0.0f)
-                        atomicAdd(P.dry + size_t(c)*kLine + i, val);
+
                 }
                 if(t == 0)
                     S.newGain[c] = early ? (cg + step*float(fadeLen)) : tg;
@@ -799,7 +803,7 @@ k_mix_voices(const MixParams P)
         if(t == 0)
         {
             // Gains.Current write-back, after every thread has read the old values
-            if(!isHrtf && !defer)
+            if(!isHrtf && !defer && !parkDry)
                 for(uint32_t c = 0;c < P.cd;++c)
                     P.dry_cur[size_t(v)*P.cd + c] = S.newGain[c];
         }
@@ -1254,55 +1258,62 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
 {
     constexpr float F1[4] = {0.479400865589f, 0.876218493539f, 0.976597589508f, 0.997499255936f};
     constexpr float F2[4] = {0.161758498368f, 0.733028932341f, 0.945349700329f, 0.990599156684f};
+    // chain inputs and outputs live in shared memory: the serial recurrences never wait on
+    // a global load (row stride 1025+8 keeps the five chain threads on different banks)
+    constexpr int kRow = kLine + 9;
+    __shared__ float sIn[5][kRow];
+    __shared__ float sOut[5][kRow];
     const uint32_t n = Q.frames;
     const float *w = Q.dry, *x = Q.dry + kLine, *y = Q.dry + 2*kLine;
     float *left = Q.real + size_t(Q.real_left)*kLine, *right = Q.real + size_t(Q.real_right)*kLine;
-    float *outS = Q.scratch, *outWX = Q.scratch + 1025, *outD = Q.scratch + 2*1025;
-    float *outL = Q.scratch + 3*1025, *outR = Q.scratch + 4*1025;
-    const int chain = threadIdx.x;
-    if(chain < 5)
+    for(uint32_t k = threadIdx.x;k < n;k += blockDim.x)
+    {
+        const float wk = w[k], xk = x[k];
+        sIn[0][k] = 0.4698463f*wk + 0.0757602682546f*xk;
+        sIn[1][k] = -0.17101005f*wk + 0.208149636675f*xk;
+        sIn[2][k] = y[k];
+        sIn[3][k] = left[k];
+        sIn[4][k] = right[k];
+    }
+    __syncthreads();
+    // one warp per chain so the five chains run on five schedulers' worth of issue slots
+    const int chain = threadIdx.x >> 5;
+    if(chain < 5 && (threadIdx.x & 31) == 0)
     {
         float *st = Q.state + chain*8;
-        float z0[4], z1[4];
+        float z0[4], z1[4], c[4];
         #pragma unroll
-        for(int i = 0;i < 4;++i) { z0[i] = st[i*2]; z1[i] = st[i*2+1]; }
-        const bool second = chain == 1;
-        float *dst = chain == 0 ? outS+1 : chain == 1 ? outWX : chain == 2 ? outD+1
-            : chain == 3 ? outL+1 : outR+1;
+        for(int i = 0;i < 4;++i) { z0[i] = st[i*2]; z1[i] = st[i*2+1]; c[i] = chain == 1 ? F2[i] : F1[i]; }
+        // the Filter1 chains are delayed by one sample: out[0] is last update's final output
+        const int off = chain == 1 ? 0 : 1;
+        const float *src = sIn[chain];
+        float *dst = sOut[chain] + off;
+        #pragma unroll 4
         for(uint32_t k = 0;k < n;++k)
         {
-            float v;
-            if(chain == 0) v = 0.4698463f*w[k] + 0.0757602682546f*x[k];
-            else if(chain == 1) v = -0.17101005f*w[k] + 0.208149636675f*x[k];
-            else if(chain == 2) v = y[k];
-            else if(chain == 3) v = left[k];
-            else v = right[k];
+            float v = src[k];
             #pragma unroll
             for(int i = 0;i < 4;++i)
             {
-                const float c = second ? F2[i] : F1[i];
-                const float yy = v*c + z0[i];
+                const float yy = v*c[i] + z0[i];
                 z0[i] = z1[i];
-                z1[i] = yy*c - v;
+                z1[i] = yy*c[i] - v;
                 v = yy;
             }
             dst[k] = v;
         }
         #pragma unroll
         for(int i = 0;i < 4;++i) { st[i*2] = z0[i]; st[i*2+1] = z1[i]; }
-        // the one-sample output delay of the Filter1 chains
         float *delay = Q.state + 40;
-        if(chain == 0) { outS[0] = delay[0]; delay[0] = outS[n]; }
-        else if(chain == 2) { outD[0] = delay[1]; delay[1] = outD[n]; }
-        else if(chain == 3) { outL[0] = delay[2]; delay[2] = outL[n]; }
-        else if(chain == 4) { outR[0] = delay[3]; delay[3] = outR[n]; }
+        const int di = chain == 0 ? 0 : chain == 2 ? 1 : chain == 3 ? 2 : 3;
+        if(chain != 1) { sOut[chain][0] = delay[di]; delay[di] = sOut[chain][n]; }
     }
     __syncthreads();
     for(uint32_t i = threadIdx.x;i < n;i += blockDim.x)
     {
-        const float dd = outWX[i] + 0.267586995182f*outD[i];
-        left[i] = outS[i] + dd + outL[i];
-        right[i] = outS[i] - dd + outR[i];
+        const float dd = sOut[1][i] + 0.267586995182f*sOut[2][i];
+        left[i] = sOut[0][i] + dd + sOut[3][i];
+        right[i] = sOut[0][i] - dd + sOut[4][i];
     }
 }
 
