@@ -293,6 +293,11 @@ B200MIX_API int64_t b200mix_get_resampler_table(b200mix_device *dev, uint32_t wh
  * bracketed by CUDA events on the device's stream; b200mix_last_mix_kernel_ms returns the
  * duration of the most recent one (synchronises the stream), <0 if unavailable. */
 B200MIX_API int b200mix_profile(b200mix_device *dev, int enable);
+/* With b200mix_profile(dev, 2) every update also records stage marks; this returns the
+ * durations (ms) of the last update's 8 stages: 0 clear, 1 voice kernel, 2 direct filters +
+ * deferred voice pass, 3 row reduction, 4 parked dry bus, 5 aux sends, 6 effect slots +
+ * slot output mix, 7 post-process.  Returns the stage count, <0 if unavailable. */
+B200MIX_API int b200mix_last_stage_ms(b200mix_device *dev, float *ms, uint32_t count);
 B200MIX_API float b200mix_last_mix_kernel_ms(b200mix_device *dev);
 /* Number of CUDA kernels this device has launched so far. */
 B200MIX_API uint64_t b200mix_launch_count(const b200mix_device *dev);

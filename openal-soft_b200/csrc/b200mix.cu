@@ -123,9 +123,18 @@ struct b200mix_device {
     uint32_t num_dry_entries{0};
     bool dry_entries_dirty{true};
     float *d_dry_partial{nullptr};           // [kDryChunksMax][cd][1024]
+    float *d_dry_geff{nullptr};              // [max_voices][cd]
+    float *d_send_geff{nullptr};             // [max_voices*num_sends][cw]
+    float4 *d_dry_gramp{nullptr}, *d_send_gramp{nullptr};
+    float *d_send_partial{nullptr};          // [send_chunks][max_slots][cw][1024]
+    uint32_t send_partial_chunks{0}, max_slot_entries{0};
     bool profile{false};
     cudaEvent_t ev_mix0{nullptr}, ev_mix1{nullptr};
     bool ev_valid{false};
+    // stage marks of the last update (profile >= 2): see b200mix_last_stage_ms
+    static constexpr int kStages = 8;
+    cudaEvent_t ev_stage[kStages + 1]{};
+    bool stage_valid{false}; int profile_level{0};
 
     // mixing order (host mirror of which voices are configured active, and their cost)
     std::vector<uint8_t> h_active;
@@ -181,7 +190,7 @@ Variant get_variant(int idx)
     }
 }
 
-constexpr uint32_t kDryChunksMax = 32;
+constexpr uint32_t kDryChunksMax = 128;
 
 // Storage of the parked dry bus (variants with CDR == 0 that meet a non-HRTF voice).
 int ensure_dry_park(b200mix_device *d)
@@ -195,6 +204,8 @@ int ensure_dry_park(b200mix_device *d)
     if(int rc = dev_alloc(d, d->d_dry_entries, dd.max_voices)) return rc;
     if(int rc = dev_alloc(d, d->d_dry_slot_start, 2)) return rc;
     if(int rc = dev_alloc(d, d->d_dry_partial, size_t(kDryChunksMax)*dd.dry_channels*kLine)) return rc;
+    if(int rc = dev_alloc(d, d->d_dry_geff, size_t(dd.max_voices)*dd.dry_channels)) return rc;
+    if(int rc = dev_alloc(d, d->d_dry_gramp, size_t(dd.max_voices)*dd.dry_channels)) return rc;
     return B200MIX_OK;
 }
 
@@ -363,6 +374,8 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             if(int rc = dev_alloc(d, d->d_slots, dd.max_slots)) return rc;
             if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
             if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
+            if(int rc = dev_alloc(d, d->d_send_geff, size_t(dd.max_voices)*dd.num_sends*dd.wet_channels)) return rc;
+            if(int rc = dev_alloc(d, d->d_send_gramp, size_t(dd.max_voices)*dd.num_sends*dd.wet_channels)) return rc;
             d->h_send_slot.assign(size_t(dd.max_voices)*B200MIX_MAX_SENDS, B200MIX_NO_SLOT);
             if(int rc = dev_alloc(d, d->d_slot_start, dd.max_slots + 1)) return rc;
             if(int rc = dev_alloc(d, d->d_entries, size_t(dd.max_voices)*dd.num_sends)) return rc;
@@ -421,6 +434,8 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
     cudaFree(d->d_dline); cudaFree(d->d_order2);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
+    cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
+    cudaFree(d->d_dry_gramp); cudaFree(d->d_send_gramp);
     if(d->h_fupd) cudaFreeHost(d->h_fupd);
     if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
@@ -429,6 +444,7 @@ void b200mix_destroy(b200mix_device *d)
     if(d->stage_done) cudaEventDestroy(d->stage_done);
     if(d->ev_mix0) cudaEventDestroy(d->ev_mix0);
     if(d->ev_mix1) cudaEventDestroy(d->ev_mix1);
+    for(cudaEvent_t e : d->ev_stage) if(e) cudaEventDestroy(e);
     if(d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -905,6 +921,9 @@ int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, 
     return B200MIX_OK;
 }
 
+static inline void stage_mark(b200mix_device *d, int i)
+{ if(d->profile_level >= 2) cudaEventRecord(d->ev_stage[i], d->stream); }
+
 // Phase A of an update: clear the mix buffers, mix every voice, reduce the partial rows and
 // finish the aux sends -> the slots' Wet buffers are complete (alc/alu.cpp:2196-2206).
 static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results, bool force_sends)
@@ -918,6 +937,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     { d->error = "render: ambisonic decoder not set"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
 
+    stage_mark(d, 0);
     // clear MixBuffer (alc/alu.cpp:2417) and the wet buffers (alc/alu.cpp:2196-2198)
     CUDA_TRY(d, cudaMemsetAsync(d->d_dry, 0, size_t(d->dry_alloc_ch)*kLine*sizeof(float), d->stream));
     if(d->d_real != d->d_dry)
@@ -977,12 +997,14 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     P.order = d->d_order; P.num_order = d->num_order;
     P.xscratch = d->d_xscratch; P.sendinfo = d->d_sendinfo;
     P.filt = d->d_filt; P.filt_paths = 1u + dd.num_sends;
+    stage_mark(d, 1);
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
     if(d->profile) { cudaEventRecord(d->ev_mix1, d->stream); d->ev_valid = true; }
     ++d->launches;
     CUDA_TRY(d, cudaGetLastError());
 
+    stage_mark(d, 2);
     // ---- voices with an active direct filter: filter the parked lines, then mix them ----
     size_t rows2 = 0;
     if(d->d_filt && d->num_order2)
@@ -1005,6 +1027,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
         CUDA_TRY(d, cudaGetLastError());
     }
 
+    stage_mark(d, 3);
     if(var.hrtf)
     {
         const uint32_t len = 2*kAccumLen;
@@ -1033,6 +1056,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     }
     CUDA_TRY(d, cudaGetLastError());
 
+    stage_mark(d, 4);
     // ---- parked dry bus: non-HRTF voices of a variant without register accumulators ----
     if(var.cdr == 0 && d->d_dry_entries)
     {
@@ -1057,11 +1081,18 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             DM.xscratch = d->d_xscratch; DM.send_cur = d->d_dry_cur; DM.send_tgt = d->d_dry_tgt;
             DM.wet = d->d_dry; DM.frames = frames; DM.cw = dd.dry_channels; DM.num_sends = 1;
             DM.valid_bit = kSiDry; DM.dline = d->d_dline ? d->d_dline : d->d_xscratch;
-            // enough CTAs to fill the GPU: 8 sample tiles x chunks of >= 64 entries
+            // a CTA's 8 warps share its entries evenly: chunks of 64 entries keep the first
+            // (fading) tile's serial work per warp short
             const uint32_t chunks = std::max(1u, std::min(kDryChunksMax, (d->num_dry_entries + 63u)/64u));
-            DM.chunks = chunks; DM.partial = d->d_dry_partial;
+            DM.chunks = chunks; DM.partial = d->d_dry_partial; DM.geff = d->d_dry_geff; DM.gramp = d->d_dry_gramp;
+            {
+                const uint32_t tot = d->num_dry_entries*dd.dry_channels;
+                k_send_gains_prepare<<<(tot + 127)/128, 128, 0, d->stream>>>(DM, d->num_dry_entries);
+                ++d->launches;
+            }
             const uint32_t tiles = chunks > 1u ? uint32_t(kLine/128) : (frames + 127u)/128u;
-            k_send_mix<<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
+            if(dd.dry_channels > 4u) k_send_mix<16><<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
+            else k_send_mix<4><<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
             ++d->launches;
             if(chunks > 1u)
             {
@@ -1077,6 +1108,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
         }
     }
 
+    stage_mark(d, 5);
     // ---- aux sends (core/voice.cpp:967-980) ----
     if((d->active_slots || force_sends) && d->d_wet && d->d_slot_start)
     {
@@ -1095,6 +1127,9 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             }
             d->h_slot_start[dd.max_slots] = uint32_t(d->h_entries.size());
             d->num_entries = uint32_t(d->h_entries.size());
+            d->max_slot_entries = 0;
+            for(uint32_t sl = 0;sl < dd.max_slots;++sl)
+                d->max_slot_entries = std::max(d->max_slot_entries, d->h_slot_start[sl+1] - d->h_slot_start[sl]);
             CUDA_TRY(d, cudaMemcpyAsync(d->d_slot_start, d->h_slot_start.data(),
                 (dd.max_slots + 1)*sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
             if(d->num_entries)
@@ -1127,8 +1162,37 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             k_filters<<<(d->num_entries + 31u)/32u, 32, 0, d->stream>>>(FP);
             ++d->launches;
         }
-        k_send_mix<<<dim3(dd.max_slots, (frames + 127)/128, 1), 256, 0, d->stream>>>(SM);
-        ++d->launches;
+        SM.geff = d->d_send_geff; SM.gramp = d->d_send_gramp;
+        if(d->num_entries)
+        {
+            const uint32_t tot = d->num_entries*dd.wet_channels;
+            k_send_gains_prepare<<<(tot + 127)/128, 128, 0, d->stream>>>(SM, d->num_entries);
+            ++d->launches;
+        }
+        {
+            // a CTA's 8 warps share its entries evenly: chunks of 128 entries per slot
+            const uint32_t chunks = std::max(1u, std::min(16u, (d->max_slot_entries + 127u)/128u));
+            if(chunks > 1u && d->send_partial_chunks < chunks)
+            {
+                CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+                cudaFree(d->d_send_partial); d->d_send_partial = nullptr; d->send_partial_chunks = 0;
+                CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_send_partial),
+                    size_t(chunks)*dd.max_slots*dd.wet_channels*kLine*sizeof(float)));
+                d->send_partial_chunks = chunks;
+            }
+            SM.chunks = chunks; SM.partial = d->d_send_partial;
+            const uint32_t tiles = chunks > 1u ? uint32_t(kLine/128) : (frames + 127u)/128u;
+            if(dd.wet_channels > 4u) k_send_mix<16><<<dim3(dd.max_slots, tiles, chunks), 256, 0, d->stream>>>(SM);
+            else k_send_mix<4><<<dim3(dd.max_slots, tiles, chunks), 256, 0, d->stream>>>(SM);
+            ++d->launches;
+            if(chunks > 1u)
+            {
+                const uint32_t len = dd.max_slots*dd.wet_channels*kLine;
+                k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(
+                    d->d_send_partial, chunks, len, d->d_wet, 1);
+                ++d->launches;
+            }
+        }
         if(d->num_entries)
         {
             const uint32_t tot = d->num_entries*dd.wet_channels;
@@ -1145,6 +1209,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
 static int render_phase_b(b200mix_device *d, uint32_t frames)
 {
     const b200mix_device_desc &dd = d->desc;
+    stage_mark(d, 6);
     if(d->active_slots)
     {
         ConvParams CP{};
@@ -1172,6 +1237,7 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         CUDA_TRY(d, cudaGetLastError());
     }
 
+    stage_mark(d, 7);
     switch(dd.post_process)
     {
     case B200MIX_POST_HRTF:
@@ -1222,6 +1288,8 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
     }
     default: break;
     }
+    stage_mark(d, 8);
+    if(d->profile_level >= 2) d->stage_valid = true;
     CUDA_TRY(d, cudaGetLastError());
     return B200MIX_OK;
 }
@@ -1338,9 +1406,21 @@ int b200mix_profile(b200mix_device *d, int enable)
         CUDA_TRY(d, cudaEventCreate(&d->ev_mix0));
         CUDA_TRY(d, cudaEventCreate(&d->ev_mix1));
     }
+    if(enable >= 2 && !d->ev_stage[0])
+        for(cudaEvent_t &e : d->ev_stage) CUDA_TRY(d, cudaEventCreate(&e));
     d->profile = enable != 0;
-    d->ev_valid = false;
+    d->profile_level = enable;
+    d->ev_valid = false; d->stage_valid = false;
     return B200MIX_OK;
+}
+
+int b200mix_last_stage_ms(b200mix_device *d, float *ms, uint32_t count)
+{
+    if(!d || !ms || !d->stage_valid) return B200MIX_ERR_INVALID;
+    if(cudaEventSynchronize(d->ev_stage[b200mix_device::kStages]) != cudaSuccess) return B200MIX_ERR_CUDA;
+    for(uint32_t i = 0;i < count && i < uint32_t(b200mix_device::kStages);++i)
+        if(cudaEventElapsedTime(&ms[i], d->ev_stage[i], d->ev_stage[i+1]) != cudaSuccess) return B200MIX_ERR_CUDA;
+    return int(b200mix_device::kStages);
 }
 
 float b200mix_last_mix_kernel_ms(b200mix_device *d)

@@ -61,6 +61,9 @@ struct SendMixParams {
     const float *dline;             // dry bus only: [max_voices][1024] (deferred voices), else null
     uint32_t chunks;                // gridDim.z: entry ranges summed by separate CTAs
     float *partial;                 // [chunks][slots][cw][1024] when chunks > 1 (then k_reduce_rows)
+    float *geff;                    // [entries][cw] gain of every entry-channel once its fade is over
+                                    // (k_send_gains_prepare), 0 for entries not mixed this update
+    float4 *gramp;                  // [entries][cw] {a, b, flat, L}: gain(i) = i < L ? a + b*i : flat
 };
 
 // ---- direct and send filters ------------------------------------------------------------
@@ -262,12 +265,16 @@ __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
     }
 }
 
-// grid (slot, tile of 128 samples, entry chunk), 256 threads = 8 warps.  Each warp takes
-// every 8th (voice, send) entry of the chunk; a lane owns 4 consecutive samples (one float4
-// load of the parked line) and up to 4 wet channels.  The 8 warps' partial sums are combined
-// through shared memory in warp order, chunks through k_reduce_rows, so the result does not
-// depend on scheduling.
-__global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
+// grid (slot, tile of 128 samples, entry chunk), 256 threads = 8 warps.  A warp takes
+// blocks of 32 consecutive (voice, send) entries of the chunk: one coalesced load brings the
+// block's entries and their sendinfo words, which are then broadcast by shuffle, so the only
+// dependent global loads inside the entry loop are the parked line (one float4 per lane,
+// 4 consecutive samples) and the gains.  All wet channels of an entry are accumulated in
+// registers in one pass (CH per pass).  The 8 warps' partial sums are combined through
+// shared memory in warp order, chunks through k_reduce_rows: the result does not depend on
+// scheduling.
+template<int CH>
+__global__ void __launch_bounds__(256, 2) k_send_mix(const SendMixParams Q)
 {
     __shared__ float part[8][4][128];
     const uint32_t slot = blockIdx.x;
@@ -281,83 +288,183 @@ __global__ void __launch_bounds__(256) k_send_mix(const SendMixParams Q)
         e0 = min(e0 + blockIdx.z*per, e1);
         e1 = min(e0 + per, e1);
     }
+    // the CTA's entries are split evenly over its 8 warps (contiguous ranges)
+    const uint32_t wblock = (e1 - e0 + 7u)/8u;
     float *outBase = Q.chunks > 1u
         ? Q.partial + (size_t(blockIdx.z)*gridDim.x + slot)*Q.cw*kLine
         : Q.wet + size_t(slot)*Q.cw*kLine;
-    for(uint32_t c0 = 0;c0 < Q.cw;c0 += 4u)
+    for(uint32_t c0 = 0;c0 < Q.cw;c0 += CH)
     {
-        float acc[4][4];
+        float acc[CH][4];
         #pragma unroll
-        for(int c = 0;c < 4;++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f; }
-        for(uint32_t e = e0 + warp;e < e1;e += 8u)
+        for(int c = 0;c < CH;++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f; }
+        // Tiles that start at sample 128 or later are past every fade (Counter <= 64): the gain
+        // of an entry-channel is the constant k_send_gains_prepare left in geff.  Full tiles
+        // only, so no per-sample bound checks: one float4 of the line, CH broadcast gains,
+        // 4*CH FMAs per entry.
+        const bool plainTile = blockIdx.y > 0u && (blockIdx.y + 1u)*128u <= n && (Q.cw & 3u) == 0u;
+        if(plainTile)
         {
-            const SendEntry en = Q.entries[e];
-            const uint32_t info = Q.sendinfo[en.voice];
-            if(!(info & Q.valid_bit)) continue;
-            const bool playing = (info & kSiPlaying) != 0;
-            const uint32_t counter = (info >> 8) & 0xffu;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float *line = Q.xscratch + size_t(en.voice)*kLine;
-            if(Q.dline)
+            for(uint32_t base = e0 + warp*wblock;base < min(e0 + (warp + 1u)*wblock, e1);base += 32u)
             {
-                if(info & kSiDeferred) line = Q.dline + size_t(en.voice)*kLine;
-            }
-            else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active)
-                line = Q.fscratch + size_t(e)*kLine;
-            if(i0 < n) x = *reinterpret_cast<const float4*>(line + i0);
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            const float delta = counter ? 1.0f/float(counter) : 0.0f;
-            const uint32_t fadeLen = counter < n ? counter : n;
-            const size_t gbase = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw;
-            #pragma unroll
-            for(uint32_t cc = 0;cc < 4u;++cc)
-            {
-                const uint32_t c = c0 + cc;
-                if(c < Q.cw)
+                const uint32_t cnt = min(32u, min(e0 + (warp + 1u)*wblock, e1) - base);
+                uint32_t myVoice = 0u, myLine = 0u;     // myLine: 0 xscratch, 1 dline, 2 fscratch
+                if(lane < cnt)
                 {
-                    // Mix_ semantics (core/mixer/mixer_c.cpp:150-186)
-                    const float tg0 = Q.send_tgt[gbase + c];
-                    const float cg = counter ? Q.send_cur[gbase + c] : tg0;
-                    const float tg = playing ? tg0 : 0.0f;
-                    const float step = (tg - cg)*delta;
-                    const bool fade = fabsf(step) > kEps;
-                    const bool early = fade && fadeLen < counter;
-                    const float flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
-                    const uint32_t start = fade ? fadeLen : 0u;
+                    const SendEntry en = Q.entries[base + lane];
+                    myVoice = en.voice;
+                    if(Q.dline) myLine = (Q.sendinfo[en.voice] & kSiDeferred) ? 1u : 0u;
+                    else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active) myLine = 2u;
+                }
+                constexpr int U = (CH > 4) ? 2 : 4;
+                for(uint32_t u0 = 0;u0 < cnt;u0 += U)
+                {
+                    float4 xU[U]; float4 gU[U][CH/4];
                     #pragma unroll
-                    for(uint32_t k = 0;k < 4u;++k)
+                    for(int q = 0;q < U;++q)
                     {
-                        const uint32_t i = i0 + k;
-                        const float g = (i >= n) ? 0.0f : ((fade && i < fadeLen) ? (cg + step*float(i))
-                            : (i >= start ? flat : 0.0f));
-                        acc[cc][k] += xs[k]*g;
+                        const uint32_t u = min(u0 + uint32_t(q), cnt - 1u);
+                        const uint32_t voice = __shfl_sync(0xffffffffu, myVoice, int(u));
+                        const uint32_t which = __shfl_sync(0xffffffffu, myLine, int(u));
+                        const float *line = which == 0u ? Q.xscratch + size_t(voice)*kLine
+                            : (which == 1u ? Q.dline + size_t(voice)*kLine : Q.fscratch + size_t(base + u)*kLine);
+                        xU[q] = *reinterpret_cast<const float4*>(line + i0);
+                        const float4 *gp = reinterpret_cast<const float4*>(Q.geff + size_t(base + u)*Q.cw + c0);
+                        #pragma unroll
+                        for(int g4 = 0;g4 < CH/4;++g4)
+                            gU[q][g4] = (c0 + uint32_t(g4)*4u < Q.cw && u0 + uint32_t(q) < cnt) ? gp[g4]
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    #pragma unroll
+                    for(int q = 0;q < U;++q)
+                    {
+                        const float xs[4] = {xU[q].x, xU[q].y, xU[q].z, xU[q].w};
+                        #pragma unroll
+                        for(int g4 = 0;g4 < CH/4;++g4)
+                        {
+                            const float gg[4] = {gU[q][g4].x, gU[q][g4].y, gU[q][g4].z, gU[q][g4].w};
+                            #pragma unroll
+                            for(int cc = 0;cc < 4;++cc)
+                                #pragma unroll
+                                for(int k = 0;k < 4;++k)
+                                    acc[g4*4 + cc][k] = fmaf(xs[k], gg[cc], acc[g4*4 + cc][k]);
+                        }
                     }
                 }
             }
         }
-        #pragma unroll
-        for(int cc = 0;cc < 4;++cc)
-            #pragma unroll
-            for(int k = 0;k < 4;++k) part[warp][cc][lane*4 + k] = acc[cc][k];
-        __syncthreads();
-        // threads 0..127 own one sample each; sum the 8 warp partials in order
-        if(threadIdx.x < 128u)
+        else
+        for(uint32_t base = e0 + warp*wblock;base < min(e0 + (warp + 1u)*wblock, e1);base += 32u)
         {
-            const uint32_t i = blockIdx.y*128u + threadIdx.x;
-            #pragma unroll
-            for(uint32_t cc = 0;cc < 4u;++cc)
+            // first tile (fades) or a partial tile: gain(i) = i < L ? a + b*i : flat from the
+            // ramp k_send_gains_prepare left per entry-channel (Mix_, mixer_c.cpp:150-186)
+            const uint32_t cnt = min(32u, min(e0 + (warp + 1u)*wblock, e1) - base);
+            uint32_t myVoice = 0u, myLine = 0u;
+            if(lane < cnt)
             {
-                if(c0 + cc < Q.cw && (i < n || Q.chunks > 1u))
+                const SendEntry en = Q.entries[base + lane];
+                myVoice = en.voice;
+                if(Q.dline) myLine = (Q.sendinfo[en.voice] & kSiDeferred) ? 1u : 0u;
+                else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active) myLine = 2u;
+            }
+            for(uint32_t u = 0;u < cnt;++u)
+            {
+                const uint32_t voice = __shfl_sync(0xffffffffu, myVoice, int(u));
+                const uint32_t which = __shfl_sync(0xffffffffu, myLine, int(u));
+                const float *line = which == 0u ? Q.xscratch + size_t(voice)*kLine
+                    : (which == 1u ? Q.dline + size_t(voice)*kLine : Q.fscratch + size_t(base + u)*kLine);
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if(i0 < n) x = *reinterpret_cast<const float4*>(line + i0);
+                const float4 *gp = Q.gramp + size_t(base + u)*Q.cw + c0;
+                float xs[4] = {x.x, x.y, x.z, x.w};
+                float fi[4];
+                #pragma unroll
+                for(int k = 0;k < 4;++k)
                 {
-                    float sum = part[0][cc][threadIdx.x];
+                    if(i0 + k >= n) xs[k] = 0.0f;
+                    fi[k] = float(i0 + k);
+                }
+                #pragma unroll
+                for(int g4 = 0;g4 < CH/4;++g4)
+                {
+                    float4 rp[4];
                     #pragma unroll
-                    for(int wv = 1;wv < 8;++wv) sum += part[wv][cc][threadIdx.x];
-                    outBase[size_t(c0 + cc)*kLine + i] = sum;
+                    for(int cc = 0;cc < 4;++cc)
+                        rp[cc] = (c0 + g4*4 + cc < Q.cw) ? gp[g4*4 + cc] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    #pragma unroll
+                    for(int cc = 0;cc < 4;++cc)
+                    {
+                        #pragma unroll
+                        for(int k = 0;k < 4;++k)
+                        {
+                            const float g = (fi[k] < rp[cc].w) ? fmaf(rp[cc].y, fi[k], rp[cc].x) : rp[cc].z;
+                            acc[g4*4 + cc][k] = fmaf(xs[k], g, acc[g4*4 + cc][k]);
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();
+        // combine the 8 warps' partials, four channels at a time, in warp order
+        #pragma unroll
+        for(int g4 = 0;g4 < CH/4;++g4)
+        {
+            #pragma unroll
+            for(int cc = 0;cc < 4;++cc)
+                #pragma unroll
+                for(int k = 0;k < 4;++k) part[warp][cc][lane*4 + k] = acc[g4*4 + cc][k];
+            __syncthreads();
+            if(threadIdx.x < 128u)
+            {
+                const uint32_t i = blockIdx.y*128u + threadIdx.x;
+                #pragma unroll
+                for(uint32_t cc = 0;cc < 4u;++cc)
+                {
+                    const uint32_t c = c0 + uint32_t(g4)*4u + cc;
+                    if(c < Q.cw && (i < n || Q.chunks > 1u))
+                    {
+                        float sum = part[0][cc][threadIdx.x];
+                        #pragma unroll
+                        for(int wv = 1;wv < 8;++wv) sum += part[wv][cc][threadIdx.x];
+                        outBase[size_t(c)*kLine + i] = sum;
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
+}
+
+// Gain of every (entry, channel) once its fade has ended (Mix_, mixer_c.cpp:150-186: the
+// target, or silence below GainSilenceThreshold / when the voice is stopping); runs before
+// k_send_mix.  One thread per entry-channel.
+__global__ void k_send_gains_prepare(const SendMixParams Q, uint32_t num_entries)
+{
+    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;
+    const uint32_t e = idx / Q.cw, c = idx - e*Q.cw;
+    if(e >= num_entries) return;
+    const SendEntry en = Q.entries[e];
+    const uint32_t info = Q.sendinfo[en.voice];
+    float flat = 0.0f;
+    float4 ramp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(info & Q.valid_bit)
+    {
+        const bool playing = (info & kSiPlaying) != 0;
+        const uint32_t counter = (info >> 8) & 0xffu, n = Q.frames;
+        const float delta = counter ? 1.0f/float(counter) : 0.0f;
+        const uint32_t fadeLen = counter < n ? counter : n;
+        const size_t g = (size_t(en.voice)*Q.num_sends + en.send)*Q.cw + c;
+        const float tg0 = Q.send_tgt[g];
+        const float cg = counter ? Q.send_cur[g] : tg0;
+        const float tg = playing ? tg0 : 0.0f;
+        const float step = (tg - cg)*delta;
+        const bool fade = fabsf(step) > kEps;
+        const bool early = fade && fadeLen < counter;
+        flat = (!early && fabsf(tg) > kSilence) ? tg : 0.0f;
+        // fading: cg + step*i for i < fadeLen, then flat; not fading: flat from sample 0
+        ramp = fade ? make_float4(cg, step, flat, float(fadeLen)) : make_float4(0.f, 0.f, flat, 0.f);
+    }
+    Q.geff[size_t(e)*Q.cw + c] = flat;
+    Q.gramp[size_t(e)*Q.cw + c] = ramp;
 }
 
 // New Current gains of the sends (runs after k_send_mix; one thread per entry-channel).

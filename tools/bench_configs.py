@@ -201,8 +201,9 @@ def main():
     for _ in range(args.warmup):
         update()
     torch.cuda.synchronize()
-    lib.b200mix_profile(h, 1)
-    ms, mix = [], []
+    lib.b200mix_profile(h, 2)
+    lib.b200mix_last_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    ms, mix, stages = [], [], []
     for _ in range(args.steps):
         with torch.cuda.stream(stream):
             flush.zero_()
@@ -216,6 +217,9 @@ def main():
         e1.synchronize()
         ms.append(e0.elapsed_time(e1))
         mix.append(lib.b200mix_last_mix_kernel_ms(h))
+        st = np.zeros(8, dtype=np.float32)
+        if lib.b200mix_last_stage_ms(h, st.ctypes.data, 8) == 8:
+            stages.append(st)
     t = torch.tensor([float(np.mean(ms))], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -226,6 +230,10 @@ def main():
             "voices_per_gpu": nv, "slots": nslots, "slots_installed_rank0": installed,
             "conv_taps": args.taps if cfg["conv"] else None, "direct_filters": bool(args.filters),
             "ms_per_update": ms_update, "mix_kernel_ms_rank0": float(np.mean(mix)),
+            "stage_us_rank0": dict(zip(["clear", "voices", "filters+deferred", "reduce", "dry_bus", "sends",
+                                        "effects", "post"],
+                                       [round(float(x) * 1e3, 1) for x in np.mean(stages, axis=0)]))
+            if stages else None,
             "voice_samples_per_s": total * 1024 / (ms_update * 1e-3),
             "rt_voices": total * (1000.0 * 1024 / 48000) / ms_update,
             "timing": "CUDA events on the mixer stream, L2 flushed between updates, max over ranks"}))
