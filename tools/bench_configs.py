@@ -53,6 +53,9 @@ def main():
                     help="install only every k-th slot (one GPU standing for 1/k of the box)")
     ap.add_argument("--taps", type=int, default=96000)
     ap.add_argument("--filters", action="store_true")
+    ap.add_argument("--pcm-pool", type=int, default=0,
+                    help="distinct PCM contents (0 = one per voice up to 8192 voices per rank, else 256); "
+                         "every voice still owns its own device buffer")
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     args = ap.parse_args()
@@ -137,8 +140,13 @@ def main():
 
     # ---- voices ----
     hrtf = bench.load_hrtf(lib) if kind == "hrtf" else None
+    pool = args.pcm_pool or (nv if nv <= 8192 else 256)
+    pcms = {}
     for k in range(nv):
-        pcm = scene.voice_buffer_fast(first + k)
+        key = (first + k) % pool
+        if key not in pcms:
+            pcms[key] = scene.voice_buffer_fast(first + k)
+        pcm = pcms[key]
         lib.b200mix_buffer_data(h, k, abi.FMT_I16, 1, pcm.shape[0], pcm.ctypes.data, pcm.nbytes)
     params, coeffs, pitches = bench.synth_voices(first, nv, total, lib, hrtf)
     dry = None
@@ -228,7 +236,7 @@ def main():
         print(json.dumps({
             "config": args.config, "kind": kind, "n_gpus": world, "voices_total": total,
             "voices_per_gpu": nv, "slots": nslots, "slots_installed_rank0": installed,
-            "conv_taps": args.taps if cfg["conv"] else None, "direct_filters": bool(args.filters),
+            "conv_taps": args.taps if cfg["conv"] else None, "pcm_pool": pool, "direct_filters": bool(args.filters),
             "ms_per_update": ms_update, "mix_kernel_ms_rank0": float(np.mean(mix)),
             "stage_us_rank0": dict(zip(["clear", "voices", "filters+deferred", "reduce", "dry_bus", "sends",
                                         "effects", "post"],
