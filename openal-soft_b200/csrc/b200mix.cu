@@ -115,6 +115,7 @@ struct b200mix_device {
     uint32_t reverb_slots{0};
 
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
+    bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
     std::vector<uint8_t> h_hrtf;             // host mirror: voice mixes through its own HRIR
     std::vector<SendEntry> h_dry_entries;
@@ -939,8 +940,13 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
 
     stage_mark(d, 0);
     // clear MixBuffer (alc/alu.cpp:2417) and the wet buffers (alc/alu.cpp:2196-2198)
-    CUDA_TRY(d, cudaMemsetAsync(d->d_dry, 0, size_t(d->dry_alloc_ch)*kLine*sizeof(float), d->stream));
-    if(d->d_real != d->d_dry)
+    // (the dry mix is left alone while nothing can write or read it: HRTF-only scenes; an
+    // HRTF post-process whose RealOut is just L/R overwrites it instead of accumulating)
+    if(d->dry_active || dd.post_process != B200MIX_POST_HRTF)
+        CUDA_TRY(d, cudaMemsetAsync(d->d_dry, 0, size_t(d->dry_alloc_ch)*kLine*sizeof(float), d->stream));
+    d->real_overwrite = dd.post_process == B200MIX_POST_HRTF && dd.real_channels == 2
+        && dd.real_left != dd.real_right;
+    if(d->d_real != d->d_dry && !d->real_overwrite)
         CUDA_TRY(d, cudaMemsetAsync(d->d_real, 0, size_t(dd.real_channels)*kLine*sizeof(float), d->stream));
     if(d->d_wet)
         CUDA_TRY(d, cudaMemsetAsync(d->d_wet, 0, size_t(dd.max_slots)*dd.wet_channels*kLine*sizeof(float), d->stream));
@@ -1254,8 +1260,8 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
             k_post_hrtf_split<<<dd.dry_channels, 32, 0, d->stream>>>(Q);
             ++d->launches;
         }
-        const uint32_t total = 2u*(frames + kHrirLen);
-        k_post_hrtf_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
+        Q.overwrite = d->real_overwrite ? 1u : 0u;
+        k_post_hrtf_mix<<<dim3((frames + kHrirLen + 127)/128, 2), 128, 0, d->stream>>>(Q);
         ++d->launches;
         d->carry_idx ^= 1;
         break;

@@ -889,11 +889,28 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
         const float B2A[4][4] = {{0.5f, 0.5f, 0.5f, 0.5f}, {0.5f, -0.5f, -0.5f, 0.5f},
             {0.5f, 0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, 0.5f, -0.5f}};
         float *dl = R.main_d + size_t(line)*R.main_len;
-        for(uint32_t i = lane;i < n;i += 32)
+        // (all loads of a batch are issued before the first store: the delay lines are plain
+        // pointers, so the compiler must assume a store may alias the next load)
+        for(uint32_t i0 = lane;i0 < n;i0 += 8u*32u)
         {
-            float a = 0.0f;
-            for(uint32_t k = 0;k < numInput;++k) a = a + wet[size_t(k)*kLine + i]*B2A[line][k];
-            dl[(offset0 + i) & (R.main_len-1)] = a;
+            float w[8][4];
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+                #pragma unroll
+                for(int k = 0;k < 4;++k)
+                {
+                    const uint32_t i = i0 + uint32_t(u)*32u;
+                    w[u][k] = (i < n && uint32_t(k) < numInput) ? wet[size_t(k)*kLine + i] : 0.0f;
+                }
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = i0 + uint32_t(u)*32u;
+                float a = 0.0f;
+                #pragma unroll
+                for(int k = 0;k < 4;++k) if(uint32_t(k) < numInput) a = a + w[u][k]*B2A[line][k];
+                if(i < n) dl[(offset0 + i) & (R.main_len-1)] = a;
+            }
         }
     }
     __syncthreads();
@@ -912,11 +929,20 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             const float *input = R.main_d + size_t(line)*R.main_len;
             const uint32_t t0 = offset - tapCur, t1 = offset - R.early_tap[line];
             tapCur = R.early_tap[line];
-            for(uint32_t i = lane;i < todo;i += 32)
+            float v0[8], v1[8];
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
             {
-                const float in0 = input[(t0+i) & (R.main_len-1)], in1 = input[(t1+i) & (R.main_len-1)];
-                const float a = in0*c0, b = in1*c1;
-                temp[line][i] = a + (b-a)*(fadeStep*float(i));
+                const uint32_t i = lane + uint32_t(u)*32u;
+                v0[u] = i < todo ? input[(t0+i) & (R.main_len-1)] : 0.0f;
+                v1[u] = i < todo ? input[(t1+i) & (R.main_len-1)] : 0.0f;
+            }
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = lane + uint32_t(u)*32u;
+                const float a = v0[u]*c0, b = v1[u]*c1;
+                if(i < todo) temp[line][i] = a + (b-a)*(fadeStep*float(i));
             }
         }
         __syncwarp();
@@ -931,12 +957,24 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             for(uint32_t sb = 0;sb < todo;sb += off)
             {
                 const uint32_t td = (todo - sb < off) ? todo - sb : off;
-                for(uint32_t i = lane;i < td;i += 32)
+                float dv[8];
+                #pragma unroll
+                for(int u = 0;u < 8;++u)
                 {
-                    const float x = temp[line][sb+i];
-                    const float y = buf[(offset + sb + i - off) & m] - fc*x;
-                    buf[(offset + sb + i) & m] = x + fc*y;
-                    temp[line][sb+i] = y;
+                    const uint32_t i = lane + uint32_t(u)*32u;
+                    dv[u] = i < td ? buf[(offset + sb + i - off) & m] : 0.0f;
+                }
+                #pragma unroll
+                for(int u = 0;u < 8;++u)
+                {
+                    const uint32_t i = lane + uint32_t(u)*32u;
+                    if(i < td)
+                    {
+                        const float x = temp[line][sb+i];
+                        const float y = dv[u] - fc*x;
+                        buf[(offset + sb + i) & m] = x + fc*y;
+                        temp[line][sb+i] = y;
+                    }
                 }
                 __syncwarp();
             }
@@ -956,8 +994,20 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
         {
             const float *dl = R.early_d + size_t(line)*R.early_len;
             const uint32_t tap = offset - R.early_offset[line];
-            for(uint32_t i = lane;i < todo;i += 32)
-                earlyOut[size_t(line)*kLine + base + i] = dl[(tap+i) & (R.early_len-1)]*R.early_coeff + temp[line][i];
+            float dv[8];
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = lane + uint32_t(u)*32u;
+                dv[u] = i < todo ? dl[(tap+i) & (R.early_len-1)] : 0.0f;
+            }
+            const float ec = R.early_coeff;
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = lane + uint32_t(u)*32u;
+                if(i < todo) earlyOut[size_t(line)*kLine + base + i] = dv[u]*ec + temp[line][i];
+            }
         }
         __syncthreads();
         // VectorScatter + late-input write (reverb.cpp:1649-1655)
@@ -1002,15 +1052,24 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             const uint32_t m = R.late_len-1;
             const float midGain = R.t60_mid_gain[line];
             const uint32_t tap = offset - R.late_offset[line];
-            for(uint32_t i = lane;i < todo;i += 32)
+            float o[8][4], cb[8][4];
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
             {
-                const uint32_t idelay = moddel[i];
+                const uint32_t i = lane + uint32_t(u)*32u;
+                const uint32_t idelay = i < todo ? moddel[i] : 0u;
                 const uint32_t delay = tap + i - (idelay>>8), doff = idelay & 255u;
-                const float o0 = input[delay & m], o1 = input[(delay-1u) & m];
-                const float o2 = input[(delay-2u) & m], o3 = input[(delay-3u) & m];
-                const float out = o0*Q.cubic[256u+doff] + o1*Q.cubic[doff] + o2*Q.cubic[256u-doff]
-                    + o3*Q.cubic[512u-doff];
-                temp[line][i] = out*midGain;
+                #pragma unroll
+                for(int k = 0;k < 4;++k) o[u][k] = i < todo ? input[(delay - uint32_t(k)) & m] : 0.0f;
+                cb[u][0] = Q.cubic[256u+doff]; cb[u][1] = Q.cubic[doff];
+                cb[u][2] = Q.cubic[256u-doff]; cb[u][3] = Q.cubic[512u-doff];
+            }
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = lane + uint32_t(u)*32u;
+                const float out = o[u][0]*cb[u][0] + o[u][1]*cb[u][1] + o[u][2]*cb[u][2] + o[u][3]*cb[u][3];
+                if(i < todo) temp[line][i] = out*midGain;
             }
         }
         __syncwarp();
@@ -1026,11 +1085,21 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             const float fadeStep = 1.0f/float(todo);
             const float dg = R.density_gain;
             const float ds = (t0 != t1) ? dg*fadeStep : 0.0f;
-            for(uint32_t i = lane;i < todo;i += 32)
+            float v0[8], v1[8];
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
             {
+                const uint32_t i = lane + uint32_t(u)*32u;
+                v0[u] = i < todo ? input[(t0+i) & m] : 0.0f;
+                v1[u] = i < todo ? input[(t1+i) & m] : 0.0f;
+            }
+            #pragma unroll
+            for(int u = 0;u < 8;++u)
+            {
+                const uint32_t i = lane + uint32_t(u)*32u;
                 const float fc = float(i);
                 const float fade0 = dg - ds*fc, fade1 = ds*fc;
-                temp[line][i] = input[(t0+i) & m]*fade0 + input[(t1+i) & m]*fade1 + temp[line][i];
+                if(i < todo) temp[line][i] = v0[u]*fade0 + v1[u]*fade1 + temp[line][i];
             }
         }
         __syncthreads();
@@ -1043,21 +1112,48 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             for(uint32_t sb = 0;sb < todo;sb += minOff)
             {
                 const uint32_t td = (todo - sb < minOff) ? todo - sb : minOff;
-                for(uint32_t i = lane;i < td;i += 32)
+                float dv[8];
+                #pragma unroll
+                for(int u = 0;u < 8;++u)
                 {
-                    const float input = temp[line][sb+i];
-                    const float out = buf[size_t((offset + sb + i - myOff) & m)*NL + line] - fc*input;
-                    buf[size_t((offset + sb + i) & m)*NL + line] = input + fc*out;
-                    temp[line][sb+i] = out;
+                    const uint32_t i = lane + uint32_t(u)*32u;
+                    dv[u] = i < td ? buf[size_t((offset + sb + i - myOff) & m)*NL + line] : 0.0f;
+                }
+                #pragma unroll
+                for(int u = 0;u < 8;++u)
+                {
+                    const uint32_t i = lane + uint32_t(u)*32u;
+                    if(i < td)
+                    {
+                        const float input = temp[line][sb+i];
+                        const float out = dv[u] - fc*input;
+                        buf[size_t((offset + sb + i) & m)*NL + line] = input + fc*out;
+                        temp[line][sb+i] = out;
+                    }
                 }
                 __syncthreads();
-                for(uint32_t i = tid;i < td;i += 128)
                 {
-                    float *d = buf + size_t((offset + sb + i) & m)*NL;
-                    const float in[4] = {d[0], d[1], d[2], d[3]};
-                    float f[4];
-                    scatter4(in, R.mix_x, R.mix_y, f);
-                    d[0] = f[0]; d[1] = f[1]; d[2] = f[2]; d[3] = f[3];
+                    float4 dq[2];
+                    #pragma unroll
+                    for(int u = 0;u < 2;++u)
+                    {
+                        const uint32_t i = tid + uint32_t(u)*128u;
+                        dq[u] = i < td ? *reinterpret_cast<const float4*>(buf + size_t((offset + sb + i) & m)*NL)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    #pragma unroll
+                    for(int u = 0;u < 2;++u)
+                    {
+                        const uint32_t i = tid + uint32_t(u)*128u;
+                        if(i < td)
+                        {
+                            const float in[4] = {dq[u].x, dq[u].y, dq[u].z, dq[u].w};
+                            float f[4];
+                            scatter4(in, R.mix_x, R.mix_y, f);
+                            *reinterpret_cast<float4*>(buf + size_t((offset + sb + i) & m)*NL)
+                                = make_float4(f[0], f[1], f[2], f[3]);
+                        }
+                    }
                 }
                 __syncthreads();
             }

@@ -1099,6 +1099,7 @@ struct PostHrtfParams {
     const float *dec_hfscale; float *dec_state;   // state: [cd][4] = coeff, lp_z1, lp_z2, ap_z1
     float *temp;                 // [cd][1024] band-split dry
     uint32_t frames, cd, dec_ir, real_left, real_right, dry_active;
+    uint32_t overwrite;          // RealOut L/R were not cleared: store instead of accumulate
 };
 
 // Stage 1 (only when the dry mix is non-silent): BandSplitter::processHfScale per dry
@@ -1151,36 +1152,50 @@ __global__ void __launch_bounds__(32) k_post_hrtf_split(const PostHrtfParams Q)
 }
 
 // Stage 2: total[t] = carry[t] + voices[t] + decoder FIR of the dry channels;
-// RealOut L/R += total[0..n); carry_out = total[n..n+128).
+// RealOut L/R (+)= total[0..n); carry_out = total[n..n+128).
+// grid (tiles of 128 outputs, ear); the channels' input spans and this ear's decoder taps are
+// staged in shared memory one channel at a time, so the FIR runs without global loads.
 __global__ void __launch_bounds__(128) k_post_hrtf_mix(const PostHrtfParams Q)
 {
-    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;   // [ear][t]
+    __shared__ float xs[128 + kHrirLen];
+    __shared__ float cf[kHrirLen];
     const uint32_t span = Q.frames + kHrirLen;
-    if(idx >= 2u*span) return;
-    const uint32_t ear = idx / span, tt = idx - ear*span;
-    float tot = Q.accum_sum[ear*kAccumLen + tt];
-    if(tt < uint32_t(kHrirLen)) tot += Q.carry_in[ear*kHrirLen + tt];
+    const uint32_t ear = blockIdx.y;
+    const uint32_t t0 = blockIdx.x*128u, tt = t0 + threadIdx.x;
+    float tot = 0.0f;
+    if(tt < span)
+    {
+        tot = Q.accum_sum[ear*kAccumLen + tt];
+        if(tt < uint32_t(kHrirLen)) tot += Q.carry_in[ear*kHrirLen + tt];
+    }
     if(Q.dry_active)
     {
+        const uint32_t jmax = Q.dec_ir;                // <= kHrirLen
         for(uint32_t c = 0;c < Q.cd;++c)
         {
             const float *x = Q.temp + size_t(c)*kLine;
-            const float2 *cf = Q.dec_coef + size_t(c)*Q.dec_ir;
-            float s = 0.0f;
-            const uint32_t jmax = Q.dec_ir;
-            for(uint32_t j = 0;j < jmax;++j)
+            const float2 *cg = Q.dec_coef + size_t(c)*Q.dec_ir;
+            __syncthreads();
+            // xs[k] = x[t0 - kHrirLen + k], zero outside [0, frames)
+            for(uint32_t k = threadIdx.x;k < 128u + kHrirLen;k += 128u)
             {
-                const int src = int(tt) - int(j);
-                if(src >= 0 && src < int(Q.frames))
-                    s = fmaf(ear ? cf[j].y : cf[j].x, x[src], s);
+                const int src = int(t0) - int(kHrirLen) + int(k);
+                xs[k] = (src >= 0 && src < int(Q.frames)) ? x[src] : 0.0f;
             }
+            if(threadIdx.x < jmax) cf[threadIdx.x] = ear ? cg[threadIdx.x].y : cg[threadIdx.x].x;
+            __syncthreads();
+            float s = 0.0f;
+            const float *w = xs + kHrirLen + threadIdx.x;
+            for(uint32_t j = 0;j < jmax;++j)
+                s = fmaf(cf[j], w[-int(j)], s);
             tot += s;
         }
     }
+    if(tt >= span) return;
     if(tt < Q.frames)
     {
         float *o = Q.real + size_t(ear ? Q.real_right : Q.real_left)*kLine + tt;
-        *o += tot;
+        *o = Q.overwrite ? tot : (*o + tot);
     }
     else
         Q.carry_out[ear*kHrirLen + (tt - Q.frames)] = tot;
