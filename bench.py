@@ -65,6 +65,8 @@ def load_product():
     lib.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                             C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.b200mix_hrtf_attach.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200mix_voices_update_dirs.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 4
     return lib
 
 
@@ -80,13 +82,20 @@ def load_hrtf(lib):
     return h if lib.b200mix_hrtf_load(data, len(data), C.byref(h)) == 0 else None
 
 
-def hrir_for(lib, hrtf, pos, out, delays):
-    """CalcHrtfPanning's lookup (alc/alu.cpp:1210-1216) for a source at `pos`."""
+def direction_of(pos):
+    """{elevation, azimuth, distance, spread} as CalcHrtfPanning derives them for a source
+    at `pos` (alc/alu.cpp:1210-1216)."""
     x, y, z = pos
     d = math.sqrt(x * x + y * y + z * z)
     ev = math.asin(max(-1.0, min(1.0, y / d)))
     az = math.atan2(x / d, -z / d)
-    lib.b200mix_hrtf_get_coeffs(hrtf, ev, az, d, 0.0, out.ctypes.data, delays)
+    return ev, az, d, 0.0
+
+
+def hrir_for(lib, hrtf, pos, out, delays):
+    """HrtfStore::getCoeffs on the host for a source at `pos`."""
+    ev, az, d, sp = direction_of(pos)
+    lib.b200mix_hrtf_get_coeffs(hrtf, ev, az, d, sp, out.ctypes.data, delays)
 
 
 def synth_voices(first, count, total, lib=None, hrtf=None, shift=0.0):
@@ -383,11 +392,26 @@ def main_cuda(args):
             if hrtf is None:
                 mp[j].hrtf_delay[0] = (params[k].hrtf_delay[0] + 3 * base + 1) % 40
         mc = np.ascontiguousarray(c2[base::8][:nmove] * np.float32(1.0 if hrtf is not None else 1.0 - 0.02 * base))
-        move_sets.append((mp, mc))
+        md = np.zeros((nmove, 4), dtype=np.float32)
+        cs, sn = math.cos(0.05 * (base + 1)), math.sin(0.05 * (base + 1))
+        for j in range(nmove):
+            x, y, z = scene.voice_position(first + base + 8 * j)
+            md[j] = direction_of((x * cs - z * sn, y, x * sn + z * cs))
+        move_sets.append((mp, mc, md))
+
+    # With the data set attached the application only sends the moved sources' DIRECTIONS
+    # and the 4-HRIR blend runs on the GPU (b200mix_voices_update_dirs);
+    # otherwise it sends host-blended HRIRs.
+    use_dirs = hrtf is not None and lib.b200mix_hrtf_attach(h, hrtf) == 0
+    if use_dirs:
+        h2d = nmove * (C.sizeof(abi.VoiceParams) + 16)
 
     def step_e2e(it):
-        mp, mc = move_sets[it % 8]
-        ck(lib.b200mix_voices_update(h, nmove, mp, mc.ctypes.data, None, None), "voices_update")
+        mp, mc, md = move_sets[it % 8]
+        if use_dirs:
+            ck(lib.b200mix_voices_update_dirs(h, nmove, mp, md.ctypes.data, None, None), "voices_update_dirs")
+        else:
+            ck(lib.b200mix_voices_update(h, nmove, mp, mc.ctypes.data, None, None), "voices_update")
         ck(lib.b200mix_render(h, FRAMES, ptrs, results), "render")
 
     for it in range(args.warmup):
@@ -431,7 +455,9 @@ def main_cuda(args):
                        "parallelism": f"voices sharded over {world} GPU(s); one NCCL reduce of RealOut per update"},
             "rt_voices": total * UPDATE_MS / ms_per_step,
             "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000.0 * te / args.steps},
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000.0 * te / args.steps,
+                    "update": ("b200mix_voices_update_dirs (directions; HRIR blend on the GPU)" if use_dirs
+                               else "b200mix_voices_update (host-blended HRIRs)") + f", {nmove} moved voices/GPU/update"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_mix_voices", "achieved": achieved, "peak": peak,

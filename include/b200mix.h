@@ -282,6 +282,19 @@ B200MIX_API int b200mix_hrtf_info(const b200mix_hrtf *hrtf, uint32_t *sample_rat
 B200MIX_API int b200mix_hrtf_get_coeffs(const b200mix_hrtf *hrtf, float elevation, float azimuth,
     float distance, float spread, float *coeffs, uint32_t delays[2]);
 
+/* Device-side parameter stage: with a data set attached, voices can be
+ * updated with their DIRECTIONS instead of pre-blended HRIRs — dirs is [n][4] floats
+ * {elevation, azimuth, distance, spread} exactly as CalcHrtfPanning hands them to
+ * HrtfStore::getCoeffs (alc/alu.cpp, core/hrtf.cpp:192-260).  The 4-HRIR blend and the
+ * delays are then computed on the GPU (16 bytes per moved voice cross the bus instead of
+ * ir_size*8), bit-identically to b200mix_hrtf_get_coeffs.  params[i].hrtf_delay is ignored;
+ * non-HRTF voices in the same call ignore their dirs row.  The data set's ir_size must not
+ * exceed the device's. */
+B200MIX_API int b200mix_hrtf_attach(b200mix_device *dev, const b200mix_hrtf *hrtf);
+B200MIX_API int b200mix_voices_update_dirs(b200mix_device *dev, uint32_t n,
+    const b200mix_voice_params *params, const float *dirs, const float *dry_gains,
+    const float *send_gains);
+
 /* ---- introspection (tests, profiling) ------------------------------------ */
 /* Copies the Dry mix of the last update: [dry_channels][1024]. */
 B200MIX_API int b200mix_get_dry(b200mix_device *dev, float *dry);

@@ -20,6 +20,7 @@
 #include "mixer_kernels.cuh"
 #include "effect_kernels.cuh"
 #include "resampler_tables.hpp"
+#include "hrtf_store.hpp"
 
 using namespace b200mix;
 
@@ -114,6 +115,9 @@ struct b200mix_device {
     float *d_cubic_filter{nullptr};          // gCubicTable (reverb modulation taps)
     uint32_t reverb_slots{0};
 
+    // attached HRTF data set (device-side HrtfStore::getCoeffs)
+    float2 *d_st_fields{nullptr}; uint2 *d_st_elevs{nullptr}; float2 *d_st_coeffs{nullptr};
+    uint8_t *d_st_delays{nullptr}; uint32_t st_num_fields{0}, st_ir{0};
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -434,6 +438,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
     cudaFree(d->d_dline); cudaFree(d->d_order2);
+    cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
     cudaFree(d->d_dry_gramp); cudaFree(d->d_send_gramp);
@@ -708,8 +713,56 @@ int b200mix_slot_output_gains(b200mix_device *d, uint32_t slot, uint32_t lines, 
     return B200MIX_OK;
 }
 
+int b200mix_hrtf_attach(b200mix_device *d, const b200mix_hrtf *h)
+{
+    if(!d || !h) return B200MIX_ERR_INVALID;
+    if(h->ir_size > d->desc.ir_size)
+    { d->error = "hrtf_attach: data set HRIRs are longer than the device's ir_size"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
+    d->d_st_fields = nullptr; d->d_st_elevs = nullptr; d->d_st_coeffs = nullptr; d->d_st_delays = nullptr;
+    std::vector<float2> fields(h->fields.size());
+    for(size_t i = 0;i < fields.size();++i)
+    {
+        uint32_t ev = h->fields[i].ev_count; float evf;
+        std::memcpy(&evf, &ev, sizeof(evf));
+        fields[i] = make_float2(h->fields[i].distance, evf);
+    }
+    std::vector<uint2> elevs(h->elevs.size());
+    for(size_t i = 0;i < elevs.size();++i) elevs[i] = make_uint2(h->elevs[i].az_count, h->elevs[i].ir_offset);
+    if(int rc = dev_alloc(d, d->d_st_fields, fields.size(), false)) return rc;
+    if(int rc = dev_alloc(d, d->d_st_elevs, elevs.size(), false)) return rc;
+    if(int rc = dev_alloc(d, d->d_st_coeffs, h->coeffs.size()/2, false)) return rc;
+    if(int rc = dev_alloc(d, d->d_st_delays, h->delays.size(), false)) return rc;
+    CUDA_TRY(d, cudaMemcpy(d->d_st_fields, fields.data(), fields.size()*sizeof(float2), cudaMemcpyHostToDevice));
+    CUDA_TRY(d, cudaMemcpy(d->d_st_elevs, elevs.data(), elevs.size()*sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(d, cudaMemcpy(d->d_st_coeffs, h->coeffs.data(), h->coeffs.size()*sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(d, cudaMemcpy(d->d_st_delays, h->delays.data(), h->delays.size(), cudaMemcpyHostToDevice));
+    d->st_num_fields = uint32_t(fields.size()); d->st_ir = h->ir_size;
+    return B200MIX_OK;
+}
+
+static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
+    const float *hrtf_coeffs, const float *dirs, const float *dry_gains, const float *send_gains);
+
 int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains)
+{
+    return voices_update_impl(d, n, params, hrtf_coeffs, nullptr, dry_gains, send_gains);
+}
+
+int b200mix_voices_update_dirs(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
+    const float *dirs, const float *dry_gains, const float *send_gains)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(!dirs) { d->error = "voices_update_dirs: null directions"; return B200MIX_ERR_INVALID; }
+    if(!d->d_st_coeffs) { d->error = "voices_update_dirs: no HRTF data set attached"; return B200MIX_ERR_INVALID; }
+    return voices_update_impl(d, n, params, nullptr, dirs, dry_gains, send_gains);
+}
+
+static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice_params *params,
+    const float *hrtf_coeffs, const float *dirs, const float *dry_gains, const float *send_gains)
 {
     if(!d) return B200MIX_ERR_INVALID;
     if(n == 0) return B200MIX_OK;
@@ -742,6 +795,7 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
             u.bsinc_sf = st.sf; u.bsinc_m = st.m; u.bsinc_l = st.l; u.bsinc_off = st.offset;
         }
         u.delay0 = p.hrtf_delay[0]; u.delay1 = p.hrtf_delay[1]; u.gain = p.hrtf_gain;
+        if(dirs) { u.delay0 = 0; u.delay1 = 0; }        // computed on the device
         if(u.delay0 >= B200MIX_HRTF_HISTORY || u.delay1 >= B200MIX_HRTF_HISTORY)
         { d->error = "voices_update: HRTF delay out of range"; return B200MIX_ERR_INVALID; }
         for(uint32_t s = 0;s < B200MIX_MAX_SENDS;++s)
@@ -757,7 +811,7 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
                 const uint32_t nv2 = (p.flags & B200MIX_VF_STOPPED) ? B200MIX_NO_SLOT : u.send_slot[s2];
                 if(m != nv2) { m = nv2; d->sends_dirty = true; }
             }
-        u.has_coeffs = hrtf_coeffs != nullptr && dd.ir_size > 0;
+        u.has_coeffs = (hrtf_coeffs != nullptr || (dirs != nullptr && (p.flags & B200MIX_VF_HRTF))) && dd.ir_size > 0;
         u.has_dry = dry_gains != nullptr;
         if(!(p.flags & B200MIX_VF_HRTF) && !(p.flags & B200MIX_VF_STOPPED))
         {
@@ -783,7 +837,15 @@ int b200mix_voices_update(b200mix_device *d, uint32_t n, const b200mix_voice_par
     CUDA_TRY(d, cudaMemcpyAsync(d->d_upd, d->h_upd, n*sizeof(VoiceUpdate), cudaMemcpyHostToDevice, d->stream));
     ApplyParams A{};
     A.voices = d->d_voices; A.updates = d->d_upd;
-    if(hrtf_coeffs && dd.ir_size)
+    if(dirs && dd.ir_size)
+    {
+        std::memcpy(d->h_coef, dirs, size_t(n)*4*sizeof(float));
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_coef, d->h_coef, size_t(n)*4*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        A.dirs = reinterpret_cast<const float4*>(d->d_coef);
+        A.st_fields = d->d_st_fields; A.st_elevs = d->d_st_elevs; A.st_coeffs = d->d_st_coeffs;
+        A.st_delays = d->d_st_delays; A.st_num_fields = d->st_num_fields; A.st_ir = d->st_ir;
+    }
+    else if(hrtf_coeffs && dd.ir_size)
     {
         const size_t cnt = size_t(n)*dd.ir_size*2;
         std::memcpy(d->h_coef, hrtf_coeffs, cnt*sizeof(float));

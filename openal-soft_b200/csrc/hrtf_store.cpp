@@ -5,6 +5,7 @@
 // bench.py — derive b200mix_voice_params HRIRs from source directions with the
 // reference's own data set (hrtf/Default HRTF.mhr) instead of synthetic filters.
 #include "../../include/b200mix.h"
+#include "hrtf_store.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -12,16 +13,6 @@
 #include <new>
 #include <numbers>
 #include <vector>
-
-struct b200mix_hrtf {
-    uint32_t sample_rate{}, ir_size{};
-    struct Field { float distance; uint32_t ev_count; };
-    struct Elev { uint32_t az_count, ir_offset; };
-    std::vector<Field> fields;
-    std::vector<Elev> elevs;
-    std::vector<float> coeffs;      // [ir_count][ir_size][2]
-    std::vector<uint8_t> delays;    // [ir_count][2], quarter samples
-};
 
 namespace {
 

@@ -956,7 +956,75 @@ struct ApplyParams {
     float2 *hrtf_tgt; float2 *hrtf_old; float *dry_cur, *dry_tgt, *send_cur, *send_tgt;
     uint32_t ir, ir_pad, cd, cw, num_sends;
     FilterRec *filt; uint32_t filt_paths;
+    // device-side HrtfStore::getCoeffs (b200mix_voices_update_dirs): per update
+    // {elevation, azimuth, distance, spread}; the attached data set
+    const float4 *dirs;
+    const float2 *st_fields;     // {distance, ev_count as float bits}
+    const uint2 *st_elevs;       // {az_count, ir_offset}
+    const float2 *st_coeffs;     // [ir_count][st_ir]
+    const uint8_t *st_delays;    // [ir_count][2]
+    uint32_t st_num_fields, st_ir;
 };
+
+// HrtfStore::getCoeffs (core/hrtf.cpp:192-260) on the device, in the exact operation order of
+// the host restatement (csrc/hrtf_store.cpp: b200mix_hrtf_get_coeffs) with explicit
+// round-to-nearest mul/add, so both give bit-identical HRIRs and delays.
+struct HrirBlend { uint32_t idx[4]; float w[4]; float passthru; uint32_t delay[2]; };
+
+__device__ __forceinline__ void hrir_index(uint32_t count, float v, bool elev, uint32_t &idx, float &blend)
+{
+    const float inv_pi = 0.318309886183790671538f;
+    if(elev)
+    {
+        v = __fmul_rn(__fadd_rn(__fmul_rn(inv_pi, v), 0.5f), float(count-1u));
+        const uint32_t i = v > 0.0f ? uint32_t(v) : 0u;
+        idx = min(i, count-1u); blend = __fsub_rn(v, float(i));
+    }
+    else
+    {
+        v = __fmul_rn(__fadd_rn(__fmul_rn(inv_pi*0.5f, v), 1.0f), float(count));
+        const uint32_t i = v > 0.0f ? uint32_t(v) : 0u;
+        idx = i % count; blend = __fsub_rn(v, float(i));
+    }
+}
+
+__device__ __forceinline__ void hrir_blend(const ApplyParams &A, const float4 dir, HrirBlend &B)
+{
+    const float inv_pi = 0.318309886183790671538f;
+    const float elevation = dir.x, azimuth = dir.y, distance = dir.z, spread = dir.w;
+    const float dirfact = __fsub_rn(1.0f, __fmul_rn(inv_pi/2.0f, spread));
+    uint32_t ebase = 0, fi = 0;
+    for(;fi + 1u < A.st_num_fields;++fi)
+    {
+        if(distance >= A.st_fields[fi].x) break;
+        ebase += __float_as_uint(A.st_fields[fi].y);
+    }
+    const uint32_t evCount = __float_as_uint(A.st_fields[fi].y);
+    uint32_t e0i; float e0b;
+    hrir_index(evCount, elevation, true, e0i, e0b);
+    const uint32_t e1i = min(e0i + 1u, evCount - 1u);
+    const uint2 el0 = A.st_elevs[ebase + e0i], el1 = A.st_elevs[ebase + e1i];
+    uint32_t a0i, a1i; float a0b, a1b;
+    hrir_index(el0.x, azimuth, false, a0i, a0b);
+    hrir_index(el1.x, azimuth, false, a1i, a1b);
+    B.idx[0] = el0.y + a0i; B.idx[1] = el0.y + ((a0i + 1u) % el0.x);
+    B.idx[2] = el1.y + a1i; B.idx[3] = el1.y + ((a1i + 1u) % el1.x);
+    const float ne = __fsub_rn(1.0f, e0b);
+    B.w[0] = __fmul_rn(__fmul_rn(ne, __fsub_rn(1.0f, a0b)), dirfact);
+    B.w[1] = __fmul_rn(__fmul_rn(ne, a0b), dirfact);
+    B.w[2] = __fmul_rn(__fmul_rn(e0b, __fsub_rn(1.0f, a1b)), dirfact);
+    B.w[3] = __fmul_rn(__fmul_rn(e0b, a1b), dirfact);
+    #pragma unroll
+    for(int ear = 0;ear < 2;++ear)
+    {
+        float dsum = __fmul_rn(float(A.st_delays[B.idx[0]*2u + ear]), B.w[0]);
+        dsum = __fadd_rn(dsum, __fmul_rn(float(A.st_delays[B.idx[1]*2u + ear]), B.w[1]));
+        dsum = __fadd_rn(dsum, __fmul_rn(float(A.st_delays[B.idx[2]*2u + ear]), B.w[2]));
+        dsum = __fadd_rn(dsum, __fmul_rn(float(A.st_delays[B.idx[3]*2u + ear]), B.w[3]));
+        B.delay[ear] = uint32_t(__float2int_rn(__fmul_rn(dsum, 0.25f)));
+    }
+    B.passthru = __fmul_rn(0.70710678118654752440f, __fsub_rn(1.0f, dirfact));
+}
 
 // BiquadInterpFilter::reset (biquad.h:144-150) for one record; lane k < 32 writes word k.
 __device__ __forceinline__ void filter_reset_word(FilterRec *fr, int k)
@@ -1034,17 +1102,40 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
             for(uint32_t k = t;k < A.filt_paths*32u;k += 64)
                 filter_reset_word(A.filt + size_t(up.voice)*A.filt_paths + (k >> 5), int(k & 31u));
     }
+    __shared__ HrirBlend sB;
+    const bool fromDirs = A.dirs != nullptr && up.has_coeffs && A.hrtf_tgt;
+    if(fromDirs)
+    {
+        if(t == 0) hrir_blend(A, A.dirs[u], sB);
+        __syncthreads();
+    }
     if(up.has_coeffs && A.hrtf_tgt)
     {
         float2 *tg = A.hrtf_tgt + size_t(up.voice)*A.ir_pad;
         float2 *ol = A.hrtf_old + size_t(up.voice)*A.ir_pad;
-        const float *src = A.coeffs + size_t(u)*A.ir*2;
+        const float *src = fromDirs ? nullptr : A.coeffs + size_t(u)*A.ir*2;
         for(uint32_t k = t;k < A.ir_pad;k += 64)
         {
             // keep "old" = the filter used by the last mix unless a newer target is
-            // already pending (see DESIGN.md §3.4)
+            // already pending (see DESIGN.md §3.6)
             if(!wasDirty && !reset) ol[k] = tg[k];
-            tg[k] = (k < A.ir) ? make_float2(src[k*2], src[k*2+1]) : make_float2(0.f, 0.f);
+            float2 val = make_float2(0.f, 0.f);
+            if(fromDirs)
+            {
+                if(k < A.st_ir && k < A.ir)
+                {
+                    val = (k == 0) ? make_float2(sB.passthru, sB.passthru) : val;
+                    #pragma unroll
+                    for(int c = 0;c < 4;++c)
+                    {
+                        const float2 sv = A.st_coeffs[size_t(sB.idx[c])*A.st_ir + k];
+                        val.x = __fadd_rn(__fmul_rn(sv.x, sB.w[c]), val.x);
+                        val.y = __fadd_rn(__fmul_rn(sv.y, sB.w[c]), val.y);
+                    }
+                }
+            }
+            else if(k < A.ir) val = make_float2(src[k*2], src[k*2+1]);
+            tg[k] = val;
         }
     }
     if(up.has_dry && A.dry_tgt)
@@ -1076,7 +1167,9 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
         rec.loop_start = up.loop_start; rec.loop_end = up.loop_end; rec.step = up.step;
         rec.bsinc_sf = up.bsinc_sf; rec.bsinc_m = up.bsinc_m; rec.bsinc_l = up.bsinc_l;
         rec.bsinc_off = up.bsinc_off;
-        rec.tgt_delay0 = up.delay0; rec.tgt_delay1 = up.delay1; rec.tgt_gain = up.gain;
+        rec.tgt_delay0 = fromDirs ? sB.delay[0] : up.delay0;
+        rec.tgt_delay1 = fromDirs ? sB.delay[1] : up.delay1;
+        rec.tgt_gain = up.gain;
         uint32_t mask = 0;
         for(int s = 0;s < kMaxSends;++s)
         {

@@ -354,3 +354,85 @@ def test_two_device_slot_ownership_equals_single_device():
     for dev in ranks:
         dev.close()
     _check(np.concatenate(outs, axis=1), ref, "two-device slot ownership")
+
+
+def test_device_side_hrir_lookup_is_bit_identical_to_host_helper():
+    """b200mix_voices_update_dirs computes HrtfStore::getCoeffs on the GPU.
+    Two devices mix the same scene — one fed HRIRs from the host helper (itself pinned to the
+    reference's ALU in test_hrtf_params.py), one fed only directions — through moving voices
+    and ragged updates; the outputs must be identical to the bit."""
+    import ctypes as C
+    import os
+    mhr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "openal-soft_b200", "data", "Default HRTF.mhr")
+    if not os.path.exists(mhr):
+        pytest.skip("HRTF data set not staged (run build())")
+    lib = mixlib.product().lib
+    lib.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.b200mix_hrtf_free.argtypes = [C.c_void_p]
+    lib.b200mix_hrtf_attach.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200mix_voices_update_dirs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+    data = open(mhr, "rb").read()
+    hs = C.c_void_p()
+    assert lib.b200mix_hrtf_load(data, len(data), C.byref(hs)) == 0
+    rng = np.random.default_rng(4242)
+    nv, ir = 48, 64
+    desc = synth.hrtf_desc(nv, ir)
+    params, _, dry = synth.voice_set(rng, nv, ir)
+
+    def directions(seed):
+        r = np.random.default_rng(seed)
+        d = np.zeros((nv, 4), dtype=np.float32)
+        d[:, 0] = r.uniform(-np.pi / 2, np.pi / 2, nv)        # elevation
+        d[:, 1] = r.uniform(-np.pi, np.pi, nv)                # azimuth
+        d[:, 2] = r.uniform(0.05, 3.0, nv)                    # distance (field selection)
+        d[:, 3] = r.uniform(0.0, np.pi, nv) * (r.random(nv) < 0.3)   # spread on a third
+        d[0] = [np.pi / 2, 0.0, 1.0, 0.0]                     # poles and seams
+        d[1] = [-np.pi / 2, np.pi, 1.0, 0.0]
+        d[2] = [0.0, -np.pi, 1.0, 2 * np.pi]
+        return d
+
+    def host_lookup(dirs, plist):
+        coeffs = np.zeros((len(plist), ir, 2), dtype=np.float32)
+        dl = (C.c_uint32 * 2)()
+        for k, p in enumerate(plist):
+            e, a, dist, sp = [float(x) for x in dirs[k]]
+            assert lib.b200mix_hrtf_get_coeffs(hs, e, a, dist, sp, coeffs[k].ctypes.data, dl) == 0
+            p.hrtf_delay[0], p.hrtf_delay[1] = dl[0], dl[1]
+        return coeffs
+
+    devs = [MixDevice(mixlib.product(), desc), MixDevice(mixlib.product(), desc)]
+    assert lib.b200mix_hrtf_attach(devs[1].h, hs) == 0
+    for dev in devs:
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+    outs = [[], []]
+    for u, f in enumerate((1024, 1024, 300, 1024, 64, 1024)):
+        if u in (0, 2, 3):
+            dirs = directions(100 + u)
+            sub = list(range(nv)) if u == 0 else list(range(u, nv, 3))
+            plist = []
+            for k in sub:
+                q = abi.VoiceParams.from_buffer_copy(bytes(params[k]))
+                if u:
+                    q.flags &= ~abi.VF_RESET
+                plist.append(q)
+            coeffs = host_lookup(dirs[sub], plist)
+            devs[0].voices_update(plist, coeffs, dry[sub], None)
+            arr = (abi.VoiceParams * len(plist))(*plist)
+            dsub = np.ascontiguousarray(dirs[sub])
+            dd = np.ascontiguousarray(dry[sub])
+            assert lib.b200mix_voices_update_dirs(devs[1].h, len(plist), arr, dsub.ctypes.data,
+                                                  dd.ctypes.data, None) == 0
+        for j, dev in enumerate(devs):
+            outs[j].append(dev.render(f))
+    for dev in devs:
+        dev.close()
+    lib.b200mix_hrtf_free(hs)
+    a, b = np.concatenate(outs[0], axis=1), np.concatenate(outs[1], axis=1)
+    assert np.abs(a).max() > 1e-4
+    assert np.array_equal(a, b), f"max diff {np.abs(a - b).max():.3e}"
