@@ -441,6 +441,12 @@ def main_cuda(args):
         alg_bytes = algorithmic_bytes_per_voice(mean_pitch) * nv
         mix_avg = float(np.mean([m for m in mix_ms if m > 0])) if any(m > 0 for m in mix_ms) else None
         achieved = alg_bytes / (mix_avg * 1e-3) / 1e9 if mix_avg else None
+        traffic = None
+        try:
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                            ["k_mix_voices"]["dram_bytes_per_launch"])
+        except Exception:
+            pass
         line = {
             "metric": "voice-samples/s mixed (HRTF, bsinc24, 1024-frame updates)",
             "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": args.steps,
@@ -462,7 +468,9 @@ def main_cuda(args):
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_mix_voices", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read+write "
+                                                               "of one ncu --set full capture of this workload)",
+                         "peak_source": peak_src,
                          "kernel_ms": mix_avg, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "HRTF voices are FP32-FMA/shared-memory bound (~100 flop/B), not "
                                  "HBM bound; see DESIGN.md"},
