@@ -41,6 +41,8 @@ extern "C" {
 #define B200MIX_MAX_WET_CHANNELS   25u /* MaxAmbiChannels         core/ambidefs.h:19 */
 #define B200MIX_RESAMPLER_PADDING  48u /* MaxResamplerPadding     core/resampler_limits.h:8 */
 #define B200MIX_NO_SLOT   0xffffffffu
+#define B200MIX_NO_LOOP   0xffffffffu
+#define B200MIX_MAX_QUEUE          32u /* items of a streaming queue the mixer looks ahead over */
 
 enum { B200MIX_OK = 0, B200MIX_ERR_INVALID = -1, B200MIX_ERR_CUDA = -2,
        B200MIX_ERR_NOMEM = -3, B200MIX_ERR_UNSUPPORTED = -4 };
@@ -202,6 +204,20 @@ typedef struct b200mix_voice_params {
 B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
     const b200mix_voice_params *params, const float *hrtf_coeffs, const float *dry_gains,
     const float *send_gains);
+
+/* Streaming sources: the VoiceBufferItem list behind alSourceQueueBuffers
+ * (core/voice.h:84-99; LoadBufferQueue core/voice.cpp:546-595; queue advance :1183-1196).
+ * A voice updated WITHOUT B200MIX_VF_STATIC plays this list instead of `buffer`:
+ * buffers[0] is the current item (mCurrentBuffer), the following ones its mNext chain;
+ * loop_index is the item playback continues with after the last one (mLoopBuffer: 0 for a
+ * looping source) or B200MIX_NO_LOOP.  position/position_frac count from the start of the
+ * current item.  Every update reports how many items were finished in
+ * b200mix_voice_result.buffers_done (AsyncBufferCompleteEvent); the mixer advances its own
+ * head, and the host re-sends the list (from the then-current item) whenever the
+ * application queues or unqueues buffers.  At most B200MIX_MAX_QUEUE items are looked at;
+ * count 0 detaches the queue (the voice ends like one whose buffer ran out). */
+B200MIX_API int b200mix_voice_queue(b200mix_device *dev, uint32_t voice, uint32_t count,
+    const uint32_t *buffers, uint32_t loop_index);
 
 /* Direct and send filters: DoFilters -> BiquadInterpFilter::dualProcess
  * (core/voice.cpp:255-268, core/filters/biquad.cpp:254-343).  One entry is the RESULT of

@@ -118,6 +118,7 @@ struct b200mix_device {
     // attached HRTF data set (device-side HrtfStore::getCoeffs)
     float2 *d_st_fields{nullptr}; uint2 *d_st_elevs{nullptr}; float2 *d_st_coeffs{nullptr};
     uint8_t *d_st_delays{nullptr}; uint32_t st_num_fields{0}, st_ir{0};
+    uint4 *d_qhdr{nullptr}; uint32_t *d_queue{nullptr};   // streaming queues (first b200mix_voice_queue)
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -437,7 +438,7 @@ void b200mix_destroy(b200mix_device *d)
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
-    cudaFree(d->d_dline); cudaFree(d->d_order2);
+    cudaFree(d->d_dline); cudaFree(d->d_order2); cudaFree(d->d_qhdr); cudaFree(d->d_queue);
     cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
@@ -872,11 +873,43 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
     A.ir = dd.ir_size; A.ir_pad = d->ir_pad; A.cd = dd.dry_channels; A.cw = dd.wet_channels;
     A.num_sends = dd.num_sends;
     A.filt = d->d_filt; A.filt_paths = 1u + dd.num_sends;
+    A.qhdr = d->d_qhdr;
     k_apply_updates<<<n, 64, 0, d->stream>>>(A);
     ++d->launches;
     CUDA_TRY(d, cudaGetLastError());
     CUDA_TRY(d, cudaEventRecord(d->stage_done, d->stream));
     d->stage_busy = true;
+    return B200MIX_OK;
+}
+
+int b200mix_voice_queue(b200mix_device *d, uint32_t voice, uint32_t count, const uint32_t *buffers,
+    uint32_t loop_index)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    if(voice >= dd.max_voices || (count && !buffers))
+    { d->error = "voice_queue: bad arguments"; return B200MIX_ERR_INVALID; }
+    if(count > B200MIX_MAX_QUEUE)
+    { d->error = "voice_queue: more than B200MIX_MAX_QUEUE items"; return B200MIX_ERR_UNSUPPORTED; }
+    if(loop_index != B200MIX_NO_LOOP && loop_index >= count)
+    { d->error = "voice_queue: loop index outside the list"; return B200MIX_ERR_INVALID; }
+    QueueSet Q{};
+    Q.voice = voice; Q.count = count; Q.loop = loop_index;
+    for(uint32_t i = 0;i < count;++i)
+    {
+        if(buffers[i] >= dd.max_buffers || !d->h_buffers[buffers[i]].data)
+        { d->error = "voice_queue: buffer id without data"; return B200MIX_ERR_INVALID; }
+        Q.items[i] = buffers[i];
+    }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    if(!d->d_qhdr)
+    {
+        if(int rc = dev_alloc(d, d->d_qhdr, dd.max_voices)) return rc;
+        if(int rc = dev_alloc(d, d->d_queue, size_t(dd.max_voices)*kMaxQueue)) return rc;
+    }
+    k_set_queue<<<1, 32, 0, d->stream>>>(d->d_voices, d->d_qhdr, d->d_queue, Q);
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
     return B200MIX_OK;
 }
 
@@ -1065,6 +1098,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     P.order = d->d_order; P.num_order = d->num_order;
     P.xscratch = d->d_xscratch; P.sendinfo = d->d_sendinfo;
     P.filt = d->d_filt; P.filt_paths = 1u + dd.num_sends;
+    P.qhdr = d->d_qhdr; P.queue = d->d_queue;
     stage_mark(d, 1);
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);

@@ -102,7 +102,12 @@ struct MixParams {
     // pass 0 resamples and parks the line (xscratch), pass 1 mixes the filtered line (dline).
     uint32_t pass;
     const float *dline;                       // [max_voices][1024] filtered direct-path lines
+    // streaming queues (null until the first b200mix_voice_queue): per voice
+    // {count, head, loop, -} and kMaxQueue buffer ids
+    uint4 *qhdr; const uint32_t *queue;
 };
+
+constexpr uint32_t kMaxQueue = 32, kNoLoop = 0xffffffffu;
 
 // sendinfo bits
 constexpr uint32_t kSiSend = 1u, kSiPlaying = 2u, kSiDeferred = 4u, kSiDirty = 8u, kSiDry = 16u;
@@ -357,6 +362,11 @@ k_mix_voices(const MixParams P)
             && uint32_t(intPos) >= loopEnd)
             looping = false;                                     // core/voice.cpp:1015-1019
         const uint32_t resampler = h0.w;
+        // streaming source (neither IsStatic nor callback): plays the voice's buffer queue
+        const bool isQueue = !(flags & kVfStatic) && P.qhdr != nullptr;
+        uint4 qh = make_uint4(0u, 0u, kNoLoop, 0u);
+        if(isQueue && !second) qh = P.qhdr[v];
+        const uint32_t *qitems = P.queue + size_t(v)*kMaxQueue;
         const bool isHrtf = HRTF && (flags & kVfHrtf);
         const bool dirty = second ? ((info & kSiDirty) != 0) : ((flags & kVfCoefDirty) != 0);
         FilterRec *dfilt = P.filt ? P.filt + size_t(v)*P.filt_paths : nullptr;
@@ -475,26 +485,68 @@ k_mix_voices(const MixParams P)
                     const uint32_t count = srcn - srcDelay;
                     float *dst = srcBuffer + srcDelay;
                     for(uint32_t k = t;k < srcDelay;k += GS) srcBuffer[k] = 0.0f;
-                    // LoadBufferStatic (core/voice.cpp:500-544).  Element k of the run maps to
-                    // buffer frame q(k); loads are issued 8 at a time before any conversion.
-                    const uint32_t loopSize = looping ? (loopEnd - loopStart) : 1u;
-                    const uint32_t q0 = !looping ? uintPos : ((uintPos < loopEnd) ? uintPos
-                        : ((uintPos-loopStart)%loopSize + loopStart));
-                    const uint32_t firstRun = looping ? (loopEnd - q0) : 0u;
-                    const uint32_t lastFrame = buf.frames ? buf.frames-1u : 0u;
-                    const bool pastEnd = !looping && !(buf.frames > uintPos);
-                    const bool simpleWrap = looping && count <= firstRun + loopSize;
-                    const FillArgs fa{dst, count, uintPos, q0, firstRun, loopStart, loopSize,
-                        lastFrame, buf.channels, looping, pastEnd, simpleWrap};
-                    switch(buf.type)
+                    // LoadBufferStatic (core/voice.cpp:500-544): one run; element k maps to buffer
+                    // frame q(k).  LoadBufferQueue (:546-595): one run per queue item crossed, then
+                    // the last sample held.  Loads are issued 8 at a time before any conversion.
+                    uint32_t done = 0, item = qh.x ? qh.y : kNoLoop, qpos = uintPos;
+                    bool more = true;
+                    while(more)
                     {
-                    case 0: fill_window<uint8_t, GS>(fa, static_cast<const uint8_t*>(buf.data), t); break;
-                    case 1: fill_window<int16_t, GS>(fa, static_cast<const int16_t*>(buf.data), t); break;
-                    case 2: fill_window<int32_t, GS>(fa, static_cast<const int32_t*>(buf.data), t); break;
-                    case 3: fill_window<float, GS>(fa, static_cast<const float*>(buf.data), t); break;
-                    case 4: fill_window<double, GS>(fa, static_cast<const double*>(buf.data), t); break;
-                    case 5: fill_window<MulawByte, GS>(fa, static_cast<const MulawByte*>(buf.data), t); break;
-                    default: fill_window<AlawByte, GS>(fa, static_cast<const AlawByte*>(buf.data), t); break;
+                        BufferRec rb = buf;
+                        FillArgs fa;
+                        if(!isQueue)
+                        {
+                            const uint32_t loopSize = looping ? (loopEnd - loopStart) : 1u;
+                            const uint32_t q0 = !looping ? uintPos : ((uintPos < loopEnd) ? uintPos
+                                : ((uintPos-loopStart)%loopSize + loopStart));
+                            const uint32_t firstRun = looping ? (loopEnd - q0) : 0u;
+                            const uint32_t lastFrame = buf.frames ? buf.frames-1u : 0u;
+                            const bool pastEnd = !looping && !(buf.frames > uintPos);
+                            const bool simpleWrap = looping && count <= firstRun + loopSize;
+                            fa = FillArgs{dst, count, uintPos, q0, firstRun, loopStart, loopSize,
+                                lastFrame, buf.channels, looping, pastEnd, simpleWrap};
+                            done = count; more = false;
+                        }
+                        else
+                        {
+                            bool found = false;
+                            while(item != kNoLoop && done < count)
+                            {
+                                rb = P.buffers[qitems[item]];
+                                if(qpos >= rb.frames)
+                                {
+                                    qpos -= rb.frames;
+                                    item = (item + 1u < qh.x) ? item + 1u : qh.z;
+                                    continue;
+                                }
+                                found = true;
+                                break;
+                            }
+                            if(!found) break;
+                            const uint32_t run = min(count - done, rb.frames - qpos);
+                            fa = FillArgs{dst + done, run, qpos, qpos, 0u, 0u, 1u, rb.frames-1u,
+                                rb.channels, false, false, false};
+                            done += run; qpos = 0u;
+                            item = (item + 1u < qh.x) ? item + 1u : qh.z;
+                            more = done < count;
+                        }
+                        switch(rb.type)
+                        {
+                        case 0: fill_window<uint8_t, GS>(fa, static_cast<const uint8_t*>(rb.data), t); break;
+                        case 1: fill_window<int16_t, GS>(fa, static_cast<const int16_t*>(rb.data), t); break;
+                        case 2: fill_window<int32_t, GS>(fa, static_cast<const int32_t*>(rb.data), t); break;
+                        case 3: fill_window<float, GS>(fa, static_cast<const float*>(rb.data), t); break;
+                        case 4: fill_window<double, GS>(fa, static_cast<const double*>(rb.data), t); break;
+                        case 5: fill_window<MulawByte, GS>(fa, static_cast<const MulawByte*>(rb.data), t); break;
+                        default: fill_window<AlawByte, GS>(fa, static_cast<const AlawByte*>(rb.data), t); break;
+                        }
+                    }
+                    if(done < count)
+                    {
+                        // queue ran out inside the window: hold the last sample (0 if none)
+                        group_sync(bar, GS);
+                        const float held = done ? dst[done-1u] : 0.0f;
+                        for(uint32_t k = done + t;k < count;k += GS) dst[k] = held;
                     }
                 }
                 group_sync(bar, GS);       // window complete
@@ -769,6 +821,7 @@ k_mix_voices(const MixParams P)
         {
             uint32_t newFlags = (flags | kVfFading) & ~kVfCoefDirty;
             uint32_t newState = vstate;
+            uint32_t buffersDone = 0u;
             int32_t pos = int32_t(h1.x); uint32_t frac = h1.y;
             if(vstate == 2u) newState = 0u;
             else
@@ -777,7 +830,22 @@ k_mix_voices(const MixParams P)
                 const uint32_t done = frac >> 16;
                 pos = add_sat(pos, int32_t(done));
                 frac &= 0xffffu;
-                if(haveBuffer && pos > 0)
+                if(haveBuffer && pos > 0 && isQueue)
+                {
+                    // streaming source: finished items leave the queue (core/voice.cpp:1183-1196)
+                    uint32_t item = qh.x ? qh.y : kNoLoop;
+                    while(item != kNoLoop)
+                    {
+                        const uint32_t len = P.buffers[qitems[item]].frames;
+                        if(len > uint32_t(pos)) break;
+                        pos -= int32_t(len);
+                        ++buffersDone;
+                        item = (item + 1u < qh.x) ? item + 1u : qh.z;
+                    }
+                    if(item == kNoLoop) { newFlags &= ~kVfHaveBuffer; newState = 2u; }
+                    else if(item != qh.y) P.qhdr[v].y = item;
+                }
+                else if(haveBuffer && pos > 0)
                 {
                     if(looping)
                     {
@@ -797,7 +865,7 @@ k_mix_voices(const MixParams P)
             rec.state = newState;
             if(P.results)
                 P.results[v] = VoiceResult{pos, frac,
-                    newState == 1u ? 1u : (newState == 2u ? 2u : (1u<<7)), 0u};
+                    newState == 1u ? 1u : (newState == 2u ? 2u : (1u<<7)), buffersDone};
         }
         group_sync(bar, GS);               // smem free for the next voice
         if(t == 0)
@@ -964,6 +1032,7 @@ struct ApplyParams {
     const float2 *st_coeffs;     // [ir_count][st_ir]
     const uint8_t *st_delays;    // [ir_count][2]
     uint32_t st_num_fields, st_ir;
+    uint4 *qhdr;                 // streaming queues (null: none): a restart rewinds the head
 };
 
 // HrtfStore::getCoeffs (core/hrtf.cpp:192-260) on the device, in the exact operation order of
@@ -1034,6 +1103,22 @@ __device__ __forceinline__ void filter_reset_word(FilterRec *fr, int k)
     if(k == 0 || k == 5 || k == 10 || k == 15) val = __float_as_uint(1.0f);   // b0 of cur/tgt
     else if(k == 24 || k == 25) val = 0xffffffffu;                             // mCounter = -1
     w[k] = val;
+}
+
+// b200mix_voice_queue: installs a voice's buffer list (items by value in the launch
+// parameters) and keeps VoiceFlag "has a current buffer" in step with it.
+struct QueueSet { uint32_t voice, count, loop; uint32_t items[kMaxQueue]; };
+__global__ void k_set_queue(VoiceRec *voices, uint4 *qhdr, uint32_t *queue, const QueueSet Q)
+{
+    const uint32_t t = threadIdx.x;
+    if(t < Q.count) queue[size_t(Q.voice)*kMaxQueue + t] = Q.items[t];
+    if(t == 0)
+    {
+        qhdr[Q.voice] = make_uint4(Q.count, 0u, Q.loop, 0u);
+        uint32_t fl = voices[Q.voice].flags;
+        fl = Q.count ? (fl | kVfHaveBuffer) : (fl & ~kVfHaveBuffer);
+        voices[Q.voice].flags = fl;
+    }
 }
 
 __global__ void k_filter_init(FilterRec *filt, size_t count)
@@ -1153,6 +1238,7 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
             fl |= kVfHaveBuffer;
             if(up.flags & (1u<<6)) fl |= kVfFading;
             rec.old_delay0 = 0; rec.old_delay1 = 0; rec.old_gain = 0.0f;
+            if(A.qhdr) A.qhdr[up.voice].y = 0u;
         }
         else
         {

@@ -10,6 +10,8 @@ MAX_DRY = 32
 MAX_WET = 25
 PADDING = 48
 NO_SLOT = 0xFFFFFFFF
+NO_LOOP = 0xFFFFFFFF
+MAX_QUEUE = 32
 
 (RS_POINT, RS_LINEAR, RS_SPLINE, RS_GAUSSIAN, RS_FAST_BSINC12, RS_BSINC12, RS_FAST_BSINC24,
  RS_BSINC24, RS_FAST_BSINC48, RS_BSINC48) = range(10)

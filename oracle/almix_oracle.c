@@ -202,6 +202,11 @@ typedef struct {
     uint32_t send_slot[B200MIX_MAX_SENDS];
     float send_cur[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
     float send_tgt[B200MIX_MAX_SENDS][B200MIX_MAX_WET_CHANNELS];
+    /* streaming queue (VoiceBufferItem list, core/voice.h:84-99): buffer ids from the
+     * current item on; q_loop = index playback continues at after the last item */
+    uint32_t q_count, q_head, q_loop;
+    uint32_t q_items[B200MIX_MAX_QUEUE];
+    uint32_t buffers_done;
     /* DirectParams/SendParams LowPass+HighPass, path 0 = direct, 1+s = send s */
     struct { obiquad lp, hp; int active; } filt[1 + B200MIX_MAX_SENDS];
 } ovoice;
@@ -427,7 +432,13 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
         if(p->flags & B200MIX_VF_RESET)
         {
             /* Voice::prepare + InitVoice: core/voice.cpp:1235-1400, al/source.cpp:639-669 */
+            /* the buffer list is the source's, not the voice's: it survives a restart */
+            const uint32_t qc = v->q_count, ql = v->q_loop;
+            uint32_t qi[B200MIX_MAX_QUEUE];
+            memcpy(qi, v->q_items, sizeof(qi));
             memset(v, 0, sizeof(*v));
+            v->q_count = qc; v->q_loop = ql; v->q_head = 0;
+            memcpy(v->q_items, qi, sizeof(qi));
             for(uint32_t f = 0;f < 1 + B200MIX_MAX_SENDS;++f)
             { obiquad_reset(&v->filt[f].lp); obiquad_reset(&v->filt[f].hp); }
             v->pos = p->position; v->frac = p->position_frac;
@@ -457,6 +468,59 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
                     v->send_tgt[s][c] = send_gains[((size_t)i*ns + s)*cw + c];
     }
     return B200MIX_OK;
+}
+
+int oracle_voice_queue(oracle_device *d, uint32_t voice, uint32_t count, const uint32_t *buffers,
+    uint32_t loop_index)
+{
+    if(voice >= d->desc.max_voices || count > B200MIX_MAX_QUEUE || (count && !buffers))
+        return B200MIX_ERR_INVALID;
+    if(loop_index != B200MIX_NO_LOOP && loop_index >= count) return B200MIX_ERR_INVALID;
+    ovoice *v = &d->voices[voice];
+    for(uint32_t i = 0;i < count;++i)
+    {
+        if(buffers[i] >= d->desc.max_buffers) return B200MIX_ERR_INVALID;
+        v->q_items[i] = buffers[i];
+    }
+    v->q_count = count; v->q_head = 0; v->q_loop = loop_index;
+    v->have_buffer = count > 0;
+    return B200MIX_OK;
+}
+
+static void load_samples(float *dst, size_t count, const obuffer *b, size_t offset);
+
+/* next item of the queue: mNext, or the loop item past the end (core/voice.cpp:563-565) */
+static uint32_t queue_next(const ovoice *v, uint32_t item)
+{
+    if(item + 1 < v->q_count) return item + 1;
+    return v->q_loop;            /* B200MIX_NO_LOOP ends the list */
+}
+
+/* LoadBufferQueue, core/voice.cpp:546-595 */
+static void load_buffer_queue(const oracle_device *d, const ovoice *v, size_t dataPosInt, float *dst,
+    size_t count)
+{
+    float lastSample = 0.0f;
+    uint32_t item = v->q_head;
+    while(item != B200MIX_NO_LOOP && count > 0)
+    {
+        const obuffer *b = &d->buffers[v->q_items[item]];
+        if(dataPosInt >= b->frames)
+        {
+            dataPosInt -= b->frames;
+            item = queue_next(v, item);
+            continue;
+        }
+        size_t remaining = b->frames - dataPosInt;
+        if(remaining > count) remaining = count;
+        load_samples(dst, remaining, b, dataPosInt);
+        lastSample = dst[remaining-1];
+        dst += remaining; count -= remaining;
+        if(!count) break;
+        dataPosInt = 0;
+        item = queue_next(v, item);
+    }
+    for(size_t i = 0;i < count;++i) dst[i] = lastSample;
 }
 
 /* BiquadInterpFilter::setParams after SetParams filled mTargetCoeffs
@@ -733,7 +797,8 @@ static void load_resampled(oracle_device *d, ovoice *v, int vstate, int looping,
     int32_t intPos = v->pos;
     uint32_t fracPos = v->frac;
     const uint32_t increment = v->step;
-    const obuffer *buf = v->have_buffer ? &d->buffers[v->buffer] : NULL;
+    const int is_queue = !(v->flags & B200MIX_VF_STATIC);
+    const obuffer *buf = v->have_buffer ? &d->buffers[is_queue ? v->q_items[v->q_head] : v->buffer] : NULL;
 
     for(uint32_t loaded = 0;loaded < samplesToMix;)
     {
@@ -777,8 +842,11 @@ static void load_resampled(oracle_device *d, ovoice *v, int vstate, int looping,
         else
         {
             const uint32_t uintPos = (intPos < 0) ? 0u : (uint32_t)intPos;
-            load_buffer_static(buf, looping, v->loop_start, v->loop_end, uintPos,
-                srcBuffer+srcSampleDelay, srcn-srcSampleDelay);
+            if(is_queue)
+                load_buffer_queue(d, v, uintPos, srcBuffer+srcSampleDelay, srcn-srcSampleDelay);
+            else
+                load_buffer_static(buf, looping, v->loop_start, v->loop_end, uintPos,
+                    srcBuffer+srcSampleDelay, srcn-srcSampleDelay);
         }
 
         if(increment == FRAC_ONE && fracPos == 0)
@@ -963,7 +1031,8 @@ static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_res
         if(vstate == 2) v->state = 0;
         return;
     }
-    const obuffer *buf = v->have_buffer ? &d->buffers[v->buffer] : NULL;
+    const int is_queue = !(v->flags & B200MIX_VF_STATIC);
+    const obuffer *buf = v->have_buffer ? &d->buffers[is_queue ? v->q_items[v->q_head] : v->buffer] : NULL;
     int looping = (v->flags & B200MIX_VF_LOOPING) != 0;
     if((v->flags & B200MIX_VF_STATIC) && looping && buf)
     {
@@ -1023,7 +1092,22 @@ static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_res
     const uint32_t samplesDone = frac >> FRAC_BITS;
     int32_t pos = add_sat_i32(v->pos, (int32_t)samplesDone);
     frac &= FRAC_MASK;
-    if(buf && pos > 0)
+    if(buf && pos > 0 && is_queue)
+    {
+        /* streaming source, core/voice.cpp:1183-1196 */
+        uint32_t item = v->q_head;
+        while(item != B200MIX_NO_LOOP)
+        {
+            const uint32_t len = d->buffers[v->q_items[item]].frames;
+            if(len > (uint32_t)pos) break;
+            pos -= (int32_t)len;
+            ++v->buffers_done;
+            item = queue_next(v, item);
+        }
+        if(item == B200MIX_NO_LOOP) v->have_buffer = 0;
+        else v->q_head = item;
+    }
+    else if(buf && pos > 0)
     {
         if(looping)
         {
@@ -1237,6 +1321,7 @@ int oracle_render_begin(oracle_device *d, uint32_t frames, float **wet_host, siz
     for(uint32_t i = 0;i < dd->max_voices;++i)
     {
         ovoice *v = &d->voices[i];
+        v->buffers_done = 0;
         if(v->state == 1 || v->state == 2)
             voice_mix(d, v, frames, NULL);
     }
@@ -1286,7 +1371,7 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
             results[i].position = v->pos; results[i].position_frac = v->frac;
             results[i].flags = (v->state == 1) ? B200MIX_VF_PLAYING
                 : (v->state == 2) ? B200MIX_VF_STOPPING : B200MIX_VF_STOPPED;
-            results[i].buffers_done = 0;
+            results[i].buffers_done = d->voices[i].buffers_done;
         }
     return B200MIX_OK;
 }

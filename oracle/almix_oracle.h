@@ -70,6 +70,8 @@ int  oracle_buffer_data(oracle_device *dev, uint32_t buffer, uint32_t sample_typ
 int  oracle_buffer_free(oracle_device *dev, uint32_t buffer);
 int  oracle_voices_update(oracle_device *dev, uint32_t n, const b200mix_voice_params *params,
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains);
+int  oracle_voice_queue(oracle_device *dev, uint32_t voice, uint32_t count, const uint32_t *buffers,
+    uint32_t loop_index);
 int  oracle_voices_filters(oracle_device *dev, uint32_t n, const b200mix_voice_filter *filters);
 int  oracle_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5]);
 int  oracle_render(oracle_device *dev, uint32_t frames, float *const *real_out,

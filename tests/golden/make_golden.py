@@ -59,7 +59,13 @@ SCENES = {
     "hrtf_bsinc24_dfilter_v6": (6, 1, 7, 6, True, 48000, None, "i16", 0, None, "direct"),
     "stereo_spline_dfilter_v5": (5, 0, 2, 5, True, 48000, None, "i16", 0, None, "direct"),
     "hrtf_spline_reverb_sfilter_v4": (4, 1, 2, 6, True, 48000, None, "i16", 0, {}, "send"),
+    # streaming sources (alSourceQueueBuffers -> LoadBufferQueue, core/voice.cpp:546-595): every
+    # voice plays QUEUE_LENS buffers back to back, even voices loop the queue, odd ones run out
+    "hrtf_bsinc24_queue_v6": (6, 1, 7, 12, True, 48000, None, "i16", 0, None, None, "queue"),
+    "stereo_spline_queue_v4": (4, 0, 2, 12, True, 48000, None, "i16", 0, None, None, "queue"),
 }
+
+QUEUE_LENS = (3000, 1500, 5000)
 
 # Filter scripts: {update index (applied BEFORE that render; 0 = before play):
 #                  [(voice, path, gainHF, gainLF or None)]}; path 0 = direct, 1 = send 0.
@@ -101,12 +107,20 @@ ATTRS = {
 
 def run_scene(name):
     from helpers import refal, scenes
-    from pyb200mix import abi
+    from pyb200mix import abi, scene
     V, hrtf, rs, U, looping, frames = SCENES[name][:6]
     spec = SCENES[name]
     attrs = ATTRS[spec[6]](refal) if len(spec) > 6 and spec[6] else None
     fmt = spec[7] if len(spec) > 7 else "i16"
-    ref, pcms = scenes.make_ref_scene(V, hrtf, rs, attrs=attrs, looping=looping, frames=frames, fmt=fmt)
+    queue = len(spec) > 11 and spec[11] == "queue"
+    if queue:
+        ref, pcms = scenes.make_ref_scene(0, hrtf, rs, attrs=attrs, max_sources=V)
+        for i in range(V):
+            parts = [scene.voice_buffer_fmt(i * len(QUEUE_LENS) + j, n, fmt) for j, n in enumerate(QUEUE_LENS)]
+            ref.add_queue_voice(parts, scene.BUFFER_RATE, scene.voice_pitch(i), scene.voice_position(i),
+                                scene.voice_gain(V), rs, looping=(i % 2 == 0), fmt=scene.FORMATS[fmt][1])
+    else:
+        ref, pcms = scenes.make_ref_scene(V, hrtf, rs, attrs=attrs, looping=looping, frames=frames, fmt=fmt)
     taps = spec[8] if len(spec) > 8 else 0
     if taps:
         slot = ref.add_convolution_slot(conv_ir(taps), 48000, 0.5)
@@ -118,7 +132,7 @@ def run_scene(name):
         slot = ref.add_reverb_slot(props=rvprops)
         for src in ref.sources:
             ref.connect_send(src, slot)
-    script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 else None
+    script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 and spec[10] else None
     if script:
         apply_filter_script(ref, script, 0, slot)
     ref.play_all()
@@ -153,6 +167,8 @@ def run_scene(name):
                    send=send[:V].copy(), wet_channels=np.int64(wet[0]))
     if script:
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
+    if queue:
+        res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
     if d.post_process == abi.POST_HRTF:
         c, hf, sc = ref.hrtf_decoder()
         res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)

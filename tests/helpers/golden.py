@@ -25,7 +25,7 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
     V, hrtf, rs, U, looping, buf_frames = [int(x) for x in fx["meta"]]
     desc = abi.DeviceDesc.from_buffer_copy(fx["desc"].tobytes())
     desc.max_voices = V
-    desc.max_buffers = V
+    desc.max_buffers = V * (len(fx["queue_lens"]) if "queue_lens" in fx else 1)
     desc.max_slots = 0
     taps = int(fx["conv_taps"]) if "conv_taps" in fx else 0
     reverb = "reverb_params" in fx
@@ -39,8 +39,13 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
         elif desc.post_process == abi.POST_AMBIDEC:
             dev.set_ambi_decoder(fx["amb_hf"], fx.get("amb_lf"), float(fx["amb_xover"]))
         fmt = str(fx["fmt"]) if "fmt" in fx else "i16"
-        for i in range(V):
-            dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, buf_frames, fmt))
+        qlens = [int(x) for x in fx["queue_lens"]] if "queue_lens" in fx else None
+        if qlens:
+            for i in range(V * len(qlens)):
+                dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, qlens[i % len(qlens)], fmt))
+        else:
+            for i in range(V):
+                dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, buf_frames, fmt))
         if taps:
             rng = np.random.default_rng(taps)      # same IR as tests/golden/make_golden.py:conv_ir
             ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
@@ -60,6 +65,10 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             q.position_frac = 0
             plist.append(q)
         dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if (taps or reverb) else None)
+        if qlens:
+            for k in range(V):
+                ids = [k * len(qlens) + j for j in range(len(qlens))]
+                dev.voice_queue(k, ids, 0 if (plist[k].flags & abi.VF_LOOPING) else abi.NO_LOOP)
         outs = []
         res = None
         for u in range(updates or U):

@@ -49,6 +49,8 @@ class MixLib:
         self.voices_filters.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         self.biquad_coeffs = f("biquad_coeffs")
         self.biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        self.voice_queue = f("voice_queue")
+        self.voice_queue.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
         self.render_begin = f("render_begin")
         self.render_begin.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         self.render_end = f("render_end")
@@ -151,6 +153,11 @@ class MixDevice:
         rc = self.m.render(self.h, frames, ptrs, res)
         assert rc == 0, f"render -> {rc}"
         return (out, res) if want_results else out
+
+    def voice_queue(self, voice, buffer_ids, loop_index):
+        arr = (C.c_uint32 * max(len(buffer_ids), 1))(*buffer_ids)
+        rc = self.m.voice_queue(self.h, voice, len(buffer_ids), arr, loop_index)
+        assert rc == 0, rc
 
     def render_begin(self, frames=1024):
         """Returns (wet pointer, float count): a host pointer on the oracle, a device pointer

@@ -122,6 +122,7 @@ def libs(conf_text: str | None = None):
     al.alSourcef.argtypes = [C.c_uint, C.c_int, C.c_float]
     al.alSource3f.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_float, C.c_float]
     al.alSource3i.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+    al.alSourceQueueBuffers.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_uint)]
     al.alSourcePlayv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alSourceStopv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alDistanceModel.argtypes = [C.c_int]
@@ -218,6 +219,30 @@ class RefDevice:
         self.buffers.append(b.value)
         self.sources.append(s.value)
         self._keep.append(pcm)
+        return s.value
+
+    def add_queue_voice(self, pcms, rate: int, pitch: float, pos, gain: float,
+                        resampler: int | None, looping: bool = False, fmt=AL_FORMAT_MONO16):
+        """A streaming source: alSourceQueueBuffers with one buffer per PCM array."""
+        ids = (C.c_uint * len(pcms))()
+        self.al.alGenBuffers(len(pcms), ids)
+        for i, pcm in enumerate(pcms):
+            pcm = np.ascontiguousarray(pcm)
+            self.al.alBufferData(ids[i], fmt, pcm.ctypes.data, pcm.nbytes, rate)
+            self._keep.append(pcm)
+        s = C.c_uint(0)
+        self.al.alGenSources(1, C.byref(s))
+        self.al.alSourceQueueBuffers(s, len(pcms), ids)
+        self.al.alSourcei(s, AL_LOOPING, 1 if looping else 0)
+        self.al.alSourcef(s, AL_PITCH, pitch)
+        self.al.alSourcef(s, AL_GAIN, gain)
+        self.al.alSource3f(s, AL_POSITION, *[float(x) for x in pos])
+        if resampler is not None:
+            self.al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x}"
+        self.buffers += list(ids)
+        self.sources.append(s.value)
         return s.value
 
     def add_convolution_slot(self, ir_pcm: np.ndarray, rate: int, slot_gain: float = 1.0,

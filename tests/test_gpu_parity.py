@@ -34,8 +34,8 @@ def test_golden_vectors_from_reference(name):
     out_o, res_o = golden.replay(mixlib.oracle(), fx)
     V = int(fx["meta"][0])
     for k in range(V):
-        assert (res[k].position, res[k].position_frac, res[k].flags) == \
-            (res_o[k].position, res_o[k].position_frac, res_o[k].flags), k
+        assert (res[k].position, res[k].position_frac, res[k].flags, res[k].buffers_done) == \
+            (res_o[k].position, res_o[k].position_frac, res_o[k].flags, res_o[k].buffers_done), k
 
 
 def _run_pair(desc_fn, nv, updates, **kw):
@@ -436,3 +436,61 @@ def test_device_side_hrir_lookup_is_bit_identical_to_host_helper():
     a, b = np.concatenate(outs[0], axis=1), np.concatenate(outs[1], axis=1)
     assert np.abs(a).max() > 1e-4
     assert np.array_equal(a, b), f"max diff {np.abs(a - b).max():.3e}"
+
+
+@pytest.mark.parametrize("hrtf", [True, False])
+def test_streaming_queues_vs_oracle(hrtf):
+    """LoadBufferQueue + queue advance: short items (several crossed per window), loop back to
+    a middle item, queues that run out (Stopping fade), a start position beyond the first
+    item, re-queuing mid-stream, ragged updates; audio AND per-update voice results
+    (position, state, buffers_done) must match the oracle."""
+    rng = np.random.default_rng(909)
+    nv, ir = 20, 64
+    desc = synth.hrtf_desc(nv, ir) if hrtf else synth.stereo_desc(nv)
+    nbuf = nv * 4
+    desc.max_buffers = nbuf
+    params, coeffs, dry = synth.voice_set(rng, nv, ir if hrtf else 0, hrtf=hrtf,
+                                          dry_channels=desc.dry_channels, pitch_lo=0.4, pitch_hi=3.0)
+    lens = [int(x) for x in rng.integers(40, 2500, size=nbuf)]
+    for k, p in enumerate(params):
+        p.flags &= ~abi.VF_STATIC
+        p.flags &= ~abi.VF_LOOPING
+        p.position = int(rng.integers(0, 3000)) if k % 5 == 0 else 0
+        p.loop_start, p.loop_end = 0, 0
+
+    def queue_of(k, phase):
+        ids = [k * 4 + j for j in range(4)]
+        if phase == 1:
+            ids = ids[::-1][:3]
+        loop = abi.NO_LOOP if k % 3 == 0 else (k % 3 - 1)       # none / item 0 / item 1
+        return ids, loop
+
+    outs, results = [], []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        if hrtf:
+            dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        else:
+            dev.set_ambi_decoder((np.random.default_rng(3).standard_normal((desc.dry_channels, 2)) * 0.5
+                                  ).astype(np.float32), None, 0.0)
+        for i in range(nbuf):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i, lens[i]))
+        dev.voices_update(params, coeffs if hrtf else None, dry, None)
+        for k in range(nv):
+            dev.voice_queue(k, *queue_of(k, 0))
+        o, rs = [], []
+        for u, f in enumerate((1024, 37, 1024, 512, 1024, 1, 1000, 1024, 1024)):
+            if u == 3:
+                # the application re-queues: a new list from the current item on
+                for k in range(1, nv, 4):
+                    dev.voice_queue(k, *queue_of(k, 1))
+            out, res = dev.render(f, want_results=True)
+            o.append(out)
+            rs.append([(res[k].position, res[k].position_frac, res[k].flags, res[k].buffers_done)
+                       for k in range(nv)])
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+        results.append(rs)
+    assert results[0] == results[1]
+    assert sum(r[3] for upd in results[0] for r in upd) > 10        # items really were consumed
+    _check(outs[1], outs[0], "streaming queues")
