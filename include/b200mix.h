@@ -180,6 +180,11 @@ enum {
     B200MIX_VF_FADING    = 1u<<6, /* with RESET: start with IsFading set (al/source.cpp:775,2714) */
     B200MIX_VF_STOPPED   = 1u<<7  /* Voice::Stopped: remove from the active set */
 };
+/* Multi-channel sources: the reference mixes every buffer channel as its own mixing channel
+ * with its own panning/HRIR (Voice::mChans[c], core/voice.h:236-257; LoadSamples' srcChannel,
+ * core/voice.cpp:271-287).  Here each mixing channel is a voice of its own: same buffer,
+ * position and step, its own targets, and the buffer channel it reads in bits 16..23. */
+#define B200MIX_VF_CHANNEL(c)  (((uint32_t)(c) & 0xffu) << 16)
 
 typedef struct b200mix_voice_params {
     uint32_t voice;           /* index in the device voice array, < max_voices */

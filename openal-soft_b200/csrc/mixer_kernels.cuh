@@ -34,6 +34,7 @@ constexpr float kEps = 1.1920929e-07f;
 // internal voice flag bits (low 8 bits are the ABI's B200MIX_VF_*)
 constexpr uint32_t kVfStatic = 1u<<2, kVfLooping = 1u<<3, kVfHrtf = 1u<<4;
 constexpr uint32_t kVfFading = 1u<<8, kVfHaveBuffer = 1u<<9, kVfCoefDirty = 1u<<10;
+constexpr uint32_t kVfChannelMask = 0xffu<<16;       // B200MIX_VF_CHANNEL: buffer channel read
 
 struct alignas(16) BufferRec {
     const void *data;
@@ -530,15 +531,18 @@ k_mix_voices(const MixParams P)
                             item = (item + 1u < qh.x) ? item + 1u : qh.z;
                             more = done < count;
                         }
+                        // srcChannel of LoadSamples (core/voice.cpp:271-287); a channel the buffer
+                        // does not have reads channel 0
+                        const uint32_t ch = ((flags >> 16) & 0xffu) < rb.channels ? ((flags >> 16) & 0xffu) : 0u;
                         switch(rb.type)
                         {
-                        case 0: fill_window<uint8_t, GS>(fa, static_cast<const uint8_t*>(rb.data), t); break;
-                        case 1: fill_window<int16_t, GS>(fa, static_cast<const int16_t*>(rb.data), t); break;
-                        case 2: fill_window<int32_t, GS>(fa, static_cast<const int32_t*>(rb.data), t); break;
-                        case 3: fill_window<float, GS>(fa, static_cast<const float*>(rb.data), t); break;
-                        case 4: fill_window<double, GS>(fa, static_cast<const double*>(rb.data), t); break;
-                        case 5: fill_window<MulawByte, GS>(fa, static_cast<const MulawByte*>(rb.data), t); break;
-                        default: fill_window<AlawByte, GS>(fa, static_cast<const AlawByte*>(rb.data), t); break;
+                        case 0: fill_window<uint8_t, GS>(fa, static_cast<const uint8_t*>(rb.data) + ch, t); break;
+                        case 1: fill_window<int16_t, GS>(fa, static_cast<const int16_t*>(rb.data) + ch, t); break;
+                        case 2: fill_window<int32_t, GS>(fa, static_cast<const int32_t*>(rb.data) + ch, t); break;
+                        case 3: fill_window<float, GS>(fa, static_cast<const float*>(rb.data) + ch, t); break;
+                        case 4: fill_window<double, GS>(fa, static_cast<const double*>(rb.data) + ch, t); break;
+                        case 5: fill_window<MulawByte, GS>(fa, static_cast<const MulawByte*>(rb.data) + ch, t); break;
+                        default: fill_window<AlawByte, GS>(fa, static_cast<const AlawByte*>(rb.data) + ch, t); break;
                         }
                     }
                     if(done < count)
@@ -1231,7 +1235,7 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
             A.send_tgt[size_t(up.voice)*A.num_sends*A.cw + c] = A.send[size_t(u)*A.num_sends*A.cw + c];
     if(t == 0)
     {
-        uint32_t fl = up.flags & (kVfStatic|kVfLooping|kVfHrtf);
+        uint32_t fl = up.flags & (kVfStatic|kVfLooping|kVfHrtf|kVfChannelMask);
         if(reset)
         {
             rec.pos = up.position; rec.frac = up.position_frac;

@@ -13,6 +13,12 @@ NO_SLOT = 0xFFFFFFFF
 NO_LOOP = 0xFFFFFFFF
 MAX_QUEUE = 32
 
+
+def vf_channel(c):
+    """B200MIX_VF_CHANNEL(c): the buffer channel a voice reads."""
+    return (int(c) & 0xff) << 16
+
+
 (RS_POINT, RS_LINEAR, RS_SPLINE, RS_GAUSSIAN, RS_FAST_BSINC12, RS_BSINC12, RS_FAST_BSINC24,
  RS_BSINC24, RS_FAST_BSINC48, RS_BSINC48) = range(10)
 FMT_U8, FMT_I16, FMT_I32, FMT_F32, FMT_F64, FMT_MULAW, FMT_ALAW = range(7)

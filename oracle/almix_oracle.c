@@ -448,7 +448,7 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
         if(p->flags & B200MIX_VF_STOPPED) v->state = 0;
         else if(p->flags & B200MIX_VF_STOPPING) v->state = 2;
         else if(p->flags & B200MIX_VF_PLAYING) v->state = 1;
-        v->flags = p->flags & (B200MIX_VF_STATIC|B200MIX_VF_LOOPING|B200MIX_VF_HRTF);
+        v->flags = p->flags & (B200MIX_VF_STATIC|B200MIX_VF_LOOPING|B200MIX_VF_HRTF|B200MIX_VF_CHANNEL(0xff));
         v->buffer = p->buffer; v->resampler = p->resampler;
         v->loop_start = p->loop_start; v->loop_end = p->loop_end; v->step = p->step;
         v->tgt_delay[0] = p->hrtf_delay[0]; v->tgt_delay[1] = p->hrtf_delay[1];
@@ -723,10 +723,12 @@ static float to_float(const obuffer *b, size_t idx)
     }
     return 0.0f;
 }
+static size_t g_src_channel;   /* srcChannel of the voice being loaded (single-threaded oracle) */
 static void load_samples(float *dst, size_t count, const obuffer *b, size_t offset)
 {
+    const size_t ch = g_src_channel < b->channels ? g_src_channel : 0;
     for(size_t i = 0;i < count;++i)
-        dst[i] = to_float(b, (offset+i)*b->channels);
+        dst[i] = to_float(b, (offset+i)*b->channels + ch);
 }
 
 /* LoadBufferStatic, core/voice.cpp:500-544 */
@@ -799,6 +801,7 @@ static void load_resampled(oracle_device *d, ovoice *v, int vstate, int looping,
     const uint32_t increment = v->step;
     const int is_queue = !(v->flags & B200MIX_VF_STATIC);
     const obuffer *buf = v->have_buffer ? &d->buffers[is_queue ? v->q_items[v->q_head] : v->buffer] : NULL;
+    g_src_channel = (v->flags >> 16) & 0xffu;
 
     for(uint32_t loaded = 0;loaded < samplesToMix;)
     {

@@ -180,6 +180,11 @@ int refh_ambi_decoder(ALCdevice *adev, float *gains_hf, float *gains_lf, float *
     return static_cast<int>(db.size());
 }
 
+/* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
+ * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
+static size_t g_snap_channel = 0;
+void refh_set_snapshot_channel(int c) { g_snap_channel = c < 0 ? 0u : size_t(c); }
+
 int refh_voice_count(ALCcontext *actx)
 { return static_cast<int>(ctx_of(actx)->getVoicesSpan().size()); }
 
@@ -205,7 +210,7 @@ int refh_snapshot_voices(ALCcontext *actx, b200mix_voice_params *params, float *
     auto n = 0u;
     for(auto *voice : voices)
     {
-        auto &ch = voice->mChans[0];
+        auto &ch = voice->mChans[std::min(g_snap_channel, voice->mChans.size()-1)];
         const auto pstate = voice->mPlayState.load();
         auto *item = voice->mCurrentBuffer.load();
         auto *loop = voice->mLoopBuffer.load();

@@ -63,6 +63,9 @@ SCENES = {
     # voice plays QUEUE_LENS buffers back to back, even voices loop the queue, odd ones run out
     "hrtf_bsinc24_queue_v6": (6, 1, 7, 12, True, 48000, None, "i16", 0, None, None, "queue"),
     "stereo_spline_queue_v4": (4, 0, 2, 12, True, 48000, None, "i16", 0, None, None, "queue"),
+    # stereo sources: two mixing channels per voice (Voice::mChans[0..1]), virtual speakers at +-30 deg
+    "hrtf_bsinc24_stereo_src_v4": (4, 1, 7, 4, True, 20000, None, "i16", 0, None, None, "stereo_src"),
+    "basic_spline_stereo_src_v3": (3, 0, 2, 3, True, 20000, None, "i16", 0, None, None, "stereo_src"),
 }
 
 QUEUE_LENS = (3000, 1500, 5000)
@@ -113,7 +116,17 @@ def run_scene(name):
     attrs = ATTRS[spec[6]](refal) if len(spec) > 6 and spec[6] else None
     fmt = spec[7] if len(spec) > 7 else "i16"
     queue = len(spec) > 11 and spec[11] == "queue"
-    if queue:
+    stereo_src = len(spec) > 11 and spec[11] == "stereo_src"
+    if stereo_src:
+        a2 = dict(attrs or {})
+        a2[refal.ALC_STEREO_SOURCES] = V
+        ref, pcms = scenes.make_ref_scene(0, hrtf, rs, attrs=a2, max_sources=1)
+        for i in range(V):
+            lr = np.stack([scene.voice_buffer_fmt(2 * i, frames, fmt), scene.voice_buffer_fmt(2 * i + 1, frames, fmt)],
+                          axis=1)
+            ref.add_voice(np.ascontiguousarray(lr), scene.BUFFER_RATE, scene.voice_pitch(i), scene.voice_position(i),
+                          scene.voice_gain(V), rs, looping=looping, fmt=refal.AL_FORMAT_STEREO16)
+    elif queue:
         ref, pcms = scenes.make_ref_scene(0, hrtf, rs, attrs=attrs, max_sources=V)
         for i in range(V):
             parts = [scene.voice_buffer_fmt(i * len(QUEUE_LENS) + j, n, fmt) for j, n in enumerate(QUEUE_LENS)]
@@ -150,6 +163,7 @@ def run_scene(name):
             filt_coef.append(np.array([[lp, hp] for _, _, _, lp, hp in ents], dtype=np.float32))
         if u == 0:
             snap = ref.snapshot(wet_channels=wet[0] if nslots else 0)
+            snap1 = ref.snapshot(channel=1) if stereo_src else None
             if rvprops is not None:
                 rvp, rvg, rvstate = ref.reverb_params(0)
                 assert rvstate == 4, rvstate     # ReverbState::Normal
@@ -169,6 +183,10 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if stereo_src:
+        n1, params1, coeffs1, dry1, _, _ = snap1
+        res.update(params_c1=np.frombuffer(bytes(params1), dtype=np.uint8)[:V * C.sizeof(abi.VoiceParams)].copy(),
+                   coeffs_c1=coeffs1[:V].copy(), dry_c1=dry1[:V].copy())
     if d.post_process == abi.POST_HRTF:
         c, hf, sc = ref.hrtf_decoder()
         res.update(dec_coeffs=c, dec_hf=hf, dec_sc=sc)

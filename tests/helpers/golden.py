@@ -24,7 +24,8 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
     """Returns (out [U][ch][frames], final voice results)."""
     V, hrtf, rs, U, looping, buf_frames = [int(x) for x in fx["meta"]]
     desc = abi.DeviceDesc.from_buffer_copy(fx["desc"].tobytes())
-    desc.max_voices = V
+    stereo_src = "params_c1" in fx
+    desc.max_voices = V * (2 if stereo_src else 1)
     desc.max_buffers = V * (len(fx["queue_lens"]) if "queue_lens" in fx else 1)
     desc.max_slots = 0
     taps = int(fx["conv_taps"]) if "conv_taps" in fx else 0
@@ -43,6 +44,11 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
         if qlens:
             for i in range(V * len(qlens)):
                 dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, qlens[i % len(qlens)], fmt))
+        elif stereo_src:
+            for i in range(V):
+                lr = np.stack([scene.voice_buffer_fmt(2 * i, buf_frames, fmt),
+                               scene.voice_buffer_fmt(2 * i + 1, buf_frames, fmt)], axis=1)
+                dev.buffer_data(i, scene.FORMATS[fmt][0], np.ascontiguousarray(lr), channels=2)
         else:
             for i in range(V):
                 dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, buf_frames, fmt))
@@ -64,7 +70,25 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             q.position = 0
             q.position_frac = 0
             plist.append(q)
-        dev.voices_update(plist, fx["coeffs"], fx["dry"], fx["send"] if (taps or reverb) else None)
+        coeffs, dry = fx["coeffs"], fx["dry"]
+        if stereo_src:
+            # one voice per mixing channel: voice 2k+c = channel c of source k, in the order the
+            # reference mixes them (voice by voice, channel by channel)
+            params1 = (abi.VoiceParams * V).from_buffer_copy(fx["params_c1"].tobytes())
+            both = []
+            for k in range(V):
+                for c, src in ((0, plist[k]), (1, params1[k])):
+                    q = abi.VoiceParams()
+                    C.memmove(C.byref(q), C.byref(plist[k]), C.sizeof(q))
+                    q.voice = 2 * k + c
+                    q.hrtf_delay[0], q.hrtf_delay[1] = src.hrtf_delay[0], src.hrtf_delay[1]
+                    q.hrtf_gain = src.hrtf_gain
+                    q.flags |= abi.vf_channel(c)
+                    both.append(q)
+            plist = both
+            coeffs = np.stack([fx["coeffs"], fx["coeffs_c1"]], axis=1).reshape((2 * V,) + fx["coeffs"].shape[1:])
+            dry = np.stack([fx["dry"], fx["dry_c1"]], axis=1).reshape((2 * V,) + fx["dry"].shape[1:])
+        dev.voices_update(plist, coeffs, dry, fx["send"] if (taps or reverb) else None)
         if qlens:
             for k in range(V):
                 ids = [k * len(qlens) + j for j in range(len(qlens))]

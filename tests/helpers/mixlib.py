@@ -112,9 +112,9 @@ class MixDevice:
         rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)
         assert rc == 0, rc
 
-    def buffer_data(self, buf_id, sample_type, pcm):
+    def buffer_data(self, buf_id, sample_type, pcm, channels=1):
         pcm = np.ascontiguousarray(pcm)
-        rc = self.m.buffer_data(self.h, buf_id, sample_type, 1, pcm.shape[0], pcm.ctypes.data,
+        rc = self.m.buffer_data(self.h, buf_id, sample_type, channels, pcm.shape[0], pcm.ctypes.data,
                                 pcm.nbytes)
         assert rc == 0, rc
 

@@ -26,6 +26,7 @@ AL_ROLLOFF_FACTOR = 0x1021
 AL_FORMAT_MONO8 = 0x1100
 AL_FORMAT_MONO16 = 0x1101
 AL_FORMAT_MONO_FLOAT32 = 0x10010
+AL_FORMAT_STEREO16 = 0x1103
 AL_DISTANCE_MODEL = 0xD000
 AL_SOURCE_RESAMPLER_SOFT = 0x1212
 AL_SOURCE_SPATIALIZE_SOFT = 0x1214
@@ -137,6 +138,8 @@ def libs(conf_text: str | None = None):
     hz.refh_slot_count.argtypes = [C.c_void_p]
     hz.refh_slot_wet_channels.argtypes = [C.c_void_p, C.c_int]
     hz.refh_mono_line_gains.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    hz.refh_set_snapshot_channel.argtypes = [C.c_int]
+    hz.refh_set_snapshot_channel.restype = None
     hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     hz.refh_biquad_coeffs.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
     hz.refh_biquad_coeffs.restype = None
@@ -356,7 +359,9 @@ class RefDevice:
         return np.ascontiguousarray(buf.T)
 
     # ---- taps ----
-    def snapshot(self, wet_channels: int = 0):
+    def snapshot(self, wet_channels: int = 0, channel: int = 0):
+        """channel: which mixing channel (Voice::mChans[channel]) of every voice to read."""
+        self.hz.refh_set_snapshot_channel(channel)
         n = self.hz.refh_voice_count(self.ctx)
         d = self.desc
         params = (abi.VoiceParams * max(n, 1))()
