@@ -55,10 +55,11 @@ enum b200mix_resampler {
     B200MIX_RESAMPLER_BSINC48
 };
 
-/* enum FmtType, core/storage_formats.h (PCM subset; IMA4/MSADPCM are §8f-next). */
+/* enum FmtType, core/storage_formats.h. */
 enum b200mix_sample_type {
     B200MIX_FMT_U8 = 0, B200MIX_FMT_I16, B200MIX_FMT_I32, B200MIX_FMT_F32, B200MIX_FMT_F64,
-    B200MIX_FMT_MULAW, B200MIX_FMT_ALAW
+    B200MIX_FMT_MULAW, B200MIX_FMT_ALAW,
+    B200MIX_FMT_IMA4, B200MIX_FMT_MSADPCM     /* only through b200mix_buffer_data_adpcm */
 };
 
 /* PostProcess variant of DeviceBase (core/device.h:200-222). */
@@ -112,6 +113,14 @@ B200MIX_API int b200mix_set_ambi_decoder(b200mix_device *dev, uint32_t in_channe
 /* Uploads an immutable copy (AL semantics: a buffer cannot change while attached). */
 B200MIX_API int b200mix_buffer_data(b200mix_device *dev, uint32_t buffer, uint32_t sample_type,
     uint32_t channels, uint32_t frames, const void *data, size_t bytes);
+/* Block-compressed buffers (AL_EXT_IMA4, AL_SOFT_MSADPCM): `blocks` blocks of
+ * samples_per_block sample frames each (BufferStorage::mBlockAlign; AL's defaults are 65 for
+ * IMA4 and 64 for MSADPCM), laid out exactly as alBufferData receives them.  The reference
+ * decodes these inside the mixer (LoadSamples<IMA4Data>/<MSADPCMData>, core/voice.cpp:289-484);
+ * both are integer recurrences, so the library decodes once here to the identical int16
+ * samples and the mixer streams those.  The buffer then has blocks*samples_per_block frames. */
+B200MIX_API int b200mix_buffer_data_adpcm(b200mix_device *dev, uint32_t buffer, uint32_t sample_type,
+    uint32_t channels, uint32_t samples_per_block, uint32_t blocks, const void *data, size_t bytes);
 B200MIX_API int b200mix_buffer_free(b200mix_device *dev, uint32_t buffer);
 
 /* ---- auxiliary effect slots: EffectSlotBase + EffectState (core/effectslot.h:50-82,

@@ -21,6 +21,7 @@
 #include "effect_kernels.cuh"
 #include "resampler_tables.hpp"
 #include "hrtf_store.hpp"
+#include "adpcm.hpp"
 
 using namespace b200mix;
 
@@ -532,6 +533,27 @@ int b200mix_buffer_data(b200mix_device *d, uint32_t buffer, uint32_t sample_type
     CUDA_TRY(d, cudaMemcpyAsync(d->d_buffers + buffer, &h, sizeof(BufferRec), cudaMemcpyHostToDevice,
         d->stream));
     return B200MIX_OK;
+}
+
+int b200mix_buffer_data_adpcm(b200mix_device *d, uint32_t buffer, uint32_t sample_type,
+    uint32_t channels, uint32_t samples_per_block, uint32_t blocks, const void *data, size_t bytes)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const bool ms = sample_type == B200MIX_FMT_MSADPCM;
+    if((sample_type != B200MIX_FMT_IMA4 && !ms) || channels < 1 || channels > 2 || !data
+        || !AdpcmBlockValid(ms, samples_per_block))
+    { d->error = "buffer_data_adpcm: bad arguments"; return B200MIX_ERR_INVALID; }
+    if(bytes < AdpcmBlockBytes(ms, channels, samples_per_block)*blocks
+        || uint64_t(blocks)*samples_per_block > 0x7fffffffull)
+    { d->error = "buffer_data_adpcm: short data"; return B200MIX_ERR_INVALID; }
+    std::vector<int16_t> pcm(size_t(blocks)*samples_per_block*channels);
+    if(ms) DecodeMSADPCM(static_cast<const uint8_t*>(data), channels, samples_per_block, blocks, pcm.data());
+    else DecodeIMA4(static_cast<const uint8_t*>(data), channels, samples_per_block, blocks, pcm.data());
+    const int rc = b200mix_buffer_data(d, buffer, B200MIX_FMT_I16, channels, blocks*samples_per_block,
+        pcm.data(), pcm.size()*sizeof(int16_t));
+    // the upload above reads pageable memory: make sure it is consumed before pcm goes away
+    if(rc == B200MIX_OK) CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return rc;
 }
 
 int b200mix_buffer_free(b200mix_device *d, uint32_t buffer)

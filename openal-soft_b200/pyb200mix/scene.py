@@ -73,7 +73,55 @@ def voice_gain(num_voices: int) -> float:
 
 # sample formats for the format-coverage scenes: (abi FMT_*, AL format enum)
 FORMATS = {"i16": (1, 0x1101), "u8": (0, 0x1100), "f32": (3, 0x10010), "mulaw": (5, 0x10014),
-           "alaw": (6, 0x10016)}
+           "alaw": (6, 0x10016), "ima4": (7, 0x1300), "msadpcm": (8, 0x1302)}
+ADPCM_BLOCK = {"ima4": (65, 36), "msadpcm": (64, 38)}     # AL default block: (samples, bytes) mono
+
+_IMA_STEP = [7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45, 50, 55, 60, 66, 73, 80,
+             88, 97, 107, 118, 130, 143, 157, 173, 190, 209, 230, 253, 279, 307, 337, 371, 408, 449, 494, 544,
+             598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066, 2272, 2499, 2749,
+             3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635,
+             13899, 15289, 16818, 18500, 20350, 22358, 24633, 27086, 29794, 32767]
+_IMA_ADJ = [-1, -1, -1, -1, 2, 4, 6, 8]
+
+
+def adpcm_blocks(i: int, kind: str, blocks: int) -> np.ndarray:
+    """Mono block-compressed test data for voice i (bytes as alBufferData takes them).
+    ima4: the voice's synthetic signal through a plain IMA encoder (65-sample blocks).
+    msadpcm: well-formed 64-sample blocks (predictor, scale, two history samples) whose
+    nibbles come from a seeded generator — every byte pattern is a valid stream."""
+    spb, nbytes = ADPCM_BLOCK[kind]
+    out = np.zeros((blocks, nbytes), dtype=np.uint8)
+    if kind == "ima4":
+        pcm = voice_buffer_i16(i, blocks * spb).astype(np.int64)
+        idx = 0
+        for b in range(blocks):
+            blk = pcm[b * spb:(b + 1) * spb]
+            pred = int(blk[0])
+            out[b, 0], out[b, 1] = pred & 0xFF, (pred >> 8) & 0xFF
+            out[b, 2], out[b, 3] = idx & 0xFF, 0
+            for n in range(spb - 1):
+                step = _IMA_STEP[idx]
+                diff = int(blk[n + 1]) - pred
+                code = 8 if diff < 0 else 0
+                code |= min(7, (abs(diff) * 4) // step)
+                delta = (2 * (code & 7) + 1) * step // 8
+                pred = max(-32768, min(32767, pred - delta if code & 8 else pred + delta))
+                idx = max(0, min(88, idx + _IMA_ADJ[code & 7]))
+                out[b, 4 + (n >> 1)] |= code << ((n & 1) * 4)
+        return out.reshape(-1)
+    rng = np.random.default_rng(0xAD9C + i)
+    pcm = voice_buffer_i16(i, blocks * 2)
+    for b in range(blocks):
+        out[b, 0] = (i + b) % 7
+        out[b, 1], out[b, 2] = 48, 0                     # scale 48
+        h0, h1 = int(pcm[2 * b + 1]) & 0xFFFF, int(pcm[2 * b]) & 0xFFFF
+        out[b, 3], out[b, 4] = h0 & 0xFF, h0 >> 8
+        out[b, 5], out[b, 6] = h1 & 0xFF, h1 >> 8
+        # small nibbles (-2..2) keep the random walk away from the rails most of the time
+        nib = rng.choice(np.array([0, 1, 2, 15, 14, 0, 1, 15], dtype=np.uint8), size=(nbytes - 7) * 2)
+        out[b, 7:] = (nib[0::2] << 4) | nib[1::2]
+    return out.reshape(-1)
+
 
 
 def voice_buffer_fmt(i: int, frames: int, fmt: str) -> np.ndarray:

@@ -411,6 +411,79 @@ int oracle_buffer_data(oracle_device *d, uint32_t buffer, uint32_t type, uint32_
     return B200MIX_OK;
 }
 
+/* LoadSamples<IMA4Data> / LoadSamples<MSADPCMData> (core/voice.cpp:289-484; tables :199-238)
+ * evaluated for whole blocks at upload time: the decoders are integer recurrences, so the
+ * int16 results are exactly the values the reference's mixer converts with /32768.0f. */
+static const int ima_step[89] = {
+    7,8,9,10,11,12,13,14,16,17,19,21,23,25,28,31,34,37,41,45,50,55,60,66,73,80,88,97,107,118,130,143,
+    157,173,190,209,230,253,279,307,337,371,408,449,494,544,598,658,724,796,876,963,1060,1166,1282,
+    1411,1552,1707,1878,2066,2272,2499,2749,3024,3327,3660,4026,4428,4871,5358,5894,6484,7132,7845,
+    8630,9493,10442,11487,12635,13899,15289,16818,18500,20350,22358,24633,27086,29794,32767};
+static const int ima_codeword[16] = {1,3,5,7,9,11,13,15,-1,-3,-5,-7,-9,-11,-13,-15};
+static const int ima_adjust[16] = {-1,-1,-1,-1,2,4,6,8,-1,-1,-1,-1,2,4,6,8};
+static const int ms_adaption[16] = {230,230,230,230,307,409,512,614,768,614,512,409,307,230,230,230};
+static const int ms_coeff[7][2] = {{256,0},{512,-256},{0,0},{192,64},{240,0},{460,-208},{392,-232}};
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static int rd_s16(const uint8_t *p) { return (int)(int16_t)((uint16_t)p[0] | ((uint16_t)p[1] << 8)); }
+
+int oracle_buffer_data_adpcm(oracle_device *d, uint32_t buffer, uint32_t type, uint32_t channels,
+    uint32_t spb, uint32_t blocks, const void *data, size_t bytes)
+{
+    const int ms = type == B200MIX_FMT_MSADPCM;
+    if((type != B200MIX_FMT_IMA4 && !ms) || channels < 1 || channels > 2 || !data) return B200MIX_ERR_INVALID;
+    if(ms ? (spb < 2 || (spb & 1)) : (spb < 1 || ((spb-1) & 7))) return B200MIX_ERR_INVALID;
+    const size_t blockBytes = ms ? ((size_t)(spb-2)/2 + 7)*channels : ((size_t)(spb-1)/2 + 4)*channels;
+    if(bytes < blockBytes*blocks) return B200MIX_ERR_INVALID;
+    int16_t *pcm = malloc(sizeof(int16_t)*(size_t)blocks*spb*channels);
+    if(!pcm) return B200MIX_ERR_NOMEM;
+    const uint8_t *src = data;
+    int16_t *dst = pcm;
+    for(uint32_t b = 0;b < blocks;++b, src += blockBytes, dst += (size_t)spb*channels)
+        for(uint32_t c = 0;c < channels;++c)
+        {
+            if(!ms)
+            {
+                /* :309-351 */
+                int sample = rd_s16(src + c*4), idx = clampi(rd_s16(src + c*4 + 2), 0, 88);
+                const uint8_t *nib = src + (channels + c)*4;
+                dst[c] = (int16_t)sample;
+                for(uint32_t n = 0;n + 1 < spb;++n)
+                {
+                    const uint32_t shift = (n&1)*4, word = (n>>1) & ~3u;
+                    const uint32_t code = (nib[word*channels + ((n>>1)&3)] >> shift) & 0xf;
+                    sample = clampi(sample + ima_codeword[code]*ima_step[idx]/8, -32768, 32767);
+                    idx = clampi(idx + ima_adjust[code], 0, 88);
+                    dst[(size_t)(n+1)*channels + c] = (int16_t)sample;
+                }
+            }
+            else
+            {
+                /* :400-462 */
+                const uint32_t pred = src[c] < 6 ? src[c] : 6;
+                int scale = rd_s16(src + channels + 2*c);
+                int h0 = rd_s16(src + 3*channels + 2*c), h1 = rd_s16(src + 5*channels + 2*c);
+                const uint8_t *nib = src + 7*channels;
+                dst[c] = (int16_t)h1;
+                dst[(size_t)channels + c] = (int16_t)h0;
+                uint32_t off = c;
+                for(uint32_t n = 2;n < spb;++n, off += channels)
+                {
+                    const int nval = (nib[off>>1] >> (((off&1)^1)*4)) & 0xf;
+                    const int p = ((nval^0x08) - 0x08)*scale;
+                    const int diff = (h0*ms_coeff[pred][0] + h1*ms_coeff[pred][1])/256;
+                    const int sample = clampi(p + diff, -32768, 32767);
+                    h1 = h0; h0 = sample;
+                    scale = ms_adaption[nval]*scale/256; if(scale < 16) scale = 16;
+                    dst[(size_t)n*channels + c] = (int16_t)sample;
+                }
+            }
+        }
+    const int rc = oracle_buffer_data(d, buffer, B200MIX_FMT_I16, channels, blocks*spb, pcm,
+        sizeof(int16_t)*(size_t)blocks*spb*channels);
+    free(pcm);
+    return rc;
+}
+
 int oracle_buffer_free(oracle_device *d, uint32_t buffer)
 {
     if(buffer >= d->desc.max_buffers) return B200MIX_ERR_INVALID;

@@ -67,6 +67,8 @@ int  oracle_set_ambi_decoder(oracle_device *dev, uint32_t in_channels, const flo
     const float *gains_lf, float xover_coeff);
 int  oracle_buffer_data(oracle_device *dev, uint32_t buffer, uint32_t sample_type,
     uint32_t channels, uint32_t frames, const void *data, size_t bytes);
+int  oracle_buffer_data_adpcm(oracle_device *dev, uint32_t buffer, uint32_t sample_type,
+    uint32_t channels, uint32_t samples_per_block, uint32_t blocks, const void *data, size_t bytes);
 int  oracle_buffer_free(oracle_device *dev, uint32_t buffer);
 int  oracle_voices_update(oracle_device *dev, uint32_t n, const b200mix_voice_params *params,
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains);

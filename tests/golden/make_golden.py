@@ -66,7 +66,11 @@ SCENES = {
     # stereo sources: two mixing channels per voice (Voice::mChans[0..1]), virtual speakers at +-30 deg
     "hrtf_bsinc24_stereo_src_v4": (4, 1, 7, 4, True, 20000, None, "i16", 0, None, None, "stereo_src"),
     "basic_spline_stereo_src_v3": (3, 0, 2, 3, True, 20000, None, "i16", 0, None, None, "stereo_src"),
+    # block-compressed buffers: even voices AL_FORMAT_MONO_IMA4, odd AL_FORMAT_MONO_MSADPCM_SOFT
+    "hrtf_spline_adpcm_v4": (4, 1, 2, 4, True, 0, None, "i16", 0, None, None, "adpcm"),
 }
+
+ADPCM_BLOCKS = 120
 
 QUEUE_LENS = (3000, 1500, 5000)
 
@@ -117,7 +121,15 @@ def run_scene(name):
     fmt = spec[7] if len(spec) > 7 else "i16"
     queue = len(spec) > 11 and spec[11] == "queue"
     stereo_src = len(spec) > 11 and spec[11] == "stereo_src"
-    if stereo_src:
+    adpcm = len(spec) > 11 and spec[11] == "adpcm"
+    if adpcm:
+        ref, pcms = scenes.make_ref_scene(0, hrtf, rs, attrs=attrs, max_sources=V)
+        for i in range(V):
+            kind = "ima4" if i % 2 == 0 else "msadpcm"
+            ref.add_voice(scene.adpcm_blocks(i, kind, ADPCM_BLOCKS), scene.BUFFER_RATE, scene.voice_pitch(i),
+                          scene.voice_position(i), scene.voice_gain(V), rs, looping=looping,
+                          fmt=scene.FORMATS[kind][1])
+    elif stereo_src:
         a2 = dict(attrs or {})
         a2[refal.ALC_STEREO_SOURCES] = V
         ref, pcms = scenes.make_ref_scene(0, hrtf, rs, attrs=a2, max_sources=1)
@@ -183,6 +195,8 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if adpcm:
+        res.update(adpcm_blocks=np.int64(ADPCM_BLOCKS))
     if stereo_src:
         n1, params1, coeffs1, dry1, _, _ = snap1
         res.update(params_c1=np.frombuffer(bytes(params1), dtype=np.uint8)[:V * C.sizeof(abi.VoiceParams)].copy(),

@@ -41,7 +41,12 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             dev.set_ambi_decoder(fx["amb_hf"], fx.get("amb_lf"), float(fx["amb_xover"]))
         fmt = str(fx["fmt"]) if "fmt" in fx else "i16"
         qlens = [int(x) for x in fx["queue_lens"]] if "queue_lens" in fx else None
-        if qlens:
+        if "adpcm_blocks" in fx:
+            for i in range(V):
+                kind = "ima4" if i % 2 == 0 else "msadpcm"
+                dev.buffer_data_adpcm(i, scene.FORMATS[kind][0], scene.ADPCM_BLOCK[kind][0],
+                                      int(fx["adpcm_blocks"]), scene.adpcm_blocks(i, kind, int(fx["adpcm_blocks"])))
+        elif qlens:
             for i in range(V * len(qlens)):
                 dev.buffer_data(i, scene.FORMATS[fmt][0], scene.voice_buffer_fmt(i, qlens[i % len(qlens)], fmt))
         elif stereo_src:

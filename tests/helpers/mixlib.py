@@ -32,6 +32,8 @@ class MixLib:
         self.buffer_data = f("buffer_data")
         self.buffer_data.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_void_p, C.c_size_t]
+        self.buffer_data_adpcm = f("buffer_data_adpcm")
+        self.buffer_data_adpcm.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_void_p, C.c_size_t]
         self.voices_update = f("voices_update")
         self.voices_update.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
@@ -116,6 +118,12 @@ class MixDevice:
         pcm = np.ascontiguousarray(pcm)
         rc = self.m.buffer_data(self.h, buf_id, sample_type, channels, pcm.shape[0], pcm.ctypes.data,
                                 pcm.nbytes)
+        assert rc == 0, rc
+
+    def buffer_data_adpcm(self, buf_id, sample_type, samples_per_block, blocks, data, channels=1):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        rc = self.m.buffer_data_adpcm(self.h, buf_id, sample_type, channels, samples_per_block, blocks,
+                                      data.ctypes.data, data.nbytes)
         assert rc == 0, rc
 
     def voices_update(self, params, coeffs=None, dry=None, send=None):
