@@ -285,6 +285,21 @@ B200MIX_API int b200mix_render(b200mix_device *dev, uint32_t frames, float *cons
 B200MIX_API int b200mix_render_device(b200mix_device *dev, uint32_t frames,
     const float **real_out_dev);
 
+/* Output stage on the device, for hosts that run WITHOUT the gain limiter (float output, or
+ * ALC_OUTPUT_LIMITER_SOFT off): ApplyDither (alc/alu.cpp:2309-2333) followed by the
+ * interleaving Write<T> (alc/alu.cpp:2362-2390, SampleConv :2335-2360) of the same update
+ * b200mix_render performs.  out receives frames*frame_step samples of out_type (enum DevFmtType
+ * order below); frame_step >= real_channels, extra channels get SampleConv<T>(0).
+ * dither_depth is DeviceBase::DitherDepth (0 = off; 32768 for 16-bit output), *dither_seed
+ * DeviceBase::DitherSeed (22222 at device open), advanced exactly as the reference's LCG.
+ * The limiter (core/mastering.cpp) is not implemented: hosts that need it take float output
+ * from b200mix_render and keep the reference's Limiter/Dither/Write on the CPU. */
+enum b200mix_out_type { B200MIX_OUT_I8 = 0, B200MIX_OUT_U8, B200MIX_OUT_I16, B200MIX_OUT_U16,
+    B200MIX_OUT_I32, B200MIX_OUT_U32, B200MIX_OUT_F32 };
+B200MIX_API int b200mix_render_interleaved(b200mix_device *dev, uint32_t frames, void *out,
+    uint32_t out_type, uint32_t frame_step, float dither_depth, uint32_t *dither_seed,
+    b200mix_voice_result *results);
+
 /* The same update in two halves, for voice-sharded multi-GPU mixing: effects
  * consume the SUMMED wet input of all ranks, so the host reduces the wet buffers between
  * the halves.  b200mix_render_begin clears the mix buffers, mixes this device's voices and

@@ -120,6 +120,7 @@ struct b200mix_device {
     float2 *d_st_fields{nullptr}; uint2 *d_st_elevs{nullptr}; float2 *d_st_coeffs{nullptr};
     uint8_t *d_st_delays{nullptr}; uint32_t st_num_fields{0}, st_ir{0};
     uint4 *d_qhdr{nullptr}; uint32_t *d_queue{nullptr};   // streaming queues (first b200mix_voice_queue)
+    void *d_outbuf{nullptr}, *h_outbuf{nullptr};          // interleaved output staging (render_interleaved)
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -440,6 +441,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
     cudaFree(d->d_dline); cudaFree(d->d_order2); cudaFree(d->d_qhdr); cudaFree(d->d_queue);
+    cudaFree(d->d_outbuf); if(d->h_outbuf) cudaFreeHost(d->h_outbuf);
     cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
@@ -1456,6 +1458,49 @@ int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
     if(!d) return B200MIX_ERR_INVALID;
     if(int rc = render_launch(d, frames, results != nullptr)) return rc;
     return render_collect(d, frames, real_out, results);
+}
+
+static uint32_t lcg_skip_host(uint32_t x, uint64_t k)
+{
+    uint32_t a = 96314165u, c = 907633515u, accA = 1u, accC = 0u;
+    while(k)
+    {
+        if(k & 1u) { accA = accA*a; accC = accC*a + c; }
+        c = c*a + c; a = a*a;
+        k >>= 1;
+    }
+    return accA*x + accC;
+}
+
+int b200mix_render_interleaved(b200mix_device *d, uint32_t frames, void *out, uint32_t out_type,
+    uint32_t frame_step, float dither_depth, uint32_t *dither_seed, b200mix_voice_result *results)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    if(!out || out_type > B200MIX_OUT_F32 || frame_step < dd.real_channels || frame_step > 64u
+        || (dither_depth > 0.0f && !dither_seed))
+    { d->error = "render_interleaved: bad arguments"; return B200MIX_ERR_INVALID; }
+    if(int rc = render_launch(d, frames, results != nullptr)) return rc;
+    static const size_t sz[] = {1, 1, 2, 2, 4, 4, 4};
+    if(!d->d_outbuf)
+    {
+        CUDA_TRY(d, cudaMalloc(&d->d_outbuf, size_t(kLine)*64*4));
+        CUDA_TRY(d, cudaMallocHost(&d->h_outbuf, size_t(kLine)*64*4));
+    }
+    OutputParams Q{};
+    Q.real = d->d_real; Q.out = d->d_outbuf; Q.frames = frames; Q.channels = dd.real_channels;
+    Q.frame_step = frame_step; Q.out_type = out_type; Q.dither_depth = dither_depth;
+    Q.seed = dither_seed ? *dither_seed : 0u;
+    const uint32_t total = frames*frame_step;
+    k_output_write<<<(total + 255)/256, 256, 0, d->stream>>>(Q);
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
+    const size_t bytes = size_t(total)*sz[out_type];
+    CUDA_TRY(d, cudaMemcpyAsync(d->h_outbuf, d->d_outbuf, bytes, cudaMemcpyDeviceToHost, d->stream));
+    if(int rc = render_collect(d, frames, nullptr, results)) return rc;     // synchronises the stream
+    std::memcpy(out, d->h_outbuf, bytes);
+    if(dither_depth > 0.0f) *dither_seed = lcg_skip_host(*dither_seed, uint64_t(2)*dd.real_channels*frames);
+    return B200MIX_OK;
 }
 
 int b200mix_render_begin(b200mix_device *d, uint32_t frames, float **wet_dev, size_t *wet_floats)

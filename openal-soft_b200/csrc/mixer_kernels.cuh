@@ -1515,4 +1515,76 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     }
 }
 
+// Output stage: ApplyDither (alc/alu.cpp:2309-2333) + Write<T> (alc/alu.cpp:2362-2390).
+// The reference draws two LCG values per sample, channel after channel; sample i of channel c
+// therefore uses draws 2(c*n+i)+1 and +2 from the incoming seed — reached directly with the
+// LCG's closed form x_k = A^k x_0 + C(A^k-1)/(A-1) (mod 2^32), so every thread is independent.
+struct OutputParams {
+    const float *real; void *out;
+    uint32_t frames, channels, frame_step, out_type, seed;
+    float dither_depth;
+};
+
+__device__ __forceinline__ uint32_t lcg_skip(uint32_t x, uint32_t k)
+{
+    // k steps of x -> x*96314165 + 907633515 (dither_rng, alc/alu.cpp:444-448)
+    uint32_t a = 96314165u, c = 907633515u;      // one step
+    uint32_t accA = 1u, accC = 0u;               // identity
+    while(k)
+    {
+        if(k & 1u) { accA = accA*a; accC = accC*a + c; }
+        c = c*a + c; a = a*a;
+        k >>= 1;
+    }
+    return accA*x + accC;
+}
+
+__global__ void k_output_write(const OutputParams Q)
+{
+    const uint32_t idx = blockIdx.x*blockDim.x + threadIdx.x;
+    const uint32_t n = Q.frames;
+    if(idx >= n*Q.frame_step) return;
+    const uint32_t i = idx / Q.frame_step, c = idx - i*Q.frame_step;
+    float val = 0.0f;
+    if(c < Q.channels)
+    {
+        val = Q.real[size_t(c)*kLine + i];
+        if(Q.dither_depth > 0.0f)
+        {
+            const uint32_t k = 2u*(c*n + i);
+            const uint32_t r0 = lcg_skip(Q.seed, k + 1u);
+            const uint32_t r1 = r0*96314165u + 907633515u;
+            const double inv = 1.0/4294967295.0;
+            float v = __fmul_rn(val, Q.dither_depth);
+            v = __fadd_rn(v, float(double(r0)*inv - double(r1)*inv));
+            val = __fmul_rn(rintf(v), __fdiv_rn(1.0f, Q.dither_depth));
+        }
+    }
+    // SampleConv<T>, alc/alu.cpp:2335-2360 (fastf2i rounds to nearest even)
+    switch(Q.out_type)
+    {
+    case 0: case 1:
+    {
+        int v = __float2int_rn(fminf(fmaxf(__fmul_rn(val, 128.0f), -128.0f), 127.0f));
+        if(Q.out_type == 1) v += 128;
+        static_cast<uint8_t*>(Q.out)[idx] = uint8_t(v);
+        break;
+    }
+    case 2: case 3:
+    {
+        int v = __float2int_rn(fminf(fmaxf(__fmul_rn(val, 32768.0f), -32768.0f), 32767.0f));
+        if(Q.out_type == 3) v += 32768;
+        static_cast<uint16_t*>(Q.out)[idx] = uint16_t(v);
+        break;
+    }
+    case 4: case 5:
+    {
+        const int v = __float2int_rn(fminf(fmaxf(__fmul_rn(val, 2147483648.0f), -2147483648.0f), 2147483520.0f));
+        static_cast<uint32_t*>(Q.out)[idx] = Q.out_type == 5 ? uint32_t(v) + 2147483648u : uint32_t(v);
+        break;
+    }
+    default: static_cast<float*>(Q.out)[idx] = val; break;
+    }
+}
+
 } // namespace b200mix

@@ -1460,6 +1460,62 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
     return oracle_render_end(d, real_out, results, NULL);
 }
 
+/* ApplyDither (alc/alu.cpp:2309-2333) + Write<T> (alc/alu.cpp:2362-2390) after a normal update;
+ * no limiter.  lrintf rounds to nearest even like fastf2i / fast_roundf. */
+int oracle_render_interleaved(oracle_device *d, uint32_t frames, void *out, uint32_t out_type,
+    uint32_t frame_step, float dither_depth, uint32_t *dither_seed, b200mix_voice_result *results)
+{
+    const b200mix_device_desc *dd = &d->desc;
+    if(!out || out_type > B200MIX_OUT_F32 || frame_step < dd->real_channels) return B200MIX_ERR_INVALID;
+    const int rc = oracle_render(d, frames, NULL, results);
+    if(rc) return rc;
+    if(dither_depth > 0.0f)
+    {
+        const double invRNGRange = 1.0 / 4294967295.0;
+        const float invscale = 1.0f / dither_depth;
+        uint32_t seed = *dither_seed;
+        for(uint32_t c = 0;c < dd->real_channels;++c)
+            for(uint32_t i = 0;i < frames;++i)
+            {
+                float val = d->real[c][i] * dither_depth;
+                seed = seed*96314165u + 907633515u; const uint32_t rng0 = seed;
+                seed = seed*96314165u + 907633515u; const uint32_t rng1 = seed;
+                val += (float)(rng0*invRNGRange - rng1*invRNGRange);
+                d->real[c][i] = (float)lrintf(val) * invscale;
+            }
+        *dither_seed = seed;
+    }
+    for(uint32_t i = 0;i < frames;++i)
+        for(uint32_t c = 0;c < frame_step;++c)
+        {
+            const float val = c < dd->real_channels ? d->real[c][i] : 0.0f;
+            const size_t idx = (size_t)i*frame_step + c;
+            switch(out_type)
+            {
+            case B200MIX_OUT_I8: case B200MIX_OUT_U8:
+            {
+                int v = (int)lrintf(fminf(fmaxf(val*128.0f, -128.0f), 127.0f));
+                ((uint8_t*)out)[idx] = (uint8_t)(out_type == B200MIX_OUT_U8 ? v + 128 : v);
+                break;
+            }
+            case B200MIX_OUT_I16: case B200MIX_OUT_U16:
+            {
+                int v = (int)lrintf(fminf(fmaxf(val*32768.0f, -32768.0f), 32767.0f));
+                ((uint16_t*)out)[idx] = (uint16_t)(out_type == B200MIX_OUT_U16 ? v + 32768 : v);
+                break;
+            }
+            case B200MIX_OUT_I32: case B200MIX_OUT_U32:
+            {
+                const int32_t v = (int32_t)lrintf(fminf(fmaxf(val*2147483648.0f, -2147483648.0f), 2147483520.0f));
+                ((uint32_t*)out)[idx] = out_type == B200MIX_OUT_U32 ? (uint32_t)v + 2147483648u : (uint32_t)v;
+                break;
+            }
+            default: ((float*)out)[idx] = val; break;
+            }
+        }
+    return B200MIX_OK;
+}
+
 int oracle_get_dry(oracle_device *d, float *dry)
 {
     memcpy(dry, d->dry, sizeof(float[LINE])*d->desc.dry_channels);

@@ -81,6 +81,8 @@ int  oracle_render(oracle_device *dev, uint32_t frames, float *const *real_out,
 int  oracle_render_begin(oracle_device *dev, uint32_t frames, float **wet_host, size_t *wet_floats);
 int  oracle_render_end(oracle_device *dev, float *const *real_out, b200mix_voice_result *results,
     const float **real_out_host);
+int  oracle_render_interleaved(oracle_device *dev, uint32_t frames, void *out, uint32_t out_type,
+    uint32_t frame_step, float dither_depth, uint32_t *dither_seed, b200mix_voice_result *results);
 int  oracle_slot_convolution(oracle_device *dev, uint32_t slot, uint32_t ir_channels,
     uint32_t ir_frames, const float *ir);
 int  oracle_slot_output_gains(oracle_device *dev, uint32_t slot, uint32_t lines, const float *gains);

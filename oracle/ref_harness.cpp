@@ -180,6 +180,9 @@ int refh_ambi_decoder(ALCdevice *adev, float *gains_hf, float *gains_lf, float *
     return static_cast<int>(db.size());
 }
 
+/* DeviceBase::DitherDepth as the device open chose it (alc/alc.cpp:1690-1716). */
+float refh_dither_depth(ALCdevice *adev) { return dev_of(adev)->DitherDepth; }
+
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
 static size_t g_snap_channel = 0;

@@ -68,6 +68,9 @@ SCENES = {
     "basic_spline_stereo_src_v3": (3, 0, 2, 3, True, 20000, None, "i16", 0, None, None, "stereo_src"),
     # block-compressed buffers: even voices AL_FORMAT_MONO_IMA4, odd AL_FORMAT_MONO_MSADPCM_SOFT
     "hrtf_spline_adpcm_v4": (4, 1, 2, 4, True, 0, None, "i16", 0, None, None, "adpcm"),
+    # integer output without the limiter: ApplyDither + Write<T> (16-bit dithered, 8-bit unsigned)
+    "hrtf_spline_out_i16_v6": (6, 1, 2, 3, True, 48000, "out_i16"),
+    "stereo_spline_out_u8_v6": (6, 0, 2, 3, True, 48000, "out_u8"),
 }
 
 ADPCM_BLOCKS = 120
@@ -104,7 +107,11 @@ def conv_ir(taps):
     rng = np.random.default_rng(taps)
     return (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
 
+OUT_TYPES = {"out_i16": (np.int16, 2), "out_u8": (np.uint8, 1)}    # numpy type, b200mix_out_type
+
 ATTRS = {
+    "out_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
+    "out_u8": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_UNSIGNED_BYTE_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
     "ambi3": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 3,
                         r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
@@ -160,6 +167,7 @@ def run_scene(name):
     script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 and spec[10] else None
     if script:
         apply_filter_script(ref, script, 0, slot)
+    out_np, out_type = OUT_TYPES.get(spec[6] if len(spec) > 6 else None, (np.float32, None))
     ref.play_all()
     outs = []
     snap = None
@@ -168,7 +176,7 @@ def run_scene(name):
     for u in range(U):
         if script and u:
             apply_filter_script(ref, script, u, slot)
-        outs.append(ref.render())
+        outs.append(ref.render(dtype=out_np))
         if script:
             ents, _ = ref.voice_filters(V)
             filt_meta.append(np.array([[v, p, a] for v, p, a, _, _ in ents], dtype=np.int32))
@@ -195,6 +203,8 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if out_type is not None:
+        res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
     if adpcm:
         res.update(adpcm_blocks=np.int64(ADPCM_BLOCKS))
     if stereo_src:
@@ -246,7 +256,7 @@ def main():
         out["meta"] = np.array([V, hrtf, rs, U, int(looping), frames], dtype=np.int64)
         out["fmt"] = np.array(SCENES[name][7] if len(SCENES[name]) > 7 else "i16")
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-        d = np.abs(a["out"].astype(np.float64) - b["out"]).max()
+        d = np.abs(a["out"].astype(np.float64) - b["out"].astype(np.float64)).max()
         print(f"{name}: wrote, |sse-c|max = {d:.3e}")
 
 

@@ -100,12 +100,17 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
                 dev.voice_queue(k, ids, 0 if (plist[k].flags & abi.VF_LOOPING) else abi.NO_LOOP)
         outs = []
         res = None
+        seed = 22222            # DitherRNGSeed, alc/alc.cpp:329
         for u in range(updates or U):
             if "filt_meta" in fx:
                 # the reference's filter targets during update u, every path of every voice
                 dev.voices_filters((int(m[0]), int(m[1]), int(m[2]), c[0], c[1])
                                    for m, c in zip(fx["filt_meta"][u], fx["filt_coef"][u]))
-            o, res = dev.render(frames, want_results=True)
+            if "out_type" in fx:
+                o, res, seed = dev.render_interleaved(frames, int(fx["out_type"]), float(fx["dither_depth"]), seed)
+                o = np.ascontiguousarray(o.T)        # planar like the fixture
+            else:
+                o, res = dev.render(frames, want_results=True)
             outs.append(o)
         return np.stack(outs), res
     finally:

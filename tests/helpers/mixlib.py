@@ -53,6 +53,9 @@ class MixLib:
         self.biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
         self.voice_queue = f("voice_queue")
         self.voice_queue.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        self.render_interleaved = f("render_interleaved")
+        self.render_interleaved.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                            C.c_float, C.POINTER(C.c_uint32), C.c_void_p]
         self.render_begin = f("render_begin")
         self.render_begin.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         self.render_end = f("render_end")
@@ -166,6 +169,19 @@ class MixDevice:
         arr = (C.c_uint32 * max(len(buffer_ids), 1))(*buffer_ids)
         rc = self.m.voice_queue(self.h, voice, len(buffer_ids), arr, loop_index)
         assert rc == 0, rc
+
+    OUT_NP = {0: np.int8, 1: np.uint8, 2: np.int16, 3: np.uint16, 4: np.int32, 5: np.uint32, 6: np.float32}
+
+    def render_interleaved(self, frames, out_type, dither_depth, seed, frame_step=None):
+        """Returns (out [frames][frame_step], results, new seed)."""
+        step = frame_step or self.desc.real_channels
+        out = np.zeros((frames, step), dtype=self.OUT_NP[out_type])
+        sd = C.c_uint32(seed)
+        res = (abi.VoiceResult * max(self.desc.max_voices, 1))()
+        rc = self.m.render_interleaved(self.h, frames, out.ctypes.data, out_type, step, dither_depth,
+                                       C.byref(sd), res)
+        assert rc == 0, f"render_interleaved -> {rc}"
+        return out, res, sd.value
 
     def render_begin(self, frames=1024):
         """Returns (wet pointer, float count): a host pointer on the oracle, a device pointer

@@ -54,6 +54,8 @@ ALC_STEREO_SOURCES = 0x1011
 ALC_FORMAT_CHANNELS_SOFT = 0x1990
 ALC_FORMAT_TYPE_SOFT = 0x1991
 ALC_FLOAT_SOFT = 0x1406
+ALC_SHORT_SOFT = 0x1402
+ALC_UNSIGNED_BYTE_SOFT = 0x1401
 ALC_STEREO_SOFT = 0x1501
 ALC_BFORMAT3D_SOFT = 0x1507
 ALC_HRTF_SOFT = 0x1992
@@ -138,6 +140,8 @@ def libs(conf_text: str | None = None):
     hz.refh_slot_count.argtypes = [C.c_void_p]
     hz.refh_slot_wet_channels.argtypes = [C.c_void_p, C.c_int]
     hz.refh_mono_line_gains.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    hz.refh_dither_depth.argtypes = [C.c_void_p]
+    hz.refh_dither_depth.restype = C.c_float
     hz.refh_set_snapshot_channel.argtypes = [C.c_int]
     hz.refh_set_snapshot_channel.restype = None
     hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -338,6 +342,9 @@ class RefDevice:
         err = self.al.alGetError()
         assert err == 0, f"AL error {err:#x} connecting send"
 
+    def dither_depth(self) -> float:
+        return float(self.hz.refh_dither_depth(self.dev))
+
     def slot_info(self):
         n = self.hz.refh_slot_count(self.ctx)
         return n, [self.hz.refh_slot_wet_channels(self.ctx, i) for i in range(n)]
@@ -351,10 +358,10 @@ class RefDevice:
         arr = (C.c_uint * len(self.sources))(*self.sources)
         self.al.alSourcePlayv(len(self.sources), arr)
 
-    def render(self, frames: int = 1024, channels: int | None = None) -> np.ndarray:
-        """Returns planar [channels][frames] float32 (de-interleaved)."""
+    def render(self, frames: int = 1024, channels: int | None = None, dtype=np.float32) -> np.ndarray:
+        """Returns planar [channels][frames] (de-interleaved) of the device's sample type."""
         ch = channels or self.out_channels
-        buf = np.zeros((frames, ch), dtype=np.float32)
+        buf = np.zeros((frames, ch), dtype=dtype)
         self.al.alcRenderSamplesSOFT(self.dev, buf.ctypes.data, frames)
         return np.ascontiguousarray(buf.T)
 

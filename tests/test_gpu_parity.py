@@ -28,8 +28,18 @@ def _check(out, ref, what="", rms_tol=RMS_TOL, max_tol=MAX_TOL):
 def test_golden_vectors_from_reference(name):
     fx = golden.load(name)
     out, res = golden.replay(mixlib.product(), fx)
-    _check(out, fx["out_sse"], name + " vs reference SSE kernels")
-    _check(out, fx["out_c"], name + " vs reference C kernels")
+    if "out_type" in fx:
+        # integer output (dither + Write<T>): the float mix ahead of the rounding differs from the
+        # reference's in the last bits, so a sample may land on the neighbouring integer — never
+        # further, and rarely (the dither noise itself is reproduced exactly)
+        for key in ("out_sse", "out_c"):
+            diff = np.abs(out.astype(np.int64) - fx[key].astype(np.int64))
+            assert diff.max() <= 1, (name, key, int(diff.max()))
+            assert (diff != 0).mean() <= 0.01, (name, key, float((diff != 0).mean()))
+        assert np.ptp(fx["out_c"].astype(np.int64)) > 8
+    else:
+        _check(out, fx["out_sse"], name + " vs reference SSE kernels")
+        _check(out, fx["out_c"], name + " vs reference C kernels")
     # voice bookkeeping agrees with the oracle (positions are integers: exact)
     out_o, res_o = golden.replay(mixlib.oracle(), fx)
     V = int(fx["meta"][0])
