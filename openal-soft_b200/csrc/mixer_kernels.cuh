@@ -198,6 +198,21 @@ template<> __device__ __forceinline__ MulawByte ld_raw(const MulawByte *p)
 template<> __device__ __forceinline__ AlawByte ld_raw(const AlawByte *p)
 { return AlawByte{__ldg(reinterpret_cast<const uint8_t*>(p))}; }
 
+// word offset of the second 16-bit window copy: 16 (mod 32) banks away from the first, so lanes
+// on an even and on an odd window position never meet in a bank while the warp's span stays
+// within 32 samples
+constexpr int kPackB = 688;
+static_assert(kPackB >= (kResBuf + 8 + 1)/2 && kPackB + (kResBuf + 8 + 1)/2 <= kResBuf + 8 + 24
+    && (kPackB % 32) == 16, "16-bit window copies must fit the float window's storage");
+
+// sample k of the resample window, whichever representation it is in
+__device__ __forceinline__ float win_at(const float *win, bool packed, uint32_t k)
+{
+    if(!packed) return win[k];
+    const uint16_t y = reinterpret_cast<const uint16_t*>(win)[k];
+    return float(int(y) - 32768) * (1.0f/32768.0f);
+}
+
 struct FillArgs {
     float *dst; uint32_t count, uintPos, q0, firstRun, loopStart, loopSize, lastFrame, channels;
     bool looping, pastEnd, simpleWrap;
@@ -249,7 +264,7 @@ struct GroupSmem {
     static constexpr int kOLen = FP + kHist + FP + 32;  // old-coefficient pass input
     // The resample stage (window + phase tables) and the FIR stage (per-ear inputs) never
     // live at the same time: they share storage.
-    struct ResampleStage { float win[kResBuf + 8]; alignas(8) float tabF[32*kTabStride]; alignas(8) float tabD[32*kTabStride]; };
+    struct ResampleStage { float win[kResBuf + 8 + 24]; alignas(8) float tabF[32*kTabStride]; alignas(8) float tabD[32*kTabStride]; };
     struct FirStage { float2 lLR[kLLen]; float2 oLR[kOLen]; };   // {left, right} per input sample
     union { ResampleStage rs; FirStage fs; } u;
     float x[kHist + kLine];
@@ -454,6 +469,7 @@ k_mix_voices(const MixParams P)
             calc_buffer_size(fracPos, increment, n-loaded, dstn, srcn);
             uint32_t srcDelay = 0;
             bool silent = false;
+            bool packedWin = false;        // the window currently holds the two 16-bit copies
             if(intPos < 0)
             {
                 srcDelay = uint32_t(-intPos);
@@ -468,6 +484,7 @@ k_mix_voices(const MixParams P)
             else
             {
                 float *srcBuffer = S.u.rs.win + kEdge;
+                bool winInt = false;       // every sample of this window came from a <=16-bit format
                 if(!haveBuffer)
                 {
                     // voice ended: hold the sample closest to 0 (core/voice.cpp:704-719)
@@ -491,6 +508,7 @@ k_mix_voices(const MixParams P)
                     // the last sample held.  Loads are issued 8 at a time before any conversion.
                     uint32_t done = 0, item = qh.x ? qh.y : kNoLoop, qpos = uintPos;
                     bool more = true;
+                    winInt = true;
                     while(more)
                     {
                         BufferRec rb = buf;
@@ -531,6 +549,7 @@ k_mix_voices(const MixParams P)
                             item = (item + 1u < qh.x) ? item + 1u : qh.z;
                             more = done < count;
                         }
+                        winInt = winInt && (rb.type <= 1u || rb.type >= 5u);
                         // srcChannel of LoadSamples (core/voice.cpp:271-287); a channel the buffer
                         // does not have reads channel 0
                         const uint32_t ch = ((flags >> 16) & 0xffu) < rb.channels ? ((flags >> 16) & 0xffu) : 0u;
@@ -555,10 +574,96 @@ k_mix_voices(const MixParams P)
                 }
                 group_sync(bar, GS);       // window complete
 
+                // ---- 16-bit window for the bsinc resamplers ----
+                // u8/i16/mu-law/A-law samples are exact multiples of 2^-15, so the window can be
+                // re-stored as biased 16-bit integers y = 32768*s + 32768 without loss.  Two
+                // copies (A: pairs (y0,y1),(y2,y3)..; B: pairs (y1,y2),(y3,y4)..) give every
+                // window position an aligned pair, so ONE 32-bit shared load feeds two taps: the
+                // resampler is bound by shared-memory wavefronts (3 per lane-tap: F, D, sample)
+                // and this removes half of the sample loads and their bank conflicts at pitch > 1.
+                // Converting back costs a PRMT and half an add per tap on the idle ALU; the
+                // 2^-15 scale is applied once to the result (exact), so xs is unchanged bit for bit.
+                packedWin = resampler >= 4u && winInt && !(increment == 65536u && fracPos == 0u);
+                if(packedWin)
+                {
+                    constexpr int PER = (kResBuf + 8 + GS - 1)/GS;
+                    const uint32_t L = min(uint32_t(kEdge) + srcn + 8u, uint32_t(kResBuf + 8));
+                    float v[PER];
+                    #pragma unroll
+                    for(int u = 0;u < PER;++u)
+                    {
+                        const uint32_t k = uint32_t(t) + uint32_t(u)*GS;
+                        v[u] = k < L ? S.u.rs.win[k] : 0.0f;
+                    }
+                    group_sync(bar, GS);
+                    uint16_t *pa = reinterpret_cast<uint16_t*>(S.u.rs.win);
+                    uint16_t *pb = pa + 2*kPackB;
+                    #pragma unroll
+                    for(int u = 0;u < PER;++u)
+                    {
+                        const uint32_t k = uint32_t(t) + uint32_t(u)*GS;
+                        if(k < L)
+                        {
+                            const uint16_t y = uint16_t(__float2int_rn(v[u]*32768.0f) + 32768);
+                            pa[k] = y;
+                            if(k) pb[k-1u] = y;
+                        }
+                    }
+                    group_sync(bar, GS);
+                }
+
                 // ---- resample dstn outputs (core/voice.cpp:764-769) ----
                 if(increment == 65536u && fracPos == 0u)
                 {
                     for(uint32_t k = t;k < dstn;k += GS) xs[loaded+k] = srcBuffer[k];
+                }
+                else if(packedWin)
+                {
+                    const uint32_t *wordsA = reinterpret_cast<const uint32_t*>(S.u.rs.win);
+                    const uint32_t *wordsB = wordsA + kPackB;
+                    const float2 bias = make_float2(-8421376.0f, -8421376.0f);   // -(2^23 + 32768)
+                    const float2 one = make_float2(1.0f, 1.0f);
+                    for(uint32_t k = t;k < dstn;k += 2u*GS)
+                    {
+                        const uint32_t kB = k + GS;
+                        const bool hasB = kB < dstn;
+                        const uint64_t fpA = uint64_t(k)*increment + fracPos;
+                        const uint64_t fpB = uint64_t(hasB ? kB : k)*increment + fracPos;
+                        const uint32_t fracA = uint32_t(fpA) & 0xffffu, fracB = uint32_t(fpB) & 0xffffu;
+                        const float pfA = float(fracA & 2047u) * (1.0f/2048.0f);
+                        const float pfB = float(fracB & 2047u) * (1.0f/2048.0f);
+                        const float *FA = S.u.rs.tabF + (fracA>>11)*ms, *DA = S.u.rs.tabD + (fracA>>11)*ms;
+                        const float *FB = S.u.rs.tabF + (fracB>>11)*ms, *DB = S.u.rs.tabD + (fracB>>11)*ms;
+                        const uint32_t posA = tapOff + uint32_t(fpA>>16), posB = tapOff + uint32_t(fpB>>16);
+                        const uint32_t *wA = ((posA & 1u) ? wordsB : wordsA) + (posA >> 1);
+                        const uint32_t *wB = ((posB & 1u) ? wordsB : wordsA) + (posB >> 1);
+                        const float2 pA = make_float2(pfA, pfA), pB = make_float2(pfB, pfB);
+                        float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, b0 = a0, b1 = a0;
+                        for(uint32_t j = 0;j < m;j += 4)
+                        {
+                            const uint32_t wa0 = wA[(j>>1)], wa1 = wA[(j>>1)+1u];
+                            const uint32_t wb0 = wB[(j>>1)], wb1 = wB[(j>>1)+1u];
+                            // (0x4B000000 | y) is the float 2^23 + y: subtract the bias to get 32768*s
+                            const float2 sA0 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wa0, 0x4B00u, 0x5410u)),
+                                __uint_as_float(__byte_perm(wa0, 0x4B00u, 0x5432u))), one, bias);
+                            const float2 sA1 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wa1, 0x4B00u, 0x5410u)),
+                                __uint_as_float(__byte_perm(wa1, 0x4B00u, 0x5432u))), one, bias);
+                            const float2 sB0 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wb0, 0x4B00u, 0x5410u)),
+                                __uint_as_float(__byte_perm(wb0, 0x4B00u, 0x5432u))), one, bias);
+                            const float2 sB1 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wb1, 0x4B00u, 0x5410u)),
+                                __uint_as_float(__byte_perm(wb1, 0x4B00u, 0x5432u))), one, bias);
+                            const float2 cA0 = __ffma2_rn(pA, make_float2(DA[j+0], DA[j+1]), make_float2(FA[j+0], FA[j+1]));
+                            const float2 cB0 = __ffma2_rn(pB, make_float2(DB[j+0], DB[j+1]), make_float2(FB[j+0], FB[j+1]));
+                            const float2 cA1 = __ffma2_rn(pA, make_float2(DA[j+2], DA[j+3]), make_float2(FA[j+2], FA[j+3]));
+                            const float2 cB1 = __ffma2_rn(pB, make_float2(DB[j+2], DB[j+3]), make_float2(FB[j+2], FB[j+3]));
+                            a0 = __ffma2_rn(cA0, sA0, a0);
+                            b0 = __ffma2_rn(cB0, sB0, b0);
+                            a1 = __ffma2_rn(cA1, sA1, a1);
+                            b1 = __ffma2_rn(cB1, sB1, b1);
+                        }
+                        xs[loaded+k] = ((a0.x + a1.x) + (a0.y + a1.y)) * (1.0f/32768.0f);
+                        if(hasB) xs[loaded+kB] = ((b0.x + b1.x) + (b0.y + b1.y)) * (1.0f/32768.0f);
+                    }
                 }
                 else if(resampler >= 2u)
                 {
@@ -620,7 +725,7 @@ k_mix_voices(const MixParams P)
             {
                 const uint32_t dstOffset = n - loaded;
                 const uint32_t srcOffset = uint32_t((uint64_t(dstOffset)*increment + fracPos) >> 16);
-                for(int k = t;k < kPad;k += GS) rec.prev[k] = S.u.rs.win[srcOffset + k];
+                for(int k = t;k < kPad;k += GS) rec.prev[k] = win_at(S.u.rs.win, packedWin, srcOffset + uint32_t(k));
             }
             loaded = loadEnd;
             if(loaded < n)
@@ -635,9 +740,9 @@ k_mix_voices(const MixParams P)
                     else intPos = add_sat(intPos, int32_t(srcOffset));
                     // slide the window tail to the front (core/voice.cpp:808-809)
                     float carry = 0.0f;
-                    if(t < kPad) carry = S.u.rs.win[srcOffset + t];
+                    if(t < kPad) carry = win_at(S.u.rs.win, packedWin, srcOffset + uint32_t(t));
                     float carry2 = 0.0f;
-                    if(GS < kPad && t + GS < kPad) carry2 = S.u.rs.win[srcOffset + t + GS];
+                    if(GS < kPad && t + GS < kPad) carry2 = win_at(S.u.rs.win, packedWin, srcOffset + uint32_t(t) + GS);
                     group_sync(bar, GS);
                     if(t < kPad) S.u.rs.win[t] = carry;
                     if(GS < kPad && t + GS < kPad) S.u.rs.win[t + GS] = carry2;
