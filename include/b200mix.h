@@ -164,15 +164,31 @@ typedef struct b200mix_reverb_params {
     float    mod_depth;           /* mLate.Mod.Depth */
     float    late_ap_coeff;       /* mLate.VecAp.Coeff */
     uint32_t late_ap_offset[4];   /* mLate.VecAp.Offset */
+    uint32_t fade_samples;        /* mFadeSampleCount of this pipeline: how long it keeps ringing
+                                     out once a later full update has replaced it */
 } b200mix_reverb_params;
 
 /* ReverbState::deviceUpdate + the first (full) update: allocates and clears the delay
- * lines and installs the parameters.  Output mix gains (8 lines: 4 early then 4 late,
- * EarlyReflections::Gains / LateReverb::Gains) go through b200mix_slot_output_gains.
- * Only the plain output path (MixOutPlain, device ambisonic order 1) is implemented;
- * a later full parameter change (pipeline cross-fade) must re-install the slot. */
+ * lines of both pipelines and installs the parameters.  Output mix gains (8 lines: 4 early
+ * then 4 late, EarlyReflections::Gains / LateReverb::Gains) go through
+ * b200mix_slot_output_gains and always address the CURRENT pipeline.
+ * Only the plain output path (MixOutPlain, device ambisonic order 1) is implemented. */
 B200MIX_API int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot,
     const b200mix_reverb_params *params);
+/* A later ReverbState::update (alc/effects/reverb.cpp:1222-1351) on an installed reverb.
+ * params = the post-update values of the pipeline that is current AFTER the update (line
+ * lengths must equal the installed ones).
+ * full_update == 0: the values are applied to the current pipeline in place; its state is kept
+ *   and changed delay taps / tap coefficient cross-fade over the next block exactly as
+ *   processEarly/processLate do.
+ * full_update != 0 (density, diffusion, decay times, modulation or reference frequencies
+ *   changed, reverb.cpp:1243-1262): the reference switches to its other pipeline; the old one
+ *   gets its input tap coefficient faded to zero and keeps ringing out beside the new one for
+ *   its fade_samples, then its output gains fade to zero and it is cleared
+ *   (ReverbState::process :1840-1878, ReverbPipeline::clear :550-566).  The library runs that
+ *   state machine; send the new pipeline's output gains with b200mix_slot_output_gains. */
+B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
+    const b200mix_reverb_params *params, uint32_t full_update);
 
 /* Detaches the effect (EffectSlotType::None): the slot's wet input is ignored. */
 B200MIX_API int b200mix_slot_disable(b200mix_device *dev, uint32_t slot);

@@ -121,6 +121,16 @@ struct b200mix_device {
     uint8_t *d_st_delays{nullptr}; uint32_t st_num_fields{0}, st_ir{0};
     uint4 *d_qhdr{nullptr}; uint32_t *d_queue{nullptr};   // streaming queues (first b200mix_voice_queue)
     void *d_outbuf{nullptr}, *h_outbuf{nullptr};          // interleaved output staging (render_interleaved)
+    // reverb slots: host side of ReverbState's two-pipeline state machine
+    struct RvHost {
+        bool used{false};
+        int cur{0}, state{4};                   // PipelineState: 1 StartFade, 2 Fading, 3 Cleanup, 4 Normal
+        uint32_t fade[2]{1u, 1u};               // mFadeSampleCount per pipeline object
+        uint32_t offset{0};                     // mOffset
+        ReverbDev h[2];                         // host mirrors (parameters + pointers)
+        ReverbDev *dev{nullptr};                // device array [2]
+    };
+    std::vector<RvHost> rv;
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -581,6 +591,7 @@ static void free_slot(b200mix_device *d, uint32_t slot)
     d->slot_allocs[slot].clear();
     if(d->h_slots[slot].type) --d->active_slots;
     if(d->h_slots[slot].type == B200MIX_EFFECT_REVERB) --d->reverb_slots;
+    if(slot < d->rv.size()) d->rv[slot].used = false;
     d->h_slots[slot] = SlotRec{};
 }
 
@@ -664,29 +675,9 @@ int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_chann
     return B200MIX_OK;
 }
 
-int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_params *p)
+// b200mix_reverb_params -> the parameter part of a ReverbDev (state and pointers untouched)
+static void reverb_fill_params(ReverbDev &h, const b200mix_reverb_params *p)
 {
-    if(!d || slot >= d->h_slots.size() || !p || p->struct_size != sizeof(*p))
-    { if(d) d->error = "slot_reverb: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
-    auto pow2 = [](uint32_t v) { return v >= 4u && !(v & (v-1u)); };
-    if(!pow2(p->main_len) || !pow2(p->late_in_len) || !pow2(p->early_ap_len) || !pow2(p->early_len)
-        || !pow2(p->late_ap_len) || !pow2(p->late_len) || !p->late_offset[0] || !p->late_ap_offset[0])
-    { d->error = "slot_reverb: line lengths must be powers of two, feedback delays non-zero"; return B200MIX_ERR_INVALID; }
-    for(int j = 0;j < 4;++j)
-        if(!p->early_ap_offset[j] || p->late_ap_offset[j] < p->late_ap_offset[0])
-        { d->error = "slot_reverb: all-pass delays must be non-zero, late all-pass sorted"; return B200MIX_ERR_INVALID; }
-    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
-    free_slot(d, slot);
-    SlotRec r{};
-    r.type = B200MIX_EFFECT_REVERB; r.channels = 8;
-    auto alloc = [&](auto *&ptr, size_t count) -> int {
-        if(int rc = dev_alloc(d, ptr, count)) return rc;
-        d->slot_allocs[slot].push_back(ptr);
-        return B200MIX_OK;
-    };
-    ReverbDev h{};
-    h.main_len = p->main_len; h.late_in_len = p->late_in_len; h.early_ap_len = p->early_ap_len;
-    h.early_len = p->early_len; h.late_ap_len = p->late_ap_len; h.late_len = p->late_len;
     std::memcpy(h.early_tap, p->early_tap, sizeof(h.early_tap)); h.early_tap_coeff = p->early_tap_coeff;
     std::memcpy(h.late_tap, p->late_tap, sizeof(h.late_tap));
     h.mix_x = p->mix_x; h.mix_y = p->mix_y;
@@ -702,19 +693,98 @@ int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_p
     std::memcpy(h.t60_hf, p->t60_hf, sizeof(h.t60_hf)); std::memcpy(h.t60_lf, p->t60_lf, sizeof(h.t60_lf));
     h.mod_step = p->mod_step; h.mod_depth = p->mod_depth; h.late_ap_coeff = p->late_ap_coeff;
     std::memcpy(h.late_ap_offset, p->late_ap_offset, sizeof(h.late_ap_offset));
-    if(int rc = alloc(h.main_d, size_t(4)*p->main_len)) return rc;
-    if(int rc = alloc(h.late_in, size_t(4)*p->late_in_len)) return rc;
-    if(int rc = alloc(h.early_ap, size_t(4)*p->early_ap_len)) return rc;
-    if(int rc = alloc(h.early_d, size_t(4)*p->early_len)) return rc;
-    if(int rc = alloc(h.late_ap, size_t(4)*p->late_ap_len)) return rc;
-    if(int rc = alloc(h.late_d, size_t(4)*p->late_len)) return rc;
-    ReverbDev *dh = nullptr;
-    if(int rc = alloc(dh, 1)) return rc;
-    r.H = reinterpret_cast<float*>(dh);            // SlotRec::H carries the ReverbDev block
-    if(int rc = alloc(r.lines, size_t(8)*kLine)) return rc;
-    if(int rc = alloc(r.gains, size_t(2)*8*32)) return rc;
-    if(int rc = alloc(r.gtgt, size_t(8)*32)) return rc;
-    CUDA_TRY(d, cudaMemcpyAsync(dh, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
+}
+
+static int reverb_check_params(b200mix_device *d, const b200mix_reverb_params *p)
+{
+    auto pow2 = [](uint32_t v) { return v >= 4u && !(v & (v-1u)); };
+    if(!pow2(p->main_len) || !pow2(p->late_in_len) || !pow2(p->early_ap_len) || !pow2(p->early_len)
+        || !pow2(p->late_ap_len) || !pow2(p->late_len) || !p->late_offset[0] || !p->late_ap_offset[0])
+    { d->error = "slot_reverb: line lengths must be powers of two, feedback delays non-zero"; return B200MIX_ERR_INVALID; }
+    for(int j = 0;j < 4;++j)
+        if(!p->early_ap_offset[j] || p->late_ap_offset[j] < p->late_ap_offset[0])
+        { d->error = "slot_reverb: all-pass delays must be non-zero, late all-pass sorted"; return B200MIX_ERR_INVALID; }
+    return B200MIX_OK;
+}
+
+// the parameter prefix of ReverbDev (everything before the filter states)
+static constexpr size_t kReverbParamBytes = offsetof(ReverbDev, z_lp);
+
+// ReverbPipeline::clear (reverb.cpp:550-566) for one pipeline object: delay lines, filter and
+// tap state, the parameters clear() resets, and the object's output gains.
+static int reverb_clear_pipeline(b200mix_device *d, uint32_t slot, int obj)
+{
+    b200mix_device::RvHost &R = d->rv[slot];
+    ReverbDev &h = R.h[obj];
+    CUDA_TRY(d, cudaMemsetAsync(h.late_in, 0, size_t(4)*h.late_in_len*sizeof(float), d->stream));
+    CUDA_TRY(d, cudaMemsetAsync(h.early_ap, 0, size_t(4)*h.early_ap_len*sizeof(float), d->stream));
+    CUDA_TRY(d, cudaMemsetAsync(h.early_d, 0, size_t(4)*h.early_len*sizeof(float), d->stream));
+    CUDA_TRY(d, cudaMemsetAsync(h.late_ap, 0, size_t(4)*h.late_ap_len*sizeof(float), d->stream));
+    CUDA_TRY(d, cudaMemsetAsync(h.late_d, 0, size_t(4)*h.late_len*sizeof(float), d->stream));
+    std::memset(h.early_tap, 0, sizeof(h.early_tap)); std::memset(h.late_tap, 0, sizeof(h.late_tap));
+    h.early_tap_coeff = 0.0f; h.mod_step = 1u; h.mod_depth = 0.0f;
+    std::memset(h.z_lp, 0, sizeof(h.z_lp)); std::memset(h.z_hp, 0, sizeof(h.z_hp));
+    std::memset(h.z_t60hf, 0, sizeof(h.z_t60hf)); std::memset(h.z_t60lf, 0, sizeof(h.z_t60lf));
+    std::memset(h.early_tap_cur, 0, sizeof(h.early_tap_cur)); std::memset(h.late_tap_cur, 0, sizeof(h.late_tap_cur));
+    h.early_coeff_cur = 0.0f; h.mod_index = 0u; h.offset = R.offset;
+    CUDA_TRY(d, cudaMemcpyAsync(R.dev + obj, &h, sizeof(ReverbDev), cudaMemcpyHostToDevice, d->stream));
+    const SlotRec &S = d->h_slots[slot];
+    CUDA_TRY(d, cudaMemsetAsync(S.gtgt + size_t(obj)*8*32, 0, size_t(8)*32*sizeof(float), d->stream));
+    for(int sel = 0;sel < 2;++sel)
+        CUDA_TRY(d, cudaMemsetAsync(S.gains + (size_t(sel)*16 + size_t(obj)*8)*32, 0, size_t(8)*32*sizeof(float), d->stream));
+    // the host mirrors were read by pageable-memory copies above: wait before they change again
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return B200MIX_OK;
+}
+
+int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_params *p)
+{
+    if(!d || slot >= d->h_slots.size() || !p || p->struct_size != sizeof(*p))
+    { if(d) d->error = "slot_reverb: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
+    if(int rc = reverb_check_params(d, p)) return rc;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    free_slot(d, slot);
+    if(d->rv.size() < d->h_slots.size()) d->rv.resize(d->h_slots.size());
+    b200mix_device::RvHost &R = d->rv[slot];
+    R = b200mix_device::RvHost{};
+    SlotRec r{};
+    r.type = B200MIX_EFFECT_REVERB; r.channels = 16;       // 2 pipeline objects x (4 early + 4 late) lines
+    auto alloc = [&](auto *&ptr, size_t count) -> int {
+        if(int rc = dev_alloc(d, ptr, count)) return rc;
+        d->slot_allocs[slot].push_back(ptr);
+        return B200MIX_OK;
+    };
+    float *main_d = nullptr;
+    if(int rc = alloc(main_d, size_t(4)*p->main_len)) return rc;
+    for(int obj = 0;obj < 2;++obj)
+    {
+        ReverbDev &h = R.h[obj];
+        h = ReverbDev{};
+        h.main_len = p->main_len; h.late_in_len = p->late_in_len; h.early_ap_len = p->early_ap_len;
+        h.early_len = p->early_len; h.late_ap_len = p->late_ap_len; h.late_len = p->late_len;
+        // a pipeline that has not been updated yet is in ReverbPipeline::clear()'s state
+        reverb_fill_params(h, p);
+        std::memset(h.early_tap, 0, sizeof(h.early_tap)); std::memset(h.late_tap, 0, sizeof(h.late_tap));
+        h.early_tap_coeff = 0.0f; h.mod_step = 1u; h.mod_depth = 0.0f;
+        h.main_d = main_d;
+        if(int rc = alloc(h.late_in, size_t(4)*p->late_in_len)) return rc;
+        if(int rc = alloc(h.early_ap, size_t(4)*p->early_ap_len)) return rc;
+        if(int rc = alloc(h.early_d, size_t(4)*p->early_len)) return rc;
+        if(int rc = alloc(h.late_ap, size_t(4)*p->late_ap_len)) return rc;
+        if(int rc = alloc(h.late_d, size_t(4)*p->late_len)) return rc;
+    }
+    // deviceUpdate leaves DeviceClear; the first update is a full one: it switches to pipeline
+    // object 1 and goes straight to Normal (reverb.cpp:1243-1280)
+    R.used = true; R.cur = 1; R.state = 4; R.offset = 0;
+    reverb_fill_params(R.h[1], p);
+    R.fade[1] = p->fade_samples; R.fade[0] = 1u;
+    if(int rc = alloc(R.dev, 2)) return rc;
+    r.H = reinterpret_cast<float*>(R.dev);         // SlotRec::H carries the ReverbDev[2] block
+    if(int rc = alloc(r.lines, size_t(16)*kLine)) return rc;
+    if(int rc = alloc(r.gains, size_t(2)*16*32)) return rc;
+    if(int rc = alloc(r.gtgt, size_t(16)*32)) return rc;
+    r.rv_cur = 1u; r.rv_mask = 2u;
+    CUDA_TRY(d, cudaMemcpyAsync(R.dev, R.h, 2*sizeof(ReverbDev), cudaMemcpyHostToDevice, d->stream));
     d->h_slots[slot] = r;
     CUDA_TRY(d, cudaMemcpyAsync(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
@@ -723,17 +793,57 @@ int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_p
     return B200MIX_OK;
 }
 
+int b200mix_slot_reverb_update(b200mix_device *d, uint32_t slot, const b200mix_reverb_params *p,
+    uint32_t full_update)
+{
+    if(!d || slot >= d->h_slots.size() || !p || p->struct_size != sizeof(*p)
+        || d->h_slots[slot].type != B200MIX_EFFECT_REVERB)
+    { if(d) d->error = "slot_reverb_update: no reverb installed on this slot / bad arguments"; return B200MIX_ERR_INVALID; }
+    if(int rc = reverb_check_params(d, p)) return rc;
+    b200mix_device::RvHost &R = d->rv[slot];
+    const ReverbDev &h0 = R.h[0];
+    if(p->main_len != h0.main_len || p->late_in_len != h0.late_in_len || p->early_ap_len != h0.early_ap_len
+        || p->early_len != h0.early_len || p->late_ap_len != h0.late_ap_len || p->late_len != h0.late_len)
+    { d->error = "slot_reverb_update: line lengths differ from the installed ones"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));      // host mirrors are about to change
+    if(full_update)
+    {
+        // reverb.cpp:1275-1279
+        R.state = 1;
+        R.cur ^= 1;
+        const int old = R.cur ^ 1;
+        R.h[old].early_tap_coeff = 0.0f;
+        CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(R.dev + old) + offsetof(ReverbDev, early_tap_coeff),
+            &R.h[old].early_tap_coeff, sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        // the object coming back into use has not advanced mOffset while it was idle
+        R.h[R.cur].offset = R.offset;
+        CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(R.dev + R.cur) + offsetof(ReverbDev, offset),
+            &R.h[R.cur].offset, sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+        d->h_slots[slot].rv_cur = uint32_t(R.cur);
+    }
+    reverb_fill_params(R.h[R.cur], p);
+    R.fade[R.cur] = p->fade_samples;
+    CUDA_TRY(d, cudaMemcpyAsync(R.dev + R.cur, &R.h[R.cur], kReverbParamBytes, cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    return B200MIX_OK;
+}
+
 int b200mix_slot_output_gains(b200mix_device *d, uint32_t slot, uint32_t lines, const float *gains)
 {
-    if(!d || slot >= d->h_slots.size() || !d->h_slots[slot].type || lines != d->h_slots[slot].channels || !gains)
+    if(!d || slot >= d->h_slots.size() || !d->h_slots[slot].type || !gains)
     { if(d) d->error = "slot_output_gains: bad arguments"; return B200MIX_ERR_INVALID; }
+    const bool reverb = d->h_slots[slot].type == B200MIX_EFFECT_REVERB;
+    if(lines != (reverb ? 8u : d->h_slots[slot].channels))
+    { d->error = "slot_output_gains: wrong line count"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
     std::vector<float> g(size_t(lines)*32, 0.0f);
     for(uint32_t c = 0;c < lines;++c)
         for(uint32_t o = 0;o < d->desc.dry_channels;++o)
             g[c*32 + o] = gains[c*d->desc.dry_channels + o];
-    CUDA_TRY(d, cudaMemcpyAsync(d->h_slots[slot].gtgt, g.data(), g.size()*sizeof(float),
-        cudaMemcpyHostToDevice, d->stream));
+    // a reverb's gains are those of its CURRENT pipeline object (update3DPanning, reverb.cpp:1293-1296)
+    float *dst = d->h_slots[slot].gtgt + (reverb ? size_t(d->rv[slot].cur)*8*32 : 0);
+    CUDA_TRY(d, cudaMemcpyAsync(dst, g.data(), g.size()*sizeof(float), cudaMemcpyHostToDevice, d->stream));
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     return B200MIX_OK;
 }
@@ -1345,10 +1455,47 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         for(const SlotRec &sr : d->h_slots) if(sr.type) maxch = std::max(maxch, sr.channels);
         if(d->reverb_slots)
         {
+            // ReverbState::process's pipeline state machine (reverb.cpp:1840-1878), host side
+            for(uint32_t sl = 0;sl < d->rv.size();++sl)
+            {
+                b200mix_device::RvHost &R = d->rv[sl];
+                if(!R.used || d->h_slots[sl].type != B200MIX_EFFECT_REVERB) continue;
+                uint32_t mask = 1u << R.cur;
+                if(R.state < 2) R.state = 2;                         // StartFade -> Fading
+                if(R.state != 4)
+                {
+                    const int old = R.cur ^ 1;
+                    if(R.state == 3)
+                    {
+                        if(int rc = reverb_clear_pipeline(d, sl, old)) return rc;
+                        R.state = 4;
+                    }
+                    else
+                    {
+                        if(frames >= R.fade[old])
+                        {
+                            // final mix of the old pipeline: its gains fade to silence
+                            CUDA_TRY(d, cudaMemsetAsync(d->h_slots[sl].gtgt + size_t(old)*8*32, 0,
+                                size_t(8)*32*sizeof(float), d->stream));
+                            R.fade[old] = 0; R.state = 3;
+                        }
+                        else R.fade[old] -= frames;
+                        mask |= 1u << old;
+                    }
+                }
+                R.offset += frames;
+                if(d->h_slots[sl].rv_mask != mask || d->h_slots[sl].rv_cur != uint32_t(R.cur))
+                {
+                    d->h_slots[sl].rv_mask = mask; d->h_slots[sl].rv_cur = uint32_t(R.cur);
+                    CUDA_TRY(d, cudaMemcpyAsync(d->d_slots + sl, &d->h_slots[sl], sizeof(SlotRec),
+                        cudaMemcpyHostToDevice, d->stream));
+                    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+                }
+            }
             ReverbParamsK RP{};
             RP.slots = d->d_slots; RP.wet = d->d_wet; RP.cubic = d->d_cubic_filter;
             RP.frames = frames; RP.cw = dd.wet_channels;
-            k_reverb_process<<<dd.max_slots, 128, 0, d->stream>>>(RP);
+            k_reverb_process<<<dim3(dd.max_slots, 2), 128, 0, d->stream>>>(RP);
             ++d->launches;
         }
         k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);

@@ -28,7 +28,9 @@ constexpr int kConvMaxBlocks = 9;   // blocks that can complete in one 1024-fram
 struct SlotRec {
     uint32_t type, channels, frames, segs;     // segs = mNumConvolveSegs
     uint32_t cur, fifo, nb_last, f_last;       // ring position, FIFO fill; last update's record
-    uint32_t cur_last, pad0, pad1, pad2;
+    uint32_t cur_last;
+    uint32_t rv_cur, rv_mask;                  // reverb: current pipeline object; objects to run now
+    uint32_t pad2;
     float *H;         // [channels][segs][256]  filter spectra (pre-scaled by 1/256)
     float *X;         // [segs+kConvMaxBlocks][256] input spectra ring (our own ring: long enough that
                       //                        a whole update's blocks never overwrite live history)
@@ -741,10 +743,10 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
 {
     // per-(slot,line) constants are staged once per CTA; the sample loop then only streams
     // the output lines (coalesced, independent loads)
-    constexpr int kMaxLines = 8;
+    constexpr int kMaxLines = 16;
     __shared__ float s_cg[64][kMaxLines], s_tg[64][kMaxLines];
     __shared__ const float *s_line[64];
-    __shared__ uint32_t s_ch[64];
+    __shared__ uint32_t s_ch[64], s_first[64];
     const uint32_t o = blockIdx.y;
     const uint32_t i = blockIdx.x*128u + threadIdx.x;
     const uint32_t n = Q.frames;
@@ -757,27 +759,39 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
         if(threadIdx.x < cnt)
         {
             const SlotRec &S = Q.slots[sb + threadIdx.x];
-            const uint32_t ch = (S.type == 0u) ? 0u : (S.channels < uint32_t(kMaxLines) ? S.channels : uint32_t(kMaxLines));
+            uint32_t ch = (S.type == 0u) ? 0u : (S.channels < uint32_t(kMaxLines) ? S.channels : uint32_t(kMaxLines));
+            uint32_t first = 0u;
+            if(S.type == 2u)
+            {
+                // reverb: lines 0-7 belong to pipeline object 0, 8-15 to object 1; the current
+                // pipeline is mixed first, then (while it rings out) the old one
+                // (ReverbState::process, reverb.cpp:1843-1877)
+                first = S.rv_cur*8u;
+                ch = (S.rv_mask == 3u) ? 16u : 8u;
+            }
             s_ch[threadIdx.x] = ch;
+            s_first[threadIdx.x] = first;
             s_line[threadIdx.x] = S.lines;
             const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
             for(uint32_t c = 0;c < ch;++c)
             {
-                s_cg[threadIdx.x][c] = gcur[c*32u + o];
-                s_tg[threadIdx.x][c] = S.gtgt[c*32u + o];
+                const uint32_t li = (c + first) & (kMaxLines - 1u);
+                s_cg[threadIdx.x][c] = gcur[li*32u + o];
+                s_tg[threadIdx.x][c] = S.gtgt[li*32u + o];
             }
         }
         __syncthreads();
         for(uint32_t s = 0;s < cnt;++s)
         {
-            const uint32_t ch = s_ch[s];
+            const uint32_t ch = s_ch[s], first = s_first[s];
             const float *lines = s_line[s];
             #pragma unroll 4
             for(uint32_t c = 0;c < ch;++c)
             {
                 const float cg = s_cg[s][c], tg = s_tg[s][c];
                 const float step = (tg - cg)*delta;
-                const float x = (i < n) ? lines[size_t(c)*kLine + i] : 0.0f;
+                const uint32_t li = (c + first) & (kMaxLines - 1u);
+                const float x = (i < n) ? lines[size_t(li)*kLine + i] : 0.0f;
                 if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
                 else if(fabsf(tg) > kSilence) acc += x*tg;
             }
@@ -793,7 +807,12 @@ __global__ void k_slot_gains_commit(const SlotMixParams Q)
     SlotRec &S = Q.slots[s];
     if(S.type == 0u) return;
     float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
-    for(uint32_t k = threadIdx.x;k < S.channels*32u;k += blockDim.x) gcur[k] = S.gtgt[k];
+    for(uint32_t k = threadIdx.x;k < S.channels*32u;k += blockDim.x)
+    {
+        // a reverb pipeline object that did not run this update keeps its Current gains
+        if(S.type == 2u && !((S.rv_mask >> (k >> 8)) & 1u)) continue;
+        gcur[k] = S.gtgt[k];
+    }
 }
 
 } // namespace b200mix
@@ -875,14 +894,16 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     __shared__ float temp[NL][MAXUPD];
     __shared__ uint32_t moddel[MAXUPD];
     SlotRec &S = Q.slots[blockIdx.x];
-    if(S.type != 2u) return;
-    ReverbDev &R = *reinterpret_cast<ReverbDev*>(S.H);
+    if(S.type != 2u || !((S.rv_mask >> blockIdx.y) & 1u)) return;
+    // blockIdx.y = pipeline object (ReverbState::mPipelines[2]); both share the main delay line,
+    // each CTA writes this update's input into it itself (identical values) before reading it
+    ReverbDev &R = reinterpret_cast<ReverbDev*>(S.H)[blockIdx.y];
     const int tid = threadIdx.x, line = tid >> 5, lane = tid & 31;
     const uint32_t n = Q.frames;
     const uint32_t offset0 = R.offset;
     const float *wet = Q.wet + size_t(blockIdx.x)*Q.cw*kLine;
     const uint32_t numInput = Q.cw < 4u ? Q.cw : 4u;
-    float *earlyOut = S.lines, *lateOut = S.lines + 4*kLine;
+    float *earlyOut = S.lines + size_t(blockIdx.y)*8*kLine, *lateOut = earlyOut + 4*kLine;
 
     // B-Format -> A-Format into the main delay (reverb.cpp:1824-1838, B2A :91-97)
     {

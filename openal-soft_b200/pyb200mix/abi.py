@@ -69,4 +69,15 @@ class ReverbParams(C.Structure):
                 ("t60_mid_gain", C.c_float * 4),
                 ("t60_hf", (C.c_float * 5) * 4), ("t60_lf", (C.c_float * 5) * 4),
                 ("mod_step", C.c_uint32), ("mod_depth", C.c_float),
-                ("late_ap_coeff", C.c_float), ("late_ap_offset", C.c_uint32 * 4)]
+                ("late_ap_coeff", C.c_float), ("late_ap_offset", C.c_uint32 * 4),
+                ("fade_samples", C.c_uint32)]
+
+
+def reverb_params_from(raw) -> "ReverbParams":
+    """ReverbParams from stored bytes (fixtures written before a field was appended are
+    zero-extended; struct_size is refreshed)."""
+    raw = bytes(raw)
+    n = C.sizeof(ReverbParams)
+    p = ReverbParams.from_buffer_copy(raw[:n].ljust(n, b"\0"))
+    p.struct_size = n
+    return p

@@ -355,6 +355,17 @@ int oracle_slot_reverb(oracle_device *d, uint32_t slot, const b200mix_reverb_par
     return B200MIX_OK;
 }
 
+int oracle_slot_reverb_update(oracle_device *d, uint32_t slot, const b200mix_reverb_params *params,
+    uint32_t full_update)
+{
+    if(slot >= d->desc.max_slots || !params || params->struct_size != sizeof(*params))
+        return B200MIX_ERR_INVALID;
+    oslot *s = &d->slots[slot];
+    if(s->type != B200MIX_EFFECT_REVERB) return B200MIX_ERR_INVALID;
+    oreverb_update(s->reverb, params, full_update != 0);
+    return B200MIX_OK;
+}
+
 int oracle_slot_convolution(oracle_device *d, uint32_t slot, uint32_t ir_channels,
     uint32_t ir_frames, const float *ir)
 {

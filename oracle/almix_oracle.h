@@ -87,6 +87,8 @@ int  oracle_slot_convolution(oracle_device *dev, uint32_t slot, uint32_t ir_chan
     uint32_t ir_frames, const float *ir);
 int  oracle_slot_output_gains(oracle_device *dev, uint32_t slot, uint32_t lines, const float *gains);
 int  oracle_slot_reverb(oracle_device *dev, uint32_t slot, const b200mix_reverb_params *params);
+int  oracle_slot_reverb_update(oracle_device *dev, uint32_t slot, const b200mix_reverb_params *params,
+    uint32_t full_update);
 int  oracle_slot_disable(oracle_device *dev, uint32_t slot);
 int  oracle_get_dry(oracle_device *dev, float *dry);
 /* test-only: wet mix of one slot [wet_channels][1024] */

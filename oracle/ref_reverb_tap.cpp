@@ -58,7 +58,8 @@ int refh_reverb_params(ALCcontext *actx, int idx, b200mix_reverb_params *out, fl
     auto *st = static_cast<ReverbState*>(slot->mEffectState.get());
     if(st->mUpmixOutput) return -3;
     auto &p = st->mPipelines[st->mCurrentPipeline];
-    *pipeline_state = int(st->mPipelineState);
+    /* low byte: mPipelineState; bit 8: mCurrentPipeline (flips on every full update) */
+    *pipeline_state = int(st->mPipelineState) | (int(st->mCurrentPipeline) << 8);
     auto *dev = static_cast<DeviceBase*>(ctx->mDevice);
     const auto cd = dev->Dry.Buffer.size();
 
@@ -97,6 +98,7 @@ int refh_reverb_params(ALCcontext *actx, int idx, b200mix_reverb_params *out, fl
     out->mod_step = p.mLate.Mod.Step;
     out->mod_depth = p.mLate.Mod.Depth;
     out->late_ap_coeff = p.mLate.VecAp.Coeff;
+    out->fade_samples = uint32_t(p.mFadeSampleCount);
     return 0;
 }
 

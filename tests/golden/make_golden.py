@@ -71,7 +71,19 @@ SCENES = {
     # integer output without the limiter: ApplyDither + Write<T> (16-bit dithered, 8-bit unsigned)
     "hrtf_spline_out_i16_v6": (6, 1, 2, 3, True, 48000, "out_i16"),
     "stereo_spline_out_u8_v6": (6, 0, 2, 3, True, 48000, "out_u8"),
+    # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
+    # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
+    # running out and being cleared, and a full update arriving while the previous fade still runs
+    "hrtf_spline_reverb_xfade_v4": (4, 1, 2, 18, True, 48000, None, "i16", 0,
+                                    {0x0006: 0.1, 0x000A: 0.004, 0x000D: 0.006}, None, "rvscript"),
 }
+
+# {update index (applied before that render): {AL_EAXREVERB_* : value}}
+REVERB_SCRIPT = {2: {0x0006: 0.5, 0x0001: 0.6},                 # decay time + density: full update
+                 4: {0x0003: 0.5, 0x000A: 0.02, 0x0009: 0.1},   # gain, reflections delay+gain: in place
+                 11: {0x0002: 0.4},                             # diffusion: full, from the Normal state
+                 13: {0x0006: 0.2},                             # full ...
+                 14: {0x0006: 0.8, 0x0012: 0.6}}                # ... and full again while still fading
 
 ADPCM_BLOCKS = 120
 
@@ -164,10 +176,19 @@ def run_scene(name):
         slot = ref.add_reverb_slot(props=rvprops)
         for src in ref.sources:
             ref.connect_send(src, slot)
+    if len(spec) > 11 and spec[11] == "rvscript":
+        # keep the voices' send gains independent of the slot's decay parameters (the automatic
+        # wet-gain adjustment of CalcAttnSourceParams would change them with every reverb change):
+        # this scene is about the effect's own state machine
+        for src in ref.sources:
+            ref.al.alSourcei(src, 0x2000B, 0)      # AL_AUXILIARY_SEND_FILTER_GAIN_AUTO
+            ref.al.alSourcei(src, 0x2000C, 0)      # AL_AUXILIARY_SEND_FILTER_GAINHF_AUTO
     script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 and spec[10] else None
     if script:
         apply_filter_script(ref, script, 0, slot)
     out_np, out_type = OUT_TYPES.get(spec[6] if len(spec) > 6 else None, (np.float32, None))
+    rvscript = len(spec) > 11 and spec[11] == "rvscript"
+    rv_steps = []
     ref.play_all()
     outs = []
     snap = None
@@ -176,7 +197,12 @@ def run_scene(name):
     for u in range(U):
         if script and u:
             apply_filter_script(ref, script, u, slot)
+        if rvscript and u in REVERB_SCRIPT:
+            ref.change_reverb(slot, REVERB_SCRIPT[u])
         outs.append(ref.render(dtype=out_np))
+        if rvscript:
+            rvp_u, rvg_u, rvst_u = ref.reverb_params(0)
+            rv_steps.append((np.frombuffer(bytes(rvp_u), dtype=np.uint8).copy(), rvg_u, rvst_u))
         if script:
             ents, _ = ref.voice_filters(V)
             filt_meta.append(np.array([[v, p, a] for v, p, a, _, _ in ents], dtype=np.int32))
@@ -186,7 +212,7 @@ def run_scene(name):
             snap1 = ref.snapshot(channel=1) if stereo_src else None
             if rvprops is not None:
                 rvp, rvg, rvstate = ref.reverb_params(0)
-                assert rvstate == 4, rvstate     # ReverbState::Normal
+                assert (rvstate & 0xff) == 4, rvstate     # ReverbState::Normal
     n, params, coeffs, dry, send, state = snap
     d = ref.desc
     res = dict(out=np.stack(outs),
@@ -203,6 +229,9 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if rvscript:
+        res.update(rv_params=np.stack([x[0] for x in rv_steps]), rv_gains=np.stack([x[1] for x in rv_steps]),
+                   rv_state=np.array([x[2] for x in rv_steps], dtype=np.int64))
     if out_type is not None:
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
     if adpcm:

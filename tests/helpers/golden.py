@@ -62,7 +62,7 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
             dev.slot_convolution(0, ir[None, :], fx["conv_gains"][None, :])
         if reverb:
-            dev.slot_reverb(0, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+            dev.slot_reverb(0, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                             fx["reverb_gains"])
         params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
         plist = []
@@ -106,6 +106,16 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
                 # the reference's filter targets during update u, every path of every voice
                 dev.voices_filters((int(m[0]), int(m[1]), int(m[2]), c[0], c[1])
                                    for m, c in zip(fx["filt_meta"][u], fx["filt_coef"][u]))
+            if "rv_state" in fx and u > 0:
+                # replay the reference's ReverbState::update calls: a flipped mCurrentPipeline bit
+                # marks a full update; otherwise changed values are applied in place
+                st, prev = int(fx["rv_state"][u]), int(fx["rv_state"][u - 1])
+                full = (st >> 8) != (prev >> 8)
+                changed = full or not np.array_equal(fx["rv_params"][u], fx["rv_params"][u - 1]) \
+                    or not np.array_equal(fx["rv_gains"][u], fx["rv_gains"][u - 1])
+                if changed:
+                    dev.slot_reverb_update(0, abi.reverb_params_from(fx["rv_params"][u].tobytes()), full,
+                                           fx["rv_gains"][u])
             if "out_type" in fx:
                 o, res, seed = dev.render_interleaved(frames, int(fx["out_type"]), float(fx["dither_depth"]), seed)
                 o = np.ascontiguousarray(o.T)        # planar like the fixture

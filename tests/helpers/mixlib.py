@@ -45,6 +45,8 @@ class MixLib:
         self.slot_output_gains.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         self.slot_reverb = f("slot_reverb")
         self.slot_reverb.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams)]
+        self.slot_reverb_update = f("slot_reverb_update")
+        self.slot_reverb_update.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams), C.c_uint32]
         self.slot_disable = f("slot_disable")
         self.slot_disable.argtypes = [C.c_void_p, C.c_uint32]
         self.voices_filters = f("voices_filters")
@@ -112,6 +114,14 @@ class MixDevice:
         """params: abi.ReverbParams; gains: [8][dry_channels] (early 0-3, late 0-3)."""
         params.struct_size = C.sizeof(abi.ReverbParams)
         rc = self.m.slot_reverb(self.h, slot, C.byref(params))
+        assert rc == 0, rc
+        gains = np.ascontiguousarray(gains, dtype=np.float32)
+        rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)
+        assert rc == 0, rc
+
+    def slot_reverb_update(self, slot, params, full, gains):
+        params.struct_size = C.sizeof(abi.ReverbParams)
+        rc = self.m.slot_reverb_update(self.h, slot, C.byref(params), 1 if full else 0)
         assert rc == 0, rc
         gains = np.ascontiguousarray(gains, dtype=np.float32)
         rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)

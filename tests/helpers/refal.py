@@ -285,7 +285,18 @@ class RefDevice:
         self.al.alAuxiliaryEffectSloti(s, AL_EFFECTSLOT_EFFECT, e.value)
         err = self.al.alGetError()
         assert err == 0, f"AL error {err:#x} creating reverb slot"
+        self._slot_effect = getattr(self, "_slot_effect", {})
+        self._slot_effect[s.value] = e.value
         return s.value
+
+    def change_reverb(self, slot: int, props: dict):
+        """Changes properties of the slot's reverb effect and re-applies it (ReverbState::update)."""
+        e = self._slot_effect[slot]
+        for k, v in props.items():
+            self.al.alEffectf(e, k, float(v))
+        self.al.alAuxiliaryEffectSloti(slot, AL_EFFECTSLOT_EFFECT, e)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} changing reverb"
 
     def reverb_params(self, idx: int):
         if not hasattr(self, "_rv"):

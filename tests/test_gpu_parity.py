@@ -212,7 +212,7 @@ def test_reverb_slots_vs_oracle_ragged_updates():
         for i in range(nv):
             dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
         for s, fx in enumerate(fxs):
-            dev.slot_reverb(s, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+            dev.slot_reverb(s, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                             fx["reverb_gains"])
         dev.voices_update(params, coeffs, dry, send)
         o = [dev.render(f) for f in (1024, 300, 1024, 17, 1024, 1024, 700, 1024)]
@@ -264,7 +264,7 @@ def test_direct_and_send_filters_vs_oracle_ragged_updates(hrtf):
                                   ).astype(np.float32), None, 0.0)
         for i in range(nv):
             dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
-        dev.slot_reverb(0, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+        dev.slot_reverb(0, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                         np.ascontiguousarray(fx["reverb_gains"][:, :desc.dry_channels]))
         dev.voices_update(params, coeffs if hrtf else None, dry, send)
         o = []
@@ -331,7 +331,7 @@ def test_two_device_slot_ownership_equals_single_device():
             dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
         for s, fx in enumerate(fxs):
             if s in owned:
-                dev.slot_reverb(s, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+                dev.slot_reverb(s, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                                 fx["reverb_gains"])
         dev.voices_update([params[i] for i in voices], coeffs[voices], dry[voices], send[voices])
         return dev
@@ -504,3 +504,45 @@ def test_streaming_queues_vs_oracle(hrtf):
     assert results[0] == results[1]
     assert sum(r[3] for upd in results[0] for r in upd) > 10        # items really were consumed
     _check(outs[1], outs[0], "streaming queues")
+
+
+def test_reverb_parameter_changes_vs_oracle_ragged_updates():
+    """ReverbState::update while playing: the reference's own parameter blocks of the cross-fade
+    golden (full updates, an in-place one, the old pipeline ringing out and being cleared, a full
+    update while the previous fade still runs) replayed with ragged update sizes, so fade counts
+    run out mid-way and pipelines are re-entered at odd offsets."""
+    fx = golden.load("hrtf_spline_reverb_xfade_v4")
+    rng = np.random.default_rng(31337)
+    nv, ir = 16, 64
+    desc = synth.hrtf_desc(nv, ir)
+    desc.num_sends = 1
+    desc.wet_channels = 4
+    desc.max_slots = 1
+    params, coeffs, dry = synth.voice_set(rng, nv, ir)
+    send = (rng.standard_normal((nv, 1, 4)) * 0.3).astype(np.float32)
+    for p in params:
+        p.send_slot[0] = 0
+    sizes = (1024, 300, 1024, 17, 1024, 1024, 700, 1024, 1, 1024, 1024, 512, 1024, 1024, 1024, 90, 1024, 1024)
+    U = len(sizes)
+    assert U == fx["rv_state"].shape[0]
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.slot_reverb(0, abi.reverb_params_from(fx["rv_params"][0].tobytes()), fx["rv_gains"][0])
+        dev.voices_update(params, coeffs, dry, send)
+        o = []
+        for u, f in enumerate(sizes):
+            if u > 0:
+                st, prev = int(fx["rv_state"][u]), int(fx["rv_state"][u - 1])
+                full = (st >> 8) != (prev >> 8)
+                if full or not np.array_equal(fx["rv_params"][u], fx["rv_params"][u - 1]) \
+                        or not np.array_equal(fx["rv_gains"][u], fx["rv_gains"][u - 1]):
+                    dev.slot_reverb_update(0, abi.reverb_params_from(fx["rv_params"][u].tobytes()), full,
+                                           fx["rv_gains"][u])
+            o.append(dev.render(f))
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], "reverb parameter changes")

@@ -114,7 +114,7 @@ def _mix_slots(voices, total, updates, rank, world):
         dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i, 6000))
     for s_, fx in enumerate(fxs):
         if shard.slot_owner(s_, world) == rank:
-            dev.slot_reverb(s_, abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes()),
+            dev.slot_reverb(s_, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                             fx["reverb_gains"])
     dev.voices_update([params[i] for i in voices], coeffs[voices], dry[voices], send[voices])
     outs = []

@@ -120,7 +120,7 @@ def main():
     installed = 0
     if nslots:
         fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "hrtf_bsinc24_reverb_v6.npz")))
-        rp = abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes())
+        rp = abi.reverb_params_from(fx["reverb_params"].tobytes())
         rp.struct_size = C.sizeof(abi.ReverbParams)
         rg = np.ascontiguousarray(fx["reverb_gains"], dtype=np.float32)
         for s in range(nslots):

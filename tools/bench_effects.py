@@ -52,7 +52,7 @@ def main():
     lib.b200mix_set_hrtf_decoder(h, 4, 91, dec.ctypes.data, hf.ctypes.data, sc.ctypes.data)
     if args.effect == "reverb":
         fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "hrtf_bsinc24_reverb_v6.npz")))
-        rp = abi.ReverbParams.from_buffer_copy(fx["reverb_params"].tobytes())
+        rp = abi.reverb_params_from(fx["reverb_params"].tobytes())
         rp.struct_size = C.sizeof(abi.ReverbParams)
         g = np.ascontiguousarray(fx["reverb_gains"], dtype=np.float32)
         for s in range(ns):
