@@ -11,6 +11,7 @@ rendered output for U consecutive 1024-frame updates from BOTH kernel sets:
 The PCM inputs are regenerated from the seeds at test time.
 """
 import ctypes as C
+import math
 import os
 import subprocess
 import sys
@@ -74,6 +75,12 @@ SCENES = {
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
+    # sources that MOVE between updates (a new position for half of them before every render):
+    # MixHrtfBlend with really different old/new HRIRs and delays, gain ramps of Mix_ (per-update
+    # voice parameter snapshots are replayed); 20 updates, also the ">= 16 consecutive updates"
+    # run of SURVEY §8d
+    "hrtf_bsinc24_moving_v6": (6, 1, 7, 20, True, 48000, None, "i16", 0, None, None, "moving"),
+    "stereo_spline_moving_v6": (6, 0, 2, 8, True, 48000, None, "i16", 0, None, None, "moving"),
     "hrtf_spline_reverb_xfade_v4": (4, 1, 2, 18, True, 48000, None, "i16", 0,
                                     {0x0006: 0.1, 0x000A: 0.004, 0x000D: 0.006}, None, "rvscript"),
 }
@@ -189,6 +196,8 @@ def run_scene(name):
     out_np, out_type = OUT_TYPES.get(spec[6] if len(spec) > 6 else None, (np.float32, None))
     rvscript = len(spec) > 11 and spec[11] == "rvscript"
     rv_steps = []
+    moving = len(spec) > 11 and spec[11] == "moving"
+    mv_steps = []
     ref.play_all()
     outs = []
     snap = None
@@ -199,7 +208,20 @@ def run_scene(name):
             apply_filter_script(ref, script, u, slot)
         if rvscript and u in REVERB_SCRIPT:
             ref.change_reverb(slot, REVERB_SCRIPT[u])
+        if moving and u:
+            for i in range(u % 2, V, 2):
+                x, y, z = scene.voice_position(i)
+                ang = 0.35 * u + 0.2 * i
+                cs, sn = math.cos(ang), math.sin(ang)
+                r = 1.0 + 0.15 * ((u + i) % 5)
+                ref.al.alSource3f(ref.sources[i], refal.AL_POSITION, float((x * cs - z * sn) * r),
+                                  float(y * (1.0 - 0.1 * (u % 3))), float((x * sn + z * cs) * r))
+                ref.al.alSourcef(ref.sources[i], refal.AL_GAIN, scene.voice_gain(V) * (0.6 + 0.1 * ((u + i) % 4)))
         outs.append(ref.render(dtype=out_np))
+        if moving:
+            _, mp, mc, md, _, _ = ref.snapshot()
+            mv_steps.append((np.frombuffer(bytes(mp), dtype=np.uint8)[:V * C.sizeof(abi.VoiceParams)].copy(),
+                             mc[:V].copy(), md[:V].copy()))
         if rvscript:
             rvp_u, rvg_u, rvst_u = ref.reverb_params(0)
             rv_steps.append((np.frombuffer(bytes(rvp_u), dtype=np.uint8).copy(), rvg_u, rvst_u))
@@ -229,6 +251,9 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if moving:
+        res.update(mv_params=np.stack([x[0] for x in mv_steps]), mv_coeffs=np.stack([x[1] for x in mv_steps]),
+                   mv_dry=np.stack([x[2] for x in mv_steps]))
     if rvscript:
         res.update(rv_params=np.stack([x[0] for x in rv_steps]), rv_gains=np.stack([x[1] for x in rv_steps]),
                    rv_state=np.array([x[2] for x in rv_steps], dtype=np.int64))

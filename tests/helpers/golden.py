@@ -106,6 +106,28 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
                 # the reference's filter targets during update u, every path of every voice
                 dev.voices_filters((int(m[0]), int(m[1]), int(m[2]), c[0], c[1])
                                    for m, c in zip(fx["filt_meta"][u], fx["filt_coef"][u]))
+            if "mv_params" in fx and u > 0:
+                # the reference recomputed the moved sources' targets before this update: resend
+                # the voices whose snapshot differs from the previous one
+                mp = (abi.VoiceParams * V).from_buffer_copy(fx["mv_params"][u].tobytes())
+                mprev = (abi.VoiceParams * V).from_buffer_copy(fx["mv_params"][u - 1].tobytes())
+                sel = []
+                for k in range(V):
+                    same = (np.array_equal(fx["mv_coeffs"][u][k], fx["mv_coeffs"][u - 1][k])
+                            and np.array_equal(fx["mv_dry"][u][k], fx["mv_dry"][u - 1][k])
+                            and mp[k].hrtf_gain == mprev[k].hrtf_gain
+                            and list(mp[k].hrtf_delay) == list(mprev[k].hrtf_delay))
+                    if not same:
+                        sel.append(k)
+                if sel:
+                    ql = []
+                    for k in sel:
+                        q = abi.VoiceParams()
+                        C.memmove(C.byref(q), C.byref(mp[k]), C.sizeof(q))
+                        q.buffer = k
+                        q.flags = (q.flags & ~(abi.VF_STOPPING | abi.VF_STOPPED | abi.VF_RESET)) | abi.VF_PLAYING
+                        ql.append(q)
+                    dev.voices_update(ql, fx["mv_coeffs"][u][sel], fx["mv_dry"][u][sel], None)
             if "rv_state" in fx and u > 0:
                 # replay the reference's ReverbState::update calls: a flipped mCurrentPipeline bit
                 # marks a full update; otherwise changed values are applied in place
