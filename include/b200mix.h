@@ -190,6 +190,13 @@ B200MIX_API int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot,
 B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
     const b200mix_reverb_params *params, uint32_t full_update);
 
+/* EffectSlotBase::Target (AL_SOFT_effect_target, core/effectslot.h:64; alc/alu.cpp:626-633): the
+ * slot's effect output is mixed into `target`'s Wet buffer instead of the Dry mix
+ * (B200MIX_NO_SLOT restores Dry).  A targeting slot's output gains are then
+ * [lines][wet_channels].  Slots run in the reference's order — every slot before its target
+ * (alc/alu.cpp:2211-2251); chains must be acyclic. */
+B200MIX_API int b200mix_slot_target(b200mix_device *dev, uint32_t slot, uint32_t target);
+
 /* Detaches the effect (EffectSlotType::None): the slot's wet input is ignored. */
 B200MIX_API int b200mix_slot_disable(b200mix_device *dev, uint32_t slot);
 

@@ -131,6 +131,8 @@ struct b200mix_device {
         ReverbDev *dev{nullptr};                // device array [2]
     };
     std::vector<RvHost> rv;
+    std::vector<uint32_t> h_target;          // EffectSlotBase::Target per slot (NO_SLOT = Dry)
+    uint32_t num_stages{1}; bool any_target{false};
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -584,6 +586,36 @@ int b200mix_buffer_free(b200mix_device *d, uint32_t buffer)
     return B200MIX_OK;
 }
 
+// Processing stages (alc/alu.cpp:2211-2251: every slot before its target): stage = (longest
+// chain length) - (hops from the slot to a slot that outputs to Dry); uploads stage/target of
+// every slot record.
+static int update_stages(b200mix_device *d)
+{
+    const uint32_t ns = uint32_t(d->h_slots.size());
+    if(d->h_target.size() != ns) d->h_target.assign(ns, B200MIX_NO_SLOT);
+    std::vector<uint32_t> depth(ns, 0);
+    uint32_t maxd = 0; d->any_target = false;
+    for(uint32_t sl = 0;sl < ns;++sl)
+    {
+        uint32_t hops = 0;
+        for(uint32_t t = d->h_target[sl];t != B200MIX_NO_SLOT && hops <= ns;t = d->h_target[t]) ++hops;
+        depth[sl] = hops;
+        if(d->h_slots[sl].type) { maxd = std::max(maxd, hops); if(hops) d->any_target = true; }
+    }
+    d->num_stages = maxd + 1u;
+    for(uint32_t sl = 0;sl < ns;++sl)
+    {
+        d->h_slots[sl].stage = d->h_slots[sl].type ? maxd - std::min(depth[sl], maxd) : 0u;
+        d->h_slots[sl].target = d->h_target[sl];
+    }
+    if(ns && d->d_slots)
+    {
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_slots, d->h_slots.data(), ns*sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    }
+    return B200MIX_OK;
+}
+
 static void free_slot(b200mix_device *d, uint32_t slot)
 {
     cudaStreamSynchronize(d->stream);
@@ -600,8 +632,7 @@ int b200mix_slot_disable(b200mix_device *d, uint32_t slot)
     if(!d || slot >= d->h_slots.size()) { if(d) d->error = "slot_disable: bad slot"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
     free_slot(d, slot);
-    CUDA_TRY(d, cudaMemcpy(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice));
-    return B200MIX_OK;
+    return update_stages(d);
 }
 
 int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_channels,
@@ -672,7 +703,7 @@ int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_chann
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     ++d->active_slots;
     d->dry_active = true;
-    return B200MIX_OK;
+    return update_stages(d);
 }
 
 // b200mix_reverb_params -> the parameter part of a ReverbDev (state and pointers untouched)
@@ -790,7 +821,22 @@ int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_p
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     ++d->active_slots; ++d->reverb_slots;
     d->dry_active = true;
-    return B200MIX_OK;
+    return update_stages(d);
+}
+
+int b200mix_slot_target(b200mix_device *d, uint32_t slot, uint32_t target)
+{
+    if(!d || slot >= d->h_slots.size() || (target != B200MIX_NO_SLOT && target >= d->h_slots.size()))
+    { if(d) d->error = "slot_target: slot out of range"; return B200MIX_ERR_INVALID; }
+    if(d->h_target.size() != d->h_slots.size()) d->h_target.assign(d->h_slots.size(), B200MIX_NO_SLOT);
+    uint32_t hops = 0;
+    for(uint32_t t = target;t != B200MIX_NO_SLOT;t = d->h_target[t])
+        if(t == slot || ++hops > d->h_slots.size())
+        { d->error = "slot_target: the chain would loop"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    d->h_target[slot] = target;
+    return update_stages(d);
 }
 
 int b200mix_slot_reverb_update(b200mix_device *d, uint32_t slot, const b200mix_reverb_params *p,
@@ -837,10 +883,13 @@ int b200mix_slot_output_gains(b200mix_device *d, uint32_t slot, uint32_t lines, 
     if(lines != (reverb ? 8u : d->h_slots[slot].channels))
     { d->error = "slot_output_gains: wrong line count"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    // gains address the slot's output target: the Dry mix or the target slot's Wet mix
+    const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
+    const uint32_t width = toSlot ? d->desc.wet_channels : d->desc.dry_channels;
     std::vector<float> g(size_t(lines)*32, 0.0f);
     for(uint32_t c = 0;c < lines;++c)
-        for(uint32_t o = 0;o < d->desc.dry_channels;++o)
-            g[c*32 + o] = gains[c*d->desc.dry_channels + o];
+        for(uint32_t o = 0;o < width;++o)
+            g[c*32 + o] = gains[c*width + o];
     // a reverb's gains are those of its CURRENT pipeline object (update3DPanning, reverb.cpp:1293-1296)
     float *dst = d->h_slots[slot].gtgt + (reverb ? size_t(d->rv[slot].cur)*8*32 : 0);
     CUDA_TRY(d, cudaMemcpyAsync(dst, g.data(), g.size()*sizeof(float), cudaMemcpyHostToDevice, d->stream));
@@ -1492,21 +1541,35 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
                     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
                 }
             }
-            ReverbParamsK RP{};
-            RP.slots = d->d_slots; RP.wet = d->d_wet; RP.cubic = d->d_cubic_filter;
-            RP.frames = frames; RP.cw = dd.wet_channels;
-            k_reverb_process<<<dim3(dd.max_slots, 2), 128, 0, d->stream>>>(RP);
-            ++d->launches;
         }
-        k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
-        k_conv_mac<<<dim3(dd.max_slots, maxch), 512, 0, d->stream>>>(CP);
-        k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
         SlotMixParams SP{};
         SP.slots = d->d_slots; SP.dry = d->d_dry; SP.frames = frames; SP.cd = dd.dry_channels;
-        SP.num_slots = dd.max_slots;
-        k_slot_output_mix<<<dim3((frames + 127)/128, dd.dry_channels), 128, 0, d->stream>>>(SP);
+        SP.num_slots = dd.max_slots; SP.wet = d->d_wet; SP.cw = dd.wet_channels;
+        // one pass per stage of the slot graph (a single pass unless slots target other slots)
+        for(uint32_t st = 0;st < d->num_stages;++st)
+        {
+            if(d->reverb_slots)
+            {
+                ReverbParamsK RP{};
+                RP.slots = d->d_slots; RP.wet = d->d_wet; RP.cubic = d->d_cubic_filter;
+                RP.frames = frames; RP.cw = dd.wet_channels; RP.stage = st;
+                k_reverb_process<<<dim3(dd.max_slots, 2), 128, 0, d->stream>>>(RP);
+                ++d->launches;
+            }
+            CP.stage = st; SP.stage = st;
+            k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
+            k_conv_mac<<<dim3(dd.max_slots, maxch), 512, 0, d->stream>>>(CP);
+            k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
+            k_slot_output_mix<<<dim3((frames + 127)/128, dd.dry_channels), 128, 0, d->stream>>>(SP);
+            d->launches += 4;
+            if(d->any_target)
+            {
+                k_slot_target_mix<<<dim3((frames + 127)/128, dd.max_slots), 128, 0, d->stream>>>(SP);
+                ++d->launches;
+            }
+        }
         k_slot_gains_commit<<<dd.max_slots, 64, 0, d->stream>>>(SP);
-        d->launches += 5;
+        ++d->launches;
         CUDA_TRY(d, cudaGetLastError());
     }
 

@@ -30,7 +30,7 @@ struct SlotRec {
     uint32_t cur, fifo, nb_last, f_last;       // ring position, FIFO fill; last update's record
     uint32_t cur_last;
     uint32_t rv_cur, rv_mask;                  // reverb: current pipeline object; objects to run now
-    uint32_t pad2;
+    uint32_t stage;                            // processing stage: every slot runs before its target
     float *H;         // [channels][segs][256]  filter spectra (pre-scaled by 1/256)
     float *X;         // [segs+kConvMaxBlocks][256] input spectra ring (our own ring: long enough that
                       //                        a whole update's blocks never overwrite live history)
@@ -41,7 +41,7 @@ struct SlotRec {
     float *lines;     // [channels][1024]       this update's output lines
     float *gains;     // [2][channels][32]      ping-pong Current gains
     float *gtgt;      // [channels][32]         Target gains
-    uint32_t gsel, pad3;
+    uint32_t gsel, target;                     // target: slot whose Wet takes the output, or 0xffffffff (Dry)
 };
 
 // ---- send mix --------------------------------------------------------------------------
@@ -515,7 +515,7 @@ __device__ __forceinline__ void fft256_inplace(float2 *data, const float2 *__res
 
 struct ConvParams {
     SlotRec *slots; const float *wet; const float2 *twiddle;
-    uint32_t frames, cw, num_slots;
+    uint32_t frames, cw, num_slots, stage;
 };
 
 // grid = slots, 128 threads
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
     __shared__ float2 fbuf[kConvFft];
     __shared__ float hsm[kConvBlock];
     SlotRec &S = Q.slots[blockIdx.x];
-    if(S.type != 1u) return;
+    if(S.type != 1u || S.stage != Q.stage) return;
     const int t = threadIdx.x;
     const uint32_t n = Q.frames, f = S.fifo, cur = S.cur, ring = S.segs + kConvMaxBlocks;
     const uint32_t nb = (f + n) / kConvBlock;
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
     constexpr int NB = kConvMaxBlocks;
     __shared__ float2 part[3][NB][128];
     const SlotRec &S = Q.slots[blockIdx.x];
-    if(S.type != 1u || blockIdx.y >= S.channels) return;
+    if(S.type != 1u || S.stage != Q.stage || blockIdx.y >= S.channels) return;
     const uint32_t nb = S.nb_last;
     if(nb == 0) return;
     const int t = threadIdx.x & 127, grp = threadIdx.x >> 7;
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
     __shared__ float2 fbuf[kConvFft];
     __shared__ float first[kConvBlock], tail[kConvBlock];
     SlotRec &S = Q.slots[blockIdx.x];
-    if(S.type != 1u || blockIdx.y >= S.channels) return;
+    if(S.type != 1u || S.stage != Q.stage || blockIdx.y >= S.channels) return;
     const int t = threadIdx.x;
     const uint32_t c = blockIdx.y, n = Q.frames, nb = S.nb_last, f = S.f_last;
     float *ov = S.ov + size_t(c)*kConvFft;
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
 
 // Dry[o][i] += sum over slots/lines of line[i]*gain(i): MixSamples(Counter = samplesToDo)
 // (ConvolutionState::NormalMix, convolution.cpp:298-304), slots and lines in index order.
-struct SlotMixParams { SlotRec *slots; float *dry; uint32_t frames, cd, num_slots; };
+struct SlotMixParams { SlotRec *slots; float *dry; uint32_t frames, cd, num_slots, stage; float *wet; uint32_t cw; };
 
 __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
 {
@@ -759,7 +759,9 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
         if(threadIdx.x < cnt)
         {
             const SlotRec &S = Q.slots[sb + threadIdx.x];
-            uint32_t ch = (S.type == 0u) ? 0u : (S.channels < uint32_t(kMaxLines) ? S.channels : uint32_t(kMaxLines));
+            // only this stage's slots whose output goes to the Dry mix (no target slot)
+            uint32_t ch = (S.type == 0u || S.stage != Q.stage || S.target != 0xffffffffu) ? 0u
+                : (S.channels < uint32_t(kMaxLines) ? S.channels : uint32_t(kMaxLines));
             uint32_t first = 0u;
             if(S.type == 2u)
             {
@@ -767,7 +769,7 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
                 // pipeline is mixed first, then (while it rings out) the old one
                 // (ReverbState::process, reverb.cpp:1843-1877)
                 first = S.rv_cur*8u;
-                ch = (S.rv_mask == 3u) ? 16u : 8u;
+                if(ch) ch = (S.rv_mask == 3u) ? 16u : 8u;
             }
             s_ch[threadIdx.x] = ch;
             s_first[threadIdx.x] = first;
@@ -798,6 +800,40 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
         }
     }
     if(i < n) Q.dry[size_t(o)*kLine + i] = acc;
+}
+
+// Slots with a target slot (EffectSlotBase::Target): their output lines are mixed into the
+// target's Wet buffer before the target's stage runs.  grid (tile of 128 samples, target slot);
+// the sources of one target are added in slot order (deterministic).
+__global__ void __launch_bounds__(128) k_slot_target_mix(const SlotMixParams Q)
+{
+    const uint32_t t = blockIdx.y;
+    const uint32_t i = blockIdx.x*128u + threadIdx.x;
+    const uint32_t n = Q.frames;
+    if(i >= n) return;
+    const float delta = 1.0f/float(n);
+    for(uint32_t s = 0;s < Q.num_slots;++s)
+    {
+        const SlotRec &S = Q.slots[s];
+        if(S.type == 0u || S.stage != Q.stage || S.target != t) continue;
+        uint32_t ch = S.channels, first = 0u;
+        if(S.type == 2u) { first = S.rv_cur*8u; ch = (S.rv_mask == 3u) ? 16u : 8u; }
+        const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
+        for(uint32_t o = 0;o < Q.cw;++o)
+        {
+            float acc = Q.wet[(size_t(t)*Q.cw + o)*kLine + i];
+            for(uint32_t c = 0;c < ch;++c)
+            {
+                const uint32_t li = S.type == 2u ? ((c + first) & 15u) : c;
+                const float cg = gcur[li*32u + o], tg = S.gtgt[li*32u + o];
+                const float step = (tg - cg)*delta;
+                const float x = S.lines[size_t(li)*kLine + i];
+                if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
+                else if(fabsf(tg) > kSilence) acc += x*tg;
+            }
+            Q.wet[(size_t(t)*Q.cw + o)*kLine + i] = acc;
+        }
+    }
 }
 
 // Current <- Target for every slot line (the fade always completes: Counter == frames).
@@ -844,7 +880,7 @@ struct ReverbDev {
     float *main_d, *late_in, *early_ap, *early_d, *late_ap, *late_d;
 };
 
-struct ReverbParamsK { SlotRec *slots; const float *wet; const float *cubic; uint32_t frames, cw; };
+struct ReverbParamsK { SlotRec *slots; const float *wet; const float *cubic; uint32_t frames, cw, stage; };
 
 __device__ __forceinline__ void scatter4(const float in[4], float x, float y, float out[4])
 {
@@ -894,7 +930,7 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     __shared__ float temp[NL][MAXUPD];
     __shared__ uint32_t moddel[MAXUPD];
     SlotRec &S = Q.slots[blockIdx.x];
-    if(S.type != 2u || !((S.rv_mask >> blockIdx.y) & 1u)) return;
+    if(S.type != 2u || S.stage != Q.stage || !((S.rv_mask >> blockIdx.y) & 1u)) return;
     // blockIdx.y = pipeline object (ReverbState::mPipelines[2]); both share the main delay line,
     // each CTA writes this update's input into it itself (identical values) before reading it
     ReverbDev &R = reinterpret_cast<ReverbDev*>(S.H)[blockIdx.y];

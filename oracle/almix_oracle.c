@@ -227,6 +227,7 @@ typedef struct {
     uint32_t hist_pos;
     float *cur, *tgt;          /* output mix gains [channels][MAX_DRY] */
     oreverb *reverb;           /* type == B200MIX_EFFECT_REVERB */
+    uint32_t target;           /* EffectSlotBase::Target as a slot index, B200MIX_NO_SLOT = the Dry mix */
 } oslot;
 
 struct oracle_device {
@@ -277,6 +278,7 @@ int oracle_create(const b200mix_device_desc *desc, oracle_device **out)
     size_t nwet = (size_t)desc->max_slots*desc->wet_channels;
     d->wet = calloc(nwet ? nwet : 1, sizeof(float[LINE]));
     d->slots = calloc(desc->max_slots ? desc->max_slots : 1, sizeof(oslot));
+    if(d->slots) for(uint32_t i = 0;i < (desc->max_slots ? desc->max_slots : 1);++i) d->slots[i].target = B200MIX_NO_SLOT;
     *out = d;
     return B200MIX_OK;
 }
@@ -339,7 +341,9 @@ int oracle_slot_disable(oracle_device *d, uint32_t slot)
     oslot *s = &d->slots[slot];
     free(s->ir); free(s->hist); free(s->cur); free(s->tgt);
     oreverb_destroy(s->reverb);
+    const uint32_t target = s->target;       /* the target belongs to the slot, not to its effect */
     memset(s, 0, sizeof(*s));
+    s->target = target;
     return B200MIX_OK;
 }
 
@@ -352,6 +356,18 @@ int oracle_slot_reverb(oracle_device *d, uint32_t slot, const b200mix_reverb_par
     s->reverb = oreverb_create(params);
     if(!s->reverb) return B200MIX_ERR_NOMEM;
     s->type = B200MIX_EFFECT_REVERB; s->channels = 8;
+    return B200MIX_OK;
+}
+
+/* EffectSlotBase::Target (AL_EFFECTSLOT_TARGET_SOFT): the slot's output feeds `target`'s Wet
+ * buffer instead of the Dry mix.  Chains must be acyclic (al/auxeffectslot.cpp rejects loops). */
+int oracle_slot_target(oracle_device *d, uint32_t slot, uint32_t target)
+{
+    if(slot >= d->desc.max_slots || (target != B200MIX_NO_SLOT && target >= d->desc.max_slots))
+        return B200MIX_ERR_INVALID;
+    for(uint32_t t = target, hops = 0;t != B200MIX_NO_SLOT;t = d->slots[t].target)
+        if(t == slot || ++hops > d->desc.max_slots) return B200MIX_ERR_INVALID;
+    d->slots[slot].target = target;
     return B200MIX_OK;
 }
 
@@ -386,14 +402,16 @@ int oracle_slot_output_gains(oracle_device *d, uint32_t slot, uint32_t lines, co
     if(slot >= d->desc.max_slots || !d->slots[slot].type || lines != d->slots[slot].channels)
         return B200MIX_ERR_INVALID;
     oslot *s = &d->slots[slot];
+    /* gains address the slot's output target: the Dry mix or the target slot's Wet mix */
+    const uint32_t width = s->target != B200MIX_NO_SLOT ? d->desc.wet_channels : d->desc.dry_channels;
     if(s->type == B200MIX_EFFECT_REVERB)
     {
-        oreverb_set_gains(s->reverb, gains, d->desc.dry_channels);
+        oreverb_set_gains(s->reverb, gains, width);
         return B200MIX_OK;
     }
     for(uint32_t c = 0;c < lines;++c)
-        for(uint32_t o = 0;o < d->desc.dry_channels;++o)
-            s->tgt[c*B200MIX_MAX_DRY_CHANNELS + o] = gains[c*d->desc.dry_channels + o];
+        for(uint32_t o = 0;o < width;++o)
+            s->tgt[c*B200MIX_MAX_DRY_CHANNELS + o] = gains[c*width + o];
     return B200MIX_OK;
 }
 
@@ -1355,10 +1373,15 @@ static void post_uhj(oracle_device *d, size_t n)
 }
 
 /* MixSamples(line, Dry, Current, Target, Counter = n): ReverbState::MixOutPlain */
+/* mOutTarget of the slot being processed (alc/alu.cpp:626-633): the Dry mix or the target
+ * slot's Wet buffer */
+static float (*g_out_buf)[LINE];
+static size_t g_out_channels;
+
 static void reverb_mix_cb(void *ctx, const float *in, size_t n, float *cur, const float *tgt)
 {
-    oracle_device *d = ctx;
-    mix_samples(in, n, d->dry, d->desc.dry_channels, cur, tgt, n);
+    (void)ctx;
+    mix_samples(in, n, g_out_buf, g_out_channels, cur, tgt, n);
 }
 
 /* ConvolutionState::process + NormalMix (alc/effects/convolution.cpp:623-714,298-304):
@@ -1389,7 +1412,7 @@ static void slot_convolution_process(oracle_device *d, oslot *s, const float *in
             }
             d->temp[i] = (float)acc;
         }
-        mix_samples(d->temp, n, d->dry, d->desc.dry_channels, s->cur + c*B200MIX_MAX_DRY_CHANNELS,
+        mix_samples(d->temp, n, g_out_buf, g_out_channels, s->cur + c*B200MIX_MAX_DRY_CHANNELS,
             s->tgt + c*B200MIX_MAX_DRY_CHANNELS, n);
     }
 }
@@ -1428,8 +1451,53 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
     d->mid_frames = 0;
     /* EffectState::process for every slot (alc/alu.cpp:2252-2256); slots here have no
      * slot targets, so each mixes straight into Dry (mOutTarget, alc/alu.cpp:626-633). */
-    for(uint32_t si = 0;si < dd->max_slots;++si)
+    /* Slot order (alc/alu.cpp:2211-2251): slots without a target last, in their own order;
+     * before them the slots targeting those, and so on — a slot always runs before its target.
+     * sorted[] is filled from the back exactly like the reference's partition passes. */
+    uint32_t sorted[256], nsl = 0, split;
     {
+        uint32_t act[256], na = 0;
+        for(uint32_t si = 0;si < dd->max_slots && na < 256;++si) if(d->slots[si].type) act[na++] = si;
+        nsl = na;
+        /* partition_copy over the REVERSED list: targeted-away slots to the front (in reverse
+         * order), the rest to the back in original order */
+        uint32_t front = 0, back = na;
+        for(uint32_t k = na;k-- > 0;)
+        {
+            if(d->slots[act[k]].target != B200MIX_NO_SLOT) sorted[front++] = act[k];
+            else sorted[--back] = act[k];
+        }
+        /* partition_copy writes the no-target ones through a reverse iterator while walking the
+         * source backwards: they end up in original order */
+        split = front;
+        uint32_t next_target = na;
+        while(split > 1)
+        {
+            if(next_target == split) break;
+            --next_target;
+            /* std::partition(begin, split, not_next): elements NOT targeting sorted[next_target]
+             * first; the unstable order of std::partition only matters for slots of one level,
+             * which are independent of each other except for float summation order into a
+             * shared target — we keep the relative order (stable) */
+            uint32_t tmp[256], a = 0, b = 0, hold[256];
+            for(uint32_t k = 0;k < split;++k)
+            {
+                if(d->slots[sorted[k]].target != sorted[next_target]) tmp[a++] = sorted[k];
+                else hold[b++] = sorted[k];
+            }
+            for(uint32_t k = 0;k < b;++k) tmp[a+k] = hold[k];
+            memcpy(sorted, tmp, sizeof(uint32_t)*split);
+            split = a;
+        }
+    }
+    for(uint32_t k = 0;k < nsl;++k)
+    {
+        const uint32_t si = sorted[k];
+        const uint32_t tg = d->slots[si].target;
+        if(tg != B200MIX_NO_SLOT)
+        { g_out_buf = d->wet + (size_t)tg*dd->wet_channels; g_out_channels = dd->wet_channels; }
+        else
+        { g_out_buf = d->dry; g_out_channels = dd->dry_channels; }
         if(d->slots[si].type == B200MIX_EFFECT_CONVOLUTION)
             slot_convolution_process(d, &d->slots[si], d->wet[(size_t)si*dd->wet_channels], frames);
         else if(d->slots[si].type == B200MIX_EFFECT_REVERB)

@@ -402,6 +402,22 @@ void refh_mono_line_gains(ALCdevice *adev, float slot_gain, float *out)
 }
 
 /* HrtfAccumData as [1024+128][2]. */
+/* As refh_mono_line_gains, but panned into active slot `target_idx`'s Wet mix (a slot whose
+ * EffectSlotBase::Target is that slot, alc/alu.cpp:626-633).  out has wet_channels entries. */
+int refh_mono_line_gains_slot(ALCcontext *actx, int target_idx, float slot_gain, float *out)
+{
+    auto *arr = ctx_of(actx)->mActiveAuxSlots.load(std::memory_order_acquire);
+    if(!arr || target_idx < 0 || size_t(target_idx) >= (arr->size()>>1)) return -1;
+    auto *tslot = (*arr)[size_t(target_idx)];
+    const auto pos = std::array{0.0f, 0.0f, -1.0f};
+    const auto coeffs = CalcDirectionCoeffs(pos, 0.0f);
+    auto gains = std::array<float, MaxAmbiChannels>{};
+    ComputePanGains(&tslot->Wet, coeffs, slot_gain, gains);
+    for(auto c = 0_uz;c < tslot->Wet.Buffer.size() && c < MaxAmbiChannels;++c)
+        out[c] = gains[c];
+    return int(tslot->Wet.Buffer.size());
+}
+
 void refh_get_hrtf_accum(ALCdevice *adev, float *out)
 {
     auto *dev = dev_of(adev);

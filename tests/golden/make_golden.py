@@ -75,6 +75,9 @@ SCENES = {
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
+    # slot chaining (AL_EFFECTSLOT_TARGET_SOFT): a convolution slot feeding a reverb slot; even voices
+    # send to the convolution, odd ones straight to the reverb
+    "hrtf_spline_chain_v6": (6, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "chain"),
     # sources that MOVE between updates (a new position for half of them before every render):
     # MixHrtfBlend with really different old/new HRIRs and delays, gain ramps of Mix_ (per-update
     # voice parameter snapshots are replayed); 20 updates, also the ">= 16 consecutive updates"
@@ -190,6 +193,13 @@ def run_scene(name):
         for src in ref.sources:
             ref.al.alSourcei(src, 0x2000B, 0)      # AL_AUXILIARY_SEND_FILTER_GAIN_AUTO
             ref.al.alSourcei(src, 0x2000C, 0)      # AL_AUXILIARY_SEND_FILTER_GAINHF_AUTO
+    chain = len(spec) > 11 and spec[11] == "chain"
+    if chain:
+        slot_a = ref.add_convolution_slot(conv_ir(600), 48000, 0.5)
+        slot_b = ref.add_reverb_slot(props={0x0006: 0.8})
+        ref.set_slot_target(slot_a, slot_b)
+        for i, src in enumerate(ref.sources):
+            ref.connect_send(src, slot_a if i % 2 == 0 else slot_b)
     script = FILTER_SCRIPTS[spec[10]] if len(spec) > 10 and spec[10] else None
     if script:
         apply_filter_script(ref, script, 0, slot)
@@ -202,7 +212,7 @@ def run_scene(name):
     outs = []
     snap = None
     filt_meta, filt_coef = [], []
-    nslots, wet = ref.slot_info() if (taps or rvprops is not None) else (0, [])
+    nslots, wet = ref.slot_info() if (taps or rvprops is not None or chain) else (0, [])
     for u in range(U):
         if script and u:
             apply_filter_script(ref, script, u, slot)
@@ -251,6 +261,14 @@ def run_scene(name):
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))
     if queue:
         res.update(queue_lens=np.array(QUEUE_LENS, dtype=np.int64))
+    if chain:
+        # which active-slot index carries the reverb (the other one is the convolution)
+        b_idx = 0 if ref.try_reverb(0) else 1
+        rvp_c, rvg_c, _ = ref.reverb_params(b_idx)
+        res.update(chain_conv_idx=np.int64(1 - b_idx), chain_reverb_idx=np.int64(b_idx), conv_taps_chain=np.int64(600),
+                   chain_conv_gains=ref.mono_line_gains_slot(b_idx, 0.5),
+                   chain_reverb_params=np.frombuffer(bytes(rvp_c), dtype=np.uint8).copy(), chain_reverb_gains=rvg_c,
+                   send=snap[4][:V].copy(), wet_channels=np.int64(wet[0]))
     if moving:
         res.update(mv_params=np.stack([x[0] for x in mv_steps]), mv_coeffs=np.stack([x[1] for x in mv_steps]),
                    mv_dry=np.stack([x[2] for x in mv_steps]))

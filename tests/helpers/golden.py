@@ -30,8 +30,12 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
     desc.max_slots = 0
     taps = int(fx["conv_taps"]) if "conv_taps" in fx else 0
     reverb = "reverb_params" in fx
+    chain = "chain_conv_idx" in fx
     if taps or reverb:
         desc.max_slots = 1
+        desc.wet_channels = int(fx["wet_channels"])
+    if chain:
+        desc.max_slots = 2
         desc.wet_channels = int(fx["wet_channels"])
     dev = MixDevice(mixlib, desc)
     try:
@@ -64,6 +68,14 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
         if reverb:
             dev.slot_reverb(0, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                             fx["reverb_gains"])
+        if chain:
+            a, b = int(fx["chain_conv_idx"]), int(fx["chain_reverb_idx"])
+            dev.slot_target(a, b)
+            n600 = int(fx["conv_taps_chain"])
+            rng = np.random.default_rng(n600)      # make_golden.py:conv_ir
+            ir = (rng.standard_normal(n600) * np.exp(-np.arange(n600) / (n600 / 5.0)) * 0.05).astype(np.float32)
+            dev.slot_convolution(a, ir[None, :], fx["chain_conv_gains"][None, :])
+            dev.slot_reverb(b, abi.reverb_params_from(fx["chain_reverb_params"].tobytes()), fx["chain_reverb_gains"])
         params = (abi.VoiceParams * V).from_buffer_copy(fx["params"].tobytes())
         plist = []
         for k in range(V):
@@ -93,7 +105,7 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             plist = both
             coeffs = np.stack([fx["coeffs"], fx["coeffs_c1"]], axis=1).reshape((2 * V,) + fx["coeffs"].shape[1:])
             dry = np.stack([fx["dry"], fx["dry_c1"]], axis=1).reshape((2 * V,) + fx["dry"].shape[1:])
-        dev.voices_update(plist, coeffs, dry, fx["send"] if (taps or reverb) else None)
+        dev.voices_update(plist, coeffs, dry, fx["send"] if (taps or reverb or chain) else None)
         if qlens:
             for k in range(V):
                 ids = [k * len(qlens) + j for j in range(len(qlens))]

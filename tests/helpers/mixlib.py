@@ -47,6 +47,8 @@ class MixLib:
         self.slot_reverb.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams)]
         self.slot_reverb_update = f("slot_reverb_update")
         self.slot_reverb_update.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.ReverbParams), C.c_uint32]
+        self.slot_target = f("slot_target")
+        self.slot_target.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         self.slot_disable = f("slot_disable")
         self.slot_disable.argtypes = [C.c_void_p, C.c_uint32]
         self.voices_filters = f("voices_filters")
@@ -117,6 +119,10 @@ class MixDevice:
         assert rc == 0, rc
         gains = np.ascontiguousarray(gains, dtype=np.float32)
         rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)
+        assert rc == 0, rc
+
+    def slot_target(self, slot, target):
+        rc = self.m.slot_target(self.h, slot, target)
         assert rc == 0, rc
 
     def slot_reverb_update(self, slot, params, full, gains):

@@ -140,6 +140,7 @@ def libs(conf_text: str | None = None):
     hz.refh_slot_count.argtypes = [C.c_void_p]
     hz.refh_slot_wet_channels.argtypes = [C.c_void_p, C.c_int]
     hz.refh_mono_line_gains.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    hz.refh_mono_line_gains_slot.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
     hz.refh_dither_depth.argtypes = [C.c_void_p]
     hz.refh_dither_depth.restype = C.c_float
     hz.refh_set_snapshot_channel.argtypes = [C.c_int]
@@ -348,6 +349,18 @@ class RefDevice:
                 counters.append((cnt[2 * p], cnt[2 * p + 1]))
         return out, counters
 
+    def try_reverb(self, idx: int) -> bool:
+        """True if active slot idx holds a reverb."""
+        if not hasattr(self, "_rv"):
+            self.reverb_params.__func__  # noqa: B018  (make sure the attribute exists)
+            self._rv = C.CDLL(os.path.join(REF_DIR, "libref_reverb_tap.so"))
+            self._rv.refh_reverb_params.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.ReverbParams),
+                                                    C.c_void_p, C.POINTER(C.c_int)]
+        p = abi.ReverbParams()
+        gains = np.zeros((8, abi.MAX_WET), dtype=np.float32)
+        st = C.c_int(0)
+        return self._rv.refh_reverb_params(self.ctx, idx, C.byref(p), gains.ctypes.data, C.byref(st)) == 0
+
     def connect_send(self, source: int, slot: int, send: int = 0, filt: int = AL_FILTER_NULL):
         self.al.alSource3i(source, AL_AUXILIARY_SEND_FILTER, slot, send, filt)
         err = self.al.alGetError()
@@ -355,6 +368,17 @@ class RefDevice:
 
     def dither_depth(self) -> float:
         return float(self.hz.refh_dither_depth(self.dev))
+
+    def set_slot_target(self, slot: int, target: int):
+        self.al.alAuxiliaryEffectSloti(slot, 0x199C, target)      # AL_EFFECTSLOT_TARGET_SOFT
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} setting slot target"
+
+    def mono_line_gains_slot(self, target_idx: int, slot_gain: float) -> np.ndarray:
+        out = np.zeros(abi.MAX_WET, dtype=np.float32)
+        n = self.hz.refh_mono_line_gains_slot(self.ctx, target_idx, slot_gain, out.ctypes.data)
+        assert n > 0, n
+        return out[:n].copy()
 
     def slot_info(self):
         n = self.hz.refh_slot_count(self.ctx)
