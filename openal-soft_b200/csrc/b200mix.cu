@@ -54,8 +54,9 @@ struct b200mix_device {
     std::vector<BufferRec> h_buffers;
     float2 *d_hrtf_tgt{nullptr}, *d_hrtf_old{nullptr};
     float *d_dry_cur{nullptr}, *d_dry_tgt{nullptr}, *d_send_cur{nullptr}, *d_send_tgt{nullptr};
-    VoiceResult *d_results{nullptr};
-    b200mix_voice_result *h_results{nullptr};     // pinned
+    VoiceResult *d_results{nullptr};              // inside d_outblock
+    b200mix_voice_result *h_results{nullptr};     // inside h_outblock (pinned)
+    char *d_outblock{nullptr}, *h_outblock{nullptr}; size_t out_real_bytes{0};
 
     // mix buffers
     uint32_t dry_alloc_ch{0};
@@ -76,10 +77,8 @@ struct b200mix_device {
     float *d_uhj_state{nullptr}, *d_uhj_scratch{nullptr};
 
     // update staging (pinned host + device)
-    VoiceUpdate *h_upd{nullptr}, *d_upd{nullptr};
-    float *h_coef{nullptr}, *d_coef{nullptr};
-    float *h_dryg{nullptr}, *d_dryg{nullptr};
-    float *h_sendg{nullptr}, *d_sendg{nullptr};
+    char *h_arena{nullptr}, *d_arena{nullptr};    // staging arena (see ensure_stage)
+    VoiceUpdate *h_upd{nullptr};                  // == h_arena
     uint32_t stage_cap{0};
     cudaEvent_t stage_done{nullptr};
     bool stage_busy{false};
@@ -229,6 +228,11 @@ int ensure_dry_park(b200mix_device *d)
     return B200MIX_OK;
 }
 
+// One pinned + one device staging arena for b200mix_voices_update: a call packs
+// [VoiceUpdate n][coefficients or directions][dry gains][send gains] back to back (16-byte
+// aligned parts) and ships them with ONE host-to-device copy.
+static size_t align16(size_t v) { return (v + 15u) & ~size_t(15); }
+
 int ensure_stage(b200mix_device *d, uint32_t n)
 {
     if(n <= d->stage_cap) return B200MIX_OK;
@@ -236,32 +240,17 @@ int ensure_stage(b200mix_device *d, uint32_t n)
     if(d->stage_cap)
     {
         cudaStreamSynchronize(d->stream);
-        cudaFreeHost(d->h_upd); cudaFree(d->d_upd);
-        cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
-        cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg);
-        cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
-        d->h_upd = nullptr; d->h_coef = d->h_dryg = d->h_sendg = nullptr;
-        d->d_upd = nullptr; d->d_coef = d->d_dryg = d->d_sendg = nullptr;
+        cudaFreeHost(d->h_arena); cudaFree(d->d_arena);
+        d->h_arena = nullptr; d->d_arena = nullptr;
     }
     const uint32_t cap = std::max<uint32_t>(n, 256u);
-    CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_upd), cap*sizeof(VoiceUpdate)));
-    CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_upd), cap*sizeof(VoiceUpdate)));
-    if(dd.ir_size)
-    {
-        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_coef), size_t(cap)*dd.ir_size*2*sizeof(float)));
-        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_coef), size_t(cap)*dd.ir_size*2*sizeof(float)));
-    }
-    if(dd.dry_channels)
-    {
-        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_dryg), size_t(cap)*dd.dry_channels*sizeof(float)));
-        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_dryg), size_t(cap)*dd.dry_channels*sizeof(float)));
-    }
-    if(dd.num_sends && dd.wet_channels)
-    {
-        const size_t per = size_t(dd.num_sends)*dd.wet_channels;
-        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_sendg), cap*per*sizeof(float)));
-        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_sendg), cap*per*sizeof(float)));
-    }
+    const size_t bytes = align16(size_t(cap)*sizeof(VoiceUpdate))
+        + align16(size_t(cap)*std::max<size_t>(size_t(dd.ir_size)*2, 4)*sizeof(float))
+        + align16(size_t(cap)*dd.dry_channels*sizeof(float))
+        + align16(size_t(cap)*dd.num_sends*dd.wet_channels*sizeof(float)) + 64;
+    CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_arena), bytes));
+    CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_arena), bytes));
+    d->h_upd = reinterpret_cast<VoiceUpdate*>(d->h_arena);
     d->stage_cap = cap;
     return B200MIX_OK;
 }
@@ -352,13 +341,10 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
             if(int rc = dev_alloc(d, d->d_send_cur, dd.max_voices*per)) return rc;
             if(int rc = dev_alloc(d, d->d_send_tgt, dd.max_voices*per)) return rc;
         }
-        if(int rc = dev_alloc(d, d->d_results, dd.max_voices)) return rc;
         if(int rc = dev_alloc(d, d->d_order, dd.max_voices)) return rc;
         d->h_active.assign(dd.max_voices, 0);
         d->h_cost.assign(dd.max_voices, 0);
         d->h_hrtf.assign(dd.max_voices, 0);
-        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_results),
-            size_t(dd.max_voices)*sizeof(b200mix_voice_result)));
 
         // launch variant
         const bool hrtfDev = dd.ir_size > 0;
@@ -372,8 +358,23 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
 
         d->dry_alloc_ch = std::max<uint32_t>(std::max(dd.dry_channels, 1u), uint32_t(var.cdr));
         if(int rc = dev_alloc(d, d->d_dry, size_t(d->dry_alloc_ch)*kLine)) return rc;
-        if(dd.post_process == B200MIX_POST_NONE) d->d_real = d->d_dry;
-        else if(int rc = dev_alloc(d, d->d_real, size_t(std::max(dd.real_channels, 1u))*kLine)) return rc;
+        // RealOut and the voice results share one block (and one pinned mirror): a render that
+        // returns both needs ONE device-to-host copy
+        {
+            const size_t realFloats = size_t(std::max(dd.real_channels, 1u))*kLine;
+            static_assert(sizeof(VoiceResult) == 16 && sizeof(b200mix_voice_result) == 16, "result layout");
+            const size_t blockBytes = realFloats*sizeof(float) + size_t(dd.max_voices)*sizeof(VoiceResult);
+            char *blk = nullptr;
+            if(int rc = dev_alloc(d, blk, blockBytes)) return rc;
+            d->d_outblock = blk;
+            d->d_results = reinterpret_cast<VoiceResult*>(blk + realFloats*sizeof(float));
+            CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_outblock), blockBytes));
+            d->h_real = reinterpret_cast<float*>(d->h_outblock);
+            d->h_results = reinterpret_cast<b200mix_voice_result*>(d->h_outblock + realFloats*sizeof(float));
+            d->out_real_bytes = realFloats*sizeof(float);
+            if(dd.post_process == B200MIX_POST_NONE) d->d_real = d->d_dry;
+            else d->d_real = reinterpret_cast<float*>(blk);
+        }
         if(dd.max_slots && dd.wet_channels)
             if(int rc = dev_alloc(d, d->d_wet, size_t(dd.max_slots)*dd.wet_channels*kLine)) return rc;
         const size_t maxRows = size_t(d->num_sms)*d->mix_blocks_per_sm;
@@ -383,8 +384,6 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         if(int rc = dev_alloc(d, d->d_accum_sum, 2*kAccumLen)) return rc;
         if(int rc = dev_alloc(d, d->d_carry[0], 2*kHrirLen)) return rc;
         if(int rc = dev_alloc(d, d->d_carry[1], 2*kHrirLen)) return rc;
-        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_real),
-            size_t(std::max(dd.real_channels, 1u))*kLine*sizeof(float)));
         if(int rc = dev_alloc(d, d->d_temp, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
         if(int rc = dev_alloc(d, d->d_temp2, size_t(std::max(dd.dry_channels, 1u))*kLine)) return rc;
         if(dd.max_slots && dd.wet_channels && dd.num_sends)
@@ -441,10 +440,9 @@ void b200mix_destroy(b200mix_device *d)
     for(int i = 0;i < 2;++i) cudaFree(d->d_cubic[i]);
     cudaFree(d->d_voices); cudaFree(d->d_buffers); cudaFree(d->d_hrtf_tgt); cudaFree(d->d_hrtf_old);
     cudaFree(d->d_dry_cur); cudaFree(d->d_dry_tgt); cudaFree(d->d_send_cur); cudaFree(d->d_send_tgt);
-    cudaFree(d->d_results); cudaFreeHost(d->h_results); cudaFree(d->d_order);
-    if(d->d_real != d->d_dry) cudaFree(d->d_real);
+    cudaFree(d->d_outblock); cudaFreeHost(d->h_outblock); cudaFree(d->d_order);
     cudaFree(d->d_dry); cudaFree(d->d_wet); cudaFree(d->d_partial); cudaFree(d->d_accum_sum);
-    cudaFree(d->d_carry[0]); cudaFree(d->d_carry[1]); cudaFreeHost(d->h_real);
+    cudaFree(d->d_carry[0]); cudaFree(d->d_carry[1]);
     cudaFree(d->d_dec_coef); cudaFree(d->d_dec_hfscale); cudaFree(d->d_dec_state);
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
@@ -461,8 +459,7 @@ void b200mix_destroy(b200mix_device *d)
     if(d->h_fupd) cudaFreeHost(d->h_fupd);
     if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
-    cudaFreeHost(d->h_upd); cudaFree(d->d_upd); cudaFreeHost(d->h_coef); cudaFree(d->d_coef);
-    cudaFreeHost(d->h_dryg); cudaFree(d->d_dryg); cudaFreeHost(d->h_sendg); cudaFree(d->d_sendg);
+    cudaFreeHost(d->h_arena); cudaFree(d->d_arena);
     if(d->stage_done) cudaEventDestroy(d->stage_done);
     if(d->ev_mix0) cudaEventDestroy(d->ev_mix0);
     if(d->ev_mix1) cudaEventDestroy(d->ev_mix1);
@@ -1018,38 +1015,28 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
         if((p.flags & B200MIX_VF_RESET) && !d->h_dfilt.empty() && d->h_dfilt[p.voice])
         { d->h_dfilt[p.voice] = 0; d->order2_dirty = true; }
     }
-    CUDA_TRY(d, cudaMemcpyAsync(d->d_upd, d->h_upd, n*sizeof(VoiceUpdate), cudaMemcpyHostToDevice, d->stream));
     ApplyParams A{};
-    A.voices = d->d_voices; A.updates = d->d_upd;
+    A.voices = d->d_voices; A.updates = reinterpret_cast<const VoiceUpdate*>(d->d_arena);
+    size_t off = align16(size_t(n)*sizeof(VoiceUpdate));
+    auto pack = [&](const float *src, size_t count) -> const float* {
+        std::memcpy(d->h_arena + off, src, count*sizeof(float));
+        const float *dev = reinterpret_cast<const float*>(d->d_arena + off);
+        off += align16(count*sizeof(float));
+        return dev;
+    };
     if(dirs && dd.ir_size)
     {
-        std::memcpy(d->h_coef, dirs, size_t(n)*4*sizeof(float));
-        CUDA_TRY(d, cudaMemcpyAsync(d->d_coef, d->h_coef, size_t(n)*4*sizeof(float), cudaMemcpyHostToDevice, d->stream));
-        A.dirs = reinterpret_cast<const float4*>(d->d_coef);
+        A.dirs = reinterpret_cast<const float4*>(pack(dirs, size_t(n)*4));
         A.st_fields = d->d_st_fields; A.st_elevs = d->d_st_elevs; A.st_coeffs = d->d_st_coeffs;
         A.st_delays = d->d_st_delays; A.st_num_fields = d->st_num_fields; A.st_ir = d->st_ir;
     }
     else if(hrtf_coeffs && dd.ir_size)
-    {
-        const size_t cnt = size_t(n)*dd.ir_size*2;
-        std::memcpy(d->h_coef, hrtf_coeffs, cnt*sizeof(float));
-        CUDA_TRY(d, cudaMemcpyAsync(d->d_coef, d->h_coef, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
-        A.coeffs = d->d_coef;
-    }
+        A.coeffs = pack(hrtf_coeffs, size_t(n)*dd.ir_size*2);
     if(dry_gains && dd.dry_channels)
-    {
-        const size_t cnt = size_t(n)*dd.dry_channels;
-        std::memcpy(d->h_dryg, dry_gains, cnt*sizeof(float));
-        CUDA_TRY(d, cudaMemcpyAsync(d->d_dryg, d->h_dryg, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
-        A.dry = d->d_dryg;
-    }
+        A.dry = pack(dry_gains, size_t(n)*dd.dry_channels);
     if(send_gains && dd.num_sends && dd.wet_channels)
-    {
-        const size_t cnt = size_t(n)*dd.num_sends*dd.wet_channels;
-        std::memcpy(d->h_sendg, send_gains, cnt*sizeof(float));
-        CUDA_TRY(d, cudaMemcpyAsync(d->d_sendg, d->h_sendg, cnt*sizeof(float), cudaMemcpyHostToDevice, d->stream));
-        A.send = d->d_sendg;
-    }
+        A.send = pack(send_gains, size_t(n)*dd.num_sends*dd.wet_channels);
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_arena, d->h_arena, off, cudaMemcpyHostToDevice, d->stream));
     A.hrtf_tgt = d->d_hrtf_tgt; A.hrtf_old = d->d_hrtf_old;
     A.dry_cur = d->d_dry_cur; A.dry_tgt = d->d_dry_tgt;
     A.send_cur = d->d_send_cur; A.send_tgt = d->d_send_tgt;
@@ -1641,13 +1628,20 @@ static int render_collect(b200mix_device *d, uint32_t frames, float *const *real
     b200mix_voice_result *results)
 {
     const b200mix_device_desc &dd = d->desc;
-    if(real_out)
-        CUDA_TRY(d, cudaMemcpyAsync(d->h_real, d->d_real, size_t(dd.real_channels)*kLine*sizeof(float),
-            cudaMemcpyDeviceToHost, d->stream));
     const uint32_t nv = std::max(d->voice_hi, 1u);
-    if(results)
-        CUDA_TRY(d, cudaMemcpyAsync(d->h_results, d->d_results, size_t(nv)*sizeof(VoiceResult),
+    const bool contiguous = d->d_real == reinterpret_cast<float*>(d->d_outblock);
+    if(real_out && results && contiguous)
+        CUDA_TRY(d, cudaMemcpyAsync(d->h_outblock, d->d_outblock, d->out_real_bytes + size_t(nv)*sizeof(VoiceResult),
             cudaMemcpyDeviceToHost, d->stream));
+    else
+    {
+        if(real_out)
+            CUDA_TRY(d, cudaMemcpyAsync(d->h_real, d->d_real, size_t(dd.real_channels)*kLine*sizeof(float),
+                cudaMemcpyDeviceToHost, d->stream));
+        if(results)
+            CUDA_TRY(d, cudaMemcpyAsync(d->h_results, d->d_results, size_t(nv)*sizeof(VoiceResult),
+                cudaMemcpyDeviceToHost, d->stream));
+    }
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     d->stage_busy = false;
     if(real_out)
