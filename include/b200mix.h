@@ -166,13 +166,20 @@ typedef struct b200mix_reverb_params {
     uint32_t late_ap_offset[4];   /* mLate.VecAp.Offset */
     uint32_t fade_samples;        /* mFadeSampleCount of this pipeline: how long it keeps ringing
                                      out once a later full update has replaced it */
+    /* MixOutAmbiUp (reverb.cpp:658-699), used when the device mixes above first order
+     * (ReverbState::mUpmixOutput, :834-850): the A-format lines are first turned into four
+     * B-format rows (EarlyA2B/LateA2B), each row's HF band is scaled for the device order by a
+     * BandSplitter, and the 8 output gain rows then pan those B-format rows. */
+    uint32_t upmix;               /* mUpmixOutput */
+    float    order_scale[2];      /* mOrderScales[0], [1] */
+    float    splitter_coeff;      /* mAmbiSplitter[*][*].mCoeff */
 } b200mix_reverb_params;
 
 /* ReverbState::deviceUpdate + the first (full) update: allocates and clears the delay
  * lines of both pipelines and installs the parameters.  Output mix gains (8 lines: 4 early
  * then 4 late, EarlyReflections::Gains / LateReverb::Gains) go through
  * b200mix_slot_output_gains and always address the CURRENT pipeline.
- * Only the plain output path (MixOutPlain, device ambisonic order 1) is implemented. */
+ * Both output paths are implemented: MixOutPlain (first-order devices) and MixOutAmbiUp. */
 B200MIX_API int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot,
     const b200mix_reverb_params *params);
 /* A later ReverbState::update (alc/effects/reverb.cpp:1222-1351) on an installed reverb.

@@ -132,6 +132,7 @@ struct b200mix_device {
     std::vector<RvHost> rv;
     std::vector<uint32_t> h_target;          // EffectSlotBase::Target per slot (NO_SLOT = Dry)
     uint32_t num_stages{1}; bool any_target{false};
+    bool reverb_upmix{false};                // some reverb slot uses MixOutAmbiUp
     bool mid_render{false}; uint32_t mid_frames{0};   // between render_begin and render_end
     bool real_overwrite{false};
     // parked dry bus (kernel variants without register dry accumulators)
@@ -721,6 +722,8 @@ static void reverb_fill_params(ReverbDev &h, const b200mix_reverb_params *p)
     std::memcpy(h.t60_hf, p->t60_hf, sizeof(h.t60_hf)); std::memcpy(h.t60_lf, p->t60_lf, sizeof(h.t60_lf));
     h.mod_step = p->mod_step; h.mod_depth = p->mod_depth; h.late_ap_coeff = p->late_ap_coeff;
     std::memcpy(h.late_ap_offset, p->late_ap_offset, sizeof(h.late_ap_offset));
+    h.upmix = p->upmix ? 1u : 0u; h.order_scale[0] = p->order_scale[0]; h.order_scale[1] = p->order_scale[1];
+    h.split_coeff = p->splitter_coeff;
 }
 
 static int reverb_check_params(b200mix_device *d, const b200mix_reverb_params *p)
@@ -753,6 +756,7 @@ static int reverb_clear_pipeline(b200mix_device *d, uint32_t slot, int obj)
     h.early_tap_coeff = 0.0f; h.mod_step = 1u; h.mod_depth = 0.0f;
     std::memset(h.z_lp, 0, sizeof(h.z_lp)); std::memset(h.z_hp, 0, sizeof(h.z_hp));
     std::memset(h.z_t60hf, 0, sizeof(h.z_t60hf)); std::memset(h.z_t60lf, 0, sizeof(h.z_t60lf));
+    std::memset(h.z_split, 0, sizeof(h.z_split));
     std::memset(h.early_tap_cur, 0, sizeof(h.early_tap_cur)); std::memset(h.late_tap_cur, 0, sizeof(h.late_tap_cur));
     h.early_coeff_cur = 0.0f; h.mod_index = 0u; h.offset = R.offset;
     CUDA_TRY(d, cudaMemcpyAsync(R.dev + obj, &h, sizeof(ReverbDev), cudaMemcpyHostToDevice, d->stream));
@@ -804,6 +808,12 @@ int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_p
     // deviceUpdate leaves DeviceClear; the first update is a full one: it switches to pipeline
     // object 1 and goes straight to Normal (reverb.cpp:1243-1280)
     R.used = true; R.cur = 1; R.state = 4; R.offset = 0;
+    if(p->upmix)
+    {
+        d->reverb_upmix = true;
+        CUDA_TRY(d, cudaFuncSetAttribute(k_reverb_upmix, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            int(8*kLine*sizeof(float))));
+    }
     reverb_fill_params(R.h[1], p);
     R.fade[1] = p->fade_samples; R.fade[0] = 1u;
     if(int rc = alloc(R.dev, 2)) return rc;
@@ -1542,6 +1552,11 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
                 RP.frames = frames; RP.cw = dd.wet_channels; RP.stage = st;
                 k_reverb_process<<<dim3(dd.max_slots, 2), 128, 0, d->stream>>>(RP);
                 ++d->launches;
+                if(d->reverb_upmix)
+                {
+                    k_reverb_upmix<<<dim3(dd.max_slots, 2), 256, 8*kLine*sizeof(float), d->stream>>>(RP);
+                    ++d->launches;
+                }
             }
             CP.stage = st; SP.stage = st;
             k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);

@@ -872,8 +872,10 @@ struct ReverbDev {
     uint32_t late_offset[4]; float density_gain; float t60_mid_gain[4];
     float t60_hf[4][5], t60_lf[4][5];
     uint32_t mod_step; float mod_depth; float late_ap_coeff; uint32_t late_ap_offset[4];
+    uint32_t upmix; float order_scale[2]; float split_coeff;      // MixOutAmbiUp
     // state
     float z_lp[4][2], z_hp[4][2], z_t60hf[4][2], z_t60lf[4][2];
+    float z_split[2][4][3];                                        // mAmbiSplitter {lp_z1, lp_z2, ap_z1}
     uint32_t early_tap_cur[4], late_tap_cur[4]; float early_coeff_cur;
     uint32_t mod_index; uint32_t offset;
     // delay lines
@@ -1236,6 +1238,76 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
         R.early_tap_cur[line] = tapCur; R.late_tap_cur[line] = ltapCur;
         if(line == 0) { R.early_coeff_cur = coeffCur; R.mod_index = modIdx; R.offset = offset0 + n; }
     }
+}
+
+// MixOutAmbiUp's front half (reverb.cpp:618-634,658-699) for higher-order devices: turns a
+// pipeline's 4 early + 4 late A-format lines IN PLACE into 4 + 4 B-format rows
+// (EarlyA2B / LateA2B, DoMixRow) and scales each row's HF band with its BandSplitter
+// (in-place processHfScale, core/filters/splitter.cpp:99-131); k_slot_output_mix then pans the
+// rows with the 8 gain rows as usual.  grid (slot, pipeline object), 8 warps = the 8 rows; the
+// splitter recurrence runs on lane 0 of each warp from shared memory.
+__global__ void __launch_bounds__(256) k_reverb_upmix(const ReverbParamsK Q)
+{
+    extern __shared__ float rows[];                 // [8][1024]
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 2u || S.stage != Q.stage || !((S.rv_mask >> blockIdx.y) & 1u)) return;
+    ReverbDev &R = reinterpret_cast<ReverbDev*>(S.H)[blockIdx.y];
+    if(!R.upmix) return;
+    const float inv_sqrt2 = 0.707106781186547524400844362104849039f;
+    const float A2B[2][4][4] = {
+        {{0.5f, 0.5f, 0.5f, 0.5f}, {0.5f, -0.5f, 0.5f, -0.5f}, {0.5f, -0.5f, -0.5f, 0.5f}, {0.5f, 0.5f, -0.5f, -0.5f}},
+        {{0.5f, 0.5f, 0.5f, 0.5f}, {inv_sqrt2, -inv_sqrt2, 0.0f, 0.0f}, {0.0f, 0.0f, -inv_sqrt2, inv_sqrt2},
+         {0.5f, 0.5f, -0.5f, -0.5f}}};
+    const uint32_t n = Q.frames;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int which = warp >> 2, row = warp & 3;
+    float *lines = S.lines + (size_t(blockIdx.y)*8 + size_t(which)*4)*kLine;     // this group's 4 A lines
+    float *mine = rows + size_t(warp)*kLine;
+    for(uint32_t i = lane;i < n;i += 32)
+    {
+        float acc = 0.0f;
+        #pragma unroll
+        for(int k = 0;k < 4;++k)
+        {
+            const float g = A2B[which][row][k];
+            if(fabsf(g) > kSilence) acc = acc + lines[size_t(k)*kLine + i]*g;
+        }
+        mine[i] = acc;
+    }
+    __syncthreads();                                 // every row has read the A-format lines
+    if(lane == 0)
+    {
+        const float hfscale = R.order_scale[row ? 1 : 0];
+        const float ap_coeff = R.split_coeff, lp_coeff = R.split_coeff*0.5f + 0.5f;
+        float lp_z1 = R.z_split[which][row][0], lp_z2 = R.z_split[which][row][1];
+        float ap_z1 = R.z_split[which][row][2];
+        for(uint32_t i0 = 0;i0 < n;i0 += 8)
+        {
+            float x[8], y[8];
+            #pragma unroll
+            for(int k = 0;k < 8;++k) x[k] = (i0 + k < n) ? mine[i0+k] : 0.0f;
+            #pragma unroll
+            for(int k = 0;k < 8;++k)
+            {
+                const float in0 = x[k];
+                const float d0 = (in0 - lp_z1) * lp_coeff;
+                const float lp_y0 = lp_z1 + d0;
+                const float n1 = lp_y0 + d0;
+                const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+                const float lp_y1 = lp_z2 + d1;
+                const float n2 = lp_y1 + d1;
+                const float ap_y = in0*ap_coeff + ap_z1;
+                const float n3 = in0 - ap_y*ap_coeff;
+                y[k] = (ap_y-lp_y1)*hfscale + lp_y1;
+                if(i0 + k < n) { lp_z1 = n1; lp_z2 = n2; ap_z1 = n3; }
+            }
+            #pragma unroll
+            for(int k = 0;k < 8;++k) if(i0 + k < n) mine[i0+k] = y[k];
+        }
+        R.z_split[which][row][0] = lp_z1; R.z_split[which][row][1] = lp_z2; R.z_split[which][row][2] = ap_z1;
+    }
+    __syncwarp();
+    for(uint32_t i = lane;i < n;i += 32) lines[size_t(row)*kLine + i] = mine[i];
 }
 
 } // namespace b200mix

@@ -70,7 +70,8 @@ class ReverbParams(C.Structure):
                 ("t60_hf", (C.c_float * 5) * 4), ("t60_lf", (C.c_float * 5) * 4),
                 ("mod_step", C.c_uint32), ("mod_depth", C.c_float),
                 ("late_ap_coeff", C.c_float), ("late_ap_offset", C.c_uint32 * 4),
-                ("fade_samples", C.c_uint32)]
+                ("fade_samples", C.c_uint32), ("upmix", C.c_uint32), ("order_scale", C.c_float * 2),
+                ("splitter_coeff", C.c_float)]
 
 
 def reverb_params_from(raw) -> "ReverbParams":

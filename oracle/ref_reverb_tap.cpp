@@ -46,7 +46,7 @@ extern "C" {
 
 /* Fills `out` from the CURRENT pipeline of the ReverbState on active slot `idx`;
  * gains is [8][dry_channels]: early lines 0-3 then late lines 0-3 (Target gains).
- * Returns 0, or <0 if the slot holds no reverb / the upmix path is active. */
+ * Returns 0, or <0 if the slot holds no reverb. */
 int refh_reverb_params(ALCcontext *actx, int idx, b200mix_reverb_params *out, float *gains,
     int *pipeline_state)
 {
@@ -56,7 +56,6 @@ int refh_reverb_params(ALCcontext *actx, int idx, b200mix_reverb_params *out, fl
     auto *slot = (*arr)[size_t(idx)];
     if(slot->EffectType != EffectSlotType::Reverb) return -2;
     auto *st = static_cast<ReverbState*>(slot->mEffectState.get());
-    if(st->mUpmixOutput) return -3;
     auto &p = st->mPipelines[st->mCurrentPipeline];
     /* low byte: mPipelineState; bit 8: mCurrentPipeline (flips on every full update) */
     *pipeline_state = int(st->mPipelineState) | (int(st->mCurrentPipeline) << 8);
@@ -99,6 +98,10 @@ int refh_reverb_params(ALCcontext *actx, int idx, b200mix_reverb_params *out, fl
     out->mod_depth = p.mLate.Mod.Depth;
     out->late_ap_coeff = p.mLate.VecAp.Coeff;
     out->fade_samples = uint32_t(p.mFadeSampleCount);
+    out->upmix = st->mUpmixOutput ? 1u : 0u;
+    out->order_scale[0] = st->mOrderScales[0];
+    out->order_scale[1] = st->mOrderScales[1];
+    out->splitter_coeff = p.mAmbiSplitter[0][0].mCoeff;
     return 0;
 }
 

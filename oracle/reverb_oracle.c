@@ -10,6 +10,7 @@
 #include "almix_oracle.h"
 #include "reverb_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,6 +36,7 @@ typedef struct opipe {
     float early_coeff_cur;
     uint32_t mod_index;
     size_t fade_samples;              /* mFadeSampleCount */
+    struct { float lp_z1, lp_z2, ap_z1; } split[2][NL];   /* mAmbiSplitter (MixOutAmbiUp) */
     float gcur[8][B200MIX_MAX_DRY_CHANNELS], gtgt[8][B200MIX_MAX_DRY_CHANNELS];
 } opipe;
 
@@ -73,6 +75,7 @@ static void pipe_clear(opipe *q)
     q->early_coeff_cur = 0.0f; q->p.early_tap_coeff = 0.0f;
     q->mod_index = 0; q->p.mod_step = 1; q->p.mod_depth = 0.0f;
     memset(q->gcur, 0, sizeof(q->gcur)); memset(q->gtgt, 0, sizeof(q->gtgt));
+    memset(q->split, 0, sizeof(q->split));
 }
 
 /* ReverbState::update as far as the mixer sees it (reverb.cpp:1222-1351): `p` holds the
@@ -376,9 +379,59 @@ static void process_late(oreverb *r, opipe *q, size_t offset, size_t n)
     }
 }
 
-/* mixOut -> MixOutPlain, reverb.cpp:637-656 */
+/* EarlyA2B / LateA2B, reverb.cpp:102-122 */
+#define INV_SQRT2 0.707106781186547524400844362104849039f
+static const float EarlyA2B[NL][NL] = {
+    { 0.5f,  0.5f,  0.5f,  0.5f }, { 0.5f, -0.5f,  0.5f, -0.5f },
+    { 0.5f, -0.5f, -0.5f,  0.5f }, { 0.5f,  0.5f, -0.5f, -0.5f } };
+static const float LateA2B[NL][NL] = {
+    { 0.5f, 0.5f, 0.5f, 0.5f }, { INV_SQRT2, -INV_SQRT2, 0.0f, 0.0f },
+    { 0.0f, 0.0f, -INV_SQRT2, INV_SQRT2 }, { 0.5f, 0.5f, -0.5f, -0.5f } };
+
+/* MixOutAmbiUp's per-row work (reverb.cpp:618-634,658-699): DoMixRow, then the in-place
+ * BandSplitter::processHfScale (core/filters/splitter.cpp:99-131), then MixSamples */
+static void mix_row_up(oreverb *r, opipe *q, int which, int row, const float a2b[NL],
+    float (*in)[B200MIX_LINE_SIZE], size_t n, float *cur, const float *tgt, oreverb_mix_fn mix, void *mixctx)
+{
+    float tmp[B200MIX_LINE_SIZE];
+    for(size_t i = 0;i < n;++i) tmp[i] = 0.0f;
+    for(int k = 0;k < NL;++k)
+        if(fabsf(a2b[k]) > 0.00001f)                 /* GainSilenceThreshold */
+            for(size_t i = 0;i < n;++i) tmp[i] = tmp[i] + in[k][i]*a2b[k];
+    const float hfscale = q->p.order_scale[row ? 1 : 0];
+    const float ap_coeff = q->p.splitter_coeff, lp_coeff = q->p.splitter_coeff*0.5f + 0.5f;
+    float lp_z1 = q->split[which][row].lp_z1, lp_z2 = q->split[which][row].lp_z2;
+    float ap_z1 = q->split[which][row].ap_z1;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float in0 = tmp[i];
+        const float d0 = (in0 - lp_z1) * lp_coeff;
+        const float lp_y0 = lp_z1 + d0;
+        lp_z1 = lp_y0 + d0;
+        const float d1 = (lp_y0 - lp_z2) * lp_coeff;
+        const float lp_y1 = lp_z2 + d1;
+        lp_z2 = lp_y1 + d1;
+        const float ap_y = in0*ap_coeff + ap_z1;
+        ap_z1 = in0 - ap_y*ap_coeff;
+        tmp[i] = (ap_y-lp_y1)*hfscale + lp_y1;
+    }
+    q->split[which][row].lp_z1 = lp_z1; q->split[which][row].lp_z2 = lp_z2;
+    q->split[which][row].ap_z1 = ap_z1;
+    mix(mixctx, tmp, n, cur, tgt);
+    (void)r;
+}
+
+/* mixOut -> MixOutPlain / MixOutAmbiUp, reverb.cpp:637-705 */
 static void mix_out(oreverb *r, opipe *q, size_t n, oreverb_mix_fn mix, void *mixctx)
 {
+    if(q->p.upmix)
+    {
+        for(int j = 0;j < NL;++j)
+            mix_row_up(r, q, 0, j, EarlyA2B[j], r->early_out, n, q->gcur[j], q->gtgt[j], mix, mixctx);
+        for(int j = 0;j < NL;++j)
+            mix_row_up(r, q, 1, j, LateA2B[j], r->late_out, n, q->gcur[4+j], q->gtgt[4+j], mix, mixctx);
+        return;
+    }
     for(int j = 0;j < NL;++j) mix(mixctx, r->early_out[j], n, q->gcur[j], q->gtgt[j]);
     for(int j = 0;j < NL;++j) mix(mixctx, r->late_out[j], n, q->gcur[4+j], q->gtgt[4+j]);
 }

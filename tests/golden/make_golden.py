@@ -75,6 +75,8 @@ SCENES = {
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
+    # reverb on a second-order device: MixOutAmbiUp (A2B rows, HF scaling by band splitters, up-mix)
+    "ambi2_spline_reverb_upmix_v4": (4, 0, 2, 5, True, 48000, "ambi2", "i16", 0, {0x0006: 0.8}),
     # slot chaining (AL_EFFECTSLOT_TARGET_SOFT): a convolution slot feeding a reverb slot; even voices
     # send to the convolution, odd ones straight to the reverb
     "hrtf_spline_chain_v6": (6, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "chain"),
@@ -135,6 +137,9 @@ ATTRS = {
     "out_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
     "out_u8": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_UNSIGNED_BYTE_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
+    "ambi2": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 2,
+                        r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
+                        r.ALC_AMBISONIC_SCALING_SOFT: r.ALC_N3D_SOFT},
     "ambi3": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 3,
                         r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
                         r.ALC_AMBISONIC_SCALING_SOFT: r.ALC_N3D_SOFT},
