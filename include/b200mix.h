@@ -315,20 +315,48 @@ B200MIX_API int b200mix_render(b200mix_device *dev, uint32_t frames, float *cons
 B200MIX_API int b200mix_render_device(b200mix_device *dev, uint32_t frames,
     const float **real_out_dev);
 
-/* Output stage on the device, for hosts that run WITHOUT the gain limiter (float output, or
- * ALC_OUTPUT_LIMITER_SOFT off): ApplyDither (alc/alu.cpp:2309-2333) followed by the
+/* Output stage on the device: ApplyDither (alc/alu.cpp:2309-2333) followed by the
  * interleaving Write<T> (alc/alu.cpp:2362-2390, SampleConv :2335-2360) of the same update
  * b200mix_render performs.  out receives frames*frame_step samples of out_type (enum DevFmtType
  * order below); frame_step >= real_channels, extra channels get SampleConv<T>(0).
  * dither_depth is DeviceBase::DitherDepth (0 = off; 32768 for 16-bit output), *dither_seed
  * DeviceBase::DitherSeed (22222 at device open), advanced exactly as the reference's LCG.
- * The limiter (core/mastering.cpp) is not implemented: hosts that need it take float output
- * from b200mix_render and keep the reference's Limiter/Dither/Write on the CPU. */
+ * With a limiter installed (b200mix_set_limiter) it runs ahead of the dither, as in
+ * DeviceBase::renderSamples (alc/alu.cpp:2446). */
 enum b200mix_out_type { B200MIX_OUT_I8 = 0, B200MIX_OUT_U8, B200MIX_OUT_I16, B200MIX_OUT_U16,
     B200MIX_OUT_I32, B200MIX_OUT_U32, B200MIX_OUT_F32 };
 B200MIX_API int b200mix_render_interleaved(b200mix_device *dev, uint32_t frames, void *out,
     uint32_t out_type, uint32_t frame_step, float dither_depth, uint32_t *dither_seed,
     b200mix_voice_result *results);
+
+/* The output gain limiter: Compressor (core/mastering.h:25-117, core/mastering.cpp).  The
+ * fields are Compressor::Params (core/mastering.h:88-114) — NumChans and SampleRate come from
+ * the device — and b200mix_set_limiter derives the state exactly as Compressor::Create
+ * (core/mastering.cpp:108-166).  The reference's device limiter (CreateDeviceLimiter,
+ * alc/alc.cpp:1079-1091) is {auto_flags = all five, look_ahead_time 0.001, hold_time 0.002,
+ * 0 dB pre/post gain, ratio INFINITY, knee 0, attack 0.02, release 0.2} with threshold_db
+ * from the output type (alc/alc.cpp:1750-1770).  Once installed, every render applies
+ * Compressor::process (core/mastering.cpp:261-379) to RealOut after the post-process stage and
+ * before dither/conversion (alc/alu.cpp:2446), keeping its look-ahead delay, peak hold and
+ * envelope state in device memory.  desc == NULL removes it (device->Limiter = nullptr).
+ * *look_ahead (nullable) receives Compressor::getLookAhead() in samples. */
+enum { B200MIX_LIM_AUTO_KNEE = 1u, B200MIX_LIM_AUTO_ATTACK = 2u, B200MIX_LIM_AUTO_RELEASE = 4u,
+    B200MIX_LIM_AUTO_POSTGAIN = 8u, B200MIX_LIM_AUTO_DECLIP = 16u };
+typedef struct b200mix_limiter_desc {
+    uint32_t struct_size;
+    uint32_t auto_flags;        /* B200MIX_LIM_AUTO_* (Compressor::FlagBits) */
+    float look_ahead_time;      /* seconds */
+    float hold_time;            /* seconds */
+    float pre_gain_db;
+    float post_gain_db;
+    float threshold_db;
+    float ratio;                /* INFINITY for true limiting */
+    float knee_db;
+    float attack_time;          /* seconds */
+    float release_time;         /* seconds */
+} b200mix_limiter_desc;
+B200MIX_API int b200mix_set_limiter(b200mix_device *dev, const b200mix_limiter_desc *desc,
+    uint32_t *look_ahead);
 
 /* The same update in two halves, for voice-sharded multi-GPU mixing: effects
  * consume the SUMMED wet input of all ranks, so the host reduces the wet buffers between

@@ -119,6 +119,8 @@ struct b200mix_device {
     float2 *d_st_fields{nullptr}; uint2 *d_st_elevs{nullptr}; float2 *d_st_coeffs{nullptr};
     uint8_t *d_st_delays{nullptr}; uint32_t st_num_fields{0}, st_ir{0};
     uint4 *d_qhdr{nullptr}; uint32_t *d_queue{nullptr};   // streaming queues (first b200mix_voice_queue)
+    LimiterDev *d_limiter{nullptr};                      // DeviceBase::Limiter (b200mix_set_limiter)
+    float *d_limiter_delay{nullptr};                     // Compressor::mDelay [real_channels][1024]
     void *d_outbuf{nullptr}, *h_outbuf{nullptr};          // interleaved output staging (render_interleaved)
     // reverb slots: host side of ReverbState's two-pipeline state machine
     struct RvHost {
@@ -453,6 +455,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
     cudaFree(d->d_dline); cudaFree(d->d_order2); cudaFree(d->d_qhdr); cudaFree(d->d_queue);
     cudaFree(d->d_outbuf); if(d->h_outbuf) cudaFreeHost(d->h_outbuf);
+    cudaFree(d->d_limiter); cudaFree(d->d_limiter_delay);
     cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
@@ -1626,6 +1629,13 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
     }
     default: break;
     }
+    if(d->d_limiter)
+    {
+        // if(Limiter) Limiter->process(samplesToDo, RealOut.Buffer), alc/alu.cpp:2446
+        LimiterParams LQ{d->d_limiter, d->d_real, d->d_limiter_delay, frames};
+        k_limiter<<<1, 1024, 0, d->stream>>>(LQ);
+        ++d->launches;
+    }
     stage_mark(d, 8);
     if(d->profile_level >= 2) d->stage_valid = true;
     CUDA_TRY(d, cudaGetLastError());
@@ -1677,6 +1687,56 @@ int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
     if(!d) return B200MIX_ERR_INVALID;
     if(int rc = render_launch(d, frames, results != nullptr)) return rc;
     return render_collect(d, frames, real_out, results);
+}
+
+// Compressor::Create (core/mastering.cpp:108-166): the same float/double expressions, by the
+// host's libm, so the derived constants are the reference's bit for bit.
+int b200mix_set_limiter(b200mix_device *d, const b200mix_limiter_desc *p, uint32_t *look_ahead)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(look_ahead) *look_ahead = 0;
+    if(d->mid_render) { d->error = "set_limiter: a render_begin is pending"; return B200MIX_ERR_INVALID; }
+    const b200mix_device_desc &dd = d->desc;
+    if(!p)
+    {
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        cudaFree(d->d_limiter); d->d_limiter = nullptr;
+        cudaFree(d->d_limiter_delay); d->d_limiter_delay = nullptr;
+        return B200MIX_OK;
+    }
+    if(p->struct_size != sizeof(*p)) { d->error = "set_limiter: struct_size"; return B200MIX_ERR_INVALID; }
+    const float rate = float(dd.sample_rate);
+    auto clampf = [](float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); };
+    LimiterDev h{};
+    h.look_ahead = uint32_t(clampf(std::round(p->look_ahead_time*rate), 0.0f, float(kLine) - 1.0f));
+    const uint32_t hold = uint32_t(clampf(std::round(p->hold_time*rate), 0.0f, float(kLine) - 1.0f));
+    h.flags = p->auto_flags & 31u;
+    if(!(h.flags & B200MIX_LIM_AUTO_POSTGAIN)) h.flags &= ~uint32_t(B200MIX_LIM_AUTO_DECLIP);
+    h.num_chans = dd.real_channels;
+    h.pre_gain = std::pow(10.0f, p->pre_gain_db / 20.0f);
+    h.post_gain = float(std::log(10.0)/20.0 * double(p->post_gain_db));
+    h.threshold = float(std::log(10.0)/20.0 * double(p->threshold_db));
+    h.slope = 1.0f/std::max(1.0f, p->ratio) - 1.0f;
+    h.knee = float(std::max(0.0, std::log(10.0)/20.0 * double(p->knee_db)));
+    h.attack = std::max(1.0f, p->attack_time * rate);
+    h.release = std::max(1.0f, p->release_time * rate);
+    if(h.flags & B200MIX_LIM_AUTO_KNEE) h.slope = -1.0f;
+    // the hold needs a look-ahead and more than one sample (:141-153)
+    h.hold = (h.look_ahead > 0 && hold > 1) ? hold : 0u;
+    h.crest_coeff = std::exp(-1.0f / (0.200f * rate));
+    h.gain_estimate = h.threshold * -0.5f * h.slope;
+    h.adapt_coeff = std::exp(-1.0f / (2.0f * rate));
+    for(float &v : h.hold_hist) v = -INFINITY;
+    if(!d->d_limiter)
+    {
+        if(int rc = dev_alloc(d, d->d_limiter, 1)) return rc;
+        if(int rc = dev_alloc(d, d->d_limiter_delay, size_t(std::max(dd.real_channels, 1u))*kLine)) return rc;
+    }
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    CUDA_TRY(d, cudaMemcpy(d->d_limiter, &h, sizeof(h), cudaMemcpyHostToDevice));
+    CUDA_TRY(d, cudaMemset(d->d_limiter_delay, 0, size_t(std::max(dd.real_channels, 1u))*kLine*sizeof(float)));
+    if(look_ahead) *look_ahead = h.look_ahead;
+    return B200MIX_OK;
 }
 
 static uint32_t lcg_skip_host(uint32_t x, uint64_t k)

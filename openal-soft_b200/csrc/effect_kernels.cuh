@@ -91,9 +91,6 @@ struct FilterRunParams {
 
 struct BiquadCoefs { float b0, b1, b2, a1, a2; };
 
-__device__ __forceinline__ float lerp_rn(float a, float b, float mu)     // lerpf, alnumeric.h:115
-{ return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), mu)); }
-
 __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
 {
     __shared__ float tile[32][33];

@@ -1620,6 +1620,296 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     }
 }
 
+// Output limiter: Compressor::process (core/mastering.cpp:261-379) on RealOut, one CTA.
+// The reference's stages are kept, each in the most parallel form its arithmetic allows:
+//  1. pre-gain, linked peak max_c|x_c| (one thread per sample);
+//  2. the crest-factor detectors (:288-308) are first-order recurrences — one thread walks them
+//     in the reference's order while the other warps take the logarithm and the peak hold: the
+//     sliding hold (:46-105, a descending-maxima queue) IS the maximum over the last `hold`
+//     detector values, so every sample takes it over a window of [history | this update];
+//  3. attack/release coefficients exp(-1/t) from the crest factor, one thread per sample;
+//  4. gain computer + ballistics + deviation tracking (gainCompressor, :177-259): a serial,
+//     nonlinear chain (the automated knee feeds back), one thread, the reference's operation
+//     order with explicitly rounded operations;
+//  5. exp() of the control signal, the look-ahead FIFO (:331-358) and the gain, per sample.
+struct LimiterDev {
+    uint32_t flags, look_ahead, hold, num_chans;
+    float pre_gain, post_gain, threshold, slope, knee, attack, release;
+    float crest_coeff, gain_estimate, adapt_coeff;
+    // state carried between updates
+    float last_peak_sq, last_rms_sq, last_release, last_attack, last_gain_dev;
+    uint32_t pad;
+    float side_carry[kLine];      // mSideChain[0..look_ahead)
+    float hold_hist[kLine];       // the hold's last hold-1 detector values (-inf at start)
+};
+struct LimiterParams { LimiterDev *lim; float *real; float *delay; uint32_t frames; };
+
+__device__ __forceinline__ float lerp_rn(float a, float b, float mu)
+{ return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), mu)); }       // lerpf, common/altypes.hpp:1197
+
+// exp/log as the host libm rounds them (glibc's expf/logf are correctly rounded but for rare
+// half-way cases): evaluated in double and rounded once.  The smoothing coefficients
+// exp(-1/t) sit just below 1, where one float ulp changes the release RATE (1-a) by 1e-4
+// relative — CUDA's 2-ulp expf would make the envelope drift away from the reference's.
+__device__ __forceinline__ float exp_cr(float x) { return float(exp(double(x))); }
+__device__ __forceinline__ float log_cr(float x) { return float(log(double(x))); }
+
+struct LimiterChainArgs {
+    LimiterDev *lim;
+    const float *yg, *side, *rel, *att;     // shared memory: x_over / y_G, mSideChain, a_rel, a_att
+    float *out;                             // shared memory: postGain - y_L per sample
+    uint32_t n; float thr;
+};
+
+// Gain computer + ballistics + deviation tracking of gainCompressor (core/mastering.cpp:196-253),
+// one thread, the reference's operation order.
+template<bool AUTO_KNEE, bool AUTO_POST, bool AUTO_DECLIP>
+__device__ __noinline__ void limiter_chain(const LimiterChainArgs A)
+{
+    LimiterDev &L = *A.lim;
+    const uint32_t n = A.n;
+    const float thr = A.thr, nslope = -L.slope, c_est = L.gain_estimate, a_adp = L.adapt_coeff;
+    float postGain = L.post_gain;
+    float y_1 = L.last_release, y_L = L.last_attack, c_dev = L.last_gain_dev;
+
+    // one sample of the chain after the static curve
+    auto ballistics = [&](float y_G, float input, float a_rel, float a_att) -> float
+    {
+        const float x_L = __fmul_rn(nslope, y_G);
+        y_1 = fmaxf(x_L, lerp_rn(x_L, y_1, a_rel));
+        y_L = lerp_rn(y_1, y_L, a_att);
+        c_dev = lerp_rn(-__fadd_rn(y_L, c_est), c_dev, a_adp);
+        if(AUTO_POST)
+        {
+            if(AUTO_DECLIP)
+                c_dev = fmaxf(c_dev, __fsub_rn(__fsub_rn(__fsub_rn(input, y_L), thr), c_est));
+            postGain = -__fadd_rn(c_dev, c_est);
+        }
+        return __fsub_rn(postGain, y_L);
+    };
+    // half the automated knee: 0.5*max(0, 2.5*(c_dev+c_est)) == max(0, 1.25*(c_dev+c_est))
+    auto knee_half = [&]() -> float
+    { return fmaxf(0.0f, __fmul_rn(1.25f, __fadd_rn(c_dev, c_est))); };
+    // the static curve with a knee (:205-210); 2*knee == 4*knee_half
+    auto curve = [&](float x_over, float knee_h) -> float
+    {
+        if(x_over <= -knee_h) return 0.0f;
+        if(fabsf(x_over) < knee_h)
+        {
+            const float t = __fadd_rn(x_over, knee_h);
+            return __fdiv_rn(__fmul_rn(t, t), __fmul_rn(4.0f, knee_h));
+        }
+        return x_over;
+    };
+
+    uint32_t k = 0;
+    for(;k + 8u <= n;k += 8u)
+    {
+        float xo[8], in[8], ar[8], aa[8], o[8];
+        #pragma unroll
+        for(int j = 0;j < 8;++j)
+        { xo[j] = A.yg[k + j]; in[j] = A.side[k + j]; ar[j] = A.rel[k + j]; aa[j] = A.att[k + j]; }
+        if(!AUTO_KNEE)
+        {
+            // no feedback into the static curve (y_G came from phase 3): three short
+            // pipelined recurrences
+            #pragma unroll
+            for(int j = 0;j < 8;++j) o[j] = ballistics(xo[j], in[j], ar[j], aa[j]);
+        }
+        else
+        {
+            // The automated knee feeds the deviation c_dev back into the curve, which makes
+            // every sample wait for the previous one's whole chain.  But the curve only asks
+            // on which side of -knee/2 the sample lies (the knee region itself is rare), and
+            // the knee moves slowly: run the block with the knee frozen at its first sample's
+            // value, then check every sample's decision against the knee it should have seen;
+            // on any difference redo the block one sample at a time.  Exact either way.
+            const float sy1 = y_1, syL = y_L, scd = c_dev, spg = postGain;
+            const float kh0 = knee_half();
+            float kh[8];
+            #pragma unroll
+            for(int j = 0;j < 8;++j)
+            {
+                kh[j] = knee_half();
+                o[j] = ballistics(xo[j] <= -kh0 ? 0.0f : xo[j], in[j], ar[j], aa[j]);
+            }
+            bool bad = false;
+            #pragma unroll
+            for(int j = 0;j < 8;++j)
+            {
+                const bool below0 = xo[j] <= -kh0, below = xo[j] <= -kh[j];
+                bad |= (below != below0) | (!below & (fabsf(xo[j]) < kh[j]));
+            }
+            if(bad)
+            {
+                y_1 = sy1; y_L = syL; c_dev = scd; postGain = spg;
+                #pragma unroll
+                for(int j = 0;j < 8;++j)
+                    o[j] = ballistics(curve(xo[j], knee_half()), in[j], ar[j], aa[j]);
+            }
+        }
+        #pragma unroll
+        for(int j = 0;j < 8;++j) A.out[k + j] = o[j];
+    }
+    for(;k < n;++k)
+    {
+        const float x_over = A.yg[k];
+        const float y_G = AUTO_KNEE ? curve(x_over, knee_half()) : x_over;
+        A.out[k] = ballistics(y_G, A.side[k], A.rel[k], A.att[k]);
+    }
+    L.last_release = y_1; L.last_attack = y_L; L.last_gain_dev = c_dev;
+}
+
+__global__ void __launch_bounds__(1024) k_limiter(const LimiterParams Q)
+{
+    __shared__ float s_side[2*kLine];     // [carried look-ahead part | this update's detector]
+    __shared__ float s_xg[2*kLine];       // [hold history | log peak of this update]
+    __shared__ float s_x2[kLine];         // squared peak, later the log-domain gain
+    __shared__ float s_att[kLine], s_rel[kLine];
+    __shared__ float s_yg[kLine];         // x_over, or the static curve's y_G with a fixed knee
+    LimiterDev &L = *Q.lim;
+    const uint32_t n = Q.frames, i = threadIdx.x, la = L.look_ahead, C = L.num_chans;
+    const uint32_t flags = L.flags;
+    const bool autoKnee = flags & 1u, autoAtt = flags & 2u, autoRel = flags & 4u;
+    const bool autoPost = flags & 8u, autoDeclip = flags & 16u;
+    const uint32_t hh = L.hold > 1u ? L.hold - 1u : 0u;
+    const float pre = L.pre_gain;
+
+    // 1
+    if(i < n)
+    {
+        float xabs = 0.0f;
+        for(uint32_t c = 0;c < C;++c)
+        {
+            float v = Q.real[size_t(c)*kLine + i];
+            if(pre != 1.0f) { v = __fmul_rn(v, pre); Q.real[size_t(c)*kLine + i] = v; }
+            xabs = fmaxf(xabs, fabsf(v));
+        }
+        s_x2[i] = fminf(fmaxf(__fmul_rn(xabs, xabs), 0.000001f), 1000000.0f);
+        s_xg[hh + i] = log_cr(fmaxf(0.000001f, xabs));
+    }
+    if(i < la) s_side[i] = L.side_carry[i];
+    if(i < hh) s_xg[i] = L.hold_hist[i];
+    __syncthreads();
+
+    // 2
+    if(i == 0 || i == 32u)
+    {
+        // the two detectors are independent recurrences: one thread each (different warps),
+        // eight samples loaded ahead of the dependent chain
+        if(autoAtt || autoRel)
+        {
+            const float a = L.crest_coeff;
+            const bool peak = i == 0;
+            float y = peak ? L.last_peak_sq : L.last_rms_sq;
+            float *dst = peak ? s_att : s_rel;
+            uint32_t k = 0;
+            for(;k + 8u <= n;k += 8u)
+            {
+                float x2[8];
+                #pragma unroll
+                for(int j = 0;j < 8;++j) x2[j] = s_x2[k + j];
+                #pragma unroll
+                for(int j = 0;j < 8;++j)
+                {
+                    const float t = lerp_rn(x2[j], y, a);
+                    y = peak ? fmaxf(x2[j], t) : t;
+                    dst[k + j] = y;
+                }
+            }
+            for(;k < n;++k)
+            {
+                const float x2 = s_x2[k];
+                const float t = lerp_rn(x2, y, a);
+                y = peak ? fmaxf(x2, t) : t;
+                dst[k] = y;
+            }
+            if(peak) L.last_peak_sq = y; else L.last_rms_sq = y;
+        }
+    }
+    else if(i >= 64u)
+    {
+        for(uint32_t k = i - 64u;k < n;k += 960u)
+        {
+            float m = s_xg[hh + k];
+            for(uint32_t j = 0;j < hh;++j) m = fmaxf(m, s_xg[k + j]);
+            s_side[la + k] = m;
+        }
+    }
+    __syncthreads();
+    if(i < hh) L.hold_hist[i] = s_xg[n + i];
+
+    // 3
+    const float thr = L.threshold;
+    if(i < n)
+    {
+        float t_att = L.attack, t_rel = __fsub_rn(L.release, L.attack);
+        float a_att, a_rel;
+        if(autoAtt || autoRel)
+        {
+            const float crest = __fdiv_rn(s_att[i], s_rel[i]);
+            if(autoAtt) t_att = __fdiv_rn(__fmul_rn(2.0f, L.attack), crest);
+            if(autoRel) t_rel = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, L.release), crest), t_att);
+        }
+        a_att = exp_cr(__fdiv_rn(-1.0f, t_att));
+        a_rel = exp_cr(__fdiv_rn(-1.0f, t_rel));
+        s_att[i] = a_att; s_rel[i] = a_rel;
+        // x_over; with a fixed knee the whole static curve is known here
+        const float x_over = __fsub_rn(s_side[la + i], thr);
+        float y_G = x_over;
+        if(!autoKnee)
+        {
+            const float knee = L.knee, knee_h = __fmul_rn(0.5f, knee);
+            if(x_over <= -knee_h) y_G = 0.0f;
+            else if(fabsf(x_over) < knee_h)
+            {
+                const float t = __fadd_rn(x_over, knee_h);
+                y_G = __fdiv_rn(__fmul_rn(t, t), __fmul_rn(2.0f, knee));
+            }
+        }
+        s_yg[i] = y_G;
+    }
+    __syncthreads();
+
+    // 4
+    if(i == 0)
+    {
+        const LimiterChainArgs A{&L, s_yg, s_side, s_rel, s_att, s_x2, n, thr};
+        // the automation flags are compile-time in the chain: a flag test inside the unrolled
+        // block would cut it into short dependent pieces
+        if(autoKnee)
+        {
+            if(autoDeclip) limiter_chain<true, true, true>(A);
+            else if(autoPost) limiter_chain<true, true, false>(A);
+            else limiter_chain<true, false, false>(A);
+        }
+        else
+        {
+            if(autoDeclip) limiter_chain<false, true, true>(A);
+            else if(autoPost) limiter_chain<false, true, false>(A);
+            else limiter_chain<false, false, false>(A);
+        }
+    }
+    __syncthreads();
+
+    // 5
+    const float g = i < n ? exp_cr(s_x2[i]) : 0.0f;
+    if(i < la) L.side_carry[i] = s_side[n + i];
+    for(uint32_t c = 0;c < C;++c)
+    {
+        float *x = Q.real + size_t(c)*kLine;
+        float *dl = Q.delay + size_t(c)*kLine;
+        // stream = [delay line | this update]: output i is stream[i], the new delay line is the
+        // stream's last look_ahead samples
+        float v = 0.0f, nd = 0.0f;
+        if(i < n) v = i < la ? dl[i] : x[i - la];
+        if(i < la) nd = (n + i < la) ? dl[n + i] : x[n + i - la];
+        __syncthreads();
+        if(i < n) x[i] = __fmul_rn(g, v);
+        if(i < la) dl[i] = nd;
+    }
+}
+
 // Output stage: ApplyDither (alc/alu.cpp:2309-2333) + Write<T> (alc/alu.cpp:2362-2390).
 // The reference draws two LCG values per sample, channel after channel; sample i of channel c
 // therefore uses draws 2(c*n+i)+1 and +2 from the incoming seed — reached directly with the

@@ -56,6 +56,24 @@ class VoiceResult(C.Structure):
                 ("flags", C.c_uint32), ("buffers_done", C.c_uint32)]
 
 
+class LimiterDesc(C.Structure):
+    """b200mix_limiter_desc (Compressor::Params, core/mastering.h:88-114)."""
+    _fields_ = [("struct_size", C.c_uint32), ("auto_flags", C.c_uint32),
+                ("look_ahead_time", C.c_float), ("hold_time", C.c_float),
+                ("pre_gain_db", C.c_float), ("post_gain_db", C.c_float),
+                ("threshold_db", C.c_float), ("ratio", C.c_float), ("knee_db", C.c_float),
+                ("attack_time", C.c_float), ("release_time", C.c_float)]
+
+
+LIM_AUTO_ALL = 31
+
+
+def device_limiter(threshold_db: float) -> "LimiterDesc":
+    """The reference's device limiter (CreateDeviceLimiter, alc/alc.cpp:1079-1091)."""
+    return LimiterDesc(C.sizeof(LimiterDesc), LIM_AUTO_ALL, 0.001, 0.002, 0.0, 0.0, threshold_db,
+                       float("inf"), 0.0, 0.02, 0.2)
+
+
 class ReverbParams(C.Structure):
     _fields_ = [("struct_size", C.c_uint32),
                 ("main_len", C.c_uint32), ("late_in_len", C.c_uint32), ("early_ap_len", C.c_uint32),

@@ -10,6 +10,7 @@
  */
 #include "almix_oracle.h"
 #include "reverb_oracle.h"
+#include "limiter_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -257,6 +258,7 @@ struct oracle_device {
     float samples[LINE];
     float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
     uint32_t mid_frames;       /* between oracle_render_begin and oracle_render_end */
+    olimiter *limiter;         /* DeviceBase::Limiter */
     float hrtf_samples[LINE+HIST];
     float temp[LINE], temp2[LINE];
 };
@@ -295,6 +297,7 @@ void oracle_destroy(oracle_device *d)
         oreverb_destroy(d->slots[i].reverb);
     }
     free(d->slots);
+    olimiter_destroy(d->limiter);
     free(d->dry); free(d->wet);
     free(d->dec_coef); free(d->dec_hfscale); free(d->dec_split);
     free(d->amb_hf); free(d->amb_lf); free(d->amb_split);
@@ -332,6 +335,19 @@ int oracle_set_ambi_decoder(oracle_device *d, uint32_t in_channels, const float 
     if(gains_lf) { d->amb_lf = malloc(n*sizeof(float)); memcpy(d->amb_lf, gains_lf, n*sizeof(float)); }
     d->amb_split = calloc(in_channels, sizeof(osplitter));
     for(uint32_t c = 0;c < in_channels;++c) d->amb_split[c].coeff = xover_coeff;
+    return B200MIX_OK;
+}
+
+/* CreateDeviceLimiter / device->Limiter = nullptr (alc/alc.cpp:1079-1091,1508,1771-1774) */
+int oracle_set_limiter(oracle_device *d, const b200mix_limiter_desc *desc, uint32_t *look_ahead)
+{
+    olimiter_destroy(d->limiter); d->limiter = NULL;
+    if(look_ahead) *look_ahead = 0;
+    if(!desc) return B200MIX_OK;
+    if(desc->struct_size != sizeof(*desc)) return B200MIX_ERR_INVALID;
+    d->limiter = olimiter_create(desc, d->desc.real_channels, (float)d->desc.sample_rate);
+    if(!d->limiter) return B200MIX_ERR_NOMEM;
+    if(look_ahead) *look_ahead = olimiter_look_ahead(d->limiter);
     return B200MIX_OK;
 }
 
@@ -1515,6 +1531,9 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
     default: return B200MIX_ERR_UNSUPPORTED;
     }
 
+    /* if(Limiter) Limiter->process(samplesToDo, RealOut.Buffer), alc/alu.cpp:2446 */
+    if(d->limiter) olimiter_process(d->limiter, frames, d->real);
+
     if(real_out_host) *real_out_host = &d->real[0][0];
     if(real_out)
         for(uint32_t c = 0;c < dd->real_channels;++c)
@@ -1540,7 +1559,7 @@ int oracle_render(oracle_device *d, uint32_t frames, float *const *real_out,
 }
 
 /* ApplyDither (alc/alu.cpp:2309-2333) + Write<T> (alc/alu.cpp:2362-2390) after a normal update;
- * no limiter.  lrintf rounds to nearest even like fastf2i / fast_roundf. */
+ * the limiter, when installed, has already run in oracle_render_end.  lrintf rounds to nearest even like fastf2i / fast_roundf. */
 int oracle_render_interleaved(oracle_device *d, uint32_t frames, void *out, uint32_t out_type,
     uint32_t frame_step, float dither_depth, uint32_t *dither_seed, b200mix_voice_result *results)
 {

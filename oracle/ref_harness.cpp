@@ -60,6 +60,8 @@
 #include "core/mixer.h"
 #include "core/mixer/hrtfdefs.h"
 #include "core/voice.h"
+#include "core/mastering.h"
+#include <limits>
 
 #include "../include/b200mix.h"
 
@@ -182,6 +184,35 @@ int refh_ambi_decoder(ALCdevice *adev, float *gains_hf, float *gains_lf, float *
 
 /* DeviceBase::DitherDepth as the device open chose it (alc/alc.cpp:1690-1716). */
 float refh_dither_depth(ALCdevice *adev) { return dev_of(adev)->DitherDepth; }
+
+/* The device limiter as UpdateDeviceParams set it up: returns 0 when device->Limiter is null,
+ * else fills the Compressor::Params of CreateDeviceLimiter (alc/alc.cpp:1079-1091) with the
+ * threshold of alc/alc.cpp:1750-1770 (the same float expressions, evaluated here by the same
+ * libm) — what a maintainer's binding hands to b200mix_set_limiter. */
+int refh_limiter_desc(ALCdevice *adev, b200mix_limiter_desc *out)
+{
+    auto *device = dev_of(adev);
+    if(!device->Limiter) return 0;
+    auto thrshld = 1.0f;
+    switch(device->FmtType)
+    {
+    case DevFmtByte: case DevFmtUByte: thrshld = 127.0f / 128.0f; break;
+    case DevFmtShort: case DevFmtUShort: thrshld = 32767.0f / 32768.0f; break;
+    case DevFmtInt: case DevFmtUInt: case DevFmtFloat: break;
+    }
+    if(device->DitherDepth > 0.0f)
+        thrshld -= 1.0f / device->DitherDepth;
+    *out = b200mix_limiter_desc{};
+    out->struct_size = sizeof(*out);
+    out->auto_flags = B200MIX_LIM_AUTO_KNEE | B200MIX_LIM_AUTO_ATTACK | B200MIX_LIM_AUTO_RELEASE
+        | B200MIX_LIM_AUTO_POSTGAIN | B200MIX_LIM_AUTO_DECLIP;
+    out->look_ahead_time = 0.001f; out->hold_time = 0.002f;
+    out->pre_gain_db = 0.0f; out->post_gain_db = 0.0f;
+    out->threshold_db = std::log10(thrshld) * 20.0f;
+    out->ratio = std::numeric_limits<float>::infinity();
+    out->knee_db = 0.0f; out->attack_time = 0.02f; out->release_time = 0.2f;
+    return static_cast<int>(device->Limiter->getLookAhead()) + 1;
+}
 
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */

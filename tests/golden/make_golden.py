@@ -72,6 +72,11 @@ SCENES = {
     # integer output without the limiter: ApplyDither + Write<T> (16-bit dithered, 8-bit unsigned)
     "hrtf_spline_out_i16_v6": (6, 1, 2, 3, True, 48000, "out_i16"),
     "stereo_spline_out_u8_v6": (6, 0, 2, 3, True, 48000, "out_u8"),
+    # the output limiter (Compressor, core/mastering.cpp) on a mix driven well past full scale by
+    # the listener gain: 16-bit output (limiter on by default, then dither + Write<T>; the voices
+    # run out, so the release side is covered too) and float output with ALC_OUTPUT_LIMITER_SOFT
+    "hrtf_spline_limiter_i16_v6": (6, 1, 2, 8, False, 4000, "lim_i16", "i16", 0, None, None, "limiter"),
+    "stereo_spline_limiter_f32_v6": (6, 0, 2, 5, True, 48000, "lim_f32", "i16", 0, None, None, "limiter"),
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
@@ -127,15 +132,20 @@ def apply_filter_script(ref, script, u, slot):
             ref.connect_send(src, slot, path - 1, filt)
 
 
+LIMITER_LISTENER_GAIN = 5.0
+
+
 def conv_ir(taps):
     rng = np.random.default_rng(taps)
     return (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.05).astype(np.float32)
 
-OUT_TYPES = {"out_i16": (np.int16, 2), "out_u8": (np.uint8, 1)}    # numpy type, b200mix_out_type
+OUT_TYPES = {"out_i16": (np.int16, 2), "out_u8": (np.uint8, 1), "lim_i16": (np.int16, 2)}    # numpy type, b200mix_out_type
 
 ATTRS = {
     "out_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
     "out_u8": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_UNSIGNED_BYTE_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
+    "lim_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT},
+    "lim_f32": lambda r: {r.ALC_OUTPUT_LIMITER_SOFT: 1},
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
     "ambi2": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 2,
                         r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
@@ -210,6 +220,10 @@ def run_scene(name):
         apply_filter_script(ref, script, 0, slot)
     out_np, out_type = OUT_TYPES.get(spec[6] if len(spec) > 6 else None, (np.float32, None))
     rvscript = len(spec) > 11 and spec[11] == "rvscript"
+    limiter = len(spec) > 11 and spec[11] == "limiter"
+    if limiter:
+        ref.al.alListenerf.argtypes = [C.c_int, C.c_float]
+        ref.al.alListenerf(refal.AL_GAIN, LIMITER_LISTENER_GAIN)
     rv_steps = []
     moving = len(spec) > 11 and spec[11] == "moving"
     mv_steps = []
@@ -282,6 +296,9 @@ def run_scene(name):
                    rv_state=np.array([x[2] for x in rv_steps], dtype=np.int64))
     if out_type is not None:
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
+    if limiter:
+        ld, la = ref.limiter_desc()
+        res.update(limiter_desc=np.frombuffer(bytes(ld), dtype=np.uint8).copy(), limiter_look_ahead=np.int64(la))
     if adpcm:
         res.update(adpcm_blocks=np.int64(ADPCM_BLOCKS))
     if stereo_src:

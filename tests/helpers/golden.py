@@ -110,6 +110,9 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             for k in range(V):
                 ids = [k * len(qlens) + j for j in range(len(qlens))]
                 dev.voice_queue(k, ids, 0 if (plist[k].flags & abi.VF_LOOPING) else abi.NO_LOOP)
+        if "limiter_desc" in fx:
+            la = dev.set_limiter(abi.LimiterDesc.from_buffer_copy(fx["limiter_desc"].tobytes()))
+            assert la == int(fx["limiter_look_ahead"]), (la, int(fx["limiter_look_ahead"]))
         outs = []
         res = None
         seed = 22222            # DitherRNGSeed, alc/alc.cpp:329

@@ -60,6 +60,8 @@ class MixLib:
         self.render_interleaved = f("render_interleaved")
         self.render_interleaved.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
                                             C.c_float, C.POINTER(C.c_uint32), C.c_void_p]
+        self.set_limiter = f("set_limiter")
+        self.set_limiter.argtypes = [C.c_void_p, C.POINTER(abi.LimiterDesc), C.POINTER(C.c_uint32)]
         self.render_begin = f("render_begin")
         self.render_begin.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         self.render_end = f("render_end")
@@ -198,6 +200,13 @@ class MixDevice:
                                        C.byref(sd), res)
         assert rc == 0, f"render_interleaved -> {rc}"
         return out, res, sd.value
+
+    def set_limiter(self, desc):
+        """Installs (or with None removes) the output limiter; returns its look-ahead."""
+        la = C.c_uint32(0)
+        rc = self.m.set_limiter(self.h, C.byref(desc) if desc is not None else None, C.byref(la))
+        assert rc == 0, f"set_limiter -> {rc}"
+        return la.value
 
     def render_begin(self, frames=1024):
         """Returns (wet pointer, float count): a host pointer on the oracle, a device pointer

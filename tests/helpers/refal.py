@@ -143,6 +143,7 @@ def libs(conf_text: str | None = None):
     hz.refh_mono_line_gains_slot.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
     hz.refh_dither_depth.argtypes = [C.c_void_p]
     hz.refh_dither_depth.restype = C.c_float
+    hz.refh_limiter_desc.argtypes = [C.c_void_p, C.c_void_p]
     hz.refh_set_snapshot_channel.argtypes = [C.c_int]
     hz.refh_set_snapshot_channel.restype = None
     hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -368,6 +369,13 @@ class RefDevice:
 
     def dither_depth(self) -> float:
         return float(self.hz.refh_dither_depth(self.dev))
+
+    def limiter_desc(self):
+        """(abi.LimiterDesc, look-ahead) of the device's limiter, or None when it has none."""
+        from pyb200mix import abi
+        d = abi.LimiterDesc()
+        rc = self.hz.refh_limiter_desc(self.dev, C.byref(d))
+        return (d, rc - 1) if rc else None
 
     def set_slot_target(self, slot: int, target: int):
         self.al.alAuxiliaryEffectSloti(slot, 0x199C, target)      # AL_EFFECTSLOT_TARGET_SOFT

@@ -4,6 +4,8 @@
 (3) size-independent properties at BASELINE.json's config-2 size.
 Tolerance (north_star): RMS <= 1e-5 and max-abs <= 1e-4 on float32 output; we hold the
 CUDA path to a 10x tighter bound against the oracle since both follow the same math."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -127,6 +129,50 @@ def test_partial_update_sizes_vs_oracle():
         dev.close()
         outs.append(np.concatenate(o, axis=1))
     _check(outs[1], outs[0], "ragged update sizes")
+
+
+LIMITER_DESCS = {
+    # the reference's device limiter (CreateDeviceLimiter, alc/alc.cpp:1079-1091), 16-bit threshold
+    "device": abi.device_limiter(-0.00053),
+    # a plain 4:1 compressor: nothing automated, soft knee, pre/post gain, no hold
+    "manual": abi.LimiterDesc(C.sizeof(abi.LimiterDesc), 0, 0.002, 0.0, 3.0, -1.5, -9.0, 4.0, 6.0, 0.005, 0.1),
+    # automation without look-ahead (no delay lines, no hold)
+    "no_lookahead": abi.LimiterDesc(C.sizeof(abi.LimiterDesc), abi.LIM_AUTO_ALL, 0.0, 0.002, 0.0, 0.0, -3.0,
+                                    float("inf"), 0.0, 0.02, 0.2),
+}
+
+
+@pytest.mark.parametrize("kind", sorted(LIMITER_DESCS))
+def test_limiter_vs_oracle_ragged_updates(kind):
+    """Compressor::process on a mix driven past full scale, with update sizes below and above the
+    look-ahead (48) and hold (96) lengths; the unlimited mix is checked to be much louder."""
+    rng = np.random.default_rng(21)
+    nv, ir = 16, 64
+    desc = synth.hrtf_desc(nv, ir)
+    params, coeffs, dry = synth.voice_set(rng, nv, ir)
+    for p in params:
+        p.hrtf_gain *= 12.0
+    sizes = (1024, 37, 512, 1, 1000, 64, 20, 20, 100, 1024)
+    outs = []
+    for lib, lim in ((mixlib.oracle(), True), (mixlib.product(), True), (mixlib.product(), False)):
+        dev = MixDevice(lib, desc)
+        dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.voices_update(params, coeffs, dry, None)
+        if lim:
+            la = dev.set_limiter(LIMITER_DESCS[kind])
+            assert la == round(LIMITER_DESCS[kind].look_ahead_time * desc.sample_rate)
+        o = [dev.render(f) for f in sizes]
+        if lim:
+            dev.set_limiter(None)      # device->Limiter = nullptr
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    # the tolerances are for full-scale output: a compressor that leaves the mix above 1.0 is
+    # judged relative to its peak
+    scale = max(1.0, float(np.abs(outs[0]).max()))
+    _check(outs[1] / scale, outs[0] / scale, f"limiter {kind}")
+    assert np.abs(outs[2]).max() > 2.0 * np.abs(outs[1]).max()
 
 
 def test_config2_size_linearity_and_subsample():

@@ -27,6 +27,12 @@ def test_oracle_matches_reference_sse_kernels(name):
     out, _ = golden.replay(mixlib.oracle(), fx)
     ref = fx["out_sse"].astype(np.float64)
     err = out - ref
+    if "out_type" in fx:
+        # integer output: the SSE kernels' last-bit differences can move a sample across a
+        # rounding boundary — by one step at most, and rarely
+        assert np.abs(err).max() <= 1 and (err != 0).mean() <= 0.01
+        assert np.ptp(ref) > 8
+        return
     assert np.sqrt((err ** 2).mean()) <= 1e-7
     assert np.abs(err).max() <= 1e-6
     assert np.abs(ref).max() > 1e-3  # the scene is not silent

@@ -151,3 +151,38 @@ def test_filters_ragged_updates_vs_reference_live(hrtf):
         if dev is not None:
             dev.close()
         ref.close()
+
+
+@pytest.mark.parametrize("hrtf", [1, 0])
+def test_limiter_ragged_updates_vs_reference_live(hrtf):
+    """Pins the oracle's Compressor (look-ahead FIFO, sliding hold, envelope state carried
+    across updates) against the live reference: float output with ALC_OUTPUT_LIMITER_SOFT, a mix
+    driven past full scale, update sizes below and above the look-ahead (48) and hold (96)."""
+    import ctypes as C
+    from helpers import scenes
+    V = 6
+    ref, pcms = scenes.make_ref_scene(V, hrtf, abi.RS_SPLINE, attrs={refal.ALC_OUTPUT_LIMITER_SOFT: 1})
+    ref.al.alListenerf.argtypes = [C.c_int, C.c_float]
+    ref.al.alListenerf(refal.AL_GAIN, 6.0)
+    sizes = [1024, 37, 500, 1, 1000, 64, 20, 20, 100, 333, 1024]
+    ref.play_all()
+    dev = None
+    peak = 0.0
+    try:
+        for u, n in enumerate(sizes):
+            out_ref = ref.render(n)
+            if dev is None:
+                dev = scenes.mirror_device(mixlib.oracle(), ref, V, pcms)
+                scenes.feed_params(dev, ref, True, V)
+                ld, la = ref.limiter_desc()
+                assert dev.set_limiter(ld) == la == 48
+            out = dev.render(n)
+            err = np.abs(out.astype(np.float64) - out_ref).max()
+            assert err <= 2e-6, (u, n, err)
+            peak = max(peak, float(np.abs(out_ref).max()))
+    finally:
+        if dev is not None:
+            dev.close()
+        ref.close()
+    # the limiter did hold the mix at full scale (the unlimited mix peaks far above 1)
+    assert 0.5 < peak <= 1.0 + 1e-6, peak
