@@ -358,6 +358,15 @@ typedef struct b200mix_limiter_desc {
 B200MIX_API int b200mix_set_limiter(b200mix_device *dev, const b200mix_limiter_desc *desc,
     uint32_t *look_ahead);
 
+/* Speaker distance compensation: ApplyDistanceComp (alc/alu.cpp:2276-2307) with the per-channel
+ * delays and gains InitDistanceComp derived from a custom decoder's speaker distances
+ * (alc/panning.cpp:301-371: DistanceComp::ChanData{Buffer.size(), Gain} per RealOut channel).
+ * Runs after the limiter and before dither/conversion (alc/alu.cpp:2449-2450).  delays[c] in
+ * samples (< 1024 = DistanceComp::MaxDelay, core/device.h:88), 0 = channel untouched (the
+ * reference skips channels without a buffer, gain included).  channels == 0 removes it. */
+B200MIX_API int b200mix_set_distance_comp(b200mix_device *dev, uint32_t channels,
+    const uint32_t *delays, const float *gains);
+
 /* The same update in two halves, for voice-sharded multi-GPU mixing: effects
  * consume the SUMMED wet input of all ranks, so the host reduces the wet buffers between
  * the halves.  b200mix_render_begin clears the mix buffers, mixes this device's voices and

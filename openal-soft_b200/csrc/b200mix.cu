@@ -121,6 +121,7 @@ struct b200mix_device {
     uint4 *d_qhdr{nullptr}; uint32_t *d_queue{nullptr};   // streaming queues (first b200mix_voice_queue)
     LimiterDev *d_limiter{nullptr};                      // DeviceBase::Limiter (b200mix_set_limiter)
     float *d_limiter_delay{nullptr};                     // Compressor::mDelay [real_channels][1024]
+    uint32_t *d_dc_delay{nullptr}; float *d_dc_gain{nullptr}, *d_dc_buf{nullptr};   // DeviceBase::ChannelDelays
     void *d_outbuf{nullptr}, *h_outbuf{nullptr};          // interleaved output staging (render_interleaved)
     // reverb slots: host side of ReverbState's two-pipeline state machine
     struct RvHost {
@@ -456,6 +457,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_dline); cudaFree(d->d_order2); cudaFree(d->d_qhdr); cudaFree(d->d_queue);
     cudaFree(d->d_outbuf); if(d->h_outbuf) cudaFreeHost(d->h_outbuf);
     cudaFree(d->d_limiter); cudaFree(d->d_limiter_delay);
+    cudaFree(d->d_dc_delay); cudaFree(d->d_dc_gain); cudaFree(d->d_dc_buf);
     cudaFree(d->d_st_fields); cudaFree(d->d_st_elevs); cudaFree(d->d_st_coeffs); cudaFree(d->d_st_delays);
     cudaFree(d->d_dry_entries); cudaFree(d->d_dry_slot_start); cudaFree(d->d_dry_partial);
     cudaFree(d->d_dry_geff); cudaFree(d->d_send_geff); cudaFree(d->d_send_partial);
@@ -1636,6 +1638,13 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         k_limiter<<<1, 1024, 0, d->stream>>>(LQ);
         ++d->launches;
     }
+    if(d->d_dc_delay)
+    {
+        // if(ChannelDelays) ApplyDistanceComp(RealOut.Buffer, ...), alc/alu.cpp:2449-2450
+        DistCompParams DQ{d->d_real, d->d_dc_buf, d->d_dc_delay, d->d_dc_gain, frames};
+        k_distance_comp<<<dd.real_channels, 1024, 0, d->stream>>>(DQ);
+        ++d->launches;
+    }
     stage_mark(d, 8);
     if(d->profile_level >= 2) d->stage_valid = true;
     CUDA_TRY(d, cudaGetLastError());
@@ -1687,6 +1696,33 @@ int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
     if(!d) return B200MIX_ERR_INVALID;
     if(int rc = render_launch(d, frames, results != nullptr)) return rc;
     return render_collect(d, frames, real_out, results);
+}
+
+int b200mix_set_distance_comp(b200mix_device *d, uint32_t channels, const uint32_t *delays, const float *gains)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(d->mid_render) { d->error = "set_distance_comp: a render_begin is pending"; return B200MIX_ERR_INVALID; }
+    const b200mix_device_desc &dd = d->desc;
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    cudaFree(d->d_dc_delay); cudaFree(d->d_dc_gain); cudaFree(d->d_dc_buf);
+    d->d_dc_delay = nullptr; d->d_dc_gain = nullptr; d->d_dc_buf = nullptr;
+    if(!channels) return B200MIX_OK;
+    if(channels > dd.real_channels || !delays || !gains)
+    { d->error = "set_distance_comp: bad arguments"; return B200MIX_ERR_INVALID; }
+    std::vector<uint32_t> hd(dd.real_channels, 0u);
+    std::vector<float> hg(dd.real_channels, 1.0f);
+    for(uint32_t c = 0;c < channels;++c)
+    {
+        if(delays[c] >= kLine) { d->error = "set_distance_comp: delay >= 1024"; return B200MIX_ERR_INVALID; }
+        hd[c] = delays[c]; hg[c] = gains[c];
+    }
+    if(int rc = dev_alloc(d, d->d_dc_delay, dd.real_channels)) return rc;
+    if(int rc = dev_alloc(d, d->d_dc_gain, dd.real_channels)) return rc;
+    if(int rc = dev_alloc(d, d->d_dc_buf, size_t(dd.real_channels)*kLine)) return rc;
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    CUDA_TRY(d, cudaMemcpy(d->d_dc_delay, hd.data(), hd.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(d, cudaMemcpy(d->d_dc_gain, hg.data(), hg.size()*sizeof(float), cudaMemcpyHostToDevice));
+    return B200MIX_OK;
 }
 
 // Compressor::Create (core/mastering.cpp:108-166): the same float/double expressions, by the

@@ -1910,6 +1910,24 @@ __global__ void __launch_bounds__(1024) k_limiter(const LimiterParams Q)
     }
 }
 
+// Speaker distance compensation: ApplyDistanceComp (alc/alu.cpp:2276-2307).  Per channel a
+// FIFO of `delay` samples ([delay line | this update] -> output, the rest is the new delay
+// line), then the channel's gain on what comes out; channels without a delay are left alone.
+struct DistCompParams { float *real; float *buf; const uint32_t *delay; const float *gain; uint32_t frames; };
+
+__global__ void __launch_bounds__(1024) k_distance_comp(const DistCompParams Q)
+{
+    const uint32_t c = blockIdx.x, i = threadIdx.x, n = Q.frames, base = Q.delay[c];
+    if(base < 1u) return;
+    float *x = Q.real + size_t(c)*kLine, *dl = Q.buf + size_t(c)*kLine;
+    float v = 0.0f, nd = 0.0f;
+    if(i < n) v = i < base ? dl[i] : x[i - base];
+    if(i < base) nd = (n + i < base) ? dl[n + i] : x[n + i - base];
+    __syncthreads();
+    if(i < n) x[i] = __fmul_rn(v, Q.gain[c]);
+    if(i < base) dl[i] = nd;
+}
+
 // Output stage: ApplyDither (alc/alu.cpp:2309-2333) + Write<T> (alc/alu.cpp:2362-2390).
 // The reference draws two LCG values per sample, channel after channel; sample i of channel c
 // therefore uses draws 2(c*n+i)+1 and +2 from the incoming seed — reached directly with the

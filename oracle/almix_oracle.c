@@ -259,6 +259,9 @@ struct oracle_device {
     float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
     uint32_t mid_frames;       /* between oracle_render_begin and oracle_render_end */
     olimiter *limiter;         /* DeviceBase::Limiter */
+    uint32_t *dc_delay;        /* DeviceBase::ChannelDelays: Buffer.size() per RealOut channel */
+    float *dc_gain;
+    float (*dc_buf)[LINE];
     float hrtf_samples[LINE+HIST];
     float temp[LINE], temp2[LINE];
 };
@@ -298,6 +301,7 @@ void oracle_destroy(oracle_device *d)
     }
     free(d->slots);
     olimiter_destroy(d->limiter);
+    free(d->dc_delay); free(d->dc_gain); free(d->dc_buf);
     free(d->dry); free(d->wet);
     free(d->dec_coef); free(d->dec_hfscale); free(d->dec_split);
     free(d->amb_hf); free(d->amb_lf); free(d->amb_split);
@@ -348,6 +352,22 @@ int oracle_set_limiter(oracle_device *d, const b200mix_limiter_desc *desc, uint3
     d->limiter = olimiter_create(desc, d->desc.real_channels, (float)d->desc.sample_rate);
     if(!d->limiter) return B200MIX_ERR_NOMEM;
     if(look_ahead) *look_ahead = olimiter_look_ahead(d->limiter);
+    return B200MIX_OK;
+}
+
+/* InitDistanceComp's result (alc/panning.cpp:301-371) */
+int oracle_set_distance_comp(oracle_device *d, uint32_t channels, const uint32_t *delays, const float *gains)
+{
+    free(d->dc_delay); free(d->dc_gain); free(d->dc_buf);
+    d->dc_delay = NULL; d->dc_gain = NULL; d->dc_buf = NULL;
+    if(!channels) return B200MIX_OK;
+    if(channels > d->desc.real_channels || !delays || !gains) return B200MIX_ERR_INVALID;
+    for(uint32_t c = 0;c < channels;++c) if(delays[c] >= LINE) return B200MIX_ERR_INVALID;
+    const uint32_t rc = d->desc.real_channels;
+    d->dc_delay = calloc(rc, sizeof(uint32_t)); d->dc_gain = calloc(rc, sizeof(float));
+    d->dc_buf = calloc(rc, sizeof(float[LINE]));
+    if(!d->dc_delay || !d->dc_gain || !d->dc_buf) return B200MIX_ERR_NOMEM;
+    for(uint32_t c = 0;c < channels;++c) { d->dc_delay[c] = delays[c]; d->dc_gain[c] = gains[c]; }
     return B200MIX_OK;
 }
 
@@ -1533,6 +1553,31 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
 
     /* if(Limiter) Limiter->process(samplesToDo, RealOut.Buffer), alc/alu.cpp:2446 */
     if(d->limiter) olimiter_process(d->limiter, frames, d->real);
+
+    /* if(ChannelDelays) ApplyDistanceComp(...), alc/alu.cpp:2449-2450 and :2276-2307: a FIFO of
+     * `base` samples per channel (the rotate/swap pair), then the gain on what comes out */
+    if(d->dc_delay)
+        for(uint32_t c = 0;c < dd->real_channels;++c)
+        {
+            const uint32_t base = d->dc_delay[c];
+            if(base < 1) continue;
+            float *buf = d->real[c], *dl = d->dc_buf[c], tmp[LINE];
+            if(frames >= base)
+            {
+                memcpy(tmp, buf + (frames-base), sizeof(float)*base);
+                memmove(buf + base, buf, sizeof(float)*(frames-base));
+                memcpy(buf, dl, sizeof(float)*base);
+                memcpy(dl, tmp, sizeof(float)*base);
+            }
+            else
+            {
+                memcpy(tmp, buf, sizeof(float)*frames);
+                memcpy(buf, dl, sizeof(float)*frames);
+                memmove(dl, dl + frames, sizeof(float)*(base-frames));
+                memcpy(dl + (base-frames), tmp, sizeof(float)*frames);
+            }
+            for(uint32_t i = 0;i < frames;++i) buf[i] = buf[i]*d->dc_gain[c];
+        }
 
     if(real_out_host) *real_out_host = &d->real[0][0];
     if(real_out)

@@ -214,6 +214,22 @@ int refh_limiter_desc(ALCdevice *adev, b200mix_limiter_desc *out)
     return static_cast<int>(device->Limiter->getLookAhead()) + 1;
 }
 
+/* DeviceBase::ChannelDelays (core/device.h:85-100) as InitDistanceComp built it: per RealOut
+ * channel the delay line length and gain.  Returns the channel count, 0 without distance comp. */
+int refh_distance_comp(ALCdevice *adev, uint32_t *delays, float *gains)
+{
+    auto *device = dev_of(adev);
+    if(!device->ChannelDelays) return 0;
+    const auto n = device->RealOut.Buffer.size();
+    for(size_t c{0};c < n;++c)
+    {
+        const auto &cd = device->ChannelDelays->mChannels[c];
+        delays[c] = static_cast<uint32_t>(cd.Buffer.size());
+        gains[c] = cd.Gain;
+    }
+    return static_cast<int>(n);
+}
+
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
 static size_t g_snap_channel = 0;

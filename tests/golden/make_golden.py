@@ -77,6 +77,9 @@ SCENES = {
     # run out, so the release side is covered too) and float output with ALC_OUTPUT_LIMITER_SOFT
     "hrtf_spline_limiter_i16_v6": (6, 1, 2, 8, False, 4000, "lim_i16", "i16", 0, None, None, "limiter"),
     "stereo_spline_limiter_f32_v6": (6, 0, 2, 5, True, 48000, "lim_f32", "i16", 0, None, None, "limiter"),
+    # a custom quad decoder (QUAD_AMBDEC below, speakers at unequal distances): BFormatDec from the
+    # .ambdec matrices + ApplyDistanceComp with the delays/gains InitDistanceComp derives
+    "quad_spline_distcomp_v6": (6, 0, 2, 4, True, 48000, "quad", "i16", 0, None, None, "distcomp"),
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
@@ -134,6 +137,36 @@ def apply_filter_script(ref, script, u, slot):
 
 LIMITER_LISTENER_GAIN = 5.0
 
+# A first-order horizontal decoder of our own for a quad rig whose speakers stand at different
+# distances (2.0, 1.5, 2.5 and 1.0 m): single band, plain projection rows (W, Y, X in ACN order).
+QUAD_AMBDEC = """/description quad_unequal_distances
+/version 3
+/dec/chan_mask b
+/dec/freq_bands 1
+/dec/speakers 4
+/dec/coeff_scale n3d
+/opt/input_scale n3d
+/opt/nfeff_comp input
+/opt/delay_comp on
+/opt/level_comp on
+/opt/xover_freq 400
+/opt/xover_ratio 0
+/speakers/{
+add_spkr LF 2.0 45 0
+add_spkr RF 1.5 -45 0
+add_spkr LB 2.5 135 0
+add_spkr RB 1.0 -135 0
+/}
+/matrix/{
+order_gain 1 1 0 0
+add_row 0.25 0.204124 0.204124
+add_row 0.25 -0.204124 0.204124
+add_row 0.25 0.204124 -0.204124
+add_row 0.25 -0.204124 -0.204124
+/}
+/end
+"""
+
 
 def conv_ir(taps):
     rng = np.random.default_rng(taps)
@@ -146,6 +179,7 @@ ATTRS = {
     "out_u8": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_UNSIGNED_BYTE_SOFT, r.ALC_OUTPUT_LIMITER_SOFT: 0},
     "lim_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT},
     "lim_f32": lambda r: {r.ALC_OUTPUT_LIMITER_SOFT: 1},
+    "quad": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_QUAD_SOFT},
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
     "ambi2": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 2,
                         r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
@@ -296,6 +330,17 @@ def run_scene(name):
                    rv_state=np.array([x[2] for x in rv_steps], dtype=np.int64))
     if out_type is not None:
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
+    if len(spec) > 11 and spec[11] == "distcomp":
+        dl, dg = ref.distance_comp()
+        assert dl.max() > 0, dl
+        res.update(distcomp_delays=dl, distcomp_gains=dg)
+        # DistanceComp::Create (core/device.h:98-99) does not clear mSamples: what the first
+        # update plays out of the delay lines is uninitialised heap memory in the reference
+        # (seen: 1e32 in one run, zeros in the next).  Those samples are not part of the
+        # contract; they are zeroed here and in the replay.
+        res.update(undefined_head=dl.astype(np.int64))
+        for c, n in enumerate(dl):
+            res["out"][0, c, :int(n)] = 0
     if limiter:
         ld, la = ref.limiter_desc()
         res.update(limiter_desc=np.frombuffer(bytes(ld), dtype=np.uint8).copy(), limiter_look_ahead=np.int64(la))
@@ -320,6 +365,12 @@ def run_scene(name):
 def child(name, mode, path):
     from helpers import refal
     conf = "[general]\n" + ("disable-cpu-exts = all\n" if mode == "c" else "")
+    spec = SCENES[name]
+    if len(spec) > 11 and spec[11] == "distcomp":
+        amb = os.path.join(HERE, f"_tmp_{os.getpid()}.ambdec")
+        with open(amb, "w") as f:
+            f.write(QUAD_AMBDEC)
+        conf += f"[decoder]\nquad = {amb}\n"
     refal.libs(conf)
     res = run_scene(name)
     np.savez(path, **res)

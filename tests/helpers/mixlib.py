@@ -62,6 +62,8 @@ class MixLib:
                                             C.c_float, C.POINTER(C.c_uint32), C.c_void_p]
         self.set_limiter = f("set_limiter")
         self.set_limiter.argtypes = [C.c_void_p, C.POINTER(abi.LimiterDesc), C.POINTER(C.c_uint32)]
+        self.set_distance_comp = f("set_distance_comp")
+        self.set_distance_comp.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         self.render_begin = f("render_begin")
         self.render_begin.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         self.render_end = f("render_end")
@@ -207,6 +209,17 @@ class MixDevice:
         rc = self.m.set_limiter(self.h, C.byref(desc) if desc is not None else None, C.byref(la))
         assert rc == 0, f"set_limiter -> {rc}"
         return la.value
+
+    def set_distance_comp(self, delays, gains):
+        """Installs per-channel output delays/gains (None removes them)."""
+        if delays is None:
+            rc = self.m.set_distance_comp(self.h, 0, None, None)
+        else:
+            dl = np.ascontiguousarray(delays, dtype=np.uint32)
+            g = np.ascontiguousarray(gains, dtype=np.float32)
+            assert dl.shape == g.shape
+            rc = self.m.set_distance_comp(self.h, len(dl), dl.ctypes.data, g.ctypes.data)
+        assert rc == 0, f"set_distance_comp -> {rc}"
 
     def render_begin(self, frames=1024):
         """Returns (wet pointer, float count): a host pointer on the oracle, a device pointer

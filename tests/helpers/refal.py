@@ -57,6 +57,7 @@ ALC_FLOAT_SOFT = 0x1406
 ALC_SHORT_SOFT = 0x1402
 ALC_UNSIGNED_BYTE_SOFT = 0x1401
 ALC_STEREO_SOFT = 0x1501
+ALC_QUAD_SOFT = 0x1503
 ALC_BFORMAT3D_SOFT = 0x1507
 ALC_HRTF_SOFT = 0x1992
 ALC_HRTF_STATUS_SOFT = 0x1993
@@ -144,6 +145,7 @@ def libs(conf_text: str | None = None):
     hz.refh_dither_depth.argtypes = [C.c_void_p]
     hz.refh_dither_depth.restype = C.c_float
     hz.refh_limiter_desc.argtypes = [C.c_void_p, C.c_void_p]
+    hz.refh_distance_comp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     hz.refh_set_snapshot_channel.argtypes = [C.c_int]
     hz.refh_set_snapshot_channel.restype = None
     hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -369,6 +371,13 @@ class RefDevice:
 
     def dither_depth(self) -> float:
         return float(self.hz.refh_dither_depth(self.dev))
+
+    def distance_comp(self):
+        """(delays uint32[real], gains float32[real]) of DeviceBase::ChannelDelays, or None."""
+        dl = np.zeros(64, dtype=np.uint32)
+        g = np.zeros(64, dtype=np.float32)
+        n = self.hz.refh_distance_comp(self.dev, dl.ctypes.data, g.ctypes.data)
+        return (dl[:n].copy(), g[:n].copy()) if n else None
 
     def limiter_desc(self):
         """(abi.LimiterDesc, look-ahead) of the device's limiter, or None when it has none."""

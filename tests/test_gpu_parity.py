@@ -175,6 +175,35 @@ def test_limiter_vs_oracle_ragged_updates(kind):
     assert np.abs(outs[2]).max() > 2.0 * np.abs(outs[1]).max()
 
 
+def test_distance_comp_vs_oracle_ragged_updates():
+    """ApplyDistanceComp after an ambisonic decode: per-channel FIFOs longer and shorter than the
+    update sizes, a channel without delay (left untouched, gain included), then removal."""
+    rng = np.random.default_rng(31)
+    nv = 12
+    desc = synth.stereo_desc(nv)
+    params, coeffs, dry = synth.voice_set(rng, nv, 0, hrtf=False, dry_channels=desc.dry_channels)
+    delays = np.array([700, 0][:desc.real_channels] + [13] * max(desc.real_channels - 2, 0), dtype=np.uint32)
+    gains = np.array([0.6, 0.25][:desc.real_channels] + [0.9] * max(desc.real_channels - 2, 0), dtype=np.float32)
+    sizes = (1024, 37, 512, 1, 1000, 64, 5, 1024)
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        g = np.random.default_rng(8).standard_normal((desc.dry_channels, desc.real_channels))
+        dev.set_ambi_decoder(g.astype(np.float32), None, 0.0)
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.voices_update(params, None, dry, None)
+        dev.set_distance_comp(delays, gains)
+        o = [dev.render(f) for f in sizes]
+        dev.set_distance_comp(None, None)
+        o.append(dev.render(256))
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], "distance compensation")
+    # channel 0 starts with 700 samples of (zeroed) delay line
+    assert not outs[1][0, :700].any() and outs[1][0, 700:1024].any()
+
+
 def test_config2_size_linearity_and_subsample():
     """BASELINE config 2 size (4096 HRTF voices, bsinc24): the oracle only mixes a
     deterministic 1/16 subsample; the full mix is checked by linearity — the sum of
