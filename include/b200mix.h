@@ -358,6 +358,14 @@ typedef struct b200mix_limiter_desc {
 B200MIX_API int b200mix_set_limiter(b200mix_device *dev, const b200mix_limiter_desc *desc,
     uint32_t *look_ahead);
 
+/* Which UHJ encoder a B200MIX_POST_UHJ device runs (UhjEncodeQuality, alc/alc.cpp:564-574;
+ * core/uhjfilter.h): filter_length 0 = UhjEncoderIIR (the default), 256 / 512 = UhjEncoder<N>
+ * (core/uhjfilter.cpp:83-205: the +90 degree shift as an N-tap linear-phase FIR, every other
+ * signal delayed by N/2 + 128 samples).  Resets the encoder state; *delay (nullable) receives
+ * EncoderBase::getDelay() in samples. */
+B200MIX_API int b200mix_set_uhj_encoder(b200mix_device *dev, uint32_t filter_length,
+    uint32_t *delay);
+
 /* Speaker distance compensation: ApplyDistanceComp (alc/alu.cpp:2276-2307) with the per-channel
  * delays and gains InitDistanceComp derived from a custom decoder's speaker distances
  * (alc/panning.cpp:301-371: DistanceComp::ChanData{Buffer.size(), Gain} per RealOut channel).

@@ -75,6 +75,8 @@ struct b200mix_device {
     float *d_amb_hf{nullptr}, *d_amb_lf{nullptr}, *d_amb_state{nullptr};
     bool dry_active{false};
     float *d_uhj_state{nullptr}, *d_uhj_scratch{nullptr};
+    uint32_t uhj_fir{0};                                  // 0 = IIR, 256 / 512 = UhjEncoder<N>
+    float *d_uhj_fir_state{nullptr}, *d_uhj_fir_coef{nullptr};
 
     // update staging (pinned host + device)
     char *h_arena{nullptr}, *d_arena{nullptr};    // staging arena (see ensure_stage)
@@ -451,6 +453,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
+    cudaFree(d->d_uhj_fir_state); cudaFree(d->d_uhj_fir_coef);
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
@@ -1625,7 +1628,14 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         PostUhjParams Q{};
         Q.dry = d->d_dry; Q.real = d->d_real; Q.state = d->d_uhj_state; Q.scratch = d->d_uhj_scratch;
         Q.frames = frames; Q.real_left = dd.real_left; Q.real_right = dd.real_right;
-        k_post_uhj<<<1, 1024, 0, d->stream>>>(Q);
+        if(d->uhj_fir)
+        {
+            PostUhjFirParams F{d->d_dry, d->d_real, d->d_uhj_fir_state, d->d_uhj_fir_coef, frames,
+                dd.real_left, dd.real_right, d->uhj_fir};
+            k_post_uhj_fir<<<1, 1024, 0, d->stream>>>(F);
+        }
+        else
+            k_post_uhj<<<1, 1024, 0, d->stream>>>(Q);
         ++d->launches;
         break;
     }
@@ -1696,6 +1706,44 @@ int b200mix_render(b200mix_device *d, uint32_t frames, float *const *real_out,
     if(!d) return B200MIX_ERR_INVALID;
     if(int rc = render_launch(d, frames, results != nullptr)) return rc;
     return render_collect(d, frames, real_out, results);
+}
+
+int b200mix_set_uhj_encoder(b200mix_device *d, uint32_t filter_length, uint32_t *delay)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    if(d->mid_render || dd.post_process != B200MIX_POST_UHJ || dd.dry_channels < 3
+        || (filter_length != 0 && filter_length != 256 && filter_length != 512))
+    { d->error = "set_uhj_encoder: needs a UHJ device and a length of 0, 256 or 512"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    CUDA_TRY(d, cudaMemset(d->d_uhj_state, 0, 64*sizeof(float)));
+    if(filter_length)
+    {
+        if(!d->d_uhj_fir_state)
+        {
+            if(int rc = dev_alloc(d, d->d_uhj_fir_state, kUhjFirStateFloats)) return rc;
+            if(int rc = dev_alloc(d, d->d_uhj_fir_coef, 256)) return rc;
+            CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        }
+        CUDA_TRY(d, cudaMemset(d->d_uhj_fir_state, 0, kUhjFirStateFloats*sizeof(float)));
+        // SegmentedFilter's desired response (core/allpass_conv.hpp:56-75): Blackman-Nuttall
+        // windowed 2/(pi k) at the odd taps
+        const uint32_t half = filter_length/2u;
+        std::vector<float> coef(256, 0.0f);
+        const double pi = 3.14159265358979323846;
+        for(uint32_t i = 0;i < half;++i)
+        {
+            const int k = int(half) - int(i*2u + 1u);
+            const double w = 2.0*pi/double(half - 1u) * double(i);
+            const double window = 0.3635819 - 0.4891775*std::cos(w) + 0.1365995*std::cos(2.0*w)
+                - 0.0106411*std::cos(3.0*w);
+            coef[i] = float(window * 2.0 / (pi * double(k)));
+        }
+        CUDA_TRY(d, cudaMemcpy(d->d_uhj_fir_coef, coef.data(), 256*sizeof(float), cudaMemcpyHostToDevice));
+    }
+    d->uhj_fir = filter_length;
+    if(delay) *delay = filter_length ? filter_length/2u + 128u : 1u;
+    return B200MIX_OK;
 }
 
 int b200mix_set_distance_comp(b200mix_device *d, uint32_t channels, const uint32_t *delays, const float *gains)

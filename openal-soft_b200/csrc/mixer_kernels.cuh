@@ -1620,6 +1620,64 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     }
 }
 
+// UhjEncoder<N>::encode (core/uhjfilter.cpp:83-205), N = 256 or 512.  The reference shifts
+// -0.171 W + 0.208 X by +90 degrees with a segmented FFT overlap-add (core/allpass_conv.hpp);
+// that is a linear convolution with an N-tap response (every second tap zero) delivered one
+// 128-sample segment late, evaluated here directly from shared memory — 64/128 k MACs per
+// update.  W, X, Y and the existing Left/Right content are delayed by N/2 + 128 samples.
+struct PostUhjFirParams {
+    const float *dry; float *real; float *state; const float *coef;   // coef[j] = h[2j+1]
+    uint32_t frames, real_left, real_right, taps;
+};
+constexpr uint32_t kUhjFirHist = 640u, kUhjFirDelay = 384u;            // state: hist | 3 in | 2 out
+constexpr uint32_t kUhjFirStateFloats = kUhjFirHist + 5u*kUhjFirDelay;
+
+__global__ void __launch_bounds__(1024) k_post_uhj_fir(const PostUhjFirParams Q)
+{
+    constexpr uint32_t kSeg = 128u;
+    __shared__ float sExt[kUhjFirHist + kLine];
+    __shared__ float sCoef[256];
+    const uint32_t n = Q.frames, N = Q.taps, hist = N + kSeg - 1u, delay = N/2u + kSeg;
+    const uint32_t i = threadIdx.x;
+    float *wxh = Q.state;
+    const float *w = Q.dry, *x = Q.dry + kLine, *y = Q.dry + 2*kLine;
+    float *lines[5] = {const_cast<float*>(w), const_cast<float*>(x), const_cast<float*>(y),
+        Q.real + size_t(Q.real_left)*kLine, Q.real + size_t(Q.real_right)*kLine};
+
+    if(i < hist) sExt[i] = wxh[i];
+    if(i < n) sExt[hist + i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    if(i < N/2u) sCoef[i] = Q.coef[i];
+    // the five delayed signals: [delay line | this update] -> value i; the tail is the new line
+    float dv[5], nd[5];
+    #pragma unroll
+    for(int c = 0;c < 5;++c)
+    {
+        const float *dl = Q.state + kUhjFirHist + c*kUhjFirDelay;
+        dv[c] = 0.0f; nd[c] = 0.0f;
+        if(i < n) dv[c] = i < delay ? dl[i] : lines[c][i - delay];
+        if(i < delay) nd[c] = (n + i < delay) ? dl[n + i] : lines[c][n + i - delay];
+    }
+    __syncthreads();
+    if(i < n)
+    {
+        const float *src = sExt + hist + i - kSeg - 1u;     // tap k = 2j+1 reads src[-2j]
+        float acc0 = 0.0f, acc1 = 0.0f;
+        for(uint32_t j = 0;j < N/2u;j += 2u)
+        {
+            acc0 = fmaf(sCoef[j], src[-int(2u*j)], acc0);
+            acc1 = fmaf(sCoef[j + 1u], src[-int(2u*j + 2u)], acc1);
+        }
+        const float S = 0.4698463f*dv[0] + 0.0757602682546f*dv[1];
+        const float D = (acc0 + acc1) + 0.267586995182f*dv[2];
+        lines[3][i] = dv[3] + (S + D);
+        lines[4][i] = dv[4] + (S - D);
+    }
+    #pragma unroll
+    for(int c = 0;c < 5;++c)
+        if(i < delay) Q.state[kUhjFirHist + c*kUhjFirDelay + i] = nd[c];
+    if(i < hist) wxh[i] = sExt[n + i];
+}
+
 // Output limiter: Compressor::process (core/mastering.cpp:261-379) on RealOut, one CTA.
 // The reference's stages are kept, each in the most parallel form its arithmetic allows:
 //  1. pre-gain, linked peak max_c|x_c| (one thread per sample);

@@ -12,6 +12,8 @@
 #include "reverb_oracle.h"
 #include "limiter_oracle.h"
 
+#define ORACLE_PI 3.14159265358979323846   /* std::numbers::pi */
+
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -253,6 +255,12 @@ struct oracle_device {
     float uhj_f1wx[4][2], uhj_f2wx[4][2], uhj_f1y[4][2], uhj_f1d[2][4][2];
     float uhj_delay_wx, uhj_delay_y, uhj_delay_d[2];
     float uhj_s[LINE+1], uhj_d[LINE+1], uhj_wx[LINE], uhj_t[LINE+1];
+    /* UHJ FIR encoder (UhjEncoder<N>, core/uhjfilter.h:27-70): N = 0 selects the IIR one */
+    uint32_t uhj_fir;                   /* 0, 256 or 512 */
+    double uhj_fir_h[512];              /* the phase-shift response (odd taps only are non-zero) */
+    float uhj_wxhist[512+128];          /* the last N+127 values of -0.171 W + 0.208 X */
+    float uhj_in_delay[3][512/2+128];   /* W, X, Y delayed by sFilterDelay = N/2 + 128 */
+    float uhj_out_delay[2][512/2+128];  /* mDirectDelay */
     /* scratch */
     float resample_data[RESBUF];
     float samples[LINE];
@@ -352,6 +360,38 @@ int oracle_set_limiter(oracle_device *d, const b200mix_limiter_desc *desc, uint3
     d->limiter = olimiter_create(desc, d->desc.real_channels, (float)d->desc.sample_rate);
     if(!d->limiter) return B200MIX_ERR_NOMEM;
     if(look_ahead) *look_ahead = olimiter_look_ahead(d->limiter);
+    return B200MIX_OK;
+}
+
+/* UhjEncodeQuality (alc/alc.cpp:564-574): 0 = UhjEncoderIIR, 256/512 = UhjEncoder<N>; resets the
+ * encoder state like a device reset does.  *delay = EncoderBase::getDelay(). */
+int oracle_set_uhj_encoder(oracle_device *d, uint32_t filter_length, uint32_t *delay)
+{
+    if(filter_length != 0 && filter_length != 256 && filter_length != 512) return B200MIX_ERR_INVALID;
+    if(d->desc.post_process != B200MIX_POST_UHJ) return B200MIX_ERR_INVALID;
+    d->uhj_fir = filter_length;
+    memset(d->uhj_f1wx, 0, sizeof(d->uhj_f1wx)); memset(d->uhj_f2wx, 0, sizeof(d->uhj_f2wx));
+    memset(d->uhj_f1y, 0, sizeof(d->uhj_f1y)); memset(d->uhj_f1d, 0, sizeof(d->uhj_f1d));
+    d->uhj_delay_wx = d->uhj_delay_y = d->uhj_delay_d[0] = d->uhj_delay_d[1] = 0.0f;
+    memset(d->uhj_wxhist, 0, sizeof(d->uhj_wxhist));
+    memset(d->uhj_in_delay, 0, sizeof(d->uhj_in_delay));
+    memset(d->uhj_out_delay, 0, sizeof(d->uhj_out_delay));
+    if(filter_length)
+    {
+        /* SegmentedFilter's desired response, core/allpass_conv.hpp:56-75 */
+        const size_t N = filter_length, half = N/2;
+        memset(d->uhj_fir_h, 0, sizeof(d->uhj_fir_h));
+        for(size_t i = 0;i < half;++i)
+        {
+            const int k = (int)half - (int)(i*2 + 1);
+            const double w = 2.0*ORACLE_PI/(double)(half-1) * (double)i;
+            const double window = 0.3635819 - 0.4891775*cos(w) + 0.1365995*cos(2.0*w)
+                - 0.0106411*cos(3.0*w);
+            const double pk = ORACLE_PI * (double)k;
+            d->uhj_fir_h[i*2 + 1] = window * 2.0 / pk;
+        }
+    }
+    if(delay) *delay = filter_length ? filter_length/2 + 128 : 1;
     return B200MIX_OK;
 }
 
@@ -1408,6 +1448,66 @@ static void post_uhj(oracle_device *d, size_t n)
     for(size_t i = 0;i < n;++i) right[i] = d->uhj_s[i] - d->uhj_d[i] + d->uhj_t[i];
 }
 
+/* A FIFO of `len` samples in front of a line: [delay | inout] -> inout, the tail stays behind
+ * (the rotate/swap_ranges pairs of core/uhjfilter.cpp:174-193). */
+static void fifo_delay(float *dl, size_t len, float *inout, size_t n)
+{
+    float tmp[LINE];
+    if(n >= len)
+    {
+        memcpy(tmp, inout + (n-len), sizeof(float)*len);
+        memmove(inout + len, inout, sizeof(float)*(n-len));
+        memcpy(inout, dl, sizeof(float)*len);
+        memcpy(dl, tmp, sizeof(float)*len);
+    }
+    else
+    {
+        memcpy(tmp, inout, sizeof(float)*n);
+        memcpy(inout, dl, sizeof(float)*n);
+        memmove(dl, dl + n, sizeof(float)*(len-n));
+        memcpy(dl + (len-n), tmp, sizeof(float)*n);
+    }
+}
+
+/* UhjEncoder<N>::encode, core/uhjfilter.cpp:83-205.  The reference applies the wide-band +90
+ * degree shift j() by segmented FFT overlap-add (core/allpass_conv.hpp:42-103): a linear
+ * convolution with the N-tap response built at :61-75, delivered one 128-sample segment late.
+ * Restated by its definition — the direct convolution, accumulated in double — so it agrees
+ * with the reference within float rounding, not bitwise (like the convolution effect).  The
+ * other signals are delayed by sFilterDelay = N/2 + 128 to line up with it. */
+static void post_uhj_fir(oracle_device *d, size_t n)
+{
+    const size_t N = d->uhj_fir, seg = 128, delay = N/2 + seg, hist = N + seg - 1;
+    float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
+    float w[LINE], x[LINE], y[LINE], ext[512+128+LINE];
+    memcpy(w, d->dry[0], sizeof(float)*n); memcpy(x, d->dry[1], sizeof(float)*n);
+    memcpy(y, d->dry[2], sizeof(float)*n);
+
+    /* j(-0.17101005*W + 0.208149636675*X) of the NON-delayed input (:112-114) */
+    memcpy(ext, d->uhj_wxhist, sizeof(float)*hist);
+    for(size_t i = 0;i < n;++i) ext[hist + i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    for(size_t t = 0;t < n;++t)
+    {
+        double acc = 0.0;
+        for(size_t k = 1;k < N;k += 2) acc += d->uhj_fir_h[k] * (double)ext[hist + t - seg - k];
+        d->uhj_wx[t] = (float)acc;
+    }
+    memmove(d->uhj_wxhist, ext + n, sizeof(float)*hist);
+
+    fifo_delay(d->uhj_in_delay[0], delay, w, n);
+    fifo_delay(d->uhj_in_delay[1], delay, x, n);
+    fifo_delay(d->uhj_in_delay[2], delay, y, n);
+    fifo_delay(d->uhj_out_delay[0], delay, left, n);
+    fifo_delay(d->uhj_out_delay[1], delay, right, n);
+    for(size_t i = 0;i < n;++i)
+    {
+        const float S = 0.4698463f*w[i] + 0.0757602682546f*x[i];
+        const float D = d->uhj_wx[i] + 0.267586995182f*y[i];
+        left[i] += S + D;
+        right[i] += S - D;
+    }
+}
+
 /* MixSamples(line, Dry, Current, Target, Counter = n): ReverbState::MixOutPlain */
 /* mOutTarget of the slot being processed (alc/alu.cpp:626-633): the Dry mix or the target
  * slot's Wet buffer */
@@ -1546,7 +1646,9 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
     {
     case B200MIX_POST_HRTF: if(d->dec_channels) post_hrtf(d, frames); break;
     case B200MIX_POST_AMBIDEC: if(d->amb_in) post_ambidec(d, frames); break;
-    case B200MIX_POST_UHJ: if(dd->dry_channels >= 3) post_uhj(d, frames); break;
+    case B200MIX_POST_UHJ:
+        if(dd->dry_channels >= 3) { if(d->uhj_fir) post_uhj_fir(d, frames); else post_uhj(d, frames); }
+        break;
     case B200MIX_POST_NONE: break;
     default: return B200MIX_ERR_UNSUPPORTED;
     }

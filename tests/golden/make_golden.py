@@ -80,6 +80,9 @@ SCENES = {
     # a custom quad decoder (QUAD_AMBDEC below, speakers at unequal distances): BFormatDec from the
     # .ambdec matrices + ApplyDistanceComp with the delays/gains InitDistanceComp derives
     "quad_spline_distcomp_v6": (6, 0, 2, 4, True, 48000, "quad", "i16", 0, None, None, "distcomp"),
+    # the FIR UHJ encoders (uhj/encode-filter = fir256 / fir512): UhjEncoder<N>, core/uhjfilter.cpp:83-205
+    "uhj_spline_fir256_v6": (6, 0, 2, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir256"),
+    "uhj_bsinc12_fir512_v5": (5, 0, 4, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir512"),
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
@@ -330,6 +333,8 @@ def run_scene(name):
                    rv_state=np.array([x[2] for x in rv_steps], dtype=np.int64))
     if out_type is not None:
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
+    if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
+        res.update(uhj_fir=np.int64(int(spec[11][6:])))
     if len(spec) > 11 and spec[11] == "distcomp":
         dl, dg = ref.distance_comp()
         assert dl.max() > 0, dl
@@ -371,6 +376,8 @@ def child(name, mode, path):
         with open(amb, "w") as f:
             f.write(QUAD_AMBDEC)
         conf += f"[decoder]\nquad = {amb}\n"
+    if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
+        conf += f"[uhj]\nencode-filter = fir{spec[11][6:]}\n"
     refal.libs(conf)
     res = run_scene(name)
     np.savez(path, **res)

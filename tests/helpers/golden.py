@@ -110,6 +110,9 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             for k in range(V):
                 ids = [k * len(qlens) + j for j in range(len(qlens))]
                 dev.voice_queue(k, ids, 0 if (plist[k].flags & abi.VF_LOOPING) else abi.NO_LOOP)
+        if "uhj_fir" in fx:
+            n = int(fx["uhj_fir"])
+            assert dev.set_uhj_encoder(n) == n // 2 + 128
         if "distcomp_delays" in fx:
             dev.set_distance_comp(fx["distcomp_delays"], fx["distcomp_gains"])
         if "limiter_desc" in fx:

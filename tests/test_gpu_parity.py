@@ -204,6 +204,32 @@ def test_distance_comp_vs_oracle_ragged_updates():
     assert not outs[1][0, :700].any() and outs[1][0, 700:1024].any()
 
 
+@pytest.mark.parametrize("taps", [0, 256, 512])
+def test_uhj_encoders_vs_oracle_ragged_updates(taps):
+    """UhjEncoderIIR (taps 0) and UhjEncoder<256/512> on a 3-channel dry mix, update sizes below
+    and above the encoder delay (N/2 + 128) and the FIR history."""
+    rng = np.random.default_rng(41 + taps)
+    nv = 12
+    desc = synth.stereo_desc(nv)
+    desc.post_process = abi.POST_UHJ
+    params, coeffs, dry = synth.voice_set(rng, nv, 0, hrtf=False, dry_channels=desc.dry_channels)
+    sizes = (1024, 37, 512, 1, 1000, 64, 300, 5, 1024)
+    outs = []
+    for lib in (mixlib.oracle(), mixlib.product()):
+        dev = MixDevice(lib, desc)
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.voices_update(params, None, dry, None)
+        assert dev.set_uhj_encoder(taps) == (taps // 2 + 128 if taps else 1)
+        o = [dev.render(f) for f in sizes]
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], f"uhj encoder {taps}")
+    if taps:
+        d = taps // 2 + 128
+        assert not outs[1][:, :128].any() and outs[1][:, d:d + 512].any()
+
+
 def test_config2_size_linearity_and_subsample():
     """BASELINE config 2 size (4096 HRTF voices, bsinc24): the oracle only mixes a
     deterministic 1/16 subsample; the full mix is checked by linearity — the sum of

@@ -12,9 +12,10 @@ def test_oracle_matches_reference_c_kernels_bit_exact(name):
     out, _ = golden.replay(mixlib.oracle(), fx)
     ref = fx["out_c"]
     assert out.shape == ref.shape
-    if "conv_taps" in fx or "conv_taps_chain" in fx:
-        # the convolution slot is restated by its definition (direct linear convolution, f64
-        # accumulation), not by pffft's float butterflies: equal within rounding, not bitwise
+    if "conv_taps" in fx or "conv_taps_chain" in fx or "uhj_fir" in fx:
+        # the convolution slot (and the FIR UHJ encoder's phase shifter) is restated by its
+        # definition (direct linear convolution, f64 accumulation), not by pffft's float
+        # butterflies: equal within rounding, not bitwise
         assert np.abs(out.astype(np.float64) - ref).max() <= 5e-7
         return
     # the restatement follows the reference's C kernels operation for operation
