@@ -371,6 +371,7 @@ def child(name, mode, path):
     from helpers import refal
     conf = "[general]\n" + ("disable-cpu-exts = all\n" if mode == "c" else "")
     spec = SCENES[name]
+    amb = None
     if len(spec) > 11 and spec[11] == "distcomp":
         amb = os.path.join(HERE, f"_tmp_{os.getpid()}.ambdec")
         with open(amb, "w") as f:
@@ -379,7 +380,11 @@ def child(name, mode, path):
     if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
         conf += f"[uhj]\nencode-filter = fir{spec[11][6:]}\n"
     refal.libs(conf)
-    res = run_scene(name)
+    try:
+        res = run_scene(name)
+    finally:
+        if amb:
+            os.remove(amb)
     np.savez(path, **res)
 
 
