@@ -366,6 +366,14 @@ B200MIX_API int b200mix_set_limiter(b200mix_device *dev, const b200mix_limiter_d
 B200MIX_API int b200mix_set_uhj_encoder(b200mix_device *dev, uint32_t filter_length,
     uint32_t *delay);
 
+/* BS2B headphone crossfeed on a stereo B200MIX_POST_AMBIDEC device: Bs2bPostProcess
+ * (alc/alu.cpp:408-434; set up at alc/panning.cpp:1421-1432 from the cf_level option) =
+ * the ambisonic decode followed by Bs2b::bs2b_processor::cross_feed (core/bs2b.cpp:104-163) on
+ * FrontLeft/FrontRight, with the coefficients of core/bs2b.cpp:41-91 for `level` 1..6
+ * (Bs2b::LowCLevel .. HighECLevel) at the device rate.  level 0 removes it.  Clears the
+ * filter history. */
+B200MIX_API int b200mix_set_bs2b(b200mix_device *dev, uint32_t level);
+
 /* Speaker distance compensation: ApplyDistanceComp (alc/alu.cpp:2276-2307) with the per-channel
  * delays and gains InitDistanceComp derived from a custom decoder's speaker distances
  * (alc/panning.cpp:301-371: DistanceComp::ChanData{Buffer.size(), Gain} per RealOut channel).

@@ -75,6 +75,8 @@ struct b200mix_device {
     float *d_amb_hf{nullptr}, *d_amb_lf{nullptr}, *d_amb_state{nullptr};
     bool dry_active{false};
     float *d_uhj_state{nullptr}, *d_uhj_scratch{nullptr};
+    uint32_t bs2b_level{0};                               // Bs2bPostProcess: 0 = off
+    float *d_bs2b{nullptr};                               // [0..3] history, [4..8] coefficients
     uint32_t uhj_fir{0};                                  // 0 = IIR, 256 / 512 = UhjEncoder<N>
     float *d_uhj_fir_state{nullptr}, *d_uhj_fir_coef{nullptr};
 
@@ -453,7 +455,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
-    cudaFree(d->d_uhj_fir_state); cudaFree(d->d_uhj_fir_coef);
+    cudaFree(d->d_uhj_fir_state); cudaFree(d->d_uhj_fir_coef); cudaFree(d->d_bs2b);
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
@@ -1621,6 +1623,15 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         const uint32_t total = dd.real_channels*frames;
         k_post_ambi_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
         ++d->launches;
+        if(d->bs2b_level)
+        {
+            // RealOut holds nothing but the decode here (no direct-channel voices), so the
+            // copy-out / add-back of the direct signal around the filter (alc/alu.cpp:414-433)
+            // has nothing to move
+            Bs2bParams B{d->d_real, d->d_bs2b, d->d_bs2b + 4, frames, dd.real_left, dd.real_right};
+            k_post_bs2b<<<1, 128, 0, d->stream>>>(B);
+            ++d->launches;
+        }
         break;
     }
     case B200MIX_POST_UHJ:
@@ -1743,6 +1754,44 @@ int b200mix_set_uhj_encoder(b200mix_device *d, uint32_t filter_length, uint32_t 
     }
     d->uhj_fir = filter_length;
     if(delay) *delay = filter_length ? filter_length/2u + 128u : 1u;
+    return B200MIX_OK;
+}
+
+int b200mix_set_bs2b(b200mix_device *d, uint32_t level)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    if(d->mid_render || level > 6 || dd.post_process != B200MIX_POST_AMBIDEC || dd.real_left == dd.real_right
+        || dd.real_left >= dd.real_channels || dd.real_right >= dd.real_channels)
+    { d->error = "set_bs2b: needs a stereo ambisonic-decode device and a level of 0..6"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    if(!d->d_bs2b)
+    {
+        if(int rc = dev_alloc(d, d->d_bs2b, 16)) return rc;
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    }
+    float h[9] = {};
+    if(level)
+    {
+        // init(), core/bs2b.cpp:41-91 (same float expressions, host libm)
+        static const float tab[6][4] = {
+            {360.0f,  501.0f, 0.398107170553497f, 0.205671765275719f},
+            {500.0f,  711.0f, 0.459726988530872f, 0.228208484414988f},
+            {700.0f, 1021.0f, 0.530884444230988f, 0.250105790667544f},
+            {360.0f,  494.0f, 0.316227766016838f, 0.168236228897329f},
+            {500.0f,  689.0f, 0.354813389233575f, 0.187169483835901f},
+            {700.0f,  975.0f, 0.398107170553497f, 0.205671765275719f}};
+        const float Fc_lo = tab[level-1][0], Fc_hi = tab[level-1][1];
+        const float G_lo = tab[level-1][2], G_hi = tab[level-1][3];
+        const float pi = 3.14159265358979323846f;
+        const float g = 1.0f / (1.0f - G_hi + G_lo);
+        float x = std::exp(-pi*2.0f*Fc_lo/float(dd.sample_rate));
+        h[4+1] = x; h[4+0] = G_lo * (1.0f - x) * g;
+        x = std::exp(-pi*2.0f*Fc_hi/float(dd.sample_rate));
+        h[4+4] = x; h[4+2] = (1.0f - G_hi * (1.0f - x)) * g; h[4+3] = -x * g;
+    }
+    CUDA_TRY(d, cudaMemcpy(d->d_bs2b, h, sizeof(h), cudaMemcpyHostToDevice));
+    d->bs2b_level = level;
     return B200MIX_OK;
 }
 

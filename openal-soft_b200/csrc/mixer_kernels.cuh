@@ -1620,6 +1620,62 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     }
 }
 
+// BS2B crossfeed after the ambisonic decode (Bs2bPostProcess, alc/alu.cpp:408-434):
+// bs2b_processor::cross_feed (core/bs2b.cpp:104-163) on FrontLeft/FrontRight.  Four first-order
+// recurrences (a high-shelf "direct" and a low-pass "crossfeed" path per input channel), one
+// thread each on its own warp, inputs and outputs staged in shared memory; operations in the
+// reference's order with explicit rounding.  coef = {a0_lo, b1_lo, a0_hi, a1_hi, b1_hi},
+// state = history[2]{lo, hi}.
+struct Bs2bParams { float *real; float *state; const float *coef; uint32_t frames, real_left, real_right; };
+
+__global__ void __launch_bounds__(128) k_post_bs2b(const Bs2bParams Q)
+{
+    __shared__ float sIn[2][kLine];
+    __shared__ float sOut[4][kLine + 8];     // L hi, L lo, R lo, R hi
+    const uint32_t n = Q.frames;
+    float *left = Q.real + size_t(Q.real_left)*kLine, *right = Q.real + size_t(Q.real_right)*kLine;
+    for(uint32_t k = threadIdx.x;k < n;k += blockDim.x) { sIn[0][k] = left[k]; sIn[1][k] = right[k]; }
+    __syncthreads();
+    const int chain = threadIdx.x >> 5;
+    if((threadIdx.x & 31) == 0)
+    {
+        const float a0lo = Q.coef[0], b1lo = Q.coef[1], a0hi = Q.coef[2], a1hi = Q.coef[3], b1hi = Q.coef[4];
+        // chain 0: left hi, 1: left lo, 2: right lo, 3: right hi
+        const bool hi = chain == 0 || chain == 3;
+        const float *src = sIn[chain >> 1];
+        float *st = Q.state + (chain >> 1)*2 + (hi ? 1 : 0);
+        float z = *st;
+        float *dst = sOut[chain];
+        uint32_t k = 0;
+        for(;k + 8u <= n;k += 8u)
+        {
+            float x[8];
+            #pragma unroll
+            for(int j = 0;j < 8;++j) x[j] = src[k + j];
+            #pragma unroll
+            for(int j = 0;j < 8;++j)
+            {
+                const float y = __fadd_rn(__fmul_rn(hi ? a0hi : a0lo, x[j]), z);
+                z = hi ? __fadd_rn(__fmul_rn(a1hi, x[j]), __fmul_rn(b1hi, y)) : __fmul_rn(b1lo, y);
+                dst[k + j] = y;
+            }
+        }
+        for(;k < n;++k)
+        {
+            const float y = __fadd_rn(__fmul_rn(hi ? a0hi : a0lo, src[k]), z);
+            z = hi ? __fadd_rn(__fmul_rn(a1hi, src[k]), __fmul_rn(b1hi, y)) : __fmul_rn(b1lo, y);
+            dst[k] = y;
+        }
+        *st = z;
+    }
+    __syncthreads();
+    for(uint32_t k = threadIdx.x;k < n;k += blockDim.x)
+    {
+        left[k] = __fadd_rn(sOut[0][k], sOut[2][k]);
+        right[k] = __fadd_rn(sOut[1][k], sOut[3][k]);
+    }
+}
+
 // UhjEncoder<N>::encode (core/uhjfilter.cpp:83-205), N = 256 or 512.  The reference shifts
 // -0.171 W + 0.208 X by +90 degrees with a segmented FFT overlap-add (core/allpass_conv.hpp);
 // that is a linear convolution with an N-tap response (every second tap zero) delivered one

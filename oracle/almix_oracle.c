@@ -267,6 +267,10 @@ struct oracle_device {
     float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
     uint32_t mid_frames;       /* between oracle_render_begin and oracle_render_end */
     olimiter *limiter;         /* DeviceBase::Limiter */
+    /* Bs2b::bs2b_processor (core/bs2b.h:50-89): level 0 = off */
+    uint32_t bs2b_level;
+    float bs2b_a0_lo, bs2b_b1_lo, bs2b_a0_hi, bs2b_a1_hi, bs2b_b1_hi;
+    float bs2b_hist[2][2];     /* history[ch]{lo, hi} */
     uint32_t *dc_delay;        /* DeviceBase::ChannelDelays: Buffer.size() per RealOut channel */
     float *dc_gain;
     float (*dc_buf)[LINE];
@@ -392,6 +396,22 @@ int oracle_set_uhj_encoder(oracle_device *d, uint32_t filter_length, uint32_t *d
         }
     }
     if(delay) *delay = filter_length ? filter_length/2 + 128 : 1;
+    return B200MIX_OK;
+}
+
+/* bs2b->set_params(cf_level, rate), alc/panning.cpp:1426-1427 */
+int oracle_set_bs2b(oracle_device *d, uint32_t level)
+{
+    if(level > 6 || d->desc.post_process != B200MIX_POST_AMBIDEC
+        || d->desc.real_left == d->desc.real_right) return B200MIX_ERR_INVALID;
+    memset(d->bs2b_hist, 0, sizeof(d->bs2b_hist));
+    d->bs2b_level = level;
+    if(level)
+    {
+        float c[5];
+        oracle_bs2b_coeffs(level, d->desc.sample_rate, c);
+        d->bs2b_a0_lo = c[0]; d->bs2b_b1_lo = c[1]; d->bs2b_a0_hi = c[2]; d->bs2b_a1_hi = c[3]; d->bs2b_b1_hi = c[4];
+    }
     return B200MIX_OK;
 }
 
@@ -1401,6 +1421,69 @@ static void post_ambidec(oracle_device *d, size_t n)
     }
 }
 
+/* init(), core/bs2b.cpp:41-91 */
+int oracle_bs2b_coeffs(uint32_t level, uint32_t srate, float out[5])
+{
+    static const float tab[6][4] = {
+        {360.0f,  501.0f, 0.398107170553497f, 0.205671765275719f},
+        {500.0f,  711.0f, 0.459726988530872f, 0.228208484414988f},
+        {700.0f, 1021.0f, 0.530884444230988f, 0.250105790667544f},
+        {360.0f,  494.0f, 0.316227766016838f, 0.168236228897329f},
+        {500.0f,  689.0f, 0.354813389233575f, 0.187169483835901f},
+        {700.0f,  975.0f, 0.398107170553497f, 0.205671765275719f}};
+    if(level < 1 || level > 6 || srate < 1) return B200MIX_ERR_INVALID;
+    const float Fc_lo = tab[level-1][0], Fc_hi = tab[level-1][1];
+    const float G_lo = tab[level-1][2], G_hi = tab[level-1][3];
+    const float pi = 3.14159265358979323846f;
+    const float g = 1.0f / (1.0f - G_hi + G_lo);
+    float x = expf(-pi*2.0f*Fc_lo/(float)srate);
+    out[1] = x;                              /* b1_lo */
+    out[0] = G_lo * (1.0f - x) * g;          /* a0_lo */
+    x = expf(-pi*2.0f*Fc_hi/(float)srate);
+    out[4] = x;                              /* b1_hi */
+    out[2] = (1.0f - G_hi * (1.0f - x)) * g; /* a0_hi */
+    out[3] = -x * g;                         /* a1_hi */
+    return B200MIX_OK;
+}
+
+/* bs2b_processor::cross_feed, core/bs2b.cpp:104-163 (the 128-sample blocking only bounds a
+ * temporary; the recurrences run straight through).  coef = {a0_lo,b1_lo,a0_hi,a1_hi,b1_hi},
+ * hist = history[2]{lo,hi}. */
+void oracle_bs2b_cross_feed(const float coef[5], float hist[2][2], float *left, float *right, size_t n)
+{
+    const float a0lo = coef[0], b1lo = coef[1], a0hi = coef[2], a1hi = coef[3], b1hi = coef[4];
+    float lz_lo = hist[0][0], lz_hi = hist[0][1], rz_lo = hist[1][0], rz_hi = hist[1][1];
+    for(size_t i = 0;i < n;++i)
+    {
+        float x = left[i];
+        const float l0 = a0hi*x + lz_hi;
+        lz_hi = a1hi*x + b1hi*l0;
+        const float l1 = a0lo*x + lz_lo;
+        lz_lo = b1lo*l1;
+        x = right[i];
+        const float r0 = a0lo*x + rz_lo;
+        rz_lo = b1lo*r0;
+        const float r1 = a0hi*x + rz_hi;
+        rz_hi = a1hi*x + b1hi*r1;
+        left[i] = l0 + r0;
+        right[i] = l1 + r1;
+    }
+    hist[0][0] = lz_lo; hist[0][1] = lz_hi; hist[1][0] = rz_lo; hist[1][1] = rz_hi;
+}
+
+/* DeviceBase::Process(Bs2bPostProcess), alc/alu.cpp:408-434 */
+static void post_bs2b(oracle_device *d, size_t n)
+{
+    float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
+    float ldirect[LINE], rdirect[LINE];
+    memcpy(ldirect, left, sizeof(float)*n); memcpy(rdirect, right, sizeof(float)*n);
+    memset(left, 0, sizeof(float)*n); memset(right, 0, sizeof(float)*n);
+    post_ambidec(d, n);
+    const float coef[5] = {d->bs2b_a0_lo, d->bs2b_b1_lo, d->bs2b_a0_hi, d->bs2b_a1_hi, d->bs2b_b1_hi};
+    oracle_bs2b_cross_feed(coef, d->bs2b_hist, left, right, n);
+    for(size_t i = 0;i < n;++i) { left[i] += ldirect[i]; right[i] += rdirect[i]; }
+}
+
 /* process(AllPassFilter&...), core/allpass_iir.hpp:53-70 */
 static void allpass_process(float st[4][2], const float coeffs[4], const float *src, float *dst,
     size_t n)
@@ -1645,7 +1728,9 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
     switch(dd->post_process)
     {
     case B200MIX_POST_HRTF: if(d->dec_channels) post_hrtf(d, frames); break;
-    case B200MIX_POST_AMBIDEC: if(d->amb_in) post_ambidec(d, frames); break;
+    case B200MIX_POST_AMBIDEC:
+        if(d->amb_in) { if(d->bs2b_level) post_bs2b(d, frames); else post_ambidec(d, frames); }
+        break;
     case B200MIX_POST_UHJ:
         if(dd->dry_channels >= 3) { if(d->uhj_fir) post_uhj_fir(d, frames); else post_uhj(d, frames); }
         break;

@@ -61,6 +61,7 @@
 #include "core/mixer/hrtfdefs.h"
 #include "core/voice.h"
 #include "core/mastering.h"
+#include "core/bs2b.h"
 #include <limits>
 
 #include "../include/b200mix.h"
@@ -228,6 +229,23 @@ int refh_distance_comp(ALCdevice *adev, uint32_t *delays, float *gains)
         gains[c] = cd.Gain;
     }
     return static_cast<int>(n);
+}
+
+/* Kernel-level tap (SURVEY 8c ii): the reference's Bs2b::bs2b_processor, set up by set_params
+ * and run over [left|right] in place; state (4 floats: history[0].lo/.hi, history[1].lo/.hi)
+ * goes in and comes back so ragged runs can be chained; coef receives
+ * {a0_lo, b1_lo, a0_hi, a1_hi, b1_hi}.  (The loopback device never selects Bs2bPostProcess,
+ * alc/panning.cpp:1421, so the filter is pinned here.) */
+void refh_bs2b_cross_feed(int level, int srate, float *left, float *right, int n, float *state, float *coef)
+{
+    Bs2b::bs2b_processor p{};
+    p.set_params(level, srate);
+    p.history[0].lo = state[0]; p.history[0].hi = state[1];
+    p.history[1].lo = state[2]; p.history[1].hi = state[3];
+    p.cross_feed(std::span{left, size_t(n)}, std::span{right, size_t(n)});
+    state[0] = p.history[0].lo; state[1] = p.history[0].hi;
+    state[2] = p.history[1].lo; state[3] = p.history[1].hi;
+    coef[0] = p.a0_lo; coef[1] = p.b1_lo; coef[2] = p.a0_hi; coef[3] = p.a1_hi; coef[4] = p.b1_hi;
 }
 
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one

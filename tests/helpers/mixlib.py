@@ -62,6 +62,8 @@ class MixLib:
                                             C.c_float, C.POINTER(C.c_uint32), C.c_void_p]
         self.set_limiter = f("set_limiter")
         self.set_limiter.argtypes = [C.c_void_p, C.POINTER(abi.LimiterDesc), C.POINTER(C.c_uint32)]
+        self.set_bs2b = f("set_bs2b")
+        self.set_bs2b.argtypes = [C.c_void_p, C.c_uint32]
         self.set_uhj_encoder = f("set_uhj_encoder")
         self.set_uhj_encoder.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         self.set_distance_comp = f("set_distance_comp")
@@ -211,6 +213,10 @@ class MixDevice:
         rc = self.m.set_limiter(self.h, C.byref(desc) if desc is not None else None, C.byref(la))
         assert rc == 0, f"set_limiter -> {rc}"
         return la.value
+
+    def set_bs2b(self, level):
+        rc = self.m.set_bs2b(self.h, level)
+        assert rc == 0, f"set_bs2b -> {rc}"
 
     def set_uhj_encoder(self, filter_length):
         """0 = IIR, 256/512 = FIR; returns the encoder's delay in samples."""

@@ -230,6 +230,31 @@ def test_uhj_encoders_vs_oracle_ragged_updates(taps):
         assert not outs[1][:, :128].any() and outs[1][:, d:d + 512].any()
 
 
+@pytest.mark.parametrize("level", [1, 3, 6])
+def test_bs2b_crossfeed_vs_oracle_ragged_updates(level):
+    """Bs2bPostProcess: ambisonic decode + BS2B crossfeed (the oracle's filter is bit-exact with
+    the reference's Bs2b::bs2b_processor, tests/test_oracle_vs_ref.py), ragged updates, removal."""
+    rng = np.random.default_rng(51 + level)
+    nv = 12
+    desc = synth.stereo_desc(nv)
+    params, coeffs, dry = synth.voice_set(rng, nv, 0, hrtf=False, dry_channels=desc.dry_channels)
+    sizes = (1024, 37, 512, 1, 1000, 64, 7, 1024)
+    outs = []
+    for lib, lev in ((mixlib.oracle(), level), (mixlib.product(), level), (mixlib.product(), 0)):
+        dev = MixDevice(lib, desc)
+        g = np.random.default_rng(8).standard_normal((desc.dry_channels, desc.real_channels))
+        dev.set_ambi_decoder(g.astype(np.float32), None, 0.0)
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.voices_update(params, None, dry, None)
+        dev.set_bs2b(lev)
+        o = [dev.render(f) for f in sizes]
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], f"bs2b level {level}")
+    assert np.abs(outs[1] - outs[2]).max() > 1e-3       # the crossfeed did change the output
+
+
 def test_config2_size_linearity_and_subsample():
     """BASELINE config 2 size (4096 HRTF voices, bsinc24): the oracle only mixes a
     deterministic 1/16 subsample; the full mix is checked by linearity — the sum of

@@ -186,3 +186,36 @@ def test_limiter_ragged_updates_vs_reference_live(hrtf):
         ref.close()
     # the limiter did hold the mix at full scale (the unlimited mix peaks far above 1)
     assert 0.5 < peak <= 1.0 + 1e-6, peak
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6])
+def test_bs2b_crossfeed_bit_exact(level):
+    """The oracle's BS2B coefficients and cross-feed recurrences against the reference's
+    Bs2b::bs2b_processor (kernel-level tap), chained over ragged chunks."""
+    import ctypes as C
+    _, hz = refal.libs()
+    hz.refh_bs2b_cross_feed.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2
+    hz.refh_bs2b_cross_feed.restype = None
+    lib = _oracle_lib()
+    lib.oracle_bs2b_coeffs.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.oracle_bs2b_cross_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.oracle_bs2b_cross_feed.restype = None
+    rng = np.random.default_rng(100 + level)
+    for srate in (44100, 48000, 96000):
+        coef_o = np.zeros(5, dtype=np.float32)
+        assert lib.oracle_bs2b_coeffs(level, srate, coef_o.ctypes.data) == 0
+        st_r = np.zeros(4, dtype=np.float32)
+        st_o = np.zeros(4, dtype=np.float32)
+        coef_r = np.zeros(5, dtype=np.float32)
+        for n in (1024, 37, 500, 1, 129, 1000):
+            l = (rng.standard_normal(n) * 0.3).astype(np.float32)
+            r = (rng.standard_normal(n) * 0.3).astype(np.float32)
+            lr, rr = l.copy(), r.copy()
+            hz.refh_bs2b_cross_feed(level, srate, lr.ctypes.data, rr.ctypes.data, n, st_r.ctypes.data,
+                                    coef_r.ctypes.data)
+            assert np.array_equal(coef_o.view(np.uint32), coef_r.view(np.uint32)), (coef_o, coef_r)
+            lo, ro = l.copy(), r.copy()
+            lib.oracle_bs2b_cross_feed(coef_o.ctypes.data, st_o.ctypes.data, lo.ctypes.data, ro.ctypes.data, n)
+            assert np.array_equal(lo.view(np.uint32), lr.view(np.uint32)), (srate, n)
+            assert np.array_equal(ro.view(np.uint32), rr.view(np.uint32)), (srate, n)
+            assert np.array_equal(st_o.view(np.uint32), st_r.view(np.uint32))
