@@ -374,6 +374,17 @@ B200MIX_API int b200mix_set_uhj_encoder(b200mix_device *dev, uint32_t filter_len
  * filter history. */
 B200MIX_API int b200mix_set_bs2b(b200mix_device *dev, uint32_t level);
 
+/* Front image stabilizer on a B200MIX_POST_AMBIDEC device with FrontLeft, FrontRight and a
+ * FrontCenter output the decoder does not feed: StablizerPostProcess (alc/alu.cpp:330-406; set up
+ * by InitPanning/CreateStablizer, alc/panning.cpp:160-172,806-834, front-stablizer option).  After
+ * the decode the mid signal L+R is band-split (BandSplitter::process, crossover 5 kHz), part of it
+ * is moved to the centre channel, and every other channel passes the splitter's all-pass
+ * (BandSplitter::processAllPass) to stay in phase.  splitter_coeff is
+ * FrontStablizer::MidFilter.mCoeff (BandSplitter::init(5000/rate), core/filters/splitter.cpp:15-26).
+ * center_channel = B200MIX_NO_SLOT removes it.  Clears the filter states. */
+B200MIX_API int b200mix_set_front_stabilizer(b200mix_device *dev, uint32_t center_channel,
+    float splitter_coeff);
+
 /* Speaker distance compensation: ApplyDistanceComp (alc/alu.cpp:2276-2307) with the per-channel
  * delays and gains InitDistanceComp derived from a custom decoder's speaker distances
  * (alc/panning.cpp:301-371: DistanceComp::ChanData{Buffer.size(), Gain} per RealOut channel).

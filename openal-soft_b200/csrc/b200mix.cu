@@ -75,6 +75,9 @@ struct b200mix_device {
     float *d_amb_hf{nullptr}, *d_amb_lf{nullptr}, *d_amb_state{nullptr};
     bool dry_active{false};
     float *d_uhj_state{nullptr}, *d_uhj_scratch{nullptr};
+    uint32_t stab_center{B200MIX_NO_SLOT};                // StablizerPostProcess: FrontCenter index
+    float stab_coeff{0.0f};
+    float *d_stab_state{nullptr};                         // [0..2] MidFilter, [4+i] ChannelFilters[i].mApZ1
     uint32_t bs2b_level{0};                               // Bs2bPostProcess: 0 = off
     float *d_bs2b{nullptr};                               // [0..3] history, [4..8] coefficients
     uint32_t uhj_fir{0};                                  // 0 = IIR, 256 / 512 = UhjEncoder<N>
@@ -455,7 +458,7 @@ void b200mix_destroy(b200mix_device *d)
     cudaFree(d->d_temp); cudaFree(d->d_temp2);
     cudaFree(d->d_amb_hf); cudaFree(d->d_amb_lf); cudaFree(d->d_amb_state);
     cudaFree(d->d_uhj_state); cudaFree(d->d_uhj_scratch);
-    cudaFree(d->d_uhj_fir_state); cudaFree(d->d_uhj_fir_coef); cudaFree(d->d_bs2b);
+    cudaFree(d->d_uhj_fir_state); cudaFree(d->d_uhj_fir_coef); cudaFree(d->d_bs2b); cudaFree(d->d_stab_state);
     for(auto &v : d->slot_allocs) for(void *p : v) cudaFree(p);
     cudaFree(d->d_slots); cudaFree(d->d_xscratch); cudaFree(d->d_sendinfo);
     cudaFree(d->d_filt); cudaFree(d->d_fupd); cudaFree(d->d_fscratch);
@@ -1623,7 +1626,20 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         const uint32_t total = dd.real_channels*frames;
         k_post_ambi_mix<<<(total + 127)/128, 128, 0, d->stream>>>(Q);
         ++d->launches;
-        if(d->bs2b_level)
+        if(d->stab_center != B200MIX_NO_SLOT)
+        {
+            StabParams S{};
+            S.real = d->d_real; S.state = d->d_stab_state; S.frames = frames;
+            S.real_channels = dd.real_channels; S.lidx = dd.real_left; S.ridx = dd.real_right;
+            S.cidx = d->stab_center; S.coeff = d->stab_coeff;
+            const float halfPi = 3.14159265358979323846f*0.5f;
+            S.mid_lf = std::cos(1.0f/3.0f * halfPi); S.mid_hf = std::cos(1.0f/4.0f * halfPi);
+            S.center_lf = std::sin(1.0f/3.0f * halfPi); S.center_hf = std::sin(1.0f/4.0f * halfPi);
+            const size_t smem = size_t(2u + dd.real_channels)*kLine*sizeof(float);
+            k_post_stabilizer<<<1, 32u*dd.real_channels, smem, d->stream>>>(S);
+            ++d->launches;
+        }
+        else if(d->bs2b_level)
         {
             // RealOut holds nothing but the decode here (no direct-channel voices), so the
             // copy-out / add-back of the direct signal around the filter (alc/alu.cpp:414-433)
@@ -1754,6 +1770,29 @@ int b200mix_set_uhj_encoder(b200mix_device *d, uint32_t filter_length, uint32_t 
     }
     d->uhj_fir = filter_length;
     if(delay) *delay = filter_length ? filter_length/2u + 128u : 1u;
+    return B200MIX_OK;
+}
+
+int b200mix_set_front_stabilizer(b200mix_device *d, uint32_t center_channel, float splitter_coeff)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    if(d->mid_render) { d->error = "set_front_stabilizer: a render_begin is pending"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    if(center_channel == B200MIX_NO_SLOT) { d->stab_center = B200MIX_NO_SLOT; return B200MIX_OK; }
+    if(dd.post_process != B200MIX_POST_AMBIDEC || center_channel >= dd.real_channels
+        || dd.real_left == dd.real_right || dd.real_left >= dd.real_channels || dd.real_right >= dd.real_channels
+        || center_channel == dd.real_left || center_channel == dd.real_right || dd.real_channels > 32u)
+    { d->error = "set_front_stabilizer: needs an ambisonic-decode device with left, right and centre outputs"; return B200MIX_ERR_INVALID; }
+    if(!d->d_stab_state)
+    {
+        if(int rc = dev_alloc(d, d->d_stab_state, 4 + 32)) return rc;
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    }
+    CUDA_TRY(d, cudaMemset(d->d_stab_state, 0, (4 + 32)*sizeof(float)));
+    CUDA_TRY(d, cudaFuncSetAttribute(k_post_stabilizer, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        int(size_t(2u + dd.real_channels)*kLine*sizeof(float))));
+    d->stab_center = center_channel; d->stab_coeff = splitter_coeff;
     return B200MIX_OK;
 }
 

@@ -1620,6 +1620,153 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     }
 }
 
+// Front image stabilizer after the ambisonic decode (StablizerPostProcess, alc/alu.cpp:330-406).
+// RealOut holds only the decode here (nothing mixes into it directly), so the "direct" mid/side
+// signals the reference moves out of the way first are zero and the left channel's all-pass
+// (which only ever sees that zero mid signal) keeps a zero state.  One warp per serial filter:
+// warp 0 the mid band splitter (BandSplitter::process), warp 1 the side signal's all-pass
+// (ChannelFilters[right]), warps 2.. the all-pass of every other output channel
+// (BandSplitter::processAllPass); rows staged in shared memory, operations in the reference's
+// order with explicit rounding.  state: [0..2] MidFilter lp_z1, lp_z2, ap_z1; [4+i] mApZ1 of
+// ChannelFilters[i].
+struct StabParams {
+    float *real; float *state;
+    uint32_t frames, real_channels, lidx, ridx, cidx;
+    float coeff;
+    float mid_lf, mid_hf, center_lf, center_hf;   // cos/sin(1/3 * pi/2), cos/sin(1/4 * pi/2) by the host libm
+};
+
+__global__ void __launch_bounds__(1024) k_post_stabilizer(const StabParams Q)
+{
+    extern __shared__ float sRows[];            // [2 + real_channels][kLine]: tmp->LF, HF, side, others
+    const uint32_t n = Q.frames, C = Q.real_channels;
+    float *left = Q.real + size_t(Q.lidx)*kLine, *right = Q.real + size_t(Q.ridx)*kLine;
+    float *rowLF = sRows, *rowHF = sRows + kLine, *rowSide = sRows + 2*kLine;
+    for(uint32_t k = threadIdx.x;k < n;k += blockDim.x)
+    {
+        const float l = left[k], r = right[k];
+        rowLF[k] = __fadd_rn(l, r);             // the decoded mid signal (splitter input)
+        rowSide[k] = __fadd_rn(0.0f, __fsub_rn(l, r));   // side[i] (= 0) += leftout - rightout
+    }
+    // the other channels, in output-channel order, rows 3..
+    uint32_t other = 0;
+    for(uint32_t c = 0;c < C;++c)
+    {
+        if(c == Q.lidx || c == Q.ridx) continue;
+        float *row = sRows + size_t(3u + other)*kLine;
+        const float *src = Q.real + size_t(c)*kLine;
+        for(uint32_t k = threadIdx.x;k < n;k += blockDim.x) row[k] = src[k];
+        ++other;
+    }
+    __syncthreads();
+
+    const uint32_t chain = threadIdx.x >> 5;
+    const float coeff = Q.coeff;
+    if((threadIdx.x & 31u) == 0u && chain < C)
+    {
+        if(chain == 0)
+        {
+            const float lp_coeff = __fadd_rn(__fmul_rn(coeff, 0.5f), 0.5f);
+            float lp_z1 = Q.state[0], lp_z2 = Q.state[1], ap_z1 = Q.state[2];
+            uint32_t k = 0;
+            for(;k < n;)
+            {
+                float x[8];
+                const uint32_t m = min(8u, n - k);
+                #pragma unroll
+                for(uint32_t j = 0;j < 8u;++j) x[j] = j < m ? rowLF[k + j] : 0.0f;
+                #pragma unroll
+                for(uint32_t j = 0;j < 8u;++j)
+                {
+                    if(j < m)
+                    {
+                        const float d0 = __fmul_rn(__fsub_rn(x[j], lp_z1), lp_coeff);
+                        const float lp_y0 = __fadd_rn(lp_z1, d0);
+                        lp_z1 = __fadd_rn(lp_y0, d0);
+                        const float d1 = __fmul_rn(__fsub_rn(lp_y0, lp_z2), lp_coeff);
+                        const float lp_y1 = __fadd_rn(lp_z2, d1);
+                        lp_z2 = __fadd_rn(lp_y1, d1);
+                        const float ap_y = __fadd_rn(__fmul_rn(x[j], coeff), ap_z1);
+                        ap_z1 = __fsub_rn(x[j], __fmul_rn(ap_y, coeff));
+                        rowLF[k + j] = lp_y1;
+                        rowHF[k + j] = __fsub_rn(ap_y, lp_y1);
+                    }
+                }
+                k += m;
+            }
+            Q.state[0] = lp_z1; Q.state[1] = lp_z2; Q.state[2] = ap_z1;
+        }
+        else
+        {
+            // chain 1: side with ChannelFilters[ridx]; chain 2+o: other channel o with its own
+            uint32_t ch = Q.ridx;
+            float *row = rowSide;
+            if(chain >= 2u)
+            {
+                uint32_t o = chain - 2u, c = 0;
+                for(;c < C;++c)
+                {
+                    if(c == Q.lidx || c == Q.ridx) continue;
+                    if(o == 0u) break;
+                    --o;
+                }
+                ch = c;
+                row = sRows + size_t(3u + (chain - 2u))*kLine;
+            }
+            float z1 = Q.state[4u + ch];
+            uint32_t k = 0;
+            for(;k < n;)
+            {
+                float x[8];
+                const uint32_t m = min(8u, n - k);
+                #pragma unroll
+                for(uint32_t j = 0;j < 8u;++j) x[j] = j < m ? row[k + j] : 0.0f;
+                #pragma unroll
+                for(uint32_t j = 0;j < 8u;++j)
+                {
+                    if(j < m)
+                    {
+                        const float y = __fadd_rn(__fmul_rn(x[j], coeff), z1);
+                        z1 = __fsub_rn(x[j], __fmul_rn(y, coeff));
+                        row[k + j] = y;
+                    }
+                }
+                k += m;
+            }
+            Q.state[4u + ch] = z1;
+        }
+    }
+    __syncthreads();
+
+    // pan the mid bands between centre and left+right (alc/alu.cpp:380-405)
+    const float mid_lf = Q.mid_lf, mid_hf = Q.mid_hf, center_lf = Q.center_lf, center_hf = Q.center_hf;
+    float *center = Q.real + size_t(Q.cidx)*kLine;
+    const float *rowCenter = nullptr;
+    other = 0;
+    for(uint32_t c = 0;c < C;++c)
+    {
+        if(c == Q.lidx || c == Q.ridx) continue;
+        float *row = sRows + size_t(3u + other)*kLine;
+        if(c == Q.cidx) rowCenter = row;
+        else
+        {
+            float *dst = Q.real + size_t(c)*kLine;
+            for(uint32_t k = threadIdx.x;k < n;k += blockDim.x) dst[k] = row[k];
+        }
+        ++other;
+    }
+    for(uint32_t k = threadIdx.x;k < n;k += blockDim.x)
+    {
+        const float lf = rowLF[k], hf = rowHF[k];
+        const float m = __fadd_rn(__fadd_rn(__fmul_rn(lf, mid_lf), __fmul_rn(hf, mid_hf)), 0.0f);
+        const float cc = __fadd_rn(__fmul_rn(lf, center_lf), __fmul_rn(hf, center_hf));
+        const float sd = rowSide[k];
+        left[k] = __fmul_rn(__fadd_rn(m, sd), 0.5f);
+        right[k] = __fmul_rn(__fsub_rn(m, sd), 0.5f);
+        center[k] = __fadd_rn(rowCenter[k], __fmul_rn(cc, 0.5f));
+    }
+}
+
 // BS2B crossfeed after the ambisonic decode (Bs2bPostProcess, alc/alu.cpp:408-434):
 // bs2b_processor::cross_feed (core/bs2b.cpp:104-163) on FrontLeft/FrontRight.  Four first-order
 // recurrences (a high-shelf "direct" and a low-pass "crossfeed" path per input channel), one

@@ -267,6 +267,10 @@ struct oracle_device {
     float filtered[LINE];      /* DeviceBase::FilteredData core/device.h */
     uint32_t mid_frames;       /* between oracle_render_begin and oracle_render_end */
     olimiter *limiter;         /* DeviceBase::Limiter */
+    /* FrontStablizer (core/front_stablizer.h): MidFilter + one all-pass state per RealOut channel */
+    uint32_t stab_center;      /* B200MIX_NO_SLOT = off */
+    osplitter stab_mid;
+    float stab_ap_z1[B200MIX_MAX_DRY_CHANNELS*2];
     /* Bs2b::bs2b_processor (core/bs2b.h:50-89): level 0 = off */
     uint32_t bs2b_level;
     float bs2b_a0_lo, bs2b_b1_lo, bs2b_a0_hi, bs2b_a1_hi, bs2b_b1_hi;
@@ -287,6 +291,7 @@ int oracle_create(const b200mix_device_desc *desc, oracle_device **out)
     oracle_device *d = calloc(1, sizeof(*d));
     if(!d) return B200MIX_ERR_NOMEM;
     d->desc = *desc;
+    d->stab_center = B200MIX_NO_SLOT;
     d->buffers = calloc(desc->max_buffers ? desc->max_buffers : 1, sizeof(obuffer));
     d->voices = calloc(desc->max_voices ? desc->max_voices : 1, sizeof(ovoice));
     d->dry = calloc(desc->dry_channels ? desc->dry_channels : 1, sizeof(float[LINE]));
@@ -396,6 +401,22 @@ int oracle_set_uhj_encoder(oracle_device *d, uint32_t filter_length, uint32_t *d
         }
     }
     if(delay) *delay = filter_length ? filter_length/2 + 128 : 1;
+    return B200MIX_OK;
+}
+
+/* CreateStablizer, alc/panning.cpp:160-172 */
+int oracle_set_front_stabilizer(oracle_device *d, uint32_t center_channel, float splitter_coeff)
+{
+    const b200mix_device_desc *dd = &d->desc;
+    memset(&d->stab_mid, 0, sizeof(d->stab_mid)); memset(d->stab_ap_z1, 0, sizeof(d->stab_ap_z1));
+    d->stab_center = B200MIX_NO_SLOT;
+    if(center_channel == B200MIX_NO_SLOT) return B200MIX_OK;
+    if(dd->post_process != B200MIX_POST_AMBIDEC || center_channel >= dd->real_channels
+        || dd->real_left == dd->real_right || center_channel == dd->real_left
+        || center_channel == dd->real_right || dd->real_channels > B200MIX_MAX_DRY_CHANNELS*2)
+        return B200MIX_ERR_INVALID;
+    d->stab_center = center_channel;
+    d->stab_mid.coeff = splitter_coeff;
     return B200MIX_OK;
 }
 
@@ -1421,6 +1442,56 @@ static void post_ambidec(oracle_device *d, size_t n)
     }
 }
 
+/* BandSplitter::processAllPass, core/filters/splitter.cpp:163-174 */
+static void splitter_allpass(float coeff, float *z1p, float *samples, size_t n)
+{
+    float z1 = *z1p;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x = samples[i];
+        const float y = x*coeff + z1;
+        z1 = x - y*coeff;
+        samples[i] = y;
+    }
+    *z1p = z1;
+}
+
+/* DeviceBase::Process(StablizerPostProcess), alc/alu.cpp:330-406 */
+static void post_stabilizer(oracle_device *d, size_t n)
+{
+    const uint32_t lidx = d->desc.real_left, ridx = d->desc.real_right, cidx = d->stab_center;
+    float *leftout = d->real[lidx], *rightout = d->real[ridx];
+    float mid[LINE], side[LINE], tmp[LINE], midhf[LINE], midlf[LINE];
+    for(size_t i = 0;i < n;++i) { mid[i] = leftout[i] + rightout[i]; side[i] = leftout[i] - rightout[i]; }
+    memset(leftout, 0, sizeof(float)*n); memset(rightout, 0, sizeof(float)*n);
+
+    post_ambidec(d, n);
+
+    for(size_t i = 0;i < n;++i) side[i] += leftout[i] - rightout[i];
+    for(size_t i = 0;i < n;++i) tmp[i] = leftout[i] + rightout[i];
+    splitter_process(&d->stab_mid, tmp, midhf, midlf, n);
+
+    for(uint32_t i = 0;i < d->desc.real_channels;++i)
+    {
+        float *buf = (i == lidx) ? mid : (i == ridx) ? side : d->real[i];
+        splitter_allpass(d->stab_mid.coeff, &d->stab_ap_z1[i], buf, n);
+    }
+
+    const float half_pi = 3.14159265358979323846f*0.5f;
+    const float mid_lf = cosf(1.0f/3.0f * half_pi), mid_hf = cosf(1.0f/4.0f * half_pi);
+    const float center_lf = sinf(1.0f/3.0f * half_pi), center_hf = sinf(1.0f/4.0f * half_pi);
+    float *centerout = d->real[cidx];
+    for(size_t i = 0;i < n;++i)
+    {
+        const float m = midlf[i]*mid_lf + midhf[i]*mid_hf + mid[i];
+        const float c = midlf[i]*center_lf + midhf[i]*center_hf;
+        const float s = side[i];
+        leftout[i] = (m + s) * 0.5f;
+        rightout[i] = (m - s) * 0.5f;
+        centerout[i] += c * 0.5f;
+    }
+}
+
 /* init(), core/bs2b.cpp:41-91 */
 int oracle_bs2b_coeffs(uint32_t level, uint32_t srate, float out[5])
 {
@@ -1729,7 +1800,12 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
     {
     case B200MIX_POST_HRTF: if(d->dec_channels) post_hrtf(d, frames); break;
     case B200MIX_POST_AMBIDEC:
-        if(d->amb_in) { if(d->bs2b_level) post_bs2b(d, frames); else post_ambidec(d, frames); }
+        if(d->amb_in)
+        {
+            if(d->stab_center != B200MIX_NO_SLOT) post_stabilizer(d, frames);
+            else if(d->bs2b_level) post_bs2b(d, frames);
+            else post_ambidec(d, frames);
+        }
         break;
     case B200MIX_POST_UHJ:
         if(dd->dry_channels >= 3) { if(d->uhj_fir) post_uhj_fir(d, frames); else post_uhj(d, frames); }

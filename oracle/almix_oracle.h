@@ -93,6 +93,7 @@ int  oracle_slot_disable(oracle_device *dev, uint32_t slot);
 int  oracle_slot_target(oracle_device *dev, uint32_t slot, uint32_t target);
 int  oracle_set_distance_comp(oracle_device *dev, uint32_t channels, const uint32_t *delays, const float *gains);
 int  oracle_set_uhj_encoder(oracle_device *dev, uint32_t filter_length, uint32_t *delay);
+int  oracle_set_front_stabilizer(oracle_device *dev, uint32_t center_channel, float splitter_coeff);
 int  oracle_set_bs2b(oracle_device *dev, uint32_t level);
 int  oracle_bs2b_coeffs(uint32_t level, uint32_t srate, float out[5]);
 void oracle_bs2b_cross_feed(const float coef[5], float hist[2][2], float *left, float *right, size_t n);

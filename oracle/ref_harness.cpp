@@ -62,6 +62,7 @@
 #include "core/voice.h"
 #include "core/mastering.h"
 #include "core/bs2b.h"
+#include "core/front_stablizer.h"
 #include <limits>
 
 #include "../include/b200mix.h"
@@ -107,8 +108,9 @@ int refh_device_desc(ALCdevice *adev, b200mix_device_desc *out)
     out->num_sends = dev->NumAuxSends;
     out->ir_size = dev->mIrSize;
     out->wet_channels = 0; /* filled by refh_wet_channels once a slot exists */
-    if(std::holds_alternative<AmbiDecPostProcess>(dev->mPostProcess))
-        out->post_process = B200MIX_POST_AMBIDEC;
+    if(std::holds_alternative<AmbiDecPostProcess>(dev->mPostProcess)
+        || std::holds_alternative<StablizerPostProcess>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_AMBIDEC;   /* + refh_front_stabilizer for the latter */
     else if(std::holds_alternative<HrtfPostProcess>(dev->mPostProcess))
         out->post_process = B200MIX_POST_HRTF;
     else if(std::holds_alternative<UhjPostProcess>(dev->mPostProcess))
@@ -159,9 +161,11 @@ int refh_ambi_decoder(ALCdevice *adev, float *gains_hf, float *gains_lf, float *
     int *dual)
 {
     auto *dev = dev_of(adev);
-    auto *proc = std::get_if<AmbiDecPostProcess>(&dev->mPostProcess);
-    if(!proc) return -1;
-    auto &dec = *proc->mAmbiDecoder;
+    BFormatDec *decp{nullptr};
+    if(auto *proc = std::get_if<AmbiDecPostProcess>(&dev->mPostProcess)) decp = proc->mAmbiDecoder.get();
+    else if(auto *sproc = std::get_if<StablizerPostProcess>(&dev->mPostProcess)) decp = sproc->mAmbiDecoder.get();
+    if(!decp) return -1;
+    auto &dec = *decp;
     const auto outs = dev->RealOut.Buffer.size();
     if(auto *sb = std::get_if<BFormatDec::SBandDecoderVector>(&dec.mChannelDec))
     {
@@ -246,6 +250,17 @@ void refh_bs2b_cross_feed(int level, int srate, float *left, float *right, int n
     state[0] = p.history[0].lo; state[1] = p.history[0].hi;
     state[2] = p.history[1].lo; state[3] = p.history[1].hi;
     coef[0] = p.a0_lo; coef[1] = p.b1_lo; coef[2] = p.a0_hi; coef[3] = p.a1_hi; coef[4] = p.b1_hi;
+}
+
+/* StablizerPostProcess (core/device.h:176-179): returns the FrontCenter RealOut index and the
+ * band-splitter coefficient of FrontStablizer::MidFilter, or -1 when the device has none. */
+int refh_front_stabilizer(ALCdevice *adev, float *splitter_coeff)
+{
+    auto *dev = dev_of(adev);
+    auto *proc = std::get_if<StablizerPostProcess>(&dev->mPostProcess);
+    if(!proc) return -1;
+    *splitter_coeff = proc->mStablizer->MidFilter.mCoeff;
+    return static_cast<int>(dev->RealOut.ChannelIndex[FrontCenter].c_val);
 }
 
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one

@@ -83,6 +83,8 @@ SCENES = {
     # the FIR UHJ encoders (uhj/encode-filter = fir256 / fir512): UhjEncoder<N>, core/uhjfilter.cpp:83-205
     "uhj_spline_fir256_v6": (6, 0, 2, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir256"),
     "uhj_bsinc12_fir512_v5": (5, 0, 4, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir512"),
+    # 5.1 output with the front image stabilizer (front-stablizer = true): StablizerPostProcess
+    "surround51_spline_stabilizer_v6": (6, 0, 2, 4, True, 48000, "x51", "i16", 0, None, None, "stabilizer"),
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
     # ReverbState::process): REVERB_SCRIPT below — full updates, a non-full one, the old pipeline
     # running out and being cleared, and a full update arriving while the previous fade still runs
@@ -140,6 +142,38 @@ def apply_filter_script(ref, script, u, slot):
 
 LIMITER_LISTENER_GAIN = 5.0
 
+# A first-order 5.1 decoder of our own that leaves the centre speaker silent (zero row): the
+# condition under which InitPanning creates the front stabilizer (alc/panning.cpp:806-834).
+X51_NOCENTER_AMBDEC = """/description surround51_no_centre
+/version 3
+/dec/chan_mask b
+/dec/freq_bands 1
+/dec/speakers 5
+/dec/coeff_scale n3d
+/opt/input_scale n3d
+/opt/nfeff_comp input
+/opt/delay_comp off
+/opt/level_comp off
+/opt/xover_freq 400
+/opt/xover_ratio 0
+/speakers/{
+add_spkr LF 1.0 30 0
+add_spkr RF 1.0 -30 0
+add_spkr CE 1.0 0 0
+add_spkr LS 1.0 110 0
+add_spkr RS 1.0 -110 0
+/}
+/matrix/{
+order_gain 1 1 0 0
+add_row 0.30 0.125 0.2165
+add_row 0.30 -0.125 0.2165
+add_row 0 0 0
+add_row 0.35 0.235 -0.0855
+add_row 0.35 -0.235 -0.0855
+/}
+/end
+"""
+
 # A first-order horizontal decoder of our own for a quad rig whose speakers stand at different
 # distances (2.0, 1.5, 2.5 and 1.0 m): single band, plain projection rows (W, Y, X in ACN order).
 QUAD_AMBDEC = """/description quad_unequal_distances
@@ -183,6 +217,7 @@ ATTRS = {
     "lim_i16": lambda r: {r.ALC_FORMAT_TYPE_SOFT: r.ALC_SHORT_SOFT},
     "lim_f32": lambda r: {r.ALC_OUTPUT_LIMITER_SOFT: 1},
     "quad": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_QUAD_SOFT},
+    "x51": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_5POINT1_SOFT},
     "uhj": lambda r: {r.ALC_OUTPUT_MODE_SOFT: r.ALC_STEREO_UHJ_SOFT},
     "ambi2": lambda r: {r.ALC_FORMAT_CHANNELS_SOFT: r.ALC_BFORMAT3D_SOFT, r.ALC_AMBISONIC_ORDER_SOFT: 2,
                         r.ALC_AMBISONIC_LAYOUT_SOFT: r.ALC_ACN_SOFT,
@@ -335,6 +370,10 @@ def run_scene(name):
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
     if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
         res.update(uhj_fir=np.int64(int(spec[11][6:])))
+    if len(spec) > 11 and spec[11] == "stabilizer":
+        st = ref.front_stabilizer()
+        assert st is not None, "the reference did not enable the front stabilizer"
+        res.update(stab_center=np.int64(st[0]), stab_coeff=np.float32(st[1]))
     if len(spec) > 11 and spec[11] == "distcomp":
         dl, dg = ref.distance_comp()
         assert dl.max() > 0, dl
@@ -377,6 +416,11 @@ def child(name, mode, path):
         with open(amb, "w") as f:
             f.write(QUAD_AMBDEC)
         conf += f"[decoder]\nquad = {amb}\n"
+    if len(spec) > 11 and spec[11] == "stabilizer":
+        amb = os.path.join(HERE, f"_tmp_{os.getpid()}.ambdec")
+        with open(amb, "w") as f:
+            f.write(X51_NOCENTER_AMBDEC)
+        conf += f"front-stablizer = true\n[decoder]\nsurround51 = {amb}\n"
     if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
         conf += f"[uhj]\nencode-filter = fir{spec[11][6:]}\n"
     refal.libs(conf)

@@ -110,6 +110,8 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             for k in range(V):
                 ids = [k * len(qlens) + j for j in range(len(qlens))]
                 dev.voice_queue(k, ids, 0 if (plist[k].flags & abi.VF_LOOPING) else abi.NO_LOOP)
+        if "stab_center" in fx:
+            dev.set_front_stabilizer(int(fx["stab_center"]), float(fx["stab_coeff"]))
         if "uhj_fir" in fx:
             n = int(fx["uhj_fir"])
             assert dev.set_uhj_encoder(n) == n // 2 + 128

@@ -62,6 +62,8 @@ class MixLib:
                                             C.c_float, C.POINTER(C.c_uint32), C.c_void_p]
         self.set_limiter = f("set_limiter")
         self.set_limiter.argtypes = [C.c_void_p, C.POINTER(abi.LimiterDesc), C.POINTER(C.c_uint32)]
+        self.set_front_stabilizer = f("set_front_stabilizer")
+        self.set_front_stabilizer.argtypes = [C.c_void_p, C.c_uint32, C.c_float]
         self.set_bs2b = f("set_bs2b")
         self.set_bs2b.argtypes = [C.c_void_p, C.c_uint32]
         self.set_uhj_encoder = f("set_uhj_encoder")
@@ -213,6 +215,10 @@ class MixDevice:
         rc = self.m.set_limiter(self.h, C.byref(desc) if desc is not None else None, C.byref(la))
         assert rc == 0, f"set_limiter -> {rc}"
         return la.value
+
+    def set_front_stabilizer(self, center_channel, splitter_coeff):
+        rc = self.m.set_front_stabilizer(self.h, center_channel, splitter_coeff)
+        assert rc == 0, f"set_front_stabilizer -> {rc}"
 
     def set_bs2b(self, level):
         rc = self.m.set_bs2b(self.h, level)

@@ -58,6 +58,7 @@ ALC_SHORT_SOFT = 0x1402
 ALC_UNSIGNED_BYTE_SOFT = 0x1401
 ALC_STEREO_SOFT = 0x1501
 ALC_QUAD_SOFT = 0x1503
+ALC_5POINT1_SOFT = 0x1504
 ALC_BFORMAT3D_SOFT = 0x1507
 ALC_HRTF_SOFT = 0x1992
 ALC_HRTF_STATUS_SOFT = 0x1993
@@ -146,6 +147,7 @@ def libs(conf_text: str | None = None):
     hz.refh_dither_depth.restype = C.c_float
     hz.refh_limiter_desc.argtypes = [C.c_void_p, C.c_void_p]
     hz.refh_distance_comp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_front_stabilizer.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     hz.refh_set_snapshot_channel.argtypes = [C.c_int]
     hz.refh_set_snapshot_channel.restype = None
     hz.refh_voice_filters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -371,6 +373,12 @@ class RefDevice:
 
     def dither_depth(self) -> float:
         return float(self.hz.refh_dither_depth(self.dev))
+
+    def front_stabilizer(self):
+        """(FrontCenter index, splitter coefficient) of StablizerPostProcess, or None."""
+        co = C.c_float(0.0)
+        idx = self.hz.refh_front_stabilizer(self.dev, C.byref(co))
+        return (idx, co.value) if idx >= 0 else None
 
     def distance_comp(self):
         """(delays uint32[real], gains float32[real]) of DeviceBase::ChannelDelays, or None."""

@@ -255,6 +255,36 @@ def test_bs2b_crossfeed_vs_oracle_ragged_updates(level):
     assert np.abs(outs[1] - outs[2]).max() > 1e-3       # the crossfeed did change the output
 
 
+def test_front_stabilizer_vs_oracle_ragged_updates():
+    """StablizerPostProcess on a 6-channel decode (the oracle is bit-exact with the reference on
+    the 5.1 golden): mid band split, centre feed, all-pass on the other channels; then removal."""
+    rng = np.random.default_rng(61)
+    nv = 12
+    desc = synth.stereo_desc(nv, dry_channels=4)
+    desc.real_channels = 6
+    params, coeffs, dry = synth.voice_set(rng, nv, 0, hrtf=False, dry_channels=desc.dry_channels)
+    sizes = (1024, 37, 512, 1, 1000, 64, 7, 1024)
+    outs = []
+    for lib, on in ((mixlib.oracle(), True), (mixlib.product(), True), (mixlib.product(), False)):
+        dev = MixDevice(lib, desc)
+        g = np.random.default_rng(8).standard_normal((desc.dry_channels, desc.real_channels)) * 0.5
+        g[:, 2] = 0.0          # the decoder leaves the centre speaker to the stabilizer
+        dev.set_ambi_decoder(g.astype(np.float32), None, 0.0)
+        for i in range(nv):
+            dev.buffer_data(i, abi.FMT_I16, scene.voice_buffer_fast(i))
+        dev.voices_update(params, None, dry, None)
+        if on:
+            dev.set_front_stabilizer(2, -0.49314544)
+        o = [dev.render(f) for f in sizes]
+        if on:
+            dev.set_front_stabilizer(abi.NO_SLOT, 0.0)
+            o.append(dev.render(128))
+        dev.close()
+        outs.append(np.concatenate(o, axis=1))
+    _check(outs[1], outs[0], "front stabilizer")
+    assert np.abs(outs[1][2]).max() > 1e-3 and not outs[2][2].any()     # only the stabilizer feeds the centre
+
+
 def test_config2_size_linearity_and_subsample():
     """BASELINE config 2 size (4096 HRTF voices, bsinc24): the oracle only mixes a
     deterministic 1/16 subsample; the full mix is checked by linearity — the sum of
