@@ -67,7 +67,8 @@ enum b200mix_post_process {
     B200MIX_POST_NONE = 0,   /* RealOut aliases Dry (e.g. ALC_BFORMAT3D_SOFT output) */
     B200MIX_POST_AMBIDEC,    /* BFormatDec::process        core/bformatdec.cpp:60-97 */
     B200MIX_POST_HRTF,       /* MixDirectHrtf              core/mixer/hrtfbase.h:91-133 */
-    B200MIX_POST_UHJ         /* UhjEncoderIIR::encode      core/uhjfilter.cpp:231-283 */
+    B200MIX_POST_UHJ,        /* UhjEncoderIIR::encode      core/uhjfilter.cpp:231-283 */
+    B200MIX_POST_TSME        /* TsmeEncoderIIR::encode     core/tsmefilter.cpp:280-329 (4 dry channels W,Y,Z,X) */
 };
 
 typedef struct b200mix_device b200mix_device;
@@ -358,10 +359,11 @@ typedef struct b200mix_limiter_desc {
 B200MIX_API int b200mix_set_limiter(b200mix_device *dev, const b200mix_limiter_desc *desc,
     uint32_t *look_ahead);
 
-/* Which UHJ encoder a B200MIX_POST_UHJ device runs (UhjEncodeQuality, alc/alc.cpp:564-574;
- * core/uhjfilter.h): filter_length 0 = UhjEncoderIIR (the default), 256 / 512 = UhjEncoder<N>
- * (core/uhjfilter.cpp:83-205: the +90 degree shift as an N-tap linear-phase FIR, every other
- * signal delayed by N/2 + 128 samples).  Resets the encoder state; *delay (nullable) receives
+/* Which encoder a B200MIX_POST_UHJ / B200MIX_POST_TSME device runs (UhjEncodeQuality /
+ * TsmeEncodeQuality, alc/alc.cpp:564-597; core/uhjfilter.h, core/tsmefilter.hpp): filter_length
+ * 0 = UhjEncoderIIR / TsmeEncoderIIR (the default), 256 / 512 = UhjEncoder<N> / TsmeEncoder<N>
+ * (core/uhjfilter.cpp:83-205, core/tsmefilter.cpp:137-278: the +90 degree shift as an N-tap
+ * linear-phase FIR, every other signal delayed by N/2 + 128 samples).  Resets the encoder state; *delay (nullable) receives
  * EncoderBase::getDelay() in samples. */
 B200MIX_API int b200mix_set_uhj_encoder(b200mix_device *dev, uint32_t filter_length,
     uint32_t *delay);

@@ -290,7 +290,8 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         || desc->num_sends > B200MIX_MAX_SENDS || desc->ir_size > B200MIX_HRIR_LENGTH
         || desc->real_channels > B200MIX_MAX_DRY_CHANNELS || desc->max_voices == 0)
     { g_create_error = "descriptor out of range"; return B200MIX_ERR_INVALID; }
-    if(desc->post_process == B200MIX_POST_UHJ && desc->dry_channels < 3)
+    if((desc->post_process == B200MIX_POST_UHJ && desc->dry_channels < 3)
+        || (desc->post_process == B200MIX_POST_TSME && desc->dry_channels < 4))
     { g_create_error = "UHJ post-process needs W,X,Y dry channels"; return B200MIX_ERR_INVALID; }
 
     auto *d = new(std::nothrow) b200mix_device{};
@@ -425,7 +426,7 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
                 cudaMemcpyHostToDevice, d->stream));
             CUDA_TRY(d, cudaStreamSynchronize(d->stream));
         }
-        if(dd.post_process == B200MIX_POST_UHJ)
+        if(dd.post_process == B200MIX_POST_UHJ || dd.post_process == B200MIX_POST_TSME)
         {
             if(int rc = dev_alloc(d, d->d_uhj_state, 64)) return rc;
             if(int rc = dev_alloc(d, d->d_uhj_scratch, 5*1025)) return rc;
@@ -1650,15 +1651,16 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         }
         break;
     }
-    case B200MIX_POST_UHJ:
+    case B200MIX_POST_UHJ: case B200MIX_POST_TSME:
     {
+        const MatrixEncSpec spec = dd.post_process == B200MIX_POST_TSME ? kTsmeEncSpec : kUhjEncSpec;
         PostUhjParams Q{};
         Q.dry = d->d_dry; Q.real = d->d_real; Q.state = d->d_uhj_state; Q.scratch = d->d_uhj_scratch;
-        Q.frames = frames; Q.real_left = dd.real_left; Q.real_right = dd.real_right;
+        Q.frames = frames; Q.real_left = dd.real_left; Q.real_right = dd.real_right; Q.enc = spec;
         if(d->uhj_fir)
         {
             PostUhjFirParams F{d->d_dry, d->d_real, d->d_uhj_fir_state, d->d_uhj_fir_coef, frames,
-                dd.real_left, dd.real_right, d->uhj_fir};
+                dd.real_left, dd.real_right, d->uhj_fir, spec};
             k_post_uhj_fir<<<1, 1024, 0, d->stream>>>(F);
         }
         else
@@ -1739,7 +1741,8 @@ int b200mix_set_uhj_encoder(b200mix_device *d, uint32_t filter_length, uint32_t 
 {
     if(!d) return B200MIX_ERR_INVALID;
     const b200mix_device_desc &dd = d->desc;
-    if(d->mid_render || dd.post_process != B200MIX_POST_UHJ || dd.dry_channels < 3
+    if(d->mid_render || (dd.post_process != B200MIX_POST_UHJ && dd.post_process != B200MIX_POST_TSME)
+        || dd.dry_channels < 3
         || (filter_length != 0 && filter_length != 256 && filter_length != 512))
     { d->error = "set_uhj_encoder: needs a UHJ device and a length of 0, 256 or 512"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));

@@ -1552,9 +1552,20 @@ __global__ void __launch_bounds__(128) k_post_ambi_mix(const PostAmbiParams Q)
 // UhjEncoderIIR::encode (core/uhjfilter.cpp:231-283): five 4-stage all-pass chains
 // (core/allpass_iir.hpp:53-70), each a serial recurrence -> one thread per chain, then
 // the whole block combines.  state: [5 chains][4 stages][2] + 4 delay samples.
+// The two stereo matrix encoders share their structure and differ in constants and in the Dry
+// channels they read: UhjEncoder* (core/uhjfilter.cpp:59-70; Dry 0,1,2 = W,X,Y) and TsmeEncoder*
+// (core/tsmefilter.cpp:156-163,289-309; Dry 0,1,2,3 = W,Y,Z,X).  S = sw W + sx X [+ sz Z],
+// D = j(dw W + dx X) + dy Y, Left = S + D, Right = S - D.
+struct MatrixEncSpec { uint32_t w, x, y, z; float sw, sx, sz, dw, dx, dy; };   // z = ~0u: none
+constexpr MatrixEncSpec kUhjEncSpec{0u, 1u, 2u, ~0u, 0.4698463f, 0.0757602682546f, 0.0f,
+    -0.17101005f, 0.208149636675f, 0.267586995182f};
+constexpr MatrixEncSpec kTsmeEncSpec{0u, 3u, 1u, 2u, 0.288397341271f, 0.166565447888f, 0.187684284734f,
+    0.444008050325f, -0.256439256487f, 0.333238912931f};
+
 struct PostUhjParams {
     const float *dry; float *real; float *state; float *scratch;   // scratch [5][1025]
     uint32_t frames, real_left, real_right;
+    MatrixEncSpec enc;
 };
 
 __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
@@ -1567,13 +1578,17 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     __shared__ float sIn[5][kRow];
     __shared__ float sOut[5][kRow];
     const uint32_t n = Q.frames;
-    const float *w = Q.dry, *x = Q.dry + kLine, *y = Q.dry + 2*kLine;
+    const MatrixEncSpec E = Q.enc;
+    const float *w = Q.dry + size_t(E.w)*kLine, *x = Q.dry + size_t(E.x)*kLine, *y = Q.dry + size_t(E.y)*kLine;
+    const float *z = E.z != ~0u ? Q.dry + size_t(E.z)*kLine : nullptr;
     float *left = Q.real + size_t(Q.real_left)*kLine, *right = Q.real + size_t(Q.real_right)*kLine;
     for(uint32_t k = threadIdx.x;k < n;k += blockDim.x)
     {
         const float wk = w[k], xk = x[k];
-        sIn[0][k] = 0.4698463f*wk + 0.0757602682546f*xk;
-        sIn[1][k] = -0.17101005f*wk + 0.208149636675f*xk;
+        float sv = E.sw*wk + E.sx*xk;
+        if(z) sv = sv + E.sz*z[k];
+        sIn[0][k] = sv;
+        sIn[1][k] = E.dw*wk + E.dx*xk;
         sIn[2][k] = y[k];
         sIn[3][k] = left[k];
         sIn[4][k] = right[k];
@@ -1614,7 +1629,7 @@ __global__ void __launch_bounds__(1024) k_post_uhj(const PostUhjParams Q)
     __syncthreads();
     for(uint32_t i = threadIdx.x;i < n;i += blockDim.x)
     {
-        const float dd = sOut[1][i] + 0.267586995182f*sOut[2][i];
+        const float dd = sOut[1][i] + E.dy*sOut[2][i];
         left[i] = sOut[0][i] + dd + sOut[3][i];
         right[i] = sOut[0][i] - dd + sOut[4][i];
     }
@@ -1831,9 +1846,10 @@ __global__ void __launch_bounds__(128) k_post_bs2b(const Bs2bParams Q)
 struct PostUhjFirParams {
     const float *dry; float *real; float *state; const float *coef;   // coef[j] = h[2j+1]
     uint32_t frames, real_left, real_right, taps;
+    MatrixEncSpec enc;
 };
-constexpr uint32_t kUhjFirHist = 640u, kUhjFirDelay = 384u;            // state: hist | 3 in | 2 out
-constexpr uint32_t kUhjFirStateFloats = kUhjFirHist + 5u*kUhjFirDelay;
+constexpr uint32_t kUhjFirHist = 640u, kUhjFirDelay = 384u;            // state: hist | W X Y L R Z lines
+constexpr uint32_t kUhjFirStateFloats = kUhjFirHist + 6u*kUhjFirDelay;
 
 __global__ void __launch_bounds__(1024) k_post_uhj_fir(const PostUhjFirParams Q)
 {
@@ -1843,20 +1859,24 @@ __global__ void __launch_bounds__(1024) k_post_uhj_fir(const PostUhjFirParams Q)
     const uint32_t n = Q.frames, N = Q.taps, hist = N + kSeg - 1u, delay = N/2u + kSeg;
     const uint32_t i = threadIdx.x;
     float *wxh = Q.state;
-    const float *w = Q.dry, *x = Q.dry + kLine, *y = Q.dry + 2*kLine;
-    float *lines[5] = {const_cast<float*>(w), const_cast<float*>(x), const_cast<float*>(y),
-        Q.real + size_t(Q.real_left)*kLine, Q.real + size_t(Q.real_right)*kLine};
+    const MatrixEncSpec E = Q.enc;
+    const bool hasZ = E.z != ~0u;
+    const float *w = Q.dry + size_t(E.w)*kLine, *x = Q.dry + size_t(E.x)*kLine, *y = Q.dry + size_t(E.y)*kLine;
+    float *lines[6] = {const_cast<float*>(w), const_cast<float*>(x), const_cast<float*>(y),
+        Q.real + size_t(Q.real_left)*kLine, Q.real + size_t(Q.real_right)*kLine,
+        const_cast<float*>(hasZ ? Q.dry + size_t(E.z)*kLine : w)};
 
     if(i < hist) sExt[i] = wxh[i];
-    if(i < n) sExt[hist + i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    if(i < n) sExt[hist + i] = E.dw*w[i] + E.dx*x[i];
     if(i < N/2u) sCoef[i] = Q.coef[i];
-    // the five delayed signals: [delay line | this update] -> value i; the tail is the new line
-    float dv[5], nd[5];
+    // the delayed signals: [delay line | this update] -> value i; the tail is the new line
+    float dv[6], nd[6];
     #pragma unroll
-    for(int c = 0;c < 5;++c)
+    for(int c = 0;c < 6;++c)
     {
         const float *dl = Q.state + kUhjFirHist + c*kUhjFirDelay;
         dv[c] = 0.0f; nd[c] = 0.0f;
+        if(c == 5 && !hasZ) continue;
         if(i < n) dv[c] = i < delay ? dl[i] : lines[c][i - delay];
         if(i < delay) nd[c] = (n + i < delay) ? dl[n + i] : lines[c][n + i - delay];
     }
@@ -1870,14 +1890,15 @@ __global__ void __launch_bounds__(1024) k_post_uhj_fir(const PostUhjFirParams Q)
             acc0 = fmaf(sCoef[j], src[-int(2u*j)], acc0);
             acc1 = fmaf(sCoef[j + 1u], src[-int(2u*j + 2u)], acc1);
         }
-        const float S = 0.4698463f*dv[0] + 0.0757602682546f*dv[1];
-        const float D = (acc0 + acc1) + 0.267586995182f*dv[2];
+        float S = E.sw*dv[0] + E.sx*dv[1];
+        if(hasZ) S = S + E.sz*dv[5];
+        const float D = (acc0 + acc1) + E.dy*dv[2];
         lines[3][i] = dv[3] + (S + D);
         lines[4][i] = dv[4] + (S - D);
     }
     #pragma unroll
-    for(int c = 0;c < 5;++c)
-        if(i < delay) Q.state[kUhjFirHist + c*kUhjFirDelay + i] = nd[c];
+    for(int c = 0;c < 6;++c)
+        if(i < delay && (c < 5 || hasZ)) Q.state[kUhjFirHist + c*kUhjFirDelay + i] = nd[c];
     if(i < hist) wxh[i] = sExt[n + i];
 }
 

@@ -259,7 +259,7 @@ struct oracle_device {
     uint32_t uhj_fir;                   /* 0, 256 or 512 */
     double uhj_fir_h[512];              /* the phase-shift response (odd taps only are non-zero) */
     float uhj_wxhist[512+128];          /* the last N+127 values of -0.171 W + 0.208 X */
-    float uhj_in_delay[3][512/2+128];   /* W, X, Y delayed by sFilterDelay = N/2 + 128 */
+    float uhj_in_delay[4][512/2+128];   /* W, X, Y (and Z) delayed by sFilterDelay = N/2 + 128 */
     float uhj_out_delay[2][512/2+128];  /* mDirectDelay */
     /* scratch */
     float resample_data[RESBUF];
@@ -377,7 +377,8 @@ int oracle_set_limiter(oracle_device *d, const b200mix_limiter_desc *desc, uint3
 int oracle_set_uhj_encoder(oracle_device *d, uint32_t filter_length, uint32_t *delay)
 {
     if(filter_length != 0 && filter_length != 256 && filter_length != 512) return B200MIX_ERR_INVALID;
-    if(d->desc.post_process != B200MIX_POST_UHJ) return B200MIX_ERR_INVALID;
+    if(d->desc.post_process != B200MIX_POST_UHJ && d->desc.post_process != B200MIX_POST_TSME)
+        return B200MIX_ERR_INVALID;
     d->uhj_fir = filter_length;
     memset(d->uhj_f1wx, 0, sizeof(d->uhj_f1wx)); memset(d->uhj_f2wx, 0, sizeof(d->uhj_f2wx));
     memset(d->uhj_f1y, 0, sizeof(d->uhj_f1y)); memset(d->uhj_f1d, 0, sizeof(d->uhj_f1d));
@@ -1573,25 +1574,43 @@ static void allpass_process(float st[4][2], const float coeffs[4], const float *
     }
 }
 
+/* The two stereo matrix encoders share their structure (S from W, X [and Z]; D = j(W, X) + Y;
+ * Left = S + D, Right = S - D) and differ in constants and in which Dry channels they read:
+ * UhjEncoder* (core/uhjfilter.cpp:59-70; Dry 0,1,2 = W,X,Y, alc/alu.cpp:307-311) and TsmeEncoder*
+ * (core/tsmefilter.cpp:156-163,289-309; Dry 0,1,2,3 = W,Y,Z,X, alc/alu.cpp:322-327). */
+typedef struct { int w, x, y, z; float sw, sx, sz, dw, dx, dy; } oencspec;
+static const oencspec kUhjSpec = {0, 1, 2, -1, 0.4698463f, 0.0757602682546f, 0.0f,
+    -0.17101005f, 0.208149636675f, 0.267586995182f};
+static const oencspec kTsmeSpec = {0, 3, 1, 2, 0.288397341271f, 0.166565447888f, 0.187684284734f,
+    0.444008050325f, -0.256439256487f, 0.333238912931f};
+static const oencspec *enc_spec(const oracle_device *d)
+{ return d->desc.post_process == B200MIX_POST_TSME ? &kTsmeSpec : &kUhjSpec; }
+
 /* UhjEncoderIIR::encode, core/uhjfilter.cpp:231-283 (DeviceBase::Process(UhjPostProcess),
  * alc/alu.cpp:300-312) */
 static void post_uhj(oracle_device *d, size_t n)
 {
     static const float F1[4] = {0.479400865589f, 0.876218493539f, 0.976597589508f, 0.997499255936f};
     static const float F2[4] = {0.161758498368f, 0.733028932341f, 0.945349700329f, 0.990599156684f};
-    const float *w = d->dry[0], *x = d->dry[1], *y = d->dry[2];
+    const oencspec *e = enc_spec(d);
+    const float *w = d->dry[e->w], *x = d->dry[e->x], *y = d->dry[e->y];
     float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
 
-    for(size_t i = 0;i < n;++i) d->temp[i] = 0.4698463f*w[i] + 0.0757602682546f*x[i];
+    for(size_t i = 0;i < n;++i) d->temp[i] = e->sw*w[i] + e->sx*x[i];
+    if(e->z >= 0)
+    {
+        const float *z = d->dry[e->z];
+        for(size_t i = 0;i < n;++i) d->temp[i] = d->temp[i] + e->sz*z[i];
+    }
     allpass_process(d->uhj_f1wx, F1, d->temp, d->uhj_s+1, n);
     d->uhj_s[0] = d->uhj_delay_wx; d->uhj_delay_wx = d->uhj_s[n];
 
-    for(size_t i = 0;i < n;++i) d->temp[i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    for(size_t i = 0;i < n;++i) d->temp[i] = e->dw*w[i] + e->dx*x[i];
     allpass_process(d->uhj_f2wx, F2, d->temp, d->uhj_wx, n);
 
     allpass_process(d->uhj_f1y, F1, y, d->uhj_d+1, n);
     d->uhj_d[0] = d->uhj_delay_y; d->uhj_delay_y = d->uhj_d[n];
-    for(size_t i = 0;i < n;++i) d->uhj_d[i] = d->uhj_wx[i] + 0.267586995182f*d->uhj_d[i];
+    for(size_t i = 0;i < n;++i) d->uhj_d[i] = d->uhj_wx[i] + e->dy*d->uhj_d[i];
 
     allpass_process(d->uhj_f1d[0], F1, left, d->uhj_t+1, n);
     d->uhj_t[0] = d->uhj_delay_d[0]; d->uhj_delay_d[0] = d->uhj_t[n];
@@ -1633,13 +1652,15 @@ static void post_uhj_fir(oracle_device *d, size_t n)
 {
     const size_t N = d->uhj_fir, seg = 128, delay = N/2 + seg, hist = N + seg - 1;
     float *left = d->real[d->desc.real_left], *right = d->real[d->desc.real_right];
-    float w[LINE], x[LINE], y[LINE], ext[512+128+LINE];
-    memcpy(w, d->dry[0], sizeof(float)*n); memcpy(x, d->dry[1], sizeof(float)*n);
-    memcpy(y, d->dry[2], sizeof(float)*n);
+    const oencspec *e = enc_spec(d);
+    float w[LINE], x[LINE], y[LINE], z[LINE], ext[512+128+LINE];
+    memcpy(w, d->dry[e->w], sizeof(float)*n); memcpy(x, d->dry[e->x], sizeof(float)*n);
+    memcpy(y, d->dry[e->y], sizeof(float)*n);
+    if(e->z >= 0) memcpy(z, d->dry[e->z], sizeof(float)*n);
 
     /* j(-0.17101005*W + 0.208149636675*X) of the NON-delayed input (:112-114) */
     memcpy(ext, d->uhj_wxhist, sizeof(float)*hist);
-    for(size_t i = 0;i < n;++i) ext[hist + i] = -0.17101005f*w[i] + 0.208149636675f*x[i];
+    for(size_t i = 0;i < n;++i) ext[hist + i] = e->dw*w[i] + e->dx*x[i];
     for(size_t t = 0;t < n;++t)
     {
         double acc = 0.0;
@@ -1651,12 +1672,14 @@ static void post_uhj_fir(oracle_device *d, size_t n)
     fifo_delay(d->uhj_in_delay[0], delay, w, n);
     fifo_delay(d->uhj_in_delay[1], delay, x, n);
     fifo_delay(d->uhj_in_delay[2], delay, y, n);
+    if(e->z >= 0) fifo_delay(d->uhj_in_delay[3], delay, z, n);
     fifo_delay(d->uhj_out_delay[0], delay, left, n);
     fifo_delay(d->uhj_out_delay[1], delay, right, n);
     for(size_t i = 0;i < n;++i)
     {
-        const float S = 0.4698463f*w[i] + 0.0757602682546f*x[i];
-        const float D = d->uhj_wx[i] + 0.267586995182f*y[i];
+        float S = e->sw*w[i] + e->sx*x[i];
+        if(e->z >= 0) S = S + e->sz*z[i];
+        const float D = d->uhj_wx[i] + e->dy*y[i];
         left[i] += S + D;
         right[i] += S - D;
     }
@@ -1807,8 +1830,9 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
             else post_ambidec(d, frames);
         }
         break;
-    case B200MIX_POST_UHJ:
-        if(dd->dry_channels >= 3) { if(d->uhj_fir) post_uhj_fir(d, frames); else post_uhj(d, frames); }
+    case B200MIX_POST_UHJ: case B200MIX_POST_TSME:
+        if(dd->dry_channels >= (dd->post_process == B200MIX_POST_TSME ? 4u : 3u))
+        { if(d->uhj_fir) post_uhj_fir(d, frames); else post_uhj(d, frames); }
         break;
     case B200MIX_POST_NONE: break;
     default: return B200MIX_ERR_UNSUPPORTED;

@@ -115,6 +115,8 @@ int refh_device_desc(ALCdevice *adev, b200mix_device_desc *out)
         out->post_process = B200MIX_POST_HRTF;
     else if(std::holds_alternative<UhjPostProcess>(dev->mPostProcess))
         out->post_process = B200MIX_POST_UHJ;
+    else if(std::holds_alternative<TsmePostProcess>(dev->mPostProcess))
+        out->post_process = B200MIX_POST_TSME;
     else if(std::holds_alternative<std::monostate>(dev->mPostProcess))
         out->post_process = B200MIX_POST_NONE;
     else

@@ -83,6 +83,9 @@ SCENES = {
     # the FIR UHJ encoders (uhj/encode-filter = fir256 / fir512): UhjEncoder<N>, core/uhjfilter.cpp:83-205
     "uhj_spline_fir256_v6": (6, 0, 2, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir256"),
     "uhj_bsinc12_fir512_v5": (5, 0, 4, 4, True, 48000, "uhj", "i16", 0, None, None, "uhjfir512"),
+    # Tetraphonic surround matrix encoding (stereo-encoding = tsme): TsmeEncoderIIR and TsmeEncoder<256>
+    "tsme_spline_iir_v6": (6, 0, 2, 4, True, 48000, None, "i16", 0, None, None, "tsme0"),
+    "tsme_bsinc12_fir256_v5": (5, 0, 4, 4, True, 48000, None, "i16", 0, None, None, "tsme256"),
     # 5.1 output with the front image stabilizer (front-stablizer = true): StablizerPostProcess
     "surround51_spline_stabilizer_v6": (6, 0, 2, 4, True, 48000, "x51", "i16", 0, None, None, "stabilizer"),
     # reverb parameter changes while playing (ReverbState::update + the two-pipeline cross-fade of
@@ -370,6 +373,8 @@ def run_scene(name):
         res.update(out_type=np.int64(out_type), dither_depth=np.float32(ref.dither_depth()))
     if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
         res.update(uhj_fir=np.int64(int(spec[11][6:])))
+    if len(spec) > 11 and str(spec[11]).startswith("tsme") and int(spec[11][4:]):
+        res.update(uhj_fir=np.int64(int(spec[11][4:])))
     if len(spec) > 11 and spec[11] == "stabilizer":
         st = ref.front_stabilizer()
         assert st is not None, "the reference did not enable the front stabilizer"
@@ -421,6 +426,10 @@ def child(name, mode, path):
         with open(amb, "w") as f:
             f.write(X51_NOCENTER_AMBDEC)
         conf += f"front-stablizer = true\n[decoder]\nsurround51 = {amb}\n"
+    if len(spec) > 11 and str(spec[11]).startswith("tsme"):
+        conf += "stereo-encoding = tsme\n"
+        if int(spec[11][4:]):
+            conf += f"[tsme]\nencode-filter = fir{spec[11][4:]}\n"
     if len(spec) > 11 and str(spec[11]).startswith("uhjfir"):
         conf += f"[uhj]\nencode-filter = fir{spec[11][6:]}\n"
     refal.libs(conf)

@@ -204,14 +204,15 @@ def test_distance_comp_vs_oracle_ragged_updates():
     assert not outs[1][0, :700].any() and outs[1][0, 700:1024].any()
 
 
-@pytest.mark.parametrize("taps", [0, 256, 512])
-def test_uhj_encoders_vs_oracle_ragged_updates(taps):
-    """UhjEncoderIIR (taps 0) and UhjEncoder<256/512> on a 3-channel dry mix, update sizes below
-    and above the encoder delay (N/2 + 128) and the FIR history."""
-    rng = np.random.default_rng(41 + taps)
+@pytest.mark.parametrize("post,taps", [(abi.POST_UHJ, 0), (abi.POST_UHJ, 256), (abi.POST_UHJ, 512),
+                                       (abi.POST_TSME, 0), (abi.POST_TSME, 256), (abi.POST_TSME, 512)])
+def test_matrix_encoders_vs_oracle_ragged_updates(post, taps):
+    """Uhj/TsmeEncoderIIR (taps 0) and Uhj/TsmeEncoder<256/512> on a 3- / 4-channel dry mix, update
+    sizes below and above the encoder delay (N/2 + 128) and the FIR history."""
+    rng = np.random.default_rng(41 + taps + post)
     nv = 12
-    desc = synth.stereo_desc(nv)
-    desc.post_process = abi.POST_UHJ
+    desc = synth.stereo_desc(nv, dry_channels=4 if post == abi.POST_TSME else 3)
+    desc.post_process = post
     params, coeffs, dry = synth.voice_set(rng, nv, 0, hrtf=False, dry_channels=desc.dry_channels)
     sizes = (1024, 37, 512, 1, 1000, 64, 300, 5, 1024)
     outs = []
@@ -224,7 +225,7 @@ def test_uhj_encoders_vs_oracle_ragged_updates(taps):
         o = [dev.render(f) for f in sizes]
         dev.close()
         outs.append(np.concatenate(o, axis=1))
-    _check(outs[1], outs[0], f"uhj encoder {taps}")
+    _check(outs[1], outs[0], f"matrix encoder {post} {taps}")
     if taps:
         d = taps // 2 + 128
         assert not outs[1][:, :128].any() and outs[1][:, d:d + 512].any()
