@@ -287,6 +287,21 @@ typedef struct b200mix_voice_filter {
 B200MIX_API int b200mix_voices_filters(b200mix_device *dev, uint32_t n,
     const b200mix_voice_filter *filters);
 
+/* Host helpers, no GPU: the panning half of the parameter stage.
+ * b200mix_ambi_coeffs = CalcDirectionCoeffs(dir, spread) (core/mixer.h:68-73 -> CalcAmbiCoeffs,
+ * core/mixer.cpp:16-91, core/ambidefs.h:219-272): the 25 N3D/ACN encoder coefficients of the unit
+ * vector dir (OpenAL axes), widened by `spread` radians (0..tau).
+ * b200mix_pan_gains = ComputePanGains (core/mixer.cpp:93-102) on a mix whose AmbiMap is
+ * {scale[c], index[c]} for c < channels (DeviceBase::Dry.AmbiMap or an effect slot's Wet.AmbiMap,
+ * core/device.h:109-121): gains[c] = scale[c]*coeffs[index[c]]*ingain, the rest up to gains_len
+ * zero — what goes into dry_gains / send_gains of b200mix_voices_update.  Both are bit-identical
+ * to the reference's results. */
+#define B200MIX_MAX_AMBI_CHANNELS 25u /* MaxAmbiChannels core/ambidefs.h:18-19 */
+B200MIX_API int b200mix_ambi_coeffs(const float dir[3], float spread,
+    float coeffs[B200MIX_MAX_AMBI_CHANNELS]);
+B200MIX_API int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *index,
+    const float coeffs[B200MIX_MAX_AMBI_CHANNELS], float ingain, float *gains, uint32_t gains_len);
+
 /* Host helper, no GPU: BiquadFilter::SetParams via setParamsFromSlope
  * (core/filters/biquad.h:92-97, biquad.cpp:48-129).  type follows enum BiquadType:
  * 0 HighShelf, 1 LowShelf, 2 Peaking, 3 LowPass, 4 HighPass, 5 BandPass.

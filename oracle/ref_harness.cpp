@@ -265,6 +265,36 @@ int refh_front_stabilizer(ALCdevice *adev, float *splitter_coeff)
     return static_cast<int>(dev->RealOut.ChannelIndex[FrontCenter].c_val);
 }
 
+/* Kernel-level taps for the panning helpers: CalcDirectionCoeffs (core/mixer.h:68-73) and
+ * ComputePanGains (core/mixer.cpp:93-102) on the device's Dry mix; refh_dry_ambi_map returns the
+ * Dry.AmbiMap entries ({Scale, Index}, core/device.h:109-121) a binding passes to
+ * b200mix_pan_gains. */
+void refh_calc_direction_coeffs(const float *dir, float spread, float *out25)
+{
+    const auto c = CalcDirectionCoeffs(std::span<const float,3>{dir, 3}, spread);
+    std::copy(c.begin(), c.end(), out25);
+}
+
+int refh_dry_ambi_map(ALCdevice *adev, float *scale, uint32_t *index)
+{
+    auto *dev = dev_of(adev);
+    const auto n = dev->Dry.Buffer.size();
+    for(size_t c{0};c < n;++c)
+    {
+        scale[c] = dev->Dry.AmbiMap[c].Scale;
+        index[c] = static_cast<uint32_t>(dev->Dry.AmbiMap[c].Index);
+    }
+    return static_cast<int>(n);
+}
+
+void refh_dry_pan_gains(ALCdevice *adev, const float *coeffs25, float ingain, float *gains)
+{
+    auto *dev = dev_of(adev);
+    std::array<float,MaxAmbiChannels> g{};
+    ComputePanGains(&dev->Dry, std::span<const float,MaxAmbiChannels>{coeffs25, MaxAmbiChannels}, ingain, g);
+    std::copy(g.begin(), g.end(), gains);
+}
+
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
 static size_t g_snap_channel = 0;

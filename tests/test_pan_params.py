@@ -1,0 +1,91 @@
+"""Host-side panning helpers of the product (b200mix_ambi_coeffs, b200mix_pan_gains; no GPU
+involved) against the compiled reference's CalcDirectionCoeffs / ComputePanGains through the
+kernel-level taps of oracle/ref_harness.cpp: bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import mixlib, refal
+
+pytestmark = pytest.mark.ref
+
+
+def _bind():
+    prod = mixlib.product().lib
+    prod.b200mix_ambi_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    prod.b200mix_pan_gains.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_uint32]
+    _, hz = refal.libs()
+    hz.refh_calc_direction_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    hz.refh_calc_direction_coeffs.restype = None
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_dry_pan_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    hz.refh_dry_pan_gains.restype = None
+    return prod, hz
+
+
+def _dirs(rng, n):
+    v = rng.standard_normal((n, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float32)
+    return np.concatenate([axes, v.astype(np.float32)])
+
+
+def test_ambi_coeffs_bit_exact():
+    prod, hz = _bind()
+    rng = np.random.default_rng(71)
+    spreads = [0.0, 0.0, 1e-3, 0.5, 1.0, np.pi, 5.0, 2.0 * np.pi]
+    for k, d in enumerate(_dirs(rng, 1500)):
+        spread = float(spreads[k % len(spreads)] if k % 3 else rng.uniform(0.0, 2.0 * np.pi))
+        a = np.zeros(25, dtype=np.float32)
+        b = np.zeros(25, dtype=np.float32)
+        dd = np.ascontiguousarray(d)
+        hz.refh_calc_direction_coeffs(dd.ctypes.data, spread, a.ctypes.data)
+        assert prod.b200mix_ambi_coeffs(dd.ctypes.data, spread, b.ctypes.data) == 0
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (d, spread, a, b)
+
+
+@pytest.mark.parametrize("attrs", ["stereo", "hrtf", "ambi3"])
+def test_pan_gains_on_reference_devices_bit_exact(attrs):
+    prod, hz = _bind()
+    a = {"stereo": {refal.ALC_HRTF_SOFT: 0},
+         "hrtf": {refal.ALC_HRTF_SOFT: 1},
+         "ambi3": {refal.ALC_FORMAT_CHANNELS_SOFT: refal.ALC_BFORMAT3D_SOFT, refal.ALC_AMBISONIC_ORDER_SOFT: 3,
+                   refal.ALC_AMBISONIC_LAYOUT_SOFT: refal.ALC_ACN_SOFT,
+                   refal.ALC_AMBISONIC_SCALING_SOFT: refal.ALC_N3D_SOFT}}[attrs]
+    ref = refal.RefDevice(a)
+    try:
+        scale = np.zeros(32, dtype=np.float32)
+        index = np.zeros(32, dtype=np.uint32)
+        n = hz.refh_dry_ambi_map(ref.dev, scale.ctypes.data, index.ctypes.data)
+        assert n == ref.desc.dry_channels
+        rng = np.random.default_rng(72)
+        for d in _dirs(rng, 300):
+            spread = float(rng.uniform(0.0, 3.0)) if rng.random() < 0.5 else 0.0
+            gain = float(rng.uniform(0.0, 2.0))
+            co = np.zeros(25, dtype=np.float32)
+            dd = np.ascontiguousarray(d)
+            assert prod.b200mix_ambi_coeffs(dd.ctypes.data, spread, co.ctypes.data) == 0
+            g_ref = np.zeros(25, dtype=np.float32)
+            hz.refh_dry_pan_gains(ref.dev, co.ctypes.data, gain, g_ref.ctypes.data)
+            g = np.full(32, 7.0, dtype=np.float32)
+            assert prod.b200mix_pan_gains(n, scale.ctypes.data, index.ctypes.data, co.ctypes.data, gain,
+                                          g.ctypes.data, 32) == 0
+            assert np.array_equal(g[:25].view(np.uint32), g_ref.view(np.uint32)), (d, spread, gain)
+            assert not g[25:].any()
+    finally:
+        ref.close()
+
+
+def test_pan_helpers_reject_bad_arguments():
+    prod, _ = _bind()
+    co = np.zeros(25, dtype=np.float32)
+    d = np.array([0, 0, -1], dtype=np.float32)
+    assert prod.b200mix_ambi_coeffs(None, 0.0, co.ctypes.data) < 0
+    assert prod.b200mix_ambi_coeffs(d.ctypes.data, 0.0, None) < 0
+    scale = np.ones(4, dtype=np.float32)
+    bad = np.array([0, 1, 2, 25], dtype=np.uint32)
+    g = np.zeros(4, dtype=np.float32)
+    assert prod.b200mix_pan_gains(4, scale.ctypes.data, bad.ctypes.data, co.ctypes.data, 1.0, g.ctypes.data, 4) < 0
+    assert prod.b200mix_pan_gains(5, scale.ctypes.data, bad.ctypes.data, co.ctypes.data, 1.0, g.ctypes.data, 4) < 0
