@@ -176,6 +176,41 @@ typedef struct b200mix_reverb_params {
     float    splitter_coeff;      /* mAmbiSplitter[*][*].mCoeff */
 } b200mix_reverb_params;
 
+/* Host helpers, no GPU: the reverb's own parameter stage.  b200mix_efx_reverb is ReverbProps
+ * (core/effects/base.h:62-86, the AL_EAXREVERB_* properties after the AL layer's clamping).
+ * b200mix_reverb_params_from_efx restates ReverbState::deviceUpdate/allocLines
+ * (alc/effects/reverb.cpp:728-851) and ReverbState::update (:1222-1351) for one pipeline:
+ * every field of b200mix_reverb_params, and — when gains is not NULL — the 8 output gain rows
+ * [4 early, 4 late][out_channels] of update3DPanning (:1151-1220) on the target mix described by
+ * b200mix_reverb_target.  All values are bit-identical to the reference's.
+ * b200mix_reverb_full_update_needed(prev, next) is the fullUpdate test of :1243-1262 (prev NULL:
+ * the first update after deviceUpdate, always full). */
+typedef struct b200mix_efx_reverb {
+    uint32_t struct_size;
+    float density, diffusion, gain, gain_hf, gain_lf, decay_time, decay_hf_ratio, decay_lf_ratio;
+    float reflections_gain, reflections_delay, reflections_pan[3];
+    float late_reverb_gain, late_reverb_delay, late_reverb_pan[3];
+    float echo_time, echo_depth, modulation_time, modulation_depth;
+    float air_absorption_gain_hf, hf_reference, lf_reference, room_rolloff_factor;
+    uint32_t decay_hf_limit;
+} b200mix_efx_reverb;
+typedef struct b200mix_reverb_target {
+    uint32_t struct_size;
+    uint32_t sample_rate;           /* DeviceBase::mSampleRate */
+    uint32_t device_ambi_order;     /* DeviceBase::mAmbiOrder (above 1: MixOutAmbiUp) */
+    uint32_t device_2d;             /* DeviceBase::m2DMixing */
+    float    xover_freq;            /* DeviceBase::mXOverFreq (400 Hz by default, core/device.h:238) */
+    float    slot_gain;             /* EffectSlotBase::Gain */
+    float    reverb_boost;          /* ReverbBoost (alc/effects/base.h:11; 1 unless the reverb/boost option is set) */
+    uint32_t out_channels;          /* target.Main->Buffer.size(): Dry, or the target slot's Wet */
+    const float *out_scale;         /* target.Main->AmbiMap[c].Scale */
+    const uint32_t *out_index;      /* target.Main->AmbiMap[c].Index */
+} b200mix_reverb_target;
+B200MIX_API int b200mix_reverb_params_from_efx(const b200mix_efx_reverb *props,
+    const b200mix_reverb_target *target, struct b200mix_reverb_params *params, float *gains);
+B200MIX_API int b200mix_reverb_full_update_needed(const b200mix_efx_reverb *prev,
+    const b200mix_efx_reverb *next);
+
 /* ReverbState::deviceUpdate + the first (full) update: allocates and clears the delay
  * lines of both pipelines and installs the parameters.  Output mix gains (8 lines: 4 early
  * then 4 late, EarlyReflections::Gains / LateReverb::Gains) go through

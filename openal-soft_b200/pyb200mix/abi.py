@@ -56,6 +56,27 @@ class VoiceResult(C.Structure):
                 ("flags", C.c_uint32), ("buffers_done", C.c_uint32)]
 
 
+class EfxReverb(C.Structure):
+    """b200mix_efx_reverb (ReverbProps, core/effects/base.h:62-86)."""
+    _fields_ = [("struct_size", C.c_uint32),
+                ("density", C.c_float), ("diffusion", C.c_float), ("gain", C.c_float), ("gain_hf", C.c_float),
+                ("gain_lf", C.c_float), ("decay_time", C.c_float), ("decay_hf_ratio", C.c_float),
+                ("decay_lf_ratio", C.c_float), ("reflections_gain", C.c_float), ("reflections_delay", C.c_float),
+                ("reflections_pan", C.c_float * 3), ("late_reverb_gain", C.c_float),
+                ("late_reverb_delay", C.c_float), ("late_reverb_pan", C.c_float * 3), ("echo_time", C.c_float),
+                ("echo_depth", C.c_float), ("modulation_time", C.c_float), ("modulation_depth", C.c_float),
+                ("air_absorption_gain_hf", C.c_float), ("hf_reference", C.c_float), ("lf_reference", C.c_float),
+                ("room_rolloff_factor", C.c_float), ("decay_hf_limit", C.c_uint32)]
+
+
+class ReverbTarget(C.Structure):
+    """b200mix_reverb_target."""
+    _fields_ = [("struct_size", C.c_uint32), ("sample_rate", C.c_uint32), ("device_ambi_order", C.c_uint32),
+                ("device_2d", C.c_uint32), ("xover_freq", C.c_float), ("slot_gain", C.c_float),
+                ("reverb_boost", C.c_float), ("out_channels", C.c_uint32), ("out_scale", C.c_void_p),
+                ("out_index", C.c_void_p)]
+
+
 class LimiterDesc(C.Structure):
     """b200mix_limiter_desc (Compressor::Params, core/mastering.h:88-114)."""
     _fields_ = [("struct_size", C.c_uint32), ("auto_flags", C.c_uint32),

@@ -295,6 +295,13 @@ void refh_dry_pan_gains(ALCdevice *adev, const float *coeffs25, float ingain, fl
     std::copy(g.begin(), g.end(), gains);
 }
 
+/* What ReverbState::deviceUpdate reads from the device (alc/effects/reverb.cpp:834-850). */
+void refh_device_ambi(ALCdevice *adev, uint32_t *order, uint32_t *is2d, float *xover_freq)
+{
+    auto *dev = dev_of(adev);
+    *order = dev->mAmbiOrder; *is2d = dev->m2DMixing ? 1u : 0u; *xover_freq = dev->mXOverFreq;
+}
+
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
 static size_t g_snap_channel = 0;
