@@ -176,6 +176,17 @@ typedef struct b200mix_reverb_params {
     float    splitter_coeff;      /* mAmbiSplitter[*][*].mCoeff */
 } b200mix_reverb_params;
 
+/* Host helper, no GPU: the rate conversion of a convolution effect's impulse response.
+ * ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:356-361,417-431) runs an IR whose
+ * buffer rate differs from the device's through PPhaseResampler (common/polyphase_resampler.cpp,
+ * Kaiser-windowed sinc, 180 dB rejection, double precision) and stores it as float; this is that
+ * conversion for one channel, bit-identical.  out_frames is normally
+ * b200mix_resampled_ir_frames(src, dst, in_frames) = ceil(in_frames*dst/src); the result feeds
+ * b200mix_slot_convolution. */
+B200MIX_API int64_t b200mix_resampled_ir_frames(uint32_t src_rate, uint32_t dst_rate, uint32_t frames);
+B200MIX_API int b200mix_resample_ir(uint32_t src_rate, uint32_t dst_rate, const float *in,
+    uint32_t in_frames, float *out, uint32_t out_frames);
+
 /* Host helpers, no GPU: the reverb's own parameter stage.  b200mix_efx_reverb is ReverbProps
  * (core/effects/base.h:62-86, the AL_EAXREVERB_* properties after the AL layer's clamping).
  * b200mix_reverb_params_from_efx restates ReverbState::deviceUpdate/allocLines

@@ -63,6 +63,7 @@
 #include "core/mastering.h"
 #include "core/bs2b.h"
 #include "core/front_stablizer.h"
+#include "polyphase_resampler.h"
 #include <limits>
 
 #include "../include/b200mix.h"
@@ -300,6 +301,19 @@ void refh_device_ambi(ALCdevice *adev, uint32_t *order, uint32_t *is2d, float *x
 {
     auto *dev = dev_of(adev);
     *order = dev->mAmbiOrder; *is2d = dev->m2DMixing ? 1u : 0u; *xover_freq = dev->mXOverFreq;
+}
+
+/* Kernel-level tap: PPhaseResampler (common/polyphase_resampler.h) as ConvolutionState::deviceUpdate
+ * uses it — float samples widened to double, resampled, narrowed back with one rounding. */
+void refh_pphase_resample(unsigned src_rate, unsigned dst_rate, const float *in, unsigned n_in,
+    float *out, unsigned n_out)
+{
+    auto rs = PPhaseResampler{};
+    rs.init(src_rate, dst_rate);
+    auto din = std::vector<double>(in, in + n_in);
+    auto dout = std::vector<double>(n_out);
+    rs.process(din, dout);
+    std::ranges::transform(dout, out, [](double d) { return static_cast<float>(d); });
 }
 
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
