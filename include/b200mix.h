@@ -176,6 +176,74 @@ typedef struct b200mix_reverb_params {
     float    splitter_coeff;      /* mAmbiSplitter[*][*].mCoeff */
 } b200mix_reverb_params;
 
+/* Host helpers, no GPU: the source half of the parameter stage for point sources.
+ * b200mix_calc_source_params restates CalcAttnVoiceParams (alc/alu.cpp:1712-2010): listener
+ * transform, distance model, cones, gain limits, air absorption and the send decay adjustment,
+ * doppler, the resampler step and the source spread.  b200mix_listener_params is ContextParams
+ * (core/context.h:67-84; matrix row-major as al::Matrix), b200mix_source_props the VoiceProps
+ * fields that function reads (core/voice.h:101-157) with the slot values it takes from
+ * EffectSlotBase (core/effectslot.h:70-75) folded into each send.  The result feeds
+ * CalcPanningAndFilters' steps (alc/alu.cpp:1519-1656), each of which has its helper:
+ *   HRTF device: hrtf_elevation/hrtf_azimuth/distance/spread -> b200mix_hrtf_get_coeffs or
+ *     b200mix_voices_update_dirs, hrtf_gain = dry_gain;
+ *   other devices: b200mix_ambi_coeffs(pos or b200mix_pairwise_azimuth(pos), spread) ->
+ *     b200mix_pan_gains(Dry map, dry_gain);
+ *   sends: b200mix_ambi_coeffs(pos, spread) -> b200mix_pan_gains(slot Wet map, wet_gain[i]);
+ *   filters: b200mix_biquad_coeffs(HighShelf, hf_reference/rate, gain_hf, 1) and
+ *     (LowShelf, lf_reference/rate, gain_lf, 1), active iff gain_hf != 1 || gain_lf != 1.
+ * b200mix_pairwise_azimuth is ScaleAzimuthFront3_2 (alc/alu.cpp:675-708), used when the device
+ * renders stereo pair-wise (RenderMode::Pairwise).  Everything is bit-identical to the reference
+ * (the ReverseX/Y/Z, nfc-scale and half-angle-cone compatibility options at their defaults). */
+typedef struct b200mix_listener_params {
+    uint32_t struct_size;
+    float position[3];
+    float matrix[16];
+    float velocity[3];
+    float gain, meters_per_unit, air_absorption_gain_hf, doppler_factor, speed_of_sound;
+    uint32_t source_distance_model;     /* ContextParams::SourceDistanceModel */
+    uint32_t distance_model;            /* enum DistanceModel order: Disable, Inverse, InverseClamped,
+                                           Linear, LinearClamped, Exponent, ExponentClamped */
+} b200mix_listener_params;
+/* ContextProps (core/context.h:46-64) -> b200mix_calc_listener_params = CalcContextParams
+ * (alc/alu.cpp:508-555); gain_boost is ContextBase::mGainBoost (1 unless volume-adjust is set). */
+typedef struct b200mix_listener_props {
+    uint32_t struct_size;
+    float position[3], velocity[3], orient_at[3], orient_up[3];
+    float gain, gain_boost, meters_per_unit, air_absorption_gain_hf;
+    float doppler_factor, doppler_velocity, speed_of_sound;
+    uint32_t source_distance_model, distance_model;
+} b200mix_listener_props;
+typedef struct b200mix_source_send {
+    float gain, gain_hf, hf_reference, gain_lf, lf_reference;   /* VoiceProps::SendData */
+    uint32_t active;                    /* Slot != null && EffectType != None */
+    float slot_room_rolloff, slot_decay_time, slot_air_absorption_gain_hf;   /* EffectSlotBase */
+} b200mix_source_send;
+typedef struct b200mix_source_props {
+    uint32_t struct_size;
+    float pitch, gain, outer_gain, min_gain, max_gain, inner_angle, outer_angle;
+    float ref_distance, max_distance, rolloff_factor;
+    float position[3], velocity[3], direction[3];
+    uint32_t head_relative, distance_model;
+    uint32_t dry_gain_hf_auto, wet_gain_auto, wet_gain_hf_auto;
+    float outer_gain_hf, air_absorption_factor, room_rolloff_factor, doppler_factor, radius;
+    struct { float gain, gain_hf, hf_reference, gain_lf, lf_reference; } direct;
+    b200mix_source_send sends[B200MIX_MAX_SENDS];
+} b200mix_source_props;
+typedef struct b200mix_source_result {
+    uint32_t step;                      /* Voice::mStep */
+    float pos[3];                       /* unit vector to the source, listener space */
+    float distance, spread;
+    float hrtf_elevation, hrtf_azimuth; /* CalcHrtfPanning's src_ev / src_az */
+    float dry_gain, dry_gain_hf, dry_gain_lf;                   /* drygain {Base, HF, LF} */
+    float wet_gain[B200MIX_MAX_SENDS], wet_gain_hf[B200MIX_MAX_SENDS], wet_gain_lf[B200MIX_MAX_SENDS];
+} b200mix_source_result;
+B200MIX_API int b200mix_calc_source_params(const b200mix_source_props *props,
+    const b200mix_listener_params *listener, uint32_t num_sends, uint32_t buffer_rate,
+    uint32_t device_rate, b200mix_source_result *result);
+B200MIX_API int b200mix_calc_listener_params(const b200mix_listener_props *props,
+    b200mix_listener_params *listener);
+B200MIX_API int b200mix_pairwise_azimuth(const float pos[3], float out[3]);
+
 /* Host helper, no GPU: the rate conversion of a convolution effect's impulse response.
  * ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:356-361,417-431) runs an IR whose
  * buffer rate differs from the device's through PPhaseResampler (common/polyphase_resampler.cpp,

@@ -316,6 +316,78 @@ void refh_pphase_resample(unsigned src_rate, unsigned dst_rate, const float *in,
     std::ranges::transform(dout, out, [](double d) { return static_cast<float>(d); });
 }
 
+/* Taps for the source parameter helper: ContextParams (core/context.h:67-84), the VoiceProps of
+ * voice idx with the EffectSlotBase values CalcAttnVoiceParams reads through its send slots
+ * (alc/alu.cpp:1712-1742,1925-1961), the device's render mode, and an active slot's Wet.AmbiMap. */
+void refh_listener_params(ALCcontext *actx, b200mix_listener_params *out)
+{
+    auto &p = ctx_of(actx)->mParams;
+    *out = b200mix_listener_params{};
+    out->struct_size = sizeof(*out);
+    for(size_t i{0};i < 3;++i) { out->position[i] = p.Position[i]; out->velocity[i] = p.Velocity[i]; }
+    for(size_t r{0};r < 4;++r) for(size_t c{0};c < 4;++c) out->matrix[r*4 + c] = p.Matrix[r][c];
+    out->gain = p.Gain; out->meters_per_unit = p.MetersPerUnit;
+    out->air_absorption_gain_hf = p.AirAbsorptionGainHF; out->doppler_factor = p.DopplerFactor;
+    out->speed_of_sound = p.SpeedOfSound;
+    out->source_distance_model = p.SourceDistanceModel ? 1u : 0u;
+    out->distance_model = static_cast<uint32_t>(p.mDistanceModel);
+}
+
+int refh_source_props(ALCcontext *actx, int idx, b200mix_source_props *out, uint32_t *buffer_rate)
+{
+    auto voices = ctx_of(actx)->getVoicesSpan();
+    if(idx < 0 || size_t(idx) >= voices.size()) return -1;
+    auto *voice = voices[size_t(idx)];
+    auto const &P = voice->mProps;
+    *out = b200mix_source_props{};
+    out->struct_size = sizeof(*out);
+    out->pitch = P.Pitch; out->gain = P.Gain; out->outer_gain = P.OuterGain;
+    out->min_gain = P.MinGain; out->max_gain = P.MaxGain;
+    out->inner_angle = P.InnerAngle; out->outer_angle = P.OuterAngle;
+    out->ref_distance = P.RefDistance; out->max_distance = P.MaxDistance; out->rolloff_factor = P.RolloffFactor;
+    for(size_t i{0};i < 3;++i)
+    { out->position[i] = P.Position[i]; out->velocity[i] = P.Velocity[i]; out->direction[i] = P.Direction[i]; }
+    out->head_relative = P.HeadRelative ? 1u : 0u;
+    out->distance_model = static_cast<uint32_t>(P.mDistanceModel);
+    out->dry_gain_hf_auto = P.DryGainHFAuto; out->wet_gain_auto = P.WetGainAuto;
+    out->wet_gain_hf_auto = P.WetGainHFAuto; out->outer_gain_hf = P.OuterGainHF;
+    out->air_absorption_factor = P.AirAbsorptionFactor; out->room_rolloff_factor = P.RoomRolloffFactor;
+    out->doppler_factor = P.DopplerFactor; out->radius = P.Radius;
+    out->direct.gain = P.Direct.Gain; out->direct.gain_hf = P.Direct.GainHF;
+    out->direct.hf_reference = P.Direct.HFReference; out->direct.gain_lf = P.Direct.GainLF;
+    out->direct.lf_reference = P.Direct.LFReference;
+    for(size_t i{0};i < MaxSendCount;++i)
+    {
+        auto &S = out->sends[i];
+        S.gain = P.Send[i].Gain; S.gain_hf = P.Send[i].GainHF; S.hf_reference = P.Send[i].HFReference;
+        S.gain_lf = P.Send[i].GainLF; S.lf_reference = P.Send[i].LFReference;
+        auto *slot = P.Send[i].Slot;
+        S.active = (slot && slot->EffectType != EffectSlotType::None) ? 1u : 0u;
+        if(S.active)
+        {
+            S.slot_room_rolloff = slot->RoomRolloff; S.slot_decay_time = slot->DecayTime;
+            S.slot_air_absorption_gain_hf = slot->AirAbsorptionGainHF;
+        }
+    }
+    *buffer_rate = voice->mFrequency;
+    return 0;
+}
+
+int refh_device_render_mode(ALCdevice *adev) { return static_cast<int>(dev_of(adev)->mRenderMode); }
+
+int refh_slot_ambi_map(ALCcontext *actx, int idx, float *scale, uint32_t *index)
+{
+    auto *arr = ctx_of(actx)->mActiveAuxSlots.load(std::memory_order_acquire);
+    if(!arr || idx < 0 || size_t(idx) >= (arr->size()>>1)) return -1;
+    auto &wet = (*arr)[size_t(idx)]->Wet;
+    for(size_t c{0};c < wet.Buffer.size();++c)
+    {
+        scale[c] = wet.AmbiMap[c].Scale;
+        index[c] = static_cast<uint32_t>(wet.AmbiMap[c].Index);
+    }
+    return static_cast<int>(wet.Buffer.size());
+}
+
 /* Which Voice::mChans[] entry refh_snapshot_voices reads (multi-channel sources: one
  * mixing channel per buffer channel, core/voice.h:236-257).  Default 0. */
 static size_t g_snap_channel = 0;

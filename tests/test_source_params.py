@@ -1,0 +1,306 @@
+"""Host-side source parameter stage of the product (b200mix_calc_source_params and the panning /
+filter helpers it feeds; no GPU involved) against live voices of the compiled reference: random
+listeners and sources (all distance models, cones, doppler, air absorption, radius, direct and
+send filters, a reverb send with decay) are set up through the AL API, the reference's ALU computes
+its voice parameters, and the helpers must reproduce them bit for bit from the same properties:
+resampler step, HRIR coefficients / delays / gain or dry panning gains, send panning gains and the
+direct / send filter coefficient sets."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import mixlib, refal, scenes
+from pyb200mix import abi, scene
+
+pytestmark = pytest.mark.ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MHR = os.path.join(ROOT, "openal-soft_b200", "data", "Default HRTF.mhr")
+MODELS = [0, 0xD001, 0xD002, 0xD003, 0xD004, 0xD005, 0xD006]     # AL_NONE, AL_INVERSE_DISTANCE, ...
+
+
+class ListenerParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("matrix", C.c_float * 16),
+                ("velocity", C.c_float * 3), ("gain", C.c_float), ("meters_per_unit", C.c_float),
+                ("air_absorption_gain_hf", C.c_float), ("doppler_factor", C.c_float),
+                ("speed_of_sound", C.c_float), ("source_distance_model", C.c_uint32),
+                ("distance_model", C.c_uint32)]
+
+
+class SourceSend(C.Structure):
+    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
+                ("gain_lf", C.c_float), ("lf_reference", C.c_float), ("active", C.c_uint32),
+                ("slot_room_rolloff", C.c_float), ("slot_decay_time", C.c_float),
+                ("slot_air_absorption_gain_hf", C.c_float)]
+
+
+class Direct(C.Structure):
+    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
+                ("gain_lf", C.c_float), ("lf_reference", C.c_float)]
+
+
+class SourceProps(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32)] + [(n, C.c_float) for n in (
+        "pitch", "gain", "outer_gain", "min_gain", "max_gain", "inner_angle", "outer_angle", "ref_distance",
+        "max_distance", "rolloff_factor")] + [("position", C.c_float * 3), ("velocity", C.c_float * 3),
+        ("direction", C.c_float * 3), ("head_relative", C.c_uint32), ("distance_model", C.c_uint32),
+        ("dry_gain_hf_auto", C.c_uint32), ("wet_gain_auto", C.c_uint32), ("wet_gain_hf_auto", C.c_uint32),
+        ("outer_gain_hf", C.c_float), ("air_absorption_factor", C.c_float), ("room_rolloff_factor", C.c_float),
+        ("doppler_factor", C.c_float), ("radius", C.c_float), ("direct", Direct),
+        ("sends", SourceSend * abi.MAX_SENDS)]
+
+
+class SourceResult(C.Structure):
+    _fields_ = [("step", C.c_uint32), ("pos", C.c_float * 3), ("distance", C.c_float), ("spread", C.c_float),
+                ("hrtf_elevation", C.c_float), ("hrtf_azimuth", C.c_float), ("dry_gain", C.c_float),
+                ("dry_gain_hf", C.c_float), ("dry_gain_lf", C.c_float), ("wet_gain", C.c_float * abi.MAX_SENDS),
+                ("wet_gain_hf", C.c_float * abi.MAX_SENDS), ("wet_gain_lf", C.c_float * abi.MAX_SENDS)]
+
+
+class ListenerProps(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("velocity", C.c_float * 3),
+                ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3), ("gain", C.c_float),
+                ("gain_boost", C.c_float), ("meters_per_unit", C.c_float), ("air_absorption_gain_hf", C.c_float),
+                ("doppler_factor", C.c_float), ("doppler_velocity", C.c_float), ("speed_of_sound", C.c_float),
+                ("source_distance_model", C.c_uint32), ("distance_model", C.c_uint32)]
+
+
+def test_listener_params_match_calc_context_params():
+    """b200mix_calc_listener_params against the ContextParams the reference derives from the same
+    listener / context properties set through the AL API."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_listener_params.argtypes = [C.POINTER(ListenerProps), C.POINTER(ListenerParams)]
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    for seed in range(8):
+        rng = np.random.default_rng(700 + seed)
+        ref, _ = scenes.make_ref_scene(1, 0, abi.RS_LINEAR)
+        try:
+            al = ref.al
+            al.alListenerfv.argtypes = [C.c_int, C.POINTER(C.c_float)]
+            al.alListener3f.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+            al.alListenerf.argtypes = [C.c_int, C.c_float]
+            al.alDopplerFactor.argtypes = [C.c_float]
+            al.alSpeedOfSound.argtypes = [C.c_float]
+            al.alEnable.argtypes = [C.c_int]
+            lp = ListenerProps()
+            lp.struct_size = C.sizeof(lp)
+            pos, vel = _f3(rng, 3.0), _f3(rng, 8.0)
+            at = rng.standard_normal(3)
+            up = rng.standard_normal(3) if seed % 2 else np.cross(np.cross(at, rng.standard_normal(3)), at)
+            ori = [float(np.float32(x)) for x in np.concatenate([at, up])]
+            for i in range(3):
+                lp.position[i], lp.velocity[i], lp.orient_at[i], lp.orient_up[i] = pos[i], vel[i], ori[i], ori[3 + i]
+            lp.gain = float(rng.uniform(0.1, 2.0)); lp.gain_boost = 1.0
+            lp.meters_per_unit = float(rng.uniform(0.1, 4.0)); lp.air_absorption_gain_hf = 0.99426
+            lp.doppler_factor = float(rng.uniform(0.0, 3.0)); lp.doppler_velocity = 1.0
+            lp.speed_of_sound = float(rng.uniform(50.0, 900.0))
+            lp.source_distance_model = seed % 2
+            model = int(rng.integers(0, 7)); lp.distance_model = model
+            al.alListener3f(0x1004, *pos); al.alListener3f(0x1006, *vel)
+            al.alListenerfv(0x100F, (C.c_float * 6)(*ori))
+            al.alListenerf(refal.AL_GAIN, lp.gain); al.alListenerf(0x20004, lp.meters_per_unit)
+            al.alDopplerFactor(lp.doppler_factor); al.alSpeedOfSound(lp.speed_of_sound)
+            al.alDistanceModel(MODELS[model])
+            if seed % 2:
+                al.alEnable(0x200)
+            assert al.alGetError() == 0
+            ref.play_all()
+            ref.render(16)
+            want = ListenerParams()
+            hz.refh_listener_params(ref.ctx, C.byref(want))
+            got = ListenerParams()
+            assert prod.b200mix_calc_listener_params(C.byref(lp), C.byref(got)) == 0
+            assert bytes(want) == bytes(got), (seed, list(want.matrix), list(got.matrix))
+        finally:
+            ref.close()
+
+
+def _f3(rng, s):
+    return [float(np.float32(x)) for x in rng.standard_normal(3) * s]
+
+
+def _build_scene(rng, devname, V):
+    attrs = {"hrtf": {refal.ALC_HRTF_SOFT: 1}, "stereo": {refal.ALC_HRTF_SOFT: 0},
+             "ambi3": {refal.ALC_FORMAT_CHANNELS_SOFT: refal.ALC_BFORMAT3D_SOFT, refal.ALC_AMBISONIC_ORDER_SOFT: 3,
+                       refal.ALC_AMBISONIC_LAYOUT_SOFT: refal.ALC_ACN_SOFT,
+                       refal.ALC_AMBISONIC_SCALING_SOFT: refal.ALC_N3D_SOFT}}[devname]
+    ref, pcms = scenes.make_ref_scene(V, 1 if devname == "hrtf" else 0, abi.RS_LINEAR, attrs=attrs)
+    al = ref.al
+    al.alListenerfv.argtypes = [C.c_int, C.POINTER(C.c_float)]
+    al.alListener3f.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    al.alListenerf.argtypes = [C.c_int, C.c_float]
+    al.alDopplerFactor.argtypes = [C.c_float]
+    al.alSpeedOfSound.argtypes = [C.c_float]
+    al.alEnable.argtypes = [C.c_int]
+    # listener
+    al.alListener3f(0x1004, *_f3(rng, 2.0))
+    al.alListener3f(0x1006, *_f3(rng, 5.0))
+    at = rng.standard_normal(3)
+    up = np.cross(np.cross(at, rng.standard_normal(3)), at)
+    al.alListenerfv(0x100F, (C.c_float * 6)(*[float(x) for x in np.concatenate([at, up])]))
+    al.alListenerf(refal.AL_GAIN, float(rng.uniform(0.3, 1.5)))
+    al.alListenerf(0x20004, float(rng.uniform(0.2, 3.0)))              # AL_METERS_PER_UNIT
+    al.alDopplerFactor(float(rng.uniform(0.0, 2.0)))
+    al.alSpeedOfSound(float(rng.uniform(100.0, 600.0)))
+    al.alDistanceModel(int(rng.choice(MODELS)))
+    if rng.random() < 0.5:
+        al.alEnable(0x200)                                             # AL_SOURCE_DISTANCE_MODEL
+    slot = ref.add_reverb_slot(props={0x0006: float(rng.uniform(0.5, 5.0)), 0x0013: float(rng.uniform(0.9, 1.0)),
+                                      0x0016: float(rng.uniform(0.0, 2.0))})
+    for k, src in enumerate(ref.sources):
+        r = rng.uniform(0.05, 30.0)
+        d = rng.standard_normal(3)
+        d /= np.linalg.norm(d)
+        al.alSource3f(src, 0x1004, *[float(np.float32(x)) for x in d * r])
+        al.alSource3f(src, 0x1006, *_f3(rng, 20.0))
+        if k % 3:
+            al.alSource3f(src, 0x1005, *_f3(rng, 1.0))
+            inner = float(rng.uniform(0.0, 300.0))
+            al.alSourcef(src, 0x1001, inner)
+            al.alSourcef(src, 0x1002, float(rng.uniform(inner, 360.0)))
+            al.alSourcef(src, 0x1022, float(rng.uniform(0.0, 1.0)))
+            al.alSourcef(src, 0x20009, float(rng.uniform(0.0, 1.0)))
+        ref_d = float(rng.uniform(0.1, 5.0))
+        al.alSourcef(src, 0x1020, ref_d)
+        al.alSourcef(src, 0x1023, float(rng.uniform(0.05, 60.0)))
+        al.alSourcef(src, 0x1021, float(rng.uniform(0.0, 3.0)))
+        al.alSourcef(src, 0x100D, float(rng.uniform(0.0, 0.2)))
+        al.alSourcef(src, 0x100E, float(rng.uniform(0.5, 1.0)))
+        al.alSourcef(src, refal.AL_GAIN, float(rng.uniform(0.1, 2.0)))
+        al.alSourcef(src, refal.AL_PITCH, float(rng.uniform(0.3, 3.0)))
+        al.alSourcei(src, 0x202, int(k % 4 == 0))
+        al.alSourcei(src, 0xD000, int(rng.choice(MODELS)))             # AL_DISTANCE_MODEL (per source)
+        al.alSourcef(src, 0x20007, float(rng.uniform(0.0, 10.0)))
+        al.alSourcef(src, 0x20008, float(rng.uniform(0.0, 1.0)))
+        al.alSourcef(src, 0xC000, float(rng.uniform(0.0, 1.0)))        # AL_DOPPLER_FACTOR (source)
+        if k % 2:
+            al.alSourcef(src, 0x1031, float(rng.uniform(0.0, 2.0 * r)))
+        al.alSourcei(src, 0x2000A, int(rng.integers(0, 2)))
+        al.alSourcei(src, 0x2000B, int(rng.integers(0, 2)))
+        al.alSourcei(src, 0x2000C, int(rng.integers(0, 2)))
+        if k % 2 == 0:
+            ref.set_direct_filter(src, ref.make_filter(float(rng.uniform(0.2, 1.0)), float(rng.uniform(0.1, 1.0)),
+                                                      float(rng.uniform(0.1, 1.0)) if k % 4 == 0 else None))
+        sf = refal.AL_FILTER_NULL if k % 3 == 0 else ref.make_filter(float(rng.uniform(0.2, 1.0)),
+                                                                     float(rng.uniform(0.1, 1.0)))
+        if k % 5 != 4:
+            ref.connect_send(src, slot, 0, sf)
+    err = al.alGetError()
+    assert err == 0, hex(err)
+    return ref
+
+
+@pytest.mark.skipif(not os.path.exists(MHR), reason="HRTF data set not staged (run build())")
+@pytest.mark.parametrize("devname", ["hrtf", "stereo", "ambi3"])
+def test_source_params_reproduce_the_references_voices(devname):
+    prod = mixlib.product().lib
+    prod.b200mix_calc_source_params.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.c_uint32,
+                                                C.c_uint32, C.c_uint32, C.POINTER(SourceResult)]
+    prod.b200mix_pairwise_azimuth.argtypes = [C.c_void_p, C.c_void_p]
+    prod.b200mix_ambi_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    prod.b200mix_pan_gains.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_uint32]
+    prod.b200mix_biquad_coeffs.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    prod.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    prod.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                             C.POINTER(C.c_uint32)]
+    prod.b200mix_hrtf_free.argtypes = [C.c_void_p]
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    hz.refh_source_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(SourceProps), C.POINTER(C.c_uint32)]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hrtf = C.c_void_p()
+    data = open(MHR, "rb").read()
+    assert prod.b200mix_hrtf_load(data, len(data), C.byref(hrtf)) == 0
+
+    V = 24
+    checked = dict(cone=0, doppler=0, absorb=0, filt=0, sends=0)
+    for seed in range(3):
+        rng = np.random.default_rng(900 + seed)
+        ref = _build_scene(rng, devname, V)
+        try:
+            ref.play_all()
+            ref.render(64)
+            nslots, wet = ref.slot_info()
+            n, params, coeffs, dry, send, _ = ref.snapshot(wet_channels=wet[0])
+            assert n >= V
+            ents, _ = ref.voice_filters(V)
+            filt = {(v, p): (a, lp, hp) for v, p, a, lp, hp in ents}
+            lis = ListenerParams()
+            hz.refh_listener_params(ref.ctx, C.byref(lis))
+            mode = hz.refh_device_render_mode(ref.dev)          # 0 normal, 1 pairwise, 2 hrtf
+            assert (mode == 2) == (devname == "hrtf")
+            dscale = np.zeros(32, dtype=np.float32); dindex = np.zeros(32, dtype=np.uint32)
+            nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
+            wscale = np.zeros(32, dtype=np.float32); windex = np.zeros(32, dtype=np.uint32)
+            nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
+            assert nw == wet[0]
+            rate = ref.desc.sample_rate
+            ns = ref.desc.num_sends
+            for k in range(V):
+                sp = SourceProps()
+                brate = C.c_uint32(0)
+                assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
+                res = SourceResult()
+                assert prod.b200mix_calc_source_params(C.byref(sp), C.byref(lis), ns, brate.value, rate,
+                                                       C.byref(res)) == 0
+                assert res.step == params[k].step, (devname, seed, k, res.step, params[k].step)
+                assert res.distance > 1e-6
+                pos = np.array(list(res.pos), dtype=np.float32)
+                co = np.zeros(25, dtype=np.float32)
+                if mode == 2:
+                    out = np.zeros((ref.desc.ir_size, 2), dtype=np.float32)
+                    dl = (C.c_uint32 * 2)()
+                    assert prod.b200mix_hrtf_get_coeffs(hrtf, res.hrtf_elevation, res.hrtf_azimuth, res.distance,
+                                                        res.spread, out.ctypes.data, dl) == 0
+                    assert np.array_equal(out.view(np.uint32), coeffs[k].view(np.uint32)), (devname, seed, k)
+                    assert list(dl) == list(params[k].hrtf_delay)
+                    assert np.float32(res.dry_gain).view(np.uint32) == np.float32(params[k].hrtf_gain).view(np.uint32)
+                else:
+                    ppos = pos.copy()
+                    if mode == 1:
+                        assert prod.b200mix_pairwise_azimuth(pos.ctypes.data, ppos.ctypes.data) == 0
+                    assert prod.b200mix_ambi_coeffs(ppos.ctypes.data, res.spread, co.ctypes.data) == 0
+                    g = np.zeros(nd, dtype=np.float32)
+                    assert prod.b200mix_pan_gains(nd, dscale.ctypes.data, dindex.ctypes.data, co.ctypes.data,
+                                                  res.dry_gain, g.ctypes.data, nd) == 0
+                    assert np.array_equal(g.view(np.uint32), dry[k].view(np.uint32)), (devname, seed, k, g, dry[k])
+                # sends: always the unscaled direction (alc/alu.cpp:1218-1225,1356-1361 use the same coeffs as
+                # the dry path; with pairwise scaling they share the scaled position)
+                wpos = pos.copy()
+                if mode == 1:
+                    assert prod.b200mix_pairwise_azimuth(pos.ctypes.data, wpos.ctypes.data) == 0
+                assert prod.b200mix_ambi_coeffs(wpos.ctypes.data, res.spread, co.ctypes.data) == 0
+                if sp.sends[0].active:
+                    g = np.zeros(nw, dtype=np.float32)
+                    assert prod.b200mix_pan_gains(nw, wscale.ctypes.data, windex.ctypes.data, co.ctypes.data,
+                                                  res.wet_gain[0], g.ctypes.data, nw) == 0
+                    assert np.array_equal(g.view(np.uint32), send[k][0].view(np.uint32)), (devname, seed, k)
+                    checked["sends"] += 1
+                # filters (alc/alu.cpp:1619-1656)
+                for path, (ghf, glf, hfref, lfref) in enumerate(
+                        [(res.dry_gain_hf, res.dry_gain_lf, sp.direct.hf_reference, sp.direct.lf_reference)]
+                        + [(res.wet_gain_hf[s], res.wet_gain_lf[s], sp.sends[s].hf_reference, sp.sends[s].lf_reference)
+                           for s in range(ns)]):
+                    act, lp, hp = filt[(k, path)]
+                    inv = np.float32(1.0) / np.float32(rate)
+                    a = np.zeros(5, dtype=np.float32); b = np.zeros(5, dtype=np.float32)
+                    assert prod.b200mix_biquad_coeffs(0, float(np.float32(hfref) * inv), ghf, 1.0, a.ctypes.data) == 0
+                    assert prod.b200mix_biquad_coeffs(1, float(np.float32(lfref) * inv), glf, 1.0, b.ctypes.data) == 0
+                    assert bool(act) == (ghf != 1.0 or glf != 1.0), (devname, seed, k, path)
+                    assert np.array_equal(a.view(np.uint32), lp.view(np.uint32)), (devname, seed, k, path, a, lp)
+                    assert np.array_equal(b.view(np.uint32), hp.view(np.uint32)), (devname, seed, k, path)
+                    checked["filt"] += int(bool(act))
+                checked["cone"] += int(sp.inner_angle < 360.0 and any(sp.direction))
+                checked["doppler"] += int(sp.doppler_factor * lis.doppler_factor > 0)
+                checked["absorb"] += int(res.distance > sp.ref_distance)
+        finally:
+            ref.close()
+    prod.b200mix_hrtf_free(hrtf)
+    assert all(v > 5 for v in checked.values()), checked
