@@ -364,6 +364,29 @@ B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
     const b200mix_voice_params *params, const float *hrtf_coeffs, const float *dry_gains,
     const float *send_gains);
 
+/* CalcVoiceParams for a point source in one call (host, no GPU): b200mix_calc_source_params
+ * followed by CalcPanningAndFilters' steps (alc/alu.cpp:1196-1226,1318-1361,1619-1656).  Fills, for
+ * the voice that plays the source: voice->step, voice->hrtf_gain and the HRTF flag; on HRTF
+ * devices (render_mode 2) dir = {elevation, azimuth, distance, spread} for
+ * b200mix_voices_update_dirs, otherwise dry_gains[dry.channels] (render_mode 1 = pair-wise stereo);
+ * send_gains[num_sends][wet_stride]; filters[1 + num_sends] for b200mix_voices_filters.  The other
+ * fields of *voice (buffer, positions, flags, send_slot) are the caller's.  Returns
+ * B200MIX_ERR_UNSUPPORTED for a source exactly at the listener (the reference's no-distance
+ * path).  Bit-identical to the reference's voices (tests/test_source_params.py). */
+typedef struct b200mix_mix_map { uint32_t channels; const float *scale; const uint32_t *index; } b200mix_mix_map;
+typedef struct b200mix_voice_env {
+    uint32_t struct_size;
+    uint32_t device_rate, num_sends;
+    uint32_t render_mode;               /* DeviceBase::mRenderMode: 0 Normal, 1 Pairwise, 2 Hrtf */
+    uint32_t wet_stride;                /* floats per send in send_gains (>= every wet map's channels) */
+    b200mix_mix_map dry;                /* DeviceBase::Dry.AmbiMap */
+    b200mix_mix_map wet[B200MIX_MAX_SENDS];   /* the send's slot Wet.AmbiMap; channels 0 = no slot */
+} b200mix_voice_env;
+B200MIX_API int b200mix_calc_voice(const b200mix_source_props *props,
+    const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,
+    b200mix_voice_params *voice, float dir[4], float *dry_gains, float *send_gains,
+    struct b200mix_voice_filter *filters);
+
 /* Streaming sources: the VoiceBufferItem list behind alSourceQueueBuffers
  * (core/voice.h:84-99; LoadBufferQueue core/voice.cpp:546-595; queue advance :1183-1196).
  * A voice updated WITHOUT B200MIX_VF_STATIC plays this list instead of `buffer`:

@@ -292,4 +292,69 @@ int b200mix_calc_source_params(const b200mix_source_props *props, const b200mix_
     return B200MIX_OK;
 }
 
+int b200mix_calc_voice(const b200mix_source_props *props, const b200mix_listener_params *listener,
+    const b200mix_voice_env *env, uint32_t buffer_rate, b200mix_voice_params *voice, float dir[4],
+    float *dry_gains, float *send_gains, b200mix_voice_filter *filters)
+{
+    if(!props || !listener || !env || !voice || !filters || env->struct_size != sizeof(*env)
+        || env->num_sends > B200MIX_MAX_SENDS || env->render_mode > 2u)
+        return B200MIX_ERR_INVALID;
+    b200mix_source_result r{};
+    if(int rc = b200mix_calc_source_params(props, listener, env->num_sends, buffer_rate, env->device_rate, &r))
+        return rc;
+    // CalcPanningAndFilters for a point source at a distance (alc/alu.cpp:1196-1226,1318-1361);
+    // a source sitting on the listener takes the reference's separate no-distance path
+    if(!(r.distance > kEps)) return B200MIX_ERR_UNSUPPORTED;
+    voice->step = r.step;
+    float coeffs[B200MIX_MAX_AMBI_CHANNELS];
+    float pos[3] = {r.pos[0], r.pos[1], r.pos[2]};
+    if(env->render_mode == 2u)
+    {
+        // CalcHrtfPanning: the HRIR pair comes from the direction (b200mix_voices_update_dirs or
+        // b200mix_hrtf_get_coeffs), the voice carries the gain
+        if(!dir) return B200MIX_ERR_INVALID;
+        dir[0] = r.hrtf_elevation; dir[1] = r.hrtf_azimuth; dir[2] = r.distance; dir[3] = r.spread;
+        voice->hrtf_gain = r.dry_gain;
+        voice->flags |= B200MIX_VF_HRTF;
+    }
+    else
+    {
+        if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
+        if(env->render_mode == 1u) b200mix_pairwise_azimuth(r.pos, pos);
+        b200mix_ambi_coeffs(pos, r.spread, coeffs);
+        if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
+            dry_gains, env->dry.channels)) return rc;
+        voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
+        if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
+    }
+    // sends share the dry path's encoder coefficients (HRTF devices: the unscaled direction)
+    if(env->render_mode == 2u) b200mix_ambi_coeffs(r.pos, r.spread, coeffs);
+    for(uint32_t s = 0;s < env->num_sends;++s)
+    {
+        const b200mix_mix_map &w = env->wet[s];
+        if(!send_gains || !env->wet_stride) break;
+        float *g = send_gains + size_t(s)*env->wet_stride;
+        for(uint32_t c = 0;c < env->wet_stride;++c) g[c] = 0.0f;
+        if(!props->sends[s].active || !w.channels) continue;
+        if(w.channels > env->wet_stride || !w.scale || !w.index) return B200MIX_ERR_INVALID;
+        if(int rc = b200mix_pan_gains(w.channels, w.scale, w.index, coeffs, r.wet_gain[s], g, w.channels)) return rc;
+    }
+    // filters (alc/alu.cpp:1619-1656)
+    const float inv_samplerate = 1.0f / float(env->device_rate);
+    for(uint32_t path = 0;path <= env->num_sends;++path)
+    {
+        b200mix_voice_filter &f = filters[path];
+        const float ghf = path ? r.wet_gain_hf[path-1] : r.dry_gain_hf;
+        const float glf = path ? r.wet_gain_lf[path-1] : r.dry_gain_lf;
+        const float hfref = path ? props->sends[path-1].hf_reference : props->direct.hf_reference;
+        const float lfref = path ? props->sends[path-1].lf_reference : props->direct.lf_reference;
+        f.voice = voice->voice; f.path = path;
+        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
+        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
+            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
+            return B200MIX_ERR_INVALID;
+    }
+    return B200MIX_OK;
+}
+
 } // extern "C"

@@ -304,3 +304,98 @@ def test_source_params_reproduce_the_references_voices(devname):
             ref.close()
     prod.b200mix_hrtf_free(hrtf)
     assert all(v > 5 for v in checked.values()), checked
+
+
+class MixMap(C.Structure):
+    _fields_ = [("channels", C.c_uint32), ("scale", C.c_void_p), ("index", C.c_void_p)]
+
+
+class VoiceEnv(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device_rate", C.c_uint32), ("num_sends", C.c_uint32),
+                ("render_mode", C.c_uint32), ("wet_stride", C.c_uint32), ("dry", MixMap),
+                ("wet", MixMap * abi.MAX_SENDS)]
+
+
+@pytest.mark.skipif(not os.path.exists(MHR), reason="HRTF data set not staged (run build())")
+@pytest.mark.parametrize("devname", ["hrtf", "stereo", "ambi3"])
+def test_calc_voice_single_call(devname):
+    """b200mix_calc_voice (the whole CalcVoiceParams of a point source in one call) against the same
+    live voices: the structs it fills are what b200mix_voices_update(_dirs) / _filters take."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_voice.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                        C.c_uint32, C.POINTER(abi.VoiceParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+    prod.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    prod.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                             C.POINTER(C.c_uint32)]
+    prod.b200mix_hrtf_free.argtypes = [C.c_void_p]
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    hz.refh_source_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(SourceProps), C.POINTER(C.c_uint32)]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hrtf = C.c_void_p()
+    data = open(MHR, "rb").read()
+    assert prod.b200mix_hrtf_load(data, len(data), C.byref(hrtf)) == 0
+    V = 16
+    rng = np.random.default_rng(950)
+    ref = _build_scene(rng, devname, V)
+    try:
+        ref.play_all()
+        ref.render(64)
+        nslots, wet = ref.slot_info()
+        n, params, coeffs, dry, send, _ = ref.snapshot(wet_channels=wet[0])
+        ents, _ = ref.voice_filters(V)
+        filt = {(v, p): (a, lp, hp) for v, p, a, lp, hp in ents}
+        lis = ListenerParams()
+        hz.refh_listener_params(ref.ctx, C.byref(lis))
+        dscale = np.zeros(32, dtype=np.float32); dindex = np.zeros(32, dtype=np.uint32)
+        nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
+        wscale = np.zeros(32, dtype=np.float32); windex = np.zeros(32, dtype=np.uint32)
+        nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
+        ns = ref.desc.num_sends
+        env = VoiceEnv()
+        env.struct_size = C.sizeof(env)
+        env.device_rate, env.num_sends = ref.desc.sample_rate, ns
+        env.render_mode = hz.refh_device_render_mode(ref.dev)
+        env.wet_stride = nw
+        env.dry = MixMap(nd, dscale.ctypes.data, dindex.ctypes.data)
+        env.wet[0] = MixMap(nw, wscale.ctypes.data, windex.ctypes.data)
+        for k in range(V):
+            sp = SourceProps()
+            brate = C.c_uint32(0)
+            assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
+            vp = abi.VoiceParams()
+            vp.voice = k
+            d4 = np.zeros(4, dtype=np.float32)
+            dg = np.full(nd, 9.0, dtype=np.float32)
+            sg = np.full((ns, nw), 9.0, dtype=np.float32)
+            fl = (abi.VoiceFilter * (1 + abi.MAX_SENDS))()
+            rc = prod.b200mix_calc_voice(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(vp),
+                                         d4.ctypes.data, dg.ctypes.data, sg.ctypes.data, fl)
+            assert rc == 0, rc
+            assert vp.step == params[k].step
+            if env.render_mode == 2:
+                assert vp.flags & abi.VF_HRTF
+                out = np.zeros((ref.desc.ir_size, 2), dtype=np.float32)
+                dl = (C.c_uint32 * 2)()
+                assert prod.b200mix_hrtf_get_coeffs(hrtf, d4[0], d4[1], d4[2], d4[3], out.ctypes.data, dl) == 0
+                assert np.array_equal(out.view(np.uint32), coeffs[k].view(np.uint32))
+                assert list(dl) == list(params[k].hrtf_delay)
+                assert np.float32(vp.hrtf_gain).view(np.uint32) == np.float32(params[k].hrtf_gain).view(np.uint32)
+            else:
+                assert not (vp.flags & abi.VF_HRTF)
+                assert np.array_equal(dg.view(np.uint32), dry[k].view(np.uint32)), (k, dg, dry[k])
+            want_send = send[k][0] if sp.sends[0].active else np.zeros(nw, dtype=np.float32)
+            assert np.array_equal(sg[0].view(np.uint32), want_send.view(np.uint32)), (k, sg[0], want_send)
+            for path in range(1 + ns):
+                act, lp, hp = filt[(k, path)]
+                f = fl[path]
+                assert (f.voice, f.path, bool(f.active)) == (k, path, bool(act))
+                assert np.array_equal(np.array(list(f.lowpass), dtype=np.float32).view(np.uint32), lp.view(np.uint32))
+                assert np.array_equal(np.array(list(f.highpass), dtype=np.float32).view(np.uint32), hp.view(np.uint32))
+    finally:
+        ref.close()
+        prod.b200mix_hrtf_free(hrtf)
