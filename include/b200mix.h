@@ -370,9 +370,9 @@ B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
  * devices (render_mode 2) dir = {elevation, azimuth, distance, spread} for
  * b200mix_voices_update_dirs, otherwise dry_gains[dry.channels] (render_mode 1 = pair-wise stereo);
  * send_gains[num_sends][wet_stride]; filters[1 + num_sends] for b200mix_voices_filters.  The other
- * fields of *voice (buffer, positions, flags, send_slot) are the caller's.  Returns
- * B200MIX_ERR_UNSUPPORTED for a source exactly at the listener (the reference's no-distance
- * path).  Bit-identical to the reference's voices (tests/test_source_params.py). */
+ * fields of *voice (buffer, positions, flags, send_slot) are the caller's.  A source exactly at
+ * the listener takes the reference's no-distance path (front-centre position, distance = inf for
+ * the HRIR lookup, :1268-1310,1420-1466).  Bit-identical to the reference's voices (tests/test_source_params.py). */
 typedef struct b200mix_mix_map { uint32_t channels; const float *scale; const uint32_t *index; } b200mix_mix_map;
 typedef struct b200mix_voice_env {
     uint32_t struct_size;

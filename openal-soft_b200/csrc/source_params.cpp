@@ -302,33 +302,59 @@ int b200mix_calc_voice(const b200mix_source_props *props, const b200mix_listener
     b200mix_source_result r{};
     if(int rc = b200mix_calc_source_params(props, listener, env->num_sends, buffer_rate, env->device_rate, &r))
         return rc;
-    // CalcPanningAndFilters for a point source at a distance (alc/alu.cpp:1196-1226,1318-1361);
-    // a source sitting on the listener takes the reference's separate no-distance path
-    if(!(r.distance > kEps)) return B200MIX_ERR_UNSUPPORTED;
     voice->step = r.step;
     float coeffs[B200MIX_MAX_AMBI_CHANNELS];
-    float pos[3] = {r.pos[0], r.pos[1], r.pos[2]};
-    if(env->render_mode == 2u)
+    if(r.distance > kEps)
     {
-        // CalcHrtfPanning: the HRIR pair comes from the direction (b200mix_voices_update_dirs or
-        // b200mix_hrtf_get_coeffs), the voice carries the gain
-        if(!dir) return B200MIX_ERR_INVALID;
-        dir[0] = r.hrtf_elevation; dir[1] = r.hrtf_azimuth; dir[2] = r.distance; dir[3] = r.spread;
-        voice->hrtf_gain = r.dry_gain;
-        voice->flags |= B200MIX_VF_HRTF;
+        // CalcPanningAndFilters for a point source at a distance (alc/alu.cpp:1196-1226,1318-1361)
+        float pos[3] = {r.pos[0], r.pos[1], r.pos[2]};
+        if(env->render_mode == 2u)
+        {
+            // CalcHrtfPanning: the HRIR pair comes from the direction (b200mix_voices_update_dirs or
+            // b200mix_hrtf_get_coeffs), the voice carries the gain
+            if(!dir) return B200MIX_ERR_INVALID;
+            dir[0] = r.hrtf_elevation; dir[1] = r.hrtf_azimuth; dir[2] = r.distance; dir[3] = r.spread;
+            voice->hrtf_gain = r.dry_gain;
+            voice->flags |= B200MIX_VF_HRTF;
+            b200mix_ambi_coeffs(r.pos, r.spread, coeffs);      // the sends' encoder coefficients
+        }
+        else
+        {
+            if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
+            if(env->render_mode == 1u) b200mix_pairwise_azimuth(r.pos, pos);
+            b200mix_ambi_coeffs(pos, r.spread, coeffs);        // shared by the dry mix and the sends
+            if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
+                dry_gains, env->dry.channels)) return rc;
+            voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
+            if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
+        }
     }
     else
     {
-        if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
-        if(env->render_mode == 1u) b200mix_pairwise_azimuth(r.pos, pos);
-        b200mix_ambi_coeffs(pos, r.spread, coeffs);
-        if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
-            dry_gains, env->dry.channels)) return rc;
-        voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
-        if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
+        // A source on the listener (alc/alu.cpp:1268-1310,1420-1466): the mono channel sits at the
+        // front-centre position of MonoMap (:1471-1473, pan gain 1 with VoiceProps::Panning at its
+        // default 0), spread is all or nothing
+        const float front[3] = {0.0f, 0.0f, -1.0f};
+        if(env->render_mode == 2u)
+        {
+            if(!dir) return B200MIX_ERR_INVALID;
+            dir[0] = std::asin(front[1]); dir[1] = std::atan2(front[0], -front[2]);
+            dir[2] = std::numeric_limits<float>::infinity(); dir[3] = r.spread;
+            voice->hrtf_gain = r.dry_gain;
+            voice->flags |= B200MIX_VF_HRTF;
+        }
+        else
+        {
+            if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
+            // ScaleAzimuthFront3 leaves the front-centre direction where it is
+            b200mix_ambi_coeffs(front, r.spread, coeffs);
+            if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
+                dry_gains, env->dry.channels)) return rc;
+            voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
+            if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
+        }
+        b200mix_ambi_coeffs(front, r.spread, coeffs);
     }
-    // sends share the dry path's encoder coefficients (HRTF devices: the unscaled direction)
-    if(env->render_mode == 2u) b200mix_ambi_coeffs(r.pos, r.spread, coeffs);
     for(uint32_t s = 0;s < env->num_sends;++s)
     {
         const b200mix_mix_map &w = env->wet[s];

@@ -137,7 +137,8 @@ def _build_scene(rng, devname, V):
     al.alSpeedOfSound.argtypes = [C.c_float]
     al.alEnable.argtypes = [C.c_int]
     # listener
-    al.alListener3f(0x1004, *_f3(rng, 2.0))
+    lpos = _f3(rng, 2.0)
+    al.alListener3f(0x1004, *lpos)
     al.alListener3f(0x1006, *_f3(rng, 5.0))
     at = rng.standard_normal(3)
     up = np.cross(np.cross(at, rng.standard_normal(3)), at)
@@ -173,6 +174,9 @@ def _build_scene(rng, devname, V):
         al.alSourcef(src, refal.AL_GAIN, float(rng.uniform(0.1, 2.0)))
         al.alSourcef(src, refal.AL_PITCH, float(rng.uniform(0.3, 3.0)))
         al.alSourcei(src, 0x202, int(k % 4 == 0))
+        if k % 7 == 3:
+            # a source sitting exactly on the listener: the reference's no-distance panning path
+            al.alSource3f(src, 0x1004, *([0.0, 0.0, 0.0] if k % 4 == 0 else lpos))
         al.alSourcei(src, 0xD000, int(rng.choice(MODELS)))             # AL_DISTANCE_MODEL (per source)
         al.alSourcef(src, 0x20007, float(rng.uniform(0.0, 10.0)))
         al.alSourcef(src, 0x20008, float(rng.uniform(0.0, 1.0)))
@@ -251,7 +255,8 @@ def test_source_params_reproduce_the_references_voices(devname):
                 assert prod.b200mix_calc_source_params(C.byref(sp), C.byref(lis), ns, brate.value, rate,
                                                        C.byref(res)) == 0
                 assert res.step == params[k].step, (devname, seed, k, res.step, params[k].step)
-                assert res.distance > 1e-6
+                if not res.distance > 1e-6:
+                    continue            # the no-distance path is covered by test_calc_voice_single_call
                 pos = np.array(list(res.pos), dtype=np.float32)
                 co = np.zeros(25, dtype=np.float32)
                 if mode == 2:
@@ -363,6 +368,7 @@ def test_calc_voice_single_call(devname):
         env.wet_stride = nw
         env.dry = MixMap(nd, dscale.ctypes.data, dindex.ctypes.data)
         env.wet[0] = MixMap(nw, wscale.ctypes.data, windex.ctypes.data)
+        zero_dist = 0
         for k in range(V):
             sp = SourceProps()
             brate = C.c_uint32(0)
@@ -377,6 +383,7 @@ def test_calc_voice_single_call(devname):
                                          d4.ctypes.data, dg.ctypes.data, sg.ctypes.data, fl)
             assert rc == 0, rc
             assert vp.step == params[k].step
+            zero_dist += int(np.isinf(d4[2]) or (env.render_mode != 2 and k % 7 == 3))
             if env.render_mode == 2:
                 assert vp.flags & abi.VF_HRTF
                 out = np.zeros((ref.desc.ir_size, 2), dtype=np.float32)
@@ -396,6 +403,7 @@ def test_calc_voice_single_call(devname):
                 assert (f.voice, f.path, bool(f.active)) == (k, path, bool(act))
                 assert np.array_equal(np.array(list(f.lowpass), dtype=np.float32).view(np.uint32), lp.view(np.uint32))
                 assert np.array_equal(np.array(list(f.highpass), dtype=np.float32).view(np.uint32), hp.view(np.uint32))
+        assert zero_dist >= 2, zero_dist
     finally:
         ref.close()
         prod.b200mix_hrtf_free(hrtf)
