@@ -387,6 +387,29 @@ B200MIX_API int b200mix_calc_voice(const b200mix_source_props *props,
     b200mix_voice_params *voice, float dir[4], float *dry_gains, float *send_gains,
     struct b200mix_voice_filter *filters);
 
+/* The same for a multi-channel source that is not spatialized (stereo music and the like:
+ * CalcNonAttnVoiceParams, alc/alu.cpp:1658-1710, then the no-distance branches of
+ * CalcHrtfPanning / CalcNormalPanning, :1268-1310,1420-1466): one mixing channel per buffer
+ * channel (one ABI voice each, B200MIX_VF_CHANNEL(c)) at the layout's speaker position.  Returns
+ * the channel count (or < 0); per channel c: hrtf_gains[c] and dirs[c][4] on HRTF devices,
+ * dry_gains[c][dry.channels] otherwise, send_gains[c][num_sends][wet_stride]; *step and
+ * filters[1 + num_sends] are shared by all channels.  setup: the buffer's channel layout,
+ * VoiceProps::StereoPan (radians, {pi/6, -pi/6} by default) and ::Panning, and the index of the
+ * LFE channel in the Dry mix when the Dry mix is the output mix itself (else B200MIX_NO_SLOT). */
+enum b200mix_channel_layout { B200MIX_LAYOUT_STEREO = 2, B200MIX_LAYOUT_REAR, B200MIX_LAYOUT_QUAD,
+    B200MIX_LAYOUT_X51, B200MIX_LAYOUT_X61, B200MIX_LAYOUT_X71 };
+typedef struct b200mix_channel_setup {
+    uint32_t struct_size;
+    uint32_t layout;                    /* enum b200mix_channel_layout */
+    float stereo_pan[2];
+    float panning;
+    uint32_t lfe_dry_index;
+} b200mix_channel_setup;
+B200MIX_API int b200mix_calc_voice_channels(const b200mix_source_props *props,
+    const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,
+    const b200mix_channel_setup *setup, uint32_t *step, float *hrtf_gains, float *dirs,
+    float *dry_gains, float *send_gains, struct b200mix_voice_filter *filters);
+
 /* Streaming sources: the VoiceBufferItem list behind alSourceQueueBuffers
  * (core/voice.h:84-99; LoadBufferQueue core/voice.cpp:546-595; queue advance :1183-1196).
  * A voice updated WITHOUT B200MIX_VF_STATIC plays this list instead of `buffer`:

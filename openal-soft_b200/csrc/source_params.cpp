@@ -383,4 +383,148 @@ int b200mix_calc_voice(const b200mix_source_props *props, const b200mix_listener
     return B200MIX_OK;
 }
 
+int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix_listener_params *listener,
+    const b200mix_voice_env *env, uint32_t buffer_rate, const b200mix_channel_setup *setup,
+    uint32_t *step, float *hrtf_gains, float *dirs, float *dry_gains, float *send_gains,
+    b200mix_voice_filter *filters)
+{
+    if(!props || !listener || !env || !setup || !step || !filters || env->struct_size != sizeof(*env)
+        || props->struct_size != sizeof(*props) || listener->struct_size != sizeof(*listener)
+        || setup->struct_size != sizeof(*setup) || env->num_sends > B200MIX_MAX_SENDS || env->render_mode > 2u
+        || !env->device_rate)
+        return B200MIX_ERR_INVALID;
+    const b200mix_source_props &P = *props;
+
+    // channel positions (alc/alu.cpp:892-897,1471-1517; StereoMap :1525-1528 with StereoPan :1553-1562)
+    enum Kind { L, R, C, Lfe };
+    struct Chan { Kind kind; float pos[3]; };
+    constexpr float sin30 = 0.5f, cos30 = 0.866025403785f;
+    constexpr float sin45 = 1.41421356237309504880f*0.5f, cos45 = 1.41421356237309504880f*0.5f;
+    constexpr float sin110 = 0.939692620786f, cos110 = -0.342020143326f;
+    Chan chans[8];
+    uint32_t nch = 0;
+    auto add = [&](Kind k, float x, float y, float z) { chans[nch++] = Chan{k, {x, y, z}}; };
+    switch(setup->layout)
+    {
+    case B200MIX_LAYOUT_STEREO:
+        add(L, -std::sin(setup->stereo_pan[0]), 0.0f, -std::cos(setup->stereo_pan[0]));
+        add(R, -std::sin(setup->stereo_pan[1]), 0.0f, -std::cos(setup->stereo_pan[1]));
+        break;
+    case B200MIX_LAYOUT_REAR: add(L, -sin30, 0.0f, cos30); add(R, sin30, 0.0f, cos30); break;
+    case B200MIX_LAYOUT_QUAD:
+        add(L, -sin45, 0.0f, -cos45); add(R, sin45, 0.0f, -cos45); add(L, -sin45, 0.0f, cos45); add(R, sin45, 0.0f, cos45);
+        break;
+    case B200MIX_LAYOUT_X51:
+        add(L, -sin30, 0.0f, -cos30); add(R, sin30, 0.0f, -cos30); add(C, 0.0f, 0.0f, -1.0f); add(Lfe, 0.0f, 0.0f, 0.0f);
+        add(L, -sin110, 0.0f, -cos110); add(R, sin110, 0.0f, -cos110);
+        break;
+    case B200MIX_LAYOUT_X61:
+        add(L, -sin30, 0.0f, -cos30); add(R, sin30, 0.0f, -cos30); add(C, 0.0f, 0.0f, -1.0f); add(Lfe, 0.0f, 0.0f, 0.0f);
+        add(C, 0.0f, 0.0f, 1.0f); add(L, -1.0f, 0.0f, 0.0f); add(R, 1.0f, 0.0f, 0.0f);
+        break;
+    case B200MIX_LAYOUT_X71:
+        add(L, -sin30, 0.0f, -cos30); add(R, sin30, 0.0f, -cos30); add(C, 0.0f, 0.0f, -1.0f); add(Lfe, 0.0f, 0.0f, 0.0f);
+        add(L, -sin30, 0.0f, cos30); add(R, sin30, 0.0f, cos30); add(L, -1.0f, 0.0f, 0.0f); add(R, 1.0f, 0.0f, 0.0f);
+        break;
+    default: return B200MIX_ERR_INVALID;
+    }
+
+    // CalcNonAttnVoiceParams (alc/alu.cpp:1658-1710)
+    const float pitch = float(buffer_rate) / float(env->device_rate) * P.pitch;
+    if(pitch > float(kMaxPitch)) *step = kMaxPitch << kFracBits;
+    else *step = std::max(uint32_t(std::lrintf(pitch * kFracOne)), 1u);
+    const float mingain = std::min(P.min_gain, P.max_gain);
+    const float srcgain = std::clamp(P.gain, mingain, P.max_gain);
+    const float dryBase = std::min(kGainMixMax, srcgain * P.direct.gain * listener->gain);
+    float wetBase[B200MIX_MAX_SENDS];
+    for(uint32_t i = 0;i < env->num_sends;++i)
+        wetBase[i] = std::min(kGainMixMax, srcgain * P.sends[i].gain * listener->gain);
+
+    // GetPanGainSelector (:1078-1116)
+    const float lgain = std::min(1.0f - setup->panning, 1.0f), rgain = std::min(1.0f + setup->panning, 1.0f);
+    const float cgain = std::min(lgain, rgain);
+
+    // the no-distance paths of CalcHrtfPanning (:1268-1310) and CalcNormalPanning (:1420-1466); a
+    // multi-channel source has no spread of its own here (spreadmult = 0)
+    const uint32_t nd = env->dry.channels;
+    for(uint32_t c = 0;c < nch;++c)
+    {
+        const Chan &ch = chans[c];
+        const float pangain = ch.kind == L ? lgain : ch.kind == R ? rgain : cgain;
+        float *dg = dry_gains ? dry_gains + size_t(c)*nd : nullptr;
+        float *sg = (send_gains && env->wet_stride) ? send_gains + size_t(c)*env->num_sends*env->wet_stride : nullptr;
+        if(dg) for(uint32_t k = 0;k < nd;++k) dg[k] = 0.0f;
+        if(sg) for(uint32_t k = 0;k < env->num_sends*env->wet_stride;++k) sg[k] = 0.0f;
+        if(hrtf_gains) hrtf_gains[c] = 0.0f;
+        if(dirs) { dirs[c*4+0] = 0.0f; dirs[c*4+1] = 0.0f; dirs[c*4+2] = std::numeric_limits<float>::infinity(); dirs[c*4+3] = 0.0f; }
+        float coeffs[B200MIX_MAX_AMBI_CHANNELS];
+        if(ch.kind == Lfe)
+        {
+            // LFE plays only where the Dry mix IS the output mix and has an LFE channel (:1441-1450)
+            if(env->render_mode != 2u && dg && setup->lfe_dry_index < nd) dg[setup->lfe_dry_index] = dryBase*pangain;
+            continue;
+        }
+        if(env->render_mode == 2u)
+        {
+            if(!hrtf_gains || !dirs) return B200MIX_ERR_INVALID;
+            dirs[c*4+0] = std::asin(ch.pos[1]);
+            dirs[c*4+1] = std::atan2(ch.pos[0], -ch.pos[2]);
+            hrtf_gains[c] = dryBase * pangain;
+            b200mix_ambi_coeffs(ch.pos, 0.0f, coeffs);
+        }
+        else
+        {
+            if(!dg || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
+            float pos[3] = {ch.pos[0], ch.pos[1], ch.pos[2]};
+            if(env->render_mode == 1u && pos[2] < 0.0f)
+            {
+                // ScaleAzimuthFront3 (:642-673)
+                const float len2d = std::sqrt(pos[0]*pos[0] + pos[2]*pos[2]);
+                float z = -pos[2] / len2d;
+                if(z > 0.866025403785f)
+                {
+                    float x = pos[0] / len2d;
+                    x = x*3.0f - x*x*x*4.0f;
+                    z = z*z*z*4.0f - z*3.0f;
+                    pos[0] = x * len2d;
+                    pos[2] = -z * len2d;
+                }
+                else
+                {
+                    pos[0] = std::copysign(len2d, pos[0]);
+                    pos[2] = 0.0f;
+                }
+            }
+            b200mix_ambi_coeffs(pos, 0.0f, coeffs);
+            if(int rc = b200mix_pan_gains(nd, env->dry.scale, env->dry.index, coeffs, dryBase * pangain, dg, nd))
+                return rc;
+        }
+        for(uint32_t i = 0;i < env->num_sends && sg;++i)
+        {
+            const b200mix_mix_map &w = env->wet[i];
+            if(!P.sends[i].active || !w.channels) continue;
+            if(w.channels > env->wet_stride || !w.scale || !w.index) return B200MIX_ERR_INVALID;
+            if(int rc = b200mix_pan_gains(w.channels, w.scale, w.index, coeffs, wetBase[i] * pangain,
+                sg + size_t(i)*env->wet_stride, w.channels)) return rc;
+        }
+    }
+
+    // filters (:1619-1656): every channel shares channel 0's
+    const float inv_samplerate = 1.0f / float(env->device_rate);
+    for(uint32_t path = 0;path <= env->num_sends;++path)
+    {
+        b200mix_voice_filter &f = filters[path];
+        const float ghf = path ? P.sends[path-1].gain_hf : P.direct.gain_hf;
+        const float glf = path ? P.sends[path-1].gain_lf : P.direct.gain_lf;
+        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
+        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
+        f.path = path;
+        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
+        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
+            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
+            return B200MIX_ERR_INVALID;
+    }
+    return int(nch);
+}
+
 } // extern "C"

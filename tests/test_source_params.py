@@ -407,3 +407,131 @@ def test_calc_voice_single_call(devname):
     finally:
         ref.close()
         prod.b200mix_hrtf_free(hrtf)
+
+
+class ChannelSetup(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
+                ("panning", C.c_float), ("lfe_dry_index", C.c_uint32)]
+
+
+LAYOUTS = {  # name: (AL format, channels, b200mix_channel_layout)
+    "stereo": (0x1103, 2, 2), "rear": (0x1208, 2, 3), "quad": (0x1205, 4, 4),
+    "x51": (0x120B, 6, 5), "x61": (0x120E, 7, 6), "x71": (0x1211, 8, 7)}
+
+
+@pytest.mark.skipif(not os.path.exists(MHR), reason="HRTF data set not staged (run build())")
+@pytest.mark.parametrize("devname", ["hrtf", "stereo", "ambi3"])
+def test_calc_voice_channels_for_unspatialized_multichannel_sources(devname):
+    """b200mix_calc_voice_channels against live stereo / rear / quad / 5.1 / 6.1 / 7.1 sources of the
+    reference (CalcNonAttnVoiceParams + the no-distance panning): every mixing channel's HRIR pair
+    and gain or dry panning gains, send gains, the shared step and filters, bit for bit."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_voice_channels.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                                 C.c_uint32, C.POINTER(ChannelSetup), C.POINTER(C.c_uint32)] + [C.c_void_p] * 5
+    prod.b200mix_hrtf_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    prod.b200mix_hrtf_get_coeffs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                             C.POINTER(C.c_uint32)]
+    prod.b200mix_hrtf_free.argtypes = [C.c_void_p]
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    hz.refh_source_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(SourceProps), C.POINTER(C.c_uint32)]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hrtf = C.c_void_p()
+    data = open(MHR, "rb").read()
+    assert prod.b200mix_hrtf_load(data, len(data), C.byref(hrtf)) == 0
+    attrs = {"hrtf": {refal.ALC_HRTF_SOFT: 1}, "stereo": {refal.ALC_HRTF_SOFT: 0},
+             "ambi3": {refal.ALC_FORMAT_CHANNELS_SOFT: refal.ALC_BFORMAT3D_SOFT, refal.ALC_AMBISONIC_ORDER_SOFT: 3,
+                       refal.ALC_AMBISONIC_LAYOUT_SOFT: refal.ALC_ACN_SOFT,
+                       refal.ALC_AMBISONIC_SCALING_SOFT: refal.ALC_N3D_SOFT}}[devname]
+    a2 = dict(attrs)
+    a2[refal.ALC_STEREO_SOURCES] = 16
+    rng = np.random.default_rng(990)
+    ref, _ = scenes.make_ref_scene(0, 1 if devname == "hrtf" else 0, abi.RS_LINEAR, attrs=a2, max_sources=1)
+    try:
+        al = ref.al
+        al.alListenerf.argtypes = [C.c_int, C.c_float]
+        al.alSourcefv.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_float)]
+        al.alListenerf(refal.AL_GAIN, 0.8)
+        slot = ref.add_reverb_slot()
+        names = list(LAYOUTS) + ["stereo"]
+        angles = {}
+        for k, name in enumerate(names):
+            fmt, nch, _ = LAYOUTS[name]
+            pcm = (rng.standard_normal((2000, nch)) * 3000).astype(np.int16)
+            ref.add_voice(np.ascontiguousarray(pcm), 44100, float(rng.uniform(0.5, 2.0)), (1.0, 2.0, 3.0),
+                          float(rng.uniform(0.2, 1.5)), abi.RS_LINEAR, looping=True, fmt=fmt)
+            src = ref.sources[-1]
+            if k == len(names) - 1:
+                ang = [float(np.float32(rng.uniform(0.1, 1.5))), float(np.float32(-rng.uniform(0.1, 1.5)))]
+                al.alSourcefv(src, 0x1030, (C.c_float * 2)(*ang))       # AL_STEREO_ANGLES
+                angles[k] = ang
+            if k % 2 == 0:
+                ref.set_direct_filter(src, ref.make_filter(float(rng.uniform(0.3, 1.0)), float(rng.uniform(0.1, 1.0))))
+            ref.connect_send(src, slot, 0, refal.AL_FILTER_NULL if k % 3 else
+                             ref.make_filter(float(rng.uniform(0.3, 1.0)), float(rng.uniform(0.1, 1.0))))
+        assert al.alGetError() == 0
+        ref.play_all()
+        ref.render(64)
+        nslots, wet = ref.slot_info()
+        lis = ListenerParams()
+        hz.refh_listener_params(ref.ctx, C.byref(lis))
+        dscale = np.zeros(32, dtype=np.float32); dindex = np.zeros(32, dtype=np.uint32)
+        nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
+        wscale = np.zeros(32, dtype=np.float32); windex = np.zeros(32, dtype=np.uint32)
+        nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
+        ns = ref.desc.num_sends
+        env = VoiceEnv()
+        env.struct_size = C.sizeof(env)
+        env.device_rate, env.num_sends = ref.desc.sample_rate, ns
+        env.render_mode = hz.refh_device_render_mode(ref.dev)
+        env.wet_stride = nw
+        env.dry = MixMap(nd, dscale.ctypes.data, dindex.ctypes.data)
+        env.wet[0] = MixMap(nw, wscale.ctypes.data, windex.ctypes.data)
+        V = len(names)
+        snaps = [ref.snapshot(wet_channels=wet[0], channel=c) for c in range(8)]
+        ents, _ = ref.voice_filters(V)
+        filt = {(v, p): (a, lp, hp) for v, p, a, lp, hp in ents}
+        for k, name in enumerate(names):
+            _, nch, layout = LAYOUTS[name]
+            sp = SourceProps()
+            brate = C.c_uint32(0)
+            assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
+            ang = angles.get(k, [float(np.float32(np.pi / 6)), float(np.float32(-np.pi / 6))])
+            setup = ChannelSetup(C.sizeof(ChannelSetup), layout, (C.c_float * 2)(*ang), 0.0, abi.NO_SLOT)
+            step = C.c_uint32(0)
+            hg = np.zeros(8, dtype=np.float32)
+            dirs = np.zeros((8, 4), dtype=np.float32)
+            dg = np.full((8, nd), 9.0, dtype=np.float32)
+            sg = np.full((8, ns, nw), 9.0, dtype=np.float32)
+            fl = (abi.VoiceFilter * (1 + abi.MAX_SENDS))()
+            rc = prod.b200mix_calc_voice_channels(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                                  C.byref(step), hg.ctypes.data, dirs.ctypes.data, dg.ctypes.data,
+                                                  sg.ctypes.data, fl)
+            assert rc == nch, (name, rc)
+            for c in range(nch):
+                n, params, coeffs, dry, send, _ = snaps[c]
+                assert step.value == params[k].step, (name, step.value, params[k].step)
+                if env.render_mode == 2:
+                    out = np.zeros((ref.desc.ir_size, 2), dtype=np.float32)
+                    dl = (C.c_uint32 * 2)()
+                    if hg[c] != 0.0 or np.abs(coeffs[k]).max() > 0:
+                        assert prod.b200mix_hrtf_get_coeffs(hrtf, dirs[c][0], dirs[c][1], dirs[c][2], dirs[c][3],
+                                                            out.ctypes.data, dl) == 0
+                        assert np.array_equal(out.view(np.uint32), coeffs[k].view(np.uint32)), (name, c)
+                        assert list(dl) == list(params[k].hrtf_delay), (name, c)
+                    assert np.float32(hg[c]).view(np.uint32) == np.float32(params[k].hrtf_gain).view(np.uint32), (name, c)
+                else:
+                    assert np.array_equal(dg[c].view(np.uint32), dry[k].view(np.uint32)), (name, c, dg[c], dry[k])
+                assert np.array_equal(sg[c][0].view(np.uint32), send[k][0].view(np.uint32)), (name, c, sg[c][0], send[k][0])
+            for path in range(1 + ns):
+                act, lp, hp = filt[(k, path)]
+                f = fl[path]
+                assert bool(f.active) == bool(act), (name, path)
+                assert np.array_equal(np.array(list(f.lowpass), dtype=np.float32).view(np.uint32), lp.view(np.uint32))
+                assert np.array_equal(np.array(list(f.highpass), dtype=np.float32).view(np.uint32), hp.view(np.uint32))
+    finally:
+        ref.close()
+        prod.b200mix_hrtf_free(hrtf)
