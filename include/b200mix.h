@@ -228,6 +228,7 @@ typedef struct b200mix_source_props {
     float outer_gain_hf, air_absorption_factor, room_rolloff_factor, doppler_factor, radius;
     struct { float gain, gain_hf, hf_reference, gain_lf, lf_reference; } direct;
     b200mix_source_send sends[B200MIX_MAX_SENDS];
+    float orient_at[3], orient_up[3];   /* VoiceProps::OrientAt/OrientUp (B-Format sources) */
 } b200mix_source_props;
 typedef struct b200mix_source_result {
     uint32_t step;                      /* Voice::mStep */
@@ -409,6 +410,26 @@ B200MIX_API int b200mix_calc_voice_channels(const b200mix_source_props *props,
     const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,
     const b200mix_channel_setup *setup, uint32_t *step, float *hrtf_gains, float *dirs,
     float *dry_gains, float *send_gains, struct b200mix_voice_filter *filters);
+
+/* And for a first-order B-Format source (ambient beds: AL_FORMAT_BFORMAT2D/3D_*) that is not
+ * spatialized, on a device that mixes first order: CalcNonAttnVoiceParams, then
+ * CalcAmbisonicPanning at no distance (alc/alu.cpp:911-1077 with coverage 1): the source's
+ * orientation (and the listener's, unless head-relative) rotates the X/Y/Z channels, the buffer's
+ * channel order and normalisation are folded in, and each buffer channel becomes one non-HRTF
+ * voice whose dry/send gains are a row of that matrix.  Returns the channel count (3 for 2D, 4 for
+ * 3D) or < 0; B200MIX_ERR_UNSUPPORTED when the device mixes above first order (the reference then
+ * up-samples and band-splits the source, core/voice.cpp:1082-1089). */
+typedef struct b200mix_bformat_setup {
+    uint32_t struct_size;
+    uint32_t is_2d;                     /* FmtBFormat2D (W, X, Y) instead of FmtBFormat3D */
+    uint32_t layout;                    /* AmbiLayout: 0 FuMa, 1 ACN */
+    uint32_t scaling;                   /* AmbiScaling: 0 FuMa, 1 SN3D, 2 N3D */
+    uint32_t device_ambi_order;         /* DeviceBase::mAmbiOrder */
+} b200mix_bformat_setup;
+B200MIX_API int b200mix_calc_voice_bformat(const b200mix_source_props *props,
+    const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,
+    const b200mix_bformat_setup *setup, uint32_t *step, float *dry_gains, float *send_gains,
+    struct b200mix_voice_filter *filters);
 
 /* Streaming sources: the VoiceBufferItem list behind alSourceQueueBuffers
  * (core/voice.h:84-99; LoadBufferQueue core/voice.cpp:546-595; queue advance :1183-1196).

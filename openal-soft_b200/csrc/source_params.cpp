@@ -527,4 +527,111 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
     return int(nch);
 }
 
+int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_listener_params *listener,
+    const b200mix_voice_env *env, uint32_t buffer_rate, const b200mix_bformat_setup *setup, uint32_t *step,
+    float *dry_gains, float *send_gains, b200mix_voice_filter *filters)
+{
+    if(!props || !listener || !env || !setup || !step || !filters || !dry_gains
+        || env->struct_size != sizeof(*env) || props->struct_size != sizeof(*props)
+        || listener->struct_size != sizeof(*listener) || setup->struct_size != sizeof(*setup)
+        || env->num_sends > B200MIX_MAX_SENDS || env->render_mode > 2u || !env->device_rate
+        || setup->layout > 1u || setup->scaling > 2u || !env->dry.scale || !env->dry.index)
+        return B200MIX_ERR_INVALID;
+    if(setup->device_ambi_order != 1u) return B200MIX_ERR_UNSUPPORTED;
+    const b200mix_source_props &P = *props;
+
+    // CalcNonAttnVoiceParams (alc/alu.cpp:1658-1710)
+    const float pitch = float(buffer_rate) / float(env->device_rate) * P.pitch;
+    if(pitch > float(kMaxPitch)) *step = kMaxPitch << kFracBits;
+    else *step = std::max(uint32_t(std::lrintf(pitch * kFracOne)), 1u);
+    const float mingain = std::min(P.min_gain, P.max_gain);
+    const float srcgain = std::clamp(P.gain, mingain, P.max_gain);
+    const float dryBase = std::min(kGainMixMax, srcgain * P.direct.gain * listener->gain);
+    float wetBase[B200MIX_MAX_SENDS];
+    for(uint32_t i = 0;i < env->num_sends;++i)
+        wetBase[i] = std::min(kGainMixMax, srcgain * P.sends[i].gain * listener->gain);
+
+    // CalcAmbisonicPanning with no distance: coverage 1 (:946-949)
+    const float coverage = 1.0f;
+    // AmbiScale::FromFuMa / FromSN3D / FromN3D, first order (core/ambidefs.h:33-92)
+    static const float scaleTab[3][4] = {
+        {1.414213562f, 1.732050808f, 1.732050808f, 1.732050808f},
+        {1.0f, 1.732050808f, 1.732050808f, 1.732050808f},
+        {1.0f, 1.0f, 1.0f, 1.0f}};
+    const float *scales = scaleTab[setup->scaling];
+    // AmbiIndex::FromFuMa / FromACN / FromFuMa2D / FromACN2D, first order
+    static const unsigned idx3d[2][4] = {{0, 3, 1, 2}, {0, 1, 2, 3}};
+    static const unsigned idx2d[2][3] = {{0, 3, 1}, {0, 1, 3}};
+    const unsigned nch = setup->is_2d ? 3u : 4u;
+    const unsigned *index_map = setup->is_2d ? idx2d[setup->layout] : idx3d[setup->layout];
+
+    // the panned W term (:951-957), then scaled by (1 - coverage) (:1049-1050)
+    float pan[B200MIX_MAX_AMBI_CHANNELS];
+    {
+        const float front[3] = {0.0f, 0.0f, -1.0f};
+        float pos[3] = {front[0], front[1], front[2]};
+        if(env->render_mode == 1u) b200mix_pairwise_azimuth(front, pos);
+        b200mix_ambi_coeffs(pos, 0.0f, pan);
+        const float scale = (1.0f-coverage)*scales[0];
+        for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k) pan[k] = pan[k] * scale;
+    }
+
+    // orientation -> first-order rotation (:976-999)
+    Vec N{{P.orient_at[0], P.orient_at[1], P.orient_at[2], 0.0f}};
+    normalize(N);
+    Vec V{{P.orient_up[0], P.orient_up[1], P.orient_up[2], 0.0f}};
+    normalize(V);
+    if(!P.head_relative) { N = mul(listener->matrix, N); V = mul(listener->matrix, V); }
+    Vec U{{N.v[1]*V.v[2] - N.v[2]*V.v[1], N.v[2]*V.v[0] - N.v[0]*V.v[2], N.v[0]*V.v[1] - N.v[1]*V.v[0], 0.0f}};
+    normalize(U);
+    float shrot[4][4] = {};
+    shrot[0][0] = 1.0f;
+    shrot[1][1] =  U.v[0]; shrot[1][2] = -U.v[1]; shrot[1][3] =  U.v[2];
+    shrot[2][1] = -V.v[0]; shrot[2][2] =  V.v[1]; shrot[2][3] = -V.v[2];
+    shrot[3][1] = -N.v[0]; shrot[3][2] =  N.v[1]; shrot[3][3] = -N.v[2];
+
+    const uint32_t nd = env->dry.channels;
+    float coeffs[B200MIX_MAX_AMBI_CHANNELS];
+    for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k) coeffs[k] = pan[k];
+    for(unsigned c = 0;c < nch;++c)
+    {
+        const unsigned acn = index_map[c];
+        const float scale = scales[acn] * coverage;
+        for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k)
+            coeffs[k] = (k < 4u ? shrot[acn][k] : 0.0f)*scale + coeffs[k];
+        if(int rc = b200mix_pan_gains(nd, env->dry.scale, env->dry.index, coeffs, dryBase,
+            dry_gains + size_t(c)*nd, nd)) return rc;
+        if(send_gains && env->wet_stride)
+        {
+            float *sg = send_gains + size_t(c)*env->num_sends*env->wet_stride;
+            for(uint32_t k = 0;k < env->num_sends*env->wet_stride;++k) sg[k] = 0.0f;
+            for(uint32_t i = 0;i < env->num_sends;++i)
+            {
+                const b200mix_mix_map &w = env->wet[i];
+                if(!P.sends[i].active || !w.channels) continue;
+                if(w.channels > env->wet_stride || !w.scale || !w.index) return B200MIX_ERR_INVALID;
+                if(int rc = b200mix_pan_gains(w.channels, w.scale, w.index, coeffs, wetBase[i],
+                    sg + size_t(i)*env->wet_stride, w.channels)) return rc;
+            }
+        }
+        for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k) coeffs[k] = 0.0f;      // :1074
+    }
+
+    const float inv_samplerate = 1.0f / float(env->device_rate);
+    for(uint32_t path = 0;path <= env->num_sends;++path)
+    {
+        b200mix_voice_filter &f = filters[path];
+        const float ghf = path ? P.sends[path-1].gain_hf : P.direct.gain_hf;
+        const float glf = path ? P.sends[path-1].gain_lf : P.direct.gain_lf;
+        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
+        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
+        f.path = path;
+        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
+        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
+            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
+            return B200MIX_ERR_INVALID;
+    }
+    return int(nch);
+}
+
 } // extern "C"

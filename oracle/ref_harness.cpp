@@ -346,7 +346,10 @@ int refh_source_props(ALCcontext *actx, int idx, b200mix_source_props *out, uint
     out->inner_angle = P.InnerAngle; out->outer_angle = P.OuterAngle;
     out->ref_distance = P.RefDistance; out->max_distance = P.MaxDistance; out->rolloff_factor = P.RolloffFactor;
     for(size_t i{0};i < 3;++i)
-    { out->position[i] = P.Position[i]; out->velocity[i] = P.Velocity[i]; out->direction[i] = P.Direction[i]; }
+    {
+        out->position[i] = P.Position[i]; out->velocity[i] = P.Velocity[i]; out->direction[i] = P.Direction[i];
+        out->orient_at[i] = P.OrientAt[i]; out->orient_up[i] = P.OrientUp[i];
+    }
     out->head_relative = P.HeadRelative ? 1u : 0u;
     out->distance_model = static_cast<uint32_t>(P.mDistanceModel);
     out->dry_gain_hf_auto = P.DryGainHFAuto; out->wet_gain_auto = P.WetGainAuto;

@@ -49,7 +49,7 @@ class SourceProps(C.Structure):
         ("dry_gain_hf_auto", C.c_uint32), ("wet_gain_auto", C.c_uint32), ("wet_gain_hf_auto", C.c_uint32),
         ("outer_gain_hf", C.c_float), ("air_absorption_factor", C.c_float), ("room_rolloff_factor", C.c_float),
         ("doppler_factor", C.c_float), ("radius", C.c_float), ("direct", Direct),
-        ("sends", SourceSend * abi.MAX_SENDS)]
+        ("sends", SourceSend * abi.MAX_SENDS), ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3)]
 
 
 class SourceResult(C.Structure):
@@ -535,3 +535,118 @@ def test_calc_voice_channels_for_unspatialized_multichannel_sources(devname):
     finally:
         ref.close()
         prod.b200mix_hrtf_free(hrtf)
+
+
+class BFormatSetup(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("is_2d", C.c_uint32), ("layout", C.c_uint32),
+                ("scaling", C.c_uint32), ("device_ambi_order", C.c_uint32)]
+
+
+@pytest.mark.parametrize("devname", ["hrtf", "stereo"])
+def test_calc_voice_bformat_first_order(devname):
+    """b200mix_calc_voice_bformat against live first-order B-Format sources of the reference (2D and
+    3D buffers, FuMa / ACN channel order, FuMa / SN3D / N3D normalisation, arbitrary source
+    orientation, head-relative or not, rotated listener): every channel's dry and send gain rows,
+    step and filters, bit for bit."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_voice_bformat.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                                C.c_uint32, C.POINTER(BFormatSetup), C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    hz.refh_source_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(SourceProps), C.POINTER(C.c_uint32)]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    hz.refh_device_ambi.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    hz.refh_device_ambi.restype = None
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1200)
+    attrs = {"hrtf": {refal.ALC_HRTF_SOFT: 1}, "stereo": {refal.ALC_HRTF_SOFT: 0}}[devname]
+    a2 = dict(attrs)
+    a2[refal.ALC_STEREO_SOURCES] = 16
+    ref, _ = scenes.make_ref_scene(0, 1 if devname == "hrtf" else 0, abi.RS_LINEAR, attrs=a2, max_sources=1)
+    try:
+        al = ref.al
+        al.alListenerfv.argtypes = [C.c_int, C.POINTER(C.c_float)]
+        al.alListenerf.argtypes = [C.c_int, C.c_float]
+        al.alSourcefv.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_float)]
+        al.alBufferi.argtypes = [C.c_uint, C.c_int, C.c_int]
+        at = rng.standard_normal(3)
+        up = np.cross(np.cross(at, rng.standard_normal(3)), at)
+        al.alListenerfv(0x100F, (C.c_float * 6)(*[float(x) for x in np.concatenate([at, up])]))
+        al.alListenerf(refal.AL_GAIN, 0.9)
+        slot = ref.add_reverb_slot()
+        combos = [(is2d, layout, scaling) for is2d in (0, 1) for layout in (0, 1) for scaling in (0, 1, 2)]
+        for k, (is2d, layout, scaling) in enumerate(combos):
+            nch = 3 if is2d else 4
+            pcm = np.ascontiguousarray((rng.standard_normal((1500, nch)) * 3000).astype(np.int16))
+            b = C.c_uint(0); s = C.c_uint(0)
+            al.alGenBuffers(1, C.byref(b))
+            al.alBufferi(b, 0x1997, layout)           # AL_AMBISONIC_LAYOUT_SOFT: AL_FUMA_SOFT / AL_ACN_SOFT
+            al.alBufferi(b, 0x1998, scaling)          # AL_AMBISONIC_SCALING_SOFT: FuMa / SN3D / N3D
+            al.alBufferData(b, 0x20022 if is2d else 0x20032, pcm.ctypes.data, pcm.nbytes, 32000)
+            al.alGenSources(1, C.byref(s))
+            al.alSourcei(s, refal.AL_BUFFER, b.value)
+            al.alSourcei(s, refal.AL_LOOPING, 1)
+            al.alSourcef(s, refal.AL_GAIN, float(rng.uniform(0.2, 1.2)))
+            al.alSourcef(s, refal.AL_PITCH, float(rng.uniform(0.5, 1.5)))
+            sat = rng.standard_normal(3)
+            sup = np.cross(np.cross(sat, rng.standard_normal(3)), sat)
+            al.alSourcefv(s, 0x100F, (C.c_float * 6)(*[float(x) for x in np.concatenate([sat, sup])]))
+            al.alSourcei(s, 0x202, k % 2)             # AL_SOURCE_RELATIVE
+            ref.buffers.append(b.value); ref.sources.append(s.value); ref._keep.append(pcm)
+            if k % 3 == 0:
+                ref.set_direct_filter(s.value, ref.make_filter(0.8, float(rng.uniform(0.1, 1.0))))
+            ref.connect_send(s.value, slot)
+        assert al.alGetError() == 0
+        ref.play_all()
+        ref.render(64)
+        nslots, wet = ref.slot_info()
+        lis = ListenerParams()
+        hz.refh_listener_params(ref.ctx, C.byref(lis))
+        order, is2d_dev, xover = C.c_uint32(0), C.c_uint32(0), C.c_float(0.0)
+        hz.refh_device_ambi(ref.dev, C.byref(order), C.byref(is2d_dev), C.byref(xover))
+        assert order.value == 1
+        dscale = np.zeros(32, dtype=np.float32); dindex = np.zeros(32, dtype=np.uint32)
+        nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
+        wscale = np.zeros(32, dtype=np.float32); windex = np.zeros(32, dtype=np.uint32)
+        nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
+        ns = ref.desc.num_sends
+        env = VoiceEnv()
+        env.struct_size = C.sizeof(env)
+        env.device_rate, env.num_sends = ref.desc.sample_rate, ns
+        env.render_mode = hz.refh_device_render_mode(ref.dev)
+        env.wet_stride = nw
+        env.dry = MixMap(nd, dscale.ctypes.data, dindex.ctypes.data)
+        env.wet[0] = MixMap(nw, wscale.ctypes.data, windex.ctypes.data)
+        snaps = [ref.snapshot(wet_channels=wet[0], channel=c) for c in range(4)]
+        ents, _ = ref.voice_filters(len(combos))
+        filt = {(v, p): (a, lp, hp) for v, p, a, lp, hp in ents}
+        for k, (is2d, layout, scaling) in enumerate(combos):
+            sp = SourceProps()
+            brate = C.c_uint32(0)
+            assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
+            setup = BFormatSetup(C.sizeof(BFormatSetup), is2d, layout, scaling, order.value)
+            step = C.c_uint32(0)
+            dg = np.full((4, nd), 9.0, dtype=np.float32)
+            sg = np.full((4, ns, nw), 9.0, dtype=np.float32)
+            fl = (abi.VoiceFilter * (1 + abi.MAX_SENDS))()
+            rc = prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                                 C.byref(step), dg.ctypes.data, sg.ctypes.data, fl)
+            assert rc == (3 if is2d else 4), rc
+            for c in range(rc):
+                n, params, coeffs, dry, send, _ = snaps[c]
+                assert step.value == params[k].step
+                assert np.array_equal(dg[c].view(np.uint32), dry[k].view(np.uint32)), ((is2d, layout, scaling), c, dg[c], dry[k])
+                assert np.array_equal(sg[c][0].view(np.uint32), send[k][0].view(np.uint32)), ((is2d, layout, scaling), c)
+            assert np.abs(dg[:rc]).max() > 0
+            for path in range(1 + ns):
+                act, lp, hp = filt[(k, path)]
+                f = fl[path]
+                assert bool(f.active) == bool(act)
+                assert np.array_equal(np.array(list(f.lowpass), dtype=np.float32).view(np.uint32), lp.view(np.uint32))
+        setup = BFormatSetup(C.sizeof(BFormatSetup), 0, 1, 2, 3)
+        assert prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                               C.byref(step), dg.ctypes.data, sg.ctypes.data, fl) < 0
+    finally:
+        ref.close()
