@@ -405,6 +405,8 @@ typedef struct b200mix_channel_setup {
     float stereo_pan[2];
     float panning;
     uint32_t lfe_dry_index;
+    uint32_t spatialized;               /* AL_SOURCE_SPATIALIZE_SOFT forced on: CalcAttnVoiceParams, the
+                                           channels drawn toward the source (alc/alu.cpp:1228-1266,1363-1418) */
 } b200mix_channel_setup;
 B200MIX_API int b200mix_calc_voice_channels(const b200mix_source_props *props,
     const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,

@@ -429,16 +429,38 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
     default: return B200MIX_ERR_INVALID;
     }
 
-    // CalcNonAttnVoiceParams (alc/alu.cpp:1658-1710)
-    const float pitch = float(buffer_rate) / float(env->device_rate) * P.pitch;
-    if(pitch > float(kMaxPitch)) *step = kMaxPitch << kFracBits;
-    else *step = std::max(uint32_t(std::lrintf(pitch * kFracOne)), 1u);
-    const float mingain = std::min(P.min_gain, P.max_gain);
-    const float srcgain = std::clamp(P.gain, mingain, P.max_gain);
-    const float dryBase = std::min(kGainMixMax, srcgain * P.direct.gain * listener->gain);
-    float wetBase[B200MIX_MAX_SENDS];
-    for(uint32_t i = 0;i < env->num_sends;++i)
-        wetBase[i] = std::min(kGainMixMax, srcgain * P.sends[i].gain * listener->gain);
+    float dryBase, wetBase[B200MIX_MAX_SENDS] = {};
+    float gainHF[1 + B200MIX_MAX_SENDS], gainLF[1 + B200MIX_MAX_SENDS];
+    b200mix_source_result attn{};
+    bool warp = false;
+    if(setup->spatialized)
+    {
+        // AL_SOURCE_SPATIALIZE_SOFT on a multi-channel source: CalcAttnVoiceParams (:1712-2010)
+        if(int rc = b200mix_calc_source_params(props, listener, env->num_sends, buffer_rate, env->device_rate, &attn))
+            return rc;
+        *step = attn.step;
+        dryBase = attn.dry_gain;
+        gainHF[0] = attn.dry_gain_hf; gainLF[0] = attn.dry_gain_lf;
+        for(uint32_t i = 0;i < env->num_sends;++i)
+        { wetBase[i] = attn.wet_gain[i]; gainHF[1+i] = attn.wet_gain_hf[i]; gainLF[1+i] = attn.wet_gain_lf[i]; }
+        warp = attn.distance > kEps;
+    }
+    else
+    {
+        // CalcNonAttnVoiceParams (alc/alu.cpp:1658-1710)
+        const float pitch = float(buffer_rate) / float(env->device_rate) * P.pitch;
+        if(pitch > float(kMaxPitch)) *step = kMaxPitch << kFracBits;
+        else *step = std::max(uint32_t(std::lrintf(pitch * kFracOne)), 1u);
+        const float mingain = std::min(P.min_gain, P.max_gain);
+        const float srcgain = std::clamp(P.gain, mingain, P.max_gain);
+        dryBase = std::min(kGainMixMax, srcgain * P.direct.gain * listener->gain);
+        gainHF[0] = P.direct.gain_hf; gainLF[0] = P.direct.gain_lf;
+        for(uint32_t i = 0;i < env->num_sends;++i)
+        {
+            wetBase[i] = std::min(kGainMixMax, srcgain * P.sends[i].gain * listener->gain);
+            gainHF[1+i] = P.sends[i].gain_hf; gainLF[1+i] = P.sends[i].gain_lf;
+        }
+    }
 
     // GetPanGainSelector (:1078-1116)
     const float lgain = std::min(1.0f - setup->panning, 1.0f), rgain = std::min(1.0f + setup->panning, 1.0f);
@@ -464,18 +486,29 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
             if(env->render_mode != 2u && dg && setup->lfe_dry_index < nd) dg[setup->lfe_dry_index] = dryBase*pangain;
             continue;
         }
+        float cpos[3] = {ch.pos[0], ch.pos[1], ch.pos[2]};
+        if(warp)
+        {
+            // a spatialized source pulls its channels toward its direction as the spread shrinks
+            // (:1234-1250,1380-1396)
+            const float a = 1.0f - (0.318309886183790671538f*0.5f)*attn.spread;
+            for(int k = 0;k < 3;++k) cpos[k] = lerpf(ch.pos[k], attn.pos[k], a);
+            if(const float len = std::sqrt(cpos[0]*cpos[0] + cpos[1]*cpos[1] + cpos[2]*cpos[2]); len < 1.0f)
+            { cpos[0] /= len; cpos[1] /= len; cpos[2] /= len; }
+        }
         if(env->render_mode == 2u)
         {
             if(!hrtf_gains || !dirs) return B200MIX_ERR_INVALID;
-            dirs[c*4+0] = std::asin(ch.pos[1]);
-            dirs[c*4+1] = std::atan2(ch.pos[0], -ch.pos[2]);
+            dirs[c*4+0] = warp ? std::asin(std::clamp(cpos[1], -1.0f, 1.0f)) : std::asin(cpos[1]);
+            dirs[c*4+1] = std::atan2(cpos[0], -cpos[2]);
+            if(warp) dirs[c*4+2] = attn.distance;
             hrtf_gains[c] = dryBase * pangain;
-            b200mix_ambi_coeffs(ch.pos, 0.0f, coeffs);
+            b200mix_ambi_coeffs(cpos, 0.0f, coeffs);
         }
         else
         {
             if(!dg || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
-            float pos[3] = {ch.pos[0], ch.pos[1], ch.pos[2]};
+            float pos[3] = {cpos[0], cpos[1], cpos[2]};
             if(env->render_mode == 1u && pos[2] < 0.0f)
             {
                 // ScaleAzimuthFront3 (:642-673)
@@ -514,8 +547,7 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
     for(uint32_t path = 0;path <= env->num_sends;++path)
     {
         b200mix_voice_filter &f = filters[path];
-        const float ghf = path ? P.sends[path-1].gain_hf : P.direct.gain_hf;
-        const float glf = path ? P.sends[path-1].gain_lf : P.direct.gain_lf;
+        const float ghf = gainHF[path], glf = gainLF[path];
         const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
         const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
         f.path = path;

@@ -411,7 +411,7 @@ def test_calc_voice_single_call(devname):
 
 class ChannelSetup(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
-                ("panning", C.c_float), ("lfe_dry_index", C.c_uint32)]
+                ("panning", C.c_float), ("lfe_dry_index", C.c_uint32), ("spatialized", C.c_uint32)]
 
 
 LAYOUTS = {  # name: (AL format, channels, b200mix_channel_layout)
@@ -472,6 +472,12 @@ def test_calc_voice_channels_for_unspatialized_multichannel_sources(devname):
                 ref.set_direct_filter(src, ref.make_filter(float(rng.uniform(0.3, 1.0)), float(rng.uniform(0.1, 1.0))))
             ref.connect_send(src, slot, 0, refal.AL_FILTER_NULL if k % 3 else
                              ref.make_filter(float(rng.uniform(0.3, 1.0)), float(rng.uniform(0.1, 1.0))))
+            if k % 2:
+                # spatialized multi-channel source (AL_SOURCE_SPATIALIZE_SOFT): attenuated, its channels
+                # drawn toward the source direction according to the radius
+                al.alSourcei(src, 0x1214, 1)
+                al.alSource3f(src, 0x1004, *_f3(rng, 4.0))
+                al.alSourcef(src, 0x1031, float(rng.uniform(0.0, 3.0)))
         assert al.alGetError() == 0
         ref.play_all()
         ref.render(64)
@@ -500,7 +506,7 @@ def test_calc_voice_channels_for_unspatialized_multichannel_sources(devname):
             brate = C.c_uint32(0)
             assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
             ang = angles.get(k, [float(np.float32(np.pi / 6)), float(np.float32(-np.pi / 6))])
-            setup = ChannelSetup(C.sizeof(ChannelSetup), layout, (C.c_float * 2)(*ang), 0.0, abi.NO_SLOT)
+            setup = ChannelSetup(C.sizeof(ChannelSetup), layout, (C.c_float * 2)(*ang), 0.0, abi.NO_SLOT, k % 2)
             step = C.c_uint32(0)
             hg = np.zeros(8, dtype=np.float32)
             dirs = np.zeros((8, 4), dtype=np.float32)
