@@ -365,6 +365,7 @@ B200MIX_API int b200mix_voices_update(b200mix_device *dev, uint32_t n,
     const b200mix_voice_params *params, const float *hrtf_coeffs, const float *dry_gains,
     const float *send_gains);
 
+struct b200mix_voice_filter;     /* defined with b200mix_voices_filters below */
 /* CalcVoiceParams for a point source in one call (host, no GPU): b200mix_calc_source_params
  * followed by CalcPanningAndFilters' steps (alc/alu.cpp:1196-1226,1318-1361,1619-1656).  Fills, for
  * the voice that plays the source: voice->step, voice->hrtf_gain and the HRTF flag; on HRTF

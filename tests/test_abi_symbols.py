@@ -55,3 +55,37 @@ def test_create_fails_loudly_without_a_gpu():
     rc = lib.b200mix_create(C.byref(d), C.byref(h))
     assert rc == -2 and not h.value          # B200MIX_ERR_CUDA: there is no CPU fallback
     assert b"CUDA" in lib.b200mix_last_error(None)
+
+
+def test_header_is_plain_c_and_cpp():
+    """include/b200mix.h must compile on its own as C99 and as C++ without warnings (it is the
+    interface a C host or a cgo/JNI/ctypes binding reads)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "b200mix.h")
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+
+
+def test_c_host_can_call_the_parameter_stage():
+    """A plain C program (tools/bench_param_stage.c) builds against the header and the library and
+    runs the host parameter stage."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no host compiler")
+    libdir = os.path.dirname(mixlib.PRODUCT_SO)
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "bps")
+        subprocess.check_call([gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tools", "bench_param_stage.c"), "-L", libdir, "-lb200mix", "-lm",
+                               "-o", exe])
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = libdir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+        out = subprocess.check_output([exe], env=env, text=True)
+        assert "sources/s" in out
