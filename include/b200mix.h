@@ -389,6 +389,16 @@ B200MIX_API int b200mix_calc_voice(const b200mix_source_props *props,
     b200mix_voice_params *voice, float dir[4], float *dry_gains, float *send_gains,
     struct b200mix_voice_filter *filters);
 
+/* b200mix_calc_voice over n independent sources, split over `threads` host threads (the caller's
+ * included; 0 or 1 = in the calling thread).  Arrays are indexed like props[]: voices[n],
+ * buffer_rates[n], dirs[n][4], dry_gains[n][dry.channels], send_gains[n][num_sends][wet_stride],
+ * filters[n][1 + num_sends] — the layout b200mix_voices_update(_dirs) and b200mix_voices_filters
+ * take.  Returns the first error any source produced. */
+B200MIX_API int b200mix_calc_voices(uint32_t n, const b200mix_source_props *props,
+    const b200mix_listener_params *listener, const b200mix_voice_env *env, const uint32_t *buffer_rates,
+    b200mix_voice_params *voices, float *dirs, float *dry_gains, float *send_gains,
+    struct b200mix_voice_filter *filters, uint32_t threads);
+
 /* The same for a multi-channel source that is not spatialized (stereo music and the like:
  * CalcNonAttnVoiceParams, alc/alu.cpp:1658-1710, then the no-distance branches of
  * CalcHrtfPanning / CalcNormalPanning, :1268-1310,1420-1466): one mixing channel per buffer

@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -664,6 +666,38 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
             return B200MIX_ERR_INVALID;
     }
     return int(nch);
+}
+
+int b200mix_calc_voices(uint32_t n, const b200mix_source_props *props, const b200mix_listener_params *listener,
+    const b200mix_voice_env *env, const uint32_t *buffer_rates, b200mix_voice_params *voices, float *dirs,
+    float *dry_gains, float *send_gains, b200mix_voice_filter *filters, uint32_t threads)
+{
+    if(!n) return B200MIX_OK;
+    if(!props || !listener || !env || !buffer_rates || !voices || !filters || env->struct_size != sizeof(*env))
+        return B200MIX_ERR_INVALID;
+    const size_t nd = env->dry.channels, ns = size_t(env->num_sends)*env->wet_stride;
+    const size_t nf = 1u + env->num_sends;
+    auto run = [&](uint32_t first, uint32_t last, int *status)
+    {
+        for(uint32_t i = first;i < last;++i)
+        {
+            const int rc = b200mix_calc_voice(&props[i], listener, env, buffer_rates[i], &voices[i],
+                dirs ? dirs + size_t(i)*4 : nullptr, dry_gains ? dry_gains + size_t(i)*nd : nullptr,
+                send_gains ? send_gains + size_t(i)*ns : nullptr, filters + size_t(i)*nf);
+            if(rc && !*status) *status = rc;
+        }
+    };
+    // sources are independent: split them evenly over the threads (the caller's included)
+    const uint32_t nt = std::max(1u, std::min(threads ? threads : 1u, (n + 63u)/64u));
+    std::vector<int> status(nt, 0);
+    std::vector<std::thread> pool;
+    const uint32_t per = (n + nt - 1u)/nt;
+    for(uint32_t t = 1;t < nt;++t)
+        pool.emplace_back(run, std::min(n, t*per), std::min(n, (t + 1u)*per), &status[t]);
+    run(0u, std::min(n, per), &status[0]);
+    for(auto &th : pool) th.join();
+    for(int st : status) if(st) return st;
+    return B200MIX_OK;
 }
 
 } // extern "C"

@@ -656,3 +656,72 @@ def test_calc_voice_bformat_first_order(devname):
                                                C.byref(step), dg.ctypes.data, sg.ctypes.data, fl) < 0
     finally:
         ref.close()
+
+
+def test_calc_voices_batch_equals_the_single_calls():
+    """b200mix_calc_voices (threaded batch) returns exactly what b200mix_calc_voice returns per source."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_voice.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                        C.c_uint32, C.POINTER(abi.VoiceParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+    prod.b200mix_calc_voices.argtypes = [C.c_uint32, C.c_void_p, C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint32]
+    rng = np.random.default_rng(77)
+    n, ns, nd, nw = 1000, 2, 4, 4
+    lis = ListenerParams()
+    lis.struct_size = C.sizeof(lis)
+    for i in range(4):
+        lis.matrix[i * 4 + i] = 1.0
+    lis.gain, lis.meters_per_unit, lis.air_absorption_gain_hf = 1.0, 1.0, 0.99426
+    lis.doppler_factor, lis.speed_of_sound, lis.distance_model = 1.0, 343.3, 2
+    scale = np.ones(4, dtype=np.float32); index = np.arange(4, dtype=np.uint32)
+    props = (SourceProps * n)()
+    rates = np.full(n, 44100, dtype=np.uint32)
+    for k in range(n):
+        p = props[k]
+        p.struct_size = C.sizeof(SourceProps)
+        p.pitch, p.gain, p.max_gain = float(rng.uniform(0.5, 2)), float(rng.uniform(0.1, 1)), 1.0
+        p.inner_angle = p.outer_angle = 360.0
+        p.ref_distance, p.max_distance, p.rolloff_factor = 1.0, 1e6, float(rng.uniform(0, 2))
+        for i in range(3):
+            p.position[i] = float(rng.standard_normal() * 10)
+            p.velocity[i] = float(rng.standard_normal() * 5)
+        p.distance_model, p.doppler_factor = 2, 1.0
+        p.direct.gain, p.direct.gain_hf, p.direct.gain_lf = 1.0, float(rng.uniform(0.2, 1)), 1.0
+        p.direct.hf_reference, p.direct.lf_reference = 5000.0, 250.0
+        for s in range(ns):
+            p.sends[s].gain, p.sends[s].gain_hf, p.sends[s].gain_lf = 1.0, 1.0, 1.0
+            p.sends[s].hf_reference, p.sends[s].lf_reference, p.sends[s].active = 5000.0, 250.0, 1
+    for mode in (2, 0):
+        env = VoiceEnv()
+        env.struct_size = C.sizeof(env)
+        env.device_rate, env.num_sends, env.render_mode, env.wet_stride = 48000, ns, mode, nw
+        env.dry = MixMap(nd, scale.ctypes.data, index.ctypes.data)
+        for s in range(ns):
+            env.wet[s] = MixMap(nw, scale.ctypes.data, index.ctypes.data)
+        want_v = (abi.VoiceParams * n)(); want_d = np.zeros((n, 4), np.float32)
+        want_g = np.zeros((n, nd), np.float32); want_s = np.zeros((n, ns, nw), np.float32)
+        want_f = (abi.VoiceFilter * (n * (1 + ns)))()
+        for k in range(n):
+            fl = (abi.VoiceFilter * (1 + abi.MAX_SENDS))()
+            want_v[k].voice = k
+            assert prod.b200mix_calc_voice(C.byref(props[k]), C.byref(lis), C.byref(env), int(rates[k]),
+                                           C.byref(want_v[k]), want_d[k].ctypes.data, want_g[k].ctypes.data,
+                                           want_s[k].ctypes.data, fl) == 0
+            for j in range(1 + ns):
+                want_f[k * (1 + ns) + j] = fl[j]
+        for threads in (1, 8):
+            got_v = (abi.VoiceParams * n)(); got_d = np.zeros((n, 4), np.float32)
+            got_g = np.zeros((n, nd), np.float32); got_s = np.zeros((n, ns, nw), np.float32)
+            got_f = (abi.VoiceFilter * (n * (1 + ns)))()
+            for k in range(n):
+                got_v[k].voice = k
+            assert prod.b200mix_calc_voices(n, props, C.byref(lis), C.byref(env), rates.ctypes.data, got_v,
+                                            got_d.ctypes.data, got_g.ctypes.data, got_s.ctypes.data, got_f,
+                                            threads) == 0
+            assert bytes(got_v) == bytes(want_v)
+            assert bytes(got_f) == bytes(want_f)
+            assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+            assert np.array_equal(got_g.view(np.uint32), want_g.view(np.uint32))
+            assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
