@@ -496,6 +496,15 @@ B200MIX_API int b200mix_ambi_coeffs(const float dir[3], float spread,
 B200MIX_API int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *index,
     const float coeffs[B200MIX_MAX_AMBI_CHANNELS], float ingain, float *gains, uint32_t gains_len);
 
+/* Host helper, no GPU: the output gains of a convolution effect whose impulse response is a
+ * plain channel layout — ConvolutionState::update (alc/effects/convolution.cpp:541-620).  layout:
+ * 1 = mono, else enum b200mix_channel_layout (stereo ... 7.1); pairwise: the device renders stereo
+ * pair-wise (RenderMode::Pairwise); slot_gain: EffectSlotBase::Gain; {channels, scale, index}: the
+ * target mix's AmbiMap.  gains receives one row of gains_stride floats per IR channel (the LFE row
+ * is zero) for b200mix_slot_output_gains; returns the row count.  Bit-identical to the reference. */
+B200MIX_API int b200mix_convolution_gains(uint32_t layout, uint32_t pairwise, float slot_gain,
+    uint32_t channels, const float *scale, const uint32_t *index, float *gains, uint32_t gains_stride);
+
 /* Host helper, no GPU: BiquadFilter::SetParams via setParamsFromSlope
  * (core/filters/biquad.h:92-97, biquad.cpp:48-129).  type follows enum BiquadType:
  * 0 HighShelf, 1 LowShelf, 2 Peaking, 3 LowPass, 4 HighPass, 5 BandPass.

@@ -96,4 +96,72 @@ int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *ind
     return B200MIX_OK;
 }
 
+int b200mix_convolution_gains(uint32_t layout, uint32_t pairwise, float slot_gain, uint32_t channels,
+    const float *scale, const uint32_t *index, float *gains, uint32_t gains_stride)
+{
+    // ConvolutionState::update for a non-ambisonic impulse response (alc/effects/convolution.cpp:
+    // 541-620): every IR channel's output line is panned to its speaker position (MonoMap ... X71Map,
+    // :144-196), the front pair stretched for pair-wise stereo devices (ScaleAzimuthFront, :552-576);
+    // the LFE line gets no gains
+    if(!scale || !index || !gains || gains_stride < channels) return B200MIX_ERR_INVALID;
+    constexpr float sin30 = 0.5f, cos30 = 0.866025403785f;
+    constexpr float sin45 = 1.41421356237309504880f*0.5f, cos45 = 1.41421356237309504880f*0.5f;
+    constexpr float sin110 = 0.939692620786f, cos110 = -0.342020143326f;
+    struct Chan { bool lfe; float pos[3]; };
+    Chan chans[8];
+    uint32_t n = 0;
+    auto add = [&](float x, float y, float z, bool lfe = false) { chans[n++] = Chan{lfe, {x, y, z}}; };
+    switch(layout)
+    {
+    case 1u: add(0.0f, 0.0f, -1.0f); break;
+    case B200MIX_LAYOUT_STEREO: add(-sin30, 0.0f, -cos30); add(sin30, 0.0f, -cos30); break;
+    case B200MIX_LAYOUT_REAR: add(-sin30, 0.0f, cos30); add(sin30, 0.0f, cos30); break;
+    case B200MIX_LAYOUT_QUAD:
+        add(-sin45, 0.0f, -cos45); add(sin45, 0.0f, -cos45); add(-sin45, 0.0f, cos45); add(sin45, 0.0f, cos45);
+        break;
+    case B200MIX_LAYOUT_X51:
+        add(-sin30, 0.0f, -cos30); add(sin30, 0.0f, -cos30); add(0.0f, 0.0f, -1.0f); add(0.0f, 0.0f, 0.0f, true);
+        add(-sin110, 0.0f, -cos110); add(sin110, 0.0f, -cos110);
+        break;
+    case B200MIX_LAYOUT_X61:
+        add(-sin30, 0.0f, -cos30); add(sin30, 0.0f, -cos30); add(0.0f, 0.0f, -1.0f); add(0.0f, 0.0f, 0.0f, true);
+        add(0.0f, 0.0f, 1.0f); add(-1.0f, 0.0f, 0.0f); add(1.0f, 0.0f, 0.0f);
+        break;
+    case B200MIX_LAYOUT_X71:
+        add(-sin30, 0.0f, -cos30); add(sin30, 0.0f, -cos30); add(0.0f, 0.0f, -1.0f); add(0.0f, 0.0f, 0.0f, true);
+        add(-sin30, 0.0f, cos30); add(sin30, 0.0f, cos30); add(-1.0f, 0.0f, 0.0f); add(1.0f, 0.0f, 0.0f);
+        break;
+    default: return B200MIX_ERR_INVALID;
+    }
+    for(uint32_t c = 0;c < n;++c)
+    {
+        float *g = gains + size_t(c)*gains_stride;
+        for(uint32_t k = 0;k < gains_stride;++k) g[k] = 0.0f;
+        if(chans[c].lfe) continue;
+        float pos[3] = {chans[c].pos[0], chans[c].pos[1], chans[c].pos[2]};
+        if(pairwise && pos[2] < 0.0f)
+        {
+            const float len2d = std::sqrt(pos[0]*pos[0] + pos[2]*pos[2]);
+            float x = pos[0] / len2d;
+            float z = -pos[2] / len2d;
+            if(z > cos30)
+            {
+                x = x*3.0f - x*x*x*4.0f;
+                z = z*z*z*4.0f - z*3.0f;
+                pos[0] = x * len2d;
+                pos[2] = -z * len2d;
+            }
+            else
+            {
+                pos[0] = std::copysign(len2d, pos[0]);
+                pos[2] = 0.0f;
+            }
+        }
+        float coeffs[B200MIX_MAX_AMBI_CHANNELS];
+        b200mix_ambi_coeffs(pos, 0.0f, coeffs);
+        if(int rc = b200mix_pan_gains(channels, scale, index, coeffs, slot_gain, g, channels)) return rc;
+    }
+    return int(n);
+}
+
 } // extern "C"

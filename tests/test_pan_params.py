@@ -89,3 +89,46 @@ def test_pan_helpers_reject_bad_arguments():
     g = np.zeros(4, dtype=np.float32)
     assert prod.b200mix_pan_gains(4, scale.ctypes.data, bad.ctypes.data, co.ctypes.data, 1.0, g.ctypes.data, 4) < 0
     assert prod.b200mix_pan_gains(5, scale.ctypes.data, bad.ctypes.data, co.ctypes.data, 1.0, g.ctypes.data, 4) < 0
+
+
+@pytest.mark.parametrize("devname", ["hrtf", "stereo", "ambi3"])
+def test_convolution_gains_bit_exact(devname):
+    """b200mix_convolution_gains against ConvolutionState::update on live convolution slots with
+    mono, stereo, quad, 5.1 and 7.1 impulse responses (oracle/ref_conv_tap.cpp reads mChans[].Target)."""
+    import os
+    prod, hz = _bind()
+    prod.b200mix_convolution_gains.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_uint32]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    tap = C.CDLL(os.path.join(refal.REF_DIR, "libref_conv_tap.so"))
+    tap.refh_conv_gains.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    attrs = {"stereo": {refal.ALC_HRTF_SOFT: 0}, "hrtf": {refal.ALC_HRTF_SOFT: 1},
+             "ambi3": {refal.ALC_FORMAT_CHANNELS_SOFT: refal.ALC_BFORMAT3D_SOFT, refal.ALC_AMBISONIC_ORDER_SOFT: 3,
+                       refal.ALC_AMBISONIC_LAYOUT_SOFT: refal.ALC_ACN_SOFT,
+                       refal.ALC_AMBISONIC_SCALING_SOFT: refal.ALC_N3D_SOFT}}[devname]
+    # AL float32 formats: mono, stereo, quad, 5.1, 7.1 and the layout ids of the helper
+    cases = [(0x10010, 1, 1), (0x10011, 2, 2), (0x1206, 4, 4), (0x120C, 6, 5), (0x1212, 8, 7)]
+    rng = np.random.default_rng(5)
+    for fmt, nch, layout in cases:
+        from helpers import scenes
+        from pyb200mix import abi
+        ref, _ = scenes.make_ref_scene(1, 1 if devname == "hrtf" else 0, abi.RS_LINEAR, attrs=attrs)
+        try:
+            ir = (rng.standard_normal((600, nch)) * 0.05).astype(np.float32)
+            slot_gain = float(np.float32(rng.uniform(0.2, 1.0)))
+            slot = ref.add_convolution_slot(ir, 48000, slot_gain, fmt=fmt)
+            ref.connect_send(ref.sources[0], slot)
+            ref.play_all()
+            ref.render(64)
+            want = np.zeros((8, 25), dtype=np.float32)
+            assert tap.refh_conv_gains(ref.ctx, 0, want.ctypes.data) == nch
+            scale = np.zeros(32, dtype=np.float32); index = np.zeros(32, dtype=np.uint32)
+            n = hz.refh_dry_ambi_map(ref.dev, scale.ctypes.data, index.ctypes.data)
+            got = np.full((8, 25), 7.0, dtype=np.float32)
+            rc = prod.b200mix_convolution_gains(layout, int(hz.refh_device_render_mode(ref.dev) == 1), slot_gain, n,
+                                                scale.ctypes.data, index.ctypes.data, got.ctypes.data, 25)
+            assert rc == nch, (devname, layout, rc)
+            assert np.array_equal(got[:nch].view(np.uint32), want[:nch].view(np.uint32)), (devname, layout, got[:nch], want[:nch])
+            assert np.abs(want[:nch]).max() > 0
+        finally:
+            ref.close()
