@@ -641,6 +641,16 @@ B200MIX_API int b200mix_hrtf_info(const b200mix_hrtf *hrtf, uint32_t *sample_rat
 B200MIX_API int b200mix_hrtf_get_coeffs(const b200mix_hrtf *hrtf, float elevation, float azimuth,
     float distance, float spread, float *coeffs, uint32_t delays[2]);
 
+/* The HRTF decoder of a first-order device from the data set alone (host, no GPU): the
+ * virtual-speaker set-up of InitHrtfPanning (alc/panning.cpp:847-1137, hrtf-mode full / ambi1)
+ * through DirectHrtfState::build (core/hrtf.cpp:265-366) — what b200mix_set_hrtf_decoder takes.
+ * voice_ir_size = DeviceBase::mIrSize (0: the data set's).  coeffs must hold 4*128*2 floats and is
+ * filled as [4][*ir_size][2]; returns the channel count (4).  Bit-identical to the reference's
+ * DirectHrtfState; B200MIX_ERR_UNSUPPORTED for other ambisonic orders (their decoder matrices
+ * are not restated yet). */
+B200MIX_API int b200mix_hrtf_build_decoder(const b200mix_hrtf *hrtf, uint32_t ambi_order,
+    uint32_t voice_ir_size, uint32_t *ir_size, float *coeffs, float hf_scale[4], float *splitter_coeff);
+
 /* Device-side parameter stage: with a data set attached, voices can be
  * updated with their DIRECTIONS instead of pre-blended HRIRs — dirs is [n][4] floats
  * {elevation, azimuth, distance, spread} exactly as CalcHrtfPanning hands them to

@@ -171,4 +171,86 @@ int b200mix_hrtf_get_coeffs(const b200mix_hrtf *h, float elevation, float azimut
     return B200MIX_OK;
 }
 
+int b200mix_hrtf_build_decoder(const b200mix_hrtf *h, uint32_t ambi_order, uint32_t voice_ir_size,
+    uint32_t *ir_size, float *coeffs, float hf_scale[4], float *splitter_coeff)
+{
+    // InitHrtfPanning's first-order set-up (alc/panning.cpp:847-1137: AmbiPoints1O, AmbiMatrix1O,
+    // AmbiOrderHFGain1O, 700 Hz crossover) handed to DirectHrtfState::build (core/hrtf.cpp:265-366)
+    if(!h || !ir_size || !coeffs || !hf_scale || !splitter_coeff || h->fields.empty()) return B200MIX_ERR_INVALID;
+    if(ambi_order != 1u) return B200MIX_ERR_UNSUPPORTED;
+    constexpr uint32_t kChannels = 4, kHrirLength = B200MIX_HRIR_LENGTH;
+    constexpr float Deg180 = std::numbers::pi_v<float>, Deg_90 = Deg180 / 2.0f, Deg_45 = Deg_90 / 2.0f;
+    constexpr float Deg135 = Deg_45 * 3.0f, Deg_35 = 6.154797087e-01f;
+    const float pts[8][2] = {      // {elevation, azimuth}
+        { Deg_35, -Deg_45}, { Deg_35, -Deg135}, { Deg_35, Deg_45}, { Deg_35, Deg135},
+        {-Deg_35, -Deg_45}, {-Deg_35, -Deg135}, {-Deg_35, Deg_45}, {-Deg_35, Deg135}};
+    static const float mtx[8][4] = {
+        {0.125f,  0.125f,  0.125f,  0.125f}, {0.125f,  0.125f,  0.125f, -0.125f},
+        {0.125f, -0.125f,  0.125f,  0.125f}, {0.125f, -0.125f,  0.125f, -0.125f},
+        {0.125f,  0.125f, -0.125f,  0.125f}, {0.125f,  0.125f, -0.125f, -0.125f},
+        {0.125f, -0.125f, -0.125f,  0.125f}, {0.125f, -0.125f, -0.125f, -0.125f}};
+    const float orderHF[2] = {2.000000000e+00f, 1.154700538e+00f};
+
+    // the channels' band splitter (BandSplitter::init, core/filters/splitter.cpp:15-26)
+    {
+        const double xover_norm = double(700.0f) / h->sample_rate;
+        const float w = std::numbers::pi_v<float>*2.0f * std::min(float(xover_norm), 0.49f);
+        const float cw = std::cos(w);
+        *splitter_coeff = cw > std::numeric_limits<float>::epsilon() ? (std::sin(w) - 1.0f) / cw : cw * -0.5f;
+    }
+    hf_scale[0] = orderHF[0];
+    hf_scale[1] = hf_scale[2] = hf_scale[3] = orderHF[1];
+
+    // the HRIR nearest to every virtual speaker (:292-326)
+    struct Impulse { const float *hrir; uint32_t ldelay, rdelay; };
+    Impulse imp[8];
+    uint32_t min_delay = B200MIX_HRTF_HISTORY * 4u, max_delay = 0u;
+    const uint32_t evCount = h->fields[0].ev_count;
+    for(int k = 0;k < 8;++k)
+    {
+        const IdxBlend elev0 = EvIndex(evCount, pts[k][0]);
+        const uint32_t elev1_idx = std::min(elev0.idx + 1u, evCount - 1u);
+        const uint32_t ir0offset = h->elevs[elev0.idx].ir_offset, ir1offset = h->elevs[elev1_idx].ir_offset;
+        const IdxBlend az0 = AzIndex(h->elevs[elev0.idx].az_count, pts[k][1]);
+        const IdxBlend az1 = AzIndex(h->elevs[elev1_idx].az_count, pts[k][1]);
+        const uint32_t idx[4] = {
+            ir0offset + az0.idx, ir0offset + ((az0.idx+1u) % h->elevs[elev0.idx].az_count),
+            ir1offset + az1.idx, ir1offset + ((az1.idx+1u) % h->elevs[elev1_idx].az_count)};
+        const uint32_t irOffset = idx[(elev0.blend >= 0.5f ? 2u : 0u) + (az1.blend >= 0.5f ? 1u : 0u)];
+        imp[k] = Impulse{&h->coeffs[size_t(irOffset)*h->ir_size*2u], h->delays[irOffset*2u], h->delays[irOffset*2u + 1u]};
+        min_delay = std::min(min_delay, std::min(imp[k].ldelay, imp[k].rdelay));
+        max_delay = std::max(max_delay, std::max(imp[k].ldelay, imp[k].rdelay));
+    }
+
+    auto delay_round = [](uint32_t d) { return (d + 2u) >> 2; };      // HrirDelayFracHalf / FracBits
+    std::vector<double> tmp(size_t(kChannels)*kHrirLength*2u, 0.0);
+    max_delay = 0u;
+    for(int k = 0;k < 8;++k)
+    {
+        const uint32_t base_delay = min_delay;                         // perHrirMin is false at first order
+        const uint32_t ldelay = delay_round(imp[k].ldelay - base_delay);
+        const uint32_t rdelay = delay_round(imp[k].rdelay - base_delay);
+        max_delay = std::max(max_delay, std::max(imp[k].ldelay, imp[k].rdelay) - base_delay);
+        for(uint32_t c = 0;c < kChannels;++c)
+        {
+            const double mult = mtx[k][c];
+            double *res = &tmp[size_t(c)*kHrirLength*2u];
+            for(uint32_t i = 0;i < h->ir_size && ldelay + i < kHrirLength;++i)
+                res[(ldelay + i)*2u] = double(imp[k].hrir[i*2u])*mult + res[(ldelay + i)*2u];
+            for(uint32_t i = 0;i < h->ir_size && rdelay + i < kHrirLength;++i)
+                res[(rdelay + i)*2u + 1u] = double(imp[k].hrir[i*2u + 1u])*mult + res[(rdelay + i)*2u + 1u];
+        }
+    }
+    const uint32_t max_length = std::min(delay_round(max_delay) + (voice_ir_size ? voice_ir_size : h->ir_size), kHrirLength);
+    *ir_size = max_length;
+    // [channels][max_length][2]
+    for(uint32_t c = 0;c < kChannels;++c)
+        for(uint32_t i = 0;i < max_length;++i)
+        {
+            coeffs[(size_t(c)*max_length + i)*2u] = float(tmp[(size_t(c)*kHrirLength + i)*2u]);
+            coeffs[(size_t(c)*max_length + i)*2u + 1u] = float(tmp[(size_t(c)*kHrirLength + i)*2u + 1u]);
+        }
+    return int(kChannels);
+}
+
 } // extern "C"

@@ -83,6 +83,18 @@ def test_calc_voice_drives_a_mixer_to_the_references_audio(hrtf):
             out_ref = ref.render(1024)
             if dev is None:
                 dev = scenes.mirror_device(mixlib.oracle(), ref, V, pcms)
+                if hrtf:
+                    # the HRTF decoder too comes from the library's own builder, not from the reference
+                    prod.b200mix_hrtf_build_decoder.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32,
+                                                                C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p,
+                                                                C.POINTER(C.c_float)]
+                    irs, sc = C.c_uint32(0), C.c_float(0.0)
+                    dco = np.zeros(4 * 128 * 2, dtype=np.float32)
+                    dhf = np.zeros(4, dtype=np.float32)
+                    assert prod.b200mix_hrtf_build_decoder(hstore, 1, ref.desc.ir_size, C.byref(irs), dco.ctypes.data,
+                                                           dhf.ctypes.data, C.byref(sc)) == 4
+                    dev.set_hrtf_decoder(dco[:4 * irs.value * 2].reshape(4, irs.value, 2), dhf,
+                                         np.full(4, sc.value, dtype=np.float32))
                 nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
                 nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
                 ns = ref.desc.num_sends

@@ -60,3 +60,36 @@ def test_loader_rejects_garbage():
     junk = b"MinPHR03" + bytes(40)
     assert lib.b200mix_hrtf_load(junk, len(junk), C.byref(h)) != 0
     assert lib.b200mix_hrtf_load(b"RIFFxxxxWAVEfmt xxxx", 20, C.byref(h)) != 0
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not os.path.exists(MHR), reason="HRTF data set not staged (run build())")
+def test_build_decoder_matches_the_references_direct_hrtf_state():
+    """b200mix_hrtf_build_decoder against the DirectHrtfState of a live HRTF device of the compiled
+    reference (default data set, hrtf-mode full): coefficients, HF scales, splitter coefficient and
+    the decoder's IR length, bit for bit."""
+    from helpers import refal
+    lib = _lib()
+    lib.b200mix_hrtf_build_decoder.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p,
+                                               C.c_void_p, C.POINTER(C.c_float)]
+    data = open(MHR, "rb").read()
+    h = C.c_void_p()
+    assert lib.b200mix_hrtf_load(data, len(data), C.byref(h)) == 0
+    ref = refal.RefDevice({refal.ALC_HRTF_SOFT: 1})
+    try:
+        want_c, want_hf, want_sc = ref.hrtf_decoder()
+        irs = C.c_uint32(0)
+        got = np.zeros(4 * 128 * 2, dtype=np.float32)
+        hf = np.zeros(4, dtype=np.float32)
+        sc = C.c_float(0.0)
+        assert lib.b200mix_hrtf_build_decoder(h, 1, ref.desc.ir_size, C.byref(irs), got.ctypes.data, hf.ctypes.data,
+                                              C.byref(sc)) == 4
+        assert irs.value == want_c.shape[1], (irs.value, want_c.shape)
+        got = got[:4 * irs.value * 2].reshape(4, irs.value, 2)
+        assert np.array_equal(got.view(np.uint32), want_c.view(np.uint32)), np.abs(got - want_c).max()
+        assert np.array_equal(hf.view(np.uint32), want_hf.view(np.uint32)), (hf, want_hf)
+        assert np.float32(sc.value).view(np.uint32) == want_sc[0].view(np.uint32)
+        assert lib.b200mix_hrtf_build_decoder(h, 3, 0, C.byref(irs), got.ctypes.data, hf.ctypes.data, C.byref(sc)) < 0
+    finally:
+        ref.close()
+        lib.b200mix_hrtf_free(h)
