@@ -496,6 +496,22 @@ B200MIX_API int b200mix_ambi_coeffs(const float dir[3], float spread,
 B200MIX_API int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *index,
     const float coeffs[B200MIX_MAX_AMBI_CHANNELS], float ingain, float *gains, uint32_t gains_len);
 
+/* Host helper, no GPU: the reference's built-in decoders for mono (0), stereo (1) and quad (2)
+ * output — InitPanning (alc/panning.cpp:542-577,718-845) — as the arguments of b200mix_create
+ * (dry_channels, real_channels, B200MIX_POST_AMBIDEC) and b200mix_set_ambi_decoder, plus the Dry
+ * mix's AmbiMap for the panning helpers.  hq_mode = the decoder/hq-mode option (default on: the
+ * quad decoder is dual-band).  gains_* are [dry_channels][real_channels].  Bit-identical to a
+ * reference device of that format. */
+typedef struct b200mix_builtin_decoder_out {
+    uint32_t struct_size;
+    uint32_t ambi_order, is_2d, dry_channels, real_channels, dual_band;
+    float map_scale[3]; uint32_t map_index[3];
+    float gains_hf[3*4], gains_lf[3*4];
+    float xover_coeff;
+} b200mix_builtin_decoder_out;
+B200MIX_API int b200mix_builtin_decoder(uint32_t layout, uint32_t hq_mode, uint32_t sample_rate,
+    b200mix_builtin_decoder_out *out);
+
 /* Host helper, no GPU: the output gains of a convolution effect whose impulse response is a
  * plain channel layout — ConvolutionState::update (alc/effects/convolution.cpp:541-620).  layout:
  * 1 = mono, else enum b200mix_channel_layout (stereo ... 7.1); pairwise: the device renders stereo

@@ -6,6 +6,7 @@
 // Gains.Target arrays (tests/test_pan_params.py pins both against the compiled reference).
 #include "../../include/b200mix.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace {
@@ -162,6 +163,58 @@ int b200mix_convolution_gains(uint32_t layout, uint32_t pairwise, float slot_gai
         if(int rc = b200mix_pan_gains(channels, scale, index, coeffs, slot_gain, g, channels)) return rc;
     }
     return int(n);
+}
+
+int b200mix_builtin_decoder(uint32_t layout, uint32_t hq_mode, uint32_t sample_rate, b200mix_builtin_decoder_out *out)
+{
+    // InitPanning with one of the built-in layouts (alc/panning.cpp:542-577,718-845): the decoder
+    // rows times the per-order gains, transposed into BFormatDec's [input][output] gains
+    // (core/bformatdec.cpp:28-58), the Dry mix's AmbiMap, and the dual-band crossover (400 Hz,
+    // core/device.h:238) when decoder/hq-mode is on and the layout has LF rows
+    if(!out || out->struct_size != sizeof(*out) || !sample_rate) return B200MIX_ERR_INVALID;
+    struct Row { uint32_t real_index; float c[3]; };
+    const Row mono[1] = {{0u, {1.0f, 0.0f, 0.0f}}};
+    const Row stereo[2] = {{0u, {5.00000000e-1f, 2.88675135e-1f, 5.52305643e-2f}},
+                           {1u, {5.00000000e-1f, -2.88675135e-1f, 5.52305643e-2f}}};
+    // QuadConfig lists BackLeft, FrontLeft, FrontRight, BackRight; DevFmtQuad's channels are
+    // FrontLeft, FrontRight, BackLeft, BackRight
+    const Row quad[4] = {{2u, {2.50000000e-1f, 2.04124145e-1f, -2.04124145e-1f}},
+                         {0u, {2.50000000e-1f, 2.04124145e-1f, 2.04124145e-1f}},
+                         {1u, {2.50000000e-1f, -2.04124145e-1f, 2.04124145e-1f}},
+                         {3u, {2.50000000e-1f, -2.04124145e-1f, -2.04124145e-1f}}};
+    const Row *rows; uint32_t nrows, order; bool hasLF = false;
+    float orderHF[2] = {1.0f, 1.0f}, orderLF[2] = {1.0f, 1.0f};
+    switch(layout)
+    {
+    case 0u: rows = mono; nrows = 1; order = 0; break;
+    case 1u: rows = stereo; nrows = 2; order = 1; break;
+    case 2u: rows = quad; nrows = 4; order = 1; hasLF = true; orderHF[0] = 1.41421356e+0f; break;
+    default: return B200MIX_ERR_INVALID;
+    }
+    const uint32_t ambicount = order*2u + 1u;             // Ambi2DChannelsFromOrder (all three are pantaphonic)
+    static const uint32_t acn2d[3] = {0u, 1u, 3u};        // AmbiIndex::FromACN2D
+    static const uint32_t order2d[3] = {0u, 1u, 1u};      // AmbiIndex::OrderFrom2DChannel
+    out->ambi_order = order; out->is_2d = 1u;
+    out->dry_channels = ambicount; out->real_channels = nrows;
+    for(uint32_t k = 0;k < ambicount;++k) { out->map_scale[k] = 1.0f/1.0f; out->map_index[k] = acn2d[k]; }   // N3D scales
+    const bool dual = hq_mode && hasLF;
+    out->dual_band = dual ? 1u : 0u;
+    for(uint32_t k = 0;k < 3u*4u;++k) { out->gains_hf[k] = 0.0f; out->gains_lf[k] = 0.0f; }
+    for(uint32_t r = 0;r < nrows;++r)
+        for(uint32_t k = 0;k < ambicount;++k)
+        {
+            out->gains_hf[k*nrows + rows[r].real_index] = rows[r].c[k] * orderHF[order2d[k]];
+            if(dual) out->gains_lf[k*nrows + rows[r].real_index] = rows[r].c[k] * orderLF[order2d[k]];
+        }
+    out->xover_coeff = 0.0f;
+    if(dual)
+    {
+        const float f0norm = 400.0f / float(sample_rate);
+        const float w = 3.14159265358979323846f*2.0f * std::min(f0norm, 0.49f);
+        const float cw = std::cos(w);
+        out->xover_coeff = cw > 1.1920928955078125e-7f ? (std::sin(w) - 1.0f) / cw : cw * -0.5f;
+    }
+    return B200MIX_OK;
 }
 
 } // extern "C"

@@ -132,3 +132,44 @@ def test_convolution_gains_bit_exact(devname):
             assert np.abs(want[:nch]).max() > 0
         finally:
             ref.close()
+
+
+class BuiltinDecoder(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("ambi_order", C.c_uint32), ("is_2d", C.c_uint32),
+                ("dry_channels", C.c_uint32), ("real_channels", C.c_uint32), ("dual_band", C.c_uint32),
+                ("map_scale", C.c_float * 3), ("map_index", C.c_uint32 * 3), ("gains_hf", C.c_float * 12),
+                ("gains_lf", C.c_float * 12), ("xover_coeff", C.c_float)]
+
+
+@pytest.mark.parametrize("layout,fmt", [(0, 0x1500), (1, 0x1501), (2, 0x1503)])
+def test_builtin_decoders_bit_exact(layout, fmt):
+    """b200mix_builtin_decoder against a live reference device of that output format: channel
+    counts, the Dry AmbiMap, the BFormatDec gain matrices and the crossover coefficient."""
+    prod, hz = _bind()
+    prod.b200mix_builtin_decoder.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(BuiltinDecoder)]
+    hz.refh_device_ambi.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    hz.refh_device_ambi.restype = None
+    ref = refal.RefDevice({refal.ALC_FORMAT_CHANNELS_SOFT: fmt, refal.ALC_HRTF_SOFT: 0})
+    try:
+        out = BuiltinDecoder()
+        out.struct_size = C.sizeof(out)
+        assert prod.b200mix_builtin_decoder(layout, 1, ref.desc.sample_rate, C.byref(out)) == 0
+        assert (out.dry_channels, out.real_channels) == (ref.desc.dry_channels, ref.desc.real_channels)
+        order, is2d, xover = C.c_uint32(0), C.c_uint32(0), C.c_float(0.0)
+        hz.refh_device_ambi(ref.dev, C.byref(order), C.byref(is2d), C.byref(xover))
+        assert (out.ambi_order, out.is_2d) == (order.value, is2d.value)
+        scale = np.zeros(32, dtype=np.float32); index = np.zeros(32, dtype=np.uint32)
+        n = hz.refh_dry_ambi_map(ref.dev, scale.ctypes.data, index.ctypes.data)
+        assert list(out.map_index)[:n] == list(index[:n])
+        assert np.array_equal(np.array(list(out.map_scale)[:n], dtype=np.float32).view(np.uint32), scale[:n].view(np.uint32))
+        hfm, lfm, xo = ref.ambi_decoder()
+        cnt = out.dry_channels * out.real_channels
+        got_hf = np.array(list(out.gains_hf)[:cnt], dtype=np.float32).reshape(hfm.shape)
+        assert np.array_equal(got_hf.view(np.uint32), hfm.view(np.uint32)), (got_hf, hfm)
+        assert bool(out.dual_band) == (lfm is not None)
+        if lfm is not None:
+            got_lf = np.array(list(out.gains_lf)[:cnt], dtype=np.float32).reshape(lfm.shape)
+            assert np.array_equal(got_lf.view(np.uint32), lfm.view(np.uint32))
+            assert np.float32(out.xover_coeff).view(np.uint32) == np.float32(xo).view(np.uint32)
+    finally:
+        ref.close()
