@@ -89,3 +89,31 @@ def test_c_host_can_call_the_parameter_stage():
         env["LD_LIBRARY_PATH"] = libdir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
         out = subprocess.check_output([exe], env=env, text=True)
         assert "sources/s" in out
+
+
+def test_standalone_c_example_builds_and_fails_loudly_without_a_gpu():
+    """examples/standalone_host.c (a host using only the library) compiles against the header as C,
+    sets up its HRTF device from the data set and — on this CPU-only box — stops at b200mix_create."""
+    import shutil
+    import subprocess
+    import tempfile
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    gcc = shutil.which("gcc")
+    mhr = os.path.join(ROOT, "openal-soft_b200", "data", "Default HRTF.mhr")
+    if not gcc or not os.path.exists(mhr):
+        pytest.skip("no host compiler / data set")
+    libdir = os.path.dirname(mixlib.PRODUCT_SO)
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "standalone_host")
+        subprocess.check_call([gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "examples", "standalone_host.c"), "-L", libdir, "-lb200mix", "-lm",
+                               "-o", exe])
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = libdir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+        out = subprocess.check_output([exe, mhr], env=env, text=True)
+        assert "no CPU path" in out
