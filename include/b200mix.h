@@ -496,8 +496,8 @@ B200MIX_API int b200mix_ambi_coeffs(const float dir[3], float spread,
 B200MIX_API int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *index,
     const float coeffs[B200MIX_MAX_AMBI_CHANNELS], float ingain, float *gains, uint32_t gains_len);
 
-/* Host helper, no GPU: the reference's built-in decoders for mono (0), stereo (1) and quad (2)
- * output — InitPanning (alc/panning.cpp:542-577,718-845) — as the arguments of b200mix_create
+/* Host helper, no GPU: the reference's built-in decoders for mono (0), stereo (1), quad (2), 5.1
+ * (3), 6.1 (4) and 7.1 (5) output — InitPanning (alc/panning.cpp:542-577,718-845) — as the arguments of b200mix_create
  * (dry_channels, real_channels, B200MIX_POST_AMBIDEC) and b200mix_set_ambi_decoder, plus the Dry
  * mix's AmbiMap for the panning helpers.  hq_mode = the decoder/hq-mode option (default on: the
  * quad decoder is dual-band).  gains_* are [dry_channels][real_channels].  Bit-identical to a
@@ -505,8 +505,8 @@ B200MIX_API int b200mix_pan_gains(uint32_t channels, const float *scale, const u
 typedef struct b200mix_builtin_decoder_out {
     uint32_t struct_size;
     uint32_t ambi_order, is_2d, dry_channels, real_channels, dual_band;
-    float map_scale[3]; uint32_t map_index[3];
-    float gains_hf[3*4], gains_lf[3*4];
+    float map_scale[5]; uint32_t map_index[5];
+    float gains_hf[5*8], gains_lf[5*8];
     float xover_coeff;
 } b200mix_builtin_decoder_out;
 B200MIX_API int b200mix_builtin_decoder(uint32_t layout, uint32_t hq_mode, uint32_t sample_rate,

@@ -137,11 +137,11 @@ def test_convolution_gains_bit_exact(devname):
 class BuiltinDecoder(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("ambi_order", C.c_uint32), ("is_2d", C.c_uint32),
                 ("dry_channels", C.c_uint32), ("real_channels", C.c_uint32), ("dual_band", C.c_uint32),
-                ("map_scale", C.c_float * 3), ("map_index", C.c_uint32 * 3), ("gains_hf", C.c_float * 12),
-                ("gains_lf", C.c_float * 12), ("xover_coeff", C.c_float)]
+                ("map_scale", C.c_float * 5), ("map_index", C.c_uint32 * 5), ("gains_hf", C.c_float * 40),
+                ("gains_lf", C.c_float * 40), ("xover_coeff", C.c_float)]
 
 
-@pytest.mark.parametrize("layout,fmt", [(0, 0x1500), (1, 0x1501), (2, 0x1503)])
+@pytest.mark.parametrize("layout,fmt", [(0, 0x1500), (1, 0x1501), (2, 0x1503), (3, 0x1504), (4, 0x1505), (5, 0x1506)])
 def test_builtin_decoders_bit_exact(layout, fmt):
     """b200mix_builtin_decoder against a live reference device of that output format: channel
     counts, the Dry AmbiMap, the BFormatDec gain matrices and the crossover coefficient."""
