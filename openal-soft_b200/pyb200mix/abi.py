@@ -121,3 +121,70 @@ def reverb_params_from(raw) -> "ReverbParams":
     p = ReverbParams.from_buffer_copy(raw[:n].ljust(n, b"\0"))
     p.struct_size = n
     return p
+
+
+# ---- host parameter stage (b200mix_calc_listener_params / _source_params / _voice*) ----
+class ListenerParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("matrix", C.c_float * 16),
+                ("velocity", C.c_float * 3), ("gain", C.c_float), ("meters_per_unit", C.c_float),
+                ("air_absorption_gain_hf", C.c_float), ("doppler_factor", C.c_float),
+                ("speed_of_sound", C.c_float), ("source_distance_model", C.c_uint32),
+                ("distance_model", C.c_uint32)]
+
+
+class ListenerProps(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("velocity", C.c_float * 3),
+                ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3), ("gain", C.c_float),
+                ("gain_boost", C.c_float), ("meters_per_unit", C.c_float), ("air_absorption_gain_hf", C.c_float),
+                ("doppler_factor", C.c_float), ("doppler_velocity", C.c_float), ("speed_of_sound", C.c_float),
+                ("source_distance_model", C.c_uint32), ("distance_model", C.c_uint32)]
+
+
+class SourceSend(C.Structure):
+    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
+                ("gain_lf", C.c_float), ("lf_reference", C.c_float), ("active", C.c_uint32),
+                ("slot_room_rolloff", C.c_float), ("slot_decay_time", C.c_float),
+                ("slot_air_absorption_gain_hf", C.c_float)]
+
+
+class SourceDirect(C.Structure):
+    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
+                ("gain_lf", C.c_float), ("lf_reference", C.c_float)]
+
+
+class SourceProps(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32)] + [(n, C.c_float) for n in (
+        "pitch", "gain", "outer_gain", "min_gain", "max_gain", "inner_angle", "outer_angle", "ref_distance",
+        "max_distance", "rolloff_factor")] + [("position", C.c_float * 3), ("velocity", C.c_float * 3),
+        ("direction", C.c_float * 3), ("head_relative", C.c_uint32), ("distance_model", C.c_uint32),
+        ("dry_gain_hf_auto", C.c_uint32), ("wet_gain_auto", C.c_uint32), ("wet_gain_hf_auto", C.c_uint32),
+        ("outer_gain_hf", C.c_float), ("air_absorption_factor", C.c_float), ("room_rolloff_factor", C.c_float),
+        ("doppler_factor", C.c_float), ("radius", C.c_float), ("direct", SourceDirect),
+        ("sends", SourceSend * MAX_SENDS), ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3)]
+
+
+class SourceResult(C.Structure):
+    _fields_ = [("step", C.c_uint32), ("pos", C.c_float * 3), ("distance", C.c_float), ("spread", C.c_float),
+                ("hrtf_elevation", C.c_float), ("hrtf_azimuth", C.c_float), ("dry_gain", C.c_float),
+                ("dry_gain_hf", C.c_float), ("dry_gain_lf", C.c_float), ("wet_gain", C.c_float * MAX_SENDS),
+                ("wet_gain_hf", C.c_float * MAX_SENDS), ("wet_gain_lf", C.c_float * MAX_SENDS)]
+
+
+class MixMap(C.Structure):
+    _fields_ = [("channels", C.c_uint32), ("scale", C.c_void_p), ("index", C.c_void_p)]
+
+
+class VoiceEnv(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device_rate", C.c_uint32), ("num_sends", C.c_uint32),
+                ("render_mode", C.c_uint32), ("wet_stride", C.c_uint32), ("dry", MixMap),
+                ("wet", MixMap * MAX_SENDS)]
+
+
+class ChannelSetup(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
+                ("panning", C.c_float), ("lfe_dry_index", C.c_uint32), ("spatialized", C.c_uint32)]
+
+
+class BFormatSetup(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("is_2d", C.c_uint32), ("layout", C.c_uint32),
+                ("scaling", C.c_uint32), ("device_ambi_order", C.c_uint32)]

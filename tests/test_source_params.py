@@ -13,6 +13,8 @@ import pytest
 
 from helpers import mixlib, refal, scenes
 from pyb200mix import abi, scene
+from pyb200mix.abi import (ListenerParams, ListenerProps, SourceSend, SourceProps, SourceResult, MixMap, VoiceEnv,
+                            ChannelSetup, BFormatSetup)
 
 pytestmark = pytest.mark.ref
 
@@ -21,50 +23,16 @@ MHR = os.path.join(ROOT, "openal-soft_b200", "data", "Default HRTF.mhr")
 MODELS = [0, 0xD001, 0xD002, 0xD003, 0xD004, 0xD005, 0xD006]     # AL_NONE, AL_INVERSE_DISTANCE, ...
 
 
-class ListenerParams(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("matrix", C.c_float * 16),
-                ("velocity", C.c_float * 3), ("gain", C.c_float), ("meters_per_unit", C.c_float),
-                ("air_absorption_gain_hf", C.c_float), ("doppler_factor", C.c_float),
-                ("speed_of_sound", C.c_float), ("source_distance_model", C.c_uint32),
-                ("distance_model", C.c_uint32)]
 
 
-class SourceSend(C.Structure):
-    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
-                ("gain_lf", C.c_float), ("lf_reference", C.c_float), ("active", C.c_uint32),
-                ("slot_room_rolloff", C.c_float), ("slot_decay_time", C.c_float),
-                ("slot_air_absorption_gain_hf", C.c_float)]
 
 
-class Direct(C.Structure):
-    _fields_ = [("gain", C.c_float), ("gain_hf", C.c_float), ("hf_reference", C.c_float),
-                ("gain_lf", C.c_float), ("lf_reference", C.c_float)]
 
 
-class SourceProps(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32)] + [(n, C.c_float) for n in (
-        "pitch", "gain", "outer_gain", "min_gain", "max_gain", "inner_angle", "outer_angle", "ref_distance",
-        "max_distance", "rolloff_factor")] + [("position", C.c_float * 3), ("velocity", C.c_float * 3),
-        ("direction", C.c_float * 3), ("head_relative", C.c_uint32), ("distance_model", C.c_uint32),
-        ("dry_gain_hf_auto", C.c_uint32), ("wet_gain_auto", C.c_uint32), ("wet_gain_hf_auto", C.c_uint32),
-        ("outer_gain_hf", C.c_float), ("air_absorption_factor", C.c_float), ("room_rolloff_factor", C.c_float),
-        ("doppler_factor", C.c_float), ("radius", C.c_float), ("direct", Direct),
-        ("sends", SourceSend * abi.MAX_SENDS), ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3)]
 
 
-class SourceResult(C.Structure):
-    _fields_ = [("step", C.c_uint32), ("pos", C.c_float * 3), ("distance", C.c_float), ("spread", C.c_float),
-                ("hrtf_elevation", C.c_float), ("hrtf_azimuth", C.c_float), ("dry_gain", C.c_float),
-                ("dry_gain_hf", C.c_float), ("dry_gain_lf", C.c_float), ("wet_gain", C.c_float * abi.MAX_SENDS),
-                ("wet_gain_hf", C.c_float * abi.MAX_SENDS), ("wet_gain_lf", C.c_float * abi.MAX_SENDS)]
 
 
-class ListenerProps(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("position", C.c_float * 3), ("velocity", C.c_float * 3),
-                ("orient_at", C.c_float * 3), ("orient_up", C.c_float * 3), ("gain", C.c_float),
-                ("gain_boost", C.c_float), ("meters_per_unit", C.c_float), ("air_absorption_gain_hf", C.c_float),
-                ("doppler_factor", C.c_float), ("doppler_velocity", C.c_float), ("speed_of_sound", C.c_float),
-                ("source_distance_model", C.c_uint32), ("distance_model", C.c_uint32)]
 
 
 def test_listener_params_match_calc_context_params():
@@ -311,14 +279,8 @@ def test_source_params_reproduce_the_references_voices(devname):
     assert all(v > 5 for v in checked.values()), checked
 
 
-class MixMap(C.Structure):
-    _fields_ = [("channels", C.c_uint32), ("scale", C.c_void_p), ("index", C.c_void_p)]
 
 
-class VoiceEnv(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("device_rate", C.c_uint32), ("num_sends", C.c_uint32),
-                ("render_mode", C.c_uint32), ("wet_stride", C.c_uint32), ("dry", MixMap),
-                ("wet", MixMap * abi.MAX_SENDS)]
 
 
 @pytest.mark.skipif(not os.path.exists(MHR), reason="HRTF data set not staged (run build())")
@@ -409,9 +371,6 @@ def test_calc_voice_single_call(devname):
         prod.b200mix_hrtf_free(hrtf)
 
 
-class ChannelSetup(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
-                ("panning", C.c_float), ("lfe_dry_index", C.c_uint32), ("spatialized", C.c_uint32)]
 
 
 LAYOUTS = {  # name: (AL format, channels, b200mix_channel_layout)
@@ -543,9 +502,6 @@ def test_calc_voice_channels_for_unspatialized_multichannel_sources(devname):
         prod.b200mix_hrtf_free(hrtf)
 
 
-class BFormatSetup(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("is_2d", C.c_uint32), ("layout", C.c_uint32),
-                ("scaling", C.c_uint32), ("device_ambi_order", C.c_uint32)]
 
 
 @pytest.mark.parametrize("devname", ["hrtf", "stereo"])
