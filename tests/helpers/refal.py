@@ -107,6 +107,8 @@ def libs(conf_text: str | None = None):
     with open(conf_path, "w") as f:
         f.write(conf_text or "[general]\n")
     os.environ["ALSOFT_CONF"] = conf_path
+    import atexit
+    atexit.register(lambda: os.path.exists(conf_path) and os.remove(conf_path))
     os.environ.setdefault("ALSOFT_LOGLEVEL", "1")
     al = C.CDLL(os.path.join(REF_DIR, "libopenal_ref.so"), mode=C.RTLD_GLOBAL)
     hz = C.CDLL(os.path.join(REF_DIR, "libref_harness.so"))
