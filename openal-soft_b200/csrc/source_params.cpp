@@ -53,6 +53,29 @@ float lerpf(float a, float b, float mu) { return a + (b-a)*mu; }
 
 enum Model { Disable, Inverse, InverseClamped, Linear, LinearClamped, Exponent, ExponentClamped };
 
+// The filter block of CalcPanningAndFilters (alc/alu.cpp:1619-1656): per path (0 = direct, 1+s = send s)
+// a high-shelf at HFReference and a low-shelf at LFReference with the path's HF / LF gains; the
+// path's filter is active iff either gain differs from 1.
+int design_filters(const b200mix_source_props &P, uint32_t device_rate, uint32_t num_sends, const float *gainHF,
+    const float *gainLF, const uint32_t *voice, b200mix_voice_filter *filters)
+{
+    const float inv_samplerate = 1.0f / float(device_rate);
+    for(uint32_t path = 0;path <= num_sends;++path)
+    {
+        b200mix_voice_filter &f = filters[path];
+        const float ghf = gainHF[path], glf = gainLF[path];
+        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
+        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
+        if(voice) f.voice = *voice;
+        f.path = path;
+        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
+        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
+            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
+            return B200MIX_ERR_INVALID;
+    }
+    return B200MIX_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -367,21 +390,11 @@ int b200mix_calc_voice(const b200mix_source_props *props, const b200mix_listener
         if(w.channels > env->wet_stride || !w.scale || !w.index) return B200MIX_ERR_INVALID;
         if(int rc = b200mix_pan_gains(w.channels, w.scale, w.index, coeffs, r.wet_gain[s], g, w.channels)) return rc;
     }
-    // filters (alc/alu.cpp:1619-1656)
-    const float inv_samplerate = 1.0f / float(env->device_rate);
-    for(uint32_t path = 0;path <= env->num_sends;++path)
-    {
-        b200mix_voice_filter &f = filters[path];
-        const float ghf = path ? r.wet_gain_hf[path-1] : r.dry_gain_hf;
-        const float glf = path ? r.wet_gain_lf[path-1] : r.dry_gain_lf;
-        const float hfref = path ? props->sends[path-1].hf_reference : props->direct.hf_reference;
-        const float lfref = path ? props->sends[path-1].lf_reference : props->direct.lf_reference;
-        f.voice = voice->voice; f.path = path;
-        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
-        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
-            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
-            return B200MIX_ERR_INVALID;
-    }
+    float gainHF[1 + B200MIX_MAX_SENDS], gainLF[1 + B200MIX_MAX_SENDS];
+    gainHF[0] = r.dry_gain_hf; gainLF[0] = r.dry_gain_lf;
+    for(uint32_t i = 0;i < B200MIX_MAX_SENDS;++i) { gainHF[1+i] = r.wet_gain_hf[i]; gainLF[1+i] = r.wet_gain_lf[i]; }
+    if(int rc = design_filters(*props, env->device_rate, env->num_sends, gainHF, gainLF, &voice->voice, filters))
+        return rc;
     return B200MIX_OK;
 }
 
@@ -544,20 +557,8 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
         }
     }
 
-    // filters (:1619-1656): every channel shares channel 0's
-    const float inv_samplerate = 1.0f / float(env->device_rate);
-    for(uint32_t path = 0;path <= env->num_sends;++path)
-    {
-        b200mix_voice_filter &f = filters[path];
-        const float ghf = gainHF[path], glf = gainLF[path];
-        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
-        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
-        f.path = path;
-        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
-        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
-            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
-            return B200MIX_ERR_INVALID;
-    }
+    // every channel shares channel 0's filters
+    if(int rc = design_filters(P, env->device_rate, env->num_sends, gainHF, gainLF, nullptr, filters)) return rc;
     return int(nch);
 }
 
@@ -651,20 +652,10 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
         for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k) coeffs[k] = 0.0f;      // :1074
     }
 
-    const float inv_samplerate = 1.0f / float(env->device_rate);
-    for(uint32_t path = 0;path <= env->num_sends;++path)
-    {
-        b200mix_voice_filter &f = filters[path];
-        const float ghf = path ? P.sends[path-1].gain_hf : P.direct.gain_hf;
-        const float glf = path ? P.sends[path-1].gain_lf : P.direct.gain_lf;
-        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
-        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
-        f.path = path;
-        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
-        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
-            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
-            return B200MIX_ERR_INVALID;
-    }
+    float gainHF[1 + B200MIX_MAX_SENDS], gainLF[1 + B200MIX_MAX_SENDS];
+    gainHF[0] = P.direct.gain_hf; gainLF[0] = P.direct.gain_lf;
+    for(uint32_t i = 0;i < B200MIX_MAX_SENDS;++i) { gainHF[1+i] = P.sends[i].gain_hf; gainLF[1+i] = P.sends[i].gain_lf; }
+    if(int rc = design_filters(P, env->device_rate, env->num_sends, gainHF, gainLF, nullptr, filters)) return rc;
     return int(nch);
 }
 
