@@ -53,6 +53,23 @@ int main(void)
     const double s = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec)*1e-9;
     printf("b200mix_calc_voice: %d sources in %.3f s = %.0f ns/source, %.2f M sources/s on one core (checksum %g)\n",
         N, s, s/N*1e9, N/s*1e-6, acc);
+
+    /* the threaded batch form */
+    uint32_t *rates = malloc(N*sizeof(*rates));
+    b200mix_voice_params *vps = calloc(N, sizeof(*vps));
+    float *dirs = malloc((size_t)N*4*sizeof(float)), *dry = malloc((size_t)N*4*sizeof(float));
+    float *snd = malloc((size_t)N*4*sizeof(float));
+    b200mix_voice_filter *fl = malloc((size_t)N*2*sizeof(*fl));
+    for(int i = 0;i < N;++i) rates[i] = 48000;
+    for(unsigned th = 1;th <= 16;th *= 2)
+    {
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        if(b200mix_calc_voices(N, sp, &lis, &env, rates, vps, dirs, dry, snd, fl, th) != 0) return 3;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double sb = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec)*1e-9;
+        printf("b200mix_calc_voices, %2u thread(s): %.2f M sources/s\n", th, N/sb*1e-6);
+    }
+    free(rates); free(vps); free(dirs); free(dry); free(snd); free(fl);
     free(sp);
     return 0;
 }
