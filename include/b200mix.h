@@ -645,6 +645,41 @@ B200MIX_API int b200mix_render_begin(b200mix_device *dev, uint32_t frames, float
 B200MIX_API int b200mix_render_end(b200mix_device *dev, float *const *real_out,
     b200mix_voice_result *results, const float **real_out_dev);
 
+/* ---- voice-sharded device sets: one device per GPU, one process per device ----
+ * Voices are independent until they add into the mix buffers (core/voice.cpp:962,978;
+ * hrtfbase.h:28), so the host deals its voices over `world` devices (each holds only its own
+ * voices and buffers) and the LIBRARY performs the two exchanges of an update inside
+ * b200mix_render / _render_device / _render_interleaved, on the device's own stream:
+ *   1. after the voice loop: the slots' Wet buffers are reduce-scattered — slot s is OWNED by
+ *      rank s mod world, which installs its effect (b200mix_slot_*) and receives the sum of
+ *      every rank's sends to it (effects consume the summed input, alc/alu.cpp:2252-2256);
+ *   2. after the post-process (linear, alc/alu.cpp:2439-2443): the RealOut blocks are summed
+ *      onto rank 0; the nonlinear output stage (limiter, distance compensation, dither,
+ *      conversion) then runs on rank 0 only.  On the other ranks real_out receives that
+ *      rank's partial mix.
+ * Two transports:
+ *   - peer stores over NVLink (default): b200mix_shard_init allocates this device's receive
+ *     block and returns its CUDA IPC handle (B200MIX_SHARD_HANDLE_BYTES); the host gathers the
+ *     handles of all ranks by whatever means it has (MPI, a socket, torch.distributed) and
+ *     passes the rank-ordered array to b200mix_shard_connect.  Each update a rank writes its
+ *     block straight into the receiver's memory and publishes an epoch flag; the receiver sums
+ *     in rank order (bit-reproducible).  A peer that stops answering makes render fail with
+ *     B200MIX_ERR_CUDA after a time-out instead of hanging.
+ *   - NCCL: b200mix_shard_nccl_id (rank 0) creates the ncclUniqueId (128 bytes) the host
+ *     broadcasts; b200mix_shard_nccl joins the communicator; an update is one ncclAllReduce of
+ *     the Wet buffers (when the device has slots) and one ncclReduce of RealOut.  NCCL is
+ *     dlopen()ed (libnccl.so.2): B200MIX_ERR_UNSUPPORTED when it is not installed.
+ * b200mix_render_begin/_end are for hosts that exchange the wet buffers themselves and are
+ * refused on a sharded device.  b200mix_shard_last_us: with b200mix_profile on, the device time
+ * of the last update's two exchanges in microseconds (<0: none). */
+#define B200MIX_SHARD_HANDLE_BYTES 64u
+#define B200MIX_NCCL_ID_BYTES     128u
+B200MIX_API int b200mix_shard_init(b200mix_device *dev, uint32_t rank, uint32_t world, void *handle_out);
+B200MIX_API int b200mix_shard_connect(b200mix_device *dev, const void *handles);
+B200MIX_API int b200mix_shard_nccl_id(void *id_out);
+B200MIX_API int b200mix_shard_nccl(b200mix_device *dev, uint32_t rank, uint32_t world, const void *nccl_id);
+B200MIX_API int b200mix_shard_last_us(b200mix_device *dev, float *wet_us, float *real_us);
+
 /* ---- host-side parameter helpers (no GPU involved) -------------------------- */
 /* The HRTF data set and the per-voice HRIR lookup of the parameter stage:
  * LoadHrtf03 (core/hrtf_loader.cpp:583-721, "MinPHR03" files such as hrtf/Default HRTF.mhr)
@@ -687,6 +722,12 @@ B200MIX_API int b200mix_get_dry(b200mix_device *dev, float *dry);
  * reference's in tests): which = enum b200mix_resampler; returns float count. */
 B200MIX_API int64_t b200mix_get_resampler_table(b200mix_device *dev, uint32_t which,
     float *out, size_t max_floats);
+/* Taps per output sample a voice with this resampler and step costs (BsincPrepare's m,
+ * alc/alu.cpp:140-165; 4 cubic, 2 linear, 1 point) and, in *full (nullable), whether the bsinc
+ * runs with scale interpolation (step > 1.0, Resample_BSinc instead of _FastBSinc) — the terms
+ * of SURVEY §8(d)'s algorithmic flop count.  < 0 on bad arguments. */
+B200MIX_API int b200mix_resampler_taps(b200mix_device *dev, uint32_t resampler, uint32_t step,
+    uint32_t *full);
 /* Kernel timing for roofline reports: when enabled, the voice kernel of every update is
  * bracketed by CUDA events on the device's stream; b200mix_last_mix_kernel_ms returns the
  * duration of the most recent one (synchronises the stream), <0 if unavailable. */

@@ -17,8 +17,11 @@
 
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include "mixer_kernels.cuh"
 #include "effect_kernels.cuh"
+#include "shard_kernels.cuh"
 #include "resampler_tables.hpp"
 #include "hrtf_store.hpp"
 #include "adpcm.hpp"
@@ -52,6 +55,8 @@ struct b200mix_device {
     VoiceRec *d_voices{nullptr};
     BufferRec *d_buffers{nullptr};
     std::vector<BufferRec> h_buffers;
+    std::vector<uint32_t> h_vbuf;                 // static buffer an active voice plays (or NO_SLOT)
+    std::vector<uint32_t> h_bufrefs;              // active static voices per buffer
     float2 *d_hrtf_tgt{nullptr}, *d_hrtf_old{nullptr};
     float *d_dry_cur{nullptr}, *d_dry_tgt{nullptr}, *d_send_cur{nullptr}, *d_send_tgt{nullptr};
     VoiceResult *d_results{nullptr};              // inside d_outblock
@@ -174,6 +179,25 @@ struct b200mix_device {
     uint32_t num_order{0};
     bool order_dirty{true};
 
+    // voice-sharded device set (b200mix_shard_*): transport 0 none, 1 peer stores, 2 NCCL
+    struct Shard {
+        uint32_t rank{0}, world{1}; int transport{0};
+        char *own{nullptr}; size_t bytes{0};
+        char *peer[kShardMaxWorld]{};
+        size_t off_real{0}, off_wet{0}, real_floats{0}, wet_src_floats{0};
+        uint32_t owned_max{0};
+        uint32_t epoch{0};
+        uint32_t *d_counters{nullptr};         // [0] real push, [1] real sum, [2] wet sum, [4..] wet push per owner
+        uint32_t *h_status{nullptr};           // pinned copy of ShardCtl::status
+        cudaEvent_t ev[4]{};                   // wet exchange begin/end, RealOut reduce begin/end
+        bool ev_wet{false}, ev_real{false};
+        // NCCL transport (dlopen'ed: the library carries no link-time NCCL dependency)
+        void *nccl_lib{nullptr}; void *comm{nullptr};
+        int (*reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t){nullptr};
+        int (*allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t){nullptr};
+        int (*comm_destroy)(void*){nullptr};
+    } shard;
+
     uint32_t ir_pad{0};
     uint32_t voice_hi{0};          // 1 + highest voice index ever configured
     // launch geometry (resolved at create)
@@ -277,7 +301,9 @@ const BsincTable *bsinc_for(const b200mix_device *d, uint32_t resampler)
 
 extern "C" {
 
-uint32_t b200mix_version(void) { return (1u<<16) | 0u; }
+static void shard_release(b200mix_device *d);
+
+uint32_t b200mix_version(void) { return (1u<<16) | 1u; }
 
 const char *b200mix_last_error(const b200mix_device *dev)
 { return dev ? dev->error.c_str() : g_create_error.c_str(); }
@@ -293,6 +319,10 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
     if((desc->post_process == B200MIX_POST_UHJ && desc->dry_channels < 3)
         || (desc->post_process == B200MIX_POST_TSME && desc->dry_channels < 4))
     { g_create_error = "UHJ post-process needs W,X,Y dry channels"; return B200MIX_ERR_INVALID; }
+    if((desc->post_process == B200MIX_POST_HRTF || desc->post_process == B200MIX_POST_UHJ
+        || desc->post_process == B200MIX_POST_TSME)
+        && (desc->real_left >= desc->real_channels || desc->real_right >= desc->real_channels))
+    { g_create_error = "real_left/real_right outside RealOut"; return B200MIX_ERR_INVALID; }
 
     auto *d = new(std::nothrow) b200mix_device{};
     if(!d) { g_create_error = "out of host memory"; return B200MIX_ERR_NOMEM; }
@@ -340,6 +370,8 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
         if(int rc = dev_alloc(d, d->d_voices, dd.max_voices)) return rc;
         if(int rc = dev_alloc(d, d->d_buffers, std::max(dd.max_buffers, 1u))) return rc;
         d->h_buffers.assign(std::max(dd.max_buffers, 1u), BufferRec{});
+        d->h_vbuf.assign(dd.max_voices, B200MIX_NO_SLOT);
+        d->h_bufrefs.assign(std::max(dd.max_buffers, 1u), 0u);
         if(dd.ir_size)
         {
             if(int rc = dev_alloc(d, d->d_hrtf_tgt, size_t(dd.max_voices)*d->ir_pad)) return rc;
@@ -447,6 +479,7 @@ void b200mix_destroy(b200mix_device *d)
 {
     if(!d) return;
     if(d->stream) cudaStreamSynchronize(d->stream);
+    shard_release(d);
     for(auto &b : d->h_buffers) if(b.data) cudaFree(const_cast<void*>(b.data));
     for(int i = 0;i < 3;++i) cudaFree(d->d_bsinc[i]);
     for(int i = 0;i < 2;++i) cudaFree(d->d_cubic[i]);
@@ -545,6 +578,8 @@ int b200mix_buffer_data(b200mix_device *d, uint32_t buffer, uint32_t sample_type
     if(bytes < need) { d->error = "buffer_data: short data"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
     BufferRec &h = d->h_buffers[buffer];
+    if(h.data && d->h_bufrefs[buffer])
+    { d->error = "buffer_data: the buffer is attached to an active voice (AL_INVALID_OPERATION)"; return B200MIX_ERR_INVALID; }
     if(h.data)
     {
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
@@ -587,6 +622,8 @@ int b200mix_buffer_free(b200mix_device *d, uint32_t buffer)
     if(!d || buffer >= d->desc.max_buffers) return B200MIX_ERR_INVALID;
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
     BufferRec &h = d->h_buffers[buffer];
+    if(h.data && d->h_bufrefs[buffer])
+    { d->error = "buffer_free: the buffer is attached to an active voice; stop the voice first"; return B200MIX_ERR_INVALID; }
     if(h.data)
     {
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
@@ -989,6 +1026,27 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
         { d->error = "voices_update: voice/buffer/resampler out of range"; return B200MIX_ERR_INVALID; }
         if((p.flags & B200MIX_VF_LOOPING) && p.loop_end <= p.loop_start)
         { d->error = "voices_update: empty loop"; return B200MIX_ERR_INVALID; }
+        // MaxPitch clamp of the parameter stage (alc/alu.cpp:1682-1685,1996-1999): CalculateBufferSize
+        // relies on it
+        if(p.step > (10u << 16))
+        { d->error = "voices_update: step above MaxPitch<<16"; return B200MIX_ERR_INVALID; }
+        if(!(p.flags & B200MIX_VF_STOPPED))
+        {
+            if(p.flags & B200MIX_VF_STATIC)
+            {
+                const BufferRec &hb = d->h_buffers[p.buffer];
+                if(!hb.data || !hb.frames)
+                { d->error = "voices_update: static voice on a buffer without data"; return B200MIX_ERR_INVALID; }
+                if((p.flags & B200MIX_VF_LOOPING) && p.loop_end > hb.frames)
+                { d->error = "voices_update: loop end beyond the buffer"; return B200MIX_ERR_INVALID; }
+            }
+            else if(!d->d_qhdr)
+            {
+                // a streaming voice reads its queue: make sure the (empty) queue table exists
+                if(int rc = dev_alloc(d, d->d_qhdr, dd.max_voices)) return rc;
+                if(int rc = dev_alloc(d, d->d_queue, size_t(dd.max_voices)*kMaxQueue)) return rc;
+            }
+        }
         VoiceUpdate &u = d->h_upd[i];
         u.voice = p.voice; u.flags = p.flags; u.buffer = p.buffer; u.resampler = p.resampler;
         u.position = p.position; u.position_frac = p.position_frac;
@@ -1036,6 +1094,17 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
             d->h_active[p.voice] = act; d->h_cost[p.voice] = cost;
         }
         d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
+        {
+            const uint32_t nb = (!(p.flags & B200MIX_VF_STOPPED) && (p.flags & B200MIX_VF_STATIC))
+                ? p.buffer : B200MIX_NO_SLOT;
+            uint32_t &ob = d->h_vbuf[p.voice];
+            if(ob != nb)
+            {
+                if(ob != B200MIX_NO_SLOT) --d->h_bufrefs[ob];
+                if(nb != B200MIX_NO_SLOT) ++d->h_bufrefs[nb];
+                ob = nb;
+            }
+        }
         if((p.flags & B200MIX_VF_RESET) && !d->h_dfilt.empty() && d->h_dfilt[p.voice])
         { d->h_dfilt[p.voice] = 0; d->order2_dirty = true; }
     }
@@ -1670,6 +1739,18 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
     }
     default: break;
     }
+    stage_mark(d, 8);
+    if(d->profile_level >= 2) d->stage_valid = true;
+    CUDA_TRY(d, cudaGetLastError());
+    return B200MIX_OK;
+}
+
+// The nonlinear output stage (limiter, speaker distance compensation): after the RealOut
+// reduce of a sharded device set, on the root only (alc/alu.cpp:2446-2450).
+static int render_output_stage(b200mix_device *d, uint32_t frames)
+{
+    const b200mix_device_desc &dd = d->desc;
+    if(d->shard.transport && d->shard.rank != 0u) return B200MIX_OK;
     if(d->d_limiter)
     {
         // if(Limiter) Limiter->process(samplesToDo, RealOut.Buffer), alc/alu.cpp:2446
@@ -1684,17 +1765,98 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         k_distance_comp<<<dd.real_channels, 1024, 0, d->stream>>>(DQ);
         ++d->launches;
     }
-    stage_mark(d, 8);
-    if(d->profile_level >= 2) d->stage_valid = true;
     CUDA_TRY(d, cudaGetLastError());
+    return B200MIX_OK;
+}
+
+// ---- voice-sharded device sets: the two exchanges of an update -------------
+// Wet reduce-scatter: every owner ends up with the summed send input of its slots.
+static int shard_wet_exchange(b200mix_device *d)
+{
+    b200mix_device::Shard &S = d->shard;
+    const b200mix_device_desc &dd = d->desc;
+    if(!S.transport || !d->d_wet) return B200MIX_OK;
+    if(d->profile) { cudaEventRecord(S.ev[0], d->stream); }
+    const size_t wetFloats = size_t(dd.max_slots)*dd.wet_channels*kLine;
+    if(S.transport == 2)
+    {
+        if(S.allreduce(d->d_wet, d->d_wet, wetFloats, 7 /*ncclFloat*/, 0 /*ncclSum*/, S.comm, d->stream) != 0)
+        { d->error = "ncclAllReduce of the wet buffers failed"; return B200MIX_ERR_CUDA; }
+    }
+    else
+    {
+        const uint32_t slotFloats = dd.wet_channels*uint32_t(kLine);
+        ShardPushParams P{};
+        P.src = d->d_wet; P.rank = S.rank; P.world = S.world; P.epoch = S.epoch;
+        P.wet = 1u; P.num_slots = dd.max_slots; P.slot_floats = slotFloats; P.owned_max = S.owned_max;
+        P.own = reinterpret_cast<ShardCtl*>(S.own);
+        for(uint32_t r = 0;r < S.world;++r) P.peer[r] = S.peer[r];
+        P.off_data = S.off_wet; P.per_src_floats = S.wet_src_floats;
+        P.counters = S.d_counters + 4;
+        const uint32_t chunks = std::max(1u, std::min(32u, slotFloats*S.owned_max/(4u*256u*4u)));
+        k_shard_push<<<dim3(chunks, S.world), 256, 0, d->stream>>>(P);
+        ShardSumParams Q{};
+        Q.dst = d->d_wet; Q.rank = S.rank; Q.world = S.world; Q.epoch = S.epoch;
+        Q.wet = 1u; Q.num_slots = dd.max_slots; Q.slot_floats = slotFloats; Q.owned_max = S.owned_max;
+        Q.own = P.own; for(uint32_t r = 0;r < S.world;++r) Q.peer[r] = S.peer[r];
+        Q.off_data = S.off_wet; Q.per_src_floats = S.wet_src_floats; Q.counter = S.d_counters + 2;
+        k_shard_sum<<<std::max(1u, std::min(64u, slotFloats*S.owned_max/(4u*256u*2u))), 256, 0, d->stream>>>(Q);
+        d->launches += 2;
+        CUDA_TRY(d, cudaGetLastError());
+    }
+    if(d->profile) { cudaEventRecord(S.ev[1], d->stream); S.ev_wet = true; }
+    return B200MIX_OK;
+}
+
+// RealOut reduce onto rank 0.
+static int shard_real_reduce(b200mix_device *d)
+{
+    b200mix_device::Shard &S = d->shard;
+    const b200mix_device_desc &dd = d->desc;
+    if(!S.transport) return B200MIX_OK;
+    if(d->profile) { cudaEventRecord(S.ev[2], d->stream); }
+    const uint32_t floats = dd.real_channels*uint32_t(kLine);
+    if(S.transport == 2)
+    {
+        if(S.reduce(d->d_real, d->d_real, floats, 7, 0, 0, S.comm, d->stream) != 0)
+        { d->error = "ncclReduce of RealOut failed"; return B200MIX_ERR_CUDA; }
+    }
+    else if(S.rank != 0u)
+    {
+        ShardPushParams P{};
+        P.src = d->d_real; P.rank = S.rank; P.world = S.world; P.epoch = S.epoch; P.floats = floats;
+        P.own = reinterpret_cast<ShardCtl*>(S.own);
+        for(uint32_t r = 0;r < S.world;++r) P.peer[r] = S.peer[r];
+        P.off_data = S.off_real; P.per_src_floats = S.real_floats; P.counters = S.d_counters;
+        k_shard_push<<<dim3(std::max(1u, floats/(4u*256u*2u)), 1), 256, 0, d->stream>>>(P);
+        ++d->launches;
+    }
+    else
+    {
+        ShardSumParams Q{};
+        Q.dst = d->d_real; Q.rank = 0u; Q.world = S.world; Q.epoch = S.epoch; Q.floats = floats;
+        Q.own = reinterpret_cast<ShardCtl*>(S.own);
+        for(uint32_t r = 0;r < S.world;++r) Q.peer[r] = S.peer[r];
+        Q.off_data = S.off_real; Q.per_src_floats = S.real_floats; Q.counter = S.d_counters + 1;
+        k_shard_sum<<<std::max(1u, floats/(4u*256u*2u)), 256, 0, d->stream>>>(Q);
+        ++d->launches;
+    }
+    CUDA_TRY(d, cudaGetLastError());
+    if(d->profile) { cudaEventRecord(S.ev[3], d->stream); S.ev_real = true; }
     return B200MIX_OK;
 }
 
 static int render_launch(b200mix_device *d, uint32_t frames, bool want_results)
 {
     if(d->mid_render) { d->error = "render: a render_begin is pending"; return B200MIX_ERR_INVALID; }
-    if(int rc = render_phase_a(d, frames, want_results, false)) return rc;
-    return render_phase_b(d, frames);
+    const bool sharded = d->shard.transport != 0;
+    if(sharded) ++d->shard.epoch;
+    // a sharded set always finishes its sends: another rank may own the slots they feed
+    if(int rc = render_phase_a(d, frames, want_results, sharded)) return rc;
+    if(sharded) if(int rc = shard_wet_exchange(d)) return rc;
+    if(int rc = render_phase_b(d, frames)) return rc;
+    if(sharded) if(int rc = shard_real_reduce(d)) return rc;
+    return render_output_stage(d, frames);
 }
 
 static int render_collect(b200mix_device *d, uint32_t frames, float *const *real_out,
@@ -1715,8 +1877,13 @@ static int render_collect(b200mix_device *d, uint32_t frames, float *const *real
             CUDA_TRY(d, cudaMemcpyAsync(d->h_results, d->d_results, size_t(nv)*sizeof(VoiceResult),
                 cudaMemcpyDeviceToHost, d->stream));
     }
+    if(d->shard.transport == 1)
+        CUDA_TRY(d, cudaMemcpyAsync(d->shard.h_status, d->shard.own + offsetof(ShardCtl, status),
+            sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     d->stage_busy = false;
+    if(d->shard.transport == 1 && *d->shard.h_status)
+    { d->error = "render: a peer of the sharded device set did not answer in time"; return B200MIX_ERR_CUDA; }
     if(real_out)
         for(uint32_t c = 0;c < dd.real_channels;++c)
             if(real_out[c]) std::memcpy(real_out[c], d->h_real + size_t(c)*kLine, frames*sizeof(float));
@@ -1961,6 +2128,8 @@ int b200mix_render_begin(b200mix_device *d, uint32_t frames, float **wet_dev, si
 {
     if(!d) return B200MIX_ERR_INVALID;
     if(d->mid_render) { d->error = "render_begin: already begun"; return B200MIX_ERR_INVALID; }
+    if(d->shard.transport)
+    { d->error = "render_begin: a sharded device set exchanges its wet buffers itself — use b200mix_render"; return B200MIX_ERR_INVALID; }
     if(int rc = render_phase_a(d, frames, true, true)) return rc;
     d->mid_render = true; d->mid_frames = frames;
     if(wet_dev) *wet_dev = d->d_wet;
@@ -1975,6 +2144,7 @@ int b200mix_render_end(b200mix_device *d, float *const *real_out, b200mix_voice_
     if(!d->mid_render) { d->error = "render_end: no render_begin pending"; return B200MIX_ERR_INVALID; }
     d->mid_render = false;
     if(int rc = render_phase_b(d, d->mid_frames)) return rc;
+    if(int rc = render_output_stage(d, d->mid_frames)) return rc;
     if(real_out_dev) *real_out_dev = d->d_real;
     if(!real_out && !results) return B200MIX_OK;
     return render_collect(d, d->mid_frames, real_out, results);
@@ -1985,6 +2155,145 @@ int b200mix_render_device(b200mix_device *d, uint32_t frames, const float **real
     if(!d) return B200MIX_ERR_INVALID;
     if(int rc = render_launch(d, frames, false)) return rc;
     if(real_out_dev) *real_out_dev = d->d_real;
+    return B200MIX_OK;
+}
+
+// ---- voice-sharded device sets ---------------------------------------------------------
+static void shard_release(b200mix_device *d)
+{
+    b200mix_device::Shard &S = d->shard;
+    if(S.transport == 1)
+        for(uint32_t r = 0;r < S.world;++r)
+            if(r != S.rank && S.peer[r]) cudaIpcCloseMemHandle(S.peer[r]);
+    if(S.comm && S.comm_destroy) S.comm_destroy(S.comm);
+    if(S.nccl_lib) dlclose(S.nccl_lib);
+    cudaFree(S.own); cudaFree(S.d_counters);
+    if(S.h_status) cudaFreeHost(S.h_status);
+    for(cudaEvent_t e : S.ev) if(e) cudaEventDestroy(e);
+    S = b200mix_device::Shard{};
+}
+
+static int shard_common(b200mix_device *d, uint32_t rank, uint32_t world)
+{
+    if(world < 1u || world > kShardMaxWorld || rank >= world)
+    { d->error = "shard: rank/world out of range (world <= 16)"; return B200MIX_ERR_INVALID; }
+    if(d->mid_render) { d->error = "shard: a render_begin is pending"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    shard_release(d);
+    d->shard.rank = rank; d->shard.world = world;
+    for(cudaEvent_t &e : d->shard.ev) CUDA_TRY(d, cudaEventCreate(&e));
+    return B200MIX_OK;
+}
+
+int b200mix_shard_init(b200mix_device *d, uint32_t rank, uint32_t world, void *handle_out)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(!handle_out) { d->error = "shard_init: null handle"; return B200MIX_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200MIX_SHARD_HANDLE_BYTES, "IPC handle size");
+    if(int rc = shard_common(d, rank, world)) return rc;
+    b200mix_device::Shard &S = d->shard;
+    const b200mix_device_desc &dd = d->desc;
+    S.real_floats = size_t(std::max(dd.real_channels, 1u))*kLine;
+    S.owned_max = dd.max_slots ? (dd.max_slots + world - 1u)/world : 0u;
+    S.wet_src_floats = size_t(S.owned_max)*dd.wet_channels*kLine;
+    S.off_real = sizeof(ShardCtl);
+    S.off_wet = S.off_real + size_t(2)*world*S.real_floats*sizeof(float);
+    S.bytes = S.off_wet + size_t(2)*world*S.wet_src_floats*sizeof(float);
+    CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&S.own), S.bytes));
+    CUDA_TRY(d, cudaMemset(S.own, 0, S.bytes));
+    if(int rc = dev_alloc(d, S.d_counters, 4 + kShardMaxWorld)) return rc;
+    CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&S.h_status), sizeof(uint32_t)));
+    *S.h_status = 0u;
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(d, cudaIpcGetMemHandle(&h, S.own));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return B200MIX_OK;
+}
+
+int b200mix_shard_connect(b200mix_device *d, const void *handles)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    b200mix_device::Shard &S = d->shard;
+    if(!handles || !S.own || S.transport)
+    { d->error = "shard_connect: call b200mix_shard_init first (once)"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    for(uint32_t r = 0;r < S.world;++r)
+    {
+        if(r == S.rank) { S.peer[r] = S.own; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + size_t(r)*sizeof(h), sizeof(h));
+        void *p = nullptr;
+        CUDA_TRY(d, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        S.peer[r] = static_cast<char*>(p);
+    }
+    S.transport = 1; S.epoch = 0;
+    return B200MIX_OK;
+}
+
+namespace { struct NcclId { char internal[128]; }; }
+
+static void *nccl_open(std::string &err)
+{
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if(!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if(!lib) err = std::string("NCCL not found: ") + dlerror();
+    return lib;
+}
+
+int b200mix_shard_nccl_id(void *id_out)
+{
+    if(!id_out) return B200MIX_ERR_INVALID;
+    std::string err;
+    void *lib = nccl_open(err);
+    if(!lib) { g_create_error = err; return B200MIX_ERR_UNSUPPORTED; }
+    auto get = reinterpret_cast<int(*)(NcclId*)>(dlsym(lib, "ncclGetUniqueId"));
+    NcclId id{};
+    const int rc = get ? get(&id) : 1;
+    if(rc == 0) std::memcpy(id_out, &id, sizeof(id));
+    dlclose(lib);
+    return rc == 0 ? B200MIX_OK : B200MIX_ERR_CUDA;
+}
+
+int b200mix_shard_nccl(b200mix_device *d, uint32_t rank, uint32_t world, const void *nccl_id)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(!nccl_id) { d->error = "shard_nccl: null id"; return B200MIX_ERR_INVALID; }
+    if(int rc = shard_common(d, rank, world)) return rc;
+    b200mix_device::Shard &S = d->shard;
+    S.nccl_lib = nccl_open(d->error);
+    if(!S.nccl_lib) return B200MIX_ERR_UNSUPPORTED;
+    auto init = reinterpret_cast<int(*)(void**, int, NcclId, int)>(dlsym(S.nccl_lib, "ncclCommInitRank"));
+    S.reduce = reinterpret_cast<decltype(S.reduce)>(dlsym(S.nccl_lib, "ncclReduce"));
+    S.allreduce = reinterpret_cast<decltype(S.allreduce)>(dlsym(S.nccl_lib, "ncclAllReduce"));
+    S.comm_destroy = reinterpret_cast<decltype(S.comm_destroy)>(dlsym(S.nccl_lib, "ncclCommDestroy"));
+    if(!init || !S.reduce || !S.allreduce || !S.comm_destroy)
+    { d->error = "shard_nccl: NCCL symbols missing"; return B200MIX_ERR_UNSUPPORTED; }
+    NcclId id; std::memcpy(&id, nccl_id, sizeof(id));
+    if(init(&S.comm, int(world), id, int(rank)) != 0)
+    { d->error = "ncclCommInitRank failed"; S.comm = nullptr; return B200MIX_ERR_CUDA; }
+    S.transport = 2; S.epoch = 0;
+    return B200MIX_OK;
+}
+
+int b200mix_shard_last_us(b200mix_device *d, float *wet_us, float *real_us)
+{
+    if(!d || !d->shard.transport) return B200MIX_ERR_INVALID;
+    b200mix_device::Shard &S = d->shard;
+    float ms = 0.0f;
+    if(wet_us)
+    {
+        *wet_us = -1.0f;
+        if(S.ev_wet && cudaEventSynchronize(S.ev[1]) == cudaSuccess
+            && cudaEventElapsedTime(&ms, S.ev[0], S.ev[1]) == cudaSuccess) *wet_us = ms*1000.0f;
+    }
+    if(real_us)
+    {
+        *real_us = -1.0f;
+        if(S.ev_real && cudaEventSynchronize(S.ev[3]) == cudaSuccess
+            && cudaEventElapsedTime(&ms, S.ev[2], S.ev[3]) == cudaSuccess) *real_us = ms*1000.0f;
+    }
     return B200MIX_OK;
 }
 
@@ -2018,6 +2327,22 @@ int64_t b200mix_get_resampler_table(b200mix_device *d, uint32_t which, float *ou
             != cudaSuccess) return -1;
     }
     return int64_t(n);
+}
+
+// Taps per output sample the resampler of a voice with this step runs (BsincPrepare's m for
+// the bsinc family, alc/alu.cpp:140-165; 4 for the cubic family, 2 linear, 1 point; 0 for the
+// pitch-1.0 copy) and whether it is the full BSinc form (scale interpolation, mixer_c.cpp:84-105).
+int b200mix_resampler_taps(b200mix_device *d, uint32_t resampler, uint32_t step, uint32_t *full)
+{
+    if(!d || resampler > B200MIX_RESAMPLER_BSINC48) return B200MIX_ERR_INVALID;
+    if(full) *full = 0u;
+    if(const BsincTable *t = bsinc_for(d, resampler))
+    {
+        const BsincState st = PrepareBsinc(*t, step);
+        if(full) *full = (step > 65536u && (resampler & 1u)) ? 1u : 0u;
+        return int(st.m);
+    }
+    return resampler >= 2u ? 4 : (resampler == 1u ? 2 : 1);
 }
 
 int b200mix_profile(b200mix_device *d, int enable)

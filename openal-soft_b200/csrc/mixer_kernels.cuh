@@ -470,6 +470,9 @@ k_mix_voices(const MixParams P)
             uint32_t srcDelay = 0;
             bool silent = false;
             bool packedWin = false;        // the window currently holds the two 16-bit copies
+            // defence in depth (the host rejects steps above MaxPitch): a chunk that cannot
+            // produce any output would never end this loop
+            if(dstn == 0u) { dstn = n - loaded; silent = true; }
             if(intPos < 0)
             {
                 srcDelay = uint32_t(-intPos);

@@ -1,11 +1,17 @@
-"""Voice sharding across ranks and the single per-update collective.
+"""Voice sharding across ranks — launcher-side plumbing only.
 
-Voices are independent until they `+=` into the device mix buffers, and the
-post-process (HRTF decoder / B-Format decode) is linear, so every rank mixes its own
-voices all the way to RealOut and ONE sum-reduce of the [real_channels][1024] block
-per update combines them.  This module holds the rank arithmetic and the collective
-so the same code runs under NCCL (bench.py, GPUs) and gloo (CPU tests)."""
+The exchange itself lives in the library (include/b200mix.h, "voice-sharded device sets"):
+b200mix_render reduce-scatters the slots' Wet buffers and reduces RealOut onto rank 0 on the
+device's own stream.  What is left for the host is (1) dealing voices and slots over the ranks
+and (2) carrying 64-byte CUDA IPC handles (or the 128-byte NCCL id) between the processes
+once at start-up.  A C++ host does (2) with whatever it has (MPI, a socket); the Python
+launchers here (bench.py, tools/) use a torch.distributed group."""
 from __future__ import annotations
+
+import ctypes as C
+
+HANDLE_BYTES = 64       # B200MIX_SHARD_HANDLE_BYTES
+NCCL_ID_BYTES = 128     # B200MIX_NCCL_ID_BYTES
 
 
 def shard_range(total_voices: int, world: int, rank: int) -> tuple[int, int]:
@@ -23,25 +29,44 @@ def owner_of(voice: int, total_voices: int, world: int) -> int:
     return rem + (voice - cut) // max(base, 1)
 
 
-def reduce_real_out(block, dst: int = 0):
-    """Sum-reduces one rank-local RealOut block (a torch tensor, CUDA for NCCL or CPU
-    for gloo) onto rank `dst`; in place.  A no-op for world size 1."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(block, dst=dst, op=dist.ReduceOp.SUM)
-    return block
-
-
 def slot_owner(slot: int, world: int) -> int:
-    """Effect slots are independent of each other: slot s runs on rank s mod G."""
+    """The library's ownership rule: slot s is processed by rank s mod world, which is the
+    rank that installs its effect and receives the summed send input."""
     return slot % world
 
 
-def allreduce_wet(wet):
-    """Sums the slots' Wet buffers of all ranks in place (torch tensor viewing the device's
-    wet storage between b200mix_render_begin and b200mix_render_end): effects consume the
-    summed send input.  Under NCCL call it with the mixer's stream current."""
+def owned_slots(num_slots: int, world: int, rank: int) -> list[int]:
+    return list(range(rank, num_slots, world))
+
+
+def connect(lib, dev, rank: int, world: int, transport: str = "p2p", group=None) -> None:
+    """Joins device `dev` (a b200mix_device*) of ctypes library `lib` to the sharded set.
+    transport "p2p": b200mix_shard_init -> all-gather of the IPC handles over `group` ->
+    b200mix_shard_connect.  transport "nccl": rank 0's b200mix_shard_nccl_id is broadcast,
+    then b200mix_shard_nccl.  `group` is a torch.distributed group whose backend can move
+    Python objects from host memory (gloo); None = the default group."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(wet, op=dist.ReduceOp.SUM)
-    return wet
+
+    def ck(rc, what):
+        if rc != 0:
+            lib.b200mix_last_error.restype = C.c_char_p
+            lib.b200mix_last_error.argtypes = [C.c_void_p]
+            raise RuntimeError(f"{what} failed ({rc}): {(lib.b200mix_last_error(dev) or b'').decode()}")
+
+    if transport == "p2p":
+        buf = C.create_string_buffer(HANDLE_BYTES)
+        ck(lib.b200mix_shard_init(dev, rank, world, buf), "b200mix_shard_init")
+        blobs = [None] * world
+        dist.all_gather_object(blobs, buf.raw, group=group)
+        assert all(len(b) == HANDLE_BYTES for b in blobs)
+        ck(lib.b200mix_shard_connect(dev, b"".join(blobs)), "b200mix_shard_connect")
+    elif transport == "nccl":
+        box = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(NCCL_ID_BYTES)
+            ck(lib.b200mix_shard_nccl_id(buf), "b200mix_shard_nccl_id")
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=0, group=group)
+        ck(lib.b200mix_shard_nccl(dev, rank, world, box[0]), "b200mix_shard_nccl")
+    else:
+        raise ValueError(transport)

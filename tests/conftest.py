@@ -25,6 +25,9 @@ def _has_gpu():
 def pytest_collection_modifyitems(config, items):
     from helpers import refal
     have_ref = refal.available()
+    have_gpu = _has_gpu()
     for item in items:
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device here (runs on the B200 box)"))
         if "ref" in item.keywords and not have_ref:
             item.add_marker(pytest.mark.skip(reason="oracle/_ref not built"))

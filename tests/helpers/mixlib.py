@@ -76,6 +76,17 @@ class MixLib:
         self.render_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
         self.get_dry = f("get_dry")
         self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
+        if prefix == "b200mix_":          # sharded device sets exist on the product only
+            self.shard_init = f("shard_init")
+            self.shard_init.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+            self.shard_connect = f("shard_connect")
+            self.shard_connect.argtypes = [C.c_void_p, C.c_void_p]
+            self.shard_nccl_id = f("shard_nccl_id")
+            self.shard_nccl_id.argtypes = [C.c_void_p]
+            self.shard_nccl = f("shard_nccl")
+            self.shard_nccl.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+            self.shard_last_us = f("shard_last_us")
+            self.shard_last_us.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
 
 
 class MixDevice:
@@ -259,6 +270,24 @@ class MixDevice:
         rc = self.m.render_end(self.h, ptrs, None, None)
         assert rc == 0, f"render_end -> {rc}"
         return out
+
+    def shard_init(self, rank, world):
+        """Returns this device's 64-byte IPC handle (peer-store transport)."""
+        buf = C.create_string_buffer(64)
+        rc = self.m.shard_init(self.h, rank, world, buf)
+        assert rc == 0, f"shard_init -> {rc}: {self.last_error()}"
+        return buf.raw
+
+    def shard_connect(self, handles):
+        blob = b"".join(handles)
+        rc = self.m.shard_connect(self.h, blob)
+        assert rc == 0, f"shard_connect -> {rc}: {self.last_error()}"
+
+    def last_error(self):
+        fn = getattr(self.m.lib, self.m.prefix + "last_error")
+        fn.restype = C.c_char_p
+        fn.argtypes = [C.c_void_p]
+        return (fn(self.h) or b"").decode()
 
     def dry(self):
         out = np.zeros((self.desc.dry_channels, abi.LINE), dtype=np.float32)

@@ -1,7 +1,9 @@
 """The N>1 path on CPU: world_size-2 gloo.  Each rank mixes its shard of the voices
-(with the CPU oracle standing in for the device mixer — the host-side sharding and the
-collective are what is under test) and the reduced RealOut must equal the single-process
-mix of all voices."""
+(with the CPU oracle standing in for the device mixer — the host-side dealing of voices and
+slots is what is under test; gloo stands in for the library's own exchange, which is tested
+on hardware in test_gpu_shard.py) and the reduced RealOut must equal the single-process mix of
+all voices.  The handle exchange of pyb200mix.shard.connect runs here against a recording
+stand-in for the library."""
 import os
 import socket
 import sys
@@ -15,6 +17,20 @@ import torch.multiprocessing as mp
 from pyb200mix import shard
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def reduce_real_out(block, dst=0):
+    """gloo stand-in for the library's RealOut reduce (b200mix_render on a sharded set)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(block, dst=dst, op=dist.ReduceOp.SUM)
+    return block
+
+
+def allreduce_wet(wet):
+    """gloo stand-in for the library's wet exchange: every owner sees the summed send input."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(wet, op=dist.ReduceOp.SUM)
+    return wet
 
 
 def test_shard_ranges_partition_the_voices():
@@ -57,7 +73,7 @@ def _worker(rank, world, port, total, updates, ret):
     first, count = shard.shard_range(total, world, rank)
     out = _mix(list(range(first, first + count)), total, updates)
     block = torch.from_numpy(out.copy())
-    shard.reduce_real_out(block, dst=0)
+    reduce_real_out(block, dst=0)
     if rank == 0:
         ret.put(block.numpy())
     dist.barrier()
@@ -121,7 +137,7 @@ def _mix_slots(voices, total, updates, rank, world):
     for _ in range(updates):
         ptr, cnt = dev.render_begin()
         wet = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(cnt,))
-        shard.allreduce_wet(torch.from_numpy(wet))        # in place on the oracle's storage
+        allreduce_wet(torch.from_numpy(wet))        # in place on the oracle's storage
         outs.append(dev.render_end())
     dev.close()
     return np.stack(outs)
@@ -134,7 +150,7 @@ def _slot_worker(rank, world, port, total, updates, ret):
     first, count = shard.shard_range(total, world, rank)
     out = _mix_slots(list(range(first, first + count)), total, updates, rank, world)
     block = torch.from_numpy(out.copy())
-    shard.reduce_real_out(block, dst=0)
+    reduce_real_out(block, dst=0)
     if rank == 0:
         ret.put(block.numpy())
     dist.barrier()
@@ -160,3 +176,75 @@ def test_two_rank_slot_ownership_equals_single_process_mix():
     scale = float(np.abs(single).max())
     assert scale > 1e-3
     assert np.abs(reduced - single).max() <= 5e-6 * max(scale, 1.0)
+
+
+# ---- pyb200mix.shard.connect: the start-up exchange, against a recording stand-in -----------
+class _FakeLib:
+    """Records the b200mix_shard_* calls connect() makes (no GPU here)."""
+
+    def __init__(self, rank):
+        self.rank, self.calls = rank, []
+
+    def b200mix_shard_init(self, dev, rank, world, buf):
+        buf.raw = bytes([0x40 + rank]) * 64
+        self.calls.append(("init", rank, world))
+        return 0
+
+    def b200mix_shard_connect(self, dev, blob):
+        self.calls.append(("connect", bytes(blob)))
+        return 0
+
+    def b200mix_shard_nccl_id(self, buf):
+        buf.raw = bytes(range(128))
+        self.calls.append(("nccl_id",))
+        return 0
+
+    def b200mix_shard_nccl(self, dev, rank, world, ident):
+        self.calls.append(("nccl", rank, world, bytes(ident)))
+        return 0
+
+
+def _connect_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _FakeLib(rank)
+    shard.connect(lib, None, rank, world, "p2p")
+    shard.connect(lib, None, rank, world, "nccl")
+    ret.put((rank, lib.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_connect_gathers_handles_in_rank_order_and_broadcasts_the_nccl_id():
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_connect_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    want_blob = bytes([0x40]) * 64 + bytes([0x41]) * 64
+    for r in range(world):
+        calls = got[r]
+        assert calls[0] == ("init", r, world)
+        assert calls[1] == ("connect", want_blob)          # every rank sees the rank-ordered table
+        assert calls[-1] == ("nccl", r, world, bytes(range(128)))
+    assert ("nccl_id",) in got[0] and ("nccl_id",) not in got[1]
+
+
+def test_slot_ownership_rule():
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            mine = shard.owned_slots(13, world, r)
+            assert all(shard.slot_owner(s, world) == r for s in mine)
+            seen += mine
+        assert sorted(seen) == list(range(13))
