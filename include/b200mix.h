@@ -711,6 +711,45 @@ B200MIX_API int b200mix_hrtf_build_decoder(const b200mix_hrtf *hrtf, uint32_t am
  * non-HRTF voices in the same call ignore their dirs row.  The data set's ir_size must not
  * exceed the device's. */
 B200MIX_API int b200mix_hrtf_attach(b200mix_device *dev, const b200mix_hrtf *hrtf);
+/* The whole parameter stage of point sources on the GPU: CalcVoiceParams ->
+ * CalcAttnVoiceParams + CalcPanningAndFilters (alc/alu.cpp:1512-1657,1712-2010).  The host sends,
+ * for every source the application touched, its PROPERTIES (b200mix_source_props, what
+ * alSourcefv set — the same struct b200mix_calc_voice takes), the listener and the device's mix
+ * maps; a kernel computes per source what b200mix_calc_voice computes on a host core — listener
+ * transform, distance model, cones, air absorption, send decay, doppler -> step and
+ * BsincPrepare, spread, the HRIR direction (then blended from the attached data set exactly as
+ * b200mix_voices_update_dirs does) or the dry pan gains, the send gains, and the high-/low-shelf
+ * pair of every path with BiquadInterpFilter::setParams' rule — and writes the voice records
+ * directly.  What stays with the host is what the AL layer decides: which voice plays the
+ * source, its buffer / queue, start offset, loop points, resampler and send slots
+ * (b200mix_source_voice; flags as in b200mix_voice_params — the HRTF flag is set by the
+ * library from env->render_mode).  env->dry / env->wet[] point at HOST arrays (copied).
+ * Requires b200mix_hrtf_attach when env->render_mode == 2.  The arithmetic is the same source
+ * text as the host helpers' (csrc/param_math.hpp) compiled without FMA contraction, libm calls in
+ * double rounded once: voices come out bit-identical to b200mix_calc_voice's except where the host
+ * libm is not correctly rounded (<= 1 ulp). */
+typedef struct b200mix_source_voice {
+    uint32_t voice;           /* index in the device voice array */
+    uint32_t flags;           /* B200MIX_VF_* (HRTF is decided by the library) */
+    uint32_t buffer;          /* buffer id (static sources) */
+    uint32_t resampler;       /* enum b200mix_resampler */
+    int32_t  position;        /* mPosition      (RESET only) */
+    uint32_t position_frac;   /* mPositionFrac  (RESET only) */
+    uint32_t loop_start, loop_end;
+    uint32_t buffer_rate;     /* BufferStorage::mSampleRate (the step is pitch * buffer_rate / device_rate) */
+    uint32_t send_slot[B200MIX_MAX_SENDS];
+} b200mix_source_voice;
+B200MIX_API int b200mix_sources_update(b200mix_device *dev, uint32_t n, const b200mix_source_voice *voices,
+    const b200mix_source_props *props, const b200mix_listener_params *listener,
+    const b200mix_voice_env *env);
+/* Reads back what the parameter stage left in a voice's record (tests): step, the BsincPrepare
+ * state {sf, m, l, offset as float bits}, HRTF target gain and delays, dry target gains
+ * [dry_channels], send target gains [num_sends][wet_channels], and the filter targets of every
+ * path [1 + num_sends] x {active, lowpass[5], highpass[5]} (11 floats, active as 0/1).  Any
+ * pointer may be NULL. */
+B200MIX_API int b200mix_get_voice_targets(b200mix_device *dev, uint32_t voice, uint32_t *step,
+    float bsinc[4], float *hrtf_gain, uint32_t hrtf_delay[2], float *hrtf_coeffs, float *dry_gains,
+    float *send_gains, float *filters);
 B200MIX_API int b200mix_voices_update_dirs(b200mix_device *dev, uint32_t n,
     const b200mix_voice_params *params, const float *dirs, const float *dry_gains,
     const float *send_gains);

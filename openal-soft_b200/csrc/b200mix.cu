@@ -22,6 +22,7 @@
 #include "mixer_kernels.cuh"
 #include "effect_kernels.cuh"
 #include "shard_kernels.cuh"
+#include "param_kernels.hpp"
 #include "resampler_tables.hpp"
 #include "hrtf_store.hpp"
 #include "adpcm.hpp"
@@ -179,6 +180,11 @@ struct b200mix_device {
     uint32_t num_order{0};
     bool order_dirty{true};
 
+    // GPU parameter stage (b200mix_sources_update): pinned input staging + device scratch
+    char *h_src{nullptr}, *d_src{nullptr}; uint32_t src_cap{0};
+    cudaEvent_t src_done{nullptr}; bool src_busy{false};
+    bool dev_filters{false};                 // filter activity is decided on the device: order2 = order
+
     // voice-sharded device set (b200mix_shard_*): transport 0 none, 1 peer stores, 2 NCCL
     struct Shard {
         uint32_t rank{0}, world{1}; int transport{0};
@@ -302,6 +308,7 @@ const BsincTable *bsinc_for(const b200mix_device *d, uint32_t resampler)
 extern "C" {
 
 static void shard_release(b200mix_device *d);
+static int ensure_filters(b200mix_device *d);
 
 uint32_t b200mix_version(void) { return (1u<<16) | 1u; }
 
@@ -508,6 +515,9 @@ void b200mix_destroy(b200mix_device *d)
     if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
     cudaFreeHost(d->h_arena); cudaFree(d->d_arena);
+    if(d->h_src) cudaFreeHost(d->h_src);
+    cudaFree(d->d_src);
+    if(d->src_done) cudaEventDestroy(d->src_done);
     if(d->stage_done) cudaEventDestroy(d->stage_done);
     if(d->ev_mix0) cudaEventDestroy(d->ev_mix0);
     if(d->ev_mix1) cudaEventDestroy(d->ev_mix1);
@@ -706,7 +716,7 @@ int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_chann
     if(int rc = alloc(r.head, size_t(ir_channels)*kConvBlock)) return rc;
     if(int rc = alloc(r.inbuf, kConvFft)) return rc;
     if(int rc = alloc(r.ov, size_t(ir_channels)*kConvFft)) return rc;
-    if(int rc = alloc(r.yspec, size_t(ir_channels)*kConvMaxBlocks*kConvFft)) return rc;
+    if(int rc = alloc(r.yspec, size_t(ir_channels)*kConvMaxChunks*kConvMaxBlocks*kConvFft)) return rc;
     if(int rc = alloc(r.lines, size_t(ir_channels)*kLine)) return rc;
     if(int rc = alloc(r.gains, size_t(2)*ir_channels*32)) return rc;
     if(int rc = alloc(r.gtgt, size_t(ir_channels)*32)) return rc;
@@ -1145,6 +1155,247 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
     return B200MIX_OK;
 }
 
+// Could any path of this source need a filter?  (All of these leave GainHF == GainLF == 1 exactly
+// when false, alc/alu.cpp:1854-1961 — a cheap scan so that scenes without filters never allocate
+// or run the filter stage.)
+static bool source_may_filter(const b200mix_source_props &P, uint32_t num_sends)
+{
+    if(P.direct.gain_hf != 1.0f || P.direct.gain_lf != 1.0f || P.air_absorption_factor != 0.0f) return true;
+    if(P.inner_angle < 360.0f && (P.outer_gain_hf != 1.0f)) return true;
+    for(uint32_t s = 0;s < num_sends;++s)
+        if(P.sends[s].gain_hf != 1.0f || P.sends[s].gain_lf != 1.0f
+            || (P.sends[s].active && P.sends[s].slot_air_absorption_gain_hf < 1.0f)) return true;
+    return false;
+}
+
+int b200mix_sources_update(b200mix_device *d, uint32_t n, const b200mix_source_voice *voices,
+    const b200mix_source_props *props, const b200mix_listener_params *listener, const b200mix_voice_env *env)
+{
+    if(!d) return B200MIX_ERR_INVALID;
+    if(n == 0) return B200MIX_OK;
+    const b200mix_device_desc &dd = d->desc;
+    if(!voices || !props || !listener || !env || env->struct_size != sizeof(*env)
+        || listener->struct_size != sizeof(*listener) || env->render_mode > 2u
+        || env->num_sends != dd.num_sends || !env->device_rate || listener->distance_model > 6u)
+    { d->error = "sources_update: bad arguments (env->num_sends must equal the device's)"; return B200MIX_ERR_INVALID; }
+    if(env->render_mode == 2u && (!dd.ir_size || !d->d_st_coeffs))
+    { d->error = "sources_update: HRTF rendering needs an HRTF device and b200mix_hrtf_attach"; return B200MIX_ERR_INVALID; }
+    if(env->render_mode != 2u && (env->dry.channels != dd.dry_channels || !env->dry.scale || !env->dry.index))
+    { d->error = "sources_update: env->dry must describe the device's Dry mix"; return B200MIX_ERR_INVALID; }
+    if(dd.num_sends && (env->wet_stride != dd.wet_channels))
+    { d->error = "sources_update: env->wet_stride must equal the device's wet_channels"; return B200MIX_ERR_INVALID; }
+    for(uint32_t s = 0;s < dd.num_sends;++s)
+        if(env->wet[s].channels > dd.wet_channels || (env->wet[s].channels && (!env->wet[s].scale || !env->wet[s].index)))
+        { d->error = "sources_update: bad wet map"; return B200MIX_ERR_INVALID; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+
+    bool mayFilter = d->d_filt != nullptr;
+    const bool hrtfMode = env->render_mode == 2u;
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const b200mix_source_voice &p = voices[i];
+        const b200mix_source_props &P = props[i];
+        if(P.struct_size != sizeof(P) || P.distance_model > 6u)
+        { d->error = "sources_update: bad source props"; return B200MIX_ERR_INVALID; }
+        if(p.voice >= dd.max_voices || p.resampler > B200MIX_RESAMPLER_BSINC48
+            || (!(p.flags & B200MIX_VF_STOPPED) && p.buffer >= dd.max_buffers))
+        { d->error = "sources_update: voice/buffer/resampler out of range"; return B200MIX_ERR_INVALID; }
+        if((p.flags & B200MIX_VF_LOOPING) && p.loop_end <= p.loop_start)
+        { d->error = "sources_update: empty loop"; return B200MIX_ERR_INVALID; }
+        if(!(p.flags & B200MIX_VF_STOPPED))
+        {
+            if(p.flags & B200MIX_VF_STATIC)
+            {
+                const BufferRec &hb = d->h_buffers[p.buffer];
+                if(!hb.data || !hb.frames)
+                { d->error = "sources_update: static voice on a buffer without data"; return B200MIX_ERR_INVALID; }
+                if((p.flags & B200MIX_VF_LOOPING) && p.loop_end > hb.frames)
+                { d->error = "sources_update: loop end beyond the buffer"; return B200MIX_ERR_INVALID; }
+            }
+            else if(!d->d_qhdr)
+            {
+                if(int rc = dev_alloc(d, d->d_qhdr, dd.max_voices)) return rc;
+                if(int rc = dev_alloc(d, d->d_queue, size_t(dd.max_voices)*kMaxQueue)) return rc;
+            }
+        }
+        for(uint32_t s = 0;s < dd.num_sends;++s)
+            if(p.send_slot[s] != B200MIX_NO_SLOT && p.send_slot[s] >= dd.max_slots)
+            { d->error = "sources_update: send slot out of range"; return B200MIX_ERR_INVALID; }
+        if(!mayFilter && source_may_filter(P, dd.num_sends)) mayFilter = true;
+    }
+    if(mayFilter)
+    {
+        if(int rc = ensure_filters(d)) return rc;
+        if(!d->dev_filters) { d->dev_filters = true; d->order2_dirty = true; }
+    }
+    // host mirrors (as b200mix_voices_update keeps them); the step is not known here: the cost
+    // key of the mixing order takes the resampler's widest filter
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const b200mix_source_voice &p = voices[i];
+        const bool stopped = (p.flags & B200MIX_VF_STOPPED) != 0;
+        if(!d->h_send_slot.empty())
+            for(uint32_t s2 = 0;s2 < B200MIX_MAX_SENDS;++s2)
+            {
+                uint32_t &m = d->h_send_slot[size_t(p.voice)*B200MIX_MAX_SENDS + s2];
+                const uint32_t nv2 = (stopped || s2 >= dd.num_sends) ? B200MIX_NO_SLOT : p.send_slot[s2];
+                if(m != nv2) { m = nv2; d->sends_dirty = true; }
+            }
+        if(!hrtfMode && !stopped)
+        {
+            d->dry_active = true;
+            if(d->mix_cdr == 0)
+                if(int rc = ensure_dry_park(d)) return rc;
+        }
+        const uint8_t hv = hrtfMode ? 1 : 0;
+        if(d->h_hrtf[p.voice] != hv) { d->h_hrtf[p.voice] = hv; d->dry_entries_dirty = true; }
+        const uint8_t act = stopped ? 0 : 1;
+        uint32_t cost = p.resampler >= 2u ? 4u : 2u;
+        if(const BsincTable *t = bsinc_for(d, p.resampler)) cost = t->m[0];
+        if(d->h_active[p.voice] != act || (!d->h_cost[p.voice] && act)) { d->order_dirty = true; d->h_cost[p.voice] = cost; }
+        d->h_active[p.voice] = act;
+        d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
+        const uint32_t nb = (!stopped && (p.flags & B200MIX_VF_STATIC)) ? p.buffer : B200MIX_NO_SLOT;
+        uint32_t &ob = d->h_vbuf[p.voice];
+        if(ob != nb)
+        {
+            if(ob != B200MIX_NO_SLOT) --d->h_bufrefs[ob];
+            if(nb != B200MIX_NO_SLOT) ++d->h_bufrefs[nb];
+            ob = nb;
+        }
+    }
+
+    // staging: [voices n][props n] in, [VoiceUpdate n][dirs n][dry][send][hf/lf][FilterUpdate] scratch
+    const uint32_t paths = 1u + dd.num_sends;
+    const size_t inBytes = align16(size_t(n)*sizeof(b200mix_source_voice)) + align16(size_t(n)*sizeof(b200mix_source_props));
+    if(d->src_busy) { CUDA_TRY(d, cudaEventSynchronize(d->src_done)); d->src_busy = false; }
+    if(n > d->src_cap)
+    {
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        if(d->h_src) cudaFreeHost(d->h_src);
+        cudaFree(d->d_src); d->h_src = nullptr; d->d_src = nullptr;
+        const uint32_t cap = std::max(n, 2u*d->src_cap);
+        const size_t in = align16(size_t(cap)*sizeof(b200mix_source_voice)) + align16(size_t(cap)*sizeof(b200mix_source_props));
+        const size_t out = align16(size_t(cap)*sizeof(VoiceUpdate)) + align16(size_t(cap)*16)
+            + align16(size_t(cap)*std::max(dd.dry_channels, 1u)*4) + align16(size_t(cap)*std::max(dd.num_sends*dd.wet_channels, 1u)*4)
+            + align16(size_t(cap)*(1u + B200MIX_MAX_SENDS)*8) + align16(size_t(cap)*paths*sizeof(FilterUpdate));
+        CUDA_TRY(d, cudaMallocHost(reinterpret_cast<void**>(&d->h_src), in));
+        CUDA_TRY(d, cudaMalloc(reinterpret_cast<void**>(&d->d_src), in + out + 64));
+        if(!d->src_done) CUDA_TRY(d, cudaEventCreateWithFlags(&d->src_done, cudaEventDisableTiming));
+        d->src_cap = cap;
+    }
+    std::memcpy(d->h_src, voices, size_t(n)*sizeof(b200mix_source_voice));
+    const size_t offProps = align16(size_t(n)*sizeof(b200mix_source_voice));
+    std::memcpy(d->h_src + offProps, props, size_t(n)*sizeof(b200mix_source_props));
+    CUDA_TRY(d, cudaMemcpyAsync(d->d_src, d->h_src, inBytes, cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaEventRecord(d->src_done, d->stream));
+    d->src_busy = true;
+
+    CalcVoicesParams Q{};
+    Q.voices = reinterpret_cast<const b200mix_source_voice*>(d->d_src);
+    Q.props = reinterpret_cast<const b200mix_source_props*>(d->d_src + offProps);
+    Q.n = n; Q.listener = *listener;
+    Q.device_rate = env->device_rate; Q.num_sends = dd.num_sends; Q.render_mode = env->render_mode;
+    Q.cd = dd.dry_channels; Q.cw = dd.wet_channels; Q.ir = dd.ir_size;
+    if(!hrtfMode)
+    {
+        Q.dry_channels = env->dry.channels;
+        for(uint32_t c = 0;c < env->dry.channels;++c) { Q.dry_scale[c] = env->dry.scale[c]; Q.dry_index[c] = env->dry.index[c]; }
+    }
+    for(uint32_t s = 0;s < dd.num_sends;++s)
+    {
+        Q.wet_channels[s] = env->wet[s].channels;
+        for(uint32_t c = 0;c < env->wet[s].channels;++c) { Q.wet_scale[s][c] = env->wet[s].scale[c]; Q.wet_index[s][c] = env->wet[s].index[c]; }
+    }
+    for(int t = 0;t < 3;++t)
+    {
+        Q.bsinc[t].scaleBase = d->bsinc[t].scaleBase; Q.bsinc[t].scaleRange = d->bsinc[t].scaleRange;
+        for(unsigned k = 0;k < kBsincScales;++k) { Q.bsinc[t].m[k] = d->bsinc[t].m[k]; Q.bsinc[t].filterOffset[k] = d->bsinc[t].filterOffset[k]; }
+    }
+    size_t off = inBytes;
+    auto carve = [&](size_t bytes) { char *p = d->d_src + off; off += align16(bytes); return p; };
+    Q.updates = reinterpret_cast<VoiceUpdate*>(carve(size_t(n)*sizeof(VoiceUpdate)));
+    Q.dirs = reinterpret_cast<float4*>(carve(size_t(n)*16));
+    Q.dry = reinterpret_cast<float*>(carve(size_t(n)*std::max(dd.dry_channels, 1u)*4));
+    Q.send = (dd.num_sends && dd.wet_channels)
+        ? reinterpret_cast<float*>(carve(size_t(n)*dd.num_sends*dd.wet_channels*4)) : nullptr;
+    Q.gains_hflf = reinterpret_cast<float*>(carve(size_t(n)*(1u + B200MIX_MAX_SENDS)*8));
+    Q.fupd = reinterpret_cast<FilterUpdate*>(carve(size_t(n)*paths*sizeof(FilterUpdate)));
+    const bool filters = d->d_filt != nullptr;
+    CUDA_TRY(d, launch_calc_voices(Q, filters, d->stream));
+    d->launches += filters ? 2 : 1;
+
+    ApplyParams A{};
+    A.voices = d->d_voices; A.updates = Q.updates;
+    if(hrtfMode)
+    {
+        A.dirs = Q.dirs;
+        A.st_fields = d->d_st_fields; A.st_elevs = d->d_st_elevs; A.st_coeffs = d->d_st_coeffs;
+        A.st_delays = d->d_st_delays; A.st_num_fields = d->st_num_fields; A.st_ir = d->st_ir;
+    }
+    else A.dry = Q.dry;
+    A.send = Q.send;
+    A.hrtf_tgt = d->d_hrtf_tgt; A.hrtf_old = d->d_hrtf_old;
+    A.dry_cur = d->d_dry_cur; A.dry_tgt = d->d_dry_tgt;
+    A.send_cur = d->d_send_cur; A.send_tgt = d->d_send_tgt;
+    A.ir = dd.ir_size; A.ir_pad = d->ir_pad; A.cd = dd.dry_channels; A.cw = dd.wet_channels;
+    A.num_sends = dd.num_sends;
+    A.filt = d->d_filt; A.filt_paths = paths;
+    A.qhdr = d->d_qhdr;
+    k_apply_updates<<<n, 64, 0, d->stream>>>(A);
+    ++d->launches;
+    if(filters)
+    {
+        k_apply_filter_updates<<<(2u*n*paths + 127u)/128u, 128, 0, d->stream>>>(d->d_filt, paths, Q.fupd, n*paths);
+        ++d->launches;
+    }
+    CUDA_TRY(d, cudaGetLastError());
+    return B200MIX_OK;
+}
+
+int b200mix_get_voice_targets(b200mix_device *d, uint32_t voice, uint32_t *step, float bsinc[4],
+    float *hrtf_gain, uint32_t hrtf_delay[2], float *hrtf_coeffs, float *dry_gains, float *send_gains,
+    float *filters)
+{
+    if(!d || voice >= d->desc.max_voices) return B200MIX_ERR_INVALID;
+    const b200mix_device_desc &dd = d->desc;
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    VoiceRec rec;
+    CUDA_TRY(d, cudaMemcpy(&rec, d->d_voices + voice, offsetof(VoiceRec, prev), cudaMemcpyDeviceToHost));
+    if(step) *step = rec.step;
+    if(bsinc)
+    {
+        bsinc[0] = rec.bsinc_sf;
+        std::memcpy(&bsinc[1], &rec.bsinc_m, 4); std::memcpy(&bsinc[2], &rec.bsinc_l, 4);
+        std::memcpy(&bsinc[3], &rec.bsinc_off, 4);
+    }
+    if(hrtf_gain) *hrtf_gain = rec.tgt_gain;
+    if(hrtf_delay) { hrtf_delay[0] = rec.tgt_delay0; hrtf_delay[1] = rec.tgt_delay1; }
+    if(hrtf_coeffs && d->d_hrtf_tgt)
+        CUDA_TRY(d, cudaMemcpy(hrtf_coeffs, d->d_hrtf_tgt + size_t(voice)*d->ir_pad, size_t(dd.ir_size)*8, cudaMemcpyDeviceToHost));
+    if(dry_gains && dd.dry_channels)
+        CUDA_TRY(d, cudaMemcpy(dry_gains, d->d_dry_tgt + size_t(voice)*dd.dry_channels, size_t(dd.dry_channels)*4, cudaMemcpyDeviceToHost));
+    if(send_gains && d->d_send_tgt)
+        CUDA_TRY(d, cudaMemcpy(send_gains, d->d_send_tgt + size_t(voice)*dd.num_sends*dd.wet_channels,
+            size_t(dd.num_sends)*dd.wet_channels*4, cudaMemcpyDeviceToHost));
+    if(filters)
+    {
+        const uint32_t paths = 1u + dd.num_sends;
+        for(uint32_t pth = 0;pth < paths;++pth)
+        {
+            float *o = filters + size_t(pth)*11;
+            for(int k = 0;k < 11;++k) o[k] = k == 1 ? 1.0f : (k == 6 ? 1.0f : 0.0f);
+            if(!d->d_filt) continue;
+            FilterRec fr;
+            CUDA_TRY(d, cudaMemcpy(&fr, d->d_filt + size_t(voice)*paths + pth, sizeof(fr), cudaMemcpyDeviceToHost));
+            o[0] = fr.active ? 1.0f : 0.0f;
+            for(int k = 0;k < 5;++k) { o[1+k] = fr.tgt[0][k]; o[6+k] = fr.tgt[1][k]; }
+        }
+    }
+    return B200MIX_OK;
+}
+
 int b200mix_voice_queue(b200mix_device *d, uint32_t voice, uint32_t count, const uint32_t *buffers,
     uint32_t loop_index)
 {
@@ -1176,6 +1427,29 @@ int b200mix_voice_queue(b200mix_device *d, uint32_t voice, uint32_t count, const
     return B200MIX_OK;
 }
 
+// Filter state of every voice path (allocated by the first filter a host or the GPU parameter
+// stage sets; a device that never sees one pays nothing).
+static int ensure_filters(b200mix_device *d)
+{
+    if(d->d_filt) return B200MIX_OK;
+    const b200mix_device_desc &dd = d->desc;
+    const uint32_t paths = 1u + dd.num_sends;
+    const size_t count = size_t(dd.max_voices)*paths;
+    if(int rc = dev_alloc(d, d->d_filt, count, false)) return rc;
+    k_filter_init<<<unsigned((count*32u + 255u)/256u), 256, 0, d->stream>>>(d->d_filt, count);
+    ++d->launches;
+    CUDA_TRY(d, cudaGetLastError());
+    CUDA_TRY(d, cudaEventCreateWithFlags(&d->fstage_done, cudaEventDisableTiming));
+    if(!d->d_xscratch)
+        if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
+    if(!d->d_sendinfo)
+        if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
+    if(int rc = dev_alloc(d, d->d_dline, size_t(dd.max_voices)*kLine)) return rc;
+    if(int rc = dev_alloc(d, d->d_order2, dd.max_voices)) return rc;
+    d->h_dfilt.assign(dd.max_voices, 0);
+    return B200MIX_OK;
+}
+
 int b200mix_voices_filters(b200mix_device *d, uint32_t n, const b200mix_voice_filter *filters)
 {
     static_assert(sizeof(FilterUpdate) == sizeof(b200mix_voice_filter), "FilterUpdate mirrors the ABI struct");
@@ -1188,22 +1462,7 @@ int b200mix_voices_filters(b200mix_device *d, uint32_t n, const b200mix_voice_fi
         if(filters[i].voice >= dd.max_voices || filters[i].path >= paths)
         { d->error = "voices_filters: voice/path out of range"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
-    if(!d->d_filt)
-    {
-        const size_t count = size_t(dd.max_voices)*paths;
-        if(int rc = dev_alloc(d, d->d_filt, count, false)) return rc;
-        k_filter_init<<<unsigned((count*32u + 255u)/256u), 256, 0, d->stream>>>(d->d_filt, count);
-        ++d->launches;
-        CUDA_TRY(d, cudaGetLastError());
-        CUDA_TRY(d, cudaEventCreateWithFlags(&d->fstage_done, cudaEventDisableTiming));
-        if(!d->d_xscratch)
-            if(int rc = dev_alloc(d, d->d_xscratch, size_t(dd.max_voices)*kLine)) return rc;
-        if(!d->d_sendinfo)
-            if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
-        if(int rc = dev_alloc(d, d->d_dline, size_t(dd.max_voices)*kLine)) return rc;
-        if(int rc = dev_alloc(d, d->d_order2, dd.max_voices)) return rc;
-        d->h_dfilt.assign(dd.max_voices, 0);
-    }
+    if(int rc = ensure_filters(d)) return rc;
     for(uint32_t i = 0;i < n;++i)
         if(filters[i].path == 0)
         {
@@ -1234,49 +1493,6 @@ int b200mix_voices_filters(b200mix_device *d, uint32_t n, const b200mix_voice_fi
     CUDA_TRY(d, cudaGetLastError());
     CUDA_TRY(d, cudaEventRecord(d->fstage_done, d->stream));
     d->fstage_busy = true;
-    return B200MIX_OK;
-}
-
-// BiquadFilter::SetParams behind setParamsFromSlope (core/filters/biquad.h:61-62,92-97;
-// biquad.cpp:48-129).  Host arithmetic only.
-int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5])
-{
-    if(type > 5u || !coeffs || !(slope > 0.0f)) return B200MIX_ERR_INVALID;
-    gain = std::max(gain, 0.001f);
-    const float rcpQ = std::sqrt((gain + 1.0f/gain)*(1.0f/slope - 1.0f) + 2.0f);
-    gain = std::max(gain, 0.00001f);
-    const float w0 = 3.14159265358979323846f*2.0f * std::min(f0norm, 0.49f);
-    const float sin_w0 = std::sin(w0), cos_w0 = std::cos(w0);
-    const float alpha = sin_w0/2.0f * rcpQ;
-    float a[3] = {1.0f, 0.0f, 0.0f}, b[3] = {1.0f, 0.0f, 0.0f};
-    const float gp = gain + 1.0f, gm = gain - 1.0f;
-    if(type <= 1u)
-    {
-        // shelves: the low shelf is the high shelf with cos(w0) negated
-        const float sg = 2.0f * std::sqrt(gain) * alpha;
-        const float sgn = type == 0u ? 1.0f : -1.0f;
-        const float cw = sgn*cos_w0;
-        b[0] =            gain*(gp + gm*cw + sg);
-        b[1] = sgn*-2.0f*gain*(gm + gp*cw);
-        b[2] =            gain*(gp + gm*cw - sg);
-        a[0] =                  gp - gm*cw + sg;
-        a[1] = sgn*2.0f*       (gm - gp*cw);
-        a[2] =                  gp - gm*cw - sg;
-    }
-    else if(type == 2u)
-    {
-        b[0] = 1.0f + alpha*gain; b[1] = -2.0f*cos_w0; b[2] = 1.0f - alpha*gain;
-        a[0] = 1.0f + alpha/gain; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha/gain;
-    }
-    else
-    {
-        a[0] = 1.0f + alpha; a[1] = -2.0f*cos_w0; a[2] = 1.0f - alpha;
-        if(type == 3u) { b[0] = (1.0f - cos_w0)/2.0f; b[1] = 1.0f - cos_w0; b[2] = b[0]; }
-        else if(type == 4u) { b[0] = (1.0f + cos_w0)/2.0f; b[1] = -(1.0f + cos_w0); b[2] = b[0]; }
-        else { b[0] = alpha; b[1] = 0.0f; b[2] = -alpha; }
-    }
-    coeffs[0] = b[0]/a[0]; coeffs[1] = b[1]/a[0]; coeffs[2] = b[2]/a[0];
-    coeffs[3] = a[1]/a[0]; coeffs[4] = a[2]/a[0];
     return B200MIX_OK;
 }
 
@@ -1330,7 +1546,9 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     if(d->d_filt && d->order2_dirty)
     {
         d->h_order2.clear();
-        for(uint32_t v : d->h_order) if(d->h_dfilt[v]) d->h_order2.push_back(v);
+        // with the GPU parameter stage the host does not know which direct filters are active:
+        // the second pass then looks at every voice's kSiDeferred bit
+        for(uint32_t v : d->h_order) if(d->dev_filters || d->h_dfilt[v]) d->h_order2.push_back(v);
         d->num_order2 = uint32_t(d->h_order2.size());
         if(d->num_order2)
         {
@@ -1580,8 +1798,18 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         ConvParams CP{};
         CP.slots = d->d_slots; CP.wet = d->d_wet; CP.twiddle = d->d_twiddle;
         CP.frames = frames; CP.cw = dd.wet_channels; CP.num_slots = dd.max_slots;
-        uint32_t maxch = 1;
-        for(const SlotRec &sr : d->h_slots) if(sr.type) maxch = std::max(maxch, sr.channels);
+        uint32_t maxch = 1, convWork = 0, convSegs = 0;
+        for(const SlotRec &sr : d->h_slots)
+        {
+            if(sr.type) maxch = std::max(maxch, sr.channels);
+            if(sr.type == B200MIX_EFFECT_CONVOLUTION) { convWork += sr.channels; convSegs = std::max(convSegs, sr.segs); }
+        }
+        // segment chunks of k_conv_mac: ~3 CTAs per SM over all convolution slot-channels, at
+        // least 16 segments per chunk
+        CP.chunks = 1u;
+        if(convWork)
+            CP.chunks = std::max(1u, std::min(std::min(uint32_t(kConvMaxChunks), (convSegs + 15u)/16u),
+                (3u*uint32_t(d->num_sms) + convWork - 1u)/convWork));
         if(d->reverb_slots)
         {
             // ReverbState::process's pipeline state machine (reverb.cpp:1840-1878), host side
@@ -1643,10 +1871,11 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
             }
             CP.stage = st; SP.stage = st;
             k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
-            k_conv_mac<<<dim3(dd.max_slots, maxch), 512, 0, d->stream>>>(CP);
+            k_conv_mac<<<dim3(dd.max_slots, maxch, CP.chunks), 512, 0, d->stream>>>(CP);
+            k_conv_ifft<<<dim3(dd.max_slots, maxch, kConvMaxBlocks), 128, 0, d->stream>>>(CP);
             k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
             k_slot_output_mix<<<dim3((frames + 127)/128, dd.dry_channels), 128, 0, d->stream>>>(SP);
-            d->launches += 4;
+            d->launches += 5;
             if(d->any_target)
             {
                 k_slot_target_mix<<<dim3((frames + 127)/128, dd.max_slots), 128, 0, d->stream>>>(SP);

@@ -24,6 +24,7 @@ namespace b200mix {
 constexpr int kConvBlock = 128;     // ConvolveUpdateSamples
 constexpr int kConvFft = 256;       // ConvolveUpdateSize
 constexpr int kConvMaxBlocks = 9;   // blocks that can complete in one 1024-frame update
+constexpr int kConvMaxChunks = 24;  // segment-range chunks of k_conv_mac (gridDim.z), partials in yspec
 
 struct SlotRec {
     uint32_t type, channels, frames, segs;     // segs = mNumConvolveSegs
@@ -37,7 +38,7 @@ struct SlotRec {
     float *head;      // [channels][128]        first 128 IR taps
     float *inbuf;     // [256]                  mInput
     float *ov;        // [channels][256]        mOutput
-    float *yspec;     // [channels][kConvMaxBlocks][256]
+    float *yspec;     // [channels][kConvMaxChunks][kConvMaxBlocks][256] partial sums per segment chunk
     float *lines;     // [channels][1024]       this update's output lines
     float *gains;     // [2][channels][32]      ping-pong Current gains
     float *gtgt;      // [channels][32]         Target gains
@@ -513,7 +514,12 @@ __device__ __forceinline__ void fft256_inplace(float2 *data, const float2 *__res
 struct ConvParams {
     SlotRec *slots; const float *wet; const float2 *twiddle;
     uint32_t frames, cw, num_slots, stage;
+    uint32_t chunks;                  // gridDim.z of k_conv_mac
 };
+
+// segment range of chunk z of `chunks` over `segs` segments; zcnt = chunks that are not empty
+__device__ __forceinline__ uint32_t conv_chunk_len(uint32_t segs, uint32_t chunks)
+{ return (segs + chunks - 1u)/chunks; }
 
 // grid = slots, 128 threads
 __global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
@@ -584,7 +590,11 @@ __global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
     }
 }
 
-// grid (slots, channels), 512 threads = 4 segment ranges x 128 packed bins.  A thread keeps the
+// grid (slots, channels, segment chunks), 512 threads = 4 segment ranges x 128 packed bins.  The
+// filter spectra are the one HBM-bound stream of the effects stage (2 s IR: 767 KB per slot and
+// channel, plus as much input-spectrum history): the chunks spread one slot's stream over many
+// SMs (16 slots x 24 chunks = 384 CTAs), every chunk leaves its partial sums in yspec and
+// k_conv_output adds them in chunk order (deterministic).  A thread keeps the
 // accumulators of ALL blocks completed this update (<= 9) and walks its range of filter
 // segments once: X[(cur0 - b + s)] is a sliding window over the spectrum ring, so each
 // iteration loads ONE new input spectrum bin and ONE filter bin for up to 9 complex MACs.
@@ -600,8 +610,12 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
     if(nb == 0) return;
     const int t = threadIdx.x & 127, grp = threadIdx.x >> 7;
     const uint32_t segs = S.segs, cur0 = S.cur_last, ring = segs + kConvMaxBlocks;
-    const uint32_t per = (segs + 3u)/4u;
-    const uint32_t s0 = uint32_t(grp)*per, s1 = (s0 + per < segs) ? s0 + per : segs;
+    const uint32_t clen = conv_chunk_len(segs, gridDim.z);
+    const uint32_t z0 = blockIdx.z*clen;
+    if(z0 >= segs) return;                                   // empty chunk (short IR)
+    const uint32_t z1 = (z0 + clen < segs) ? z0 + clen : segs;
+    const uint32_t per = (z1 - z0 + 3u)/4u;
+    const uint32_t s0 = min(z0 + uint32_t(grp)*per, z1), s1 = (s0 + per < z1) ? s0 + per : z1;
     const float2 *__restrict__ X = reinterpret_cast<const float2*>(S.X) + t;
     const float2 *__restrict__ H = reinterpret_cast<const float2*>(S.H + size_t(blockIdx.y)*segs*kConvFft) + t;
     float2 acc[NB], xw[NB];          // xw[s mod NB] holds X[(cur0 + s) mod ring]
@@ -631,7 +645,9 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
         {
             const uint32_t s = sb + uint32_t(u);
             const bool ok = s >= s0 && s < s1;
-            xn[u] = ok ? X[size_t((cur0 + s) % ring)*128] : make_float2(0.f, 0.f);
+            uint32_t q = cur0 + s;                 // cur0 < ring, s < segs < ring
+            q = q >= ring ? q - ring : q;
+            xn[u] = ok ? X[size_t(q)*128] : make_float2(0.f, 0.f);
             hn[u] = ok ? H[size_t(s)*128] : make_float2(0.f, 0.f);
         }
         #pragma unroll
@@ -668,7 +684,8 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
     __syncthreads();
     if(grp == 0)
     {
-        float2 *Y = reinterpret_cast<float2*>(S.yspec + size_t(blockIdx.y)*kConvMaxBlocks*kConvFft) + t;
+        float2 *Y = reinterpret_cast<float2*>(S.yspec
+            + (size_t(blockIdx.y)*kConvMaxChunks + blockIdx.z)*kConvMaxBlocks*kConvFft) + t;
         #pragma unroll
         for(int b = 0;b < NB;++b)
         {
@@ -680,56 +697,77 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
     }
 }
 
-// grid (slots, channels), 128 threads
-__global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
+// grid (slots, channels, blocks), 128 threads: the accumulated spectrum of one completed block
+// (sum of the segment chunks' partials, in chunk order) through the inverse FFT; the 256
+// time-domain samples replace chunk 0's partial of that block in yspec.
+__global__ void __launch_bounds__(128) k_conv_ifft(const ConvParams Q)
 {
     __shared__ float2 fbuf[kConvFft];
-    __shared__ float first[kConvBlock], tail[kConvBlock];
+    __shared__ float2 ysp[kConvBlock];
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 1u || S.stage != Q.stage || blockIdx.y >= S.channels || blockIdx.z >= S.nb_last) return;
+    const int t = threadIdx.x;
+    const uint32_t c = blockIdx.y, b = blockIdx.z;
+    const uint32_t clen = conv_chunk_len(S.segs, Q.chunks);
+    const uint32_t zcnt = (S.segs + clen - 1u)/clen;
+    float2 ysum = make_float2(0.f, 0.f);
+    for(uint32_t z = 0;z < zcnt;++z)
+    {
+        const float2 a = reinterpret_cast<const float2*>(S.yspec
+            + ((size_t(c)*kConvMaxChunks + z)*kConvMaxBlocks + b)*kConvFft)[t];
+        ysum.x += a.x; ysum.y += a.y;
+    }
+    ysp[t] = ysum;
+    __syncthreads();
+    // inverse FFT: ifft(x) = conj(fft(conj(x)))
+    const float2 y0 = ysp[0];
+    for(int k = t;k < kConvFft;k += 128)
+    {
+        float2 v;
+        if(k == 0) v = make_float2(y0.x, 0.0f);
+        else if(k == 128) v = make_float2(y0.y, 0.0f);
+        else if(k < 128) { const float2 a = ysp[k]; v = make_float2(a.x, -a.y); }       // conj(x_k)
+        else { const float2 a = ysp[256-k]; v = make_float2(a.x, a.y); }                // conj(conj(x_{N-k}))
+        fbuf[bitrev8(uint32_t(k))] = v;
+    }
+    __syncthreads();
+    fft256_inplace(fbuf, Q.twiddle, t);
+    float *yt = S.yspec + ((size_t(c)*kConvMaxChunks + 0u)*kConvMaxBlocks + b)*kConvFft;
+    yt[t] = fbuf[t].x; yt[kConvBlock + t] = fbuf[kConvBlock + t].x;
+}
+
+// grid (slots, channels), 128 threads: overlap-add of the blocks' time-domain outputs
+// (convolution.cpp:699-706) into the slot's output lines.
+__global__ void __launch_bounds__(128) k_conv_output(const ConvParams Q)
+{
     SlotRec &S = Q.slots[blockIdx.x];
     if(S.type != 1u || S.stage != Q.stage || blockIdx.y >= S.channels) return;
     const int t = threadIdx.x;
     const uint32_t c = blockIdx.y, n = Q.frames, nb = S.nb_last, f = S.f_last;
     float *ov = S.ov + size_t(c)*kConvFft;
     float *line = S.lines + size_t(c)*kLine;
-    first[t] = ov[t]; tail[t] = ov[kConvBlock + t];
-    __syncthreads();
-    // samples of the block that was in progress when the update started
+    float first = ov[t], tail = ov[kConvBlock + t];
+    // every thread owns sample t of each 128-sample block: no exchange between threads.
+    // samples of the block that was in progress when the update started: line[i] += mOutput[f + i]
     {
         const uint32_t cnt = (kConvBlock - f < n) ? kConvBlock - f : n;
-        if(uint32_t(t) < cnt) line[t] += first[f + t];
+        if(uint32_t(t) >= f && uint32_t(t) - f < cnt) line[uint32_t(t) - f] += first;
     }
     for(uint32_t b = 0;b < nb;++b)
     {
-        // inverse FFT of the accumulated spectrum: ifft(x) = conj(fft(conj(x)))
-        const float2 *Y = reinterpret_cast<const float2*>(S.yspec + (size_t(c)*kConvMaxBlocks + b)*kConvFft);
-        const float2 y0 = Y[0];
-        __syncthreads();
-        for(int k = t;k < kConvFft;k += 128)
-        {
-            float2 v;
-            if(k == 0) v = make_float2(y0.x, 0.0f);
-            else if(k == 128) v = make_float2(y0.y, 0.0f);
-            else if(k < 128) { const float2 a = Y[k]; v = make_float2(a.x, -a.y); }       // conj(x_k)
-            else { const float2 a = Y[256-k]; v = make_float2(a.x, a.y); }                // conj(conj(x_{N-k}))
-            fbuf[bitrev8(uint32_t(k))] = v;
-        }
-        __syncthreads();
-        fft256_inplace(fbuf, Q.twiddle, t);
+        const float *yt = S.yspec + ((size_t(c)*kConvMaxChunks + 0u)*kConvMaxBlocks + b)*kConvFft;
         // O_b = y[0..128) + previous tail ; new tail = y[128..256)   (convolution.cpp:702-706)
-        const float o = fbuf[t].x + tail[t];
-        const float tl = fbuf[kConvBlock + t].x;
-        __syncthreads();
-        first[t] = o; tail[t] = tl;
-        __syncthreads();
+        first = yt[t] + tail;
+        tail = yt[kConvBlock + t];
         // the samples following this block boundary
         const uint32_t base = (b+1u)*kConvBlock - f;       // output index of the block start
         if(base < n)
         {
             const uint32_t cnt = (n - base < uint32_t(kConvBlock)) ? n - base : uint32_t(kConvBlock);
-            if(uint32_t(t) < cnt) line[base + t] += first[t];
+            if(uint32_t(t) < cnt) line[base + t] += first;
         }
     }
-    ov[t] = first[t]; ov[kConvBlock + t] = tail[t];
+    ov[t] = first; ov[kConvBlock + t] = tail;
 }
 
 // Dry[o][i] += sum over slots/lines of line[i]*gain(i): MixSamples(Counter = samplesToDo)

@@ -17,6 +17,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "voice_structs.hpp"
+
 namespace b200mix {
 
 constexpr int kLine = 1024;          // BufferLineSize
@@ -26,7 +28,6 @@ constexpr int kEdge = 24;            // MaxResamplerEdge
 constexpr int kPad = 48;             // MaxResamplerPadding
 constexpr int kResBuf = kLine + 256 + kPad;   // DeviceBase::mResampleData (core/device.h:282)
 constexpr int kSrcSizeMax = kResBuf - kEdge;
-constexpr int kMaxSends = 6;
 constexpr int kAccumLen = kLine + kHrirLen;   // HrtfAccumData (core/device.h:288)
 constexpr float kSilence = 0.00001f;          // GainSilenceThreshold
 constexpr float kEps = 1.1920929e-07f;
@@ -55,14 +56,6 @@ struct alignas(16) VoiceRec {
     float hist[kHist];         // Hrtf.History
 };
 
-struct alignas(16) VoiceUpdate {   // staged by b200mix_voices_update
-    uint32_t voice, flags, buffer, resampler;
-    int32_t  position; uint32_t position_frac, loop_start, loop_end;
-    uint32_t step; float bsinc_sf; uint32_t bsinc_m, bsinc_l;
-    uint32_t bsinc_off, delay0, delay1; float gain;
-    uint32_t send_slot[kMaxSends]; uint32_t has_coeffs, has_dry;
-};
-
 struct VoiceResult { int32_t position; uint32_t position_frac, flags, buffers_done; };
 
 // Device-resident BiquadInterpFilter pair of one voice path (core/voice.h:50-53,70-73;
@@ -76,10 +69,6 @@ struct alignas(16) FilterRec {
     uint32_t pad[5];
 };
 static_assert(sizeof(FilterRec) == 128, "FilterRec layout");
-
-struct FilterUpdate {      // == b200mix_voice_filter
-    uint32_t voice, path, active; float lp[5], hp[5];
-};
 
 struct MixParams {
     VoiceRec *voices; const BufferRec *buffers;

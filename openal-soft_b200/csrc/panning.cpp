@@ -9,52 +9,14 @@
 #include <algorithm>
 #include <cmath>
 
+#include "param_math.hpp"
+
 namespace {
-
-// real N3D spherical harmonics up to fourth order, ACN order, ambisonic axes (x front, y left, z up)
-void sh_n3d(const float y, const float z, const float x, float c[B200MIX_MAX_AMBI_CHANNELS])
-{
-    const float xx = x*x, yy = y*y, zz = z*z;
-    const float xy = x*y, yz = y*z, xz = x*z;
-    const float x4 = xx*xx, y4 = yy*yy, x2y2 = xx*yy, z4 = zz*zz;
-    constexpr float kSqrt3 = 1.7320508075688772935f;       // std::numbers::sqrt3_v<float>
-    constexpr float kSqrt15 = 3.872983346e+00f, kSqrt5h = 1.118033989e+00f, kSqrt15h = 1.936491673e+00f;
-    constexpr float k3a = 2.091650066e+00f, k3b = 1.024695076e+01f, k3c = 1.620185175e+00f;
-    constexpr float k3d = 1.322875656e+00f, k3e = 5.123475383e+00f;
-    constexpr float k4a = 8.874119675e+00f, k4b = 6.274950199e+00f, k4c = 3.354101966e+00f;
-    constexpr float k4d = 2.371708245e+00f, k4e = 3.750000000e-01f, k4f = 1.677050983e+00f;
-    constexpr float k4g = 2.218529919e+00f;
-
-    c[0] = 1.0f;
-    c[1] = kSqrt3 * y;
-    c[2] = kSqrt3 * z;
-    c[3] = kSqrt3 * x;
-
-    c[4] = kSqrt15 * xy;
-    c[5] = kSqrt15 * yz;
-    c[6] = kSqrt5h * (3.0f*zz - 1.0f);
-    c[7] = kSqrt15 * xz;
-    c[8] = kSqrt15h * (xx - yy);
-
-    c[9] = k3a * (y*(3.0f*xx - yy));
-    c[10] = k3b * (z*xy);
-    c[11] = k3c * (y*(5.0f*zz - 1.0f));
-    c[12] = k3d * (z*(5.0f*zz - 3.0f));
-    c[13] = k3c * (x*(5.0f*zz - 1.0f));
-    c[14] = k3e * (z*(xx - yy));
-    c[15] = k3a * (x*(xx - 3.0f*yy));
-
-    c[16] = k4a * (xy*(xx - yy));
-    c[17] = k4b * ((3.0f*xx - yy) * yz);
-    c[18] = k4c * (xy * (7.0f*zz - 1.0f));
-    c[19] = k4d * (yz * (7.0f*zz - 3.0f));
-    c[20] = k4e * (35.0f*z4 - 30.0f*zz + 3.0f);
-    c[21] = k4d * (xz * (7.0f*zz - 3.0f));
-    c[22] = k4f * ((xx - yy) * (7.0f*zz - 1.0f));
-    c[23] = k4b * ((xx - 3.0f*yy) * xz);
-    c[24] = k4g * (x4 - 6.0f*x2y2 + y4);
-}
-
+struct HostMath {
+    static float sqrt(float x) { return std::sqrt(x); }
+    static float sin(float x) { return std::sin(x); }
+    static float cos(float x) { return std::cos(x); }
+};
 } // namespace
 
 extern "C" {
@@ -62,25 +24,7 @@ extern "C" {
 int b200mix_ambi_coeffs(const float dir[3], float spread, float coeffs[B200MIX_MAX_AMBI_CHANNELS])
 {
     if(!dir || !coeffs) return B200MIX_ERR_INVALID;
-    // OpenAL to ambisonic axes: Y = -x, Z = y, X = -z (core/mixer.h:68-73)
-    sh_n3d(-dir[0], dir[1], -dir[2], coeffs);
-    if(spread > 0.0f)
-    {
-        // a spherical cap subtending `spread`, loudness-compensated zonal weights per order and
-        // up to +3 dB for a full spread (core/mixer.cpp:21-88)
-        const float ca = std::cos(spread * 0.5f);
-        const float scale = std::sqrt(1.0f + 0.318309886183790671538f*0.5f*spread);   // inv_pi_v<float>
-        const float caca = ca*ca;
-        const float zh[5] = {
-            scale,
-            scale * 0.5f * (ca+1.0f),
-            scale * 0.5f * ((ca+1.0f)*ca),
-            scale * 0.125f * ((ca+1.0f)*(5.0f*caca - 1.0f)),
-            scale * 0.125f * ((ca+1.0f)*(7.0f*caca - 3.0f)*ca)};
-        static const unsigned char order_of[B200MIX_MAX_AMBI_CHANNELS] = {
-            0, 1,1,1, 2,2,2,2,2, 3,3,3,3,3,3,3, 4,4,4,4,4,4,4,4,4};
-        for(unsigned i = 0;i < B200MIX_MAX_AMBI_CHANNELS;++i) coeffs[i] *= zh[order_of[i]];
-    }
+    b200mix::pm::ambi_coeffs<HostMath>(dir, spread, coeffs);
     return B200MIX_OK;
 }
 
@@ -88,12 +32,16 @@ int b200mix_pan_gains(uint32_t channels, const float *scale, const uint32_t *ind
     const float coeffs[B200MIX_MAX_AMBI_CHANNELS], float ingain, float *gains, uint32_t gains_len)
 {
     if(!scale || !index || !coeffs || !gains || channels > gains_len) return B200MIX_ERR_INVALID;
-    for(uint32_t c = 0;c < channels;++c)
-    {
-        if(index[c] >= B200MIX_MAX_AMBI_CHANNELS) return B200MIX_ERR_INVALID;
-        gains[c] = scale[c] * coeffs[index[c]] * ingain;
-    }
-    for(uint32_t c = channels;c < gains_len;++c) gains[c] = 0.0f;
+    return b200mix::pm::pan_gains(channels, scale, index, coeffs, ingain, gains, gains_len)
+        ? B200MIX_OK : B200MIX_ERR_INVALID;
+}
+
+// BiquadFilter::SetParams behind setParamsFromSlope (core/filters/biquad.h:61-62,92-97;
+// biquad.cpp:48-129).  Host arithmetic only.
+int b200mix_biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5])
+{
+    if(type > 5u || !coeffs || !(slope > 0.0f)) return B200MIX_ERR_INVALID;
+    b200mix::pm::biquad_coeffs<HostMath>(type, f0norm, gain, slope, coeffs);
     return B200MIX_OK;
 }
 

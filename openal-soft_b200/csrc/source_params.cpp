@@ -14,64 +14,38 @@
 #include <thread>
 #include <vector>
 
+#include "param_math.hpp"
+
 namespace {
 
-constexpr float kGainMixMax = 1000.0f;            // alc/alu.h:18
-constexpr float kSpeedOfSound = 343.3f;           // core/context.h:32
-constexpr float kReverbDecayGain = 0.001f;        // core/effects/base.h:22
-constexpr unsigned kMaxPitch = 10u, kFracBits = 16u;
-constexpr float kFracOne = 65536.0f;
-constexpr float kPi = 3.14159265358979323846f;
+using namespace b200mix::pm;
+
+// <cmath>: the reference's own libm calls (see param_math.hpp)
+struct HostMath {
+    static float sqrt(float x) { return std::sqrt(x); }
+    static float pow(float a, float b) { return std::pow(a, b); }
+    static float acos(float x) { return std::acos(x); }
+    static float asin(float x) { return std::asin(x); }
+    static float atan2(float y, float x) { return std::atan2(y, x); }
+    static float sin(float x) { return std::sin(x); }
+    static float cos(float x) { return std::cos(x); }
+    static float copysign(float a, float b) { return std::copysign(a, b); }
+    static long lrint(float x) { return std::lrintf(x); }
+    static float infinity() { return std::numeric_limits<float>::infinity(); }
+};
+
 constexpr float kEps = std::numeric_limits<float>::epsilon();
 
-struct Vec { float v[4]; };
+float normalize(Vec &a) { return b200mix::pm::normalize<HostMath>(a); }
 
-// al::Vector::normalize (common/vecmat.h:51-65)
-float normalize(Vec &a)
-{
-    const float length_sqr = a.v[0]*a.v[0] + a.v[1]*a.v[1] + a.v[2]*a.v[2];
-    if(length_sqr > kEps)
-    {
-        const float length = std::sqrt(length_sqr);
-        const float inv_length = 1.0f / length;
-        a.v[0] *= inv_length; a.v[1] *= inv_length; a.v[2] *= inv_length;
-        return length;
-    }
-    a.v[0] = a.v[1] = a.v[2] = 0.0f;
-    return 0.0f;
-}
-float dot(const Vec &a, const Vec &b) { return a.v[0]*b.v[0] + a.v[1]*b.v[1] + a.v[2]*b.v[2]; }
-// operator*(Matrix, Vector) (common/vecmat.h:113-120), m row-major
-Vec mul(const float *m, const Vec &x)
-{
-    Vec r;
-    for(int c = 0;c < 4;++c)
-        r.v[c] = x.v[0]*m[0*4+c] + x.v[1]*m[1*4+c] + x.v[2]*m[2*4+c] + x.v[3]*m[3*4+c];
-    return r;
-}
-float lerpf(float a, float b, float mu) { return a + (b-a)*mu; }
-
-enum Model { Disable, Inverse, InverseClamped, Linear, LinearClamped, Exponent, ExponentClamped };
-
-// The filter block of CalcPanningAndFilters (alc/alu.cpp:1619-1656): per path (0 = direct, 1+s = send s)
-// a high-shelf at HFReference and a low-shelf at LFReference with the path's HF / LF gains; the
-// path's filter is active iff either gain differs from 1.
+// The filter block of CalcPanningAndFilters (alc/alu.cpp:1619-1656) for every path of one voice
 int design_filters(const b200mix_source_props &P, uint32_t device_rate, uint32_t num_sends, const float *gainHF,
     const float *gainLF, const uint32_t *voice, b200mix_voice_filter *filters)
 {
-    const float inv_samplerate = 1.0f / float(device_rate);
     for(uint32_t path = 0;path <= num_sends;++path)
     {
-        b200mix_voice_filter &f = filters[path];
-        const float ghf = gainHF[path], glf = gainLF[path];
-        const float hfref = path ? P.sends[path-1].hf_reference : P.direct.hf_reference;
-        const float lfref = path ? P.sends[path-1].lf_reference : P.direct.lf_reference;
-        if(voice) f.voice = *voice;
-        f.path = path;
-        f.active = (ghf != 1.0f || glf != 1.0f) ? 1u : 0u;
-        if(b200mix_biquad_coeffs(0u, hfref * inv_samplerate, ghf, 1.0f, f.lowpass)
-            || b200mix_biquad_coeffs(1u, lfref * inv_samplerate, glf, 1.0f, f.highpass))
-            return B200MIX_ERR_INVALID;
+        if(voice) filters[path].voice = *voice;
+        design_filter<HostMath>(P, device_rate, path, gainHF[path], gainLF[path], filters[path]);
     }
     return B200MIX_OK;
 }
@@ -115,29 +89,7 @@ int b200mix_calc_listener_params(const b200mix_listener_props *props, b200mix_li
 int b200mix_pairwise_azimuth(const float pos[3], float out[3])
 {
     if(!pos || !out) return B200MIX_ERR_INVALID;
-    // ScaleAzimuthFront3_2 (alc/alu.cpp:675-708): stretch front azimuths by 3/2 for the pairwise stereo mix
-    float p[3] = {pos[0], pos[1], pos[2]};
-    if(p[2] < 0.0f)
-    {
-        const float len2d = std::sqrt(p[0]*p[0] + p[2]*p[2]);
-        float z = -p[2] / len2d;
-        if(z > 0.5f)
-        {
-            float x = p[0] / len2d;
-            x = std::copysign(std::sqrt((1.0f - z) * 0.5f), x);
-            z = std::sqrt((1.0f + z) * 0.5f);
-            x = x*3.0f - x*x*x*4.0f;
-            z = z*z*z*4.0f - z*3.0f;
-            p[0] = x * len2d;
-            p[2] = -z * len2d;
-        }
-        else
-        {
-            p[0] = std::copysign(len2d, p[0]);
-            p[2] = 0.0f;
-        }
-    }
-    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+    pairwise_azimuth<HostMath>(pos, out);
     return B200MIX_OK;
 }
 
@@ -148,172 +100,7 @@ int b200mix_calc_source_params(const b200mix_source_props *props, const b200mix_
         || num_sends > B200MIX_MAX_SENDS || !device_rate || props->distance_model > ExponentClamped
         || lis->distance_model > ExponentClamped)
         return B200MIX_ERR_INVALID;
-    const b200mix_source_props &P = *props;
-
-    float roomrolloff[B200MIX_MAX_SENDS] = {};
-    for(uint32_t i = 0;i < num_sends;++i)
-        if(P.sends[i].active) roomrolloff[i] = P.room_rolloff_factor + P.sends[i].slot_room_rolloff;
-
-    // listener space (:1743-1760)
-    Vec position{{P.position[0], P.position[1], P.position[2], 1.0f}};
-    Vec velocity{{P.velocity[0], P.velocity[1], P.velocity[2], 0.0f}};
-    Vec direction{{P.direction[0], P.direction[1], P.direction[2], 0.0f}};
-    const Vec lvelocity{{lis->velocity[0], lis->velocity[1], lis->velocity[2], 0.0f}};
-    if(!P.head_relative)
-    {
-        const Vec rel{{position.v[0] - lis->position[0], position.v[1] - lis->position[1],
-            position.v[2] - lis->position[2], position.v[3] - 1.0f}};
-        position = mul(lis->matrix, rel);
-        velocity = mul(lis->matrix, velocity);
-        direction = mul(lis->matrix, direction);
-    }
-    else
-        for(int k = 0;k < 4;++k) velocity.v[k] += lvelocity.v[k];
-
-    Vec tosource{{position.v[0], position.v[1], position.v[2], 0.0f}};
-    const float distance = normalize(tosource);
-    const bool directional = normalize(direction) > 0.0f;
-
-    // distance attenuation (:1762-1852)
-    const uint32_t model = lis->source_distance_model ? P.distance_model : lis->distance_model;
-    float attenDistance = distance;
-    if(model == InverseClamped || model == LinearClamped || model == ExponentClamped)
-    {
-        if(!(P.ref_distance <= P.max_distance)) attenDistance = P.ref_distance;
-        else attenDistance = std::clamp(distance, P.ref_distance, P.max_distance);
-    }
-
-    float dryBase = P.gain, dryHF = 1.0f, dryLF = 1.0f;
-    float wetBase[B200MIX_MAX_SENDS], wetHF[B200MIX_MAX_SENDS], wetLF[B200MIX_MAX_SENDS];
-    for(uint32_t i = 0;i < B200MIX_MAX_SENDS;++i) { wetBase[i] = P.gain; wetHF[i] = 1.0f; wetLF[i] = 1.0f; }
-
-    float dryAttnBase = 1.0f;
-    switch(model)
-    {
-    case Inverse: case InverseClamped:
-        if(P.ref_distance > 0.0f)
-        {
-            if(const float dist = lerpf(P.ref_distance, attenDistance, P.rolloff_factor); dist > 0.0f)
-            {
-                dryAttnBase = P.ref_distance / dist;
-                dryBase *= dryAttnBase;
-            }
-            for(uint32_t i = 0;i < num_sends;++i)
-                if(const float dist = lerpf(P.ref_distance, attenDistance, roomrolloff[i]); dist > 0.0f)
-                    wetBase[i] = wetBase[i] * (P.ref_distance / dist);
-        }
-        break;
-    case Linear: case LinearClamped:
-        if(P.max_distance != P.ref_distance)
-        {
-            const float scale = (attenDistance-P.ref_distance) / (P.max_distance-P.ref_distance);
-            dryAttnBase = std::max(1.0f - scale*P.rolloff_factor, 0.0f);
-            dryBase *= dryAttnBase;
-            for(uint32_t i = 0;i < num_sends;++i)
-                wetBase[i] = wetBase[i] * std::max(1.0f - scale*roomrolloff[i], 0.0f);
-        }
-        break;
-    case Exponent: case ExponentClamped:
-        if(attenDistance > 0.0f && P.ref_distance > 0.0f)
-        {
-            const float dist_ratio = attenDistance / P.ref_distance;
-            dryAttnBase = std::pow(dist_ratio, -P.rolloff_factor);
-            dryBase *= dryAttnBase;
-            for(uint32_t i = 0;i < num_sends;++i)
-                wetBase[i] = wetBase[i] * std::pow(dist_ratio, -roomrolloff[i]);
-        }
-        break;
-    default: break;
-    }
-
-    // sound cones (:1854-1883); ConeScale is 1 unless __ALSOFT_HALF_ANGLE_CONES is set (:92-104)
-    float wetcone = 1.0f, wetconehf = 1.0f;
-    if(directional && P.inner_angle < 360.0f)
-    {
-        constexpr float Rad2Deg = static_cast<float>(180.0 / 3.14159265358979323846);
-        const float angle = Rad2Deg*2.0f * std::acos(-dot(direction, tosource)) * 1.0f;
-        float conegain = 1.0f, conehf = 1.0f;
-        if(angle >= P.outer_angle) { conegain = P.outer_gain; conehf = P.outer_gain_hf; }
-        else if(angle >= P.inner_angle)
-        {
-            const float scale = (angle-P.inner_angle) / (P.outer_angle-P.inner_angle);
-            conegain = lerpf(1.0f, P.outer_gain, scale);
-            conehf = lerpf(1.0f, P.outer_gain_hf, scale);
-        }
-        dryBase *= conegain;
-        if(P.dry_gain_hf_auto) dryHF *= conehf;
-        if(P.wet_gain_auto) wetcone = conegain;
-        if(P.wet_gain_hf_auto) wetconehf = conehf;
-    }
-
-    // gain limits and filters (:1885-1907)
-    const float mingain = std::min(P.min_gain, P.max_gain), maxgain = P.max_gain;
-    dryBase = std::clamp(dryBase, mingain, maxgain) * P.direct.gain;
-    dryBase = std::min(kGainMixMax, dryBase * lis->gain);
-    dryHF = dryHF * P.direct.gain_hf;
-    dryLF = P.direct.gain_lf;
-    for(uint32_t i = 0;i < num_sends;++i)
-    {
-        const float gain = std::clamp(wetBase[i]*wetcone, mingain, maxgain) * P.sends[i].gain;
-        wetBase[i] = std::min(kGainMixMax, gain * lis->gain);
-        wetHF[i] = P.sends[i].gain_hf * wetconehf;
-        wetLF[i] = P.sends[i].gain_lf;
-    }
-
-    // air absorption and initial send decay (:1909-1961)
-    if(distance > P.ref_distance)
-    {
-        const float distance_units = (distance-P.ref_distance) * P.rolloff_factor;
-        const float distance_meters = distance_units * lis->meters_per_unit;
-        const float absorb = distance_meters * P.air_absorption_factor;
-        if(absorb > kEps) dryHF *= std::pow(lis->air_absorption_gain_hf, absorb);
-        for(uint32_t i = P.wet_gain_auto ? 0u : num_sends;i < num_sends;++i)
-        {
-            const b200mix_source_send &S = P.sends[i];
-            if(!S.active || !(S.slot_decay_time > 0.0f)) continue;
-            if(S.slot_air_absorption_gain_hf < 1.0f && absorb > kEps)
-                wetHF[i] *= std::pow(S.slot_air_absorption_gain_hf, absorb);
-            const float DecayDistance = S.slot_decay_time * kSpeedOfSound;
-            const float fact = distance_meters / DecayDistance;
-            const float gain = std::pow(kReverbDecayGain, fact)*(1.0f-dryAttnBase) + dryAttnBase;
-            wetBase[i] *= gain;
-        }
-    }
-
-    // doppler and the resampler step (:1964-2001)
-    float pitch = P.pitch;
-    if(const float DopplerFactor = P.doppler_factor * lis->doppler_factor; DopplerFactor > 0.0f)
-    {
-        const float vss = dot(velocity, tosource) * -DopplerFactor;
-        const float vls = dot(lvelocity, tosource) * -DopplerFactor;
-        const float SpeedOfSound = lis->speed_of_sound;
-        if(!(vls < SpeedOfSound)) pitch = 0.0f;
-        else if(!(vss < SpeedOfSound)) pitch = std::numeric_limits<float>::infinity();
-        else pitch *= (SpeedOfSound-vls) / (SpeedOfSound-vss);
-    }
-    pitch *= float(buffer_rate) / float(device_rate);
-    if(pitch > float(kMaxPitch)) out->step = kMaxPitch << kFracBits;
-    else out->step = std::max(uint32_t(std::lrintf(pitch * kFracOne)), 1u);
-
-    // source radius (:2003-2007)
-    float spread = 0.0f;
-    if(P.radius > distance) spread = kPi*2.0f - distance/P.radius*kPi;
-    else if(distance > 0.0f) spread = std::asin(P.radius/distance) * 2.0f;
-
-    // XScale/YScale/ZScale are 1 unless the reverse-x/y/z compatibility options are set (:109-111)
-    out->pos[0] = tosource.v[0]*1.0f; out->pos[1] = tosource.v[1]*1.0f; out->pos[2] = tosource.v[2]*1.0f;
-    out->distance = distance; out->spread = spread;
-    out->dry_gain = dryBase; out->dry_gain_hf = dryHF; out->dry_gain_lf = dryLF;
-    for(uint32_t i = 0;i < B200MIX_MAX_SENDS;++i)
-    {
-        const bool on = i < num_sends;
-        out->wet_gain[i] = on ? wetBase[i] : 0.0f;
-        out->wet_gain_hf[i] = on ? wetHF[i] : 1.0f;
-        out->wet_gain_lf[i] = on ? wetLF[i] : 1.0f;
-    }
-    // CalcHrtfPanning's direction for a point source (:1209-1214)
-    out->hrtf_elevation = std::asin(std::clamp(out->pos[1], -1.0f, 1.0f));
-    out->hrtf_azimuth = std::atan2(out->pos[0], -out->pos[2]);
+    calc_source_params<HostMath>(*props, *lis, num_sends, buffer_rate, device_rate, *out);
     return B200MIX_OK;
 }
 
@@ -328,74 +115,17 @@ int b200mix_calc_voice(const b200mix_source_props *props, const b200mix_listener
     if(int rc = b200mix_calc_source_params(props, listener, env->num_sends, buffer_rate, env->device_rate, &r))
         return rc;
     voice->step = r.step;
-    float coeffs[B200MIX_MAX_AMBI_CHANNELS];
-    if(r.distance > kEps)
-    {
-        // CalcPanningAndFilters for a point source at a distance (alc/alu.cpp:1196-1226,1318-1361)
-        float pos[3] = {r.pos[0], r.pos[1], r.pos[2]};
-        if(env->render_mode == 2u)
-        {
-            // CalcHrtfPanning: the HRIR pair comes from the direction (b200mix_voices_update_dirs or
-            // b200mix_hrtf_get_coeffs), the voice carries the gain
-            if(!dir) return B200MIX_ERR_INVALID;
-            dir[0] = r.hrtf_elevation; dir[1] = r.hrtf_azimuth; dir[2] = r.distance; dir[3] = r.spread;
-            voice->hrtf_gain = r.dry_gain;
-            voice->flags |= B200MIX_VF_HRTF;
-            b200mix_ambi_coeffs(r.pos, r.spread, coeffs);      // the sends' encoder coefficients
-        }
-        else
-        {
-            if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
-            if(env->render_mode == 1u) b200mix_pairwise_azimuth(r.pos, pos);
-            b200mix_ambi_coeffs(pos, r.spread, coeffs);        // shared by the dry mix and the sends
-            if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
-                dry_gains, env->dry.channels)) return rc;
-            voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
-            if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
-        }
-    }
-    else
-    {
-        // A source on the listener (alc/alu.cpp:1268-1310,1420-1466): the mono channel sits at the
-        // front-centre position of MonoMap (:1471-1473, pan gain 1 with VoiceProps::Panning at its
-        // default 0), spread is all or nothing
-        const float front[3] = {0.0f, 0.0f, -1.0f};
-        if(env->render_mode == 2u)
-        {
-            if(!dir) return B200MIX_ERR_INVALID;
-            dir[0] = std::asin(front[1]); dir[1] = std::atan2(front[0], -front[2]);
-            dir[2] = std::numeric_limits<float>::infinity(); dir[3] = r.spread;
-            voice->hrtf_gain = r.dry_gain;
-            voice->flags |= B200MIX_VF_HRTF;
-        }
-        else
-        {
-            if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
-            // ScaleAzimuthFront3 leaves the front-centre direction where it is
-            b200mix_ambi_coeffs(front, r.spread, coeffs);
-            if(int rc = b200mix_pan_gains(env->dry.channels, env->dry.scale, env->dry.index, coeffs, r.dry_gain,
-                dry_gains, env->dry.channels)) return rc;
-            voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
-            if(dir) { dir[0] = dir[1] = dir[2] = dir[3] = 0.0f; }
-        }
-        b200mix_ambi_coeffs(front, r.spread, coeffs);
-    }
-    for(uint32_t s = 0;s < env->num_sends;++s)
-    {
-        const b200mix_mix_map &w = env->wet[s];
-        if(!send_gains || !env->wet_stride) break;
-        float *g = send_gains + size_t(s)*env->wet_stride;
-        for(uint32_t c = 0;c < env->wet_stride;++c) g[c] = 0.0f;
-        if(!props->sends[s].active || !w.channels) continue;
-        if(w.channels > env->wet_stride || !w.scale || !w.index) return B200MIX_ERR_INVALID;
-        if(int rc = b200mix_pan_gains(w.channels, w.scale, w.index, coeffs, r.wet_gain[s], g, w.channels)) return rc;
-    }
+    if(env->render_mode == 2u) { if(!dir) return B200MIX_ERR_INVALID; }
+    else if(!dry_gains || !env->dry.scale || !env->dry.index) return B200MIX_ERR_INVALID;
+    float hrtf_gain = 0.0f; bool is_hrtf = false;
+    if(!calc_panning<HostMath>(*props, r, *env, &hrtf_gain, &is_hrtf, dir, dry_gains, send_gains))
+        return B200MIX_ERR_INVALID;
+    if(is_hrtf) { voice->hrtf_gain = hrtf_gain; voice->flags |= B200MIX_VF_HRTF; }
+    else voice->flags &= ~uint32_t(B200MIX_VF_HRTF);
     float gainHF[1 + B200MIX_MAX_SENDS], gainLF[1 + B200MIX_MAX_SENDS];
     gainHF[0] = r.dry_gain_hf; gainLF[0] = r.dry_gain_lf;
     for(uint32_t i = 0;i < B200MIX_MAX_SENDS;++i) { gainHF[1+i] = r.wet_gain_hf[i]; gainLF[1+i] = r.wet_gain_lf[i]; }
-    if(int rc = design_filters(*props, env->device_rate, env->num_sends, gainHF, gainLF, &voice->voice, filters))
-        return rc;
-    return B200MIX_OK;
+    return design_filters(*props, env->device_rate, env->num_sends, gainHF, gainLF, &voice->voice, filters);
 }
 
 int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix_listener_params *listener,
@@ -518,7 +248,7 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
             dirs[c*4+1] = std::atan2(cpos[0], -cpos[2]);
             if(warp) dirs[c*4+2] = attn.distance;
             hrtf_gains[c] = dryBase * pangain;
-            b200mix_ambi_coeffs(cpos, 0.0f, coeffs);
+            ambi_coeffs<HostMath>(cpos, 0.0f, coeffs);
         }
         else
         {

@@ -180,6 +180,13 @@ class VoiceEnv(C.Structure):
                 ("wet", MixMap * MAX_SENDS)]
 
 
+class SourceVoice(C.Structure):
+    """b200mix_source_voice: what the host still decides per voice for b200mix_sources_update."""
+    _fields_ = [("voice", C.c_uint32), ("flags", C.c_uint32), ("buffer", C.c_uint32), ("resampler", C.c_uint32),
+                ("position", C.c_int32), ("position_frac", C.c_uint32), ("loop_start", C.c_uint32),
+                ("loop_end", C.c_uint32), ("buffer_rate", C.c_uint32), ("send_slot", C.c_uint32 * MAX_SENDS)]
+
+
 class ChannelSetup(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
                 ("panning", C.c_float), ("lfe_dry_index", C.c_uint32), ("spatialized", C.c_uint32)]

@@ -13,8 +13,9 @@ Configs (BASELINE.json `configs`); voices are sharded by index a
   4a  65536 voices into a third-order B-Format output (16 dry channels, no post-process)
   4b  65536 voices, 2-D first order + UHJ encode
   5   1M HRTF voices + 128 convolution (96000-tap IR) + 128 reverb slots
-With --gpus N>1 slots are owned by rank (slot mod N): every update runs
-render_begin -> ncclAllReduce(wet) -> render_end -> ncclReduce(RealOut).
+With --gpus N>1 the ranks form a sharded device set (b200mix_shard_*): slots are owned by rank
+(slot mod N) and b200mix_render_device itself reduce-scatters the wet buffers and reduces
+RealOut onto rank 0 (--transport p2p: peer stores over NVLink; nccl: ncclAllReduce + ncclReduce).
 --voices overrides the TOTAL voice count (a single GPU can run its 1/N share of config 4/5
 with --voices and --slot-share).  --filters adds an active direct low-pass to every voice.
 Time: CUDA events on the mixer's stream around the whole update, L2 flushed between
@@ -56,6 +57,7 @@ def main():
     ap.add_argument("--pcm-pool", type=int, default=0,
                     help="distinct PCM contents (0 = one per voice up to 8192 voices per rank, else 256); "
                          "every voice still owns its own device buffer")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     args = ap.parse_args()
@@ -67,8 +69,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"launch with torchrun --nproc-per-node {args.gpus}"
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")
     total = args.voices or cfg["voices"]
     first, nv = shard.shard_range(total, world, rank)
     nslots = cfg["conv"] + cfg["reverb"]
@@ -148,7 +152,7 @@ def main():
             pcms[key] = scene.voice_buffer_fast(first + k)
         pcm = pcms[key]
         lib.b200mix_buffer_data(h, k, abi.FMT_I16, 1, pcm.shape[0], pcm.ctypes.data, pcm.nbytes)
-    params, coeffs, pitches = bench.synth_voices(first, nv, total, lib, hrtf)
+    params, coeffs, pitches = bench.synth_voices(range(first, first + nv), total, lib, hrtf)
     dry = None
     for k in range(nv):
         params[k].resampler = cfg["resampler"]
@@ -193,18 +197,12 @@ def main():
     wet_ptr, wet_cnt = C.c_void_p(), C.c_size_t()
     real_floats = desc.real_channels * 1024
 
+    if world > 1:
+        shard.connect(lib, h, rank, world, args.transport, gloo)
+
     def update():
-        if world > 1 and nslots:
-            assert lib.b200mix_render_begin(h, 1024, C.byref(wet_ptr), C.byref(wet_cnt)) == 0, \
-                lib.b200mix_last_error(h)
-            with torch.cuda.stream(stream):
-                shard.allreduce_wet(bench._as_tensor(wet_ptr.value, wet_cnt.value, local))
-            assert lib.b200mix_render_end(h, None, None, C.byref(out)) == 0, lib.b200mix_last_error(h)
-        else:
-            assert lib.b200mix_render_device(h, 1024, C.byref(out)) == 0, lib.b200mix_last_error(h)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                shard.reduce_real_out(bench._as_tensor(out.value, real_floats, local), dst=0)
+        # sharded: the wet reduce-scatter and the RealOut reduce happen inside this call
+        assert lib.b200mix_render_device(h, 1024, C.byref(out)) == 0, lib.b200mix_last_error(h)
 
     for _ in range(args.warmup):
         update()
@@ -236,7 +234,9 @@ def main():
         print(json.dumps({
             "config": args.config, "kind": kind, "n_gpus": world, "voices_total": total,
             "voices_per_gpu": nv, "slots": nslots, "slots_installed_rank0": installed,
-            "conv_taps": args.taps if cfg["conv"] else None, "pcm_pool": pool, "direct_filters": bool(args.filters),
+            "conv_taps": args.taps if cfg["conv"] else None,
+            "transport": args.transport if world > 1 else None,
+            "buffers": f"{nv} private device buffers per rank, {pool} distinct host waveforms", "direct_filters": bool(args.filters),
             "ms_per_update": ms_update, "mix_kernel_ms_rank0": float(np.mean(mix)),
             "stage_us_rank0": dict(zip(["clear", "voices", "filters+deferred", "reduce", "dry_bus", "sends",
                                         "effects", "post"],

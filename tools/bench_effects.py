@@ -69,7 +69,7 @@ def main():
     for k in range(nv):
         pcm = scene.voice_buffer_fast(k)
         lib.b200mix_buffer_data(h, k, abi.FMT_I16, 1, pcm.shape[0], pcm.ctypes.data, pcm.nbytes)
-    params, coeffs, pitches = bench.synth_voices(0, nv, nv, lib, hrtf)
+    params, coeffs, pitches = bench.synth_voices(range(nv), nv, lib, hrtf)
     send = np.zeros((nv, 1, 4), dtype=np.float32)
     send[:, 0, :] = np.array([0.5, 0.2, -0.1, 0.3], dtype=np.float32) * scene.voice_gain(nv)
     for k in range(nv):
