@@ -126,7 +126,15 @@ B200MIX_API int b200mix_buffer_free(b200mix_device *dev, uint32_t buffer);
 
 /* ---- auxiliary effect slots: EffectSlotBase + EffectState (core/effectslot.h:50-82,
  *      core/effects/base.h:197-222) ------------------------------------------------ */
-enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B200MIX_EFFECT_REVERB = 2 };
+enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B200MIX_EFFECT_REVERB = 2,
+    /* the EFX effects behind b200mix_slot_efx */
+    B200MIX_EFFECT_ECHO = 3,          /* EchoState        alc/effects/echo.cpp */
+    B200MIX_EFFECT_MODULATOR = 4,     /* ModulatorState   alc/effects/modulator.cpp (ring modulator) */
+    B200MIX_EFFECT_EQUALIZER = 5,     /* EqualizerState   alc/effects/equalizer.cpp */
+    B200MIX_EFFECT_COMPRESSOR = 6,    /* CompressorState  alc/effects/compressor.cpp */
+    B200MIX_EFFECT_DEDICATED = 7,     /* DedicatedState   alc/effects/dedicated.cpp (dialogue / LFE) */
+    B200MIX_EFFECT_DISTORTION = 8     /* DistortionState  alc/effects/distortion.cpp */
+};
 
 /* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
  * device-rate impulse response (planar [ir_channels][ir_frames] floats; the host applies
@@ -312,6 +320,51 @@ B200MIX_API int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot,
  *   state machine; send the new pipeline's output gains with b200mix_slot_output_gains. */
 B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
     const b200mix_reverb_params *params, uint32_t full_update);
+
+/* The other EFX effects: EffectState::deviceUpdate + update + process of
+ *   echo        alc/effects/echo.cpp:82-157         (two-tap delay line, damped feedback, L/R spread)
+ *   modulator   alc/effects/modulator.cpp:96-199    (ring modulator: sine / saw / square carrier, high-pass)
+ *   equalizer   alc/effects/equalizer.cpp:112-183   (low shelf, two peaking bands, high shelf per channel)
+ *   compressor  alc/effects/compressor.cpp:80-177   (envelope follower on channel 0 -> gain on all)
+ *   dedicated   alc/effects/dedicated.cpp:62-109    (dialogue to front-centre / LFE)
+ *   distortion  alc/effects/distortion.cpp:113-303  (B2A, 4x oversampled low-pass -> waveshaper -> band-pass, A2B)
+ * b200mix_efx_props carries the effect's PROPERTIES (the EffectProps variant of
+ * core/effects/base.h:62-178 after the AL layer's clamping); b200mix_efx_target what update() reads
+ * from the slot and its output target: EffectSlotBase::Gain, the target mix's AmbiMap
+ * (target.Main: the Dry mix, or the target slot's Wet mix) and the slot's own Wet.AmbiMap
+ * indices (setAmbiMixParams, core/device.h:126-147).  The library runs the reference's update()
+ * arithmetic on the host (same float expressions, host libm: bit-identical coefficients) and
+ * process() on the GPU.  The first call on a slot (or a change of `type`) is deviceUpdate +
+ * update: the effect state is created and cleared; later calls are update(): parameters and
+ * gain targets change, delay lines / filter histories / current gains are kept.
+ * B200MIX_ERR_UNSUPPORTED: more than 16 wet channels; dedicated effects that resolve to a RealOut
+ * channel (FrontCenter / LFE present: the reference then writes RealOut, not the mix);
+ * distortion on a device mixing above first order (its up-sampler). */
+typedef struct b200mix_efx_props {
+    uint32_t struct_size;
+    uint32_t type;                      /* enum b200mix_effect, >= B200MIX_EFFECT_ECHO */
+    struct { float delay, lr_delay, damping, feedback, spread; } echo;                    /* EchoProps */
+    struct { float frequency, high_pass_cutoff; uint32_t waveform; } modulator;           /* 0 sinusoid, 1 sawtooth, 2 square */
+    struct { float low_cutoff, low_gain, mid1_center, mid1_gain, mid1_width,
+             mid2_center, mid2_gain, mid2_width, high_cutoff, high_gain; } equalizer;     /* EqualizerProps */
+    struct { uint32_t on_off; } compressor;                                               /* CompressorProps */
+    struct { uint32_t target; float gain; } dedicated;                                    /* 0 dialogue, 1 LFE */
+    struct { float edge, gain, lowpass_cutoff, eq_center, eq_bandwidth; } distortion;     /* DistortionProps */
+} b200mix_efx_props;
+typedef struct b200mix_efx_target {
+    uint32_t struct_size;
+    uint32_t sample_rate;               /* DeviceBase::mSampleRate */
+    float    slot_gain;                 /* EffectSlotBase::Gain */
+    uint32_t out_channels;              /* target.Main->Buffer.size() */
+    const float *out_scale;             /* target.Main->AmbiMap[c].Scale */
+    const uint32_t *out_index;          /* target.Main->AmbiMap[c].Index */
+    uint32_t wet_channels;              /* slot->Wet.Buffer.size() (== the device's wet_channels) */
+    const uint32_t *wet_index;          /* slot->Wet.AmbiMap[c].Index */
+    uint32_t real_center, real_lfe;     /* RealOut.ChannelIndex[FrontCenter] / [LFE] or B200MIX_NO_SLOT */
+    uint32_t device_ambi_order;         /* DeviceBase::mAmbiOrder */
+} b200mix_efx_target;
+B200MIX_API int b200mix_slot_efx(b200mix_device *dev, uint32_t slot, const b200mix_efx_props *props,
+    const b200mix_efx_target *target);
 
 /* EffectSlotBase::Target (AL_SOFT_effect_target, core/effectslot.h:64; alc/alu.cpp:626-633): the
  * slot's effect output is mixed into `target`'s Wet buffer instead of the Dry mix

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -22,7 +23,9 @@
 #include "mixer_kernels.cuh"
 #include "effect_kernels.cuh"
 #include "shard_kernels.cuh"
+#include "panmix_tc.cuh"
 #include "param_kernels.hpp"
+#include "efx_kernels.hpp"
 #include "resampler_tables.hpp"
 #include "hrtf_store.hpp"
 #include "adpcm.hpp"
@@ -124,6 +127,12 @@ struct b200mix_device {
     SendEntry *d_entries{nullptr};
     uint32_t num_entries{0};
     bool sends_dirty{true};
+    // EFX effect slots (b200mix_slot_efx): host mirrors + the per-slot views the kernel walks
+    struct EfxHost { bool used{false}; EfxParams p{}; EfxDev *dev{nullptr}; uint32_t mod_index{0}, mod_range{1}; };
+    std::vector<EfxHost> efx;
+    EfxSlotView *d_efx_views{nullptr};
+    uint32_t efx_slots{0};
+    bool efx_ready{false};
     float2 *d_twiddle{nullptr};
     float *d_cubic_filter{nullptr};          // gCubicTable (reverb modulation taps)
     uint32_t reverb_slots{0};
@@ -184,6 +193,8 @@ struct b200mix_device {
     char *h_src{nullptr}, *d_src{nullptr}; uint32_t src_cap{0};
     cudaEvent_t src_done{nullptr}; bool src_busy{false};
     bool dev_filters{false};                 // filter activity is decided on the device: order2 = order
+    bool panmix_tc{false};                   // wide dry buses: pan-mix past the fades on the tensor cores
+    bool mix_gather_only{false};             // B200MIX_MIX_GATHER=1: no TMA staging in k_mix_voices (A/B runs)
 
     // voice-sharded device set (b200mix_shard_*): transport 0 none, 1 peer stores, 2 NCCL
     struct Shard {
@@ -262,6 +273,14 @@ int ensure_dry_park(b200mix_device *d)
     if(!d->d_sendinfo)
         if(int rc = dev_alloc(d, d->d_sendinfo, dd.max_voices)) return rc;
     if(int rc = dev_alloc(d, d->d_dry_entries, dd.max_voices)) return rc;
+    if(dd.dry_channels > 4u && dd.dry_channels <= uint32_t(kPmN))
+    {
+        CUDA_TRY(d, cudaFuncSetAttribute(k_panmix_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            kPmStages*kPmStageBytes + 1024));
+        // B200MIX_PANMIX_SIMT=1 keeps the whole pan-mix on k_send_mix (A/B measurements only)
+        const char *simt = std::getenv("B200MIX_PANMIX_SIMT");
+        d->panmix_tc = !(simt && simt[0] == '1');
+    }
     if(int rc = dev_alloc(d, d->d_dry_slot_start, 2)) return rc;
     if(int rc = dev_alloc(d, d->d_dry_partial, size_t(kDryChunksMax)*dd.dry_channels*kLine)) return rc;
     if(int rc = dev_alloc(d, d->d_dry_geff, size_t(dd.max_voices)*dd.dry_channels)) return rc;
@@ -334,6 +353,7 @@ int b200mix_create(const b200mix_device_desc *desc, b200mix_device **out)
     auto *d = new(std::nothrow) b200mix_device{};
     if(!d) { g_create_error = "out of host memory"; return B200MIX_ERR_NOMEM; }
     d->desc = *desc;
+    if(const char *g = std::getenv("B200MIX_MIX_GATHER")) d->mix_gather_only = g[0] == '1';
     auto fail = [&](int code) { g_create_error = d->error; b200mix_destroy(d); return code; };
 
     int count = 0;
@@ -514,6 +534,7 @@ void b200mix_destroy(b200mix_device *d)
     if(d->h_fupd) cudaFreeHost(d->h_fupd);
     if(d->fstage_done) cudaEventDestroy(d->fstage_done);
     cudaFree(d->d_slot_start); cudaFree(d->d_entries); cudaFree(d->d_twiddle); cudaFree(d->d_cubic_filter);
+    cudaFree(d->d_efx_views);
     cudaFreeHost(d->h_arena); cudaFree(d->d_arena);
     if(d->h_src) cudaFreeHost(d->h_src);
     cudaFree(d->d_src);
@@ -672,6 +693,15 @@ static int update_stages(b200mix_device *d)
         CUDA_TRY(d, cudaMemcpyAsync(d->d_slots, d->h_slots.data(), ns*sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream));
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     }
+    if(ns && d->d_efx_views)
+    {
+        std::vector<EfxSlotView> views(ns, EfxSlotView{nullptr, nullptr, 0u, 0u});
+        for(uint32_t sl = 0;sl < ns;++sl)
+            if(d->h_slots[sl].type >= B200MIX_EFFECT_ECHO && sl < d->efx.size() && d->efx[sl].used)
+                views[sl] = EfxSlotView{d->efx[sl].dev, d->h_slots[sl].lines, d->h_slots[sl].stage, 0u};
+        CUDA_TRY(d, cudaMemcpyAsync(d->d_efx_views, views.data(), ns*sizeof(EfxSlotView), cudaMemcpyHostToDevice, d->stream));
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    }
     return B200MIX_OK;
 }
 
@@ -682,6 +712,11 @@ static void free_slot(b200mix_device *d, uint32_t slot)
     d->slot_allocs[slot].clear();
     if(d->h_slots[slot].type) --d->active_slots;
     if(d->h_slots[slot].type == B200MIX_EFFECT_REVERB) --d->reverb_slots;
+    if(d->h_slots[slot].type >= B200MIX_EFFECT_ECHO)
+    {
+        --d->efx_slots;
+        if(slot < d->efx.size()) d->efx[slot] = b200mix_device::EfxHost{};
+    }
     if(slot < d->rv.size()) d->rv[slot].used = false;
     d->h_slots[slot] = SlotRec{};
 }
@@ -701,6 +736,7 @@ int b200mix_slot_convolution(b200mix_device *d, uint32_t slot, uint32_t ir_chann
     { if(d) d->error = "slot_convolution: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
     CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
     free_slot(d, slot);
+    CUDA_TRY(d, cudaFuncSetAttribute(k_conv_mac, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(ConvMacSmem))));
     SlotRec r{};
     r.type = B200MIX_EFFECT_CONVOLUTION; r.channels = ir_channels; r.frames = ir_frames;
     // mNumConvolveSegs (alc/effects/convolution.cpp:375-376)
@@ -889,6 +925,86 @@ int b200mix_slot_reverb(b200mix_device *d, uint32_t slot, const b200mix_reverb_p
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     ++d->active_slots; ++d->reverb_slots;
     d->dry_active = true;
+    return update_stages(d);
+}
+
+int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *props,
+    const b200mix_efx_target *target)
+{
+    if(!d || slot >= d->h_slots.size() || !props || !target || props->struct_size != sizeof(*props)
+        || target->struct_size != sizeof(*target) || props->type < B200MIX_EFFECT_ECHO
+        || props->type > B200MIX_EFFECT_DISTORTION)
+    { if(d) d->error = "slot_efx: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
+    const b200mix_device_desc &dd = d->desc;
+    const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
+    if(target->wet_channels != dd.wet_channels || target->out_channels != (toSlot ? dd.wet_channels : dd.dry_channels))
+    { d->error = "slot_efx: the target maps do not match the device's wet / output mix"; return B200MIX_ERR_INVALID; }
+    EfxParams P;
+    if(int rc = efx_update(*props, *target, P))
+    { d->error = rc == B200MIX_ERR_UNSUPPORTED ? "slot_efx: not supported in this configuration (see b200mix.h)"
+        : "slot_efx: bad properties / maps"; return rc; }
+    CUDA_TRY(d, cudaSetDevice(d->cuda_dev));
+    if(!d->efx_ready) { CUDA_TRY(d, efx_kernels_init()); d->efx_ready = true; }
+    if(d->efx.size() < d->h_slots.size()) d->efx.resize(d->h_slots.size());
+    if(!d->d_efx_views)
+        if(int rc = dev_alloc(d, d->d_efx_views, d->h_slots.size())) return rc;
+    b200mix_device::EfxHost &H = d->efx[slot];
+    const bool fresh = !H.used || d->h_slots[slot].type != props->type || H.p.lines != P.lines
+        || H.p.echo_len != P.echo_len;
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    if(fresh)
+    {
+        // EffectState::deviceUpdate: new state, cleared
+        free_slot(d, slot);
+        SlotRec r{};
+        r.type = props->type; r.channels = P.lines; r.fade_len = P.fade_len;
+        auto alloc = [&](auto *&ptr, size_t count) -> int {
+            if(int rc = dev_alloc(d, ptr, count)) return rc;
+            d->slot_allocs[slot].push_back(ptr);
+            return B200MIX_OK;
+        };
+        EfxDev *dev = nullptr;
+        if(int rc = alloc(dev, 1)) return rc;
+        if(int rc = alloc(r.lines, size_t(P.lines)*kLine)) return rc;
+        if(int rc = alloc(r.gains, size_t(2)*P.lines*32)) return rc;
+        if(int rc = alloc(r.gtgt, size_t(P.lines)*32)) return rc;
+        EfxDev h{};
+        h.p = P; h.comp_env = 1.0f;
+        if(P.echo_len) { if(int rc = alloc(h.echo_buf, P.echo_len)) return rc; }
+        r.H = reinterpret_cast<float*>(dev);
+        CUDA_TRY(d, cudaMemcpyAsync(dev, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+        H = b200mix_device::EfxHost{};
+        H.used = true; H.dev = dev; H.mod_index = 0u; H.mod_range = P.mod_range ? P.mod_range : 1u;
+        d->h_slots[slot] = r;
+        ++d->active_slots; ++d->efx_slots;
+        d->dry_active = true;
+    }
+    else
+    {
+        // EffectState::update: new parameters, state kept.  The ring modulator rescales its
+        // phase index to the new range (modulator.cpp:117-118); the host mirrors the index
+        EfxDev hdr{};
+        hdr.p = P;
+        CUDA_TRY(d, cudaMemcpyAsync(H.dev, &hdr, sizeof(EfxParams), cudaMemcpyHostToDevice, d->stream));
+        if(props->type == B200MIX_EFFECT_MODULATOR)
+        {
+            H.mod_index = uint32_t(uint64_t(H.mod_index) * P.mod_range_new / H.mod_range);
+            H.mod_range = P.mod_range;
+            CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, mod_index), &H.mod_index,
+                sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+        }
+        d->h_slots[slot].fade_len = P.fade_len;
+        CUDA_TRY(d, cudaStreamSynchronize(d->stream));
+    }
+    H.p = P;
+    const SlotRec &S = d->h_slots[slot];
+    CUDA_TRY(d, cudaMemcpyAsync(S.gtgt, P.gains, size_t(P.lines)*32*sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    if(P.snap_gains)
+        for(int sel = 0;sel < 2;++sel)
+            CUDA_TRY(d, cudaMemcpyAsync(S.gains + size_t(sel)*P.lines*32, P.gains, size_t(P.lines)*32*sizeof(float),
+                cudaMemcpyHostToDevice, d->stream));
+    CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     return update_stages(d);
 }
 
@@ -1580,6 +1696,7 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
     P.xscratch = d->d_xscratch; P.sendinfo = d->d_sendinfo;
     P.filt = d->d_filt; P.filt_paths = 1u + dd.num_sends;
     P.qhdr = d->d_qhdr; P.queue = d->d_queue;
+    P.gather_only = d->mix_gather_only ? 1u : 0u;
     stage_mark(d, 1);
     if(d->profile) cudaEventRecord(d->ev_mix0, d->stream);
     var.fn<<<blocks, var.gs*var.groups, var.smem, d->stream>>>(P);
@@ -1673,10 +1790,22 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
                 k_send_gains_prepare<<<(tot + 127)/128, 128, 0, d->stream>>>(DM, d->num_dry_entries);
                 ++d->launches;
             }
-            const uint32_t tiles = chunks > 1u ? uint32_t(kLine/128) : (frames + 127u)/128u;
+            // Above 4 dry channels (third-order output) a full update's pan-mix past the gain fades
+            // is a dense GEMM over the voices: samples 128..1023 go to the tensor cores
+            // (k_panmix_tc), k_send_mix keeps the first tile with the fades
+            const bool tc = d->panmix_tc && dd.dry_channels > 4u && dd.dry_channels <= uint32_t(kPmN)
+                && frames == uint32_t(kLine) && chunks > 1u;
+            const uint32_t tiles = tc ? 1u : (chunks > 1u ? uint32_t(kLine/128) : (frames + 127u)/128u);
             if(dd.dry_channels > 4u) k_send_mix<16><<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
             else k_send_mix<4><<<dim3(1, tiles, chunks), 256, 0, d->stream>>>(DM);
             ++d->launches;
+            if(tc)
+            {
+                PanMixTcParams TQ{d->d_dry_slot_start, d->d_dry_entries, d->d_sendinfo, d->d_xscratch,
+                    d->d_dline, d->d_dry_geff, dd.dry_channels, chunks, d->d_dry_partial};
+                k_panmix_tc<<<chunks, 128, kPmStages*kPmStageBytes + 1024, d->stream>>>(TQ);
+                ++d->launches;
+            }
             if(chunks > 1u)
             {
                 const uint32_t len = dd.dry_channels*kLine;
@@ -1798,18 +1927,16 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         ConvParams CP{};
         CP.slots = d->d_slots; CP.wet = d->d_wet; CP.twiddle = d->d_twiddle;
         CP.frames = frames; CP.cw = dd.wet_channels; CP.num_slots = dd.max_slots;
-        uint32_t maxch = 1, convWork = 0, convSegs = 0;
+        uint32_t convCh = 1, convWork = 0, convSegs = 0;
         for(const SlotRec &sr : d->h_slots)
-        {
-            if(sr.type) maxch = std::max(maxch, sr.channels);
-            if(sr.type == B200MIX_EFFECT_CONVOLUTION) { convWork += sr.channels; convSegs = std::max(convSegs, sr.segs); }
-        }
-        // segment chunks of k_conv_mac: ~3 CTAs per SM over all convolution slot-channels, at
-        // least 16 segments per chunk
+            if(sr.type == B200MIX_EFFECT_CONVOLUTION)
+            { convCh = std::max(convCh, sr.channels); convWork += sr.channels; convSegs = std::max(convSegs, sr.segs); }
+        // segment chunks of k_conv_mac: ~4 CTAs (of 128 threads) per SM over all convolution
+        // slot-channels, at least 18 segments per chunk
         CP.chunks = 1u;
         if(convWork)
-            CP.chunks = std::max(1u, std::min(std::min(uint32_t(kConvMaxChunks), (convSegs + 15u)/16u),
-                (3u*uint32_t(d->num_sms) + convWork - 1u)/convWork));
+            CP.chunks = std::max(1u, std::min(std::min(uint32_t(kConvMaxChunks), (convSegs + 17u)/18u),
+                (4u*uint32_t(d->num_sms) + convWork - 1u)/convWork));
         if(d->reverb_slots)
         {
             // ReverbState::process's pipeline state machine (reverb.cpp:1840-1878), host side
@@ -1870,12 +1997,22 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
                 }
             }
             CP.stage = st; SP.stage = st;
-            k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
-            k_conv_mac<<<dim3(dd.max_slots, maxch, CP.chunks), 512, 0, d->stream>>>(CP);
-            k_conv_ifft<<<dim3(dd.max_slots, maxch, kConvMaxBlocks), 128, 0, d->stream>>>(CP);
-            k_conv_output<<<dim3(dd.max_slots, maxch), 128, 0, d->stream>>>(CP);
+            if(d->efx_slots)
+            {
+                EfxRunParams EQ{d->d_efx_views, d->d_wet, frames, dd.wet_channels, st};
+                CUDA_TRY(d, launch_efx_process(EQ, dd.max_slots, d->stream));
+                ++d->launches;
+            }
+            if(convWork)
+            {
+                k_conv_input<<<dd.max_slots, 128, 0, d->stream>>>(CP);
+                k_conv_mac<<<dim3(dd.max_slots, convCh, CP.chunks), 128, sizeof(ConvMacSmem), d->stream>>>(CP);
+                k_conv_ifft<<<dim3(dd.max_slots, convCh, kConvMaxBlocks), 128, 0, d->stream>>>(CP);
+                k_conv_output<<<dim3(dd.max_slots, convCh), 128, 0, d->stream>>>(CP);
+                d->launches += 4;
+            }
             k_slot_output_mix<<<dim3((frames + 127)/128, dd.dry_channels), 128, 0, d->stream>>>(SP);
-            d->launches += 5;
+            ++d->launches;
             if(d->any_target)
             {
                 k_slot_target_mix<<<dim3((frames + 127)/128, dd.max_slots), 128, 0, d->stream>>>(SP);
@@ -1884,6 +2021,8 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         }
         k_slot_gains_commit<<<dd.max_slots, 64, 0, d->stream>>>(SP);
         ++d->launches;
+        for(auto &eh : d->efx)
+            if(eh.used && eh.p.type == B200MIX_EFFECT_MODULATOR) eh.mod_index = (eh.mod_index + frames) % eh.mod_range;
         CUDA_TRY(d, cudaGetLastError());
     }
 

@@ -18,13 +18,14 @@
 #include <cuda_runtime.h>
 
 #include "mixer_kernels.cuh"
+#include "async_ptx.cuh"
 
 namespace b200mix {
 
 constexpr int kConvBlock = 128;     // ConvolveUpdateSamples
 constexpr int kConvFft = 256;       // ConvolveUpdateSize
 constexpr int kConvMaxBlocks = 9;   // blocks that can complete in one 1024-frame update
-constexpr int kConvMaxChunks = 24;  // segment-range chunks of k_conv_mac (gridDim.z), partials in yspec
+constexpr int kConvMaxChunks = 48;  // segment-range chunks of k_conv_mac (gridDim.z), partials in yspec
 
 struct SlotRec {
     uint32_t type, channels, frames, segs;     // segs = mNumConvolveSegs
@@ -43,6 +44,8 @@ struct SlotRec {
     float *gains;     // [2][channels][32]      ping-pong Current gains
     float *gtgt;      // [channels][32]         Target gains
     uint32_t gsel, target;                     // target: slot whose Wet takes the output, or 0xffffffff (Dry)
+    uint32_t fade_len;                         // MixSamples Counter of the output mix: 0 = samplesToDo, else min(n, fade_len)
+    uint32_t pad_;
 };
 
 // ---- send mix --------------------------------------------------------------------------
@@ -590,74 +593,108 @@ __global__ void __launch_bounds__(128) k_conv_input(const ConvParams Q)
     }
 }
 
-// grid (slots, channels, segment chunks), 512 threads = 4 segment ranges x 128 packed bins.  The
-// filter spectra are the one HBM-bound stream of the effects stage (2 s IR: 767 KB per slot and
-// channel, plus as much input-spectrum history): the chunks spread one slot's stream over many
-// SMs (16 slots x 24 chunks = 384 CTAs), every chunk leaves its partial sums in yspec and
-// k_conv_output adds them in chunk order (deterministic).  A thread keeps the
-// accumulators of ALL blocks completed this update (<= 9) and walks its range of filter
-// segments once: X[(cur0 - b + s)] is a sliding window over the spectrum ring, so each
-// iteration loads ONE new input spectrum bin and ONE filter bin for up to 9 complex MACs.
-// The loop is unrolled by 9 so the window rotation is a compile-time renaming and the 18
-// loads of a round are issued before their use.  Range partials are combined in order.
-__global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
+// grid (slots, channels, segment chunks), 128 threads = the 128 packed bins.  The filter spectra
+// are the one HBM-bound stream of the effects stage (2 s IR: 767 KB per slot and channel, plus
+// as much input-spectrum history).  A chunk's filter and input rows (1 KB each) are streamed
+// into a 3-stage shared-memory ring by bulk copies (cp.async.bulk, the 1-D form of TMA) that
+// complete on mbarriers: one thread issues the copies of the stage after next while all threads
+// accumulate the current one, so HBM stays busy during the arithmetic; the chunks spread one
+// slot's stream over the SMs and leave partial sums in yspec that k_conv_ifft adds in chunk
+// order (deterministic).  A thread keeps the accumulators of ALL blocks completed this update
+// (<= 9) in registers: X[(cur0 - b + s)] is a sliding window over the spectrum ring, so each
+// segment costs ONE new input bin and ONE filter bin for up to 9 complex MACs.  Stages hold 9
+// segments aligned to multiples of 9, so the window rotation is a compile-time renaming.
+constexpr int kConvStages = 3;
+struct ConvMacSmem {
+    float2 H[kConvStages][kConvMaxBlocks][128];
+    float2 X[kConvStages][kConvMaxBlocks][128];
+    uint64_t full[kConvStages];
+};
+
+__global__ void __launch_bounds__(128) k_conv_mac(const ConvParams Q)
 {
     constexpr int NB = kConvMaxBlocks;
-    __shared__ float2 part[3][NB][128];
+    extern __shared__ __align__(128) unsigned char conv_smem_raw[];
+    ConvMacSmem &M = *reinterpret_cast<ConvMacSmem*>(conv_smem_raw);
     const SlotRec &S = Q.slots[blockIdx.x];
     if(S.type != 1u || S.stage != Q.stage || blockIdx.y >= S.channels) return;
     const uint32_t nb = S.nb_last;
     if(nb == 0) return;
-    const int t = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    const int t = threadIdx.x;
     const uint32_t segs = S.segs, cur0 = S.cur_last, ring = segs + kConvMaxBlocks;
     const uint32_t clen = conv_chunk_len(segs, gridDim.z);
-    const uint32_t z0 = blockIdx.z*clen;
-    if(z0 >= segs) return;                                   // empty chunk (short IR)
-    const uint32_t z1 = (z0 + clen < segs) ? z0 + clen : segs;
-    const uint32_t per = (z1 - z0 + 3u)/4u;
-    const uint32_t s0 = min(z0 + uint32_t(grp)*per, z1), s1 = (s0 + per < z1) ? s0 + per : z1;
-    const float2 *__restrict__ X = reinterpret_cast<const float2*>(S.X) + t;
-    const float2 *__restrict__ H = reinterpret_cast<const float2*>(S.H + size_t(blockIdx.y)*segs*kConvFft) + t;
+    const uint32_t s0 = blockIdx.z*clen;
+    if(s0 >= segs) return;                                   // empty chunk (short IR)
+    const uint32_t s1 = (s0 + clen < segs) ? s0 + clen : segs;
+    const float *Xg = S.X;
+    const float *Hg = S.H + size_t(blockIdx.y)*segs*kConvFft;
+    // rounds of NB segments aligned to multiples of NB: the window slot (s mod NB) is static
+    const uint32_t r0 = s0 - (s0 % uint32_t(NB));
+    const uint32_t rounds = (s1 - r0 + uint32_t(NB) - 1u)/uint32_t(NB);
+
+    if(t == 0)
+    {
+        for(int st = 0;st < kConvStages;++st) mbar_init(&M.full[st], 1u);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // producer: the rows of round r go to stage r % kConvStages
+    auto issue = [&](uint32_t r) {
+        const uint32_t sb = r0 + r*uint32_t(NB);
+        const int st = int(r % uint32_t(kConvStages));
+        uint32_t rows = 0;
+        for(int u = 0;u < NB;++u) { const uint32_t s = sb + uint32_t(u); if(s >= s0 && s < s1) ++rows; }
+        mbar_expect_tx(&M.full[st], rows*2u*uint32_t(kConvFft)*4u);
+        for(int u = 0;u < NB;++u)
+        {
+            const uint32_t s = sb + uint32_t(u);
+            if(s < s0 || s >= s1) continue;
+            uint32_t q = cur0 + s;                 // cur0 < ring, s < segs < ring
+            q = q >= ring ? q - ring : q;
+            bulk_g2s(M.X[st][u], Xg + size_t(q)*kConvFft, kConvFft*4u, &M.full[st]);
+            bulk_g2s(M.H[st][u], Hg + size_t(s)*kConvFft, kConvFft*4u, &M.full[st]);
+        }
+    };
+    if(t == 0)
+        for(uint32_t r = 0;r < rounds && r < uint32_t(kConvStages);++r) issue(r);
+
     float2 acc[NB], xw[NB];          // xw[s mod NB] holds X[(cur0 + s) mod ring]
     #pragma unroll
     for(int b = 0;b < NB;++b) acc[b] = make_float2(0.f, 0.f);
     #pragma unroll
     for(int u = 0;u < NB;++u) xw[u] = make_float2(0.f, 0.f);
-    if(s0 < s1)
     {
         // history the first segments of the range look back at: X[cur0 + s0 - d], d = 1..NB-1
+        // (plain loads, in flight together with the first stages)
+        const float2 *X = reinterpret_cast<const float2*>(Xg) + t;
+        float2 hv[NB];
+        #pragma unroll
         for(int d = 1;d < NB;++d)
         {
             const uint32_t q = (cur0 + 2u*ring + s0 - uint32_t(d)) % ring;
+            hv[d] = X[size_t(q)*128];
+        }
+        #pragma unroll
+        for(int d = 1;d < NB;++d)
+        {
             const int slotIdx = int((s0 + uint32_t(NB)*8u - uint32_t(d)) % uint32_t(NB));
-            const float2 v = X[size_t(q)*128];
             #pragma unroll
-            for(int u = 0;u < NB;++u) if(u == slotIdx) xw[u] = v;
+            for(int u = 0;u < NB;++u) if(u == slotIdx) xw[u] = hv[d];
         }
     }
-    // rounds of NB segments aligned to multiples of NB: the window slot (s mod NB) is static
-    const uint32_t r0 = s0 - (s0 % uint32_t(NB));
-    for(uint32_t sb = r0;sb < s1;sb += uint32_t(NB))
+    for(uint32_t r = 0;r < rounds;++r)
     {
-        float2 xn[NB], hn[NB];
-        #pragma unroll
-        for(int u = 0;u < NB;++u)
-        {
-            const uint32_t s = sb + uint32_t(u);
-            const bool ok = s >= s0 && s < s1;
-            uint32_t q = cur0 + s;                 // cur0 < ring, s < segs < ring
-            q = q >= ring ? q - ring : q;
-            xn[u] = ok ? X[size_t(q)*128] : make_float2(0.f, 0.f);
-            hn[u] = ok ? H[size_t(s)*128] : make_float2(0.f, 0.f);
-        }
+        const int st = int(r % uint32_t(kConvStages));
+        mbar_wait(&M.full[st], (r / uint32_t(kConvStages)) & 1u);
+        const uint32_t sb = r0 + r*uint32_t(NB);
         #pragma unroll
         for(int u = 0;u < NB;++u)
         {
             const uint32_t s = sb + uint32_t(u);
             if(s >= s0 && s < s1)
             {
-                xw[u] = xn[u];
-                const float2 h = hn[u];
+                xw[u] = M.X[st][u][t];
+                const float2 h = M.H[st][u][t];
                 #pragma unroll
                 for(int b = 0;b < NB;++b)
                 {
@@ -675,26 +712,14 @@ __global__ void __launch_bounds__(512) k_conv_mac(const ConvParams Q)
                 }
             }
         }
+        __syncthreads();                       // every thread is done with this stage
+        if(t == 0 && r + uint32_t(kConvStages) < rounds) issue(r + uint32_t(kConvStages));
     }
-    if(grp > 0)
-    {
-        #pragma unroll
-        for(int b = 0;b < NB;++b) part[grp-1][b][t] = acc[b];
-    }
-    __syncthreads();
-    if(grp == 0)
-    {
-        float2 *Y = reinterpret_cast<float2*>(S.yspec
-            + (size_t(blockIdx.y)*kConvMaxChunks + blockIdx.z)*kConvMaxBlocks*kConvFft) + t;
-        #pragma unroll
-        for(int b = 0;b < NB;++b)
-        {
-            float2 v = acc[b];
-            #pragma unroll
-            for(int gq = 0;gq < 3;++gq) { v.x += part[gq][b][t].x; v.y += part[gq][b][t].y; }
-            if(uint32_t(b) < nb) Y[size_t(b)*128] = v;
-        }
-    }
+    float2 *Y = reinterpret_cast<float2*>(S.yspec
+        + (size_t(blockIdx.y)*kConvMaxChunks + blockIdx.z)*kConvMaxBlocks*kConvFft) + t;
+    #pragma unroll
+    for(int b = 0;b < NB;++b)
+        if(uint32_t(b) < nb) Y[size_t(b)*128] = acc[b];
 }
 
 // grid (slots, channels, blocks), 128 threads: the accumulated spectrum of one completed block
@@ -781,7 +806,7 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
     constexpr int kMaxLines = 16;
     __shared__ float s_cg[64][kMaxLines], s_tg[64][kMaxLines];
     __shared__ const float *s_line[64];
-    __shared__ uint32_t s_ch[64], s_first[64];
+    __shared__ uint32_t s_ch[64], s_first[64], s_fade[64];
     const uint32_t o = blockIdx.y;
     const uint32_t i = blockIdx.x*128u + threadIdx.x;
     const uint32_t n = Q.frames;
@@ -808,6 +833,7 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
             }
             s_ch[threadIdx.x] = ch;
             s_first[threadIdx.x] = first;
+            s_fade[threadIdx.x] = S.fade_len ? min(S.fade_len, n) : n;
             s_line[threadIdx.x] = S.lines;
             const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
             for(uint32_t c = 0;c < ch;++c)
@@ -820,16 +846,18 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
         __syncthreads();
         for(uint32_t s = 0;s < cnt;++s)
         {
-            const uint32_t ch = s_ch[s], first = s_first[s];
+            const uint32_t ch = s_ch[s], first = s_first[s], L = s_fade[s];
             const float *lines = s_line[s];
+            const float dl = (L == n) ? delta : 1.0f/float(L);
             #pragma unroll 4
             for(uint32_t c = 0;c < ch;++c)
             {
                 const float cg = s_cg[s][c], tg = s_tg[s][c];
-                const float step = (tg - cg)*delta;
+                const float step = (tg - cg)*dl;
                 const uint32_t li = (c + first) & (kMaxLines - 1u);
                 const float x = (i < n) ? lines[size_t(li)*kLine + i] : 0.0f;
-                if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
+                // MixLine (mixer_c.cpp:150-186): the ramp over the first L samples, then the target
+                if(fabsf(step) > kEps && i < L) acc += x*(cg + step*float(i));
                 else if(fabsf(tg) > kSilence) acc += x*tg;
             }
         }
@@ -853,6 +881,8 @@ __global__ void __launch_bounds__(128) k_slot_target_mix(const SlotMixParams Q)
         if(S.type == 0u || S.stage != Q.stage || S.target != t) continue;
         uint32_t ch = S.channels, first = 0u;
         if(S.type == 2u) { first = S.rv_cur*8u; ch = (S.rv_mask == 3u) ? 16u : 8u; }
+        const uint32_t L = S.fade_len ? min(S.fade_len, n) : n;
+        const float dl = (L == n) ? delta : 1.0f/float(L);
         const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
         for(uint32_t o = 0;o < Q.cw;++o)
         {
@@ -861,9 +891,9 @@ __global__ void __launch_bounds__(128) k_slot_target_mix(const SlotMixParams Q)
             {
                 const uint32_t li = S.type == 2u ? ((c + first) & 15u) : c;
                 const float cg = gcur[li*32u + o], tg = S.gtgt[li*32u + o];
-                const float step = (tg - cg)*delta;
+                const float step = (tg - cg)*dl;
                 const float x = S.lines[size_t(li)*kLine + i];
-                if(fabsf(step) > kEps) acc += x*(cg + step*float(i));
+                if(fabsf(step) > kEps && i < L) acc += x*(cg + step*float(i));
                 else if(fabsf(tg) > kSilence) acc += x*tg;
             }
             Q.wet[(size_t(t)*Q.cw + o)*kLine + i] = acc;

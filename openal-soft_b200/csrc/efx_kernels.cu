@@ -1,0 +1,275 @@
+// efx_kernels.cu — EffectState::process of the EFX effects behind b200mix_slot_efx on the GPU:
+// echo, ring modulator, equalizer, compressor, dedicated, distortion
+// (alc/effects/{echo,modulator,equalizer,compressor,dedicated,distortion}.cpp).
+//
+// Every one of these is a handful of per-sample recurrences (biquads, an envelope follower, a
+// feedback delay) around trivially parallel arithmetic, and a scene has few of them: one CTA per
+// slot, the recurrences each on their own thread reading and writing shared memory (so only the
+// filter state is on the dependency chain), everything else spread over the CTA.  The kernel
+// leaves the effect's output LINES in the slot record; the slot output mix
+// (k_slot_output_mix / k_slot_target_mix) applies the pan gains with MixSamples' fade.
+//
+// Built with -fmad=false like the parameter kernels: the recurrences are written as the
+// reference writes them and are evaluated operation for operation (no FMA contraction; the
+// reference's x86-64 baseline build has none either), with flush-to-zero as the mixer thread
+// runs (core/fpu_ctrl.cpp).  The one libm call inside a process() — the ring modulator's
+// std::sin per sample — is evaluated in double and rounded once.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "efx_kernels.hpp"
+
+namespace b200mix {
+
+namespace {
+
+constexpr int kLine = 1024;
+
+// BiquadFilter::process (core/filters/biquad.cpp:175-200), in place on shared memory
+__device__ __forceinline__ void biquad_run(const float *c, float *z, const float *src, float *dst, uint32_t n)
+{
+    const float b0 = c[0], b1 = c[1], b2 = c[2], a1 = c[3], a2 = c[4];
+    float z1 = z[0], z2 = z[1];
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const float x = src[i];
+        const float y = x*b0 + z1;
+        z1 = x*b1 - y*a1 + z2;
+        z2 = x*b2 - y*a2;
+        dst[i] = y;
+    }
+    z[0] = z1; z[1] = z2;
+}
+
+// BiquadFilter::dualProcess (core/filters/biquad.cpp:254-283)
+__device__ __forceinline__ void dual_biquad_run(const float *c0, const float *c1, float *z0, float *z1,
+    const float *src, float *dst, uint32_t n)
+{
+    const float b00 = c0[0], b01 = c0[1], b02 = c0[2], a01 = c0[3], a02 = c0[4];
+    const float b10 = c1[0], b11 = c1[1], b12 = c1[2], a11 = c1[3], a12 = c1[4];
+    float z01 = z0[0], z02 = z0[1], z11 = z1[0], z12 = z1[1];
+    for(uint32_t i = 0;i < n;++i)
+    {
+        const float x0 = src[i];
+        const float y0 = x0*b00 + z01;
+        z01 = x0*b01 - y0*a01 + z02;
+        z02 = x0*b02 - y0*a02;
+        const float y1 = y0*b10 + z11;
+        z11 = y0*b11 - y1*a11 + z12;
+        z12 = y0*b12 - y1*a12;
+        dst[i] = y1;
+    }
+    z0[0] = z01; z0[1] = z02; z1[0] = z11; z1[1] = z12;
+}
+
+constexpr float kDecodeCoeff = static_cast<float>(0.25 / 1.7320508075688772935);     // distortion.cpp:52
+constexpr float kEncodeCoeff = static_cast<float>(0.5 * 1.7320508075688772935);      // distortion.cpp:62
+__constant__ float kB2A[4][4] = {{0.25f,  kDecodeCoeff,  kDecodeCoeff,  kDecodeCoeff},
+                                 {0.25f, -kDecodeCoeff, -kDecodeCoeff,  kDecodeCoeff},
+                                 {0.25f,  kDecodeCoeff, -kDecodeCoeff, -kDecodeCoeff},
+                                 {0.25f, -kDecodeCoeff,  kDecodeCoeff, -kDecodeCoeff}};
+__constant__ float kA2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f},
+                                 {kEncodeCoeff, -kEncodeCoeff,  kEncodeCoeff, -kEncodeCoeff},
+                                 {kEncodeCoeff, -kEncodeCoeff, -kEncodeCoeff,  kEncodeCoeff},
+                                 {kEncodeCoeff,  kEncodeCoeff, -kEncodeCoeff, -kEncodeCoeff}};
+
+// grid = slots, 128 threads, dynamic shared memory: 2*kEfxMaxLines + 1 lines (input copies + work)
+__global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
+{
+    extern __shared__ float sm[];
+    const EfxSlotView V = Q.slots[blockIdx.x];
+    if(!V.dev || V.stage != Q.stage) return;
+    EfxDev &E = *V.dev;
+    const EfxParams &P = E.p;
+    const uint32_t t = threadIdx.x, n = Q.frames;
+    const float *wet = Q.wet + size_t(blockIdx.x)*Q.cw*kLine;
+    float *lines = V.lines;
+    const uint32_t nin = min(P.in_channels, Q.cw);
+    float *sIn = sm;                                   // [kEfxMaxLines][1024]
+    float *sWork = sm + kEfxMaxLines*kLine;            // [.. ][1024]
+
+    switch(P.type)
+    {
+    case B200MIX_EFFECT_DEDICATED:
+        // MixSamples(samplesIn[0], ...): the line IS wet channel 0 (dedicated.cpp:105-109)
+        for(uint32_t i = t;i < n;i += blockDim.x) lines[i] = wet[i];
+        break;
+
+    case B200MIX_EFFECT_ECHO:
+    {
+        // EchoState::process (echo.cpp:133-171).  Inside a chunk no longer than the shorter tap
+        // delay every tap read refers to samples written before the chunk: the reads, the
+        // delay-line write and the output lines are sample-parallel; only the damping filter on
+        // the feedback tap is a recurrence (one thread, shared memory).
+        const uint32_t mask = P.echo_len - 1u;
+        float *buf = E.echo_buf;
+        uint32_t offset = E.echo_offset;
+        for(uint32_t base = 0;base < n;)
+        {
+            const uint32_t td = min(n - base, P.echo_tap[0]);
+            for(uint32_t i = t;i < td;i += blockDim.x)
+            {
+                const float o1 = buf[(offset + i - P.echo_tap[0]) & mask];
+                const float o2 = buf[(offset + i - P.echo_tap[1]) & mask];
+                lines[base + i] = o1;
+                lines[kLine + base + i] = o2;
+                sWork[i] = o2;
+            }
+            __syncthreads();
+            if(t == 0) biquad_run(P.echo_filter, E.echo_z, sWork, sWork, td);
+            __syncthreads();
+            for(uint32_t i = t;i < td;i += blockDim.x)
+                buf[(offset + i) & mask] = wet[base + i] + sWork[i] * P.echo_feed;
+            __threadfence_block();
+            __syncthreads();
+            offset += td; base += td;
+        }
+        if(t == 0) E.echo_offset = offset & mask;
+        break;
+    }
+
+    case B200MIX_EFFECT_MODULATOR:
+    {
+        // ModulatorState::process (modulator.cpp:157-199)
+        const uint32_t range = P.mod_range, index0 = E.mod_index;
+        for(uint32_t i = t;i < n;i += blockDim.x)
+        {
+            const uint32_t idx = (index0 + i) % range;
+            float m = 1.0f;
+            if(P.mod_wave == 1u) m = float(::sin(double(float(idx) * P.mod_scale)));
+            else if(P.mod_wave == 2u) m = float(idx)*P.mod_scale - 1.0f;
+            else if(P.mod_wave == 3u) m = float(float(idx)*P.mod_scale < 0.5f)*2.0f - 1.0f;
+            sWork[kLine*kEfxMaxLines + i] = m;         // mModSamples: the extra work row
+        }
+        for(uint32_t c = 0;c < nin;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x) sIn[c*kLine + i] = wet[size_t(c)*kLine + i];
+        __syncthreads();
+        if(t < nin && P.line_on[t]) biquad_run(P.mod_hp, E.chan_z[t][0], sIn + t*kLine, sWork + t*kLine, n);
+        __syncthreads();
+        const float *mod = sWork + kLine*kEfxMaxLines;
+        for(uint32_t c = 0;c < P.lines;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+                lines[size_t(c)*kLine + i] = (c < nin && P.line_on[c]) ? sWork[c*kLine + i] * mod[i] : 0.0f;
+        if(t == 0) E.mod_index = (index0 + n) % range;
+        break;
+    }
+
+    case B200MIX_EFFECT_EQUALIZER:
+    {
+        // EqualizerState::process (equalizer.cpp:165-183): two DualBiquad passes per channel
+        for(uint32_t c = 0;c < nin;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x) sIn[c*kLine + i] = wet[size_t(c)*kLine + i];
+        __syncthreads();
+        if(t < nin && P.line_on[t])
+        {
+            dual_biquad_run(P.eq[0], P.eq[1], E.chan_z[t][0], E.chan_z[t][1], sIn + t*kLine, sWork + t*kLine, n);
+            dual_biquad_run(P.eq[2], P.eq[3], E.chan_z[t][2], E.chan_z[t][3], sWork + t*kLine, sWork + t*kLine, n);
+        }
+        __syncthreads();
+        for(uint32_t c = 0;c < P.lines;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+                lines[size_t(c)*kLine + i] = (c < nin && P.line_on[c]) ? sWork[c*kLine + i] : 0.0f;
+        break;
+    }
+
+    case B200MIX_EFFECT_COMPRESSOR:
+    {
+        // CompressorState::process (compressor.cpp:111-177): envelope follower on channel 0
+        for(uint32_t i = t;i < n;i += blockDim.x) sIn[i] = wet[i];
+        __syncthreads();
+        if(t == 0)
+        {
+            float env = E.comp_env;
+            const float am = P.comp_attack, rm = P.comp_release;
+            for(uint32_t i = 0;i < n;++i)
+            {
+                float amplitude = 1.0f;
+                if(P.comp_enabled)
+                {
+                    amplitude = fabsf(sIn[i]);
+                    amplitude = amplitude < 0.5f ? 0.5f : (2.0f < amplitude ? 2.0f : amplitude);
+                }
+                if(amplitude > env) { const float e = env*am; env = amplitude < e ? amplitude : e; }
+                else if(amplitude < env) { const float e = env*rm; env = e < amplitude ? amplitude : e; }
+                sWork[i] = 1.0f / env;
+            }
+            E.comp_env = env;
+        }
+        __syncthreads();
+        for(uint32_t c = 0;c < P.lines;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+                lines[size_t(c)*kLine + i] = (c < nin && P.line_on[c]) ? wet[size_t(c)*kLine + i] * sWork[i] : 0.0f;
+        break;
+    }
+
+    case B200MIX_EFFECT_DISTORTION:
+    {
+        // DistortionState::process (distortion.cpp:198-303), first-order devices
+        const uint32_t numInput = min(nin, 4u);
+        // B-Format -> A-Format, accumulated in input order like the reference's transform loop
+        for(uint32_t i = t;i < n;i += blockDim.x)
+            for(uint32_t c = 0;c < 4u;++c)
+            {
+                float a = 0.0f;
+                for(uint32_t k = 0;k < numInput;++k) a = a + wet[size_t(k)*kLine + i]*kB2A[c][k];
+                sIn[c*kLine + i] = a;
+            }
+        // mBBuffer rows 4..7 of sIn accumulate the result
+        for(uint32_t i = t;i < 4u*kLine;i += blockDim.x) sIn[4*kLine + i] = 0.0f;
+        __syncthreads();
+        const float fc = P.dist_edge;
+        for(uint32_t base = 0;base < n;)
+        {
+            const uint32_t todo = min(uint32_t(kLine), (n - base)*4u);
+            for(uint32_t c = 0;c < 4u;++c)
+            {
+                float *t0 = sWork, *t1 = sWork + kLine;
+                // zero stuffing x4 (keeps the signal's power)
+                for(uint32_t i = t;i < todo;i += blockDim.x)
+                    t0[i] = !(i & 3u) ? sIn[c*kLine + (i >> 2) + base] * 4.0f : 0.0f;
+                __syncthreads();
+                if(t == 0) biquad_run(P.dist_lp, E.chan_z[c][0], t0, t1, todo);
+                __syncthreads();
+                // three waveshaper steps
+                for(uint32_t i = t;i < todo;i += blockDim.x)
+                {
+                    float smp = t1[i];
+                    smp = ( 1.0f + fc) * smp/(1.0f + fc*fabsf(smp));
+                    smp = (-1.0f - fc) * smp/(1.0f + fc*fabsf(smp));
+                    smp = ( 1.0f + fc) * smp/(1.0f + fc*fabsf(smp));
+                    t0[i] = smp;
+                }
+                __syncthreads();
+                if(t == 0) biquad_run(P.dist_bp, E.chan_z[c][1], t0, t1, todo);
+                __syncthreads();
+                // A-Format -> B-Format, decimated (every fourth sample)
+                for(uint32_t i = t;i < (todo >> 2);i += blockDim.x)
+                    for(uint32_t k = 0;k < 4u;++k)
+                        sIn[(4u + k)*kLine + base + i] = sIn[(4u + k)*kLine + base + i] + t1[i*4u]*kA2B[k][c];
+                __syncthreads();
+            }
+            base += todo >> 2;
+        }
+        for(uint32_t c = 0;c < 4u;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+                lines[size_t(c)*kLine + i] = P.line_on[c] ? sIn[(4u + c)*kLine + i] : 0.0f;
+        break;
+    }
+    default: break;
+    }
+}
+
+} // namespace
+
+constexpr int kEfxSmem = int((2u*kEfxMaxLines + 1u)*kLine*sizeof(float));
+
+cudaError_t efx_kernels_init()
+{ return cudaFuncSetAttribute(k_efx_process, cudaFuncAttributeMaxDynamicSharedMemorySize, kEfxSmem); }
+
+cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream)
+{
+    k_efx_process<<<num_slots, 128, kEfxSmem, stream>>>(Q);
+    return cudaGetLastError();
+}
+
+} // namespace b200mix

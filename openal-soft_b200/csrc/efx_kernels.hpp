@@ -1,0 +1,28 @@
+// efx_kernels.hpp — interface between the library's host side (b200mix.cu) and the EFX effect
+// kernels (efx_kernels.cu, compiled separately with -fmad=false).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "efx_math.hpp"
+
+namespace b200mix {
+
+// Device-resident effect state: the parameters update() produced + what process() carries over.
+struct EfxDev {
+    EfxParams p;
+    float *echo_buf;                       // EchoState::mSampleBuffer [echo_len]
+    uint32_t echo_offset; float echo_z[2]; // mOffset, mFilter z1/z2
+    uint32_t mod_index;                    // ModulatorState::mIndex
+    float comp_env;                        // CompressorState::mEnvFollower
+    float chan_z[kEfxMaxLines][4][2];      // per-channel biquad histories (modulator [0], equalizer [0..3],
+                                           // distortion [0] low-pass, [1] band-pass)
+};
+
+struct EfxSlotView { EfxDev *dev; float *lines; uint32_t stage, pad; };   // dev == null: not an EFX slot
+struct EfxRunParams { const EfxSlotView *slots; const float *wet; uint32_t frames, cw, stage; };
+
+cudaError_t efx_kernels_init();            // per CUDA device: dynamic shared memory opt-in
+cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream);
+
+} // namespace b200mix

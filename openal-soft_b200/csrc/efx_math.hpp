@@ -1,0 +1,189 @@
+// efx_math.hpp — EffectState::deviceUpdate + update of the EFX effects behind b200mix_slot_efx:
+// effect PROPERTIES -> the coefficients, tap offsets and gain targets process() consumes
+// (alc/effects/{echo,modulator,equalizer,compressor,dedicated,distortion}.cpp).  Host arithmetic,
+// the reference's own float expressions and <cmath> calls (param_math.hpp's biquad designs), so the
+// values are bit-identical to the reference's; the GPU kernels (efx_kernels.cu) only run process().
+// Shared with the test oracle (oracle/efx_oracle.cpp), which keeps its own process().
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "param_math.hpp"
+
+namespace b200mix {
+
+constexpr uint32_t kEfxMaxLines = 16;     // output lines / input channels handled per slot
+
+// What update() leaves behind (parameters only; state lives with the process side).
+struct EfxParams {
+    uint32_t type, in_channels, lines;
+    uint32_t fade_len;                    // MixSamples Counter of the output mix: 0 = samplesToDo, else min(n, fade_len)
+    uint32_t snap_gains;                  // 1: the gain applies at once (compressor: no Current/Target fade)
+    uint32_t line_on[kEfxMaxLines];       // line feeds an output channel (mTargetChannel != InvalidChannelIndex)
+    float gains[kEfxMaxLines][32];        // target gains [line][output channel of the target mix]
+    // echo
+    uint32_t echo_tap[2], echo_len; float echo_filter[5], echo_feed;
+    // modulator
+    uint32_t mod_range_new;               // the range update() rescales mIndex with (before the square's rounding)
+    uint32_t mod_range, mod_wave; float mod_scale, mod_hp[5];      // wave: 0 one, 1 sin, 2 saw, 3 square
+    // equalizer
+    float eq[4][5];
+    // compressor
+    uint32_t comp_enabled; float comp_attack, comp_release;
+    // distortion
+    float dist_edge, dist_lp[5], dist_bp[5];
+};
+
+namespace efx_detail {
+struct HostMath {
+    static float sqrt(float x) { return std::sqrt(x); }
+    static float sin(float x) { return std::sin(x); }
+    static float cos(float x) { return std::cos(x); }
+    static float sinh(float x) { return std::sinh(x); }
+    static float log(float x) { return std::log(x); }
+};
+inline uint32_t next_pow2(uint32_t v)     // NextPowerOf2, common/alnumeric.h:121-135
+{
+    if(v > 0) { v--; v |= v>>1; v |= v>>2; v |= v>>4; v |= v>>8; v |= v>>16; }
+    return v + 1u;
+}
+inline uint32_t f2u(float f) { return static_cast<uint32_t>(static_cast<int32_t>(f)); }   // float2uint
+// MixParams::setAmbiMixParams (core/device.h:126-147): wet channel i -> the output channel carrying
+// the same ambisonic index
+inline void ambi_mix_params(const b200mix_efx_target &T, float gainbase, uint32_t max_lines, EfxParams &P)
+{
+    for(uint32_t i = 0;i < T.wet_channels && i < max_lines;++i)
+    {
+        P.line_on[i] = 0u;
+        for(uint32_t j = 0;j < T.out_channels;++j)
+            if(T.out_index[j] == T.wet_index[i])
+            {
+                P.line_on[i] = 1u;
+                P.gains[i][j] = T.out_scale[j] * gainbase;
+                break;
+            }
+    }
+}
+} // namespace efx_detail
+
+// Returns B200MIX_OK / _ERR_INVALID / _ERR_UNSUPPORTED.
+inline int efx_update(const b200mix_efx_props &E, const b200mix_efx_target &T, EfxParams &P)
+{
+    using namespace efx_detail;
+    std::memset(&P, 0, sizeof(P));
+    if(T.out_channels > 32u || T.wet_channels < 1u || !T.out_scale || !T.out_index || !T.wet_index || !T.sample_rate)
+        return B200MIX_ERR_INVALID;
+    if(T.wet_channels > kEfxMaxLines) return B200MIX_ERR_UNSUPPORTED;
+    const float frequency = static_cast<float>(T.sample_rate);
+    P.type = E.type; P.in_channels = T.wet_channels;
+    switch(E.type)
+    {
+    case B200MIX_EFFECT_ECHO:
+    {
+        // EchoState::deviceUpdate / update (echo.cpp:82-131)
+        P.echo_len = next_pow2(f2u(0.207f*frequency + 0.5f) + f2u(0.404f*frequency + 0.5f));
+        P.echo_tap[0] = std::max(f2u(std::round(E.echo.delay*frequency)), 1u);
+        P.echo_tap[1] = f2u(std::round(E.echo.lr_delay*frequency)) + P.echo_tap[0];
+        const float gainhf = std::max(1.0f - E.echo.damping, 0.0625f);
+        pm::biquad_coeffs<HostMath>(0u, 5000.0f/frequency, gainhf, 1.0f, P.echo_filter);
+        P.echo_feed = E.echo.feedback;
+        const float x = E.echo.spread, z = std::sqrt(1.0f - x*x);
+        float c0[B200MIX_MAX_AMBI_CHANNELS], c1[B200MIX_MAX_AMBI_CHANNELS];
+        pm::sh_n3d(x, 0.0f, z, c0);           // CalcAmbiCoeffs( x, 0, z, 0)
+        pm::sh_n3d(-x, 0.0f, z, c1);          // CalcAmbiCoeffs(-x, 0, z, 0)
+        P.lines = 2u; P.line_on[0] = P.line_on[1] = 1u;
+        if(!pm::pan_gains(T.out_channels, T.out_scale, T.out_index, c0, T.slot_gain, P.gains[0], 32u)
+            || !pm::pan_gains(T.out_channels, T.out_scale, T.out_index, c1, T.slot_gain, P.gains[1], 32u))
+            return B200MIX_ERR_INVALID;
+        break;
+    }
+    case B200MIX_EFFECT_MODULATOR:
+    {
+        // ModulatorState::update (modulator.cpp:101-155)
+        const float samplesPerCycle = E.modulator.frequency > 0.0f ? frequency/E.modulator.frequency + 0.5f : 1.0f;
+        const uint32_t range = static_cast<uint32_t>(std::clamp(samplesPerCycle, 1.0f, frequency));
+        P.mod_range_new = range; P.mod_range = range;
+        if(range == 1u) { P.mod_scale = 0.0f; P.mod_wave = 0u; }
+        else if(E.modulator.waveform == 0u)
+        { P.mod_scale = 3.14159265358979323846f*2.0f / static_cast<float>(range); P.mod_wave = 1u; }
+        else if(E.modulator.waveform == 1u)
+        { P.mod_scale = 2.0f / static_cast<float>(range-1u); P.mod_wave = 2u; }
+        else if(E.modulator.waveform == 2u)
+        {
+            P.mod_range = (range+1u) & ~1u;
+            P.mod_scale = 1.0f / static_cast<float>(P.mod_range-1u);
+            P.mod_wave = 3u;
+        }
+        else return B200MIX_ERR_INVALID;
+        const float f0norm = std::clamp(E.modulator.high_pass_cutoff / frequency, 1.0f/512.0f, 0.49f);
+        pm::biquad_coeffs_bandwidth<HostMath>(4u, f0norm, 1.0f, 0.75f, P.mod_hp);
+        P.lines = T.wet_channels; P.fade_len = 64u;
+        ambi_mix_params(T, T.slot_gain, kEfxMaxLines, P);
+        break;
+    }
+    case B200MIX_EFFECT_EQUALIZER:
+    {
+        // EqualizerState::update (equalizer.cpp:117-163)
+        float gain = std::sqrt(E.equalizer.low_gain);
+        pm::biquad_coeffs<HostMath>(1u, E.equalizer.low_cutoff/frequency, gain, 0.75f, P.eq[0]);
+        gain = std::sqrt(E.equalizer.mid1_gain);
+        pm::biquad_coeffs_bandwidth<HostMath>(2u, E.equalizer.mid1_center/frequency, gain, E.equalizer.mid1_width, P.eq[1]);
+        gain = std::sqrt(E.equalizer.mid2_gain);
+        pm::biquad_coeffs_bandwidth<HostMath>(2u, E.equalizer.mid2_center/frequency, gain, E.equalizer.mid2_width, P.eq[2]);
+        gain = std::sqrt(E.equalizer.high_gain);
+        pm::biquad_coeffs<HostMath>(0u, E.equalizer.high_cutoff/frequency, gain, 0.75f, P.eq[3]);
+        P.lines = T.wet_channels;
+        ambi_mix_params(T, T.slot_gain, kEfxMaxLines, P);
+        break;
+    }
+    case B200MIX_EFFECT_COMPRESSOR:
+    {
+        // CompressorState::deviceUpdate / update (compressor.cpp:80-109)
+        const float attackCount = frequency * 0.1f, releaseCount = frequency * 0.2f;
+        P.comp_attack = std::pow(2.0f/0.5f, 1.0f/attackCount);
+        P.comp_release = std::pow(0.5f/2.0f, 1.0f/releaseCount);
+        P.comp_enabled = E.compressor.on_off ? 1u : 0u;
+        P.lines = T.wet_channels; P.snap_gains = 1u;
+        ambi_mix_params(T, T.slot_gain, kEfxMaxLines, P);
+        break;
+    }
+    case B200MIX_EFFECT_DEDICATED:
+    {
+        // DedicatedState::update (dedicated.cpp:67-103)
+        const float Gain = T.slot_gain * E.dedicated.gain;
+        P.lines = 1u; P.line_on[0] = 1u;
+        if(E.dedicated.target == 0u)
+        {
+            if(T.real_center != B200MIX_NO_SLOT) return B200MIX_ERR_UNSUPPORTED;
+            float c[B200MIX_MAX_AMBI_CHANNELS];
+            pm::sh_n3d(-0.0f, 0.0f, 1.0f, c);        // CalcDirectionCoeffs({0, 0, -1})
+            if(!pm::pan_gains(T.out_channels, T.out_scale, T.out_index, c, Gain, P.gains[0], 32u))
+                return B200MIX_ERR_INVALID;
+        }
+        else if(T.real_lfe != B200MIX_NO_SLOT) return B200MIX_ERR_UNSUPPORTED;
+        break;
+    }
+    case B200MIX_EFFECT_DISTORTION:
+    {
+        // DistortionState::update (distortion.cpp:140-196), first-order devices (no up-sampler)
+        if(T.device_ambi_order > 1u) return B200MIX_ERR_UNSUPPORTED;
+        const float edge = std::min(std::sin(3.14159265358979323846f*0.5f * E.distortion.edge), 0.99f);
+        P.dist_edge = 2.0f * edge / (1.0f-edge);
+        float cutoff = E.distortion.lowpass_cutoff;
+        float bandwidth = 0.746268656716f;
+        pm::biquad_coeffs_bandwidth<HostMath>(3u, cutoff/frequency*0.25f, 1.0f, bandwidth, P.dist_lp);
+        cutoff = E.distortion.eq_center;
+        bandwidth = E.distortion.eq_bandwidth / (cutoff * 0.67f);
+        pm::biquad_coeffs_bandwidth<HostMath>(5u, cutoff/frequency*0.25f, 1.0f, bandwidth, P.dist_bp);
+        P.lines = 4u;
+        ambi_mix_params(T, T.slot_gain*E.distortion.gain, 4u, P);
+        break;
+    }
+    default: return B200MIX_ERR_INVALID;
+    }
+    return B200MIX_OK;
+}
+
+} // namespace b200mix

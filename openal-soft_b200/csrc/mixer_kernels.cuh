@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "voice_structs.hpp"
+#include "async_ptx.cuh"
 
 namespace b200mix {
 
@@ -95,6 +96,7 @@ struct MixParams {
     // streaming queues (null until the first b200mix_voice_queue): per voice
     // {count, head, loop, -} and kMaxQueue buffer ids
     uint4 *qhdr; const uint32_t *queue;
+    uint32_t gather_only;                     // A/B measurements: skip the TMA staging of source spans
 };
 
 constexpr uint32_t kMaxQueue = 32, kNoLoop = 0xffffffffu;
@@ -246,7 +248,7 @@ __device__ __forceinline__ void fill_window(const FillArgs &A, const T *__restri
 
 // Shared-memory carve-up of one voice group.
 template<int GS, int OPT, int FP>
-struct GroupSmem {
+struct alignas(16) GroupSmem {
     static constexpr int kTabStride = kPad + 2;         // max row stride; rows use m+2 (even, half odd:
                                                         // 8-byte aligned AND conflict-free for LDS.64)
     static constexpr int kLLen = FP + OPT*GS;           // FIR input incl. front zero pad
@@ -259,6 +261,7 @@ struct GroupSmem {
     float x[kHist + kLine];
     float2 coefT[kHrirLen], coefO[kHrirLen];
     float newGain[32];                  // dry Current gains written back after the voice
+    uint64_t tmaBar;                    // mbarrier of the group's source-span bulk copies
 };
 
 // One FIR pass for BOTH ears: acc[r].{x,y} += sum_j c[j].{x,y} * in[FP + t0 + r - j].{x,y}
@@ -316,6 +319,9 @@ k_mix_voices(const MixParams P)
 
     const uint32_t n = P.frames;
     const int t0 = OPT*t;
+    if(t == 0) { mbar_init(&S.tmaBar, 1u); mbar_fence_init(); }
+    uint32_t tmaPhase = 0u;                       // parity of the next completion of tmaBar
+    group_sync(bar, GS);
 
     // Voices are visited in the host's mixing order (active voices only, sorted by
     // resampler cost) with a grid-strided assignment: every round of the persistent loop
@@ -501,6 +507,67 @@ k_mix_voices(const MixParams P)
                     uint32_t done = 0, item = qh.x ? qh.y : kNoLoop, qpos = uintPos;
                     bool more = true;
                     winInt = true;
+                    // ---- TMA staging of the source span (the common case: a static mono int16
+                    // buffer, the span inside the buffer, at most one loop wrap).  The span is one
+                    // or two CONTIGUOUS runs of the buffer: one thread issues a bulk copy
+                    // (cp.async.bulk: global -> shared, completion on the group's mbarrier) per run
+                    // into the unused tail of the window storage; the group then converts from
+                    // shared memory.  Replaces ~1300 two-byte gathers per voice-chunk by one or two
+                    // asynchronous copies; the lines were pulled into L2 a round earlier.
+                    if(!P.gather_only && !isQueue && buf.type == 1u && buf.channels == 1u
+                        && ((flags >> 16) & 0xffu) == 0u && count > 0u)
+                    {
+                        const uint32_t loopSize = looping ? (loopEnd - loopStart) : 1u;
+                        const uint32_t q0 = !looping ? uintPos : ((uintPos < loopEnd) ? uintPos
+                            : ((uintPos-loopStart)%loopSize + loopStart));
+                        const uint32_t run1 = looping ? min(count, loopEnd - q0) : count;
+                        const uint32_t run2 = count - run1;
+                        const bool fits = looping ? (run2 <= loopSize && loopEnd <= buf.frames)
+                                                  : (uintPos + count <= buf.frames);
+                        if(fits)
+                        {
+                            const int16_t *base = static_cast<const int16_t*>(buf.data);
+                            const uintptr_t a1 = reinterpret_cast<uintptr_t>(base + q0);
+                            const uintptr_t a2 = reinterpret_cast<uintptr_t>(base + loopStart);
+                            const uint32_t lead1 = uint32_t(a1 & 15u) >> 1, lead2 = uint32_t(a2 & 15u) >> 1;
+                            const uint32_t bytes1 = ((run1 + lead1)*2u + 15u) & ~15u;
+                            const uint32_t bytes2 = run2 ? (((run2 + lead2)*2u + 15u) & ~15u) : 0u;
+                            constexpr uint32_t kWinBytes = uint32_t(sizeof(S.u.rs.win));
+                            unsigned char *wbytes = reinterpret_cast<unsigned char*>(S.u.rs.win);
+                            unsigned char *raw2 = wbytes + kWinBytes - bytes2;
+                            unsigned char *raw1 = raw2 - bytes1;
+                            if(t == 0)
+                            {
+                                fence_proxy_async_smem();
+                                mbar_expect_tx(&S.tmaBar, bytes1 + bytes2);
+                                bulk_g2s(raw1, reinterpret_cast<const void*>(a1 & ~uintptr_t(15)), bytes1, &S.tmaBar);
+                                if(run2)
+                                    bulk_g2s(raw2, reinterpret_cast<const void*>(a2 & ~uintptr_t(15)), bytes2, &S.tmaBar);
+                            }
+                            mbar_wait(&S.tmaBar, tmaPhase);
+                            tmaPhase ^= 1u;
+                            const int16_t *r1 = reinterpret_cast<const int16_t*>(raw1) + lead1;
+                            const int16_t *r2 = reinterpret_cast<const int16_t*>(raw2) + lead2;
+                            constexpr int PERW = (kSrcSizeMax + GS - 1)/GS;
+                            float v[PERW];
+                            #pragma unroll
+                            for(int u = 0;u < PERW;++u)
+                            {
+                                const uint32_t k = uint32_t(t) + uint32_t(u)*GS;
+                                int16_t x = 0;
+                                if(k < count) x = k < run1 ? r1[k] : r2[k - run1];
+                                v[u] = to_float(x);
+                            }
+                            group_sync(bar, GS);                 // raw span consumed: the floats may overwrite it
+                            #pragma unroll
+                            for(int u = 0;u < PERW;++u)
+                            {
+                                const uint32_t k = uint32_t(t) + uint32_t(u)*GS;
+                                if(k < count) dst[k] = v[u];
+                            }
+                            done = count; more = false;
+                        }
+                    }
                     while(more)
                     {
                         BufferRec rb = buf;

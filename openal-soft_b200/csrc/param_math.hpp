@@ -69,10 +69,27 @@ enum Model { Disable, Inverse, InverseClamped, Linear, LinearClamped, Exponent, 
 
 // BiquadFilter::SetParams behind setParamsFromSlope (core/filters/biquad.h:61-62,92-97;
 // biquad.cpp:48-129).  type: 0 HighShelf, 1 LowShelf, 2 Peaking, 3 LowPass, 4 HighPass, 5 BandPass.
+// BiquadFilter::SetParams (core/filters/biquad.cpp:48-129) with an explicit rcpQ.
+template<class M> PM_HD void biquad_set_params(uint32_t type, float f0norm, float gain, float rcpQ, float coeffs[5]);
+// rcpQFromBandwidth (core/filters/biquad.h:70-76)
+template<class M> PM_HD float biquad_rcpq_from_bandwidth(float f0norm, float bandwidth)
+{
+    const float w0 = 3.14159265358979323846f*2.0f * f0norm;
+    return 2.0f*M::sinh(M::log(2.0f)/2.0f*bandwidth*w0/M::sin(w0));
+}
+// setParamsFromBandwidth (core/filters/biquad.h:110-112)
+template<class M> PM_HD void biquad_coeffs_bandwidth(uint32_t type, float f0norm, float gain, float bandwidth, float coeffs[5])
+{ biquad_set_params<M>(type, f0norm, gain, biquad_rcpq_from_bandwidth<M>(f0norm, bandwidth), coeffs); }
+
 template<class M> PM_HD void biquad_coeffs(uint32_t type, float f0norm, float gain, float slope, float coeffs[5])
 {
     gain = fmaxf_(gain, 0.001f);
     const float rcpQ = M::sqrt((gain + 1.0f/gain)*(1.0f/slope - 1.0f) + 2.0f);
+    biquad_set_params<M>(type, f0norm, gain, rcpQ, coeffs);
+}
+
+template<class M> PM_HD void biquad_set_params(uint32_t type, float f0norm, float gain, float rcpQ, float coeffs[5])
+{
     gain = fmaxf_(gain, 0.00001f);
     const float w0 = 3.14159265358979323846f*2.0f * fminf_(f0norm, 0.49f);
     const float sin_w0 = M::sin(w0), cos_w0 = M::cos(w0);

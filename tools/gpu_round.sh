@@ -22,5 +22,29 @@ fx)
   timeout 300 python tools/bench_effects.py --effect conv --voices 4096 --slots 32 > gpurun_out/${tag}_fx_conv.log 2>&1
   timeout 300 python tools/bench_effects.py --effect conv --voices 4096 --slots 16 >> gpurun_out/${tag}_fx_conv.log 2>&1
   tail -2 gpurun_out/${tag}_fx_conv.log; grep k_conv_mac gpurun_out/${tag}_launches_fx_conv.csv | tail -3 ;;
+params)
+  timeout 900 python -m pytest tests/test_gpu_params.py tests/test_gpu_parity.py -m gpu -q --timeout 600 -x -s -k "sources_update or convolution or config2 or golden" > gpurun_out/${tag}_pytest_params.log 2>&1
+  tail -8 gpurun_out/${tag}_pytest_params.log ;;
+ncu_conv)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv_mac -s 4 -c 1 -o gpurun_out/${tag}_prof_conv_mac -f \
+     python tools/bench_effects.py --effect conv --voices 4096 --slots 32 --steps 2 > gpurun_out/${tag}_ncu_conv.log 2>&1
+  tail -2 gpurun_out/${tag}_ncu_conv.log ;;
+ab4a)
+  for env in "X=0" "B200MIX_PANMIX_SIMT=1" "B200MIX_MIX_GATHER=1" "B200MIX_PANMIX_SIMT=1 B200MIX_MIX_GATHER=1"; do
+    echo "== $env" >> gpurun_out/${tag}_ab4a.log
+    env $env timeout 600 python -m pytest tests/test_gpu_atsize.py -m gpu -q --timeout 600 -x -k "config4a" 2>&1 | grep -E "passed|failed|^E .*rms" >> gpurun_out/${tag}_ab4a.log
+  done
+  cat gpurun_out/${tag}_ab4a.log ;;
+probe)
+  ./tools/ubench/umma_probe > gpurun_out/${tag}_umma_probe.log 2>&1; cat gpurun_out/${tag}_umma_probe.log ;;
+tc)
+  ./tools/ubench/panmix_tc_test 1000 16 > gpurun_out/${tag}_panmix_tc.log 2>&1
+  ./tools/ubench/panmix_tc_test 8192 16 >> gpurun_out/${tag}_panmix_tc.log 2>&1
+  ./tools/ubench/panmix_tc_test 77 9 >> gpurun_out/${tag}_panmix_tc.log 2>&1
+  cat gpurun_out/${tag}_panmix_tc.log
+  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_atsize.py -m gpu -q --timeout 600 -x -k "ambi3 or config4a or dry_mix" > gpurun_out/${tag}_pytest_tc.log 2>&1
+  tail -5 gpurun_out/${tag}_pytest_tc.log
+  for m in 0 1; do B200MIX_PANMIX_SIMT=$m timeout 300 python tools/bench_configs.py --config 4a --voices 8192 --steps 8 >> gpurun_out/${tag}_cfg4a.jsonl 2>> gpurun_out/${tag}_cfg4a.err; done
+  cat gpurun_out/${tag}_cfg4a.jsonl ;;
 esac
 done
