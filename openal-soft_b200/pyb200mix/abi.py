@@ -187,6 +187,64 @@ class SourceVoice(C.Structure):
                 ("loop_end", C.c_uint32), ("buffer_rate", C.c_uint32), ("send_slot", C.c_uint32 * MAX_SENDS)]
 
 
+(EFFECT_NONE, EFFECT_CONVOLUTION, EFFECT_REVERB, EFFECT_ECHO, EFFECT_MODULATOR, EFFECT_EQUALIZER,
+ EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION) = range(9)
+
+
+class _EfxEcho(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("delay", "lr_delay", "damping", "feedback", "spread")]
+
+
+class _EfxModulator(C.Structure):
+    _fields_ = [("frequency", C.c_float), ("high_pass_cutoff", C.c_float), ("waveform", C.c_uint32)]
+
+
+class _EfxEqualizer(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("low_cutoff", "low_gain", "mid1_center", "mid1_gain", "mid1_width",
+                                          "mid2_center", "mid2_gain", "mid2_width", "high_cutoff", "high_gain")]
+
+
+class _EfxCompressor(C.Structure):
+    _fields_ = [("on_off", C.c_uint32)]
+
+
+class _EfxDedicated(C.Structure):
+    _fields_ = [("target", C.c_uint32), ("gain", C.c_float)]
+
+
+class _EfxDistortion(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("edge", "gain", "lowpass_cutoff", "eq_center", "eq_bandwidth")]
+
+
+class EfxProps(C.Structure):
+    """b200mix_efx_props: the EFX effect's properties (EffectProps, core/effects/base.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("type", C.c_uint32), ("echo", _EfxEcho), ("modulator", _EfxModulator),
+                ("equalizer", _EfxEqualizer), ("compressor", _EfxCompressor), ("dedicated", _EfxDedicated),
+                ("distortion", _EfxDistortion)]
+
+
+class EfxTarget(C.Structure):
+    """b200mix_efx_target: what EffectState::update reads from the slot and its output target."""
+    _fields_ = [("struct_size", C.c_uint32), ("sample_rate", C.c_uint32), ("slot_gain", C.c_float),
+                ("out_channels", C.c_uint32), ("out_scale", C.c_void_p), ("out_index", C.c_void_p),
+                ("wet_channels", C.c_uint32), ("wet_index", C.c_void_p), ("real_center", C.c_uint32),
+                ("real_lfe", C.c_uint32), ("device_ambi_order", C.c_uint32)]
+
+
+def efx_defaults(effect_type):
+    """The EFX defaults of include/AL/efx.h (AL_*_DEFAULT_*) for one effect type."""
+    p = EfxProps()
+    p.struct_size = C.sizeof(EfxProps)
+    p.type = effect_type
+    p.echo = _EfxEcho(0.1, 0.1, 0.5, 0.5, -1.0)
+    p.modulator = _EfxModulator(440.0, 800.0, 0)
+    p.equalizer = _EfxEqualizer(200.0, 1.0, 500.0, 1.0, 1.0, 3000.0, 1.0, 1.0, 6000.0, 1.0)
+    p.compressor = _EfxCompressor(1)
+    p.dedicated = _EfxDedicated(0, 1.0)
+    p.distortion = _EfxDistortion(0.2, 0.05, 8000.0, 3600.0, 3600.0)
+    return p
+
+
 class ChannelSetup(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("layout", C.c_uint32), ("stereo_pan", C.c_float * 2),
                 ("panning", C.c_float), ("lfe_dry_index", C.c_uint32), ("spatialized", C.c_uint32)]

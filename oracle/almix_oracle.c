@@ -11,6 +11,7 @@
 #include "almix_oracle.h"
 #include "reverb_oracle.h"
 #include "limiter_oracle.h"
+#include "efx_oracle.h"
 
 #define ORACLE_PI 3.14159265358979323846   /* std::numbers::pi */
 
@@ -230,6 +231,7 @@ typedef struct {
     uint32_t hist_pos;
     float *cur, *tgt;          /* output mix gains [channels][MAX_DRY] */
     oreverb *reverb;           /* type == B200MIX_EFFECT_REVERB */
+    oefx *efx;                 /* type >= B200MIX_EFFECT_ECHO (efx_oracle.cpp) */
     uint32_t target;           /* EffectSlotBase::Target as a slot index, B200MIX_NO_SLOT = the Dry mix */
 } oslot;
 
@@ -459,6 +461,7 @@ int oracle_slot_disable(oracle_device *d, uint32_t slot)
     oslot *s = &d->slots[slot];
     free(s->ir); free(s->hist); free(s->cur); free(s->tgt);
     oreverb_destroy(s->reverb);
+    if(s->efx) oefx_free(s->efx);
     const uint32_t target = s->target;       /* the target belongs to the slot, not to its effect */
     memset(s, 0, sizeof(*s));
     s->target = target;
@@ -474,6 +477,25 @@ int oracle_slot_reverb(oracle_device *d, uint32_t slot, const b200mix_reverb_par
     s->reverb = oreverb_create(params);
     if(!s->reverb) return B200MIX_ERR_NOMEM;
     s->type = B200MIX_EFFECT_REVERB; s->channels = 8;
+    return B200MIX_OK;
+}
+
+/* The other EFX effects: deviceUpdate + update on the first call / a change of type, update()
+ * afterwards (efx_oracle.cpp). */
+int oracle_slot_efx(oracle_device *d, uint32_t slot, const b200mix_efx_props *props,
+    const b200mix_efx_target *target)
+{
+    if(slot >= d->desc.max_slots || !props || !target || props->struct_size != sizeof(*props)
+        || target->struct_size != sizeof(*target))
+        return B200MIX_ERR_INVALID;
+    oslot *s = &d->slots[slot];
+    if(s->efx && s->type == props->type && oefx_update(s->efx, props, target) == B200MIX_OK)
+        return B200MIX_OK;
+    oracle_slot_disable(d, slot);
+    int rc = B200MIX_OK;
+    s->efx = oefx_create(props, target, &rc);
+    if(!s->efx) return rc;
+    s->type = props->type; s->channels = 1;
     return B200MIX_OK;
 }
 
@@ -1817,6 +1839,9 @@ int oracle_render_end(oracle_device *d, float *const *real_out, b200mix_voice_re
             oreverb_process(d->slots[si].reverb, frames,
                 (const float(*)[LINE])d->wet[(size_t)si*dd->wet_channels], dd->wet_channels,
                 reverb_mix_cb, d);
+        else if(d->slots[si].efx)
+            oefx_process(d->slots[si].efx, frames, (const float(*)[LINE])d->wet[(size_t)si*dd->wet_channels],
+                dd->wet_channels, g_out_buf, g_out_channels);
     }
 
     switch(dd->post_process)

@@ -91,6 +91,8 @@ int  oracle_slot_reverb_update(oracle_device *dev, uint32_t slot, const b200mix_
     uint32_t full_update);
 int  oracle_slot_disable(oracle_device *dev, uint32_t slot);
 int  oracle_slot_target(oracle_device *dev, uint32_t slot, uint32_t target);
+int  oracle_slot_efx(oracle_device *dev, uint32_t slot, const b200mix_efx_props *props,
+    const b200mix_efx_target *target);
 int  oracle_set_distance_comp(oracle_device *dev, uint32_t channels, const uint32_t *delays, const float *gains);
 int  oracle_set_uhj_encoder(oracle_device *dev, uint32_t filter_length, uint32_t *delay);
 int  oracle_set_front_stabilizer(oracle_device *dev, uint32_t center_channel, float splitter_coeff);

@@ -1,0 +1,276 @@
+// efx_oracle.cpp — CPU restatement of EffectState::process for the EFX effects the product runs
+// on the GPU (echo, ring modulator, equalizer, compressor, dedicated, distortion).  TEST
+// INFRASTRUCTURE ONLY: linked into oracle/liboracle.so, used by tests/, smoke() and nothing else.
+//
+// Each process() below follows the reference line by line (file:line cited); the parameter side
+// (deviceUpdate + update: coefficient designs, tap offsets, gain targets) is the shared
+// restatement in openal-soft_b200/csrc/efx_math.hpp, whose values are pinned — together with
+// these loops — by the golden vectors rendered by the compiled reference (tests/golden/efx_*).
+// Compiled with -ffp-contract=off: plain mul/add like the reference's x86-64 build.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "efx_oracle.h"
+#include "../openal-soft_b200/csrc/efx_math.hpp"
+
+using b200mix::EfxParams;
+namespace {
+constexpr size_t LINE = 1024;
+constexpr float kSilence = 0.00001f;      // GainSilenceThreshold, core/mixer/defs.h:28
+
+struct Biquad { float z1{0.0f}, z2{0.0f}; };
+// BiquadFilter::process, core/filters/biquad.cpp:175-200
+void biquad_process(const float *c, Biquad &f, const float *src, float *dst, size_t n)
+{
+    float z1 = f.z1, z2 = f.z2;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x = src[i];
+        const float y = x*c[0] + z1;
+        z1 = x*c[1] - y*c[3] + z2;
+        z2 = x*c[2] - y*c[4];
+        dst[i] = y;
+    }
+    f.z1 = z1; f.z2 = z2;
+}
+// BiquadFilter::dualProcess, core/filters/biquad.cpp:254-283
+void dual_process(const float *c0, const float *c1, Biquad &f0, Biquad &f1, const float *src, float *dst, size_t n)
+{
+    float z01 = f0.z1, z02 = f0.z2, z11 = f1.z1, z12 = f1.z2;
+    for(size_t i = 0;i < n;++i)
+    {
+        const float x0 = src[i];
+        const float y0 = x0*c0[0] + z01;
+        z01 = x0*c0[1] - y0*c0[3] + z02;
+        z02 = x0*c0[2] - y0*c0[4];
+        const float y1 = y0*c1[0] + z11;
+        z11 = y0*c1[1] - y1*c1[3] + z12;
+        z12 = y0*c1[2] - y1*c1[4];
+        dst[i] = y1;
+    }
+    f0.z1 = z01; f0.z2 = z02; f1.z1 = z11; f1.z2 = z12;
+}
+// MixLine, core/mixer/mixer_c.cpp:150-186
+void mix_line(const float *in, size_t n, float *dst, float &cur, float target, float delta, size_t fade_len, size_t counter)
+{
+    const float step = (target - cur) * delta;
+    size_t pos = 0;
+    if(std::fabs(step) > 1.1920929e-07f)
+    {
+        const float gain = cur;
+        float step_count = 0.0f;
+        for(;pos < fade_len;++pos) { dst[pos] += in[pos] * (gain + step*step_count); step_count += 1.0f; }
+        if(fade_len < counter) { cur = gain + step*step_count; return; }
+    }
+    cur = target;
+    if(!(std::fabs(target) > kSilence)) return;
+    for(;pos < n;++pos) dst[pos] += in[pos]*target;
+}
+// Mix_C 1 -> many and 1 -> 1, mixer_c.cpp:247-268
+void mix_many(const float *in, size_t n, float (*out)[LINE], size_t nout, float *cur, const float *tgt, size_t counter)
+{
+    const float delta = counter > 0 ? 1.0f/float(counter) : 0.0f;
+    const size_t fade_len = std::min(counter, n);
+    for(size_t c = 0;c < nout;++c) mix_line(in, n, out[c], cur[c], tgt[c], delta, fade_len, counter);
+}
+} // namespace
+
+struct oefx {
+    EfxParams p{};
+    float cur[b200mix::kEfxMaxLines][32]{};       // Current gains per line and output channel
+    // echo
+    std::vector<float> echo_buf; size_t echo_offset{0}; Biquad echo_f;
+    // modulator
+    uint32_t mod_index{0}, mod_range{1};
+    Biquad chan[b200mix::kEfxMaxLines][4];
+    // compressor
+    float env{1.0f};
+};
+
+extern "C" {
+
+oefx *oefx_create(const b200mix_efx_props *props, const b200mix_efx_target *target, int *rc)
+{
+    auto *e = new(std::nothrow) oefx{};
+    if(!e) { *rc = B200MIX_ERR_NOMEM; return nullptr; }
+    *rc = b200mix::efx_update(*props, *target, e->p);
+    if(*rc != B200MIX_OK) { delete e; return nullptr; }
+    if(e->p.echo_len) e->echo_buf.assign(e->p.echo_len, 0.0f);
+    e->mod_range = e->p.mod_range ? e->p.mod_range : 1u;
+    if(e->p.snap_gains) std::memcpy(e->cur, e->p.gains, sizeof(e->cur));
+    return e;
+}
+
+int oefx_update(oefx *e, const b200mix_efx_props *props, const b200mix_efx_target *target)
+{
+    EfxParams P;
+    if(int rc = b200mix::efx_update(*props, *target, P)) return rc;
+    if(P.type != e->p.type || P.lines != e->p.lines || P.echo_len != e->p.echo_len) return B200MIX_ERR_INVALID;
+    if(P.type == B200MIX_EFFECT_MODULATOR)
+    {   // mIndex rescale, modulator.cpp:117-118
+        e->mod_index = uint32_t(uint64_t(e->mod_index) * P.mod_range_new / e->mod_range);
+        e->mod_range = P.mod_range;
+    }
+    e->p = P;
+    if(P.snap_gains) std::memcpy(e->cur, P.gains, sizeof(e->cur));
+    return B200MIX_OK;
+}
+
+uint32_t oefx_type(const oefx *e) { return e->p.type; }
+void oefx_free(oefx *e) { delete e; }
+
+void oefx_process(oefx *e, size_t n, const float (*in)[1024], size_t nin_, float (*out)[1024], size_t nout)
+{
+    const EfxParams &P = e->p;
+    const size_t nin = std::min<size_t>(nin_, P.in_channels);
+    static thread_local float buf[LINE], tmp0[LINE], tmp1[LINE], mod[LINE];
+    switch(P.type)
+    {
+    case B200MIX_EFFECT_DEDICATED:
+        // dedicated.cpp:105-109
+        mix_many(in[0], n, out, nout, e->cur[0], P.gains[0], n);
+        break;
+    case B200MIX_EFFECT_ECHO:
+    {
+        // echo.cpp:133-157
+        const size_t mask = e->echo_buf.size() - 1;
+        float *delaybuf = e->echo_buf.data();
+        size_t offset = e->echo_offset;
+        size_t tap1 = offset - P.echo_tap[0], tap2 = offset - P.echo_tap[1];
+        for(size_t i = 0;i < n;++i)
+        {
+            offset &= mask; tap1 &= mask; tap2 &= mask;
+            delaybuf[offset] = in[0][i];
+            tmp0[i] = delaybuf[tap1++];
+            tmp1[i] = delaybuf[tap2++];
+            const float feedb = tmp1[i];
+            const float y = feedb*P.echo_filter[0] + e->echo_f.z1;                 // processOne
+            e->echo_f.z1 = feedb*P.echo_filter[1] - y*P.echo_filter[3] + e->echo_f.z2;
+            e->echo_f.z2 = feedb*P.echo_filter[2] - y*P.echo_filter[4];
+            delaybuf[offset++] += y * P.echo_feed;
+        }
+        e->echo_offset = offset;
+        mix_many(tmp0, n, out, nout, e->cur[0], P.gains[0], n);
+        mix_many(tmp1, n, out, nout, e->cur[1], P.gains[1], n);
+        break;
+    }
+    case B200MIX_EFFECT_MODULATOR:
+    {
+        // modulator.cpp:157-199
+        uint32_t index = e->mod_index;
+        for(size_t i = 0;i < n;++i)
+        {
+            float m = 1.0f;
+            if(P.mod_wave == 1u) m = std::sin(float(index) * P.mod_scale);
+            else if(P.mod_wave == 2u) m = float(index)*P.mod_scale - 1.0f;
+            else if(P.mod_wave == 3u) m = float(float(index)*P.mod_scale < 0.5f)*2.0f - 1.0f;
+            mod[i] = m;
+            if(++index == P.mod_range) index = 0;
+        }
+        e->mod_index = index;
+        for(size_t c = 0;c < nin;++c)
+        {
+            if(!P.line_on[c]) continue;
+            biquad_process(P.mod_hp, e->chan[c][0], in[c], buf, n);
+            for(size_t i = 0;i < n;++i) buf[i] = buf[i] * mod[i];
+            // MixSamples 1 -> 1 to the channel of the same ambisonic index, Counter = min(n, 64)
+            for(size_t o = 0;o < nout;++o)
+                if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                {
+                    const size_t counter = std::min<size_t>(n, 64);
+                    mix_line(buf, n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(counter), counter, counter);
+                }
+        }
+        break;
+    }
+    case B200MIX_EFFECT_EQUALIZER:
+        // equalizer.cpp:165-183
+        for(size_t c = 0;c < nin;++c)
+        {
+            if(!P.line_on[c]) continue;
+            dual_process(P.eq[0], P.eq[1], e->chan[c][0], e->chan[c][1], in[c], buf, n);
+            dual_process(P.eq[2], P.eq[3], e->chan[c][2], e->chan[c][3], buf, buf, n);
+            for(size_t o = 0;o < nout;++o)
+                if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                    mix_line(buf, n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        }
+        break;
+    case B200MIX_EFFECT_COMPRESSOR:
+    {
+        // compressor.cpp:111-177
+        float env = e->env;
+        for(size_t i = 0;i < n;++i)
+        {
+            const float amplitude = P.comp_enabled ? std::clamp(std::fabs(in[0][i]), 0.5f, 2.0f) : 1.0f;
+            if(amplitude > env) env = std::min(env*P.comp_attack, amplitude);
+            else if(amplitude < env) env = std::max(env*P.comp_release, amplitude);
+            buf[i] = 1.0f / env;
+        }
+        e->env = env;
+        for(size_t c = 0;c < nin;++c)
+        {
+            if(!P.line_on[c]) continue;
+            for(size_t o = 0;o < nout;++o)
+            {
+                const float gain = P.gains[c][o];
+                if(std::fabs(gain) > kSilence)
+                    for(size_t i = 0;i < n;++i) out[o][i] += in[c][i] * buf[i] * gain;
+            }
+        }
+        break;
+    }
+    case B200MIX_EFFECT_DISTORTION:
+    {
+        // distortion.cpp:198-303 (first-order devices)
+        static const float dc = static_cast<float>(0.25 / 1.7320508075688772935);
+        static const float ec = static_cast<float>(0.5 * 1.7320508075688772935);
+        static const float B2A[4][4] = {{0.25f, dc, dc, dc}, {0.25f, -dc, -dc, dc}, {0.25f, dc, -dc, -dc}, {0.25f, -dc, dc, -dc}};
+        static const float A2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {ec, -ec, ec, -ec}, {ec, -ec, -ec, ec}, {ec, ec, -ec, -ec}};
+        static thread_local float A[4][LINE], B[4][LINE];
+        const size_t numInput = std::min<size_t>(nin, 4);
+        for(size_t c = 0;c < 4;++c)
+        {
+            for(size_t i = 0;i < n;++i) A[c][i] = 0.0f;
+            for(size_t k = 0;k < numInput;++k)
+                for(size_t i = 0;i < n;++i) A[c][i] = A[c][i] + in[k][i]*B2A[c][k];
+        }
+        for(auto &row : B) std::fill_n(row, n, 0.0f);
+        const float fc = P.dist_edge;
+        for(size_t base = 0;base < n;)
+        {
+            const size_t todo = std::min<size_t>(LINE, (n-base)*4);
+            for(size_t c = 0;c < 4;++c)
+            {
+                for(size_t i = 0;i < todo;++i) tmp0[i] = !(i&3) ? A[c][(i>>2)+base] * 4.0f : 0.0f;
+                biquad_process(P.dist_lp, e->chan[c][0], tmp0, tmp1, todo);
+                for(size_t i = 0;i < todo;++i)
+                {
+                    float smp = tmp1[i];
+                    smp = ( 1.0f + fc) * smp/(1.0f + fc*std::fabs(smp));
+                    smp = (-1.0f - fc) * smp/(1.0f + fc*std::fabs(smp));
+                    smp = ( 1.0f + fc) * smp/(1.0f + fc*std::fabs(smp));
+                    tmp0[i] = smp;
+                }
+                biquad_process(P.dist_bp, e->chan[c][1], tmp0, tmp1, todo);
+                for(size_t k = 0;k < 4;++k)
+                    for(size_t i = 0;i < (todo>>2);++i) B[k][base+i] += tmp1[i*4] * A2B[k][c];
+            }
+            base += todo >> 2;
+        }
+        for(size_t c = 0;c < 4;++c)
+        {
+            if(!P.line_on[c]) continue;
+            for(size_t o = 0;o < nout;++o)
+                if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                    mix_line(B[c], n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        }
+        break;
+    }
+    default: break;
+    }
+}
+
+} // extern "C"

@@ -104,7 +104,75 @@ SCENES = {
     "stereo_spline_moving_v6": (6, 0, 2, 8, True, 48000, None, "i16", 0, None, None, "moving"),
     "hrtf_spline_reverb_xfade_v4": (4, 1, 2, 18, True, 48000, None, "i16", 0,
                                     {0x0006: 0.1, 0x000A: 0.004, 0x000D: 0.006}, None, "rvscript"),
+    # the other EFX effects on an aux slot (alc/effects/*.cpp), every voice sends to it; EFX_SCENES
+    # below gives the effect, its properties and the property changes applied between updates
+    # (EffectState::update on a running effect)
+    "efx_echo_hrtf_v5": (5, 1, 2, 10, True, 48000, None, "i16", 0, None, None, "efx:echo"),
+    "efx_echo_short_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:echo_short"),
+    "efx_modulator_sin_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:mod_sin"),
+    "efx_modulator_saw_square_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:mod_saw"),
+    "efx_equalizer_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:eq"),
+    "efx_compressor_hrtf_v5": (5, 1, 2, 8, False, 9000, None, "i16", 0, None, None, "efx:comp"),
+    "efx_dedicated_dialog_hrtf_v4": (4, 1, 2, 4, True, 48000, None, "i16", 0, None, None, "efx:dialog"),
+    "efx_distortion_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:dist"),
 }
+
+# name: (our effect type, AL effect enum, {AL float props}, {AL int props}, slot gain,
+#        {update index: ({float props}, {int props})})
+EFX_SCENES = {
+    "echo": (3, 0x0004, {0x0001: 0.05, 0x0002: 0.03, 0x0003: 0.4, 0x0004: 0.6, 0x0005: -0.7}, {}, 0.8,
+             {4: ({0x0001: 0.08, 0x0004: 0.3, 0x0005: 0.5}, {}), 7: ({0x0003: 0.9}, {})}),
+    # a tap delay shorter than the update (chunked feedback) and down to one sample
+    "echo_short": (3, 0x0004, {0x0001: 0.004, 0x0002: 0.0, 0x0003: 0.2, 0x0004: 0.8, 0x0005: 1.0}, {}, 1.0,
+                   {3: ({0x0001: 0.0, 0x0002: 0.001}, {})}),
+    "mod_sin": (4, 0x0009, {0x0001: 700.0, 0x0002: 300.0}, {0x0003: 0}, 0.9,
+                {3: ({0x0001: 1234.5, 0x0002: 1500.0}, {})}),
+    "mod_saw": (4, 0x0009, {0x0001: 330.0, 0x0002: 50.0}, {0x0003: 1}, 1.0,
+                {2: ({0x0001: 215.0}, {0x0003: 2}), 4: ({0x0001: 0.0}, {})}),
+    "eq": (5, 0x000C, {0x0001: 0.3, 0x0002: 300.0, 0x0003: 3.0, 0x0004: 900.0, 0x0005: 0.6, 0x0006: 0.2,
+                       0x0007: 2500.0, 0x0008: 0.3, 0x0009: 4.0, 0x000A: 7000.0}, {}, 0.7,
+           {3: ({0x0001: 2.0, 0x0009: 0.5}, {})}),
+    "comp": (6, 0x000B, {}, {0x0001: 1}, 1.0, {3: ({}, {0x0001: 0}), 6: ({}, {0x0001: 1})}),
+    "dialog": (7, 0x9001, {0x0001: 0.6}, {}, 0.9, {2: ({0x0001: 0.2}, {})}),
+    "dist": (8, 0x0003, {0x0001: 0.6, 0x0002: 0.3, 0x0003: 6000.0, 0x0004: 2000.0, 0x0005: 1500.0}, {}, 1.0,
+             {3: ({0x0001: 0.2, 0x0004: 4000.0}, {})}),
+}
+
+
+def efx_props_struct(kind, fprops, iprops):
+    """The AL properties of EFX_SCENES as b200mix_efx_props (EFX defaults for what is not set)."""
+    from pyb200mix import abi
+    typ = EFX_SCENES[kind][0]
+    p = abi.efx_defaults(typ)
+    f, i = fprops, iprops
+    if typ == 3:
+        for k, n in {1: "delay", 2: "lr_delay", 3: "damping", 4: "feedback", 5: "spread"}.items():
+            if k in f:
+                setattr(p.echo, n, f[k])
+    elif typ == 4:
+        for k, n in {1: "frequency", 2: "high_pass_cutoff"}.items():
+            if k in f:
+                setattr(p.modulator, n, f[k])
+        if 3 in i:
+            p.modulator.waveform = i[3]
+    elif typ == 5:
+        names = {1: "low_gain", 2: "low_cutoff", 3: "mid1_gain", 4: "mid1_center", 5: "mid1_width",
+                 6: "mid2_gain", 7: "mid2_center", 8: "mid2_width", 9: "high_gain", 10: "high_cutoff"}
+        for k, n in names.items():
+            if k in f:
+                setattr(p.equalizer, n, f[k])
+    elif typ == 6:
+        if 1 in i:
+            p.compressor.on_off = i[1]
+    elif typ == 7:
+        p.dedicated.target = 0
+        if 1 in f:
+            p.dedicated.gain = f[1]
+    elif typ == 8:
+        for k, n in {1: "edge", 2: "gain", 3: "lowpass_cutoff", 4: "eq_center", 5: "eq_bandwidth"}.items():
+            if k in f:
+                setattr(p.distortion, n, f[k])
+    return p
 
 # {update index (applied before that render): {AL_EAXREVERB_* : value}}
 REVERB_SCRIPT = {2: {0x0006: 0.5, 0x0001: 0.6},                 # decay time + density: full update
@@ -283,6 +351,14 @@ def run_scene(name):
         for src in ref.sources:
             ref.al.alSourcei(src, 0x2000B, 0)      # AL_AUXILIARY_SEND_FILTER_GAIN_AUTO
             ref.al.alSourcei(src, 0x2000C, 0)      # AL_AUXILIARY_SEND_FILTER_GAINHF_AUTO
+    efx_kind = spec[11][4:] if len(spec) > 11 and str(spec[11]).startswith("efx:") else None
+    efx_f, efx_i = {}, {}
+    if efx_kind:
+        _, al_type, efx_f, efx_i, efx_gain, efx_script = EFX_SCENES[efx_kind]
+        efx_f, efx_i = dict(efx_f), dict(efx_i)
+        slot = ref.add_efx_slot(al_type, efx_f, efx_i, efx_gain)
+        for src in ref.sources:
+            ref.connect_send(src, slot)
     chain = len(spec) > 11 and spec[11] == "chain"
     if chain:
         slot_a = ref.add_convolution_slot(conv_ir(600), 48000, 0.5)
@@ -306,8 +382,14 @@ def run_scene(name):
     outs = []
     snap = None
     filt_meta, filt_coef = [], []
-    nslots, wet = ref.slot_info() if (taps or rvprops is not None or chain) else (0, [])
+    nslots, wet = ref.slot_info() if (taps or rvprops is not None or chain or efx_kind) else (0, [])
+    efx_steps = []
     for u in range(U):
+        if efx_kind and u in efx_script:
+            df, di = efx_script[u]
+            efx_f.update(df); efx_i.update(di)
+            ref.change_efx(slot, df, di)
+            efx_steps.append((u, np.frombuffer(bytes(efx_props_struct(efx_kind, efx_f, efx_i)), dtype=np.uint8).copy()))
         if script and u:
             apply_filter_script(ref, script, u, slot)
         if rvscript and u in REVERB_SCRIPT:
@@ -350,6 +432,17 @@ def run_scene(name):
                    wet_channels=np.int64(wet[0]))
     if rvprops is not None:
         res.update(reverb_params=np.frombuffer(bytes(rvp), dtype=np.uint8).copy(), reverb_gains=rvg,
+                   send=send[:V].copy(), wet_channels=np.int64(wet[0]))
+    if efx_kind:
+        _, _, f0, i0, efx_gain, _ = EFX_SCENES[efx_kind]
+        dsc, dix = ref.dry_ambi_map()
+        _, wix = ref.slot_ambi_map(0)
+        res.update(efx_props=np.frombuffer(bytes(efx_props_struct(efx_kind, f0, i0)), dtype=np.uint8).copy(),
+                   efx_slot_gain=np.float32(efx_gain), efx_out_scale=dsc, efx_out_index=dix, efx_wet_index=wix,
+                   efx_ambi_order=np.int64(ref.device_ambi_order()),
+                   efx_step_updates=np.array([x[0] for x in efx_steps], dtype=np.int64),
+                   efx_step_props=(np.stack([x[1] for x in efx_steps]) if efx_steps
+                                   else np.zeros((0, 1), dtype=np.uint8)),
                    send=send[:V].copy(), wet_channels=np.int64(wet[0]))
     if script:
         res.update(filt_meta=np.stack(filt_meta), filt_coef=np.stack(filt_coef))

@@ -76,6 +76,8 @@ class MixLib:
         self.render_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
         self.get_dry = f("get_dry")
         self.get_dry.argtypes = [C.c_void_p, C.c_void_p]
+        self.slot_efx = f("slot_efx")
+        self.slot_efx.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.EfxProps), C.POINTER(abi.EfxTarget)]
         if prefix == "b200mix_":          # sharded device sets exist on the product only
             self.shard_init = f("shard_init")
             self.shard_init.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -141,6 +143,24 @@ class MixDevice:
         gains = np.ascontiguousarray(gains, dtype=np.float32)
         rc = self.m.slot_output_gains(self.h, slot, 8, gains.ctypes.data)
         assert rc == 0, rc
+
+    def slot_efx(self, slot, props, slot_gain, out_scale, out_index, wet_index, ambi_order=1,
+                 real_center=abi.NO_SLOT, real_lfe=abi.NO_SLOT, expect=0):
+        """b200mix_slot_efx: props = abi.EfxProps; the maps are the target mix's AmbiMap and the slot's
+        Wet.AmbiMap indices."""
+        out_scale = np.ascontiguousarray(out_scale, dtype=np.float32)
+        out_index = np.ascontiguousarray(out_index, dtype=np.uint32)
+        wet_index = np.ascontiguousarray(wet_index, dtype=np.uint32)
+        t = abi.EfxTarget()
+        t.struct_size = C.sizeof(abi.EfxTarget)
+        t.sample_rate = self.desc.sample_rate
+        t.slot_gain = slot_gain
+        t.out_channels, t.out_scale, t.out_index = len(out_scale), out_scale.ctypes.data, out_index.ctypes.data
+        t.wet_channels, t.wet_index = len(wet_index), wet_index.ctypes.data
+        t.real_center, t.real_lfe, t.device_ambi_order = real_center, real_lfe, ambi_order
+        props.struct_size = C.sizeof(abi.EfxProps)
+        rc = self.m.slot_efx(self.h, slot, C.byref(props), C.byref(t))
+        assert rc == expect, f"slot_efx -> {rc}"
 
     def slot_target(self, slot, target):
         rc = self.m.slot_target(self.h, slot, target)

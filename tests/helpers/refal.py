@@ -297,6 +297,61 @@ class RefDevice:
         self._slot_effect[s.value] = e.value
         return s.value
 
+    def add_efx_slot(self, al_type: int, fprops: dict | None = None, iprops: dict | None = None,
+                     slot_gain: float = 1.0):
+        """Any EFX effect on an aux slot: fprops {AL_param: float} via alEffectf, iprops via alEffecti."""
+        e = C.c_uint(0)
+        s = C.c_uint(0)
+        self.al.alGenEffects(1, C.byref(e))
+        self.al.alEffecti(e, AL_EFFECT_TYPE, al_type)
+        for k, v in (fprops or {}).items():
+            self.al.alEffectf(e, k, float(v))
+        for k, v in (iprops or {}).items():
+            self.al.alEffecti(e, k, int(v))
+        self.al.alGenAuxiliaryEffectSlots(1, C.byref(s))
+        self.al.alAuxiliaryEffectSlotf(s, AL_EFFECTSLOT_GAIN, slot_gain)
+        self.al.alAuxiliaryEffectSloti(s, AL_EFFECTSLOT_EFFECT, e.value)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} creating effect slot {al_type:#x}"
+        self._slot_effect = getattr(self, "_slot_effect", {})
+        self._slot_effect[s.value] = e.value
+        return s.value
+
+    def change_efx(self, slot: int, fprops: dict | None = None, iprops: dict | None = None):
+        """Changes properties of the slot's effect and re-applies it (EffectState::update)."""
+        e = self._slot_effect[slot]
+        for k, v in (fprops or {}).items():
+            self.al.alEffectf(e, k, float(v))
+        for k, v in (iprops or {}).items():
+            self.al.alEffecti(e, k, int(v))
+        self.al.alAuxiliaryEffectSloti(slot, AL_EFFECTSLOT_EFFECT, e)
+        err = self.al.alGetError()
+        assert err == 0, f"AL error {err:#x} changing effect"
+
+    def dry_ambi_map(self):
+        """DeviceBase::Dry.AmbiMap: (scale [n] f32, index [n] u32)."""
+        self.hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        sc = np.zeros(64, dtype=np.float32)
+        ix = np.zeros(64, dtype=np.uint32)
+        n = self.hz.refh_dry_ambi_map(self.dev, sc.ctypes.data, ix.ctypes.data)
+        return sc[:n].copy(), ix[:n].copy()
+
+    def slot_ambi_map(self, idx: int):
+        """The idx-th active slot's Wet.AmbiMap: (scale, index)."""
+        self.hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        sc = np.zeros(64, dtype=np.float32)
+        ix = np.zeros(64, dtype=np.uint32)
+        n = self.hz.refh_slot_ambi_map(self.ctx, idx, sc.ctypes.data, ix.ctypes.data)
+        assert n > 0, n
+        return sc[:n].copy(), ix[:n].copy()
+
+    def device_ambi_order(self) -> int:
+        self.hz.refh_device_ambi.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                             C.POINTER(C.c_float)]
+        o, d2, xo = C.c_uint32(), C.c_uint32(), C.c_float()
+        self.hz.refh_device_ambi(self.dev, C.byref(o), C.byref(d2), C.byref(xo))
+        return int(o.value)
+
     def change_reverb(self, slot: int, props: dict):
         """Changes properties of the slot's reverb effect and re-applies it (ReverbState::update)."""
         e = self._slot_effect[slot]

@@ -34,6 +34,7 @@ def test_oracle_matches_reference_sse_kernels(name):
         assert np.abs(err).max() <= 1 and (err != 0).mean() <= 0.01
         assert np.ptp(ref) > 8
         return
-    assert np.sqrt((err ** 2).mean()) <= 1e-7
-    assert np.abs(err).max() <= 1e-6
+    gap_rms, gap_max = golden.kernel_set_gap(fx)
+    assert np.sqrt((err ** 2).mean()) <= max(1e-7, 1.5 * gap_rms)
+    assert np.abs(err).max() <= max(1e-6, 1.5 * gap_max)
     assert np.abs(ref).max() > 1e-3  # the scene is not silent
