@@ -42,6 +42,7 @@ extern "C" {
 #define B200MIX_RESAMPLER_PADDING  48u /* MaxResamplerPadding     core/resampler_limits.h:8 */
 #define B200MIX_NO_SLOT   0xffffffffu
 #define B200MIX_NO_LOOP   0xffffffffu
+#define B200MIX_NO_BUFFER 0xffffffffu
 #define B200MIX_MAX_QUEUE          32u /* items of a streaming queue the mixer looks ahead over */
 
 enum { B200MIX_OK = 0, B200MIX_ERR_INVALID = -1, B200MIX_ERR_CUDA = -2,
@@ -133,7 +134,9 @@ enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B
     B200MIX_EFFECT_EQUALIZER = 5,     /* EqualizerState   alc/effects/equalizer.cpp */
     B200MIX_EFFECT_COMPRESSOR = 6,    /* CompressorState  alc/effects/compressor.cpp */
     B200MIX_EFFECT_DEDICATED = 7,     /* DedicatedState   alc/effects/dedicated.cpp (dialogue / LFE) */
-    B200MIX_EFFECT_DISTORTION = 8     /* DistortionState  alc/effects/distortion.cpp */
+    B200MIX_EFFECT_DISTORTION = 8,    /* DistortionState  alc/effects/distortion.cpp */
+    B200MIX_EFFECT_CHORUS = 9,        /* ChorusState      alc/effects/chorus.cpp (AL_EFFECT_CHORUS and AL_EFFECT_FLANGER) */
+    B200MIX_EFFECT_AUTOWAH = 10       /* AutowahState     alc/effects/autowah.cpp */
 };
 
 /* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
@@ -328,6 +331,8 @@ B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
  *   compressor  alc/effects/compressor.cpp:80-177   (envelope follower on channel 0 -> gain on all)
  *   dedicated   alc/effects/dedicated.cpp:62-109    (dialogue to front-centre / LFE)
  *   distortion  alc/effects/distortion.cpp:113-303  (B2A, 4x oversampled low-pass -> waveshaper -> band-pass, A2B)
+ *   chorus      alc/effects/chorus.cpp:132-425      (chorus and flanger: LFO-modulated cubic taps + feedback, B2A/A2B)
+ *   autowah     alc/effects/autowah.cpp:94-205      (envelope follower -> per-sample peaking filter)
  * b200mix_efx_props carries the effect's PROPERTIES (the EffectProps variant of
  * core/effects/base.h:62-178 after the AL layer's clamping); b200mix_efx_target what update() reads
  * from the slot and its output target: EffectSlotBase::Gain, the target mix's AmbiMap
@@ -339,7 +344,7 @@ B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
  * gain targets change, delay lines / filter histories / current gains are kept.
  * B200MIX_ERR_UNSUPPORTED: more than 16 wet channels; dedicated effects that resolve to a RealOut
  * channel (FrontCenter / LFE present: the reference then writes RealOut, not the mix);
- * distortion on a device mixing above first order (its up-sampler). */
+ * distortion / chorus on a device mixing above first order (their up-sampler). */
 typedef struct b200mix_efx_props {
     uint32_t struct_size;
     uint32_t type;                      /* enum b200mix_effect, >= B200MIX_EFFECT_ECHO */
@@ -350,6 +355,8 @@ typedef struct b200mix_efx_props {
     struct { uint32_t on_off; } compressor;                                               /* CompressorProps */
     struct { uint32_t target; float gain; } dedicated;                                    /* 0 dialogue, 1 LFE */
     struct { float edge, gain, lowpass_cutoff, eq_center, eq_bandwidth; } distortion;     /* DistortionProps */
+    struct { uint32_t waveform; int32_t phase; float rate, depth, feedback, delay; } chorus; /* ChorusProps (0 sinusoid, 1 triangle) */
+    struct { float attack_time, release_time, resonance, peak_gain; } autowah;            /* AutowahProps */
 } b200mix_efx_props;
 typedef struct b200mix_efx_target {
     uint32_t struct_size;
@@ -397,7 +404,10 @@ enum {
 typedef struct b200mix_voice_params {
     uint32_t voice;           /* index in the device voice array, < max_voices */
     uint32_t flags;           /* B200MIX_VF_* */
-    uint32_t buffer;          /* buffer id of mCurrentBuffer (static sources) */
+    uint32_t buffer;          /* buffer id of mCurrentBuffer (static sources); B200MIX_NO_BUFFER =
+                               * mCurrentBuffer is null (alSourceStop / rewind, alc/alu.cpp:2069-2083):
+                               * the voice holds its near-zero sample while it fades
+                               * (core/voice.cpp:704-719) */
     uint32_t resampler;       /* enum b200mix_resampler (VoiceProps::mResampler) */
     int32_t  position;        /* mPosition      (RESET only) */
     uint32_t position_frac;   /* mPositionFrac  (RESET only) */

@@ -1,0 +1,22 @@
+/* b200mix_seam.h — the seam a maintainer adds to OpenAL Soft to mix on a B200 through
+ * libb200mix.so (include/b200mix.h).  Declared here, called from the two patched places of
+ * alc/alu.cpp (integration/alu_seam.patch), implemented in b200mix_seam.cpp. */
+#ifndef B200MIX_SEAM_H
+#define B200MIX_SEAM_H
+
+struct DeviceBase;
+
+/* True when this device mixes on the GPU (ALSOFT_B200MIX=1 in the environment and
+ * libb200mix.so could be loaded).  ProcessContexts then skips its voice loop and effect loop
+ * (alc/alu.cpp:2201-2206, 2252-2256) — parameter updates still run on the host. */
+bool b200seam_enabled(const DeviceBase *device /* may be null: the switch is process-wide */) noexcept;
+
+/* Replaces the voice loop, the slot loop and DeviceBase::Process(mPostProcess) of
+ * DeviceBase::renderSamples(unsigned) (alc/alu.cpp:2412-2443): snapshots the post-ALU voices
+ * of the device's contexts into b200mix_voice_params, renders `samplesToDo` frames on the GPU
+ * and leaves the result in RealOut.Buffer; positions and play states go back into the Voice
+ * objects.  Limiter, distance compensation, dither and Write<T> stay the host's.  A failure
+ * (CUDA error, unsupported configuration) disconnects the device (DeviceBase::handleDisconnect). */
+void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept;
+
+#endif

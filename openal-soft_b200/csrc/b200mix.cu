@@ -128,7 +128,8 @@ struct b200mix_device {
     uint32_t num_entries{0};
     bool sends_dirty{true};
     // EFX effect slots (b200mix_slot_efx): host mirrors + the per-slot views the kernel walks
-    struct EfxHost { bool used{false}; EfxParams p{}; EfxDev *dev{nullptr}; uint32_t mod_index{0}, mod_range{1}; };
+    struct EfxHost { bool used{false}; EfxParams p{}; EfxDev *dev{nullptr}; uint32_t mod_index{0}, mod_range{1};
+        uint32_t lfo_offset{0}, lfo_range{1}; };
     std::vector<EfxHost> efx;
     EfxSlotView *d_efx_views{nullptr};
     uint32_t efx_slots{0};
@@ -933,7 +934,7 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
 {
     if(!d || slot >= d->h_slots.size() || !props || !target || props->struct_size != sizeof(*props)
         || target->struct_size != sizeof(*target) || props->type < B200MIX_EFFECT_ECHO
-        || props->type > B200MIX_EFFECT_DISTORTION)
+        || props->type > B200MIX_EFFECT_AUTOWAH)
     { if(d) d->error = "slot_efx: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
     const b200mix_device_desc &dd = d->desc;
     const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
@@ -950,7 +951,9 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
         if(int rc = dev_alloc(d, d->d_efx_views, d->h_slots.size())) return rc;
     b200mix_device::EfxHost &H = d->efx[slot];
     const bool fresh = !H.used || d->h_slots[slot].type != props->type || H.p.lines != P.lines
-        || H.p.echo_len != P.echo_len;
+        || H.p.echo_len != P.echo_len || H.p.cho_len != P.cho_len;
+    if(P.type == B200MIX_EFFECT_AUTOWAH && P.lines > kEfxMaxLines - 2u)
+    { d->error = "slot_efx: autowah handles up to 14 wet channels"; return B200MIX_ERR_UNSUPPORTED; }
     CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     if(fresh)
     {
@@ -971,11 +974,13 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
         EfxDev h{};
         h.p = P; h.comp_env = 1.0f;
         if(P.echo_len) { if(int rc = alloc(h.echo_buf, P.echo_len)) return rc; }
+        if(P.cho_len) { if(int rc = alloc(h.cho_buf, size_t(4)*P.cho_len)) return rc; }
         r.H = reinterpret_cast<float*>(dev);
         CUDA_TRY(d, cudaMemcpyAsync(dev, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
         H = b200mix_device::EfxHost{};
         H.used = true; H.dev = dev; H.mod_index = 0u; H.mod_range = P.mod_range ? P.mod_range : 1u;
+        H.lfo_offset = 0u; H.lfo_range = P.cho_lfo_range ? P.cho_lfo_range : 1u;
         d->h_slots[slot] = r;
         ++d->active_slots; ++d->efx_slots;
         d->dry_active = true;
@@ -992,6 +997,14 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
             H.mod_index = uint32_t(uint64_t(H.mod_index) * P.mod_range_new / H.mod_range);
             H.mod_range = P.mod_range;
             CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, mod_index), &H.mod_index,
+                sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+        }
+        if(props->type == B200MIX_EFFECT_CHORUS)
+        {
+            // mLfoOffset follows the LFO range (chorus.cpp:185-211)
+            H.lfo_offset = P.cho_rate_on ? H.lfo_offset * P.cho_lfo_range_new / H.lfo_range : 0u;
+            H.lfo_range = P.cho_lfo_range;
+            CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, cho_lfo_offset), &H.lfo_offset,
                 sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
         }
         d->h_slots[slot].fade_len = P.fade_len;
@@ -1147,8 +1160,9 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
     for(uint32_t i = 0;i < n;++i)
     {
         const b200mix_voice_params &p = params[i];
+        const bool nobuf = p.buffer == B200MIX_NO_BUFFER;
         if(p.voice >= dd.max_voices || p.resampler > B200MIX_RESAMPLER_BSINC48
-            || (!(p.flags & B200MIX_VF_STOPPED) && p.buffer >= dd.max_buffers))
+            || (!(p.flags & B200MIX_VF_STOPPED) && !nobuf && p.buffer >= dd.max_buffers))
         { d->error = "voices_update: voice/buffer/resampler out of range"; return B200MIX_ERR_INVALID; }
         if((p.flags & B200MIX_VF_LOOPING) && p.loop_end <= p.loop_start)
         { d->error = "voices_update: empty loop"; return B200MIX_ERR_INVALID; }
@@ -1158,7 +1172,8 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
         { d->error = "voices_update: step above MaxPitch<<16"; return B200MIX_ERR_INVALID; }
         if(!(p.flags & B200MIX_VF_STOPPED))
         {
-            if(p.flags & B200MIX_VF_STATIC)
+            if(nobuf) { /* nothing to read */ }
+            else if(p.flags & B200MIX_VF_STATIC)
             {
                 const BufferRec &hb = d->h_buffers[p.buffer];
                 if(!hb.data || !hb.frames)
@@ -1175,6 +1190,7 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
         }
         VoiceUpdate &u = d->h_upd[i];
         u.voice = p.voice; u.flags = p.flags; u.buffer = p.buffer; u.resampler = p.resampler;
+        if(nobuf) { u.flags |= kUpNoBuffer; u.buffer = 0u; }
         u.position = p.position; u.position_frac = p.position_frac;
         u.loop_start = p.loop_start; u.loop_end = p.loop_end; u.step = p.step;
         u.bsinc_sf = 0.0f; u.bsinc_m = 0; u.bsinc_l = 0; u.bsinc_off = 0;
@@ -1221,7 +1237,7 @@ static int voices_update_impl(b200mix_device *d, uint32_t n, const b200mix_voice
         }
         d->voice_hi = std::max(d->voice_hi, p.voice + 1u);
         {
-            const uint32_t nb = (!(p.flags & B200MIX_VF_STOPPED) && (p.flags & B200MIX_VF_STATIC))
+            const uint32_t nb = (!(p.flags & B200MIX_VF_STOPPED) && (p.flags & B200MIX_VF_STATIC) && !nobuf)
                 ? p.buffer : B200MIX_NO_SLOT;
             uint32_t &ob = d->h_vbuf[p.voice];
             if(ob != nb)
@@ -1999,7 +2015,7 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
             CP.stage = st; SP.stage = st;
             if(d->efx_slots)
             {
-                EfxRunParams EQ{d->d_efx_views, d->d_wet, frames, dd.wet_channels, st};
+                EfxRunParams EQ{d->d_efx_views, d->d_wet, frames, dd.wet_channels, st, d->d_cubic_filter};
                 CUDA_TRY(d, launch_efx_process(EQ, dd.max_slots, d->stream));
                 ++d->launches;
             }
@@ -2022,7 +2038,10 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
         k_slot_gains_commit<<<dd.max_slots, 64, 0, d->stream>>>(SP);
         ++d->launches;
         for(auto &eh : d->efx)
+        {
             if(eh.used && eh.p.type == B200MIX_EFFECT_MODULATOR) eh.mod_index = (eh.mod_index + frames) % eh.mod_range;
+            if(eh.used && eh.p.type == B200MIX_EFFECT_CHORUS) eh.lfo_offset = (eh.lfo_offset + frames) % eh.lfo_range;
+        }
         CUDA_TRY(d, cudaGetLastError());
     }
 

@@ -255,6 +255,127 @@ __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
                 lines[size_t(c)*kLine + i] = P.line_on[c] ? sIn[(4u + c)*kLine + i] : 0.0f;
         break;
     }
+    case B200MIX_EFFECT_CHORUS:
+    {
+        // ChorusState::process (chorus.cpp:326-425), first-order devices.  The feedback tap sits
+        // only (mDelay + 2^15) >> 16 samples back — a per-sample recurrence through the delay
+        // line: one thread per A-format line, the line's delay buffer in shared memory.
+        static const float dc = kDecodeCoeff, ec = kEncodeCoeff;
+        const float B2A[4][4] = {{0.25f, dc, dc, dc}, {0.25f, dc, -dc, -dc}, {0.25f, -dc, -dc, dc}, {0.25f, -dc, dc, -dc}};
+        const float A2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {ec, ec, -ec, -ec}, {ec, -ec, -ec, ec}, {ec, -ec, ec, -ec}};
+        const uint32_t numInput = min(nin, 4u);
+        for(uint32_t i = t;i < n;i += blockDim.x)
+            for(uint32_t c = 0;c < 4u;++c)
+            {
+                float a = 0.0f;
+                for(uint32_t k = 0;k < numInput;++k) a = a + wet[size_t(k)*kLine + i]*B2A[c][k];
+                sIn[c*kLine + i] = a;
+            }
+        // mModDelays[0] / [1] (calcTriangleDelays / calcSinusoidDelays, chorus.cpp:235-323)
+        uint32_t *md = reinterpret_cast<uint32_t*>(sWork);          // rows 0,1
+        const uint32_t range = P.cho_lfo_range, lfo0 = E.cho_lfo_offset;
+        for(uint32_t i = t;i < 2u*n;i += blockDim.x)
+        {
+            const uint32_t side = i / n, k = i - side*n;
+            const uint32_t off = ((side ? lfo0 + P.cho_lfo_disp : lfo0) % range + k) % range;
+            const float offset_norm = float(off) * P.cho_lfo_scale;
+            const float v = P.cho_wave == 1u ? (1.0f - fabsf(2.0f - offset_norm)) * P.cho_depth
+                                              : float(::sin(double(offset_norm))) * P.cho_depth;
+            md[side*kLine + k] = uint32_t(__float2int_rn(v) + P.cho_delay);        // fastf2i: round to nearest even
+        }
+        const uint32_t len = P.cho_len, mask = len - 1u;
+        const bool inSmem = 4u*len <= 12u*uint32_t(kLine);
+        float *dl = inSmem ? sWork + 4*kLine : E.cho_buf;              // rows 4..15 when it fits
+        if(inSmem) for(uint32_t i = t;i < 4u*len;i += blockDim.x) dl[i] = E.cho_buf[i];
+        __syncthreads();
+        if(t < 4u)
+        {
+            float *d = dl + size_t(t)*len;
+            const uint32_t *mds = md + (t < 2u ? 0 : kLine);
+            const float fb = P.cho_feedback;
+            const uint32_t avgdelay = (uint32_t(P.cho_delay) + 32768u) >> 16;
+            uint32_t offset = E.cho_offset;
+            float *tmp = sIn + (4u + t)*kLine;                         // mTempLine of this line
+            for(uint32_t i = 0;i < n;++i)
+            {
+                d[offset & mask] = sIn[t*kLine + i];
+                const uint32_t moddelay = mds[i];
+                const uint32_t delay = offset - (moddelay >> 8), phase = moddelay & 255u;
+                const float sample = d[(delay+1u) & mask]*Q.cubic[256u + phase] + d[delay & mask]*Q.cubic[phase]
+                    + d[(delay-1u) & mask]*Q.cubic[256u - phase] + d[(delay-2u) & mask]*Q.cubic[512u - phase];
+                d[offset & mask] += d[(offset - avgdelay) & mask] * fb;
+                ++offset;
+                tmp[i] = sample;
+            }
+        }
+        __syncthreads();
+        for(uint32_t c = 0;c < 4u;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+            {
+                float b = 0.0f;
+                for(uint32_t k = 0;k < 4u;++k) b = b + sIn[(4u + k)*kLine + i]*A2B[c][k];
+                lines[size_t(c)*kLine + i] = P.line_on[c] ? b : 0.0f;
+            }
+        if(inSmem) for(uint32_t i = t;i < 4u*len;i += blockDim.x) E.cho_buf[i] = dl[i];
+        if(t == 0) { E.cho_offset += n; E.cho_lfo_offset = (lfo0 + n) % range; }
+        break;
+    }
+
+    case B200MIX_EFFECT_AUTOWAH:
+    {
+        // AutowahState::process (autowah.cpp:136-205): envelope follower on channel 0 (a
+        // recurrence), the per-sample filter terms from it (parallel), then one peaking filter
+        // with per-sample coefficients per channel (a recurrence per channel)
+        for(uint32_t c = 0;c < nin;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x) sIn[c*kLine + i] = wet[size_t(c)*kLine + i];
+        __syncthreads();
+        float *env = sWork + kEfxMaxLines*kLine;                       // the extra row
+        if(t == 0)
+        {
+            float env_delay = E.wah_env;
+            for(uint32_t i = 0;i < n;++i)
+            {
+                const float sample = P.wah_peak_gain * fabsf(sIn[i]);
+                const float a = (sample > env_delay) ? P.wah_attack : P.wah_release;
+                env_delay = sample + (env_delay - sample)*a;            // lerpf(sample, env_delay, a)
+                env[i] = env_delay;
+            }
+            E.wah_env = env_delay;
+        }
+        __syncthreads();
+        float *cosw = sWork + (kEfxMaxLines - 1)*kLine, *alpha = sWork + (kEfxMaxLines - 2)*kLine;
+        for(uint32_t i = t;i < n;i += blockDim.x)
+        {
+            const float f = P.wah_bandwidth*env[i] + P.wah_freq_min;
+            const float w0 = (f < 0.46f ? f : 0.46f) * (3.14159265358979323846f*2.0f);
+            cosw[i] = float(::cos(double(w0)));
+            alpha[i] = float(::sin(double(w0)))*(0.5f/5.0f);
+        }
+        __syncthreads();
+        if(t < nin && t < kEfxMaxLines - 2u && P.line_on[t])
+        {
+            float z1 = E.chan_z[t][0][0], z2 = E.chan_z[t][0][1];
+            const float rg = P.wah_res_gain;
+            const float *src = sIn + t*kLine;
+            float *dst = sWork + t*kLine;
+            for(uint32_t i = 0;i < n;++i)
+            {
+                const float al = alpha[i], cw = cosw[i], input = src[i];
+                const float b0 = 1.0f + al*rg, b1 = -2.0f * cw, b2 = 1.0f - al*rg;
+                const float a0 = 1.0f / (1.0f + al/rg), a1 = -2.0f * cw, a2 = 1.0f - al/rg;
+                const float output = input*(b0*a0) + z1;
+                z1 = input*(b1*a0) - output*(a1*a0) + z2;
+                z2 = input*(b2*a0) - output*(a2*a0);
+                dst[i] = output;
+            }
+            E.chan_z[t][0][0] = z1; E.chan_z[t][0][1] = z2;
+        }
+        __syncthreads();
+        for(uint32_t c = 0;c < P.lines;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+                lines[size_t(c)*kLine + i] = (c < nin && c < kEfxMaxLines - 2u && P.line_on[c]) ? sWork[c*kLine + i] : 0.0f;
+        break;
+    }
     default: break;
     }
 }

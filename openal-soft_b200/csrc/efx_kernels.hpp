@@ -15,12 +15,15 @@ struct EfxDev {
     uint32_t echo_offset; float echo_z[2]; // mOffset, mFilter z1/z2
     uint32_t mod_index;                    // ModulatorState::mIndex
     float comp_env;                        // CompressorState::mEnvFollower
+    float *cho_buf;                        // ChorusState::mDelayBuffers [4][cho_len]
+    uint32_t cho_offset, cho_lfo_offset;   // mOffset, mLfoOffset
+    float wah_env;                         // AutowahState::mEnvDelay
     float chan_z[kEfxMaxLines][4][2];      // per-channel biquad histories (modulator [0], equalizer [0..3],
                                            // distortion [0] low-pass, [1] band-pass)
 };
 
 struct EfxSlotView { EfxDev *dev; float *lines; uint32_t stage, pad; };   // dev == null: not an EFX slot
-struct EfxRunParams { const EfxSlotView *slots; const float *wet; uint32_t frames, cw, stage; };
+struct EfxRunParams { const EfxSlotView *slots; const float *wet; uint32_t frames, cw, stage; const float *cubic; /* gCubicTable [513] */ };
 
 cudaError_t efx_kernels_init();            // per CUDA device: dynamic shared memory opt-in
 cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream);

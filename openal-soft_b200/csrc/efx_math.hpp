@@ -34,6 +34,12 @@ struct EfxParams {
     uint32_t comp_enabled; float comp_attack, comp_release;
     // distortion
     float dist_edge, dist_lp[5], dist_bp[5];
+    // chorus / flanger
+    uint32_t cho_len;                     // delay buffer length per line (power of two)
+    uint32_t cho_wave; int32_t cho_delay; float cho_depth, cho_feedback;
+    uint32_t cho_lfo_range_new, cho_lfo_range, cho_lfo_disp, cho_rate_on; float cho_lfo_scale;
+    // autowah
+    float wah_attack, wah_release, wah_res_gain, wah_peak_gain, wah_freq_min, wah_bandwidth;
 };
 
 namespace efx_detail {
@@ -44,6 +50,13 @@ struct HostMath {
     static float sinh(float x) { return std::sinh(x); }
     static float log(float x) { return std::log(x); }
 };
+// float2int (common/alnumeric.h:195-222): truncation, out-of-range values clamped
+inline int f2i(float f)
+{
+    if(!(f < 2147483648.0f)) return 2147483647;
+    if(!(f > -2147483648.0f)) return -2147483647 - 1;
+    return static_cast<int>(f);
+}
 inline uint32_t next_pow2(uint32_t v)     // NextPowerOf2, common/alnumeric.h:121-135
 {
     if(v > 0) { v--; v |= v>>1; v |= v>>2; v |= v>>4; v |= v>>8; v |= v>>16; }
@@ -179,6 +192,50 @@ inline int efx_update(const b200mix_efx_props &E, const b200mix_efx_target &T, E
         pm::biquad_coeffs_bandwidth<HostMath>(5u, cutoff/frequency*0.25f, 1.0f, bandwidth, P.dist_bp);
         P.lines = 4u;
         ambi_mix_params(T, T.slot_gain*E.distortion.gain, 4u, P);
+        break;
+    }
+    case B200MIX_EFFECT_CHORUS:
+    {
+        // ChorusState::deviceUpdate / update (chorus.cpp:132-232), first-order devices
+        if(T.device_ambi_order > 1u) return B200MIX_ERR_UNSUPPORTED;
+        P.cho_len = next_pow2(f2u(0.016f*2.0f*frequency) + 1u);           // max(ChorusMaxDelay, FlangerMaxDelay)
+        constexpr int mindelay = 24 << 8;                                  // MaxResamplerEdge << sTableBits
+        if(E.chorus.waveform > 1u) return B200MIX_ERR_INVALID;
+        P.cho_wave = E.chorus.waveform;
+        const float stepscale = frequency * 256.0f;
+        P.cho_delay = std::max(f2i(std::round(E.chorus.delay * stepscale)), mindelay);
+        P.cho_depth = std::min(static_cast<float>(P.cho_delay) * E.chorus.depth,
+            static_cast<float>(P.cho_delay - mindelay));
+        P.cho_feedback = E.chorus.feedback;
+        if(!(E.chorus.rate > 0.0f))
+        { P.cho_rate_on = 0u; P.cho_lfo_range = 1u; P.cho_lfo_range_new = 1u; P.cho_lfo_scale = 0.0f; P.cho_lfo_disp = 0u; }
+        else
+        {
+            constexpr int range_limit = 2147483647/360 - 180;
+            const float range = std::round(frequency / E.chorus.rate);
+            const uint32_t lfo_range = f2u(std::min(range, float(range_limit)));
+            P.cho_rate_on = 1u; P.cho_lfo_range = lfo_range; P.cho_lfo_range_new = lfo_range;
+            P.cho_lfo_scale = (P.cho_wave == 1u ? 4.0f : 3.14159265358979323846f*2.0f) / static_cast<float>(lfo_range);
+            int phase = E.chorus.phase;
+            if(phase < 0) phase += 360;
+            P.cho_lfo_disp = (lfo_range*static_cast<uint32_t>(phase) + 180u) / 360u;
+        }
+        P.lines = 4u;
+        ambi_mix_params(T, T.slot_gain, 4u, P);
+        break;
+    }
+    case B200MIX_EFFECT_AUTOWAH:
+    {
+        // AutowahState::update (autowah.cpp:110-134)
+        const float ReleaseTime = std::clamp(E.autowah.release_time, 0.001f, 1.0f);
+        P.wah_attack = std::exp(-1.0f / (E.autowah.attack_time*frequency));
+        P.wah_release = std::exp(-1.0f / (ReleaseTime*frequency));
+        P.wah_res_gain = std::sqrt(std::log10(E.autowah.resonance)*10.0f / 3.0f);
+        P.wah_peak_gain = 1.0f - std::log10(E.autowah.peak_gain / 31621.0f);
+        P.wah_freq_min = 20.0f / frequency;
+        P.wah_bandwidth = (2500.0f-20.0f) / frequency;
+        P.lines = T.wet_channels;
+        ambi_mix_params(T, T.slot_gain, kEfxMaxLines, P);
         break;
     }
     default: return B200MIX_ERR_INVALID;

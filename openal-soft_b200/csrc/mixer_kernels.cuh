@@ -36,6 +36,8 @@ constexpr float kEps = 1.1920929e-07f;
 // internal voice flag bits (low 8 bits are the ABI's B200MIX_VF_*)
 constexpr uint32_t kVfStatic = 1u<<2, kVfLooping = 1u<<3, kVfHrtf = 1u<<4;
 constexpr uint32_t kVfFading = 1u<<8, kVfHaveBuffer = 1u<<9, kVfCoefDirty = 1u<<10;
+// VoiceUpdate::flags only: mCurrentBuffer is null (B200MIX_NO_BUFFER)
+constexpr uint32_t kUpNoBuffer = 1u<<11;
 constexpr uint32_t kVfChannelMask = 0xffu<<16;       // B200MIX_VF_CHANNEL: buffer channel read
 
 struct alignas(16) BufferRec {
@@ -1413,6 +1415,7 @@ __global__ void __launch_bounds__(64) k_apply_updates(const ApplyParams A)
             fl |= oldFlags & (kVfFading|kVfHaveBuffer|kVfCoefDirty);
         }
         if(up.has_coeffs && !reset) fl |= kVfCoefDirty;
+        if(up.flags & kUpNoBuffer) fl &= ~kVfHaveBuffer;
         rec.flags = fl;
         if(up.flags & (1u<<7)) rec.state = 0u;
         else if(up.flags & (1u<<1)) rec.state = 2u;

@@ -188,7 +188,7 @@ class SourceVoice(C.Structure):
 
 
 (EFFECT_NONE, EFFECT_CONVOLUTION, EFFECT_REVERB, EFFECT_ECHO, EFFECT_MODULATOR, EFFECT_EQUALIZER,
- EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION) = range(9)
+ EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION, EFFECT_CHORUS, EFFECT_AUTOWAH) = range(11)
 
 
 class _EfxEcho(C.Structure):
@@ -216,11 +216,20 @@ class _EfxDistortion(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("edge", "gain", "lowpass_cutoff", "eq_center", "eq_bandwidth")]
 
 
+class _EfxChorus(C.Structure):
+    _fields_ = [("waveform", C.c_uint32), ("phase", C.c_int32), ("rate", C.c_float), ("depth", C.c_float),
+                ("feedback", C.c_float), ("delay", C.c_float)]
+
+
+class _EfxAutowah(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("attack_time", "release_time", "resonance", "peak_gain")]
+
+
 class EfxProps(C.Structure):
     """b200mix_efx_props: the EFX effect's properties (EffectProps, core/effects/base.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("type", C.c_uint32), ("echo", _EfxEcho), ("modulator", _EfxModulator),
                 ("equalizer", _EfxEqualizer), ("compressor", _EfxCompressor), ("dedicated", _EfxDedicated),
-                ("distortion", _EfxDistortion)]
+                ("distortion", _EfxDistortion), ("chorus", _EfxChorus), ("autowah", _EfxAutowah)]
 
 
 class EfxTarget(C.Structure):
@@ -242,6 +251,8 @@ def efx_defaults(effect_type):
     p.compressor = _EfxCompressor(1)
     p.dedicated = _EfxDedicated(0, 1.0)
     p.distortion = _EfxDistortion(0.2, 0.05, 8000.0, 3600.0, 3600.0)
+    p.chorus = _EfxChorus(1, 90, 1.1, 0.1, 0.25, 0.016)
+    p.autowah = _EfxAutowah(0.06, 0.06, 1000.0, 11.22)
     return p
 
 

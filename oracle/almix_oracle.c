@@ -692,6 +692,7 @@ int oracle_voices_update(oracle_device *d, uint32_t n, const b200mix_voice_param
         else if(p->flags & B200MIX_VF_PLAYING) v->state = 1;
         v->flags = p->flags & (B200MIX_VF_STATIC|B200MIX_VF_LOOPING|B200MIX_VF_HRTF|B200MIX_VF_CHANNEL(0xff));
         v->buffer = p->buffer; v->resampler = p->resampler;
+        if(p->buffer == B200MIX_NO_BUFFER) { v->buffer = 0; v->have_buffer = 0; }   /* alc/alu.cpp:2071 */
         v->loop_start = p->loop_start; v->loop_end = p->loop_end; v->step = p->step;
         v->tgt_delay[0] = p->hrtf_delay[0]; v->tgt_delay[1] = p->hrtf_delay[1];
         v->tgt_gain = p->hrtf_gain;

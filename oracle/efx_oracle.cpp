@@ -88,7 +88,14 @@ struct oefx {
     Biquad chan[b200mix::kEfxMaxLines][4];
     // compressor
     float env{1.0f};
+    // chorus
+    std::vector<float> cho_buf; uint32_t cho_offset{0}, lfo_offset{0}, lfo_range{1};
+    float cubic[513]{};
+    // autowah
+    float wah_env{0.0f};
 };
+
+extern "C" void oracle_build_cubic_filter(float filter[513]);      // tables.c (gCubicTable)
 
 extern "C" {
 
@@ -99,6 +106,8 @@ oefx *oefx_create(const b200mix_efx_props *props, const b200mix_efx_target *targ
     *rc = b200mix::efx_update(*props, *target, e->p);
     if(*rc != B200MIX_OK) { delete e; return nullptr; }
     if(e->p.echo_len) e->echo_buf.assign(e->p.echo_len, 0.0f);
+    if(e->p.cho_len) { e->cho_buf.assign(size_t(4)*e->p.cho_len, 0.0f); oracle_build_cubic_filter(e->cubic); }
+    e->lfo_range = e->p.cho_lfo_range ? e->p.cho_lfo_range : 1u;
     e->mod_range = e->p.mod_range ? e->p.mod_range : 1u;
     if(e->p.snap_gains) std::memcpy(e->cur, e->p.gains, sizeof(e->cur));
     return e;
@@ -108,7 +117,13 @@ int oefx_update(oefx *e, const b200mix_efx_props *props, const b200mix_efx_targe
 {
     EfxParams P;
     if(int rc = b200mix::efx_update(*props, *target, P)) return rc;
-    if(P.type != e->p.type || P.lines != e->p.lines || P.echo_len != e->p.echo_len) return B200MIX_ERR_INVALID;
+    if(P.type != e->p.type || P.lines != e->p.lines || P.echo_len != e->p.echo_len || P.cho_len != e->p.cho_len)
+        return B200MIX_ERR_INVALID;
+    if(P.type == B200MIX_EFFECT_CHORUS)
+    {   // mLfoOffset follows the LFO range, chorus.cpp:185-211
+        e->lfo_offset = P.cho_rate_on ? e->lfo_offset * P.cho_lfo_range_new / e->lfo_range : 0u;
+        e->lfo_range = P.cho_lfo_range;
+    }
     if(P.type == B200MIX_EFFECT_MODULATOR)
     {   // mIndex rescale, modulator.cpp:117-118
         e->mod_index = uint32_t(uint64_t(e->mod_index) * P.mod_range_new / e->mod_range);
@@ -266,6 +281,104 @@ void oefx_process(oefx *e, size_t n, const float (*in)[1024], size_t nin_, float
             for(size_t o = 0;o < nout;++o)
                 if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
                     mix_line(B[c], n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        }
+        break;
+    }
+    case B200MIX_EFFECT_CHORUS:
+    {
+        // chorus.cpp:326-425 (first-order devices)
+        static const float dc = static_cast<float>(0.25 / 1.7320508075688772935);
+        static const float ec = static_cast<float>(0.5 * 1.7320508075688772935);
+        static const float B2A[4][4] = {{0.25f, dc, dc, dc}, {0.25f, dc, -dc, -dc}, {0.25f, -dc, -dc, dc}, {0.25f, -dc, dc, -dc}};
+        static const float A2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {ec, ec, -ec, -ec}, {ec, -ec, -ec, ec}, {ec, -ec, ec, -ec}};
+        static thread_local float A[4][LINE], B[4][LINE];
+        static thread_local uint32_t md[2][LINE];
+        const size_t numInput = std::min<size_t>(nin, 4);
+        for(size_t c = 0;c < 4;++c)
+        {
+            for(size_t i = 0;i < n;++i) A[c][i] = 0.0f;
+            for(size_t k = 0;k < numInput;++k)
+                for(size_t i = 0;i < n;++i) A[c][i] = A[c][i] + in[k][i]*B2A[c][k];
+        }
+        for(auto &row : B) std::fill_n(row, n, 0.0f);
+        // calcTriangleDelays / calcSinusoidDelays, chorus.cpp:235-323
+        auto gen = [&P](uint32_t offset) -> uint32_t {
+            const float offset_norm = float(offset) * P.cho_lfo_scale;
+            const float v = P.cho_wave == 1u ? (1.0f - std::fabs(2.0f - offset_norm)) * P.cho_depth
+                                              : std::sin(offset_norm) * P.cho_depth;
+            return uint32_t(int(std::lrintf(v)) + P.cho_delay);            // fastf2i = cvtss2si (current rounding mode)
+        };
+        const uint32_t range = e->lfo_range;
+        uint32_t off = e->lfo_offset;
+        for(size_t i = 0;i < n;++i) { md[0][i] = gen(off++); if(off == range) off = 0; }
+        off = (e->lfo_offset + P.cho_lfo_disp) % range;
+        for(size_t i = 0;i < n;++i) { md[1][i] = gen(off++); if(off == range) off = 0; }
+        e->lfo_offset = uint32_t(e->lfo_offset + n) % range;
+        const uint32_t bufmask = P.cho_len - 1u;
+        const uint32_t avgdelay = (uint32_t(P.cho_delay) + 32768u) >> 16;
+        for(size_t c = 0;c < 4;++c)
+        {
+            const uint32_t *moddelays = md[c < 2 ? 0 : 1];
+            float *delaybuf = e->cho_buf.data() + size_t(c)*P.cho_len;
+            uint32_t offset = e->cho_offset;
+            for(size_t i = 0;i < n;++i)
+            {
+                delaybuf[offset&bufmask] = A[c][i];
+                const uint32_t delay = offset - (moddelays[i] >> 8), phase = moddelays[i] & 255u;
+                const float sample = delaybuf[(delay+1) & bufmask]*e->cubic[256 + phase] +
+                    delaybuf[(delay  ) & bufmask]*e->cubic[phase] +
+                    delaybuf[(delay-1) & bufmask]*e->cubic[256 - phase] +
+                    delaybuf[(delay-2) & bufmask]*e->cubic[512 - phase];
+                delaybuf[offset&bufmask] += delaybuf[(offset-avgdelay) & bufmask] * P.cho_feedback;
+                ++offset;
+                tmp0[i] = sample;
+            }
+            for(size_t k = 0;k < 4;++k)
+                for(size_t i = 0;i < n;++i) B[k][i] = B[k][i] + tmp0[i]*A2B[k][c];
+        }
+        e->cho_offset += uint32_t(n);
+        for(size_t c = 0;c < 4;++c)
+        {
+            if(!P.line_on[c]) continue;
+            for(size_t o = 0;o < nout;++o)
+                if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                    mix_line(B[c], n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        }
+        break;
+    }
+    case B200MIX_EFFECT_AUTOWAH:
+    {
+        // autowah.cpp:136-205
+        static thread_local float cosw[LINE], alpha[LINE];
+        float env_delay = e->wah_env;
+        for(size_t i = 0;i < n;++i)
+        {
+            const float sample = P.wah_peak_gain * std::fabs(in[0][i]);
+            const float a = (sample > env_delay) ? P.wah_attack : P.wah_release;
+            env_delay = sample + (env_delay - sample)*a;
+            const float w0 = std::min(P.wah_bandwidth*env_delay + P.wah_freq_min, 0.46f) * (3.14159265358979323846f*2.0f);
+            cosw[i] = std::cos(w0); alpha[i] = std::sin(w0)*(0.5f/5.0f);
+        }
+        e->wah_env = env_delay;
+        for(size_t c = 0;c < nin;++c)
+        {
+            if(!P.line_on[c]) continue;
+            float z1 = e->chan[c][0].z1, z2 = e->chan[c][0].z2;
+            const float rg = P.wah_res_gain;
+            for(size_t i = 0;i < n;++i)
+            {
+                const float b0 = 1.0f + alpha[i]*rg, b1 = -2.0f * cosw[i], b2 = 1.0f - alpha[i]*rg;
+                const float a0 = 1.0f / (1.0f + alpha[i]/rg), a1 = -2.0f * cosw[i], a2 = 1.0f - alpha[i]/rg;
+                const float input = in[c][i];
+                const float output = input*(b0*a0) + z1;
+                z1 = input*(b1*a0) - output*(a1*a0) + z2;
+                z2 = input*(b2*a0) - output*(a2*a0);
+                buf[i] = output;
+            }
+            e->chan[c][0].z1 = z1; e->chan[c][0].z2 = z2;
+            for(size_t o = 0;o < nout;++o)
+                if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                    mix_line(buf, n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
         }
         break;
     }

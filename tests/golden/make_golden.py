@@ -115,6 +115,9 @@ SCENES = {
     "efx_compressor_hrtf_v5": (5, 1, 2, 8, False, 9000, None, "i16", 0, None, None, "efx:comp"),
     "efx_dedicated_dialog_hrtf_v4": (4, 1, 2, 4, True, 48000, None, "i16", 0, None, None, "efx:dialog"),
     "efx_distortion_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:dist"),
+    "efx_chorus_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:chorus"),
+    "efx_flanger_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:flanger"),
+    "efx_autowah_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:autowah"),
 }
 
 # name: (our effect type, AL effect enum, {AL float props}, {AL int props}, slot gain,
@@ -136,6 +139,13 @@ EFX_SCENES = {
     "dialog": (7, 0x9001, {0x0001: 0.6}, {}, 0.9, {2: ({0x0001: 0.2}, {})}),
     "dist": (8, 0x0003, {0x0001: 0.6, 0x0002: 0.3, 0x0003: 6000.0, 0x0004: 2000.0, 0x0005: 1500.0}, {}, 1.0,
              {3: ({0x0001: 0.2, 0x0004: 4000.0}, {})}),
+    # chorus (sinusoid LFO, then triangle with another rate / phase) and flanger (feedback close to -1)
+    "chorus": (9, 0x0002, {0x0003: 2.5, 0x0004: 0.4, 0x0005: 0.4, 0x0006: 0.012}, {0x0001: 0, 0x0002: 120}, 0.8,
+               {4: ({0x0003: 0.7, 0x0004: 0.9}, {0x0001: 1, 0x0002: -90})}),
+    "flanger": (9, 0x0005, {0x0003: 0.9, 0x0004: 1.0, 0x0005: -0.8, 0x0006: 0.003}, {0x0001: 1, 0x0002: 0}, 1.0,
+                {3: ({0x0003: 0.0}, {})}),
+    "autowah": (10, 0x000A, {0x0001: 0.02, 0x0002: 0.1, 0x0003: 300.0, 0x0004: 5000.0}, {}, 0.9,
+                {3: ({0x0003: 20.0, 0x0004: 100.0}, {})}),
 }
 
 
@@ -172,6 +182,21 @@ def efx_props_struct(kind, fprops, iprops):
         for k, n in {1: "edge", 2: "gain", 3: "lowpass_cutoff", 4: "eq_center", 5: "eq_bandwidth"}.items():
             if k in f:
                 setattr(p.distortion, n, f[k])
+    elif typ == 9:
+        if kind == "flanger":            # AL_FLANGER_* defaults (include/AL/efx.h)
+            p.chorus.waveform, p.chorus.phase, p.chorus.rate = 1, 0, 0.27
+            p.chorus.depth, p.chorus.feedback, p.chorus.delay = 1.0, -0.5, 0.002
+        for k, n in {3: "rate", 4: "depth", 5: "feedback", 6: "delay"}.items():
+            if k in f:
+                setattr(p.chorus, n, f[k])
+        if 1 in i:
+            p.chorus.waveform = i[1]
+        if 2 in i:
+            p.chorus.phase = i[2]
+    elif typ == 10:
+        for k, n in {1: "attack_time", 2: "release_time", 3: "resonance", 4: "peak_gain"}.items():
+            if k in f:
+                setattr(p.autowah, n, f[k])
     return p
 
 # {update index (applied before that render): {AL_EAXREVERB_* : value}}

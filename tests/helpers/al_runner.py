@@ -1,0 +1,116 @@
+#!/usr/bin/env python3
+"""Drives ONE OpenAL library (a path given on the command line) through the public AL/ALC API
+only — loopback device, buffers, sources, alcRenderSamplesSOFT — on a seeded scene, and writes
+the rendered updates to an .npz.  tests/test_gpu_dropin.py runs it once on the stock compiled
+reference and once on the patched libopenal_b200.so (ALSOFT_B200MIX=1): the application code is
+identical, only the mixer behind alcRenderSamplesSOFT differs.
+
+usage: al_runner.py <libopenal path> <out.npz> <voices> <updates> <hrtf 0|1> [resampler]"""
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "openal-soft_b200"))
+from pyb200mix import scene  # noqa: E402
+
+ALC_FREQUENCY, ALC_MONO_SOURCES = 0x1007, 0x1010
+ALC_FORMAT_CHANNELS_SOFT, ALC_FORMAT_TYPE_SOFT = 0x1990, 0x1991
+ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT = 0x1501, 0x1406, 0x1992
+AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 0x100A, 0x1004
+AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
+AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
+
+
+def main():
+    lib, out_path, V, U, hrtf = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    resampler = int(sys.argv[6]) if len(sys.argv) > 6 else 7          # bsinc24
+    conf = os.path.join(os.path.dirname(out_path), f"alsoft_{os.getpid()}.conf")
+    open(conf, "w").write("[general]\n")
+    os.environ["ALSOFT_CONF"] = conf
+    os.environ.setdefault("ALSOFT_LOGLEVEL", "1")
+    al = C.CDLL(lib, mode=C.RTLD_GLOBAL)
+    al.alcLoopbackOpenDeviceSOFT.restype = C.c_void_p
+    al.alcLoopbackOpenDeviceSOFT.argtypes = [C.c_char_p]
+    al.alcCreateContext.restype = C.c_void_p
+    al.alcCreateContext.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    al.alcMakeContextCurrent.argtypes = [C.c_void_p]
+    al.alcDestroyContext.argtypes = [C.c_void_p]
+    al.alcCloseDevice.argtypes = [C.c_void_p]
+    al.alcRenderSamplesSOFT.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    al.alcGetIntegerv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    al.alGenBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alGenSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alBufferData.argtypes = [C.c_uint, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    al.alSourcei.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alSourcef.argtypes = [C.c_uint, C.c_int, C.c_float]
+    al.alSource3f.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_float, C.c_float]
+    al.alSourcePlayv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alSourceStop.argtypes = [C.c_uint]
+    al.alSourcePlay.argtypes = [C.c_uint]
+    al.alGetSourcei.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_int)]
+    dev = al.alcLoopbackOpenDeviceSOFT(None)
+    assert dev
+    attrs = [ALC_FORMAT_CHANNELS_SOFT, ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT, ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
+             ALC_MONO_SOURCES, max(V, 1), ALC_HRTF_SOFT, hrtf, 0]
+    ctx = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
+    assert ctx
+    al.alcMakeContextCurrent(ctx)
+    keep, sources = [], (C.c_uint * V)()
+    for i in range(V):
+        b, s = C.c_uint(0), C.c_uint(0)
+        # every fourth voice is a short one-shot (runs out, fades, stops by itself)
+        oneshot = i % 4 == 3
+        pcm = np.ascontiguousarray(scene.voice_buffer_fast(i, 3000 + 37 * i if oneshot else scene.BUFFER_FRAMES))
+        keep.append(pcm)
+        al.alGenBuffers(1, C.byref(b))
+        al.alBufferData(b, AL_FORMAT_MONO16, pcm.ctypes.data, pcm.nbytes, 48000)
+        al.alGenSources(1, C.byref(s))
+        al.alSourcei(s, AL_BUFFER, b.value)
+        al.alSourcei(s, AL_LOOPING, 0 if oneshot else 1)
+        al.alSourcef(s, AL_PITCH, scene.voice_pitch(i))
+        al.alSourcef(s, AL_GAIN, scene.voice_gain(V))
+        al.alSource3f(s, AL_POSITION, *[float(x) for x in scene.voice_position(i)])
+        al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
+        sources[i] = s.value
+    err = al.alGetError()
+    assert err == 0, hex(err)
+    al.alSourcePlayv(V, sources)
+    outs, states, offsets = [], [], []
+    for u in range(U):
+        # the application moves a quarter of its sources, stops one and restarts another
+        for i in range(u % 4, V, 4):
+            x, y, z = scene.voice_position(i)
+            ang = 0.3 * u + 0.1 * i
+            cs, sn = math.cos(ang), math.sin(ang)
+            al.alSource3f(sources[i], AL_POSITION, float(x * cs - z * sn), float(y), float(x * sn + z * cs))
+        if u == 3 and V > 2:
+            al.alSourceStop(sources[2])
+        if u == 5 and V > 2:
+            al.alSourcePlay(sources[2])
+        buf = np.zeros((1024, 2), dtype=np.float32)
+        al.alcRenderSamplesSOFT(dev, buf.ctypes.data, 1024)
+        outs.append(buf.T.copy())
+        st, off = [], []
+        for i in range(min(V, 64)):
+            v = C.c_int(0)
+            al.alGetSourcei(sources[i], AL_SOURCE_STATE, C.byref(v))
+            st.append(v.value)
+            al.alGetSourcei(sources[i], AL_SAMPLE_OFFSET, C.byref(v))
+            off.append(v.value)
+        states.append(st)
+        offsets.append(off)
+    hv = C.c_int(0)
+    al.alcGetIntegerv(dev, 0x1993, 1, C.byref(hv))             # ALC_HRTF_STATUS_SOFT
+    np.savez(out_path, out=np.stack(outs), states=np.array(states), offsets=np.array(offsets), hrtf_status=hv.value)
+    al.alcMakeContextCurrent(None)
+    al.alcDestroyContext(ctx)
+    al.alcCloseDevice(dev)
+    os.remove(conf)
+
+
+if __name__ == "__main__":
+    main()

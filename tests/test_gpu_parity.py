@@ -722,6 +722,12 @@ EFX_CASES = {
     "dedicated": (abi.EFFECT_DEDICATED, lambda p: setattr(p.dedicated, "gain", 0.7), lambda p: setattr(p.dedicated, "gain", 0.1)),
     "distortion": (abi.EFFECT_DISTORTION, lambda p: (setattr(p.distortion, "edge", 0.8), setattr(p.distortion, "gain", 0.4)),
                    lambda p: (setattr(p.distortion, "edge", 0.1), setattr(p.distortion, "eq_center", 5000.0))),
+    "chorus": (abi.EFFECT_CHORUS, lambda p: (setattr(p.chorus, "waveform", 0), setattr(p.chorus, "rate", 3.3),
+                                             setattr(p.chorus, "depth", 0.6), setattr(p.chorus, "feedback", 0.5)),
+               lambda p: (setattr(p.chorus, "waveform", 1), setattr(p.chorus, "rate", 0.9), setattr(p.chorus, "phase", -120),
+                          setattr(p.chorus, "delay", 0.003), setattr(p.chorus, "feedback", -0.7))),
+    "autowah": (abi.EFFECT_AUTOWAH, lambda p: (setattr(p.autowah, "resonance", 200.0), setattr(p.autowah, "peak_gain", 3000.0)),
+                lambda p: (setattr(p.autowah, "attack_time", 0.005), setattr(p.autowah, "resonance", 40.0))),
 }
 
 

@@ -1,0 +1,50 @@
+"""The drop-in seam's host logic without a GPU: the patched reference (integration/alu_seam.patch +
+integration/b200mix_seam.cpp) runs the application in tests/helpers/al_runner.py with
+ALSOFT_B200MIX_LIB pointing at oracle/liboracle_abi.so — the oracle behind the b200mix_* names —
+and must reproduce the stock reference: audio within the oracle's own distance from the
+reference's SSE kernels, source states and offsets exactly.  What this pins is the binding
+(voice snapshots, change detection, stop / restart / end-of-buffer bookkeeping, cursor
+write-back); tests/test_gpu_dropin.py repeats it with libb200mix.so on the GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+RUNNER = os.path.join(ROOT, "tests", "helpers", "al_runner.py")
+SHIM = os.path.join(ROOT, "oracle", "liboracle_abi.so")
+
+
+def _run(lib, tag, voices, updates, hrtf, seam, tmp_path):
+    out = os.path.join(str(tmp_path), f"{tag}.npz")
+    env = dict(os.environ)
+    env.pop("ALSOFT_B200MIX", None)
+    if seam:
+        env["ALSOFT_B200MIX"] = "1"
+        env["ALSOFT_B200MIX_LIB"] = SHIM
+    p = subprocess.run([sys.executable, RUNNER, os.path.join(REF, lib), out, str(voices), str(updates), str(hrtf)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "b200mix:" not in p.stderr, p.stderr[-2000:]          # the seam's own error lines
+    return dict(np.load(out))
+
+
+@pytest.mark.parametrize("voices,updates,hrtf", [(24, 8, 1), (24, 8, 0), (300, 4, 1)])
+def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, tmp_path):
+    for f in ("libopenal_ref.so", "libopenal_b200.so"):
+        if not os.path.exists(os.path.join(REF, f)):
+            pytest.skip(f"oracle/_ref/{f} not built")
+    if not os.path.exists(SHIM):
+        pytest.skip("oracle/liboracle_abi.so not built")
+    cpu = _run("libopenal_ref.so", "cpu", voices, updates, hrtf, False, tmp_path)
+    via = _run("libopenal_b200.so", "seam", voices, updates, hrtf, True, tmp_path)
+    ref, out = cpu["out"].astype(np.float64), via["out"].astype(np.float64)
+    assert np.abs(ref).max() > 1e-2
+    err = out - ref
+    rms, mx = float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())
+    assert rms <= 1e-7 and mx <= 1e-6, f"rms {rms:.3e} max {mx:.3e}"
+    assert np.array_equal(cpu["states"], via["states"])
+    assert np.array_equal(cpu["offsets"], via["offsets"])

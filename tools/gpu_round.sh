@@ -35,6 +35,13 @@ ab4a)
     env $env timeout 600 python -m pytest tests/test_gpu_atsize.py -m gpu -q --timeout 600 -x -k "config4a" 2>&1 | grep -E "passed|failed|^E .*rms" >> gpurun_out/${tag}_ab4a.log
   done
   cat gpurun_out/${tag}_ab4a.log ;;
+l4a)
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 24 -c 40 --csv \
+     --log-file gpurun_out/${tag}_launches_cfg4a.csv python tools/bench_configs.py --config 4a --voices 8192 --steps 2 --warmup 2 > gpurun_out/${tag}_cfg4a_ncu.log 2>&1
+  grep -E "k_send|k_panmix|k_reduce|k_mix" gpurun_out/${tag}_launches_cfg4a.csv | awk -F'","' '{print $5, $9, $NF}' | tail -14 ;;
+dropin)
+  timeout 900 python -m pytest tests/test_gpu_dropin.py tests/test_gpu_params.py -m gpu -q --timeout 800 > gpurun_out/${tag}_pytest_dropin.log 2>&1
+  tail -8 gpurun_out/${tag}_pytest_dropin.log ;;
 probe)
   ./tools/ubench/umma_probe > gpurun_out/${tag}_umma_probe.log 2>&1; cat gpurun_out/${tag}_umma_probe.log ;;
 tc)
