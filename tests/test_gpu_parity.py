@@ -41,10 +41,16 @@ def test_golden_vectors_from_reference(name):
         assert np.ptp(fx["out_c"].astype(np.int64)) > 8
     else:
         gap_rms, gap_max = golden.kernel_set_gap(fx)      # the reference against itself (SSE vs C)
-        _check(out, fx["out_sse"], name + " vs reference SSE kernels", max(RMS_TOL, 2 * gap_rms),
-               max(MAX_TOL, 2 * gap_max))
-        _check(out, fx["out_c"], name + " vs reference C kernels", max(RMS_TOL, 2 * gap_rms),
-               max(MAX_TOL, 2 * gap_max))
+        max_tol = max(MAX_TOL, 2 * gap_max)
+        if name.startswith(("efx_chorus", "efx_flanger")):
+            # The sinusoid LFO is rounded to a 24.8 fixed-point delay per sample (fastf2i,
+            # chorus.cpp:300-323).  glibc's sinf is not correctly rounded (<= 0.56 ulp); the kernel's
+            # sine is (double sin, rounded once), so on isolated samples the delay lands 1/256 sample
+            # away and the cubic-interpolated tap differs by ~slope/256.  RMS keeps the 10x-tighter
+            # bar; the peak gets north_star's own budget (1e-4).
+            max_tol = max(max_tol, 1e-4)
+        _check(out, fx["out_sse"], name + " vs reference SSE kernels", max(RMS_TOL, 2 * gap_rms), max_tol)
+        _check(out, fx["out_c"], name + " vs reference C kernels", max(RMS_TOL, 2 * gap_rms), max_tol)
     # voice bookkeeping agrees with the oracle (positions are integers: exact)
     out_o, res_o = golden.replay(mixlib.oracle(), fx)
     V = int(fx["meta"][0])
@@ -750,8 +756,8 @@ def test_efx_effects_vs_oracle_ragged_updates(kind):
     wscale = np.ones(4, dtype=np.float32)
     windex = np.array([0, 1, 2, 3], dtype=np.uint32)
     sizes = (1024, 100, 1024, 7, 640, 1024, 333, 1024)
-    outs = []
-    for lib in (mixlib.oracle(), mixlib.product()):
+
+    def run(lib, send_gains):
         dev = MixDevice(lib, desc)
         dev.set_hrtf_decoder(*synth.decoder(np.random.default_rng(7)))
         for i in range(nv):
@@ -761,7 +767,7 @@ def test_efx_effects_vs_oracle_ragged_updates(kind):
         dev.slot_target(1, 0)                     # slot 1 feeds slot 0's Wet mix
         dev.slot_efx(0, props, 0.8, dscale, dindex, windex)
         dev.slot_efx(1, props, 0.6, wscale, windex, windex)
-        dev.voices_update(params, coeffs, dry, send)
+        dev.voices_update(params, coeffs, dry, send_gains)
         o = []
         for u, f in enumerate(sizes):
             if u == 4:
@@ -770,5 +776,15 @@ def test_efx_effects_vs_oracle_ragged_updates(kind):
                 dev.slot_efx(1, props, 0.5, wscale, windex, windex)
             o.append(dev.render(f))
         dev.close()
-        outs.append(np.concatenate(o, axis=1))
-    _check(outs[1], outs[0], f"efx {kind} vs oracle", 3e-6, 3e-5)
+        return np.concatenate(o, axis=1)
+
+    ref = run(mixlib.oracle(), send)
+    out = run(mixlib.product(), send)
+    # Conditioning: the waveshaper (small-signal gain (1+fc)^3), the high-gain peaking filters and
+    # the envelope-driven wah amplify last-bit differences of their INPUT (the send mix sums in a
+    # different order on the GPU) by orders of magnitude.  The oracle itself, fed send gains two
+    # ulps away, moves by `sens`; the comparison cannot be tighter than a few times that.
+    ptb = run(mixlib.oracle(), (send * np.float32(1.0 + 3e-7)).astype(np.float32))
+    d = ptb.astype(np.float64) - ref.astype(np.float64)
+    sens_rms, sens_max = float(np.sqrt((d ** 2).mean())), float(np.abs(d).max())
+    _check(out, ref, f"efx {kind} vs oracle", max(3e-6, 3.0 * sens_rms), max(3e-5, 3.0 * sens_max))

@@ -8,14 +8,45 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for s in $sections; do
 case $s in
 tests)
-  timeout 1700 python -m pytest tests -m gpu -q --timeout 1500 -x > gpurun_out/${tag}_pytest_gpu.log 2>&1
-  tail -5 gpurun_out/${tag}_pytest_gpu.log ;;
+  timeout 1700 python -m pytest tests -m gpu -q --timeout 1500 > gpurun_out/${tag}_pytest_gpu.log 2>&1
+  grep -E '^(FAILED|ERROR)' gpurun_out/${tag}_pytest_gpu.log | head -30; tail -3 gpurun_out/${tag}_pytest_gpu.log ;;
 tests_fast)
   timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x --deselect tests/test_gpu_atsize.py > gpurun_out/${tag}_pytest_gpu_fast.log 2>&1
   tail -5 gpurun_out/${tag}_pytest_gpu_fast.log ;;
 bench)
   timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
   tail -c 3000 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
+launches)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+     --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu.log 2>&1
+  grep -c k_ gpurun_out/${tag}_launches_bench.csv ;;
+configs)
+  for c in 1 2 3 "4a --voices 8192" "4b --voices 8192"; do timeout 600 python tools/bench_configs.py --config $c >> gpurun_out/${tag}_configs_n1.jsonl 2>> gpurun_out/${tag}_configs_n1.err; done
+  timeout 900 python tools/bench_configs.py --config 5 --voices 131072 --slot-share 8 --steps 8 >> gpurun_out/${tag}_configs_n1.jsonl 2>> gpurun_out/${tag}_configs_n1.err
+  python - <<PY
+import json
+for l in open('gpurun_out/${tag}_configs_n1.jsonl'):
+    j=json.loads(l); print(j['config'], j['voices_total'], j['slots'], round(j['ms_per_update'],4), j.get('stage_us_rank0'))
+PY
+  ;;
+multi)
+  NG=$(nvidia-smi -L | wc -l)
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+  timeout 900 python -m pytest tests/test_gpu_shard.py -m gpu -q --timeout 600 > gpurun_out/${tag}_pytest_shard_n${NG}.log 2>&1
+  tail -3 gpurun_out/${tag}_pytest_shard_n${NG}.log
+  timeout 900 $TR --master-port 29511 bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n${NG}.json 2> gpurun_out/${tag}_bench_n${NG}.err
+  tail -c 2500 gpurun_out/${tag}_bench_n${NG}.json; tail -3 gpurun_out/${tag}_bench_n${NG}.err
+  timeout 600 $TR --master-port 29512 bench.py --impl reference --gpus $NG --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref_n${NG}.json 2>> gpurun_out/${tag}_bench_n${NG}.err
+  tail -c 600 gpurun_out/${tag}_bench_ref_n${NG}.json
+  for c in "2" "2 --transport nccl" "3" "5 --voices $((131072*NG)) --slot-share $((8/NG)) --steps 8"; do
+    timeout 900 $TR --master-port 29513 tools/bench_configs.py --config $c --gpus $NG >> gpurun_out/${tag}_configs_n${NG}.jsonl 2>> gpurun_out/${tag}_configs_n${NG}.err
+  done
+  python - <<PY
+import json
+for l in open('gpurun_out/${tag}_configs_n${NG}.jsonl'):
+    j=json.loads(l); print(j['config'], j['n_gpus'], j['voices_total'], j['slots'], j.get('transport'), round(j['ms_per_update'],4), j.get('stage_us_rank0'), j.get('collective'))
+PY
+  ;;
 fx)
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_conv -c 60 --csv \
      --log-file gpurun_out/${tag}_launches_fx_conv.csv python tools/bench_effects.py --effect conv --voices 4096 --slots 32 --steps 4 > gpurun_out/${tag}_fx_conv_ncu.log 2>&1
@@ -25,6 +56,10 @@ fx)
 params)
   timeout 900 python -m pytest tests/test_gpu_params.py tests/test_gpu_parity.py -m gpu -q --timeout 600 -x -s -k "sources_update or convolution or config2 or golden" > gpurun_out/${tag}_pytest_params.log 2>&1
   tail -8 gpurun_out/${tag}_pytest_params.log ;;
+ncu_mix)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mix_voices -s 4 -c 1 -o gpurun_out/${tag}_prof_mix -f \
+     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sustained > gpurun_out/${tag}_ncu_mix.log 2>&1
+  tail -2 gpurun_out/${tag}_ncu_mix.log; ls -la gpurun_out/${tag}_prof_mix.ncu-rep ;;
 ncu_conv)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv_mac -s 4 -c 1 -o gpurun_out/${tag}_prof_conv_mac -f \
      python tools/bench_effects.py --effect conv --voices 4096 --slots 32 --steps 2 > gpurun_out/${tag}_ncu_conv.log 2>&1
