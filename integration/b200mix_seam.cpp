@@ -7,12 +7,16 @@
  *   ALSOFT_B200MIX=1            enables the seam (else the library behaves as stock OpenAL Soft)
  *   ALSOFT_B200MIX_LIB=<path>   libb200mix.so (default: "libb200mix.so" on the loader path)
  *
- * Scope of this binding (v1): HRTF and ambisonic-decode devices, static mono sources of any
+ * Scope of this binding (v2): HRTF and ambisonic-decode devices, static mono sources of any
  * PCM sample type, any resampler, moving sources (targets are re-sent when the ALU changed
- * them), source start / stop / loop.  Streaming queues, multi-channel sources, direct/send
- * filters and auxiliary effect slots are forwarded by the C ABI (b200mix_voice_queue,
- * B200MIX_VF_CHANNEL, b200mix_voices_filters, b200mix_slot_*) but not wired up here yet: the
- * seam disconnects the device with a message rather than mixing them wrong.
+ * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
+ * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
+ * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah), slot gain, slot
+ * targets (AL_SOFT_effect_target), property changes while playing.  Streaming queues,
+ * multi-channel sources, direct / send filters and convolution slots are forwarded by the C
+ * ABI (b200mix_voice_queue, B200MIX_VF_CHANNEL, b200mix_voices_filters,
+ * b200mix_slot_convolution) but not wired up here yet: the seam disconnects the device with
+ * a message rather than mixing them wrong.
  */
 #include "config.h"
 
@@ -52,6 +56,8 @@
 #include "core/context.h"
 #include "core/device.h"
 #include "core/effectslot.h"
+#include "core/effects/base.h"
+#include "alc/effects/base.h"
 #include "core/hrtf.h"
 #include "core/logging.h"
 #include "core/voice.h"
@@ -72,6 +78,14 @@ struct Api {
     decltype(&b200mix_buffer_data) buffer_data{};
     decltype(&b200mix_voices_update) voices_update{};
     decltype(&b200mix_render) render{};
+    decltype(&b200mix_slot_efx) slot_efx{};
+    decltype(&b200mix_slot_reverb) slot_reverb{};
+    decltype(&b200mix_slot_reverb_update) slot_reverb_update{};
+    decltype(&b200mix_slot_output_gains) slot_output_gains{};
+    decltype(&b200mix_slot_target) slot_target{};
+    decltype(&b200mix_slot_disable) slot_disable{};
+    decltype(&b200mix_reverb_params_from_efx) reverb_params_from_efx{};
+    decltype(&b200mix_reverb_full_update_needed) reverb_full_update_needed{};
     bool ok{false};
 };
 
@@ -87,9 +101,13 @@ Api &api()
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
         LOAD(buffer_data); LOAD(voices_update); LOAD(render);
+        LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
+        LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
-            && r.buffer_data && r.voices_update && r.render;
+            && r.buffer_data && r.voices_update && r.render && r.slot_efx && r.slot_reverb
+            && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
+            && r.reverb_params_from_efx && r.reverb_full_update_needed;
         if(!r.ok) ERR("b200mix: the mixer library lacks entry points of include/b200mix.h");
         return r;
     }();
@@ -100,7 +118,18 @@ struct VoiceCache {                  /* what was last sent for a voice: resend o
     unsigned source_id{0};
     bool live{false};
     b200mix_voice_params params{};
-    std::vector<float> coeffs, dry;
+    std::vector<float> coeffs, dry, send;
+};
+
+struct SlotCache {                   /* what was last installed for an effect slot */
+    const EffectSlotBase *slot{nullptr};
+    const EffectState *state{nullptr};   /* a new EffectState object = deviceUpdate (al/auxeffectslot.cpp initEffect) */
+    bool live{false};
+    uint32_t kind{0};                /* 0 none, 1 reverb, 2 b200mix_slot_efx */
+    b200mix_efx_props efx{};
+    b200mix_efx_reverb reverb{};
+    float gain{0.0f};
+    uint32_t target{B200MIX_NO_SLOT};
 };
 
 struct Seam {
@@ -115,12 +144,16 @@ struct Seam {
     std::vector<b200mix_voice_result> results;
     std::vector<Voice*> vptr;
     std::vector<ContextBase*> vctx;
+    std::vector<SlotCache> slots;
+    std::unordered_map<const EffectSlotBase*, uint32_t> slot_ids;
+    std::unordered_map<const void*, uint32_t> wet_ids;                        /* Wet.Buffer.data() -> slot id */
+    std::vector<float> upd_send;
 };
 
 std::mutex g_lock;
 std::unordered_map<const DeviceBase*, Seam> g_seams;
 
-constexpr uint32_t kMaxVoices = 16384, kMaxBuffers = 16384;
+constexpr uint32_t kMaxVoices = 16384, kMaxBuffers = 16384, kMaxSlots = 64;   /* 64: alc/alc.cpp:3427 */
 
 int sample_type_of(const SampleVariant &sv, const void **data)
 {
@@ -161,6 +194,9 @@ bool open_device(DeviceBase *device, Seam &S)
     d.real_left = device->RealOut.ChannelIndex[FrontLeft].c_val;
     d.real_right = device->RealOut.ChannelIndex[FrontRight].c_val;
     d.max_voices = kMaxVoices; d.max_buffers = kMaxBuffers;
+    d.num_sends = std::min<uint32_t>(device->NumAuxSends, B200MIX_MAX_SENDS);
+    d.wet_channels = d.num_sends ? static_cast<uint32_t>(AmbiChannelsFromOrder(device->mAmbiOrder)) : 0u; /* aluInitEffectPanning */
+    d.max_slots = d.num_sends ? kMaxSlots : 0u;
     if(std::holds_alternative<HrtfPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_HRTF;
     else if(std::holds_alternative<AmbiDecPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_AMBIDEC;
     else if(std::holds_alternative<std::monostate>(device->mPostProcess)) d.post_process = B200MIX_POST_NONE;
@@ -212,7 +248,200 @@ bool open_device(DeviceBase *device, Seam &S)
             return fail(device, S, "b200mix_set_ambi_decoder failed:");
     }
     S.cache.assign(kMaxVoices, VoiceCache{});
+    S.slots.assign(kMaxSlots, SlotCache{});
     S.results.assign(kMaxVoices, b200mix_voice_result{});
+    return true;
+}
+
+
+/* EffectProps (core/effects/base.h:62-178) -> the ABI's plain structs.  Returns the slot kind:
+ * 0 none, 1 reverb, 2 b200mix_slot_efx, -1 not wired. */
+int effect_of(const EffectSlotBase *slot, b200mix_efx_props &o, b200mix_efx_reverb &rv)
+{
+    std::memset(&o, 0, sizeof(o)); o.struct_size = sizeof(o);
+    std::memset(&rv, 0, sizeof(rv)); rv.struct_size = sizeof(rv);
+    const EffectProps &props = slot->mEffectProps;
+    switch(slot->EffectType)
+    {
+    case EffectSlotType::None: return 0;
+    case EffectSlotType::Reverb:
+        if(auto *p = std::get_if<ReverbProps>(&props))
+        {
+            rv.density = p->Density; rv.diffusion = p->Diffusion; rv.gain = p->Gain; rv.gain_hf = p->GainHF;
+            rv.gain_lf = p->GainLF; rv.decay_time = p->DecayTime; rv.decay_hf_ratio = p->DecayHFRatio;
+            rv.decay_lf_ratio = p->DecayLFRatio; rv.reflections_gain = p->ReflectionsGain;
+            rv.reflections_delay = p->ReflectionsDelay; rv.late_reverb_gain = p->LateReverbGain;
+            rv.late_reverb_delay = p->LateReverbDelay;
+            for(int k = 0;k < 3;++k) { rv.reflections_pan[k] = p->ReflectionsPan[size_t(k)]; rv.late_reverb_pan[k] = p->LateReverbPan[size_t(k)]; }
+            rv.echo_time = p->EchoTime; rv.echo_depth = p->EchoDepth; rv.modulation_time = p->ModulationTime;
+            rv.modulation_depth = p->ModulationDepth; rv.air_absorption_gain_hf = p->AirAbsorptionGainHF;
+            rv.hf_reference = p->HFReference; rv.lf_reference = p->LFReference;
+            rv.room_rolloff_factor = p->RoomRolloffFactor; rv.decay_hf_limit = p->DecayHFLimit ? 1u : 0u;
+            return 1;
+        }
+        return -1;
+    case EffectSlotType::Echo:
+        if(auto *p = std::get_if<EchoProps>(&props))
+        { o.type = B200MIX_EFFECT_ECHO; o.echo.delay = p->Delay; o.echo.lr_delay = p->LRDelay; o.echo.damping = p->Damping;
+          o.echo.feedback = p->Feedback; o.echo.spread = p->Spread; return 2; }
+        return -1;
+    case EffectSlotType::RingModulator:
+        if(auto *p = std::get_if<ModulatorProps>(&props))
+        { o.type = B200MIX_EFFECT_MODULATOR; o.modulator.frequency = p->Frequency; o.modulator.high_pass_cutoff = p->HighPassCutoff;
+          o.modulator.waveform = static_cast<uint32_t>(p->Waveform); return 2; }
+        return -1;
+    case EffectSlotType::Equalizer:
+        if(auto *p = std::get_if<EqualizerProps>(&props))
+        { o.type = B200MIX_EFFECT_EQUALIZER; auto &e = o.equalizer;
+          e.low_cutoff = p->LowCutoff; e.low_gain = p->LowGain; e.mid1_center = p->Mid1Center; e.mid1_gain = p->Mid1Gain;
+          e.mid1_width = p->Mid1Width; e.mid2_center = p->Mid2Center; e.mid2_gain = p->Mid2Gain; e.mid2_width = p->Mid2Width;
+          e.high_cutoff = p->HighCutoff; e.high_gain = p->HighGain; return 2; }
+        return -1;
+    case EffectSlotType::Compressor:
+        if(auto *p = std::get_if<CompressorProps>(&props))
+        { o.type = B200MIX_EFFECT_COMPRESSOR; o.compressor.on_off = p->OnOff ? 1u : 0u; return 2; }
+        return -1;
+    case EffectSlotType::Dedicated:
+        if(auto *p = std::get_if<DedicatedProps>(&props))
+        { o.type = B200MIX_EFFECT_DEDICATED; o.dedicated.target = p->Target == DedicatedProps::Lfe ? 1u : 0u;
+          o.dedicated.gain = p->Gain; return 2; }
+        return -1;
+    case EffectSlotType::Distortion:
+        if(auto *p = std::get_if<DistortionProps>(&props))
+        { o.type = B200MIX_EFFECT_DISTORTION; o.distortion.edge = p->Edge; o.distortion.gain = p->Gain;
+          o.distortion.lowpass_cutoff = p->LowpassCutoff; o.distortion.eq_center = p->EQCenter;
+          o.distortion.eq_bandwidth = p->EQBandwidth; return 2; }
+        return -1;
+    case EffectSlotType::Chorus:
+    case EffectSlotType::Flanger:
+        if(auto *p = std::get_if<ChorusProps>(&props))
+        { o.type = B200MIX_EFFECT_CHORUS; o.chorus.waveform = static_cast<uint32_t>(p->Waveform); o.chorus.phase = p->Phase;
+          o.chorus.rate = p->Rate; o.chorus.depth = p->Depth; o.chorus.feedback = p->Feedback; o.chorus.delay = p->Delay; return 2; }
+        return -1;
+    case EffectSlotType::Autowah:
+        if(auto *p = std::get_if<AutowahProps>(&props))
+        { o.type = B200MIX_EFFECT_AUTOWAH; o.autowah.attack_time = p->AttackTime; o.autowah.release_time = p->ReleaseTime;
+          o.autowah.resonance = p->Resonance; o.autowah.peak_gain = p->PeakGain; return 2; }
+        return -1;
+    default: return -1;          /* convolution, frequency / pitch shifter, vocal morpher */
+    }
+}
+
+uint32_t slot_id_of(Seam &S, const EffectSlotBase *slot)
+{
+    if(auto it = S.slot_ids.find(slot); it != S.slot_ids.end()) return it->second;
+    for(uint32_t i = 0;i < kMaxSlots;++i)
+        if(!S.slots[i].slot) { S.slots[i] = SlotCache{}; S.slots[i].slot = slot; S.slot_ids[slot] = i; return i; }
+    return B200MIX_NO_SLOT;
+}
+
+/* CalcEffectSlotParams' result (alc/alu.cpp:557-636) -> b200mix_slot_*: every active slot whose
+ * effect object, properties, gain or target differ from what the device has is (re)installed. */
+bool sync_slots(DeviceBase *device, Seam &S)
+{
+    Api &A = api();
+    std::array<bool, kMaxSlots> seen{};
+    S.wet_ids.clear();
+    for(ContextBase *ctx : *device->mContexts.load(std::memory_order_acquire))
+    {
+        auto *arr = ctx->mActiveAuxSlots.load(std::memory_order_acquire);
+        if(!arr) continue;
+        for(EffectSlotBase *slot : *arr)
+        {
+            if(!S.desc.max_slots) return fail(device, S, "effect slots on a device without auxiliary sends");
+            const uint32_t id = slot_id_of(S, slot);
+            if(id == B200MIX_NO_SLOT) return fail(device, S, "more effect slots than the seam's device was created for");
+            seen[id] = true;
+            if(slot->Wet.Buffer.size() != S.desc.wet_channels) return fail(device, S, "unexpected Wet buffer size");
+            S.wet_ids[slot->Wet.Buffer.data()] = id;
+        }
+    }
+    for(uint32_t id = 0;id < kMaxSlots;++id)
+    {
+        SlotCache &C = S.slots[id];
+        if(!C.slot) continue;
+        if(!seen[id])
+        {   /* left the active list (deleted, or nothing plays into it any more) */
+            if(C.live && C.kind && A.slot_disable(S.dev, id) != B200MIX_OK) return fail(device, S, "b200mix_slot_disable failed:");
+            S.slot_ids.erase(C.slot);
+            C = SlotCache{};
+            continue;
+        }
+        const EffectSlotBase *slot = C.slot;
+        b200mix_efx_props efx; b200mix_efx_reverb rv;
+        const int kind = effect_of(slot, efx, rv);
+        if(kind < 0) return fail(device, S, "this effect type is not wired into the seam yet");
+        uint32_t target = B200MIX_NO_SLOT;
+        if(slot->Target)
+        {
+            target = slot_id_of(S, slot->Target);
+            if(target == B200MIX_NO_SLOT || !seen[target]) return fail(device, S, "effect slot target outside the active set");
+        }
+        const EffectState *state = slot->mEffectState.get();
+        const bool fresh = !C.live || C.state != state || C.kind != uint32_t(kind);
+        const bool changed = fresh || C.gain != slot->Gain || C.target != target
+            || std::memcmp(&C.efx, &efx, sizeof(efx)) != 0 || std::memcmp(&C.reverb, &rv, sizeof(rv)) != 0;
+        if(!changed) continue;
+
+        if(C.target != target || fresh)
+            if(A.slot_target(S.dev, id, target) != B200MIX_OK) return fail(device, S, "b200mix_slot_target failed:");
+        /* EffectTarget (alc/alu.cpp:627-633): the target slot's Wet mix, or the Dry mix */
+        const MixParams &out = slot->Target ? slot->Target->Wet : device->Dry;
+        std::array<float, MaxAmbiChannels> oscale{};
+        std::array<uint32_t, MaxAmbiChannels> oindex{}, windex{};
+        const auto nout = static_cast<uint32_t>(out.Buffer.size());
+        if(nout > MaxAmbiChannels) return fail(device, S, "effect target wider than an ambisonic mix");
+        for(uint32_t c = 0;c < nout;++c) { oscale[c] = out.AmbiMap[c].Scale; oindex[c] = out.AmbiMap[c].Index; }
+        for(uint32_t c = 0;c < S.desc.wet_channels;++c) windex[c] = slot->Wet.AmbiMap[c].Index;
+        if(kind == 0)
+        {
+            if(C.live && C.kind && A.slot_disable(S.dev, id) != B200MIX_OK) return fail(device, S, "b200mix_slot_disable failed:");
+        }
+        else if(kind == 1)
+        {
+            b200mix_reverb_target t{};
+            t.struct_size = sizeof(t);
+            t.sample_rate = device->mSampleRate; t.device_ambi_order = device->mAmbiOrder;
+            t.device_2d = device->m2DMixing ? 1u : 0u; t.xover_freq = device->mXOverFreq;
+            t.slot_gain = slot->Gain; t.reverb_boost = ReverbBoost;
+            t.out_channels = nout; t.out_scale = oscale.data(); t.out_index = oindex.data();
+            b200mix_reverb_params rp{};
+            rp.struct_size = sizeof(rp);
+            std::vector<float> gains(size_t(8)*nout);
+            if(A.reverb_params_from_efx(&rv, &t, &rp, gains.data()) != B200MIX_OK)
+                return fail(device, S, "b200mix_reverb_params_from_efx failed");
+            if(fresh)
+            {
+                if(C.live && C.kind && A.slot_disable(S.dev, id) != B200MIX_OK) return fail(device, S, "b200mix_slot_disable failed:");
+                if(A.slot_reverb(S.dev, id, &rp) != B200MIX_OK) return fail(device, S, "b200mix_slot_reverb failed:");
+            }
+            else
+            {
+                const uint32_t full = uint32_t(A.reverb_full_update_needed(&C.reverb, &rv));
+                if(A.slot_reverb_update(S.dev, id, &rp, full) != B200MIX_OK)
+                    return fail(device, S, "b200mix_slot_reverb_update failed:");
+            }
+            if(A.slot_output_gains(S.dev, id, 8u, gains.data()) != B200MIX_OK)
+                return fail(device, S, "b200mix_slot_output_gains failed:");
+        }
+        else
+        {
+            b200mix_efx_target t{};
+            t.struct_size = sizeof(t);
+            t.sample_rate = device->mSampleRate; t.slot_gain = slot->Gain;
+            t.out_channels = nout; t.out_scale = oscale.data(); t.out_index = oindex.data();
+            t.wet_channels = S.desc.wet_channels; t.wet_index = windex.data();
+            const auto rc = device->RealOut.ChannelIndex[FrontCenter].c_val, rl = device->RealOut.ChannelIndex[LFE].c_val;
+            t.real_center = (slot->Target || rc == InvalidChannelIndex.c_val) ? B200MIX_NO_SLOT : rc;
+            t.real_lfe = (slot->Target || rl == InvalidChannelIndex.c_val) ? B200MIX_NO_SLOT : rl;
+            t.device_ambi_order = device->mAmbiOrder;
+            if(fresh && C.live && C.kind && A.slot_disable(S.dev, id) != B200MIX_OK)
+                return fail(device, S, "b200mix_slot_disable failed:");
+            if(A.slot_efx(S.dev, id, &efx, &t) != B200MIX_OK) return fail(device, S, "b200mix_slot_efx failed:");
+        }
+        C.live = true; C.state = state; C.kind = uint32_t(kind); C.efx = efx; C.reverb = rv;
+        C.gain = slot->Gain; C.target = target;
+    }
     return true;
 }
 
@@ -233,13 +462,14 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     S.vptr.clear(); S.vctx.clear();
     for(ContextBase *ctx : *device->mContexts.load(std::memory_order_acquire))
     {
-        if(auto *arr = ctx->mActiveAuxSlots.load(std::memory_order_acquire); arr && !arr->empty())
-        { fail(device, S, "auxiliary effect slots are not wired into the seam yet"); return; }
         for(Voice *voice : ctx->getVoicesSpanAcquired()) { S.vptr.push_back(voice); S.vctx.push_back(ctx); }
     }
+    if(!sync_slots(device, S)) return;
     if(S.vptr.size() > kMaxVoices) { fail(device, S, "more voices than the seam's device was created for"); return; }
 
-    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear();
+    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear();
+    const uint32_t ns = S.desc.num_sends, cw = S.desc.wet_channels;
+    std::vector<float> sg(size_t(ns)*cw);
     for(size_t n = 0;n < S.vptr.size();++n)
     {
         Voice *voice = S.vptr[n];
@@ -255,6 +485,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                 S.upd.push_back(p);
                 S.upd_coeffs.insert(S.upd_coeffs.end(), size_t(ir)*2, 0.0f);
                 S.upd_dry.insert(S.upd_dry.end(), cd, 0.0f);
+                S.upd_send.insert(S.upd_send.end(), size_t(ns)*cw, 0.0f);
                 C.live = false;
             }
             continue;
@@ -277,6 +508,19 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         p.hrtf_delay[1] = ch.mDryParams.Hrtf.Target.Delay[1];
         p.hrtf_gain = ch.mDryParams.Hrtf.Target.Gain;
         for(auto &s : p.send_slot) s = B200MIX_NO_SLOT;
+        /* auxiliary sends (core/voice.cpp:967-980): the slot by its Wet buffer, the gains the ALU set */
+        std::fill(sg.begin(), sg.end(), 0.0f);
+        for(uint32_t snd = 0;snd < ns;++snd)
+        {
+            const auto &tgt = voice->mSend[snd];
+            if(tgt.Buffer.empty()) continue;
+            auto wit = S.wet_ids.find(tgt.Buffer.data());
+            if(wit == S.wet_ids.end() || tgt.FilterActive)
+            { fail(device, S, "send into an inactive slot, or a send filter: not wired into the seam yet"); return; }
+            p.send_slot[snd] = wit->second;
+            const float *wg = ch.mWetParams[snd].Gains.Target.data();
+            std::copy_n(wg, cw, sg.begin() + size_t(snd)*cw);
+        }
         if(item)
         {
             const void *data = nullptr;
@@ -315,11 +559,14 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         bool changed = fresh || std::memcmp(&C.params, &p, sizeof(p)) != 0;
         if(!changed && hrtf && ir) changed = std::memcmp(C.coeffs.data(), co, size_t(ir)*2*sizeof(float)) != 0;
         if(!changed && !hrtf) changed = std::memcmp(C.dry.data(), dg, cd*sizeof(float)) != 0;
+        if(!changed && !sg.empty()) changed = std::memcmp(C.send.data(), sg.data(), sg.size()*sizeof(float)) != 0;
         if(changed)
         {
             S.upd.push_back(p);
             S.upd_coeffs.insert(S.upd_coeffs.end(), co, co + size_t(ir)*2);
             S.upd_dry.insert(S.upd_dry.end(), dg, dg + cd);
+            S.upd_send.insert(S.upd_send.end(), sg.begin(), sg.end());
+            C.send = sg;
             b200mix_voice_params keep = p;
             keep.flags &= ~uint32_t(B200MIX_VF_RESET | B200MIX_VF_FADING);
             keep.position = 0; keep.position_frac = 0;
@@ -331,7 +578,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     }
     if(!S.upd.empty()
         && A.voices_update(S.dev, uint32_t(S.upd.size()), S.upd.data(), ir ? S.upd_coeffs.data() : nullptr,
-            S.upd_dry.data(), nullptr) != B200MIX_OK)
+            S.upd_dry.data(), sg.empty() ? nullptr : S.upd_send.data()) != B200MIX_OK)
     { fail(device, S, "b200mix_voices_update failed:"); return; }
 
     /* ---- the update itself: RealOut comes back planar, where Limiter / Write<T> expect it ---- */

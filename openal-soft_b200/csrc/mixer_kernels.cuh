@@ -299,7 +299,7 @@ __device__ __forceinline__ void fir_pass(float2 (&acc)[OPT], const float2 *__res
 //   OPT/FP : FIR outputs per thread / front pad (17/64 for ir<=64, 19/128 for ir<=128)
 // ---------------------------------------------------------------------------
 template<int GS, int GROUPS, bool HRTF, int CDR, int OPT, int FP>
-__global__ void __launch_bounds__(GS*GROUPS, (GS*GROUPS == 128 && (HRTF || CDR == 0)) ? 4 : 1)
+__global__ void __launch_bounds__(GS*GROUPS, GS*GROUPS != 128 ? 1 : ((HRTF || CDR == 0) ? 4 : 3))
 k_mix_voices(const MixParams P)
 {
     using Smem = GroupSmem<GS, OPT, FP>;
