@@ -12,10 +12,10 @@
  * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
  * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah), slot gain, slot
- * targets (AL_SOFT_effect_target), property changes while playing.  Streaming queues,
- * multi-channel sources, direct / send filters and convolution slots are forwarded by the C
- * ABI (b200mix_voice_queue, B200MIX_VF_CHANNEL, b200mix_voices_filters,
- * b200mix_slot_convolution) but not wired up here yet: the seam disconnects the device with
+ * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
+ * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass).  Streaming queues,
+ * multi-channel sources and convolution slots are forwarded by the C ABI (b200mix_voice_queue,
+ * B200MIX_VF_CHANNEL, b200mix_slot_convolution) but not wired up here yet: the seam disconnects the device with
  * a message rather than mixing them wrong.
  */
 #include "config.h"
@@ -34,7 +34,7 @@
 
 #include <dlfcn.h>
 
-/* BandSplitter::mCoeff and BFormatDec's matrices are private: a maintainer would add two
+/* BandSplitter::mCoeff, BiquadInterpFilter::mTargetCoeffs and BFormatDec's matrices are private: a maintainer would add two
  * accessors; the out-of-tree build opens them up instead of touching more reference files. */
 #include "opthelpers.h"
 #include "core/ambidefs.h"
@@ -47,6 +47,7 @@
 #define private public
 #define protected public
 #include "core/filters/splitter.h"
+#include "core/filters/biquad.h"
 #include "core/bformatdec.h"
 #undef protected
 #undef private
@@ -77,6 +78,7 @@ struct Api {
     decltype(&b200mix_set_ambi_decoder) set_ambi_decoder{};
     decltype(&b200mix_buffer_data) buffer_data{};
     decltype(&b200mix_voices_update) voices_update{};
+    decltype(&b200mix_voices_filters) voices_filters{};
     decltype(&b200mix_render) render{};
     decltype(&b200mix_slot_efx) slot_efx{};
     decltype(&b200mix_slot_reverb) slot_reverb{};
@@ -100,12 +102,12 @@ Api &api()
         if(!r.lib) { ERR("b200mix: cannot load the mixer library: {}", dlerror()); return r; }
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
-        LOAD(buffer_data); LOAD(voices_update); LOAD(render);
+        LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(render);
         LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
         LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
-            && r.buffer_data && r.voices_update && r.render && r.slot_efx && r.slot_reverb
+            && r.buffer_data && r.voices_update && r.voices_filters && r.render && r.slot_efx && r.slot_reverb
             && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
             && r.reverb_params_from_efx && r.reverb_full_update_needed;
         if(!r.ok) ERR("b200mix: the mixer library lacks entry points of include/b200mix.h");
@@ -119,6 +121,7 @@ struct VoiceCache {                  /* what was last sent for a voice: resend o
     bool live{false};
     b200mix_voice_params params{};
     std::vector<float> coeffs, dry, send;
+    std::vector<b200mix_voice_filter> filt;      /* per path: what the device has (empty: never sent) */
 };
 
 struct SlotCache {                   /* what was last installed for an effect slot */
@@ -148,6 +151,7 @@ struct Seam {
     std::unordered_map<const EffectSlotBase*, uint32_t> slot_ids;
     std::unordered_map<const void*, uint32_t> wet_ids;                        /* Wet.Buffer.data() -> slot id */
     std::vector<float> upd_send;
+    std::vector<b200mix_voice_filter> upd_filt;
 };
 
 std::mutex g_lock;
@@ -346,7 +350,9 @@ bool sync_slots(DeviceBase *device, Seam &S)
     {
         auto *arr = ctx->mActiveAuxSlots.load(std::memory_order_acquire);
         if(!arr) continue;
-        for(EffectSlotBase *slot : *arr)
+        /* the array's second half is ProcessContexts' sorting scratch (alc/alu.cpp:2187-2189) */
+        const auto all = std::span{*arr};
+        for(EffectSlotBase *slot : all.first(all.size()>>1))
         {
             if(!S.desc.max_slots) return fail(device, S, "effect slots on a device without auxiliary sends");
             const uint32_t id = slot_id_of(S, slot);
@@ -467,7 +473,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     if(!sync_slots(device, S)) return;
     if(S.vptr.size() > kMaxVoices) { fail(device, S, "more voices than the seam's device was created for"); return; }
 
-    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear();
+    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear(); S.upd_filt.clear();
     const uint32_t ns = S.desc.num_sends, cw = S.desc.wet_channels;
     std::vector<float> sg(size_t(ns)*cw);
     for(size_t n = 0;n < S.vptr.size();++n)
@@ -491,8 +497,8 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             continue;
         }
         if(!voice->mFlags.test(VoiceFlag::IsStatic) || voice->mFlags.test(VoiceFlag::IsCallback)
-            || voice->mFmtChannels != FmtMono || voice->mDuplicateMono || voice->mDirect.FilterActive)
-        { fail(device, S, "streaming / multi-channel / filtered sources are not wired into the seam yet"); return; }
+            || voice->mFmtChannels != FmtMono || voice->mDuplicateMono)
+        { fail(device, S, "streaming / multi-channel sources are not wired into the seam yet"); return; }
         auto *item = voice->mCurrentBuffer.load(std::memory_order_relaxed);
         auto *loop = voice->mLoopBuffer.load(std::memory_order_relaxed);
         auto &ch = voice->mChans[0];
@@ -515,8 +521,8 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             const auto &tgt = voice->mSend[snd];
             if(tgt.Buffer.empty()) continue;
             auto wit = S.wet_ids.find(tgt.Buffer.data());
-            if(wit == S.wet_ids.end() || tgt.FilterActive)
-            { fail(device, S, "send into an inactive slot, or a send filter: not wired into the seam yet"); return; }
+            if(wit == S.wet_ids.end())
+            { fail(device, S, "send into a slot outside the active set"); return; }
             p.send_slot[snd] = wit->second;
             const float *wg = ch.mWetParams[snd].Gains.Target.data();
             std::copy_n(wg, cw, sg.begin() + size_t(snd)*cw);
@@ -574,12 +580,52 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             C.coeffs.assign(co, co + size_t(ir)*2);
             C.dry.assign(dg, dg + cd);
         }
+        /* direct / send filters: the targets the ALU's filter block left (alc/alu.cpp:1619-1656).
+         * Every reference setParams call that moved a target is forwarded in the same update, so
+         * the device's copy of BiquadInterpFilter::setParams' rule sees the same sequence. */
+        {
+            const uint32_t paths = 1u + ns;
+            if(fresh) C.filt.clear();
+            auto entry = [&](uint32_t path, const BiquadInterpFilter &lp, const BiquadInterpFilter &hp, bool act)
+            {
+                b200mix_voice_filter f{};
+                f.voice = p.voice; f.path = path; f.active = act ? 1u : 0u;
+                f.lowpass[0] = lp.mTargetCoeffs.mB0; f.lowpass[1] = lp.mTargetCoeffs.mB1; f.lowpass[2] = lp.mTargetCoeffs.mB2;
+                f.lowpass[3] = lp.mTargetCoeffs.mA1; f.lowpass[4] = lp.mTargetCoeffs.mA2;
+                f.highpass[0] = hp.mTargetCoeffs.mB0; f.highpass[1] = hp.mTargetCoeffs.mB1; f.highpass[2] = hp.mTargetCoeffs.mB2;
+                f.highpass[3] = hp.mTargetCoeffs.mA1; f.highpass[4] = hp.mTargetCoeffs.mA2;
+                return f;
+            };
+            std::array<b200mix_voice_filter, 1u + B200MIX_MAX_SENDS> now{};
+            now[0] = entry(0u, ch.mDryParams.LowPass, ch.mDryParams.HighPass, voice->mDirect.FilterActive);
+            for(uint32_t snd = 0;snd < ns;++snd)
+                now[1u + snd] = entry(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass,
+                    voice->mSend[snd].FilterActive && p.send_slot[snd] != B200MIX_NO_SLOT);
+            bool any = !C.filt.empty();
+            for(uint32_t q = 0;q < paths && !any;++q) any = now[q].active != 0u;
+            if(any)
+            {
+                if(C.filt.empty())
+                {   /* first filter of this voice: all its paths, so a later activation interpolates
+                     * from the identity shelves the reference holds meanwhile */
+                    C.filt.assign(now.begin(), now.begin() + paths);
+                    S.upd_filt.insert(S.upd_filt.end(), now.begin(), now.begin() + paths);
+                }
+                else for(uint32_t q = 0;q < paths;++q)
+                    if(std::memcmp(&C.filt[q], &now[q], sizeof(now[q])) != 0)
+                    { C.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
+            }
+        }
         C.live = true; C.source_id = sid;
     }
     if(!S.upd.empty()
         && A.voices_update(S.dev, uint32_t(S.upd.size()), S.upd.data(), ir ? S.upd_coeffs.data() : nullptr,
             S.upd_dry.data(), sg.empty() ? nullptr : S.upd_send.data()) != B200MIX_OK)
     { fail(device, S, "b200mix_voices_update failed:"); return; }
+
+    if(!S.upd_filt.empty()
+        && A.voices_filters(S.dev, uint32_t(S.upd_filt.size()), S.upd_filt.data()) != B200MIX_OK)
+    { fail(device, S, "b200mix_voices_filters failed:"); return; }
 
     /* ---- the update itself: RealOut comes back planar, where Limiter / Write<T> expect it ---- */
     std::array<float*, B200MIX_MAX_DRY_CHANNELS> outs{};

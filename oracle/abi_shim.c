@@ -25,3 +25,47 @@ EXPORT int b200mix_voices_update(b200mix_device *dev, uint32_t n, const b200mix_
 { return oracle_voices_update((oracle_device*)dev, n, params, hrtf_coeffs, dry_gains, send_gains); }
 EXPORT int b200mix_render(b200mix_device *dev, uint32_t frames, float *const *real_out, b200mix_voice_result *results)
 { return oracle_render((oracle_device*)dev, frames, real_out, results); }
+
+/* ---- effect slots (seam v2) ---- */
+EXPORT int b200mix_slot_efx(b200mix_device *dev, uint32_t slot, const b200mix_efx_props *props, const b200mix_efx_target *target)
+{ return oracle_slot_efx((oracle_device*)dev, slot, props, target); }
+EXPORT int b200mix_slot_reverb(b200mix_device *dev, uint32_t slot, const b200mix_reverb_params *params)
+{ return oracle_slot_reverb((oracle_device*)dev, slot, params); }
+EXPORT int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot, const b200mix_reverb_params *params, uint32_t full_update)
+{ return oracle_slot_reverb_update((oracle_device*)dev, slot, params, full_update); }
+EXPORT int b200mix_slot_output_gains(b200mix_device *dev, uint32_t slot, uint32_t lines, const float *gains)
+{ return oracle_slot_output_gains((oracle_device*)dev, slot, lines, gains); }
+EXPORT int b200mix_slot_target(b200mix_device *dev, uint32_t slot, uint32_t target)
+{ return oracle_slot_target((oracle_device*)dev, slot, target); }
+EXPORT int b200mix_slot_disable(b200mix_device *dev, uint32_t slot)
+{ return oracle_slot_disable((oracle_device*)dev, slot); }
+
+/* The reverb's parameter stage is host code of the product (csrc/reverb_params.cpp, pinned
+ * bit-exact against the reference by tests/test_reverb_params.py): forwarded, not restated. */
+#include <dlfcn.h>
+#include <stdlib.h>
+static void *host_lib(void)
+{
+    static void *lib;
+    if(!lib)
+    {
+        const char *path = getenv("B200MIX_HOST_LIB");
+        lib = dlopen(path ? path : "libb200mix.so", RTLD_NOW | RTLD_LOCAL);
+    }
+    return lib;
+}
+EXPORT int b200mix_reverb_params_from_efx(const b200mix_efx_reverb *props, const b200mix_reverb_target *target,
+    struct b200mix_reverb_params *params, float *gains)
+{
+    typedef int (*fn_t)(const b200mix_efx_reverb*, const b200mix_reverb_target*, struct b200mix_reverb_params*, float*);
+    fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_reverb_params_from_efx") : NULL;
+    return fn ? fn(props, target, params, gains) : B200MIX_ERR_INVALID;
+}
+EXPORT int b200mix_reverb_full_update_needed(const b200mix_efx_reverb *prev, const b200mix_efx_reverb *next)
+{
+    typedef int (*fn_t)(const b200mix_efx_reverb*, const b200mix_efx_reverb*);
+    fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_reverb_full_update_needed") : NULL;
+    return fn ? fn(prev, next) : 1;
+}
+EXPORT int b200mix_voices_filters(b200mix_device *dev, uint32_t n, const b200mix_voice_filter *filters)
+{ return oracle_voices_filters((oracle_device*)dev, n, filters); }

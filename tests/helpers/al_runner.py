@@ -5,7 +5,12 @@ the rendered updates to an .npz.  tests/test_gpu_dropin.py runs it once on the s
 reference and once on the patched libopenal_b200.so (ALSOFT_B200MIX=1): the application code is
 identical, only the mixer behind alcRenderSamplesSOFT differs.
 
-usage: al_runner.py <libopenal path> <out.npz> <voices> <updates> <hrtf 0|1> [resampler]"""
+usage: al_runner.py <libopenal path> <out.npz> <voices> <updates> <hrtf 0|1> [resampler] [fx]
+
+fx = "none" (default) | "reverb" (one EAX reverb slot, every source sends to it) | "mix" (EAX
+reverb + echo + an equalizer slot that feeds the reverb slot via AL_EFFECTSLOT_TARGET_SOFT;
+properties, slot gain and an effect type change while playing) | "filt" (direct low-pass /
+band-pass filters that change and detach while playing) | "mixfilt" (both, plus send filters)"""
 import ctypes as C
 import math
 import os
@@ -23,11 +28,21 @@ ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT = 0x1501, 0x1406, 0x1992
 AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 0x100A, 0x1004
 AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
+AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
+AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
+AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
+AL_EAXREVERB_DECAY_TIME, AL_EAXREVERB_REFLECTIONS_GAIN = 0x0006, 0x0009
+AL_ECHO_DELAY, AL_ECHO_FEEDBACK = 0x0001, 0x0004
+AL_EQUALIZER_LOW_GAIN, AL_EQUALIZER_MID1_GAIN = 0x0001, 0x0003
+AL_CHORUS_RATE = 0x0003
+AL_DIRECT_FILTER, AL_FILTER_TYPE, AL_FILTER_LOWPASS, AL_FILTER_BANDPASS = 0x20005, 0x8001, 0x0001, 0x0003
+AL_LOWPASS_GAIN, AL_LOWPASS_GAINHF, AL_BANDPASS_GAIN, AL_BANDPASS_GAINLF, AL_BANDPASS_GAINHF = 1, 2, 1, 2, 3
 
 
 def main():
     lib, out_path, V, U, hrtf = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     resampler = int(sys.argv[6]) if len(sys.argv) > 6 else 7          # bsinc24
+    fx = sys.argv[7] if len(sys.argv) > 7 else "none"
     conf = os.path.join(os.path.dirname(out_path), f"alsoft_{os.getpid()}.conf")
     open(conf, "w").write("[general]\n")
     os.environ["ALSOFT_CONF"] = conf
@@ -52,6 +67,16 @@ def main():
     al.alSourceStop.argtypes = [C.c_uint]
     al.alSourcePlay.argtypes = [C.c_uint]
     al.alGetSourcei.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_int)]
+    al.alSource3i.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+    al.alGenEffects.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alEffecti.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alEffectf.argtypes = [C.c_uint, C.c_int, C.c_float]
+    al.alGenAuxiliaryEffectSlots.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alAuxiliaryEffectSloti.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alAuxiliaryEffectSlotf.argtypes = [C.c_uint, C.c_int, C.c_float]
+    al.alGenFilters.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alFilteri.argtypes = [C.c_uint, C.c_int, C.c_int]
+    al.alFilterf.argtypes = [C.c_uint, C.c_int, C.c_float]
     dev = al.alcLoopbackOpenDeviceSOFT(None)
     assert dev
     attrs = [ALC_FORMAT_CHANNELS_SOFT, ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT, ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
@@ -60,6 +85,39 @@ def main():
     assert ctx
     al.alcMakeContextCurrent(ctx)
     keep, sources = [], (C.c_uint * V)()
+
+    def make_slot(al_type, gain=1.0, fprops=None):
+        e, sl = C.c_uint(0), C.c_uint(0)
+        al.alGenEffects(1, C.byref(e))
+        al.alEffecti(e, AL_EFFECT_TYPE, al_type)
+        for k, v in (fprops or {}).items():
+            al.alEffectf(e, k, float(v))
+        al.alGenAuxiliaryEffectSlots(1, C.byref(sl))
+        al.alAuxiliaryEffectSlotf(sl, AL_EFFECTSLOT_GAIN, gain)
+        al.alAuxiliaryEffectSloti(sl, AL_EFFECTSLOT_EFFECT, e.value)
+        return sl.value, e.value
+
+    slots = []
+    filt = fx in ("filt", "mixfilt")
+    if fx == "mixfilt":
+        fx = "mix"
+    lowpass, bandpass = C.c_uint(0), C.c_uint(0)
+    if filt:
+        al.alGenFilters(1, C.byref(lowpass))
+        al.alFilteri(lowpass, AL_FILTER_TYPE, AL_FILTER_LOWPASS)
+        al.alFilterf(lowpass, AL_LOWPASS_GAIN, 0.9)
+        al.alFilterf(lowpass, AL_LOWPASS_GAINHF, 0.25)
+        al.alGenFilters(1, C.byref(bandpass))
+        al.alFilteri(bandpass, AL_FILTER_TYPE, AL_FILTER_BANDPASS)
+        al.alFilterf(bandpass, AL_BANDPASS_GAIN, 0.8)
+        al.alFilterf(bandpass, AL_BANDPASS_GAINLF, 0.3)
+        al.alFilterf(bandpass, AL_BANDPASS_GAINHF, 0.5)
+    if fx in ("reverb", "mix"):
+        slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.9))
+    if fx == "mix":
+        slots.append(make_slot(AL_EFFECT_ECHO, 0.7, {AL_ECHO_DELAY: 0.031, AL_ECHO_FEEDBACK: 0.4}))
+        slots.append(make_slot(AL_EFFECT_EQUALIZER, 0.8, {AL_EQUALIZER_LOW_GAIN: 0.5, AL_EQUALIZER_MID1_GAIN: 2.0}))
+        al.alAuxiliaryEffectSloti(slots[2][0], AL_EFFECTSLOT_TARGET_SOFT, slots[0][0])
     for i in range(V):
         b, s = C.c_uint(0), C.c_uint(0)
         # every fourth voice is a short one-shot (runs out, fades, stops by itself)
@@ -75,6 +133,18 @@ def main():
         al.alSourcef(s, AL_GAIN, scene.voice_gain(V))
         al.alSource3f(s, AL_POSITION, *[float(x) for x in scene.voice_position(i)])
         al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
+        if fx == "reverb":
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, AL_FILTER_NULL)
+        elif fx == "mix":
+            # send 0: reverb or the equalizer that feeds it; send 1: the echo for every third source
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[2][0] if i % 4 == 1 else slots[0][0], 0,
+                          lowpass.value if (filt and i % 2 == 0) else AL_FILTER_NULL)
+            if i % 3 == 0:
+                al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[1][0], 1, AL_FILTER_NULL)
+        if filt and i % 5 == 0:
+            al.alSourcei(s, AL_DIRECT_FILTER, bandpass.value)
+        elif filt and i % 2 == 1:
+            al.alSourcei(s, AL_DIRECT_FILTER, lowpass.value)
         sources[i] = s.value
     err = al.alGetError()
     assert err == 0, hex(err)
@@ -91,6 +161,32 @@ def main():
             al.alSourceStop(sources[2])
         if u == 5 and V > 2:
             al.alSourcePlay(sources[2])
+        if filt and u == 3:
+            # the filter object changes; sources pick it up when it is attached again
+            al.alFilterf(lowpass, AL_LOWPASS_GAINHF, 0.7)
+            for i in range(1, V, 2):
+                if i % 5:
+                    al.alSourcei(sources[i], AL_DIRECT_FILTER, lowpass.value)
+        if filt and u == 5:
+            al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
+            if V > 7:
+                al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
+        if slots and u == 2:
+            # a property that needs the reverb's other pipeline (full update), then one that does not
+            al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, 2.9)
+            al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+        if slots and u == 4:
+            al.alEffectf(slots[0][1], AL_EAXREVERB_REFLECTIONS_GAIN, 0.3)
+            al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+        if fx == "mix" and u == 3:
+            al.alEffectf(slots[1][1], AL_ECHO_DELAY, 0.012)
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
+            al.alAuxiliaryEffectSlotf(slots[2][0], AL_EFFECTSLOT_GAIN, 0.4)
+        if fx == "mix" and u == 6:
+            # the echo slot becomes a chorus: a new EffectState (deviceUpdate)
+            al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_CHORUS)
+            al.alEffectf(slots[1][1], AL_CHORUS_RATE, 2.2)
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
         buf = np.zeros((1024, 2), dtype=np.float32)
         al.alcRenderSamplesSOFT(dev, buf.ctypes.data, 1024)
         outs.append(buf.T.copy())

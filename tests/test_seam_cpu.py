@@ -4,7 +4,8 @@ ALSOFT_B200MIX_LIB pointing at oracle/liboracle_abi.so — the oracle behind the
 and must reproduce the stock reference: audio within the oracle's own distance from the
 reference's SSE kernels, source states and offsets exactly.  What this pins is the binding
 (voice snapshots, change detection, stop / restart / end-of-buffer bookkeeping, cursor
-write-back); tests/test_gpu_dropin.py repeats it with libb200mix.so on the GPU."""
+write-back, effect slots: install / update / target / type change); tests/test_gpu_dropin.py
+repeats it with libb200mix.so on the GPU."""
 import os
 import subprocess
 import sys
@@ -18,33 +19,39 @@ RUNNER = os.path.join(ROOT, "tests", "helpers", "al_runner.py")
 SHIM = os.path.join(ROOT, "oracle", "liboracle_abi.so")
 
 
-def _run(lib, tag, voices, updates, hrtf, seam, tmp_path):
+def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
     out = os.path.join(str(tmp_path), f"{tag}.npz")
     env = dict(os.environ)
     env.pop("ALSOFT_B200MIX", None)
     if seam:
         env["ALSOFT_B200MIX"] = "1"
         env["ALSOFT_B200MIX_LIB"] = SHIM
-    p = subprocess.run([sys.executable, RUNNER, os.path.join(REF, lib), out, str(voices), str(updates), str(hrtf)],
+        # the shim forwards the reverb's host-side parameter stage to the product library (host code)
+        env["B200MIX_HOST_LIB"] = os.path.join(ROOT, "openal-soft_b200", "libb200mix.so")
+    p = subprocess.run([sys.executable, RUNNER, os.path.join(REF, lib), out, str(voices), str(updates), str(hrtf), "7", fx],
                        env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "b200mix:" not in p.stderr, p.stderr[-2000:]          # the seam's own error lines
     return dict(np.load(out))
 
 
-@pytest.mark.parametrize("voices,updates,hrtf", [(24, 8, 1), (24, 8, 0), (300, 4, 1)])
-def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, tmp_path):
+@pytest.mark.parametrize("voices,updates,hrtf,fx", [(24, 8, 1, "none"), (24, 8, 0, "none"), (300, 4, 1, "none"),
+                                                    (24, 8, 1, "reverb"), (24, 8, 1, "mix"), (24, 8, 0, "mix"), (24, 8, 1, "filt"),
+                                                    (24, 8, 0, "mixfilt")])
+def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
             pytest.skip(f"oracle/_ref/{f} not built")
     if not os.path.exists(SHIM):
         pytest.skip("oracle/liboracle_abi.so not built")
-    cpu = _run("libopenal_ref.so", "cpu", voices, updates, hrtf, False, tmp_path)
-    via = _run("libopenal_b200.so", "seam", voices, updates, hrtf, True, tmp_path)
+    cpu = _run("libopenal_ref.so", "cpu", voices, updates, hrtf, False, tmp_path, fx)
+    via = _run("libopenal_b200.so", "seam", voices, updates, hrtf, True, tmp_path, fx)
     ref, out = cpu["out"].astype(np.float64), via["out"].astype(np.float64)
     assert np.abs(ref).max() > 1e-2
     err = out - ref
     rms, mx = float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())
-    assert rms <= 1e-7 and mx <= 1e-6, f"rms {rms:.3e} max {mx:.3e}"
+    # effect scenes: the oracle's convolution-free effects are bit-exact with the reference's C
+    # kernels, the stock library runs its SSE kernels (tests/helpers/golden.py kernel_set_gap)
+    assert rms <= (1e-7 if fx == "none" else 1e-6) and mx <= (1e-6 if fx == "none" else 1e-5), f"rms {rms:.3e} max {mx:.3e}"
     assert np.array_equal(cpu["states"], via["states"])
     assert np.array_equal(cpu["offsets"], via["offsets"])
