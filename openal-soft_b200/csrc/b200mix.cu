@@ -720,6 +720,13 @@ static void free_slot(b200mix_device *d, uint32_t slot)
     }
     if(slot < d->rv.size()) d->rv[slot].used = false;
     d->h_slots[slot] = SlotRec{};
+    // the device's record goes with it: an install that fails half-way must not leave the old
+    // record pointing at freed lines
+    if(d->d_slots)
+    {
+        cudaMemcpyAsync(d->d_slots + slot, &d->h_slots[slot], sizeof(SlotRec), cudaMemcpyHostToDevice, d->stream);
+        cudaStreamSynchronize(d->stream);
+    }
 }
 
 int b200mix_slot_disable(b200mix_device *d, uint32_t slot)

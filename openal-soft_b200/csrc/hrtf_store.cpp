@@ -71,6 +71,7 @@ int b200mix_hrtf_load(const void *data, size_t bytes, b200mix_hrtf **out)
     const uint32_t fdCount = r.le(1);
     if(!r.ok || channelType > 1 || h->ir_size < 8 || h->ir_size > B200MIX_HRIR_LENGTH
         || fdCount < 1 || fdCount > 16) return fail(B200MIX_ERR_INVALID);
+    try {
     for(uint32_t f = 0;f < fdCount;++f)
     {
         const uint32_t dist = r.le(2), evCount = r.le(1);
@@ -83,11 +84,23 @@ int b200mix_hrtf_load(const void *data, size_t bytes, b200mix_hrtf **out)
             h->elevs.push_back({az, 0u});
         }
     }
+    } catch(const std::bad_alloc&) { return fail(B200MIX_ERR_NOMEM); }
     uint32_t total = 0;
     for(auto &e : h->elevs) { e.ir_offset = total; total += e.az_count; }
     const uint32_t irs = h->ir_size;
-    h->coeffs.assign(size_t(total)*irs*2, 0.0f);
-    h->delays.assign(size_t(total)*2, 0);
+    // the header's counts must be backed by data before anything is sized from them: 3 bytes per
+    // tap and one delay byte per response (left ear only for channelType 0)
+    {
+        const size_t ears = channelType == 0 ? 1u : 2u;
+        const size_t need = size_t(total)*ears*(size_t(irs)*3u + 1u);
+        if(r.pos > bytes || bytes - r.pos < need) return fail(B200MIX_ERR_INVALID);
+    }
+    try
+    {
+        h->coeffs.assign(size_t(total)*irs*2, 0.0f);
+        h->delays.assign(size_t(total)*2, 0);
+    }
+    catch(const std::bad_alloc&) { return fail(B200MIX_ERR_NOMEM); }
     if(channelType == 0)
     {
         for(uint32_t i = 0;i < total;++i)

@@ -44,7 +44,23 @@ multi)
   python - <<PY
 import json
 for l in open('gpurun_out/${tag}_configs_n${NG}.jsonl'):
+    if not l.startswith('{'): continue
     j=json.loads(l); print(j['config'], j['n_gpus'], j['voices_total'], j['slots'], j.get('transport'), round(j['ms_per_update'],4), j.get('stage_us_rank0'), j.get('collective'))
+PY
+  ;;
+multi8)
+  NG=$(nvidia-smi -L | wc -l)
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+  timeout 600 $TR --master-port 29511 bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n${NG}.json 2> gpurun_out/${tag}_bench_n${NG}.err
+  tail -c 1500 gpurun_out/${tag}_bench_n${NG}.json; tail -3 gpurun_out/${tag}_bench_n${NG}.err
+  for c in "2 --voices $((4096*NG))" "3 --voices $((16384*NG/8)) " "5"; do
+    timeout 900 $TR --master-port 29513 tools/bench_configs.py --config $c --gpus $NG >> gpurun_out/${tag}_configs_n${NG}.jsonl 2>> gpurun_out/${tag}_configs_n${NG}.err
+  done
+  python - <<PY
+import json
+for l in open('gpurun_out/${tag}_configs_n${NG}.jsonl'):
+    if not l.startswith('{'): continue
+    j=json.loads(l); print(j['config'], j['n_gpus'], j['voices_total'], j['slots'], j.get('transport'), round(j['ms_per_update'],4), j.get('stage_us_rank0'))
 PY
   ;;
 fx)
