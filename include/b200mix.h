@@ -136,7 +136,8 @@ enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B
     B200MIX_EFFECT_DEDICATED = 7,     /* DedicatedState   alc/effects/dedicated.cpp (dialogue / LFE) */
     B200MIX_EFFECT_DISTORTION = 8,    /* DistortionState  alc/effects/distortion.cpp */
     B200MIX_EFFECT_CHORUS = 9,        /* ChorusState      alc/effects/chorus.cpp (AL_EFFECT_CHORUS and AL_EFFECT_FLANGER) */
-    B200MIX_EFFECT_AUTOWAH = 10       /* AutowahState     alc/effects/autowah.cpp */
+    B200MIX_EFFECT_AUTOWAH = 10,      /* AutowahState     alc/effects/autowah.cpp */
+    B200MIX_EFFECT_VMORPHER = 11      /* VmorpherState    alc/effects/vmorpher.cpp (vocal morpher) */
 };
 
 /* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
@@ -333,6 +334,7 @@ B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
  *   distortion  alc/effects/distortion.cpp:113-303  (B2A, 4x oversampled low-pass -> waveshaper -> band-pass, A2B)
  *   chorus      alc/effects/chorus.cpp:132-425      (chorus and flanger: LFO-modulated cubic taps + feedback, B2A/A2B)
  *   autowah     alc/effects/autowah.cpp:94-205      (envelope follower -> per-sample peaking filter)
+ *   vmorpher    alc/effects/vmorpher.cpp:100-330    (two 4-band formant filter banks blended by an LFO)
  * b200mix_efx_props carries the effect's PROPERTIES (the EffectProps variant of
  * core/effects/base.h:62-178 after the AL layer's clamping); b200mix_efx_target what update() reads
  * from the slot and its output target: EffectSlotBase::Gain, the target mix's AmbiMap
@@ -357,6 +359,9 @@ typedef struct b200mix_efx_props {
     struct { float edge, gain, lowpass_cutoff, eq_center, eq_bandwidth; } distortion;     /* DistortionProps */
     struct { uint32_t waveform; int32_t phase; float rate, depth, feedback, delay; } chorus; /* ChorusProps (0 sinusoid, 1 triangle) */
     struct { float attack_time, release_time, resonance, peak_gain; } autowah;            /* AutowahProps */
+    struct { float rate; uint32_t phoneme_a, phoneme_b;     /* VMorpherPhenome: 0 A, 1 E, 2 I, 3 O, 4 U, 5.. (no formants) */
+             int32_t phoneme_a_coarse_tuning, phoneme_b_coarse_tuning;
+             uint32_t waveform; } vmorpher;                 /* VmorpherProps (0 sinusoid, 1 triangle, 2 sawtooth) */
 } b200mix_efx_props;
 typedef struct b200mix_efx_target {
     uint32_t struct_size;

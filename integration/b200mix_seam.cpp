@@ -11,7 +11,7 @@
  * PCM sample type, any resampler, moving sources (targets are re-sent when the ALU changed
  * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
- * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah), slot gain, slot
+ * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher), slot gain, slot
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
  * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass).  Streaming queues,
  * multi-channel sources and convolution slots are forwarded by the C ABI (b200mix_voice_queue,
@@ -327,7 +327,14 @@ int effect_of(const EffectSlotBase *slot, b200mix_efx_props &o, b200mix_efx_reve
         { o.type = B200MIX_EFFECT_AUTOWAH; o.autowah.attack_time = p->AttackTime; o.autowah.release_time = p->ReleaseTime;
           o.autowah.resonance = p->Resonance; o.autowah.peak_gain = p->PeakGain; return 2; }
         return -1;
-    default: return -1;          /* convolution, frequency / pitch shifter, vocal morpher */
+    case EffectSlotType::VocalMorpher:
+        if(auto *p = std::get_if<VmorpherProps>(&props))
+        { o.type = B200MIX_EFFECT_VMORPHER; o.vmorpher.rate = p->Rate;
+          o.vmorpher.phoneme_a = static_cast<uint32_t>(p->PhonemeA); o.vmorpher.phoneme_b = static_cast<uint32_t>(p->PhonemeB);
+          o.vmorpher.phoneme_a_coarse_tuning = p->PhonemeACoarseTuning; o.vmorpher.phoneme_b_coarse_tuning = p->PhonemeBCoarseTuning;
+          o.vmorpher.waveform = static_cast<uint32_t>(p->Waveform); return 2; }
+        return -1;
+    default: return -1;          /* convolution, frequency / pitch shifter */
     }
 }
 

@@ -941,7 +941,7 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
 {
     if(!d || slot >= d->h_slots.size() || !props || !target || props->struct_size != sizeof(*props)
         || target->struct_size != sizeof(*target) || props->type < B200MIX_EFFECT_ECHO
-        || props->type > B200MIX_EFFECT_AUTOWAH)
+        || props->type > B200MIX_EFFECT_VMORPHER)
     { if(d) d->error = "slot_efx: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
     const b200mix_device_desc &dd = d->desc;
     const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
@@ -1014,6 +1014,11 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
             CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, cho_lfo_offset), &H.lfo_offset,
                 sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
         }
+        if(props->type == B200MIX_EFFECT_VMORPHER)
+            // update() installs newly constructed formant filters: their histories restart at 0
+            // (vmorpher.cpp:252-260)
+            CUDA_TRY(d, cudaMemsetAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, vm_s), 0,
+                sizeof(EfxDev::vm_s), d->stream));
         d->h_slots[slot].fade_len = P.fade_len;
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
     }

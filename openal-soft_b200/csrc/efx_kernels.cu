@@ -376,6 +376,95 @@ __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
                 lines[size_t(c)*kLine + i] = (c < nin && c < kEfxMaxLines - 2u && P.line_on[c]) ? sWork[c*kLine + i] : 0.0f;
         break;
     }
+    case B200MIX_EFFECT_VMORPHER:
+    {
+        // VmorpherState::process (vmorpher.cpp:272-330): per 256-sample chunk the LFO, then per
+        // channel two banks of four formant filters (state-variable, vmorpher.cpp:106-140) —
+        // eight independent recurrences per channel, one thread each — whose band outputs are
+        // accumulated in formant order, blended by the LFO and mixed with MixSamples' gain ramp
+        // of that chunk (Counter = the samples left in the update).
+        for(uint32_t c = 0;c < nin;++c)
+            for(uint32_t i = t;i < n;i += blockDim.x) sIn[c*kLine + i] = wet[size_t(c)*kLine + i];
+        float *lfo = sWork + kEfxMaxLines*kLine;                       // the extra row: mLfo
+        __shared__ float vmCur[kEfxMaxLines];
+        if(t < kEfxMaxLines) vmCur[t] = E.vm_cur[t];
+        const uint32_t step = P.vm_step, wave = P.vm_wave, index0 = E.vm_index;
+        for(uint32_t i = t;i < n;i += blockDim.x)
+        {
+            const uint32_t idx = (index0 + step*(i + 1u)) & 0xffffffu;
+            float v;
+            if(wave == 0u) v = 0.5f;
+            else if(wave == 1u) v = float(::sin(double(float(idx) * (3.14159265358979323846f*2.0f / 16777216.0f))))*0.5f + 0.5f;
+            else if(wave == 2u) v = fabsf(float(idx)*(2.0f/16777216.0f) - 1.0f);
+            else v = float(idx) / 16777216.0f;
+            lfo[i] = v;
+        }
+        __syncthreads();
+        constexpr uint32_t kChunk = 256u, kGroup = 8u;                  // channels per pass: 8 ch x 8 filters x 256
+        for(uint32_t base = 0;base < n;base += kChunk)
+        {
+            const uint32_t td = min(kChunk, n - base);
+            const uint32_t counter = n - base;
+            for(uint32_t c0 = 0;c0 < nin;c0 += kGroup)
+            {
+                if(t < kGroup*8u)
+                {
+                    const uint32_t c = c0 + (t >> 3), v = (t >> 2) & 1u, f = t & 3u;
+                    if(c < nin && P.vm_target[c] != 0xffffffffu)
+                    {
+                        const float g = P.vm_coeff[v][f], gain = P.vm_fgain[v][f];
+                        const float h = 1.0f / (1.0f + (g*(1.0f/5.0f)) + (g*g));
+                        const float coeff = (1.0f/5.0f) + g;
+                        float s1 = E.vm_s[c][v][f][0], s2 = E.vm_s[c][v][f][1];
+                        const float *src = sIn + c*kLine + base;
+                        float *dst = sWork + size_t(t)*kChunk;
+                        for(uint32_t k = 0;k < td;++k)
+                        {
+                            const float in = src[k];
+                            const float H = (in - coeff*s1 - s2)*h;
+                            const float B = g*H + s1;
+                            const float L = g*B + s2;
+                            s1 = g*H + B;
+                            s2 = g*B + L;
+                            dst[k] = B*gain;
+                        }
+                        E.vm_s[c][v][f][0] = s1; E.vm_s[c][v][f][1] = s2;
+                    }
+                }
+                __syncthreads();
+                for(uint32_t e = t;e < kGroup*td;e += blockDim.x)
+                {
+                    const uint32_t cl = e / td, k = e - cl*td, c = c0 + cl;
+                    if(c >= nin) continue;
+                    float outv = 0.0f;
+                    if(P.vm_target[c] != 0xffffffffu)
+                    {
+                        const float *bg = sWork + size_t(cl)*8u*kChunk + k;
+                        const float A = (((0.0f + bg[0]) + bg[kChunk]) + bg[2u*kChunk]) + bg[3u*kChunk];
+                        const float Bv = (((0.0f + bg[4u*kChunk]) + bg[5u*kChunk]) + bg[6u*kChunk]) + bg[7u*kChunk];
+                        const float blended = A + (Bv - A)*lfo[base + k];             // lerpf
+                        // MixLine (mixer_c.cpp:150-186) with fade_len = td, Counter = counter
+                        const float cur = vmCur[c], tg = P.vm_tgain[c];
+                        const float stp = (tg - cur) * (1.0f / float(counter));
+                        if(fabsf(stp) > 1.1920929e-07f) outv = blended * (cur + stp*float(k));
+                        else if(fabsf(tg) > 0.00001f) outv = blended * tg;
+                    }
+                    lines[size_t(c)*kLine + base + k] = outv;
+                }
+                __syncthreads();
+            }
+            if(t < nin && P.vm_target[t] != 0xffffffffu)
+            {
+                const float cur = vmCur[t], tg = P.vm_tgain[t];
+                const float stp = (tg - cur) * (1.0f / float(counter));
+                vmCur[t] = (fabsf(stp) > 1.1920929e-07f && td < counter) ? cur + stp*float(td) : tg;
+            }
+            __syncthreads();
+        }
+        if(t < kEfxMaxLines) E.vm_cur[t] = vmCur[t];
+        if(t == 0) E.vm_index = (index0 + step*n) & 0xffffffu;
+        break;
+    }
     default: break;
     }
 }

@@ -18,6 +18,8 @@ struct EfxDev {
     float *cho_buf;                        // ChorusState::mDelayBuffers [4][cho_len]
     uint32_t cho_offset, cho_lfo_offset;   // mOffset, mLfoOffset
     float wah_env;                         // AutowahState::mEnvDelay
+    uint32_t vm_index; float vm_cur[kEfxMaxLines];   // VmorpherState::mIndex, OutParams::mCurrentGain
+    float vm_s[kEfxMaxLines][2][4][2];     // FormantFilter::mS1/mS2 [channel][vowel][formant]
     float chan_z[kEfxMaxLines][4][2];      // per-channel biquad histories (modulator [0], equalizer [0..3],
                                            // distortion [0] low-pass, [1] band-pass)
 };

@@ -40,6 +40,11 @@ struct EfxParams {
     uint32_t cho_lfo_range_new, cho_lfo_range, cho_lfo_disp, cho_rate_on; float cho_lfo_scale;
     // autowah
     float wah_attack, wah_release, wah_res_gain, wah_peak_gain, wah_freq_min, wah_bandwidth;
+    // vocal morpher
+    uint32_t vm_step, vm_wave;            // wave: 0 half, 1 sin, 2 triangle, 3 saw (Oscillate<>, vmorpher.cpp:73-96)
+    float vm_coeff[2][4], vm_fgain[2][4]; // FormantFilter::mCoeff / mGain of vowel A and B
+    uint32_t vm_target[kEfxMaxLines];     // mTargetChannel per wet channel (0xffffffff: none)
+    float vm_tgain[kEfxMaxLines];         // mTargetGain
 };
 
 namespace efx_detail {
@@ -236,6 +241,48 @@ inline int efx_update(const b200mix_efx_props &E, const b200mix_efx_target &T, E
         P.wah_bandwidth = (2500.0f-20.0f) / frequency;
         P.lines = T.wet_channels;
         ambi_mix_params(T, T.slot_gain, kEfxMaxLines, P);
+        break;
+    }
+    case B200MIX_EFFECT_VMORPHER:
+    {
+        // VmorpherState::update (vmorpher.cpp:232-270)
+        const float step = E.vmorpher.rate / frequency;
+        P.vm_step = static_cast<uint32_t>(std::lrint(std::clamp(step*16777216.0f, 0.0f, 16777216.0f-1.0f)));   // fastf2u
+        P.vm_wave = P.vm_step == 0u ? 0u : (E.vmorpher.waveform == 0u ? 1u : (E.vmorpher.waveform == 1u ? 2u : 3u));
+        const float pitch[2] = {std::pow(2.0f, static_cast<float>(E.vmorpher.phoneme_a_coarse_tuning) / 12.0f),
+                                std::pow(2.0f, static_cast<float>(E.vmorpher.phoneme_b_coarse_tuning) / 12.0f)};
+        // getFiltersByPhoneme (vmorpher.cpp:169-225): soprano formants of A E I O U
+        static const float kFreq[5][4] = {{800, 1150, 2900, 3900}, {350, 2000, 2800, 3600}, {270, 2140, 2950, 3900},
+                                          {450, 800, 2830, 3800}, {325, 700, 2700, 3800}};
+        static const float kGain[5][4] = {{1.000000f, 0.501187f, 0.025118f, 0.100000f}, {1.000000f, 0.100000f, 0.177827f, 0.009999f},
+                                          {1.000000f, 0.251188f, 0.050118f, 0.050118f}, {1.000000f, 0.281838f, 0.079432f, 0.079432f},
+                                          {1.000000f, 0.158489f, 0.017782f, 0.009999f}};
+        const uint32_t ph[2] = {E.vmorpher.phoneme_a, E.vmorpher.phoneme_b};
+        for(int v = 0;v < 2;++v)
+            for(int f = 0;f < 4;++f)
+            {
+                if(ph[v] < 5u)
+                {
+                    const float f0norm = (kFreq[ph[v]][f] * pitch[v]) / frequency;
+                    P.vm_coeff[v][f] = std::tan(3.14159265358979323846f * f0norm);
+                    P.vm_fgain[v][f] = kGain[ph[v]][f];
+                }
+                else { P.vm_coeff[v][f] = 0.0f; P.vm_fgain[v][f] = 1.0f; }      // FormantFilter{}
+            }
+        // the kernel applies the per-chunk gain ramp itself (MixSamples once per 256 samples,
+        // vmorpher.cpp:317-318): the generic output mix gets unit gains, set at once
+        P.lines = T.wet_channels; P.snap_gains = 1u;
+        for(uint32_t i = 0;i < T.wet_channels;++i)
+        {
+            P.vm_target[i] = 0xffffffffu; P.vm_tgain[i] = 0.0f;
+            for(uint32_t j = 0;j < T.out_channels;++j)
+                if(T.out_index[j] == T.wet_index[i])
+                {
+                    P.vm_target[i] = j; P.vm_tgain[i] = T.out_scale[j] * T.slot_gain;
+                    P.line_on[i] = 1u; P.gains[i][j] = 1.0f;
+                    break;
+                }
+        }
         break;
     }
     default: return B200MIX_ERR_INVALID;

@@ -188,7 +188,7 @@ class SourceVoice(C.Structure):
 
 
 (EFFECT_NONE, EFFECT_CONVOLUTION, EFFECT_REVERB, EFFECT_ECHO, EFFECT_MODULATOR, EFFECT_EQUALIZER,
- EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION, EFFECT_CHORUS, EFFECT_AUTOWAH) = range(11)
+ EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION, EFFECT_CHORUS, EFFECT_AUTOWAH, EFFECT_VMORPHER) = range(12)
 
 
 class _EfxEcho(C.Structure):
@@ -225,11 +225,17 @@ class _EfxAutowah(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("attack_time", "release_time", "resonance", "peak_gain")]
 
 
+class _EfxVmorpher(C.Structure):
+    _fields_ = [("rate", C.c_float), ("phoneme_a", C.c_uint32), ("phoneme_b", C.c_uint32),
+                ("phoneme_a_coarse_tuning", C.c_int32), ("phoneme_b_coarse_tuning", C.c_int32), ("waveform", C.c_uint32)]
+
+
 class EfxProps(C.Structure):
     """b200mix_efx_props: the EFX effect's properties (EffectProps, core/effects/base.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("type", C.c_uint32), ("echo", _EfxEcho), ("modulator", _EfxModulator),
                 ("equalizer", _EfxEqualizer), ("compressor", _EfxCompressor), ("dedicated", _EfxDedicated),
-                ("distortion", _EfxDistortion), ("chorus", _EfxChorus), ("autowah", _EfxAutowah)]
+                ("distortion", _EfxDistortion), ("chorus", _EfxChorus), ("autowah", _EfxAutowah),
+                ("vmorpher", _EfxVmorpher)]
 
 
 class EfxTarget(C.Structure):
@@ -253,6 +259,7 @@ def efx_defaults(effect_type):
     p.distortion = _EfxDistortion(0.2, 0.05, 8000.0, 3600.0, 3600.0)
     p.chorus = _EfxChorus(1, 90, 1.1, 0.1, 0.25, 0.016)
     p.autowah = _EfxAutowah(0.06, 0.06, 1000.0, 11.22)
+    p.vmorpher = _EfxVmorpher(1.41, 0, 10, 0, 0, 0)       # phoneme A -> ER, sinusoid
     return p
 
 

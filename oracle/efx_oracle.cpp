@@ -1,5 +1,6 @@
 // efx_oracle.cpp — CPU restatement of EffectState::process for the EFX effects the product runs
-// on the GPU (echo, ring modulator, equalizer, compressor, dedicated, distortion).  TEST
+// on the GPU (echo, ring modulator, equalizer, compressor, dedicated, distortion, chorus / flanger,
+// autowah, vocal morpher).  TEST
 // INFRASTRUCTURE ONLY: linked into oracle/liboracle.so, used by tests/, smoke() and nothing else.
 //
 // Each process() below follows the reference line by line (file:line cited); the parameter side
@@ -93,6 +94,8 @@ struct oefx {
     float cubic[513]{};
     // autowah
     float wah_env{0.0f};
+    // vocal morpher
+    uint32_t vm_index{0}; float vm_cur[b200mix::kEfxMaxLines]{}; float vm_s[b200mix::kEfxMaxLines][2][4][2]{};
 };
 
 extern "C" void oracle_build_cubic_filter(float filter[513]);      // tables.c (gCubicTable)
@@ -129,6 +132,8 @@ int oefx_update(oefx *e, const b200mix_efx_props *props, const b200mix_efx_targe
         e->mod_index = uint32_t(uint64_t(e->mod_index) * P.mod_range_new / e->mod_range);
         e->mod_range = P.mod_range;
     }
+    if(P.type == B200MIX_EFFECT_VMORPHER)
+        std::memset(e->vm_s, 0, sizeof(e->vm_s));       // update() installs new FormantFilters, vmorpher.cpp:252-260
     e->p = P;
     if(P.snap_gains) std::memcpy(e->cur, P.gains, sizeof(e->cur));
     return B200MIX_OK;
@@ -379,6 +384,63 @@ void oefx_process(oefx *e, size_t n, const float (*in)[1024], size_t nin_, float
             for(size_t o = 0;o < nout;++o)
                 if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
                     mix_line(buf, n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        }
+        break;
+    }
+    case B200MIX_EFFECT_VMORPHER:
+    {
+        // vmorpher.cpp:272-330
+        static thread_local float lfo[256], bufA[256], bufB[256], blended[256];
+        for(size_t base = 0;base < n;)
+        {
+            const size_t td = std::min<size_t>(256, n - base);
+            {   // Oscillate<func>, vmorpher.cpp:86-96
+                uint32_t index = e->vm_index;
+                for(size_t i = 0;i < td;++i)
+                {
+                    index += P.vm_step; index &= 0xffffffu;
+                    switch(P.vm_wave)
+                    {
+                    case 0: lfo[i] = 0.5f; break;
+                    case 1: lfo[i] = std::sin(static_cast<float>(index) * (3.14159265358979323846f*2.0f / 16777216.0f))*0.5f + 0.5f; break;
+                    case 2: lfo[i] = std::fabs(static_cast<float>(index)*(2.0f/16777216.0f) - 1.0f); break;
+                    default: lfo[i] = static_cast<float>(index) / 16777216.0f; break;
+                    }
+                }
+            }
+            e->vm_index += uint32_t(P.vm_step * td);
+            e->vm_index &= 0xffffffu;
+            for(size_t c = 0;c < nin;++c)
+            {
+                const uint32_t outidx = P.vm_target[c];
+                if(outidx == 0xffffffffu) continue;
+                float *acc[2] = {bufA, bufB};
+                for(int v = 0;v < 2;++v)
+                {
+                    std::fill_n(acc[v], td, 0.0f);
+                    for(int f = 0;f < 4;++f)
+                    {   // FormantFilter::process, vmorpher.cpp:106-140
+                        const float g = P.vm_coeff[v][f], gain = P.vm_fgain[v][f];
+                        const float h = 1.0f / (1.0f + (g*(1.0f/5.0f)) + (g*g));
+                        const float coeff = (1.0f/5.0f) + g;
+                        float s1 = e->vm_s[c][v][f][0], s2 = e->vm_s[c][v][f][1];
+                        for(size_t i = 0;i < td;++i)
+                        {
+                            const float H = (in[c][base+i] - coeff*s1 - s2)*h;
+                            const float B = g*H + s1;
+                            const float L = g*B + s2;
+                            s1 = g*H + B;
+                            s2 = g*B + L;
+                            acc[v][i] = acc[v][i] + B*gain;
+                        }
+                        e->vm_s[c][v][f][0] = s1; e->vm_s[c][v][f][1] = s2;
+                    }
+                }
+                for(size_t i = 0;i < td;++i) blended[i] = bufA[i] + (bufB[i] - bufA[i])*lfo[i];
+                const size_t counter = n - base;
+                mix_line(blended, td, out[outidx] + base, e->vm_cur[c], P.vm_tgain[c], 1.0f/float(counter), std::min(counter, td), counter);
+            }
+            base += td;
         }
         break;
     }

@@ -118,6 +118,8 @@ SCENES = {
     "efx_chorus_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:chorus"),
     "efx_flanger_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:flanger"),
     "efx_autowah_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:autowah"),
+    "efx_vmorpher_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:vmorpher"),
+    "efx_vmorpher_saw_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:vmorpher_saw"),
 }
 
 # name: (our effect type, AL effect enum, {AL float props}, {AL int props}, slot gain,
@@ -146,6 +148,13 @@ EFX_SCENES = {
                 {3: ({0x0003: 0.0}, {})}),
     "autowah": (10, 0x000A, {0x0001: 0.02, 0x0002: 0.1, 0x0003: 300.0, 0x0004: 5000.0}, {}, 0.9,
                 {3: ({0x0003: 20.0, 0x0004: 100.0}, {})}),
+    # vocal morpher: AL_VOCAL_MORPHER_PHONEMEA 1, _PHONEMEA_COARSE_TUNING 2, _PHONEMEB 3, _PHONEMEB_COARSE_TUNING 4,
+    # _WAVEFORM 5 (0 sinusoid, 1 triangle, 2 sawtooth), _RATE 6.  A -> O at 3 Hz, then I -> U detuned with a
+    # triangle LFO; a sawtooth LFO, then rate 0 (the blend stays at 0.5) and a phoneme without formants (silence)
+    "vmorpher": (11, 0x0007, {0x0006: 3.0}, {0x0001: 0, 0x0003: 3, 0x0005: 0}, 0.9,
+                 {4: ({0x0006: 7.5}, {0x0001: 2, 0x0002: 5, 0x0003: 4, 0x0004: -7, 0x0005: 1})}),
+    "vmorpher_saw": (11, 0x0007, {0x0006: 1.41}, {0x0001: 1, 0x0003: 0, 0x0005: 2}, 1.0,
+                     {2: ({0x0006: 0.0}, {}), 4: ({0x0006: 2.0}, {0x0001: 9})}),
 }
 
 
@@ -197,6 +206,13 @@ def efx_props_struct(kind, fprops, iprops):
         for k, n in {1: "attack_time", 2: "release_time", 3: "resonance", 4: "peak_gain"}.items():
             if k in f:
                 setattr(p.autowah, n, f[k])
+    elif typ == 11:
+        if 6 in f:
+            p.vmorpher.rate = f[6]
+        for k, n in {1: "phoneme_a", 2: "phoneme_a_coarse_tuning", 3: "phoneme_b", 4: "phoneme_b_coarse_tuning",
+                     5: "waveform"}.items():
+            if k in i:
+                setattr(p.vmorpher, n, i[k])
     return p
 
 # {update index (applied before that render): {AL_EAXREVERB_* : value}}

@@ -82,7 +82,10 @@ def replay(mixlib, fx, updates=None, frames=abi.LINE):
             dev.slot_reverb(0, abi.reverb_params_from(fx["reverb_params"].tobytes()),
                             fx["reverb_gains"])
         def set_efx(raw):
-            props = abi.EfxProps.from_buffer_copy(bytes(raw))
+            # fixtures written before an effect was added hold a shorter b200mix_efx_props: the new
+            # sub-structs are unused by their effect type, zero-extend
+            props = abi.EfxProps.from_buffer_copy(bytes(raw).ljust(C.sizeof(abi.EfxProps), b"\0"))
+            props.struct_size = C.sizeof(abi.EfxProps)
             dev.slot_efx(0, props, float(fx["efx_slot_gain"]), fx["efx_out_scale"], fx["efx_out_index"],
                          fx["efx_wet_index"], int(fx["efx_ambi_order"]))
         if efx:
