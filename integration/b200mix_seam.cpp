@@ -13,9 +13,11 @@
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
  * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher), slot gain, slot
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
- * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass).  Streaming queues,
- * multi-channel sources and convolution slots are forwarded by the C ABI (b200mix_voice_queue,
- * B200MIX_VF_CHANNEL, b200mix_slot_convolution) but not wired up here yet: the seam disconnects the device with
+ * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass), streaming sources
+ * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events) and
+ * multi-channel sources (stereo … 7.1 buffers: one device voice per mixing channel).
+ * Convolution slots, ambisonic / UHJ sources, NFC, direct channels and callback buffers are not
+ * wired up here: the seam disconnects the device with
  * a message rather than mixing them wrong.
  */
 #include "config.h"
@@ -79,6 +81,7 @@ struct Api {
     decltype(&b200mix_buffer_data) buffer_data{};
     decltype(&b200mix_voices_update) voices_update{};
     decltype(&b200mix_voices_filters) voices_filters{};
+    decltype(&b200mix_voice_queue) voice_queue{};
     decltype(&b200mix_render) render{};
     decltype(&b200mix_slot_efx) slot_efx{};
     decltype(&b200mix_slot_reverb) slot_reverb{};
@@ -102,12 +105,12 @@ Api &api()
         if(!r.lib) { ERR("b200mix: cannot load the mixer library: {}", dlerror()); return r; }
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
-        LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(render);
+        LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(voice_queue); LOAD(render);
         LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
         LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
-            && r.buffer_data && r.voices_update && r.voices_filters && r.render && r.slot_efx && r.slot_reverb
+            && r.buffer_data && r.voices_update && r.voices_filters && r.voice_queue && r.render && r.slot_efx && r.slot_reverb
             && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
             && r.reverb_params_from_efx && r.reverb_full_update_needed;
         if(!r.ok) ERR("b200mix: the mixer library lacks entry points of include/b200mix.h");
@@ -116,12 +119,17 @@ Api &api()
     return a;
 }
 
-struct VoiceCache {                  /* what was last sent for a voice: resend only on change */
-    unsigned source_id{0};
-    bool live{false};
+struct ChanCache {                   /* one mixing channel = one device voice: what was last sent */
+    uint32_t id{0};
     b200mix_voice_params params{};
     std::vector<float> coeffs, dry, send;
     std::vector<b200mix_voice_filter> filt;      /* per path: what the device has (empty: never sent) */
+};
+struct VoiceCache {                  /* a Voice of the reference: resend only on change */
+    unsigned source_id{0};
+    bool live{false};
+    std::vector<ChanCache> ch;
+    std::vector<const VoiceBufferItem*> queue;   /* streaming sources: the list the device walks */
 };
 
 struct SlotCache {                   /* what was last installed for an effect slot */
@@ -152,6 +160,9 @@ struct Seam {
     std::unordered_map<const void*, uint32_t> wet_ids;                        /* Wet.Buffer.data() -> slot id */
     std::vector<float> upd_send;
     std::vector<b200mix_voice_filter> upd_filt;
+    std::vector<uint32_t> free_ids, qids;      /* device voice ids; scratch */
+    uint32_t next_id{0};
+    std::vector<const VoiceBufferItem*> qnow;
 };
 
 std::mutex g_lock;
@@ -483,6 +494,53 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear(); S.upd_filt.clear();
     const uint32_t ns = S.desc.num_sends, cw = S.desc.wet_channels;
     std::vector<float> sg(size_t(ns)*cw);
+    auto push_stopped = [&](const ChanCache &cc)
+    {   /* remove a device voice from the active set */
+        b200mix_voice_params p = cc.params;
+        p.voice = cc.id; p.flags = B200MIX_VF_STOPPED;
+        S.upd.push_back(p);
+        S.upd_coeffs.insert(S.upd_coeffs.end(), size_t(ir)*2, 0.0f);
+        S.upd_dry.insert(S.upd_dry.end(), cd, 0.0f);
+        S.upd_send.insert(S.upd_send.end(), size_t(ns)*cw, 0.0f);
+    };
+    auto release = [&](VoiceCache &C)
+    {
+        for(const ChanCache &cc : C.ch) S.free_ids.push_back(cc.id);
+        C = VoiceCache{};
+    };
+    /* one upload per (data pointer, length): BufferStorage is immutable while attached */
+    auto buffer_of = [&](const VoiceBufferItem *item, uint32_t channels, uint32_t *out) -> bool
+    {
+        const void *data = nullptr;
+        const int type = sample_type_of(item->mSamples, &data);
+        if(type < 0) return fail(device, S, "buffer format not wired into the seam yet");
+        auto it = S.buffers.find(data);
+        if(it == S.buffers.end() || it->second.second != item->mSampleLen)
+        {
+            static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
+            const uint32_t id = it == S.buffers.end() ? S.next_buffer++ : it->second.first;
+            if(id >= kMaxBuffers) return fail(device, S, "more buffers than the seam's device was created for");
+            if(A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data,
+                size_t(item->mSampleLen)*channels*sz[type]) != B200MIX_OK)
+                return fail(device, S, "b200mix_buffer_data failed:");
+            it = S.buffers.insert_or_assign(data, std::make_pair(id, item->mSampleLen)).first;
+        }
+        *out = it->second.first;
+        return true;
+    };
+    /* the queue as the mixer will walk it: [current .. last] and, for a looping queue, the items
+     * before the current one (mLoopBuffer is the queue's head; core/voice.cpp:1183-1196) */
+    auto queue_of = [](const Voice *voice, std::vector<const VoiceBufferItem*> &out)
+    {
+        out.clear();
+        const VoiceBufferItem *cur = voice->mCurrentBuffer.load(std::memory_order_relaxed);
+        const VoiceBufferItem *loop = voice->mLoopBuffer.load(std::memory_order_relaxed);
+        for(auto *it = cur;it && out.size() < B200MIX_MAX_QUEUE;it = it->mNext.load(std::memory_order_relaxed))
+            out.push_back(it);
+        for(auto *it = loop;it && it != cur && out.size() < B200MIX_MAX_QUEUE;it = it->mNext.load(std::memory_order_relaxed))
+            out.push_back(it);
+    };
+
     for(size_t n = 0;n < S.vptr.size();++n)
     {
         Voice *voice = S.vptr[n];
@@ -493,26 +551,71 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         {
             if(C.live)
             {   /* the host stopped it (alSourceStop / rewind): remove it from the active set */
-                b200mix_voice_params p = C.params;
-                p.flags = B200MIX_VF_STOPPED;
-                S.upd.push_back(p);
-                S.upd_coeffs.insert(S.upd_coeffs.end(), size_t(ir)*2, 0.0f);
-                S.upd_dry.insert(S.upd_dry.end(), cd, 0.0f);
-                S.upd_send.insert(S.upd_send.end(), size_t(ns)*cw, 0.0f);
-                C.live = false;
+                for(const ChanCache &cc : C.ch) push_stopped(cc);
+                release(C);
             }
             continue;
         }
-        if(!voice->mFlags.test(VoiceFlag::IsStatic) || voice->mFlags.test(VoiceFlag::IsCallback)
-            || voice->mFmtChannels != FmtMono || voice->mDuplicateMono)
-        { fail(device, S, "streaming / multi-channel sources are not wired into the seam yet"); return; }
+        const bool mono = voice->mFmtChannels == FmtMono;
+        if(voice->mFlags.test(VoiceFlag::IsCallback) || voice->mFlags.test(VoiceFlag::IsAmbisonic)
+            || voice->mFlags.test(VoiceFlag::HasNfc) || voice->mDecoder
+            || voice->mFmtChannels == FmtUHJ2 || voice->mFmtChannels == FmtSuperStereo
+            /* direct channels mix straight into RealOut (alc/alu.cpp:1592-1598); HRTF voices name RealOut too */
+            || (!voice->mFlags.test(VoiceFlag::HasHrtf) && !voice->mDirect.Buffer.empty()
+                && voice->mDirect.Buffer.data() != device->Dry.Buffer.data()))
+        { fail(device, S, "callback / ambisonic / UHJ / NFC / direct-channel sources are not wired into the seam yet"); return; }
+        const bool isStatic = voice->mFlags.test(VoiceFlag::IsStatic);
+        const uint32_t nch = (mono && !voice->mDuplicateMono) ? 1u : static_cast<uint32_t>(voice->mChans.size());
+        const uint32_t bufch = std::max(voice->mFrameStep, 1u);
         auto *item = voice->mCurrentBuffer.load(std::memory_order_relaxed);
         auto *loop = voice->mLoopBuffer.load(std::memory_order_relaxed);
-        auto &ch = voice->mChans[0];
 
+        const unsigned sid = voice->mSourceID.load(std::memory_order_relaxed);
+        /* a stop clears mSourceID while the voice fades out: that is not a new voice */
+        const bool fresh = !C.live || (sid != 0u && C.source_id != sid) || C.ch.size() != nch;
+        if(fresh)
+        {
+            if(C.live) { for(const ChanCache &cc : C.ch) push_stopped(cc); release(C); }
+            C.ch.resize(nch);
+            for(ChanCache &cc : C.ch)
+            {
+                if(!S.free_ids.empty()) { cc.id = S.free_ids.back(); S.free_ids.pop_back(); }
+                else cc.id = S.next_id++;
+                if(cc.id >= kMaxVoices) { fail(device, S, "more mixing channels than the seam's device was created for"); return; }
+            }
+        }
+
+        uint32_t bufid = B200MIX_NO_BUFFER;
+        if(!isStatic)
+        {   /* streaming source: (re)send the list when it is not what the device walks */
+            queue_of(voice, S.qnow);
+            if(fresh || S.qnow != C.queue)
+            {
+                S.qids.clear();
+                for(const VoiceBufferItem *qi : S.qnow)
+                {
+                    uint32_t id = 0;
+                    if(!buffer_of(qi, bufch, &id)) return;
+                    S.qids.push_back(id);
+                }
+                for(const ChanCache &cc : C.ch)
+                    if(A.voice_queue(S.dev, cc.id, uint32_t(S.qids.size()), S.qids.data(),
+                        loop ? 0u : B200MIX_NO_LOOP) != B200MIX_OK)
+                    { fail(device, S, "b200mix_voice_queue failed:"); return; }
+                C.queue = S.qnow;
+            }
+            bufid = item ? 0u : B200MIX_NO_BUFFER;
+        }
+        else if(item && !buffer_of(item, bufch, &bufid)) return;
+
+        for(uint32_t c = 0;c < nch;++c)
+        {
+        auto &ch = voice->mChans[c];
+        ChanCache &CC = C.ch[c];
         b200mix_voice_params p{};
-        p.voice = static_cast<uint32_t>(n);
-        p.flags = (pstate == Voice::Playing ? B200MIX_VF_PLAYING : B200MIX_VF_STOPPING) | B200MIX_VF_STATIC;
+        p.voice = CC.id;
+        p.flags = (pstate == Voice::Playing ? B200MIX_VF_PLAYING : B200MIX_VF_STOPPING)
+            | (isStatic ? B200MIX_VF_STATIC : 0u) | B200MIX_VF_CHANNEL(mono ? 0u : c);
         if(loop) p.flags |= B200MIX_VF_LOOPING;
         if(voice->mFlags.test(VoiceFlag::HasHrtf)) p.flags |= B200MIX_VF_HRTF;
         p.resampler = static_cast<uint32_t>(voice->mProps.mResampler);
@@ -534,30 +637,8 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             const float *wg = ch.mWetParams[snd].Gains.Target.data();
             std::copy_n(wg, cw, sg.begin() + size_t(snd)*cw);
         }
-        if(item)
-        {
-            const void *data = nullptr;
-            const int type = sample_type_of(item->mSamples, &data);
-            if(type < 0 || voice->mFrameStep != 1u) { fail(device, S, "buffer format not wired into the seam yet"); return; }
-            auto it = S.buffers.find(data);
-            if(it == S.buffers.end() || it->second.second != item->mSampleLen)
-            {
-                /* BufferStorage is immutable while attached: one upload per (data, length) */
-                static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
-                const uint32_t id = it == S.buffers.end() ? S.next_buffer++ : it->second.first;
-                if(id >= kMaxBuffers) { fail(device, S, "more buffers than the seam's device was created for"); return; }
-                if(A.buffer_data(S.dev, id, uint32_t(type), 1u, item->mSampleLen, data,
-                    size_t(item->mSampleLen)*sz[type]) != B200MIX_OK)
-                { fail(device, S, "b200mix_buffer_data failed:"); return; }
-                it = S.buffers.insert_or_assign(data, std::make_pair(id, item->mSampleLen)).first;
-            }
-            p.buffer = it->second.first;
-            p.loop_start = item->mLoopStart; p.loop_end = item->mLoopEnd;
-        }
-        else p.buffer = B200MIX_NO_BUFFER;      /* alSourceStop / rewind took the buffer (alc/alu.cpp:2071) */
-        const unsigned sid = voice->mSourceID.load(std::memory_order_relaxed);
-        /* a stop clears mSourceID while the voice fades out: that is not a new voice */
-        const bool fresh = !C.live || (sid != 0u && C.source_id != sid);
+        p.buffer = bufid;                       /* B200MIX_NO_BUFFER: alSourceStop / rewind took it (alc/alu.cpp:2071) */
+        if(item && isStatic) { p.loop_start = item->mLoopStart; p.loop_end = item->mLoopEnd; }
         if(fresh)
         {
             /* Voice::prepare + the start offset the AL layer set (al/source.cpp) */
@@ -569,30 +650,30 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         const float *co = &ch.mDryParams.Hrtf.Target.Coeffs[0][0];
         const float *dg = ch.mDryParams.Gains.Target.data();
         const bool hrtf = (p.flags & B200MIX_VF_HRTF) != 0;
-        bool changed = fresh || std::memcmp(&C.params, &p, sizeof(p)) != 0;
-        if(!changed && hrtf && ir) changed = std::memcmp(C.coeffs.data(), co, size_t(ir)*2*sizeof(float)) != 0;
-        if(!changed && !hrtf) changed = std::memcmp(C.dry.data(), dg, cd*sizeof(float)) != 0;
-        if(!changed && !sg.empty()) changed = std::memcmp(C.send.data(), sg.data(), sg.size()*sizeof(float)) != 0;
+        bool changed = fresh || std::memcmp(&CC.params, &p, sizeof(p)) != 0;
+        if(!changed && hrtf && ir) changed = std::memcmp(CC.coeffs.data(), co, size_t(ir)*2*sizeof(float)) != 0;
+        if(!changed && !hrtf) changed = std::memcmp(CC.dry.data(), dg, cd*sizeof(float)) != 0;
+        if(!changed && !sg.empty()) changed = std::memcmp(CC.send.data(), sg.data(), sg.size()*sizeof(float)) != 0;
         if(changed)
         {
             S.upd.push_back(p);
             S.upd_coeffs.insert(S.upd_coeffs.end(), co, co + size_t(ir)*2);
             S.upd_dry.insert(S.upd_dry.end(), dg, dg + cd);
             S.upd_send.insert(S.upd_send.end(), sg.begin(), sg.end());
-            C.send = sg;
+            CC.send = sg;
             b200mix_voice_params keep = p;
             keep.flags &= ~uint32_t(B200MIX_VF_RESET | B200MIX_VF_FADING);
             keep.position = 0; keep.position_frac = 0;
-            C.params = keep;
-            C.coeffs.assign(co, co + size_t(ir)*2);
-            C.dry.assign(dg, dg + cd);
+            CC.params = keep;
+            CC.coeffs.assign(co, co + size_t(ir)*2);
+            CC.dry.assign(dg, dg + cd);
         }
         /* direct / send filters: the targets the ALU's filter block left (alc/alu.cpp:1619-1656).
          * Every reference setParams call that moved a target is forwarded in the same update, so
          * the device's copy of BiquadInterpFilter::setParams' rule sees the same sequence. */
         {
             const uint32_t paths = 1u + ns;
-            if(fresh) C.filt.clear();
+            if(fresh) CC.filt.clear();
             auto entry = [&](uint32_t path, const BiquadInterpFilter &lp, const BiquadInterpFilter &hp, bool act)
             {
                 b200mix_voice_filter f{};
@@ -608,21 +689,22 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             for(uint32_t snd = 0;snd < ns;++snd)
                 now[1u + snd] = entry(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass,
                     voice->mSend[snd].FilterActive && p.send_slot[snd] != B200MIX_NO_SLOT);
-            bool any = !C.filt.empty();
+            bool any = !CC.filt.empty();
             for(uint32_t q = 0;q < paths && !any;++q) any = now[q].active != 0u;
             if(any)
             {
-                if(C.filt.empty())
+                if(CC.filt.empty())
                 {   /* first filter of this voice: all its paths, so a later activation interpolates
                      * from the identity shelves the reference holds meanwhile */
-                    C.filt.assign(now.begin(), now.begin() + paths);
+                    CC.filt.assign(now.begin(), now.begin() + paths);
                     S.upd_filt.insert(S.upd_filt.end(), now.begin(), now.begin() + paths);
                 }
                 else for(uint32_t q = 0;q < paths;++q)
-                    if(std::memcmp(&C.filt[q], &now[q], sizeof(now[q])) != 0)
-                    { C.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
+                    if(std::memcmp(&CC.filt[q], &now[q], sizeof(now[q])) != 0)
+                    { CC.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
             }
         }
+        }   /* channels */
         C.live = true; C.source_id = sid;
     }
     if(!S.upd.empty()
@@ -646,28 +728,53 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         Voice *voice = S.vptr[n];
         VoiceCache &C = S.cache[n];
         if(!C.live) continue;
-        const b200mix_voice_result &r = S.results[n];
+        ContextBase *ctx = S.vctx[n];
+        const b200mix_voice_result &r = S.results[C.ch[0].id];       /* all channels move together */
         voice->mPosition.store(r.position, std::memory_order_relaxed);
         voice->mPositionFrac.store(r.position_frac, std::memory_order_relaxed);
         voice->mFlags.set(VoiceFlag::IsFading);
+        const unsigned sid = voice->mSourceID.load(std::memory_order_relaxed);
+        if(r.buffers_done && !voice->mFlags.test(VoiceFlag::IsStatic))
+        {
+            /* streaming source: the queue advance of core/voice.cpp:1183-1196 and its event (:1211-1221) */
+            auto *it = voice->mCurrentBuffer.load(std::memory_order_relaxed);
+            auto *lp = voice->mLoopBuffer.load(std::memory_order_relaxed);
+            for(uint32_t k = 0;k < r.buffers_done && it;++k)
+            {
+                it = it->mNext.load(std::memory_order_relaxed);
+                if(!it) it = lp;
+            }
+            voice->mCurrentBuffer.store(it, std::memory_order_release);
+            queue_of(voice, C.queue);            /* what the device now walks */
+            if(sid && ctx->mEnabledEvts.load(std::memory_order_acquire).test(AsyncEnableBits::BufferCompleted))
+            {
+                auto *ring = ctx->mAsyncEvents.get();
+                if(auto vec = ring->getWriteVector(); !vec[0].empty())
+                {
+                    auto &evt = InitAsyncEvent<AsyncBufferCompleteEvent>(vec[0].front());
+                    evt.mId = sid;
+                    evt.mCount = r.buffers_done;
+                    ring->writeAdvance(1);
+                }
+            }
+        }
         if(r.flags & B200MIX_VF_STOPPED)
         {
             voice->mCurrentBuffer.store(nullptr, std::memory_order_relaxed);
             voice->mLoopBuffer.store(nullptr, std::memory_order_relaxed);
             voice->mSourceID.store(0u, std::memory_order_relaxed);
             voice->mPlayState.store(Voice::Stopped, std::memory_order_release);
-            C.live = false;
+            release(C);
         }
         else if((r.flags & B200MIX_VF_STOPPING) && voice->mPlayState.load(std::memory_order_relaxed) == Voice::Playing)
         {
             /* ran out of data: the source reads as stopped from now on, the voice fades for
              * one more update (core/voice.cpp:1198-1232) */
-            const unsigned sid = voice->mSourceID.load(std::memory_order_relaxed);
             voice->mCurrentBuffer.store(nullptr, std::memory_order_release);
             voice->mLoopBuffer.store(nullptr, std::memory_order_relaxed);
             voice->mSourceID.store(0u, std::memory_order_release);
             voice->mPlayState.store(Voice::Stopping, std::memory_order_release);
-            ContextBase *ctx = S.vctx[n];
+            C.queue.clear();
             if(ctx->mEnabledEvts.load(std::memory_order_acquire).test(AsyncEnableBits::SourceState))
             {
                 auto *ring = ctx->mAsyncEvents.get();

@@ -69,3 +69,5 @@ EXPORT int b200mix_reverb_full_update_needed(const b200mix_efx_reverb *prev, con
 }
 EXPORT int b200mix_voices_filters(b200mix_device *dev, uint32_t n, const b200mix_voice_filter *filters)
 { return oracle_voices_filters((oracle_device*)dev, n, filters); }
+EXPORT int b200mix_voice_queue(b200mix_device *dev, uint32_t voice, uint32_t count, const uint32_t *buffers, uint32_t loop_index)
+{ return oracle_voice_queue((oracle_device*)dev, voice, count, buffers, loop_index); }

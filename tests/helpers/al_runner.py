@@ -10,7 +10,9 @@ usage: al_runner.py <libopenal path> <out.npz> <voices> <updates> <hrtf 0|1> [re
 fx = "none" (default) | "reverb" (one EAX reverb slot, every source sends to it) | "mix" (EAX
 reverb + echo + an equalizer slot that feeds the reverb slot via AL_EFFECTSLOT_TARGET_SOFT;
 properties, slot gain and an effect type change while playing) | "filt" (direct low-pass /
-band-pass filters that change and detach while playing) | "mixfilt" (both, plus send filters)"""
+band-pass filters that change and detach while playing) | "mixfilt" (both, plus send filters)
+| "stream" (alSourceQueueBuffers: queues that run out, looping queues, buffers queued and
+unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones)"""
 import ctypes as C
 import math
 import os
@@ -28,6 +30,7 @@ ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT = 0x1501, 0x1406, 0x1992
 AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 0x100A, 0x1004
 AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
+AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
 AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
 AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
 AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
@@ -67,6 +70,8 @@ def main():
     al.alSourceStop.argtypes = [C.c_uint]
     al.alSourcePlay.argtypes = [C.c_uint]
     al.alGetSourcei.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_int)]
+    al.alSourceQueueBuffers.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_uint)]
+    al.alSourceUnqueueBuffers.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_uint)]
     al.alSource3i.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
     al.alGenEffects.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alEffecti.argtypes = [C.c_uint, C.c_int, C.c_int]
@@ -97,7 +102,7 @@ def main():
         al.alAuxiliaryEffectSloti(sl, AL_EFFECTSLOT_EFFECT, e.value)
         return sl.value, e.value
 
-    slots = []
+    slots, streams = [], []
     filt = fx in ("filt", "mixfilt")
     if fx == "mixfilt":
         fx = "mix"
@@ -123,12 +128,32 @@ def main():
         # every fourth voice is a short one-shot (runs out, fades, stops by itself)
         oneshot = i % 4 == 3
         pcm = np.ascontiguousarray(scene.voice_buffer_fast(i, 3000 + 37 * i if oneshot else scene.BUFFER_FRAMES))
+        fmt = AL_FORMAT_MONO16
+        if fx == "stereo" and i % 2 == 0:
+            # a stereo buffer: left = this voice's waveform, right = the next one's (interleaved)
+            other = scene.voice_buffer_fast(i + 1, len(pcm))
+            pcm = np.ascontiguousarray(np.stack([pcm, other], axis=1).reshape(-1))
+            fmt = AL_FORMAT_STEREO16
         keep.append(pcm)
-        al.alGenBuffers(1, C.byref(b))
-        al.alBufferData(b, AL_FORMAT_MONO16, pcm.ctypes.data, pcm.nbytes, 48000)
         al.alGenSources(1, C.byref(s))
-        al.alSourcei(s, AL_BUFFER, b.value)
-        al.alSourcei(s, AL_LOOPING, 0 if oneshot else 1)
+        if fx == "stream" and i % 3 != 2:
+            # a streaming source: three queued buffers of different lengths; every third source loops its queue
+            qb = (C.c_uint * 3)()
+            al.alGenBuffers(3, qb)
+            off = 0
+            for k, ln in enumerate((2000 + 13 * i, 1500, 3100)):
+                part = np.ascontiguousarray(pcm[off:off + ln])
+                keep.append(part)
+                al.alBufferData(qb[k], fmt, part.ctypes.data, part.nbytes, 48000)
+                off += ln
+            al.alSourceQueueBuffers(s, 3, qb)
+            al.alSourcei(s, AL_LOOPING, 1 if i % 3 == 1 else 0)
+            streams.append((i, qb))
+        else:
+            al.alGenBuffers(1, C.byref(b))
+            al.alBufferData(b, fmt, pcm.ctypes.data, pcm.nbytes, 48000)
+            al.alSourcei(s, AL_BUFFER, b.value)
+            al.alSourcei(s, AL_LOOPING, 0 if oneshot else 1)
         al.alSourcef(s, AL_PITCH, scene.voice_pitch(i))
         al.alSourcef(s, AL_GAIN, scene.voice_gain(V))
         al.alSource3f(s, AL_POSITION, *[float(x) for x in scene.voice_position(i)])
@@ -171,6 +196,23 @@ def main():
             al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
             if V > 7:
                 al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
+        if streams and u == 1:
+            # the application keeps a stream fed: one more buffer on the first streaming source
+            i0, _ = streams[0]
+            extra = C.c_uint(0)
+            al.alGenBuffers(1, C.byref(extra))
+            part = np.ascontiguousarray(scene.voice_buffer_fast(i0 + 5, 2500))
+            keep.append(part)
+            al.alBufferData(extra, AL_FORMAT_MONO16, part.ctypes.data, part.nbytes, 48000)
+            al.alSourceQueueBuffers(sources[i0], 1, C.byref(extra))
+        if streams and u == 3:
+            # ... and takes back what has been played
+            i0, _ = streams[0]
+            done = C.c_int(0)
+            al.alGetSourcei(sources[i0], AL_BUFFERS_PROCESSED, C.byref(done))
+            if done.value > 0:
+                got = (C.c_uint * done.value)()
+                al.alSourceUnqueueBuffers(sources[i0], done.value, got)
         if slots and u == 2:
             # a property that needs the reverb's other pipeline (full update), then one that does not
             al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, 2.9)
@@ -197,6 +239,8 @@ def main():
             st.append(v.value)
             al.alGetSourcei(sources[i], AL_SAMPLE_OFFSET, C.byref(v))
             off.append(v.value)
+            al.alGetSourcei(sources[i], AL_BUFFERS_PROCESSED, C.byref(v))
+            st.append(v.value)
         states.append(st)
         offsets.append(off)
     hv = C.c_int(0)
