@@ -11,7 +11,7 @@
  * PCM sample type, any resampler, moving sources (targets are re-sent when the ALU changed
  * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
- * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher), slot gain, slot
+ * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher, frequency shifter), slot gain, slot
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
  * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass), streaming sources
  * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events) and
@@ -345,7 +345,13 @@ int effect_of(const EffectSlotBase *slot, b200mix_efx_props &o, b200mix_efx_reve
           o.vmorpher.phoneme_a_coarse_tuning = p->PhonemeACoarseTuning; o.vmorpher.phoneme_b_coarse_tuning = p->PhonemeBCoarseTuning;
           o.vmorpher.waveform = static_cast<uint32_t>(p->Waveform); return 2; }
         return -1;
-    default: return -1;          /* convolution, frequency / pitch shifter */
+    case EffectSlotType::FrequencyShifter:
+        if(auto *p = std::get_if<FshifterProps>(&props))
+        { o.type = B200MIX_EFFECT_FSHIFTER; o.fshifter.frequency = p->Frequency;
+          o.fshifter.left_direction = static_cast<uint32_t>(p->LeftDirection);
+          o.fshifter.right_direction = static_cast<uint32_t>(p->RightDirection); return 2; }
+        return -1;
+    default: return -1;          /* convolution, pitch shifter */
     }
 }
 

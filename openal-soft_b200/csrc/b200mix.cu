@@ -941,7 +941,7 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
 {
     if(!d || slot >= d->h_slots.size() || !props || !target || props->struct_size != sizeof(*props)
         || target->struct_size != sizeof(*target) || props->type < B200MIX_EFFECT_ECHO
-        || props->type > B200MIX_EFFECT_VMORPHER)
+        || props->type > B200MIX_EFFECT_FSHIFTER)
     { if(d) d->error = "slot_efx: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
     const b200mix_device_desc &dd = d->desc;
     const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
@@ -982,6 +982,13 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
         h.p = P; h.comp_env = 1.0f;
         if(P.echo_len) { if(int rc = alloc(h.echo_buf, P.echo_len)) return rc; }
         if(P.cho_len) { if(int rc = alloc(h.cho_buf, size_t(4)*P.cho_len)) return rc; }
+        if(P.type == B200MIX_EFFECT_FSHIFTER)
+        {   // FshifterState::deviceUpdate (fshifter.cpp:140-148): cleared FIFOs, mPos = HilSize - HilStep
+            if(int rc = alloc(h.fs_in, size_t(4)*1024)) return rc;
+            if(int rc = alloc(h.fs_outfifo, size_t(4)*256)) return rc;
+            if(int rc = alloc(h.fs_accum, size_t(4)*1024)) return rc;
+            h.fs_count = 0u; h.fs_pos = 1024u - 256u;
+        }
         r.H = reinterpret_cast<float*>(dev);
         CUDA_TRY(d, cudaMemcpyAsync(dev, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
@@ -1013,6 +1020,14 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
             H.lfo_range = P.cho_lfo_range;
             CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, cho_lfo_offset), &H.lfo_offset,
                 sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+        }
+        if(props->type == B200MIX_EFFECT_FSHIFTER)
+        {   // a direction switched off zeroes that side's phase accumulators (fshifter.cpp:189-192,205-208)
+            static const uint32_t zero = 0u;
+            for(int c = 0;c < 4;++c)
+                if(P.fs_reset_phase[c])
+                    CUDA_TRY(d, cudaMemcpyAsync(reinterpret_cast<char*>(H.dev) + offsetof(EfxDev, fs_phase) + c*sizeof(uint32_t),
+                        &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
         }
         if(props->type == B200MIX_EFFECT_VMORPHER)
             // update() installs newly constructed formant filters: their histories restart at 0

@@ -74,6 +74,69 @@ __constant__ float kA2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f},
                                  {kEncodeCoeff,  kEncodeCoeff, -kEncodeCoeff, -kEncodeCoeff}};
 
 // grid = slots, 128 threads, dynamic shared memory: 2*kEfxMaxLines + 1 lines (input copies + work)
+// ---- frequency shifter helpers: 1024-point complex FFT in double, one warp per transform, data in
+// shared memory (complex_fft, common/alcomplex.cpp:110-197 computes the same radix-2 DIT butterflies
+// with recursively multiplied twiddles; direct table twiddles differ in the last bits of a double
+// only) and the discrete Hilbert transform built on it (complex_hilbert, :199-215).
+__device__ double2 g_fs_tw[512];          // exp(+i 2 pi k / 1024)
+__device__ float g_fs_hann[1024];         // gHannWindow<1024>, common/hann_window.hpp:11-26
+
+__global__ void k_efx_tables()
+{
+    const uint32_t k = threadIdx.x;
+    if(k < 512u)
+    {
+        double sn, cs;
+        sincospi(double(k) / 512.0, &sn, &cs);
+        g_fs_tw[k] = make_double2(cs, sn);
+        const double v = ::sin((double(k) + 1.0) * (3.14159265358979323846 / 1025.0));
+        const float w = float(v * v);
+        g_fs_hann[k] = w; g_fs_hann[1023u - k] = w;
+    }
+}
+
+__device__ __forceinline__ void fft1024_warp(double2 *x, uint32_t lane, double sign)
+{
+    for(uint32_t i = lane;i < 1024u;i += 32u)
+    {
+        const uint32_t j = __brev(i) >> 22;
+        if(i < j) { const double2 a = x[i]; x[i] = x[j]; x[j] = a; }
+    }
+    __syncwarp();
+    for(uint32_t s = 0;s < 10u;++s)
+    {
+        const uint32_t half = 1u << s;
+        for(uint32_t b = lane;b < 512u;b += 32u)
+        {
+            const uint32_t j = b & (half - 1u), k = ((b >> s) << (s + 1u)) + j;
+            const double2 w = g_fs_tw[j * (512u >> s)];
+            const double wi = w.y * sign;
+            const double2 v = x[k + half];
+            const double2 tmp = make_double2(v.x*w.x - v.y*wi, v.x*wi + v.y*w.x);
+            const double2 u = x[k];
+            x[k + half] = make_double2(u.x - tmp.x, u.y - tmp.y);
+            x[k] = make_double2(u.x + tmp.x, u.y + tmp.y);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void hilbert1024_warp(double2 *x, uint32_t lane)
+{
+    fft1024_warp(x, lane, 1.0);                       // inverse_fft
+    const double inv = 1.0 / 1024.0;
+    for(uint32_t i = lane;i < 1024u;i += 32u)
+    {
+        double2 v = x[i];
+        if(i == 0u || i == 512u) { v.x *= inv; v.y *= inv; }
+        else if(i < 512u) { v.x *= inv*2.0; v.y *= inv*2.0; }
+        else v = make_double2(0.0, 0.0);
+        x[i] = v;
+    }
+    __syncwarp();
+    fft1024_warp(x, lane, -1.0);                      // forward_fft
+}
+
 __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
 {
     extern __shared__ float sm[];
@@ -465,6 +528,87 @@ __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
         if(t == 0) E.vm_index = (index0 + step*n) & 0xffffffu;
         break;
     }
+    case B200MIX_EFFECT_FSHIFTER:
+    {
+        // FshifterState::process (fshifter.cpp:235-366), first-order devices.  One warp per A-format
+        // line: B2A into the input FIFO, every 256 samples one STFT frame (Hann window, analytic
+        // signal through the Hilbert transform, window again, overlap-add), then the analytic
+        // signal is rotated by the phase accumulator and encoded back to B-Format.
+        static const float dc = kDecodeCoeff, ec = kEncodeCoeff;
+        const float B2A[4][4] = {{0.25f, dc, dc, dc}, {0.25f, dc, -dc, -dc}, {0.25f, -dc, -dc, dc}, {0.25f, -dc, dc, -dc}};
+        const float A2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {ec, ec, -ec, -ec}, {ec, -ec, -ec, ec}, {ec, -ec, ec, -ec}};
+        double2 *ana = reinterpret_cast<double2*>(sIn);                 // [4][1024] mAnalytic, one per warp
+        double2 *outd = reinterpret_cast<double2*>(sWork);              // [4][1024] mOutdata
+        const uint32_t c = t >> 5, lane = t & 31u;
+        double *infifo = E.fs_in + size_t(c)*1024u;
+        double2 *outfifo = E.fs_outfifo + size_t(c)*256u;
+        double2 *accum = E.fs_accum + size_t(c)*1024u;
+        double2 *myAna = ana + size_t(c)*1024u, *myOut = outd + size_t(c)*1024u;
+        uint32_t count = E.fs_count, pos = E.fs_pos;
+        const uint32_t numInput = min(nin, 4u);
+        __syncthreads();                                                // everybody has read count / pos
+        for(uint32_t base = 0;base < n;)
+        {
+            const uint32_t todo = min(256u - count, n - base);
+            for(uint32_t i = lane;i < todo;i += 32u)
+            {
+                double a = 0.0;
+                for(uint32_t k = 0;k < numInput;++k)
+                    a = a + double(wet[size_t(k)*kLine + base + i]) * double(B2A[c][k]);
+                infifo[pos + count + i] = a;
+                myOut[base + i] = outfifo[count + i];
+            }
+            __syncwarp();
+            count += todo; base += todo;
+            if(count < 256u) break;
+            count = 0u; pos = (pos + 256u) & 1023u;
+            for(uint32_t k = lane;k < 1024u;k += 32u)
+                myAna[k] = make_double2(infifo[(pos + k) & 1023u] * double(g_fs_hann[k]), 0.0);
+            __syncwarp();
+            hilbert1024_warp(myAna, lane);
+            for(uint32_t k = lane;k < 1024u;k += 32u)
+            {
+                const double sc = (2.0/4.0) * double(g_fs_hann[k]);
+                const double2 v = myAna[k];
+                const uint32_t q = (pos + k) & 1023u;
+                double2 acc = accum[q];
+                acc.x += sc*v.x; acc.y += sc*v.y;
+                accum[q] = acc;
+            }
+            __syncwarp();
+            for(uint32_t j = lane;j < 256u;j += 32u)
+            {
+                outfifo[j] = accum[pos + j];
+                accum[pos + j] = make_double2(0.0, 0.0);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        float *temp = reinterpret_cast<float*>(sIn);                    // [4][1024] mTempLine per line
+        {
+            const uint32_t pstep = P.fs_phase_step[c], ph0 = E.fs_phase[c];
+            const double sign = double(P.fs_sign[c]);
+            for(uint32_t i = lane;i < n;i += 32u)
+            {
+                const uint32_t pidx = (ph0 + pstep*i) & 0xffffu;
+                const double phase = double(pidx) * (3.14159265358979323846*2.0 / 65536.0);
+                const double2 in = myOut[i];
+                temp[c*kLine + i] = float(in.x*::cos(phase) + in.y*::sin(phase)*sign);
+            }
+            __syncwarp();
+            if(lane == 0u) E.fs_phase[c] = (ph0 + pstep*n) & 0xffffu;
+        }
+        __syncthreads();
+        for(uint32_t i4 = 0;i4 < 4u;++i4)
+            for(uint32_t i = t;i < n;i += blockDim.x)
+            {
+                float b = 0.0f;
+                for(uint32_t k = 0;k < 4u;++k) b = b + temp[k*kLine + i]*A2B[i4][k];
+                lines[size_t(i4)*kLine + i] = P.line_on[i4] ? b : 0.0f;
+            }
+        if(t == 0u) { E.fs_count = count; E.fs_pos = pos; }
+        break;
+    }
     default: break;
     }
 }
@@ -474,7 +618,11 @@ __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
 constexpr int kEfxSmem = int((2u*kEfxMaxLines + 1u)*kLine*sizeof(float));
 
 cudaError_t efx_kernels_init()
-{ return cudaFuncSetAttribute(k_efx_process, cudaFuncAttributeMaxDynamicSharedMemorySize, kEfxSmem); }
+{
+    k_efx_tables<<<1, 512>>>();            // twiddles + Hann window of the frequency shifter (per CUDA device)
+    if(cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_efx_process, cudaFuncAttributeMaxDynamicSharedMemorySize, kEfxSmem);
+}
 
 cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream)
 {

@@ -20,6 +20,10 @@ struct EfxDev {
     float wah_env;                         // AutowahState::mEnvDelay
     uint32_t vm_index; float vm_cur[kEfxMaxLines];   // VmorpherState::mIndex, OutParams::mCurrentGain
     float vm_s[kEfxMaxLines][2][4][2];     // FormantFilter::mS1/mS2 [channel][vowel][formant]
+    // frequency shifter (double precision like the reference): mInFIFO [4][1024], mOutFIFO [4][256] complex,
+    // mOutputAccum [4][1024] complex; mCount, mPos, mPhase[4]
+    double *fs_in; double2 *fs_outfifo; double2 *fs_accum;
+    uint32_t fs_count, fs_pos, fs_phase[4];
     float chan_z[kEfxMaxLines][4][2];      // per-channel biquad histories (modulator [0], equalizer [0..3],
                                            // distortion [0] low-pass, [1] band-pass)
 };

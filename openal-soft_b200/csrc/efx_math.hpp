@@ -45,6 +45,8 @@ struct EfxParams {
     float vm_coeff[2][4], vm_fgain[2][4]; // FormantFilter::mCoeff / mGain of vowel A and B
     uint32_t vm_target[kEfxMaxLines];     // mTargetChannel per wet channel (0xffffffff: none)
     float vm_tgain[kEfxMaxLines];         // mTargetGain
+    // frequency shifter
+    uint32_t fs_phase_step[4]; float fs_sign[4]; uint32_t fs_reset_phase[4];   // ProcessParams::mPhaseStep / mSign; Off: mPhase = 0
 };
 
 namespace efx_detail {
@@ -283,6 +285,24 @@ inline int efx_update(const b200mix_efx_props &E, const b200mix_efx_target &T, E
                     break;
                 }
         }
+        break;
+    }
+    case B200MIX_EFFECT_FSHIFTER:
+    {
+        // FshifterState::update (fshifter.cpp:171-233); the up-sampler of higher-order devices (:150-168) is not built
+        if(T.device_ambi_order > 1u) return B200MIX_ERR_UNSUPPORTED;
+        const float step = E.fshifter.frequency / frequency;
+        const uint32_t pstep = static_cast<uint32_t>(std::lrint(std::min(step, 1.0f) * 65536.0f));    // fastf2u
+        const uint32_t dir[4] = {E.fshifter.left_direction, E.fshifter.left_direction,
+                                 E.fshifter.right_direction, E.fshifter.right_direction};
+        for(int c = 0;c < 4;++c)
+        {
+            P.fs_phase_step[c] = pstep; P.fs_sign[c] = 1.0f; P.fs_reset_phase[c] = 0u;
+            if(dir[c] == 0u) P.fs_sign[c] = -1.0f;
+            else if(dir[c] == 2u) { P.fs_phase_step[c] = 0u; P.fs_reset_phase[c] = 1u; }   // with phase 0 the sign is moot
+        }
+        P.lines = 4u;
+        ambi_mix_params(T, T.slot_gain, 4u, P);
         break;
     }
     default: return B200MIX_ERR_INVALID;

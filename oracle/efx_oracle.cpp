@@ -1,6 +1,6 @@
 // efx_oracle.cpp — CPU restatement of EffectState::process for the EFX effects the product runs
 // on the GPU (echo, ring modulator, equalizer, compressor, dedicated, distortion, chorus / flanger,
-// autowah, vocal morpher).  TEST
+// autowah, vocal morpher, frequency shifter).  TEST
 // INFRASTRUCTURE ONLY: linked into oracle/liboracle.so, used by tests/, smoke() and nothing else.
 //
 // Each process() below follows the reference line by line (file:line cited); the parameter side
@@ -10,6 +10,7 @@
 // Compiled with -ffp-contract=off: plain mul/add like the reference's x86-64 build.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -79,6 +80,59 @@ void mix_many(const float *in, size_t n, float (*out)[LINE], size_t nout, float 
 }
 } // namespace
 
+// complex_fft / complex_hilbert (common/alcomplex.cpp:110-215): radix-2 decimation in time in double.
+// The reference multiplies its twiddles up recursively from tabulated angles; evaluating them
+// directly differs in the last bits of a double, far below the float the effect outputs.
+using cplx = std::complex<double>;
+void fft_pow2(cplx *x, size_t n, double sign)
+{
+    for(size_t i = 1, j = 0;i < n;++i)
+    {
+        size_t bit = n >> 1;
+        for(;j & bit;bit >>= 1) j ^= bit;
+        j ^= bit;
+        if(i < j) std::swap(x[i], x[j]);
+    }
+    for(size_t half = 1;half < n;half <<= 1)
+        for(size_t j = 0;j < half;++j)
+        {
+            const double ang = 3.14159265358979323846 * double(j) / double(half);
+            const cplx w{std::cos(ang), sign*std::sin(ang)};
+            for(size_t k = j;k < n;k += half << 1)
+            {
+                const cplx t = x[k + half] * w;
+                x[k + half] = x[k] - t;
+                x[k] += t;
+            }
+        }
+}
+void hilbert_pow2(cplx *x, size_t n)
+{
+    fft_pow2(x, n, 1.0);
+    const double inv = 1.0 / double(n);
+    x[0] *= inv;
+    for(size_t i = 1;i < n/2;++i) x[i] *= inv*2.0;
+    x[n/2] *= inv;
+    for(size_t i = n/2 + 1;i < n;++i) x[i] = cplx{};
+    fft_pow2(x, n, -1.0);
+}
+// gHannWindow<1024>, common/hann_window.hpp:11-26
+const float *hann1024()
+{
+    static float w[1024];
+    static bool done = false;
+    if(!done)
+    {
+        for(unsigned i = 0;i < 512;++i)
+        {
+            const double v = std::sin((i + 1.0) * (3.14159265358979323846 / 1025.0));
+            w[i] = static_cast<float>(v * v); w[1023 - i] = w[i];
+        }
+        done = true;
+    }
+    return w;
+}
+
 struct oefx {
     EfxParams p{};
     float cur[b200mix::kEfxMaxLines][32]{};       // Current gains per line and output channel
@@ -94,6 +148,10 @@ struct oefx {
     float cubic[513]{};
     // autowah
     float wah_env{0.0f};
+    // frequency shifter (fshifter.cpp:92-118)
+    size_t fs_count{0}, fs_pos{1024 - 256};
+    std::vector<double> fs_in; std::vector<std::complex<double>> fs_outfifo, fs_accum, fs_outdata;
+    uint32_t fs_phase[4]{};
     // vocal morpher
     uint32_t vm_index{0}; float vm_cur[b200mix::kEfxMaxLines]{}; float vm_s[b200mix::kEfxMaxLines][2][4][2]{};
 };
@@ -110,6 +168,11 @@ oefx *oefx_create(const b200mix_efx_props *props, const b200mix_efx_target *targ
     if(*rc != B200MIX_OK) { delete e; return nullptr; }
     if(e->p.echo_len) e->echo_buf.assign(e->p.echo_len, 0.0f);
     if(e->p.cho_len) { e->cho_buf.assign(size_t(4)*e->p.cho_len, 0.0f); oracle_build_cubic_filter(e->cubic); }
+    if(e->p.type == B200MIX_EFFECT_FSHIFTER)
+    {
+        e->fs_in.assign(4*1024, 0.0); e->fs_outfifo.assign(4*256, {}); e->fs_accum.assign(4*1024, {});
+        e->fs_outdata.assign(4*1024, {});
+    }
     e->lfo_range = e->p.cho_lfo_range ? e->p.cho_lfo_range : 1u;
     e->mod_range = e->p.mod_range ? e->p.mod_range : 1u;
     if(e->p.snap_gains) std::memcpy(e->cur, e->p.gains, sizeof(e->cur));
@@ -132,6 +195,8 @@ int oefx_update(oefx *e, const b200mix_efx_props *props, const b200mix_efx_targe
         e->mod_index = uint32_t(uint64_t(e->mod_index) * P.mod_range_new / e->mod_range);
         e->mod_range = P.mod_range;
     }
+    if(P.type == B200MIX_EFFECT_FSHIFTER)
+        for(int c = 0;c < 4;++c) if(P.fs_reset_phase[c]) e->fs_phase[c] = 0u;      // fshifter.cpp:189-192,205-208
     if(P.type == B200MIX_EFFECT_VMORPHER)
         std::memset(e->vm_s, 0, sizeof(e->vm_s));       // update() installs new FormantFilters, vmorpher.cpp:252-260
     e->p = P;
@@ -442,6 +507,69 @@ void oefx_process(oefx *e, size_t n, const float (*in)[1024], size_t nin_, float
             }
             base += td;
         }
+        break;
+    }
+    case B200MIX_EFFECT_FSHIFTER:
+    {
+        // fshifter.cpp:235-366 (first-order devices)
+        static const float dc = static_cast<float>(0.25 / 1.7320508075688772935), ec = static_cast<float>(0.5 * 1.7320508075688772935);
+        const float B2A[4][4] = {{0.25f, dc, dc, dc}, {0.25f, dc, -dc, -dc}, {0.25f, -dc, -dc, dc}, {0.25f, -dc, dc, -dc}};
+        const float A2B[4][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {ec, ec, -ec, -ec}, {ec, -ec, -ec, ec}, {ec, -ec, ec, -ec}};
+        static thread_local float bbuf[4][LINE];
+        static thread_local cplx analytic[1024];
+        const float *win = hann1024();
+        for(int i = 0;i < 4;++i) std::fill_n(bbuf[i], n, 0.0f);
+        const size_t numInput = std::min<size_t>(nin, 4);
+        for(size_t base = 0;base < n;)
+        {
+            const size_t todo = std::min<size_t>(256 - e->fs_count, n - base);
+            for(size_t c = 0;c < 4;++c)
+            {
+                double *infifo = e->fs_in.data() + c*1024 + e->fs_pos + e->fs_count;
+                std::fill_n(infifo, todo, 0.0);
+                for(size_t i = 0;i < numInput;++i)
+                    for(size_t k = 0;k < todo;++k)
+                        infifo[k] = infifo[k] + double(in[i][base+k])*double(B2A[c][i]);
+                for(size_t k = 0;k < todo;++k)
+                    e->fs_outdata[c*1024 + base + k] = e->fs_outfifo[c*256 + e->fs_count + k];
+            }
+            e->fs_count += todo; base += todo;
+            if(e->fs_count < 256) break;
+            e->fs_count = 0;
+            e->fs_pos = (e->fs_pos + 256) & 1023;
+            const size_t pos = e->fs_pos;
+            for(size_t c = 0;c < 4;++c)
+            {
+                const double *fifo = e->fs_in.data() + c*1024;
+                cplx *accum = e->fs_accum.data() + c*1024;
+                for(size_t k = 0;k < 1024;++k) analytic[k] = cplx{fifo[(pos + k) & 1023] * double(win[k]), 0.0};
+                hilbert_pow2(analytic, 1024);
+                for(size_t k = 0;k < 1024;++k) analytic[k] = (2.0/4.0*double(win[k])) * analytic[k];
+                for(size_t k = 0;k < 1024;++k) accum[(pos + k) & 1023] += analytic[k];
+                for(size_t k = 0;k < 256;++k) { e->fs_outfifo[c*256 + k] = accum[pos + k]; accum[pos + k] = cplx{}; }
+            }
+        }
+        for(size_t c = 0;c < 4;++c)
+        {
+            const double sign = double(P.fs_sign[c]);
+            const uint32_t pstep = P.fs_phase_step[c];
+            uint32_t pidx = e->fs_phase[c];
+            for(size_t k = 0;k < n;++k)
+            {
+                const double phase = pidx * (3.14159265358979323846*2.0 / 65536.0);
+                const cplx v = e->fs_outdata[c*1024 + k];
+                buf[k] = static_cast<float>(v.real()*std::cos(phase) + v.imag()*std::sin(phase)*sign);
+                pidx += pstep; pidx &= 0xffffu;
+            }
+            e->fs_phase[c] = pidx;
+            for(size_t i = 0;i < 4;++i)
+                for(size_t k = 0;k < n;++k) bbuf[i][k] = bbuf[i][k] + buf[k]*A2B[i][c];
+        }
+        for(size_t c = 0;c < 4;++c)
+            if(P.line_on[c])
+                for(size_t o = 0;o < nout;++o)
+                    if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                        mix_line(bbuf[c], n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
         break;
     }
     default: break;

@@ -120,6 +120,8 @@ SCENES = {
     "efx_autowah_hrtf_v5": (5, 1, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:autowah"),
     "efx_vmorpher_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:vmorpher"),
     "efx_vmorpher_saw_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:vmorpher_saw"),
+    "efx_fshifter_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:fshifter"),
+    "efx_fshifter_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:fshifter_off"),
 }
 
 # name: (our effect type, AL effect enum, {AL float props}, {AL int props}, slot gain,
@@ -153,6 +155,12 @@ EFX_SCENES = {
     # triangle LFO; a sawtooth LFO, then rate 0 (the blend stays at 0.5) and a phoneme without formants (silence)
     "vmorpher": (11, 0x0007, {0x0006: 3.0}, {0x0001: 0, 0x0003: 3, 0x0005: 0}, 0.9,
                  {4: ({0x0006: 7.5}, {0x0001: 2, 0x0002: 5, 0x0003: 4, 0x0004: -7, 0x0005: 1})}),
+    # frequency shifter: AL_FREQUENCY_SHIFTER_FREQUENCY 1, _LEFT_DIRECTION 2, _RIGHT_DIRECTION 3 (0 down, 1 up, 2 off):
+    # 150 Hz left down / right up, then 1200 Hz both up; one side off, then back on
+    "fshifter": (12, 0x0006, {0x0001: 150.0}, {0x0002: 0, 0x0003: 1}, 0.9,
+                 {4: ({0x0001: 1200.0}, {0x0002: 1})}),
+    "fshifter_off": (12, 0x0006, {0x0001: 440.0}, {0x0002: 2, 0x0003: 0}, 1.0,
+                     {2: ({}, {0x0002: 1, 0x0003: 2}), 4: ({0x0001: 30.0}, {0x0003: 1})}),
     "vmorpher_saw": (11, 0x0007, {0x0006: 1.41}, {0x0001: 1, 0x0003: 0, 0x0005: 2}, 1.0,
                      {2: ({0x0006: 0.0}, {}), 4: ({0x0006: 2.0}, {0x0001: 9})}),
 }
@@ -206,6 +214,13 @@ def efx_props_struct(kind, fprops, iprops):
         for k, n in {1: "attack_time", 2: "release_time", 3: "resonance", 4: "peak_gain"}.items():
             if k in f:
                 setattr(p.autowah, n, f[k])
+    elif typ == 12:
+        if 1 in f:
+            p.fshifter.frequency = f[1]
+        if 2 in i:
+            p.fshifter.left_direction = i[2]
+        if 3 in i:
+            p.fshifter.right_direction = i[3]
     elif typ == 11:
         if 6 in f:
             p.vmorpher.rate = f[6]

@@ -734,6 +734,9 @@ EFX_CASES = {
                           setattr(p.chorus, "delay", 0.003), setattr(p.chorus, "feedback", -0.7))),
     "autowah": (abi.EFFECT_AUTOWAH, lambda p: (setattr(p.autowah, "resonance", 200.0), setattr(p.autowah, "peak_gain", 3000.0)),
                 lambda p: (setattr(p.autowah, "attack_time", 0.005), setattr(p.autowah, "resonance", 40.0))),
+    "fshifter": (abi.EFFECT_FSHIFTER, lambda p: (setattr(p.fshifter, "frequency", 300.0), setattr(p.fshifter, "left_direction", 0),
+                                                 setattr(p.fshifter, "right_direction", 1)),
+                 lambda p: (setattr(p.fshifter, "frequency", 2500.0), setattr(p.fshifter, "left_direction", 2))),
     "vmorpher": (abi.EFFECT_VMORPHER, lambda p: (setattr(p.vmorpher, "rate", 5.0), setattr(p.vmorpher, "phoneme_a", 0),
                                                  setattr(p.vmorpher, "phoneme_b", 2), setattr(p.vmorpher, "waveform", 1)),
                  lambda p: (setattr(p.vmorpher, "phoneme_a", 3), setattr(p.vmorpher, "phoneme_a_coarse_tuning", 7),
