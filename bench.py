@@ -16,7 +16,8 @@ same voices.
 
 value  : voice-samples/s with everything resident in HBM, device-timed (CUDA events on the
          mixer's stream around each update incl. the RealOut reduce, L2 flushed between
-         updates), max over ranks.
+         updates; the K updates are enqueued back to back and the host synchronises once,
+         after the last one), max over ranks.
 e2e    : same metric through the C ABI with HOST buffers: per step the parameter snapshots of
          1/8 of the voices (moving sources) go host->device, the (reduced, on rank 0) planar
          output block and the per-voice results come back to host memory.
@@ -468,14 +469,17 @@ def main_cuda(args):
         torch.cuda.synchronize()
 
     def timed_device_steps(steps, warmup):
-        """K device-timed updates (events on the mixer's stream, L2 flushed before each);
-        returns (per-step ms, per-step voice-kernel ms, per-step reduce us)."""
+        """K device-timed updates: events on the mixer's stream around every update, L2 flushed
+        before each, the K updates enqueued back to back and the host synchronised once at the end
+        (the contract's bracket) — a per-update host round trip would put host wake-up jitter of
+        the slowest of N processes into every rank-0 reduce.  A short host-synchronous pass
+        afterwards samples the per-kernel / per-collective device times.
+        Returns (per-step ms, per-step voice-kernel ms, per-step reduce us, launches)."""
         for _ in range(warmup):
             mx.render_device()
         barrier()
         l0 = lib.b200mix_launch_count(h)
-        step_ms, mix_ms, red_us = [], [], []
-        ru = C.c_float(-1.0)
+        evs = []
         for _ in range(steps):
             with torch.cuda.stream(stream):
                 flush.zero_()                       # evict the voice state / sources from L2
@@ -484,14 +488,23 @@ def main_cuda(args):
             e0.record(stream)
             mx.render_device()                      # incl. the library's RealOut reduce when sharded
             e1.record(stream)
-            e1.synchronize()
-            step_ms.append(e0.elapsed_time(e1))
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        launches = lib.b200mix_launch_count(h) - l0
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        mix_ms, red_us = [], []
+        ru = C.c_float(-1.0)
+        for _ in range(min(steps, 4)):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            mx.render_device()
+            torch.cuda.synchronize()
             mix_ms.append(lib.b200mix_last_mix_kernel_ms(h))
             if world > 1:
                 lib.b200mix_shard_last_us(h, None, C.byref(ru))
                 red_us.append(ru.value)
         barrier()
-        return step_ms, mix_ms, red_us, lib.b200mix_launch_count(h) - l0
+        return step_ms, mix_ms, red_us, launches
 
     def max_over_ranks(x):
         if world == 1:
@@ -526,8 +539,8 @@ def main_cuda(args):
         collective = {"transport": "peer stores over NVLink (CUDA IPC), rank-ordered sum on rank 0",
                       "bytes": 2 * FRAMES * 4,
                       "reduce_us": max_over_ranks(float(np.mean(red_us))),
-                      "reduce_us_note": "device time of the reduce on its stream (on rank 0 it includes waiting "
-                                        "for the slowest rank's block), max over ranks",
+                      "reduce_us_note": "device time of the reduce on its stream in a host-synchronous pass (on rank 0 "
+                                        "it includes waiting for the slowest rank's block), max over ranks",
                       "nccl": {"ms_per_step": nccl_ms, "reduce_us": nccl_red,
                                "what": "same update with ncclReduce (library transport 2)"}}
 
