@@ -597,20 +597,25 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             queue_of(voice, S.qnow);
             if(fresh || S.qnow != C.queue)
             {
+                /* empty buffers in a queue are legal AL (the reference steps over them, core/voice.cpp:
+                 * 1183-1196); the device list holds the items that have samples */
                 S.qids.clear();
                 for(const VoiceBufferItem *qi : S.qnow)
                 {
+                    if(qi->mSampleLen == 0u) continue;
                     uint32_t id = 0;
                     if(!buffer_of(qi, bufch, &id)) return;
                     S.qids.push_back(id);
                 }
                 for(const ChanCache &cc : C.ch)
                     if(A.voice_queue(S.dev, cc.id, uint32_t(S.qids.size()), S.qids.data(),
-                        loop ? 0u : B200MIX_NO_LOOP) != B200MIX_OK)
+                        (loop && !S.qids.empty()) ? 0u : B200MIX_NO_LOOP) != B200MIX_OK)
                     { fail(device, S, "b200mix_voice_queue failed:"); return; }
                 C.queue = S.qnow;
             }
-            bufid = item ? 0u : B200MIX_NO_BUFFER;
+            bool hasSamples = false;
+            for(const VoiceBufferItem *qi : C.queue) hasSamples = hasSamples || qi->mSampleLen != 0u;
+            bufid = (item && hasSamples) ? 0u : B200MIX_NO_BUFFER;
         }
         else if(item && !buffer_of(item, bufch, &bufid)) return;
 
@@ -644,7 +649,8 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             std::copy_n(wg, cw, sg.begin() + size_t(snd)*cw);
         }
         p.buffer = bufid;                       /* B200MIX_NO_BUFFER: alSourceStop / rewind took it (alc/alu.cpp:2071) */
-        if(item && isStatic) { p.loop_start = item->mLoopStart; p.loop_end = item->mLoopEnd; }
+        if(item) { p.loop_start = item->mLoopStart; p.loop_end = item->mLoopEnd; }
+        if(!isStatic && p.loop_end <= p.loop_start) p.flags &= ~uint32_t(B200MIX_VF_LOOPING);   /* a queue loops through its list, not through loop points */
         if(fresh)
         {
             /* Voice::prepare + the start offset the AL layer set (al/source.cpp) */
@@ -740,17 +746,25 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         voice->mPositionFrac.store(r.position_frac, std::memory_order_relaxed);
         voice->mFlags.set(VoiceFlag::IsFading);
         const unsigned sid = voice->mSourceID.load(std::memory_order_relaxed);
-        if(r.buffers_done && !voice->mFlags.test(VoiceFlag::IsStatic))
+        uint32_t itemsDone = 0;
+        if(!voice->mFlags.test(VoiceFlag::IsStatic) && (r.position > 0 || r.buffers_done))
         {
-            /* streaming source: the queue advance of core/voice.cpp:1183-1196 and its event (:1211-1221) */
+            /* streaming source: the queue advance of core/voice.cpp:1183-1196 — the device counts
+             * the items with samples it finished; empty items in between go with them */
             auto *it = voice->mCurrentBuffer.load(std::memory_order_relaxed);
             auto *lp = voice->mLoopBuffer.load(std::memory_order_relaxed);
-            for(uint32_t k = 0;k < r.buffers_done && it;++k)
+            uint32_t real = r.buffers_done;
+            while(it && itemsDone < 4u*B200MIX_MAX_QUEUE)
             {
+                if(it->mSampleLen != 0u) { if(!real) break; --real; }
                 it = it->mNext.load(std::memory_order_relaxed);
                 if(!it) it = lp;
+                ++itemsDone;
             }
-            voice->mCurrentBuffer.store(it, std::memory_order_release);
+            if(itemsDone) voice->mCurrentBuffer.store(it, std::memory_order_release);
+        }
+        if(itemsDone)
+        {
             queue_of(voice, C.queue);            /* what the device now walks */
             if(sid && ctx->mEnabledEvts.load(std::memory_order_acquire).test(AsyncEnableBits::BufferCompleted))
             {
@@ -759,7 +773,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                 {
                     auto &evt = InitAsyncEvent<AsyncBufferCompleteEvent>(vec[0].front());
                     evt.mId = sid;
-                    evt.mCount = r.buffers_done;
+                    evt.mCount = itemsDone;
                     ring->writeAdvance(1);
                 }
             }

@@ -220,6 +220,7 @@ struct b200mix_device {
     uint32_t voice_hi{0};          // 1 + highest voice index ever configured
     // launch geometry (resolved at create)
     int mix_variant{0}; int mix_groups{2}; int mix_gs{64}; int mix_cdr{0};
+    uint32_t reverb_seq{0};          // update counter of k_reverb_process' early/late hand-off (24 bits used)
     size_t mix_smem{0}; int mix_blocks_per_sm{1};
 };
 
@@ -1852,6 +1853,9 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             if(chunks > 1u)
             {
                 const uint32_t len = dd.dry_channels*kLine;
+                if(chunks <= 16u)
+                    k_reduce_few<<<(len/4 + 255)/256, 256, 0, d->stream>>>(d->d_dry_partial, chunks, len, d->d_dry, 1);
+                else
                 k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(
                     d->d_dry_partial, chunks, len, d->d_dry, 1);
                 ++d->launches;
@@ -1943,6 +1947,9 @@ static int render_phase_a(b200mix_device *d, uint32_t frames, bool want_results,
             if(chunks > 1u)
             {
                 const uint32_t len = dd.max_slots*dd.wet_channels*kLine;
+                if(chunks <= 16u)
+                    k_reduce_few<<<(len/4 + 255)/256, 256, 0, d->stream>>>(d->d_send_partial, chunks, len, d->d_wet, 1);
+                else
                 k_reduce_rows<<<(len/4 + kReduceCols - 1)/kReduceCols, 1024, 0, d->stream>>>(
                     d->d_send_partial, chunks, len, d->d_wet, 1);
                 ++d->launches;
@@ -2031,8 +2038,10 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
                 ReverbParamsK RP{};
                 RP.slots = d->d_slots; RP.wet = d->d_wet; RP.cubic = d->d_cubic_filter;
                 RP.frames = frames; RP.cw = dd.wet_channels; RP.stage = st;
-                k_reverb_process<<<dim3(dd.max_slots, 2), 128, 0, d->stream>>>(RP);
-                ++d->launches;
+                RP.seq = ++d->reverb_seq;
+                k_reverb_process<<<dim3(dd.max_slots, 2, 2), 128, 0, d->stream>>>(RP);
+                k_reverb_commit<<<dd.max_slots, 2, 0, d->stream>>>(RP);
+                d->launches += 2;
                 if(d->reverb_upmix)
                 {
                     k_reverb_upmix<<<dim3(dd.max_slots, 2), 256, 8*kLine*sizeof(float), d->stream>>>(RP);

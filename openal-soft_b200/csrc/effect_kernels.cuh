@@ -849,16 +849,28 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
             const uint32_t ch = s_ch[s], first = s_first[s], L = s_fade[s];
             const float *lines = s_line[s];
             const float dl = (L == n) ? delta : 1.0f/float(L);
-            #pragma unroll 4
-            for(uint32_t c = 0;c < ch;++c)
+            // eight lines' samples are loaded before the first is used (the adds stay in line
+            // order): the loop is a chain of L2 round trips otherwise
+            for(uint32_t c0 = 0;c0 < ch;c0 += 8u)
             {
-                const float cg = s_cg[s][c], tg = s_tg[s][c];
-                const float step = (tg - cg)*dl;
-                const uint32_t li = (c + first) & (kMaxLines - 1u);
-                const float x = (i < n) ? lines[size_t(li)*kLine + i] : 0.0f;
-                // MixLine (mixer_c.cpp:150-186): the ramp over the first L samples, then the target
-                if(fabsf(step) > kEps && i < L) acc += x*(cg + step*float(i));
-                else if(fabsf(tg) > kSilence) acc += x*tg;
+                float xv[8];
+                #pragma unroll
+                for(uint32_t k = 0;k < 8u;++k)
+                {
+                    const uint32_t li = (c0 + k + first) & (kMaxLines - 1u);
+                    xv[k] = (i < n && c0 + k < ch) ? lines[size_t(li)*kLine + i] : 0.0f;
+                }
+                #pragma unroll
+                for(uint32_t k = 0;k < 8u;++k)
+                {
+                    const uint32_t c = c0 + k;
+                    if(c >= ch) break;
+                    const float cg = s_cg[s][c], tg = s_tg[s][c];
+                    const float step = (tg - cg)*dl;
+                    // MixLine (mixer_c.cpp:150-186): the ramp over the first L samples, then the target
+                    if(fabsf(step) > kEps && i < L) acc += xv[k]*(cg + step*float(i));
+                    else if(fabsf(tg) > kSilence) acc += xv[k]*tg;
+                }
             }
         }
     }
@@ -943,11 +955,12 @@ struct ReverbDev {
     float z_split[2][4][3];                                        // mAmbiSplitter {lp_z1, lp_z2, ap_z1}
     uint32_t early_tap_cur[4], late_tap_cur[4]; float early_coeff_cur;
     uint32_t mod_index; uint32_t offset;
+    uint32_t sync;                // (update seq << 8) | early chunks of this update that are complete
     // delay lines
     float *main_d, *late_in, *early_ap, *early_d, *late_ap, *late_d;
 };
 
-struct ReverbParamsK { SlotRec *slots; const float *wet; const float *cubic; uint32_t frames, cw, stage; };
+struct ReverbParamsK { SlotRec *slots; const float *wet; const float *cubic; uint32_t frames, cw, stage, seq; };
 
 __device__ __forceinline__ void scatter4(const float in[4], float x, float y, float out[4])
 {
@@ -999,8 +1012,13 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     SlotRec &S = Q.slots[blockIdx.x];
     if(S.type != 2u || S.stage != Q.stage || !((S.rv_mask >> blockIdx.y) & 1u)) return;
     // blockIdx.y = pipeline object (ReverbState::mPipelines[2]); both share the main delay line,
-    // each CTA writes this update's input into it itself (identical values) before reading it
+    // each early CTA writes this update's input into it itself (identical values) before reading it.
+    // blockIdx.z = half: 0 runs B2A + processEarly, 1 runs processLate CONCURRENTLY on another SM.
+    // The only data the late half takes from this update's early half is the late-input delay
+    // line, read `late tap` (>= the late reverb delay) samples back: late chunk s may start once
+    // the early chunks covering [.., base_s + todo_s - 1 - minTap] are complete (R.sync).
     ReverbDev &R = reinterpret_cast<ReverbDev*>(S.H)[blockIdx.y];
+    const bool earlyHalf = blockIdx.z == 0u;
     const int tid = threadIdx.x, line = tid >> 5, lane = tid & 31;
     const uint32_t n = Q.frames;
     const uint32_t offset0 = R.offset;
@@ -1009,6 +1027,7 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     float *earlyOut = S.lines + size_t(blockIdx.y)*8*kLine, *lateOut = earlyOut + 4*kLine;
 
     // B-Format -> A-Format into the main delay (reverb.cpp:1824-1838, B2A :91-97)
+    if(earlyHalf)
     {
         const float B2A[4][4] = {{0.5f, 0.5f, 0.5f, 0.5f}, {0.5f, -0.5f, -0.5f, 0.5f},
             {0.5f, 0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, 0.5f, -0.5f}};
@@ -1043,7 +1062,8 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     uint32_t offset = offset0;
     float coeffCur = R.early_coeff_cur;
     uint32_t tapCur = R.early_tap_cur[line];
-    for(uint32_t base = 0;base < n;)
+    uint32_t chunksDone = 0;
+    for(uint32_t base = 0;earlyHalf && base < n;)
     {
         const uint32_t todo = (n-base < MAXUPD) ? n-base : MAXUPD;
         const float fadeStep = 1.0f/float(todo);
@@ -1146,6 +1166,22 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
         }
         __syncthreads();
         base += todo; offset += todo;
+        // publish: this chunk's late-input samples are in memory
+        ++chunksDone;
+        if(tid == 0)
+        {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&R.sync), "r"((Q.seq << 8) | chunksDone) : "memory");
+        }
+    }
+    if(earlyHalf)
+    {
+        if(lane == 0)
+        {
+            R.early_tap_cur[line] = tapCur;
+            if(line == 0) R.early_coeff_cur = coeffCur;
+        }
+        return;
     }
 
     // ---- processLate, reverb.cpp:1696-1811 ----
@@ -1156,6 +1192,33 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
     {
         uint32_t todo = R.late_offset[0] < MAXUPD ? R.late_offset[0] : MAXUPD;
         if(n-base < todo) todo = n-base;
+        {
+            // early chunks (of MAXUPD samples) this chunk's late-input taps reach into
+            uint32_t minTap = 0xffffffffu;
+            for(int j = 0;j < NL;++j)
+            {
+                minTap = min(minTap, R.late_tap[j]);
+                minTap = min(minTap, R.late_tap_cur[j]);
+            }
+            const int64_t last = int64_t(base) + int64_t(todo) - 1 - int64_t(minTap);
+            const uint32_t need = last < 0 ? 0u : min(uint32_t(last / int64_t(MAXUPD)) + 1u, (n + MAXUPD - 1u)/MAXUPD);
+            if(need && tid == 0)
+            {
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for(;;)
+                {
+                    uint32_t v;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&R.sync) : "memory");
+                    if((v >> 8) == (Q.seq & 0xffffffu) && (v & 0xffu) >= need) break;
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if(t1 - t0 > 1000000000ull) break;          // never hang the GPU on a lost partner
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+        }
         // Modulation::calcDelays (reverb.cpp:1662-1681)
         {
             const float depth = R.mod_depth*256.0f;
@@ -1214,8 +1277,8 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
             for(int u = 0;u < 8;++u)
             {
                 const uint32_t i = lane + uint32_t(u)*32u;
-                v0[u] = i < todo ? input[(t0+i) & m] : 0.0f;
-                v1[u] = i < todo ? input[(t1+i) & m] : 0.0f;
+                v0[u] = i < todo ? __ldcg(input + ((t0+i) & m)) : 0.0f;      // written by the early half on another SM
+                v1[u] = i < todo ? __ldcg(input + ((t1+i) & m)) : 0.0f;
             }
             #pragma unroll
             for(int u = 0;u < 8;++u)
@@ -1300,9 +1363,17 @@ __global__ void __launch_bounds__(128) k_reverb_process(const ReverbParamsK Q)
 
     if(lane == 0)
     {
-        R.early_tap_cur[line] = tapCur; R.late_tap_cur[line] = ltapCur;
-        if(line == 0) { R.early_coeff_cur = coeffCur; R.mod_index = modIdx; R.offset = offset0 + n; }
+        R.late_tap_cur[line] = ltapCur;
+        if(line == 0) R.mod_index = modIdx;
     }
+}
+
+// After both halves of every pipeline: the write offset moves on (ReverbState::mOffset, reverb.cpp:1880).
+__global__ void k_reverb_commit(const ReverbParamsK Q)
+{
+    SlotRec &S = Q.slots[blockIdx.x];
+    if(S.type != 2u || S.stage != Q.stage || !((S.rv_mask >> threadIdx.x) & 1u)) return;
+    reinterpret_cast<ReverbDev*>(S.H)[threadIdx.x].offset += Q.frames;
 }
 
 // MixOutAmbiUp's front half (reverb.cpp:618-634,658-699) for higher-order devices: turns a

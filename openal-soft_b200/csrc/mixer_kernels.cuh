@@ -1186,6 +1186,44 @@ k_reduce_rows(const float *__restrict__ partial, uint32_t rows, uint32_t len,
     }
 }
 
+// The same sum for a handful of long rows (the chunk partials of k_send_mix: <= 16 rows of
+// slots x channels x 1024 floats): one float4 column per thread, all rows' loads in flight at
+// once, added with exactly the association k_reduce_rows' tree has for rows <= 16 (groups of
+// four rows in order, then the groups in order), so both kernels give bit-identical results.
+__global__ void __launch_bounds__(256)
+k_reduce_few(const float *__restrict__ partial, uint32_t rows, uint32_t len,
+    float *__restrict__ out, int accumulate)
+{
+    const uint32_t e4 = blockIdx.x*blockDim.x + threadIdx.x;
+    if(e4*4u >= len) return;
+    const float4 *p = reinterpret_cast<const float4*>(partial) + e4;
+    const size_t stride4 = len/4u;
+    float4 v[16];
+    #pragma unroll
+    for(uint32_t r = 0;r < 16u;++r)
+        v[r] = r < rows ? __ldg(p + size_t(r)*stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g[4];
+    #pragma unroll
+    for(uint32_t j = 0;j < 4u;++j)
+    {
+        float4 t = v[4u*j];
+        #pragma unroll
+        for(uint32_t k = 1;k < 4u;++k)
+        { t.x += v[4u*j+k].x; t.y += v[4u*j+k].y; t.z += v[4u*j+k].z; t.w += v[4u*j+k].w; }
+        g[j] = t;
+    }
+    float4 tot = g[0];
+    #pragma unroll
+    for(uint32_t j = 1;j < 4u;++j) { tot.x += g[j].x; tot.y += g[j].y; tot.z += g[j].z; tot.w += g[j].w; }
+    float4 *o = reinterpret_cast<float4*>(out) + e4;
+    if(accumulate)
+    {
+        const float4 a = *o;
+        tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
+    }
+    *o = tot;
+}
+
 // Applies staged parameter snapshots to the voice records (the device half of
 // b200mix_voices_update).  One CTA of 64 threads per update.
 struct ApplyParams {

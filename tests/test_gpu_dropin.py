@@ -29,6 +29,7 @@ def _run(lib, tag, voices, updates, hrtf, gpu, tmp_path, fx="none"):
     p = subprocess.run([sys.executable, RUNNER, os.path.join(REF, lib), out, str(voices), str(updates), str(hrtf), "7", fx],
                        env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
+    assert "b200mix:" not in p.stderr, p.stderr[-2000:]         # the seam's own error lines (device disconnected)
     return dict(np.load(out))
 
 

@@ -63,6 +63,24 @@ for l in open('gpurun_out/${tag}_configs_n${NG}.jsonl'):
     j=json.loads(l); print(j['config'], j['n_gpus'], j['voices_total'], j['slots'], j.get('transport'), round(j['ms_per_update'],4), j.get('stage_us_rank0'))
 PY
   ;;
+l3)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_send\|k_reduce\|k_reverb\|k_slot\|k_post\|k_filters -c 120 --csv \
+     --log-file gpurun_out/${tag}_launches_cfg3.csv python tools/bench_configs.py --config 3 --steps 2 --warmup 2 > gpurun_out/${tag}_cfg3_ncu.log 2>&1
+  python - <<PY
+import csv,re,collections
+rows=[r for r in csv.reader(open('gpurun_out/${tag}_launches_cfg3.csv')) if len(r)>10]
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
+agg=collections.OrderedDict()
+for r in rows[1:]:
+    n=re.sub(r'\(.*','',r[ki]).replace('void ','').replace('b200mix::','')
+    agg.setdefault(n,[]).append(float(r[vi].replace(',','')))
+for n,v in agg.items(): print('%-40s n=%3d last=%8.1f us'%(n[:40],len(v),v[-1]/1000))
+PY
+  ;;
+rv)
+  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shard.py tests/test_gpu_atsize.py -m gpu -q --timeout 800 -k "reverb or golden or config3 or chain or slot" > gpurun_out/${tag}_pytest_rv.log 2>&1
+  tail -4 gpurun_out/${tag}_pytest_rv.log
+  timeout 600 python tools/bench_configs.py --config 3 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('cfg3', round(j['ms_per_update'],4), j['stage_us_rank0'])" ;;
 fx)
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_conv -c 60 --csv \
      --log-file gpurun_out/${tag}_launches_fx_conv.csv python tools/bench_effects.py --effect conv --voices 4096 --slots 32 --steps 4 > gpurun_out/${tag}_fx_conv_ncu.log 2>&1
@@ -91,8 +109,8 @@ l4a)
      --log-file gpurun_out/${tag}_launches_cfg4a.csv python tools/bench_configs.py --config 4a --voices 8192 --steps 2 --warmup 2 > gpurun_out/${tag}_cfg4a_ncu.log 2>&1
   grep -E "k_send|k_panmix|k_reduce|k_mix" gpurun_out/${tag}_launches_cfg4a.csv | awk -F'","' '{print $5, $9, $NF}' | tail -14 ;;
 dropin)
-  timeout 900 python -m pytest tests/test_gpu_dropin.py tests/test_gpu_params.py -m gpu -q --timeout 800 > gpurun_out/${tag}_pytest_dropin.log 2>&1
-  tail -8 gpurun_out/${tag}_pytest_dropin.log ;;
+  timeout 900 python -m pytest tests/test_gpu_dropin.py -m gpu -q --timeout 800 > gpurun_out/${tag}_pytest_dropin.log 2>&1
+  grep -E '^E .*b200mix|^E .*rms' gpurun_out/${tag}_pytest_dropin.log | cut -c1-300 | head -8; tail -3 gpurun_out/${tag}_pytest_dropin.log ;;
 probe)
   ./tools/ubench/umma_probe > gpurun_out/${tag}_umma_probe.log 2>&1; cat gpurun_out/${tag}_umma_probe.log ;;
 tc)
