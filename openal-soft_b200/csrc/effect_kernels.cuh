@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) k_send_mix(const SendMixParams Q)
                     if(Q.dline) myLine = (Q.sendinfo[en.voice] & kSiDeferred) ? 1u : 0u;
                     else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active) myLine = 2u;
                 }
-                constexpr int U = (CH > 4) ? 2 : 4;
+                constexpr int U = (CH > 4) ? 2 : 8;      // entries in flight per lane (8 x 512 B per warp for first-order sends)
                 for(uint32_t u0 = 0;u0 < cnt;u0 += U)
                 {
                     float4 xU[U]; float4 gU[U][CH/4];
@@ -835,42 +835,63 @@ __global__ void __launch_bounds__(128) k_slot_output_mix(const SlotMixParams Q)
             s_first[threadIdx.x] = first;
             s_fade[threadIdx.x] = S.fade_len ? min(S.fade_len, n) : n;
             s_line[threadIdx.x] = S.lines;
-            const float *gcur = S.gains + size_t(S.gsel)*S.channels*32u;
-            for(uint32_t c = 0;c < ch;++c)
-            {
-                const uint32_t li = (c + first) & (kMaxLines - 1u);
-                s_cg[threadIdx.x][c] = gcur[li*32u + o];
-                s_tg[threadIdx.x][c] = S.gtgt[li*32u + o];
-            }
         }
         __syncthreads();
-        for(uint32_t s = 0;s < cnt;++s)
+        // the gains of every (slot, line): one thread each, all loads independent
+        for(uint32_t idx = threadIdx.x;idx < cnt*uint32_t(kMaxLines);idx += blockDim.x)
         {
-            const uint32_t ch = s_ch[s], first = s_first[s], L = s_fade[s];
-            const float *lines = s_line[s];
-            const float dl = (L == n) ? delta : 1.0f/float(L);
-            // eight lines' samples are loaded before the first is used (the adds stay in line
-            // order): the loop is a chain of L2 round trips otherwise
-            for(uint32_t c0 = 0;c0 < ch;c0 += 8u)
+            const uint32_t sl = idx / uint32_t(kMaxLines), c = idx % uint32_t(kMaxLines);
+            if(c >= s_ch[sl]) continue;
+            const SlotRec &S = Q.slots[sb + sl];
+            const uint32_t li = (c + s_first[sl]) & (kMaxLines - 1u);
+            s_cg[sl][c] = S.gains[size_t(S.gsel)*S.channels*32u + li*32u + o];
+            s_tg[sl][c] = S.gtgt[li*32u + o];
+        }
+        __syncthreads();
+        // the slots' lines as a flat list of blocks of <= 8 lines; block b+1's samples are loaded
+        // while block b is added (the adds stay in slot / line order): without the prefetch the
+        // loop is one L2 round trip per slot
+        uint32_t nblk = 0;
+        for(uint32_t sl = 0;sl < cnt;++sl) nblk += (s_ch[sl] + 7u)/8u;
+        uint32_t ps = 0, pc0 = 0;                       // the block being prefetched: (slot, first line)
+        while(ps < cnt && s_ch[ps] == 0u) ++ps;
+        float xn[8];
+        #pragma unroll
+        for(uint32_t k = 0;k < 8u;++k) xn[k] = 0.0f;
+        auto load_block = [&](uint32_t sl, uint32_t c0)
+        {
+            const uint32_t ch = s_ch[sl], first = s_first[sl];
+            const float *lines = s_line[sl];
+            #pragma unroll
+            for(uint32_t k = 0;k < 8u;++k)
             {
-                float xv[8];
-                #pragma unroll
-                for(uint32_t k = 0;k < 8u;++k)
-                {
-                    const uint32_t li = (c0 + k + first) & (kMaxLines - 1u);
-                    xv[k] = (i < n && c0 + k < ch) ? lines[size_t(li)*kLine + i] : 0.0f;
-                }
-                #pragma unroll
-                for(uint32_t k = 0;k < 8u;++k)
-                {
-                    const uint32_t c = c0 + k;
-                    if(c >= ch) break;
-                    const float cg = s_cg[s][c], tg = s_tg[s][c];
-                    const float step = (tg - cg)*dl;
-                    // MixLine (mixer_c.cpp:150-186): the ramp over the first L samples, then the target
-                    if(fabsf(step) > kEps && i < L) acc += xv[k]*(cg + step*float(i));
-                    else if(fabsf(tg) > kSilence) acc += xv[k]*tg;
-                }
+                const uint32_t li = (c0 + k + first) & (kMaxLines - 1u);
+                xn[k] = (i < n && c0 + k < ch) ? lines[size_t(li)*kLine + i] : 0.0f;
+            }
+        };
+        if(nblk) load_block(ps, pc0);
+        for(uint32_t bk = 0;bk < nblk;++bk)
+        {
+            const uint32_t sl = ps, c0 = pc0;
+            float xv[8];
+            #pragma unroll
+            for(uint32_t k = 0;k < 8u;++k) xv[k] = xn[k];
+            // advance the prefetch cursor and issue the next block's loads
+            pc0 += 8u;
+            if(pc0 >= s_ch[ps]) { pc0 = 0u; ++ps; while(ps < cnt && s_ch[ps] == 0u) ++ps; }
+            if(bk + 1u < nblk) load_block(ps, pc0);
+            const uint32_t ch = s_ch[sl], L = s_fade[sl];
+            const float dl = (L == n) ? delta : 1.0f/float(L);
+            #pragma unroll
+            for(uint32_t k = 0;k < 8u;++k)
+            {
+                const uint32_t c = c0 + k;
+                if(c >= ch) break;
+                const float cg = s_cg[sl][c], tg = s_tg[sl][c];
+                const float step = (tg - cg)*dl;
+                // MixLine (mixer_c.cpp:150-186): the ramp over the first L samples, then the target
+                if(fabsf(step) > kEps && i < L) acc += xv[k]*(cg + step*float(i));
+                else if(fabsf(tg) > kSilence) acc += xv[k]*tg;
             }
         }
     }
