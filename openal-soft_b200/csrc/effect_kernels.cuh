@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(32) k_filters(const FilterRunParams Q)
 // shared memory in warp order, chunks through k_reduce_rows: the result does not depend on
 // scheduling.
 template<int CH>
-__global__ void __launch_bounds__(256, 2) k_send_mix(const SendMixParams Q)
+__global__ void __launch_bounds__(256, (CH > 4) ? 2 : 4) k_send_mix(const SendMixParams Q)
 {
     __shared__ float part[8][4][128];
     const uint32_t slot = blockIdx.x;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) k_send_mix(const SendMixParams Q)
                     if(Q.dline) myLine = (Q.sendinfo[en.voice] & kSiDeferred) ? 1u : 0u;
                     else if(Q.filt && Q.filt[size_t(en.voice)*Q.filt_paths + 1u + en.send].active) myLine = 2u;
                 }
-                constexpr int U = (CH > 4) ? 2 : 8;      // entries in flight per lane (8 x 512 B per warp for first-order sends)
+                constexpr int U = (CH > 4) ? 2 : 4;      // entries in flight per lane
                 for(uint32_t u0 = 0;u0 < cnt;u0 += U)
                 {
                     float4 xU[U]; float4 gU[U][CH/4];
