@@ -14,10 +14,11 @@
  * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher, frequency shifter), slot gain, slot
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
  * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass), streaming sources
- * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events) and
- * multi-channel sources (stereo … 7.1 buffers: one device voice per mixing channel).
- * Convolution slots, ambisonic / UHJ sources, NFC, direct channels and callback buffers are not
- * wired up here: the seam disconnects the device with
+ * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events),
+ * multi-channel sources (stereo … 7.1 buffers: one device voice per mixing channel) and
+ * convolution slots with mono … 7.1 impulse responses (any PCM type and rate).
+ * Ambisonic / UHJ sources and impulse responses, NFC, direct channels and callback buffers are
+ * not wired up here: the seam disconnects the device with
  * a message rather than mixing them wrong.
  */
 #include "config.h"
@@ -56,6 +57,8 @@
 #undef class
 
 #include "core/async_event.h"
+#include "core/buffer_storage.h"
+#include "core/fmt_traits.h"
 #include "core/context.h"
 #include "core/device.h"
 #include "core/effectslot.h"
@@ -84,6 +87,10 @@ struct Api {
     decltype(&b200mix_voice_queue) voice_queue{};
     decltype(&b200mix_render) render{};
     decltype(&b200mix_slot_efx) slot_efx{};
+    decltype(&b200mix_slot_convolution) slot_convolution{};
+    decltype(&b200mix_convolution_gains) convolution_gains{};
+    decltype(&b200mix_resample_ir) resample_ir{};
+    decltype(&b200mix_resampled_ir_frames) resampled_ir_frames{};
     decltype(&b200mix_slot_reverb) slot_reverb{};
     decltype(&b200mix_slot_reverb_update) slot_reverb_update{};
     decltype(&b200mix_slot_output_gains) slot_output_gains{};
@@ -106,13 +113,15 @@ Api &api()
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
         LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(voice_queue); LOAD(render);
+        LOAD(slot_convolution); LOAD(convolution_gains); LOAD(resample_ir); LOAD(resampled_ir_frames);
         LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
         LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
             && r.buffer_data && r.voices_update && r.voices_filters && r.voice_queue && r.render && r.slot_efx && r.slot_reverb
             && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
-            && r.reverb_params_from_efx && r.reverb_full_update_needed;
+            && r.reverb_params_from_efx && r.reverb_full_update_needed && r.slot_convolution
+            && r.convolution_gains && r.resample_ir && r.resampled_ir_frames;
         if(!r.ok) ERR("b200mix: the mixer library lacks entry points of include/b200mix.h");
         return r;
     }();
@@ -136,7 +145,9 @@ struct SlotCache {                   /* what was last installed for an effect sl
     const EffectSlotBase *slot{nullptr};
     const EffectState *state{nullptr};   /* a new EffectState object = deviceUpdate (al/auxeffectslot.cpp initEffect) */
     bool live{false};
-    uint32_t kind{0};                /* 0 none, 1 reverb, 2 b200mix_slot_efx */
+    uint32_t kind{0};                /* 0 none, 1 reverb, 2 b200mix_slot_efx, 3 convolution */
+    uint32_t conv_layout{0};         /* kind 3: layout code of b200mix_convolution_gains, IR channels */
+    uint32_t conv_channels{0};
     b200mix_efx_props efx{};
     b200mix_efx_reverb reverb{};
     float gain{0.0f};
@@ -166,6 +177,12 @@ struct Seam {
 };
 
 std::mutex g_lock;
+
+/* Impulse responses by ConvolutionState object (b200seam_note_convolution): planar floats at the
+ * buffer's rate, converted like LoadSamples (core/voice.cpp:271-287, core/fmt_traits.h:88-175). */
+struct ConvIr { uint32_t layout{0}, rate{0}, frames{0}, channels{0}; std::vector<float> planar; };
+std::mutex g_conv_lock;
+std::unordered_map<const void*, ConvIr> g_conv;
 std::unordered_map<const DeviceBase*, Seam> g_seams;
 
 constexpr uint32_t kMaxVoices = 16384, kMaxBuffers = 16384, kMaxSlots = 64;   /* 64: alc/alc.cpp:3427 */
@@ -351,7 +368,8 @@ int effect_of(const EffectSlotBase *slot, b200mix_efx_props &o, b200mix_efx_reve
           o.fshifter.left_direction = static_cast<uint32_t>(p->LeftDirection);
           o.fshifter.right_direction = static_cast<uint32_t>(p->RightDirection); return 2; }
         return -1;
-    default: return -1;          /* convolution, pitch shifter */
+    case EffectSlotType::Convolution: return 3;
+    default: return -1;          /* pitch shifter */
     }
 }
 
@@ -454,6 +472,48 @@ bool sync_slots(DeviceBase *device, Seam &S)
             if(A.slot_output_gains(S.dev, id, 8u, gains.data()) != B200MIX_OK)
                 return fail(device, S, "b200mix_slot_output_gains failed:");
         }
+        else if(kind == 3)
+        {
+            /* ConvolutionState::deviceUpdate + update (alc/effects/convolution.cpp:318-471,541-620),
+             * plain channel layouts (mono ... 7.1 impulse responses) */
+            if(fresh)
+            {
+                ConvIr ir;
+                {
+                    std::lock_guard<std::mutex> cg{g_conv_lock};
+                    if(auto it = g_conv.find(state); it != g_conv.end()) ir = it->second;
+                }
+                if(C.live && C.kind && A.slot_disable(S.dev, id) != B200MIX_OK) return fail(device, S, "b200mix_slot_disable failed:");
+                C.conv_layout = ir.layout; C.conv_channels = ir.frames ? ir.channels : 0u;
+                if(ir.frames && !ir.layout) return fail(device, S, "this impulse response format is not wired into the seam yet");
+                if(ir.frames)
+                {
+                    uint32_t frames = ir.frames;
+                    std::vector<float> planar;
+                    if(ir.rate != device->mSampleRate)
+                    {
+                        frames = uint32_t(A.resampled_ir_frames(ir.rate, device->mSampleRate, ir.frames));
+                        planar.resize(size_t(frames)*ir.channels);
+                        for(uint32_t c = 0;c < ir.channels;++c)
+                            if(A.resample_ir(ir.rate, device->mSampleRate, ir.planar.data() + size_t(c)*ir.frames, ir.frames,
+                                planar.data() + size_t(c)*frames, frames) != B200MIX_OK)
+                                return fail(device, S, "b200mix_resample_ir failed");
+                    }
+                    else planar = std::move(ir.planar);
+                    if(A.slot_convolution(S.dev, id, ir.channels, frames, planar.data()) != B200MIX_OK)
+                        return fail(device, S, "b200mix_slot_convolution failed:");
+                }
+            }
+            if(C.conv_channels)
+            {
+                std::vector<float> gains(size_t(C.conv_channels)*nout);
+                const int rows = A.convolution_gains(C.conv_layout, device->mRenderMode == RenderMode::Pairwise ? 1u : 0u,
+                    slot->Gain, nout, oscale.data(), oindex.data(), gains.data(), nout);
+                if(rows != int(C.conv_channels)) return fail(device, S, "b200mix_convolution_gains failed");
+                if(A.slot_output_gains(S.dev, id, C.conv_channels, gains.data()) != B200MIX_OK)
+                    return fail(device, S, "b200mix_slot_output_gains failed:");
+            }
+        }
         else
         {
             b200mix_efx_target t{};
@@ -469,7 +529,7 @@ bool sync_slots(DeviceBase *device, Seam &S)
                 return fail(device, S, "b200mix_slot_disable failed:");
             if(A.slot_efx(S.dev, id, &efx, &t) != B200MIX_OK) return fail(device, S, "b200mix_slot_efx failed:");
         }
-        C.live = true; C.state = state; C.kind = uint32_t(kind); C.efx = efx; C.reverb = rv;
+        C.live = true; C.state = state; C.kind = (kind == 3 && !C.conv_channels) ? 0u : uint32_t(kind); C.efx = efx; C.reverb = rv;
         C.gain = slot->Gain; C.target = target;
     }
     return true;
@@ -808,4 +868,41 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             }
         }
     }
+}
+
+void b200seam_note_convolution(const void *state, const BufferStorage *buffer) noexcept
+{
+    if(!api().ok) return;
+    ConvIr ir;
+    if(buffer && buffer->mSampleLen >= 1)
+    {
+        switch(buffer->mChannels)
+        {
+        case FmtMono: ir.layout = 1u; break;
+        case FmtStereo: ir.layout = B200MIX_LAYOUT_STEREO; break;
+        case FmtRear: ir.layout = B200MIX_LAYOUT_REAR; break;
+        case FmtQuad: ir.layout = B200MIX_LAYOUT_QUAD; break;
+        case FmtX51: ir.layout = B200MIX_LAYOUT_X51; break;
+        case FmtX61: ir.layout = B200MIX_LAYOUT_X61; break;
+        case FmtX71: ir.layout = B200MIX_LAYOUT_X71; break;
+        default: ir.layout = 0u; break;          /* B-Format / UHJ responses: not wired */
+        }
+        ir.rate = buffer->mSampleRate; ir.frames = buffer->mSampleLen; ir.channels = buffer->channelsFromFmt();
+        const bool ok = std::visit([&ir]<typename T>(std::span<T> const &spl) -> bool
+        {
+            if constexpr(std::is_same_v<T,IMA4Data> || std::is_same_v<T,MSADPCMData>) return false;
+            else
+            {
+                if(spl.size() < size_t(ir.frames)*ir.channels) return false;
+                ir.planar.resize(size_t(ir.frames)*ir.channels);
+                for(uint32_t c = 0;c < ir.channels;++c)
+                    for(uint32_t k = 0;k < ir.frames;++k)
+                        ir.planar[size_t(c)*ir.frames + k] = SampleInfo<T>::to_float(spl[size_t(k)*ir.channels + c]);
+                return true;
+            }
+        }, buffer->mData);
+        if(!ok) { ir.layout = 0u; ir.planar.clear(); }
+    }
+    std::lock_guard<std::mutex> cg{g_conv_lock};
+    g_conv[state] = std::move(ir);
 }

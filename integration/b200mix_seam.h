@@ -1,10 +1,12 @@
 /* b200mix_seam.h — the seam a maintainer adds to OpenAL Soft to mix on a B200 through
- * libb200mix.so (include/b200mix.h).  Declared here, called from the two patched places of
- * alc/alu.cpp (integration/alu_seam.patch), implemented in b200mix_seam.cpp. */
+ * libb200mix.so (include/b200mix.h).  Declared here, called from the patched places of
+ * alc/alu.cpp (integration/alu_seam.patch) and alc/effects/convolution.cpp
+ * (integration/convolution_seam.patch), implemented in b200mix_seam.cpp. */
 #ifndef B200MIX_SEAM_H
 #define B200MIX_SEAM_H
 
 struct DeviceBase;
+struct BufferStorage;
 
 /* True when this device mixes on the GPU (ALSOFT_B200MIX=1 in the environment and
  * libb200mix.so could be loaded).  ProcessContexts then skips its voice loop and effect loop
@@ -18,5 +20,11 @@ bool b200seam_enabled(const DeviceBase *device /* may be null: the switch is pro
  * objects.  Limiter, distance compensation, dither and Write<T> stay the host's.  A failure
  * (CUDA error, unsupported configuration) disconnects the device (DeviceBase::handleDisconnect). */
 void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept;
+
+/* Called at the top of ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318,
+ * integration/convolution_seam.patch): the effect state objects are private to their source
+ * files, so this is where the seam learns the impulse response a convolution slot was given.
+ * No-op unless the seam is enabled. */
+void b200seam_note_convolution(const void *state, const BufferStorage *buffer) noexcept;
 
 #endif

@@ -71,3 +71,26 @@ EXPORT int b200mix_voices_filters(b200mix_device *dev, uint32_t n, const b200mix
 { return oracle_voices_filters((oracle_device*)dev, n, filters); }
 EXPORT int b200mix_voice_queue(b200mix_device *dev, uint32_t voice, uint32_t count, const uint32_t *buffers, uint32_t loop_index)
 { return oracle_voice_queue((oracle_device*)dev, voice, count, buffers, loop_index); }
+
+/* convolution slots: the device call goes to the oracle, the host helpers to the product library */
+EXPORT int b200mix_slot_convolution(b200mix_device *dev, uint32_t slot, uint32_t ir_channels, uint32_t ir_frames, const float *ir)
+{ return oracle_slot_convolution((oracle_device*)dev, slot, ir_channels, ir_frames, ir); }
+EXPORT int b200mix_convolution_gains(uint32_t layout, uint32_t pairwise, float slot_gain, uint32_t channels, const float *scale,
+    const uint32_t *index, float *gains, uint32_t gains_stride)
+{
+    typedef int (*fn_t)(uint32_t, uint32_t, float, uint32_t, const float*, const uint32_t*, float*, uint32_t);
+    fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_convolution_gains") : NULL;
+    return fn ? fn(layout, pairwise, slot_gain, channels, scale, index, gains, gains_stride) : B200MIX_ERR_INVALID;
+}
+EXPORT int64_t b200mix_resampled_ir_frames(uint32_t src_rate, uint32_t dst_rate, uint32_t frames)
+{
+    typedef int64_t (*fn_t)(uint32_t, uint32_t, uint32_t);
+    fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_resampled_ir_frames") : NULL;
+    return fn ? fn(src_rate, dst_rate, frames) : -1;
+}
+EXPORT int b200mix_resample_ir(uint32_t src_rate, uint32_t dst_rate, const float *in, uint32_t in_frames, float *out, uint32_t out_frames)
+{
+    typedef int (*fn_t)(uint32_t, uint32_t, const float*, uint32_t, float*, uint32_t);
+    fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_resample_ir") : NULL;
+    return fn ? fn(src_rate, dst_rate, in, in_frames, out, out_frames) : B200MIX_ERR_INVALID;
+}

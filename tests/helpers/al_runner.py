@@ -12,7 +12,9 @@ reverb + echo + an equalizer slot that feeds the reverb slot via AL_EFFECTSLOT_T
 properties, slot gain and an effect type change while playing) | "filt" (direct low-pass /
 band-pass filters that change and detach while playing) | "mixfilt" (both, plus send filters)
 | "stream" (alSourceQueueBuffers: queues that run out, looping queues, buffers queued and
-unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones)"""
+unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones) | "conv"
+(two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
+a stereo 16-bit one at the device rate; slot gain changes while playing)"""
 import ctypes as C
 import math
 import os
@@ -38,6 +40,7 @@ AL_EAXREVERB_DECAY_TIME, AL_EAXREVERB_REFLECTIONS_GAIN = 0x0006, 0x0009
 AL_ECHO_DELAY, AL_ECHO_FEEDBACK = 0x0001, 0x0004
 AL_EQUALIZER_LOW_GAIN, AL_EQUALIZER_MID1_GAIN = 0x0001, 0x0003
 AL_CHORUS_RATE = 0x0003
+AL_EFFECT_CONVOLUTION_SOFT, AL_FORMAT_MONO_FLOAT32 = 0xA000, 0x10010
 AL_DIRECT_FILTER, AL_FILTER_TYPE, AL_FILTER_LOWPASS, AL_FILTER_BANDPASS = 0x20005, 0x8001, 0x0001, 0x0003
 AL_LOWPASS_GAIN, AL_LOWPASS_GAINHF, AL_BANDPASS_GAIN, AL_BANDPASS_GAINLF, AL_BANDPASS_GAINHF = 1, 2, 1, 2, 3
 
@@ -117,6 +120,27 @@ def main():
         al.alFilterf(bandpass, AL_BANDPASS_GAIN, 0.8)
         al.alFilterf(bandpass, AL_BANDPASS_GAINLF, 0.3)
         al.alFilterf(bandpass, AL_BANDPASS_GAINHF, 0.5)
+    if fx == "conv":
+        def conv_slot(ir, fmt, rate, gain):
+            b, e, sl = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+            ir = np.ascontiguousarray(ir)
+            keep.append(ir)
+            al.alGenBuffers(1, C.byref(b))
+            al.alBufferData(b, fmt, ir.ctypes.data, ir.nbytes, rate)
+            al.alGenEffects(1, C.byref(e))
+            al.alEffecti(e, AL_EFFECT_TYPE, AL_EFFECT_CONVOLUTION_SOFT)
+            al.alGenAuxiliaryEffectSlots(1, C.byref(sl))
+            al.alAuxiliaryEffectSloti(sl, AL_BUFFER, b.value)
+            al.alAuxiliaryEffectSlotf(sl, AL_EFFECTSLOT_GAIN, gain)
+            al.alAuxiliaryEffectSloti(sl, AL_EFFECTSLOT_EFFECT, e.value)
+            return sl.value, e.value
+        rng = np.random.default_rng(0xC0FFEE)
+        t = np.arange(2200)
+        mono = (rng.standard_normal(2200) * np.exp(-t / 500.0) * 0.2).astype(np.float32)
+        t2 = np.arange(1500)
+        st = (rng.standard_normal((1500, 2)) * np.exp(-t2 / 300.0)[:, None] * 0.2 * 32767).astype(np.int16)
+        slots.append(conv_slot(mono, AL_FORMAT_MONO_FLOAT32, 44100, 0.8))
+        slots.append(conv_slot(st, AL_FORMAT_STEREO16, 48000, 0.6))
     if fx in ("reverb", "mix"):
         slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.9))
     if fx == "mix":
@@ -160,6 +184,8 @@ def main():
         al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
         if fx == "reverb":
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, AL_FILTER_NULL)
+        elif fx == "conv":
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % 2][0], 0, AL_FILTER_NULL)
         elif fx == "mix":
             # send 0: reverb or the equalizer that feeds it; send 1: the echo for every third source
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[2][0] if i % 4 == 1 else slots[0][0], 0,
@@ -213,11 +239,13 @@ def main():
             if done.value > 0:
                 got = (C.c_uint * done.value)()
                 al.alSourceUnqueueBuffers(sources[i0], done.value, got)
-        if slots and u == 2:
+        if fx == "conv" and u == 3:
+            al.alAuxiliaryEffectSlotf(slots[0][0], AL_EFFECTSLOT_GAIN, 0.3)
+        if slots and fx != "conv" and u == 2:
             # a property that needs the reverb's other pipeline (full update), then one that does not
             al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, 2.9)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
-        if slots and u == 4:
+        if slots and fx != "conv" and u == 4:
             al.alEffectf(slots[0][1], AL_EAXREVERB_REFLECTIONS_GAIN, 0.3)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
         if fx == "mix" and u == 3:
