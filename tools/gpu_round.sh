@@ -48,6 +48,17 @@ for l in open('gpurun_out/${tag}_configs_n${NG}.jsonl'):
     j=json.loads(l); print(j['config'], j['n_gpus'], j['voices_total'], j['slots'], j.get('transport'), round(j['ms_per_update'],4), j.get('stage_us_rank0'), j.get('collective'))
 PY
   ;;
+multi2)
+  NG=$(nvidia-smi -L | wc -l)
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+  timeout 600 python -m pytest tests/test_gpu_shard.py -m gpu -q --timeout 500 > gpurun_out/${tag}_pytest_shard_n${NG}.log 2>&1
+  tail -2 gpurun_out/${tag}_pytest_shard_n${NG}.log
+  timeout 600 $TR --master-port 29511 bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n${NG}.json 2> gpurun_out/${tag}_bench_n${NG}.err
+  python - <<PY
+import json
+j=json.loads(open('gpurun_out/${tag}_bench_n${NG}.json').read().strip().split('\n')[-1]); print('N', j['n_gpus'], 'ms', j['ms_per_step'], 'e2e', j['e2e']['ms_per_step'], 'reduce_us', j['collective']['reduce_us'], j['verification']['p2p'])
+PY
+  ;;
 multi8)
   NG=$(nvidia-smi -L | wc -l)
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
