@@ -154,7 +154,17 @@ struct SlotCache {                   /* what was last installed for an effect sl
     uint32_t target{B200MIX_NO_SLOT};
 };
 
+/* What a device reset changes (alcResetDeviceSOFT / reopen -> UpdateDeviceParams -> aluInitRenderer):
+ * the mixer is re-created when any of it differs from what it was opened with. */
+struct DeviceSig {
+    uint32_t rate{0}, dry{0}, real{0}, ir{0}, sends{0}, order{0};
+    size_t post{0};
+    const void *post_state{nullptr}, *dry_buf{nullptr};
+    bool operator==(const DeviceSig&) const = default;
+};
+
 struct Seam {
+    DeviceSig sig{};
     b200mix_device *dev{nullptr};
     b200mix_device_desc desc{};
     bool failed{false};
@@ -209,6 +219,19 @@ bool fail(DeviceBase *device, Seam &S, const char *what)
     ERR("b200mix: {} {}", what, detail);
     device->handleDisconnect("b200mix: {} {}", what, detail);
     return false;
+}
+
+DeviceSig sig_of(const DeviceBase *device)
+{
+    DeviceSig g;
+    g.rate = device->mSampleRate; g.dry = uint32_t(device->Dry.Buffer.size());
+    g.real = uint32_t(device->RealOut.Buffer.size()); g.ir = device->mIrSize;
+    g.sends = device->NumAuxSends; g.order = device->mAmbiOrder;
+    g.post = device->mPostProcess.index();
+    if(auto *h = std::get_if<HrtfPostProcess>(&device->mPostProcess)) g.post_state = h->mHrtfState.get();
+    else if(auto *a = std::get_if<AmbiDecPostProcess>(&device->mPostProcess)) g.post_state = a->mAmbiDecoder.get();
+    g.dry_buf = device->Dry.Buffer.data();
+    return g;
 }
 
 /* What aluInitRenderer decided -> b200mix_create + the post-process constants. */
@@ -281,6 +304,7 @@ bool open_device(DeviceBase *device, Seam &S)
     }
     S.cache.assign(kMaxVoices, VoiceCache{});
     S.slots.assign(kMaxSlots, SlotCache{});
+    S.sig = sig_of(device);
     S.results.assign(kMaxVoices, b200mix_voice_result{});
     return true;
 }
@@ -545,6 +569,13 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     std::lock_guard<std::mutex> guard{g_lock};
     Seam &S = g_seams[device];
     if(S.failed) return;
+    if(S.dev && !(S.sig == sig_of(device)))
+    {
+        /* the device was reset: a new mixer; every voice and slot is sent again from the
+         * reference's objects (positions are theirs, histories start clean like Voice::prepare) */
+        A.destroy(S.dev);
+        S = Seam{};
+    }
     if(!S.dev && !open_device(device, S)) return;
     const uint32_t ir = S.desc.ir_size, cd = S.desc.dry_channels;
 

@@ -14,7 +14,8 @@ band-pass filters that change and detach while playing) | "mixfilt" (both, plus 
 | "stream" (alSourceQueueBuffers: queues that run out, looping queues, buffers queued and
 unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones) | "conv"
 (two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
-a stereo 16-bit one at the device rate; slot gain changes while playing)"""
+a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
+alcResetDeviceSOFT toggles HRTF while the sources play)"""
 import ctypes as C
 import math
 import os
@@ -62,6 +63,7 @@ def main():
     al.alcDestroyContext.argtypes = [C.c_void_p]
     al.alcCloseDevice.argtypes = [C.c_void_p]
     al.alcRenderSamplesSOFT.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    al.alcResetDeviceSOFT.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     al.alcGetIntegerv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     al.alGenBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alGenSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
@@ -106,6 +108,9 @@ def main():
         return sl.value, e.value
 
     slots, streams = [], []
+    reset = fx == "reset"
+    if reset:
+        fx = "reverb"
     filt = fx in ("filt", "mixfilt")
     if fx == "mixfilt":
         fx = "mix"
@@ -222,6 +227,11 @@ def main():
             al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
             if V > 7:
                 al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
+        if reset and u == 4:
+            # the application switches the output mode while everything plays
+            attrs2 = list(attrs)
+            attrs2[attrs2.index(ALC_HRTF_SOFT) + 1] = 0 if hrtf else 1
+            assert al.alcResetDeviceSOFT(dev, (C.c_int * len(attrs2))(*attrs2))
         if streams and u == 1:
             # the application keeps a stream fed: one more buffer on the first streaming source
             i0, _ = streams[0]

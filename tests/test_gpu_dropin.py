@@ -42,13 +42,14 @@ def _need():
 @pytest.mark.parametrize("voices,updates,hrtf,fx", [(24, 12, 1, "none"), (24, 8, 0, "none"), (4096, 6, 1, "none"),
                                                     (24, 8, 1, "reverb"), (24, 8, 1, "mix"), (24, 8, 0, "mix"), (24, 8, 1, "filt"),
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
-                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"),
+                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"),
                                                     (2048, 6, 1, "mix")])
 def test_patched_reference_renders_through_libb200mix(voices, updates, hrtf, fx, tmp_path):
     _need()
     cpu = _run("libopenal_ref.so", "cpu", voices, updates, hrtf, False, tmp_path, fx)
     gpu = _run("libopenal_b200.so", "gpu", voices, updates, hrtf, True, tmp_path, fx)
-    assert int(cpu["hrtf_status"]) == int(gpu["hrtf_status"]) == (1 if hrtf else 0)
+    # ("reset" toggles HRTF with alcResetDeviceSOFT half-way)
+    assert int(cpu["hrtf_status"]) == int(gpu["hrtf_status"]) == ((1 if hrtf else 0) ^ (1 if fx == "reset" else 0))
     ref, out = cpu["out"].astype(np.float64), gpu["out"].astype(np.float64)
     assert np.abs(ref).max() > 1e-2
     err = out - ref
