@@ -15,7 +15,8 @@
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
  * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass), streaming sources
  * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events),
- * multi-channel sources (stereo … 7.1 buffers: one device voice per mixing channel) and
+ * multi-channel sources (stereo … 7.1 buffers, first-order B-Format on first-order devices: one
+ * device voice per mixing channel) and
  * convolution slots with mono … 7.1 impulse responses (any PCM type and rate).
  * Ambisonic / UHJ sources and impulse responses, NFC, direct channels and callback buffers are
  * not wired up here: the seam disconnects the device with
@@ -660,7 +661,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             /* direct channels mix straight into RealOut (alc/alu.cpp:1592-1598); HRTF voices name RealOut too */
             || (!voice->mFlags.test(VoiceFlag::HasHrtf) && !voice->mDirect.Buffer.empty()
                 && voice->mDirect.Buffer.data() != device->Dry.Buffer.data()))
-        { fail(device, S, "callback / ambisonic / UHJ / NFC / direct-channel sources are not wired into the seam yet"); return; }
+        { fail(device, S, "callback / up-sampled ambisonic / UHJ / NFC / direct-channel sources are not wired into the seam yet"); return; }
         const bool isStatic = voice->mFlags.test(VoiceFlag::IsStatic);
         const uint32_t nch = (mono && !voice->mDuplicateMono) ? 1u : static_cast<uint32_t>(voice->mChans.size());
         const uint32_t bufch = std::max(voice->mFrameStep, 1u);

@@ -15,7 +15,8 @@ band-pass filters that change and detach while playing) | "mixfilt" (both, plus 
 unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones) | "conv"
 (two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
 a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
-alcResetDeviceSOFT toggles HRTF while the sources play)"""
+alcResetDeviceSOFT toggles HRTF while the sources play) | "bformat" (first-order B-Format
+sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns)"""
 import ctypes as C
 import math
 import os
@@ -34,6 +35,7 @@ AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 
 AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
 AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
+AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
 AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
 AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
 AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
@@ -71,6 +73,7 @@ def main():
     al.alSourcei.argtypes = [C.c_uint, C.c_int, C.c_int]
     al.alSourcef.argtypes = [C.c_uint, C.c_int, C.c_float]
     al.alSource3f.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_float, C.c_float]
+    al.alSourcefv.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_float)]
     al.alSourcePlayv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alSourceStop.argtypes = [C.c_uint]
     al.alSourcePlay.argtypes = [C.c_uint]
@@ -163,6 +166,11 @@ def main():
             other = scene.voice_buffer_fast(i + 1, len(pcm))
             pcm = np.ascontiguousarray(np.stack([pcm, other], axis=1).reshape(-1))
             fmt = AL_FORMAT_STEREO16
+        if fx == "bformat" and i % 2 == 0:
+            # W X Y Z = four different waveforms
+            chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in (1, 2, 3)]
+            pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
+            fmt = AL_FORMAT_BFORMAT3D_16
         keep.append(pcm)
         al.alGenSources(1, C.byref(s))
         if fx == "stream" and i % 3 != 2:
@@ -227,6 +235,12 @@ def main():
             al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
             if V > 7:
                 al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
+        if fx == "bformat":
+            # the sound field of every B-Format source turns a little each update
+            for i in range(0, V, 2):
+                ang = 0.4 * u + 0.2 * i
+                ori = (C.c_float * 6)(math.sin(ang), 0.0, -math.cos(ang), 0.0, 1.0, 0.0)
+                al.alSourcefv(sources[i], AL_ORIENTATION, ori)
         if reset and u == 4:
             # the application switches the output mode while everything plays
             attrs2 = list(attrs)
