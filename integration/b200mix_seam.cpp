@@ -938,3 +938,14 @@ void b200seam_note_convolution(const void *state, const BufferStorage *buffer) n
     std::lock_guard<std::mutex> cg{g_conv_lock};
     g_conv[state] = std::move(ir);
 }
+
+void b200seam_device_closed(const DeviceBase *device) noexcept
+{
+    if(!api().ok) return;
+    std::lock_guard<std::mutex> guard{g_lock};
+    if(auto it = g_seams.find(device); it != g_seams.end())
+    {
+        if(it->second.dev) api().destroy(it->second.dev);
+        g_seams.erase(it);
+    }
+}

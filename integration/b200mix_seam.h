@@ -1,7 +1,8 @@
 /* b200mix_seam.h — the seam a maintainer adds to OpenAL Soft to mix on a B200 through
  * libb200mix.so (include/b200mix.h).  Declared here, called from the patched places of
- * alc/alu.cpp (integration/alu_seam.patch) and alc/effects/convolution.cpp
- * (integration/convolution_seam.patch), implemented in b200mix_seam.cpp. */
+ * alc/alu.cpp (integration/alu_seam.patch), alc/effects/convolution.cpp
+ * (integration/convolution_seam.patch) and core/device.cpp (integration/device_seam.patch),
+ * implemented in b200mix_seam.cpp. */
 #ifndef B200MIX_SEAM_H
 #define B200MIX_SEAM_H
 
@@ -26,5 +27,9 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept;
  * files, so this is where the seam learns the impulse response a convolution slot was given.
  * No-op unless the seam is enabled. */
 void b200seam_note_convolution(const void *state, const BufferStorage *buffer) noexcept;
+
+/* Called from DeviceBase::~DeviceBase (core/device.cpp:18, integration/device_seam.patch): the
+ * device's mixer, if it had one, is destroyed (b200mix_destroy) and its GPU memory released. */
+void b200seam_device_closed(const DeviceBase *device) noexcept;
 
 #endif
