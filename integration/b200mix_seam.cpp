@@ -169,7 +169,8 @@ struct Seam {
     b200mix_device *dev{nullptr};
     b200mix_device_desc desc{};
     bool failed{false};
-    std::unordered_map<const void*, std::pair<uint32_t, uint32_t>> buffers;   /* data -> (id, frames) */
+    struct BufferEntry { uint32_t id, frames; uint64_t hash; };
+    std::unordered_map<const void*, BufferEntry> buffers;                     /* sample data -> device copy */
     uint32_t next_buffer{0};
     std::vector<VoiceCache> cache;
     std::vector<b200mix_voice_params> upd;
@@ -606,24 +607,43 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         for(const ChanCache &cc : C.ch) S.free_ids.push_back(cc.id);
         C = VoiceCache{};
     };
-    /* one upload per (data pointer, length): BufferStorage is immutable while attached */
-    auto buffer_of = [&](const VoiceBufferItem *item, uint32_t channels, uint32_t *out) -> bool
+    /* One upload per (data pointer, length): BufferStorage is immutable while attached to a source.
+     * A deleted buffer's memory can come back with other content, so a voice that starts checks a
+     * hash of the samples too (not every update: ~6 us per 96 KB). */
+    auto content_hash = [](const void *data, size_t bytes) -> uint64_t
+    {
+        uint64_t h = 0xcbf29ce484222325ull ^ bytes;
+        const auto *w = static_cast<const unsigned char*>(data);
+        size_t i = 0;
+        for(;i + 8 <= bytes;i += 8) { uint64_t v; std::memcpy(&v, w + i, 8); h = (h ^ v) * 0x100000001b3ull; h ^= h >> 29; }
+        for(;i < bytes;++i) h = (h ^ w[i]) * 0x100000001b3ull;
+        return h;
+    };
+    auto buffer_of = [&](const VoiceBufferItem *item, uint32_t channels, uint32_t *out, bool verify) -> bool
     {
         const void *data = nullptr;
         const int type = sample_type_of(item->mSamples, &data);
         if(type < 0) return fail(device, S, "buffer format not wired into the seam yet");
+        static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
+        const size_t bytes = size_t(item->mSampleLen)*channels*sz[type];
         auto it = S.buffers.find(data);
-        if(it == S.buffers.end() || it->second.second != item->mSampleLen)
+        const bool known = it != S.buffers.end() && it->second.frames == item->mSampleLen;
+        uint64_t hash = 0;
+        if(!known || verify) hash = content_hash(data, bytes);
+        if(!known || (verify && it->second.hash != hash))
         {
-            static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
-            const uint32_t id = it == S.buffers.end() ? S.next_buffer++ : it->second.first;
+            uint32_t id = it == S.buffers.end() ? S.next_buffer++ : it->second.id;
             if(id >= kMaxBuffers) return fail(device, S, "more buffers than the seam's device was created for");
-            if(A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data,
-                size_t(item->mSampleLen)*channels*sz[type]) != B200MIX_OK)
-                return fail(device, S, "b200mix_buffer_data failed:");
-            it = S.buffers.insert_or_assign(data, std::make_pair(id, item->mSampleLen)).first;
+            if(A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data, bytes) != B200MIX_OK)
+            {
+                /* the old copy is still playing somewhere: leave it, take a new id */
+                id = S.next_buffer++;
+                if(id >= kMaxBuffers || A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data, bytes) != B200MIX_OK)
+                    return fail(device, S, "b200mix_buffer_data failed:");
+            }
+            it = S.buffers.insert_or_assign(data, Seam::BufferEntry{id, item->mSampleLen, hash}).first;
         }
-        *out = it->second.first;
+        *out = it->second.id;
         return true;
     };
     /* the queue as the mixer will walk it: [current .. last] and, for a looping queue, the items
@@ -696,7 +716,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                 {
                     if(qi->mSampleLen == 0u) continue;
                     uint32_t id = 0;
-                    if(!buffer_of(qi, bufch, &id)) return;
+                    if(!buffer_of(qi, bufch, &id, true)) return;
                     S.qids.push_back(id);
                 }
                 for(const ChanCache &cc : C.ch)
@@ -709,7 +729,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             for(const VoiceBufferItem *qi : C.queue) hasSamples = hasSamples || qi->mSampleLen != 0u;
             bufid = (item && hasSamples) ? 0u : B200MIX_NO_BUFFER;
         }
-        else if(item && !buffer_of(item, bufch, &bufid)) return;
+        else if(item && !buffer_of(item, bufch, &bufid, fresh)) return;
 
         for(uint32_t c = 0;c < nch;++c)
         {

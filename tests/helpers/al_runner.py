@@ -16,7 +16,8 @@ unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones
 (two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
 a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
 alcResetDeviceSOFT toggles HRTF while the sources play) | "bformat" (first-order B-Format
-sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns)"""
+sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns) | "rebuf" (a buffer is
+deleted and another one of the same size created — usually at the same address — and played)"""
 import ctypes as C
 import math
 import os
@@ -68,6 +69,7 @@ def main():
     al.alcResetDeviceSOFT.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     al.alcGetIntegerv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     al.alGenBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alDeleteBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alGenSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alBufferData.argtypes = [C.c_uint, C.c_int, C.c_void_p, C.c_int, C.c_int]
     al.alSourcei.argtypes = [C.c_uint, C.c_int, C.c_int]
@@ -110,7 +112,7 @@ def main():
         al.alAuxiliaryEffectSloti(sl, AL_EFFECTSLOT_EFFECT, e.value)
         return sl.value, e.value
 
-    slots, streams = [], []
+    slots, streams, bufids = [], [], []
     reset = fx == "reset"
     if reset:
         fx = "reverb"
@@ -210,6 +212,7 @@ def main():
         elif filt and i % 2 == 1:
             al.alSourcei(s, AL_DIRECT_FILTER, lowpass.value)
         sources[i] = s.value
+        bufids.append(b.value)
     err = al.alGetError()
     assert err == 0, hex(err)
     al.alSourcePlayv(V, sources)
@@ -241,6 +244,21 @@ def main():
                 ang = 0.4 * u + 0.2 * i
                 ori = (C.c_float * 6)(math.sin(ang), 0.0, -math.cos(ang), 0.0, 1.0, 0.0)
                 al.alSourcefv(sources[i], AL_ORIENTATION, ori)
+        if fx == "rebuf" and u in (2, 4) and V > 6:
+            # source 5: stop, swap its buffer for a NEW one of the same size and other content
+            k = 5
+            al.alSourceStop(sources[k])
+            al.alSourcei(sources[k], AL_BUFFER, 0)
+            old = C.c_uint(bufids[k])
+            al.alDeleteBuffers(1, C.byref(old))
+            nb = C.c_uint(0)
+            al.alGenBuffers(1, C.byref(nb))
+            pcm2 = np.ascontiguousarray(scene.voice_buffer_fast(k + 7 * u, scene.BUFFER_FRAMES))
+            keep.append(pcm2)
+            al.alBufferData(nb, AL_FORMAT_MONO16, pcm2.ctypes.data, pcm2.nbytes, 48000)
+            bufids[k] = nb.value
+            al.alSourcei(sources[k], AL_BUFFER, nb.value)
+            al.alSourcePlay(sources[k])
         if reset and u == 4:
             # the application switches the output mode while everything plays
             attrs2 = list(attrs)
