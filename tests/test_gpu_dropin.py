@@ -42,7 +42,7 @@ def _need():
 @pytest.mark.parametrize("voices,updates,hrtf,fx", [(24, 12, 1, "none"), (24, 8, 0, "none"), (4096, 6, 1, "none"),
                                                     (24, 8, 1, "reverb"), (24, 8, 1, "mix"), (24, 8, 0, "mix"), (24, 8, 1, "filt"),
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
-                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 7, 1, "rebuf"),
+                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"),
                                                     (2048, 6, 1, "mix")])
 def test_patched_reference_renders_through_libb200mix(voices, updates, hrtf, fx, tmp_path):
     _need()
