@@ -138,6 +138,7 @@ struct ChanCache {                   /* one mixing channel = one device voice: w
 struct VoiceCache {                  /* a Voice of the reference: resend only on change */
     unsigned source_id{0};
     bool live{false};
+    bool parked{false};                          /* paused: the device voice is stopped but keeps its state */
     std::vector<ChanCache> ch;
     std::vector<const VoiceBufferItem*> queue;   /* streaming sources: the list the device walks */
 };
@@ -667,6 +668,9 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         const bool active = pstate == Voice::Playing || pstate == Voice::Stopping;
         if(!active)
         {
+            const unsigned sid0 = voice->mSourceID.load(std::memory_order_relaxed);
+            if(C.live && C.parked && sid0 != 0u && sid0 == C.source_id)
+                continue;       /* paused: its (stopped) device voice waits for the resume */
             if(C.live)
             {   /* the host stopped it (alSourceStop / rewind): remove it from the active set */
                 for(const ChanCache &cc : C.ch) push_stopped(cc);
@@ -674,6 +678,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             }
             continue;
         }
+        C.parked = false;
         const bool mono = voice->mFmtChannels == FmtMono;
         if(voice->mFlags.test(VoiceFlag::IsCallback) || voice->mFlags.test(VoiceFlag::IsAmbisonic)
             || voice->mFlags.test(VoiceFlag::HasNfc) || voice->mDecoder
@@ -892,11 +897,21 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         }
         if(r.flags & B200MIX_VF_STOPPED)
         {
-            voice->mCurrentBuffer.store(nullptr, std::memory_order_relaxed);
-            voice->mLoopBuffer.store(nullptr, std::memory_order_relaxed);
-            voice->mSourceID.store(0u, std::memory_order_relaxed);
+            /* the fade-out update of a Stopping voice (core/voice.cpp:1119-1123): only the state
+             * changes.  Buffer and source id were cleared when it ran out or was stopped; a PAUSED
+             * source keeps both, and its position, for the resume. */
             voice->mPlayState.store(Voice::Stopped, std::memory_order_release);
-            release(C);
+            if(voice->mSourceID.load(std::memory_order_relaxed) != 0u
+                && voice->mCurrentBuffer.load(std::memory_order_relaxed) != nullptr)
+            {
+                /* alSourcePause: the voice stays the source's; a later alSourcePlay continues it with
+                 * its resampler / HRTF history and gains (al/source.cpp, VChangeState::Play on a
+                 * paused source) — the device voice keeps its record, only its cached flags change */
+                C.parked = true;
+                for(ChanCache &cc : C.ch)
+                    cc.params.flags = (cc.params.flags & ~uint32_t(B200MIX_VF_PLAYING | B200MIX_VF_STOPPING)) | B200MIX_VF_STOPPED;
+            }
+            else release(C);
         }
         else if((r.flags & B200MIX_VF_STOPPING) && voice->mPlayState.load(std::memory_order_relaxed) == Voice::Playing)
         {

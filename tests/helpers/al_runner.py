@@ -17,7 +17,9 @@ unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones
 a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
 alcResetDeviceSOFT toggles HRTF while the sources play) | "bformat" (first-order B-Format
 sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns) | "rebuf" (a buffer is
-deleted and another one of the same size created — usually at the same address — and played)"""
+deleted and another one of the same size created — usually at the same address — and played) |
+"misc" (pause / resume, seeking a playing source, pitch and gain changes, a moving listener,
+looping switched off while playing)"""
 import ctypes as C
 import math
 import os
@@ -37,6 +39,7 @@ AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x10
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
 AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
 AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
+AL_VELOCITY = 0x1006
 AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
 AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
 AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
@@ -79,6 +82,10 @@ def main():
     al.alSourcePlayv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alSourceStop.argtypes = [C.c_uint]
     al.alSourcePlay.argtypes = [C.c_uint]
+    al.alSourcePause.argtypes = [C.c_uint]
+    al.alSourceRewind.argtypes = [C.c_uint]
+    al.alListener3f.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    al.alListenerf.argtypes = [C.c_int, C.c_float]
     al.alGetSourcei.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_int)]
     al.alSourceQueueBuffers.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_uint)]
     al.alSourceUnqueueBuffers.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_uint)]
@@ -259,6 +266,25 @@ def main():
             bufids[k] = nb.value
             al.alSourcei(sources[k], AL_BUFFER, nb.value)
             al.alSourcePlay(sources[k])
+        if fx == "misc" and V > 10:
+            if u == 1:
+                al.alSourcePause(sources[0])
+                al.alSourcef(sources[1], AL_PITCH, 1.7)
+                al.alSourcef(sources[4], AL_GAIN, 0.05)
+            if u == 2:
+                al.alSourcei(sources[5], AL_SAMPLE_OFFSET, 30000)        # seek while playing
+                al.alListener3f(AL_POSITION, 0.5, 0.0, -0.25)
+                al.alSource3f(sources[6], AL_VELOCITY, 30.0, 0.0, 0.0)   # doppler
+            if u == 3:
+                al.alSourcePlay(sources[0])                              # resume
+                al.alListenerf(AL_GAIN, 0.6)
+                al.alSourcei(sources[8], AL_LOOPING, 0)
+            if u == 4:
+                al.alSourceRewind(sources[9])
+                al.alSourcef(sources[1], AL_PITCH, 0.61)
+            if u == 5:
+                al.alSourcePlay(sources[9])
+                al.alSourcePlay(sources[10])                             # restart a playing source
         if reset and u == 4:
             # the application switches the output mode while everything plays
             attrs2 = list(attrs)
