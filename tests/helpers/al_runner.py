@@ -19,7 +19,9 @@ alcResetDeviceSOFT toggles HRTF while the sources play) | "bformat" (first-order
 sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns) | "rebuf" (a buffer is
 deleted and another one of the same size created — usually at the same address — and played) |
 "misc" (pause / resume, seeking a playing source, pitch and gain changes, a moving listener,
-looping switched off while playing)"""
+looping switched off while playing) | "misc2" (a second context on the same device, sources that
+share one buffer, a send that moves to another slot and is removed, deferred updates through
+alcSuspendContext / alcProcessContext, all sources stopped and others started on the freed voices)"""
 import ctypes as C
 import math
 import os
@@ -68,6 +70,9 @@ def main():
     al.alcMakeContextCurrent.argtypes = [C.c_void_p]
     al.alcDestroyContext.argtypes = [C.c_void_p]
     al.alcCloseDevice.argtypes = [C.c_void_p]
+    al.alcSuspendContext.argtypes = [C.c_void_p]
+    al.alcProcessContext.argtypes = [C.c_void_p]
+    al.alSourceStopv.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alcRenderSamplesSOFT.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     al.alcResetDeviceSOFT.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     al.alcGetIntegerv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -222,6 +227,27 @@ def main():
         bufids.append(b.value)
     err = al.alGetError()
     assert err == 0, hex(err)
+    ctx2, sources2 = None, None
+    if fx == "misc2":
+        slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.8))
+        slots.append(make_slot(AL_EFFECT_ECHO, 0.7))
+        for i in range(V):
+            al.alSource3i(sources[i], AL_AUXILIARY_SEND_FILTER, slots[i % 2][0], 0, AL_FILTER_NULL)
+        # a second context on the same device: four sources that all play source 1's buffer
+        ctx2 = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
+        assert ctx2
+        al.alcMakeContextCurrent(ctx2)
+        sources2 = (C.c_uint * 4)()
+        al.alGenSources(4, sources2)
+        al.alListenerf(AL_GAIN, 0.5)
+        for k in range(4):
+            al.alSourcei(sources2[k], AL_BUFFER, bufids[1])
+            al.alSourcei(sources2[k], AL_LOOPING, 1)
+            al.alSourcef(sources2[k], AL_PITCH, 0.8 + 0.15 * k)
+            al.alSource3f(sources2[k], AL_POSITION, 1.0 - k, 0.5, -1.0)
+        al.alSourcePlayv(4, sources2)
+        assert al.alGetError() == 0
+        al.alcMakeContextCurrent(ctx)
     al.alSourcePlayv(V, sources)
     outs, states, offsets = [], [], []
     for u in range(U):
@@ -285,6 +311,27 @@ def main():
             if u == 5:
                 al.alSourcePlay(sources[9])
                 al.alSourcePlay(sources[10])                             # restart a playing source
+        if fx == "misc2" and V > 12:
+            if u == 1:
+                # a batch of changes becomes visible at once
+                al.alcSuspendContext(ctx)
+                for i in range(0, 8):
+                    al.alSource3f(sources[i], AL_POSITION, 0.3 * i - 1.0, 0.2, -1.5)
+                    al.alSourcef(sources[i], AL_GAIN, 0.02 + 0.01 * i)
+                al.alcProcessContext(ctx)
+            if u == 2:
+                al.alSource3i(sources[3], AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, AL_FILTER_NULL)   # echo -> reverb
+                al.alSource3i(sources[4], AL_AUXILIARY_SEND_FILTER, 0, 0, AL_FILTER_NULL)             # send removed
+            if u == 3:
+                al.alcMakeContextCurrent(ctx2)
+                al.alSourceStop(sources2[0])
+                al.alListener3f(AL_POSITION, 0.0, 0.0, 1.0)
+                al.alcMakeContextCurrent(ctx)
+            if u == 4:
+                al.alSourceStopv(12, sources)                      # the first dozen stop ...
+            if u == 5:
+                half = (C.c_uint * 6)(*[sources[i] for i in (11, 9, 7, 5, 3, 1)])
+                al.alSourcePlayv(6, half)                          # ... and some come back, on other voices
         if reset and u == 4:
             # the application switches the output mode while everything plays
             attrs2 = list(attrs)
@@ -343,6 +390,8 @@ def main():
     al.alcGetIntegerv(dev, 0x1993, 1, C.byref(hv))             # ALC_HRTF_STATUS_SOFT
     np.savez(out_path, out=np.stack(outs), states=np.array(states), offsets=np.array(offsets), hrtf_status=hv.value)
     al.alcMakeContextCurrent(None)
+    if ctx2:
+        al.alcDestroyContext(ctx2)
     al.alcDestroyContext(ctx)
     al.alcCloseDevice(dev)
     os.remove(conf)
