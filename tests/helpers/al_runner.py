@@ -21,7 +21,10 @@ deleted and another one of the same size created — usually at the same address
 "misc" (pause / resume, seeking a playing source, pitch and gain changes, a moving listener,
 looping switched off while playing) | "misc2" (a second context on the same device, sources that
 share one buffer, a send that moves to another slot and is removed, deferred updates through
-alcSuspendContext / alcProcessContext, all sources stopped and others started on the freed voices)"""
+alcSuspendContext / alcProcessContext, all sources stopped and others started on the freed voices)
+| "misc3" (streaming sources paused, resumed and sought; a queue that underruns, is refilled and
+played again; a stereo and a B-Format source with a filtered reverb send; the slot's effect set to
+null and back)"""
 import ctypes as C
 import math
 import os
@@ -42,6 +45,7 @@ AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
 AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
 AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
 AL_VELOCITY = 0x1006
+AL_EFFECT_NULL = 0x0000
 AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
 AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
 AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
@@ -129,6 +133,12 @@ def main():
     if reset:
         fx = "reverb"
     filt = fx in ("filt", "mixfilt")
+    sendfilter = C.c_uint(0)
+    if fx == "misc3":
+        al.alGenFilters(1, C.byref(sendfilter))
+        al.alFilteri(sendfilter, AL_FILTER_TYPE, AL_FILTER_LOWPASS)
+        al.alFilterf(sendfilter, AL_LOWPASS_GAIN, 0.8)
+        al.alFilterf(sendfilter, AL_LOWPASS_GAINHF, 0.4)
     if fx == "mixfilt":
         fx = "mix"
     lowpass, bandpass = C.c_uint(0), C.c_uint(0)
@@ -163,7 +173,7 @@ def main():
         st = (rng.standard_normal((1500, 2)) * np.exp(-t2 / 300.0)[:, None] * 0.2 * 32767).astype(np.int16)
         slots.append(conv_slot(mono, AL_FORMAT_MONO_FLOAT32, 44100, 0.8))
         slots.append(conv_slot(st, AL_FORMAT_STEREO16, 48000, 0.6))
-    if fx in ("reverb", "mix"):
+    if fx in ("reverb", "mix", "misc3"):
         slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.9))
     if fx == "mix":
         slots.append(make_slot(AL_EFFECT_ECHO, 0.7, {AL_ECHO_DELAY: 0.031, AL_ECHO_FEEDBACK: 0.4}))
@@ -175,6 +185,14 @@ def main():
         oneshot = i % 4 == 3
         pcm = np.ascontiguousarray(scene.voice_buffer_fast(i, 3000 + 37 * i if oneshot else scene.BUFFER_FRAMES))
         fmt = AL_FORMAT_MONO16
+        if fx == "misc3" and i == 20:
+            other = scene.voice_buffer_fast(i + 1, len(pcm))
+            pcm = np.ascontiguousarray(np.stack([pcm, other], axis=1).reshape(-1))
+            fmt = AL_FORMAT_STEREO16
+        if fx == "misc3" and i == 22:
+            chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in (1, 2, 3)]
+            pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
+            fmt = AL_FORMAT_BFORMAT3D_16
         if fx == "stereo" and i % 2 == 0:
             # a stereo buffer: left = this voice's waveform, right = the next one's (interleaved)
             other = scene.voice_buffer_fast(i + 1, len(pcm))
@@ -187,7 +205,7 @@ def main():
             fmt = AL_FORMAT_BFORMAT3D_16
         keep.append(pcm)
         al.alGenSources(1, C.byref(s))
-        if fx == "stream" and i % 3 != 2:
+        if (fx == "stream" and i % 3 != 2) or (fx == "misc3" and i < 6):
             # a streaming source: three queued buffers of different lengths; every third source loops its queue
             qb = (C.c_uint * 3)()
             al.alGenBuffers(3, qb)
@@ -211,6 +229,8 @@ def main():
         al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, resampler)
         if fx == "reverb":
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, AL_FILTER_NULL)
+        elif fx == "misc3" and i in (1, 20, 22):
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, sendfilter.value)
         elif fx == "conv":
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % 2][0], 0, AL_FILTER_NULL)
         elif fx == "mix":
@@ -332,6 +352,27 @@ def main():
             if u == 5:
                 half = (C.c_uint * 6)(*[sources[i] for i in (11, 9, 7, 5, 3, 1)])
                 al.alSourcePlayv(6, half)                          # ... and some come back, on other voices
+        if fx == "misc3" and V > 22:
+            if u == 1:
+                al.alSourcePause(sources[0])                               # a streaming source pauses
+                al.alSourcei(sources[1], AL_SAMPLE_OFFSET, 2500)           # seek inside a queue (2nd item)
+            if u == 2:
+                al.alEffecti(slots[0][1], AL_EFFECT_TYPE, AL_EFFECT_NULL)  # the slot's effect goes away ...
+                al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+            if u == 3:
+                al.alSourcePlay(sources[0])                                # ... the stream resumes
+            if u == 4:
+                al.alEffecti(slots[0][1], AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB)   # ... and the reverb is back
+                al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+            if u == 6:
+                # source 3's queue (non-looping) has run out: take the buffers back, refill, play again
+                done = C.c_int(0)
+                al.alGetSourcei(sources[3], AL_BUFFERS_PROCESSED, C.byref(done))
+                if done.value > 0:
+                    got = (C.c_uint * done.value)()
+                    al.alSourceUnqueueBuffers(sources[3], done.value, got)
+                    al.alSourceQueueBuffers(sources[3], done.value, got)
+                    al.alSourcePlay(sources[3])
         if reset and u == 4:
             # the application switches the output mode while everything plays
             attrs2 = list(attrs)

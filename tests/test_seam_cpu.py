@@ -39,7 +39,8 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
                                                     (24, 8, 1, "reverb"), (24, 8, 1, "mix"), (24, 8, 0, "mix"), (24, 8, 1, "filt"),
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
                                                     (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 7, 1, "rebuf"), (24, 8, 1, "misc"),
-                                                    (24, 8, 0, "misc"), (24, 8, 1, "misc2"), (24, 8, 0, "misc2")])
+                                                    (24, 8, 0, "misc"), (24, 8, 1, "misc2"), (24, 8, 0, "misc2"),
+                                                    (24, 9, 1, "misc3"), (24, 9, 0, "misc3")])
 def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
