@@ -24,7 +24,8 @@ share one buffer, a send that moves to another slot and is removed, deferred upd
 alcSuspendContext / alcProcessContext, all sources stopped and others started on the freed voices)
 | "misc3" (streaming sources paused, resumed and sought; a queue that underruns, is refilled and
 played again; a stereo and a B-Format source with a filtered reverb send; the slot's effect set to
-null and back)"""
+null and back) | "allfx" (one slot per remaining EFX effect — vocal morpher, frequency shifter,
+autowah, distortion, compressor, ring modulator, flanger — with property changes while playing)"""
 import ctypes as C
 import math
 import os
@@ -46,6 +47,8 @@ AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x
 AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
 AL_VELOCITY = 0x1006
 AL_EFFECT_NULL = 0x0000
+AL_EFFECT_DISTORTION, AL_EFFECT_FLANGER, AL_EFFECT_FREQUENCY_SHIFTER, AL_EFFECT_VOCAL_MORPHER = 0x0003, 0x0005, 0x0006, 0x0007
+AL_EFFECT_RING_MODULATOR, AL_EFFECT_AUTOWAH, AL_EFFECT_COMPRESSOR = 0x0009, 0x000A, 0x000B
 AL_AUXILIARY_SEND_FILTER, AL_FILTER_NULL = 0x20006, 0
 AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB, AL_EFFECT_ECHO, AL_EFFECT_EQUALIZER, AL_EFFECT_CHORUS = 0x8001, 0x8000, 0x0004, 0x000C, 0x0001
 AL_EFFECTSLOT_EFFECT, AL_EFFECTSLOT_GAIN, AL_EFFECTSLOT_TARGET_SOFT = 0x0001, 0x0002, 0x199C
@@ -173,6 +176,14 @@ def main():
         st = (rng.standard_normal((1500, 2)) * np.exp(-t2 / 300.0)[:, None] * 0.2 * 32767).astype(np.int16)
         slots.append(conv_slot(mono, AL_FORMAT_MONO_FLOAT32, 44100, 0.8))
         slots.append(conv_slot(st, AL_FORMAT_STEREO16, 48000, 0.6))
+    if fx == "allfx":
+        slots.append(make_slot(AL_EFFECT_VOCAL_MORPHER, 0.9, {0x0006: 2.0}))                       # rate
+        slots.append(make_slot(AL_EFFECT_FREQUENCY_SHIFTER, 0.8, {0x0001: 220.0}))                 # frequency
+        slots.append(make_slot(AL_EFFECT_AUTOWAH, 0.7, {0x0003: 100.0, 0x0004: 50.0}))             # resonance, peak gain
+        slots.append(make_slot(AL_EFFECT_DISTORTION, 0.6, {0x0001: 0.3, 0x0002: 0.2}))             # edge, gain
+        slots.append(make_slot(AL_EFFECT_COMPRESSOR, 0.9))
+        slots.append(make_slot(AL_EFFECT_RING_MODULATOR, 0.8, {0x0001: 300.0}))                    # frequency
+        slots.append(make_slot(AL_EFFECT_FLANGER, 0.8, {0x0003: 0.4, 0x0005: -0.6}))               # rate, feedback
     if fx in ("reverb", "mix", "misc3"):
         slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.9))
     if fx == "mix":
@@ -233,6 +244,8 @@ def main():
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, sendfilter.value)
         elif fx == "conv":
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % 2][0], 0, AL_FILTER_NULL)
+        elif fx == "allfx":
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % len(slots)][0], 0, AL_FILTER_NULL)
         elif fx == "mix":
             # send 0: reverb or the equalizer that feeds it; send 1: the echo for every third source
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[2][0] if i % 4 == 1 else slots[0][0], 0,
@@ -397,11 +410,16 @@ def main():
                 al.alSourceUnqueueBuffers(sources[i0], done.value, got)
         if fx == "conv" and u == 3:
             al.alAuxiliaryEffectSlotf(slots[0][0], AL_EFFECTSLOT_GAIN, 0.3)
-        if slots and fx != "conv" and u == 2:
+        if fx == "allfx" and u == 3:
+            for k, (par, val, isint) in enumerate(((0x0001, 2, True), (0x0002, 1, True), (0x0001, 0.01, False), (0x0001, 0.7, False),
+                                                   (0x0001, 0, True), (0x0003, 2, True), (0x0001, 0, True))):
+                (al.alEffecti if isint else al.alEffectf)(slots[k][1], par, val)
+                al.alAuxiliaryEffectSloti(slots[k][0], AL_EFFECTSLOT_EFFECT, slots[k][1])
+        if slots and fx not in ("conv", "allfx") and u == 2:
             # a property that needs the reverb's other pipeline (full update), then one that does not
             al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, 2.9)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
-        if slots and fx != "conv" and u == 4:
+        if slots and fx not in ("conv", "allfx") and u == 4:
             al.alEffectf(slots[0][1], AL_EAXREVERB_REFLECTIONS_GAIN, 0.3)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
         if fx == "mix" and u == 3:

@@ -40,7 +40,7 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
                                                     (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 7, 1, "rebuf"), (24, 8, 1, "misc"),
                                                     (24, 8, 0, "misc"), (24, 8, 1, "misc2"), (24, 8, 0, "misc2"),
-                                                    (24, 9, 1, "misc3"), (24, 9, 0, "misc3")])
+                                                    (24, 9, 1, "misc3"), (24, 9, 0, "misc3"), (28, 7, 1, "allfx"), (28, 7, 0, "allfx")])
 def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
@@ -55,6 +55,11 @@ def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp
     rms, mx = float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())
     # effect scenes: the oracle's convolution-free effects are bit-exact with the reference's C
     # kernels, the stock library runs its SSE kernels (tests/helpers/golden.py kernel_set_gap)
-    assert rms <= (1e-7 if fx == "none" else 1e-6) and mx <= (1e-6 if fx == "none" else 1e-5), f"rms {rms:.3e} max {mx:.3e}"
+    tol = (1e-7, 1e-6) if fx == "none" else (1e-6, 1e-5)
+    if fx == "allfx":
+        # autowah / distortion / ring modulator: the reference's SSE and C kernel sets are themselves up
+        # to 4e-5 apart on such scenes (tests/helpers/golden.py kernel_set_gap); north_star's budget
+        tol = (1e-5, 1e-4)
+    assert rms <= tol[0] and mx <= tol[1], f"rms {rms:.3e} max {mx:.3e}"
     assert np.array_equal(cpu["states"], via["states"])
     assert np.array_equal(cpu["offsets"], via["offsets"])
