@@ -25,7 +25,8 @@ alcSuspendContext / alcProcessContext, all sources stopped and others started on
 | "misc3" (streaming sources paused, resumed and sought; a queue that underruns, is refilled and
 played again; a stereo and a B-Format source with a filtered reverb send; the slot's effect set to
 null and back) | "allfx" (one slot per remaining EFX effect — vocal morpher, frequency shifter,
-autowah, distortion, compressor, ring modulator, flanger — with property changes while playing)"""
+autowah, distortion, compressor, ring modulator, flanger — with property changes while playing) | "i16" (16-bit output: the host's limiter, dither and Write<i16> run
+on the block the mixer delivered; the .npz then holds the samples scaled to +-1)"""
 import ctypes as C
 import math
 import os
@@ -39,7 +40,7 @@ from pyb200mix import scene  # noqa: E402
 
 ALC_FREQUENCY, ALC_MONO_SOURCES = 0x1007, 0x1010
 ALC_FORMAT_CHANNELS_SOFT, ALC_FORMAT_TYPE_SOFT = 0x1990, 0x1991
-ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT = 0x1501, 0x1406, 0x1992
+ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT, ALC_SHORT_SOFT = 0x1501, 0x1406, 0x1992, 0x1402
 AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 0x100A, 0x1004
 AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
@@ -113,7 +114,8 @@ def main():
     al.alFilterf.argtypes = [C.c_uint, C.c_int, C.c_float]
     dev = al.alcLoopbackOpenDeviceSOFT(None)
     assert dev
-    attrs = [ALC_FORMAT_CHANNELS_SOFT, ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT, ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
+    out16 = fx == "i16"
+    attrs = [ALC_FORMAT_CHANNELS_SOFT, ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT, ALC_SHORT_SOFT if out16 else ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
              ALC_MONO_SOURCES, max(V, 1), ALC_HRTF_SOFT, hrtf, 0]
     ctx = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
     assert ctx
@@ -431,9 +433,9 @@ def main():
             al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_CHORUS)
             al.alEffectf(slots[1][1], AL_CHORUS_RATE, 2.2)
             al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
-        buf = np.zeros((1024, 2), dtype=np.float32)
+        buf = np.zeros((1024, 2), dtype=np.int16 if out16 else np.float32)
         al.alcRenderSamplesSOFT(dev, buf.ctypes.data, 1024)
-        outs.append(buf.T.copy())
+        outs.append((buf.astype(np.float32) / 32768.0).T.copy() if out16 else buf.T.copy())
         st, off = [], []
         for i in range(min(V, 64)):
             v = C.c_int(0)

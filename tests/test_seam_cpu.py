@@ -40,7 +40,7 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
                                                     (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 7, 1, "rebuf"), (24, 8, 1, "misc"),
                                                     (24, 8, 0, "misc"), (24, 8, 1, "misc2"), (24, 8, 0, "misc2"),
-                                                    (24, 9, 1, "misc3"), (24, 9, 0, "misc3"), (28, 7, 1, "allfx"), (28, 7, 0, "allfx")])
+                                                    (24, 9, 1, "misc3"), (24, 9, 0, "misc3"), (28, 7, 1, "allfx"), (28, 7, 0, "allfx"), (24, 8, 1, "i16")])
 def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
@@ -60,6 +60,10 @@ def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp
         # autowah / distortion / ring modulator: the reference's SSE and C kernel sets are themselves up
         # to 4e-5 apart on such scenes (tests/helpers/golden.py kernel_set_gap); north_star's budget
         tol = (1e-5, 1e-4)
+    if fx == "i16":
+        # 16-bit output after the host's limiter and dither: a 1e-8 difference can move a sample by one LSB
+        tol = (1e-6, 1.01 / 32768.0)
+        assert float((err != 0).mean()) <= 0.002
     assert rms <= tol[0] and mx <= tol[1], f"rms {rms:.3e} max {mx:.3e}"
     assert np.array_equal(cpu["states"], via["states"])
     assert np.array_equal(cpu["offsets"], via["offsets"])
