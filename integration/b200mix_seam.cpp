@@ -7,7 +7,8 @@
  *   ALSOFT_B200MIX=1            enables the seam (else the library behaves as stock OpenAL Soft)
  *   ALSOFT_B200MIX_LIB=<path>   libb200mix.so (default: "libb200mix.so" on the loader path)
  *
- * Scope of this binding (v2): HRTF and ambisonic-decode devices, static mono sources of any
+ * Scope of this binding (v2): every output the reference renders to — HRTF, ambisonic decodes
+ * (mono … 7.1, with the front stabilizer or BS2B), UHJ / TSME encoded stereo, B-Format —, static mono sources of any
  * PCM sample type, any resampler, moving sources (targets are re-sent when the ALU changed
  * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
@@ -65,7 +66,11 @@
 #include "core/effectslot.h"
 #include "core/effects/base.h"
 #include "alc/effects/base.h"
+#include "core/front_stablizer.h"
+#include "core/bs2b.h"
 #include "core/hrtf.h"
+#include "core/uhjfilter.h"
+#include "core/tsmefilter.hpp"
 #include "core/logging.h"
 #include "core/voice.h"
 #include "ringbuffer.h"
@@ -82,6 +87,9 @@ struct Api {
     decltype(&b200mix_last_error) last_error{};
     decltype(&b200mix_set_hrtf_decoder) set_hrtf_decoder{};
     decltype(&b200mix_set_ambi_decoder) set_ambi_decoder{};
+    decltype(&b200mix_set_uhj_encoder) set_uhj_encoder{};
+    decltype(&b200mix_set_bs2b) set_bs2b{};
+    decltype(&b200mix_set_front_stabilizer) set_front_stabilizer{};
     decltype(&b200mix_buffer_data) buffer_data{};
     decltype(&b200mix_voices_update) voices_update{};
     decltype(&b200mix_voices_filters) voices_filters{};
@@ -113,12 +121,14 @@ Api &api()
         if(!r.lib) { ERR("b200mix: cannot load the mixer library: {}", dlerror()); return r; }
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
+        LOAD(set_uhj_encoder); LOAD(set_bs2b); LOAD(set_front_stabilizer);
         LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(voice_queue); LOAD(render);
         LOAD(slot_convolution); LOAD(convolution_gains); LOAD(resample_ir); LOAD(resampled_ir_frames);
         LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
         LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
+            && r.set_uhj_encoder && r.set_bs2b && r.set_front_stabilizer
             && r.buffer_data && r.voices_update && r.voices_filters && r.voice_queue && r.render && r.slot_efx && r.slot_reverb
             && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
             && r.reverb_params_from_efx && r.reverb_full_update_needed && r.slot_convolution
@@ -233,6 +243,10 @@ DeviceSig sig_of(const DeviceBase *device)
     g.post = device->mPostProcess.index();
     if(auto *h = std::get_if<HrtfPostProcess>(&device->mPostProcess)) g.post_state = h->mHrtfState.get();
     else if(auto *a = std::get_if<AmbiDecPostProcess>(&device->mPostProcess)) g.post_state = a->mAmbiDecoder.get();
+    else if(auto *u = std::get_if<UhjPostProcess>(&device->mPostProcess)) g.post_state = u->mUhjEncoder.get();
+    else if(auto *t = std::get_if<TsmePostProcess>(&device->mPostProcess)) g.post_state = t->mTsmeEncoder.get();
+    else if(auto *sp = std::get_if<StablizerPostProcess>(&device->mPostProcess)) g.post_state = sp->mAmbiDecoder.get();
+    else if(auto *bp = std::get_if<Bs2bPostProcess>(&device->mPostProcess)) g.post_state = bp->mAmbiDecoder.get();
     g.dry_buf = device->Dry.Buffer.data();
     return g;
 }
@@ -256,7 +270,11 @@ bool open_device(DeviceBase *device, Seam &S)
     d.wet_channels = d.num_sends ? static_cast<uint32_t>(AmbiChannelsFromOrder(device->mAmbiOrder)) : 0u; /* aluInitEffectPanning */
     d.max_slots = d.num_sends ? kMaxSlots : 0u;
     if(std::holds_alternative<HrtfPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_HRTF;
-    else if(std::holds_alternative<AmbiDecPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_AMBIDEC;
+    else if(std::holds_alternative<AmbiDecPostProcess>(device->mPostProcess)
+        || std::holds_alternative<StablizerPostProcess>(device->mPostProcess)
+        || std::holds_alternative<Bs2bPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_AMBIDEC;
+    else if(std::holds_alternative<UhjPostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_UHJ;
+    else if(std::holds_alternative<TsmePostProcess>(device->mPostProcess)) d.post_process = B200MIX_POST_TSME;
     else if(std::holds_alternative<std::monostate>(device->mPostProcess)) d.post_process = B200MIX_POST_NONE;
     else return fail(device, S, "this post-process is not wired into the seam yet");
     if(A.create(&d, &S.dev) != B200MIX_OK) return fail(device, S, "b200mix_create failed:");
@@ -279,9 +297,13 @@ bool open_device(DeviceBase *device, Seam &S)
         if(A.set_hrtf_decoder(S.dev, static_cast<uint32_t>(c), ir, coeffs.data(), hf.data(), sc.data()) != B200MIX_OK)
             return fail(device, S, "b200mix_set_hrtf_decoder failed:");
     }
-    else if(auto *aproc = std::get_if<AmbiDecPostProcess>(&device->mPostProcess))
+    const BFormatDec *bdec = nullptr;
+    if(auto *aproc = std::get_if<AmbiDecPostProcess>(&device->mPostProcess)) bdec = aproc->mAmbiDecoder.get();
+    else if(auto *sproc = std::get_if<StablizerPostProcess>(&device->mPostProcess)) bdec = sproc->mAmbiDecoder.get();
+    else if(auto *bproc = std::get_if<Bs2bPostProcess>(&device->mPostProcess)) bdec = bproc->mAmbiDecoder.get();
+    if(bdec)
     {
-        auto &dec = *aproc->mAmbiDecoder;
+        auto &dec = *bdec;
         const auto outs = device->RealOut.Buffer.size();
         std::vector<float> ghf(d.dry_channels*outs), glf(d.dry_channels*outs);
         float xover = 0.0f; bool dual = false;
@@ -304,6 +326,34 @@ bool open_device(DeviceBase *device, Seam &S)
         }
         if(A.set_ambi_decoder(S.dev, d.dry_channels, ghf.data(), dual ? glf.data() : nullptr, xover) != B200MIX_OK)
             return fail(device, S, "b200mix_set_ambi_decoder failed:");
+    }
+    if(auto *sproc = std::get_if<StablizerPostProcess>(&device->mPostProcess))
+    {   /* alc/alu.cpp:330-406: the decode, then the front image stabilizer */
+        if(A.set_front_stabilizer(S.dev, device->RealOut.ChannelIndex[FrontCenter].c_val,
+            sproc->mStablizer->MidFilter.mCoeff) != B200MIX_OK)
+            return fail(device, S, "b200mix_set_front_stabilizer failed:");
+    }
+    if(auto *bproc = std::get_if<Bs2bPostProcess>(&device->mPostProcess))
+    {   /* alc/alu.cpp:408-434: the decode, then the BS2B crossfeed */
+        if(A.set_bs2b(S.dev, static_cast<uint32_t>(bproc->mBs2b->level)) != B200MIX_OK)
+            return fail(device, S, "b200mix_set_bs2b failed:");
+    }
+    {   /* UhjEncodeQuality / TsmeEncodeQuality picked the encoder class (alc/alc.cpp:564-597) */
+        uint32_t flen = 0u; bool enc = false;
+        if(auto *uproc = std::get_if<UhjPostProcess>(&device->mPostProcess))
+        {
+            enc = true;
+            if(dynamic_cast<UhjEncoder<256>*>(uproc->mUhjEncoder.get())) flen = 256u;
+            else if(dynamic_cast<UhjEncoder<512>*>(uproc->mUhjEncoder.get())) flen = 512u;
+        }
+        else if(auto *tproc = std::get_if<TsmePostProcess>(&device->mPostProcess))
+        {
+            enc = true;
+            if(dynamic_cast<TsmeEncoder<256>*>(tproc->mTsmeEncoder.get())) flen = 256u;
+            else if(dynamic_cast<TsmeEncoder<512>*>(tproc->mTsmeEncoder.get())) flen = 512u;
+        }
+        if(enc && A.set_uhj_encoder(S.dev, flen, nullptr) != B200MIX_OK)
+            return fail(device, S, "b200mix_set_uhj_encoder failed:");
     }
     S.cache.assign(kMaxVoices, VoiceCache{});
     S.slots.assign(kMaxSlots, SlotCache{});

@@ -94,3 +94,11 @@ EXPORT int b200mix_resample_ir(uint32_t src_rate, uint32_t dst_rate, const float
     fn_t fn = host_lib() ? (fn_t)dlsym(host_lib(), "b200mix_resample_ir") : NULL;
     return fn ? fn(src_rate, dst_rate, in, in_frames, out, out_frames) : B200MIX_ERR_INVALID;
 }
+
+/* the other post-process variants */
+EXPORT int b200mix_set_uhj_encoder(b200mix_device *dev, uint32_t filter_length, uint32_t *delay)
+{ return oracle_set_uhj_encoder((oracle_device*)dev, filter_length, delay); }
+EXPORT int b200mix_set_bs2b(b200mix_device *dev, uint32_t level)
+{ return oracle_set_bs2b((oracle_device*)dev, level); }
+EXPORT int b200mix_set_front_stabilizer(b200mix_device *dev, uint32_t center_channel, float splitter_coeff)
+{ return oracle_set_front_stabilizer((oracle_device*)dev, center_channel, splitter_coeff); }

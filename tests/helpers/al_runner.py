@@ -26,7 +26,10 @@ alcSuspendContext / alcProcessContext, all sources stopped and others started on
 played again; a stereo and a B-Format source with a filtered reverb send; the slot's effect set to
 null and back) | "allfx" (one slot per remaining EFX effect — vocal morpher, frequency shifter,
 autowah, distortion, compressor, ring modulator, flanger — with property changes while playing) | "i16" (16-bit output: the host's limiter, dither and Write<i16> run
-on the block the mixer delivered; the .npz then holds the samples scaled to +-1)"""
+on the block the mixer delivered; the .npz then holds the samples scaled to +-1) | "quad", "x51",
+"mono", "uhj", "uhj512", "tsme", "stab51", "bs2b" (other outputs: quad / 5.1 / mono speakers, UHJ-
+encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front stabilizer, stereo
+with BS2B crossfeed — the last four through the reference's own configuration file)"""
 import ctypes as C
 import math
 import os
@@ -41,6 +44,8 @@ from pyb200mix import scene  # noqa: E402
 ALC_FREQUENCY, ALC_MONO_SOURCES = 0x1007, 0x1010
 ALC_FORMAT_CHANNELS_SOFT, ALC_FORMAT_TYPE_SOFT = 0x1990, 0x1991
 ALC_STEREO_SOFT, ALC_FLOAT_SOFT, ALC_HRTF_SOFT, ALC_SHORT_SOFT = 0x1501, 0x1406, 0x1992, 0x1402
+ALC_MONO_SOFT, ALC_QUAD_SOFT, ALC_5POINT1_SOFT = 0x1500, 0x1503, 0x1504
+ALC_OUTPUT_MODE_SOFT, ALC_STEREO_UHJ_SOFT = 0x19AC, 0x19AF
 AL_BUFFER, AL_LOOPING, AL_PITCH, AL_GAIN, AL_POSITION = 0x1009, 0x1007, 0x1003, 0x100A, 0x1004
 AL_SOURCE_STATE, AL_PLAYING, AL_STOPPED, AL_SAMPLE_OFFSET = 0x1010, 0x1012, 0x1014, 0x1025
 AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
@@ -67,7 +72,9 @@ def main():
     resampler = int(sys.argv[6]) if len(sys.argv) > 6 else 7          # bsinc24
     fx = sys.argv[7] if len(sys.argv) > 7 else "none"
     conf = os.path.join(os.path.dirname(out_path), f"alsoft_{os.getpid()}.conf")
-    open(conf, "w").write("[general]\n")
+    conf_lines = {"tsme": "[general]\nstereo-encoding=tsme\n", "stab51": "[general]\nfront-stablizer=true\n",
+                  "bs2b": "[general]\ncf_level=4\n", "uhj512": "[general]\n[uhj]\nencode-filter=fir512\n"}
+    open(conf, "w").write(conf_lines.get(fx, "[general]\n"))
     os.environ["ALSOFT_CONF"] = conf
     os.environ.setdefault("ALSOFT_LOGLEVEL", "1")
     al = C.CDLL(lib, mode=C.RTLD_GLOBAL)
@@ -115,8 +122,10 @@ def main():
     dev = al.alcLoopbackOpenDeviceSOFT(None)
     assert dev
     out16 = fx == "i16"
-    attrs = [ALC_FORMAT_CHANNELS_SOFT, ALC_STEREO_SOFT, ALC_FORMAT_TYPE_SOFT, ALC_SHORT_SOFT if out16 else ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
-             ALC_MONO_SOURCES, max(V, 1), ALC_HRTF_SOFT, hrtf, 0]
+    layout, nout = {"quad": (ALC_QUAD_SOFT, 4), "x51": (ALC_5POINT1_SOFT, 6), "stab51": (ALC_5POINT1_SOFT, 6),
+                    "mono": (ALC_MONO_SOFT, 1)}.get(fx, (ALC_STEREO_SOFT, 2))
+    attrs = [ALC_FORMAT_CHANNELS_SOFT, layout, ALC_FORMAT_TYPE_SOFT, ALC_SHORT_SOFT if out16 else ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
+             ALC_MONO_SOURCES, max(V, 1), ALC_HRTF_SOFT, hrtf] + ([ALC_OUTPUT_MODE_SOFT, ALC_STEREO_UHJ_SOFT] if fx in ("uhj", "uhj512") else []) + [0]
     ctx = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
     assert ctx
     al.alcMakeContextCurrent(ctx)
@@ -433,7 +442,7 @@ def main():
             al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_CHORUS)
             al.alEffectf(slots[1][1], AL_CHORUS_RATE, 2.2)
             al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
-        buf = np.zeros((1024, 2), dtype=np.int16 if out16 else np.float32)
+        buf = np.zeros((1024, nout), dtype=np.int16 if out16 else np.float32)
         al.alcRenderSamplesSOFT(dev, buf.ctypes.data, 1024)
         outs.append((buf.astype(np.float32) / 32768.0).T.copy() if out16 else buf.T.copy())
         st, off = [], []
