@@ -69,3 +69,43 @@ def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp
     assert rms <= tol[0] and mx <= tol[1], f"rms {rms:.3e} max {mx:.3e}"
     assert np.array_equal(cpu["states"], via["states"])
     assert np.array_equal(cpu["offsets"], via["offsets"])
+
+
+def _wav_frames(path):
+    import struct
+    d = open(path, "rb").read()
+    i = d.find(b"data")
+    raw = d[i + 8:]
+    x = np.frombuffer(raw[:len(raw) // 8 * 8], dtype=np.float32).reshape(-1, 2)
+    nz = np.nonzero(np.abs(x).sum(axis=1))[0]
+    return x[nz[0]:] if len(nz) else x[:0]
+
+
+def test_playback_backend_mixes_through_the_seam(tmp_path):
+    """SURVEY §8(f) "a real output backend adapter": none is needed — every backend's mixer thread
+    ends in DeviceBase::renderSamples.  The reference's Wave File Writer backend, stock vs patched."""
+    for f in ("libopenal_ref.so", "libopenal_b200.so"):
+        if not os.path.exists(os.path.join(REF, f)):
+            pytest.skip(f"oracle/_ref/{f} not built")
+    runner = os.path.join(ROOT, "tests", "helpers", "wave_runner.py")
+    wavs = []
+    for lib, seam in (("libopenal_ref.so", False), ("libopenal_b200.so", True)):
+        wav = os.path.join(str(tmp_path), lib + ".wav")
+        env = dict(os.environ)
+        env.pop("ALSOFT_B200MIX", None)
+        if seam:
+            env["ALSOFT_B200MIX"] = "1"
+            env["ALSOFT_B200MIX_LIB"] = SHIM
+            env["B200MIX_HOST_LIB"] = os.path.join(ROOT, "openal-soft_b200", "libb200mix.so")
+        p = subprocess.run([sys.executable, runner, os.path.join(REF, lib), wav], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert "b200mix:" not in p.stderr, p.stderr[-2000:]
+        wavs.append(_wav_frames(wav))
+    a, b = wavs
+    n = min(len(a), len(b))
+    assert n >= 8 * 1024                     # at least eight updates were written by both
+    err = a[:n].astype(np.float64) - b[:n]
+    assert np.abs(a[:n]).max() > 1e-2
+    rms, mx = float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())
+    assert rms <= 1e-7 and mx <= 1e-6, f"rms {rms:.3e} max {mx:.3e}"
