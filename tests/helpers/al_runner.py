@@ -29,7 +29,8 @@ autowah, distortion, compressor, ring modulator, flanger — with property chang
 on the block the mixer delivered; the .npz then holds the samples scaled to +-1) | "quad", "x51",
 "mono", "uhj", "uhj512", "tsme", "stab51", "bs2b" (other outputs: quad / 5.1 / mono speakers, UHJ-
 encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front stabilizer, stereo
-with BS2B crossfeed — the last four through the reference's own configuration file)"""
+with BS2B crossfeed — the last four through the reference's own configuration file) | "ragged"
+(reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames)"""
 import ctypes as C
 import math
 import os
@@ -144,7 +145,8 @@ def main():
 
     slots, streams, bufids = [], [], []
     reset = fx == "reset"
-    if reset:
+    ragged = fx == "ragged"
+    if reset or ragged:
         fx = "reverb"
     filt = fx in ("filt", "mixfilt")
     sendfilter = C.c_uint(0)
@@ -442,8 +444,9 @@ def main():
             al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_CHORUS)
             al.alEffectf(slots[1][1], AL_CHORUS_RATE, 2.2)
             al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
+        frames = (1024, 100, 7, 640, 1, 333, 1024, 480, 480, 512)[u % 10] if ragged else 1024
         buf = np.zeros((1024, nout), dtype=np.int16 if out16 else np.float32)
-        al.alcRenderSamplesSOFT(dev, buf.ctypes.data, 1024)
+        al.alcRenderSamplesSOFT(dev, buf.ctypes.data, frames)
         outs.append((buf.astype(np.float32) / 32768.0).T.copy() if out16 else buf.T.copy())
         st, off = [], []
         for i in range(min(V, 64)):
