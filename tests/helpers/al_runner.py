@@ -30,7 +30,8 @@ on the block the mixer delivered; the .npz then holds the samples scaled to +-1)
 "mono", "uhj", "uhj512", "tsme", "stab51", "bs2b" (other outputs: quad / 5.1 / mono speakers, UHJ-
 encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front stabilizer, stereo
 with BS2B crossfeed — the last four through the reference's own configuration file) | "ragged"
-(reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames)"""
+(reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames) | "direct" (a stereo source
+with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
 import math
 import os
@@ -53,6 +54,7 @@ AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
 AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
 AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
 AL_VELOCITY = 0x1006
+AL_DIRECT_CHANNELS_SOFT, ALC_CONNECTED = 0x1033, 0x313
 AL_EFFECT_NULL = 0x0000
 AL_EFFECT_DISTORTION, AL_EFFECT_FLANGER, AL_EFFECT_FREQUENCY_SHIFTER, AL_EFFECT_VOCAL_MORPHER = 0x0003, 0x0005, 0x0006, 0x0007
 AL_EFFECT_RING_MODULATOR, AL_EFFECT_AUTOWAH, AL_EFFECT_COMPRESSOR = 0x0009, 0x000A, 0x000B
@@ -217,7 +219,7 @@ def main():
             chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in (1, 2, 3)]
             pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
             fmt = AL_FORMAT_BFORMAT3D_16
-        if fx == "stereo" and i % 2 == 0:
+        if (fx == "stereo" and i % 2 == 0) or (fx == "direct" and i == 0):
             # a stereo buffer: left = this voice's waveform, right = the next one's (interleaved)
             other = scene.voice_buffer_fast(i + 1, len(pcm))
             pcm = np.ascontiguousarray(np.stack([pcm, other], axis=1).reshape(-1))
@@ -269,6 +271,8 @@ def main():
             al.alSourcei(s, AL_DIRECT_FILTER, bandpass.value)
         elif filt and i % 2 == 1:
             al.alSourcei(s, AL_DIRECT_FILTER, lowpass.value)
+        if fx == "direct" and i == 0:
+            al.alSourcei(s, AL_DIRECT_CHANNELS_SOFT, 1)
         sources[i] = s.value
         bufids.append(b.value)
     err = al.alGetError()
@@ -461,7 +465,10 @@ def main():
         offsets.append(off)
     hv = C.c_int(0)
     al.alcGetIntegerv(dev, 0x1993, 1, C.byref(hv))             # ALC_HRTF_STATUS_SOFT
-    np.savez(out_path, out=np.stack(outs), states=np.array(states), offsets=np.array(offsets), hrtf_status=hv.value)
+    cv = C.c_int(1)
+    al.alcGetIntegerv(dev, ALC_CONNECTED, 1, C.byref(cv))
+    np.savez(out_path, out=np.stack(outs), states=np.array(states), offsets=np.array(offsets), hrtf_status=hv.value,
+             connected=cv.value)
     al.alcMakeContextCurrent(None)
     if ctx2:
         al.alcDestroyContext(ctx2)

@@ -109,3 +109,23 @@ def test_playback_backend_mixes_through_the_seam(tmp_path):
     assert np.abs(a[:n]).max() > 1e-2
     rms, mx = float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())
     assert rms <= 1e-7 and mx <= 1e-6, f"rms {rms:.3e} max {mx:.3e}"
+
+
+def test_unsupported_configuration_disconnects_the_device(tmp_path):
+    """A source the binding does not cover (AL_DIRECT_CHANNELS_SOFT) must not be mixed wrong or
+    crash: the seam disconnects the device through the reference's own mechanism."""
+    lib = os.path.join(REF, "libopenal_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(SHIM):
+        pytest.skip("oracle/_ref/libopenal_b200.so or the shim not built")
+    out = os.path.join(str(tmp_path), "direct.npz")
+    env = dict(os.environ)
+    env["ALSOFT_B200MIX"] = "1"
+    env["ALSOFT_B200MIX_LIB"] = SHIM
+    env["B200MIX_HOST_LIB"] = os.path.join(ROOT, "openal-soft_b200", "libb200mix.so")
+    p = subprocess.run([sys.executable, RUNNER, lib, out, "8", "3", "0", "7", "direct"], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "b200mix:" in p.stderr and "not wired" in p.stderr
+    res = dict(np.load(out))
+    assert int(res["connected"]) == 0
+    assert np.abs(res["out"]).max() == 0.0
