@@ -91,6 +91,7 @@ struct Api {
     decltype(&b200mix_set_bs2b) set_bs2b{};
     decltype(&b200mix_set_front_stabilizer) set_front_stabilizer{};
     decltype(&b200mix_buffer_data) buffer_data{};
+    decltype(&b200mix_buffer_data_adpcm) buffer_data_adpcm{};
     decltype(&b200mix_voices_update) voices_update{};
     decltype(&b200mix_voices_filters) voices_filters{};
     decltype(&b200mix_voice_queue) voice_queue{};
@@ -122,14 +123,14 @@ Api &api()
 #define LOAD(n) r.n = reinterpret_cast<decltype(r.n)>(dlsym(r.lib, "b200mix_" #n))
         LOAD(create); LOAD(destroy); LOAD(last_error); LOAD(set_hrtf_decoder); LOAD(set_ambi_decoder);
         LOAD(set_uhj_encoder); LOAD(set_bs2b); LOAD(set_front_stabilizer);
-        LOAD(buffer_data); LOAD(voices_update); LOAD(voices_filters); LOAD(voice_queue); LOAD(render);
+        LOAD(buffer_data); LOAD(buffer_data_adpcm); LOAD(voices_update); LOAD(voices_filters); LOAD(voice_queue); LOAD(render);
         LOAD(slot_convolution); LOAD(convolution_gains); LOAD(resample_ir); LOAD(resampled_ir_frames);
         LOAD(slot_efx); LOAD(slot_reverb); LOAD(slot_reverb_update); LOAD(slot_output_gains); LOAD(slot_target);
         LOAD(slot_disable); LOAD(reverb_params_from_efx); LOAD(reverb_full_update_needed);
 #undef LOAD
         r.ok = r.create && r.destroy && r.last_error && r.set_hrtf_decoder && r.set_ambi_decoder
             && r.set_uhj_encoder && r.set_bs2b && r.set_front_stabilizer
-            && r.buffer_data && r.voices_update && r.voices_filters && r.voice_queue && r.render && r.slot_efx && r.slot_reverb
+            && r.buffer_data && r.buffer_data_adpcm && r.voices_update && r.voices_filters && r.voice_queue && r.render && r.slot_efx && r.slot_reverb
             && r.slot_reverb_update && r.slot_output_gains && r.slot_target && r.slot_disable
             && r.reverb_params_from_efx && r.reverb_full_update_needed && r.slot_convolution
             && r.convolution_gains && r.resample_ir && r.resampled_ir_frames;
@@ -210,10 +211,11 @@ std::unordered_map<const DeviceBase*, Seam> g_seams;
 
 constexpr uint32_t kMaxVoices = 16384, kMaxBuffers = 16384, kMaxSlots = 64;   /* 64: alc/alc.cpp:3427 */
 
-int sample_type_of(const SampleVariant &sv, const void **data)
+int sample_type_of(const SampleVariant &sv, const void **data, size_t *span_bytes)
 {
-    return std::visit([data]<typename T>(std::span<T> const &spl) -> int {
+    return std::visit([data,span_bytes]<typename T>(std::span<T> const &spl) -> int {
         *data = spl.data();
+        *span_bytes = spl.size_bytes();
         if constexpr(std::is_same_v<T,u8>) return B200MIX_FMT_U8;
         else if constexpr(std::is_same_v<T,i16>) return B200MIX_FMT_I16;
         else if constexpr(std::is_same_v<T,i32>) return B200MIX_FMT_I32;
@@ -221,6 +223,8 @@ int sample_type_of(const SampleVariant &sv, const void **data)
         else if constexpr(std::is_same_v<T,f64>) return B200MIX_FMT_F64;
         else if constexpr(std::is_same_v<T,MulawSample>) return B200MIX_FMT_MULAW;
         else if constexpr(std::is_same_v<T,AlawSample>) return B200MIX_FMT_ALAW;
+        else if constexpr(std::is_same_v<T,IMA4Data>) return B200MIX_FMT_IMA4;
+        else if constexpr(std::is_same_v<T,MSADPCMData>) return B200MIX_FMT_MSADPCM;
         else return -1;
     }, sv);
 }
@@ -673,10 +677,23 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     auto buffer_of = [&](const VoiceBufferItem *item, uint32_t channels, uint32_t *out, bool verify) -> bool
     {
         const void *data = nullptr;
-        const int type = sample_type_of(item->mSamples, &data);
+        size_t span_bytes = 0;
+        const int type = sample_type_of(item->mSamples, &data, &span_bytes);
         if(type < 0) return fail(device, S, "buffer format not wired into the seam yet");
+        /* IMA4 / MSADPCM stay block-compressed in BufferStorage (the reference decodes them in the
+         * mixer, core/voice.cpp:289-484): the library decodes them once at upload. */
+        const bool adpcm = type == B200MIX_FMT_IMA4 || type == B200MIX_FMT_MSADPCM;
+        if(adpcm && (!item->mBlockAlign || item->mSampleLen % item->mBlockAlign))
+            return fail(device, S, "block-compressed buffer with a partial block");
         static const size_t sz[] = {1, 2, 4, 4, 8, 1, 1};
-        const size_t bytes = size_t(item->mSampleLen)*channels*sz[type];
+        const size_t bytes = adpcm ? span_bytes : size_t(item->mSampleLen)*channels*sz[type];
+        auto upload = [&](uint32_t id) -> bool
+        {
+            if(adpcm)
+                return A.buffer_data_adpcm(S.dev, id, uint32_t(type), channels, item->mBlockAlign,
+                    item->mSampleLen / item->mBlockAlign, data, bytes) == B200MIX_OK;
+            return A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data, bytes) == B200MIX_OK;
+        };
         auto it = S.buffers.find(data);
         const bool known = it != S.buffers.end() && it->second.frames == item->mSampleLen;
         uint64_t hash = 0;
@@ -685,11 +702,11 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         {
             uint32_t id = it == S.buffers.end() ? S.next_buffer++ : it->second.id;
             if(id >= kMaxBuffers) return fail(device, S, "more buffers than the seam's device was created for");
-            if(A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data, bytes) != B200MIX_OK)
+            if(!upload(id))
             {
                 /* the old copy is still playing somewhere: leave it, take a new id */
                 id = S.next_buffer++;
-                if(id >= kMaxBuffers || A.buffer_data(S.dev, id, uint32_t(type), channels, item->mSampleLen, data, bytes) != B200MIX_OK)
+                if(id >= kMaxBuffers || !upload(id))
                     return fail(device, S, "b200mix_buffer_data failed:");
             }
             it = S.buffers.insert_or_assign(data, Seam::BufferEntry{id, item->mSampleLen, hash}).first;

@@ -21,7 +21,7 @@ def vf_channel(c):
 
 (RS_POINT, RS_LINEAR, RS_SPLINE, RS_GAUSSIAN, RS_FAST_BSINC12, RS_BSINC12, RS_FAST_BSINC24,
  RS_BSINC24, RS_FAST_BSINC48, RS_BSINC48) = range(10)
-FMT_U8, FMT_I16, FMT_I32, FMT_F32, FMT_F64, FMT_MULAW, FMT_ALAW = range(7)
+FMT_U8, FMT_I16, FMT_I32, FMT_F32, FMT_F64, FMT_MULAW, FMT_ALAW, FMT_IMA4, FMT_MSADPCM = range(9)
 POST_NONE, POST_AMBIDEC, POST_HRTF, POST_UHJ, POST_TSME = range(5)
 VF_PLAYING, VF_STOPPING, VF_STATIC, VF_LOOPING, VF_HRTF, VF_RESET, VF_FADING, VF_STOPPED = (
     1 << i for i in range(8))

@@ -20,6 +20,9 @@ EXPORT int b200mix_set_ambi_decoder(b200mix_device *dev, uint32_t in_channels, c
 EXPORT int b200mix_buffer_data(b200mix_device *dev, uint32_t buffer, uint32_t sample_type, uint32_t channels,
     uint32_t frames, const void *data, size_t bytes)
 { return oracle_buffer_data((oracle_device*)dev, buffer, sample_type, channels, frames, data, bytes); }
+EXPORT int b200mix_buffer_data_adpcm(b200mix_device *dev, uint32_t buffer, uint32_t sample_type, uint32_t channels,
+    uint32_t samples_per_block, uint32_t blocks, const void *data, size_t bytes)
+{ return oracle_buffer_data_adpcm((oracle_device*)dev, buffer, sample_type, channels, samples_per_block, blocks, data, bytes); }
 EXPORT int b200mix_voices_update(b200mix_device *dev, uint32_t n, const b200mix_voice_params *params,
     const float *hrtf_coeffs, const float *dry_gains, const float *send_gains)
 { return oracle_voices_update((oracle_device*)dev, n, params, hrtf_coeffs, dry_gains, send_gains); }

@@ -30,7 +30,9 @@ on the block the mixer delivered; the .npz then holds the samples scaled to +-1)
 "mono", "uhj", "uhj512", "tsme", "stab51", "bs2b" (other outputs: quad / 5.1 / mono speakers, UHJ-
 encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front stabilizer, stereo
 with BS2B crossfeed — the last four through the reference's own configuration file) | "ragged"
-(reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames) | "direct" (a stereo source
+(reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames) | "formats" (one source per
+buffer storage format: 8-bit, 16-bit, 32-bit integer, float32, double, mu-law, A-law, IMA4 and
+MS-ADPCM mono and stereo, and quad / 5.1 16-bit sources) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
 import math
@@ -68,6 +70,56 @@ AL_CHORUS_RATE = 0x0003
 AL_EFFECT_CONVOLUTION_SOFT, AL_FORMAT_MONO_FLOAT32 = 0xA000, 0x10010
 AL_DIRECT_FILTER, AL_FILTER_TYPE, AL_FILTER_LOWPASS, AL_FILTER_BANDPASS = 0x20005, 0x8001, 0x0001, 0x0003
 AL_LOWPASS_GAIN, AL_LOWPASS_GAINHF, AL_BANDPASS_GAIN, AL_BANDPASS_GAINLF, AL_BANDPASS_GAINHF = 1, 2, 1, 2, 3
+
+
+def format_buffer(i, frames):
+    """voice i's buffer in the i-th storage format (core/fmt_traits.h; al/buffer.cpp:640-720)."""
+    k = i % 13
+    pcm = scene.voice_buffer_fast(i, frames)
+    if k == 0:
+        return np.ascontiguousarray(scene.voice_buffer_fmt(i, frames, "u8")), 0x1100
+    if k == 1:
+        return np.ascontiguousarray(pcm), AL_FORMAT_MONO16
+    if k == 2:
+        return np.ascontiguousarray(pcm.astype(np.float32) / np.float32(32768.0)), 0x10010
+    if k == 3:
+        return np.ascontiguousarray(pcm.astype(np.float64) / 32768.0 * 0.9), 0x10012
+    if k == 4:
+        return np.ascontiguousarray(scene.voice_buffer_fmt(i, frames, "mulaw")), 0x10014
+    if k == 5:
+        return np.ascontiguousarray(scene.voice_buffer_fmt(i, frames, "alaw")), 0x10016
+    if k == 6:
+        return np.ascontiguousarray(scene.adpcm_blocks(i, "ima4", min(frames, 6500) // 65)), 0x1300
+    if k == 7:
+        return np.ascontiguousarray(scene.adpcm_blocks(i, "msadpcm", frames // 64)), 0x1302
+    if k == 8:
+        return np.ascontiguousarray(pcm.astype(np.int32) * 65536 + 12345), 0x19DB
+    rng = np.random.default_rng(0xF0 + i)
+    if k == 9:
+        # stereo IMA4: per channel a 4-byte header (predictor, step index), then 4-byte groups per channel
+        blocks = min(frames, 6500) // 65
+        out = rng.choice(np.array([0x00, 0x11, 0x19, 0x91, 0x08, 0x80, 0x21, 0x12], dtype=np.uint8), size=(blocks, 72))
+        hdr = scene.voice_buffer_fast(i, blocks * 2).astype(np.int64) & 0xFFFF
+        for c in range(2):
+            out[:, 4 * c] = hdr[c::2] & 0xFF
+            out[:, 4 * c + 1] = hdr[c::2] >> 8
+            out[:, 4 * c + 2] = 20 + c
+            out[:, 4 * c + 3] = 0
+        return np.ascontiguousarray(out.reshape(-1)), 0x1301
+    if k == 10:
+        # stereo MS-ADPCM: predictor index, scale and two history samples per channel, then nibbles
+        blocks = frames // 64
+        out = rng.choice(np.array([0x00, 0x11, 0x1F, 0xF1, 0x0F, 0xF0, 0x21, 0xEF], dtype=np.uint8), size=(blocks, 76))
+        hist = scene.voice_buffer_fast(i, blocks * 4).astype(np.int64) & 0xFFFF
+        for c in range(2):
+            out[:, c] = (i + c) % 7
+            out[:, 2 + 2 * c], out[:, 3 + 2 * c] = 40 + c, 0
+            out[:, 6 + 2 * c], out[:, 7 + 2 * c] = hist[c::4] & 0xFF, hist[c::4] >> 8
+            out[:, 10 + 2 * c], out[:, 11 + 2 * c] = hist[2 + c::4] & 0xFF, hist[2 + c::4] >> 8
+        return np.ascontiguousarray(out.reshape(-1)), 0x1303
+    nch, fmt = (4, 0x1205) if k == 11 else (6, 0x120B)
+    chans = [scene.voice_buffer_fast(i + c, frames) for c in range(nch)]
+    return np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1)), fmt
 
 
 def main():
@@ -229,6 +281,8 @@ def main():
             chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in (1, 2, 3)]
             pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
             fmt = AL_FORMAT_BFORMAT3D_16
+        if fx == "formats":
+            pcm, fmt = format_buffer(i, len(pcm))
         keep.append(pcm)
         al.alGenSources(1, C.byref(s))
         if (fx == "stream" and i % 3 != 2) or (fx == "misc3" and i < 6):
