@@ -152,6 +152,7 @@ struct VoiceCache {                  /* a Voice of the reference: resend only on
     bool parked{false};                          /* paused: the device voice is stopped but keeps its state */
     std::vector<ChanCache> ch;
     std::vector<const VoiceBufferItem*> queue;   /* streaming sources: the list the device walks */
+    bool queue_loops{false};                     /* ... and whether it wraps to its first item (mLoopBuffer) */
 };
 
 struct SlotCache {                   /* what was last installed for an effect slot */
@@ -194,7 +195,7 @@ struct Seam {
     std::unordered_map<const EffectSlotBase*, uint32_t> slot_ids;
     std::unordered_map<const void*, uint32_t> wet_ids;                        /* Wet.Buffer.data() -> slot id */
     std::vector<float> upd_send;
-    std::vector<b200mix_voice_filter> upd_filt;
+    std::vector<b200mix_voice_filter> upd_filt, upd_filt_first;
     std::vector<uint32_t> free_ids, qids;      /* device voice ids; scratch */
     uint32_t next_id{0};
     std::vector<const VoiceBufferItem*> qnow;
@@ -645,7 +646,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     if(!sync_slots(device, S)) return;
     if(S.vptr.size() > kMaxVoices) { fail(device, S, "more voices than the seam's device was created for"); return; }
 
-    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear(); S.upd_filt.clear();
+    S.upd.clear(); S.upd_coeffs.clear(); S.upd_dry.clear(); S.upd_send.clear(); S.upd_filt.clear(); S.upd_filt_first.clear();
     const uint32_t ns = S.desc.num_sends, cw = S.desc.wet_channels;
     std::vector<float> sg(size_t(ns)*cw);
     auto push_stopped = [&](const ChanCache &cc)
@@ -745,15 +746,33 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             }
             continue;
         }
+        if(pstate == Voice::Stopping && !C.live && !voice->mCurrentBuffer.load(std::memory_order_relaxed))
+        {
+            /* started and stopped (or its source deleted) between two updates: the parameter stage
+             * never ran for it (alc/alu.cpp:2168-2172 skips voices without a source), its history is
+             * the silence Voice::prepare left, and Voice::mix would fade that silence out
+             * (core/voice.cpp:704-719) and leave the voice stopped */
+            voice->mPlayState.store(Voice::Stopped, std::memory_order_release);
+            continue;
+        }
         C.parked = false;
         const bool mono = voice->mFmtChannels == FmtMono;
-        if(voice->mFlags.test(VoiceFlag::IsCallback) || voice->mFlags.test(VoiceFlag::IsAmbisonic)
-            || voice->mFlags.test(VoiceFlag::HasNfc) || voice->mDecoder
-            || voice->mFmtChannels == FmtUHJ2 || voice->mFmtChannels == FmtSuperStereo
-            /* direct channels mix straight into RealOut (alc/alu.cpp:1592-1598); HRTF voices name RealOut too */
-            || (!voice->mFlags.test(VoiceFlag::HasHrtf) && !voice->mDirect.Buffer.empty()
-                && voice->mDirect.Buffer.data() != device->Dry.Buffer.data()))
-        { fail(device, S, "callback / up-sampled ambisonic / UHJ / NFC / direct-channel sources are not wired into the seam yet"); return; }
+        const char *unwired = nullptr;
+        if(voice->mFlags.test(VoiceFlag::IsCallback)) unwired = "callback buffers";
+        else if(voice->mFlags.test(VoiceFlag::IsAmbisonic)) unwired = "up-sampled ambisonic sources";
+        else if(voice->mFlags.test(VoiceFlag::HasNfc)) unwired = "near-field control filters";
+        else if(voice->mDecoder || voice->mFmtChannels == FmtUHJ2 || voice->mFmtChannels == FmtSuperStereo)
+            unwired = "UHJ / super-stereo sources";
+        /* direct channels mix straight into RealOut (alc/alu.cpp:1592-1598); HRTF voices name RealOut too */
+        else if(!voice->mFlags.test(VoiceFlag::HasHrtf) && !voice->mDirect.Buffer.empty()
+            && voice->mDirect.Buffer.data() != device->Dry.Buffer.data())
+            unwired = "direct-channel sources";
+        if(unwired)
+        {
+            ERR("b200mix: {} are not wired into the seam yet", unwired);
+            fail(device, S, "a source uses a feature outside the seam:");
+            return;
+        }
         const bool isStatic = voice->mFlags.test(VoiceFlag::IsStatic);
         const uint32_t nch = (mono && !voice->mDuplicateMono) ? 1u : static_cast<uint32_t>(voice->mChans.size());
         const uint32_t bufch = std::max(voice->mFrameStep, 1u);
@@ -779,7 +798,9 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         if(!isStatic)
         {   /* streaming source: (re)send the list when it is not what the device walks */
             queue_of(voice, S.qnow);
-            if(fresh || S.qnow != C.queue)
+            /* (a looping queue whose current item is its head lists the same items as the same
+             * queue with looping just switched off: the loop point is part of the comparison) */
+            if(fresh || S.qnow != C.queue || C.queue_loops != (loop != nullptr))
             {
                 /* empty buffers in a queue are legal AL (the reference steps over them, core/voice.cpp:
                  * 1183-1196); the device list holds the items that have samples */
@@ -796,6 +817,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                         (loop && !S.qids.empty()) ? 0u : B200MIX_NO_LOOP) != B200MIX_OK)
                     { fail(device, S, "b200mix_voice_queue failed:"); return; }
                 C.queue = S.qnow;
+                C.queue_loops = loop != nullptr;
             }
             bool hasSamples = false;
             for(const VoiceBufferItem *qi : C.queue) hasSamples = hasSamples || qi->mSampleLen != 0u;
@@ -885,20 +907,35 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             for(uint32_t snd = 0;snd < ns;++snd)
                 now[1u + snd] = entry(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass,
                     voice->mSend[snd].FilterActive && p.send_slot[snd] != B200MIX_NO_SLOT);
-            bool any = !CC.filt.empty();
-            for(uint32_t q = 0;q < paths && !any;++q) any = now[q].active != 0u;
-            if(any)
-            {
-                if(CC.filt.empty())
-                {   /* first filter of this voice: all its paths, so a later activation interpolates
-                     * from the identity shelves the reference holds meanwhile */
-                    CC.filt.assign(now.begin(), now.begin() + paths);
-                    S.upd_filt.insert(S.upd_filt.end(), now.begin(), now.begin() + paths);
-                }
-                else for(uint32_t q = 0;q < paths;++q)
-                    if(std::memcmp(&CC.filt[q], &now[q], sizeof(now[q])) != 0)
-                    { CC.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
+            if(CC.filt.empty())
+            {   /* a voice that starts: all its paths, active or not.  The reference designs the
+                 * (identity) shelves of an unfiltered path too, and DoFilters' clear() keeps
+                 * mCoeffs on them, so a filter attached later interpolates from THOSE coefficients
+                 * (core/filters/biquad.cpp:131-149) — the device needs the same starting point */
+                CC.filt.assign(now.begin(), now.begin() + paths);
+                S.upd_filt.insert(S.upd_filt.end(), now.begin(), now.begin() + paths);
+                /* ... and one that starts with an interpolation already pending (its source was
+                 * paused, sought — which moves it to a new Voice — and given another filter before
+                 * it resumed: the parameter stage runs for every voice that has a source,
+                 * alc/alu.cpp:2168-2172): the coefficients it starts from go first */
+                auto pending = [](const BiquadInterpFilter &f) { return f.mCounter > 0; };
+                auto current = [&](uint32_t q, const BiquadInterpFilter &lp, const BiquadInterpFilter &hp)
+                {
+                    if(!pending(lp) && !pending(hp)) return;
+                    b200mix_voice_filter f = now[q];
+                    f.lowpass[0] = lp.mCoeffs.mB0; f.lowpass[1] = lp.mCoeffs.mB1; f.lowpass[2] = lp.mCoeffs.mB2;
+                    f.lowpass[3] = lp.mCoeffs.mA1; f.lowpass[4] = lp.mCoeffs.mA2;
+                    f.highpass[0] = hp.mCoeffs.mB0; f.highpass[1] = hp.mCoeffs.mB1; f.highpass[2] = hp.mCoeffs.mB2;
+                    f.highpass[3] = hp.mCoeffs.mA1; f.highpass[4] = hp.mCoeffs.mA2;
+                    S.upd_filt_first.push_back(f);
+                };
+                current(0u, ch.mDryParams.LowPass, ch.mDryParams.HighPass);
+                for(uint32_t snd = 0;snd < ns;++snd)
+                    current(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass);
             }
+            else for(uint32_t q = 0;q < paths;++q)
+                if(std::memcmp(&CC.filt[q], &now[q], sizeof(now[q])) != 0)
+                { CC.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
         }
         }   /* channels */
         C.live = true; C.source_id = sid;
@@ -908,6 +945,10 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             S.upd_dry.data(), sg.empty() ? nullptr : S.upd_send.data()) != B200MIX_OK)
     { fail(device, S, "b200mix_voices_update failed:"); return; }
 
+    /* two calls, in this order: the library applies one call's entries concurrently */
+    if(!S.upd_filt_first.empty()
+        && A.voices_filters(S.dev, uint32_t(S.upd_filt_first.size()), S.upd_filt_first.data()) != B200MIX_OK)
+    { fail(device, S, "b200mix_voices_filters failed:"); return; }
     if(!S.upd_filt.empty()
         && A.voices_filters(S.dev, uint32_t(S.upd_filt.size()), S.upd_filt.data()) != B200MIX_OK)
     { fail(device, S, "b200mix_voices_filters failed:"); return; }

@@ -32,7 +32,10 @@ encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front
 with BS2B crossfeed — the last four through the reference's own configuration file) | "ragged"
 (reverb scene rendered in updates of 1024, 100, 7, 640, 1, 333 … frames) | "formats" (one source per
 buffer storage format: 8-bit, 16-bit, 32-bit integer, float32, double, mu-law, A-law, IMA4 and
-MS-ADPCM mono and stereo, and quad / 5.1 16-bit sources) | "direct" (a stereo source
+MS-ADPCM mono and stereo, and quad / 5.1 16-bit sources) | "fuzzN" (the "mixfilt" scene with
+streaming sources, driven by a seeded random sequence of API calls — play / stop / pause / rewind,
+seeks, pitch / gain / position / looping changes, filters and sends attached and removed, queues
+unqueued and refilled, slot gains and effect properties, sources deleted and created) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
 import math
@@ -122,6 +125,89 @@ def format_buffer(i, frames):
     return np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1)), fmt
 
 
+class _NoCalls:
+    """stands in for the library when one fuzz action is masked out (AL_RUNNER_FUZZ_SKIP="update:action,...")"""
+    def __getattr__(self, name):
+        return lambda *a: 0
+
+
+def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0):
+    """A handful of random API calls between two updates (errors an application could provoke —
+    a seek beyond the end, looping a playing queue — are part of the sequence; both libraries see
+    the same calls)."""
+    stream_ids = {i for i, _ in streams}
+    skip = os.environ.get("AL_RUNNER_FUZZ_SKIP", "").split(",")
+    for k in range(int(rng.integers(3, 9))):
+        al = _NoCalls() if f"{u}:{k}" in skip else real_al
+        i = int(rng.integers(0, V))
+        s = sources[i]
+        op = int(rng.integers(0, 16))
+        if os.environ.get("AL_RUNNER_FUZZ_LOG"):
+            st = C.c_int(0)
+            real_al.alGetSourcei(s, AL_SOURCE_STATE, C.byref(st))
+            print(f"fuzz: source {i} (state {st.value:#x}, {'stream' if i in stream_ids else 'static'}) op {op}", file=sys.stderr)
+        if op == 0:
+            al.alSourcePlay(s)
+        elif op == 1:
+            al.alSourceStop(s)
+        elif op == 2:
+            al.alSourcePause(s)
+        elif op == 3:
+            al.alSourceRewind(s)
+        elif op == 4:
+            al.alSourcef(s, AL_PITCH, float(rng.uniform(0.3, 3.0)))
+        elif op == 5:
+            al.alSourcef(s, AL_GAIN, float(rng.uniform(0.0, 0.3)))
+        elif op == 6:
+            al.alSource3f(s, AL_POSITION, *[float(x) for x in rng.uniform(-3.0, 3.0, 3)])
+        elif op == 7:
+            al.alSourcei(s, AL_SAMPLE_OFFSET, int(rng.integers(0, 7000)))
+        elif op == 8:
+            al.alSourcei(s, AL_LOOPING, int(rng.integers(0, 2)))
+        elif op == 9:
+            al.alSourcei(s, AL_DIRECT_FILTER, int(rng.choice([AL_FILTER_NULL, filters[0], filters[1]])))
+        elif op == 10:
+            k = int(rng.integers(0, len(slots) + 1))
+            al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[k][0] if k < len(slots) else 0, int(rng.integers(0, 2)),
+                          int(rng.choice([AL_FILTER_NULL, filters[0]])))
+        elif op == 11 and i in stream_ids:
+            done = C.c_int(0)
+            al.alGetSourcei(s, AL_BUFFERS_PROCESSED, C.byref(done))
+            if done.value > 0:
+                n = int(rng.integers(1, done.value + 1))
+                got = (C.c_uint * n)()
+                al.alSourceUnqueueBuffers(s, n, got)
+                if rng.integers(0, 2):
+                    al.alSourceQueueBuffers(s, n, got)
+        elif op == 12:
+            k = int(rng.integers(0, len(slots)))
+            al.alAuxiliaryEffectSlotf(slots[k][0], AL_EFFECTSLOT_GAIN, float(rng.uniform(0.1, 1.0)))
+        elif op == 13:
+            al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, float(rng.uniform(0.4, 4.0)))
+            al.alEffectf(slots[0][1], AL_EAXREVERB_REFLECTIONS_GAIN, float(rng.uniform(0.0, 1.0)))
+            al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+        elif op == 14:
+            al.alListener3f(AL_POSITION, *[float(x) for x in rng.uniform(-1.0, 1.0, 3)])
+            al.alListenerf(AL_GAIN, float(rng.uniform(0.5, 1.0)))
+        elif op == 15 and i not in stream_ids and bufids[i]:
+            # the source goes away; a new one takes its place and its buffer
+            old = C.c_uint(s)
+            al.alDeleteSources(1, C.byref(old))
+            new = C.c_uint(0)
+            al.alGenSources(1, C.byref(new))
+            al.alSourcei(new, AL_BUFFER, bufids[i])
+            al.alSourcei(new, AL_LOOPING, int(rng.integers(0, 2)))
+            al.alSourcef(new, AL_GAIN, 0.15)
+            al.alSource3f(new, AL_POSITION, *[float(x) for x in rng.uniform(-2.0, 2.0, 3)])
+            if os.environ.get("DBG_PITCH"):
+                al.alSourcef(new, AL_PITCH, float(os.environ["DBG_PITCH"]))
+            if os.environ.get("DBG_RS"):
+                al.alSourcei(new, AL_SOURCE_RESAMPLER_SOFT, int(os.environ["DBG_RS"]))
+            sources[i] = new.value
+            al.alSourcePlay(new)
+        al.alGetError()
+
+
 def main():
     lib, out_path, V, U, hrtf = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     resampler = int(sys.argv[6]) if len(sys.argv) > 6 else 7          # bsinc24
@@ -149,6 +235,7 @@ def main():
     al.alGenBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alDeleteBuffers.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alGenSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    al.alDeleteSources.argtypes = [C.c_int, C.POINTER(C.c_uint)]
     al.alBufferData.argtypes = [C.c_uint, C.c_int, C.c_void_p, C.c_int, C.c_int]
     al.alSourcei.argtypes = [C.c_uint, C.c_int, C.c_int]
     al.alSourcef.argtypes = [C.c_uint, C.c_int, C.c_float]
@@ -200,6 +287,10 @@ def main():
     slots, streams, bufids = [], [], []
     reset = fx == "reset"
     ragged = fx == "ragged"
+    fuzz = None
+    if fx.startswith("fuzz"):
+        fuzz = np.random.default_rng(0xF22 + int(fx[4:] or 0))
+        fx = "mixfilt"
     if reset or ragged:
         fx = "reverb"
     filt = fx in ("filt", "mixfilt")
@@ -285,7 +376,7 @@ def main():
             pcm, fmt = format_buffer(i, len(pcm))
         keep.append(pcm)
         al.alGenSources(1, C.byref(s))
-        if (fx == "stream" and i % 3 != 2) or (fx == "misc3" and i < 6):
+        if (fx == "stream" and i % 3 != 2) or (fx == "misc3" and i < 6) or (fuzz is not None and i % 4 == 0):
             # a streaming source: three queued buffers of different lengths; every third source loops its queue
             qb = (C.c_uint * 3)()
             al.alGenBuffers(3, qb)
@@ -381,6 +472,10 @@ def main():
                 ang = 0.4 * u + 0.2 * i
                 ori = (C.c_float * 6)(math.sin(ang), 0.0, -math.cos(ang), 0.0, 1.0, 0.0)
                 al.alSourcefv(sources[i], AL_ORIENTATION, ori)
+        if fuzz is not None:
+            if os.environ.get("AL_RUNNER_FUZZ_LOG"):
+                print(f"fuzz: update {u}", file=sys.stderr)
+            fuzz_actions(al, fuzz, sources, V, slots, streams, (lowpass.value, bandpass.value), bufids, u)
         if fx == "rebuf" and u in (2, 4) and V > 6:
             # source 5: stop, swap its buffer for a NEW one of the same size and other content
             k = 5
@@ -448,6 +543,9 @@ def main():
             if u == 4:
                 al.alEffecti(slots[0][1], AL_EFFECT_TYPE, AL_EFFECT_EAXREVERB)   # ... and the reverb is back
                 al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+            if u == 5:
+                al.alSourceStop(sources[2])                                # a playing stream is stopped ...
+                al.alSourcePlay(sources[4])                                # ... and another restarted from its head
             if u == 6:
                 # source 3's queue (non-looping) has run out: take the buffers back, refill, play again
                 done = C.c_int(0)
