@@ -152,6 +152,7 @@ struct VoiceCache {                  /* a Voice of the reference: resend only on
     bool parked{false};                          /* paused: the device voice is stopped but keeps its state */
     std::vector<ChanCache> ch;
     std::vector<const VoiceBufferItem*> queue;   /* streaming sources: the list the device walks */
+    uint64_t seen{0};                            /* the update that last found this Voice in a context */
     bool queue_loops{false};                     /* ... and whether it wraps to its first item (mLoopBuffer) */
 };
 
@@ -182,10 +183,15 @@ struct Seam {
     b200mix_device *dev{nullptr};
     b200mix_device_desc desc{};
     bool failed{false};
+    bool reset_pending{false};           /* b200seam_device_reset since the last update */
     struct BufferEntry { uint32_t id, frames; uint64_t hash; };
     std::unordered_map<const void*, BufferEntry> buffers;                     /* sample data -> device copy */
     uint32_t next_buffer{0};
     std::vector<VoiceCache> cache;
+    std::unordered_map<const Voice*, uint32_t> cache_of;   /* Voice object -> its entry of `cache` */
+    std::vector<uint32_t> cache_free, cidx;                /* unused entries; entry of vptr[n] this update */
+    uint32_t next_cache{0};
+    uint64_t update_no{0};
     std::vector<b200mix_voice_params> upd;
     std::vector<float> upd_coeffs, upd_dry;
     std::vector<b200mix_voice_result> results;
@@ -627,7 +633,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     std::lock_guard<std::mutex> guard{g_lock};
     Seam &S = g_seams[device];
     if(S.failed) return;
-    if(S.dev && !(S.sig == sig_of(device)))
+    if(S.dev && (S.reset_pending || !(S.sig == sig_of(device))))
     {
         /* the device was reset: a new mixer; every voice and slot is sent again from the
          * reference's objects (positions are theirs, histories start clean like Voice::prepare) */
@@ -661,7 +667,9 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     auto release = [&](VoiceCache &C)
     {
         for(const ChanCache &cc : C.ch) S.free_ids.push_back(cc.id);
+        const uint64_t seen = C.seen;
         C = VoiceCache{};
+        C.seen = seen;
     };
     /* One upload per (data pointer, length): BufferStorage is immutable while attached to a source.
      * A deleted buffer's memory can come back with other content, so a voice that starts checks a
@@ -728,10 +736,40 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             out.push_back(it);
     };
 
+    /* The cache entry of every Voice object, by address: a context's voice array grows in place
+     * (ContextBase::allocVoices appends clusters) but the arrays of the contexts after it then
+     * start later in this list, and contexts come and go. */
+    ++S.update_no;
+    S.cidx.assign(S.vptr.size(), UINT32_MAX);
+    for(size_t n = 0;n < S.vptr.size();++n)
+        if(auto it = S.cache_of.find(S.vptr[n]); it != S.cache_of.end())
+        { S.cidx[n] = it->second; S.cache[it->second].seen = S.update_no; }
+    for(auto it = S.cache_of.begin();it != S.cache_of.end();)
+    {
+        VoiceCache &C = S.cache[it->second];
+        if(C.seen == S.update_no) { ++it; continue; }
+        /* its context was destroyed (alcDestroyContext drops it from mContexts, alc/alc.cpp:3130-3160):
+         * the reference stops mixing its voices there and then */
+        if(C.live) { for(const ChanCache &cc : C.ch) push_stopped(cc); release(C); }
+        S.cache_free.push_back(it->second);
+        it = S.cache_of.erase(it);
+    }
+    for(size_t n = 0;n < S.vptr.size();++n)
+    {
+        if(S.cidx[n] != UINT32_MAX) continue;
+        uint32_t idx;
+        if(!S.cache_free.empty()) { idx = S.cache_free.back(); S.cache_free.pop_back(); }
+        else idx = S.next_cache++;
+        S.cache[idx] = VoiceCache{};
+        S.cache[idx].seen = S.update_no;
+        S.cache_of.emplace(S.vptr[n], idx);
+        S.cidx[n] = idx;
+    }
+
     for(size_t n = 0;n < S.vptr.size();++n)
     {
         Voice *voice = S.vptr[n];
-        VoiceCache &C = S.cache[n];
+        VoiceCache &C = S.cache[S.cidx[n]];
         const auto pstate = voice->mPlayState.load(std::memory_order_acquire);
         const bool active = pstate == Voice::Playing || pstate == Voice::Stopping;
         if(!active)
@@ -963,7 +1001,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
     for(size_t n = 0;n < S.vptr.size();++n)
     {
         Voice *voice = S.vptr[n];
-        VoiceCache &C = S.cache[n];
+        VoiceCache &C = S.cache[S.cidx[n]];
         if(!C.live) continue;
         ContextBase *ctx = S.vctx[n];
         const b200mix_voice_result &r = S.results[C.ch[0].id];       /* all channels move together */
@@ -1090,5 +1128,16 @@ void b200seam_device_closed(const DeviceBase *device) noexcept
     {
         if(it->second.dev) api().destroy(it->second.dev);
         g_seams.erase(it);
+    }
+}
+
+void b200seam_device_reset(const DeviceBase *device) noexcept
+{
+    if(!api().ok) return;
+    std::lock_guard<std::mutex> guard{g_lock};
+    if(auto it = g_seams.find(device); it != g_seams.end())
+    {
+        it->second.reset_pending = true;
+        it->second.failed = false;       /* ResetDeviceParams reconnects the device: the mixer gets another try */
     }
 }

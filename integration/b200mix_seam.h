@@ -32,4 +32,12 @@ void b200seam_note_convolution(const void *state, const BufferStorage *buffer) n
  * device's mixer, if it had one, is destroyed (b200mix_destroy) and its GPU memory released. */
 void b200seam_device_closed(const DeviceBase *device) noexcept;
 
+/* Called where UpdateDeviceParams has re-prepared every voice and re-initialized every effect
+ * state (alc/alc.cpp:1908, integration/alc_seam.patch) — alcResetDeviceSOFT, or alcCreateContext
+ * with an attribute list on a device that is already playing.  The next update builds a new mixer
+ * from the reference's objects: positions are theirs, histories start clean like Voice::prepare's.
+ * (Most resets also change something b200seam_render can see — channel counts, the decoder
+ * objects — but one that re-creates the same configuration does not.) */
+void b200seam_device_reset(const DeviceBase *device) noexcept;
+
 #endif

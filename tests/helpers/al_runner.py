@@ -35,7 +35,11 @@ buffer storage format: 8-bit, 16-bit, 32-bit integer, float32, double, mu-law, A
 MS-ADPCM mono and stereo, and quad / 5.1 16-bit sources) | "fuzzN" (the "mixfilt" scene with
 streaming sources, driven by a seeded random sequence of API calls — play / stop / pause / rewind,
 seeks, pitch / gain / position / looping changes, filters and sends attached and removed, queues
-unqueued and refilled, slot gains and effect properties, sources deleted and created) | "direct" (a stereo source
+unqueued and refilled, slot gains and effect properties, sources deleted and created; from N = 100
+also: a slot's effect replaced by another type, slot targets, deferred updates, resampler changes,
+stereo and B-Format sources created along the way, streams fed new buffers, buffers swapped on
+stopped sources) | "ctx" (300 sources: a second context created while the first plays, the first
+one's voice array growing past 256, the second context destroyed while its sources play) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
 import math
@@ -131,17 +135,37 @@ class _NoCalls:
         return lambda *a: 0
 
 
-def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0):
+FUZZ_EXT = {"on": False, "suspended": None, "extra": [], "keep": [], "retarget": False}
+
+
+def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0, ctx=None):
     """A handful of random API calls between two updates (errors an application could provoke —
     a seek beyond the end, looping a playing queue — are part of the sequence; both libraries see
     the same calls)."""
     stream_ids = {i for i, _ in streams}
     skip = os.environ.get("AL_RUNNER_FUZZ_SKIP", "").split(",")
+    ext = FUZZ_EXT["on"]
+    if FUZZ_EXT["suspended"]:
+        real_al.alcProcessContext(ctx)                       # the batch deferred since the last update becomes visible
+        FUZZ_EXT["suspended"] = None
+    if ext and not FUZZ_EXT["extra"]:
+        # other source formats for the sources created along the way: stereo and first-order B-Format
+        for nch, fmt in ((2, AL_FORMAT_STEREO16), (4, AL_FORMAT_BFORMAT3D_16), (2, AL_FORMAT_STEREO16)):
+            chans = [scene.voice_buffer_fast(40 + nch + c + len(FUZZ_EXT["extra"]), 9000) for c in range(nch)]
+            pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
+            FUZZ_EXT["keep"].append(pcm)
+            b = C.c_uint(0)
+            real_al.alGenBuffers(1, C.byref(b))
+            real_al.alBufferData(b, fmt, pcm.ctypes.data, pcm.nbytes, 48000)
+            FUZZ_EXT["extra"].append(b.value)
     for k in range(int(rng.integers(3, 9))):
         al = _NoCalls() if f"{u}:{k}" in skip else real_al
+        only = os.environ.get("AL_RUNNER_FUZZ_ONLY")
+        if only and f"{u}:{k}" not in only.split(","):
+            al = _NoCalls()
         i = int(rng.integers(0, V))
         s = sources[i]
-        op = int(rng.integers(0, 16))
+        op = int(rng.integers(0, 24 if ext else 16))
         if os.environ.get("AL_RUNNER_FUZZ_LOG"):
             st = C.c_int(0)
             real_al.alGetSourcei(s, AL_SOURCE_STATE, C.byref(st))
@@ -205,6 +229,54 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0)
                 al.alSourcei(new, AL_SOURCE_RESAMPLER_SOFT, int(os.environ["DBG_RS"]))
             sources[i] = new.value
             al.alSourcePlay(new)
+        elif op == 16:
+            # slot 1's effect becomes another one (a new EffectState), or none
+            et = int(rng.choice([AL_EFFECT_ECHO, AL_EFFECT_CHORUS, AL_EFFECT_NULL, AL_EFFECT_RING_MODULATOR, AL_EFFECT_EQUALIZER,
+                                 AL_EFFECT_DISTORTION, AL_EFFECT_COMPRESSOR, AL_EFFECT_FLANGER, AL_EFFECT_AUTOWAH]))
+            al.alEffecti(slots[1][1], AL_EFFECT_TYPE, et)
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
+        elif op == 17:
+            # (only where the Dry mix and the slots' Wet mixes map their channels alike — HRTF output.
+            # Elsewhere a per-channel effect that moves to a mix with another channel map while it plays
+            # carries its scalar mCurrentGain along in the reference; library and oracle keep gains per
+            # output channel and fade the moved channels: DESIGN.md "known divergences")
+            tgt = int(rng.choice([0, slots[0][0]]))
+            if FUZZ_EXT["retarget"]:
+                al.alAuxiliaryEffectSloti(slots[2][0], AL_EFFECTSLOT_TARGET_SOFT, tgt)
+        elif op == 18 and ctx is not None:
+            if al is real_al:
+                real_al.alcSuspendContext(ctx)
+                FUZZ_EXT["suspended"] = True
+        elif op == 19:
+            al.alSourcei(s, AL_SOURCE_RESAMPLER_SOFT, int(rng.integers(0, 8)))
+        elif op == 20 and i not in stream_ids and bufids[i]:
+            # the source goes away; a stereo or B-Format one takes its place
+            old = C.c_uint(s)
+            al.alDeleteSources(1, C.byref(old))
+            new = C.c_uint(0)
+            al.alGenSources(1, C.byref(new))
+            al.alSourcei(new, AL_BUFFER, FUZZ_EXT["extra"][int(rng.integers(0, len(FUZZ_EXT["extra"])))])
+            al.alSourcei(new, AL_LOOPING, int(rng.integers(0, 2)))
+            al.alSourcef(new, AL_GAIN, 0.1)
+            al.alSourcef(new, AL_PITCH, float(rng.uniform(0.5, 2.0)))
+            al.alSource3i(new, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, AL_FILTER_NULL)
+            if al is real_al:
+                sources[i] = new.value
+            al.alSourcePlay(new)
+        elif op == 21 and i in stream_ids:
+            # the application feeds the stream one more buffer
+            nb = C.c_uint(0)
+            al.alGenBuffers(1, C.byref(nb))
+            part = np.ascontiguousarray(scene.voice_buffer_fast(60 + i + u, int(rng.integers(800, 3000))))
+            FUZZ_EXT["keep"].append(part)
+            al.alBufferData(nb, AL_FORMAT_MONO16, part.ctypes.data, part.nbytes, 48000)
+            al.alSourceQueueBuffers(s, 1, C.byref(nb))
+        elif op == 22 and i not in stream_ids:
+            # a stopped source takes another source's buffer (AL_INVALID_OPERATION while it plays)
+            al.alSourcei(s, AL_BUFFER, bufids[int(rng.integers(0, V))] or bufids[1])
+        elif op == 23:
+            al.alSourcei(s, 0x202, int(rng.integers(0, 2)))                 # AL_SOURCE_RELATIVE
+            al.alSourcef(s, 0x1021, float(rng.uniform(0.0, 2.0)))           # AL_ROLLOFF_FACTOR
         al.alGetError()
 
 
@@ -290,6 +362,8 @@ def main():
     fuzz = None
     if fx.startswith("fuzz"):
         fuzz = np.random.default_rng(0xF22 + int(fx[4:] or 0))
+        FUZZ_EXT["on"] = int(fx[4:] or 0) >= 100          # seeds from 100: the extended set of calls
+        FUZZ_EXT["retarget"] = bool(hrtf)
         fx = "mixfilt"
     if reset or ragged:
         fx = "reverb"
@@ -443,7 +517,7 @@ def main():
         al.alSourcePlayv(4, sources2)
         assert al.alGetError() == 0
         al.alcMakeContextCurrent(ctx)
-    al.alSourcePlayv(V, sources)
+    al.alSourcePlayv(min(V, 200) if fx == "ctx" else V, sources)
     outs, states, offsets = [], [], []
     for u in range(U):
         # the application moves a quarter of its sources, stops one and restarts another
@@ -475,7 +549,31 @@ def main():
         if fuzz is not None:
             if os.environ.get("AL_RUNNER_FUZZ_LOG"):
                 print(f"fuzz: update {u}", file=sys.stderr)
-            fuzz_actions(al, fuzz, sources, V, slots, streams, (lowpass.value, bandpass.value), bufids, u)
+            fuzz_actions(al, fuzz, sources, V, slots, streams, (lowpass.value, bandpass.value), bufids, u, ctx)
+        if fx == "ctx" and V > 260:
+            if u == 1:
+                # a second context appears while the first one plays: its voices follow the first one's
+                ctx2 = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
+                assert ctx2
+                al.alcMakeContextCurrent(ctx2)
+                sources2 = (C.c_uint * 4)()
+                al.alGenSources(4, sources2)
+                for k in range(4):
+                    al.alSourcei(sources2[k], AL_BUFFER, bufids[2 * k])
+                    al.alSourcei(sources2[k], AL_LOOPING, 1)
+                    al.alSourcef(sources2[k], AL_PITCH, 0.7 + 0.2 * k)
+                    al.alSourcef(sources2[k], AL_GAIN, 0.2)
+                    al.alSource3f(sources2[k], AL_POSITION, 1.0 - k, 0.5, -1.0)
+                al.alSourcePlayv(4, sources2)
+                al.alcMakeContextCurrent(ctx)
+            if u == 3:
+                # the first context outgrows its 256 voices (ContextBase::allocVoices): the second one's move down the list
+                rest = (C.c_uint * (V - 200))(*[sources[i] for i in range(200, V)])
+                al.alSourcePlayv(V - 200, rest)
+            if u == 5:
+                # the second context goes away with its sources still playing
+                al.alcDestroyContext(ctx2)
+                ctx2 = None
         if fx == "rebuf" and u in (2, 4) and V > 6:
             # source 5: stop, swap its buffer for a NEW one of the same size and other content
             k = 5

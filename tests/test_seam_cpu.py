@@ -44,7 +44,7 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
                                                     (24, 6, 0, "quad"), (24, 6, 0, "x51"), (24, 6, 0, "mono"), (24, 6, 0, "uhj"),
                                                     (24, 6, 0, "uhj512"), (24, 6, 0, "tsme"), (24, 12, 1, "ragged"), (24, 12, 0, "ragged"),
                                                     (26, 8, 1, "formats"), (26, 8, 0, "formats"),
-                                                    (24, 10, 1, "fuzz0"), (24, 30, 0, "fuzz2"), (24, 30, 1, "fuzz7"), (24, 24, 0, "fuzz17")])
+                                                    (300, 8, 1, "ctx"), (300, 8, 0, "ctx"), (24, 10, 1, "fuzz0"), (24, 30, 0, "fuzz2"), (24, 30, 1, "fuzz7"), (24, 24, 0, "fuzz17"), (24, 30, 1, "fuzz100"), (24, 30, 0, "fuzz103")])
 def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
