@@ -38,7 +38,7 @@ seeks, pitch / gain / position / looping changes, filters and sends attached and
 unqueued and refilled, slot gains and effect properties, sources deleted and created; from N = 100
 also: a slot's effect replaced by another type, slot targets, deferred updates, resampler changes,
 stereo and B-Format sources created along the way, streams fed new buffers, buffers swapped on
-stopped sources) | "ctx" (300 sources: a second context created while the first plays, the first
+stopped sources; from N = 200 also rendered in ragged update sizes) | "ctx" (300 sources: a second context created while the first plays, the first
 one's voice array growing past 256, the second context destroyed while its sources play) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
@@ -233,6 +233,8 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0,
             # slot 1's effect becomes another one (a new EffectState), or none
             et = int(rng.choice([AL_EFFECT_ECHO, AL_EFFECT_CHORUS, AL_EFFECT_NULL, AL_EFFECT_RING_MODULATOR, AL_EFFECT_EQUALIZER,
                                  AL_EFFECT_DISTORTION, AL_EFFECT_COMPRESSOR, AL_EFFECT_FLANGER, AL_EFFECT_AUTOWAH]))
+            if os.environ.get("AL_RUNNER_FUZZ_LOG"):
+                print(f"fuzz:   effect type {et:#x}", file=sys.stderr)
             al.alEffecti(slots[1][1], AL_EFFECT_TYPE, et)
             al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
         elif op == 17:
@@ -364,8 +366,9 @@ def main():
         fuzz = np.random.default_rng(0xF22 + int(fx[4:] or 0))
         FUZZ_EXT["on"] = int(fx[4:] or 0) >= 100          # seeds from 100: the extended set of calls
         FUZZ_EXT["retarget"] = bool(hrtf)
+        ragged = int(fx[4:] or 0) >= 200                   # seeds from 200: ... rendered in ragged update sizes
         fx = "mixfilt"
-    if reset or ragged:
+    if reset or (ragged and fuzz is None):
         fx = "reverb"
     filt = fx in ("filt", "mixfilt")
     sendfilter = C.c_uint(0)

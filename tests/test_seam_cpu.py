@@ -44,7 +44,7 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
                                                     (24, 6, 0, "quad"), (24, 6, 0, "x51"), (24, 6, 0, "mono"), (24, 6, 0, "uhj"),
                                                     (24, 6, 0, "uhj512"), (24, 6, 0, "tsme"), (24, 12, 1, "ragged"), (24, 12, 0, "ragged"),
                                                     (26, 8, 1, "formats"), (26, 8, 0, "formats"),
-                                                    (300, 8, 1, "ctx"), (300, 8, 0, "ctx"), (24, 10, 1, "fuzz0"), (24, 30, 0, "fuzz2"), (24, 30, 1, "fuzz7"), (24, 24, 0, "fuzz17"), (24, 30, 1, "fuzz100"), (24, 30, 0, "fuzz103")])
+                                                    (300, 8, 1, "ctx"), (300, 8, 0, "ctx"), (24, 10, 1, "fuzz0"), (24, 30, 0, "fuzz2"), (24, 30, 1, "fuzz7"), (24, 24, 0, "fuzz17"), (24, 30, 1, "fuzz100"), (24, 30, 0, "fuzz103"), (24, 30, 0, "fuzz201")])
 def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp_path):
     for f in ("libopenal_ref.so", "libopenal_b200.so"):
         if not os.path.exists(os.path.join(REF, f)):
@@ -60,7 +60,8 @@ def test_seam_drives_the_abi_like_the_stock_mixer(voices, updates, hrtf, fx, tmp
     # effect scenes: the oracle's convolution-free effects are bit-exact with the reference's C
     # kernels, the stock library runs its SSE kernels (tests/helpers/golden.py kernel_set_gap)
     tol = (1e-7, 1e-6) if fx == "none" else (1e-6, 1e-5)
-    if fx == "allfx":
+    if fx == "allfx" or (fx.startswith("fuzz") and int(fx[4:]) >= 100):
+        # (the extended random sequences put these effects into a slot too)
         # autowah / distortion / ring modulator: the reference's SSE and C kernel sets are themselves up
         # to 4e-5 apart on such scenes (tests/helpers/golden.py kernel_set_gap); north_star's budget
         tol = (1e-5, 1e-4)
