@@ -223,7 +223,7 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0,
             al.alSourcei(new, AL_LOOPING, int(rng.integers(0, 2)))
             al.alSourcef(new, AL_GAIN, 0.15)
             al.alSource3f(new, AL_POSITION, *[float(x) for x in rng.uniform(-2.0, 2.0, 3)])
-            if os.environ.get("DBG_PITCH"):
+            if os.environ.get("DBG_PITCH"):  # (debug knobs used while bisecting)
                 al.alSourcef(new, AL_PITCH, float(os.environ["DBG_PITCH"]))
             if os.environ.get("DBG_RS"):
                 al.alSourcei(new, AL_SOURCE_RESAMPLER_SOFT, int(os.environ["DBG_RS"]))
