@@ -38,7 +38,8 @@ seeks, pitch / gain / position / looping changes, filters and sends attached and
 unqueued and refilled, slot gains and effect properties, sources deleted and created; from N = 100
 also: a slot's effect replaced by another type, slot targets, deferred updates, resampler changes,
 stereo and B-Format sources created along the way, streams fed new buffers, buffers swapped on
-stopped sources; from N = 200 also rendered in ragged update sizes) | "ctx" (300 sources: a second context created while the first plays, the first
+stopped sources; N = 200..299 also rendered in ragged update
+sizes; from N = 300 with a slot turned into a convolution reverb and alcResetDeviceSOFT toggling HRTF) | "ctx" (300 sources: a second context created while the first plays, the first
 one's voice array growing past 256, the second context destroyed while its sources play) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
@@ -135,7 +136,8 @@ class _NoCalls:
         return lambda *a: 0
 
 
-FUZZ_EXT = {"on": False, "suspended": None, "extra": [], "keep": [], "retarget": False}
+FUZZ_EXT = {"on": False, "suspended": None, "extra": [], "keep": [], "retarget": False, "family3": False,
+            "dev": None, "attrs": None, "hrtf": 0, "irbuf": 0}
 
 
 def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0, ctx=None):
@@ -165,7 +167,7 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0,
             al = _NoCalls()
         i = int(rng.integers(0, V))
         s = sources[i]
-        op = int(rng.integers(0, 24 if ext else 16))
+        op = int(rng.integers(0, (26 if FUZZ_EXT["family3"] else 24) if ext else 16))
         if os.environ.get("AL_RUNNER_FUZZ_LOG"):
             st = C.c_int(0)
             real_al.alGetSourcei(s, AL_SOURCE_STATE, C.byref(st))
@@ -279,6 +281,29 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0,
         elif op == 23:
             al.alSourcei(s, 0x202, int(rng.integers(0, 2)))                 # AL_SOURCE_RELATIVE
             al.alSourcef(s, 0x1021, float(rng.uniform(0.0, 2.0)))           # AL_ROLLOFF_FACTOR
+        elif op == 24:
+            # slot 1 becomes a convolution reverb (the buffer goes onto the slot before the effect does)
+            if not FUZZ_EXT["irbuf"] and al is real_al:
+                g = np.random.default_rng(0x1B)
+                ir = (g.standard_normal(1800) * np.exp(-np.arange(1800) / 400.0) * 0.2).astype(np.float32)
+                FUZZ_EXT["keep"].append(ir)
+                b = C.c_uint(0)
+                real_al.alGenBuffers(1, C.byref(b))
+                real_al.alBufferData(b, AL_FORMAT_MONO_FLOAT32, ir.ctypes.data, ir.nbytes, 44100)
+                FUZZ_EXT["irbuf"] = b.value
+            al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_CONVOLUTION_SOFT)
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_BUFFER, FUZZ_EXT["irbuf"])
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
+        elif op == 25 and int(rng.integers(0, 3)) == 0:
+            # the application switches the output mode (HRTF <-> plain stereo) with everything in flight
+            # (not while updates are deferred: the reference would then mix voices whose parameters
+            # still describe the previous configuration — nothing to compare against)
+            if al is real_al and not FUZZ_EXT["suspended"]:
+                FUZZ_EXT["hrtf"] ^= 1
+                attrs2 = list(FUZZ_EXT["attrs"])
+                attrs2[attrs2.index(ALC_HRTF_SOFT) + 1] = FUZZ_EXT["hrtf"]
+                assert real_al.alcResetDeviceSOFT(FUZZ_EXT["dev"], (C.c_int * len(attrs2))(*attrs2))
+                FUZZ_EXT["retarget"] = bool(FUZZ_EXT["hrtf"])
         al.alGetError()
 
 
@@ -366,7 +391,9 @@ def main():
         fuzz = np.random.default_rng(0xF22 + int(fx[4:] or 0))
         FUZZ_EXT["on"] = int(fx[4:] or 0) >= 100          # seeds from 100: the extended set of calls
         FUZZ_EXT["retarget"] = bool(hrtf)
-        ragged = int(fx[4:] or 0) >= 200                   # seeds from 200: ... rendered in ragged update sizes
+        ragged = 200 <= int(fx[4:] or 0) < 300             # seeds 200..299: ... rendered in ragged update sizes
+        FUZZ_EXT["family3"] = int(fx[4:] or 0) >= 300      # seeds from 300: ... plus convolution slots and device resets
+        FUZZ_EXT.update(dev=dev, attrs=attrs, hrtf=hrtf)
         fx = "mixfilt"
     if reset or (ragged and fuzz is None):
         fx = "reverb"
