@@ -40,7 +40,8 @@ also: a slot's effect replaced by another type, slot targets, deferred updates, 
 stereo and B-Format sources created along the way, streams fed new buffers, buffers swapped on
 stopped sources; N = 200..299 also rendered in ragged update
 sizes; from N = 300 with a slot turned into a convolution reverb and alcResetDeviceSOFT toggling HRTF) | "ctx" (300 sources: a second context created while the first plays, the first
-one's voice array growing past 256, the second context destroyed while its sources play) | "direct" (a stereo source
+one's voice array growing past 256, the second context destroyed while its sources play) | "short" (sources of 40 ... 1500 frames that end
+inside the update they start in, restarted every other update) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
 import ctypes as C
 import math
@@ -235,11 +236,13 @@ def fuzz_actions(real_al, rng, sources, V, slots, streams, filters, bufids, u=0,
             # slot 1's effect becomes another one (a new EffectState), or none
             et = int(rng.choice([AL_EFFECT_ECHO, AL_EFFECT_CHORUS, AL_EFFECT_NULL, AL_EFFECT_RING_MODULATOR, AL_EFFECT_EQUALIZER,
                                  AL_EFFECT_DISTORTION, AL_EFFECT_COMPRESSOR, AL_EFFECT_FLANGER, AL_EFFECT_AUTOWAH]))
-            if FUZZ_EXT["family3"] and et in (AL_EFFECT_CHORUS, AL_EFFECT_FLANGER, AL_EFFECT_RING_MODULATOR, AL_EFFECT_COMPRESSOR):
-                # deviceUpdate leaves these effects' oscillator phase / envelope alone (e.g. ChorusState::
-                # mLfoOffset, alc/effects/chorus.cpp:136-168), so in the reference they run on across a
-                # device reset while a re-created mixer starts them at 0: DESIGN.md "known divergences"
-                et = AL_EFFECT_ECHO
+            if FUZZ_EXT["family3"] and et in (AL_EFFECT_CHORUS, AL_EFFECT_FLANGER, AL_EFFECT_RING_MODULATOR, AL_EFFECT_COMPRESSOR,
+                                              AL_EFFECT_ECHO):
+                # deviceUpdate leaves these effects' oscillator phase / envelope / feedback filter history
+                # alone (e.g. ChorusState::mLfoOffset, alc/effects/chorus.cpp:136-168; EchoState::mFilter,
+                # alc/effects/echo.cpp:76-89), so in the reference they run on across a device reset while a
+                # re-created mixer starts them clean: DESIGN.md "known divergences"
+                et = AL_EFFECT_EQUALIZER
             if os.environ.get("AL_RUNNER_FUZZ_LOG"):
                 print(f"fuzz:   effect type {et:#x}", file=sys.stderr)
             al.alEffecti(slots[1][1], AL_EFFECT_TYPE, et)
@@ -457,11 +460,19 @@ def main():
         slots.append(make_slot(AL_EFFECT_ECHO, 0.7, {AL_ECHO_DELAY: 0.031, AL_ECHO_FEEDBACK: 0.4}))
         slots.append(make_slot(AL_EFFECT_EQUALIZER, 0.8, {AL_EQUALIZER_LOW_GAIN: 0.5, AL_EQUALIZER_MID1_GAIN: 2.0}))
         al.alAuxiliaryEffectSloti(slots[2][0], AL_EFFECTSLOT_TARGET_SOFT, slots[0][0])
+    if fuzz is not None and FUZZ_EXT["family3"]:
+        # (see fuzz_actions, op 16: no echo in sequences with device resets)
+        al.alEffecti(slots[1][1], AL_EFFECT_TYPE, AL_EFFECT_EQUALIZER)
+        al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
     for i in range(V):
         b, s = C.c_uint(0), C.c_uint(0)
         # every fourth voice is a short one-shot (runs out, fades, stops by itself)
         oneshot = i % 4 == 3
         pcm = np.ascontiguousarray(scene.voice_buffer_fast(i, 3000 + 37 * i if oneshot else scene.BUFFER_FRAMES))
+        if fx == "short":
+            # every source ends inside the update it starts in (or the next one): 40 ... 1500 frames, no loop
+            oneshot = True
+            pcm = np.ascontiguousarray(scene.voice_buffer_fast(i, 40 + 61 * i))
         fmt = AL_FORMAT_MONO16
         if fx == "misc3" and i == 20:
             other = scene.voice_buffer_fast(i + 1, len(pcm))
@@ -581,6 +592,8 @@ def main():
                 ang = 0.4 * u + 0.2 * i
                 ori = (C.c_float * 6)(math.sin(ang), 0.0, -math.cos(ang), 0.0, 1.0, 0.0)
                 al.alSourcefv(sources[i], AL_ORIENTATION, ori)
+        if fx == "short" and u % 2 == 0 and u:
+            al.alSourcePlayv(V, sources)
         if fuzz is not None:
             if os.environ.get("AL_RUNNER_FUZZ_LOG"):
                 print(f"fuzz: update {u}", file=sys.stderr)
