@@ -145,6 +145,7 @@ struct ChanCache {                   /* one mixing channel = one device voice: w
     b200mix_voice_params params{};
     std::vector<float> coeffs, dry, send;
     std::vector<b200mix_voice_filter> filt;      /* per path: what the device has (empty: never sent) */
+    std::vector<b200mix_voice_filter> last;      /* per path: the reference's targets when this channel was last looked at */
 };
 struct VoiceCache {                  /* a Voice of the reference: resend only on change */
     unsigned source_id{0};
@@ -184,6 +185,7 @@ struct Seam {
     b200mix_device_desc desc{};
     bool failed{false};
     bool reset_pending{false};           /* b200seam_device_reset since the last update */
+    bool filters_on{false};              /* some voice has had an active direct / send filter: targets are forwarded */
     struct BufferEntry { uint32_t id, frames; uint64_t hash; };
     std::unordered_map<const void*, BufferEntry> buffers;                     /* sample data -> device copy */
     uint32_t next_buffer{0};
@@ -766,6 +768,18 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
         S.cidx[n] = idx;
     }
 
+    /* Filters cross the ABI from the first update in which any playing voice has one (most
+     * applications never attach any: the library then runs without filter records). */
+    if(!S.filters_on)
+        for(const Voice *voice : S.vptr)
+        {
+            const auto pstate = voice->mPlayState.load(std::memory_order_acquire);
+            if(pstate != Voice::Playing && pstate != Voice::Stopping) continue;
+            bool any = voice->mDirect.FilterActive;
+            for(uint32_t snd = 0;snd < ns && !any;++snd) any = voice->mSend[snd].FilterActive;
+            if(any) { S.filters_on = true; break; }
+        }
+
     for(size_t n = 0;n < S.vptr.size();++n)
     {
         Voice *voice = S.vptr[n];
@@ -929,7 +943,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
          * the device's copy of BiquadInterpFilter::setParams' rule sees the same sequence. */
         {
             const uint32_t paths = 1u + ns;
-            if(fresh) CC.filt.clear();
+            if(fresh) { CC.filt.clear(); CC.last.clear(); }
             auto entry = [&](uint32_t path, const BiquadInterpFilter &lp, const BiquadInterpFilter &hp, bool act)
             {
                 b200mix_voice_filter f{};
@@ -945,11 +959,23 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
             for(uint32_t snd = 0;snd < ns;++snd)
                 now[1u + snd] = entry(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass,
                     voice->mSend[snd].FilterActive && p.send_slot[snd] != B200MIX_NO_SLOT);
-            if(CC.filt.empty())
+            if(!S.filters_on)
+            {   /* no filter anywhere on this device yet: nothing crosses the ABI (the library then
+                 * keeps no filter records at all); the targets are remembered for the day one does */
+                CC.last.assign(now.begin(), now.begin() + paths);
+            }
+            else if(CC.filt.empty())
             {   /* a voice that starts: all its paths, active or not.  The reference designs the
                  * (identity) shelves of an unfiltered path too, and DoFilters' clear() keeps
                  * mCoeffs on them, so a filter attached later interpolates from THOSE coefficients
                  * (core/filters/biquad.cpp:131-149) — the device needs the same starting point */
+                const bool played_unfiltered = !fresh && !CC.last.empty();
+                if(played_unfiltered)
+                    /* it played before the first filter of this device came up: the shelves the
+                     * reference held for it go first (its records are still in their reset state and
+                     * adopt them at once), then this update's targets interpolate from them */
+                    S.upd_filt_first.insert(S.upd_filt_first.end(), CC.last.begin(), CC.last.end());
+                CC.last.assign(now.begin(), now.begin() + paths);
                 CC.filt.assign(now.begin(), now.begin() + paths);
                 S.upd_filt.insert(S.upd_filt.end(), now.begin(), now.begin() + paths);
                 /* ... and one that starts with an interpolation already pending (its source was
@@ -959,7 +985,7 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                 auto pending = [](const BiquadInterpFilter &f) { return f.mCounter > 0; };
                 auto current = [&](uint32_t q, const BiquadInterpFilter &lp, const BiquadInterpFilter &hp)
                 {
-                    if(!pending(lp) && !pending(hp)) return;
+                    if(played_unfiltered || (!pending(lp) && !pending(hp))) return;
                     b200mix_voice_filter f = now[q];
                     f.lowpass[0] = lp.mCoeffs.mB0; f.lowpass[1] = lp.mCoeffs.mB1; f.lowpass[2] = lp.mCoeffs.mB2;
                     f.lowpass[3] = lp.mCoeffs.mA1; f.lowpass[4] = lp.mCoeffs.mA2;
@@ -971,9 +997,13 @@ void b200seam_render(DeviceBase *device, unsigned samplesToDo) noexcept
                 for(uint32_t snd = 0;snd < ns;++snd)
                     current(1u + snd, ch.mWetParams[snd].LowPass, ch.mWetParams[snd].HighPass);
             }
-            else for(uint32_t q = 0;q < paths;++q)
-                if(std::memcmp(&CC.filt[q], &now[q], sizeof(now[q])) != 0)
-                { CC.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
+            else
+            {
+                for(uint32_t q = 0;q < paths;++q)
+                    if(std::memcmp(&CC.filt[q], &now[q], sizeof(now[q])) != 0)
+                    { CC.filt[q] = now[q]; S.upd_filt.push_back(now[q]); }
+                CC.last.assign(now.begin(), now.begin() + paths);
+            }
         }
         }   /* channels */
         C.live = true; C.source_id = sid;

@@ -237,6 +237,7 @@ typedef struct {
 
 struct oracle_device {
     b200mix_device_desc desc;
+    int filters_seen;          /* b200mix_voices_filters has been called: filter records exist (see there) */
     obuffer *buffers;
     ovoice *voices;
     float (*dry)[LINE];        /* Dry.Buffer */
@@ -789,6 +790,18 @@ static void obiquad_set_target(obiquad *f, const float tgt[5])
 
 int oracle_voices_filters(oracle_device *d, uint32_t n, const b200mix_voice_filter *filters)
 {
+    if(!d->filters_seen && n)
+    {
+        /* The library allocates its filter records on the first call and starts every one of them
+         * in BiquadInterpFilter::reset's state (mCounter = -1: the first target applies at once),
+         * also for voices that have been playing unfiltered.  A host that forwards filters only
+         * once one is in use therefore first sends the shelves the reference held so far, then the
+         * new targets (integration/b200mix_seam.cpp). */
+        for(uint32_t v = 0;v < d->desc.max_voices;++v)
+            for(uint32_t f = 0;f < 1 + B200MIX_MAX_SENDS;++f)
+            { obiquad_reset(&d->voices[v].filt[f].lp); obiquad_reset(&d->voices[v].filt[f].hp); d->voices[v].filt[f].active = 0; }
+        d->filters_seen = 1;
+    }
     for(uint32_t i = 0;i < n;++i)
     {
         const b200mix_voice_filter *q = &filters[i];
@@ -923,15 +936,20 @@ static void obiquad_dual_interp(obiquad *f0, obiquad *f1, const float *src, floa
 }
 
 /* DoFilters, core/voice.cpp:255-268 */
-static const float *do_filters(ovoice *v, uint32_t path, float *dst, const float *src, size_t n)
+static const float *do_filters(const oracle_device *d, ovoice *v, uint32_t path, float *dst, const float *src, size_t n)
 {
     if(v->filt[path].active)
     {
         obiquad_dual_interp(&v->filt[path].lp, &v->filt[path].hp, src, dst, n);
         return dst;
     }
-    obiquad_clear(&v->filt[path].lp);
-    obiquad_clear(&v->filt[path].hp);
+    /* ABI lifecycle, as the library has it: until the first b200mix_voices_filters call there are
+     * no filter records to clear */
+    if(d->filters_seen)
+    {
+        obiquad_clear(&v->filt[path].lp);
+        obiquad_clear(&v->filt[path].hp);
+    }
     return src;
 }
 
@@ -1306,7 +1324,7 @@ static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_res
     }
 
     /* DoMix, :934-984 */
-    const float *samples = do_filters(v, 0, d->filtered, d->samples, n);
+    const float *samples = do_filters(d, v, 0, d->filtered, d->samples, n);
     if(v->flags & B200MIX_VF_HRTF)
     {
         const float targetGain = v->tgt_gain * (float)(vstate == 1);
@@ -1320,7 +1338,7 @@ static void voice_mix(oracle_device *d, ovoice *v, uint32_t n, b200mix_voice_res
     for(uint32_t s = 0;s < ns;++s)
     {
         if(v->send_slot[s] == B200MIX_NO_SLOT) continue;
-        samples = do_filters(v, 1 + s, d->filtered, d->samples, n);
+        samples = do_filters(d, v, 1 + s, d->filtered, d->samples, n);
         const float *tg = (vstate == 1) ? v->send_tgt[s] : silent;
         mix_samples(samples, n, d->wet + (size_t)v->send_slot[s]*cw, cw, v->send_cur[s], tg,
             counter);

@@ -39,7 +39,8 @@ unqueued and refilled, slot gains and effect properties, sources deleted and cre
 also: a slot's effect replaced by another type, slot targets, deferred updates, resampler changes,
 stereo and B-Format sources created along the way, streams fed new buffers, buffers swapped on
 stopped sources; N = 200..299 also rendered in ragged update
-sizes; from N = 300 with a slot turned into a convolution reverb and alcResetDeviceSOFT toggling HRTF) | "ctx" (300 sources: a second context created while the first plays, the first
+sizes; N = 300..399 with a slot turned into a convolution reverb and alcResetDeviceSOFT toggling HRTF; from N = 400 the
+extended set on a scene without filters until the sequence attaches one) | "ctx" (300 sources: a second context created while the first plays, the first
 one's voice array growing past 256, the second context destroyed while its sources play) | "short" (sources of 40 ... 1500 frames that end
 inside the update they start in, restarted every other update) | "direct" (a stereo source
 with AL_DIRECT_CHANNELS_SOFT: not wired into the seam — the device must disconnect, not crash)"""
@@ -400,9 +401,10 @@ def main():
         FUZZ_EXT["on"] = int(fx[4:] or 0) >= 100          # seeds from 100: the extended set of calls
         FUZZ_EXT["retarget"] = bool(hrtf)
         ragged = 200 <= int(fx[4:] or 0) < 300             # seeds 200..299: ... rendered in ragged update sizes
-        FUZZ_EXT["family3"] = int(fx[4:] or 0) >= 300      # seeds from 300: ... plus convolution slots and device resets
+        FUZZ_EXT["family3"] = 300 <= int(fx[4:] or 0) < 400   # seeds 300..399: ... plus convolution slots and device resets
         FUZZ_EXT.update(dev=dev, attrs=attrs, hrtf=hrtf)
-        fx = "mixfilt"
+        # seeds from 400: the extended set on a scene that starts WITHOUT filters — the first one is attached by the sequence
+        fx = "mix" if int(fx[4:] or 0) >= 400 else "mixfilt"
     if reset or (ragged and fuzz is None):
         fx = "reverb"
     filt = fx in ("filt", "mixfilt")
@@ -415,7 +417,7 @@ def main():
     if fx == "mixfilt":
         fx = "mix"
     lowpass, bandpass = C.c_uint(0), C.c_uint(0)
-    if filt:
+    if filt or fuzz is not None:
         al.alGenFilters(1, C.byref(lowpass))
         al.alFilteri(lowpass, AL_FILTER_TYPE, AL_FILTER_LOWPASS)
         al.alFilterf(lowpass, AL_LOWPASS_GAIN, 0.9)
