@@ -138,7 +138,8 @@ enum b200mix_effect { B200MIX_EFFECT_NONE = 0, B200MIX_EFFECT_CONVOLUTION = 1, B
     B200MIX_EFFECT_CHORUS = 9,        /* ChorusState      alc/effects/chorus.cpp (AL_EFFECT_CHORUS and AL_EFFECT_FLANGER) */
     B200MIX_EFFECT_AUTOWAH = 10,      /* AutowahState     alc/effects/autowah.cpp */
     B200MIX_EFFECT_VMORPHER = 11,     /* VmorpherState    alc/effects/vmorpher.cpp (vocal morpher) */
-    B200MIX_EFFECT_FSHIFTER = 12      /* FshifterState    alc/effects/fshifter.cpp (frequency shifter) */
+    B200MIX_EFFECT_FSHIFTER = 12,     /* FshifterState    alc/effects/fshifter.cpp (frequency shifter) */
+    B200MIX_EFFECT_PSHIFTER = 13      /* PshifterState    alc/effects/pshifter.cpp (pitch shifter) */
 };
 
 /* ConvolutionState::deviceUpdate (alc/effects/convolution.cpp:318-471): installs the
@@ -338,6 +339,8 @@ B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
  *   vmorpher    alc/effects/vmorpher.cpp:100-330    (two 4-band formant filter banks blended by an LFO)
  *   fshifter    alc/effects/fshifter.cpp:92-366     (analytic signal by a 1024-point STFT Hilbert transform in double,
  *                                                    rotated by a phase accumulator; first-order devices)
+ *   pshifter    alc/effects/pshifter.cpp:84-472     (phase vocoder: 1024-point STFT, hop 128, up to 9 wet channels that
+ *                                                    follow the phase of channel 0; devices up to second order)
  * b200mix_efx_props carries the effect's PROPERTIES (the EffectProps variant of
  * core/effects/base.h:62-178 after the AL layer's clamping); b200mix_efx_target what update() reads
  * from the slot and its output target: EffectSlotBase::Gain, the target mix's AmbiMap
@@ -349,7 +352,8 @@ B200MIX_API int b200mix_slot_reverb_update(b200mix_device *dev, uint32_t slot,
  * gain targets change, delay lines / filter histories / current gains are kept.
  * B200MIX_ERR_UNSUPPORTED: more than 16 wet channels; dedicated effects that resolve to a RealOut
  * channel (FrontCenter / LFE present: the reference then writes RealOut, not the mix);
- * distortion / chorus / frequency shifter on a device mixing above first order (their up-sampler). */
+ * distortion / chorus / frequency shifter on a device mixing above first order, the pitch shifter above
+ * second order (their up-samplers). */
 typedef struct b200mix_efx_props {
     uint32_t struct_size;
     uint32_t type;                      /* enum b200mix_effect, >= B200MIX_EFFECT_ECHO */
@@ -366,6 +370,7 @@ typedef struct b200mix_efx_props {
              int32_t phoneme_a_coarse_tuning, phoneme_b_coarse_tuning;
              uint32_t waveform; } vmorpher;                 /* VmorpherProps (0 sinusoid, 1 triangle, 2 sawtooth) */
     struct { float frequency; uint32_t left_direction, right_direction; } fshifter;  /* FshifterProps (0 down, 1 up, 2 off) */
+    struct { int32_t coarse_tune, fine_tune; } pshifter;                                  /* PshifterProps (semitones, cents) */
 } b200mix_efx_props;
 typedef struct b200mix_efx_target {
     uint32_t struct_size;

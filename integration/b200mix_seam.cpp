@@ -12,7 +12,7 @@
  * PCM sample type, any resampler, moving sources (targets are re-sent when the ALU changed
  * them), source start / stop / loop / end of buffer, auxiliary sends into effect slots —
  * EAX / standard reverb and the EFX effects of b200mix_slot_efx (echo, ring modulator,
- * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher, frequency shifter), slot gain, slot
+ * equalizer, compressor, dedicated, distortion, chorus / flanger, autowah, vocal morpher, frequency shifter, pitch shifter), slot gain, slot
  * targets (AL_SOFT_effect_target), property changes while playing, direct and send filters
  * (AL_DIRECT_FILTER / AL_AUXILIARY_SEND_FILTER low-, high- and band-pass), streaming sources
  * (alSourceQueueBuffers: queue advance, looping queues, buffer-completed events),
@@ -458,8 +458,12 @@ int effect_of(const EffectSlotBase *slot, b200mix_efx_props &o, b200mix_efx_reve
           o.fshifter.left_direction = static_cast<uint32_t>(p->LeftDirection);
           o.fshifter.right_direction = static_cast<uint32_t>(p->RightDirection); return 2; }
         return -1;
+    case EffectSlotType::PitchShifter:
+        if(auto *p = std::get_if<PshifterProps>(&props))
+        { o.type = B200MIX_EFFECT_PSHIFTER; o.pshifter.coarse_tune = p->CoarseTune; o.pshifter.fine_tune = p->FineTune; return 2; }
+        return -1;
     case EffectSlotType::Convolution: return 3;
-    default: return -1;          /* pitch shifter */
+    default: return -1;
     }
 }
 

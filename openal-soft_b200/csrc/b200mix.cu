@@ -133,6 +133,7 @@ struct b200mix_device {
     std::vector<EfxHost> efx;
     EfxSlotView *d_efx_views{nullptr};
     uint32_t efx_slots{0};
+    uint32_t pshift_slots{0};                // EFX slots running the pitch shifter (k_efx_pshift)
     bool efx_ready{false};
     float2 *d_twiddle{nullptr};
     float *d_cubic_filter{nullptr};          // gCubicTable (reverb modulation taps)
@@ -717,6 +718,7 @@ static void free_slot(b200mix_device *d, uint32_t slot)
     if(d->h_slots[slot].type >= B200MIX_EFFECT_ECHO)
     {
         --d->efx_slots;
+        if(d->h_slots[slot].type == B200MIX_EFFECT_PSHIFTER) --d->pshift_slots;
         if(slot < d->efx.size()) d->efx[slot] = b200mix_device::EfxHost{};
     }
     if(slot < d->rv.size()) d->rv[slot].used = false;
@@ -942,7 +944,7 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
 {
     if(!d || slot >= d->h_slots.size() || !props || !target || props->struct_size != sizeof(*props)
         || target->struct_size != sizeof(*target) || props->type < B200MIX_EFFECT_ECHO
-        || props->type > B200MIX_EFFECT_FSHIFTER)
+        || props->type > B200MIX_EFFECT_PSHIFTER)
     { if(d) d->error = "slot_efx: bad arguments (or the device has no sends/slots)"; return B200MIX_ERR_INVALID; }
     const b200mix_device_desc &dd = d->desc;
     const bool toSlot = slot < d->h_target.size() && d->h_target[slot] != B200MIX_NO_SLOT;
@@ -990,6 +992,14 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
             if(int rc = alloc(h.fs_accum, size_t(4)*1024)) return rc;
             h.fs_count = 0u; h.fs_pos = 1024u - 256u;
         }
+        if(P.type == B200MIX_EFFECT_PSHIFTER)
+        {   // PshifterState::deviceUpdate (pshifter.cpp:131-145): cleared FIFOs and phases, mPos = StftSize - StftStep
+            if(int rc = alloc(h.ps_fifo, size_t(9)*1024)) return rc;
+            if(int rc = alloc(h.ps_accum, size_t(9)*1024)) return rc;
+            if(int rc = alloc(h.ps_last, size_t(513))) return rc;
+            if(int rc = alloc(h.ps_sum, size_t(513))) return rc;
+            h.ps_count = 0u; h.ps_pos = 1024u - 128u;
+        }
         r.H = reinterpret_cast<float*>(dev);
         CUDA_TRY(d, cudaMemcpyAsync(dev, &h, sizeof(h), cudaMemcpyHostToDevice, d->stream));
         CUDA_TRY(d, cudaStreamSynchronize(d->stream));
@@ -998,6 +1008,7 @@ int b200mix_slot_efx(b200mix_device *d, uint32_t slot, const b200mix_efx_props *
         H.lfo_offset = 0u; H.lfo_range = P.cho_lfo_range ? P.cho_lfo_range : 1u;
         d->h_slots[slot] = r;
         ++d->active_slots; ++d->efx_slots;
+        if(props->type == B200MIX_EFFECT_PSHIFTER) ++d->pshift_slots;
         d->dry_active = true;
     }
     else
@@ -2054,6 +2065,11 @@ static int render_phase_b(b200mix_device *d, uint32_t frames)
                 EfxRunParams EQ{d->d_efx_views, d->d_wet, frames, dd.wet_channels, st, d->d_cubic_filter};
                 CUDA_TRY(d, launch_efx_process(EQ, dd.max_slots, d->stream));
                 ++d->launches;
+                if(d->pshift_slots)
+                {
+                    CUDA_TRY(d, launch_efx_pshift(EQ, dd.max_slots, d->stream));
+                    ++d->launches;
+                }
             }
             if(convWork)
             {

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "efx_kernels.hpp"
+#include "pshift.hpp"
 
 namespace b200mix {
 
@@ -613,6 +614,72 @@ __global__ void __launch_bounds__(128) k_efx_process(const EfxRunParams Q)
     }
 }
 
+// PshifterState::process (pshifter.cpp:207-472), devices up to second order: a kernel of its own
+// beside k_efx_process (same grid, same shared-memory carve-up; launched only while a pitch
+// shifter slot exists).  One warp per wet channel (4 at a time): FIFO exchange, and every 128
+// samples one STFT frame — the frame arithmetic is csrc/pshift.hpp (lane-strided, also run on the
+// host by the CPU tests).  Channel 0's analysis fixes mLastPhase / mSumPhase of the frame before the
+// other channels read them; the next frame's channel 0 waits for every reader of this one.
+__global__ void __launch_bounds__(128) k_efx_pshift(const EfxRunParams Q)
+{
+    extern __shared__ float sm[];
+    const EfxSlotView V = Q.slots[blockIdx.x];
+    if(!V.dev || V.stage != Q.stage) return;
+    EfxDev &E = *V.dev;
+    const EfxParams &P = E.p;
+    if(P.type != B200MIX_EFFECT_PSHIFTER) return;
+    const uint32_t t = threadIdx.x, n = Q.frames;
+    const float *wet = Q.wet + size_t(blockIdx.x)*Q.cw*kLine;
+    float *lines = V.lines;
+    const uint32_t nin = min(P.in_channels, Q.cw);
+    float *sIn = sm;
+    float *sWork = sm + kEfxMaxLines*kLine;
+    namespace ps = pshift;
+    static_assert(sizeof(ps::Cplx) == sizeof(double2), "transform buffers share the double2 layout");
+    const uint32_t w = t >> 5;
+    const ps::Lanes L{t & 31u, 32u};
+    ps::Cplx *X = reinterpret_cast<ps::Cplx*>(sIn) + size_t(w)*ps::kSize;          // [4][1024] complex doubles = sIn
+    float *re = sWork + size_t(w)*2u*544u, *im = re + 544u;                       // [4][2][513 (+pad)]
+    const ps::Cplx *tw = reinterpret_cast<const ps::Cplx*>(g_fs_tw);
+    const uint32_t numInput = min(nin, ps::kMaxLines);
+    const uint32_t shift_i = P.ps_shift_i; const float shift = P.ps_shift;
+    uint32_t count = E.ps_count, pos = E.ps_pos;
+    __syncthreads();                                                // everybody has read count / pos
+    for(uint32_t base = 0;base < n;)
+    {
+        const uint32_t todo = min(ps::kStep - count, n - base);
+        for(uint32_t c = w;c < numInput;c += 4u)
+            ps::fifo_exchange(E.ps_fifo + size_t(c)*ps::kSize + pos + count, wet + size_t(c)*kLine + base,
+                lines + size_t(c)*kLine + base, todo, L);
+        count += todo; base += todo;
+        if(count < ps::kStep) break;
+        count = 0u; pos = (pos + ps::kStep) & (ps::kSize - 1u);
+        for(uint32_t c0 = 0;c0 < numInput;c0 += 4u)
+        {
+            const uint32_t c = c0 + w;
+            const bool on = c < numInput;
+            float *fifo = E.ps_fifo + size_t(c)*ps::kSize, *accum = E.ps_accum + size_t(c)*ps::kSize;
+            if(on) ps::analyse_frame(X, tw, fifo, g_fs_hann, pos, re, im, L);
+            if(c == 0u)
+            {
+                ps::bins_channel0(re, im, E.ps_last, shift, L);
+                ps::synthesise_bins<true>(X, re, im, E.ps_sum, shift_i, L);
+            }
+            if(c0 == 0u) __syncthreads();                           // mLastPhase / mSumPhase of this frame are final
+            if(on && c != 0u)
+            {
+                ps::bins_channelN(re, im, E.ps_last, L);
+                ps::synthesise_bins<false>(X, re, im, E.ps_sum, shift_i, L);
+            }
+            if(on) ps::resynthesise_frame(X, tw, fifo, accum, g_fs_hann, pos, L);
+        }
+        __syncthreads();                                            // every channel has read this frame's phases
+    }
+    for(uint32_t c = numInput;c < P.lines;++c)
+        for(uint32_t i = t;i < n;i += blockDim.x) lines[size_t(c)*kLine + i] = 0.0f;
+    if(t == 0u) { E.ps_count = count; E.ps_pos = pos; }
+}
+
 } // namespace
 
 constexpr int kEfxSmem = int((2u*kEfxMaxLines + 1u)*kLine*sizeof(float));
@@ -621,12 +688,19 @@ cudaError_t efx_kernels_init()
 {
     k_efx_tables<<<1, 512>>>();            // twiddles + Hann window of the frequency shifter (per CUDA device)
     if(cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) return e;
+    if(cudaError_t e = cudaFuncSetAttribute(k_efx_pshift, cudaFuncAttributeMaxDynamicSharedMemorySize, kEfxSmem); e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_efx_process, cudaFuncAttributeMaxDynamicSharedMemorySize, kEfxSmem);
 }
 
 cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream)
 {
     k_efx_process<<<num_slots, 128, kEfxSmem, stream>>>(Q);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_efx_pshift(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream)
+{
+    k_efx_pshift<<<num_slots, 128, kEfxSmem, stream>>>(Q);
     return cudaGetLastError();
 }
 

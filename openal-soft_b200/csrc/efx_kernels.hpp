@@ -26,6 +26,9 @@ struct EfxDev {
     uint32_t fs_count, fs_pos, fs_phase[4];
     float chan_z[kEfxMaxLines][4][2];      // per-channel biquad histories (modulator [0], equalizer [0..3],
                                            // distortion [0] low-pass, [1] band-pass)
+    // pitch shifter: ProcessParams::mFIFO / mOutputAccum [9][1024], mLastPhase / mSumPhase [513]; mCount, mPos
+    float *ps_fifo, *ps_accum, *ps_last, *ps_sum;
+    uint32_t ps_count, ps_pos;
 };
 
 struct EfxSlotView { EfxDev *dev; float *lines; uint32_t stage, pad; };   // dev == null: not an EFX slot
@@ -33,5 +36,6 @@ struct EfxRunParams { const EfxSlotView *slots; const float *wet; uint32_t frame
 
 cudaError_t efx_kernels_init();            // per CUDA device: dynamic shared memory opt-in
 cudaError_t launch_efx_process(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream);
+cudaError_t launch_efx_pshift(const EfxRunParams &Q, uint32_t num_slots, cudaStream_t stream);   // the pitch shifter's own kernel
 
 } // namespace b200mix

@@ -47,6 +47,8 @@ struct EfxParams {
     float vm_tgain[kEfxMaxLines];         // mTargetGain
     // frequency shifter
     uint32_t fs_phase_step[4]; float fs_sign[4]; uint32_t fs_reset_phase[4];   // ProcessParams::mPhaseStep / mSign; Off: mPhase = 0
+    // pitch shifter
+    uint32_t ps_shift_i; float ps_shift;  // PshifterState::mPitchShiftI (16.16) / mPitchShift
 };
 
 namespace efx_detail {
@@ -303,6 +305,19 @@ inline int efx_update(const b200mix_efx_props &E, const b200mix_efx_target &T, E
         }
         P.lines = 4u;
         ambi_mix_params(T, T.slot_gain, 4u, P);
+        break;
+    }
+    case B200MIX_EFFECT_PSHIFTER:
+    {
+        // PshifterState::update (pshifter.cpp:170-205); the up-sampler of devices above second order
+        // (:150-167, :445-461) is not built
+        if(T.device_ambi_order > 2u) return B200MIX_ERR_UNSUPPORTED;
+        const int tune = E.pshifter.coarse_tune*100 + E.pshifter.fine_tune;
+        const float pitch = std::pow(2.0f, static_cast<float>(tune) / 1200.0f);
+        P.ps_shift_i = static_cast<uint32_t>(std::lrint(std::min(std::max(pitch, 0.5f), 2.0f) * 65536.0f));   // fastf2u
+        P.ps_shift = static_cast<float>(P.ps_shift_i) * (1.0f/65536.0f);
+        P.lines = std::min(T.wet_channels, 9u);                       // NumLines: second order
+        ambi_mix_params(T, T.slot_gain, 9u, P);
         break;
     }
     default: return B200MIX_ERR_INVALID;

@@ -189,7 +189,7 @@ class SourceVoice(C.Structure):
 
 (EFFECT_NONE, EFFECT_CONVOLUTION, EFFECT_REVERB, EFFECT_ECHO, EFFECT_MODULATOR, EFFECT_EQUALIZER,
  EFFECT_COMPRESSOR, EFFECT_DEDICATED, EFFECT_DISTORTION, EFFECT_CHORUS, EFFECT_AUTOWAH, EFFECT_VMORPHER,
- EFFECT_FSHIFTER) = range(13)
+ EFFECT_FSHIFTER, EFFECT_PSHIFTER) = range(14)
 
 
 class _EfxEcho(C.Structure):
@@ -235,12 +235,16 @@ class _EfxFshifter(C.Structure):
     _fields_ = [("frequency", C.c_float), ("left_direction", C.c_uint32), ("right_direction", C.c_uint32)]
 
 
+class _EfxPshifter(C.Structure):
+    _fields_ = [("coarse_tune", C.c_int32), ("fine_tune", C.c_int32)]
+
+
 class EfxProps(C.Structure):
     """b200mix_efx_props: the EFX effect's properties (EffectProps, core/effects/base.h)."""
     _fields_ = [("struct_size", C.c_uint32), ("type", C.c_uint32), ("echo", _EfxEcho), ("modulator", _EfxModulator),
                 ("equalizer", _EfxEqualizer), ("compressor", _EfxCompressor), ("dedicated", _EfxDedicated),
                 ("distortion", _EfxDistortion), ("chorus", _EfxChorus), ("autowah", _EfxAutowah),
-                ("vmorpher", _EfxVmorpher), ("fshifter", _EfxFshifter)]
+                ("vmorpher", _EfxVmorpher), ("fshifter", _EfxFshifter), ("pshifter", _EfxPshifter)]
 
 
 class EfxTarget(C.Structure):
@@ -266,6 +270,7 @@ def efx_defaults(effect_type):
     p.autowah = _EfxAutowah(0.06, 0.06, 1000.0, 11.22)
     p.vmorpher = _EfxVmorpher(1.41, 0, 10, 0, 0, 0)       # phoneme A -> ER, sinusoid
     p.fshifter = _EfxFshifter(0.0, 0, 0)                  # 0 Hz, both sides down
+    p.pshifter = _EfxPshifter(12, 0)                      # one octave up
     return p
 
 

@@ -1,6 +1,6 @@
 // efx_oracle.cpp — CPU restatement of EffectState::process for the EFX effects the product runs
 // on the GPU (echo, ring modulator, equalizer, compressor, dedicated, distortion, chorus / flanger,
-// autowah, vocal morpher, frequency shifter).  TEST
+// autowah, vocal morpher, frequency shifter, pitch shifter).  TEST
 // INFRASTRUCTURE ONLY: linked into oracle/liboracle.so, used by tests/, smoke() and nothing else.
 //
 // Each process() below follows the reference line by line (file:line cited); the parameter side
@@ -152,6 +152,9 @@ struct oefx {
     size_t fs_count{0}, fs_pos{1024 - 256};
     std::vector<double> fs_in; std::vector<std::complex<double>> fs_outfifo, fs_accum, fs_outdata;
     uint32_t fs_phase[4]{};
+    // pitch shifter (pshifter.cpp:84-118): mCount, mPos, per-channel mFIFO / mOutputAccum, mLastPhase, mSumPhase
+    size_t ps_count{0}, ps_pos{1024 - 128};
+    std::vector<float> ps_fifo, ps_accum, ps_last, ps_sum;
     // vocal morpher
     uint32_t vm_index{0}; float vm_cur[b200mix::kEfxMaxLines]{}; float vm_s[b200mix::kEfxMaxLines][2][4][2]{};
 };
@@ -172,6 +175,11 @@ oefx *oefx_create(const b200mix_efx_props *props, const b200mix_efx_target *targ
     {
         e->fs_in.assign(4*1024, 0.0); e->fs_outfifo.assign(4*256, {}); e->fs_accum.assign(4*1024, {});
         e->fs_outdata.assign(4*1024, {});
+    }
+    if(e->p.type == B200MIX_EFFECT_PSHIFTER)
+    {   // PshifterState::deviceUpdate, pshifter.cpp:131-145
+        e->ps_fifo.assign(9*1024, 0.0f); e->ps_accum.assign(9*1024, 0.0f);
+        e->ps_last.assign(513, 0.0f); e->ps_sum.assign(513, 0.0f);
     }
     e->lfo_range = e->p.cho_lfo_range ? e->p.cho_lfo_range : 1u;
     e->mod_range = e->p.mod_range ? e->p.mod_range : 1u;
@@ -566,6 +574,118 @@ void oefx_process(oefx *e, size_t n, const float (*in)[1024], size_t nin_, float
                 for(size_t k = 0;k < n;++k) bbuf[i][k] = bbuf[i][k] + buf[k]*A2B[i][c];
         }
         for(size_t c = 0;c < 4;++c)
+            if(P.line_on[c])
+                for(size_t o = 0;o < nout;++o)
+                    if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)
+                        mix_line(bbuf[c], n, out[o], e->cur[c][o], P.gains[c][o], 1.0f/float(n), n, n);
+        break;
+    }
+    case B200MIX_EFFECT_PSHIFTER:
+    {
+        // PshifterState::process, pshifter.cpp:207-472 (devices up to second order).  The reference's
+        // real FFT (pffft, single precision, ordered output) is evaluated here as a complex FFT in
+        // double whose results are rounded to float: same transform, rounding differences only.
+        constexpr size_t N = 1024, H = 512, STEP = 128;
+        constexpr float pi = 3.14159265358979323846f, inv_pi = 0.318309886183790671538f;
+        constexpr float expected_cycles = pi*2.0f / 8.0f;
+        static thread_local float bbuf[9][LINE];
+        static thread_local cplx X[N];
+        static thread_local float fre[H+1], fim[H+1], smag[H+1], sfb[H+1];
+        const float *win = hann1024();
+        const size_t numInput = std::min<size_t>(nin, 9);
+        const uint32_t psi = P.ps_shift_i; const float ps = P.ps_shift;
+        auto f2i = [](float f) { return b200mix::efx_detail::f2i(f); };
+        for(size_t base = 0;base < n;)
+        {
+            const size_t todo = std::min<size_t>(STEP - e->ps_count, n - base);
+            for(size_t c = 0;c < numInput;++c)
+            {
+                float *fifo = e->ps_fifo.data() + c*N + e->ps_pos + e->ps_count;
+                for(size_t k = 0;k < todo;++k) { bbuf[c][base + k] = fifo[k]; fifo[k] = in[c][base + k]; }
+            }
+            e->ps_count += todo; base += todo;
+            if(e->ps_count < STEP) break;
+            e->ps_count = 0;
+            e->ps_pos = (e->ps_pos + STEP) & (N - 1);
+            const size_t pos = e->ps_pos;
+            for(size_t c = 0;c < numInput;++c)
+            {
+                float *fifo = e->ps_fifo.data() + c*N;
+                float *accum = e->ps_accum.data() + c*N;
+                for(size_t k = 0;k < N;++k) X[k] = cplx{double(fifo[(pos + k) & (N - 1)] * win[k]), 0.0};
+                fft_pow2(X, N, -1.0);
+                for(size_t k = 0;k <= H;++k) { fre[k] = float(X[k].real()); fim[k] = (k == 0 || k == H) ? 0.0f : float(X[k].imag()); }
+                for(size_t k = 0;k <= H;++k) { smag[k] = 0.0f; sfb[k] = 0.0f; }
+                if(c == 0)
+                {
+                    for(size_t k = 0;k <= H;++k)
+                    {
+                        const float magnitude = std::hypot(fre[k], fim[k]);        // std::abs(complex<float>)
+                        const float phase = std::atan2(fim[k], fre[k]);            // std::arg
+                        const float bin_offset = float(k & 7u);
+                        float tmp = (phase - e->ps_last[k]) - bin_offset*expected_cycles;
+                        e->ps_last[k] = phase;
+                        tmp *= inv_pi;
+                        const int qpd = f2i(tmp);
+                        tmp -= float(qpd + (qpd%2));
+                        tmp *= 0.5f*8.0f;
+                        const float freqbin = float(k) + tmp;
+                        const size_t j = (k*size_t(psi) + 32768u) >> 16;
+                        if(j < H+1)
+                        {
+                            if(smag[j] < magnitude) sfb[j] = freqbin * ps;
+                            smag[j] += magnitude;
+                        }
+                    }
+                    for(size_t k = 0;k <= H;++k)
+                    {
+                        const float bin_offset = float(k & ~size_t{7});
+                        float tmp = (sfb[k] - bin_offset) * expected_cycles;
+                        tmp = (tmp + e->ps_sum[k]) * inv_pi;
+                        const int qpd = f2i(tmp);
+                        tmp -= float(qpd + (qpd%2));
+                        e->ps_sum[k] = tmp * pi;
+                        fre[k] = smag[k] * std::cos(e->ps_sum[k]);                 // std::polar
+                        fim[k] = smag[k] * std::sin(e->ps_sum[k]);
+                    }
+                }
+                else
+                {
+                    constexpr uint32_t bin_limit = ((uint32_t(H)+1u) << 16) - 32768u - 1u;
+                    const size_t bin_count = std::min<size_t>(H+1, bin_limit/psi + 1u);
+                    for(size_t k = 0;k < bin_count;++k)
+                    {
+                        const float magnitude = std::hypot(fre[k], fim[k]);
+                        const float phasediff = std::atan2(fim[k], fre[k]) - e->ps_last[k];
+                        const size_t j = (k*size_t(psi) + 32768u) >> 16;
+                        if(smag[j] < magnitude) sfb[j] = phasediff;
+                        smag[j] += magnitude;
+                    }
+                    for(size_t k = 0;k <= H;++k)
+                    {
+                        float tmp = e->ps_sum[k] + sfb[k];
+                        tmp *= inv_pi;
+                        const int qpd = f2i(tmp);
+                        tmp -= float(qpd + (qpd%2));
+                        const float phase = tmp * pi;
+                        fre[k] = smag[k] * std::cos(phase);
+                        fim[k] = smag[k] * std::sin(phase);
+                    }
+                }
+                // the half-complex spectrum back to time: bins 0 and 512 contribute their real parts only
+                X[0] = cplx{double(fre[0]), 0.0}; X[H] = cplx{double(fre[H]), 0.0};
+                for(size_t k = 1;k < H;++k) { X[k] = cplx{double(fre[k]), double(fim[k])}; X[N - k] = std::conj(X[k]); }
+                fft_pow2(X, N, 1.0);
+                constexpr float scale = 3.0f / 8.0f / 1024.0f;
+                for(size_t k = 0;k < N;++k)
+                {
+                    const float v = win[k]*float(X[k].real())*scale;
+                    accum[(pos + k) & (N - 1)] += v;
+                }
+                for(size_t k = 0;k < STEP;++k) { fifo[pos + k] = accum[pos + k]; accum[pos + k] = 0.0f; }
+            }
+        }
+        for(size_t c = 0;c < numInput;++c)
             if(P.line_on[c])
                 for(size_t o = 0;o < nout;++o)
                     if(P.gains[c][o] != 0.0f || e->cur[c][o] != 0.0f)

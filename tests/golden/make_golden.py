@@ -122,6 +122,8 @@ SCENES = {
     "efx_vmorpher_saw_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:vmorpher_saw"),
     "efx_fshifter_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:fshifter"),
     "efx_fshifter_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:fshifter_off"),
+    "efx_pshifter_hrtf_v5": (5, 1, 2, 8, True, 48000, None, "i16", 0, None, None, "efx:pshifter"),
+    "efx_pshifter_down_stereo_v4": (4, 0, 2, 6, True, 48000, None, "i16", 0, None, None, "efx:pshifter_down"),
 }
 
 # name: (our effect type, AL effect enum, {AL float props}, {AL int props}, slot gain,
@@ -161,6 +163,11 @@ EFX_SCENES = {
                  {4: ({0x0001: 1200.0}, {0x0002: 1})}),
     "fshifter_off": (12, 0x0006, {0x0001: 440.0}, {0x0002: 2, 0x0003: 0}, 1.0,
                      {2: ({}, {0x0002: 1, 0x0003: 2}), 4: ({0x0001: 30.0}, {0x0003: 1})}),
+    # pitch shifter: AL_PITCH_SHIFTER_COARSE_TUNE 1 (semitones), _FINE_TUNE 2 (cents): the default octave up,
+    # then a fifth up + 30 cents; shifting down (several analysis bins land on one synthesis bin), then the
+    # octave down
+    "pshifter": (13, 0x0008, {}, {}, 0.9, {4: ({}, {0x0001: 7, 0x0002: 30})}),
+    "pshifter_down": (13, 0x0008, {}, {0x0001: -5, 0x0002: -20}, 1.0, {3: ({}, {0x0001: -12, 0x0002: 0})}),
     "vmorpher_saw": (11, 0x0007, {0x0006: 1.41}, {0x0001: 1, 0x0003: 0, 0x0005: 2}, 1.0,
                      {2: ({0x0006: 0.0}, {}), 4: ({0x0006: 2.0}, {0x0001: 9})}),
 }
@@ -221,6 +228,11 @@ def efx_props_struct(kind, fprops, iprops):
             p.fshifter.left_direction = i[2]
         if 3 in i:
             p.fshifter.right_direction = i[3]
+    elif typ == 13:
+        if 1 in i:
+            p.pshifter.coarse_tune = i[1]
+        if 2 in i:
+            p.pshifter.fine_tune = i[2]
     elif typ == 11:
         if 6 in f:
             p.vmorpher.rate = f[6]

@@ -25,7 +25,8 @@ alcSuspendContext / alcProcessContext, all sources stopped and others started on
 | "misc3" (streaming sources paused, resumed and sought; a queue that underruns, is refilled and
 played again; a stereo and a B-Format source with a filtered reverb send; the slot's effect set to
 null and back) | "allfx" (one slot per remaining EFX effect — vocal morpher, frequency shifter,
-autowah, distortion, compressor, ring modulator, flanger — with property changes while playing) | "i16" (16-bit output: the host's limiter, dither and Write<i16> run
+autowah, distortion, compressor, ring modulator, flanger — with property changes while playing) |
+"pshift" (two pitch-shifter slots, up and down, re-tuned while playing) | "i16" (16-bit output: the host's limiter, dither and Write<i16> run
 on the block the mixer delivered; the .npz then holds the samples scaled to +-1) | "quad", "x51",
 "mono", "uhj", "uhj512", "tsme", "stab51", "bs2b" (other outputs: quad / 5.1 / mono speakers, UHJ-
 encoded stereo with the IIR or the 512-tap FIR encoder, TSME, 5.1 with the front stabilizer, stereo
@@ -381,12 +382,14 @@ def main():
     al.alcMakeContextCurrent(ctx)
     keep, sources = [], (C.c_uint * V)()
 
-    def make_slot(al_type, gain=1.0, fprops=None):
+    def make_slot(al_type, gain=1.0, fprops=None, iprops=None):
         e, sl = C.c_uint(0), C.c_uint(0)
         al.alGenEffects(1, C.byref(e))
         al.alEffecti(e, AL_EFFECT_TYPE, al_type)
         for k, v in (fprops or {}).items():
             al.alEffectf(e, k, float(v))
+        for k, v in (iprops or {}).items():
+            al.alEffecti(e, k, int(v))
         al.alGenAuxiliaryEffectSlots(1, C.byref(sl))
         al.alAuxiliaryEffectSlotf(sl, AL_EFFECTSLOT_GAIN, gain)
         al.alAuxiliaryEffectSloti(sl, AL_EFFECTSLOT_EFFECT, e.value)
@@ -456,6 +459,9 @@ def main():
         slots.append(make_slot(AL_EFFECT_COMPRESSOR, 0.9))
         slots.append(make_slot(AL_EFFECT_RING_MODULATOR, 0.8, {0x0001: 300.0}))                    # frequency
         slots.append(make_slot(AL_EFFECT_FLANGER, 0.8, {0x0003: 0.4, 0x0005: -0.6}))               # rate, feedback
+    if fx == "pshift":
+        slots.append(make_slot(0x0008, 0.9))                                                       # AL_EFFECT_PITCH_SHIFTER: an octave up
+        slots.append(make_slot(0x0008, 0.8, None, {0x0001: -7, 0x0002: 20}))                       # a fifth down + 20 cents
     if fx in ("reverb", "mix", "misc3"):
         slots.append(make_slot(AL_EFFECT_EAXREVERB, 0.9))
     if fx == "mix":
@@ -526,7 +532,7 @@ def main():
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[0][0], 0, sendfilter.value)
         elif fx == "conv":
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % 2][0], 0, AL_FILTER_NULL)
-        elif fx == "allfx":
+        elif fx in ("allfx", "pshift"):
             al.alSource3i(s, AL_AUXILIARY_SEND_FILTER, slots[i % len(slots)][0], 0, AL_FILTER_NULL)
         elif fx == "mix":
             # send 0: reverb or the equalizer that feeds it; send 1: the echo for every third source
@@ -732,11 +738,17 @@ def main():
                                                    (0x0001, 0, True), (0x0003, 2, True), (0x0001, 0, True))):
                 (al.alEffecti if isint else al.alEffectf)(slots[k][1], par, val)
                 al.alAuxiliaryEffectSloti(slots[k][0], AL_EFFECTSLOT_EFFECT, slots[k][1])
-        if slots and fx not in ("conv", "allfx") and u == 2:
+        if fx == "pshift" and u == 3:
+            al.alEffecti(slots[0][1], 0x0001, 5)                                                   # coarse tune: a fourth up
+            al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
+            al.alEffecti(slots[1][1], 0x0001, -12)
+            al.alEffecti(slots[1][1], 0x0002, 0)
+            al.alAuxiliaryEffectSloti(slots[1][0], AL_EFFECTSLOT_EFFECT, slots[1][1])
+        if slots and fx not in ("conv", "allfx", "pshift") and u == 2:
             # a property that needs the reverb's other pipeline (full update), then one that does not
             al.alEffectf(slots[0][1], AL_EAXREVERB_DECAY_TIME, 2.9)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
-        if slots and fx not in ("conv", "allfx") and u == 4:
+        if slots and fx not in ("conv", "allfx", "pshift") and u == 4:
             al.alEffectf(slots[0][1], AL_EAXREVERB_REFLECTIONS_GAIN, 0.3)
             al.alAuxiliaryEffectSloti(slots[0][0], AL_EFFECTSLOT_EFFECT, slots[0][1])
         if fx == "mix" and u == 3:

@@ -18,6 +18,13 @@ def test_oracle_matches_reference_c_kernels_bit_exact(name):
         # butterflies: equal within rounding, not bitwise
         assert np.abs(out.astype(np.float64) - ref).max() <= 5e-7
         return
+    if "pshifter" in name:
+        # the pitch shifter's real FFT (pffft, single precision) is evaluated as a complex FFT in
+        # double: rounding differences only.  The reference's own SSE and C builds differ by
+        # 1.5e-6 / 1.9e-6 on these two scenes.
+        assert np.abs(out.astype(np.float64) - ref).max() <= 4e-6
+        assert np.sqrt(((out.astype(np.float64) - ref) ** 2).mean()) <= 6e-7
+        return
     # the restatement follows the reference's C kernels operation for operation
     assert np.array_equal(out, ref), f"max diff {np.abs(out - ref).max():.3e}"
 
