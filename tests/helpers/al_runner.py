@@ -15,7 +15,8 @@ band-pass filters that change and detach while playing) | "mixfilt" (both, plus 
 unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones) | "conv"
 (two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
 a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
-alcResetDeviceSOFT toggles HRTF while the sources play) | "bformat" (first-order B-Format
+alcResetDeviceSOFT toggles HRTF while the sources play) | "hoa" (second- / third-order B-Format beds,
+AL_SOFT_bformat_hoa, ACN or FuMa, on the first-order device) | "bformat" (first-order B-Format
 sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns) | "rebuf" (a buffer is
 deleted and another one of the same size created — usually at the same address — and played) |
 "misc" (pause / resume, seeking a playing source, pitch and gain changes, a moving listener,
@@ -67,6 +68,8 @@ AL_FORMAT_MONO16, AL_SOURCE_RESAMPLER_SOFT = 0x1101, 0x1212
 AL_FORMAT_STEREO16, AL_BUFFERS_PROCESSED, AL_BUFFERS_QUEUED = 0x1103, 0x1016, 0x1015
 AL_FORMAT_BFORMAT3D_16, AL_ORIENTATION = 0x20032, 0x100F
 AL_VELOCITY = 0x1006
+AL_UNPACK_AMBISONIC_ORDER_SOFT, AL_AMBISONIC_LAYOUT_SOFT, AL_AMBISONIC_SCALING_SOFT = 0x199D, 0x1997, 0x1998
+AL_ACN_SOFT, AL_SN3D_SOFT, AL_N3D_SOFT = 1, 1, 2
 AL_DIRECT_CHANNELS_SOFT, ALC_CONNECTED = 0x1033, 0x313
 AL_EFFECT_NULL = 0x0000
 AL_EFFECT_DISTORTION, AL_EFFECT_FLANGER, AL_EFFECT_FREQUENCY_SHIFTER, AL_EFFECT_VOCAL_MORPHER = 0x0003, 0x0005, 0x0006, 0x0007
@@ -500,6 +503,14 @@ def main():
             chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in (1, 2, 3)]
             pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
             fmt = AL_FORMAT_BFORMAT3D_16
+        hoa_order = 0
+        if fx == "hoa" and i % 2 == 0:
+            # AL_SOFT_bformat_hoa: second- and third-order beds (9 / 16 channels), ACN or FuMa layout
+            hoa_order = 2 + (i // 2) % 2
+            nchan = (hoa_order + 1) ** 2
+            chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in range(1, nchan)]
+            pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
+            fmt = AL_FORMAT_BFORMAT3D_16
         if fx == "formats":
             pcm, fmt = format_buffer(i, len(pcm))
         keep.append(pcm)
@@ -519,7 +530,13 @@ def main():
             streams.append((i, qb))
         else:
             al.alGenBuffers(1, C.byref(b))
+            if hoa_order:
+                al.alBufferi(b, AL_UNPACK_AMBISONIC_ORDER_SOFT, hoa_order)
+                if i % 4 == 0:
+                    al.alBufferi(b, AL_AMBISONIC_LAYOUT_SOFT, AL_ACN_SOFT)
+                    al.alBufferi(b, AL_AMBISONIC_SCALING_SOFT, AL_N3D_SOFT if i % 8 == 0 else AL_SN3D_SOFT)
             al.alBufferData(b, fmt, pcm.ctypes.data, pcm.nbytes, 48000)
+            assert al.alGetError() == 0
             al.alSourcei(s, AL_BUFFER, b.value)
             al.alSourcei(s, AL_LOOPING, 0 if oneshot else 1)
         al.alSourcef(s, AL_PITCH, scene.voice_pitch(i))
@@ -594,7 +611,7 @@ def main():
             al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
             if V > 7:
                 al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
-        if fx == "bformat":
+        if fx in ("bformat", "hoa"):
             # the sound field of every B-Format source turns a little each update
             for i in range(0, V, 2):
                 ang = 0.4 * u + 0.2 * i
