@@ -16,7 +16,9 @@ unqueued while playing) | "stereo" (AL_FORMAT_STEREO16 sources next to mono ones
 (two convolution slots: a mono float32 impulse response at 44.1 kHz — resampled by the library — and
 a stereo 16-bit one at the device rate; slot gain changes while playing) | "reset" (reverb scene;
 alcResetDeviceSOFT toggles HRTF while the sources play) | "hoa" (second- / third-order B-Format beds,
-AL_SOFT_bformat_hoa, ACN or FuMa, on the first-order device) | "bformat" (first-order B-Format
+AL_SOFT_bformat_hoa, ACN or FuMa, on the first-order device) | "hoadev2" / "hoadev3" (an ALC_BFORMAT3D_SOFT
+device of order 2 / 3; beds of that order and the next, rotated by the application: AmbiRotator) |
+"bformat" (first-order B-Format
 sources, AL_FORMAT_BFORMAT3D_16, whose orientation the application turns) | "rebuf" (a buffer is
 deleted and another one of the same size created — usually at the same address — and played) |
 "misc" (pause / resume, seeking a playing source, pitch and gain changes, a moving listener,
@@ -377,9 +379,12 @@ def main():
     assert dev
     out16 = fx == "i16"
     layout, nout = {"quad": (ALC_QUAD_SOFT, 4), "x51": (ALC_5POINT1_SOFT, 6), "stab51": (ALC_5POINT1_SOFT, 6),
-                    "mono": (ALC_MONO_SOFT, 1)}.get(fx, (ALC_STEREO_SOFT, 2))
+                    "mono": (ALC_MONO_SOFT, 1), "hoadev2": (0x1507, 9), "hoadev3": (0x1507, 16)}.get(fx, (ALC_STEREO_SOFT, 2))
     attrs = [ALC_FORMAT_CHANNELS_SOFT, layout, ALC_FORMAT_TYPE_SOFT, ALC_SHORT_SOFT if out16 else ALC_FLOAT_SOFT, ALC_FREQUENCY, 48000,
              ALC_MONO_SOURCES, max(V, 1), ALC_HRTF_SOFT, hrtf] + ([ALC_OUTPUT_MODE_SOFT, ALC_STEREO_UHJ_SOFT] if fx in ("uhj", "uhj512") else []) + [0]
+    if fx.startswith("hoadev"):
+        # ALC_BFORMAT3D_SOFT output (RealOut is the Dry mix) of order 2 / 3: ACN, order 2 in N3D, order 3 in SN3D
+        attrs = attrs[:-1] + [0x1997, 1, 0x1998, 2 if fx == "hoadev2" else 1, 0x1999, int(fx[-1]), 0]
     ctx = al.alcCreateContext(dev, (C.c_int * len(attrs))(*attrs))
     assert ctx
     al.alcMakeContextCurrent(ctx)
@@ -504,9 +509,11 @@ def main():
             pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
             fmt = AL_FORMAT_BFORMAT3D_16
         hoa_order = 0
-        if fx == "hoa" and i % 2 == 0:
+        if fx in ("hoa", "hoadev2", "hoadev3") and i % 2 == 0:
             # AL_SOFT_bformat_hoa: second- and third-order beds (9 / 16 channels), ACN or FuMa layout
-            hoa_order = 2 + (i // 2) % 2
+            # (on an ambisonic device: beds of the device's order and of the next one — lower-order
+            # beds would be up-sampled, VoiceFlag::IsAmbisonic)
+            hoa_order = (2 + (i // 2) % 2) if fx == "hoa" else (int(fx[-1]) + (i // 2) % 2)
             nchan = (hoa_order + 1) ** 2
             chans = [pcm] + [scene.voice_buffer_fast(i + k, len(pcm)) for k in range(1, nchan)]
             pcm = np.ascontiguousarray(np.stack(chans, axis=1).reshape(-1))
@@ -532,7 +539,7 @@ def main():
             al.alGenBuffers(1, C.byref(b))
             if hoa_order:
                 al.alBufferi(b, AL_UNPACK_AMBISONIC_ORDER_SOFT, hoa_order)
-                if i % 4 == 0:
+                if i % 4 == 0 or hoa_order > 3:            # FuMa stops at third order
                     al.alBufferi(b, AL_AMBISONIC_LAYOUT_SOFT, AL_ACN_SOFT)
                     al.alBufferi(b, AL_AMBISONIC_SCALING_SOFT, AL_N3D_SOFT if i % 8 == 0 else AL_SN3D_SOFT)
             al.alBufferData(b, fmt, pcm.ctypes.data, pcm.nbytes, 48000)
@@ -611,7 +618,7 @@ def main():
             al.alSourcei(sources[0], AL_DIRECT_FILTER, AL_FILTER_NULL)
             if V > 7:
                 al.alSourcei(sources[7], AL_DIRECT_FILTER, bandpass.value)
-        if fx in ("bformat", "hoa"):
+        if fx in ("bformat", "hoa", "hoadev2", "hoadev3"):
             # the sound field of every B-Format source turns a little each update
             for i in range(0, V, 2):
                 ang = 0.4 * u + 0.2 * i

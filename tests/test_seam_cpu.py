@@ -38,7 +38,7 @@ def _run(lib, tag, voices, updates, hrtf, seam, tmp_path, fx="none"):
 @pytest.mark.parametrize("voices,updates,hrtf,fx", [(24, 8, 1, "none"), (24, 8, 0, "none"), (300, 4, 1, "none"),
                                                     (24, 8, 1, "reverb"), (24, 8, 1, "mix"), (24, 8, 0, "mix"), (24, 8, 1, "filt"),
                                                     (24, 8, 0, "mixfilt"), (24, 8, 1, "stream"), (24, 8, 0, "stream"),
-                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 6, 1, "hoa"), (12, 6, 0, "hoa"), (12, 7, 1, "rebuf"), (24, 8, 1, "misc"),
+                                                    (24, 8, 1, "stereo"), (24, 8, 0, "stereo"), (24, 8, 1, "conv"), (24, 8, 0, "conv"), (24, 8, 1, "reset"), (24, 8, 0, "reset"), (12, 6, 1, "bformat"), (12, 6, 0, "bformat"), (12, 6, 1, "hoa"), (12, 6, 0, "hoa"), (12, 6, 0, "hoadev2"), (12, 6, 0, "hoadev3"), (12, 7, 1, "rebuf"), (24, 8, 1, "misc"),
                                                     (24, 8, 0, "misc"), (24, 8, 1, "misc2"), (24, 8, 0, "misc2"),
                                                     (24, 9, 1, "misc3"), (24, 9, 0, "misc3"), (28, 7, 1, "allfx"), (28, 7, 0, "allfx"), (24, 8, 1, "pshift"), (24, 8, 0, "pshift"), (24, 8, 1, "i16"),
                                                     (24, 6, 0, "quad"), (24, 6, 0, "x51"), (24, 6, 0, "mono"), (24, 6, 0, "uhj"),
