@@ -501,20 +501,27 @@ B200MIX_API int b200mix_calc_voice_channels(const b200mix_source_props *props,
     const b200mix_channel_setup *setup, uint32_t *step, float *hrtf_gains, float *dirs,
     float *dry_gains, float *send_gains, struct b200mix_voice_filter *filters);
 
-/* And for a first-order B-Format source (ambient beds: AL_FORMAT_BFORMAT2D/3D_*) that is not
- * spatialized, on a device that mixes first order: CalcNonAttnVoiceParams, then
- * CalcAmbisonicPanning at no distance (alc/alu.cpp:911-1077 with coverage 1): the source's
- * orientation (and the listener's, unless head-relative) rotates the X/Y/Z channels, the buffer's
- * channel order and normalisation are folded in, and each buffer channel becomes one non-HRTF
- * voice whose dry/send gains are a row of that matrix.  Returns the channel count (3 for 2D, 4 for
- * 3D) or < 0; B200MIX_ERR_UNSUPPORTED when the device mixes above first order (the reference then
- * up-samples and band-splits the source, core/voice.cpp:1082-1089). */
+/* And for a B-Format source of order 1..4 (ambient beds: AL_FORMAT_BFORMAT2D/3D_*, AL_SOFT_bformat_hoa)
+ * that is not spatialized, on a device that mixes at most the source's order: CalcNonAttnVoiceParams,
+ * then CalcAmbisonicPanning at no distance (alc/alu.cpp:911-1077 with coverage 1): the source's
+ * orientation (and the listener's, unless head-relative) rotates the sound field — first order by
+ * the orientation vectors, the bands above it by AmbiRotator's recursion up to the device's order
+ * (alc/alu.cpp:799-889) —, the buffer's channel order and normalisation are folded in, and each
+ * mixed buffer channel becomes one non-HRTF voice whose dry/send gains are a row of that matrix.
+ * Only the buffer's leading channels up to the device's order are mixed (Voice::prepare,
+ * core/voice.cpp:1246-1248): returns that count ((o+1)^2, or 2*o+1 for 2D, o = min(source order,
+ * device order)) or < 0; B200MIX_ERR_UNSUPPORTED when the device
+ * mixes above the source's order, or mixes a 2D bed periphonically from second order on (the
+ * reference then up-samples and band-splits the source, alc/alu.cpp:1001-1036,
+ * core/voice.cpp:1082-1089). */
 typedef struct b200mix_bformat_setup {
     uint32_t struct_size;
     uint32_t is_2d;                     /* FmtBFormat2D (W, X, Y) instead of FmtBFormat3D */
     uint32_t layout;                    /* AmbiLayout: 0 FuMa, 1 ACN */
     uint32_t scaling;                   /* AmbiScaling: 0 FuMa, 1 SN3D, 2 N3D */
     uint32_t device_ambi_order;         /* DeviceBase::mAmbiOrder */
+    uint32_t source_ambi_order;         /* Voice::mAmbiOrder (AL_UNPACK_AMBISONIC_ORDER_SOFT), 1..4; 0 reads as 1 */
+    uint32_t device_2d_mixing;          /* DeviceBase::m2DMixing */
 } b200mix_bformat_setup;
 B200MIX_API int b200mix_calc_voice_bformat(const b200mix_source_props *props,
     const b200mix_listener_params *listener, const b200mix_voice_env *env, uint32_t buffer_rate,

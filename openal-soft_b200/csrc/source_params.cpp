@@ -292,6 +292,100 @@ int b200mix_calc_voice_channels(const b200mix_source_props *props, const b200mix
     return int(nch);
 }
 
+namespace {
+
+// Rotation of real spherical harmonics above first order: the Ivanic / Ruedenberg band recursion as
+// the reference evaluates it (AmbiRotator and RotatorCoeffs, alc/alu.cpp:709-889).  `R` holds the
+// first-order block on entry (ACN rows / columns 1..3 = m -1, 0, +1); band l (rows / columns
+// l*l .. l*l + 2l) is built from band l-1 and the first-order block.  Products and sums are taken in
+// the reference's order, so the matrix is the reference's bit for bit.
+struct BandRotator {
+    float (*R)[B200MIX_MAX_AMBI_CHANNELS];
+    int l;                       // band being built
+    unsigned prev;               // ACN index of band l-1's first row / column: (l-1)^2
+
+    // one term of the recursion: first-order column i (-1, 0, +1) against band l-1's column a, for row n of band l
+    float term(int i, int a, int n) const
+    {
+        const unsigned fc = unsigned(i + 2);
+        const unsigned col = prev + unsigned((l - 1) + a);
+        const unsigned lo = prev, hi = prev + unsigned(2*(l - 1));
+        if(n == -l) return R[3][fc]*R[lo][col] + R[1][fc]*R[hi][col];
+        if(n == l) return R[3][fc]*R[hi][col] - R[1][fc]*R[lo][col];
+        return R[2][fc]*R[prev + unsigned((l - 1) + n)][col];
+    }
+    float u_term(int m, int n) const { return term(0, m, n); }
+    float v_term(int m, int n) const
+    {
+        const float sqrt2 = 1.41421356237309504880f;
+        if(m > 0)
+        {
+            const float a = term(1, m - 1, n), b = term(-1, 1 - m, n);
+            return (m == 1) ? a*sqrt2 : (a - b);
+        }
+        const float a = term(1, m + 1, n), b = term(-1, -m - 1, n);
+        return (m == -1) ? b*sqrt2 : (a + b);
+    }
+    float w_term(int m, int n) const
+    {
+        if(m > 0) return term(1, m + 1, n) + term(-1, -m - 1, n);
+        return term(1, m - 1, n) - term(-1, 1 - m, n);
+    }
+};
+
+void rotate_higher_orders(float (*R)[B200MIX_MAX_AMBI_CHANNELS], int order)
+{
+    for(int l = 2;l <= order;++l)
+    {
+        const BandRotator B{R, l, unsigned((l - 1)*(l - 1))};
+        const unsigned base = unsigned(l*l);
+        for(int n = -l;n <= l;++n)
+        {
+            // Table I of the paper (alc/alu.cpp:727-772): evaluated in double, stored as float
+            const double denom = (n == l || n == -l) ? double((2*l)*(2*l - 1)) : double(l*l - n*n);
+            for(int m = -l;m <= l;++m)
+            {
+                float u, v, w;
+                if(m == 0)
+                {
+                    u = float(std::sqrt(l*l / denom));
+                    v = float(std::sqrt((l - 1)*l / denom) * -1.0);
+                    w = 0.0f;
+                }
+                else
+                {
+                    const int am = m < 0 ? -m : m;
+                    u = float(std::sqrt((l*l - m*m) / denom));
+                    v = float(std::sqrt((l + am - 1)*(l + am) / denom) * 0.5);
+                    w = float(std::sqrt((l - am - 1)*(l - am) / denom) * -0.5);
+                }
+                float r = 0.0f;
+                if(u != 0.0f) r += u * B.u_term(m, n);
+                if(v != 0.0f) r += v * B.v_term(m, n);
+                if(w != 0.0f) r += w * B.w_term(m, n);
+                R[base + unsigned(n + l)][base + unsigned(m + l)] = r;
+            }
+        }
+    }
+}
+
+// AmbiScale::FromFuMa / FromSN3D / FromN3D (core/ambidefs.h:49-124; FuMa is defined up to third order)
+const float kAmbiScaleTab[3][B200MIX_MAX_AMBI_CHANNELS] = {
+    {1.414213562f, 1.732050808f, 1.732050808f, 1.732050808f, 1.936491673f, 1.936491673f, 2.236067978f, 1.936491673f,
+     1.936491673f, 2.091650066f, 1.972026594f, 2.231093404f, 2.645751311f, 2.231093404f, 1.972026594f, 2.091650066f,
+     0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f},
+    {1.000000000f, 1.732050808f, 1.732050808f, 1.732050808f, 2.236067978f, 2.236067978f, 2.236067978f, 2.236067978f,
+     2.236067978f, 2.645751311f, 2.645751311f, 2.645751311f, 2.645751311f, 2.645751311f, 2.645751311f, 2.645751311f,
+     3.0f, 3.0f, 3.0f, 3.0f, 3.0f, 3.0f, 3.0f, 3.0f, 3.0f},
+    {1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f,
+     1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f}};
+// AmbiIndex::FromFuMa / FromFuMa2D / FromACN2D (core/ambidefs.h:143-190): buffer channel -> ACN
+const unsigned char kFromFuMa[16] = {0, 3, 1, 2, 6, 7, 5, 8, 4, 12, 13, 11, 14, 10, 15, 9};
+const unsigned char kFromFuMa2D[7] = {0, 3, 1, 8, 4, 15, 9};
+const unsigned char kFromACN2D[9] = {0, 1, 3, 4, 8, 9, 15, 16, 24};
+
+} // namespace
+
 int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_listener_params *listener,
     const b200mix_voice_env *env, uint32_t buffer_rate, const b200mix_bformat_setup *setup, uint32_t *step,
     float *dry_gains, float *send_gains, b200mix_voice_filter *filters)
@@ -302,7 +396,14 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
         || env->num_sends > B200MIX_MAX_SENDS || env->render_mode > 2u || !env->device_rate
         || setup->layout > 1u || setup->scaling > 2u || !env->dry.scale || !env->dry.index)
         return B200MIX_ERR_INVALID;
-    if(setup->device_ambi_order != 1u) return B200MIX_ERR_UNSUPPORTED;
+    const uint32_t srcOrder = setup->source_ambi_order ? setup->source_ambi_order : 1u;
+    const uint32_t devOrder = setup->device_ambi_order;
+    if(devOrder < 1u || devOrder > 4u || srcOrder > 4u || (setup->layout == 0u && srcOrder > 3u))
+        return B200MIX_ERR_INVALID;
+    // a device of higher order than the source (or a 2D bed on a 3D mix from second order on)
+    // up-samples and band-splits the voice (alc/alu.cpp:1001-1036, core/voice.cpp:1082-1089,1362-1385)
+    if(devOrder > srcOrder || (devOrder >= 2u && !setup->device_2d_mixing && setup->is_2d))
+        return B200MIX_ERR_UNSUPPORTED;
     const b200mix_source_props &P = *props;
 
     // CalcNonAttnVoiceParams (alc/alu.cpp:1658-1710)
@@ -318,17 +419,15 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
 
     // CalcAmbisonicPanning with no distance: coverage 1 (:946-949)
     const float coverage = 1.0f;
-    // AmbiScale::FromFuMa / FromSN3D / FromN3D, first order (core/ambidefs.h:33-92)
-    static const float scaleTab[3][4] = {
-        {1.414213562f, 1.732050808f, 1.732050808f, 1.732050808f},
-        {1.0f, 1.732050808f, 1.732050808f, 1.732050808f},
-        {1.0f, 1.0f, 1.0f, 1.0f}};
-    const float *scales = scaleTab[setup->scaling];
-    // AmbiIndex::FromFuMa / FromACN / FromFuMa2D / FromACN2D, first order
-    static const unsigned idx3d[2][4] = {{0, 3, 1, 2}, {0, 1, 2, 3}};
-    static const unsigned idx2d[2][3] = {{0, 3, 1}, {0, 1, 3}};
-    const unsigned nch = setup->is_2d ? 3u : 4u;
-    const unsigned *index_map = setup->is_2d ? idx2d[setup->layout] : idx3d[setup->layout];
+    const float *scales = kAmbiScaleTab[setup->scaling];
+    // the mixed channels in ACN terms: the buffer's leading channels up to the device's order
+    // (Voice::prepare, core/voice.cpp:1246-1248) — (order+1)^2 of them, 2*order+1 for a 2D bed
+    const uint32_t mixOrder = std::min(srcOrder, devOrder);
+    const unsigned nch = setup->is_2d ? 2u*mixOrder + 1u : (mixOrder + 1u)*(mixOrder + 1u);
+    unsigned index_map[B200MIX_MAX_AMBI_CHANNELS];
+    for(unsigned c = 0;c < nch;++c)
+        index_map[c] = setup->is_2d ? (setup->layout ? kFromACN2D[c] : kFromFuMa2D[c])
+            : (setup->layout ? c : kFromFuMa[c]);
 
     // the panned W term (:951-957), then scaled by (1 - coverage) (:1049-1050)
     float pan[B200MIX_MAX_AMBI_CHANNELS];
@@ -349,11 +448,14 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
     if(!P.head_relative) { N = mul(listener->matrix, N); V = mul(listener->matrix, V); }
     Vec U{{N.v[1]*V.v[2] - N.v[2]*V.v[1], N.v[2]*V.v[0] - N.v[0]*V.v[2], N.v[0]*V.v[1] - N.v[1]*V.v[0], 0.0f}};
     normalize(U);
-    float shrot[4][4] = {};
+    // the first-order block by hand, the bands above it up to the device's order by recursion (:992-999);
+    // bands the device does not mix stay zero
+    float shrot[B200MIX_MAX_AMBI_CHANNELS][B200MIX_MAX_AMBI_CHANNELS] = {};
     shrot[0][0] = 1.0f;
     shrot[1][1] =  U.v[0]; shrot[1][2] = -U.v[1]; shrot[1][3] =  U.v[2];
     shrot[2][1] = -V.v[0]; shrot[2][2] =  V.v[1]; shrot[2][3] = -V.v[2];
     shrot[3][1] = -N.v[0]; shrot[3][2] =  N.v[1]; shrot[3][3] = -N.v[2];
+    rotate_higher_orders(shrot, int(devOrder));
 
     const uint32_t nd = env->dry.channels;
     float coeffs[B200MIX_MAX_AMBI_CHANNELS];
@@ -363,7 +465,7 @@ int b200mix_calc_voice_bformat(const b200mix_source_props *props, const b200mix_
         const unsigned acn = index_map[c];
         const float scale = scales[acn] * coverage;
         for(unsigned k = 0;k < B200MIX_MAX_AMBI_CHANNELS;++k)
-            coeffs[k] = (k < 4u ? shrot[acn][k] : 0.0f)*scale + coeffs[k];
+            coeffs[k] = shrot[acn][k]*scale + coeffs[k];
         if(int rc = b200mix_pan_gains(nd, env->dry.scale, env->dry.index, coeffs, dryBase,
             dry_gains + size_t(c)*nd, nd)) return rc;
         if(send_gains && env->wet_stride)

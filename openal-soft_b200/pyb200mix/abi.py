@@ -281,4 +281,5 @@ class ChannelSetup(C.Structure):
 
 class BFormatSetup(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("is_2d", C.c_uint32), ("layout", C.c_uint32),
-                ("scaling", C.c_uint32), ("device_ambi_order", C.c_uint32)]
+                ("scaling", C.c_uint32), ("device_ambi_order", C.c_uint32),
+                ("source_ambi_order", C.c_uint32), ("device_2d_mixing", C.c_uint32)]

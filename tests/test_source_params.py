@@ -614,6 +614,129 @@ def test_calc_voice_bformat_first_order(devname):
         ref.close()
 
 
+@pytest.mark.parametrize("devname", ["stereo", "ambi2", "ambi3", "ambi4"])
+def test_calc_voice_bformat_higher_orders(devname):
+    """b200mix_calc_voice_bformat against live B-Format sources of order 2..4 (AL_SOFT_bformat_hoa: 3D
+    and 2D buffers, FuMa up to third order / ACN, every normalisation) on a first-order device and on
+    ALC_BFORMAT3D_SOFT devices of order 2, 3 and 4 — the bands above first order turned by the
+    recursion of AmbiRotator: every channel's dry and send gain rows and the step, bit for bit.
+    Beds the reference would up-sample (device above the source's order, 2D beds on a periphonic
+    mix from second order on) are refused."""
+    prod = mixlib.product().lib
+    prod.b200mix_calc_voice_bformat.argtypes = [C.POINTER(SourceProps), C.POINTER(ListenerParams), C.POINTER(VoiceEnv),
+                                                C.c_uint32, C.POINTER(BFormatSetup), C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+    _, hz = refal.libs()
+    hz.refh_listener_params.argtypes = [C.c_void_p, C.POINTER(ListenerParams)]
+    hz.refh_listener_params.restype = None
+    hz.refh_source_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(SourceProps), C.POINTER(C.c_uint32)]
+    hz.refh_device_render_mode.argtypes = [C.c_void_p]
+    hz.refh_device_ambi.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    hz.refh_device_ambi.restype = None
+    hz.refh_dry_ambi_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    hz.refh_slot_ambi_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1300)
+    dev_order = {"stereo": 1, "ambi2": 2, "ambi3": 3, "ambi4": 4}[devname]
+    a2 = {refal.ALC_HRTF_SOFT: 0, refal.ALC_STEREO_SOURCES: 16}
+    if dev_order > 1:
+        a2.update({refal.ALC_FORMAT_CHANNELS_SOFT: refal.ALC_BFORMAT3D_SOFT, refal.ALC_AMBISONIC_LAYOUT_SOFT: 1,
+                   refal.ALC_AMBISONIC_SCALING_SOFT: 2 if dev_order == 2 else 1, refal.ALC_AMBISONIC_ORDER_SOFT: dev_order})
+    ref, _ = scenes.make_ref_scene(0, 0, abi.RS_LINEAR, attrs=a2, max_sources=1)
+    try:
+        al = ref.al
+        al.alListenerfv.argtypes = [C.c_int, C.POINTER(C.c_float)]
+        al.alSourcefv.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_float)]
+        al.alBufferi.argtypes = [C.c_uint, C.c_int, C.c_int]
+        at = rng.standard_normal(3)
+        up = np.cross(np.cross(at, rng.standard_normal(3)), at)
+        al.alListenerfv(0x100F, (C.c_float * 6)(*[float(x) for x in np.concatenate([at, up])]))
+        slot = ref.add_reverb_slot()
+        # (order, 2D, layout, scaling): FuMa layouts stop at third order; 2D beds only where the mix is first order
+        combos = [(o, 0, layout, scaling) for o in range(max(dev_order, 2), 5) for layout in (0, 1) for scaling in (0, 1, 2)
+                  if not (layout == 0 and o > 3) and not (scaling == 0 and o > 3)]
+        if dev_order == 1:
+            combos += [(o, 1, layout, 1 + (o + layout) % 2) for o in (2, 3, 4) for layout in (0, 1) if not (layout == 0 and o > 3)]
+        for k, (o, is2d, layout, scaling) in enumerate(combos):
+            nch = 2 * o + 1 if is2d else (o + 1) ** 2
+            pcm = np.ascontiguousarray((rng.standard_normal((700, nch)) * 3000).astype(np.int16))
+            b = C.c_uint(0); s = C.c_uint(0)
+            al.alGenBuffers(1, C.byref(b))
+            al.alBufferi(b, 0x199D, o)                # AL_UNPACK_AMBISONIC_ORDER_SOFT
+            al.alBufferi(b, 0x1997, layout)           # AL_AMBISONIC_LAYOUT_SOFT
+            al.alBufferi(b, 0x1998, scaling)          # AL_AMBISONIC_SCALING_SOFT
+            al.alBufferData(b, 0x20022 if is2d else 0x20032, pcm.ctypes.data, pcm.nbytes, 32000)
+            assert al.alGetError() == 0, (o, is2d, layout, scaling)
+            al.alGenSources(1, C.byref(s))
+            al.alSourcei(s, refal.AL_BUFFER, b.value)
+            al.alSourcei(s, refal.AL_LOOPING, 1)
+            al.alSourcef(s, refal.AL_GAIN, float(rng.uniform(0.2, 1.2)))
+            al.alSourcef(s, refal.AL_PITCH, float(rng.uniform(0.5, 1.5)))
+            sat = rng.standard_normal(3)
+            sup = np.cross(np.cross(sat, rng.standard_normal(3)), sat)
+            al.alSourcefv(s, 0x100F, (C.c_float * 6)(*[float(x) for x in np.concatenate([sat, sup])]))
+            al.alSourcei(s, 0x202, k % 2)             # AL_SOURCE_RELATIVE
+            ref.buffers.append(b.value); ref.sources.append(s.value); ref._keep.append(pcm)
+            ref.connect_send(s.value, slot)
+        assert al.alGetError() == 0
+        ref.play_all()
+        ref.render(64)
+        nslots, wet = ref.slot_info()
+        lis = ListenerParams()
+        hz.refh_listener_params(ref.ctx, C.byref(lis))
+        order, is2d_dev, xover = C.c_uint32(0), C.c_uint32(0), C.c_float(0.0)
+        hz.refh_device_ambi(ref.dev, C.byref(order), C.byref(is2d_dev), C.byref(xover))
+        assert order.value == dev_order
+        dscale = np.zeros(32, dtype=np.float32); dindex = np.zeros(32, dtype=np.uint32)
+        nd = hz.refh_dry_ambi_map(ref.dev, dscale.ctypes.data, dindex.ctypes.data)
+        wscale = np.zeros(32, dtype=np.float32); windex = np.zeros(32, dtype=np.uint32)
+        nw = hz.refh_slot_ambi_map(ref.ctx, 0, wscale.ctypes.data, windex.ctypes.data)
+        ns = ref.desc.num_sends
+        env = VoiceEnv()
+        env.struct_size = C.sizeof(env)
+        env.device_rate, env.num_sends = ref.desc.sample_rate, ns
+        env.render_mode = hz.refh_device_render_mode(ref.dev)
+        env.wet_stride = nw
+        env.dry = MixMap(nd, dscale.ctypes.data, dindex.ctypes.data)
+        env.wet[0] = MixMap(nw, wscale.ctypes.data, windex.ctypes.data)
+        snaps = [ref.snapshot(wet_channels=wet[0], channel=c) for c in range(25)]
+        higher = 0.0
+        for k, (o, is2d, layout, scaling) in enumerate(combos):
+            sp = SourceProps()
+            brate = C.c_uint32(0)
+            assert hz.refh_source_props(ref.ctx, k, C.byref(sp), C.byref(brate)) == 0
+            setup = BFormatSetup(C.sizeof(BFormatSetup), is2d, layout, scaling, order.value, o, is2d_dev.value)
+            step = C.c_uint32(0)
+            dg = np.full((25, nd), 9.0, dtype=np.float32)
+            sg = np.full((25, ns, nw), 9.0, dtype=np.float32)
+            fl = (abi.VoiceFilter * (1 + abi.MAX_SENDS))()
+            rc = prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                                 C.byref(step), dg.ctypes.data, sg.ctypes.data, fl)
+            mo = min(o, dev_order)        # Voice::prepare mixes the leading channels up to the device's order
+            assert rc == (2 * mo + 1 if is2d else (mo + 1) ** 2), (rc, o, is2d, layout, scaling)
+            for c in range(rc):
+                n, params, coeffs, dry, send, _ = snaps[c]
+                assert step.value == params[k].step
+                assert np.array_equal(dg[c].view(np.uint32), dry[k].view(np.uint32)), ((o, is2d, layout, scaling), c, dg[c], dry[k])
+                assert np.array_equal(sg[c][0].view(np.uint32), send[k][0].view(np.uint32)), ((o, is2d, layout, scaling), c)
+            assert np.abs(dg[:rc]).max() > 0
+            if dev_order > 1 and not is2d:
+                higher = max(higher, float(np.abs(dg[4:(dev_order + 1) ** 2]).max()))
+        if dev_order > 1:
+            assert higher > 0.05          # the rotated higher bands reach the mix
+            # a first-order bed on this device is one the reference up-samples
+            setup = BFormatSetup(C.sizeof(BFormatSetup), 0, 1, 2, order.value, 1, is2d_dev.value)
+            assert prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                                   C.byref(step), dg.ctypes.data, sg.ctypes.data, fl) == -4
+            setup = BFormatSetup(C.sizeof(BFormatSetup), 1, 1, 2, order.value, dev_order, 0)
+            assert prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                                   C.byref(step), dg.ctypes.data, sg.ctypes.data, fl) == -4
+        # fourth-order FuMa does not exist
+        setup = BFormatSetup(C.sizeof(BFormatSetup), 0, 0, 0, order.value, 4, 0)
+        assert prod.b200mix_calc_voice_bformat(C.byref(sp), C.byref(lis), C.byref(env), brate.value, C.byref(setup),
+                                               C.byref(step), dg.ctypes.data, sg.ctypes.data, fl) == -1
+    finally:
+        ref.close()
+
+
 def test_calc_voices_batch_equals_the_single_calls():
     """b200mix_calc_voices (threaded batch) returns exactly what b200mix_calc_voice returns per source."""
     prod = mixlib.product().lib
